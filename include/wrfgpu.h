@@ -1,0 +1,183 @@
+/* wrfgpu.h -- C-ABI of the B200-native WRF-ARW dry dynamical-core step.
+ *
+ * This is the drop-in boundary for the reference's
+ *     SUBROUTINE solve_em ( grid , config_flags , <dummy_new_args.inc> )
+ * (dyn_em/solve_em.F:3-7, called from share/solve_interface.F:50-55).  The
+ * Fortran host binds these symbols with ISO_C_BINDING (see
+ * wrf_b200/fortran/module_wrfgpu.F90 and INTEGRATION.md); every signature
+ * uses plain pointers, ints and floats only.
+ *
+ * Conventions
+ *   - all arrays are real*4, WRF "XZY" memory order: 3-D (ims:ime,kms:kme,jms:jme)
+ *     i fastest, 2-D (ims:ime,jms:jme), 1-D (kms:kme)
+ *     (frame/module_driver_constants.F:15, dyn_em/module_em.F:68);
+ *   - host arrays stay owned by the caller (Fortran `grid%...`); the library
+ *     owns the device mirrors and never frees or reallocates host memory;
+ *   - every entry point returns 0 on success, non-zero on error; the message
+ *     is available from wrfgpu_last_error() and the Fortran shim turns it into
+ *     CALL wrf_error_fatal(msg) (frame/module_wrf_error.F);
+ *   - unsupported namelist values fail loudly at wrfgpu_create -- there is no
+ *     CPU fallback.
+ */
+#ifndef WRFGPU_H
+#define WRFGPU_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Index triplets of one domain on one rank: domain (ids..kde), memory
+ * (ims..kme) and patch (ips..kpe) dims, as returned by get_ijk_from_grid
+ * (dyn_em/solve_em.F:288-296).  The GPU build runs numtiles=1, so the tile
+ * (its..jte) equals the patch (SURVEY 8b "Threading"). */
+typedef struct wrfgpu_dims {
+  int ids, ide, jds, jde, kds, kde;
+  int ims, ime, jms, jme, kms, kme;
+  int ips, ipe, jps, jpe, kps, kpe;
+} wrfgpu_dims;
+
+/* The column of namelist.input / grid scalars the path reads
+ * (grid_config_rec_type, generated from Registry/Registry.EM_COMMON rconfig
+ * rows; flattened to PODs because config_flags cannot cross a C ABI). */
+typedef struct wrfgpu_config {
+  /* &bdy_control */
+  int periodic_x, periodic_y;
+  int symmetric_xs, symmetric_xe, symmetric_ys, symmetric_ye;
+  int open_xs, open_xe, open_ys, open_ye;
+  int specified, nested, polar;          /* must be 0: out of scope, rejected */
+  /* &dynamics */
+  int rk_ord;                            /* 3 (2 also accepted) */
+  int time_step_sound;                   /* 0 => derived, solve_em.F:446-462 */
+  int h_mom_adv_order, v_mom_adv_order;  /* 5 / 3 */
+  int h_sca_adv_order, v_sca_adv_order;  /* 5 / 3 */
+  int moist_adv_opt, scalar_adv_opt;     /* 0 = original, 1 = positive-definite
+                                            (Registry.EM_COMMON:3275-3279) */
+  int momentum_adv_opt;                  /* 1 */
+  int non_hydrostatic;                   /* 1 */
+  int top_lid;                           /* 0/1 */
+  int damp_opt;                          /* 0, 2 (rk_rayleigh_damp), 3 (implicit w) */
+  int w_damping;                         /* 0/1 */
+  int pert_coriolis;                     /* 0/1 */
+  int use_theta_m;                       /* 0/1 */
+  int hypsometric_opt;                   /* 1/2 */
+  int phi_adv_z;                         /* 1/2 */
+  int zadvect_implicit;                  /* must be 0 */
+  int diff_opt, km_opt;                  /* must be 0 on device */
+  int diff_6th_opt;                      /* must be 0 */
+  int mp_physics;                        /* 0 = none(passive qv), 1 = Kessler */
+  int time_step;                         /* integer namelist time_step; only its
+                                            sign is used (module_advect_em.F:204) */
+  int map_proj;                          /* 0 for ideal cases; 6 rejected */
+  float dt;                              /* grid%dt */
+  float dx, dy;                          /* rdx = 1/dx, rdy = 1/dy */
+  float epssm, smdiv, emdiv;
+  float dampcoef, zdamp;
+  float w_crit_cfl;
+  float p_top;
+  float cf1, cf2, cf3, cfn, cfn1;        /* Registry.EM_COMMON:405-407, 358-359 */
+  float khdif, kvdif;
+  /* species counts: moist = qv[,qc,qr]; scalar = generic passive species
+   * advected like scalar/tracer/chem (dyn_em/solve_em.F:2200-2955) */
+  int num_moist;                         /* 0..3 (without the WRF dummy slot 1) */
+  int num_scalar;                        /* 0..8 */
+  /* RSL_LITE process mesh (external/RSL_LITE/module_dm.F:98-175) */
+  int ntasks_x, ntasks_y, mytask;        /* mytask = mytask_y*ntasks_x + mytask_x */
+} wrfgpu_config;
+
+typedef struct wrfgpu_solver wrfgpu_solver;   /* opaque */
+
+/* -- life cycle ---------------------------------------------------------- */
+/* replaces alloc_and_configure_domain's role for the device mirrors
+ * (main/module_wrf_top.F:361) */
+int  wrfgpu_create (const wrfgpu_dims *d, const wrfgpu_config *c, int device,
+                    wrfgpu_solver **out);
+int  wrfgpu_destroy(wrfgpu_solver *s);
+const char *wrfgpu_last_error(void);
+int  wrfgpu_version(void);
+
+/* -- state transfer ------------------------------------------------------ */
+/* Registry names without the grid% prefix: "u_2","t_1","mu_2","phb","fnm",
+ * "moist_qv","moist_old_qv","scalar_1",...  (Registry/Registry.EM_COMMON:158-457).
+ * n = number of floats in the host buffer; must match the field's full memory
+ * extent.  wrfgpu_field_size returns that extent (0 if the name is unknown). */
+size_t wrfgpu_field_size(const wrfgpu_solver *s, const char *name);
+int  wrfgpu_set_field(wrfgpu_solver *s, const char *name, const float *host, size_t n);
+int  wrfgpu_get_field(wrfgpu_solver *s, const char *name, float *host, size_t n);
+/* pointer-table forms used by the Fortran shim (one call per solve_em) */
+int  wrfgpu_upload  (wrfgpu_solver *s, int nfields, const char *const *names,
+                     const float *const *host);
+int  wrfgpu_download(wrfgpu_solver *s, int nfields, const char *const *names,
+                     float *const *host);
+int  wrfgpu_num_fields(const wrfgpu_solver *s);
+const char *wrfgpu_field_name(const wrfgpu_solver *s, int idx);
+void *wrfgpu_field_devptr(wrfgpu_solver *s, const char *name);
+
+/* -- the hot path -------------------------------------------------------- */
+/* one model time step of one domain = dyn_em/solve_em.F:578-4848 with the
+ * state resident in HBM */
+int  wrfgpu_step(wrfgpu_solver *s, int nsteps);
+/* strict drop-in form: upload the prognostic set from host grid% arrays, run
+ * one solve_em, download it again (what wrf.exe sees when I/O needs host data
+ * every step).  `names/host` list the fields to move in each direction. */
+int  wrfgpu_solve_em(wrfgpu_solver *s,
+                     int n_in,  const char *const *in_names,  const float *const *in_host,
+                     int n_out, const char *const *out_names, float *const *out_host);
+int  wrfgpu_sync(wrfgpu_solver *s);
+/* number of kernels this library launched since create (bench "gpu_launches") */
+long long wrfgpu_launch_count(const wrfgpu_solver *s);
+/* cudaEvent timing of the kernels launched by phase `name` since the last
+ * reset, in ms (0 if unknown); reset with name == NULL */
+double wrfgpu_phase_ms(wrfgpu_solver *s, const char *name);
+
+/* -- per-routine entry points (kernel-level parity tests) --
+ * Each runs on the resident state, same semantics as the Fortran routine named
+ * in the comment with its=ips.. tile bounds. */
+int wrfgpu_rk_step_prep     (wrfgpu_solver *s, int rk_step);  /* module_em.F:37            */
+int wrfgpu_rk_phys_bc_dry_1 (wrfgpu_solver *s);               /* solve_em.F:726-754        */
+int wrfgpu_init_zero_tendency(wrfgpu_solver *s);              /* module_em.F:1920          */
+int wrfgpu_rk_tendency      (wrfgpu_solver *s, int rk_step);  /* module_em.F:190 + :959    */
+int wrfgpu_small_step_prep  (wrfgpu_solver *s, int rk_step);  /* module_small_step_em.F:16,
+                                                                 calc_p_rho(0) :438, calc_coef_w :570,
+                                                                 bc fills solve_em.F:1186-1263 */
+int wrfgpu_advance_uv       (wrfgpu_solver *s, int rk_step);  /* module_small_step_em.F:654 */
+int wrfgpu_advance_mu_t     (wrfgpu_solver *s, int rk_step);  /* :969  */
+int wrfgpu_advance_w        (wrfgpu_solver *s, int rk_step);  /* :1178 */
+int wrfgpu_sumflux          (wrfgpu_solver *s, int rk_step, int iteration); /* :1473 */
+int wrfgpu_calc_p_rho       (wrfgpu_solver *s, int iteration);/* :438 + bc fills solve_em.F:1670-1713 */
+int wrfgpu_small_step_finish(wrfgpu_solver *s, int rk_step);  /* calc_mu_uv_1 + :295 */
+int wrfgpu_rk_scalar_step   (wrfgpu_solver *s, int rk_step);  /* solve_em.F:1850-2955: update_scalar_pd,
+                                                                 rk_scalar_tend, rk_update_scalar */
+int wrfgpu_calc_p_rho_phi   (wrfgpu_solver *s);               /* module_big_step_utilities_em.F:953 */
+int wrfgpu_rk_phys_bc_dry_2 (wrfgpu_solver *s);               /* solve_em.F:3245-3343 */
+int wrfgpu_microphysics     (wrfgpu_solver *s);               /* solve_em.F:3629-4206 (Kessler) */
+int wrfgpu_end_of_step      (wrfgpu_solver *s);               /* solve_em.F:4437-4759 */
+/* one physical-BC fill, share/module_bc.F:202 (2-D) / :651 (3-D); `var` is the
+ * reference's one-letter stagger code */
+int wrfgpu_set_physical_bc  (wrfgpu_solver *s, const char *name, char var);
+
+/* -- decomposition + halo exchange (external/RSL_LITE) -------------------- */
+/* module_dm.F:98-175 mpaspect/compute_mesh */
+int wrfgpu_compute_mesh(int ntasks, int nproc_x, int nproc_y, int *ntasks_x, int *ntasks_y);
+/* task_for_point.c:6-14 + module_dm.F:924-1003: patch + memory dims of `mytask` */
+int wrfgpu_patch_dims(int ids, int ide, int jds, int jde, int kds, int kde,
+                      int ntasks_x, int ntasks_y, int mytask, wrfgpu_dims *out);
+/* NCCL bootstrap.  The 128-byte unique id is created on rank 0 and broadcast by
+ * the host (MPI_Bcast in wrf.exe, torch.distributed in bench.py). */
+int wrfgpu_comm_unique_id(void *id128);
+int wrfgpu_comm_init(wrfgpu_solver *s, const void *id128, int rank, int nranks);
+/* run one named Registry halo ("HALO_EM_A", "HALO_EM_D2_5", ...) on the
+ * resident state; no-op on a 1x1 mesh (Registry.EM_COMMON:3418-3551) */
+int wrfgpu_halo(wrfgpu_solver *s, const char *halo_name);
+/* pack/unpack index sets of one field for one direction, for CPU-side tests of
+ * the host logic: returns the strip bounds rsl_comm_iter would produce
+ * (module_dm.F:2761) in is,ie,js,je. dir: 0=-y 1=+y 2=-x 3=+x; send=1/recv=0 */
+int wrfgpu_halo_strip(const wrfgpu_dims *d, const wrfgpu_config *c, int width,
+                      int xstag, int ystag, int dir, int send,
+                      int *is, int *ie, int *js, int *je);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WRFGPU_H */

@@ -1,0 +1,197 @@
+// oracle.h -- CPU restatement of the WRF-ARW dry dynamical-core step.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs may load it, and only as the checker / CPU baseline.
+//
+// PARITY UNPINNED: the reference ships no golden outputs for this path
+//  and no Fortran compiler exists in the build container, so this
+// restatement could not be diffed against wrf.exe here.  It follows the
+// reference routine by routine (file:line cited on each function), in real*4,
+// Fortran evaluation order, compiled with -ffp-contract=off like the GNU stanza
+// of arch/configure.defaults:774-814 (no FMA).
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <stdexcept>
+#include "../include/wrfgpu.h"
+
+namespace orc {
+
+// share/module_model_constants.F:17-89
+constexpr float g = 9.81f;
+constexpr float r_d = 287.f;
+constexpr float cp = 7.f * r_d / 2.f;
+constexpr float r_v = 461.6f;
+constexpr float cv = cp - r_d;
+constexpr float cvpm = -cv / cp;
+constexpr float rcp = r_d / cp;
+constexpr float p1000mb = 100000.f;
+constexpr float t0 = 300.f;
+constexpr float p0 = p1000mb;
+constexpr float cpovcv = cp / (cp - r_d);
+constexpr float rvovrd = r_v / r_d;
+constexpr float reradius = 1.f / 6370.0e03f;
+constexpr float cb = 25.f;
+constexpr float xlv = 2.5e6f;
+constexpr float rhowater = 1000.f;
+constexpr float svp1 = 0.6112f, svp2 = 17.67f, svp3 = 29.65f, svpt0 = 273.15f;
+constexpr float ep_2 = r_d / r_v;
+constexpr float w_alpha = 0.3f, w_beta = 1.0f;
+
+// Fortran-style array views: (ims:ime,kms:kme,jms:jme), i fastest.
+struct A3 {
+  float *p = nullptr; int ims = 0, kms = 0, jms = 0; long sk = 0, sj = 0;
+  inline float &operator()(int i, int k, int j) const {
+    return p[(long)(i - ims) + (long)(k - kms) * sk + (long)(j - jms) * sj];
+  }
+};
+struct A2 {
+  float *p = nullptr; int ims = 0, jms = 0; long sj = 0;
+  inline float &operator()(int i, int j) const { return p[(long)(i - ims) + (long)(j - jms) * sj]; }
+};
+struct A1 {
+  float *p = nullptr; int kms = 0;
+  inline float &operator()(int k) const { return p[k - kms]; }
+};
+
+// Everything a model-layer routine receives besides its arrays: the three
+// index triplets, config_flags and the grid scalars.
+struct Cx {
+  int ids, ide, jds, jde, kds, kde;
+  int ims, ime, jms, jme, kms, kme;
+  int ips, ipe, jps, jpe;
+  int its, ite, jts, jte, kts, kte;
+  wrfgpu_config c;
+  float rdx, rdy, dt;
+  float cf1, cf2, cf3, cfn, cfn1;
+  int time_step;
+  // 1-D coefficient arrays (Registry.EM_COMMON:349-354, registry.hyb_coord)
+  A1 znu, znw, fnm, fnp, rdnw, rdn, dnw, dn;
+  A1 c1h, c2h, c1f, c2f, c3h, c4h, c3f, c4f;
+  A1 u_base, v_base, t_base, qv_base, z_base;
+  // 2-D map factors etc.
+  A2 msftx, msfty, msfux, msfuy, msfvx, msfvx_inv, msfvy, f, e, sina, cosa, ht;
+};
+
+inline float sign1(float a) { return std::copysign(1.0f, a); }  // SIGN(1.,a)
+
+struct Oracle {
+  wrfgpu_dims d;
+  wrfgpu_config c;
+  std::map<std::string, std::vector<float>> data;
+  std::map<std::string, int> kind;   // 3, 2, 1
+  std::vector<std::string> names;
+  Cx x;
+  int num_sound_steps = 0;
+  float dts = 0.f;
+  long n3, n2, n1;
+
+  Oracle(const wrfgpu_dims &d, const wrfgpu_config &c);
+  void add(const std::string &n, int kind);
+  A3 a3(const std::string &n);
+  A2 a2(const std::string &n);
+  A1 a1(const std::string &n);
+  void refresh_cx();
+
+  // solve_em pieces (oracle/solve_em.cpp)
+  void rk_step_prep(int rk_step);
+  void rk_phys_bc_dry_1();
+  void init_zero_tendency();
+  void rk_tendency(int rk_step);      // rk_tendency + rk_addtend_dry
+  void small_step_prep(int rk_step);  // + calc_p_rho(0) + calc_coef_w + bc fills
+  void advance_uv(int rk_step);
+  void advance_mu_t(int rk_step);
+  void advance_w(int rk_step);
+  void sumflux(int rk_step, int iteration);
+  void calc_p_rho(int iteration);     // + bc fills
+  void small_step_finish(int rk_step);
+  void rk_scalar_step(int rk_step);
+  void calc_p_rho_phi();
+  void rk_phys_bc_dry_2();
+  void microphysics();
+  void end_of_step();
+  void step();
+  void bc(const std::string &name, char var);
+  void rk_params(int rk_step, float &dt_rk, float &dts_rk, int &nsmall) const;
+};
+
+// ---- model-layer routines (signatures follow the Fortran dummy-arg roles) ----
+// big_step.cpp
+void calculate_full(const Cx &x, A2 rfield, A2 rfieldb, A2 rfieldp);
+void calc_mu_uv(const Cx &x, A2 mu, A2 mub, A2 muu, A2 muv);
+void calc_mu_uv_1(const Cx &x, A2 mu, A2 muu, A2 muv);
+void couple_momentum(const Cx &x, A2 muu, A3 ru, A3 u, A2 msfu, A2 muv, A3 rv, A3 v, A2 msfv,
+                     A2 msfv_inv, A2 mut, A3 rw, A3 w, A2 msft);
+void calc_ww_cp(const Cx &x, A3 u, A3 v, A2 mup, A2 mub, A3 ww);
+void calc_cq(const Cx &x, std::vector<A3> &moist, A3 cqu, A3 cqv, A3 cqw);
+void calc_alt(const Cx &x, A3 alt, A3 al, A3 alb);
+void calc_php(const Cx &x, A3 php, A3 ph, A3 phb);
+void calc_p_rho_phi(const Cx &x, std::vector<A3> &moist, A3 al, A3 alb, A2 mu, A2 muts, A3 ph,
+                    A3 phb, A3 p, A3 pb, A3 t);
+void zero_tend(const Cx &x, A3 tendency);
+void zero_tend2d(const Cx &x, A2 tendency);
+void rhs_ph(const Cx &x, A3 ph_tend, A3 u, A3 v, A3 ww, A3 ph, A3 ph_old, A3 phb, A3 w, A2 mut,
+            A2 muuf, A2 muvf);
+void horizontal_pressure_gradient(const Cx &x, A3 ru_tend, A3 rv_tend, A3 ph, A3 alt, A3 p, A3 pb,
+                                  A3 al, A3 php, A3 cqu, A3 cqv, A2 muu, A2 muv, A2 mu);
+void pg_buoy_w(const Cx &x, A3 rw_tend, A3 p, A3 cqw, A2 muf, A2 mubf);
+void w_damp(const Cx &x, A3 rw_tend, float &max_vert_cfl, float &max_horiz_cfl, A3 u, A3 v, A3 ww,
+            A3 w, A2 mut);
+void coriolis(const Cx &x, A3 ru, A3 rv, A3 rw, A3 ru_tend, A3 rv_tend, A3 rw_tend);
+void perturbation_coriolis(const Cx &x, A3 ru_in, A3 rv_in, A3 rw, A3 ru_tend, A3 rv_tend,
+                           A3 rw_tend, A2 muu, A2 muv, A3 phb, A3 ph);
+void curvature(const Cx &x, A3 ru, A3 rv, A3 rw, A3 u, A3 v, A3 w, A3 ru_tend, A3 rv_tend,
+               A3 rw_tend);
+void rk_rayleigh_damp(const Cx &x, A3 ru_tendf, A3 rv_tendf, A3 rw_tendf, A3 t_tendf, A3 u, A3 v,
+                      A3 w, A3 t, A2 mut, A2 muu, A2 muv, A3 ph, A3 phb);
+void rk_addtend_dry(const Cx &x, A3 ru_tend, A3 rv_tend, A3 rw_tend, A3 ph_tend, A3 t_tend,
+                    A3 ru_tendf, A3 rv_tendf, A3 rw_tendf, A3 ph_tendf, A3 t_tendf, A3 u_save,
+                    A3 v_save, A3 w_save, A3 ph_save, A3 t_save, A2 mu_tend, A2 mu_tendf,
+                    int rk_step, A3 h_diabatic, A2 mut);
+void ww_split(const Cx &x, A3 wwE, A3 wwI, A3 ww);
+void set_w_surface(const Cx &x, A3 w, A3 u, A3 v);
+// advect.cpp
+void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut);
+void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut);
+void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut);
+void advect_scalar(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut);
+void advect_scalar_pd(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom,
+                      A2 mut, A2 mub, A2 mu_old, float dt);
+// small_step.cpp
+void small_step_prep(const Cx &x, A3 u_1, A3 u_2, A3 v_1, A3 v_2, A3 w_1, A3 w_2, A3 t_1, A3 t_2,
+                     A3 ph_1, A3 ph_2, A2 mub, A2 mu_1, A2 mu_2, A2 muu, A2 muus, A2 muv, A2 muvs,
+                     A2 mut, A2 muts, A2 mudf, A3 u_save, A3 v_save, A3 w_save, A3 t_save,
+                     A3 ph_save, A2 mu_save, A3 ww, A3 ww_save, A3 c2a, A3 pb, A3 p, A3 alt,
+                     int rk_step);
+void small_step_finish(const Cx &x, A3 u_2, A3 u_1, A3 v_2, A3 v_1, A3 w_2, A3 w_1, A3 t_2, A3 t_1,
+                       A3 ph_2, A3 ph_1, A3 ww, A3 ww1, A2 mu_2, A2 mu_1, A2 mut, A2 muts, A2 muu,
+                       A2 muus, A2 muv, A2 muvs, A3 u_save, A3 v_save, A3 w_save, A3 t_save,
+                       A3 ph_save, A2 mu_save, A3 h_diabatic, int number_of_small_timesteps,
+                       float dts, int rk_step, int rk_order);
+void calc_p_rho(const Cx &x, A3 al, A3 p, A3 ph, A3 alt, A3 t_2, A3 t_1, A3 c2a, A3 pm1, A2 mu,
+                A2 mut, float smdiv, int step);
+void calc_coef_w(const Cx &x, A3 a, A3 alpha, A3 gamma, A2 mut, A3 cqw, A3 c2a, float dts,
+                 float epssm);
+void advance_uv(const Cx &x, A3 u, A3 ru_tend, A3 v, A3 rv_tend, A3 p, A3 pb, A3 ph, A3 php,
+                A3 alt, A3 al, A2 mu, A2 muu, A3 cqu, A2 muv, A3 cqv, A2 mudf, float dts);
+void advance_mu_t(const Cx &x, A3 ww, A3 ww_1, A3 u, A3 u_1, A3 v, A3 v_1, A2 mu, A2 mut,
+                  A2 muave, A2 muts, A2 muu, A2 muv, A2 mudf, A3 t, A3 t_1, A3 t_ave, A3 ft,
+                  A2 mu_tend, float dts, float epssm);
+void advance_w(const Cx &x, A3 w, A3 rw_tend, A3 ww, A3 w_save, A3 u, A3 v, A2 mu1, A2 mut,
+               A2 muave, A2 muts, A3 t_2ave, A3 t_2, A3 t_1, A3 ph, A3 ph_1, A3 phb, A3 ph_tend,
+               A3 c2a, A3 cqw, A3 alt, A3 a, A3 alpha, A3 gamma, float dts, float epssm);
+void sumflux(const Cx &x, A3 ru, A3 rv, A3 ww, A3 u_lin, A3 v_lin, A3 ww_lin, A2 muu, A2 muv,
+             A3 ru_m, A3 rv_m, A3 ww_m, int iteration, int number_of_small_timesteps);
+// bc.cpp
+void set_physical_bc3d(const Cx &x, A3 dat, char variable_in);
+void set_physical_bc2d(const Cx &x, A2 dat, char variable_in);
+// kessler.cpp
+void kessler(const Cx &x, A3 t, A3 qv, A3 qc, A3 qr, A3 rho, A3 pii, float dt_in, A3 z, A3 dz8w,
+             A2 rainnc, A2 rainncv);
+
+}  // namespace orc

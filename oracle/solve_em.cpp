@@ -1,0 +1,492 @@
+// solve_em.cpp -- oracle restatement of the sequencing in dyn_em/solve_em.F
+// (:578-4848) and dyn_em/module_em.F (rk_step_prep :37, rk_tendency :190,
+// rk_scalar_tend :1096, rk_update_scalar :1587, rk_update_scalar_pd :1803), plus
+// the C entry points the tests bind with ctypes.
+// Test infrastructure only; see oracle.h header.
+#include "oracle.h"
+#include <cstdio>
+namespace orc {
+
+static const char *k3d[] = {
+    "u_1", "u_2", "v_1", "v_2", "w_1", "w_2", "t_1", "t_2", "ph_1", "ph_2",
+    "phb", "pb", "alb", "p", "al", "alt", "php", "ru", "rv", "rw", "ww",
+    "ru_m", "rv_m", "ww_m", "ru_tend", "rv_tend", "u_save", "v_save", "t_save", "h_diabatic",
+    "ru_tendf", "rv_tendf", "rw_tend", "rw_tendf", "w_save", "ww1", "wwE", "wwI",
+    "ph_tend", "ph_tendf", "ph_save", "t_tend", "t_tendf", "t_2save", "advect_tend",
+    "alpha", "a", "gamma", "c2a", "cqu", "cqv", "cqw", "pm1",
+    "rho", "th_phy", "pi_phy", "p_phy", "z", "z_at_w", "dz8w", "qv_diabatic", "qc_diabatic", nullptr};
+static const char *k2d[] = {"mu_1", "mu_2", "mub", "mudf", "muu", "muus", "muv", "muvs", "mut", "muts",
+                            "muave", "mu_save", "mu_tend", "mu_tendf",
+                            "msftx", "msfty", "msfux", "msfuy", "msfvx", "msfvx_inv", "msfvy",
+                            "f", "e", "sina", "cosa", "ht", "rainnc", "rainncv", nullptr};
+static const char *k1d[] = {"znu", "znw", "fnm", "fnp", "rdnw", "rdn", "dnw", "dn",
+                            "c1h", "c2h", "c1f", "c2f", "c3h", "c4h", "c3f", "c4f",
+                            "u_base", "v_base", "t_base", "qv_base", "z_base", nullptr};
+static const char *moist_names[] = {"qv", "qc", "qr"};
+
+Oracle::Oracle(const wrfgpu_dims &d_, const wrfgpu_config &c_) : d(d_), c(c_) {
+  n1 = d.kme - d.kms + 1;
+  n2 = (long)(d.ime - d.ims + 1) * (d.jme - d.jms + 1);
+  n3 = n2 * n1;
+  for (int i = 0; k3d[i]; i++) add(k3d[i], 3);
+  for (int i = 0; k2d[i]; i++) add(k2d[i], 2);
+  for (int i = 0; k1d[i]; i++) add(k1d[i], 1);
+  for (int s = 0; s < c.num_moist; s++) {
+    add(std::string("moist_") + moist_names[s], 3);
+    add(std::string("moist_old_") + moist_names[s], 3);
+    add(std::string("moist_tend_") + moist_names[s], 3);
+  }
+  for (int s = 1; s <= c.num_scalar; s++) {
+    add("scalar_" + std::to_string(s), 3);
+    add("scalar_old_" + std::to_string(s), 3);
+    add("scalar_tend_" + std::to_string(s), 3);
+  }
+  // harmless defaults so that an un-set map factor does not divide by zero
+  for (const char *m : {"msftx", "msfty", "msfux", "msfuy", "msfvx", "msfvx_inv", "msfvy"})
+    std::fill(data[m].begin(), data[m].end(), 1.f);
+  if (c.time_step_sound == 0) {
+    float spacing = std::min(c.dx, c.dy);
+    num_sound_steps = std::max(2 * ((int)(300.f * c.dt / spacing - 0.01f) + 1), 4);
+  } else {
+    num_sound_steps = c.time_step_sound;
+  }
+  dts = c.dt / (float)num_sound_steps;
+  refresh_cx();
+}
+
+void Oracle::add(const std::string &n, int k) {
+  names.push_back(n);
+  kind[n] = k;
+  data[n].assign(k == 3 ? n3 : (k == 2 ? n2 : n1), 0.f);
+}
+A3 Oracle::a3(const std::string &n) {
+  auto it = data.find(n);
+  if (it == data.end() || kind[n] != 3) throw std::runtime_error("oracle: no 3-D field " + n);
+  A3 a; a.p = it->second.data(); a.ims = d.ims; a.kms = d.kms; a.jms = d.jms;
+  a.sk = d.ime - d.ims + 1; a.sj = a.sk * (d.kme - d.kms + 1);
+  return a;
+}
+A2 Oracle::a2(const std::string &n) {
+  auto it = data.find(n);
+  if (it == data.end() || kind[n] != 2) throw std::runtime_error("oracle: no 2-D field " + n);
+  A2 a; a.p = it->second.data(); a.ims = d.ims; a.jms = d.jms; a.sj = d.ime - d.ims + 1;
+  return a;
+}
+A1 Oracle::a1(const std::string &n) {
+  auto it = data.find(n);
+  if (it == data.end() || kind[n] != 1) throw std::runtime_error("oracle: no 1-D field " + n);
+  A1 a; a.p = it->second.data(); a.kms = d.kms;
+  return a;
+}
+
+void Oracle::refresh_cx() {
+  x.ids = d.ids; x.ide = d.ide; x.jds = d.jds; x.jde = d.jde; x.kds = d.kds; x.kde = d.kde;
+  x.ims = d.ims; x.ime = d.ime; x.jms = d.jms; x.jme = d.jme; x.kms = d.kms; x.kme = d.kme;
+  x.ips = d.ips; x.ipe = d.ipe; x.jps = d.jps; x.jpe = d.jpe;
+  x.its = d.ips; x.ite = d.ipe; x.jts = d.jps; x.jte = d.jpe; x.kts = d.kds; x.kte = d.kde;
+  x.c = c;
+  x.rdx = 1.f / c.dx; x.rdy = 1.f / c.dy; x.dt = c.dt;
+  x.cf1 = c.cf1; x.cf2 = c.cf2; x.cf3 = c.cf3; x.cfn = c.cfn; x.cfn1 = c.cfn1;
+  x.time_step = c.time_step;
+  x.znu = a1("znu"); x.znw = a1("znw"); x.fnm = a1("fnm"); x.fnp = a1("fnp");
+  x.rdnw = a1("rdnw"); x.rdn = a1("rdn"); x.dnw = a1("dnw"); x.dn = a1("dn");
+  x.c1h = a1("c1h"); x.c2h = a1("c2h"); x.c1f = a1("c1f"); x.c2f = a1("c2f");
+  x.c3h = a1("c3h"); x.c4h = a1("c4h"); x.c3f = a1("c3f"); x.c4f = a1("c4f");
+  x.u_base = a1("u_base"); x.v_base = a1("v_base"); x.t_base = a1("t_base");
+  x.qv_base = a1("qv_base"); x.z_base = a1("z_base");
+  x.msftx = a2("msftx"); x.msfty = a2("msfty"); x.msfux = a2("msfux"); x.msfuy = a2("msfuy");
+  x.msfvx = a2("msfvx"); x.msfvx_inv = a2("msfvx_inv"); x.msfvy = a2("msfvy");
+  x.f = a2("f"); x.e = a2("e"); x.sina = a2("sina"); x.cosa = a2("cosa"); x.ht = a2("ht");
+}
+
+void Oracle::bc(const std::string &name, char var) {
+  if (kind.at(name) == 3) set_physical_bc3d(x, a3(name), var);
+  else set_physical_bc2d(x, a2(name), var);
+}
+
+// solve_em.F:585-615
+void Oracle::rk_params(int rk_step, float &dt_rk, float &dts_rk, int &nsmall) const {
+  const int rk_order = c.rk_ord;
+  if (rk_order == 2) {
+    if (rk_step == 1) { dt_rk = 0.5f * c.dt; dts_rk = dts; nsmall = num_sound_steps / 2; }
+    else { dt_rk = c.dt; dts_rk = dts; nsmall = num_sound_steps; }
+  } else {
+    if (rk_step == 1) { dt_rk = c.dt / 3.f; dts_rk = dt_rk; nsmall = 1; }
+    else if (rk_step == 2) { dt_rk = 0.5f * c.dt; dts_rk = dts; nsmall = num_sound_steps / 2; }
+    else { dt_rk = c.dt; dts_rk = dts; nsmall = num_sound_steps; }
+  }
+}
+
+static std::vector<A3> moist_list(Oracle &o, const char *prefix) {
+  std::vector<A3> v;
+  for (int s = 0; s < o.c.num_moist; s++) v.push_back(o.a3(std::string(prefix) + moist_names[s]));
+  return v;
+}
+
+// module_em.F:37-186
+void Oracle::rk_step_prep(int) {
+  calculate_full(x, a2("mut"), a2("mub"), a2("mu_2"));
+  calc_mu_uv(x, a2("mu_2"), a2("mub"), a2("muu"), a2("muv"));
+  couple_momentum(x, a2("muu"), a3("ru"), a3("u_2"), x.msfuy, a2("muv"), a3("rv"), a3("v_2"), x.msfvx, x.msfvx_inv,
+                  a2("mut"), a3("rw"), a3("w_2"), x.msfty);
+  calc_ww_cp(x, a3("u_2"), a3("v_2"), a2("mu_2"), a2("mub"), a3("ww"));
+  auto m = moist_list(*this, "moist_");
+  calc_cq(x, m, a3("cqu"), a3("cqv"), a3("cqw"));
+  calc_alt(x, a3("alt"), a3("al"), a3("alb"));
+  calc_php(x, a3("php"), a3("ph_2"), a3("phb"));
+}
+
+// solve_em.F:726-754 (+ rk_phys_bc_dry_1, module_bc_em.F:960-1041)
+void Oracle::rk_phys_bc_dry_1() {
+  bc("ru", 'u'); bc("rv", 'v'); bc("rw", 'w'); bc("ww", 'w'); bc("php", 'w'); bc("alt", 't'); bc("p", 'p');
+  bc("muu", 'u'); bc("muv", 'v'); bc("mut", 't');
+  bc("rho", 'p'); bc("al", 'p'); bc("ph_2", 'w');
+}
+
+// module_em.F:1920 init_zero_tendency (called from first_rk_step_part1)
+void Oracle::init_zero_tendency() {
+  for (const char *n : {"ru_tendf", "rv_tendf", "rw_tendf", "ph_tendf", "t_tendf"}) zero_tend(x, a3(n));
+  zero_tend2d(x, a2("mu_tendf"));
+  for (int s = 0; s < c.num_moist; s++) zero_tend(x, a3(std::string("moist_tend_") + moist_names[s]));
+  for (int s = 1; s <= c.num_scalar; s++) zero_tend(x, a3("scalar_tend_" + std::to_string(s)));
+}
+
+// module_em.F:190-955 rk_tendency followed by rk_addtend_dry (solve_em.F:881-1007)
+void Oracle::rk_tendency(int rk_step) {
+  A3 ru_tend = a3("ru_tend"), rv_tend = a3("rv_tend"), rw_tend = a3("rw_tend"), ph_tend = a3("ph_tend"), t_tend = a3("t_tend");
+  A3 u = a3("u_2"), v = a3("v_2"), w = a3("w_2"), t = a3("t_2"), ph = a3("ph_2");
+  A3 ru = a3("ru"), rv = a3("rv"), rw = a3("rw"), ww = a3("ww"), wwE = a3("wwE"), wwI = a3("wwI");
+  A2 mut = a2("mut"), muu = a2("muu"), muv = a2("muv"), mu = a2("mu_2"), mub = a2("mub");
+  for (A3 z : {ru_tend, rv_tend, rw_tend, t_tend, ph_tend, a3("u_save"), a3("v_save"), a3("w_save"), a3("ph_save"), a3("t_save")})
+    zero_tend(x, z);
+  zero_tend2d(x, a2("mu_tend"));
+  zero_tend2d(x, a2("mu_save"));
+  ww_split(x, wwE, wwI, ww);
+  advect_u(x, u, u, ru_tend, ru, rv, wwE, mut);
+  advect_v(x, v, v, rv_tend, ru, rv, wwE, mut);
+  advect_w(x, w, w, rw_tend, ru, rv, wwE, mut);
+  advect_scalar(x, t, t, t_tend, ru, rv, wwE, mut);
+  rhs_ph(x, ph_tend, u, v, wwE, ph, ph, a3("phb"), w, mut, muu, muv);
+  horizontal_pressure_gradient(x, ru_tend, rv_tend, ph, a3("alt"), a3("p"), a3("pb"), a3("al"), a3("php"), a3("cqu"), a3("cqv"), muu, muv, mu);
+  pg_buoy_w(x, rw_tend, a3("p"), a3("cqw"), mu, mub);
+  float mv, mh;
+  w_damp(x, rw_tend, mv, mh, u, v, ww, w, mut);
+  if (c.pert_coriolis) perturbation_coriolis(x, ru, rv, rw, ru_tend, rv_tend, rw_tend, muu, muv, a3("phb"), ph);
+  else coriolis(x, ru, rv, rw, ru_tend, rv_tend, rw_tend);
+  curvature(x, ru, rv, rw, u, v, w, ru_tend, rv_tend, rw_tend);
+  if (rk_step == 1 && c.damp_opt == 2)
+    rk_rayleigh_damp(x, a3("ru_tendf"), a3("rv_tendf"), a3("rw_tendf"), a3("t_tendf"), u, v, w, t, mut, muu, muv, ph, a3("phb"));
+  rk_addtend_dry(x, ru_tend, rv_tend, rw_tend, ph_tend, t_tend, a3("ru_tendf"), a3("rv_tendf"), a3("rw_tendf"), a3("ph_tendf"),
+                 a3("t_tendf"), a3("u_save"), a3("v_save"), a3("w_save"), a3("ph_save"), a3("t_save"), a2("mu_tend"), a2("mu_tendf"),
+                 rk_step, a3("h_diabatic"), mut);
+}
+
+// solve_em.F:1089-1263
+void Oracle::small_step_prep(int rk_step) {
+  float dt_rk, dts_rk; int ns;
+  rk_params(rk_step, dt_rk, dts_rk, ns);
+  orc::small_step_prep(x, a3("u_1"), a3("u_2"), a3("v_1"), a3("v_2"), a3("w_1"), a3("w_2"), a3("t_1"), a3("t_2"), a3("ph_1"), a3("ph_2"),
+                       a2("mub"), a2("mu_1"), a2("mu_2"), a2("muu"), a2("muus"), a2("muv"), a2("muvs"), a2("mut"), a2("muts"), a2("mudf"),
+                       a3("u_save"), a3("v_save"), a3("w_save"), a3("t_save"), a3("ph_save"), a2("mu_save"), a3("ww"), a3("ww1"),
+                       a3("c2a"), a3("pb"), a3("p"), a3("alt"), rk_step);
+  orc::calc_p_rho(x, a3("al"), a3("p"), a3("ph_2"), a3("alt"), a3("t_2"), a3("t_save"), a3("c2a"), a3("pm1"), a2("mu_2"), a2("muts"),
+                  c.smdiv, 0);
+  calc_coef_w(x, a3("a"), a3("alpha"), a3("gamma"), a2("mut"), a3("cqw"), a3("c2a"), dts_rk, c.epssm);
+  bc("ru_tend", 'u'); bc("rv_tend", 'v'); bc("ph_2", 'w'); bc("al", 'p'); bc("p", 'p'); bc("t_1", 'p'); bc("t_save", 't');
+  bc("mu_1", 't'); bc("mu_2", 't'); bc("mudf", 't');
+}
+
+void Oracle::advance_uv(int rk_step) {
+  float dt_rk, dts_rk; int ns;
+  rk_params(rk_step, dt_rk, dts_rk, ns);
+  orc::advance_uv(x, a3("u_2"), a3("ru_tend"), a3("v_2"), a3("rv_tend"), a3("p"), a3("pb"), a3("ph_2"), a3("php"), a3("alt"), a3("al"),
+                  a2("mu_2"), a2("muu"), a3("cqu"), a2("muv"), a3("cqv"), a2("mudf"), dts_rk);
+}
+void Oracle::advance_mu_t(int rk_step) {
+  float dt_rk, dts_rk; int ns;
+  rk_params(rk_step, dt_rk, dts_rk, ns);
+  orc::advance_mu_t(x, a3("ww"), a3("ww1"), a3("u_2"), a3("u_save"), a3("v_2"), a3("v_save"), a2("mu_2"), a2("mut"), a2("muave"),
+                    a2("muts"), a2("muu"), a2("muv"), a2("mudf"), a3("t_2"), a3("t_save"), a3("t_2save"), a3("t_tend"), a2("mu_tend"),
+                    dts_rk, c.epssm);
+}
+void Oracle::advance_w(int rk_step) {
+  float dt_rk, dts_rk; int ns;
+  rk_params(rk_step, dt_rk, dts_rk, ns);
+  orc::advance_w(x, a3("w_2"), a3("rw_tend"), a3("ww"), a3("w_save"), a3("u_2"), a3("v_2"), a2("mu_2"), a2("mut"), a2("muave"), a2("muts"),
+                 a3("t_2save"), a3("t_2"), a3("t_save"), a3("ph_2"), a3("ph_save"), a3("phb"), a3("ph_tend"), a3("c2a"), a3("cqw"),
+                 a3("alt"), a3("a"), a3("alpha"), a3("gamma"), dts_rk, c.epssm);
+}
+void Oracle::sumflux(int rk_step, int iteration) {
+  float dt_rk, dts_rk; int ns;
+  rk_params(rk_step, dt_rk, dts_rk, ns);
+  orc::sumflux(x, a3("u_2"), a3("v_2"), a3("ww"), a3("u_save"), a3("v_save"), a3("ww1"), a2("muu"), a2("muv"), a3("ru_m"), a3("rv_m"),
+               a3("ww_m"), iteration, ns);
+}
+void Oracle::calc_p_rho(int iteration) {
+  orc::calc_p_rho(x, a3("al"), a3("p"), a3("ph_2"), a3("alt"), a3("t_2"), a3("t_save"), a3("c2a"), a3("pm1"), a2("mu_2"), a2("muts"),
+                  c.smdiv, iteration);
+  bc("ph_2", 'w'); bc("al", 'p'); bc("p", 'p'); bc("muts", 't'); bc("mu_2", 't'); bc("mudf", 't');
+}
+// solve_em.F:1732-1800
+void Oracle::small_step_finish(int rk_step) {
+  float dt_rk, dts_rk; int ns;
+  rk_params(rk_step, dt_rk, dts_rk, ns);
+  calc_mu_uv_1(x, a2("muts"), a2("muus"), a2("muvs"));
+  orc::small_step_finish(x, a3("u_2"), a3("u_1"), a3("v_2"), a3("v_1"), a3("w_2"), a3("w_1"), a3("t_2"), a3("t_1"), a3("ph_2"), a3("ph_1"),
+                         a3("ww"), a3("ww1"), a2("mu_2"), a2("mu_1"), a2("mut"), a2("muts"), a2("muu"), a2("muus"), a2("muv"), a2("muvs"),
+                         a3("u_save"), a3("v_save"), a3("w_save"), a3("t_save"), a3("ph_save"), a2("mu_save"), a3("h_diabatic"), ns,
+                         dts_rk, rk_step, c.rk_ord);
+  if (rk_step == c.rk_ord) {
+    bc("ru_m", 'u'); bc("rv_m", 'v'); bc("ww_m", 'w'); bc("mut", 't'); bc("muts", 't');
+  }
+}
+
+// module_em.F:1803-1916
+static void rk_update_scalar_pd(const Cx &x, A3 scalar, A3 sc_tend, A2 mu_old, A2 mu_new, A2 mu_base, float dt) {
+  const int itf = std::min(x.ite, x.ide - 1), jtf = std::min(x.jte, x.jde - 1), ktf = std::min(x.kte, x.kde - 1);
+  for (int j = x.jts; j <= jtf; j++)
+    for (int k = x.kts; k <= ktf; k++)
+      for (int i = x.its; i <= itf; i++) {
+        float tendency = 0.f;
+        tendency = tendency + sc_tend(i, k, j);
+        sc_tend(i, k, j) = 0.f;
+        float muold = mu_old(i, j) + mu_base(i, j), munew = mu_new(i, j) + mu_base(i, j);
+        scalar(i, k, j) = ((x.c1h(k) * muold + x.c2h(k)) * scalar(i, k, j) + dt * tendency) / (x.c1h(k) * munew + x.c2h(k));
+      }
+}
+// module_em.F:1587-1799
+static void rk_update_scalar(const Cx &x, A3 scalar_1, A3 scalar_2, A3 sc_tend, A3 advect_tend, A2 mu_old, A2 mu_new, A2 mu_base,
+                             int rk_step, float dt) {
+  const int itf = std::min(x.ite, x.ide - 1), jtf = std::min(x.jte, x.jde - 1), ktf = std::min(x.kte, x.kde - 1);
+  for (int j = x.jts; j <= jtf; j++)
+    for (int k = x.kts; k <= ktf; k++)
+      for (int i = x.its; i <= itf; i++) {
+        float tendency = advect_tend(i, k, j) * x.msfty(i, j);
+        tendency = tendency + sc_tend(i, k, j);
+        float muold = mu_old(i, j) + mu_base(i, j), munew = mu_new(i, j) + mu_base(i, j);
+        if (rk_step == 1) scalar_1(i, k, j) = scalar_2(i, k, j);
+        scalar_2(i, k, j) = ((x.c1h(k) * muold + x.c2h(k)) * scalar_1(i, k, j) + dt * tendency) / (x.c1h(k) * munew + x.c2h(k));
+      }
+}
+
+// solve_em.F:1850-2955 (moist + generic scalar loops)
+void Oracle::rk_scalar_step(int rk_step) {
+  float dt_rk, dts_rk; int ns;
+  rk_params(rk_step, dt_rk, dts_rk, ns);
+  const int rk_order = c.rk_ord;
+  struct Sp { std::string f, o, t; int adv_opt; };
+  std::vector<Sp> sp;
+  for (int s = 0; s < c.num_moist; s++)
+    sp.push_back({std::string("moist_") + moist_names[s], std::string("moist_old_") + moist_names[s],
+                  std::string("moist_tend_") + moist_names[s], c.moist_adv_opt});
+  for (int s = 1; s <= c.num_scalar; s++)
+    sp.push_back({"scalar_" + std::to_string(s), "scalar_old_" + std::to_string(s), "scalar_tend_" + std::to_string(s), c.scalar_adv_opt});
+  if (rk_step == rk_order)
+    for (auto &s : sp)
+      if (s.adv_opt == 1) rk_update_scalar_pd(x, a3(s.o), a3(s.t), a2("mu_1"), a2("mu_1"), a2("mub"), dt_rk);
+  if (rk_step == rk_order)
+    for (auto &s : sp)
+      if (s.adv_opt == 1) bc(s.o, 'p');
+  for (auto &s : sp) {
+    // rk_scalar_tend, module_em.F:1096-1442
+    ww_split(x, a3("wwE"), a3("wwI"), a3("ww_m"));
+    zero_tend(x, a3("advect_tend"));
+    if (rk_step == rk_order && s.adv_opt == 1)
+      advect_scalar_pd(x, a3(s.f), a3(s.o), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE"), a2("muts"), a2("mub"), a2("mu_1"), dt_rk);
+    else
+      advect_scalar(x, a3(s.f), a3(s.f), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE"), a2("muts"));
+    rk_update_scalar(x, a3(s.o), a3(s.f), a3(s.t), a3("advect_tend"), a2("mu_1"), a2("mu_2"), a2("mub"), rk_step, dt_rk);
+  }
+}
+
+void Oracle::calc_p_rho_phi() {
+  auto m = moist_list(*this, "moist_");
+  orc::calc_p_rho_phi(x, m, a3("al"), a3("alb"), a2("mu_2"), a2("muts"), a3("ph_2"), a3("phb"), a3("p"), a3("pb"), a3("t_2"));
+}
+
+// solve_em.F:3245-3343 (rk_phys_bc_dry_2, module_bc_em.F:1045-1104, + species)
+void Oracle::rk_phys_bc_dry_2() {
+  bc("u_2", 'U'); bc("v_2", 'V'); bc("w_2", 'w'); bc("t_2", 'p'); bc("ph_2", 'w'); bc("mu_2", 't');
+  for (int s = 0; s < c.num_moist; s++) bc(std::string("moist_") + moist_names[s], 'p');
+  for (int s = 1; s <= c.num_scalar; s++) bc("scalar_" + std::to_string(s), 'p');
+}
+
+// moist_physics_prep_em / kessler / moist_physics_finish_em, solve_em.F:3629-4115
+void Oracle::microphysics() {
+  if (c.mp_physics == 0) return;
+  const int i_start = x.its, i_end = std::min(x.ite, x.ide - 1), j_start = x.jts, j_end = std::min(x.jte, x.jde - 1);
+  const int k_start = x.kts, kte = x.kte, k_end = std::min(x.kte, x.kde - 1);
+  const float dt = c.dt;
+  A3 t_new = a3("t_2"), rho = a3("rho"), al = a3("al"), alb = a3("alb"), p = a3("p"), pb = a3("pb"), ph = a3("ph_2"), phb = a3("phb");
+  A3 th_phy = a3("th_phy"), pii = a3("pi_phy"), pf = a3("p_phy"), z = a3("z"), z_at_w = a3("z_at_w"), dz8w = a3("dz8w");
+  A3 h_diabatic = a3("h_diabatic"), qv = a3("moist_qv"), qc = a3("moist_qc"), qr = a3("moist_qr");
+  A3 qv_diabatic = a3("qv_diabatic"), qc_diabatic = a3("qc_diabatic");
+  // module_big_step_utilities_em.F:5394-5589 (p8w is not consumed by Kessler and is omitted)
+  for (int j = j_start; j <= j_end; j++)
+    for (int k = k_start; k <= kte; k++)
+      for (int i = i_start; i <= i_end; i++) z_at_w(i, k, j) = (ph(i, k, j) + phb(i, k, j)) / g;
+  for (int j = j_start; j <= j_end; j++)
+    for (int k = k_start; k <= kte - 1; k++)
+      for (int i = i_start; i <= i_end; i++) dz8w(i, k, j) = z_at_w(i, k + 1, j) - z_at_w(i, k, j);
+  for (int j = j_start; j <= j_end; j++)
+    for (int i = i_start; i <= i_end; i++) dz8w(i, kte, j) = 0.f;
+  for (int j = j_start; j <= j_end; j++)
+    for (int k = k_start; k <= k_end; k++)
+      for (int i = i_start; i <= i_end; i++) {
+        if (c.use_theta_m == 1) th_phy(i, k, j) = (t_new(i, k, j) + t0) / (1.f + (r_v / r_d) * qv(i, k, j));
+        else th_phy(i, k, j) = t_new(i, k, j) + t0;
+      }
+  for (int j = j_start; j <= j_end; j++)
+    for (int k = k_start; k <= k_end; k++)
+      for (int i = i_start; i <= i_end; i++) {
+        h_diabatic(i, k, j) = th_phy(i, k, j);
+        qv_diabatic(i, k, j) = qv(i, k, j);
+        qc_diabatic(i, k, j) = qc(i, k, j);
+        rho(i, k, j) = 1.f / (al(i, k, j) + alb(i, k, j));
+        pii(i, k, j) = std::pow((p(i, k, j) + pb(i, k, j)) / p0, rcp);
+        z(i, k, j) = 0.5f * (z_at_w(i, k, j) + z_at_w(i, k + 1, j));
+        pf(i, k, j) = p(i, k, j) + pb(i, k, j);
+      }
+  // microphysics_driver -> kessler with kte = kde-1 (solve_em.F: KTE=min(k_end,kde-1))
+  Cx xk = x;
+  xk.ite = i_end; xk.jte = j_end; xk.kte = k_end;
+  kessler(xk, th_phy, qv, qc, qr, rho, pii, dt, z, dz8w, a2("rainnc"), a2("rainncv"));
+  // module_big_step_utilities_em.F:5593-5784 (no_mp_heating = 0, mp_tend_lim = 10.)
+  const float mp_tend_lim = 10.f;
+  for (int j = j_start; j <= j_end; j++)
+    for (int k = k_start; k <= k_end; k++)
+      for (int i = i_start; i <= i_end; i++) {
+        float mpten = th_phy(i, k, j) - h_diabatic(i, k, j);
+        float qvten = qv(i, k, j) - qv_diabatic(i, k, j);
+        float qcten = qc(i, k, j) - qc_diabatic(i, k, j);
+        mpten = std::min(mp_tend_lim * dt, mpten);
+        mpten = std::max(-mp_tend_lim * dt, mpten);
+        if (c.use_theta_m == 1) {
+          t_new(i, k, j) = h_diabatic(i, k, j) * (1.f + (r_v / r_d) * qv_diabatic(i, k, j)) + mpten * (1.f + (r_v / r_d) * qv(i, k, j)) +
+                           (r_v / r_d) * qvten * th_phy(i, k, j) - t0;
+          h_diabatic(i, k, j) = (mpten * (1.f + (r_v / r_d) * qv(i, k, j)) + (r_v / r_d) * qvten * th_phy(i, k, j)) / dt;
+        } else {
+          t_new(i, k, j) = t_new(i, k, j) + mpten;
+          h_diabatic(i, k, j) = mpten / dt;
+        }
+        qv_diabatic(i, k, j) = qvten / dt;
+        qc_diabatic(i, k, j) = qcten / dt;
+      }
+  bc("h_diabatic", 'p');
+}
+
+// solve_em.F:4175-4759: second calc_p_rho_phi, set_phys_bc_dry_2 + species BCs, set_w_surface
+void Oracle::end_of_step() {
+  calc_p_rho_phi();
+  bc("u_1", 'U'); bc("u_2", 'U'); bc("v_1", 'V'); bc("v_2", 'V'); bc("w_1", 'w'); bc("w_2", 'w');
+  bc("t_1", 'p'); bc("t_2", 'p'); bc("ph_1", 'w'); bc("ph_2", 'w'); bc("mu_1", 't'); bc("mu_2", 't');
+  for (int s = 0; s < c.num_moist; s++) bc(std::string("moist_") + moist_names[s], 'p');
+  for (int s = 1; s <= c.num_scalar; s++) bc("scalar_" + std::to_string(s), 'p');
+  set_w_surface(x, a3("w_2"), a3("u_2"), a3("v_2"));
+}
+
+void Oracle::step() {
+  const int rk_order = c.rk_ord;
+  // solve_em.F:520-550 initialize_moist_old + bc
+  if (c.num_moist >= 1) {
+    A3 mo = a3("moist_old_qv"), m = a3("moist_qv");
+    for (int j = x.jts; j <= std::min(x.jte, x.jde - 1); j++)
+      for (int k = x.kts; k <= x.kte - 1; k++)
+        for (int i = x.its; i <= std::min(x.ite, x.ide - 1); i++) mo(i, k, j) = m(i, k, j);
+    bc("moist_old_qv", 'p');
+  }
+  for (int rk_step = 1; rk_step <= rk_order; rk_step++) {
+    float dt_rk, dts_rk; int ns;
+    rk_params(rk_step, dt_rk, dts_rk, ns);
+    rk_step_prep(rk_step);
+    rk_phys_bc_dry_1();
+    if (rk_step == 1) init_zero_tendency();
+    rk_tendency(rk_step);
+    small_step_prep(rk_step);
+    for (int it = 1; it <= ns; it++) {
+      advance_uv(rk_step);
+      advance_mu_t(rk_step);
+      advance_w(rk_step);
+      sumflux(rk_step, it);
+      calc_p_rho(it);
+    }
+    small_step_finish(rk_step);
+    rk_scalar_step(rk_step);
+    calc_p_rho_phi();
+    if (rk_step < rk_order) rk_phys_bc_dry_2();
+  }
+  microphysics();
+  end_of_step();
+}
+
+}  // namespace orc
+
+// ---------------------------------------------------------------------------
+// C entry points (ctypes)
+// ---------------------------------------------------------------------------
+using orc::Oracle;
+static thread_local std::string g_err;
+#define OGUARD(body)                                  \
+  try { body; return 0; }                             \
+  catch (const std::exception &e) { g_err = e.what(); return 1; }
+
+extern "C" {
+const char *oracle_last_error() { return g_err.c_str(); }
+int oracle_create(const wrfgpu_dims *d, const wrfgpu_config *c, Oracle **out) { OGUARD(*out = new Oracle(*d, *c)) }
+int oracle_destroy(Oracle *o) { delete o; return 0; }
+size_t oracle_field_size(Oracle *o, const char *name) {
+  auto it = o->data.find(name);
+  return it == o->data.end() ? 0 : it->second.size();
+}
+int oracle_num_fields(Oracle *o) { return (int)o->names.size(); }
+const char *oracle_field_name(Oracle *o, int i) { return o->names[i].c_str(); }
+int oracle_set_field(Oracle *o, const char *name, const float *h, size_t n) {
+  OGUARD({
+    auto &v = o->data.at(name);
+    if (v.size() != n) throw std::runtime_error(std::string("oracle_set_field: size mismatch for ") + name);
+    std::memcpy(v.data(), h, n * sizeof(float));
+  })
+}
+int oracle_get_field(Oracle *o, const char *name, float *h, size_t n) {
+  OGUARD({
+    auto &v = o->data.at(name);
+    if (v.size() != n) throw std::runtime_error(std::string("oracle_get_field: size mismatch for ") + name);
+    std::memcpy(h, v.data(), n * sizeof(float));
+  })
+}
+int oracle_step(Oracle *o, int n) { OGUARD(for (int i = 0; i < n; i++) o->step()) }
+int oracle_rk_step_prep(Oracle *o, int rk) { OGUARD(o->rk_step_prep(rk)) }
+int oracle_rk_phys_bc_dry_1(Oracle *o) { OGUARD(o->rk_phys_bc_dry_1()) }
+int oracle_init_zero_tendency(Oracle *o) { OGUARD(o->init_zero_tendency()) }
+int oracle_rk_tendency(Oracle *o, int rk) { OGUARD(o->rk_tendency(rk)) }
+int oracle_small_step_prep(Oracle *o, int rk) { OGUARD(o->small_step_prep(rk)) }
+int oracle_advance_uv(Oracle *o, int rk) { OGUARD(o->advance_uv(rk)) }
+int oracle_advance_mu_t(Oracle *o, int rk) { OGUARD(o->advance_mu_t(rk)) }
+int oracle_advance_w(Oracle *o, int rk) { OGUARD(o->advance_w(rk)) }
+int oracle_sumflux(Oracle *o, int rk, int it) { OGUARD(o->sumflux(rk, it)) }
+int oracle_calc_p_rho(Oracle *o, int it) { OGUARD(o->calc_p_rho(it)) }
+int oracle_small_step_finish(Oracle *o, int rk) { OGUARD(o->small_step_finish(rk)) }
+int oracle_rk_scalar_step(Oracle *o, int rk) { OGUARD(o->rk_scalar_step(rk)) }
+int oracle_calc_p_rho_phi(Oracle *o) { OGUARD(o->calc_p_rho_phi()) }
+int oracle_rk_phys_bc_dry_2(Oracle *o) { OGUARD(o->rk_phys_bc_dry_2()) }
+int oracle_microphysics(Oracle *o) { OGUARD(o->microphysics()) }
+int oracle_end_of_step(Oracle *o) { OGUARD(o->end_of_step()) }
+int oracle_set_physical_bc(Oracle *o, const char *name, char var) { OGUARD(o->bc(name, var)) }
+}
+
+// start_domain: the subset of dyn_em/start_em.F (start_domain_em) the hot path
+// needs before step 1 -- physical-BC fills of the base state, map factors and
+// both time levels (start_em.F:1421-1433 and the set_physical_bc calls before it).
+extern "C" int oracle_start_domain(orc::Oracle *o) {
+  OGUARD({
+    for (const char *n : {"phb"}) o->bc(n, 'w');
+    for (const char *n : {"pb", "alb", "p", "al", "alt"}) o->bc(n, 't');
+    for (const char *n : {"mub", "ht", "msftx", "msfty", "f", "e", "sina", "cosa"}) o->bc(n, 't');
+    for (const char *n : {"msfux", "msfuy"}) o->bc(n, 'u');
+    for (const char *n : {"msfvx", "msfvx_inv", "msfvy"}) o->bc(n, 'v');
+    o->bc("u_1", 'U'); o->bc("u_2", 'U'); o->bc("v_1", 'V'); o->bc("v_2", 'V'); o->bc("w_1", 'w'); o->bc("w_2", 'w');
+    o->bc("t_1", 'p'); o->bc("t_2", 'p'); o->bc("ph_1", 'w'); o->bc("ph_2", 'w'); o->bc("mu_1", 't'); o->bc("mu_2", 't');
+    for (auto &n : o->names)
+      if (n.rfind("moist_", 0) == 0 || n.rfind("scalar_", 0) == 0) o->bc(n, 'p');
+  })
+}
