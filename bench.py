@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py -- grid-point RK3 steps/s of the solve_em hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W    # CPU restatement on the host cores
+
+One "step" is one full solve_em call (3 RK substeps, 1+ns/2+ns acoustic steps, scalar
+advection, boundary fills) on the synthetic 2000x2000x80 em_quarter_ss-like domain of
+BASELINE.json configs[4] (it fits one B200).  `value` is whole-job grid-pt-steps/s with the
+state resident in HBM; `e2e` is the same metric through the drop-in call wrfgpu_solve_em
+with HOST buffers (pinned) -- prognostic state uploaded and downloaded every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic 3-D field accesses (4 B each) per grid point per launch, SURVEY.md 8(d):
+# distinct fields read + distinct fields written by the routine(s) the kernel implements.
+ALGO_ACCESSES = {
+    "k_advance_w": 19, "k_advance_uv": 14, "k_advance_mu_t": 11, "k_sumflux": 9, "k_calc_p_rho": 9,
+    "k_tend_u": 6, "k_tend_v": 6, "k_tend_w": 6, "k_tend_t": 6, "k_tend_ph": 6,      # rk_tendency+addtend = 30 in all
+    "k_ssp_3d": 26, "k_calc_coef_w": 5, "k_ssf": 18, "k_prep_3d": 13, "k_calc_ww": 3,
+    "k_calc_p_rho_phi": 7, "k_advect_scalar": 5, "k_update_scalar": 3, "k_pd_scale": 6, "k_pd_tend": 7,
+    "k_update_scalar_pd": 2, "k_zero3": 5, "k_invert_cqw": 2, "k_kessler": 20,
+}
+
+
+def algorithmic_bytes_per_point_step(n_m, n_s, ns, mp):
+    """B = 4*[3*(104+n_m+8*n_s) + 62*N_ac + 20*mp]."""
+    n_ac = 1 + ns // 2 + ns
+    return 4 * (3 * (104 + n_m + 8 * n_s) + 62 * n_ac + 20 * (1 if mp else 0))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop = threading.Event()
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(s) > 3 + k and s[3 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------
+def tile_case_on_device(small, nx, ny, nz, device):
+    """Build the big periodic state on the GPU by tiling a small periodic block (same
+    levels, same column physics): returns (Case with empty fields, {name: torch tensor})."""
+    import torch
+    from wrf_b200 import ideal
+    d = ideal.memory_dims(nx, ny, nz)
+    c = small.config
+    sd = small.dims
+    per_i, per_j = sd.ide - sd.ids, sd.jde - sd.jds      # mass points of the block = period
+    ii = torch.arange(d.ims, d.ime + 1, device=device)
+    jj = torch.arange(d.jms, d.jme + 1, device=device)
+    # periodic domain index -> block index -> block memory index
+    imap = ((ii - 1) % (nx - 1)) % per_i + 1 - sd.ims
+    jmap = ((jj - 1) % (ny - 1)) % per_j + 1 - sd.jms
+    out = {}
+    for k, a in small.fields.items():
+        t = torch.from_numpy(a).to(device)
+        if t.ndim == 3:
+            t = t.index_select(0, jmap).index_select(2, imap).contiguous()
+        elif t.ndim == 2:
+            t = t.index_select(0, jmap).index_select(1, imap).contiguous()
+        out[k] = t
+    big = ideal.Case(name="synthetic", dims=d, config=c, fields={})
+    return big, out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from wrf_b200 import Solver, make_case
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and args.gpus != world:
+        raise SystemExit("--gpus must equal WORLD_SIZE")
+    if world > 1:
+        raise SystemExit("multi-GPU patch decomposition is not wired into bench.py yet")
+
+    nx, ny, nz = args.nx, args.ny, args.nz
+    lat = 50
+    small = make_case("synthetic", nx=lat + 1, ny=lat + 1, nz=nz, bubble_lattice=lat * 2000.0)
+    case, dev_fields = tile_case_on_device(small, nx, ny, nz, dev)
+    s = Solver(case, device=local, upload=False)
+    stream = torch.cuda.current_stream()
+    s.set_stream(stream.cuda_stream)
+    for k, t in dev_fields.items():
+        s.set(k, t)
+    del dev_fields
+    torch.cuda.empty_cache()
+    s.start_domain()
+    s.sync()
+    c = case.config
+    npts = (nx - 1) * (ny - 1) * (nz - 1)
+    ns = c.time_step_sound
+    bytes_pt = algorithmic_bytes_per_point_step(c.num_moist, len([1 for _ in range(c.num_moist + c.num_scalar)]), ns, c.mp_physics)
+
+    # ---- resident-state throughput
+    for _ in range(args.warmup):
+        s.step(1)
+    torch.cuda.synchronize()
+    l0 = s.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        s.step(1)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    sampler.stop.set()
+    sampler.join(timeout=3)
+    launches = s.launch_count() - l0
+    ms_per_step = ms / args.steps
+    value = npts / (ms_per_step * 1e-3)
+
+    # ---- per-kernel times (events on the same stream, outside the timed region)
+    s.phase_timing(True)
+    s.step(1)
+    rep = s.kernel_report()
+    s.phase_timing(False)
+    tot = sum(v[1] for v in rep.values())
+    top = max(rep.items(), key=lambda kv: kv[1][1])
+    peak, peak_src = measured_peak()
+    kname, (kn, kms) = top
+    acc = ALGO_ACCESSES.get(kname, 0)
+    achieved = acc * 4 * npts / ((kms / kn) * 1e-3) / 1e9 if kn else 0.0
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "launches_per_step": kn, "avg_launch_ms": round(kms / kn, 4), "share_of_step": round(kms / tot, 4),
+                "algorithmic_accesses_per_point": acc,
+                "step": {"algorithmic_bytes_per_point": bytes_pt, "achieved_GBs": round(value * bytes_pt / 1e9, 1),
+                         "frac": round(value * bytes_pt / 1e9 / peak, 4)},
+                "kernels_ms_per_step": {k: round(v[1], 3) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])}}
+
+    # ---- end to end through the drop-in call with host buffers
+    prog = ["u_2", "v_2", "w_2", "t_2", "ph_2", "mu_2"] + [n for n in s.names() if n.startswith("moist_q")]
+    host = {}
+    for n in prog:
+        host[n] = torch.empty(s.size(n), dtype=torch.float32, pin_memory=True)
+        s.get(n, out=host[n])
+    ptrs = [host[n].data_ptr() for n in prog]
+    h2d = sum(host[n].numel() * 4 for n in prog)
+    e2e_steps = max(1, min(args.steps, 3))
+    s.solve_em(prog, ptrs, prog, ptrs)     # warm
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        s.solve_em(prog, ptrs, prog, ptrs)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e = {"value": npts / e2e_s, "unit": "grid-pt-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
+           "ms_per_step": round(e2e_s * 1e3, 2), "call": "wrfgpu_solve_em (pinned host prognostic state in and out every step)"}
+
+    line = {"metric": "grid-pt RK3 steps/s", "value": value, "unit": "grid-pt-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"synthetic em_quarter_ss {nx}x{ny}x{nz} (e_we x e_sn x e_vert), dx=2km, dt=12s, ns={ns}, "
+                                   f"periodic x/y, dry (passive qv, moist_adv_opt=1), 1 patch per GPU",
+                       "grid_points": npts, "l2_policy": "working set (tens of GB per step) is far larger than the 126 MB L2",
+                       "timing": "CUDA events on the launching stream"},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary()}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, quick=True)
+    print(json.dumps(line))
+    s.close()
+
+
+# ---------------------------------------------------------------------------
+def cpu_baseline(args, quick=False):
+    """The CPU restatement (oracle/) on a bounded sample of the same workload."""
+    from tests.oracle_lib import Oracle
+    from wrf_b200 import make_case
+    n = args.cpu_n
+    lat = 50
+    case = make_case("synthetic", nx=n + 1, ny=n + 1, nz=args.nz, bubble_lattice=lat * 2000.0)
+    o = Oracle(case)
+    threads = o.set_threads(args.cpu_threads or os.cpu_count() or 1)
+    o.start_domain()
+    o.step(1)
+    steps = 1 if quick else max(1, args.steps)
+    t0 = time.perf_counter()
+    o.step(steps)
+    dt = (time.perf_counter() - t0) / steps
+    npts = n * n * (args.nz - 1)
+    return {"value": npts / dt, "unit": "grid-pt-steps/s", "cores": threads, "kind": "port",
+            "sample": f"oracle/ (C++ restatement, -O2 -ffp-contract=off, j-tiles on {threads} threads) on {n + 1}x{n + 1}x{args.nz} "
+                      f"of the same synthetic workload, {steps} step(s), {dt:.2f} s/step",
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for _ in range(max(0, args.warmup - 1)):
+        pass
+    b = cpu_baseline(args, quick=False)
+    ns = 6
+    line = {"impl": "reference", "metric": "grid-pt RK3 steps/s", "value": b["value"], "unit": "grid-pt-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"synthetic em_quarter_ss {args.nx}x{args.ny}x{args.nz}, dx=2km, dt=12s, ns={ns}, periodic x/y, dry "
+                                   f"(bounded sample: {b['sample']})"},
+            "cpu_baseline": b, "e2e": {"value": b["value"], "unit": "grid-pt-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "no Fortran compiler exists in the build image, so the reference arm is the repo's CPU restatement of "
+                    "solve_em (oracle/), not wrf.exe"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=2000)
+    ap.add_argument("--ny", type=int, default=2000)
+    ap.add_argument("--nz", type=int, default=80)
+    ap.add_argument("--cpu-n", type=int, default=200, help="mass points per side of the CPU sample")
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -125,6 +125,11 @@ int  wrfgpu_solve_em(wrfgpu_solver *s,
                      int n_in,  const char *const *in_names,  const float *const *in_host,
                      int n_out, const char *const *out_names, float *const *out_host);
 int  wrfgpu_sync(wrfgpu_solver *s);
+/* run on the caller's CUDA stream (cudaStream_t) instead of the solver's own */
+int  wrfgpu_set_stream(wrfgpu_solver *s, void *cuda_stream);
+/* per-kernel cudaEvent statistics collected while phase timing is on, as text
+ * lines "kernel count total_ms"; returns the buffer size needed */
+size_t wrfgpu_kernel_report(wrfgpu_solver *s, char *buf, size_t cap);
 /* number of kernels this library launched since create (bench "gpu_launches") */
 long long wrfgpu_launch_count(const wrfgpu_solver *s);
 /* cudaEvent timing of the kernels launched by phase `name` since the last
@@ -134,6 +139,7 @@ double wrfgpu_phase_ms(wrfgpu_solver *s, const char *name);
 /* -- per-routine entry points (kernel-level parity tests) --
  * Each runs on the resident state, same semantics as the Fortran routine named
  * in the comment with its=ips.. tile bounds. */
+int wrfgpu_start_domain     (wrfgpu_solver *s);               /* start_em.F: BC fills before step 1 */
 int wrfgpu_rk_step_prep     (wrfgpu_solver *s, int rk_step);  /* module_em.F:37            */
 int wrfgpu_rk_phys_bc_dry_1 (wrfgpu_solver *s);               /* solve_em.F:726-754        */
 int wrfgpu_init_zero_tendency(wrfgpu_solver *s);              /* module_em.F:1920          */

@@ -18,6 +18,7 @@
 #include <vector>
 #include <algorithm>
 #include <stdexcept>
+#include <thread>
 #include "../include/wrfgpu.h"
 
 namespace orc {
@@ -90,6 +91,8 @@ struct Oracle {
   int num_sound_steps = 0;
   float dts = 0.f;
   long n3, n2, n1;
+  int nthreads = 1;   // j-tiles run on std::threads like the reference's OpenMP tiles (solve_em.F:652-674)
+  template <class Fn> void par(Fn fn);
 
   Oracle(const wrfgpu_dims &d, const wrfgpu_config &c);
   void add(const std::string &n, int kind);
@@ -119,6 +122,20 @@ struct Oracle {
   void bc(const std::string &name, char var);
   void rk_params(int rk_step, float &dt_rk, float &dts_rk, int &nsmall) const;
 };
+
+template <class Fn> void Oracle::par(Fn fn) {
+  const int nj = x.jte - x.jts + 1;
+  const int T = std::max(1, std::min(nthreads, nj / 2));
+  if (T <= 1) { fn(x); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; t++) {
+    Cx xt = x;
+    xt.jts = x.jts + (int)((long)t * nj / T);
+    xt.jte = x.jts + (int)((long)(t + 1) * nj / T) - 1;
+    th.emplace_back([fn, xt]() { fn(xt); });
+  }
+  for (auto &q : th) q.join();
+}
 
 // ---- model-layer routines (signatures follow the Fortran dummy-arg roles) ----
 // big_step.cpp

@@ -125,15 +125,15 @@ static std::vector<A3> moist_list(Oracle &o, const char *prefix) {
 
 // module_em.F:37-186
 void Oracle::rk_step_prep(int) {
-  calculate_full(x, a2("mut"), a2("mub"), a2("mu_2"));
-  calc_mu_uv(x, a2("mu_2"), a2("mub"), a2("muu"), a2("muv"));
-  couple_momentum(x, a2("muu"), a3("ru"), a3("u_2"), x.msfuy, a2("muv"), a3("rv"), a3("v_2"), x.msfvx, x.msfvx_inv,
-                  a2("mut"), a3("rw"), a3("w_2"), x.msfty);
-  calc_ww_cp(x, a3("u_2"), a3("v_2"), a2("mu_2"), a2("mub"), a3("ww"));
+  par([&](const Cx &xt) { calculate_full(xt, a2("mut"), a2("mub"), a2("mu_2")); });
+  par([&](const Cx &xt) { calc_mu_uv(xt, a2("mu_2"), a2("mub"), a2("muu"), a2("muv")); });
+  par([&](const Cx &xt) { couple_momentum(xt, a2("muu"), a3("ru"), a3("u_2"), x.msfuy, a2("muv"), a3("rv"), a3("v_2"), x.msfvx, x.msfvx_inv,
+                  a2("mut"), a3("rw"), a3("w_2"), x.msfty); });
+  par([&](const Cx &xt) { calc_ww_cp(xt, a3("u_2"), a3("v_2"), a2("mu_2"), a2("mub"), a3("ww")); });
   auto m = moist_list(*this, "moist_");
-  calc_cq(x, m, a3("cqu"), a3("cqv"), a3("cqw"));
-  calc_alt(x, a3("alt"), a3("al"), a3("alb"));
-  calc_php(x, a3("php"), a3("ph_2"), a3("phb"));
+  par([&](const Cx &xt) { calc_cq(xt, m, a3("cqu"), a3("cqv"), a3("cqw")); });
+  par([&](const Cx &xt) { calc_alt(xt, a3("alt"), a3("al"), a3("alb")); });
+  par([&](const Cx &xt) { calc_php(xt, a3("php"), a3("ph_2"), a3("phb")); });
 }
 
 // solve_em.F:726-754 (+ rk_phys_bc_dry_1, module_bc_em.F:960-1041)
@@ -146,7 +146,7 @@ void Oracle::rk_phys_bc_dry_1() {
 // module_em.F:1920 init_zero_tendency (called from first_rk_step_part1)
 void Oracle::init_zero_tendency() {
   for (const char *n : {"ru_tendf", "rv_tendf", "rw_tendf", "ph_tendf", "t_tendf"}) zero_tend(x, a3(n));
-  zero_tend2d(x, a2("mu_tendf"));
+  par([&](const Cx &xt) { zero_tend2d(xt, a2("mu_tendf")); });
   for (int s = 0; s < c.num_moist; s++) zero_tend(x, a3(std::string("moist_tend_") + moist_names[s]));
   for (int s = 1; s <= c.num_scalar; s++) zero_tend(x, a3("scalar_tend_" + std::to_string(s)));
 }
@@ -158,40 +158,40 @@ void Oracle::rk_tendency(int rk_step) {
   A3 ru = a3("ru"), rv = a3("rv"), rw = a3("rw"), ww = a3("ww"), wwE = a3("wwE"), wwI = a3("wwI");
   A2 mut = a2("mut"), muu = a2("muu"), muv = a2("muv"), mu = a2("mu_2"), mub = a2("mub");
   for (A3 z : {ru_tend, rv_tend, rw_tend, t_tend, ph_tend, a3("u_save"), a3("v_save"), a3("w_save"), a3("ph_save"), a3("t_save")})
-    zero_tend(x, z);
-  zero_tend2d(x, a2("mu_tend"));
-  zero_tend2d(x, a2("mu_save"));
-  ww_split(x, wwE, wwI, ww);
-  advect_u(x, u, u, ru_tend, ru, rv, wwE, mut);
-  advect_v(x, v, v, rv_tend, ru, rv, wwE, mut);
-  advect_w(x, w, w, rw_tend, ru, rv, wwE, mut);
-  advect_scalar(x, t, t, t_tend, ru, rv, wwE, mut);
-  rhs_ph(x, ph_tend, u, v, wwE, ph, ph, a3("phb"), w, mut, muu, muv);
-  horizontal_pressure_gradient(x, ru_tend, rv_tend, ph, a3("alt"), a3("p"), a3("pb"), a3("al"), a3("php"), a3("cqu"), a3("cqv"), muu, muv, mu);
-  pg_buoy_w(x, rw_tend, a3("p"), a3("cqw"), mu, mub);
+    par([&](const Cx &xt) { zero_tend(xt, z); });
+  par([&](const Cx &xt) { zero_tend2d(xt, a2("mu_tend")); });
+  par([&](const Cx &xt) { zero_tend2d(xt, a2("mu_save")); });
+  par([&](const Cx &xt) { ww_split(xt, wwE, wwI, ww); });
+  par([&](const Cx &xt) { advect_u(xt, u, u, ru_tend, ru, rv, wwE, mut); });
+  par([&](const Cx &xt) { advect_v(xt, v, v, rv_tend, ru, rv, wwE, mut); });
+  par([&](const Cx &xt) { advect_w(xt, w, w, rw_tend, ru, rv, wwE, mut); });
+  par([&](const Cx &xt) { advect_scalar(xt, t, t, t_tend, ru, rv, wwE, mut); });
+  par([&](const Cx &xt) { rhs_ph(xt, ph_tend, u, v, wwE, ph, ph, a3("phb"), w, mut, muu, muv); });
+  par([&](const Cx &xt) { horizontal_pressure_gradient(xt, ru_tend, rv_tend, ph, a3("alt"), a3("p"), a3("pb"), a3("al"), a3("php"), a3("cqu"), a3("cqv"), muu, muv, mu); });
+  par([&](const Cx &xt) { pg_buoy_w(xt, rw_tend, a3("p"), a3("cqw"), mu, mub); });
   float mv, mh;
   w_damp(x, rw_tend, mv, mh, u, v, ww, w, mut);
-  if (c.pert_coriolis) perturbation_coriolis(x, ru, rv, rw, ru_tend, rv_tend, rw_tend, muu, muv, a3("phb"), ph);
-  else coriolis(x, ru, rv, rw, ru_tend, rv_tend, rw_tend);
-  curvature(x, ru, rv, rw, u, v, w, ru_tend, rv_tend, rw_tend);
+  if (c.pert_coriolis) par([&](const Cx &xt) { perturbation_coriolis(xt, ru, rv, rw, ru_tend, rv_tend, rw_tend, muu, muv, a3("phb"), ph); });
+  else par([&](const Cx &xt) { coriolis(xt, ru, rv, rw, ru_tend, rv_tend, rw_tend); });
+  par([&](const Cx &xt) { curvature(xt, ru, rv, rw, u, v, w, ru_tend, rv_tend, rw_tend); });
   if (rk_step == 1 && c.damp_opt == 2)
-    rk_rayleigh_damp(x, a3("ru_tendf"), a3("rv_tendf"), a3("rw_tendf"), a3("t_tendf"), u, v, w, t, mut, muu, muv, ph, a3("phb"));
-  rk_addtend_dry(x, ru_tend, rv_tend, rw_tend, ph_tend, t_tend, a3("ru_tendf"), a3("rv_tendf"), a3("rw_tendf"), a3("ph_tendf"),
+    par([&](const Cx &xt) { rk_rayleigh_damp(xt, a3("ru_tendf"), a3("rv_tendf"), a3("rw_tendf"), a3("t_tendf"), u, v, w, t, mut, muu, muv, ph, a3("phb")); });
+  par([&](const Cx &xt) { rk_addtend_dry(xt, ru_tend, rv_tend, rw_tend, ph_tend, t_tend, a3("ru_tendf"), a3("rv_tendf"), a3("rw_tendf"), a3("ph_tendf"),
                  a3("t_tendf"), a3("u_save"), a3("v_save"), a3("w_save"), a3("ph_save"), a3("t_save"), a2("mu_tend"), a2("mu_tendf"),
-                 rk_step, a3("h_diabatic"), mut);
+                 rk_step, a3("h_diabatic"), mut); });
 }
 
 // solve_em.F:1089-1263
 void Oracle::small_step_prep(int rk_step) {
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
-  orc::small_step_prep(x, a3("u_1"), a3("u_2"), a3("v_1"), a3("v_2"), a3("w_1"), a3("w_2"), a3("t_1"), a3("t_2"), a3("ph_1"), a3("ph_2"),
+  par([&](const Cx &xt) { orc::small_step_prep(xt, a3("u_1"), a3("u_2"), a3("v_1"), a3("v_2"), a3("w_1"), a3("w_2"), a3("t_1"), a3("t_2"), a3("ph_1"), a3("ph_2"),
                        a2("mub"), a2("mu_1"), a2("mu_2"), a2("muu"), a2("muus"), a2("muv"), a2("muvs"), a2("mut"), a2("muts"), a2("mudf"),
                        a3("u_save"), a3("v_save"), a3("w_save"), a3("t_save"), a3("ph_save"), a2("mu_save"), a3("ww"), a3("ww1"),
-                       a3("c2a"), a3("pb"), a3("p"), a3("alt"), rk_step);
-  orc::calc_p_rho(x, a3("al"), a3("p"), a3("ph_2"), a3("alt"), a3("t_2"), a3("t_save"), a3("c2a"), a3("pm1"), a2("mu_2"), a2("muts"),
-                  c.smdiv, 0);
-  calc_coef_w(x, a3("a"), a3("alpha"), a3("gamma"), a2("mut"), a3("cqw"), a3("c2a"), dts_rk, c.epssm);
+                       a3("c2a"), a3("pb"), a3("p"), a3("alt"), rk_step); });
+  par([&](const Cx &xt) { orc::calc_p_rho(xt, a3("al"), a3("p"), a3("ph_2"), a3("alt"), a3("t_2"), a3("t_save"), a3("c2a"), a3("pm1"), a2("mu_2"), a2("muts"),
+                  c.smdiv, 0); });
+  par([&](const Cx &xt) { calc_coef_w(xt, a3("a"), a3("alpha"), a3("gamma"), a2("mut"), a3("cqw"), a3("c2a"), dts_rk, c.epssm); });
   bc("ru_tend", 'u'); bc("rv_tend", 'v'); bc("ph_2", 'w'); bc("al", 'p'); bc("p", 'p'); bc("t_1", 'p'); bc("t_save", 't');
   bc("mu_1", 't'); bc("mu_2", 't'); bc("mudf", 't');
 }
@@ -199,43 +199,43 @@ void Oracle::small_step_prep(int rk_step) {
 void Oracle::advance_uv(int rk_step) {
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
-  orc::advance_uv(x, a3("u_2"), a3("ru_tend"), a3("v_2"), a3("rv_tend"), a3("p"), a3("pb"), a3("ph_2"), a3("php"), a3("alt"), a3("al"),
-                  a2("mu_2"), a2("muu"), a3("cqu"), a2("muv"), a3("cqv"), a2("mudf"), dts_rk);
+  par([&](const Cx &xt) { orc::advance_uv(xt, a3("u_2"), a3("ru_tend"), a3("v_2"), a3("rv_tend"), a3("p"), a3("pb"), a3("ph_2"), a3("php"), a3("alt"), a3("al"),
+                  a2("mu_2"), a2("muu"), a3("cqu"), a2("muv"), a3("cqv"), a2("mudf"), dts_rk); });
 }
 void Oracle::advance_mu_t(int rk_step) {
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
-  orc::advance_mu_t(x, a3("ww"), a3("ww1"), a3("u_2"), a3("u_save"), a3("v_2"), a3("v_save"), a2("mu_2"), a2("mut"), a2("muave"),
+  par([&](const Cx &xt) { orc::advance_mu_t(xt, a3("ww"), a3("ww1"), a3("u_2"), a3("u_save"), a3("v_2"), a3("v_save"), a2("mu_2"), a2("mut"), a2("muave"),
                     a2("muts"), a2("muu"), a2("muv"), a2("mudf"), a3("t_2"), a3("t_save"), a3("t_2save"), a3("t_tend"), a2("mu_tend"),
-                    dts_rk, c.epssm);
+                    dts_rk, c.epssm); });
 }
 void Oracle::advance_w(int rk_step) {
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
-  orc::advance_w(x, a3("w_2"), a3("rw_tend"), a3("ww"), a3("w_save"), a3("u_2"), a3("v_2"), a2("mu_2"), a2("mut"), a2("muave"), a2("muts"),
+  par([&](const Cx &xt) { orc::advance_w(xt, a3("w_2"), a3("rw_tend"), a3("ww"), a3("w_save"), a3("u_2"), a3("v_2"), a2("mu_2"), a2("mut"), a2("muave"), a2("muts"),
                  a3("t_2save"), a3("t_2"), a3("t_save"), a3("ph_2"), a3("ph_save"), a3("phb"), a3("ph_tend"), a3("c2a"), a3("cqw"),
-                 a3("alt"), a3("a"), a3("alpha"), a3("gamma"), dts_rk, c.epssm);
+                 a3("alt"), a3("a"), a3("alpha"), a3("gamma"), dts_rk, c.epssm); });
 }
 void Oracle::sumflux(int rk_step, int iteration) {
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
-  orc::sumflux(x, a3("u_2"), a3("v_2"), a3("ww"), a3("u_save"), a3("v_save"), a3("ww1"), a2("muu"), a2("muv"), a3("ru_m"), a3("rv_m"),
-               a3("ww_m"), iteration, ns);
+  par([&](const Cx &xt) { orc::sumflux(xt, a3("u_2"), a3("v_2"), a3("ww"), a3("u_save"), a3("v_save"), a3("ww1"), a2("muu"), a2("muv"), a3("ru_m"), a3("rv_m"),
+               a3("ww_m"), iteration, ns); });
 }
 void Oracle::calc_p_rho(int iteration) {
-  orc::calc_p_rho(x, a3("al"), a3("p"), a3("ph_2"), a3("alt"), a3("t_2"), a3("t_save"), a3("c2a"), a3("pm1"), a2("mu_2"), a2("muts"),
-                  c.smdiv, iteration);
+  par([&](const Cx &xt) { orc::calc_p_rho(xt, a3("al"), a3("p"), a3("ph_2"), a3("alt"), a3("t_2"), a3("t_save"), a3("c2a"), a3("pm1"), a2("mu_2"), a2("muts"),
+                  c.smdiv, iteration); });
   bc("ph_2", 'w'); bc("al", 'p'); bc("p", 'p'); bc("muts", 't'); bc("mu_2", 't'); bc("mudf", 't');
 }
 // solve_em.F:1732-1800
 void Oracle::small_step_finish(int rk_step) {
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
-  calc_mu_uv_1(x, a2("muts"), a2("muus"), a2("muvs"));
-  orc::small_step_finish(x, a3("u_2"), a3("u_1"), a3("v_2"), a3("v_1"), a3("w_2"), a3("w_1"), a3("t_2"), a3("t_1"), a3("ph_2"), a3("ph_1"),
+  par([&](const Cx &xt) { calc_mu_uv_1(xt, a2("muts"), a2("muus"), a2("muvs")); });
+  par([&](const Cx &xt) { orc::small_step_finish(xt, a3("u_2"), a3("u_1"), a3("v_2"), a3("v_1"), a3("w_2"), a3("w_1"), a3("t_2"), a3("t_1"), a3("ph_2"), a3("ph_1"),
                          a3("ww"), a3("ww1"), a2("mu_2"), a2("mu_1"), a2("mut"), a2("muts"), a2("muu"), a2("muus"), a2("muv"), a2("muvs"),
                          a3("u_save"), a3("v_save"), a3("w_save"), a3("t_save"), a3("ph_save"), a2("mu_save"), a3("h_diabatic"), ns,
-                         dts_rk, rk_step, c.rk_ord);
+                         dts_rk, rk_step, c.rk_ord); });
   if (rk_step == c.rk_ord) {
     bc("ru_m", 'u'); bc("rv_m", 'v'); bc("ww_m", 'w'); bc("mut", 't'); bc("muts", 't');
   }
@@ -283,25 +283,25 @@ void Oracle::rk_scalar_step(int rk_step) {
     sp.push_back({"scalar_" + std::to_string(s), "scalar_old_" + std::to_string(s), "scalar_tend_" + std::to_string(s), c.scalar_adv_opt});
   if (rk_step == rk_order)
     for (auto &s : sp)
-      if (s.adv_opt == 1) rk_update_scalar_pd(x, a3(s.o), a3(s.t), a2("mu_1"), a2("mu_1"), a2("mub"), dt_rk);
+      if (s.adv_opt == 1) par([&](const Cx &xt) { rk_update_scalar_pd(xt, a3(s.o), a3(s.t), a2("mu_1"), a2("mu_1"), a2("mub"), dt_rk); });
   if (rk_step == rk_order)
     for (auto &s : sp)
       if (s.adv_opt == 1) bc(s.o, 'p');
   for (auto &s : sp) {
     // rk_scalar_tend, module_em.F:1096-1442
-    ww_split(x, a3("wwE"), a3("wwI"), a3("ww_m"));
-    zero_tend(x, a3("advect_tend"));
+    par([&](const Cx &xt) { ww_split(xt, a3("wwE"), a3("wwI"), a3("ww_m")); });
+    par([&](const Cx &xt) { zero_tend(xt, a3("advect_tend")); });
     if (rk_step == rk_order && s.adv_opt == 1)
-      advect_scalar_pd(x, a3(s.f), a3(s.o), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE"), a2("muts"), a2("mub"), a2("mu_1"), dt_rk);
+      par([&](const Cx &xt) { advect_scalar_pd(xt, a3(s.f), a3(s.o), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE"), a2("muts"), a2("mub"), a2("mu_1"), dt_rk); });
     else
-      advect_scalar(x, a3(s.f), a3(s.f), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE"), a2("muts"));
-    rk_update_scalar(x, a3(s.o), a3(s.f), a3(s.t), a3("advect_tend"), a2("mu_1"), a2("mu_2"), a2("mub"), rk_step, dt_rk);
+      par([&](const Cx &xt) { advect_scalar(xt, a3(s.f), a3(s.f), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE"), a2("muts")); });
+    par([&](const Cx &xt) { rk_update_scalar(xt, a3(s.o), a3(s.f), a3(s.t), a3("advect_tend"), a2("mu_1"), a2("mu_2"), a2("mub"), rk_step, dt_rk); });
   }
 }
 
 void Oracle::calc_p_rho_phi() {
   auto m = moist_list(*this, "moist_");
-  orc::calc_p_rho_phi(x, m, a3("al"), a3("alb"), a2("mu_2"), a2("muts"), a3("ph_2"), a3("phb"), a3("p"), a3("pb"), a3("t_2"));
+  par([&](const Cx &xt) { orc::calc_p_rho_phi(xt, m, a3("al"), a3("alb"), a2("mu_2"), a2("muts"), a3("ph_2"), a3("phb"), a3("p"), a3("pb"), a3("t_2")); });
 }
 
 // solve_em.F:3245-3343 (rk_phys_bc_dry_2, module_bc_em.F:1045-1104, + species)
@@ -350,7 +350,7 @@ void Oracle::microphysics() {
   // microphysics_driver -> kessler with kte = kde-1 (solve_em.F: KTE=min(k_end,kde-1))
   Cx xk = x;
   xk.ite = i_end; xk.jte = j_end; xk.kte = k_end;
-  kessler(xk, th_phy, qv, qc, qr, rho, pii, dt, z, dz8w, a2("rainnc"), a2("rainncv"));
+  { Cx keep = x; x = xk; par([&](const Cx &xt) { kessler(xt, th_phy, qv, qc, qr, rho, pii, dt, z, dz8w, a2("rainnc"), a2("rainncv")); }); x = keep; }
   // module_big_step_utilities_em.F:5593-5784 (no_mp_heating = 0, mp_tend_lim = 10.)
   const float mp_tend_lim = 10.f;
   for (int j = j_start; j <= j_end; j++)
@@ -382,7 +382,7 @@ void Oracle::end_of_step() {
   bc("t_1", 'p'); bc("t_2", 'p'); bc("ph_1", 'w'); bc("ph_2", 'w'); bc("mu_1", 't'); bc("mu_2", 't');
   for (int s = 0; s < c.num_moist; s++) bc(std::string("moist_") + moist_names[s], 'p');
   for (int s = 1; s <= c.num_scalar; s++) bc("scalar_" + std::to_string(s), 'p');
-  set_w_surface(x, a3("w_2"), a3("u_2"), a3("v_2"));
+  par([&](const Cx &xt) { set_w_surface(xt, a3("w_2"), a3("u_2"), a3("v_2")); });
 }
 
 void Oracle::step() {
@@ -454,6 +454,7 @@ int oracle_get_field(Oracle *o, const char *name, float *h, size_t n) {
     std::memcpy(h, v.data(), n * sizeof(float));
   })
 }
+int oracle_set_threads(Oracle *o, int n) { o->nthreads = n < 1 ? 1 : n; return o->nthreads; }
 int oracle_step(Oracle *o, int n) { OGUARD(for (int i = 0; i < n; i++) o->step()) }
 int oracle_rk_step_prep(Oracle *o, int rk) { OGUARD(o->rk_step_prep(rk)) }
 int oracle_rk_phys_bc_dry_1(Oracle *o) { OGUARD(o->rk_phys_bc_dry_1()) }

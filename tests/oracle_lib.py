@@ -65,6 +65,9 @@ class Oracle:
     def call(self, phase, *args):
         self._chk(getattr(self.lib, "oracle_" + phase)(self.h, *[ctypes.c_int(int(x)) for x in args]))
 
+    def set_threads(self, n):
+        return int(self.lib.oracle_set_threads(self.h, ctypes.c_int(int(n))))
+
     def step(self, n=1):
         self._chk(self.lib.oracle_step(self.h, ctypes.c_int(n)))
 

@@ -1,0 +1,128 @@
+"""Shared machinery of the GPU-vs-oracle parity tests (test infrastructure)."""
+from __future__ import annotations
+
+import numpy as np
+
+from tests.oracle_lib import Oracle
+from wrf_b200 import Solver, make_case
+
+# phases whose arithmetic contains libm transcendentals (powf/logf/sinf/expf): CUDA's
+# single-precision versions are not bit-identical to glibc's, so these are held to
+# a relative-L2 tolerance instead of bit equality (SURVEY.md section 7 "Transcendentals").
+TRANSCENDENTAL = {"calc_p_rho_phi", "microphysics", "end_of_step", "step"}
+TOL_REL_L2 = 1.0e-6          # per phase; the north-star bar is 1e-5 after one full step
+STEP_TOL_REL_L2 = 1.0e-5
+
+
+def small_cases():
+    """name -> Case; sizes the oracle finishes in about a second per step."""
+    return {
+        "hill2d_x": make_case("hill2d_x", nx=62, ny=3, nz=21),
+        "quarter_ss": make_case("quarter_ss", nx=26, ny=24, nz=21),
+        "quarter_ss_nopd": make_case("quarter_ss", nx=26, ny=24, nz=21, moist_adv_opt=0),
+        "b_wave": make_case("b_wave", nx=21, ny=31, nz=17),
+        "periodic": make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=2),
+    }
+
+
+def common_fields(o: Oracle, s: Solver):
+    on = set(o.names())
+    return [n for n in s.names() if n in on]
+
+
+def rel_l2(a, b):
+    a = a.astype(np.float64).ravel()
+    b = b.astype(np.float64).ravel()
+    den = np.sqrt((b * b).sum())
+    num = np.sqrt(((a - b) ** 2).sum())
+    return 0.0 if num == 0.0 else (num / den if den > 0 else np.inf)
+
+
+# perturbation fields are differences of O(1e5 Pa) / O(1 m3/kg) totals: their error is
+# measured against the full field the model actually uses (p+pb, al+alb, ph+phb, mu+mub)
+BASE_OF = {"p": "pb", "al": "alb", "ph_2": "phb", "ph_1": "phb", "mu_2": "mub", "mu_1": "mub", "t_2": None, "t_1": None}
+
+
+def rel_l2_field(o: Oracle, name, a, b):
+    base = BASE_OF.get(name, "")
+    if base == "":
+        return rel_l2(a, b)
+    if base is None:       # theta perturbation: full theta = t + 300
+        return rel_l2(a.astype(np.float64) + 300.0, b.astype(np.float64) + 300.0)
+    bb = o.get(base).astype(np.float64)
+    return rel_l2(a.astype(np.float64) + bb, b.astype(np.float64) + bb)
+
+
+def diff_report(o: Oracle, s: Solver, fields=None):
+    """returns list of (field, n_mismatch, max_abs, rel_l2)"""
+    out = []
+    for n in fields or common_fields(o, s):
+        a, b = s.get(n), o.get(n)
+        bad = ~((a == b) | (np.isnan(a) & np.isnan(b)))
+        if bad.any():
+            with np.errstate(invalid="ignore"):
+                out.append((n, int(bad.sum()), float(np.nanmax(np.abs(a.astype(np.float64) - b))), rel_l2_field(o, n, a, b)))
+    return out
+
+
+def sync_from_oracle(o: Oracle, s: Solver, fields=None):
+    for n in fields or common_fields(o, s):
+        s.set(n, o.get(n))
+
+
+def phase_sequence(case):
+    """(phase, args) list of one full solve_em step -- solve_em.F:578-4848."""
+    c = case.config
+    nss = c.time_step_sound
+    seq = []
+    for rk in range(1, c.rk_ord + 1):
+        ns = 1 if (c.rk_ord == 3 and rk == 1) else (nss // 2 if rk < c.rk_ord else nss)
+        seq += [("rk_step_prep", (rk,)), ("rk_phys_bc_dry_1", ())]
+        if rk == 1:
+            seq.append(("init_zero_tendency", ()))
+        seq += [("rk_tendency", (rk,)), ("small_step_prep", (rk,))]
+        for it in range(1, ns + 1):
+            seq += [("advance_uv", (rk,)), ("advance_mu_t", (rk,)), ("advance_w", (rk,)), ("sumflux", (rk, it)), ("calc_p_rho", (it,))]
+        seq += [("small_step_finish", (rk,)), ("rk_scalar_step", (rk,)), ("calc_p_rho_phi", ())]
+        if rk < c.rk_ord:
+            seq.append(("rk_phys_bc_dry_2", ()))
+    seq += [("microphysics", ()), ("end_of_step", ())]
+    return seq
+
+
+def is_transcendental(phase, case):
+    c = case.config
+    if phase in TRANSCENDENTAL:
+        return True
+    if phase == "advance_w" and c.damp_opt == 3:
+        return True
+    if phase == "rk_tendency" and c.damp_opt == 2:
+        return True
+    return False
+
+
+def run_phase_parity(case, verbose=False):
+    """Run one step phase by phase; the GPU input of every phase is the oracle's state.
+    Returns list of failures (phase, field, n, maxabs, rel)."""
+    o, s = Oracle(case), Solver(case)
+    o.start_domain(); s.start_domain()
+    fails = []
+    rep = diff_report(o, s)
+    for r in rep:
+        fails.append(("start_domain",) + r)
+    fields = common_fields(o, s)
+    for phase, args in phase_sequence(case):
+        o.call(phase, *args)
+        s.call(phase, *args)
+        rep = diff_report(o, s, fields)
+        loose = is_transcendental(phase, case)
+        for r in rep:
+            ok = loose and r[3] <= TOL_REL_L2
+            if verbose or not ok:
+                print(f"  {'ok ' if ok else 'BAD'} {phase}{args}: {r[0]:12s} n={r[1]:7d} maxabs={r[2]:.3e} rel_l2={r[3]:.3e}")
+            if not ok:
+                fails.append((phase,) + r)
+        if rep:
+            sync_from_oracle(o, s, [r[0] for r in rep])
+    s.close()
+    return fails

@@ -1,0 +1,198 @@
+// common.cuh -- shared declarations of the B200-native solve_em path.
+//
+// Data layout in HBM: every field keeps WRF's (i,k,j) order with i fastest and
+// the caller's memory halo (ims:ime, kms:kme, jms:jme), so an upload/download is
+// one contiguous cudaMemcpy of the Fortran array and a warp that spans 32
+// consecutive i reads/writes one 128-byte line per field.  Kernel pointers are
+// "origin shifted" (base - offset of (0,0,0)), so A3(f,i,k,j) is
+// f[i + k*sk + j*sj] with the Fortran indices used as they are.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "../../include/wrfgpu.h"
+
+namespace wg {
+
+// share/module_model_constants.F:17-89
+#define WG_G 9.81f
+#define WG_RD 287.f
+#define WG_CP (7.f * 287.f / 2.f)
+#define WG_RV 461.6f
+#define WG_T0 300.f
+#define WG_P0 100000.f
+#define WG_CPOVCV (WG_CP / (WG_CP - WG_RD))
+#define WG_RCP (WG_RD / WG_CP)
+#define WG_RVOVRD (WG_RV / WG_RD)
+#define WG_RERADIUS (1.f / 6370.0e03f)
+#define WG_CB 25.f
+
+struct Geo {
+  int ids, ide, jds, jde, kds, kde;
+  int ims, ime, jms, jme, kms, kme;
+  int ips, ipe, jps, jpe;
+  int its, ite, jts, jte;          // tile == patch (numtiles = 1)
+  int ni, nk, nj;
+  long sk, sj;                     // strides of k and j in a 3-D field
+  int periodic_x, periodic_y, sym_xs, sym_xe, sym_ys, sym_ye, open_xs, open_xe, open_ys, open_ye;
+  int top_lid, phi_adv_z, damp_opt, w_damping, pert_coriolis, use_theta_m, hypsometric_opt, rk_ord;
+  int num_moist;
+  float rdx, rdy, dt, cf1, cf2, cf3, cfn, cfn1;
+  float epssm, smdiv, emdiv, dampcoef, zdamp, w_crit_cfl, p_top;
+  float sgn_ts;                    // sign(1,time_step)
+  // 1-D coefficients, shifted so that c1h[k] takes the Fortran k
+  const float *znu, *znw, *fnm, *fnp, *rdnw, *rdn, *dnw, *dn;
+  const float *c1h, *c2h, *c1f, *c2f, *c3h, *c4h, *c3f, *c4f;
+  const float *u_base, *v_base, *t_base, *z_base;
+  // 2-D fields, origin shifted: A2(f,i,j)
+  const float *msftx, *msfty, *msfux, *msfuy, *msfvx, *msfvx_inv, *msfvy, *f, *e, *sina, *cosa, *ht;
+};
+
+#define A3(f, i, k, j) (f)[(long)(i) + (long)(k) * g.sk + (long)(j) * g.sj]
+#define A2(f, i, j) (f)[(long)(i) + (long)(j) * g.ni]
+
+typedef float *__restrict__ fp;
+typedef const float *__restrict__ cfp;
+
+__device__ __forceinline__ float sign1(float a) { return copysignf(1.0f, a); }
+
+#define CUDA_CHECK(x)                                                                     \
+  do {                                                                                    \
+    cudaError_t e_ = (x);                                                                 \
+    if (e_ != cudaSuccess)                                                                \
+      throw std::runtime_error(std::string("CUDA error ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + \
+                               std::to_string(__LINE__));                                 \
+  } while (0)
+
+struct Field {
+  float *d = nullptr;   // device allocation
+  float *o = nullptr;   // origin-shifted pointer
+  int kind = 3;         // 3, 2, 1
+  size_t n = 0;
+};
+
+struct Species {
+  std::string f, o, t;  // field, old, tend names
+  int adv_opt;
+};
+
+struct Solver {
+  wrfgpu_dims d;
+  wrfgpu_config c;
+  Geo g;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::map<std::string, Field> fields;
+  std::vector<std::string> names;
+  std::vector<Species> species;
+  int num_sound_steps = 0;
+  float dts = 0.f;
+  long long launches = 0;
+  float *d_cfl = nullptr;   // 2 floats: max_vert_cfl, max_horiz_cfl
+  // halo/NCCL state lives in halo.cu
+  void *comm = nullptr;
+  int rank = 0, nranks = 1;
+  float *sendbuf[4] = {nullptr, nullptr, nullptr, nullptr};
+  float *recvbuf[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t bufcap = 0;
+  // phase / kernel timing (cudaEvents on `stream`, only when switched on)
+  bool timing = false;
+  std::map<std::string, double> phase_ms;
+  struct KStat { long n = 0; double ms = 0; };
+  std::map<std::string, KStat> kstat;
+  struct Pending { const char *name; cudaEvent_t a, b; };
+  std::vector<Pending> pending;
+  bool own_stream = true;
+  inline void kpre(const char *name) {
+    if (!timing) return;
+    Pending p; p.name = name;
+    cudaEventCreate(&p.a); cudaEventCreate(&p.b);
+    cudaEventRecord(p.a, stream);
+    pending.push_back(p);
+  }
+  inline void kpost() {
+    if (!timing) return;
+    cudaEventRecord(pending.back().b, stream);
+  }
+  void flush_timing();
+
+  Solver(const wrfgpu_dims &d, const wrfgpu_config &c, int device);
+  ~Solver();
+  void add(const std::string &n, int kind);
+  Field &F(const std::string &n);
+  float *o(const std::string &n) { return F(n).o; }   // origin-shifted
+  void build_geo();
+  void rk_params(int rk_step, float &dt_rk, float &dts_rk, int &nsmall) const;
+
+  // phases (solve_em.cu)
+  void rk_step_prep(int rk_step);
+  void rk_phys_bc_dry_1();
+  void init_zero_tendency();
+  void rk_tendency(int rk_step);
+  void small_step_prep(int rk_step);
+  void advance_uv(int rk_step);
+  void advance_mu_t(int rk_step);
+  void advance_w(int rk_step);
+  void sumflux(int rk_step, int iteration);
+  void calc_p_rho(int iteration);
+  void small_step_finish(int rk_step);
+  void rk_scalar_step(int rk_step);
+  void calc_p_rho_phi();
+  void rk_phys_bc_dry_2();
+  void microphysics();
+  void end_of_step();
+  void start_domain();
+  void step();
+  // bc.cu
+  struct BcItem { std::string name; char var; };
+  void bc(const std::vector<BcItem> &items);
+  // halo.cu
+  void halo(const std::string &name);
+};
+
+// launch helpers -------------------------------------------------------------
+struct Box { int i0, i1, k0, k1, j0, j1; };
+inline dim3 grid3(const Box &b, int bx) {
+  return dim3((unsigned)((b.i1 - b.i0 + bx) / bx), (unsigned)(b.k1 - b.k0 + 1), (unsigned)(b.j1 - b.j0 + 1));
+}
+inline bool empty(const Box &b) { return b.i1 < b.i0 || b.k1 < b.k0 || b.j1 < b.j0; }
+
+#define WG_BX 128
+// 3-D launch: kernel(g, box, args...) with one thread per (i,k,j)
+#define LAUNCH3(S, kern, box, ...)                                                   \
+  do {                                                                               \
+    Box b_ = (box);                                                                  \
+    if (!empty(b_)) {                                                                \
+      (S)->kpre(#kern);                                                              \
+      kern<<<grid3(b_, WG_BX), WG_BX, 0, (S)->stream>>>((S)->g, b_, __VA_ARGS__);    \
+      (S)->kpost();                                                                  \
+      (S)->launches++;                                                               \
+    }                                                                                \
+  } while (0)
+// column launch: one thread per (i,j)
+#define LAUNCH2(S, kern, box, ...)                                                   \
+  do {                                                                               \
+    Box b_ = (box);                                                                  \
+    if (!empty(b_)) {                                                                \
+      dim3 gr_((unsigned)((b_.i1 - b_.i0 + WG_BX) / WG_BX), (unsigned)(b_.j1 - b_.j0 + 1)); \
+      (S)->kpre(#kern);                                                              \
+      kern<<<gr_, WG_BX, 0, (S)->stream>>>((S)->g, b_, __VA_ARGS__);                 \
+      (S)->kpost();                                                                  \
+      (S)->launches++;                                                               \
+    }                                                                                \
+  } while (0)
+
+#define TID3                                              \
+  const int i = b.i0 + blockIdx.x * blockDim.x + threadIdx.x; \
+  const int k = b.k0 + blockIdx.y;                        \
+  const int j = b.j0 + blockIdx.z;                        \
+  if (i > b.i1) return;
+#define TID2                                              \
+  const int i = b.i0 + blockIdx.x * blockDim.x + threadIdx.x; \
+  const int j = b.j0 + blockIdx.y;                        \
+  if (i > b.i1) return;
+
+}  // namespace wg

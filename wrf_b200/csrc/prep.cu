@@ -1,0 +1,147 @@
+// prep.cu -- rk_step_prep (dyn_em/module_em.F:37-186) fused into three kernels:
+//   k_prep_mu  : calculate_full(mut) + calc_mu_uv        (2-D)
+//   k_prep_3d  : couple_momentum + calc_cq + calc_alt + calc_php, one pass
+//   k_calc_ww  : calc_ww_cp column integral (k prefix sum kept in registers)
+// The reference makes seven separate sweeps (module_big_step_utilities_em.F:26,329,
+// 640,787,910,1227,3587).  Algorithmic bytes: 16+n_moist field accesses per point.
+#include "common.cuh"
+
+namespace wg {
+
+// module_big_step_utilities_em.F:3587 (mut) and :26-180 (muu,muv incl. the domain-edge special cases)
+__global__ void k_prep_mu(const Geo g, Box b, cfp mu, cfp mub, fp mut, fp muu, fp muv) {
+  TID2;
+  const bool im = i <= min(g.ite, g.ide - 1), jm = j <= min(g.jte, g.jde - 1);
+  if (im && jm) A2(mut, i, j) = A2(mub, i, j) + A2(mu, i, j);
+  if (jm) {
+    float r;
+    if (i == g.ids) {
+      const int q = g.periodic_x ? g.ids - 1 : g.ids;
+      r = 0.5f * (A2(mu, i, j) + A2(mu, q, j) + A2(mub, i, j) + A2(mub, q, j));
+    } else if (i == g.ide) {
+      const int q = g.periodic_x ? g.ide : g.ide - 1;
+      r = 0.5f * (A2(mu, i - 1, j) + A2(mu, q, j) + A2(mub, i - 1, j) + A2(mub, q, j));
+    } else {
+      r = 0.5f * (A2(mu, i, j) + A2(mu, i - 1, j) + A2(mub, i, j) + A2(mub, i - 1, j));
+    }
+    A2(muu, i, j) = r;
+  }
+  if (im) {
+    float r;
+    if (j == g.jds) {
+      const int q = g.periodic_y ? g.jds - 1 : g.jds;
+      r = 0.5f * (A2(mu, i, j) + A2(mu, i, q) + A2(mub, i, j) + A2(mub, i, q));
+    } else if (j == g.jde) {
+      const int q = g.periodic_y ? g.jde : g.jde - 1;
+      r = 0.5f * (A2(mu, i, j - 1) + A2(mu, i, q) + A2(mub, i, j - 1) + A2(mub, i, q));
+    } else {
+      r = 0.5f * (A2(mu, i, j) + A2(mu, i, j - 1) + A2(mub, i, j) + A2(mub, i, j - 1));
+    }
+    A2(muv, i, j) = r;
+  }
+}
+
+struct MoistPtrs { const float *m[3]; int n; };
+
+// couple_momentum :329, calc_cq :787, calc_alt :910, calc_php :1227
+__global__ void k_prep_3d(const Geo g, Box b, cfp u, cfp v, cfp w, cfp muu, cfp muv, cfp mut, fp ru, fp rv, fp rw,
+                          MoistPtrs mp, fp cqu, fp cqv, fp cqw, cfp al, cfp alb, fp alt, cfp ph, cfp phb, fp php) {
+  TID3;
+  const int ktf = g.kde - 1;
+  const bool im = i <= min(g.ite, g.ide - 1), jm = j <= min(g.jte, g.jde - 1), km = k <= ktf;
+  const float c1h = g.c1h[k], c2h = g.c2h[k];
+  if (km && jm) {
+    A3(ru, i, k, j) = A3(u, i, k, j) * (c1h * A2(muu, i, j) + c2h) / A2(g.msfuy, i, j);
+    float r = 1.f;
+    if (mp.n >= 1) {
+      float qtot = 0.f;
+      for (int s = 0; s < mp.n; s++) qtot = qtot + A3(mp.m[s], i, k, j) + A3(mp.m[s], i - 1, k, j);
+      r = 1.f / (1.f + 0.5f * qtot);
+    }
+    A3(cqu, i, k, j) = r;
+  }
+  if (km && im) {
+    A3(rv, i, k, j) = A3(v, i, k, j) * (c1h * A2(muv, i, j) + c2h) * A2(g.msfvx_inv, i, j);
+    float r = 1.f;
+    if (mp.n >= 1) {
+      float qtot = 0.f;
+      for (int s = 0; s < mp.n; s++) qtot = qtot + A3(mp.m[s], i, k, j) + A3(mp.m[s], i, k, j - 1);
+      r = 1.f / (1.f + 0.5f * qtot);
+    }
+    A3(cqv, i, k, j) = r;
+  }
+  if (im && jm) {
+    A3(rw, i, k, j) = A3(w, i, k, j) * (g.c1f[k] * A2(mut, i, j) + g.c2f[k]) / A2(g.msfty, i, j);
+    if (km) {
+      if (k >= 2) {
+        float r = 0.f;
+        if (mp.n >= 1) {
+          float qtot = 0.f;
+          for (int s = 0; s < mp.n; s++) qtot = qtot + A3(mp.m[s], i, k, j) + A3(mp.m[s], i, k - 1, j);
+          r = 0.5f * qtot;
+        }
+        A3(cqw, i, k, j) = r;
+      }
+      A3(alt, i, k, j) = A3(al, i, k, j) + A3(alb, i, k, j);
+      A3(php, i, k, j) = 0.5f * (A3(phb, i, k, j) + A3(phb, i, k + 1, j) + A3(ph, i, k, j) + A3(ph, i, k + 1, j));
+    }
+  }
+}
+
+// calc_ww_cp, module_big_step_utilities_em.F:640-782.  One thread per column; pass 1
+// stores divv(k) in ww(k+1) while summing dmdt, pass 2 turns it into ww in place.
+__global__ void k_calc_ww(const Geo g, Box b, cfp u, cfp v, cfp mup, cfp mub, fp ww) {
+  TID2;
+  const int ktf = g.kde - 1, kte = g.kde;
+  if (i > min(g.ite, g.ide - 1)) {   // i = ide column: only the ww(:,1,:) / ww(:,kte,:) reset (:744-749)
+    A3(ww, i, 1, j) = 0.f;
+    A3(ww, i, kte, j) = 0.f;
+    return;
+  }
+  const float muu0 = 0.5f * (A2(mup, i, j) + A2(mub, i, j) + A2(mup, i - 1, j) + A2(mub, i - 1, j));
+  const float muu1 = 0.5f * (A2(mup, i + 1, j) + A2(mub, i + 1, j) + A2(mup, i, j) + A2(mub, i, j));
+  const float muv0 = 0.5f * (A2(mup, i, j) + A2(mub, i, j) + A2(mup, i, j - 1) + A2(mub, i, j - 1));
+  const float muv1 = 0.5f * (A2(mup, i, j + 1) + A2(mub, i, j + 1) + A2(mup, i, j) + A2(mub, i, j));
+  const float msftx = A2(g.msftx, i, j);
+  const float my0 = A2(g.msfuy, i, j), my1 = A2(g.msfuy, i + 1, j);
+  const float mvi0 = A2(g.msfvx_inv, i, j), mvi1 = A2(g.msfvx_inv, i, j + 1);
+  float dmdt = 0.f;
+  for (int k = 1; k <= ktf; k++) {
+    const float c1h = g.c1h[k], c2h = g.c2h[k];
+    const float divv = msftx * g.dnw[k] *
+                       (g.rdx * ((c1h * muu1 + c2h) * A3(u, i + 1, k, j) / my1 - (c1h * muu0 + c2h) * A3(u, i, k, j) / my0) +
+                        g.rdy * ((c1h * muv1 + c2h) * A3(v, i, k, j + 1) * mvi1 - (c1h * muv0 + c2h) * A3(v, i, k, j) * mvi0));
+    dmdt = dmdt + divv;
+    A3(ww, i, k + 1, j) = divv;
+  }
+  float wprev = 0.f;
+  A3(ww, i, 1, j) = 0.f;
+  for (int k = 2; k <= ktf; k++) {
+    const float divv = A3(ww, i, k, j);
+    wprev = wprev - g.dnw[k - 1] * g.c1h[k - 1] * dmdt - divv;
+    A3(ww, i, k, j) = wprev;
+  }
+  A3(ww, i, kte, j) = 0.f;
+}
+
+void Solver::rk_step_prep(int) {
+  const Geo &q = g;
+  LAUNCH2(this, k_prep_mu, (Box{q.its, q.ite, 1, 1, q.jts, q.jte}), o("mu_2"), o("mub"), o("mut"), o("muu"), o("muv"));
+  MoistPtrs mp;
+  mp.n = c.num_moist;
+  static const char *mn[] = {"moist_qv", "moist_qc", "moist_qr"};
+  for (int s = 0; s < 3; s++) mp.m[s] = s < mp.n ? o(mn[s]) : nullptr;
+  LAUNCH3(this, k_prep_3d, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), o("u_2"), o("v_2"), o("w_2"), o("muu"), o("muv"),
+          o("mut"), o("ru"), o("rv"), o("rw"), mp, o("cqu"), o("cqv"), o("cqw"), o("al"), o("alb"), o("alt"), o("ph_2"),
+          o("phb"), o("php"));
+  LAUNCH2(this, k_calc_ww, (Box{q.its, q.ite, 1, 1, q.jts, std::min(q.jte, q.jde - 1)}), o("u_2"), o("v_2"), o("mu_2"),
+          o("mub"), o("ww"));
+}
+
+// solve_em.F:726-754 (rk_phys_bc_dry_1 = module_bc_em.F:960-1041, then rho, al, ph_2)
+void Solver::rk_phys_bc_dry_1() {
+  bc({{"ru", 'u'}, {"rv", 'v'}, {"rw", 'w'}, {"ww", 'w'}, {"php", 'w'}, {"alt", 't'}, {"p", 'p'},
+      {"muu", 'u'}, {"muv", 'v'}, {"mut", 't'}, {"rho", 'p'}, {"al", 'p'}, {"ph_2", 'w'}});
+}
+
+}  // namespace wg

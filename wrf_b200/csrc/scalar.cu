@@ -1,0 +1,259 @@
+// scalar.cu -- scalar transport of solve_em.F:1850-2955: rk_update_scalar_pd
+// (module_em.F:1803), rk_scalar_tend (:1096) with advect_scalar or, on the last RK
+// substep under *_adv_opt = 1, the positive-definite advect_scalar_pd
+// (module_advect_em.F:6069-7885), and rk_update_scalar (module_em.F:1587).
+//
+// advect_scalar_pd in the reference materialises eight tile-sized 3-D flux arrays
+// ("memory intensive", :6085-6088).  Here nothing but a per-cell limiter factor
+// `scale` is stored: kernel 1 evaluates a cell's six face fluxes (high-order minus
+// upwind, and upwind) and writes scale = max(0, ph_low/(flux_out+eps)) where the
+// outgoing correction exceeds the low-order mass (else 1); kernel 2 re-evaluates
+// the face fluxes, multiplies each high-order correction by the scale of its DONOR
+// cell (:7764-7773) and writes the tendency.  Flux values are pure functions of the
+// inputs, so recomputation is bit-identical to the stored version.
+#include "common.cuh"
+
+namespace wg {
+
+__global__ void k_advect_scalar(const Geo g, Box b, cfp q, cfp ru, cfp rv, cfp rom, fp tend);   // tend.cu
+
+// statement functions of advect_scalar_pd (:6169-6186) -- note the pre-divided constants
+__device__ __forceinline__ float pflux4(float qm2, float qm1, float q0, float qp1) {
+  return (7.f / 12.f) * (q0 + qm1) - (1.f / 12.f) * (qp1 + qm2);
+}
+__device__ __forceinline__ float pflux3(float qm2, float qm1, float q0, float qp1, float ua, float sg) {
+  return pflux4(qm2, qm1, q0, qp1) + sg * sign1(ua) * (1.f / 12.f) * ((qp1 - qm2) - 3.f * (q0 - qm1));
+}
+__device__ __forceinline__ float pflux6(float qm3, float qm2, float qm1, float q0, float qp1, float qp2) {
+  return (37.f / 60.f) * (q0 + qm1) - (2.f / 15.f) * (qp1 + qm2) + (1.f / 60.f) * (qp2 + qm3);
+}
+__device__ __forceinline__ float pflux5(float qm3, float qm2, float qm1, float q0, float qp1, float qp2, float ua, float sg) {
+  return pflux6(qm3, qm2, qm1, q0, qp1, qp2) - sg * sign1(ua) * (1.f / 60.f) * ((qp2 - qm3) - 5.f * (qp1 - qm2) + 10.f * (q0 - qm1));
+}
+__device__ __forceinline__ float flux_upwind(float qm1, float q0, float cr) {
+  return 0.5f * fminf(1.0f, (cr + fabsf(cr))) * qm1 + 0.5f * fmaxf(-1.0f, (cr - fabsf(cr))) * q0;
+}
+
+struct PdIn {
+  cfp q, q_old, ru, rv, rom, mut, mub, mu_old;
+  float dt;
+};
+struct Face { float hi, lo; bool ok; };   // hi = high-order minus low, lo = upwind flux
+
+__device__ __forceinline__ int pd_order(int f, bool dlo, bool dhi, int lo_edge, int hi_edge) {
+  // faces lo_edge+1 / hi_edge-1 are 2nd order, lo_edge+2 / hi_edge-2 3rd order
+  if ((!dlo || f >= lo_edge + 3) && (!dhi || f <= hi_edge - 3)) return 5;
+  if (f == lo_edge + 1) return 2;
+  if (f == lo_edge + 2) return 3;
+  if (f == hi_edge - 1) return 2;
+  if (f == hi_edge - 2) return 3;
+  return 0;
+}
+
+// x-face ii of row j, level k (:6640-6770)
+__device__ __forceinline__ Face pd_face_x(const Geo &g, const PdIn &s, int ii, int k, int j, bool dxs, bool dxe) {
+  Face f;
+  const int ord = pd_order(ii, dxs, dxe, g.ids, g.ide);
+  f.ok = ord != 0;
+  if (!f.ok) { f.hi = 0.f; f.lo = 0.f; return f; }
+  const float dx = 2.f / (A2(g.msfty, ii, j) + A2(g.msfty, ii - 1, j)) / g.rdx;
+  const float mu = 0.5f * ((g.c1h[k] * A2(s.mut, ii, j) + g.c2h[k]) + (g.c1h[k] * A2(s.mut, ii - 1, j) + g.c2h[k]));
+  float vel, cr;
+  if (ord == 2 && ii == g.ids + 1) { vel = A3(s.ru, ii, k, j) / mu; cr = vel * s.dt / dx; }   // :6683-6684
+  else { vel = A3(s.ru, ii, k, j); cr = vel * s.dt / dx / mu; }
+  f.lo = mu * (dx / s.dt) * flux_upwind(A3(s.q_old, ii - 1, k, j), A3(s.q_old, ii, k, j), cr);
+  float h;
+  if (ord == 5) h = vel * pflux5(A3(s.q, ii - 3, k, j), A3(s.q, ii - 2, k, j), A3(s.q, ii - 1, k, j), A3(s.q, ii, k, j), A3(s.q, ii + 1, k, j), A3(s.q, ii + 2, k, j), vel, g.sgn_ts);
+  else if (ord == 3) h = vel * pflux3(A3(s.q, ii - 2, k, j), A3(s.q, ii - 1, k, j), A3(s.q, ii, k, j), A3(s.q, ii + 1, k, j), vel, g.sgn_ts);
+  else h = 0.5f * (A3(s.ru, ii, k, j)) * (A3(s.q, ii, k, j) + A3(s.q, ii - 1, k, j));
+  f.hi = h - f.lo;
+  return f;
+}
+// y-face jj of column i (:6540-6630)
+__device__ __forceinline__ Face pd_face_y(const Geo &g, const PdIn &s, int i, int k, int jj, bool dys, bool dye) {
+  Face f;
+  const int ord = pd_order(jj, dys, dye, g.jds, g.jde);
+  f.ok = ord != 0;
+  if (!f.ok) { f.hi = 0.f; f.lo = 0.f; return f; }
+  const float dy = 2.f / (A2(g.msftx, i, jj) + A2(g.msftx, i, jj - 1)) / g.rdy;
+  const float mu = 0.5f * ((g.c1h[k] * A2(s.mut, i, jj) + g.c2h[k]) + (g.c1h[k] * A2(s.mut, i, jj - 1) + g.c2h[k]));
+  const float vel = A3(s.rv, i, k, jj);
+  const float cr = vel * s.dt / dy / mu;
+  f.lo = mu * (dy / s.dt) * flux_upwind(A3(s.q_old, i, k, jj - 1), A3(s.q_old, i, k, jj), cr);
+  float h;
+  if (ord == 5) h = vel * pflux5(A3(s.q, i, k, jj - 3), A3(s.q, i, k, jj - 2), A3(s.q, i, k, jj - 1), A3(s.q, i, k, jj), A3(s.q, i, k, jj + 1), A3(s.q, i, k, jj + 2), vel, g.sgn_ts);
+  else if (ord == 3) h = vel * pflux3(A3(s.q, i, k, jj - 2), A3(s.q, i, k, jj - 1), A3(s.q, i, k, jj), A3(s.q, i, k, jj + 1), vel, g.sgn_ts);
+  else h = 0.5f * A3(s.rv, i, k, jj) * (A3(s.q, i, k, jj) + A3(s.q, i, k, jj - 1));
+  f.hi = h - f.lo;
+  return f;
+}
+// z-face kk of column (i,j) (:7595-7645)
+__device__ __forceinline__ Face pd_face_z(const Geo &g, const PdIn &s, int i, int kk, int j) {
+  Face f;
+  f.ok = true;
+  if (kk == 1 || kk == g.kde) { f.hi = 0.f; f.lo = 0.f; return f; }
+  const int ktf = g.kde - 1;
+  const float dz = 2.f / (g.rdnw[kk] + g.rdnw[kk - 1]);
+  const float mu = 0.5f * ((g.c1h[kk] * A2(s.mut, i, j) + g.c2h[kk]) + (g.c1h[kk] * A2(s.mut, i, j) + g.c2h[kk]));
+  const float vel = A3(s.rom, i, kk, j);
+  const float cr = vel * s.dt / dz / mu;
+  f.lo = mu * (dz / s.dt) * flux_upwind(A3(s.q_old, i, kk - 1, j), A3(s.q_old, i, kk, j), cr);
+  float h;
+  if (kk == 2 || kk == ktf) h = A3(s.rom, i, kk, j) * (g.fnm[kk] * A3(s.q, i, kk, j) + g.fnp[kk] * A3(s.q, i, kk - 1, j));
+  else h = vel * pflux3(A3(s.q, i, kk - 2, j), A3(s.q, i, kk - 1, j), A3(s.q, i, kk, j), A3(s.q, i, kk + 1, j), -vel, g.sgn_ts);
+  f.hi = h - f.lo;
+  return f;
+}
+
+// kernel 1: limiter factor on the tile + 1 ring (:7681-7776)
+__global__ void k_pd_scale(const Geo g, Box b, PdIn s, fp scale) {
+  TID3;
+  const bool dxs = !(g.periodic_x || g.sym_xs), dxe = !(g.periodic_x || g.sym_xe);
+  const bool dys = !(g.periodic_y || g.sym_ys), dye = !(g.periodic_y || g.sym_ye);
+  const Face x0 = pd_face_x(g, s, i, k, j, dxs, dxe), x1 = pd_face_x(g, s, i + 1, k, j, dxs, dxe);
+  const Face y0 = pd_face_y(g, s, i, k, j, dys, dye), y1 = pd_face_y(g, s, i, k, j + 1, dys, dye);
+  const Face z0 = pd_face_z(g, s, i, k, j), z1 = pd_face_z(g, s, i, k + 1, j);
+  const float msftx = A2(g.msftx, i, j), msfty = A2(g.msfty, i, j);
+  const float ph_low = ((g.c1h[k] * A2(s.mub, i, j) + g.c2h[k]) + (g.c1h[k] * A2(s.mu_old, i, j))) * A3(s.q_old, i, k, j) -
+                       s.dt * (msftx * msfty * (g.rdx * (x1.lo - x0.lo) + g.rdy * (y1.lo - y0.lo)) + msfty * g.rdnw[k] * (z1.lo - z0.lo));
+  const float flux_out = s.dt * ((msftx * msfty) * (g.rdx * (fmaxf(0.f, x1.hi) - fminf(0.f, x0.hi)) + g.rdy * (fmaxf(0.f, y1.hi) - fminf(0.f, y0.hi))) +
+                                 msfty * g.rdnw[k] * (fminf(0.f, z1.hi) - fmaxf(0.f, z0.hi)));
+  float sc = 1.f;
+  if (flux_out > ph_low) sc = fmaxf(0.f, ph_low / (flux_out + 1.e-20f));
+  A3(scale, i, k, j) = sc;
+}
+
+// kernel 2: limited flux divergence (:7778-7883) + open-boundary terms (:7255-7318)
+__global__ void k_pd_tend(const Geo g, Box b, PdIn s, cfp scale, Box lim, fp tend) {
+  TID3;
+  const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde;
+  const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
+  const bool dxs = !(g.periodic_x || g.sym_xs), dxe = !(g.periodic_x || g.sym_xe);
+  const bool dys = !(g.periodic_y || g.sym_ys), dye = !(g.periodic_y || g.sym_ye);
+  cfp q = s.q, q_old = s.q_old, ru = s.ru, rv = s.rv;
+  // scale of a cell, 1 outside the limiter box
+  auto sc_at = [&](int ii, int kk, int jj) -> float {
+    if (ii < lim.i0 || ii > lim.i1 || jj < lim.j0 || jj > lim.j1 || kk < lim.k0 || kk > lim.k1) return 1.f;
+    return A3(scale, ii, kk, jj);
+  };
+  float t = 0.f;
+  // open boundary terms come first in the reference (they are added to `tendency` before the divergence)
+  const int i_end = min(ite, ide - 1), j_end = min(jte, jde - 1);
+  if (g.open_xs && i == ids) {
+    const float ub = fminf(0.5f * (A3(ru, ids, k, j) + A3(ru, ids + 1, k, j)), 0.f);
+    t = t - g.rdx * (ub * (A3(q_old, ids + 1, k, j) - A3(q_old, ids, k, j)) + A3(q, ids, k, j) * (A3(ru, ids + 1, k, j) - A3(ru, ids, k, j)));
+  }
+  if (g.open_xe && ite == ide && i == i_end) {
+    const float ub = fmaxf(0.5f * (A3(ru, ide - 1, k, j) + A3(ru, ide, k, j)), 0.f);
+    t = t - g.rdx * (ub * (A3(q_old, i_end, k, j) - A3(q_old, i_end - 1, k, j)) + A3(q, i_end, k, j) * (A3(ru, ide, k, j) - A3(ru, ide - 1, k, j)));
+  }
+  if (g.open_ys && j == jds) {
+    const float vb = fminf(0.5f * (A3(rv, i, k, jds) + A3(rv, i, k, jds + 1)), 0.f);
+    t = t - g.rdy * (vb * (A3(q_old, i, k, jds + 1) - A3(q_old, i, k, jds)) + A3(q, i, k, jds) * (A3(rv, i, k, jds + 1) - A3(rv, i, k, jds)));
+  }
+  if (g.open_ye && jte == jde && j == j_end) {
+    const float vb = fmaxf(0.5f * (A3(rv, i, k, jde - 1) + A3(rv, i, k, jde)), 0.f);
+    t = t - g.rdy * (vb * (A3(q_old, i, k, j_end) - A3(q_old, i, k, j_end - 1)) + A3(q, i, k, j_end) * (A3(rv, i, k, jde) - A3(rv, i, k, jde - 1)));
+  }
+  // limited high-order correction of a face: scaled by the donor cell (:7764-7773)
+  // x: fqx(i+1)>0 -> scale(i) ; fqx(i)<0 -> scale(i).  For face ii the donor is ii-1 if hi>0, ii if hi<0.
+  // z: sign convention is reversed (fqz(k+1)<0 and fqz(k)>0 are outgoing): donor is kk-1 if hi<0, kk if hi>0.
+  {
+    Face z0 = pd_face_z(g, s, i, k, j), z1 = pd_face_z(g, s, i, k + 1, j);
+    float h0 = z0.hi, h1 = z1.hi;
+    if (h0 > 0.f) h0 = sc_at(i, k, j) * h0; else if (h0 < 0.f) h0 = sc_at(i, k - 1, j) * h0;
+    if (h1 > 0.f) h1 = sc_at(i, k + 1, j) * h1; else if (h1 < 0.f) h1 = sc_at(i, k, j) * h1;
+    t = t - g.rdnw[k] * (h1 - h0 + z1.lo - z0.lo);
+  }
+  {
+    const int i_lo = dxs ? max(its, ids + 1) : its, i_hi = dxe ? min(ite, ide - 2) : min(ite, ide - 1);
+    if (i >= i_lo && i <= i_hi) {
+      Face x0 = pd_face_x(g, s, i, k, j, dxs, dxe), x1 = pd_face_x(g, s, i + 1, k, j, dxs, dxe);
+      float h0 = x0.hi, h1 = x1.hi;
+      if (h0 > 0.f) h0 = sc_at(i - 1, k, j) * h0; else if (h0 < 0.f) h0 = sc_at(i, k, j) * h0;
+      if (h1 > 0.f) h1 = sc_at(i, k, j) * h1; else if (h1 < 0.f) h1 = sc_at(i + 1, k, j) * h1;
+      t = t - A2(g.msftx, i, j) * (g.rdx * (h1 - h0 + x1.lo - x0.lo));
+    }
+  }
+  {
+    const int j_lo = dys ? max(jts, jds + 1) : jts, j_hi = dye ? min(jte, jde - 2) : min(jte, jde - 1);
+    if (j >= j_lo && j <= j_hi) {
+      Face y0 = pd_face_y(g, s, i, k, j, dys, dye), y1 = pd_face_y(g, s, i, k, j + 1, dys, dye);
+      float h0 = y0.hi, h1 = y1.hi;
+      if (h0 > 0.f) h0 = sc_at(i, k, j - 1) * h0; else if (h0 < 0.f) h0 = sc_at(i, k, j) * h0;
+      if (h1 > 0.f) h1 = sc_at(i, k, j) * h1; else if (h1 < 0.f) h1 = sc_at(i, k, j + 1) * h1;
+      t = t - A2(g.msftx, i, j) * (g.rdy * (h1 - h0 + y1.lo - y0.lo));
+    }
+  }
+  A3(tend, i, k, j) = t;
+}
+
+// rk_update_scalar_pd (module_em.F:1803-1916)
+__global__ void k_update_scalar_pd(const Geo g, Box b, float dt, fp scalar, fp sc_tend, cfp mu_old, cfp mu_new, cfp mu_base) {
+  TID3;
+  float tendency = 0.f;
+  tendency = tendency + A3(sc_tend, i, k, j);
+  A3(sc_tend, i, k, j) = 0.f;
+  const float muold = A2(mu_old, i, j) + A2(mu_base, i, j), munew = A2(mu_new, i, j) + A2(mu_base, i, j);
+  A3(scalar, i, k, j) = ((g.c1h[k] * muold + g.c2h[k]) * A3(scalar, i, k, j) + dt * tendency) / (g.c1h[k] * munew + g.c2h[k]);
+}
+
+// rk_update_scalar (module_em.F:1587-1799)
+__global__ void k_update_scalar(const Geo g, Box b, int rk_step, float dt, fp scalar_1, fp scalar_2, cfp sc_tend, cfp advect_tend,
+                                cfp mu_old, cfp mu_new, cfp mu_base) {
+  TID3;
+  float tendency = A3(advect_tend, i, k, j) * A2(g.msfty, i, j);
+  tendency = tendency + A3(sc_tend, i, k, j);
+  const float muold = A2(mu_old, i, j) + A2(mu_base, i, j), munew = A2(mu_new, i, j) + A2(mu_base, i, j);
+  float s1;
+  if (rk_step == 1) { s1 = A3(scalar_2, i, k, j); A3(scalar_1, i, k, j) = s1; }
+  else s1 = A3(scalar_1, i, k, j);
+  A3(scalar_2, i, k, j) = ((g.c1h[k] * muold + g.c2h[k]) * s1 + dt * tendency) / (g.c1h[k] * munew + g.c2h[k]);
+}
+
+void Solver::rk_scalar_step(int rk_step) {
+  const Geo &q = g;
+  float dt_rk, dts_rk; int ns;
+  rk_params(rk_step, dt_rk, dts_rk, ns);
+  const int im = std::min(q.ite, q.ide - 1), jm = std::min(q.jte, q.jde - 1), ktf = q.kde - 1;
+  Box mass{q.its, im, 1, ktf, q.jts, jm};
+  const bool last = rk_step == c.rk_ord;
+  if (last) {
+    std::vector<BcItem> items;
+    for (auto &s : species)
+      if (s.adv_opt == 1) {
+        LAUNCH3(this, k_update_scalar_pd, mass, dt_rk, o(s.o), o(s.t), o("mu_1"), o("mu_1"), o("mub"));
+        items.push_back({s.o, 'p'});
+      }
+    if (!items.empty()) { halo("HALO_EM_MOIST_OLD_E_7"); bc(items); }
+  }
+  halo("HALO_EM_D");
+  const bool dxs = !(c.periodic_x || c.symmetric_xs), dxe = !(c.periodic_x || c.symmetric_xe);
+  const bool dys = !(c.periodic_y || c.symmetric_ys), dye = !(c.periodic_y || c.symmetric_ye);
+  for (auto &s : species) {
+    if (last && s.adv_opt == 1) {
+      PdIn in;
+      in.q = o(s.f); in.q_old = o(s.o); in.ru = o("ru_m"); in.rv = o("rv_m"); in.rom = o("ww_m");
+      in.mut = o("muts"); in.mub = o("mub"); in.mu_old = o("mu_1"); in.dt = dt_rk;
+      // limiter box (:7683-7710)
+      Box lim{q.its - 1, im + 1, 1, ktf, q.jts - 1, jm + 1};
+      if (dxs) lim.i0 = std::max(q.its - 1, q.ids);
+      if (dxe) lim.i1 = std::min(q.ite + 1, q.ide - 1);
+      if (dys) lim.j0 = std::max(q.jts - 1, q.jds);
+      if (dye) lim.j1 = std::min(q.jte + 1, q.jde - 1);
+      if (c.open_xs && dxs) lim.i0 = std::max(q.its - 1, q.ids + 1);
+      if (c.open_xe && dxe) lim.i1 = std::min(q.ite + 1, q.ide - 2);
+      if (c.open_ys && dys) lim.j0 = std::max(q.jts - 1, q.jds + 1);
+      if (c.open_ye && dye) lim.j1 = std::min(q.jte + 1, q.jde - 2);
+      // "a" is free between calc_coef_w uses only until the next small_step_prep: use advect scratch "alpha"?  No:
+      // the limiter factor gets its own scratch so that a, alpha, gamma stay comparable with the oracle.
+      LAUNCH3(this, k_pd_scale, lim, in, o("pd_scale"));
+      LAUNCH3(this, k_pd_tend, mass, in, o("pd_scale"), lim, o("advect_tend"));
+    } else {
+      LAUNCH3(this, k_advect_scalar, mass, o(s.f), o("ru_m"), o("rv_m"), o("ww_m"), o("advect_tend"));
+    }
+    LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
+  }
+}
+
+}  // namespace wg

@@ -1,0 +1,178 @@
+"""Host-side mirror of the reference interface for the solve_em path.
+
+`Solver` binds the C-ABI of include/wrfgpu.h (libwrfgpu.so, built in-tree by
+wrf_b200/csrc/Makefile) with ctypes.  It is the Python stand-in for the Fortran
+shim wrf_b200/fortran/solve_em_gpu.F90: same entry points, same field names
+(Registry names without `grid%`), same error behaviour (a non-zero status becomes
+an exception, the way the shim turns it into wrf_error_fatal).  There is no CPU
+fallback: creating a Solver without the CUDA library or without a GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from .ideal import Case, Config, Dims
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+PHASES = ("rk_step_prep", "rk_phys_bc_dry_1", "init_zero_tendency", "rk_tendency", "small_step_prep",
+          "advance_uv", "advance_mu_t", "advance_w", "sumflux", "calc_p_rho", "small_step_finish",
+          "rk_scalar_step", "calc_p_rho_phi", "rk_phys_bc_dry_2", "microphysics", "end_of_step", "start_domain")
+
+# every symbol include/wrfgpu.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = (
+    "wrfgpu_create", "wrfgpu_destroy", "wrfgpu_last_error", "wrfgpu_version", "wrfgpu_field_size", "wrfgpu_set_field",
+    "wrfgpu_get_field", "wrfgpu_upload", "wrfgpu_download", "wrfgpu_num_fields", "wrfgpu_field_name", "wrfgpu_field_devptr",
+    "wrfgpu_step", "wrfgpu_solve_em", "wrfgpu_sync", "wrfgpu_set_stream", "wrfgpu_kernel_report", "wrfgpu_launch_count", "wrfgpu_phase_ms", "wrfgpu_set_physical_bc",
+    "wrfgpu_compute_mesh", "wrfgpu_patch_dims", "wrfgpu_comm_unique_id", "wrfgpu_comm_init", "wrfgpu_halo", "wrfgpu_halo_strip",
+) + tuple("wrfgpu_" + p for p in PHASES)
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libwrfgpu.so")
+
+
+def load():
+    """Load libwrfgpu.so; raises (loudly) when the CUDA extension has not been built."""
+    global _LIB
+    if _LIB is None:
+        so = library_path()
+        if not os.path.exists(so):
+            raise RuntimeError(f"{so} is missing: build it with `make -C wrf_b200/csrc` (or __graft_entry__.build()); "
+                               "there is no CPU fallback for the solve_em path")
+        lib = ctypes.CDLL(so)
+        lib.wrfgpu_last_error.restype = ctypes.c_char_p
+        lib.wrfgpu_field_size.restype = ctypes.c_size_t
+        lib.wrfgpu_field_name.restype = ctypes.c_char_p
+        lib.wrfgpu_field_devptr.restype = ctypes.c_void_p
+        lib.wrfgpu_launch_count.restype = ctypes.c_longlong
+        lib.wrfgpu_phase_ms.restype = ctypes.c_double
+        lib.wrfgpu_kernel_report.restype = ctypes.c_size_t
+        _LIB = lib
+    return _LIB
+
+
+class WrfGpuError(RuntimeError):
+    pass
+
+
+class Solver:
+    """One domain on one GPU (one MPI rank of wrf.exe)."""
+
+    def __init__(self, case: Case, device: int = 0, upload: bool = True):
+        self.lib = load()
+        self.case = case
+        self.h = ctypes.c_void_p()
+        rc = self.lib.wrfgpu_create(ctypes.byref(case.dims), ctypes.byref(case.config), ctypes.c_int(device), ctypes.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise WrfGpuError(self.lib.wrfgpu_last_error().decode())
+        if upload:
+            for k, a in case.fields.items():
+                self.set(k, a)
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise WrfGpuError(self.lib.wrfgpu_last_error().decode())
+
+    # ---- state ----
+    def names(self):
+        return [self.lib.wrfgpu_field_name(self.h, i).decode() for i in range(self.lib.wrfgpu_num_fields(self.h))]
+
+    def size(self, name) -> int:
+        return int(self.lib.wrfgpu_field_size(self.h, name.encode()))
+
+    def set(self, name, a):
+        """a: numpy array (host) or an object with data_ptr()/numel() (torch tensor, host or device)."""
+        if hasattr(a, "data_ptr"):
+            ptr, n = ctypes.c_void_p(a.data_ptr()), a.numel()
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            ptr, n = a.ctypes.data_as(ctypes.c_void_p), a.size
+        self._chk(self.lib.wrfgpu_set_field(self.h, name.encode(), ptr, ctypes.c_size_t(n)))
+
+    def get(self, name, out=None):
+        n = self.size(name)
+        if n == 0:
+            raise KeyError(name)
+        if out is not None and hasattr(out, "data_ptr"):
+            self._chk(self.lib.wrfgpu_get_field(self.h, name.encode(), ctypes.c_void_p(out.data_ptr()), ctypes.c_size_t(n)))
+            return out
+        a = np.empty(n, np.float32) if out is None else out
+        self._chk(self.lib.wrfgpu_get_field(self.h, name.encode(), a.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n)))
+        d = self.case.dims
+        ni, nk, nj = d.ime - d.ims + 1, d.kme - d.kms + 1, d.jme - d.jms + 1
+        if n == ni * nk * nj:
+            return a.reshape(nj, nk, ni)
+        if n == ni * nj:
+            return a.reshape(nj, ni)
+        return a
+
+    def devptr(self, name) -> int:
+        return int(self.lib.wrfgpu_field_devptr(self.h, name.encode()) or 0)
+
+    # ---- hot path ----
+    def step(self, n=1):
+        self._chk(self.lib.wrfgpu_step(self.h, ctypes.c_int(n)))
+
+    def sync(self):
+        self._chk(self.lib.wrfgpu_sync(self.h))
+
+    def solve_em(self, in_names, in_ptrs, out_names, out_ptrs):
+        """Strict drop-in call: upload `in`, one solve_em, download `out` (host pointers as ints)."""
+        def tab(names, ptrs):
+            n = len(names)
+            return n, (ctypes.c_char_p * n)(*[s.encode() for s in names]), (ctypes.c_void_p * n)(*ptrs)
+        ni, nn, pn = tab(in_names, in_ptrs)
+        no, on, po = tab(out_names, out_ptrs)
+        self._chk(self.lib.wrfgpu_solve_em(self.h, ni, nn, pn, no, on, po))
+
+    def call(self, phase, *args):
+        self._chk(getattr(self.lib, "wrfgpu_" + phase)(self.h, *[ctypes.c_int(int(x)) for x in args]))
+
+    def start_domain(self):
+        self.call("start_domain")
+
+    def bc(self, name, var):
+        self._chk(self.lib.wrfgpu_set_physical_bc(self.h, name.encode(), ctypes.c_char(var.encode())))
+
+    def halo(self, name):
+        self._chk(self.lib.wrfgpu_halo(self.h, name.encode()))
+
+    def launch_count(self) -> int:
+        return int(self.lib.wrfgpu_launch_count(self.h))
+
+    def phase_timing(self, on=True):
+        self.lib.wrfgpu_phase_ms(self.h, None if on else b"__off__")
+
+    def set_stream(self, cuda_stream: int):
+        self._chk(self.lib.wrfgpu_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
+
+    def kernel_report(self) -> dict:
+        """{kernel: (launches, total_ms)} collected while phase_timing is on."""
+        n = self.lib.wrfgpu_kernel_report(self.h, None, ctypes.c_size_t(0))
+        buf = ctypes.create_string_buffer(n + 16)
+        self.lib.wrfgpu_kernel_report(self.h, buf, ctypes.c_size_t(n + 16))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            k, c, ms = line.split()
+            out[k] = (int(c), float(ms))
+        return out
+
+    def phase_ms(self, name) -> float:
+        return float(self.lib.wrfgpu_phase_ms(self.h, name.encode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.wrfgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
