@@ -8,6 +8,7 @@
 // 128-byte access per field and the k-recurrences (mass-divergence prefix sum,
 // Thomas forward/backward sweeps) live in registers.
 #include "common.cuh"
+#include "libm_port.h"
 
 namespace wg {
 
@@ -379,7 +380,7 @@ __global__ void k_advance_w(const Geo g, Box b, float dts, WArgs a) {
     wtop = (wtop - A3(a.a, i, k, j) * wprev) * A3(a.alpha, i, k, j);
   }
   // backward sweep (:1439-1443) + damp_opt 3 (:1445-1458) + ph (:1460-1465)
-  const float pi = 4.f * atanf(1.f);
+  const float pi = 0x1.921fb6p+1f;   // 4.*atan(1.) in real*4
   const float dampmag = dts * g.dampcoef, hdepth = g.zdamp;
   const float htop = (A3(a.ph_1, i, kde, j) + A3(a.phb, i, kde, j)) / WG_G;
   auto finish = [&](int k, float wv, float rhs) {
@@ -387,7 +388,7 @@ __global__ void k_advance_w(const Geo g, Box b, float dts, WArgs a) {
       const float hk = (A3(a.ph_1, i, k, j) + A3(a.phb, i, k, j)) / WG_G;
       const float hbot = htop - hdepth;
       float dampwt = 0.f;
-      if (hk >= hbot) dampwt = dampmag * sinf(0.5f * pi * (hk - hbot) / hdepth) * sinf(0.5f * pi * (hk - hbot) / hdepth);
+      if (hk >= hbot) dampwt = dampmag * wg_libm::sinf_(0.5f * pi * (hk - hbot) / hdepth) * wg_libm::sinf_(0.5f * pi * (hk - hbot) / hdepth);
       wv = (wv - dampwt * (g.c1f[k] * mut + g.c2f[k]) * A3(a.w_save, i, k, j)) / (1.f + dampwt);
     }
     A3(a.w, i, k, j) = wv;

@@ -3,16 +3,15 @@
 // (:5394-5589) and moist_physics_finish_em (:5593-5784), set_w_surface
 // (module_bc_em.F:1196-1270) and the end-of-step / start-of-run boundary fills.
 #include "common.cuh"
+#include "libm_port.h"
 
 namespace wg {
 
-// The reference calls libm logf/powf (LOG, vspow = x**p, frame/libmassv.F), which glibc
-// evaluates in double precision internally and rounds once.  CUDA's single-precision
-// logf/powf differ from that by 1-2 ulp, and p' = p - pb amplifies an ulp of the 1e5 Pa
-// total pressure to ~1e-4 of the perturbation.  Evaluating in double and rounding once
-// reproduces glibc's result in the great majority of cases; the kernel stays HBM-bound.
-__device__ __forceinline__ float log_f(float x) { return (float)log((double)x); }
-__device__ __forceinline__ float pow_f(float x, float y) { return (float)pow((double)x, (double)y); }
+// LOG and x**y (vspow, frame/libmassv.F) are glibc's logf/powf in the reference build;
+// libm_port.h restates those routines so the device result is bit-identical (see its header).
+__device__ __forceinline__ float log_f(float x) { return wg_libm::logf_(x); }
+__device__ __forceinline__ float pow_f(float x, float y) { return wg_libm::powf_(x, y); }
+__device__ __forceinline__ float exp_f(float x) { return wg_libm::expf_(x); }
 
 // full nonlinear diagnosis of al and p (non-hydrostatic branch)
 __global__ void k_calc_p_rho_phi(const Geo g, Box b, fp al, cfp alb, cfp mu, cfp muts, cfp ph, cfp phb, fp p, cfp pb, cfp t, cfp qv) {
@@ -91,7 +90,7 @@ __global__ void k_kessler(const Geo g, Box b, MpArgs a) {
     A3(a.qv_diabatic, i, k, j) = qvv;
     A3(a.qc_diabatic, i, k, j) = A3(a.qc, i, k, j);
     A3(a.rho, i, k, j) = 1.f / (A3(a.al, i, k, j) + A3(a.alb, i, k, j));
-    A3(a.pi_phy, i, k, j) = powf((A3(a.p, i, k, j) + A3(a.pb, i, k, j)) / WG_P0, WG_RCP);
+    A3(a.pi_phy, i, k, j) = pow_f((A3(a.p, i, k, j) + A3(a.pb, i, k, j)) / WG_P0, WG_RCP);
     A3(a.z, i, k, j) = 0.5f * (zw_k + zw_kp1);
     zw_k = zw_kp1;
   }
@@ -105,7 +104,7 @@ __global__ void k_kessler(const Geo g, Box b, MpArgs a) {
     prodk[k] = qrk;
     const float qrr = fmaxf(0.f, qrk * 0.001f * rhok);
     const float vtden = sqrtf(rho1 / rhok);
-    vt[k] = 36.34f * powf(qrr, 0.1364f) * vtden;
+    vt[k] = 36.34f * pow_f(qrr, 0.1364f) * vtden;
     const float rdzw = 1.f / A3(a.dz8w, i, k, j);
     crmax = fmaxf(vt[k] * dt * rdzw, crmax);
   }
@@ -138,7 +137,7 @@ __global__ void k_kessler(const Geo g, Box b, MpArgs a) {
         const float rhok = A3(a.rho, i, k, j);
         const float qrr = fmaxf(0.f, prodk[k] * 0.001f * rhok);
         const float vtden = sqrtf(rho1 / rhok);
-        vt[k] = 36.34f * powf(qrr, 0.1364f) * vtden;
+        vt[k] = 36.34f * pow_f(qrr, 0.1364f) * vtden;
         const float rdzw = 1.f / A3(a.dz8w, i, k, j);
         crmax = fmaxf(vt[k] * time_sediment * rdzw, crmax);
       }
@@ -153,20 +152,20 @@ __global__ void k_kessler(const Geo g, Box b, MpArgs a) {
   for (int k = 1; k <= kte; k++) {
     float qrv = A3(a.qr, i, k, j), qcv = A3(a.qc, i, k, j), qvv = A3(a.qv, i, k, j), tv = A3(a.th_phy, i, k, j);
     const float pii = A3(a.pi_phy, i, k, j);
-    const float factorn = 1.0f / (1.f + c3 * dt * powf(fmaxf(0.f, qrv), c4));
+    const float factorn = 1.0f / (1.f + c3 * dt * pow_f(fmaxf(0.f, qrv), c4));
     const float qrprod = qcv * (1.0f - factorn) + factorn * c1 * dt * fmaxf(qcv - c2, 0.f);
     const float rcgs = 0.001f * A3(a.rho, i, k, j);
     qcv = fmaxf(qcv - qrprod, 0.f);
     qrv = (qrv + prodk[k] - qrv);
     qrv = fmaxf(qrv + qrprod, 0.f);
     const float temp = pii * tv;
-    const float pressure = 1.000e+05f * powf(pii, 1004.f / 287.f);
+    const float pressure = 1.000e+05f * pow_f(pii, 1004.f / 287.f);
     const float gam = 2.5e+06f / (1004.f * pii);
-    const float es = 1000.f * svp1 * expf(svp2 * (temp - svpt0) / (temp - svp3));
+    const float es = 1000.f * svp1 * exp_f(svp2 * (temp - svpt0) / (temp - svp3));
     const float qvs = ep2 * es / (pressure - es);
     const float pr = (qvv - qvs) / (1.f + pressure / (pressure - es) * qvs * f5 / ((temp - svp3) * (temp - svp3)));
     const float dimv = fmaxf(qvs - qvv, 0.f);
-    const float ern = fminf(fminf(dt * (((1.6f + 124.9f * powf(rcgs * qrv, .2046f)) * powf(rcgs * qrv, .525f)) / (2.55e8f / (pressure * qvs) + 5.4e5f)) *
+    const float ern = fminf(fminf(dt * (((1.6f + 124.9f * pow_f(rcgs * qrv, .2046f)) * pow_f(rcgs * qrv, .525f)) / (2.55e8f / (pressure * qvs) + 5.4e5f)) *
                                        (dimv / (rcgs * qvs)),
                                    fmaxf(-pr - qcv, 0.f)),
                             qrv);

@@ -13,6 +13,7 @@
 // rule is evaluated with DOMAIN indices so that any patch decomposition gives
 // the same bits as the single-patch run.
 #include "common.cuh"
+#include "libm_port.h"
 
 namespace wg {
 
@@ -86,6 +87,36 @@ struct TendIn {
   cfp mut, muu, muv, mu, mub;
   cfp ru_tendf, rv_tendf, rw_tendf, ph_tendf, t_tendf;
 };
+
+// perturbation_coriolis (:3854-4173): ru, rv minus the mass-coupled base-state wind interpolated
+// to the height of the u / v point.  The reference fills tile-local arrays first; evaluating the
+// same expression at the point of use gives the same bits.
+__device__ __forceinline__ float pert_wind(const Geo &g, cfp r_in, cfp ph, cfp phb, cfp mass2d, const float *base, int i, int k, int j,
+                                           int di, int dj) {
+  const int ktf = g.kde - 1;
+  const float z = 0.25f * (A3(phb, i, k, j) + A3(phb, i, k + 1, j) + A3(phb, i - di, k, j - dj) + A3(phb, i - di, k + 1, j - dj) +
+                           A3(ph, i, k, j) + A3(ph, i, k + 1, j) + A3(ph, i - di, k, j - dj) + A3(ph, i - di, k + 1, j - dj)) / WG_G;
+  const float *zb = g.z_base;
+  const float mass = (g.c1h[k] * A2(mass2d, i, j) + g.c2h[k]);
+  float b;
+  if (k == 1) {
+    const float wkp1 = fminf(1.f, fmaxf(0.f, z - zb[k]) / (zb[k + 1] - zb[k]));
+    const float wk = 1.f - wkp1;
+    b = (wk * base[k] + wkp1 * base[k + 1]);
+  } else if (k == ktf) {
+    const float wkm1 = fminf(1.f, fmaxf(0.f, zb[k] - z) / (zb[k] - zb[k - 1]));
+    const float wk = 1.f - wkm1;
+    b = (wkm1 * base[k - 1] + wk * base[k]);
+  } else {
+    const float wkp1 = fminf(1.f, fmaxf(0.f, z - zb[k]) / (zb[k + 1] - zb[k]));
+    const float wkm1 = fminf(1.f, fmaxf(0.f, zb[k] - z) / (zb[k] - zb[k - 1]));
+    const float wk = 1.f - wkp1 - wkm1;
+    b = (wkm1 * base[k - 1] + wk * base[k] + wkp1 * base[k + 1]);
+  }
+  return A3(r_in, i, k, j) - mass * b;
+}
+#define PRV(i, k, j) pert_wind(g, s.rv, s.ph, s.phb, s.muv, g.v_base, i, k, j, 0, 1)
+#define PRU(i, k, j) pert_wind(g, s.ru, s.ph, s.phb, s.muu, g.u_base, i, k, j, 1, 0)
 
 // ===========================================================================
 // ru_tend: advect_u (:126) + pgf x (:2320-2400) + coriolis (:3700-3735) + curvature + addtend
@@ -235,9 +266,28 @@ __global__ void k_tend_u(const Geo g, Box b, TendIn s, fp ru_tend) {
         t = t + (A2(g.msfux, i, j) / A2(g.msfuy, i, j)) * 0.5f * (A2(g.f, i, j) + A2(g.f, i - 1, j)) * 0.25f *
                     (A3(rv, i - 1, k, j + 1) + A3(rv, i, k, j + 1) + A3(rv, i - 1, k, j) + A3(rv, i, k, j)) -
             0.5f * (A2(g.e, i, j) + A2(g.e, i - 1, j)) * 0.5f * (A2(g.cosa, i, j) + A2(g.cosa, i - 1, j)) * 0.25f * rwsum;
+      } else {
+        t = t + (A2(g.msfux, i, j) / A2(g.msfuy, i, j)) * 0.5f * (A2(g.f, i, j) + A2(g.f, i - 1, j)) * 0.25f *
+                    (PRV(i - 1, k, j + 1) + PRV(i, k, j + 1) + PRV(i - 1, k, j) + PRV(i, k, j)) -
+            0.5f * (A2(g.e, i, j) + A2(g.e, i - 1, j)) * 0.5f * (A2(g.cosa, i, j) + A2(g.cosa, i - 1, j)) * 0.25f * rwsum;
       }
       t = t + 0.5f * (vxgm_at(g, s.u, s.v, i, k, j) + vxgm_at(g, s.u, s.v, i - 1, k, j)) * rvavg -
           A3(u, i, k, j) * WG_RERADIUS * 0.25f * rwsum;
+    }
+  }
+  // perturbation_coriolis keeps the open-boundary columns the plain routine dropped (:3975-4003)
+  if (g.pert_coriolis && !g.periodic_x) {
+    if (g.open_xs && i == ids) {
+      t = t + (A2(g.msfux, i, j) / A2(g.msfuy, i, j)) * 0.5f * (A2(g.f, i, j) + A2(g.f, i, j)) * 0.25f *
+                  (PRV(i, k, j + 1) + PRV(i, k, j + 1) + PRV(i, k, j) + PRV(i, k, j)) -
+          0.5f * (A2(g.e, i, j) + A2(g.e, i, j)) * 0.5f * (A2(g.cosa, i, j) + A2(g.cosa, i, j)) * 0.25f *
+              (A3(s.rw, i, k + 1, j) + A3(s.rw, i, k, j) + A3(s.rw, i, k + 1, j) + A3(s.rw, i, k, j));
+    }
+    if (g.open_xe && i == ide) {
+      t = t + (A2(g.msfux, i, j) / A2(g.msfuy, i, j)) * 0.5f * (A2(g.f, i - 1, j) + A2(g.f, i - 1, j)) * 0.25f *
+                  (PRV(i - 1, k, j + 1) + PRV(i - 1, k, j + 1) + PRV(i - 1, k, j) + PRV(i - 1, k, j)) -
+          0.5f * (A2(g.e, i - 1, j) + A2(g.e, i - 1, j)) * 0.5f * (A2(g.cosa, i - 1, j) + A2(g.cosa, i - 1, j)) * 0.25f *
+              (A3(s.rw, i - 1, k + 1, j) + A3(s.rw, i - 1, k, j) + A3(s.rw, i - 1, k + 1, j) + A3(s.rw, i - 1, k, j));
     }
   }
   // --- rk_addtend_dry (module_em.F:1037-1043)
@@ -390,9 +440,27 @@ __global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
         t = t - mr * 0.5f * (A2(g.f, i, j) + A2(g.f, i, j - 1)) * 0.25f *
                     (A3(ru, i, k, j) + A3(ru, i + 1, k, j) + A3(ru, i, k, j - 1) + A3(ru, i + 1, k, j - 1)) +
             mr * 0.5f * (A2(g.e, i, j) + A2(g.e, i, j - 1)) * 0.5f * (A2(g.sina, i, j) + A2(g.sina, i, j - 1)) * 0.25f * rwsum;
+      } else {
+        t = t - mr * 0.5f * (A2(g.f, i, j) + A2(g.f, i, j - 1)) * 0.25f *
+                    (PRU(i, k, j) + PRU(i + 1, k, j) + PRU(i, k, j - 1) + PRU(i + 1, k, j - 1)) +
+            mr * 0.5f * (A2(g.e, i, j) + A2(g.e, i, j - 1)) * 0.5f * (A2(g.sina, i, j) + A2(g.sina, i, j - 1)) * 0.25f * rwsum;
       }
       t = t - 0.5f * (vxgm_at(g, s.u, s.v, i, k, j) + vxgm_at(g, s.u, s.v, i, k, j - 1)) * ruavg -
           mr * A3(v, i, k, j) * WG_RERADIUS * 0.25f * rwsum;
+    }
+  }
+  if (g.pert_coriolis) {   // open-boundary rows of perturbation_coriolis (:4066-4085, :4104-4123)
+    const float mr = A2(g.msfvy, i, j) / A2(g.msfvx, i, j);
+    if (g.open_ys && j == jds) {
+      t = t - mr * 0.5f * (A2(g.f, i, j) + A2(g.f, i, j)) * 0.25f * (PRU(i, k, j) + PRU(i + 1, k, j) + PRU(i, k, j) + PRU(i + 1, k, j)) +
+          mr * 0.5f * (A2(g.e, i, j) + A2(g.e, i, j)) * 0.5f * (A2(g.sina, i, j) + A2(g.sina, i, j)) * 0.25f *
+              (A3(s.rw, i, k + 1, j) + A3(s.rw, i, k, j) + A3(s.rw, i, k + 1, j) + A3(s.rw, i, k, j));
+    }
+    if (g.open_ye && j == jde) {
+      t = t - mr * 0.5f * (A2(g.f, i, j - 1) + A2(g.f, i, j - 1)) * 0.25f *
+                  (PRU(i, k, j - 1) + PRU(i + 1, k, j - 1) + PRU(i, k, j - 1) + PRU(i + 1, k, j - 1)) +
+          mr * 0.5f * (A2(g.e, i, j - 1) + A2(g.e, i, j - 1)) * 0.5f * (A2(g.sina, i, j - 1) + A2(g.sina, i, j - 1)) * 0.25f *
+              (A3(s.rw, i, k + 1, j - 1) + A3(s.rw, i, k, j - 1) + A3(s.rw, i, k + 1, j - 1) + A3(s.rw, i, k, j - 1));
     }
   }
   t = t + A3(s.rv_tendf, i, k, j) * A2(g.msfvx_inv, i, j);
@@ -517,8 +585,12 @@ __global__ void k_tend_w(const Geo g, Box b, TendIn s, fp rw_tend) {
       // --- coriolis (:3839-3844) and curvature (:4459-4463)
       const float fzm = g.fnm[k], fzp = g.fnp[k];
       const float mr = A2(g.msftx, i, j) / A2(g.msfty, i, j);
-      t = t + A2(g.e, i, j) * (A2(g.cosa, i, j) * 0.5f * (fzm * (A3(ru, i, k, j) + A3(ru, i + 1, k, j)) + fzp * (A3(ru, i, k - 1, j) + A3(ru, i + 1, k - 1, j))) -
-                               mr * A2(g.sina, i, j) * 0.5f * (fzm * (A3(rv, i, k, j) + A3(rv, i, k, j + 1)) + fzp * (A3(rv, i, k - 1, j) + A3(rv, i, k - 1, j + 1))));
+      if (!g.pert_coriolis)
+        t = t + A2(g.e, i, j) * (A2(g.cosa, i, j) * 0.5f * (fzm * (A3(ru, i, k, j) + A3(ru, i + 1, k, j)) + fzp * (A3(ru, i, k - 1, j) + A3(ru, i + 1, k - 1, j))) -
+                                 mr * A2(g.sina, i, j) * 0.5f * (fzm * (A3(rv, i, k, j) + A3(rv, i, k, j + 1)) + fzp * (A3(rv, i, k - 1, j) + A3(rv, i, k - 1, j + 1))));
+      else
+        t = t + A2(g.e, i, j) * (A2(g.cosa, i, j) * 0.5f * (fzm * (PRU(i, k, j) + PRU(i + 1, k, j)) + fzp * (PRU(i, k - 1, j) + PRU(i + 1, k - 1, j))) -
+                                 mr * A2(g.sina, i, j) * 0.5f * (fzm * (PRV(i, k, j) + PRV(i, k, j + 1)) + fzp * (PRV(i, k - 1, j) + PRV(i, k - 1, j + 1))));
       t = t + WG_RERADIUS * (0.5f * (fzm * (A3(ru, i, k, j) + A3(ru, i + 1, k, j)) + fzp * (A3(ru, i, k - 1, j) + A3(ru, i + 1, k - 1, j))) * 0.5f *
                                  (fzm * (A3(s.u, i, k, j) + A3(s.u, i + 1, k, j)) + fzp * (A3(s.u, i, k - 1, j) + A3(s.u, i + 1, k - 1, j))) +
                              mr * 0.5f * (fzm * (A3(rv, i, k, j) + A3(rv, i, k, j + 1)) + fzp * (A3(rv, i, k - 1, j) + A3(rv, i, k - 1, j + 1))) * 0.5f *
@@ -758,7 +830,7 @@ __global__ void k_rayleigh(const Geo g, Box b, int kind, cfp u, cfp v, cfp w, cf
   TID2;
   const int kde = g.kde, ktf = g.kde - 1;
   const float zdamp = g.zdamp, dampcoef = g.dampcoef;
-  const float pii = 2.0f * asinf(1.0f);
+  const float pii = 0x1.921fb6p+1f;   // 2.*asin(1.) in real*4
   const int di = kind == 0 ? 1 : 0, dj = kind == 1 ? 1 : 0;
   auto zmid = [&](int k1) -> float {
     if (kind == 2) return 0.5f * (A3(phb, i, k1, j) + A3(phb, i, k1 + 1, j) + A3(ph, i, k1, j) + A3(ph, i, k1 + 1, j)) / WG_G;
@@ -773,7 +845,7 @@ __global__ void k_rayleigh(const Geo g, Box b, int kind, cfp u, cfp v, cfp w, cf
       const float z = (A3(phb, i, k, j) + A3(ph, i, k, j)) / WG_G;
       if (z >= (ztop - zdamp)) {
         float dcoef = 1.0f - fminf(1.0f, (ztop - z) / zdamp);
-        const float sn = sinf(0.5f * pii * dcoef);
+        const float sn = wg_libm::sinf_(0.5f * pii * dcoef);
         dcoef = sn * sn;
         A3(rw_tendf, i, k, j) = A3(rw_tendf, i, k, j) - (g.c1f[k] * A2(mut, i, j) + g.c2f[k]) * (dcoef * dampcoef) * A3(w, i, k, j);
       }
@@ -797,7 +869,7 @@ __global__ void k_rayleigh(const Geo g, Box b, int kind, cfp u, cfp v, cfp w, cf
     if (k2 + 1 > ktf) b00 = base[k2] + (base[k2] - base[k2 - 1]) * (z00 - zb[k2]) / (zb[k2] - zb[k2 - 1]);
     else b00 = base[k2] + (base[k2 + 1] - base[k2]) * (z00 - zb[k2]) / (zb[k2 + 1] - zb[k2]);
     float dcoef = 1.0f - fminf(1.0f, (ztop - z00) / zdamp);
-    const float sn = sinf(0.5f * pii * dcoef);
+    const float sn = wg_libm::sinf_(0.5f * pii * dcoef);
     dcoef = sn * sn;
     if (kind == 0)
       A3(ru_tendf, i, k, j) = A3(ru_tendf, i, k, j) - (g.c1h[k] * A2(muu, i, j) + g.c2h[k]) * (dcoef * dampcoef) * (A3(u, i, k, j) - b00);
@@ -838,7 +910,6 @@ void Solver::init_zero_tendency() {
 
 void Solver::rk_tendency(int rk_step) {
   const Geo &q = g;
-  if (c.pert_coriolis) throw std::runtime_error("wrfgpu: pert_coriolis is not yet on the device path");
   Box tile{q.its, q.ite, 1, q.kde, q.jts, q.jte};
   // the *_save arrays and mu_tend/mu_save are zeroed by rk_tendency (module_em.F:370-428)
   LAUNCH3(this, k_zero3, tile, o("u_save"), o("v_save"), o("w_save"), o("ph_save"), o("t_save"));

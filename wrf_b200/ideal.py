@@ -345,7 +345,8 @@ def balance(col, v, hy, p_top, hypsometric_opt):
 def _hash_noise(shape, seed=1234):
     """Deterministic uniform [-1,1) noise (small-amplitude noise on theta)."""
     n = int(np.prod(shape))
-    x = (np.arange(n, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        x = (np.arange(n, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)) & np.uint64(0xFFFFFFFFFFFFFFFF)
     x ^= x >> np.uint64(33)
     x = (x * np.uint64(0xFF51AFD7ED558CCD)) & np.uint64(0xFFFFFFFFFFFFFFFF)
     x ^= x >> np.uint64(33)
@@ -362,6 +363,7 @@ def make_case(name="quarter_ss", nx=None, ny=None, nz=None, **over) -> Case:
     seed = over.pop("seed", 1234)
     bubble_lattice = over.pop("bubble_lattice", 0.0)
     u_scale = over.pop("u_scale", 1.0)
+    calm = over.pop("calm", False)      # no environmental wind (needed next to symmetric walls)
     if name == "quarter_ss":
         nx, ny, nz = nx or 42, ny or 42, nz or 41
         c = default_config(dt=12.0, dx=2000.0, dy=2000.0, time_step_sound=6, time_step=12, damp_opt=2, zdamp=5000.0,
@@ -479,6 +481,9 @@ def make_case(name="quarter_ss", nx=None, ny=None, nz=None, **over) -> Case:
         zprof = np.clip(zmid.T / 12000.0, 0, 1.2)            # (k-1, ni)
         jet = (35.0 * np.sin(math.pi * np.clip(yy, 0, 1)) ** 2)[:, None, None] * (zprof * np.exp(1 - zprof))[None, :, :]
         U[:, :-1, :] = jet.astype(F)
+        V[:] = 0
+    if calm:
+        U[:] = 0
         V[:] = 0
     U[:, nz - 1, :] = 0
     V[:, nz - 1, :] = 0
