@@ -130,3 +130,45 @@ def run_phase_parity(case, verbose=False):
             sync_from_oracle(o, s, [r[0] for r in rep])
     s.close()
     return fails
+
+
+def tophat_case(adv_opt, nx=91, ny=3, nz=10):
+    """The reference's own kernel harness, PROGRAM feeder (dyn_em/module_advect_em.F:10567-10870,
+    built with -DADVECT_KERNEL): 91x3x10 doubly periodic box, top-hat scalar between i=36 and 54
+    (tophat, :56-80), ru = 90, rv = rom = 0, mu = 1, rdx = rdy = 1/1000, dt = 5, levels
+    znw = 1-(k-1)/(kte-1).  One feeder `loop` is the three advect_scalar calls with dt/3, dt/2, dt,
+    i.e. exactly rk_scalar_step(1..3) of this path with scalar_adv_opt = 0 (1: the third call is
+    advect_scalar_pd)."""
+    from wrf_b200 import ideal
+    F = np.float32
+    d = ideal.memory_dims(nx, ny, nz)
+    c = ideal.default_config(dt=5.0, dx=1000.0, dy=1000.0, time_step=5, time_step_sound=4, periodic_x=1, periodic_y=1,
+                             num_moist=0, num_scalar=1, scalar_adv_opt=adv_opt, mp_physics=0)
+    v, sc = ideal.vertical_coords(nz, 10000.0, stretch=False)
+    for k_, val in sc.items():
+        setattr(c, k_, float(val))
+    nj, nk, ni = d.jme - d.jms + 1, nz, d.ime - d.ims + 1
+    fl = {n: v[n] for n in ("znu", "znw", "fnm", "fnp", "rdnw", "rdn", "dnw", "dn")}
+    one1, zero1 = np.ones(nz, F), np.zeros(nz, F)
+    fl.update(c1h=one1, c1f=one1, c2h=zero1, c2f=zero1, c3h=v["znu"], c3f=v["znw"], c4h=zero1, c4f=zero1)
+    ones2 = np.ones((nj, ni), F)
+    for n in ("msftx", "msfty", "msfux", "msfuy", "msfvx", "msfvx_inv", "msfvy", "mub", "muts", "mut"):
+        fl[n] = ones2.copy()
+    fl["ru_m"] = np.full((nj, nk, ni), 90.0, F)
+    q = np.zeros((nj, nk, ni), F)
+    ii = np.arange(d.ims, d.ime + 1)
+    jj = np.arange(d.jms, d.jme + 1)
+    hat = ((ii > 35) & (ii < 55) & (ii >= 1) & (ii <= nx))
+    q[np.ix_((jj >= 1) & (jj <= ny), np.arange(nk), hat)] = 1.0
+    fl["scalar_1"] = q
+    fl["scalar_old_1"] = q.copy()
+    return ideal.Case(name="tophat", dims=d, config=c, fields={k: np.ascontiguousarray(a, dtype=F) for k, a in fl.items()})
+
+
+def feeder_loop(m, nloops, fill_halo=True):
+    """m: Oracle or Solver.  fill_halo=False reproduces the feeder literally (it never refreshes the halo)."""
+    for _ in range(nloops):
+        for rk in (1, 2, 3):
+            m.call("rk_scalar_step", rk)
+            if fill_halo:
+                m.bc("scalar_1", "p")

@@ -1,0 +1,168 @@
+"""CPU tests of the oracle (test infrastructure): since the reference ships no golden outputs
+for this path, the oracle is held to the invariants the reference's own
+regression philosophy and documentation state, to its embedded ADVECT_KERNEL harness, and to
+frozen regression checksums (tests/golden/, produced by tests/golden/make_golden.py)."""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from tests import parity
+from tests.oracle_lib import Oracle
+from wrf_b200 import make_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def interior(o, name):
+    d = o.case.dims
+    a = o.get(name)
+    if a.ndim == 3:
+        return a[d.jds - d.jms:d.jde - d.jms, :d.kde - 1, d.ids - d.ims:d.ide - d.ims]
+    return a[d.jds - d.jms:d.jde - d.jms, d.ids - d.ims:d.ide - d.ims]
+
+
+# ---------------------------------------------------------------- ADVECT_KERNEL harness
+@pytest.mark.parametrize("adv_opt", [0, 1])
+def test_feeder_tophat(adv_opt):
+    """PROGRAM feeder (module_advect_em.F:10567): the top-hat moves at ru/mu = 90 m/s, i.e. 0.45
+    cells per loop; mass is conserved; the positive-definite variant stays >= 0 while the plain
+    5th-order scheme undershoots; nothing varies in y or z."""
+    o = Oracle(parity.tophat_case(adv_opt))
+    q0 = interior(o, "scalar_1").astype(np.float64)
+    x = np.arange(q0.shape[2], dtype=np.float64)
+    m0, c0 = q0[1, 0].sum(), (q0[1, 0] * x).sum() / q0[1, 0].sum()
+    nloops = 40
+    parity.feeder_loop(o, nloops)
+    q = interior(o, "scalar_1").astype(np.float64)
+    assert np.isfinite(q).all()
+    assert np.ptp(q, axis=0).max() == 0.0 and np.ptp(q, axis=1).max() == 0.0      # 1-D problem stays 1-D, bit for bit
+    row = q[1, 0]
+    assert abs(row.sum() - m0) <= 1e-4 * m0                                          # flux form conserves
+    assert abs((row * x).sum() / row.sum() - (c0 + 0.45 * nloops)) < 0.05            # 18 cells downstream
+    assert 0.9 < row.max() < 1.2
+    if adv_opt == 1:
+        assert row.min() >= -1e-12      # the limiter guard (1e-20) leaves rounding-level negatives
+    else:
+        assert row.min() < -1e-3                                                     # Gibbs undershoot of the unlimited scheme
+    # literal feeder (halo never refreshed): the same away from the edges, up to the dispersive
+    # ripples (~1e-8) that the periodic fill lets re-enter from the far side
+    o2 = Oracle(parity.tophat_case(adv_opt))
+    parity.feeder_loop(o2, nloops, fill_halo=False)
+    assert np.abs(interior(o2, "scalar_1")[:, :, 10:80] - interior(o, "scalar_1")[:, :, 10:80]).max() < 1e-6
+
+
+def test_feeder_column_dump_format():
+    """the feeder's output is NINT(field*100) per i (column, :82-112); after 0 loops it is the hat"""
+    o = Oracle(parity.tophat_case(0))
+    col = np.rint(interior(o, "scalar_1")[1, 0] * 100).astype(int)
+    assert col.sum() == 19 * 100 and col[35] == 100 and col[34] == 0 and col[53] == 100 and col[54] == 0
+
+
+# ---------------------------------------------------------------- BIT4BIT: serial == threaded
+@pytest.mark.parametrize("name", ["quarter_ss", "b_wave", "les"])
+def test_threads_bit_for_bit(name):
+    """tools/regtest.csh:14-18,281 -- serial and OpenMP runs must agree bit for bit; the oracle's
+    j-tiles play the role of OpenMP tiles"""
+    case = parity.small_cases()[name]
+    a, b = Oracle(case), Oracle(case)
+    b.set_threads(3)
+    for o in (a, b):
+        o.start_domain(); o.step(2)
+    for n in a.names():
+        x, y = a.get(n), b.get(n)
+        assert np.array_equal(x, y, equal_nan=True), n
+
+
+# ---------------------------------------------------------------- documented invariants
+def test_2d_case_has_no_y_variation():
+    """doc/README.test_cases:43-47 (2-D cases): v stays zero and nothing varies in y"""
+    o = Oracle(parity.small_cases()["hill2d_x"])
+    o.start_domain(); o.step(5)
+    assert np.abs(interior(o, "v_2")).max() == 0.0
+    for n in ("u_2", "w_2", "t_2", "ph_2", "mu_2", "p"):
+        a = interior(o, n)
+        assert np.ptp(a, axis=0).max() == 0.0, n
+    assert np.abs(interior(o, "w_2")).max() > 1e-3      # and the hill does force a wave
+
+
+def test_resting_atmosphere_stays_at_rest():
+    """hydrostatically balanced, horizontally uniform, calm state: the discrete pressure-gradient and
+    buoyancy terms cancel (module_initialize_ideal.F:1000-1085 balances with the model's own operators)"""
+    case = make_case("synthetic", nx=20, ny=18, nz=21, noise=0.0, calm=True, bubble_lattice=1.0e9)
+    case.fields["t_1"][:] = case.fields["t_1"][:1, :, :1]   # remove the (single, far away) bubble if any
+    o = Oracle(make_case("b_wave", nx=16, ny=20, nz=17, calm=True))
+    o.start_domain(); o.step(5)
+    assert np.abs(interior(o, "w_2")).max() < 2e-3
+    assert np.abs(interior(o, "u_2")).max() < 2e-3
+
+
+def test_dry_mass_conserved_in_periodic_box():
+    """sum of mu over a doubly periodic domain is constant (flux-form continuity, advance_mu_t :1092-1108)"""
+    o = Oracle(parity.small_cases()["periodic"])
+    o.start_domain()
+    m0 = (interior(o, "mu_2").astype(np.float64) + interior(o, "mub")).sum()
+    o.step(5)
+    m1 = (interior(o, "mu_2").astype(np.float64) + interior(o, "mub")).sum()
+    assert abs(m1 - m0) / m0 < 5e-7
+
+
+def test_positive_definite_moisture():
+    """moist_adv_opt = 1 (POSITIVEDEF, Registry.EM_COMMON:3275-3279): qc, qr never go negative"""
+    o = Oracle(parity.small_cases()["quarter_ss"])
+    o.start_domain(); o.step(10)
+    for n in ("moist_qv", "moist_qc", "moist_qr"):
+        assert interior(o, n).min() >= 0.0, n
+
+
+def test_scalar_mass_conserved_by_pd_advection():
+    o = Oracle(parity.small_cases()["periodic"])
+    o.start_domain()
+
+    def mass(o):
+        mu = (interior(o, "mu_2").astype(np.float64) + interior(o, "mub"))[:, None, :]
+        dnw = -o.get("dnw")[:o.case.dims.kde - 1].astype(np.float64)[None, :, None]
+        return (interior(o, "scalar_1").astype(np.float64) * mu * dnw).sum()
+    m0 = mass(o)
+    o.step(4)
+    assert abs(mass(o) - m0) / m0 < 1e-5
+    assert interior(o, "scalar_1").min() >= -1e-12
+
+
+def test_zonally_uniform_channel_stays_uniform():
+    """the unperturbed b_wave channel (periodic x, symmetric y walls, f-plane) has no x variation
+    and must not develop any -- the analogue of symm_check (module_solvedebug_em.F:292) for
+    this set-up -- and nothing leaks through the symmetric walls (v = 0 on them)"""
+    o = Oracle(parity.small_cases()["b_wave"])
+    o.start_domain(); o.step(3)
+    for n in ("u_2", "v_2", "w_2", "t_2", "ph_2", "mu_2"):
+        assert np.ptp(interior(o, n), axis=-1).max() == 0.0, n
+    d = o.case.dims
+    v = o.get("v_2")
+    assert np.abs(v[d.jds - d.jms]).max() == 0.0 and np.abs(v[d.jde - d.jms]).max() == 0.0
+
+
+# ---------------------------------------------------------------- frozen regression fixtures
+def crc(a):
+    return zlib.crc32(np.ascontiguousarray(a, dtype=np.float32).tobytes()) & 0xFFFFFFFF
+
+
+def test_golden_checksums():
+    """tests/golden/oracle_step.json freezes the oracle's output after start_domain + 2 steps
+    (CRC32 of the bit patterns and an L2 norm per prognostic field) so that an accidental change
+    of the restatement is caught.  CRCs are only comparable on the libm family they were made
+    with; the norms are checked everywhere."""
+    path = os.path.join(ROOT, "tests", "golden", "oracle_step.json")
+    gold = json.load(open(path))
+    same_libm = os.confstr("CS_GNU_LIBC_VERSION") == gold["_libc"]
+    cases = parity.small_cases()
+    for name, rec in gold["cases"].items():
+        o = Oracle(cases[name])
+        o.start_domain(); o.step(2)
+        for n, (c, l2) in rec.items():
+            a = o.get(n)
+            assert abs(float(np.sqrt((a.astype(np.float64) ** 2).sum())) - l2) <= 1e-5 * max(l2, 1e-30), (name, n)
+            if same_libm:
+                assert crc(a) == c, (name, n)

@@ -132,7 +132,8 @@ def wk_sounding(zmax=30000.0, dz=250.0, qv0=14.0e-3, u_scale=1.0):
     p = 1.0e5 * (1.0 - 9.81 * h / (1004.0 * 300.0)) ** (1004.0 / 287.0)
     for _ in range(3):
         T = th * (p / 1.0e5) ** (287.0 / 1004.0)
-        es = 611.2 * np.exp(17.67 * (T - 273.15) / (T - 29.65))
+        with np.errstate(over="ignore"):   # the top of the 30 km table is far below 29.65 K-offset validity; qv is capped below
+            es = 611.2 * np.exp(17.67 * (T - 273.15) / (T - 29.65))
         qv = np.minimum(qv0, rh * 0.622 * es / np.maximum(p - es, 1.0))
         thv = th * (1.0 + 0.61 * qv)
         pi = np.empty_like(h)
@@ -319,7 +320,8 @@ def balance(col, v, hy, p_top, hypsometric_opt):
         qvf1 = qvf1 * qvf2
         p[..., kk] = p[..., kk + 1] - ((c1f[k] * mu) + qvf1 * (c1f[k] * mub + c2f[k])) / qvf2 / rdn[kk + 1]
     qvf = F(1.0) + rvovrd * qv
-    alt = ((r_d / p1000mb) * (t + t0) * qvf * (((p + pb) / p1000mb) ** cvpm)).astype(F)
+    with np.errstate(divide="ignore", invalid="ignore"):   # level kde holds no mass point; zeroed next
+        alt = ((r_d / p1000mb) * (t + t0) * qvf * (((p + pb) / p1000mb) ** cvpm)).astype(F)
     alt[..., kde - 1] = 0
     al = (alt - alb).astype(F)
     al[..., kde - 1] = 0
