@@ -169,19 +169,29 @@ int wrfgpu_compute_mesh(int ntasks, int nproc_x, int nproc_y, int *ntasks_x, int
 /* task_for_point.c:6-14 + module_dm.F:924-1003: patch + memory dims of `mytask` */
 int wrfgpu_patch_dims(int ids, int ide, int jds, int jde, int kds, int kde,
                       int ntasks_x, int ntasks_y, int mytask, wrfgpu_dims *out);
-/* NCCL bootstrap.  The 128-byte unique id is created on rank 0 and broadcast by
- * the host (MPI_Bcast in wrf.exe, torch.distributed in bench.py). */
+/* Ranks as processes (one per GPU: wrf.exe under mpirun, bench.py under torchrun): NCCL over
+ * NVLink.  The 128-byte unique id is created on rank 0 and broadcast by the host (MPI_Bcast in
+ * wrf.exe where wrf_dm_initialize builds its communicator, external/RSL_LITE/module_dm.F:177-232;
+ * torch.distributed in bench.py). */
 int wrfgpu_comm_unique_id(void *id128);
 int wrfgpu_comm_init(wrfgpu_solver *s, const void *id128, int rank, int nranks);
-/* run one named Registry halo ("HALO_EM_A", "HALO_EM_D2_5", ...) on the
- * resident state; no-op on a 1x1 mesh (Registry.EM_COMMON:3418-3551) */
+/* Ranks as solvers of ONE process (one host thread each, on one or several GPUs with peer
+ * access): neighbours read each other's send buffers directly; `all` is in rank order. */
+int wrfgpu_comm_init_local(wrfgpu_solver *const *all, int n);
+/* run one named Registry halo ("HALO_EM_A", "HALO_EM_D2_5", ...) on the resident state; a no-op
+ * on a 1x1 mesh exactly as the generated HALO_*.inc are (Registry.EM_COMMON:3418-3551).  A
+ * HALO_EM_x and the PERIOD_* include that follows it in solve_em.F are one exchange. */
 int wrfgpu_halo(wrfgpu_solver *s, const char *halo_name);
-/* pack/unpack index sets of one field for one direction, for CPU-side tests of
- * the host logic: returns the strip bounds rsl_comm_iter would produce
- * (module_dm.F:2761) in is,ie,js,je. dir: 0=-y 1=+y 2=-x 3=+x; send=1/recv=0 */
-int wrfgpu_halo_strip(const wrfgpu_dims *d, const wrfgpu_config *c, int width,
-                      int xstag, int ystag, int dir, int send,
-                      int *is, int *ie, int *js, int *je);
+/* host logic behind it, callable without a GPU:
+ * the width and the comma-separated Registry field names of an exchange for this species set */
+int wrfgpu_halo_spec(const wrfgpu_config *c, const char *halo_name, int *width, char *fields, size_t cap);
+/* the index box this rank packs (send=1) or fills (send=0) in direction dir (0=-y 1=+y: Y phase,
+ * 2=-x 3=+x: X phase, run after Y so corners propagate) and the peer rank; returns 0 when the rank
+ * has no neighbour there (external/RSL_LITE/c_code.c:405-700, period.c, module_dm.F:2761) */
+int wrfgpu_halo_box(const wrfgpu_dims *d, const wrfgpu_config *c, int width, int dir, int send,
+                    int *peer, int *is, int *ie, int *js, int *je);
+/* bytes this rank has sent in halo exchanges since create (bench: NVLink traffic) */
+long long wrfgpu_halo_bytes(const wrfgpu_solver *s);
 
 #ifdef __cplusplus
 }

@@ -91,6 +91,11 @@ struct Oracle {
   int num_sound_steps = 0;
   float dts = 0.f;
   long n3, n2, n1;
+  // multi-rank runs: called at every HALO_EM_* / PERIOD_* include site of solve_em.F with the Registry
+  // name of the exchange; the test harness moves the strips between the ranks' oracles (RSL_LITE's role)
+  void (*halo_cb)(void *ctx, const char *name) = nullptr;
+  void *halo_ctx = nullptr;
+  void halo(const char *name) { if (halo_cb) halo_cb(halo_ctx, name); }
   int nthreads = 1;   // j-tiles run on std::threads like the reference's OpenMP tiles (solve_em.F:652-674)
   template <class Fn> void par(Fn fn);
 

@@ -192,6 +192,7 @@ void Oracle::small_step_prep(int rk_step) {
   par([&](const Cx &xt) { orc::calc_p_rho(xt, a3("al"), a3("p"), a3("ph_2"), a3("alt"), a3("t_2"), a3("t_save"), a3("c2a"), a3("pm1"), a2("mu_2"), a2("muts"),
                   c.smdiv, 0); });
   par([&](const Cx &xt) { calc_coef_w(xt, a3("a"), a3("alpha"), a3("gamma"), a2("mut"), a3("cqw"), a3("c2a"), dts_rk, c.epssm); });
+  halo("HALO_EM_B");   // + PERIOD_BDY_EM_B, solve_em.F:1176-1177
   bc("ru_tend", 'u'); bc("rv_tend", 'v'); bc("ph_2", 'w'); bc("al", 'p'); bc("p", 'p'); bc("t_1", 'p'); bc("t_save", 't');
   bc("mu_1", 't'); bc("mu_2", 't'); bc("mudf", 't');
 }
@@ -225,6 +226,7 @@ void Oracle::sumflux(int rk_step, int iteration) {
 void Oracle::calc_p_rho(int iteration) {
   par([&](const Cx &xt) { orc::calc_p_rho(xt, a3("al"), a3("p"), a3("ph_2"), a3("alt"), a3("t_2"), a3("t_save"), a3("c2a"), a3("pm1"), a2("mu_2"), a2("muts"),
                   c.smdiv, iteration); });
+  halo("HALO_EM_C2");  // + PERIOD_BDY_EM_B3, solve_em.F:1659-1660
   bc("ph_2", 'w'); bc("al", 'p'); bc("p", 'p'); bc("muts", 't'); bc("mu_2", 't'); bc("mudf", 't');
 }
 // solve_em.F:1732-1800
@@ -284,9 +286,14 @@ void Oracle::rk_scalar_step(int rk_step) {
   if (rk_step == rk_order)
     for (auto &s : sp)
       if (s.adv_opt == 1) par([&](const Cx &xt) { rk_update_scalar_pd(xt, a3(s.o), a3(s.t), a2("mu_1"), a2("mu_1"), a2("mub"), dt_rk); });
-  if (rk_step == rk_order)
+  if (rk_step == rk_order) {
+    bool any = false;
+    for (auto &s : sp) any |= s.adv_opt == 1;
+    if (any) halo("HALO_EM_MOIST_OLD_E_7");   // + PERIOD_BDY_EM_MOIST_OLD (and the SCALAR_OLD twins), solve_em.F:1878-2142
     for (auto &s : sp)
       if (s.adv_opt == 1) bc(s.o, 'p');
+  }
+  halo("HALO_EM_D");   // + PERIOD_EM_DA, solve_em.F:2179-2181
   for (auto &s : sp) {
     // rk_scalar_tend, module_em.F:1096-1442
     par([&](const Cx &xt) { ww_split(xt, a3("wwE"), a3("wwI"), a3("ww_m")); });
@@ -306,6 +313,8 @@ void Oracle::calc_p_rho_phi() {
 
 // solve_em.F:3245-3343 (rk_phys_bc_dry_2, module_bc_em.F:1045-1104, + species)
 void Oracle::rk_phys_bc_dry_2() {
+  halo("HALO_EM_D2_5");        // + PERIOD_BDY_EM_D, solve_em.F:3222-3236
+  halo("HALO_EM_MOIST_E_7");   // HALO_EM_MOIST_E_5/7, SCALAR_E_5/7, solve_em.F:3359-3447
   bc("u_2", 'U'); bc("v_2", 'V'); bc("w_2", 'w'); bc("t_2", 'p'); bc("ph_2", 'w'); bc("mu_2", 't');
   for (int s = 0; s < c.num_moist; s++) bc(std::string("moist_") + moist_names[s], 'p');
   for (int s = 1; s <= c.num_scalar; s++) bc("scalar_" + std::to_string(s), 'p');
@@ -372,17 +381,22 @@ void Oracle::microphysics() {
         qv_diabatic(i, k, j) = qvten / dt;
         qc_diabatic(i, k, j) = qcten / dt;
       }
+  halo("HALO_EM_THETAM");   // + PERIOD_EM_THETAM, solve_em.F:4109-4110
   bc("h_diabatic", 'p');
 }
 
 // solve_em.F:4175-4759: second calc_p_rho_phi, set_phys_bc_dry_2 + species BCs, set_w_surface
 void Oracle::end_of_step() {
   calc_p_rho_phi();
+  halo("HALO_EM_D3_5");        // + PERIOD_BDY_EM_D3, solve_em.F:4437-4449
+  halo("HALO_EM_MOIST_E_7");
   bc("u_1", 'U'); bc("u_2", 'U'); bc("v_1", 'V'); bc("v_2", 'V'); bc("w_1", 'w'); bc("w_2", 'w');
   bc("t_1", 'p'); bc("t_2", 'p'); bc("ph_1", 'w'); bc("ph_2", 'w'); bc("mu_1", 't'); bc("mu_2", 't');
   for (int s = 0; s < c.num_moist; s++) bc(std::string("moist_") + moist_names[s], 'p');
   for (int s = 1; s <= c.num_scalar; s++) bc("scalar_" + std::to_string(s), 'p');
+  halo("HALO_EM_C");           // + PERIOD_BDY_EM_E, solve_em.F:4730-4731
   par([&](const Cx &xt) { set_w_surface(xt, a3("w_2"), a3("u_2"), a3("v_2")); });
+  halo("HALO_EM_E_5");         // solve_em.F:4781-4846
 }
 
 void Oracle::step() {
@@ -393,18 +407,21 @@ void Oracle::step() {
     for (int j = x.jts; j <= std::min(x.jte, x.jde - 1); j++)
       for (int k = x.kts; k <= x.kte - 1; k++)
         for (int i = x.its; i <= std::min(x.ite, x.ide - 1); i++) mo(i, k, j) = m(i, k, j);
+    halo("HALO_EM_MOIST_OLD_E_7");   // + PERIOD_BDY_EM_MOIST_OLD, solve_em.F:535-536
     bc("moist_old_qv", 'p');
   }
   for (int rk_step = 1; rk_step <= rk_order; rk_step++) {
     float dt_rk, dts_rk; int ns;
     rk_params(rk_step, dt_rk, dts_rk, ns);
     rk_step_prep(rk_step);
+    halo("HALO_EM_A");   // + PERIOD_BDY_EM_A, solve_em.F:708,715
     rk_phys_bc_dry_1();
     if (rk_step == 1) init_zero_tendency();
     rk_tendency(rk_step);
     small_step_prep(rk_step);
     for (int it = 1; it <= ns; it++) {
       advance_uv(rk_step);
+      halo("HALO_EM_C");   // solve_em.F:1382
       advance_mu_t(rk_step);
       advance_w(rk_step);
       sumflux(rk_step, it);
@@ -454,6 +471,11 @@ int oracle_get_field(Oracle *o, const char *name, float *h, size_t n) {
     std::memcpy(h, v.data(), n * sizeof(float));
   })
 }
+int oracle_set_halo_callback(Oracle *o, void (*cb)(void *, const char *), void *ctx) { o->halo_cb = cb; o->halo_ctx = ctx; return 0; }
+float *oracle_field_ptr(Oracle *o, const char *name) {
+  auto it = o->data.find(name);
+  return it == o->data.end() ? nullptr : it->second.data();
+}
 int oracle_set_threads(Oracle *o, int n) { o->nthreads = n < 1 ? 1 : n; return o->nthreads; }
 int oracle_step(Oracle *o, int n) { OGUARD(for (int i = 0; i < n; i++) o->step()) }
 int oracle_rk_step_prep(Oracle *o, int rk) { OGUARD(o->rk_step_prep(rk)) }
@@ -480,6 +502,7 @@ int oracle_set_physical_bc(Oracle *o, const char *name, char var) { OGUARD(o->bc
 // both time levels (start_em.F:1421-1433 and the set_physical_bc calls before it).
 extern "C" int oracle_start_domain(orc::Oracle *o) {
   OGUARD({
+    o->halo("HALO_EM_INIT");   // HALO_EM_INIT_1..5, dyn_em/start_em.F
     for (const char *n : {"phb"}) o->bc(n, 'w');
     for (const char *n : {"pb", "alb", "p", "al", "alt"}) o->bc(n, 't');
     for (const char *n : {"mub", "ht", "msftx", "msfty", "f", "e", "sina", "cosa"}) o->bc(n, 't');

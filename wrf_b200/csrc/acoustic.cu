@@ -54,15 +54,15 @@ __global__ void k_ssp_3d(const Geo g, Box b, int rk_step, SspArgs a) {
   const float c1h = g.c1h[k], c2h = g.c2h[k];
   if (km && jm) {   // u points
     const float u2 = A3(a.u_2, i, k, j);
-    float u1 = A3(a.u_1, i, k, j);
-    if (rk_step == 1) { u1 = u2; A3(a.u_1, i, k, j) = u2; }
+    float u1;
+    if (rk_step == 1) { u1 = u2; A3(a.u_1, i, k, j) = u2; } else u1 = A3(a.u_1, i, k, j);
     A3(a.u_save, i, k, j) = u2;
     A3(a.u_2, i, k, j) = ((c1h * A2(a.muus, i, j) + c2h) * u1 - (c1h * A2(a.muu, i, j) + c2h) * u2) / A2(g.msfuy, i, j);
   }
   if (km && im) {   // v points
     const float v2 = A3(a.v_2, i, k, j);
-    float v1 = A3(a.v_1, i, k, j);
-    if (rk_step == 1) { v1 = v2; A3(a.v_1, i, k, j) = v2; }
+    float v1;
+    if (rk_step == 1) { v1 = v2; A3(a.v_1, i, k, j) = v2; } else v1 = A3(a.v_1, i, k, j);
     A3(a.v_save, i, k, j) = v2;
     A3(a.v_2, i, k, j) = ((c1h * A2(a.muvs, i, j) + c2h) * v1 - (c1h * A2(a.muv, i, j) + c2h) * v2) * A2(g.msfvx_inv, i, j);
   }
@@ -70,16 +70,17 @@ __global__ void k_ssp_3d(const Geo g, Box b, int rk_step, SspArgs a) {
     const float muts = A2(a.muts, i, j), mut = A2(a.mut, i, j);
     if (km) {
       const float t2 = A3(a.t_2, i, k, j);
-      float t1 = A3(a.t_1, i, k, j);
-      if (rk_step == 1) { t1 = t2; A3(a.t_1, i, k, j) = t2; }
+      float t1;
+      if (rk_step == 1) { t1 = t2; A3(a.t_1, i, k, j) = t2; } else t1 = A3(a.t_1, i, k, j);
       A3(a.c2a, i, k, j) = WG_CPOVCV * (A3(a.pb, i, k, j) + A3(a.p, i, k, j)) / A3(a.alt, i, k, j);
       A3(a.t_save, i, k, j) = t2;
       A3(a.t_2, i, k, j) = (c1h * muts + c2h) * t1 - (c1h * mut + c2h) * t2;
     }
     const float c1f = g.c1f[k], c2f = g.c2f[k];
     const float w2 = A3(a.w_2, i, k, j), p2 = A3(a.ph_2, i, k, j);
-    float w1 = A3(a.w_1, i, k, j), p1 = A3(a.ph_1, i, k, j);
+    float w1, p1;
     if (rk_step == 1) { w1 = w2; p1 = p2; A3(a.w_1, i, k, j) = w2; A3(a.ph_1, i, k, j) = p2; }
+    else { w1 = A3(a.w_1, i, k, j); p1 = A3(a.ph_1, i, k, j); }
     A3(a.w_save, i, k, j) = w2;
     A3(a.w_2, i, k, j) = ((c1f * muts + c2f) * w1 - (c1f * mut + c2f) * w2) / A2(g.msfty, i, j);
     A3(a.ph_save, i, k, j) = p2;
@@ -102,8 +103,9 @@ __global__ void k_calc_p_rho(const Geo g, Box b, int step, fp al, fp p, cfp ph, 
     A3(pm1, i, k, j) = pv;
   } else {
     const float ptmp = pv;
-    pv = pv + g.smdiv * (pv - A3(pm1, i, k, j));
-    A3(pm1, i, k, j) = ptmp;
+    const float pold = A3(pm1, i, k, j);
+    pv = pv + g.smdiv * (pv - pold);
+    A3(pm1, i, k, j) = after_load(ptmp, pold);   // see common.cuh: keep the store behind the load
   }
   A3(p, i, k, j) = pv;
 }

@@ -59,6 +59,18 @@ typedef const float *__restrict__ cfp;
 
 __device__ __forceinline__ float sign1(float a) { return copysignf(1.0f, a); }
 
+// In-place updates: on sm_100 a store that is issued while a load of the SAME address is still
+// in flight (its value not yet consumed) stalls the SM's L1 pipeline until the load returns --
+// measured with ncu on k_calc_p_rho: 7 % DRAM utilisation, every warp in long-scoreboard stall,
+// 5.3x slower than the same kernel with the store ordered after the load (profiles/).  The
+// compiler only orders such a pair in program order, not by completion, so a store whose VALUE
+// does not depend on the earlier load (pm1 <- unsmoothed p, sc_tend <- 0) must be given a data
+// dependence on it.  after_load(v, x) returns exactly v (bitwise, for every x including NaN):
+// fminf(|x|, 0) is +0 and OR-ing +0 into v's bits changes nothing.
+__device__ __forceinline__ float after_load(float v, float loaded) {
+  return __int_as_float(__float_as_int(v) | __float_as_int(fminf(fabsf(loaded), 0.f)));
+}
+
 #define CUDA_CHECK(x)                                                                     \
   do {                                                                                    \
     cudaError_t e_ = (x);                                                                 \
@@ -92,12 +104,9 @@ struct Solver {
   float dts = 0.f;
   long long launches = 0;
   float *d_cfl = nullptr;   // 2 floats: max_vert_cfl, max_horiz_cfl
-  // halo/NCCL state lives in halo.cu
+  // halo exchange state (HaloState, halo.cu)
   void *comm = nullptr;
   int rank = 0, nranks = 1;
-  float *sendbuf[4] = {nullptr, nullptr, nullptr, nullptr};
-  float *recvbuf[4] = {nullptr, nullptr, nullptr, nullptr};
-  size_t bufcap = 0;
   // phase / kernel timing (cudaEvents on `stream`, only when switched on)
   bool timing = false;
   std::map<std::string, double> phase_ms;
@@ -195,4 +204,13 @@ inline bool empty(const Box &b) { return b.i1 < b.i0 || b.k1 < b.k0 || b.j1 < b.
   const int j = b.j0 + blockIdx.y;                        \
   if (i > b.i1) return;
 
+void halo_destroy(Solver *s);   // halo.cu
+
 }  // namespace wg
+
+// the opaque handle of include/wrfgpu.h
+struct wrfgpu_solver {
+  wg::Solver s;
+  wrfgpu_solver(const wrfgpu_dims &d, const wrfgpu_config &c, int dev) : s(d, c, dev) {}
+};
+extern thread_local std::string g_wrfgpu_err;

@@ -74,33 +74,4 @@ int wrfgpu_patch_dims(int ids, int ide, int jds, int jde, int kds, int kde, int 
   return 0;
 }
 
-// returns 1 and the strip bounds when this rank exchanges in direction `dir` (0=-y 1=+y 2=-x 3=+x), else 0.
-// `periodic` neighbours (mesh wrap, external/RSL_LITE/period.c) are included when the BC flag is set
-// and the dimension is split over more than one task.
-int wrfgpu_halo_strip(const wrfgpu_dims *d, const wrfgpu_config *c, int width, int xstag, int ystag, int dir, int send,
-                      int *is, int *ie, int *js, int *je) {
-  (void)xstag; (void)ystag;   // "not used" in RSL_LITE_PACK as well (c_code.c:408)
-  const int ntx = c->ntasks_x, nty = c->ntasks_y;
-  const int mx = c->mytask % ntx, my = c->mytask / ntx;
-  const int w = width;
-  bool have;
-  switch (dir) {
-    case 0: have = my > 0 || (c->periodic_y && nty > 1); break;
-    case 1: have = my < nty - 1 || (c->periodic_y && nty > 1); break;
-    case 2: have = mx > 0 || (c->periodic_x && ntx > 1); break;
-    default: have = mx < ntx - 1 || (c->periodic_x && ntx > 1); break;
-  }
-  if (!have) return 0;
-  if (dir < 2) {   // y exchange: i range clipped to the domain (IMAX/IMIN, c_code.c:460-461)
-    *is = std::max(d->ips - w, d->ids); *ie = std::min(d->ipe + w, d->ide);
-    if (dir == 0) { if (send) { *js = d->jps; *je = d->jps + w - 1; } else { *js = d->jps - w; *je = d->jps - 1; } }
-    else { if (send) { *js = d->jpe - w + 1; *je = d->jpe; } else { *js = d->jpe + 1; *je = d->jpe + w; } }
-  } else {         // x exchange: j range includes the y halo just received, so corners propagate
-    *js = std::max(d->jps - w, d->jds); *je = std::min(d->jpe + w, d->jde);
-    if (dir == 2) { if (send) { *is = d->ips; *ie = d->ips + w - 1; } else { *is = d->ips - w; *ie = d->ips - 1; } }
-    else { if (send) { *is = d->ipe - w + 1; *ie = d->ipe; } else { *is = d->ipe + 1; *ie = d->ipe + w; } }
-  }
-  return 1;
-}
-
 }  // extern "C"

@@ -1,14 +1,502 @@
-// halo.cu -- RSL_LITE halo exchanges (external/RSL_LITE) on NCCL.  Filled in by the
-// multi-GPU milestone; on a 1x1 mesh every HALO_EM_* is a no-op exactly as the
-// generated HALO_*.inc are in a single-task run.
+// halo.cu -- the Registry-generated HALO_EM_* / PERIOD_* exchanges of the solve_em path
+// (Registry/Registry.EM_COMMON:3418-3551, inc/HALO_EM_*.inc as emitted by tools/gen_comms.c:296-672)
+// and their RSL_LITE mechanics (external/RSL_LITE/c_code.c:306-1076, period.c, module_dm.F:2761)
+// restated for one-process-per-GPU execution.
+//
+// What is kept from the reference, because N-GPU == 1-GPU bit for bit depends on it:
+//   * patch ownership (decomp.cu) and which fields travel in which exchange, with which width;
+//   * Y exchange first over i in [ips-w, ipe+w] clipped to the domain, then X over j in
+//     [jps-w, jpe+w], so corner points arrive in two hops (c_code.c:460-477, :587);
+//   * a periodic dimension that is split over ranks is closed by an exchange between the first and
+//     the last rank of the mesh row/column (period.c); one that lives on a single rank is a local
+//     copy done by set_physical_bc (share/module_bc.F:750) -- bc.cu here.
+// What is different: strips are packed by ONE kernel per phase for all fields and both directions
+// straight into device buffers and move GPU-to-GPU -- ncclSend/ncclRecv over NVLink when ranks are
+// processes (bench.py under torchrun, wrf.exe under mpirun), or a peer-memory read of the
+// neighbour's send buffer when the ranks are solvers of one process (wrfgpu_comm_init_local).
+// A HALO_EM_x and the PERIOD_* that follows it in solve_em.F are one exchange here: the periodic
+// neighbour is just another peer, with the wider PERIOD width (e.g. HALO_EM_A 1, PERIOD_BDY_EM_A 2).
 #include "common.cuh"
+#include <dlfcn.h>
+#include <algorithm>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+
 namespace wg {
+
+// ---------------------------------------------------------------------------------------------
+// exchange table
+struct HaloDef { const char *name; int width; const char *f3; const char *f2; };
+// '@moist' -> moist_q*, '@moist_old' -> moist_old_q*, '@scalar' -> scalar_n, '@scalar_old' -> scalar_old_n
+static const HaloDef kHalos[] = {
+    // start of step: initialize_moist_old (solve_em.F:520-550); HALO_EM_MOIST_OLD_E_7 :3480 + PERIOD :3530, width 4
+    {"HALO_EM_MOIST_OLD_E_7", 4, "@moist_old,@scalar_old", ""},
+    // after rk_step_prep (:708,:715): HALO_EM_A :3425 (1) + PERIOD_BDY_EM_A :3538 (2)
+    {"HALO_EM_A", 2, "ru,rv,rw,ww,php,alt,al,p,rho", "muu,muv,mut"},
+    // after small_step_prep (:1176-1177): HALO_EM_B :3447 (1) + PERIOD_BDY_EM_B :3542 (2, adds ru_tend,rv_tend)
+    {"HALO_EM_B", 2, "ph_2,al,p,t_1,t_save,u_save,v_save,php,alt,pb,ru_tend,rv_tend", "mu_1,mu_2,mudf"},
+    // after advance_uv (:1382): HALO_EM_C :3449 (1); the periodic twin is PERIOD_BDY_EM_E :3536 (2)
+    {"HALO_EM_C", 2, "u_2,v_2", ""},
+    // after calc_p_rho (:1659-1660): HALO_EM_C2 :3450 (1) + PERIOD_BDY_EM_B3 :3543 (2)
+    {"HALO_EM_C2", 2, "ph_2,al,p", "mu_2,muts,mudf"},
+    // before scalar advection (:2179-2181): HALO_EM_D :3451 (2) + PERIOD_EM_DA :3548 (2)
+    {"HALO_EM_D", 2, "ru_m,rv_m,ww_m", "mut,muts"},
+    // end of RK substeps 1,2 (:3222-3236): HALO_EM_D2_5 :3454 (3) + PERIOD_BDY_EM_D :3546 (3); the species go
+    // with HALO_EM_MOIST_E_7 / SCALAR_E_7 (:3359-3447, width 4 because advect_scalar_pd needs a tile+1 ring)
+    {"HALO_EM_D2_5", 3, "u_2,v_2,w_2,t_2,ph_2,al", "mu_2"},
+    {"HALO_EM_MOIST_E_7", 4, "@moist,@scalar", ""},
+    // after microphysics (:4109-4110): HALO_EM_THETAM :3476 (3) + PERIOD_EM_THETAM :3551
+    {"HALO_EM_THETAM", 3, "h_diabatic", ""},
+    // end of step (:4437-4449): HALO_EM_D3_5 :3456 (3) + PERIOD_BDY_EM_D3 :3547, species :3521 (4)
+    {"HALO_EM_D3_5", 3, "u_1,u_2,v_1,v_2,w_1,w_2,t_1,t_2,ph_1,ph_2", "mu_1,mu_2"},
+    // very end (:4781-4846): HALO_EM_E_5 :3458 (3) after set_w_surface
+    {"HALO_EM_E_5", 3, "u_1,u_2,v_1,v_2,w_1,w_2,t_1,t_2,ph_1,ph_2", "mu_1,mu_2"},
+    // start_domain_em (dyn_em/start_em.F): HALO_EM_INIT_1..5 carry the base state, map factors and both time levels
+    {"HALO_EM_INIT", 4,
+     "phb,pb,alb,p,al,alt,u_1,u_2,v_1,v_2,w_1,w_2,t_1,t_2,ph_1,ph_2,@moist,@moist_old,@scalar,@scalar_old",
+     "mub,ht,msftx,msfty,f,e,sina,cosa,msfux,msfuy,msfvx,msfvx_inv,msfvy,mu_1,mu_2"},
+};
+
+static void split(const std::string &s, std::vector<std::string> &out) {
+  size_t a = 0;
+  while (a < s.size()) {
+    size_t b = s.find(',', a);
+    if (b == std::string::npos) b = s.size();
+    if (b > a) out.push_back(s.substr(a, b - a));
+    a = b + 1;
+  }
+}
+
+// expands the '@' tokens for the species counts of `c`
+static bool halo_fields(const wrfgpu_config &c, const std::string &name, int &width, std::vector<std::string> &f3,
+                        std::vector<std::string> &f2) {
+  static const char *mn[] = {"qv", "qc", "qr"};
+  for (const HaloDef &h : kHalos) {
+    if (name != h.name) continue;
+    width = h.width;
+    std::vector<std::string> raw;
+    split(h.f3, raw);
+    for (auto &t : raw) {
+      if (t == "@moist") for (int s = 0; s < c.num_moist; s++) f3.push_back(std::string("moist_") + mn[s]);
+      else if (t == "@moist_old") for (int s = 0; s < c.num_moist; s++) f3.push_back(std::string("moist_old_") + mn[s]);
+      else if (t == "@scalar") for (int s = 1; s <= c.num_scalar; s++) f3.push_back("scalar_" + std::to_string(s));
+      else if (t == "@scalar_old") for (int s = 1; s <= c.num_scalar; s++) f3.push_back("scalar_old_" + std::to_string(s));
+      else f3.push_back(t);
+    }
+    split(h.f2, f2);
+    return true;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// strip geometry.  dir: 0 = -y, 1 = +y (Y phase), 2 = -x, 3 = +x (X phase)
+struct Strip { int peer; int is, ie, js, je; };
+static bool halo_box(const wrfgpu_dims &d, const wrfgpu_config &c, int w, int dir, bool send, Strip &s) {
+  const int ntx = std::max(1, c.ntasks_x), nty = std::max(1, c.ntasks_y);
+  const int mx = c.mytask % ntx, my = c.mytask / ntx;
+  bool wrap = false;
+  int px = mx, py = my;
+  switch (dir) {
+    case 0: if (my > 0) py = my - 1; else if (c.periodic_y && nty > 1) { py = nty - 1; wrap = true; } else return false; break;
+    case 1: if (my < nty - 1) py = my + 1; else if (c.periodic_y && nty > 1) { py = 0; wrap = true; } else return false; break;
+    case 2: if (mx > 0) px = mx - 1; else if (c.periodic_x && ntx > 1) { px = ntx - 1; wrap = true; } else return false; break;
+    default: if (mx < ntx - 1) px = mx + 1; else if (c.periodic_x && ntx > 1) { px = 0; wrap = true; } else return false; break;
+  }
+  s.peer = py * ntx + px;
+  // extent along the exchanged dimension: [lo, hi] of the patch, domain [ds, de]
+  const bool isy = dir < 2;
+  const int ps = isy ? d.jps : d.ips, pe = isy ? d.jpe : d.ipe, ds = isy ? d.jds : d.ids, de = isy ? d.jde : d.ide;
+  int a, b;
+  const bool low = (dir == 0 || dir == 2);
+  if (!wrap) {
+    if (low) { if (send) { a = ps; b = ps + w - 1; } else { a = ps - w; b = ps - 1; } }
+    else { if (send) { a = pe - w + 1; b = pe; } else { a = pe + 1; b = pe + w; } }
+  } else {
+    // periodic closure: dat(de+n) = dat(ds+n), n = 0..w  and  dat(ds-n) = dat(de-n), n = 1..w
+    // (share/module_bc.F:750-790 for the one-patch case; period.c for the split one).  The high side
+    // carries one point more because the point at `de` itself (the duplicate of `ds`) is replaced too.
+    if (low) { if (send) { a = ds; b = ds + w; } else { a = ds - w; b = ds - 1; } }
+    else { if (send) { a = de - w; b = de - 1; } else { a = de; b = de + w; } }
+  }
+  if (isy) {
+    s.js = a; s.je = b;
+    s.is = std::max(d.ips - w, d.ids); s.ie = std::min(d.ipe + w, d.ide);   // c_code.c:460-477
+    // a periodic x dimension that lives on this rank: the ghost columns were filled by set_physical_bc
+    // one row into the y halo only; they are refreshed by the next bc fill, not exchanged
+  } else {
+    s.is = a; s.ie = b;
+    // rows include the y halo just received, so corners arrive in two hops (c_code.c:587 JMAX/JMIN clip to
+    // the domain; with a split periodic y the ghost rows beyond the domain came from the wrap and go along)
+    const int ext = (c.periodic_y && nty > 1) ? w : 0;
+    s.js = std::max(d.jps - w, d.jds - ext); s.je = std::min(d.jpe + w, d.jde + ext);
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device pack / unpack: one launch moves every field of an exchange for up to two strips
+#define HALO_MAX 40
+struct HaloArgs {
+  float *p[HALO_MAX];       // origin-shifted field pointers
+  long off[HALO_MAX];       // element offset of the field inside a strip buffer, per unit (ni*nj) area
+  char is3d[HALO_MAX];
+  int n, nk;
+  // two strips (one per direction of the phase)
+  int is[2], ie[2], js[2], je[2];
+  float *buf[2];
+  int active[2];
+};
+
+template <bool UNPACK>
+__global__ void k_halo_copy(const Geo g, HaloArgs a) {
+  const int f = blockIdx.z % a.n, sd = blockIdx.z / a.n;
+  if (!a.active[sd]) return;
+  const int ni = a.ie[sd] - a.is[sd] + 1, nj = a.je[sd] - a.js[sd] + 1;
+  const bool is3d = a.is3d[f];
+  const int nk = is3d ? a.nk : 1;
+  const int row = blockIdx.y;                       // (j, k) row of this field
+  if (row >= nj * nk) return;
+  const int jj = row / nk, kk = row % nk;
+  float *buf = a.buf[sd] + a.off[f] * (long)ni * nj + ((long)jj * nk + kk) * ni;
+  float *fld = a.p[f];
+  const int j = a.js[sd] + jj, k = 1 + kk;
+  for (int ii = blockIdx.x * blockDim.x + threadIdx.x; ii < ni; ii += gridDim.x * blockDim.x) {
+    const int i = a.is[sd] + ii;
+    const long x = is3d ? ((long)i + (long)k * g.sk + (long)j * g.sj) : ((long)i + (long)j * g.ni);
+    if (UNPACK) fld[x] = buf[ii];
+    else buf[ii] = fld[x];
+  }
+}
+
+// A periodic dimension that lives on ONE rank is closed locally by set_physical_bc, but only on the
+// rows [jts-1, jte+1] (share/module_bc.F:752).  When the other dimension is split, the deeper halo
+// rows a rank has just received (and the ghost rows of a periodic wrap) would keep stale ghost
+// columns -- the corner points the positive-definite limiter's tile+1 ring reads.  period.c lets
+// "the extent in other dimension go into boundary region" for the same purpose; here the received
+// rows/columns get the same periodic copy set_physical_bc applies (dat(ds-n) = dat(de-n), n = 1..4;
+// dat(de+n) = dat(ds+n), n = 0..4), so that N ranks reproduce one rank bit for bit.
+// along_x: close x on rows [a0,a1]; else close y on columns [a0,a1]
+__global__ void k_halo_close(const Geo g, HaloArgs a, int along_x, int a0, int a1) {
+  const int f = blockIdx.z;
+  const bool is3d = a.is3d[f];
+  const int nk = is3d ? a.nk : 1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;      // index over the (a0..a1) x k lines
+  const int nl = a1 - a0 + 1;
+  if (t >= nl * nk) return;
+  const int l = a0 + t / nk, k = 1 + t % nk;
+  float *fld = a.p[f];
+  const int ds = along_x ? g.ids : g.jds, de = along_x ? g.ide : g.jde;
+  auto at = [&](int m) -> float & {
+    const int i = along_x ? m : l, j = along_x ? l : m;
+    return is3d ? fld[(long)i + (long)k * g.sk + (long)j * g.sj] : fld[(long)i + (long)j * g.ni];
+  };
+  for (int n = 1; n <= 4; n++) at(ds - n) = at(de - n);
+  for (int n = 0; n <= 4; n++) at(de + n) = at(ds + n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, bound at run time so that the library also loads where no NCCL exists (CPU test box)
+struct Nccl {
+  void *h = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, char[128], int) = nullptr;   // ncclUniqueId is a 128-byte struct passed by value
+  int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+struct Id128 { char b[128]; };
+static Nccl &nccl() {
+  static Nccl n;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char *env = getenv("WRFGPU_NCCL_LIB");
+    for (const char *name : {env ? env : "libnccl.so.2", "libnccl.so.2", "libnccl.so"}) {
+      n.h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (n.h) break;
+    }
+    if (!n.h) return;
+    n.GetUniqueId = (int (*)(void *))dlsym(n.h, "ncclGetUniqueId");
+    n.CommInitRank = (int (*)(void **, int, char[128], int))dlsym(n.h, "ncclCommInitRank");
+    n.Send = (int (*)(const void *, size_t, int, int, void *, cudaStream_t))dlsym(n.h, "ncclSend");
+    n.Recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))dlsym(n.h, "ncclRecv");
+    n.GroupStart = (int (*)())dlsym(n.h, "ncclGroupStart");
+    n.GroupEnd = (int (*)())dlsym(n.h, "ncclGroupEnd");
+    n.CommDestroy = (int (*)(void *))dlsym(n.h, "ncclCommDestroy");
+    n.GetErrorString = (const char *(*)(int))dlsym(n.h, "ncclGetErrorString");
+  });
+  return n;
+}
+static void nccl_check(int rc, const char *what) {
+  if (rc != 0) {
+    Nccl &n = nccl();
+    throw std::runtime_error(std::string("wrfgpu: NCCL ") + what + " failed: " + (n.GetErrorString ? n.GetErrorString(rc) : "?"));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ranks that are solvers of ONE process (one host thread each): a host barrier orders the
+// exchange, the data moves by reading the neighbour's send buffer from the unpack kernel
+struct LocalGroup {
+  std::vector<Solver *> ranks;
+  std::mutex m;
+  std::condition_variable cv;
+  int waiting = 0;
+  long generation = 0;
+  void barrier() {
+    std::unique_lock<std::mutex> lk(m);
+    const long gen = generation;
+    if (++waiting == (int)ranks.size()) { waiting = 0; generation++; cv.notify_all(); }
+    else cv.wait(lk, [&] { return generation != gen; });
+  }
+};
+
+struct HaloState {
+  void *comm = nullptr;               // ncclComm_t
+  LocalGroup *local = nullptr;
+  bool owns_local = false;
+  float *send[4] = {nullptr, nullptr, nullptr, nullptr};
+  float *recv[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t cap = 0;                     // floats per buffer
+  cudaEvent_t packed = nullptr, consumed = nullptr;
+  long long exchanges = 0, bytes_sent = 0;
+};
+
+static HaloState &hs(Solver *s) {
+  if (!s->comm) s->comm = new HaloState();
+  return *(HaloState *)s->comm;
+}
+
+static void ensure_buffers(Solver *s, size_t nfloats) {
+  HaloState &h = hs(s);
+  if (nfloats <= h.cap) return;
+  CUDA_CHECK(cudaStreamSynchronize(s->stream));
+  const size_t cap = nfloats + nfloats / 4;
+  for (int d = 0; d < 4; d++) {
+    if (h.send[d]) cudaFree(h.send[d]);
+    if (h.recv[d]) cudaFree(h.recv[d]);
+    CUDA_CHECK(cudaMalloc(&h.send[d], cap * sizeof(float)));
+    CUDA_CHECK(cudaMalloc(&h.recv[d], cap * sizeof(float)));
+  }
+  h.cap = cap;
+}
+
+void halo_destroy(Solver *s) {
+  if (!s->comm) return;
+  HaloState &h = hs(s);
+  for (int d = 0; d < 4; d++) { cudaFree(h.send[d]); cudaFree(h.recv[d]); }
+  if (h.packed) cudaEventDestroy(h.packed);
+  if (h.consumed) cudaEventDestroy(h.consumed);
+  if (h.comm && nccl().CommDestroy) nccl().CommDestroy(h.comm);
+  delete &h;
+  s->comm = nullptr;
+}
+
+static void launch_copy(Solver *s, bool unpack, HaloArgs &a) {
+  int nimax = 0, rows = 0;
+  for (int sd = 0; sd < 2; sd++)
+    if (a.active[sd]) {
+      nimax = std::max(nimax, a.ie[sd] - a.is[sd] + 1);
+      rows = std::max(rows, (a.je[sd] - a.js[sd] + 1) * a.nk);
+    }
+  if (!nimax) return;
+  dim3 grid((unsigned)std::min(8, (nimax + 127) / 128), (unsigned)rows, (unsigned)(2 * a.n));
+  s->kpre(unpack ? "k_halo_unpack" : "k_halo_pack");
+  if (unpack) k_halo_copy<true><<<grid, 128, 0, s->stream>>>(s->g, a);
+  else k_halo_copy<false><<<grid, 128, 0, s->stream>>>(s->g, a);
+  s->kpost();
+  s->launches++;
+}
+
+// one phase (Y: dirs 0,1; X: dirs 2,3) of one exchange
+static void exchange_phase(Solver *s, int width, const std::vector<Field *> &flds, int d0) {
+  HaloState &h = hs(s);
+  HaloArgs snd{}, rcv{};
+  snd.n = rcv.n = (int)flds.size();
+  snd.nk = rcv.nk = s->g.nk;
+  long unit = 0;
+  for (size_t f = 0; f < flds.size(); f++) {
+    snd.p[f] = rcv.p[f] = flds[f]->o;
+    snd.is3d[f] = rcv.is3d[f] = flds[f]->kind == 3;
+    snd.off[f] = rcv.off[f] = unit;
+    unit += flds[f]->kind == 3 ? s->g.nk : 1;
+  }
+  Strip ss[2], rs[2];
+  bool has[2];
+  size_t nsend[2] = {0, 0}, nrecv[2] = {0, 0}, need = 0;
+  for (int q = 0; q < 2; q++) {
+    has[q] = halo_box(s->d, s->c, width, d0 + q, true, ss[q]);
+    if (has[q]) {
+      halo_box(s->d, s->c, width, d0 + q, false, rs[q]);
+      nsend[q] = (size_t)unit * (ss[q].ie - ss[q].is + 1) * (ss[q].je - ss[q].js + 1);
+      nrecv[q] = (size_t)unit * (rs[q].ie - rs[q].is + 1) * (rs[q].je - rs[q].js + 1);
+      need = std::max(need, std::max(nsend[q], nrecv[q]));
+    }
+  }
+  if (!has[0] && !has[1]) {
+    if (h.local) { h.local->barrier(); h.local->barrier(); }   // keep the collective call pattern aligned
+    return;
+  }
+  if (h.local) {
+    // buffer growth must be collective-safe: peers read our pointers only after the barrier below
+    ensure_buffers(s, need);
+  } else {
+    ensure_buffers(s, need);
+  }
+  for (int q = 0; q < 2; q++) {
+    snd.active[q] = rcv.active[q] = has[q];
+    if (!has[q]) continue;
+    snd.is[q] = ss[q].is; snd.ie[q] = ss[q].ie; snd.js[q] = ss[q].js; snd.je[q] = ss[q].je; snd.buf[q] = h.send[d0 + q];
+    rcv.is[q] = rs[q].is; rcv.ie[q] = rs[q].ie; rcv.js[q] = rs[q].js; rcv.je[q] = rs[q].je; rcv.buf[q] = h.recv[d0 + q];
+  }
+  launch_copy(s, false, snd);
+  if (h.local) {
+    CUDA_CHECK(cudaEventRecord(h.packed, s->stream));
+    h.local->barrier();
+    for (int q = 0; q < 2; q++) {
+      if (!has[q]) continue;
+      Solver *peer = h.local->ranks[rs[q].peer];
+      HaloState &ph = hs(peer);
+      CUDA_CHECK(cudaStreamWaitEvent(s->stream, ph.packed, 0));
+      // my recv from direction d is the peer's send towards the opposite direction; read it in place
+      rcv.buf[q] = ph.send[(d0 + q) ^ 1];
+    }
+    launch_copy(s, true, rcv);
+    CUDA_CHECK(cudaEventRecord(h.consumed, s->stream));
+    h.local->barrier();
+    for (int q = 0; q < 2; q++)
+      if (has[q]) CUDA_CHECK(cudaStreamWaitEvent(s->stream, hs(h.local->ranks[ss[q].peer]).consumed, 0));
+  } else {
+    Nccl &n = nccl();
+    if (!h.comm) throw std::runtime_error("wrfgpu: halo exchange on a multi-rank mesh before wrfgpu_comm_init");
+    nccl_check(n.GroupStart(), "GroupStart");
+    // sends in the order (low, high), receives in the order (high, low): when both neighbours are the
+    // same rank (2 ranks, periodic) the n-th send to a peer then meets that peer's n-th receive
+    for (int q = 0; q < 2; q++)
+      if (has[q]) nccl_check(n.Send(h.send[d0 + q], nsend[q], 7 /*ncclFloat*/, ss[q].peer, h.comm, s->stream), "Send");
+    for (int q = 1; q >= 0; q--)
+      if (has[q]) nccl_check(n.Recv(h.recv[d0 + q], nrecv[q], 7, rs[q].peer, h.comm, s->stream), "Recv");
+    nccl_check(n.GroupEnd(), "GroupEnd");
+    launch_copy(s, true, rcv);
+  }
+  h.exchanges++;
+  h.bytes_sent += (long long)((nsend[0] + nsend[1]) * sizeof(float));
+  // close the other dimension on what was just received if it is periodic and lives on this rank
+  const bool isy = d0 == 0;
+  const bool close_other = isy ? (s->c.periodic_x && s->c.ntasks_x == 1) : (s->c.periodic_y && s->c.ntasks_y == 1);
+  if (close_other)
+    for (int q = 0; q < 2; q++) {
+      if (!has[q]) continue;
+      const int a0 = isy ? rs[q].js : rs[q].is, a1 = isy ? rs[q].je : rs[q].ie;
+      const int lines = (a1 - a0 + 1) * s->g.nk;
+      s->kpre("k_halo_close");
+      k_halo_close<<<dim3((unsigned)((lines + 127) / 128), 1, (unsigned)rcv.n), 128, 0, s->stream>>>(s->g, rcv, isy ? 1 : 0, a0, a1);
+      s->kpost();
+      s->launches++;
+    }
+}
+
 void Solver::halo(const std::string &name) {
-  if (nranks == 1) return;
-  throw std::runtime_error("wrfgpu: halo '" + name + "' requested on a multi-rank mesh but the communicator is not initialised");
+  if (nranks == 1) return;   // a single task: every HALO_*.inc is a no-op, periodic closure is set_physical_bc's job
+  int width = 0;
+  std::vector<std::string> f3, f2;
+  if (!halo_fields(c, name, width, f3, f2)) throw std::runtime_error("wrfgpu: unknown halo '" + name + "'");
+  std::vector<Field *> all;
+  for (auto &n : f3) if (fields.count(n)) all.push_back(&F(n));
+  for (auto &n : f2) if (fields.count(n)) all.push_back(&F(n));
+  for (size_t pos = 0; pos < all.size(); pos += HALO_MAX) {
+    std::vector<Field *> batch(all.begin() + pos, all.begin() + std::min(all.size(), pos + HALO_MAX));
+    exchange_phase(this, width, batch, 0);   // Y
+    exchange_phase(this, width, batch, 2);   // X (j range includes the rows just received)
+  }
 }
+
 }  // namespace wg
+
+// ---------------------------------------------------------------------------------------------
+using wg::Solver;
+
 extern "C" {
-int wrfgpu_comm_unique_id(void *) { return 1; }
-int wrfgpu_comm_init(wrfgpu_solver *, const void *, int, int) { return 1; }
+
+int wrfgpu_halo_spec(const wrfgpu_config *c, const char *halo_name, int *width, char *fields, size_t cap) {
+  std::vector<std::string> f3, f2;
+  int w = 0;
+  if (!wg::halo_fields(*c, halo_name, w, f3, f2)) return 1;
+  std::string out;
+  for (auto &n : f3) out += (out.empty() ? "" : ",") + n;
+  for (auto &n : f2) out += (out.empty() ? "" : ",") + n;
+  if (width) *width = w;
+  if (fields && cap) { size_t n = std::min(cap - 1, out.size()); memcpy(fields, out.data(), n); fields[n] = 0; }
+  return 0;
 }
+
+int wrfgpu_halo_box(const wrfgpu_dims *d, const wrfgpu_config *c, int width, int dir, int send, int *peer, int *is, int *ie,
+                    int *js, int *je) {
+  wg::Strip s;
+  if (!wg::halo_box(*d, *c, width, dir, send != 0, s)) return 0;
+  *peer = s.peer; *is = s.is; *ie = s.ie; *js = s.js; *je = s.je;
+  return 1;
+}
+
+int wrfgpu_comm_unique_id(void *id128) {
+  wg::Nccl &n = wg::nccl();
+  if (!n.GetUniqueId) { g_wrfgpu_err = "wrfgpu: libnccl.so.2 could not be loaded (set WRFGPU_NCCL_LIB)"; return 1; }
+  return n.GetUniqueId(id128) == 0 ? 0 : 1;
+}
+
+int wrfgpu_comm_init(wrfgpu_solver *s, const void *id128, int rank, int nranks) {
+  try {
+    Solver &S = s->s;
+    if (nranks != S.nranks || rank != S.rank) throw std::runtime_error("wrfgpu_comm_init: rank/nranks do not match the solver's mesh");
+    wg::Nccl &n = wg::nccl();
+    if (!n.CommInitRank) throw std::runtime_error("wrfgpu: libnccl.so.2 could not be loaded (set WRFGPU_NCCL_LIB)");
+    CUDA_CHECK(cudaSetDevice(S.device));
+    wg::HaloState &h = wg::hs(&S);
+    wg::Id128 id;
+    memcpy(id.b, id128, 128);
+    wg::nccl_check(n.CommInitRank(&h.comm, nranks, id.b, rank), "CommInitRank");
+    return 0;
+  } catch (const std::exception &e) { g_wrfgpu_err = e.what(); return 1; }
+}
+
+int wrfgpu_comm_init_local(wrfgpu_solver *const *all, int n) {
+  try {
+    auto *grp = new wg::LocalGroup();
+    for (int r = 0; r < n; r++) {
+      Solver &S = all[r]->s;
+      if (S.nranks != n || S.rank != r) throw std::runtime_error("wrfgpu_comm_init_local: solvers must be given in rank order");
+      grp->ranks.push_back(&S);
+    }
+    for (int r = 0; r < n; r++) {
+      Solver &S = all[r]->s;
+      CUDA_CHECK(cudaSetDevice(S.device));
+      wg::HaloState &h = wg::hs(&S);
+      h.local = grp;
+      h.owns_local = r == 0;
+      CUDA_CHECK(cudaEventCreateWithFlags(&h.packed, cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&h.consumed, cudaEventDisableTiming));
+      for (int q = 0; q < n; q++) {
+        const int pd = all[q]->s.device;
+        if (pd != S.device) {
+          int can = 0;
+          cudaDeviceCanAccessPeer(&can, S.device, pd);
+          if (!can) throw std::runtime_error("wrfgpu_comm_init_local: no peer access between the solvers' devices");
+          cudaError_t e = cudaDeviceEnablePeerAccess(pd, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(e);
+          cudaGetLastError();
+        }
+      }
+    }
+    return 0;
+  } catch (const std::exception &e) { g_wrfgpu_err = e.what(); return 1; }
+}
+
+long long wrfgpu_halo_bytes(const wrfgpu_solver *s) {
+  return s->s.comm ? ((wg::HaloState *)s->s.comm)->bytes_sent : 0;
+}
+
+}  // extern "C"

@@ -51,6 +51,7 @@ void Solver::calc_p_rho_phi() {
 // solve_em.F:3245-3343
 void Solver::rk_phys_bc_dry_2() {
   halo("HALO_EM_D2_5");
+  halo("HALO_EM_MOIST_E_7");
   std::vector<BcItem> it = {{"u_2", 'U'}, {"v_2", 'V'}, {"w_2", 'w'}, {"t_2", 'p'}, {"ph_2", 'w'}, {"mu_2", 't'}};
   for (auto &s : species) it.push_back({s.f, 'p'});
   bc(it);
@@ -231,6 +232,7 @@ void Solver::end_of_step() {
   // second calc_p_rho_phi (solve_em.F:4190) would rewrite identical values
   if (c.mp_physics) calc_p_rho_phi();
   halo("HALO_EM_D3_5");
+  halo("HALO_EM_MOIST_E_7");
   std::vector<BcItem> it = {{"u_1", 'U'}, {"u_2", 'U'}, {"v_1", 'V'}, {"v_2", 'V'}, {"w_1", 'w'}, {"w_2", 'w'},
                             {"t_1", 'p'}, {"t_2", 'p'}, {"ph_1", 'w'}, {"ph_2", 'w'}, {"mu_1", 't'}, {"mu_2", 't'}};
   for (auto &s : species) it.push_back({s.f, 'p'});

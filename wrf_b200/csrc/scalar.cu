@@ -191,11 +191,13 @@ __global__ void k_pd_tend(const Geo g, Box b, PdIn s, cfp scale, Box lim, fp ten
 // rk_update_scalar_pd (module_em.F:1803-1916)
 __global__ void k_update_scalar_pd(const Geo g, Box b, float dt, fp scalar, fp sc_tend, cfp mu_old, cfp mu_new, cfp mu_base) {
   TID3;
+  const float tend_in = A3(sc_tend, i, k, j);
+  const float s_in = A3(scalar, i, k, j);
   float tendency = 0.f;
-  tendency = tendency + A3(sc_tend, i, k, j);
-  A3(sc_tend, i, k, j) = 0.f;
+  tendency = tendency + tend_in;
   const float muold = A2(mu_old, i, j) + A2(mu_base, i, j), munew = A2(mu_new, i, j) + A2(mu_base, i, j);
-  A3(scalar, i, k, j) = ((g.c1h[k] * muold + g.c2h[k]) * A3(scalar, i, k, j) + dt * tendency) / (g.c1h[k] * munew + g.c2h[k]);
+  A3(scalar, i, k, j) = ((g.c1h[k] * muold + g.c2h[k]) * s_in + dt * tendency) / (g.c1h[k] * munew + g.c2h[k]);
+  A3(sc_tend, i, k, j) = after_load(0.f, tend_in);   // see common.cuh: keep the store behind the load
 }
 
 // rk_update_scalar (module_em.F:1587-1799)

@@ -98,7 +98,7 @@ Solver::Solver(const wrfgpu_dims &d_, const wrfgpu_config &c_, int dev) : d(d_),
 Solver::~Solver() {
   cudaSetDevice(device);
   for (auto &kv : fields) cudaFree(kv.second.d);
-  for (int i = 0; i < 4; i++) { cudaFree(sendbuf[i]); cudaFree(recvbuf[i]); }
+  halo_destroy(this);
   cudaFree(d_cfl);
   if (stream && own_stream) cudaStreamDestroy(stream);
 }
@@ -239,8 +239,8 @@ void Solver::step() {
 // C ABI
 // ---------------------------------------------------------------------------
 using wg::Solver;
-static thread_local std::string g_err;
-struct wrfgpu_solver { Solver s; wrfgpu_solver(const wrfgpu_dims &d, const wrfgpu_config &c, int dev) : s(d, c, dev) {} };
+thread_local std::string g_wrfgpu_err;
+#define g_err g_wrfgpu_err
 
 #define GUARD(body)                                                \
   try { cudaSetDevice(s->s.device); body; return 0; }              \

@@ -28,7 +28,8 @@ ABI_SYMBOLS = (
     "wrfgpu_create", "wrfgpu_destroy", "wrfgpu_last_error", "wrfgpu_version", "wrfgpu_field_size", "wrfgpu_set_field",
     "wrfgpu_get_field", "wrfgpu_upload", "wrfgpu_download", "wrfgpu_num_fields", "wrfgpu_field_name", "wrfgpu_field_devptr",
     "wrfgpu_step", "wrfgpu_solve_em", "wrfgpu_sync", "wrfgpu_set_stream", "wrfgpu_kernel_report", "wrfgpu_launch_count", "wrfgpu_phase_ms", "wrfgpu_set_physical_bc",
-    "wrfgpu_compute_mesh", "wrfgpu_patch_dims", "wrfgpu_comm_unique_id", "wrfgpu_comm_init", "wrfgpu_halo", "wrfgpu_halo_strip",
+    "wrfgpu_compute_mesh", "wrfgpu_patch_dims", "wrfgpu_comm_unique_id", "wrfgpu_comm_init", "wrfgpu_comm_init_local", "wrfgpu_halo",
+    "wrfgpu_halo_spec", "wrfgpu_halo_box", "wrfgpu_halo_bytes",
 ) + tuple("wrfgpu_" + p for p in PHASES)
 
 
