@@ -84,13 +84,15 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------
-def tile_case_on_device(small, nx, ny, nz, device):
-    """Build the big periodic state on the GPU by tiling a small periodic block (same
-    levels, same column physics): returns (Case with empty fields, {name: torch tensor})."""
+def tile_case_on_device(small, nx, ny, nz, device, ntx=1, nty=1, rank=0):
+    """Build this rank's patch of the big periodic state on the GPU by tiling a small periodic block
+    (same levels, same column physics).  Every value is a pure function of the GLOBAL index, so any
+    decomposition holds the same global state.  Returns (Case with empty fields, {name: tensor})."""
     import torch
-    from wrf_b200 import ideal
-    d = ideal.memory_dims(nx, ny, nz)
-    c = small.config
+    from wrf_b200 import decomp, ideal
+    gd = ideal.memory_dims(nx, ny, nz)
+    d = decomp.patch_dims(gd, ntx, nty, rank) if ntx * nty > 1 else gd
+    c = decomp.patch_config(small.config, ntx, nty, rank)
     sd = small.dims
     per_i, per_j = sd.ide - sd.ids, sd.jde - sd.jds      # mass points of the block = period
     ii = torch.arange(d.ims, d.ime + 1, device=device)
@@ -110,30 +112,42 @@ def tile_case_on_device(small, nx, ny, nz, device):
     return big, out
 
 
+def measured_traffic():
+    """per-kernel DRAM bytes per grid point from the last committed `ncu --set full` capture"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from wrf_b200 import Solver, make_case
+    from wrf_b200 import Solver, decomp, make_case
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1 and args.gpus != world:
-        raise SystemExit("--gpus must equal WORLD_SIZE")
     if world > 1:
-        raise SystemExit("multi-GPU patch decomposition is not wired into bench.py yet")
+        dist.init_process_group("nccl", device_id=dev)
+        if args.gpus != world:
+            raise SystemExit("--gpus must equal WORLD_SIZE")
+    ntx, nty = decomp.compute_mesh(world)        # mpaspect: 1x1, 1x2, 2x2, 2x4 (module_dm.F:98-116)
 
     nx, ny, nz = args.nx, args.ny, args.nz
     lat = 50
     small = make_case("synthetic", nx=lat + 1, ny=lat + 1, nz=nz, bubble_lattice=lat * 2000.0)
-    case, dev_fields = tile_case_on_device(small, nx, ny, nz, dev)
+    case, dev_fields = tile_case_on_device(small, nx, ny, nz, dev, ntx, nty, rank)
     s = Solver(case, device=local, upload=False)
     stream = torch.cuda.current_stream()
     s.set_stream(stream.cuda_stream)
+    if world > 1:
+        ident = [Solver.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        s.comm_init(ident[0], rank, world)
     for k, t in dev_fields.items():
         s.set(k, t)
     del dev_fields
@@ -141,15 +155,30 @@ def run_ours(args):
     s.start_domain()
     s.sync()
     c = case.config
-    npts = (nx - 1) * (ny - 1) * (nz - 1)
+    npts = (nx - 1) * (ny - 1) * (nz - 1)          # the whole job's grid points (strong scaling)
+    d = case.dims
+    my_pts = (min(d.ipe, d.ide - 1) - d.ips + 1) * (min(d.jpe, d.jde - 1) - d.jps + 1) * (nz - 1)
     ns = c.time_step_sound
-    bytes_pt = algorithmic_bytes_per_point_step(c.num_moist, len([1 for _ in range(c.num_moist + c.num_scalar)]), ns, c.mp_physics)
+    bytes_pt = algorithmic_bytes_per_point_step(c.num_moist, c.num_moist + c.num_scalar, ns, c.mp_physics)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- resident-state throughput
     for _ in range(args.warmup):
         s.step(1)
-    torch.cuda.synchronize()
-    l0 = s.launch_count()
+    barrier()
+    l0, hb0 = s.launch_count(), s.halo_bytes()
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -157,11 +186,12 @@ def run_ours(args):
     for _ in range(args.steps):
         s.step(1)
     e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
     sampler.stop.set()
     sampler.join(timeout=3)
     launches = s.launch_count() - l0
+    halo_bytes = (s.halo_bytes() - hb0) / args.steps
     ms_per_step = ms / args.steps
     value = npts / (ms_per_step * 1e-3)
 
@@ -170,19 +200,26 @@ def run_ours(args):
     s.step(1)
     rep = s.kernel_report()
     s.phase_timing(False)
+    barrier()
     tot = sum(v[1] for v in rep.values())
     top = max(rep.items(), key=lambda kv: kv[1][1])
     peak, peak_src = measured_peak()
     kname, (kn, kms) = top
     acc = ALGO_ACCESSES.get(kname, 0)
-    achieved = acc * 4 * npts / ((kms / kn) * 1e-3) / 1e9 if kn else 0.0
+    achieved = acc * 4 * my_pts / ((kms / kn) * 1e-3) / 1e9 if kn else 0.0
+    tr = measured_traffic().get(kname)
     roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": (round(tr["dram_bytes_per_point"] * my_pts) if tr else None),
+                "traffic_source": (tr.get("source") if tr else None), "peak_source": peak_src,
                 "launches_per_step": kn, "avg_launch_ms": round(kms / kn, 4), "share_of_step": round(kms / tot, 4),
                 "algorithmic_accesses_per_point": acc,
-                "step": {"algorithmic_bytes_per_point": bytes_pt, "achieved_GBs": round(value * bytes_pt / 1e9, 1),
-                         "frac": round(value * bytes_pt / 1e9 / peak, 4)},
+                "step": {"algorithmic_bytes_per_point": bytes_pt, "achieved_GBs_per_gpu": round(value * bytes_pt / 1e9 / world, 1),
+                         "frac": round(value * bytes_pt / 1e9 / world / peak, 4)},
                 "kernels_ms_per_step": {k: round(v[1], 3) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])}}
+    if world > 1:
+        roofline["halo"] = {"bytes_sent_per_rank_per_step": int(halo_bytes),
+                            "GBs_per_rank": round(halo_bytes / (ms_per_step * 1e-3) / 1e9, 2),
+                            "nvlink_peak_GBs_per_direction": 770.0, "transport": "ncclSend/ncclRecv"}
 
     # ---- end to end through the drop-in call with host buffers
     prog = ["u_2", "v_2", "w_2", "t_2", "ph_2", "mu_2"] + [n for n in s.names() if n.startswith("moist_q")]
@@ -194,27 +231,32 @@ def run_ours(args):
     h2d = sum(host[n].numel() * 4 for n in prog)
     e2e_steps = max(1, min(args.steps, 3))
     s.solve_em(prog, ptrs, prog, ptrs)     # warm
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         s.solve_em(prog, ptrs, prog, ptrs)
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     e2e = {"value": npts / e2e_s, "unit": "grid-pt-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
-           "ms_per_step": round(e2e_s * 1e3, 2), "call": "wrfgpu_solve_em (pinned host prognostic state in and out every step)"}
+           "ms_per_step": round(e2e_s * 1e3, 2),
+           "call": "wrfgpu_solve_em (pinned host prognostic state of the rank's patch in and out every step; bytes are per rank)"}
 
     line = {"metric": "grid-pt RK3 steps/s", "value": value, "unit": "grid-pt-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"synthetic em_quarter_ss {nx}x{ny}x{nz} (e_we x e_sn x e_vert), dx=2km, dt=12s, ns={ns}, "
-                                   f"periodic x/y, dry (passive qv, moist_adv_opt=1), 1 patch per GPU",
+                                   f"periodic x/y, dry (passive qv, moist_adv_opt=1), {ntx}x{nty} patch mesh, 1 patch per GPU",
                        "grid_points": npts, "l2_policy": "working set (tens of GB per step) is far larger than the 126 MB L2",
-                       "timing": "CUDA events on the launching stream"},
+                       "timing": "CUDA events on the launching stream, max over ranks"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary()}
-    if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args, quick=True)
-    print(json.dumps(line))
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, quick=True)
+        print(json.dumps(line), flush=True)
     s.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------

@@ -1,0 +1,92 @@
+"""N ranks on the device: every rank's owned points equal the single-rank GPU run bit for bit
+(the reference's BIT4BIT criterion, tools/regtest.csh:14-18).  The ranks are solvers of
+one process exchanging through peer memory (wrfgpu_comm_init_local), so the test also runs on a
+box with a single GPU; states start NaN-poisoned outside the owned points, so every value a rank
+reads must have been delivered by a halo exchange or a boundary fill."""
+import numpy as np
+import pytest
+
+import wrf_b200
+from tests import parity
+from wrf_b200 import Solver, decomp
+
+pytestmark = pytest.mark.gpu
+
+
+def _ndev():
+    import ctypes
+    n = ctypes.c_int(0)
+    ctypes.CDLL("libcudart.so").cudaGetDeviceCount(ctypes.byref(n))
+    return max(1, n.value)
+
+
+def _run(case, ntx, nty, nsteps, spread=False):
+    ref = Solver(case)
+    ref.start_domain(); ref.step(nsteps)
+    patches = decomp.split_case(case, ntx, nty, poison=True)
+    nd = _ndev() if spread else 1
+    ranks = [Solver(p, device=r % nd) for r, p in enumerate(patches)]
+    wrf_b200.comm_init_local(ranks)
+
+    def go(s):
+        s.start_domain()
+        s.step(nsteps)
+        s.sync()
+    wrf_b200.run_ranks(ranks, go)
+    names = [n for n in ref.names() if ref.size(n) > case.dims.kde]
+    bad = []
+    for s in ranks:
+        pd = s.case.dims
+        for n in names:
+            a = decomp.owned(pd, s.get(n), name=n)
+            b = decomp.owned(pd, ref.get(n), case.dims, name=n)
+            if not np.array_equal(a, b, equal_nan=True):
+                bad.append((s.case.name, n, int((~((a == b) | (np.isnan(a) & np.isnan(b)))).sum())))
+    sent = [s.halo_bytes() for s in ranks]
+    for s in ranks:
+        s.close()
+    ref.close()
+    return bad, sent
+
+
+@pytest.mark.parametrize("mesh", [(1, 2), (2, 1), (2, 2)])
+@pytest.mark.parametrize("name", ["quarter_ss", "periodic", "b_wave", "les"])
+def test_n_rank_gpu_equals_single_rank(name, mesh):
+    bad, sent = _run(parity.small_cases()[name], *mesh, nsteps=2)
+    assert not bad, bad[:8]
+    assert all(b > 0 for b in sent)
+
+
+def test_2x4_mesh_like_the_8_gpu_bench():
+    """the mesh mpaspect gives 8 tasks (module_dm.F:98-116), on a periodic domain with uneven patches"""
+    case = wrf_b200.make_case("synthetic", nx=43, ny=54, nz=13, bubble_lattice=20000.0, noise=0.05, num_scalar=1)
+    bad, _ = _run(case, 2, 4, nsteps=2, spread=True)
+    assert not bad, bad[:8]
+
+
+def test_halo_is_neighbour_interior():
+    """halo contents after an exchange are the neighbour's interior, bit for bit"""
+    case = parity.small_cases()["periodic"]
+    patches = decomp.split_case(case, 2, 2, poison=True)
+    ranks = [Solver(p) for p in patches]
+    wrf_b200.comm_init_local(ranks)
+    wrf_b200.run_ranks(ranks, lambda s: (s.halo("HALO_EM_INIT"), s.sync()))
+    gd = case.dims
+    for s in ranks:
+        pd = s.case.dims
+        for n in ("t_2", "u_2", "phb", "mub"):
+            a = s.get(n)
+            g = case.fields[n]
+            sj, si = decomp.window(gd, pd)
+            gw = g[sj, :, si] if g.ndim == 3 else g[sj, si]
+            # every in-domain point within 4 of the owned box (ghost zones beyond the domain are the
+            # periodic closure's business and are covered by the whole-step tests)
+            jj = np.arange(pd.jms, pd.jme + 1)
+            ii = np.arange(pd.ims, pd.ime + 1)
+            mj = (jj >= max(pd.jps - 4, gd.jds)) & (jj <= min(pd.jpe + 4, gd.jde - 1))
+            mi = (ii >= max(pd.ips - 4, gd.ids)) & (ii <= min(pd.ipe + 4, gd.ide - 1))
+            aa = a[mj][..., mi]
+            gg = gw[mj][..., mi]
+            assert np.array_equal(aa, gg), (s.case.name, n, int((aa != gg).sum()))
+    for s in ranks:
+        s.close()

@@ -6,4 +6,5 @@ shipped ideal configs), decomp.py (RSL_LITE patch decomposition), fortran/ (the
 ISO_C_BINDING shim a WRF build links instead of dyn_em/solve_em.o).
 """
 from .ideal import Case, Config, Dims, make_case  # noqa: F401
-from .lib import Solver, WrfGpuError, load, library_path  # noqa: F401
+from .lib import Solver, WrfGpuError, comm_init_local, load, library_path, run_ranks  # noqa: F401
+from . import decomp  # noqa: F401

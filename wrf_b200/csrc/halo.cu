@@ -198,10 +198,11 @@ __global__ void k_halo_close(const Geo g, HaloArgs a, int along_x, int a0, int a
 
 // ---------------------------------------------------------------------------------------------
 // NCCL, bound at run time so that the library also loads where no NCCL exists (CPU test box)
+struct Id128 { char b[128]; };   // ncclUniqueId: a 128-byte struct passed BY VALUE
 struct Nccl {
   void *h = nullptr;
   int (*GetUniqueId)(void *) = nullptr;
-  int (*CommInitRank)(void **, int, char[128], int) = nullptr;   // ncclUniqueId is a 128-byte struct passed by value
+  int (*CommInitRank)(void **, int, Id128, int) = nullptr;
   int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
@@ -209,7 +210,6 @@ struct Nccl {
   int (*CommDestroy)(void *) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 };
-struct Id128 { char b[128]; };
 static Nccl &nccl() {
   static Nccl n;
   static std::once_flag once;
@@ -221,7 +221,7 @@ static Nccl &nccl() {
     }
     if (!n.h) return;
     n.GetUniqueId = (int (*)(void *))dlsym(n.h, "ncclGetUniqueId");
-    n.CommInitRank = (int (*)(void **, int, char[128], int))dlsym(n.h, "ncclCommInitRank");
+    n.CommInitRank = (int (*)(void **, int, Id128, int))dlsym(n.h, "ncclCommInitRank");
     n.Send = (int (*)(const void *, size_t, int, int, void *, cudaStream_t))dlsym(n.h, "ncclSend");
     n.Recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))dlsym(n.h, "ncclRecv");
     n.GroupStart = (int (*)())dlsym(n.h, "ncclGroupStart");
@@ -458,7 +458,7 @@ int wrfgpu_comm_init(wrfgpu_solver *s, const void *id128, int rank, int nranks) 
     wg::HaloState &h = wg::hs(&S);
     wg::Id128 id;
     memcpy(id.b, id128, 128);
-    wg::nccl_check(n.CommInitRank(&h.comm, nranks, id.b, rank), "CommInitRank");
+    wg::nccl_check(n.CommInitRank(&h.comm, nranks, id, rank), "CommInitRank");
     return 0;
   } catch (const std::exception &e) { g_wrfgpu_err = e.what(); return 1; }
 }

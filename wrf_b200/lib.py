@@ -144,6 +144,26 @@ class Solver:
     def halo(self, name):
         self._chk(self.lib.wrfgpu_halo(self.h, name.encode()))
 
+    # ---- ranks ----
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        """128-byte ncclUniqueId; make it on rank 0 and broadcast it with the host's own communicator"""
+        lib = load()
+        _preload_nccl()
+        buf = ctypes.create_string_buffer(128)
+        if lib.wrfgpu_comm_unique_id(buf) != 0:
+            raise WrfGpuError(lib.wrfgpu_last_error().decode() or "ncclGetUniqueId failed")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        """ranks are processes, one per GPU: halos travel by NCCL over NVLink"""
+        _preload_nccl()
+        self._chk(self.lib.wrfgpu_comm_init(self.h, ctypes.c_char_p(unique_id), ctypes.c_int(rank), ctypes.c_int(nranks)))
+
+    def halo_bytes(self) -> int:
+        self.lib.wrfgpu_halo_bytes.restype = ctypes.c_longlong
+        return int(self.lib.wrfgpu_halo_bytes(self.h))
+
     def launch_count(self) -> int:
         return int(self.lib.wrfgpu_launch_count(self.h))
 
@@ -177,3 +197,48 @@ class Solver:
             self.close()
         except Exception:
             pass
+
+
+def _preload_nccl():
+    """make the NCCL that ships with torch visible to dlopen("libnccl.so.2") in the C library"""
+    if os.environ.get("WRFGPU_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            so = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if os.path.exists(so):
+                ctypes.CDLL(so, mode=ctypes.RTLD_GLOBAL)
+                os.environ["WRFGPU_NCCL_LIB"] = so
+    except Exception:
+        pass
+
+
+def comm_init_local(solvers):
+    """ranks are solvers of this process (rank order): neighbours read each other's send buffers"""
+    lib = load()
+    arr = (ctypes.c_void_p * len(solvers))(*[s.h for s in solvers])
+    if lib.wrfgpu_comm_init_local(arr, ctypes.c_int(len(solvers))) != 0:
+        raise WrfGpuError(lib.wrfgpu_last_error().decode())
+
+
+def run_ranks(solvers, fn):
+    """call fn(solver) for every rank concurrently (one host thread per rank, as wrf.exe has one
+    process per rank); exceptions are re-raised"""
+    import threading
+    errs = []
+
+    def work(s):
+        try:
+            fn(s)
+        except BaseException as e:   # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(s,)) for s in solvers]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if errs:
+        raise errs[0]
