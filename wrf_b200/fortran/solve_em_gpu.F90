@@ -1,0 +1,148 @@
+!WRF:MEDIATION_LAYER:SOLVER
+!
+! solve_em_gpu.F90 -- drop-in replacement for dyn_em/solve_em.F: same subroutine name, same
+! argument list (grid, config_flags, <dummy_new_args.inc>), so share/solve_interface.F:50-55 and
+! everything above it are unchanged.  dyn_em/Makefile lists this object instead of solve_em.o
+! (INTEGRATION.md).  The Registry state stays where the Registry put it -- grid%u_2, grid%t_2,
+! grid%mu_2, grid%ph_2, moist(:,:,:,P_QV) ... -- and is mirrored in HBM; between history /
+! restart alarms the device copy is the live one and the host arrays are refreshed only when
+! med_after_solve_io is about to read them (restart_flag / Is_alarm_tstep, solve_em.F:360-374).
+!
+! Not compiled in the development image (no Fortran compiler); kept deliberately small so that
+! everything that needs testing lives behind the C-ABI, where the parity tests exercise it.
+!
+SUBROUTINE solve_em ( grid , config_flags  &
+#include "dummy_new_args.inc"
+                    )
+   USE module_domain,          ONLY : domain, get_ijk_from_grid, domain_get_current_time
+   USE module_configure,       ONLY : grid_config_rec_type, PARAM_FIRST_SCALAR, P_QV, P_QC, P_QR
+   USE module_driver_constants
+   USE module_dm,              ONLY : ntasks_x, ntasks_y, mytask, local_communicator
+   USE module_wrf_error
+   USE module_wrfgpu
+   USE, INTRINSIC :: iso_c_binding
+   IMPLICIT NONE
+
+   TYPE(domain) , TARGET          :: grid
+   TYPE (grid_config_rec_type) , INTENT(IN) :: config_flags
+#include "dummy_new_decl.inc"
+
+   INTEGER, PARAMETER :: MAXF = 96
+   TYPE(c_ptr), SAVE :: handle(max_domains) = c_null_ptr
+   LOGICAL,     SAVE :: resident(max_domains) = .FALSE.
+   TYPE(wrfgpu_dims)   :: d
+   TYPE(wrfgpu_config) :: c
+   CHARACTER(len=24, kind=c_char), TARGET, SAVE :: nm(MAXF)
+   TYPE(c_ptr) :: names(MAXF), host(MAXF)
+   INTEGER :: nf, id, ierr, device
+   INTEGER :: ids, ide, jds, jde, kds, kde, ims, ime, jms, jme, kms, kme, ips, ipe, jps, jpe, kps, kpe
+   CHARACTER(kind=c_char) :: ncclid(128)
+   LOGICAL :: host_needs_state
+
+   id = grid%id
+   CALL get_ijk_from_grid ( grid , ids, ide, jds, jde, kds, kde, ims, ime, jms, jme, kms, kme, &
+                                   ips, ipe, jps, jpe, kps, kpe )
+
+   IF ( .NOT. c_associated(handle(id)) ) THEN
+      d = wrfgpu_dims(ids, ide, jds, jde, kds, kde, ims, ime, jms, jme, kms, kme, ips, ipe, jps, jpe, kps, kpe)
+      c%periodic_x   = MERGE(1,0,config_flags%periodic_x);   c%periodic_y   = MERGE(1,0,config_flags%periodic_y)
+      c%symmetric_xs = MERGE(1,0,config_flags%symmetric_xs); c%symmetric_xe = MERGE(1,0,config_flags%symmetric_xe)
+      c%symmetric_ys = MERGE(1,0,config_flags%symmetric_ys); c%symmetric_ye = MERGE(1,0,config_flags%symmetric_ye)
+      c%open_xs = MERGE(1,0,config_flags%open_xs); c%open_xe = MERGE(1,0,config_flags%open_xe)
+      c%open_ys = MERGE(1,0,config_flags%open_ys); c%open_ye = MERGE(1,0,config_flags%open_ye)
+      c%specified = MERGE(1,0,config_flags%specified); c%nested = MERGE(1,0,config_flags%nested)
+      c%polar = MERGE(1,0,config_flags%polar)
+      c%rk_ord = config_flags%rk_ord;  c%time_step_sound = config_flags%time_step_sound
+      c%h_mom_adv_order = config_flags%h_mom_adv_order; c%v_mom_adv_order = config_flags%v_mom_adv_order
+      c%h_sca_adv_order = config_flags%h_sca_adv_order; c%v_sca_adv_order = config_flags%v_sca_adv_order
+      c%moist_adv_opt = config_flags%moist_adv_opt; c%scalar_adv_opt = config_flags%scalar_adv_opt
+      c%momentum_adv_opt = config_flags%momentum_adv_opt
+      c%non_hydrostatic = MERGE(1,0,config_flags%non_hydrostatic); c%top_lid = MERGE(1,0,config_flags%top_lid)
+      c%damp_opt = config_flags%damp_opt; c%w_damping = config_flags%w_damping
+      c%pert_coriolis = MERGE(1,0,config_flags%pert_coriolis)
+      c%use_theta_m = config_flags%use_theta_m; c%hypsometric_opt = config_flags%hypsometric_opt
+      c%phi_adv_z = config_flags%phi_adv_z; c%zadvect_implicit = config_flags%zadvect_implicit
+      c%diff_opt = config_flags%diff_opt; c%km_opt = config_flags%km_opt; c%diff_6th_opt = config_flags%diff_6th_opt
+      c%mp_physics = config_flags%mp_physics; c%time_step = config_flags%time_step; c%map_proj = config_flags%map_proj
+      c%dt = grid%dt; c%dx = config_flags%dx; c%dy = config_flags%dy
+      c%epssm = config_flags%epssm; c%smdiv = config_flags%smdiv; c%emdiv = config_flags%emdiv
+      c%dampcoef = config_flags%dampcoef; c%zdamp = config_flags%zdamp; c%w_crit_cfl = config_flags%w_crit_cfl
+      c%p_top = grid%p_top; c%cf1 = grid%cf1; c%cf2 = grid%cf2; c%cf3 = grid%cf3; c%cfn = grid%cfn; c%cfn1 = grid%cfn1
+      c%khdif = config_flags%khdif; c%kvdif = config_flags%kvdif
+      c%num_moist = num_moist - PARAM_FIRST_SCALAR + 1;  c%num_scalar = 0
+      c%ntasks_x = ntasks_x; c%ntasks_y = ntasks_y; c%mytask = mytask
+      device = MOD(mytask, 8)                        ! one rank per GPU of the box
+      CALL wrfgpu_check( wrfgpu_create(d, c, device, handle(id)), 'wrfgpu_create' )
+#ifdef DM_PARALLEL
+      IF ( ntasks_x*ntasks_y > 1 ) THEN             ! NCCL bootstrap over the communicator RSL_LITE already has
+         IF ( mytask == 0 ) CALL wrfgpu_check( wrfgpu_comm_unique_id(ncclid), 'wrfgpu_comm_unique_id' )
+         CALL MPI_Bcast( ncclid, 128, MPI_CHARACTER, 0, local_communicator, ierr )
+         CALL wrfgpu_check( wrfgpu_comm_init(handle(id), ncclid, mytask, ntasks_x*ntasks_y), 'wrfgpu_comm_init' )
+      END IF
+#endif
+   END IF
+
+   ! ---- host -> device: everything the step reads, once; afterwards only what the host changed
+   IF ( .NOT. resident(id) ) THEN
+      nf = 0
+      CALL add('u_1',grid%u_1); CALL add('u_2',grid%u_2); CALL add('v_1',grid%v_1); CALL add('v_2',grid%v_2)
+      CALL add('w_1',grid%w_1); CALL add('w_2',grid%w_2); CALL add('t_1',grid%t_1); CALL add('t_2',grid%t_2)
+      CALL add('ph_1',grid%ph_1); CALL add('ph_2',grid%ph_2); CALL add('phb',grid%phb); CALL add('pb',grid%pb)
+      CALL add('alb',grid%alb); CALL add('p',grid%p); CALL add('al',grid%al); CALL add('alt',grid%alt)
+      CALL add('h_diabatic',grid%h_diabatic)
+      CALL add('moist_qv', moist(:,:,:,P_QV))
+      IF ( config_flags%mp_physics == 1 ) THEN
+         CALL add('moist_qc', moist(:,:,:,P_QC)); CALL add('moist_qr', moist(:,:,:,P_QR))
+      END IF
+      CALL add2('mu_1',grid%mu_1); CALL add2('mu_2',grid%mu_2); CALL add2('mub',grid%mub); CALL add2('ht',grid%ht)
+      CALL add2('msftx',grid%msftx); CALL add2('msfty',grid%msfty); CALL add2('msfux',grid%msfux); CALL add2('msfuy',grid%msfuy)
+      CALL add2('msfvx',grid%msfvx); CALL add2('msfvx_inv',grid%msfvx_inv); CALL add2('msfvy',grid%msfvy)
+      CALL add2('f',grid%f); CALL add2('e',grid%e); CALL add2('sina',grid%sina); CALL add2('cosa',grid%cosa)
+      CALL add2('rainnc',grid%rainnc); CALL add2('rainncv',grid%rainncv)
+      CALL add1('znu',grid%znu); CALL add1('znw',grid%znw); CALL add1('fnm',grid%fnm); CALL add1('fnp',grid%fnp)
+      CALL add1('rdnw',grid%rdnw); CALL add1('rdn',grid%rdn); CALL add1('dnw',grid%dnw); CALL add1('dn',grid%dn)
+      CALL add1('c1h',grid%c1h); CALL add1('c2h',grid%c2h); CALL add1('c1f',grid%c1f); CALL add1('c2f',grid%c2f)
+      CALL add1('c3h',grid%c3h); CALL add1('c4h',grid%c4h); CALL add1('c3f',grid%c3f); CALL add1('c4f',grid%c4f)
+      CALL add1('u_base',grid%u_base); CALL add1('v_base',grid%v_base); CALL add1('t_base',grid%t_base)
+      CALL add1('qv_base',grid%qv_base); CALL add1('z_base',grid%z_base)
+      CALL wrfgpu_check( wrfgpu_upload(handle(id), nf, names, host), 'wrfgpu_upload' )
+      CALL wrfgpu_check( wrfgpu_start_domain(handle(id)), 'wrfgpu_start_domain' )
+      resident(id) = .TRUE.
+   END IF
+
+   ! ---- the step: dyn_em/solve_em.F:578-4848 on the device
+   CALL wrfgpu_check( wrfgpu_step(handle(id), 1), 'wrfgpu_step' )
+
+   ! ---- device -> host only when the host is about to read the state (history/restart/diagnostics)
+   host_needs_state = grid%restart_flag_alarm_rings .OR. grid%history_alarm_rings   ! see INTEGRATION.md for the exact test
+   IF ( host_needs_state ) THEN
+      nf = 0
+      CALL add('u_1',grid%u_1); CALL add('u_2',grid%u_2); CALL add('v_1',grid%v_1); CALL add('v_2',grid%v_2)
+      CALL add('w_1',grid%w_1); CALL add('w_2',grid%w_2); CALL add('t_1',grid%t_1); CALL add('t_2',grid%t_2)
+      CALL add('ph_1',grid%ph_1); CALL add('ph_2',grid%ph_2); CALL add('p',grid%p); CALL add('al',grid%al)
+      CALL add('alt',grid%alt); CALL add('ww',grid%ww); CALL add('h_diabatic',grid%h_diabatic)
+      CALL add('moist_qv', moist(:,:,:,P_QV))
+      IF ( config_flags%mp_physics == 1 ) THEN
+         CALL add('moist_qc', moist(:,:,:,P_QC)); CALL add('moist_qr', moist(:,:,:,P_QR))
+      END IF
+      CALL add2('mu_1',grid%mu_1); CALL add2('mu_2',grid%mu_2); CALL add2('rainnc',grid%rainnc); CALL add2('rainncv',grid%rainncv)
+      CALL wrfgpu_check( wrfgpu_download(handle(id), nf, names, host), 'wrfgpu_download' )
+   END IF
+
+CONTAINS
+   SUBROUTINE add(name, a)
+      CHARACTER(len=*), INTENT(IN) :: name
+      REAL, TARGET, INTENT(IN) :: a(:,:,:)          ! (ims:ime,kms:kme,jms:jme), contiguous
+      nf = nf + 1; nm(nf) = TRIM(name)//c_null_char; names(nf) = c_loc(nm(nf)); host(nf) = c_loc(a)
+   END SUBROUTINE
+   SUBROUTINE add2(name, a)
+      CHARACTER(len=*), INTENT(IN) :: name
+      REAL, TARGET, INTENT(IN) :: a(:,:)
+      nf = nf + 1; nm(nf) = TRIM(name)//c_null_char; names(nf) = c_loc(nm(nf)); host(nf) = c_loc(a)
+   END SUBROUTINE
+   SUBROUTINE add1(name, a)
+      CHARACTER(len=*), INTENT(IN) :: name
+      REAL, TARGET, INTENT(IN) :: a(:)
+      nf = nf + 1; nm(nf) = TRIM(name)//c_null_char; names(nf) = c_loc(nm(nf)); host(nf) = c_loc(a)
+   END SUBROUTINE
+END SUBROUTINE solve_em
