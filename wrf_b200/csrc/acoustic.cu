@@ -172,63 +172,146 @@ __device__ __forceinline__ float dpn_uv(const Geo &g, cfp p, int i, int kk, int 
   return .5f * (g.fnm[kk] * (A3(p, i, kk, j) + A3(p, i2, kk, j2)) + g.fnp[kk] * (A3(p, i, kk - 1, j) + A3(p, i2, kk - 1, j2)));
 }
 
-// advance_uv (:654-965), one thread per (i,k,j); u and v points handled by the same thread
-__global__ void k_advance_uv(const Geo g, Box b, float dts, UvArgs a) {
-  TID3;
-  const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde;
+// advance_uv (:654-965) as a k-marching column kernel: one thread per (i,j) owns the u point and
+// the v point of that column and walks k = 1..kde-1.  Everything with a vertical stencil -- the
+// pressure at w levels dpn(k), dpn(k+1) (built from p at k-1,k,k+1 of the two columns either side
+// of the point) and the geopotential differences at k, k+1 -- lives in rolling registers, so each
+// level costs 24 loads instead of the ~50 a point-per-thread formulation needs (measured:
+// 188 M L1 sectors per launch for 1.1 GB of DRAM traffic, LSU-bound at 20 % DRAM; profiles/r1a).
+// Loads of level k+1 are issued before level k is computed (software prefetch: the loop has no
+// other way to cover HBM latency).  Expressions are the reference's, operand for operand.
+//
+// FUSE: also does the u- and v-part of sumflux (:1473-1633) -- ru_m += u'', rv_m += v'' -- which in
+// the reference runs after advance_w but reads the u'', v'' produced here (nothing in between
+// changes them on owned points).  Only wrfgpu_step uses the fused form; the per-routine entry
+// points keep the reference's split.
+struct UvLevel {      // everything read at one level: c = (i,j), w = (i-1,j), s = (i,j-1)
+  float alt_c, alt_w, alt_s, al_c, al_w, al_s, pb_c, pb_w, pb_s, php_c, php_w, php_s;
+  float cqu, cqv, rut, rvt, u, v;
+};
+struct UvPp { float p_c, p_w, p_s, ph_c, ph_w, ph_s; };
+
+__device__ __forceinline__ UvLevel uv_load_level(const Geo &g, const UvArgs &a, int i, int k, int j) {
+  UvLevel L;
+  L.alt_c = A3(a.alt, i, k, j); L.alt_w = A3(a.alt, i - 1, k, j); L.alt_s = A3(a.alt, i, k, j - 1);
+  L.al_c = A3(a.al, i, k, j); L.al_w = A3(a.al, i - 1, k, j); L.al_s = A3(a.al, i, k, j - 1);
+  L.pb_c = A3(a.pb, i, k, j); L.pb_w = A3(a.pb, i - 1, k, j); L.pb_s = A3(a.pb, i, k, j - 1);
+  L.php_c = A3(a.php, i, k, j); L.php_w = A3(a.php, i - 1, k, j); L.php_s = A3(a.php, i, k, j - 1);
+  L.cqu = A3(a.cqu, i, k, j); L.cqv = A3(a.cqv, i, k, j);
+  L.rut = A3(a.ru_tend, i, k, j); L.rvt = A3(a.rv_tend, i, k, j);
+  L.u = A3(a.u, i, k, j); L.v = A3(a.v, i, k, j);
+  return L;
+}
+__device__ __forceinline__ UvPp uv_load_pp(const Geo &g, const UvArgs &a, int i, int k, int j) {
+  UvPp q;
+  q.p_c = A3(a.p, i, k, j); q.p_w = A3(a.p, i - 1, k, j); q.p_s = A3(a.p, i, k, j - 1);
+  q.ph_c = A3(a.ph, i, k, j); q.ph_w = A3(a.ph, i - 1, k, j); q.ph_s = A3(a.ph, i, k, j - 1);
+  return q;
+}
+
+struct UvFuse { int iteration, nsmall; fp ru_m, rv_m; cfp u_lin, v_lin; };
+
+template <bool FUSE>
+__global__ void __launch_bounds__(128) k_advance_uv(const Geo g, Box b, float dts, UvArgs a, UvFuse fz) {
+  TID2;
+  const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, kde = g.kde;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
   const int i_start = its, i_end = min(ite, ide - 1), j_start = jts, j_end = min(jte, jde - 1);
-  const float c1h = g.c1h[k], c2h = g.c2h[k];
   const float dx = 1.f / g.rdx, dy = 1.f / g.rdy;
-  // ---- u
-  if (j <= j_end) {
-    int i_start_up = i_start, i_end_up = ite, i_s_t = i_start, i_e_t = ite;
-    if ((g.open_xs || g.sym_xs) && its == ids) i_start_up++;
-    if ((g.open_xe || g.sym_xe) && ite == ide) i_end_up--;
-    if (g.sym_xs && its == ids) i_s_t++;
-    if (g.sym_xe && ite == ide) i_e_t--;
-    float uv = A3(a.u, i, k, j);
-    bool wr = false;
-    if (i >= i_s_t && i <= i_e_t) { uv = uv + dts * A3(a.ru_tend, i, k, j); wr = true; }
-    if (i >= i_start_up && i <= i_end_up) {
-      const float mudf_xy = -g.emdiv * dx * (A2(a.mudf, i, j) - A2(a.mudf, i - 1, j)) / A2(g.msfuy, i, j);
-      const float mr = A2(g.msfux, i, j) / A2(g.msfuy, i, j);
-      float dpxy = mr * .5f * g.rdx * (c1h * A2(a.muu, i, j) + c2h) *
-                   (((A3(a.ph, i, k + 1, j) - A3(a.ph, i - 1, k + 1, j)) + (A3(a.ph, i, k, j) - A3(a.ph, i - 1, k, j))) +
-                    (A3(a.alt, i, k, j) + A3(a.alt, i - 1, k, j)) * (A3(a.p, i, k, j) - A3(a.p, i - 1, k, j)) +
-                    (A3(a.al, i, k, j) + A3(a.al, i - 1, k, j)) * (A3(a.pb, i, k, j) - A3(a.pb, i - 1, k, j)));
-      const float d1 = dpn_uv(g, a.p, i, k + 1, j, 1, 0), d0 = dpn_uv(g, a.p, i, k, j, 1, 0);
-      dpxy = dpxy + mr * g.rdx * (A3(a.php, i, k, j) - A3(a.php, i - 1, k, j)) *
-                        (g.rdnw[k] * (d1 - d0) - .5f * ((c1h * A2(a.mu, i - 1, j)) + (c1h * A2(a.mu, i, j))));
-      uv = uv - dts * A3(a.cqu, i, k, j) * dpxy + (c1h * mudf_xy);
-      wr = true;
+  // ---- which of the reference's loop ranges this column is in (:734-797)
+  int i_start_up = i_start, i_end_up = ite, i_s_t = i_start, i_e_t = ite;
+  if ((g.open_xs || g.sym_xs) && its == ids) i_start_up++;
+  if ((g.open_xe || g.sym_xe) && ite == ide) i_end_up--;
+  if (g.sym_xs && its == ids) i_s_t++;
+  if (g.sym_xe && ite == ide) i_e_t--;
+  int j_start_vp = j_start, j_end_vp = jte, j_s_t = j_start, j_e_t = jte;
+  if ((g.open_ys || g.sym_ys) && jts == jds) j_start_vp++;
+  if ((g.open_ye || g.sym_ye) && jte == jde) j_end_vp--;
+  if (g.sym_ys && jts == jds) j_s_t++;
+  if (g.sym_ye && jte == jde) j_e_t--;
+  const bool u_row = j <= j_end, v_col = i <= i_end;
+  const bool u_tend = u_row && i >= i_s_t && i <= i_e_t, u_pg = u_row && i >= i_start_up && i <= i_end_up;
+  const bool v_tend = v_col && j >= j_s_t && j <= j_e_t, v_pg = v_tend && j >= j_start_vp && j <= j_end_vp;
+  if (!FUSE && !u_tend && !u_pg && !v_tend) return;
+  // ---- column constants
+  const float msfux = A2(g.msfux, i, j), msfuy = A2(g.msfuy, i, j), msfvx = A2(g.msfvx, i, j), msfvy = A2(g.msfvy, i, j);
+  const float msfvx_inv = A2(g.msfvx_inv, i, j);
+  const float mu_c = A2(a.mu, i, j), mu_w = A2(a.mu, i - 1, j), mu_s = A2(a.mu, i, j - 1);
+  const float muu = A2(a.muu, i, j), muv = A2(a.muv, i, j);
+  const float mudf_c = A2(a.mudf, i, j), mudf_w = A2(a.mudf, i - 1, j), mudf_s = A2(a.mudf, i, j - 1);
+  const float mudf_x = -g.emdiv * dx * (mudf_c - mudf_w) / msfuy;
+  const float mudf_y = -g.emdiv * dy * (mudf_c - mudf_s) * msfvx_inv;
+  const float mr_u = msfux / msfuy, mr_v = msfvy / msfvx;
+  const float nst = (float)fz.nsmall;
+  // ---- prime the pipeline: p, ph at levels 1, 2 (and p at 3 for the surface extrapolation)
+  UvPp q1 = uv_load_pp(g, a, i, 1, j), q2 = uv_load_pp(g, a, i, 2, j);
+  const float p3_c = A3(a.p, i, 3, j), p3_w = A3(a.p, i - 1, 3, j), p3_s = A3(a.p, i, 3, j - 1);
+  UvLevel L = uv_load_level(g, a, i, 1, j);
+  // dpn(1) (:828-836, :902-910): cf1..3 extrapolation of p to the surface
+  float dpn_u = .5f * (g.cf1 * (q1.p_c + q1.p_w) + g.cf2 * (q2.p_c + q2.p_w) + g.cf3 * (p3_c + p3_w));
+  float dpn_v = .5f * (g.cf1 * (q1.p_c + q1.p_s) + g.cf2 * (q2.p_c + q2.p_s) + g.cf3 * (p3_c + p3_s));
+  UvPp qk = q1, qk1 = q2;           // levels k and k+1
+  for (int k = 1; k <= kde - 1; k++) {
+    // prefetch: the rest of level k+1 and p, ph of level k+2
+    UvLevel Ln;
+    UvPp qk2;
+    if (k + 1 <= kde - 1) Ln = uv_load_level(g, a, i, k + 1, j);
+    if (k + 2 <= kde) qk2 = uv_load_pp(g, a, i, k + 2, j);
+    const float c1h = g.c1h[k], c2h = g.c2h[k];
+    // dpn(k+1)
+    float dpn_u1, dpn_v1;
+    if (k + 1 == kde) {
+      if (!g.top_lid) { dpn_u1 = 0.f; dpn_v1 = 0.f; }
+      else {
+        cfp p = a.p;
+        dpn_u1 = .5f * (g.cf1 * (A3(p, i - 1, kde - 1, j) + A3(p, i, kde - 1, j)) + g.cf2 * (A3(p, i - 1, kde - 2, j) + A3(p, i, kde - 2, j)) +
+                        g.cf3 * (A3(p, i - 1, kde - 3, j) + A3(p, i, kde - 3, j)));
+        dpn_v1 = .5f * (g.cf1 * (A3(p, i, kde - 1, j - 1) + A3(p, i, kde - 1, j)) + g.cf2 * (A3(p, i, kde - 2, j - 1) + A3(p, i, kde - 2, j)) +
+                        g.cf3 * (A3(p, i, kde - 3, j - 1) + A3(p, i, kde - 3, j)));
+      }
+    } else {
+      dpn_u1 = .5f * (g.fnm[k + 1] * (qk1.p_c + qk1.p_w) + g.fnp[k + 1] * (qk.p_c + qk.p_w));
+      dpn_v1 = .5f * (g.fnm[k + 1] * (qk1.p_c + qk1.p_s) + g.fnp[k + 1] * (qk.p_c + qk.p_s));
     }
-    if (wr) A3(a.u, i, k, j) = uv;
-  }
-  // ---- v
-  if (i <= i_end) {
-    int j_start_vp = j_start, j_end_vp = jte, j_s_t = j_start, j_e_t = jte;
-    if ((g.open_ys || g.sym_ys) && jts == jds) j_start_vp++;
-    if ((g.open_ye || g.sym_ye) && jte == jde) j_end_vp--;
-    if (g.sym_ys && jts == jds) j_s_t++;
-    if (g.sym_ye && jte == jde) j_e_t--;
-    if (j >= j_s_t && j <= j_e_t) {
-      float vv = A3(a.v, i, k, j) + dts * A3(a.rv_tend, i, k, j);
-      if (j >= j_start_vp && j <= j_end_vp) {
-        const float mudf_xy = -g.emdiv * dy * (A2(a.mudf, i, j) - A2(a.mudf, i, j - 1)) * A2(g.msfvx_inv, i, j);
-        const float mr = A2(g.msfvy, i, j) / A2(g.msfvx, i, j);
-        float dpxy = mr * .5f * g.rdy * (c1h * A2(a.muv, i, j) + c2h) *
-                     (((A3(a.ph, i, k + 1, j) - A3(a.ph, i, k + 1, j - 1)) + (A3(a.ph, i, k, j) - A3(a.ph, i, k, j - 1))) +
-                      (A3(a.alt, i, k, j) + A3(a.alt, i, k, j - 1)) * (A3(a.p, i, k, j) - A3(a.p, i, k, j - 1)) +
-                      (A3(a.al, i, k, j) + A3(a.al, i, k, j - 1)) * (A3(a.pb, i, k, j) - A3(a.pb, i, k, j - 1)));
-        const float d1 = dpn_uv(g, a.p, i, k + 1, j, 0, 1), d0 = dpn_uv(g, a.p, i, k, j, 0, 1);
-        dpxy = dpxy + mr * g.rdy * (A3(a.php, i, k, j) - A3(a.php, i, k, j - 1)) *
-                          (g.rdnw[k] * (d1 - d0) - .5f * ((c1h * A2(a.mu, i, j - 1)) + (c1h * A2(a.mu, i, j))));
-        vv = vv - dts * A3(a.cqv, i, k, j) * dpxy + (c1h * mudf_xy);
+    // ---- u (:799-870)
+    float uv = L.u;
+    if (u_tend) uv = uv + dts * L.rut;
+    if (u_pg) {
+      float dpxy = mr_u * .5f * g.rdx * (c1h * muu + c2h) *
+                   (((qk1.ph_c - qk1.ph_w) + (qk.ph_c - qk.ph_w)) + (L.alt_c + L.alt_w) * (qk.p_c - qk.p_w) +
+                    (L.al_c + L.al_w) * (L.pb_c - L.pb_w));
+      dpxy = dpxy + mr_u * g.rdx * (L.php_c - L.php_w) * (g.rdnw[k] * (dpn_u1 - dpn_u) - .5f * ((c1h * mu_w) + (c1h * mu_c)));
+      uv = uv - dts * L.cqu * dpxy + (c1h * mudf_x);
+    }
+    if (u_tend || u_pg) A3(a.u, i, k, j) = uv;
+    // ---- v (:872-944)
+    float vv = L.v;
+    if (v_tend) {
+      vv = vv + dts * L.rvt;
+      if (v_pg) {
+        float dpxy = mr_v * .5f * g.rdy * (c1h * muv + c2h) *
+                     (((qk1.ph_c - qk1.ph_s) + (qk.ph_c - qk.ph_s)) + (L.alt_c + L.alt_s) * (qk.p_c - qk.p_s) +
+                      (L.al_c + L.al_s) * (L.pb_c - L.pb_s));
+        dpxy = dpxy + mr_v * g.rdy * (L.php_c - L.php_s) * (g.rdnw[k] * (dpn_v1 - dpn_v) - .5f * ((c1h * mu_s) + (c1h * mu_c)));
+        vv = vv - dts * L.cqv * dpxy + (c1h * mudf_y);
       }
       A3(a.v, i, k, j) = vv;
     }
+    if (FUSE) {   // sumflux, u and v parts
+      float ra = 0.f, rb = 0.f;
+      if (fz.iteration != 1) { ra = A3(fz.ru_m, i, k, j); rb = A3(fz.rv_m, i, k, j); }
+      if (u_row) ra = ra + uv;
+      if (v_col) rb = rb + vv;
+      if (fz.iteration == fz.nsmall) {
+        if (u_row) ra = ra / nst + (c1h * muu + c2h) * A3(fz.u_lin, i, k, j) / msfuy;
+        if (v_col) rb = rb / nst + (c1h * muv + c2h) * A3(fz.v_lin, i, k, j) * msfvx_inv;
+      }
+      A3(fz.ru_m, i, k, j) = ra; A3(fz.rv_m, i, k, j) = rb;
+    }
+    dpn_u = dpn_u1; dpn_v = dpn_v1;
+    L = Ln; qk = qk1; qk1 = qk2;
   }
+  (void)msfvx; (void)msfvy;
 }
 
 // ---------------------------------------------------------------------------
@@ -236,8 +319,27 @@ struct MuTArgs {
   fp ww, mu, muave, muts, mudf, t, t_ave;
   cfp ww_1, u, u_1, v, v_1, mut, muu, muv, t_1, ft, mu_tend;
 };
-// advance_mu_t (:969-1174), column kernel
-__global__ void k_advance_mu_t(const Geo g, Box b, float dts, MuTArgs a) {
+// advance_mu_t (:969-1174), column kernel.  Both k loops prefetch the next level's operands into
+// registers before the current level is computed: the loops carry a recurrence (dmdt, ww, wdtn), so
+// nothing else keeps enough loads in flight to cover HBM latency (ncu r1a: 26 % DRAM, latency-bound).
+struct Mt1 { float vn, vsn, v0, vs0, ue, use, u0, us0; };
+struct Mt2 { float dv, ww1, t1u, t, ft, vn, v0, t1n, t1s, ue, u0, t1e, t1w; };
+__device__ __forceinline__ Mt1 mt_load1(const Geo &g, const MuTArgs &a, int i, int k, int j) {
+  Mt1 m;
+  m.vn = A3(a.v, i, k, j + 1); m.vsn = A3(a.v_1, i, k, j + 1); m.v0 = A3(a.v, i, k, j); m.vs0 = A3(a.v_1, i, k, j);
+  m.ue = A3(a.u, i + 1, k, j); m.use = A3(a.u_1, i + 1, k, j); m.u0 = A3(a.u, i, k, j); m.us0 = A3(a.u_1, i, k, j);
+  return m;
+}
+__device__ __forceinline__ Mt2 mt_load2(const Geo &g, const MuTArgs &a, int i, int k, int j, int k_end) {
+  Mt2 m;
+  m.dv = 0.f; m.ww1 = 0.f; m.t1u = 0.f;
+  if (k + 1 <= k_end) { m.dv = A3(a.ww, i, k + 1, j); m.ww1 = A3(a.ww_1, i, k + 1, j); m.t1u = A3(a.t_1, i, k + 1, j); }
+  m.t = A3(a.t, i, k, j); m.ft = A3(a.ft, i, k, j);
+  m.vn = A3(a.v, i, k, j + 1); m.v0 = A3(a.v, i, k, j); m.t1n = A3(a.t_1, i, k, j + 1); m.t1s = A3(a.t_1, i, k, j - 1);
+  m.ue = A3(a.u, i + 1, k, j); m.u0 = A3(a.u, i, k, j); m.t1e = A3(a.t_1, i + 1, k, j); m.t1w = A3(a.t_1, i - 1, k, j);
+  return m;
+}
+__global__ void __launch_bounds__(128) k_advance_mu_t(const Geo g, Box b, float dts, MuTArgs a) {
   TID2;
   const int k_end = g.kde - 1;
   const float msftx = A2(g.msftx, i, j), msfty = A2(g.msfty, i, j);
@@ -246,15 +348,17 @@ __global__ void k_advance_mu_t(const Geo g, Box b, float dts, MuTArgs a) {
   const float mu_tend = A2(a.mu_tend, i, j);
   // pass 1: dvdxi(k) (parked in ww(k+1)) and its column integral dmdt
   float dmdt = 0.f;
+  Mt1 c1 = mt_load1(g, a, i, 1, j);
   for (int k = 1; k <= k_end; k++) {
+    Mt1 n1;
+    if (k < k_end) n1 = mt_load1(g, a, i, k + 1, j);
     const float c1h = g.c1h[k], c2h = g.c2h[k];
     const float dvdxi = msftx * msfty *
-                        (g.rdy * ((A3(a.v, i, k, j + 1) + (c1h * muv1 + c2h) * A3(a.v_1, i, k, j + 1) * mvi1) -
-                                  (A3(a.v, i, k, j) + (c1h * muv0 + c2h) * A3(a.v_1, i, k, j) * mvi0)) +
-                         g.rdx * ((A3(a.u, i + 1, k, j) + (c1h * muu1 + c2h) * A3(a.u_1, i + 1, k, j) / my1) -
-                                  (A3(a.u, i, k, j) + (c1h * muu0 + c2h) * A3(a.u_1, i, k, j) / my0)));
+                        (g.rdy * ((c1.vn + (c1h * muv1 + c2h) * c1.vsn * mvi1) - (c1.v0 + (c1h * muv0 + c2h) * c1.vs0 * mvi0)) +
+                         g.rdx * ((c1.ue + (c1h * muu1 + c2h) * c1.use / my1) - (c1.u0 + (c1h * muu0 + c2h) * c1.us0 / my0)));
     dmdt = dmdt + g.dnw[k] * dvdxi;
     if (k < k_end) A3(a.ww, i, k + 1, j) = dvdxi;
+    c1 = n1;
   }
   {
     const float mu_old = A2(a.mu, i, j);
@@ -267,34 +371,32 @@ __global__ void k_advance_mu_t(const Geo g, Box b, float dts, MuTArgs a) {
   // pass 2: ww recurrence (:1109-1121), then the theta update which needs ww(k), ww(k+1)
   // ww(1) is not touched by the recurrence; ww(k) -= ww_1(k) for k = 1..k_end
   float w_rec = A3(a.ww, i, 1, j);             // ww(i,1,j) before the subtraction
-  float wk = w_rec - A3(a.ww_1, i, 1, j);      // final ww(1)
-  A3(a.ww, i, 1, j) = wk;
+  A3(a.ww, i, 1, j) = w_rec - A3(a.ww_1, i, 1, j);
   float wdtn_k = 0.f;                          // wdtn(1) = 0
-  float t1_km1 = 0.f, t1_k = A3(a.t_1, i, 1, j);
+  float t1_k = A3(a.t_1, i, 1, j);
+  Mt2 c2 = mt_load2(g, a, i, 1, j, k_end);
   for (int k = 1; k <= k_end; k++) {
-    // ww(k+1)
-    float wkp1 = 0.f, wdtn_kp1 = 0.f;
-    float t1_kp1 = 0.f;
+    Mt2 n2;
+    if (k < k_end) n2 = mt_load2(g, a, i, k + 1, j, k_end);
+    float wdtn_kp1 = 0.f;
     if (k + 1 <= k_end) {
-      const float dvdxi = A3(a.ww, i, k + 1, j);
-      w_rec = w_rec - g.dnw[k] * ((g.c1h[k] * dmdt) + dvdxi + (g.c1h[k] * mu_tend)) / msfty;
-      wkp1 = w_rec - A3(a.ww_1, i, k + 1, j);
+      w_rec = w_rec - g.dnw[k] * ((g.c1h[k] * dmdt) + c2.dv + (g.c1h[k] * mu_tend)) / msfty;
+      const float wkp1 = w_rec - c2.ww1;
       A3(a.ww, i, k + 1, j) = wkp1;
-      t1_kp1 = A3(a.t_1, i, k + 1, j);
-      wdtn_kp1 = wkp1 * (g.fnm[k + 1] * t1_kp1 + g.fnp[k + 1] * t1_k);
+      wdtn_kp1 = wkp1 * (g.fnm[k + 1] * c2.t1u + g.fnp[k + 1] * t1_k);
     }   // else wdtn(kde) = 0
-    const float told = A3(a.t, i, k, j);
+    const float told = c2.t;
     A3(a.t_ave, i, k, j) = told;
-    float tn = told + msfty * dts * A3(a.ft, i, k, j);
+    float tn = told + msfty * dts * c2.ft;
     tn = tn - dts * msfty *
-                  (msftx * (.5f * g.rdy * (A3(a.v, i, k, j + 1) * (A3(a.t_1, i, k, j + 1) + t1_k) - A3(a.v, i, k, j) * (t1_k + A3(a.t_1, i, k, j - 1))) +
-                            .5f * g.rdx * (A3(a.u, i + 1, k, j) * (A3(a.t_1, i + 1, k, j) + t1_k) - A3(a.u, i, k, j) * (t1_k + A3(a.t_1, i - 1, k, j)))) +
+                  (msftx * (.5f * g.rdy * (c2.vn * (c2.t1n + t1_k) - c2.v0 * (t1_k + c2.t1s)) +
+                            .5f * g.rdx * (c2.ue * (c2.t1e + t1_k) - c2.u0 * (t1_k + c2.t1w))) +
                    g.rdnw[k] * (wdtn_kp1 - wdtn_k));
     A3(a.t, i, k, j) = tn;
     wdtn_k = wdtn_kp1;
-    t1_km1 = t1_k; t1_k = t1_kp1;
+    t1_k = c2.t1u;
+    c2 = n2;
   }
-  (void)t1_km1; (void)wk;
 }
 
 // ---------------------------------------------------------------------------
@@ -302,40 +404,63 @@ struct WArgs {
   fp w, ph, t_2ave;
   cfp rw_tend, ww, w_save, u, v, mut, muave, muts, t_2, t_1, ph_1, phb, ph_tend, c2a, cqw, alt, a, alpha, gamma;
 };
-// advance_w (:1178-1469), column kernel.  rhs(k) is kept in a rolling register
-// window; the explicit w and rhs are parked in w / ph during the forward sweep
-// and finished in the backward sweep.
-__global__ void k_advance_w(const Geo g, Box b, float dts, WArgs a) {
+// what the fused form adds: calc_p_rho (:438-566) and the ww part of sumflux (:1473-1633), both
+// column-local, done in the backward sweep where ph(k+1), ph(k) have just become final
+struct WFuse { int iteration, nsmall; fp al, p, pm1, ww_m, ru_m, rv_m; cfp mu, ww_lin; };
+
+// advance_w (:1178-1469), column kernel: t_2ave, rhs, the explicit part of w and the Thomas forward
+// elimination in ONE upward sweep with every vertically shifted operand (rhs(k-1..k+1), ph(k-1..k+1),
+// the layer integrals of -omega dphi/deta, c2a*alt*t_2ave at k-1) rolling in registers and the next
+// level's 15 operands prefetched; the explicit w and rhs are parked in w / ph and finished in the
+// backward sweep (back substitution, damp_opt 3, ph).  Expressions are the reference's, operand for
+// operand; a value that the reference recomputes at the next level is computed once and carried,
+// which is bit-identical.
+struct WUp { float w_kp1, pht_kp1, ph_kp1, ph1_kp2, phb_kp2, ww_kp2, rwt, cqw, c2a, alt, t2, t2a, t1, a, alpha; };
+__device__ __forceinline__ WUp w_load_up(const Geo &g, const WArgs &a, int i, int k, int j) {
+  WUp q;
+  const int kde = g.kde;
+  q.w_kp1 = A3(a.w, i, k + 1, j); q.pht_kp1 = A3(a.ph_tend, i, k + 1, j); q.ph_kp1 = A3(a.ph, i, k + 1, j);
+  q.ph1_kp2 = 0.f; q.phb_kp2 = 0.f; q.ww_kp2 = 0.f;
+  if (k + 2 <= kde) { q.ph1_kp2 = A3(a.ph_1, i, k + 2, j); q.phb_kp2 = A3(a.phb, i, k + 2, j); q.ww_kp2 = A3(a.ww, i, k + 2, j); }
+  q.rwt = A3(a.rw_tend, i, k, j); q.cqw = A3(a.cqw, i, k, j); q.c2a = A3(a.c2a, i, k, j); q.alt = A3(a.alt, i, k, j);
+  q.t2 = A3(a.t_2, i, k, j); q.t2a = A3(a.t_2ave, i, k, j); q.t1 = A3(a.t_1, i, k, j);
+  q.a = A3(a.a, i, k, j); q.alpha = A3(a.alpha, i, k, j);
+  return q;
+}
+struct WDn { float w, gamma, rhs, ph1, phb, wsave, alt, t2, t1, c2a, pm1, ww, wwm, wwlin; };
+template <bool FUSE>
+__device__ __forceinline__ WDn w_load_dn(const Geo &g, const WArgs &a, const WFuse &fz, int i, int k, int j) {
+  WDn q;
+  q.w = A3(a.w, i, k, j); q.gamma = A3(a.gamma, i, k, j); q.rhs = A3(a.ph, i, k, j);
+  q.ph1 = 0.f; q.phb = 0.f; q.wsave = 0.f;
+  if (g.damp_opt == 3) { q.ph1 = A3(a.ph_1, i, k, j); q.phb = A3(a.phb, i, k, j); q.wsave = A3(a.w_save, i, k, j); }
+  if (FUSE) {
+    q.alt = A3(a.alt, i, k, j); q.t2 = A3(a.t_2, i, k, j); q.t1 = A3(a.t_1, i, k, j); q.c2a = A3(a.c2a, i, k, j);
+    q.pm1 = fz.iteration != 0 ? A3(fz.pm1, i, k, j) : 0.f;
+    q.ww = A3(a.ww, i, k, j);
+    q.wwm = fz.iteration != 1 ? A3(fz.ww_m, i, k, j) : 0.f;
+    q.wwlin = fz.iteration == fz.nsmall ? A3(fz.ww_lin, i, k, j) : 0.f;
+  }
+  return q;
+}
+
+template <bool FUSE>
+__global__ void __launch_bounds__(128) k_advance_w(const Geo g, Box b, float dts, WArgs a, WFuse fz) {
   TID2;
   const int kde = g.kde, k_end = g.kde - 1;
+  if (FUSE) {
+    // sumflux writes its whole tile: outside the mass points ww_m is only reset on the first iteration,
+    // and level kde of ru_m, rv_m likewise (k_advance_uv<true> handles levels 1..kde-1)
+    if (fz.iteration == 1) { A3(fz.ru_m, i, kde, j) = 0.f; A3(fz.rv_m, i, kde, j) = 0.f; }
+    if (i > min(g.ite, g.ide - 1) || j > min(g.jte, g.jde - 1)) {
+      if (fz.iteration == 1) for (int k = 1; k <= kde; k++) A3(fz.ww_m, i, k, j) = 0.f;
+      return;
+    }
+  }
   const float epssm = g.epssm;
   const float msfty = A2(g.msfty, i, j), msftx = A2(g.msftx, i, j);
   const float msft_inv = 1.f / msfty;
   const float mut = A2(a.mut, i, j), muave = A2(a.muave, i, j), muts = A2(a.muts, i, j);
-  // ---- t_2ave (:1314-1317)
-  for (int k = 1; k <= k_end; k++) {
-    float tv = .5f * ((1.f + epssm) * A3(a.t_2, i, k, j) + (1.f - epssm) * A3(a.t_2ave, i, k, j));
-    tv = (tv + (g.c1h[k] * muave) * WG_T0) / ((g.c1h[k] * muts + g.c2h[k]) * (WG_T0 + A3(a.t_1, i, k, j)));
-    A3(a.t_2ave, i, k, j) = tv;
-  }
-  // ---- rhs(k), k = 1..kde (:1318-1371).  rhs(1) = 0.
-  auto phi_dz = [&](int kk) -> float {   // wdwn(kk+1) of the reference, layer kk
-    const float dphi = (A3(a.ph_1, i, kk + 1, j) - A3(a.ph_1, i, kk, j) + A3(a.phb, i, kk + 1, j) - A3(a.phb, i, kk, j));
-    if (g.phi_adv_z == 2) return g.rdnw[kk] * dphi;
-    return .5f * (A3(a.ww, i, kk + 1, j) + A3(a.ww, i, kk, j)) * g.rdnw[kk] * dphi;
-  };
-  auto rhs_at = [&](int k) -> float {
-    if (k == 1) return 0.f;
-    float r = dts * (A3(a.ph_tend, i, k, j) + .5f * WG_G * (1.f - epssm) * A3(a.w, i, k, j));
-    if (k <= k_end) {
-      const float wa = phi_dz(k), wb = phi_dz(k - 1);   // wdwn(k+1), wdwn(k)
-      if (g.phi_adv_z == 2) r = r - dts * A3(a.ww, i, k, j) * (g.fnm[k] * wa + g.fnp[k] * wb);
-      else r = r - dts * (g.fnm[k] * wa + g.fnp[k] * wb);
-    }
-    r = A3(a.ph, i, k, j) + msfty * r / (g.c1f[k] * mut + g.c2f[k]);
-    if (g.top_lid && k == k_end + 1) r = 0.f;
-    return r;
-  };
   // surface w (:1384-1394)
   const float w1 = msfty * .5f * g.rdy *
                        ((A2(g.ht, i, j + 1) - A2(g.ht, i, j)) * (g.cf1 * A3(a.v, i, 1, j + 1) + g.cf2 * A3(a.v, i, 2, j + 1) + g.cf3 * A3(a.v, i, 3, j + 1)) +
@@ -343,41 +468,91 @@ __global__ void k_advance_w(const Geo g, Box b, float dts, WArgs a) {
                    msftx * .5f * g.rdx *
                        ((A2(g.ht, i + 1, j) - A2(g.ht, i, j)) * (g.cf1 * A3(a.u, i + 1, 1, j) + g.cf2 * A3(a.u, i + 1, 2, j) + g.cf3 * A3(a.u, i + 1, 3, j)) +
                         (A2(g.ht, i, j) - A2(g.ht, i - 1, j)) * (g.cf1 * A3(a.u, i, 1, j) + g.cf2 * A3(a.u, i, 2, j) + g.cf3 * A3(a.u, i, 3, j)));
-  // forward sweep: explicit w (:1402-1431) fused with the Thomas forward elimination (:1433-1437)
-  float rhs_km1 = 0.f;                 // rhs(1)
-  float rhs_k = rhs_at(2);             // rhs(2)
-  float ph_km1 = A3(a.ph, i, 1, j);
-  float ph_k = A3(a.ph, i, 2, j);
-  float wprev = w1;                    // w(k-1) after elimination
+  // ---- level 1: t_2ave(1) (:1314-1317) and the carried products
+  float t2ave_km1, c2a_km1, alt_km1;
+  {
+    const float t1v = A3(a.t_1, i, 1, j);
+    float tv = .5f * ((1.f + epssm) * A3(a.t_2, i, 1, j) + (1.f - epssm) * A3(a.t_2ave, i, 1, j));
+    tv = (tv + (g.c1h[1] * muave) * WG_T0) / ((g.c1h[1] * muts + g.c2h[1]) * (WG_T0 + t1v));
+    A3(a.t_2ave, i, 1, j) = tv;
+    t2ave_km1 = tv; c2a_km1 = A3(a.c2a, i, 1, j); alt_km1 = A3(a.alt, i, 1, j);
+  }
+  // layer integral of -omega dphi/deta: wdwn(kk+1) of the reference (:1318-1345)
+  auto layer = [&](int kk, float ph1_hi, float ph1_lo, float phb_hi, float phb_lo, float ww_hi, float ww_lo) -> float {
+    const float dphi = (ph1_hi - ph1_lo + phb_hi - phb_lo);
+    if (g.phi_adv_z == 2) return g.rdnw[kk] * dphi;
+    return .5f * (ww_hi + ww_lo) * g.rdnw[kk] * dphi;
+  };
+  // rhs(kk) for kk >= 2 from its operands (:1347-1371)
+  auto rhs_of = [&](int kk, float pht, float wv, float phv, float ww_kk, float lay_kk, float lay_kkm1) -> float {
+    float r = dts * (pht + .5f * WG_G * (1.f - epssm) * wv);
+    if (kk <= k_end) {
+      if (g.phi_adv_z == 2) r = r - dts * ww_kk * (g.fnm[kk] * lay_kk + g.fnp[kk] * lay_kkm1);
+      else r = r - dts * (g.fnm[kk] * lay_kk + g.fnp[kk] * lay_kkm1);
+    }
+    r = phv + msfty * r / (g.c1f[kk] * mut + g.c2f[kk]);
+    if (g.top_lid && kk == k_end + 1) r = 0.f;
+    return r;
+  };
+  const float ph_1st = A3(a.ph, i, 1, j);
+  float ph1_k, phb_k, ww_k, ph1_kp1, phb_kp1, ww_kp1, lay_km1;
+  {
+    const float ph1_1 = A3(a.ph_1, i, 1, j), phb_1 = A3(a.phb, i, 1, j), ww_1 = A3(a.ww, i, 1, j);
+    ph1_k = A3(a.ph_1, i, 2, j); phb_k = A3(a.phb, i, 2, j); ww_k = A3(a.ww, i, 2, j);
+    ph1_kp1 = A3(a.ph_1, i, 3, j); phb_kp1 = A3(a.phb, i, 3, j); ww_kp1 = A3(a.ww, i, 3, j);
+    lay_km1 = layer(1, ph1_k, ph1_1, phb_k, phb_1, ww_k, ww_1);                 // layer 1
+  }
+  float lay_k = layer(2, ph1_kp1, ph1_k, phb_kp1, phb_k, ww_kp1, ww_k);          // layer 2
+  float w_k = A3(a.w, i, 2, j);
+  float ph_km1 = ph_1st, ph_k = A3(a.ph, i, 2, j);
+  float rhs_km1 = 0.f;                                                           // rhs(1)
+  float rhs_k = rhs_of(2, A3(a.ph_tend, i, 2, j), w_k, ph_k, ww_k, lay_k, lay_km1);
+  float cpre_km1 = c2a_km1 * g.rdnw[1] / (g.c1h[1] * mut + g.c2h[1]);
+  float cat_km1 = c2a_km1 * alt_km1 * t2ave_km1;
+  float wprev = w1;                                                              // w(k-1) after elimination
+  WUp q = w_load_up(g, a, i, 2, j);
   for (int k = 2; k <= k_end; k++) {
-    const float rhs_kp1 = rhs_at(k + 1);
-    const float ph_kp1 = A3(a.ph, i, k + 1, j);
-    float wv = A3(a.w, i, k, j) + dts * A3(a.rw_tend, i, k, j) +
-               msft_inv * A3(a.cqw, i, k, j) *
+    WUp qn;
+    if (k < k_end) qn = w_load_up(g, a, i, k + 1, j);
+    // t_2ave(k) (:1314-1317)
+    float tv = .5f * ((1.f + epssm) * q.t2 + (1.f - epssm) * q.t2a);
+    tv = (tv + (g.c1h[k] * muave) * WG_T0) / ((g.c1h[k] * muts + g.c2h[k]) * (WG_T0 + q.t1));
+    A3(a.t_2ave, i, k, j) = tv;
+    // rhs(k+1): needs layer k+1 (levels k+1, k+2) unless k+1 = kde
+    float lay_kp1 = 0.f;
+    if (k + 1 <= k_end) lay_kp1 = layer(k + 1, q.ph1_kp2, ph1_kp1, q.phb_kp2, phb_kp1, q.ww_kp2, ww_kp1);
+    const float rhs_kp1 = rhs_of(k + 1, q.pht_kp1, q.w_kp1, q.ph_kp1, ww_kp1, lay_kp1, lay_k);
+    const float ph_kp1 = q.ph_kp1;
+    const float cpre_k = q.c2a * g.rdnw[k] / (g.c1h[k] * mut + g.c2h[k]);
+    const float cat_k = q.c2a * q.alt * tv;
+    float wv = w_k + dts * q.rwt +
+               msft_inv * q.cqw *
                    (+.5f * dts * WG_G * g.rdn[k] *
-                    (A3(a.c2a, i, k, j) * g.rdnw[k] / (g.c1h[k] * mut + g.c2h[k]) *
-                         ((1.f + epssm) * (rhs_kp1 - rhs_k) + (1.f - epssm) * (ph_kp1 - ph_k)) -
-                     A3(a.c2a, i, k - 1, j) * g.rdnw[k - 1] / (g.c1h[k - 1] * mut + g.c2h[k - 1]) *
-                         ((1.f + epssm) * (rhs_k - rhs_km1) + (1.f - epssm) * (ph_k - ph_km1)))) +
-               dts * WG_G * msft_inv *
-                   (g.rdn[k] * (A3(a.c2a, i, k, j) * A3(a.alt, i, k, j) * A3(a.t_2ave, i, k, j) -
-                                A3(a.c2a, i, k - 1, j) * A3(a.alt, i, k - 1, j) * A3(a.t_2ave, i, k - 1, j)) -
-                    (g.c1f[k] * muave));
-    wv = (wv - A3(a.a, i, k, j) * wprev) * A3(a.alpha, i, k, j);
+                    (cpre_k * ((1.f + epssm) * (rhs_kp1 - rhs_k) + (1.f - epssm) * (ph_kp1 - ph_k)) -
+                     cpre_km1 * ((1.f + epssm) * (rhs_k - rhs_km1) + (1.f - epssm) * (ph_k - ph_km1)))) +
+               dts * WG_G * msft_inv * (g.rdn[k] * (cat_k - cat_km1) - (g.c1f[k] * muave));
+    wv = (wv - q.a * wprev) * q.alpha;
     A3(a.w, i, k, j) = wv;
     A3(a.ph, i, k, j) = rhs_k;         // park rhs(k); ph(k) itself is no longer needed below k+1
     wprev = wv;
     rhs_km1 = rhs_k; rhs_k = rhs_kp1;
     ph_km1 = ph_k; ph_k = ph_kp1;
+    w_k = q.w_kp1;
+    lay_km1 = lay_k; lay_k = lay_kp1;
+    ph1_k = ph1_kp1; phb_k = phb_kp1; ww_k = ww_kp1;
+    ph1_kp1 = q.ph1_kp2; phb_kp1 = q.phb_kp2; ww_kp1 = q.ww_kp2;
+    cpre_km1 = cpre_k; cat_km1 = cat_k;
+    c2a_km1 = q.c2a; alt_km1 = q.alt; t2ave_km1 = tv;
+    q = qn;
   }
   // top level k = kde (:1417-1431)
   float wtop;
   {
     const int k = kde;
-    wtop = A3(a.w, i, k, j) + dts * A3(a.rw_tend, i, k, j) +
-           msft_inv * (-.5f * dts * WG_G / (g.c1h[k - 1] * mut + g.c2h[k - 1]) * (g.rdnw[k - 1] * g.rdnw[k - 1]) * 2.f * A3(a.c2a, i, k - 1, j) *
+    wtop = w_k + dts * A3(a.rw_tend, i, k, j) +
+           msft_inv * (-.5f * dts * WG_G / (g.c1h[k - 1] * mut + g.c2h[k - 1]) * (g.rdnw[k - 1] * g.rdnw[k - 1]) * 2.f * c2a_km1 *
                            ((1.f + epssm) * (rhs_k - rhs_km1) + (1.f - epssm) * (ph_k - ph_km1)) -
-                       dts * WG_G * (2.f * g.rdnw[k - 1] * A3(a.c2a, i, k - 1, j) * A3(a.alt, i, k - 1, j) * A3(a.t_2ave, i, k - 1, j) + (g.c1f[k] * muave)));
+                       dts * WG_G * (2.f * g.rdnw[k - 1] * c2a_km1 * alt_km1 * t2ave_km1 + (g.c1f[k] * muave)));
     if (g.top_lid) wtop = 0.f;
     wtop = (wtop - A3(a.a, i, k, j) * wprev) * A3(a.alpha, i, k, j);
   }
@@ -385,25 +560,71 @@ __global__ void k_advance_w(const Geo g, Box b, float dts, WArgs a) {
   const float pi = 0x1.921fb6p+1f;   // 4.*atan(1.) in real*4
   const float dampmag = dts * g.dampcoef, hdepth = g.zdamp;
   const float htop = (A3(a.ph_1, i, kde, j) + A3(a.phb, i, kde, j)) / WG_G;
-  auto finish = [&](int k, float wv, float rhs) {
+  // returns the final ph(k)
+  auto finish = [&](int k, float wv, float rhs, float ph1v, float phbv, float wsave) -> float {
     if (g.damp_opt == 3) {
-      const float hk = (A3(a.ph_1, i, k, j) + A3(a.phb, i, k, j)) / WG_G;
+      const float hk = (ph1v + phbv) / WG_G;
       const float hbot = htop - hdepth;
       float dampwt = 0.f;
       if (hk >= hbot) dampwt = dampmag * wg_libm::sinf_(0.5f * pi * (hk - hbot) / hdepth) * wg_libm::sinf_(0.5f * pi * (hk - hbot) / hdepth);
-      wv = (wv - dampwt * (g.c1f[k] * mut + g.c2f[k]) * A3(a.w_save, i, k, j)) / (1.f + dampwt);
+      wv = (wv - dampwt * (g.c1f[k] * mut + g.c2f[k]) * wsave) / (1.f + dampwt);
     }
     A3(a.w, i, k, j) = wv;
-    A3(a.ph, i, k, j) = rhs + msfty * .5f * dts * WG_G * (1.f + epssm) * wv / (g.c1f[k] * muts + g.c2f[k]);
+    const float phn = rhs + msfty * .5f * dts * WG_G * (1.f + epssm) * wv / (g.c1f[k] * muts + g.c2f[k]);
+    A3(a.ph, i, k, j) = phn;
+    return phn;
+  };
+  // calc_p_rho at level k from the final ph(k+1), ph(k) (:522-567); sumflux ww_m (:1520-1596)
+  const float mu_new = FUSE ? A2(fz.mu, i, j) : 0.f;
+  auto p_rho = [&](int k, const WDn &d, float ph_hi, float ph_lo) {
+    const float c1h = g.c1h[k], c2h = g.c2h[k];
+    const float alv = -1.f / (c1h * muts + c2h) * (d.alt * (c1h * mu_new) + g.rdnw[k] * (ph_hi - ph_lo));
+    float pv = d.c2a * (d.alt * (d.t2 - (c1h * mu_new) * d.t1) / ((c1h * muts + c2h) * (WG_T0 + d.t1)) - alv);
+    A3(fz.al, i, k, j) = alv;
+    if (fz.iteration == 0) {
+      A3(fz.pm1, i, k, j) = pv;
+    } else {
+      const float ptmp = pv;
+      pv = pv + g.smdiv * (pv - d.pm1);
+      A3(fz.pm1, i, k, j) = after_load(ptmp, d.pm1);
+    }
+    A3(fz.p, i, k, j) = pv;
+    float cq = d.wwm + d.ww;
+    if (fz.iteration == fz.nsmall) cq = cq / (float)fz.nsmall + d.wwlin;
+    A3(fz.ww_m, i, k, j) = cq;
   };
   A3(a.w, i, 1, j) = w1;
   float wnext = wtop;       // un-damped w(k+1) for the back substitution
-  finish(kde, wtop, rhs_k);
+  float ph_hi;
+  {
+    float ph1v = 0.f, phbv = 0.f, wsv = 0.f;
+    if (g.damp_opt == 3) { ph1v = A3(a.ph_1, i, kde, j); phbv = A3(a.phb, i, kde, j); wsv = A3(a.w_save, i, kde, j); }
+    ph_hi = finish(kde, wtop, rhs_k, ph1v, phbv, wsv);
+    if (FUSE) {   // ww_m(kde) (sumflux covers every level)
+      float cq = (fz.iteration != 1 ? A3(fz.ww_m, i, kde, j) : 0.f) + A3(a.ww, i, kde, j);
+      if (fz.iteration == fz.nsmall) cq = cq / (float)fz.nsmall + A3(fz.ww_lin, i, kde, j);
+      A3(fz.ww_m, i, kde, j) = cq;
+    }
+  }
+  WDn d = w_load_dn<FUSE>(g, a, fz, i, k_end, j);
   for (int k = k_end; k >= 2; k--) {
-    const float wv = A3(a.w, i, k, j) - A3(a.gamma, i, k, j) * wnext;
-    const float rhs = A3(a.ph, i, k, j);
+    WDn dn;
+    if (k > 2) dn = w_load_dn<FUSE>(g, a, fz, i, k - 1, j);
+    const float wv = d.w - d.gamma * wnext;
     wnext = wv;
-    finish(k, wv, rhs);
+    const float ph_lo = finish(k, wv, d.rhs, d.ph1, d.phb, d.wsave);
+    if (FUSE) p_rho(k, d, ph_hi, ph_lo);
+    ph_hi = ph_lo;
+    d = dn;
+  }
+  if (FUSE) {   // level 1: ph(1) is not touched by advance_w
+    WDn d1;
+    d1.alt = A3(a.alt, i, 1, j); d1.t2 = A3(a.t_2, i, 1, j); d1.t1 = A3(a.t_1, i, 1, j); d1.c2a = A3(a.c2a, i, 1, j);
+    d1.pm1 = fz.iteration != 0 ? A3(fz.pm1, i, 1, j) : 0.f;
+    d1.ww = A3(a.ww, i, 1, j);
+    d1.wwm = fz.iteration != 1 ? A3(fz.ww_m, i, 1, j) : 0.f;
+    d1.wwlin = fz.iteration == fz.nsmall ? A3(fz.ww_lin, i, 1, j) : 0.f;
+    p_rho(1, d1, ph_hi, ph_1st);
   }
 }
 
@@ -502,15 +723,29 @@ void Solver::small_step_prep(int rk_step) {
       {"mu_1", 't'}, {"mu_2", 't'}, {"mudf", 't'}});
 }
 
+static UvArgs uv_args(Solver *s) {
+  UvArgs a;
+  a.u = s->o("u_2"); a.v = s->o("v_2"); a.ru_tend = s->o("ru_tend"); a.rv_tend = s->o("rv_tend"); a.p = s->o("p"); a.pb = s->o("pb");
+  a.ph = s->o("ph_2"); a.php = s->o("php"); a.alt = s->o("alt"); a.al = s->o("al"); a.mu = s->o("mu_2"); a.muu = s->o("muu");
+  a.cqu = s->o("cqu"); a.muv = s->o("muv"); a.cqv = s->o("cqv"); a.mudf = s->o("mudf");
+  return a;
+}
+
 void Solver::advance_uv(int rk_step) {
   const Geo &q = g;
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
-  UvArgs a;
-  a.u = o("u_2"); a.v = o("v_2"); a.ru_tend = o("ru_tend"); a.rv_tend = o("rv_tend"); a.p = o("p"); a.pb = o("pb");
-  a.ph = o("ph_2"); a.php = o("php"); a.alt = o("alt"); a.al = o("al"); a.mu = o("mu_2"); a.muu = o("muu"); a.cqu = o("cqu");
-  a.muv = o("muv"); a.cqv = o("cqv"); a.mudf = o("mudf");
-  LAUNCH3(this, k_advance_uv, (Box{q.its, q.ite, 1, q.kde - 1, q.jts, q.jte}), dts_rk, a);
+  UvFuse fz{0, 0, nullptr, nullptr, nullptr, nullptr};
+  LAUNCH2(this, k_advance_uv<false>, (Box{q.its, q.ite, 1, 1, q.jts, q.jte}), dts_rk, uv_args(this), fz);
+}
+
+// advance_uv + the u, v part of sumflux(iteration); the ww part is k_sumflux_w (after advance_w)
+void Solver::advance_uv_fused(int rk_step, int iteration) {
+  const Geo &q = g;
+  float dt_rk, dts_rk; int ns;
+  rk_params(rk_step, dt_rk, dts_rk, ns);
+  UvFuse fz{iteration, ns, o("ru_m"), o("rv_m"), o("u_save"), o("v_save")};
+  LAUNCH2(this, k_advance_uv<true>, (Box{q.its, q.ite, 1, 1, q.jts, q.jte}), dts_rk, uv_args(this), fz);
 }
 
 void Solver::advance_mu_t(int rk_step) {
@@ -524,16 +759,34 @@ void Solver::advance_mu_t(int rk_step) {
   LAUNCH2(this, k_advance_mu_t, (Box{q.its, std::min(q.ite, q.ide - 1), 1, 1, q.jts, std::min(q.jte, q.jde - 1)}), dts_rk, a);
 }
 
+static WArgs w_args(Solver *s) {
+  WArgs a;
+  a.w = s->o("w_2"); a.ph = s->o("ph_2"); a.t_2ave = s->o("t_2save"); a.rw_tend = s->o("rw_tend"); a.ww = s->o("ww"); a.w_save = s->o("w_save");
+  a.u = s->o("u_2"); a.v = s->o("v_2"); a.mut = s->o("mut"); a.muave = s->o("muave"); a.muts = s->o("muts"); a.t_2 = s->o("t_2");
+  a.t_1 = s->o("t_save"); a.ph_1 = s->o("ph_save"); a.phb = s->o("phb"); a.ph_tend = s->o("ph_tend"); a.c2a = s->o("c2a"); a.cqw = s->o("cqw");
+  a.alt = s->o("alt"); a.a = s->o("a"); a.alpha = s->o("alpha"); a.gamma = s->o("gamma");
+  return a;
+}
+
 void Solver::advance_w(int rk_step) {
   const Geo &q = g;
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
-  WArgs a;
-  a.w = o("w_2"); a.ph = o("ph_2"); a.t_2ave = o("t_2save"); a.rw_tend = o("rw_tend"); a.ww = o("ww"); a.w_save = o("w_save");
-  a.u = o("u_2"); a.v = o("v_2"); a.mut = o("mut"); a.muave = o("muave"); a.muts = o("muts"); a.t_2 = o("t_2");
-  a.t_1 = o("t_save"); a.ph_1 = o("ph_save"); a.phb = o("phb"); a.ph_tend = o("ph_tend"); a.c2a = o("c2a"); a.cqw = o("cqw");
-  a.alt = o("alt"); a.a = o("a"); a.alpha = o("alpha"); a.gamma = o("gamma");
-  LAUNCH2(this, k_advance_w, (Box{q.its, std::min(q.ite, q.ide - 1), 1, 1, q.jts, std::min(q.jte, q.jde - 1)}), dts_rk, a);
+  WFuse fz{};
+  LAUNCH2(this, k_advance_w<false>, (Box{q.its, std::min(q.ite, q.ide - 1), 1, 1, q.jts, std::min(q.jte, q.jde - 1)}), dts_rk, w_args(this), fz);
+}
+
+// advance_w + sumflux (ww part) + calc_p_rho(iteration) in one column kernel, then the exchange and
+// boundary fills that follow calc_p_rho in solve_em.F:1659-1713
+void Solver::advance_w_fused(int rk_step, int iteration) {
+  const Geo &q = g;
+  float dt_rk, dts_rk; int ns;
+  rk_params(rk_step, dt_rk, dts_rk, ns);
+  if (q.kde < 5) throw std::runtime_error("wrfgpu: the fused column kernel needs at least 5 levels");
+  WFuse fz{iteration, ns, o("al"), o("p"), o("pm1"), o("ww_m"), o("ru_m"), o("rv_m"), o("mu_2"), o("ww1")};
+  LAUNCH2(this, k_advance_w<true>, (Box{q.its, q.ite, 1, 1, q.jts, q.jte}), dts_rk, w_args(this), fz);
+  halo("HALO_EM_C2");
+  bc({{"ph_2", 'w'}, {"al", 'p'}, {"p", 'p'}, {"muts", 't'}, {"mu_2", 't'}, {"mudf", 't'}});
 }
 
 void Solver::sumflux(int rk_step, int iteration) {
@@ -542,6 +795,26 @@ void Solver::sumflux(int rk_step, int iteration) {
   rk_params(rk_step, dt_rk, dts_rk, ns);
   LAUNCH3(this, k_sumflux, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), iteration, ns, o("u_2"), o("v_2"), o("ww"), o("u_save"),
           o("v_save"), o("ww1"), o("muu"), o("muv"), o("ru_m"), o("rv_m"), o("ww_m"));
+}
+
+// the part of sumflux the fused advance_uv leaves: ww_m (all levels) and the level-kde reset of ru_m, rv_m
+__global__ void k_sumflux_w(const Geo g, Box b, int iteration, int nsmall, cfp ww, cfp ww_lin, fp ru_m, fp rv_m, fp ww_m) {
+  TID3;
+  const int mini = min(g.ide - 1, g.ite), minj = min(g.jde - 1, g.jte), mink = g.kde - 1;
+  const bool dw = (i <= mini && j <= minj);
+  float cq = 0.f;
+  if (iteration != 1) cq = A3(ww_m, i, k, j);
+  if (dw) cq = cq + A3(ww, i, k, j);
+  if (iteration == nsmall && dw) cq = cq / (float)nsmall + A3(ww_lin, i, k, j);
+  A3(ww_m, i, k, j) = cq;
+  if (k == g.kde && iteration == 1) { A3(ru_m, i, k, j) = 0.f; A3(rv_m, i, k, j) = 0.f; }
+}
+
+void Solver::sumflux_w(int rk_step, int iteration) {
+  const Geo &q = g;
+  float dt_rk, dts_rk; int ns;
+  rk_params(rk_step, dt_rk, dts_rk, ns);
+  LAUNCH3(this, k_sumflux_w, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), iteration, ns, o("ww"), o("ww1"), o("ru_m"), o("rv_m"), o("ww_m"));
 }
 
 void Solver::calc_p_rho(int iteration) {

@@ -146,6 +146,8 @@ void Solver::build_geo() {
   q.its = d.ips; q.ite = d.ipe; q.jts = d.jps; q.jte = d.jpe;
   q.ni = d.ime - d.ims + 1; q.nk = d.kme - d.kms + 1; q.nj = d.jme - d.jms + 1;
   q.sk = q.ni; q.sj = (long)q.ni * q.nk;
+  if ((long)q.ni * q.nk * q.nj >= (1L << 31)) throw std::runtime_error("wrfgpu: a patch of more than 2^31 points per field is not supported");
+  q.isk = q.ni; q.isj = q.ni * q.nk;
   q.periodic_x = c.periodic_x; q.periodic_y = c.periodic_y;
   q.sym_xs = c.symmetric_xs; q.sym_xe = c.symmetric_xe; q.sym_ys = c.symmetric_ys; q.sym_ye = c.symmetric_ye;
   q.open_xs = c.open_xs; q.open_xe = c.open_xe; q.open_ys = c.open_ys; q.open_ye = c.open_ye;
@@ -217,12 +219,10 @@ void Solver::step() {
     { PHASE("rk_tendency"); rk_tendency(rk_step); }
     { PHASE("small_step_prep"); small_step_prep(rk_step); }
     for (int it = 1; it <= ns; it++) {
-      { PHASE("advance_uv"); advance_uv(rk_step); }
+      { PHASE("advance_uv"); advance_uv_fused(rk_step, it); }
       halo("HALO_EM_C");
       { PHASE("advance_mu_t"); advance_mu_t(rk_step); }
-      { PHASE("advance_w"); advance_w(rk_step); }
-      { PHASE("sumflux"); sumflux(rk_step, it); }
-      { PHASE("calc_p_rho"); calc_p_rho(it); }
+      { PHASE("advance_w"); advance_w_fused(rk_step, it); }
     }
     { PHASE("small_step_finish"); small_step_finish(rk_step); }
     { PHASE("rk_scalar"); rk_scalar_step(rk_step); }
