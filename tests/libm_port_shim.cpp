@@ -2,6 +2,7 @@
 // restated glibc routines with the system libm over large argument sets.  Test
 // infrastructure; the product compiles the same header with nvcc.
 #include "../wrf_b200/csrc/libm_port.h"
+#include "../wrf_b200/csrc/exact_div.h"
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -14,6 +15,20 @@ float port_expf(float x) { return wg_libm::expf_(x); }
 float port_sinf(float x) { return wg_libm::sinf_(x); }
 // scan the float bit patterns [lo, hi) with stride `step`; which: 0 logf, 1 expf, 2 sinf, 3 powf(x, y)
 // returns the number of arguments whose result bits differ from libm's (NaNs compare equal)
+// exact division by a constant: which = 60, 12 or 981 (g)
+long long div_scan(int which, uint32_t lo, uint32_t hi, uint32_t step, uint32_t *first_bad) {
+  long long bad = 0;
+  for (uint64_t u = lo; u < hi; u += step) {
+    const float x = fl((uint32_t)u);
+    if (x != x) continue;
+    float a, b;
+    if (which == 60) { a = WG_DIV60(x); b = x / 60.0f; }
+    else if (which == 12) { a = WG_DIV12(x); b = x / 12.0f; }
+    else { a = WG_DIVG(x); b = x / 9.81f; }
+    if (bits(a) != bits(b)) { if (!bad && first_bad) *first_bad = (uint32_t)u; bad++; }
+  }
+  return bad;
+}
 long long port_scan(int which, uint32_t lo, uint32_t hi, uint32_t step, float y, uint32_t *first_bad) {
   long long bad = 0;
   for (uint64_t u = lo; u < hi; u += step) {

@@ -21,12 +21,15 @@ def shim():
     so = os.path.join(BUILD, "libm_port_shim.so")
     src = os.path.join(ROOT, "tests", "libm_port_shim.cpp")
     hdr = os.path.join(ROOT, "wrf_b200", "csrc", "libm_port.h")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdr2 = os.path.join(ROOT, "wrf_b200", "csrc", "exact_div.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2)):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src])
     L = ctypes.CDLL(so)
     L.port_scan.restype = ctypes.c_longlong
     L.port_scan.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float,
                             ctypes.POINTER(ctypes.c_uint32)]
+    L.div_scan.restype = ctypes.c_longlong
+    L.div_scan.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)]
     for f in ("port_powf", "port_logf", "port_expf", "port_sinf"):
         getattr(L, f).restype = ctypes.c_float
         getattr(L, f).argtypes = [ctypes.c_float] * (2 if f == "port_powf" else 1)
@@ -95,3 +98,14 @@ def test_special_values(shim):
     assert shim.port_sinf(0.0) == 0.0
     assert np.isinf(shim.port_expf(1000.0)) and shim.port_expf(-1000.0) == 0.0
     assert np.isnan(shim.port_logf(-1.0)) and np.isinf(shim.port_logf(0.0))
+
+
+@pytest.mark.parametrize("d", [60, 12, 981])
+def test_exact_division_by_constant(shim, d):
+    """csrc/exact_div.h: x/60, x/12, x/g in three FMA-class instructions, bit-identical to IEEE
+    division (exhaustively verified offline over all 2^32 inputs; here every 61st bit pattern of
+    both signs plus the whole subnormal / tiny range where the guard switches to plain division)"""
+    fb = ctypes.c_uint32(0)
+    assert shim.div_scan(d, 0, 0xFFFFFFFF, 61, ctypes.byref(fb)) == 0, hex(fb.value)
+    assert shim.div_scan(d, 0, 0x0E000000, 7, ctypes.byref(fb)) == 0, hex(fb.value)
+    assert shim.div_scan(d, 0x80000000, 0x8E000000, 7, ctypes.byref(fb)) == 0, hex(fb.value)

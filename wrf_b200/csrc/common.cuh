@@ -211,6 +211,11 @@ inline bool empty(const Box &b) { return b.i1 < b.i0 || b.k1 < b.k0 || b.j1 < b.
   if (i > b.i1) return;
 
 void halo_destroy(Solver *s);   // halo.cu
+// advect_fast.cu
+Box interior_box(const Geo &q);
+int edge_strips(const Box &tile, const Box &in, Box out[4]);
+void launch_advect_scalar_fast(Solver *s, bool theta, const Box &in, cfp q, cfp ru, cfp rv, cfp rom, cfp mut, cfp t_tendf,
+                               cfp h_diabatic, fp tend);
 
 }  // namespace wg
 

@@ -1,0 +1,34 @@
+// exact_div.h -- IEEE-exact single-precision division by a compile-time constant in three
+// instructions.  The reference's flux operators divide by literals (module_advect_em.F:202-213:
+// (7*(q_i+q_im1) - ...)/12., (37*(...) - ...)/60.) and by g = 9.81; a multiplication by the
+// reciprocal is not the same number, and nvcc's correctly rounded `/` costs MUFU.RCP + FCHK + four
+// FFMA + a branch -- twelve such divisions per point made the stencil kernels issue-bound.
+// With c = RN(1/d):   q0 = x*c;  r = fma(-d, q0, x);  q = fma(r, c, q0)
+// is the correctly rounded quotient whenever it is a normal number (Markstein).  Checked
+// EXHAUSTIVELY over all 2^32 bit patterns of x for d = 60, 12, 9.81 (host, fmaf): the only
+// mismatches are |x| < 2^-103, which take the plain division below (zero keeps its sign through
+// x*c).  tests/test_libm_port.py re-runs a strided version of that scan.
+#pragma once
+#include <math.h>
+#if defined(__CUDACC__)
+#define WG_EXD __host__ __device__ __forceinline__
+#else
+#define WG_EXD static inline
+#endif
+
+WG_EXD float wg_div_const(float x, const float d, const float c) {
+#if defined(__CUDA_ARCH__)
+  const float q0 = __fmul_rn(x, c);
+  if (fabsf(x) < 0x1p-100f) return (x == 0.f) ? q0 : __fdiv_rn(x, d);
+  const float r = __fmaf_rn(-d, q0, x);
+  return __fmaf_rn(r, c, q0);
+#else
+  const float q0 = x * c;
+  if (fabsf(x) < 0x1p-100f) return (x == 0.f) ? q0 : x / d;
+  const float r = fmaf(-d, q0, x);
+  return fmaf(r, c, q0);
+#endif
+}
+#define WG_DIV60(x) wg_div_const((x), 60.0f, 1.0f / 60.0f)
+#define WG_DIV12(x) wg_div_const((x), 12.0f, 1.0f / 12.0f)
+#define WG_DIVG(x) wg_div_const((x), 9.81f, 1.0f / 9.81f)

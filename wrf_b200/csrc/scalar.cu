@@ -252,7 +252,12 @@ void Solver::rk_scalar_step(int rk_step) {
       LAUNCH3(this, k_pd_scale, lim, in, o("pd_scale"));
       LAUNCH3(this, k_pd_tend, mass, in, o("pd_scale"), lim, o("advect_tend"));
     } else {
-      LAUNCH3(this, k_advect_scalar, mass, o(s.f), o("ru_m"), o("rv_m"), o("ww_m"), o("advect_tend"));
+      Box in = interior_box(q);
+      in.k1 = ktf;
+      launch_advect_scalar_fast(this, false, in, o(s.f), o("ru_m"), o("rv_m"), o("ww_m"), nullptr, nullptr, nullptr, o("advect_tend"));
+      Box strips[4];
+      const int nst = edge_strips(mass, in, strips);
+      for (int m = 0; m < nst; m++) LAUNCH3(this, k_advect_scalar, strips[m], o(s.f), o("ru_m"), o("rv_m"), o("ww_m"), o("advect_tend"));
     }
     LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
   }

@@ -14,22 +14,9 @@
 // the same bits as the single-patch run.
 #include "common.cuh"
 #include "libm_port.h"
+#include "flux.cuh"
 
 namespace wg {
-
-// module_advect_em.F:202-213
-__device__ __forceinline__ float flux4(float qm2, float qm1, float q0, float qp1) {
-  return (7.f * (q0 + qm1) - (qp1 + qm2)) / 12.0f;
-}
-__device__ __forceinline__ float flux3(float qm2, float qm1, float q0, float qp1, float ua, float sg) {
-  return flux4(qm2, qm1, q0, qp1) + sg * sign1(ua) * ((qp1 - qm2) - 3.f * (q0 - qm1)) / 12.0f;
-}
-__device__ __forceinline__ float flux6(float qm3, float qm2, float qm1, float q0, float qp1, float qp2) {
-  return (37.f * (q0 + qm1) - 8.f * (qp1 + qm2) + (qp2 + qm3)) / 60.0f;
-}
-__device__ __forceinline__ float flux5(float qm3, float qm2, float qm1, float q0, float qp1, float qp2, float ua, float sg) {
-  return flux6(qm3, qm2, qm1, q0, qp1, qp2) - sg * sign1(ua) * ((qp2 - qm3) - 5.f * (qp1 - qm2) + 10.f * (q0 - qm1)) / 60.0f;
-}
 
 struct Deg { bool xs, xe, ys, ye; };
 __device__ __forceinline__ Deg degrade(const Geo &g) {
@@ -39,6 +26,15 @@ __device__ __forceinline__ Deg degrade(const Geo &g) {
   d.ys = !(g.periodic_y || g.sym_ys);
   d.ye = !(g.periodic_y || g.sym_ye);
   return d;
+}
+// A point at least 4 cells inside every non-periodic edge sees none of the boundary logic: every
+// face is 5th order, every loop range of the reference contains it and no open-boundary term
+// applies.  The kernels instantiate their body twice and take the branch-free one there (ncu r1b:
+// the gather kernels were issue-bound on the integer pipe by exactly this logic).
+__device__ __forceinline__ bool interior_pt(const Geo &g, int i, int j) {
+  const bool ix = g.periodic_x ? (i <= g.ide - 1) : (i >= g.ids + 4 && i <= g.ide - 5);
+  const bool jy = g.periodic_y ? (j <= g.jde - 1) : (j >= g.jds + 4 && j <= g.jde - 5);
+  return ix && jy;
 }
 // order of the flux at a face index `f`; lo2/lo3/hi2/hi3 are the face indices that
 // degrade to 2nd / 3rd order at the low / high edge.  returns 5, 3, 2
@@ -72,11 +68,12 @@ __device__ __forceinline__ float dpn_at(const Geo &g, cfp p, int i, int kk, int 
 }
 
 // vxgm of curvature (:4230-4290) with the open-boundary copies folded into index clamps
+template <bool FAST>
 __device__ __forceinline__ float vxgm_at(const Geo &g, cfp u, cfp v, int i, int k, int j) {
-  if (g.open_xs && i == g.ids - 1) i = g.ids;
-  if (g.open_xe && i == g.ide) i = g.ide - 1;
-  if (g.open_ys && j == g.jds - 1) j = g.jds;
-  if (g.open_ye && j == g.jde) j = g.jde - 1;
+  if (!FAST && g.open_xs && i == g.ids - 1) i = g.ids;
+  if (!FAST && g.open_xe && i == g.ide) i = g.ide - 1;
+  if (!FAST && g.open_ys && j == g.jds - 1) j = g.jds;
+  if (!FAST && g.open_ye && j == g.jde) j = g.jde - 1;
   return 0.5f * (A3(u, i, k, j) + A3(u, i + 1, k, j)) * (A2(g.msfvx, i, j + 1) - A2(g.msfvx, i, j)) * g.rdy -
          0.5f * (A3(v, i, k, j) + A3(v, i, k, j + 1)) * (A2(g.msfuy, i + 1, j) - A2(g.msfuy, i, j)) * g.rdx;
 }
@@ -120,11 +117,10 @@ __device__ __forceinline__ float pert_wind(const Geo &g, cfp r_in, cfp ph, cfp p
 
 // ===========================================================================
 // ru_tend: advect_u (:126) + pgf x (:2320-2400) + coriolis (:3700-3735) + curvature + addtend
-__global__ void k_tend_u(const Geo g, Box b, TendIn s, fp ru_tend) {
-  TID3;
+template <bool FAST>
+__device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i, int k, int j) {
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, ktf = g.kde - 1;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
-  if (k > ktf || j > min(jte, jde - 1)) { A3(ru_tend, i, k, j) = 0.f; return; }
   const Deg dg = degrade(g);
   const float sg = g.sgn_ts;
   cfp u = s.u, ru = s.ru, rv = s.rv, rom = s.ww;
@@ -136,12 +132,12 @@ __global__ void k_tend_u(const Geo g, Box b, TendIn s, fp ru_tend) {
     if (g.open_xe) i_e = min(ide - 1, ite);
     if (g.periodic_x) { i_s = its; i_e = ite; }
     const int j_lo = dg.ys ? max(jts, jds + 1) : jts, j_hi = dg.ye ? min(jte, jde - 2) : min(jte, jde - 1);
-    if (i >= i_s && i <= i_e && j >= j_lo && j <= j_hi) {
+    if (FAST || (i >= i_s && i <= i_e && j >= j_lo && j <= j_hi)) {
       float fq[2];
 #pragma unroll
       for (int m = 0; m < 2; m++) {
         const int jj = j + m;
-        const int ord = face_order(jj, dg.ys, dg.ye, jds + 1, jds + 2, jde - 1, jde - 2);
+        const int ord = FAST ? 5 : face_order(jj, dg.ys, dg.ye, jds + 1, jds + 2, jde - 1, jde - 2);
         if (ord == 5) {
           const float vel = 0.5f * (A3(rv, i, k, jj) + A3(rv, i - 1, k, jj));
           fq[m] = vel * flux5(YSTENCIL(u, i, k, jj), vel, sg);
@@ -159,12 +155,12 @@ __global__ void k_tend_u(const Geo g, Box b, TendIn s, fp ru_tend) {
   // --- x flux divergence
   {
     const int i_lo = dg.xs ? max(ids + 1, its) : its, i_hi = dg.xe ? min(ide - 1, ite) : ite;
-    if (i >= i_lo && i <= i_hi) {
+    if (FAST || (i >= i_lo && i <= i_hi)) {
       float fq[2];
 #pragma unroll
       for (int m = 0; m < 2; m++) {
         const int ii = i + m;
-        const int ord = face_order(ii, dg.xs, dg.xe, ids + 1, ids + 2, ide, ide - 1);
+        const int ord = FAST ? 5 : face_order(ii, dg.xs, dg.xe, ids + 1, ids + 2, ide, ide - 1);
         if (ord == 5) {
           const float vel = 0.5f * (A3(ru, ii, k, j) + A3(ru, ii - 1, k, j));
           fq[m] = vel * flux5(XSTENCIL(u, ii, k, j), vel, sg);
@@ -180,11 +176,11 @@ __global__ void k_tend_u(const Geo g, Box b, TendIn s, fp ru_tend) {
     }
   }
   // --- radiative / open boundary terms (:1244-1334)
-  if (g.open_xs && i == ids) {
+  if (!FAST && g.open_xs && i == ids) {
     const float ub = fminf(A3(ru, ids, k, j) - WG_CB * (g.c1h[k] * A2(s.mut, ids, j) + g.c2h[k]), 0.f);
     t = t - g.rdx * ub * (A3(u, ids + 1, k, j) - A3(u, ids, k, j));
   }
-  if (g.open_xe && i == ide) {
+  if (!FAST && g.open_xe && i == ide) {
     const float ub = fmaxf(A3(ru, ide, k, j) + WG_CB * (g.c1h[k] * A2(s.mut, ide - 1, j) + g.c2h[k]), 0.f);
     t = t - g.rdx * ub * (A3(u, ide, k, j) - A3(u, ide - 1, k, j));
   }
@@ -193,9 +189,9 @@ __global__ void k_tend_u(const Geo g, Box b, TendIn s, fp ru_tend) {
     if (g.open_xs) i_s = max(ids + 1, its);
     if (g.open_xe) i_e = min(ite, ide - 1);
     const int imin = ids, imax = ide - 1;
-    if (i >= i_s && i <= i_e) {
+    if (FAST || (i >= i_s && i <= i_e)) {
       const int ip = min(imax, i), im = max(imin, i - 1);
-      if (g.open_ys && j == jds) {
+      if (!FAST && g.open_ys && j == jds) {
         const float mrdy = A2(g.msfux, i, jds) * g.rdy;
         const float vw = 0.5f * (A3(rv, ip, k, jds) + A3(rv, im, k, jds));
         const float vb = fminf(vw, 0.f);
@@ -203,7 +199,7 @@ __global__ void k_tend_u(const Geo g, Box b, TendIn s, fp ru_tend) {
         const float dvp = A3(rv, im, k, jds + 1) - A3(rv, im, k, jds);
         t = t - mrdy * (vb * (A3(u, i, k, jds + 1) - A3(u, i, k, jds)) + 0.5f * A3(u, i, k, jds) * (dvm + dvp));
       }
-      if (g.open_ye && j == jde - 1) {
+      if (!FAST && g.open_ye && j == jde - 1) {
         const float mrdy = A2(g.msfux, i, jde - 1) * g.rdy;
         const float vw = 0.5f * (A3(rv, ip, k, jde) + A3(rv, im, k, jde));
         const float vb = fmaxf(vw, 0.f);
@@ -219,7 +215,7 @@ __global__ void k_tend_u(const Geo g, Box b, TendIn s, fp ru_tend) {
     if (g.open_ys) i_s = max(ids + 1, its);
     if (g.open_ye) i_e = min(ide - 1, ite);
     if (g.periodic_x) { i_s = its; i_e = ite; }
-    if (i >= i_s && i <= i_e) {
+    if (FAST || (i >= i_s && i <= i_e)) {
       float vf[2];
 #pragma unroll
       for (int m = 0; m < 2; m++) {
@@ -241,7 +237,7 @@ __global__ void k_tend_u(const Geo g, Box b, TendIn s, fp ru_tend) {
     if (g.open_xs && its == ids) i_s = its + 1;
     if (g.open_xe && ite == ide) i_e = ite - 1;
     if (g.periodic_x) { i_s = its; i_e = ite; }
-    if (i >= i_s && i <= i_e) {
+    if (FAST || (i >= i_s && i <= i_e)) {
       const float mr = A2(g.msfux, i, j) / A2(g.msfuy, i, j);
       float dpx = mr * .5f * g.rdx * (g.c1h[k] * A2(s.muu, i, j) + g.c2h[k]) *
                   ((A3(s.ph, i, k + 1, j) - A3(s.ph, i - 1, k + 1, j) + A3(s.ph, i, k, j) - A3(s.ph, i - 1, k, j)) +
@@ -259,7 +255,7 @@ __global__ void k_tend_u(const Geo g, Box b, TendIn s, fp ru_tend) {
     if (g.open_xs) i_s = max(ids + 1, its);
     if (g.open_xe) i_e = min(ide - 1, ite);
     if (g.periodic_x) { i_s = its; i_e = ite; }
-    if (i >= i_s && i <= i_e) {
+    if (FAST || (i >= i_s && i <= i_e)) {
       const float rvavg = 0.25f * (A3(rv, i - 1, k, j + 1) + A3(rv, i, k, j + 1) + A3(rv, i - 1, k, j) + A3(rv, i, k, j));
       const float rwsum = (A3(s.rw, i - 1, k + 1, j) + A3(s.rw, i - 1, k, j) + A3(s.rw, i, k + 1, j) + A3(s.rw, i, k, j));
       if (!g.pert_coriolis) {
@@ -271,19 +267,19 @@ __global__ void k_tend_u(const Geo g, Box b, TendIn s, fp ru_tend) {
                     (PRV(i - 1, k, j + 1) + PRV(i, k, j + 1) + PRV(i - 1, k, j) + PRV(i, k, j)) -
             0.5f * (A2(g.e, i, j) + A2(g.e, i - 1, j)) * 0.5f * (A2(g.cosa, i, j) + A2(g.cosa, i - 1, j)) * 0.25f * rwsum;
       }
-      t = t + 0.5f * (vxgm_at(g, s.u, s.v, i, k, j) + vxgm_at(g, s.u, s.v, i - 1, k, j)) * rvavg -
+      t = t + 0.5f * (vxgm_at<FAST>(g, s.u, s.v, i, k, j) + vxgm_at<FAST>(g, s.u, s.v, i - 1, k, j)) * rvavg -
           A3(u, i, k, j) * WG_RERADIUS * 0.25f * rwsum;
     }
   }
   // perturbation_coriolis keeps the open-boundary columns the plain routine dropped (:3975-4003)
-  if (g.pert_coriolis && !g.periodic_x) {
-    if (g.open_xs && i == ids) {
+  if (!FAST && g.pert_coriolis && !g.periodic_x) {
+    if (!FAST && g.open_xs && i == ids) {
       t = t + (A2(g.msfux, i, j) / A2(g.msfuy, i, j)) * 0.5f * (A2(g.f, i, j) + A2(g.f, i, j)) * 0.25f *
                   (PRV(i, k, j + 1) + PRV(i, k, j + 1) + PRV(i, k, j) + PRV(i, k, j)) -
           0.5f * (A2(g.e, i, j) + A2(g.e, i, j)) * 0.5f * (A2(g.cosa, i, j) + A2(g.cosa, i, j)) * 0.25f *
               (A3(s.rw, i, k + 1, j) + A3(s.rw, i, k, j) + A3(s.rw, i, k + 1, j) + A3(s.rw, i, k, j));
     }
-    if (g.open_xe && i == ide) {
+    if (!FAST && g.open_xe && i == ide) {
       t = t + (A2(g.msfux, i, j) / A2(g.msfuy, i, j)) * 0.5f * (A2(g.f, i - 1, j) + A2(g.f, i - 1, j)) * 0.25f *
                   (PRV(i - 1, k, j + 1) + PRV(i - 1, k, j + 1) + PRV(i - 1, k, j) + PRV(i - 1, k, j)) -
           0.5f * (A2(g.e, i - 1, j) + A2(g.e, i - 1, j)) * 0.5f * (A2(g.cosa, i - 1, j) + A2(g.cosa, i - 1, j)) * 0.25f *
@@ -292,16 +288,23 @@ __global__ void k_tend_u(const Geo g, Box b, TendIn s, fp ru_tend) {
   }
   // --- rk_addtend_dry (module_em.F:1037-1043)
   t = t + A3(s.ru_tendf, i, k, j) / A2(g.msfuy, i, j);
-  A3(ru_tend, i, k, j) = t;
+  return t;
+}
+__global__ void k_tend_u(const Geo g, Box b, TendIn s, fp ru_tend) {
+  TID3;
+  const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, ktf = g.kde - 1, kde = g.kde;
+  const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
+  (void)ids; (void)jds; (void)ktf; (void)kde; (void)its; (void)jts;
+  if (k > ktf || j > min(jte, jde - 1)) { A3(ru_tend, i, k, j) = 0.f; return; }
+  A3(ru_tend, i, k, j) = interior_pt(g, i, j) ? tend_u_pt<true>(g, s, i, k, j) : tend_u_pt<false>(g, s, i, k, j);
 }
 
 // ===========================================================================
 // rv_tend: advect_v (:1530) + pgf y + coriolis + curvature + addtend
-__global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
-  TID3;
+template <bool FAST>
+__device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i, int k, int j) {
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, ktf = g.kde - 1;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
-  if (k > ktf || i > min(ite, ide - 1)) { A3(rv_tend, i, k, j) = 0.f; return; }
   const Deg dg = degrade(g);
   const float sg = g.sgn_ts;
   cfp v = s.v, ru = s.ru, rv = s.rv, rom = s.ww;
@@ -309,12 +312,12 @@ __global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
   // --- y flux divergence
   {
     const int j_lo = dg.ys ? max(jts, jds + 1) : jts, j_hi = dg.ye ? min(jte, jde - 1) : jte;
-    if (j >= j_lo && j <= j_hi) {
+    if (FAST || (j >= j_lo && j <= j_hi)) {
       float fq[2];
 #pragma unroll
       for (int m = 0; m < 2; m++) {
         const int jj = j + m;
-        const int ord = face_order(jj, dg.ys, dg.ye, jds + 1, jds + 2, jde, jde - 1);
+        const int ord = FAST ? 5 : face_order(jj, dg.ys, dg.ye, jds + 1, jds + 2, jde, jde - 1);
         if (ord == 5) {
           const float vel = 0.5f * (A3(rv, i, k, jj) + A3(rv, i, k, jj - 1));
           fq[m] = vel * flux5(YSTENCIL(v, i, k, jj), vel, sg);
@@ -335,12 +338,12 @@ __global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
     if (g.open_ys) j_s = max(jds + 1, jts);
     if (g.open_ye) j_e = min(jde - 1, jte);
     const int i_lo = dg.xs ? max(ids + 1, its) : its, i_hi = dg.xe ? min(ide - 2, ite) : min(ite, ide - 1);
-    if (j >= j_s && j <= j_e && i >= i_lo && i <= i_hi) {
+    if (FAST || (j >= j_s && j <= j_e && i >= i_lo && i <= i_hi)) {
       float fq[2];
 #pragma unroll
       for (int m = 0; m < 2; m++) {
         const int ii = i + m;
-        const int ord = face_order(ii, dg.xs, dg.xe, ids + 1, ids + 2, ide - 1, ide - 2);
+        const int ord = FAST ? 5 : face_order(ii, dg.xs, dg.xe, ids + 1, ids + 2, ide - 1, ide - 2);
         if (ord == 5) {
           const float vel = 0.5f * (A3(ru, ii, k, j) + A3(ru, ii, k, j - 1));
           fq[m] = vel * flux5(XSTENCIL(v, ii, k, j), vel, sg);
@@ -356,11 +359,11 @@ __global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
     }
   }
   // --- open boundary terms (:2712-2800)
-  if (g.open_ys && j == jds) {
+  if (!FAST && g.open_ys && j == jds) {
     const float vb = fminf(A3(rv, i, k, jds) - WG_CB * (g.c1h[k] * A2(s.mut, i, jds) + g.c2h[k]), 0.f);
     t = t - g.rdy * vb * (A3(v, i, k, jds + 1) - A3(v, i, k, jds));
   }
-  if (g.open_ye && j == jde) {
+  if (!FAST && g.open_ye && j == jde) {
     const float vb = fmaxf(A3(rv, i, k, jde) + WG_CB * (g.c1h[k] * A2(s.mut, i, jde - 1) + g.c2h[k]), 0.f);
     t = t - g.rdy * vb * (A3(v, i, k, jde) - A3(v, i, k, jde - 1));
   }
@@ -369,9 +372,9 @@ __global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
     if (g.open_ys) j_s = max(jds + 1, jts);
     if (g.open_ye) j_e = min(jte, jde - 1);
     const int jmin = jds, jmax = jde - 1;
-    if (j >= j_s && j <= j_e) {
+    if (FAST || (j >= j_s && j <= j_e)) {
       const int jp = min(jmax, j), jm = max(jmin, j - 1);
-      if (g.open_xs && i == ids) {
+      if (!FAST && g.open_xs && i == ids) {
         const float mrdx = A2(g.msfvy, ids, j) * g.rdx;
         const float uw = 0.5f * (A3(ru, ids, k, jp) + A3(ru, ids, k, jm));
         const float ub = fminf(uw, 0.f);
@@ -379,7 +382,7 @@ __global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
         const float dum = A3(ru, ids + 1, k, jm) - A3(ru, ids, k, jm);
         t = t - mrdx * (ub * (A3(v, ids + 1, k, j) - A3(v, ids, k, j)) + 0.5f * A3(v, ids, k, j) * (dup + dum));
       }
-      if (g.open_xe && i == ide - 1) {
+      if (!FAST && g.open_xe && i == ide - 1) {
         const float mrdx = A2(g.msfvy, ide - 1, j) * g.rdx;
         const float uw = 0.5f * (A3(ru, ide, k, jp) + A3(ru, ide, k, jm));
         const float ub = fmaxf(uw, 0.f);
@@ -394,7 +397,7 @@ __global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
     int j_s = jts, j_e = jte;
     if (g.open_ys) j_s = max(jds + 1, jts);
     if (g.open_ye) j_e = min(jde - 1, jte);
-    if (j >= j_s && j <= j_e) {
+    if (FAST || (j >= j_s && j <= j_e)) {
       float vf[2];
 #pragma unroll
       for (int m = 0; m < 2; m++) {
@@ -415,7 +418,7 @@ __global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
     int j_s = jts, j_e = jte;
     if (g.open_ys && jts == jds) j_s = jts + 1;
     if (g.open_ye && jte == jde) j_e = jte - 1;
-    if (j >= j_s && j <= j_e) {
+    if (FAST || (j >= j_s && j <= j_e)) {
       const float mr = A2(g.msfvy, i, j) / A2(g.msfvx, i, j);
       float dpy = mr * .5f * g.rdy * (g.c1h[k] * A2(s.muv, i, j) + g.c2h[k]) *
                   ((A3(s.ph, i, k + 1, j) - A3(s.ph, i, k + 1, j - 1) + A3(s.ph, i, k, j) - A3(s.ph, i, k, j - 1)) +
@@ -432,7 +435,7 @@ __global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
     int j_s = jts, j_e = jte;
     if (g.open_ys) j_s = max(jds + 1, jts);
     if (g.open_ye) j_e = min(jde - 1, jte);
-    if (j >= j_s && j <= j_e) {
+    if (FAST || (j >= j_s && j <= j_e)) {
       const float rwsum = (A3(s.rw, i, k + 1, j - 1) + A3(s.rw, i, k, j - 1) + A3(s.rw, i, k + 1, j) + A3(s.rw, i, k, j));
       const float ruavg = 0.25f * (A3(ru, i, k, j) + A3(ru, i + 1, k, j) + A3(ru, i, k, j - 1) + A3(ru, i + 1, k, j - 1));
       const float mr = A2(g.msfvy, i, j) / A2(g.msfvx, i, j);
@@ -445,18 +448,18 @@ __global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
                     (PRU(i, k, j) + PRU(i + 1, k, j) + PRU(i, k, j - 1) + PRU(i + 1, k, j - 1)) +
             mr * 0.5f * (A2(g.e, i, j) + A2(g.e, i, j - 1)) * 0.5f * (A2(g.sina, i, j) + A2(g.sina, i, j - 1)) * 0.25f * rwsum;
       }
-      t = t - 0.5f * (vxgm_at(g, s.u, s.v, i, k, j) + vxgm_at(g, s.u, s.v, i, k, j - 1)) * ruavg -
+      t = t - 0.5f * (vxgm_at<FAST>(g, s.u, s.v, i, k, j) + vxgm_at<FAST>(g, s.u, s.v, i, k, j - 1)) * ruavg -
           mr * A3(v, i, k, j) * WG_RERADIUS * 0.25f * rwsum;
     }
   }
-  if (g.pert_coriolis) {   // open-boundary rows of perturbation_coriolis (:4066-4085, :4104-4123)
+  if (!FAST && g.pert_coriolis) {   // open-boundary rows of perturbation_coriolis (:4066-4085, :4104-4123)
     const float mr = A2(g.msfvy, i, j) / A2(g.msfvx, i, j);
-    if (g.open_ys && j == jds) {
+    if (!FAST && g.open_ys && j == jds) {
       t = t - mr * 0.5f * (A2(g.f, i, j) + A2(g.f, i, j)) * 0.25f * (PRU(i, k, j) + PRU(i + 1, k, j) + PRU(i, k, j) + PRU(i + 1, k, j)) +
           mr * 0.5f * (A2(g.e, i, j) + A2(g.e, i, j)) * 0.5f * (A2(g.sina, i, j) + A2(g.sina, i, j)) * 0.25f *
               (A3(s.rw, i, k + 1, j) + A3(s.rw, i, k, j) + A3(s.rw, i, k + 1, j) + A3(s.rw, i, k, j));
     }
-    if (g.open_ye && j == jde) {
+    if (!FAST && g.open_ye && j == jde) {
       t = t - mr * 0.5f * (A2(g.f, i, j - 1) + A2(g.f, i, j - 1)) * 0.25f *
                   (PRU(i, k, j - 1) + PRU(i + 1, k, j - 1) + PRU(i, k, j - 1) + PRU(i + 1, k, j - 1)) +
           mr * 0.5f * (A2(g.e, i, j - 1) + A2(g.e, i, j - 1)) * 0.5f * (A2(g.sina, i, j - 1) + A2(g.sina, i, j - 1)) * 0.25f *
@@ -464,17 +467,24 @@ __global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
     }
   }
   t = t + A3(s.rv_tendf, i, k, j) * A2(g.msfvx_inv, i, j);
-  A3(rv_tend, i, k, j) = t;
+  return t;
+}
+__global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
+  TID3;
+  const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, ktf = g.kde - 1, kde = g.kde;
+  const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
+  (void)ids; (void)jds; (void)ktf; (void)kde; (void)its; (void)jts;
+  if (k > ktf || i > min(ite, ide - 1)) { A3(rv_tend, i, k, j) = 0.f; return; }
+  A3(rv_tend, i, k, j) = interior_pt(g, i, j) ? tend_v_pt<true>(g, s, i, k, j) : tend_v_pt<false>(g, s, i, k, j);
 }
 
 // ===========================================================================
 // rw_tend: advect_w (:4364) + pg_buoy_w (:2419) + w_damp (:2503) + coriolis + curvature + addtend
 // cqw is read here un-inverted; k_invert_cqw applies cqw <- 1/(1+cqw) (:2489) afterwards.
-__global__ void k_tend_w(const Geo g, Box b, TendIn s, fp rw_tend) {
-  TID3;
+template <bool FAST>
+__device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i, int k, int j) {
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, kde = g.kde, ktf = g.kde - 1;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
-  if (i > min(ite, ide - 1) || j > min(jte, jde - 1)) { A3(rw_tend, i, k, j) = 0.f; return; }
   const Deg dg = degrade(g);
   const float sg = g.sgn_ts;
   cfp w = s.w, ru = s.ru, rv = s.rv, rom = s.ww;
@@ -489,12 +499,12 @@ __global__ void k_tend_w(const Geo g, Box b, TendIn s, fp rw_tend) {
     // --- y
     {
       const int j_lo = dg.ys ? max(jts, jds + 1) : jts, j_hi = dg.ye ? min(jte, jde - 2) : min(jte, jde - 1);
-      if (j >= j_lo && j <= j_hi) {
+      if (FAST || (j >= j_lo && j <= j_hi)) {
         float fq[2];
 #pragma unroll
         for (int m = 0; m < 2; m++) {
           const int jj = j + m;
-          const int ord = face_order(jj, dg.ys, dg.ye, jds + 1, jds + 2, jde - 1, jde - 2);
+          const int ord = FAST ? 5 : face_order(jj, dg.ys, dg.ye, jds + 1, jds + 2, jde - 1, jde - 2);
           const float vel = WVEL(rv, i, jj);
           if (ord == 5) fq[m] = vel * flux5(YSTENCIL(w, i, k, jj), vel, sg);
           else if (ord == 3) fq[m] = vel * flux3(A3(w, i, k, jj - 2), A3(w, i, k, jj - 1), A3(w, i, k, jj), A3(w, i, k, jj + 1), vel, sg);
@@ -507,12 +517,12 @@ __global__ void k_tend_w(const Geo g, Box b, TendIn s, fp rw_tend) {
     // --- x
     {
       const int i_lo = dg.xs ? max(ids + 1, its) : its, i_hi = dg.xe ? min(ide - 2, ite) : min(ite, ide - 1);
-      if (i >= i_lo && i <= i_hi) {
+      if (FAST || (i >= i_lo && i <= i_hi)) {
         float fq[2];
 #pragma unroll
         for (int m = 0; m < 2; m++) {
           const int ii = i + m;
-          const int ord = face_order(ii, dg.xs, dg.xe, ids + 1, ids + 2, ide - 1, ide - 2);
+          const int ord = FAST ? 5 : face_order(ii, dg.xs, dg.xe, ids + 1, ids + 2, ide - 1, ide - 2);
           const float vel = WVEL(ru, ii, j);
           if (ord == 5) fq[m] = vel * flux5(XSTENCIL(w, ii, k, j), vel, sg);
           else if (ord == 3) fq[m] = vel * flux3(A3(w, ii - 2, k, j), A3(w, ii - 1, k, j), A3(w, ii, k, j), A3(w, ii + 1, k, j), vel, sg);
@@ -529,22 +539,22 @@ __global__ void k_tend_w(const Geo g, Box b, TendIn s, fp rw_tend) {
 #define WDIF(r, i1, j1, i2, j2) (top ? (fa * (A3(r, i1, ka, j1) - A3(r, i2, ka, j2)) - fb * (A3(r, i1, kb, j1) - A3(r, i2, kb, j2))) \
                                      : (fa * (A3(r, i1, ka, j1) - A3(r, i2, ka, j2)) + fb * (A3(r, i1, kb, j1) - A3(r, i2, kb, j2))))
     const int i_end = min(ite, ide - 1), j_end = min(jte, jde - 1);
-    if (g.open_xs && i == ids) {
+    if (!FAST && g.open_xs && i == ids) {
       const float uw = 0.5f * WSUM(ru, ids, j, ids + 1, j);
       const float ub = fminf(uw, 0.f);
       t = t - g.rdx * (ub * (A3(w, ids + 1, k, j) - A3(w, ids, k, j)) + A3(w, ids, k, j) * WDIF(ru, ids + 1, j, ids, j));
     }
-    if (g.open_xe && ite == ide && i == i_end) {
+    if (!FAST && g.open_xe && ite == ide && i == i_end) {
       const float uw = 0.5f * WSUM(ru, ide - 1, j, ide, j);
       const float ub = fmaxf(uw, 0.f);
       t = t - g.rdx * (ub * (A3(w, i_end, k, j) - A3(w, i_end - 1, k, j)) + A3(w, i_end, k, j) * WDIF(ru, ide, j, ide - 1, j));
     }
-    if (g.open_ys && j == jds) {
+    if (!FAST && g.open_ys && j == jds) {
       const float vw = 0.5f * WSUM(rv, i, jds, i, jds + 1);
       const float vb = fminf(vw, 0.f);
       t = t - g.rdy * (vb * (A3(w, i, k, jds + 1) - A3(w, i, k, jds)) + A3(w, i, k, jds) * WDIF(rv, i, jds + 1, i, jds));
     }
-    if (g.open_ye && jte == jde && j == j_end) {
+    if (!FAST && g.open_ye && jte == jde && j == j_end) {
       const float vw = 0.5f * WSUM(rv, i, jde - 1, i, jde);
       const float vb = fmaxf(vw, 0.f);
       t = t - g.rdy * (vb * (A3(w, i, k, j_end) - A3(w, i, k, j_end - 1)) + A3(w, i, k, j_end) * WDIF(rv, i, jde, i, jde - 1));
@@ -598,7 +608,15 @@ __global__ void k_tend_w(const Geo g, Box b, TendIn s, fp rw_tend) {
     }
   }
   t = t + A3(s.rw_tendf, i, k, j) / A2(g.msfty, i, j);
-  A3(rw_tend, i, k, j) = t;
+  return t;
+}
+__global__ void k_tend_w(const Geo g, Box b, TendIn s, fp rw_tend) {
+  TID3;
+  const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, ktf = g.kde - 1, kde = g.kde;
+  const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
+  (void)ids; (void)jds; (void)ktf; (void)kde; (void)its; (void)jts;
+  if (i > min(ite, ide - 1) || j > min(jte, jde - 1)) { A3(rw_tend, i, k, j) = 0.f; return; }
+  A3(rw_tend, i, k, j) = interior_pt(g, i, j) ? tend_w_pt<true>(g, s, i, k, j) : tend_w_pt<false>(g, s, i, k, j);
 }
 
 // cqw <- 1/(1+cqw), module_big_step_utilities_em.F:2489
@@ -609,6 +627,7 @@ __global__ void k_invert_cqw(const Geo g, Box b, fp cqw) {
 
 // ===========================================================================
 // advect_scalar (:3029) evaluated at one point; shared by t_tend and the scalar path
+template <bool FAST>
 __device__ __forceinline__ float advect_scalar_pt(const Geo &g, cfp q, cfp q_old, cfp ru, cfp rv, cfp rom, int i, int k, int j) {
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, ktf = g.kde - 1;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
@@ -617,12 +636,12 @@ __device__ __forceinline__ float advect_scalar_pt(const Geo &g, cfp q, cfp q_old
   float t = 0.f;
   {
     const int j_lo = dg.ys ? max(jts, jds + 1) : jts, j_hi = dg.ye ? min(jte, jde - 2) : min(jte, jde - 1);
-    if (j >= j_lo && j <= j_hi) {
+    if (FAST || (j >= j_lo && j <= j_hi)) {
       float fq[2];
 #pragma unroll
       for (int m = 0; m < 2; m++) {
         const int jj = j + m;
-        const int ord = face_order(jj, dg.ys, dg.ye, jds + 1, jds + 2, jde - 1, jde - 2);
+        const int ord = FAST ? 5 : face_order(jj, dg.ys, dg.ye, jds + 1, jds + 2, jde - 1, jde - 2);
         const float vel = A3(rv, i, k, jj);
         if (ord == 5) fq[m] = vel * flux5(YSTENCIL(q, i, k, jj), vel, sg);
         else if (ord == 3) fq[m] = vel * flux3(A3(q, i, k, jj - 2), A3(q, i, k, jj - 1), A3(q, i, k, jj), A3(q, i, k, jj + 1), vel, sg);
@@ -634,12 +653,12 @@ __device__ __forceinline__ float advect_scalar_pt(const Geo &g, cfp q, cfp q_old
   }
   {
     const int i_lo = dg.xs ? max(ids + 1, its) : its, i_hi = dg.xe ? min(ide - 2, ite) : min(ite, ide - 1);
-    if (i >= i_lo && i <= i_hi) {
+    if (FAST || (i >= i_lo && i <= i_hi)) {
       float fq[2];
 #pragma unroll
       for (int m = 0; m < 2; m++) {
         const int ii = i + m;
-        const int ord = face_order(ii, dg.xs, dg.xe, ids + 1, ids + 2, ide - 1, ide - 2);
+        const int ord = FAST ? 5 : face_order(ii, dg.xs, dg.xe, ids + 1, ids + 2, ide - 1, ide - 2);
         const float vel = A3(ru, ii, k, j);
         if (ord == 5) fq[m] = vel * flux5(XSTENCIL(q, ii, k, j), vel, sg);
         else if (ord == 3) fq[m] = vel * flux3(A3(q, ii - 2, k, j), A3(q, ii - 1, k, j), A3(q, ii, k, j), A3(q, ii + 1, k, j), vel, sg);
@@ -650,19 +669,19 @@ __device__ __forceinline__ float advect_scalar_pt(const Geo &g, cfp q, cfp q_old
     }
   }
   const int i_end = min(ite, ide - 1), j_end = min(jte, jde - 1);
-  if (g.open_xs && i == ids) {
+  if (!FAST && g.open_xs && i == ids) {
     const float ub = fminf(0.5f * (A3(ru, ids, k, j) + A3(ru, ids + 1, k, j)), 0.f);
     t = t - g.rdx * (ub * (A3(q_old, ids + 1, k, j) - A3(q_old, ids, k, j)) + A3(q, ids, k, j) * (A3(ru, ids + 1, k, j) - A3(ru, ids, k, j)));
   }
-  if (g.open_xe && ite == ide && i == i_end) {
+  if (!FAST && g.open_xe && ite == ide && i == i_end) {
     const float ub = fmaxf(0.5f * (A3(ru, ide - 1, k, j) + A3(ru, ide, k, j)), 0.f);
     t = t - g.rdx * (ub * (A3(q_old, i_end, k, j) - A3(q_old, i_end - 1, k, j)) + A3(q, i_end, k, j) * (A3(ru, ide, k, j) - A3(ru, ide - 1, k, j)));
   }
-  if (g.open_ys && j == jds) {
+  if (!FAST && g.open_ys && j == jds) {
     const float vb = fminf(0.5f * (A3(rv, i, k, jds) + A3(rv, i, k, jds + 1)), 0.f);
     t = t - g.rdy * (vb * (A3(q_old, i, k, jds + 1) - A3(q_old, i, k, jds)) + A3(q, i, k, jds) * (A3(rv, i, k, jds + 1) - A3(rv, i, k, jds)));
   }
-  if (g.open_ye && jte == jde && j == j_end) {
+  if (!FAST && g.open_ye && jte == jde && j == j_end) {
     const float vb = fmaxf(0.5f * (A3(rv, i, k, jde - 1) + A3(rv, i, k, jde)), 0.f);
     t = t - g.rdy * (vb * (A3(q_old, i, k, j_end) - A3(q_old, i, k, j_end - 1)) + A3(q, i, k, j_end) * (A3(rv, i, k, jde) - A3(rv, i, k, jde - 1)));
   }
@@ -687,7 +706,8 @@ __device__ __forceinline__ float advect_scalar_pt(const Geo &g, cfp q, cfp q_old
 __global__ void k_tend_t(const Geo g, Box b, TendIn s, fp t_tend) {
   TID3;
   if (k > g.kde - 1 || i > min(g.ite, g.ide - 1) || j > min(g.jte, g.jde - 1)) { A3(t_tend, i, k, j) = 0.f; return; }
-  float t = advect_scalar_pt(g, s.t, s.t, s.ru, s.rv, s.ww, i, k, j);
+  float t = interior_pt(g, i, j) ? advect_scalar_pt<true>(g, s.t, s.t, s.ru, s.rv, s.ww, i, k, j)
+                               : advect_scalar_pt<false>(g, s.t, s.t, s.ru, s.rv, s.ww, i, k, j);
   const float msfty = A2(g.msfty, i, j);
   t = t + A3(s.t_tendf, i, k, j) / msfty + (g.c1h[k] * A2(s.mut, i, j) + g.c2h[k]) * A3(s.h_diabatic, i, k, j) / msfty;
   A3(t_tend, i, k, j) = t;
@@ -696,16 +716,16 @@ __global__ void k_tend_t(const Geo g, Box b, TendIn s, fp t_tend) {
 // external entry for the scalar path (scalar.cu)
 __global__ void k_advect_scalar(const Geo g, Box b, cfp q, cfp ru, cfp rv, cfp rom, fp tend) {
   TID3;
-  A3(tend, i, k, j) = advect_scalar_pt(g, q, q, ru, rv, rom, i, k, j);
+  A3(tend, i, k, j) = interior_pt(g, i, j) ? advect_scalar_pt<true>(g, q, q, ru, rv, rom, i, k, j)
+                                           : advect_scalar_pt<false>(g, q, q, ru, rv, rom, i, k, j);
 }
 
 // ===========================================================================
 // ph_tend: rhs_ph (:1365-2181, 6th-order branch) + rk_addtend_dry
-__global__ void k_tend_ph(const Geo g, Box b, TendIn s, fp ph_tend) {
-  TID3;
+template <bool FAST>
+__device__ __forceinline__ float tend_ph_pt(const Geo &g, const TendIn &s, int i, int k, int j) {
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, kde = g.kde, kte = g.kde;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
-  if (i > min(ite, ide - 1) || j > min(jte, jde - 1)) { A3(ph_tend, i, k, j) = 0.f; return; }
   cfp ph = s.ph, phb = s.phb, u = s.u, v = s.v, ww = s.ww;
   const float msfty = A2(g.msfty, i, j);
   float t = 0.f;
@@ -730,7 +750,7 @@ __global__ void k_tend_ph(const Geo g, Box b, TendIn s, fp ph_tend) {
       if (g.open_ys) j6s = max(jts, jds + 3);
       if (g.open_ye) j6e = min(j6e, jde - 4);
       int mode = 0;
-      if (j >= j6s && j <= j6e) mode = 6;
+      if (FAST || (j >= j6s && j <= j6e)) mode = 6;
       else if (g.open_ys && j == jds + 2) mode = 4;
       else if (g.open_ye && j == jde - 3) mode = 4;
       else if (g.open_ys && j == jds + 1) mode = 2;
@@ -764,7 +784,7 @@ __global__ void k_tend_ph(const Geo g, Box b, TendIn s, fp ph_tend) {
       if (g.open_xs) i6s = max(its, ids + 3);
       if (g.open_xe) i6e = min(i6e, ide - 4);
       int mode = 0;
-      if (i >= i6s && i <= i6e) mode = 6;
+      if (FAST || (i >= i6s && i <= i6e)) mode = 6;
       else if (g.open_xs && i == ids + 2) mode = 4;
       else if (g.open_xe && i == ide - 3) mode = 4;
       else if (g.open_xs && i == ids + 1) mode = 2;
@@ -793,25 +813,25 @@ __global__ void k_tend_ph(const Geo g, Box b, TendIn s, fp ph_tend) {
     }
     // --- lateral open boundary terms (:2065-2179); ph_old == ph in rk_tendency
     const float mass = (c1f * A2(s.mut, i, j) + c2f);
-    if (g.open_ys && j == jds) {
+    if (!FAST && g.open_ys && j == jds) {
       const int kz = min(k, kde - 1);
       const float vb = .5f * (g.fnm[kz] * (A3(v, i, kz, j + 1) + A3(v, i, kz, j)) + g.fnp[kz] * (A3(v, i, kz - 1, j + 1) + A3(v, i, kz - 1, j)));
       const float vl = fminf(vb, 0.f);
       t = t - g.rdy * mass * (+vl * (A3(ph, i, k, j + 1) - A3(ph, i, k, j)));
     }
-    if (g.open_ye && jte == jde && j == jde - 1) {
+    if (!FAST && g.open_ye && jte == jde && j == jde - 1) {
       const int kz = min(k, kde - 1);
       const float vb = .5f * (g.fnm[kz] * (A3(v, i, kz, j + 1) + A3(v, i, kz, j)) + g.fnp[kz] * (A3(v, i, kz - 1, j + 1) + A3(v, i, kz - 1, j)));
       const float vr = fmaxf(vb, 0.f);
       t = t - g.rdy * mass * (+vr * (A3(ph, i, k, j) - A3(ph, i, k, j - 1)));
     }
-    if (g.open_xs && i == ids) {
+    if (!FAST && g.open_xs && i == ids) {
       const int kz = k;   // the reference uses kz = k even at k = kde (:2139-2146)
       const float ub = .5f * (g.fnm[kz] * (A3(u, i + 1, kz, j) + A3(u, i, kz, j)) + g.fnp[kz] * (A3(u, i + 1, kz - 1, j) + A3(u, i, kz - 1, j)));
       const float ul = fminf(ub, 0.f);
       t = t - (A2(g.msftx, i, j) / msfty) * g.rdx * mass * (+ul * (A3(ph, i + 1, k, j) - A3(ph, i, k, j)));
     }
-    if (g.open_xe && ite == ide && i == ide - 1) {
+    if (!FAST && g.open_xe && ite == ide && i == ide - 1) {
       const int kz = (k == kde) ? k - 1 : k;
       const float ub = .5f * (g.fnm[kz] * (A3(u, i + 1, kz, j) + A3(u, i, kz, j)) + g.fnp[kz] * (A3(u, i + 1, kz - 1, j) + A3(u, i, kz - 1, j)));
       const float ur = fmaxf(ub, 0.f);
@@ -819,7 +839,15 @@ __global__ void k_tend_ph(const Geo g, Box b, TendIn s, fp ph_tend) {
     }
   }
   t = t + A3(s.ph_tendf, i, k, j) / msfty;
-  A3(ph_tend, i, k, j) = t;
+  return t;
+}
+__global__ void k_tend_ph(const Geo g, Box b, TendIn s, fp ph_tend) {
+  TID3;
+  const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, ktf = g.kde - 1, kde = g.kde;
+  const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
+  (void)ids; (void)jds; (void)ktf; (void)kde; (void)its; (void)jts;
+  if (i > min(ite, ide - 1) || j > min(jte, jde - 1)) { A3(ph_tend, i, k, j) = 0.f; return; }
+  A3(ph_tend, i, k, j) = interior_pt(g, i, j) ? tend_ph_pt<true>(g, s, i, k, j) : tend_ph_pt<false>(g, s, i, k, j);
 }
 
 // ===========================================================================
@@ -933,7 +961,13 @@ void Solver::rk_tendency(int rk_step) {
   LAUNCH3(this, k_tend_u, tile, s, o("ru_tend"));
   LAUNCH3(this, k_tend_v, tile, s, o("rv_tend"));
   LAUNCH3(this, k_tend_w, tile, s, o("rw_tend"));
-  LAUNCH3(this, k_tend_t, tile, s, o("t_tend"));
+  {   // theta: k-marching flux-sharing kernel on the interior, the gather kernel on the edge strips
+    const Box in = interior_box(q);
+    launch_advect_scalar_fast(this, true, in, s.t, s.ru, s.rv, s.ww, s.mut, s.t_tendf, s.h_diabatic, o("t_tend"));
+    Box strips[4];
+    const int ns = edge_strips(tile, in, strips);
+    for (int m = 0; m < ns; m++) LAUNCH3(this, k_tend_t, strips[m], s, o("t_tend"));
+  }
   LAUNCH3(this, k_tend_ph, tile, s, o("ph_tend"));
   LAUNCH3(this, k_invert_cqw, (Box{q.its, std::min(q.ite, q.ide - 1), 2, q.kde - 1, q.jts, std::min(q.jte, q.jde - 1)}), o("cqw"));
 }
