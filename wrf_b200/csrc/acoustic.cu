@@ -212,7 +212,16 @@ __device__ __forceinline__ UvPp uv_load_pp(const Geo &g, const UvArgs &a, int i,
 struct UvFuse { int iteration, nsmall; fp ru_m, rv_m; cfp u_lin, v_lin; };
 
 template <bool FUSE>
-__global__ void __launch_bounds__(128) k_advance_uv(const Geo g, Box b, float dts, UvArgs a, UvFuse fz) {
+#ifndef UV_MINB
+#define UV_MINB 5
+#endif
+#ifndef W_MINB
+#define W_MINB 7
+#endif
+#ifndef MT_MINB
+#define MT_MINB 8
+#endif
+__global__ void __launch_bounds__(128, UV_MINB) k_advance_uv(const Geo g, Box b, float dts, UvArgs a, UvFuse fz) {
   TID2;
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, kde = g.kde;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
@@ -339,7 +348,7 @@ __device__ __forceinline__ Mt2 mt_load2(const Geo &g, const MuTArgs &a, int i, i
   m.ue = A3(a.u, i + 1, k, j); m.u0 = A3(a.u, i, k, j); m.t1e = A3(a.t_1, i + 1, k, j); m.t1w = A3(a.t_1, i - 1, k, j);
   return m;
 }
-__global__ void __launch_bounds__(128) k_advance_mu_t(const Geo g, Box b, float dts, MuTArgs a) {
+__global__ void __launch_bounds__(128, MT_MINB) k_advance_mu_t(const Geo g, Box b, float dts, MuTArgs a) {
   TID2;
   const int k_end = g.kde - 1;
   const float msftx = A2(g.msftx, i, j), msfty = A2(g.msfty, i, j);
@@ -445,7 +454,7 @@ __device__ __forceinline__ WDn w_load_dn(const Geo &g, const WArgs &a, const WFu
 }
 
 template <bool FUSE>
-__global__ void __launch_bounds__(128) k_advance_w(const Geo g, Box b, float dts, WArgs a, WFuse fz) {
+__global__ void __launch_bounds__(128, W_MINB) k_advance_w(const Geo g, Box b, float dts, WArgs a, WFuse fz) {
   TID2;
   const int kde = g.kde, k_end = g.kde - 1;
   if (FUSE) {

@@ -34,7 +34,8 @@ ABI_SYMBOLS = (
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libwrfgpu.so")
+    # WRFGPU_LIB: an alternative build of the same library (tuning experiments)
+    return os.environ.get("WRFGPU_LIB") or os.path.join(_HERE, "libwrfgpu.so")
 
 
 def load():
