@@ -112,6 +112,7 @@ __global__ void k_calc_p_rho(const Geo g, Box b, int step, fp al, fp p, cfp ph, 
 
 // calc_coef_w (:570-650): column recurrence for the tridiagonal factors
 __global__ void k_calc_coef_w(const Geo g, Box b, float dts, fp a, fp alpha, fp gamma, cfp mut, cfp cqw, cfp c2a) {
+  COEF_SMEM;
   TID2;
   const int kde = g.kde;
   const float lid_flag = g.top_lid ? 0.f : 1.f;
@@ -121,8 +122,8 @@ __global__ void k_calc_coef_w(const Geo g, Box b, float dts, fp a, fp alpha, fp 
   {
     const int k = kde - 1;
     A3(a, i, 2, j) = 0.f;
-    A3(a, i, kde, j) = -2.f * cof * (g.rdnw[kde - 1] * g.rdnw[kde - 1]) * A3(c2a, i, kde - 1, j) * lid_flag /
-                       ((g.c1h[k] * mt + g.c2h[k]) * (g.c1f[k] * mt + g.c2f[k]));
+    A3(a, i, kde, j) = -2.f * cof * (cf.rdnw[kde - 1] * cf.rdnw[kde - 1]) * A3(c2a, i, kde - 1, j) * lid_flag /
+                       ((cf.c1h[k] * mt + cf.c2h[k]) * (cf.c1f[k] * mt + cf.c2f[k]));
     A3(gamma, i, 1, j) = 0.f;
   }
   float gam_prev = 0.f;   // gamma(k-1)
@@ -132,12 +133,12 @@ __global__ void k_calc_coef_w(const Geo g, Box b, float dts, fp a, fp alpha, fp 
     const float c2a_k = A3(c2a, i, k, j);
     float ak;
     if (k == 2) ak = 0.f;
-    else ak = -cq * cof * g.rdn[k] * g.rdnw[k - 1] * c2a_km1 / ((g.c1h[k - 1] * mt + g.c2h[k - 1]) * (g.c1f[k - 1] * mt + g.c2f[k - 1]));
+    else ak = -cq * cof * cf.rdn[k] * cf.rdnw[k - 1] * c2a_km1 / ((cf.c1h[k - 1] * mt + cf.c2h[k - 1]) * (cf.c1f[k - 1] * mt + cf.c2f[k - 1]));
     if (k > 2) A3(a, i, k, j) = ak;
-    const float bb = 1.f + cq * cof * g.rdn[k] *
-                               (g.rdnw[k] * c2a_k / ((g.c1h[k] * mt + g.c2h[k]) * (g.c1f[k] * mt + g.c2f[k])) +
-                                g.rdnw[k - 1] * c2a_km1 / ((g.c1h[k - 1] * mt + g.c2h[k - 1]) * (g.c1f[k] * mt + g.c2f[k])));
-    const float cc = -cq * cof * g.rdn[k] * g.rdnw[k] * c2a_k / ((g.c1h[k] * mt + g.c2h[k]) * (g.c1f[k + 1] * mt + g.c2f[k + 1]));
+    const float bb = 1.f + cq * cof * cf.rdn[k] *
+                               (cf.rdnw[k] * c2a_k / ((cf.c1h[k] * mt + cf.c2h[k]) * (cf.c1f[k] * mt + cf.c2f[k])) +
+                                cf.rdnw[k - 1] * c2a_km1 / ((cf.c1h[k - 1] * mt + cf.c2h[k - 1]) * (cf.c1f[k] * mt + cf.c2f[k])));
+    const float cc = -cq * cof * cf.rdn[k] * cf.rdnw[k] * c2a_k / ((cf.c1h[k] * mt + cf.c2h[k]) * (cf.c1f[k + 1] * mt + cf.c2f[k + 1]));
     const float al = 1.f / (bb - ak * gam_prev);
     gam_prev = cc * al;
     A3(alpha, i, k, j) = al;
@@ -146,8 +147,8 @@ __global__ void k_calc_coef_w(const Geo g, Box b, float dts, fp a, fp alpha, fp 
   }
   {
     const int k = kde;
-    const float bb = 1.f + 2.f * cof * (g.rdnw[kde - 1] * g.rdnw[kde - 1]) * A3(c2a, i, kde - 1, j) /
-                               ((g.c1h[k - 1] * mt + g.c2h[k - 1]) * (g.c1f[k] * mt + g.c2f[k]));
+    const float bb = 1.f + 2.f * cof * (cf.rdnw[kde - 1] * cf.rdnw[kde - 1]) * A3(c2a, i, kde - 1, j) /
+                               ((cf.c1h[k - 1] * mt + cf.c2h[k - 1]) * (cf.c1f[k] * mt + cf.c2f[k]));
     const float cc = 0.f;
     const float al = 1.f / (bb - A3(a, i, kde, j) * gam_prev);
     A3(alpha, i, kde, j) = al;
@@ -188,11 +189,21 @@ __device__ __forceinline__ float dpn_uv(const Geo &g, cfp p, int i, int kk, int 
 struct UvLevel {      // everything read at one level: c = (i,j), w = (i-1,j), s = (i,j-1)
   float alt_c, alt_w, alt_s, al_c, al_w, al_s, pb_c, pb_w, pb_s, php_c, php_w, php_s;
   float cqu, cqv, rut, rvt, u, v;
+  float rum, rvm, ulin, vlin;   // FUSE: the sumflux operands, prefetched with the level (a load issued at its
+                                // point of use costs one full memory round trip per level: ncu r1c, 31 % of the samples)
 };
 struct UvPp { float p_c, p_w, p_s, ph_c, ph_w, ph_s; };
 
-__device__ __forceinline__ UvLevel uv_load_level(const Geo &g, const UvArgs &a, int i, int k, int j) {
+struct UvFuse { int iteration, nsmall; fp ru_m, rv_m; cfp u_lin, v_lin; };
+
+template <bool FUSE>
+__device__ __forceinline__ UvLevel uv_load_level(const Geo &g, const UvArgs &a, const UvFuse &fz, int i, int k, int j) {
   UvLevel L;
+  L.rum = 0.f; L.rvm = 0.f; L.ulin = 0.f; L.vlin = 0.f;
+  if (FUSE) {
+    if (fz.iteration != 1) { L.rum = A3(fz.ru_m, i, k, j); L.rvm = A3(fz.rv_m, i, k, j); }
+    if (fz.iteration == fz.nsmall) { L.ulin = A3(fz.u_lin, i, k, j); L.vlin = A3(fz.v_lin, i, k, j); }
+  }
   L.alt_c = A3(a.alt, i, k, j); L.alt_w = A3(a.alt, i - 1, k, j); L.alt_s = A3(a.alt, i, k, j - 1);
   L.al_c = A3(a.al, i, k, j); L.al_w = A3(a.al, i - 1, k, j); L.al_s = A3(a.al, i, k, j - 1);
   L.pb_c = A3(a.pb, i, k, j); L.pb_w = A3(a.pb, i - 1, k, j); L.pb_s = A3(a.pb, i, k, j - 1);
@@ -209,8 +220,6 @@ __device__ __forceinline__ UvPp uv_load_pp(const Geo &g, const UvArgs &a, int i,
   return q;
 }
 
-struct UvFuse { int iteration, nsmall; fp ru_m, rv_m; cfp u_lin, v_lin; };
-
 template <bool FUSE>
 #ifndef UV_MINB
 #define UV_MINB 5
@@ -222,6 +231,7 @@ template <bool FUSE>
 #define MT_MINB 8
 #endif
 __global__ void __launch_bounds__(128, UV_MINB) k_advance_uv(const Geo g, Box b, float dts, UvArgs a, UvFuse fz) {
+  COEF_CONST;
   TID2;
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, kde = g.kde;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__(128, UV_MINB) k_advance_uv(const Geo g, Box b,
   // ---- prime the pipeline: p, ph at levels 1, 2 (and p at 3 for the surface extrapolation)
   UvPp q1 = uv_load_pp(g, a, i, 1, j), q2 = uv_load_pp(g, a, i, 2, j);
   const float p3_c = A3(a.p, i, 3, j), p3_w = A3(a.p, i - 1, 3, j), p3_s = A3(a.p, i, 3, j - 1);
-  UvLevel L = uv_load_level(g, a, i, 1, j);
+  UvLevel L = uv_load_level<FUSE>(g, a, fz, i, 1, j);
   // dpn(1) (:828-836, :902-910): cf1..3 extrapolation of p to the surface
   float dpn_u = .5f * (g.cf1 * (q1.p_c + q1.p_w) + g.cf2 * (q2.p_c + q2.p_w) + g.cf3 * (p3_c + p3_w));
   float dpn_v = .5f * (g.cf1 * (q1.p_c + q1.p_s) + g.cf2 * (q2.p_c + q2.p_s) + g.cf3 * (p3_c + p3_s));
@@ -264,9 +274,9 @@ __global__ void __launch_bounds__(128, UV_MINB) k_advance_uv(const Geo g, Box b,
     // prefetch: the rest of level k+1 and p, ph of level k+2
     UvLevel Ln;
     UvPp qk2;
-    if (k + 1 <= kde - 1) Ln = uv_load_level(g, a, i, k + 1, j);
+    if (k + 1 <= kde - 1) Ln = uv_load_level<FUSE>(g, a, fz, i, k + 1, j);
     if (k + 2 <= kde) qk2 = uv_load_pp(g, a, i, k + 2, j);
-    const float c1h = g.c1h[k], c2h = g.c2h[k];
+    const float c1h = cf.c1h[k], c2h = cf.c2h[k];
     // dpn(k+1)
     float dpn_u1, dpn_v1;
     if (k + 1 == kde) {
@@ -279,8 +289,8 @@ __global__ void __launch_bounds__(128, UV_MINB) k_advance_uv(const Geo g, Box b,
                         g.cf3 * (A3(p, i, kde - 3, j - 1) + A3(p, i, kde - 3, j)));
       }
     } else {
-      dpn_u1 = .5f * (g.fnm[k + 1] * (qk1.p_c + qk1.p_w) + g.fnp[k + 1] * (qk.p_c + qk.p_w));
-      dpn_v1 = .5f * (g.fnm[k + 1] * (qk1.p_c + qk1.p_s) + g.fnp[k + 1] * (qk.p_c + qk.p_s));
+      dpn_u1 = .5f * (cf.fnm[k + 1] * (qk1.p_c + qk1.p_w) + cf.fnp[k + 1] * (qk.p_c + qk.p_w));
+      dpn_v1 = .5f * (cf.fnm[k + 1] * (qk1.p_c + qk1.p_s) + cf.fnp[k + 1] * (qk.p_c + qk.p_s));
     }
     // ---- u (:799-870)
     float uv = L.u;
@@ -289,7 +299,7 @@ __global__ void __launch_bounds__(128, UV_MINB) k_advance_uv(const Geo g, Box b,
       float dpxy = mr_u * .5f * g.rdx * (c1h * muu + c2h) *
                    (((qk1.ph_c - qk1.ph_w) + (qk.ph_c - qk.ph_w)) + (L.alt_c + L.alt_w) * (qk.p_c - qk.p_w) +
                     (L.al_c + L.al_w) * (L.pb_c - L.pb_w));
-      dpxy = dpxy + mr_u * g.rdx * (L.php_c - L.php_w) * (g.rdnw[k] * (dpn_u1 - dpn_u) - .5f * ((c1h * mu_w) + (c1h * mu_c)));
+      dpxy = dpxy + mr_u * g.rdx * (L.php_c - L.php_w) * (cf.rdnw[k] * (dpn_u1 - dpn_u) - .5f * ((c1h * mu_w) + (c1h * mu_c)));
       uv = uv - dts * L.cqu * dpxy + (c1h * mudf_x);
     }
     if (u_tend || u_pg) A3(a.u, i, k, j) = uv;
@@ -301,19 +311,18 @@ __global__ void __launch_bounds__(128, UV_MINB) k_advance_uv(const Geo g, Box b,
         float dpxy = mr_v * .5f * g.rdy * (c1h * muv + c2h) *
                      (((qk1.ph_c - qk1.ph_s) + (qk.ph_c - qk.ph_s)) + (L.alt_c + L.alt_s) * (qk.p_c - qk.p_s) +
                       (L.al_c + L.al_s) * (L.pb_c - L.pb_s));
-        dpxy = dpxy + mr_v * g.rdy * (L.php_c - L.php_s) * (g.rdnw[k] * (dpn_v1 - dpn_v) - .5f * ((c1h * mu_s) + (c1h * mu_c)));
+        dpxy = dpxy + mr_v * g.rdy * (L.php_c - L.php_s) * (cf.rdnw[k] * (dpn_v1 - dpn_v) - .5f * ((c1h * mu_s) + (c1h * mu_c)));
         vv = vv - dts * L.cqv * dpxy + (c1h * mudf_y);
       }
       A3(a.v, i, k, j) = vv;
     }
     if (FUSE) {   // sumflux, u and v parts
-      float ra = 0.f, rb = 0.f;
-      if (fz.iteration != 1) { ra = A3(fz.ru_m, i, k, j); rb = A3(fz.rv_m, i, k, j); }
+      float ra = L.rum, rb = L.rvm;
       if (u_row) ra = ra + uv;
       if (v_col) rb = rb + vv;
       if (fz.iteration == fz.nsmall) {
-        if (u_row) ra = ra / nst + (c1h * muu + c2h) * A3(fz.u_lin, i, k, j) / msfuy;
-        if (v_col) rb = rb / nst + (c1h * muv + c2h) * A3(fz.v_lin, i, k, j) * msfvx_inv;
+        if (u_row) ra = ra / nst + (c1h * muu + c2h) * L.ulin / msfuy;
+        if (v_col) rb = rb / nst + (c1h * muv + c2h) * L.vlin * msfvx_inv;
       }
       A3(fz.ru_m, i, k, j) = ra; A3(fz.rv_m, i, k, j) = rb;
     }
@@ -348,8 +357,7 @@ __device__ __forceinline__ Mt2 mt_load2(const Geo &g, const MuTArgs &a, int i, i
   m.ue = A3(a.u, i + 1, k, j); m.u0 = A3(a.u, i, k, j); m.t1e = A3(a.t_1, i + 1, k, j); m.t1w = A3(a.t_1, i - 1, k, j);
   return m;
 }
-__global__ void __launch_bounds__(128, MT_MINB) k_advance_mu_t(const Geo g, Box b, float dts, MuTArgs a) {
-  TID2;
+__device__ __forceinline__ void advance_mu_t_column(const Geo &g, const Coef &cf, float dts, const MuTArgs &a, int i, int j) {
   const int k_end = g.kde - 1;
   const float msftx = A2(g.msftx, i, j), msfty = A2(g.msfty, i, j);
   const float muu0 = A2(a.muu, i, j), muu1 = A2(a.muu, i + 1, j), muv0 = A2(a.muv, i, j), muv1 = A2(a.muv, i, j + 1);
@@ -361,11 +369,11 @@ __global__ void __launch_bounds__(128, MT_MINB) k_advance_mu_t(const Geo g, Box 
   for (int k = 1; k <= k_end; k++) {
     Mt1 n1;
     if (k < k_end) n1 = mt_load1(g, a, i, k + 1, j);
-    const float c1h = g.c1h[k], c2h = g.c2h[k];
+    const float c1h = cf.c1h[k], c2h = cf.c2h[k];
     const float dvdxi = msftx * msfty *
                         (g.rdy * ((c1.vn + (c1h * muv1 + c2h) * c1.vsn * mvi1) - (c1.v0 + (c1h * muv0 + c2h) * c1.vs0 * mvi0)) +
                          g.rdx * ((c1.ue + (c1h * muu1 + c2h) * c1.use / my1) - (c1.u0 + (c1h * muu0 + c2h) * c1.us0 / my0)));
-    dmdt = dmdt + g.dnw[k] * dvdxi;
+    dmdt = dmdt + cf.dnw[k] * dvdxi;
     if (k < k_end) A3(a.ww, i, k + 1, j) = dvdxi;
     c1 = n1;
   }
@@ -389,10 +397,10 @@ __global__ void __launch_bounds__(128, MT_MINB) k_advance_mu_t(const Geo g, Box 
     if (k < k_end) n2 = mt_load2(g, a, i, k + 1, j, k_end);
     float wdtn_kp1 = 0.f;
     if (k + 1 <= k_end) {
-      w_rec = w_rec - g.dnw[k] * ((g.c1h[k] * dmdt) + c2.dv + (g.c1h[k] * mu_tend)) / msfty;
+      w_rec = w_rec - cf.dnw[k] * ((cf.c1h[k] * dmdt) + c2.dv + (cf.c1h[k] * mu_tend)) / msfty;
       const float wkp1 = w_rec - c2.ww1;
       A3(a.ww, i, k + 1, j) = wkp1;
-      wdtn_kp1 = wkp1 * (g.fnm[k + 1] * c2.t1u + g.fnp[k + 1] * t1_k);
+      wdtn_kp1 = wkp1 * (cf.fnm[k + 1] * c2.t1u + cf.fnp[k + 1] * t1_k);
     }   // else wdtn(kde) = 0
     const float told = c2.t;
     A3(a.t_ave, i, k, j) = told;
@@ -400,12 +408,17 @@ __global__ void __launch_bounds__(128, MT_MINB) k_advance_mu_t(const Geo g, Box 
     tn = tn - dts * msfty *
                   (msftx * (.5f * g.rdy * (c2.vn * (c2.t1n + t1_k) - c2.v0 * (t1_k + c2.t1s)) +
                             .5f * g.rdx * (c2.ue * (c2.t1e + t1_k) - c2.u0 * (t1_k + c2.t1w))) +
-                   g.rdnw[k] * (wdtn_kp1 - wdtn_k));
+                   cf.rdnw[k] * (wdtn_kp1 - wdtn_k));
     A3(a.t, i, k, j) = tn;
     wdtn_k = wdtn_kp1;
     t1_k = c2.t1u;
     c2 = n2;
   }
+}
+__global__ void __launch_bounds__(128, MT_MINB) k_advance_mu_t(const Geo g, Box b, float dts, MuTArgs a) {
+  COEF_CONST;
+  TID2;
+  advance_mu_t_column(g, cf, dts, a, i, j);
 }
 
 // ---------------------------------------------------------------------------
@@ -454,8 +467,7 @@ __device__ __forceinline__ WDn w_load_dn(const Geo &g, const WArgs &a, const WFu
 }
 
 template <bool FUSE>
-__global__ void __launch_bounds__(128, W_MINB) k_advance_w(const Geo g, Box b, float dts, WArgs a, WFuse fz) {
-  TID2;
+__device__ __forceinline__ void advance_w_column(const Geo &g, const Coef &cf, float dts, const WArgs &a, const WFuse &fz, int i, int j) {
   const int kde = g.kde, k_end = g.kde - 1;
   if (FUSE) {
     // sumflux writes its whole tile: outside the mass points ww_m is only reset on the first iteration,
@@ -482,24 +494,24 @@ __global__ void __launch_bounds__(128, W_MINB) k_advance_w(const Geo g, Box b, f
   {
     const float t1v = A3(a.t_1, i, 1, j);
     float tv = .5f * ((1.f + epssm) * A3(a.t_2, i, 1, j) + (1.f - epssm) * A3(a.t_2ave, i, 1, j));
-    tv = (tv + (g.c1h[1] * muave) * WG_T0) / ((g.c1h[1] * muts + g.c2h[1]) * (WG_T0 + t1v));
+    tv = (tv + (cf.c1h[1] * muave) * WG_T0) / ((cf.c1h[1] * muts + cf.c2h[1]) * (WG_T0 + t1v));
     A3(a.t_2ave, i, 1, j) = tv;
     t2ave_km1 = tv; c2a_km1 = A3(a.c2a, i, 1, j); alt_km1 = A3(a.alt, i, 1, j);
   }
   // layer integral of -omega dphi/deta: wdwn(kk+1) of the reference (:1318-1345)
   auto layer = [&](int kk, float ph1_hi, float ph1_lo, float phb_hi, float phb_lo, float ww_hi, float ww_lo) -> float {
     const float dphi = (ph1_hi - ph1_lo + phb_hi - phb_lo);
-    if (g.phi_adv_z == 2) return g.rdnw[kk] * dphi;
-    return .5f * (ww_hi + ww_lo) * g.rdnw[kk] * dphi;
+    if (g.phi_adv_z == 2) return cf.rdnw[kk] * dphi;
+    return .5f * (ww_hi + ww_lo) * cf.rdnw[kk] * dphi;
   };
   // rhs(kk) for kk >= 2 from its operands (:1347-1371)
   auto rhs_of = [&](int kk, float pht, float wv, float phv, float ww_kk, float lay_kk, float lay_kkm1) -> float {
     float r = dts * (pht + .5f * WG_G * (1.f - epssm) * wv);
     if (kk <= k_end) {
-      if (g.phi_adv_z == 2) r = r - dts * ww_kk * (g.fnm[kk] * lay_kk + g.fnp[kk] * lay_kkm1);
-      else r = r - dts * (g.fnm[kk] * lay_kk + g.fnp[kk] * lay_kkm1);
+      if (g.phi_adv_z == 2) r = r - dts * ww_kk * (cf.fnm[kk] * lay_kk + cf.fnp[kk] * lay_kkm1);
+      else r = r - dts * (cf.fnm[kk] * lay_kk + cf.fnp[kk] * lay_kkm1);
     }
-    r = phv + msfty * r / (g.c1f[kk] * mut + g.c2f[kk]);
+    r = phv + msfty * r / (cf.c1f[kk] * mut + cf.c2f[kk]);
     if (g.top_lid && kk == k_end + 1) r = 0.f;
     return r;
   };
@@ -516,7 +528,7 @@ __global__ void __launch_bounds__(128, W_MINB) k_advance_w(const Geo g, Box b, f
   float ph_km1 = ph_1st, ph_k = A3(a.ph, i, 2, j);
   float rhs_km1 = 0.f;                                                           // rhs(1)
   float rhs_k = rhs_of(2, A3(a.ph_tend, i, 2, j), w_k, ph_k, ww_k, lay_k, lay_km1);
-  float cpre_km1 = c2a_km1 * g.rdnw[1] / (g.c1h[1] * mut + g.c2h[1]);
+  float cpre_km1 = c2a_km1 * cf.rdnw[1] / (cf.c1h[1] * mut + cf.c2h[1]);
   float cat_km1 = c2a_km1 * alt_km1 * t2ave_km1;
   float wprev = w1;                                                              // w(k-1) after elimination
   WUp q = w_load_up(g, a, i, 2, j);
@@ -525,21 +537,21 @@ __global__ void __launch_bounds__(128, W_MINB) k_advance_w(const Geo g, Box b, f
     if (k < k_end) qn = w_load_up(g, a, i, k + 1, j);
     // t_2ave(k) (:1314-1317)
     float tv = .5f * ((1.f + epssm) * q.t2 + (1.f - epssm) * q.t2a);
-    tv = (tv + (g.c1h[k] * muave) * WG_T0) / ((g.c1h[k] * muts + g.c2h[k]) * (WG_T0 + q.t1));
+    tv = (tv + (cf.c1h[k] * muave) * WG_T0) / ((cf.c1h[k] * muts + cf.c2h[k]) * (WG_T0 + q.t1));
     A3(a.t_2ave, i, k, j) = tv;
     // rhs(k+1): needs layer k+1 (levels k+1, k+2) unless k+1 = kde
     float lay_kp1 = 0.f;
     if (k + 1 <= k_end) lay_kp1 = layer(k + 1, q.ph1_kp2, ph1_kp1, q.phb_kp2, phb_kp1, q.ww_kp2, ww_kp1);
     const float rhs_kp1 = rhs_of(k + 1, q.pht_kp1, q.w_kp1, q.ph_kp1, ww_kp1, lay_kp1, lay_k);
     const float ph_kp1 = q.ph_kp1;
-    const float cpre_k = q.c2a * g.rdnw[k] / (g.c1h[k] * mut + g.c2h[k]);
+    const float cpre_k = q.c2a * cf.rdnw[k] / (cf.c1h[k] * mut + cf.c2h[k]);
     const float cat_k = q.c2a * q.alt * tv;
     float wv = w_k + dts * q.rwt +
                msft_inv * q.cqw *
-                   (+.5f * dts * WG_G * g.rdn[k] *
+                   (+.5f * dts * WG_G * cf.rdn[k] *
                     (cpre_k * ((1.f + epssm) * (rhs_kp1 - rhs_k) + (1.f - epssm) * (ph_kp1 - ph_k)) -
                      cpre_km1 * ((1.f + epssm) * (rhs_k - rhs_km1) + (1.f - epssm) * (ph_k - ph_km1)))) +
-               dts * WG_G * msft_inv * (g.rdn[k] * (cat_k - cat_km1) - (g.c1f[k] * muave));
+               dts * WG_G * msft_inv * (cf.rdn[k] * (cat_k - cat_km1) - (cf.c1f[k] * muave));
     wv = (wv - q.a * wprev) * q.alpha;
     A3(a.w, i, k, j) = wv;
     A3(a.ph, i, k, j) = rhs_k;         // park rhs(k); ph(k) itself is no longer needed below k+1
@@ -559,9 +571,9 @@ __global__ void __launch_bounds__(128, W_MINB) k_advance_w(const Geo g, Box b, f
   {
     const int k = kde;
     wtop = w_k + dts * A3(a.rw_tend, i, k, j) +
-           msft_inv * (-.5f * dts * WG_G / (g.c1h[k - 1] * mut + g.c2h[k - 1]) * (g.rdnw[k - 1] * g.rdnw[k - 1]) * 2.f * c2a_km1 *
+           msft_inv * (-.5f * dts * WG_G / (cf.c1h[k - 1] * mut + cf.c2h[k - 1]) * (cf.rdnw[k - 1] * cf.rdnw[k - 1]) * 2.f * c2a_km1 *
                            ((1.f + epssm) * (rhs_k - rhs_km1) + (1.f - epssm) * (ph_k - ph_km1)) -
-                       dts * WG_G * (2.f * g.rdnw[k - 1] * c2a_km1 * alt_km1 * t2ave_km1 + (g.c1f[k] * muave)));
+                       dts * WG_G * (2.f * cf.rdnw[k - 1] * c2a_km1 * alt_km1 * t2ave_km1 + (cf.c1f[k] * muave)));
     if (g.top_lid) wtop = 0.f;
     wtop = (wtop - A3(a.a, i, k, j) * wprev) * A3(a.alpha, i, k, j);
   }
@@ -576,18 +588,18 @@ __global__ void __launch_bounds__(128, W_MINB) k_advance_w(const Geo g, Box b, f
       const float hbot = htop - hdepth;
       float dampwt = 0.f;
       if (hk >= hbot) dampwt = dampmag * wg_libm::sinf_(0.5f * pi * (hk - hbot) / hdepth) * wg_libm::sinf_(0.5f * pi * (hk - hbot) / hdepth);
-      wv = (wv - dampwt * (g.c1f[k] * mut + g.c2f[k]) * wsave) / (1.f + dampwt);
+      wv = (wv - dampwt * (cf.c1f[k] * mut + cf.c2f[k]) * wsave) / (1.f + dampwt);
     }
     A3(a.w, i, k, j) = wv;
-    const float phn = rhs + msfty * .5f * dts * WG_G * (1.f + epssm) * wv / (g.c1f[k] * muts + g.c2f[k]);
+    const float phn = rhs + msfty * .5f * dts * WG_G * (1.f + epssm) * wv / (cf.c1f[k] * muts + cf.c2f[k]);
     A3(a.ph, i, k, j) = phn;
     return phn;
   };
   // calc_p_rho at level k from the final ph(k+1), ph(k) (:522-567); sumflux ww_m (:1520-1596)
   const float mu_new = FUSE ? A2(fz.mu, i, j) : 0.f;
   auto p_rho = [&](int k, const WDn &d, float ph_hi, float ph_lo) {
-    const float c1h = g.c1h[k], c2h = g.c2h[k];
-    const float alv = -1.f / (c1h * muts + c2h) * (d.alt * (c1h * mu_new) + g.rdnw[k] * (ph_hi - ph_lo));
+    const float c1h = cf.c1h[k], c2h = cf.c2h[k];
+    const float alv = -1.f / (c1h * muts + c2h) * (d.alt * (c1h * mu_new) + cf.rdnw[k] * (ph_hi - ph_lo));
     float pv = d.c2a * (d.alt * (d.t2 - (c1h * mu_new) * d.t1) / ((c1h * muts + c2h) * (WG_T0 + d.t1)) - alv);
     A3(fz.al, i, k, j) = alv;
     if (fz.iteration == 0) {
@@ -635,6 +647,12 @@ __global__ void __launch_bounds__(128, W_MINB) k_advance_w(const Geo g, Box b, f
     d1.wwlin = fz.iteration == fz.nsmall ? A3(fz.ww_lin, i, 1, j) : 0.f;
     p_rho(1, d1, ph_hi, ph_1st);
   }
+}
+template <bool FUSE>
+__global__ void __launch_bounds__(128, W_MINB) k_advance_w(const Geo g, Box b, float dts, WArgs a, WFuse fz) {
+  COEF_SMEM;
+  TID2;
+  advance_w_column<FUSE>(g, cf, dts, a, fz, i, j);
 }
 
 // sumflux (:1473-1633)
@@ -757,14 +775,19 @@ void Solver::advance_uv_fused(int rk_step, int iteration) {
   LAUNCH2(this, k_advance_uv<true>, (Box{q.its, q.ite, 1, 1, q.jts, q.jte}), dts_rk, uv_args(this), fz);
 }
 
+static MuTArgs mu_t_args(Solver *s) {
+  MuTArgs a;
+  a.ww = s->o("ww"); a.mu = s->o("mu_2"); a.muave = s->o("muave"); a.muts = s->o("muts"); a.mudf = s->o("mudf"); a.t = s->o("t_2");
+  a.t_ave = s->o("t_2save"); a.ww_1 = s->o("ww1"); a.u = s->o("u_2"); a.u_1 = s->o("u_save"); a.v = s->o("v_2"); a.v_1 = s->o("v_save");
+  a.mut = s->o("mut"); a.muu = s->o("muu"); a.muv = s->o("muv"); a.t_1 = s->o("t_save"); a.ft = s->o("t_tend"); a.mu_tend = s->o("mu_tend");
+  return a;
+}
+
 void Solver::advance_mu_t(int rk_step) {
   const Geo &q = g;
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
-  MuTArgs a;
-  a.ww = o("ww"); a.mu = o("mu_2"); a.muave = o("muave"); a.muts = o("muts"); a.mudf = o("mudf"); a.t = o("t_2");
-  a.t_ave = o("t_2save"); a.ww_1 = o("ww1"); a.u = o("u_2"); a.u_1 = o("u_save"); a.v = o("v_2"); a.v_1 = o("v_save");
-  a.mut = o("mut"); a.muu = o("muu"); a.muv = o("muv"); a.t_1 = o("t_save"); a.ft = o("t_tend"); a.mu_tend = o("mu_tend");
+  MuTArgs a = mu_t_args(this);
   LAUNCH2(this, k_advance_mu_t, (Box{q.its, std::min(q.ite, q.ide - 1), 1, 1, q.jts, std::min(q.jte, q.jde - 1)}), dts_rk, a);
 }
 

@@ -140,6 +140,7 @@ void launch_advect_scalar_fast(Solver *s, bool theta, const Box &in, cfp q, cfp 
   if (empty(in)) return;
   const int ni = in.i1 - in.i0 + 1, nj = in.j1 - in.j0 + 1;
   dim3 block(32, 4), grid((unsigned)((ni + 30) / 31), (unsigned)((nj + 7) / 8));
+  if (s->coef_dirty) s->sync_coef();
   s->kpre(theta ? "k_advect_scalar_fast<theta>" : "k_advect_scalar_fast");
   if (theta) k_advect_scalar_fast<true><<<grid, block, 0, s->stream>>>(s->g, in, q, ru, rv, rom, mut, t_tendf, h_diabatic, tend);
   else k_advect_scalar_fast<false><<<grid, block, 0, s->stream>>>(s->g, in, q, ru, rv, rom, mut, t_tendf, h_diabatic, tend);

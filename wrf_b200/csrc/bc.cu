@@ -27,7 +27,7 @@ struct BcInfo {
   char variable;
 };
 
-__device__ __forceinline__ BcInfo bc_info(const Geo &g, char v_in, bool is3d) {
+__device__ __forceinline__ BcInfo bc_info(const GeoBase &g, char v_in, bool is3d) {
   BcInfo q;
   char v = v_in;
   if (v >= 'A' && v <= 'Z') v = (char)(v - 'A' + 'a');
@@ -51,7 +51,7 @@ __device__ __forceinline__ BcInfo bc_info(const Geo &g, char v_in, bool is3d) {
 }
 
 // x pass: one thread per (j, k, field); loops over the few ghost columns
-__global__ void k_bc_x(const Geo g, BcBatch bb) {
+__global__ void k_bc_x(const GeoBase g, BcBatch bb) {
   const int j = g.jms + blockIdx.x * blockDim.x + threadIdx.x;
   const int k = 1 + blockIdx.y;
   const int f = blockIdx.z;
@@ -124,7 +124,7 @@ __global__ void k_bc_x(const Geo g, BcBatch bb) {
 }
 
 // y pass: one thread per (i, k, field); loops over the few ghost rows
-__global__ void k_bc_y(const Geo g, BcBatch bb) {
+__global__ void k_bc_y(const GeoBase g, BcBatch bb) {
   const int i = g.ims + blockIdx.x * blockDim.x + threadIdx.x;
   const int k = 1 + blockIdx.y;
   const int f = blockIdx.z;

@@ -30,7 +30,13 @@ namespace wg {
 #define WG_RERADIUS (1.f / 6370.0e03f)
 #define WG_CB 25.f
 
-struct Geo {
+struct Box { int i0, i1, k0, k1, j0, j1; };   // inclusive index box of a launch
+
+// levels a Geo can carry: index 0..WG_NK-1 holds Fortran k = 0..WG_NK-1 (kme <= WG_NK-2, checked at create)
+#define WG_NK 128
+// GeoBase: extents, strides, flags and scalars (what the strip kernels of bc.cu / halo.cu need);
+// Geo adds the per-level coefficient arrays.
+struct GeoBase {
   int ids, ide, jds, jde, kds, kde;
   int ims, ime, jms, jme, kms, kme;
   int ips, ipe, jps, jpe;
@@ -44,13 +50,22 @@ struct Geo {
   float rdx, rdy, dt, cf1, cf2, cf3, cfn, cfn1;
   float epssm, smdiv, emdiv, dampcoef, zdamp, w_crit_cfl, p_top;
   float sgn_ts;                    // sign(1,time_step)
-  // 1-D coefficients, shifted so that c1h[k] takes the Fortran k
-  const float *znu, *znw, *fnm, *fnp, *rdnw, *rdn, *dnw, *dn;
-  const float *c1h, *c2h, *c1f, *c2f, *c3h, *c4h, *c3f, *c4f;
+  // base-state sounding (Rayleigh damping, perturbation Coriolis only): origin-shifted global pointers
   const float *u_base, *v_base, *t_base, *z_base;
   // 2-D fields, origin shifted: A2(f,i,j)
   const float *msftx, *msfty, *msfux, *msfuy, *msfvx, *msfvx_inv, *msfvy, *f, *e, *sina, *cosa, *ht;
 };
+struct Coef {
+  // 1-D coefficients the kernels index with the (warp-uniform) Fortran k.  They travel BY VALUE in
+  // the kernel parameter block, i.e. in the constant bank: g.c1h[k] is one LDC with a uniform
+  // address.  As global loads they shared scoreboards with the k-loops' prefetch loads, so the
+  // first use of c1h[k] waited for the whole prefetch batch (ncu r1c: 32 % of k_advance_uv's
+  // stall samples on `FMUL c1h*muu`), which serialised what the prefetch was meant to overlap.
+  float fnm[WG_NK], fnp[WG_NK], rdnw[WG_NK], rdn[WG_NK], dnw[WG_NK];
+  float c1h[WG_NK], c2h[WG_NK], c1f[WG_NK], c2f[WG_NK], c3h[WG_NK], c4h[WG_NK], c3f[WG_NK], c4f[WG_NK];
+};
+#define WG_NCOEF 13
+struct Geo : GeoBase, Coef {};
 
 // 32-bit element indices: one IMAD per term and one widening add per access instead of 64-bit
 // multiplies (ncu: the stencil kernels were issue-bound on integer address arithmetic)
@@ -73,6 +88,29 @@ __device__ __forceinline__ float sign1(float a) { return copysignf(1.0f, a); }
 __device__ __forceinline__ float after_load(float v, float loaded) {
   return __int_as_float(__float_as_int(v) | __float_as_int(fminf(fabsf(loaded), 0.f)));
 }
+
+// k_advance_w reads ~20 coefficients per level; with the warps of an SM at different levels the
+// constant cache thrashes (measured: 7.6 -> 9.3 ms per launch when the coefficients moved from L1
+// to the constant bank).  It stages the levels 0..kde+1 of the 13 arrays in shared memory once per
+// block (uniform-address LDS = broadcast, short scoreboard).  Must be called by every thread of the
+// block before any early return.
+#ifdef __CUDACC__
+__device__ __forceinline__ void coef_to_smem(const Geo &g, Coef &sc) {
+  const int nk = g.kde + 2, nt = blockDim.x * blockDim.y * blockDim.z;
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  const float *src = static_cast<const Coef &>(g).fnm;
+  float *dst = sc.fnm;
+  for (int n = tid; n < WG_NCOEF * nk; n += nt) {
+    const int a = n / nk, k = n - a * nk;
+    dst[a * WG_NK + k] = src[a * WG_NK + k];
+  }
+  __syncthreads();
+}
+#endif
+// per kernel, whichever measured faster (profiles/README.md, r1e): shared memory for k_advance_w
+// (many coefficients per level), the constant bank for k_advance_uv / k_advance_mu_t (few)
+#define COEF_SMEM __shared__ Coef sc_; coef_to_smem(g, sc_); const Coef &cf = sc_
+#define COEF_CONST const Coef &cf = g
 
 #define CUDA_CHECK(x)                                                                     \
   do {                                                                                    \
@@ -118,6 +156,12 @@ struct Solver {
   struct Pending { const char *name; cudaEvent_t a, b; };
   std::vector<Pending> pending;
   bool own_stream = true;
+  // thread-block shapes: blk3 = (i, k, j) of the point kernels, blk2 = (i, j) of the column kernels;
+  // WRFGPU_BLK3 / WRFGPU_BLK2 ("32x1x4", "32x4") override for tuning (measured r1d: blocks spanning
+  // several j rows are 2-6 % slower than 128 x 1).  blk2 must hold 128 threads (__launch_bounds__).
+  dim3 blk3{128, 1, 1}, blk2{128, 1, 1};
+  bool coef_dirty = true;   // a 1-D field was uploaded since the Geo's coefficient copies were made
+  void sync_coef();         // device 1-D fields -> g.fnm ... g.c4f (kernel-parameter copies)
   inline void kpre(const char *name) {
     if (!timing) return;
     Pending p; p.name = name;
@@ -169,9 +213,8 @@ struct Solver {
 };
 
 // launch helpers -------------------------------------------------------------
-struct Box { int i0, i1, k0, k1, j0, j1; };
-inline dim3 grid3(const Box &b, int bx) {
-  return dim3((unsigned)((b.i1 - b.i0 + bx) / bx), (unsigned)(b.k1 - b.k0 + 1), (unsigned)(b.j1 - b.j0 + 1));
+inline dim3 grid3(const Box &b, const dim3 &t) {   // thread block t = (i, k, j)
+  return dim3((unsigned)((b.i1 - b.i0 + t.x) / t.x), (unsigned)((b.k1 - b.k0 + t.y) / t.y), (unsigned)((b.j1 - b.j0 + t.z) / t.z));
 }
 inline bool empty(const Box &b) { return b.i1 < b.i0 || b.k1 < b.k0 || b.j1 < b.j0; }
 
@@ -181,8 +224,9 @@ inline bool empty(const Box &b) { return b.i1 < b.i0 || b.k1 < b.k0 || b.j1 < b.
   do {                                                                               \
     Box b_ = (box);                                                                  \
     if (!empty(b_)) {                                                                \
+      if ((S)->coef_dirty) (S)->sync_coef();                                         \
       (S)->kpre(#kern);                                                              \
-      kern<<<grid3(b_, WG_BX), WG_BX, 0, (S)->stream>>>((S)->g, b_, __VA_ARGS__);    \
+      kern<<<grid3(b_, (S)->blk3), (S)->blk3, 0, (S)->stream>>>((S)->g, b_, __VA_ARGS__); \
       (S)->kpost();                                                                  \
       (S)->launches++;                                                               \
     }                                                                                \
@@ -192,9 +236,11 @@ inline bool empty(const Box &b) { return b.i1 < b.i0 || b.k1 < b.k0 || b.j1 < b.
   do {                                                                               \
     Box b_ = (box);                                                                  \
     if (!empty(b_)) {                                                                \
-      dim3 gr_((unsigned)((b_.i1 - b_.i0 + WG_BX) / WG_BX), (unsigned)(b_.j1 - b_.j0 + 1)); \
+      const dim3 &t_ = (S)->blk2;                                                    \
+      dim3 gr_((unsigned)((b_.i1 - b_.i0 + t_.x) / t_.x), (unsigned)((b_.j1 - b_.j0 + t_.y) / t_.y)); \
+      if ((S)->coef_dirty) (S)->sync_coef();                                         \
       (S)->kpre(#kern);                                                              \
-      kern<<<gr_, WG_BX, 0, (S)->stream>>>((S)->g, b_, __VA_ARGS__);                 \
+      kern<<<gr_, t_, 0, (S)->stream>>>((S)->g, b_, __VA_ARGS__);                    \
       (S)->kpost();                                                                  \
       (S)->launches++;                                                               \
     }                                                                                \
@@ -202,13 +248,13 @@ inline bool empty(const Box &b) { return b.i1 < b.i0 || b.k1 < b.k0 || b.j1 < b.
 
 #define TID3                                              \
   const int i = b.i0 + blockIdx.x * blockDim.x + threadIdx.x; \
-  const int k = b.k0 + blockIdx.y;                        \
-  const int j = b.j0 + blockIdx.z;                        \
-  if (i > b.i1) return;
+  const int k = b.k0 + blockIdx.y * blockDim.y + threadIdx.y; \
+  const int j = b.j0 + blockIdx.z * blockDim.z + threadIdx.z; \
+  if (i > b.i1 || k > b.k1 || j > b.j1) return;
 #define TID2                                              \
   const int i = b.i0 + blockIdx.x * blockDim.x + threadIdx.x; \
-  const int j = b.j0 + blockIdx.y;                        \
-  if (i > b.i1) return;
+  const int j = b.j0 + blockIdx.y * blockDim.y + threadIdx.y; \
+  if (i > b.i1 || j > b.j1) return;
 
 void halo_destroy(Solver *s);   // halo.cu
 // advect_fast.cu

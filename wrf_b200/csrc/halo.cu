@@ -150,7 +150,7 @@ struct HaloArgs {
 };
 
 template <bool UNPACK>
-__global__ void k_halo_copy(const Geo g, HaloArgs a) {
+__global__ void k_halo_copy(const GeoBase g, HaloArgs a) {
   const int f = blockIdx.z % a.n, sd = blockIdx.z / a.n;
   if (!a.active[sd]) return;
   const int ni = a.ie[sd] - a.is[sd] + 1, nj = a.je[sd] - a.js[sd] + 1;
@@ -178,7 +178,7 @@ __global__ void k_halo_copy(const Geo g, HaloArgs a) {
 // rows/columns get the same periodic copy set_physical_bc applies (dat(ds-n) = dat(de-n), n = 1..4;
 // dat(de+n) = dat(ds+n), n = 0..4), so that N ranks reproduce one rank bit for bit.
 // along_x: close x on rows [a0,a1]; else close y on columns [a0,a1]
-__global__ void k_halo_close(const Geo g, HaloArgs a, int along_x, int a0, int a1) {
+__global__ void k_halo_close(const GeoBase g, HaloArgs a, int along_x, int a0, int a1) {
   const int f = blockIdx.z;
   const bool is3d = a.is3d[f];
   const int nk = is3d ? a.nk : 1;

@@ -2,6 +2,7 @@
 // Sequencing follows dyn_em/solve_em.F:578-4848 (dry path, no nest/specified/polar).
 #include "common.cuh"
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 namespace wg {
@@ -52,6 +53,7 @@ Solver::Solver(const wrfgpu_dims &d_, const wrfgpu_config &c_, int dev) : d(d_),
   check_config(c);
   if (d.kms != 1 || d.kds != 1) throw std::runtime_error("wrfgpu: kds/kms must be 1");
   if (d.kde - d.kds < 4) throw std::runtime_error("wrfgpu: need at least 4 vertical levels");
+  if (d.kme > WG_NK - 2) throw std::runtime_error("wrfgpu: more than " + std::to_string(WG_NK - 2) + " vertical levels are not supported");
   if (d.ips - d.ims < 4 || d.ime - d.ipe < 4 || d.jps - d.jms < 4 || d.jme - d.jpe < 4)
     throw std::runtime_error("wrfgpu: memory halo must be at least 4 points");
   int ndev = 0;
@@ -90,6 +92,16 @@ Solver::Solver(const wrfgpu_dims &d_, const wrfgpu_config &c_, int dev) : d(d_),
     num_sound_steps = c.time_step_sound;
   }
   dts = c.dt / (float)num_sound_steps;
+  if (const char *e = getenv("WRFGPU_BLK3")) {
+    unsigned x = 0, y = 0, z = 0;
+    if (sscanf(e, "%ux%ux%u", &x, &y, &z) != 3 || x * y * z == 0 || x * y * z > 1024 || (x % 32) != 0) throw std::runtime_error("wrfgpu: bad WRFGPU_BLK3");
+    blk3 = dim3(x, y, z);
+  }
+  if (const char *e = getenv("WRFGPU_BLK2")) {
+    unsigned x = 0, y = 0;
+    if (sscanf(e, "%ux%u", &x, &y) != 2 || x * y != 128 || (x % 32) != 0) throw std::runtime_error("wrfgpu: bad WRFGPU_BLK2 (must hold 128 threads)");
+    blk2 = dim3(x, y, 1);
+  }
   rank = c.mytask;
   nranks = std::max(1, c.ntasks_x * c.ntasks_y);
   build_geo();
@@ -159,13 +171,26 @@ void Solver::build_geo() {
   q.epssm = c.epssm; q.smdiv = c.smdiv; q.emdiv = c.emdiv; q.dampcoef = c.dampcoef; q.zdamp = c.zdamp;
   q.w_crit_cfl = c.w_crit_cfl; q.p_top = c.p_top;
   q.sgn_ts = c.time_step >= 0 ? 1.f : -1.f;
-  q.znu = o("znu"); q.znw = o("znw"); q.fnm = o("fnm"); q.fnp = o("fnp"); q.rdnw = o("rdnw"); q.rdn = o("rdn");
-  q.dnw = o("dnw"); q.dn = o("dn"); q.c1h = o("c1h"); q.c2h = o("c2h"); q.c1f = o("c1f"); q.c2f = o("c2f");
-  q.c3h = o("c3h"); q.c4h = o("c4h"); q.c3f = o("c3f"); q.c4f = o("c4f");
+  coef_dirty = true;   // fnm ... c4f are copied from the device fields before the next launch (sync_coef)
   q.u_base = o("u_base"); q.v_base = o("v_base"); q.t_base = o("t_base"); q.z_base = o("z_base");
   q.msftx = o("msftx"); q.msfty = o("msfty"); q.msfux = o("msfux"); q.msfuy = o("msfuy"); q.msfvx = o("msfvx");
   q.msfvx_inv = o("msfvx_inv"); q.msfvy = o("msfvy"); q.f = o("f"); q.e = o("e"); q.sina = o("sina");
   q.cosa = o("cosa"); q.ht = o("ht");
+}
+
+// The 1-D coefficient arrays live in Geo by value (kernel parameter block); refresh them from the
+// device fields the caller uploaded.  Runs once after the uploads, never inside the time loop.
+void Solver::sync_coef() {
+  struct { const char *n; float *dst; } tab[] = {
+      {"fnm", g.fnm}, {"fnp", g.fnp}, {"rdnw", g.rdnw}, {"rdn", g.rdn}, {"dnw", g.dnw}, {"c1h", g.c1h}, {"c2h", g.c2h},
+      {"c1f", g.c1f}, {"c2f", g.c2f}, {"c3h", g.c3h}, {"c4h", g.c4h}, {"c3f", g.c3f}, {"c4f", g.c4f}};
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  for (auto &t : tab) {
+    Field &f = F(t.n);
+    for (int k = 0; k < WG_NK; k++) t.dst[k] = 0.f;
+    CUDA_CHECK(cudaMemcpy(t.dst + d.kms, f.d, f.n * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  coef_dirty = false;
 }
 
 // solve_em.F:585-615
@@ -277,6 +302,7 @@ static void xfer(Solver &S, const char *name, const float *in, float *out, size_
   cudaGetLastError();
   cudaMemcpyKind kind = in ? (dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
                            : (dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost);
+  if (in && f.kind == 1) S.coef_dirty = true;
   if (in) CUDA_CHECK(cudaMemcpyAsync(f.d, in, n * sizeof(float), kind, S.stream));
   else CUDA_CHECK(cudaMemcpyAsync(out, f.d, n * sizeof(float), kind, S.stream));
   if (!async) CUDA_CHECK(cudaStreamSynchronize(S.stream));

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Builds an alternative libwrfgpu for tuning experiments (selected at run time with WRFGPU_LIB):
+#   bash variant.sh <name> [-DMACRO=VALUE ...]   ->  ../variants/libwrfgpu_<name>.so
+set -e
+cd "$(dirname "$0")"
+name=$1; shift
+out=../variants; mkdir -p $out /tmp/wgv_$name
+for f in solver bc prep tend advect_fast acoustic scalar moist halo decomp; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC "$@" -c $f.cu -o /tmp/wgv_$name/$f.o &
+done
+wait
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libwrfgpu_$name.so /tmp/wgv_$name/*.o -lcudart
+echo built $out/libwrfgpu_$name.so
