@@ -263,6 +263,9 @@ int edge_strips(const Box &tile, const Box &in, Box out[4]);
 void launch_advect_scalar_fast(Solver *s, bool theta, const Box &in, cfp q, cfp ru, cfp rv, cfp rom, cfp mut, cfp t_tendf,
                                cfp h_diabatic, fp tend);
 
+// mom_fast.cu: which = 0 ru_tend, 1 rv_tend, 2 rw_tend on the interior box
+void launch_mom_fast(Solver *s, int which, const Box &in);
+
 }  // namespace wg
 
 // the opaque handle of include/wrfgpu.h

@@ -958,14 +958,24 @@ void Solver::rk_tendency(int rk_step) {
   s.mut = o("mut"); s.muu = o("muu"); s.muv = o("muv"); s.mu = o("mu_2"); s.mub = o("mub");
   s.ru_tendf = o("ru_tendf"); s.rv_tendf = o("rv_tendf"); s.rw_tendf = o("rw_tendf"); s.ph_tendf = o("ph_tendf");
   s.t_tendf = o("t_tendf");
-  LAUNCH3(this, k_tend_u, tile, s, o("ru_tend"));
-  LAUNCH3(this, k_tend_v, tile, s, o("rv_tend"));
-  LAUNCH3(this, k_tend_w, tile, s, o("rw_tend"));
+  const Box in = interior_box(q);
+  Box strips[4];
+  const int ns = edge_strips(tile, in, strips);
+  if (!c.pert_coriolis && !empty(in)) {
+    // momentum: k-marching kernels on the interior (mom_fast.cu), the gather kernels on the edge strips
+    for (int which = 0; which < 3; which++) launch_mom_fast(this, which, in);
+    for (int m = 0; m < ns; m++) {
+      LAUNCH3(this, k_tend_u, strips[m], s, o("ru_tend"));
+      LAUNCH3(this, k_tend_v, strips[m], s, o("rv_tend"));
+      LAUNCH3(this, k_tend_w, strips[m], s, o("rw_tend"));
+    }
+  } else {
+    LAUNCH3(this, k_tend_u, tile, s, o("ru_tend"));
+    LAUNCH3(this, k_tend_v, tile, s, o("rv_tend"));
+    LAUNCH3(this, k_tend_w, tile, s, o("rw_tend"));
+  }
   {   // theta: k-marching flux-sharing kernel on the interior, the gather kernel on the edge strips
-    const Box in = interior_box(q);
     launch_advect_scalar_fast(this, true, in, s.t, s.ru, s.rv, s.ww, s.mut, s.t_tendf, s.h_diabatic, o("t_tend"));
-    Box strips[4];
-    const int ns = edge_strips(tile, in, strips);
     for (int m = 0; m < ns; m++) LAUNCH3(this, k_tend_t, strips[m], s, o("t_tend"));
   }
   LAUNCH3(this, k_tend_ph, tile, s, o("ph_tend"));
