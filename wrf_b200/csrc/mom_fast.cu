@@ -28,6 +28,11 @@ struct MomIn {
   cfp ru_tendf, rv_tendf, rw_tendf;
 };
 
+#ifndef MOM_UNROLL
+#define MOM_UNROLL 1
+#endif
+#define MOM_PRAGMA_(x) _Pragma(#x)
+#define MOM_PRAGMA(x) MOM_PRAGMA_(x)
 #define MOM_THREAD_SETUP                                                     \
   const int lane = threadIdx.x;                                              \
   const int i_raw = b.i0 + blockIdx.x * 31 + lane;                           \
@@ -63,6 +68,7 @@ __global__ void __launch_bounds__(128, 4) k_mom_u_fast(const Geo g, Box b, MomIn
   float rw_c = A3(s.rw, i, 1, j), rw_w = A3(s.rw, i - 1, 1, j);
   // dpn(1): cf1..3 extrapolation to the surface (:2247-2252)
   float d0 = .5f * (g.cf1 * ps_k + g.cf2 * (A3(s.p, i - 1, 2, j) + A3(s.p, i, 2, j)) + g.cf3 * (A3(s.p, i - 1, 3, j) + A3(s.p, i, 3, j)));
+  MOM_PRAGMA(unroll MOM_UNROLL)
   for (int k = 1; k <= ktf; k++) {
     const float c1h = g.c1h[k], c2h = g.c2h[k];
     // ---- this level's operands
@@ -166,6 +172,7 @@ __global__ void __launch_bounds__(128, 4) k_mom_v_fast(const Geo g, Box b, MomIn
   float ps_km1 = 0.f, ps_k = p_s + p_c;
   float rw_c = A3(s.rw, i, 1, j), rw_s = A3(s.rw, i, 1, j - 1);
   float d0 = .5f * (g.cf1 * ps_k + g.cf2 * (A3(s.p, i, 2, j - 1) + A3(s.p, i, 2, j)) + g.cf3 * (A3(s.p, i, 3, j - 1) + A3(s.p, i, 3, j)));
+  MOM_PRAGMA(unroll MOM_UNROLL)
   for (int k = 1; k <= ktf; k++) {
     const float c1h = g.c1h[k], c2h = g.c2h[k];
     const float vy0 = A3(v, i, k, j - 3), vy1 = A3(v, i, k, j - 2), vy2 = A3(v, i, k, j - 1);
@@ -266,6 +273,7 @@ __global__ void __launch_bounds__(128, 4) k_mom_w_fast(const Geo g, Box b, MomIn
   float p_m = A3(s.p, i, 1, j), cqw_m = 0.f;
   // vertical face 2 (:5996-6031): 2nd order
   float vf = 0.25f * (rom_k + rom_m) * (w1 + w0);
+  MOM_PRAGMA(unroll MOM_UNROLL)
   for (int k = 2; k <= kde; k++) {
     const bool top = (k == kde);
     float w3 = 0.f;
