@@ -359,6 +359,84 @@ __global__ void __launch_bounds__(128, 4) k_mom_w_fast(const Geo g, Box b, MomIn
   (void)rom_m;
 }
 
+
+// ===========================================================================
+// ph_tend at (i, 1..kde, j): rhs_ph (module_big_step_utilities_em.F:1365-2181, 6th-order branch) +
+// rk_addtend_dry, the sums of tend_ph_pt<true> (tend.cu) with the vertical operands rolling in registers
+struct PhIn { cfp ph, phb, u, v, w, ww, mut, muu, muv, ph_tendf; };
+__global__ void __launch_bounds__(128, 6) k_ph_fast(const Geo g, Box b, PhIn s, fp ph_tend) {
+  TID2;
+  const int kde = g.kde;
+  cfp ph = s.ph, phb = s.phb;
+  const float msfty = A2(g.msfty, i, j), mut = A2(s.mut, i, j);
+  const float muv_n = A2(s.muv, i, j + 1), muv_c = A2(s.muv, i, j), muu_e = A2(s.muu, i + 1, j), muu_c = A2(s.muu, i, j);
+  const float ya = A2(g.msfvy, i, j + 1), yb = A2(g.msfvy, i, j), xa = A2(g.msfux, i + 1, j), xb = A2(g.msfux, i, j);
+  A3(ph_tend, i, 1, j) = 0.f + A3(s.ph_tendf, i, 1, j) / msfty;
+  float ph_k = A3(ph, i, 2, j), phb_k = A3(phb, i, 2, j), ww_k = A3(s.ww, i, 2, j);
+  float wd_k;   // wdwn(k) (:1459-1475)
+  {
+    const float ph_1 = A3(ph, i, 1, j), phb_1 = A3(phb, i, 1, j), ww_1 = A3(s.ww, i, 1, j);
+    if (g.phi_adv_z == 2) wd_k = g.rdnw[1] * (ph_k - ph_1 + phb_k - phb_1);
+    else wd_k = .5f * (ww_k + ww_1) * g.rdnw[1] * (ph_k - ph_1 + phb_k - phb_1);
+  }
+  float u_c_m = A3(s.u, i, 1, j), u_e_m = A3(s.u, i + 1, 1, j), v_c_m = A3(s.v, i, 1, j), v_n_m = A3(s.v, i, 1, j + 1);
+  float u_c_mm = 0.f, u_e_mm = 0.f, v_c_mm = 0.f, v_n_mm = 0.f;
+  for (int k = 2; k <= kde; k++) {
+    const bool top = (k == kde);
+    const float c1f = g.c1f[k], c2f = g.c2f[k];
+    const float py1 = A3(ph, i, k, j + 1), pym1 = A3(ph, i, k, j - 1), py2 = A3(ph, i, k, j + 2), pym2 = A3(ph, i, k, j - 2);
+    const float py3 = A3(ph, i, k, j + 3), pym3 = A3(ph, i, k, j - 3);
+    const float by1 = A3(phb, i, k, j + 1), bym1 = A3(phb, i, k, j - 1), by2 = A3(phb, i, k, j + 2), bym2 = A3(phb, i, k, j - 2);
+    const float by3 = A3(phb, i, k, j + 3), bym3 = A3(phb, i, k, j - 3);
+    const float px1 = A3(ph, i + 1, k, j), pxm1 = A3(ph, i - 1, k, j), px2 = A3(ph, i + 2, k, j), pxm2 = A3(ph, i - 2, k, j);
+    const float px3 = A3(ph, i + 3, k, j), pxm3 = A3(ph, i - 3, k, j);
+    const float bx1 = A3(phb, i + 1, k, j), bxm1 = A3(phb, i - 1, k, j), bx2 = A3(phb, i + 2, k, j), bxm2 = A3(phb, i - 2, k, j);
+    const float bx3 = A3(phb, i + 3, k, j), bxm3 = A3(phb, i - 3, k, j);
+    const float wk = A3(s.w, i, k, j), tendf = A3(s.ph_tendf, i, k, j);
+    float ph1 = 0.f, phb1 = 0.f, ww1 = 0.f, u_c = 0.f, u_e = 0.f, v_c = 0.f, v_n = 0.f;
+    if (!top) {
+      ph1 = A3(ph, i, k + 1, j); phb1 = A3(phb, i, k + 1, j); ww1 = A3(s.ww, i, k + 1, j);
+      u_c = A3(s.u, i, k, j); u_e = A3(s.u, i + 1, k, j); v_c = A3(s.v, i, k, j); v_n = A3(s.v, i, k, j + 1);
+    }
+    float t = 0.f;
+    float wd_k1 = 0.f;
+    if (!top) {   // -omega dphi/deta (:1459-1494)
+      if (g.phi_adv_z == 2) {
+        wd_k1 = g.rdnw[k] * (ph1 - ph_k + phb1 - phb_k);
+        t = t - ww_k * (g.fnm[k] * wd_k1 + g.fnp[k] * wd_k);
+      } else {
+        wd_k1 = .5f * (ww1 + ww_k) * g.rdnw[k] * (ph1 - ph_k + phb1 - phb_k);
+        t = t - (g.fnm[k] * wd_k1 + g.fnp[k] * wd_k);
+      }
+    }
+    // "gw" term (:1496-1508)
+    t = t + (c1f * mut + c2f) * WG_G * wk / msfty;
+    const float fac = top ? 0.5f : 0.25f;
+    {   // y advection, 6th-order centred difference of ph+phb (:1783-1815)
+      const float va = top ? (g.cfn * v_n_m + g.cfn1 * v_n_mm) : (v_n + v_n_m);
+      const float vb = top ? (g.cfn * v_c_m + g.cfn1 * v_c_mm) : (v_c + v_c_m);
+      const float ma = (c1f * muv_n + c2f), mb = (c1f * muv_c + c2f);
+      t = t - (fac * g.rdy / msfty) *
+                  ((ma * va * ya + mb * vb * yb) * (1.f / 60.f) *
+                   (45.f * (py1 - pym1) - 9.f * (py2 - pym2) + (py3 - pym3) + 45.f * (by1 - bym1) - 9.f * (by2 - bym2) + (by3 - bym3)));
+    }
+    {   // x advection (:1940-1970)
+      const float ua = top ? (g.cfn * u_e_m + g.cfn1 * u_e_mm) : (u_e + u_e_m);
+      const float ub = top ? (g.cfn * u_c_m + g.cfn1 * u_c_mm) : (u_c + u_c_m);
+      const float ma = (c1f * muu_e + c2f), mb = (c1f * muu_c + c2f);
+      t = t - (fac * g.rdx / msfty) *
+                  ((ma * ua * xa + mb * ub * xb) * (1.f / 60.f) *
+                   (45.f * (px1 - pxm1) - 9.f * (px2 - pxm2) + (px3 - pxm3) + 45.f * (bx1 - bxm1) - 9.f * (bx2 - bxm2) + (bx3 - bxm3)));
+    }
+    t = t + tendf / msfty;
+    A3(ph_tend, i, k, j) = t;
+    wd_k = wd_k1;
+    ph_k = ph1; phb_k = phb1; ww_k = ww1;
+    u_c_mm = u_c_m; u_e_mm = u_e_m; v_c_mm = v_c_m; v_n_mm = v_n_m;
+    u_c_m = u_c; u_e_m = u_e; v_c_m = v_c; v_n_m = v_n;
+  }
+}
+
 // ---------------------------------------------------------------------------
 static MomIn mom_in(Solver *s) {
   MomIn m;
@@ -371,9 +449,16 @@ static MomIn mom_in(Solver *s) {
   return m;
 }
 
-// which: 0 = ru_tend, 1 = rv_tend, 2 = rw_tend, on the interior box `in`
+// which: 0 = ru_tend, 1 = rv_tend, 2 = rw_tend, 3 = ph_tend, on the interior box `in`
 void launch_mom_fast(Solver *s, int which, const Box &in) {
   if (empty(in)) return;
+  if (which == 3) {
+    PhIn p;
+    p.ph = s->o("ph_2"); p.phb = s->o("phb"); p.u = s->o("u_2"); p.v = s->o("v_2"); p.w = s->o("w_2"); p.ww = s->o("ww");
+    p.mut = s->o("mut"); p.muu = s->o("muu"); p.muv = s->o("muv"); p.ph_tendf = s->o("ph_tendf");
+    LAUNCH2(s, k_ph_fast, in, p, s->o("ph_tend"));
+    return;
+  }
   const int ni = in.i1 - in.i0 + 1, nj = in.j1 - in.j0 + 1;
   dim3 block(32, 4), grid((unsigned)((ni + 30) / 31), (unsigned)((nj + 3) / 4));
   if (s->coef_dirty) s->sync_coef();

@@ -978,7 +978,12 @@ void Solver::rk_tendency(int rk_step) {
     launch_advect_scalar_fast(this, true, in, s.t, s.ru, s.rv, s.ww, s.mut, s.t_tendf, s.h_diabatic, o("t_tend"));
     for (int m = 0; m < ns; m++) LAUNCH3(this, k_tend_t, strips[m], s, o("t_tend"));
   }
-  LAUNCH3(this, k_tend_ph, tile, s, o("ph_tend"));
+  if (!empty(in)) {   // ph: k-marching kernel on the interior (mom_fast.cu), the gather kernel on the edge strips
+    launch_mom_fast(this, 3, in);
+    for (int m = 0; m < ns; m++) LAUNCH3(this, k_tend_ph, strips[m], s, o("ph_tend"));
+  } else {
+    LAUNCH3(this, k_tend_ph, tile, s, o("ph_tend"));
+  }
   LAUNCH3(this, k_invert_cqw, (Box{q.its, std::min(q.ite, q.ide - 1), 2, q.kde - 1, q.jts, std::min(q.jte, q.jde - 1)}), o("cqw"));
 }
 
