@@ -47,7 +47,9 @@ struct SspArgs {
 };
 
 // small_step_prep, 3-D part (:128-170, :218-290)
-__global__ void k_ssp_3d(const Geo g, Box b, int rk_step, SspArgs a) {
+// zero_rest: also write the zeros rk_tendency leaves in the parts of u_save ... t_save this kernel does not
+// define (module_em.F:370-428 zeroes the whole arrays first); wrfgpu_step then skips that zeroing pass
+__global__ void k_ssp_3d(const Geo g, Box b, int rk_step, int zero_rest, SspArgs a) {
   TID3;
   const int kde = g.kde;
   const bool im = i <= min(g.ite, g.ide - 1), jm = j <= min(g.jte, g.jde - 1), km = k <= kde - 1;
@@ -58,14 +60,14 @@ __global__ void k_ssp_3d(const Geo g, Box b, int rk_step, SspArgs a) {
     if (rk_step == 1) { u1 = u2; A3(a.u_1, i, k, j) = u2; } else u1 = A3(a.u_1, i, k, j);
     A3(a.u_save, i, k, j) = u2;
     A3(a.u_2, i, k, j) = ((c1h * A2(a.muus, i, j) + c2h) * u1 - (c1h * A2(a.muu, i, j) + c2h) * u2) / A2(g.msfuy, i, j);
-  }
+  } else if (zero_rest) A3(a.u_save, i, k, j) = 0.f;
   if (km && im) {   // v points
     const float v2 = A3(a.v_2, i, k, j);
     float v1;
     if (rk_step == 1) { v1 = v2; A3(a.v_1, i, k, j) = v2; } else v1 = A3(a.v_1, i, k, j);
     A3(a.v_save, i, k, j) = v2;
     A3(a.v_2, i, k, j) = ((c1h * A2(a.muvs, i, j) + c2h) * v1 - (c1h * A2(a.muv, i, j) + c2h) * v2) * A2(g.msfvx_inv, i, j);
-  }
+  } else if (zero_rest) A3(a.v_save, i, k, j) = 0.f;
   if (im && jm) {
     const float muts = A2(a.muts, i, j), mut = A2(a.mut, i, j);
     if (km) {
@@ -75,7 +77,7 @@ __global__ void k_ssp_3d(const Geo g, Box b, int rk_step, SspArgs a) {
       A3(a.c2a, i, k, j) = WG_CPOVCV * (A3(a.pb, i, k, j) + A3(a.p, i, k, j)) / A3(a.alt, i, k, j);
       A3(a.t_save, i, k, j) = t2;
       A3(a.t_2, i, k, j) = (c1h * muts + c2h) * t1 - (c1h * mut + c2h) * t2;
-    }
+    } else if (zero_rest) A3(a.t_save, i, k, j) = 0.f;
     const float c1f = g.c1f[k], c2f = g.c2f[k];
     const float w2 = A3(a.w_2, i, k, j), p2 = A3(a.ph_2, i, k, j);
     float w1, p1;
@@ -86,6 +88,8 @@ __global__ void k_ssp_3d(const Geo g, Box b, int rk_step, SspArgs a) {
     A3(a.ph_save, i, k, j) = p2;
     A3(a.ph_2, i, k, j) = p1 - p2;
     A3(a.ww_save, i, k, j) = A3(a.ww, i, k, j);
+  } else if (zero_rest) {
+    A3(a.w_save, i, k, j) = 0.f; A3(a.ph_save, i, k, j) = 0.f; A3(a.t_save, i, k, j) = 0.f;
   }
 }
 
@@ -726,7 +730,7 @@ __global__ void k_ssf(const Geo g, Box b, int last, float dts, int nsmall, SsfAr
 }
 
 // ---------------------------------------------------------------------------
-void Solver::small_step_prep(int rk_step) {
+void Solver::small_step_prep(int rk_step, bool zero_rest) {
   const Geo &q = g;
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
@@ -739,7 +743,7 @@ void Solver::small_step_prep(int rk_step) {
   a.u_save = o("u_save"); a.v_save = o("v_save"); a.w_save = o("w_save"); a.t_save = o("t_save"); a.ph_save = o("ph_save");
   a.ww_save = o("ww1"); a.c2a = o("c2a"); a.ww = o("ww"); a.pb = o("pb"); a.p = o("p"); a.alt = o("alt");
   a.muu = o("muu"); a.muus = o("muus"); a.muv = o("muv"); a.muvs = o("muvs"); a.mut = o("mut"); a.muts = o("muts");
-  LAUNCH3(this, k_ssp_3d, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), rk_step, a);
+  LAUNCH3(this, k_ssp_3d, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), rk_step, zero_rest ? 1 : 0, a);
   const int im = std::min(q.ite, q.ide - 1), jm = std::min(q.jte, q.jde - 1);
   LAUNCH3(this, k_calc_p_rho, (Box{q.its, im, 1, q.kde - 1, q.jts, jm}), 0, o("al"), o("p"), o("ph_2"), o("alt"), o("t_2"),
           o("t_save"), o("c2a"), o("pm1"), o("mu_2"), o("muts"));

@@ -187,8 +187,8 @@ struct Solver {
   void rk_step_prep(int rk_step);
   void rk_phys_bc_dry_1();
   void init_zero_tendency();
-  void rk_tendency(int rk_step);
-  void small_step_prep(int rk_step);
+  void rk_tendency(int rk_step, bool zero_save = true);   // zero_save = false: small_step_prep(rk_step, true) writes those zeros
+  void small_step_prep(int rk_step, bool zero_rest = false);
   void advance_uv(int rk_step);
   void advance_uv_fused(int rk_step, int iteration);
   void sumflux_w(int rk_step, int iteration);
@@ -263,6 +263,8 @@ int edge_strips(const Box &tile, const Box &in, Box out[4]);
 void launch_advect_scalar_fast(Solver *s, bool theta, const Box &in, cfp q, cfp ru, cfp rv, cfp rom, cfp mut, cfp t_tendf,
                                cfp h_diabatic, fp tend);
 
+// pd_fast.cu: pass 1 = limiter factor on bx -> out, pass 2 = limited flux divergence on bx -> out
+void launch_pd_fast(Solver *s, int pass, const Box &bx, cfp q, cfp q_old, float dt, fp out);
 // mom_fast.cu: which = 0 ru_tend, 1 rv_tend, 2 rw_tend on the interior box
 void launch_mom_fast(Solver *s, int which, const Box &in);
 

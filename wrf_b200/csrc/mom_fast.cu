@@ -28,11 +28,6 @@ struct MomIn {
   cfp ru_tendf, rv_tendf, rw_tendf;
 };
 
-#ifndef MOM_UNROLL
-#define MOM_UNROLL 1
-#endif
-#define MOM_PRAGMA_(x) _Pragma(#x)
-#define MOM_PRAGMA(x) MOM_PRAGMA_(x)
 #define MOM_THREAD_SETUP                                                     \
   const int lane = threadIdx.x;                                              \
   const int i_raw = b.i0 + blockIdx.x * 31 + lane;                           \
@@ -68,7 +63,6 @@ __global__ void __launch_bounds__(128, 4) k_mom_u_fast(const Geo g, Box b, MomIn
   float rw_c = A3(s.rw, i, 1, j), rw_w = A3(s.rw, i - 1, 1, j);
   // dpn(1): cf1..3 extrapolation to the surface (:2247-2252)
   float d0 = .5f * (g.cf1 * ps_k + g.cf2 * (A3(s.p, i - 1, 2, j) + A3(s.p, i, 2, j)) + g.cf3 * (A3(s.p, i - 1, 3, j) + A3(s.p, i, 3, j)));
-  MOM_PRAGMA(unroll MOM_UNROLL)
   for (int k = 1; k <= ktf; k++) {
     const float c1h = g.c1h[k], c2h = g.c2h[k];
     // ---- this level's operands
@@ -172,7 +166,6 @@ __global__ void __launch_bounds__(128, 4) k_mom_v_fast(const Geo g, Box b, MomIn
   float ps_km1 = 0.f, ps_k = p_s + p_c;
   float rw_c = A3(s.rw, i, 1, j), rw_s = A3(s.rw, i, 1, j - 1);
   float d0 = .5f * (g.cf1 * ps_k + g.cf2 * (A3(s.p, i, 2, j - 1) + A3(s.p, i, 2, j)) + g.cf3 * (A3(s.p, i, 3, j - 1) + A3(s.p, i, 3, j)));
-  MOM_PRAGMA(unroll MOM_UNROLL)
   for (int k = 1; k <= ktf; k++) {
     const float c1h = g.c1h[k], c2h = g.c2h[k];
     const float vy0 = A3(v, i, k, j - 3), vy1 = A3(v, i, k, j - 2), vy2 = A3(v, i, k, j - 1);
@@ -252,8 +245,9 @@ __global__ void __launch_bounds__(128, 4) k_mom_v_fast(const Geo g, Box b, MomIn
 }
 
 // ===========================================================================
-// rw_tend at (i, 1..kde, j)
-__global__ void __launch_bounds__(128, 4) k_mom_w_fast(const Geo g, Box b, MomIn s, fp rw_tend) {
+// rw_tend at (i, 1..kde, j).  Also pg_buoy_w's side effect cqw <- 1/(1+cqw) at levels 2..kde-1 (:2489):
+// the column's thread is the only reader of cqw(i,:,j) here, and it carries cqw(k-1) in a register.
+__global__ void __launch_bounds__(128, 4) k_mom_w_fast(const Geo g, Box b, MomIn s, fp rw_tend, fp cqw_inout) {
   MOM_THREAD_SETUP;
   (void)ktf;
   cfp w = s.w, ru = s.ru, rv = s.rv, rom = s.ww;
@@ -273,7 +267,6 @@ __global__ void __launch_bounds__(128, 4) k_mom_w_fast(const Geo g, Box b, MomIn
   float p_m = A3(s.p, i, 1, j), cqw_m = 0.f;
   // vertical face 2 (:5996-6031): 2nd order
   float vf = 0.25f * (rom_k + rom_m) * (w1 + w0);
-  MOM_PRAGMA(unroll MOM_UNROLL)
   for (int k = 2; k <= kde; k++) {
     const bool top = (k == kde);
     float w3 = 0.f;
@@ -329,6 +322,7 @@ __global__ void __launch_bounds__(128, 4) k_mom_w_fast(const Geo g, Box b, MomIn
     } else {
       const float cq1 = 1.f / (1.f + cqw);
       const float cq2 = cqw * cq1;
+      if (st) A3(cqw_inout, i, k, j) = cq1;
       t = t + rmsf * WG_G * (cq1 * g.rdn[k] * (p_k - p_m) - (g.c1f[k] * mu) - cq2 * (g.c1f[k] * mub + g.c2f[k]));
     }
     if (!top) {
@@ -471,7 +465,7 @@ void launch_mom_fast(Solver *s, int which, const Box &in) {
     k_mom_v_fast<<<grid, block, 0, s->stream>>>(s->g, in, m, s->o("rv_tend"));
   } else {
     s->kpre("k_mom_w_fast");
-    k_mom_w_fast<<<grid, block, 0, s->stream>>>(s->g, in, m, s->o("rw_tend"));
+    k_mom_w_fast<<<grid, block, 0, s->stream>>>(s->g, in, m, s->o("rw_tend"), s->o("cqw"));
   }
   s->kpost();
   s->launches++;

@@ -249,8 +249,18 @@ void Solver::rk_scalar_step(int rk_step) {
       if (c.open_ye && dye) lim.j1 = std::min(q.jte + 1, q.jde - 2);
       // "a" is free between calc_coef_w uses only until the next small_step_prep: use advect scratch "alpha"?  No:
       // the limiter factor gets its own scratch so that a, alpha, gamma stay comparable with the oracle.
-      LAUNCH3(this, k_pd_scale, lim, in, o("pd_scale"));
-      LAUNCH3(this, k_pd_tend, mass, in, o("pd_scale"), lim, o("advect_tend"));
+      // k-marching kernels (pd_fast.cu) where every face is 5th order, the gather kernels on the strips around
+      Box sfast = lim, tfast = interior_box(q);
+      tfast.k1 = ktf;
+      if (!c.periodic_x) { sfast.i0 = std::max(lim.i0, q.ids + 4); sfast.i1 = std::min(lim.i1, q.ide - 5); }
+      if (!c.periodic_y) { sfast.j0 = std::max(lim.j0, q.jds + 4); sfast.j1 = std::min(lim.j1, q.jde - 5); }
+      Box strips[4];
+      launch_pd_fast(this, 1, sfast, in.q, in.q_old, dt_rk, o("pd_scale"));
+      int nst = edge_strips(lim, sfast, strips);
+      for (int m = 0; m < nst; m++) LAUNCH3(this, k_pd_scale, strips[m], in, o("pd_scale"));
+      launch_pd_fast(this, 2, tfast, in.q, in.q_old, dt_rk, o("advect_tend"));
+      nst = edge_strips(mass, tfast, strips);
+      for (int m = 0; m < nst; m++) LAUNCH3(this, k_pd_tend, strips[m], in, o("pd_scale"), lim, o("advect_tend"));
     } else {
       Box in = interior_box(q);
       in.k1 = ktf;

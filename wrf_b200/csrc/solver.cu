@@ -241,8 +241,9 @@ void Solver::step() {
     halo("HALO_EM_A");
     { PHASE("bc"); rk_phys_bc_dry_1(); }
     if (rk_step == 1) { PHASE("rk_tendency"); init_zero_tendency(); }
-    { PHASE("rk_tendency"); rk_tendency(rk_step); }
-    { PHASE("small_step_prep"); small_step_prep(rk_step); }
+    // the zeroing of u_save ... t_save (module_em.F:370-428) is folded into small_step_prep's sweep: nothing reads them in between
+    { PHASE("rk_tendency"); rk_tendency(rk_step, false); }
+    { PHASE("small_step_prep"); small_step_prep(rk_step, true); }
     for (int it = 1; it <= ns; it++) {
       { PHASE("advance_uv"); advance_uv_fused(rk_step, it); }
       halo("HALO_EM_C");

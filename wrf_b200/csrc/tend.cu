@@ -936,11 +936,11 @@ void Solver::init_zero_tendency() {
   }
 }
 
-void Solver::rk_tendency(int rk_step) {
+void Solver::rk_tendency(int rk_step, bool zero_save) {
   const Geo &q = g;
   Box tile{q.its, q.ite, 1, q.kde, q.jts, q.jte};
   // the *_save arrays and mu_tend/mu_save are zeroed by rk_tendency (module_em.F:370-428)
-  LAUNCH3(this, k_zero3, tile, o("u_save"), o("v_save"), o("w_save"), o("ph_save"), o("t_save"));
+  if (zero_save) LAUNCH3(this, k_zero3, tile, o("u_save"), o("v_save"), o("w_save"), o("ph_save"), o("t_save"));
   LAUNCH2(this, k_zero2, tile, o("mu_tend"), o("mu_save"));
   if (rk_step == 1 && c.damp_opt == 2) {
     const int jm = std::min(q.jte, q.jde - 1), im = std::min(q.ite, q.ide - 1);
@@ -984,7 +984,18 @@ void Solver::rk_tendency(int rk_step) {
   } else {
     LAUNCH3(this, k_tend_ph, tile, s, o("ph_tend"));
   }
-  LAUNCH3(this, k_invert_cqw, (Box{q.its, std::min(q.ite, q.ide - 1), 2, q.kde - 1, q.jts, std::min(q.jte, q.jde - 1)}), o("cqw"));
+  {   // cqw <- 1/(1+cqw): done by k_mom_w_fast on the interior, here on what is left of the mass points
+    const Box cq{q.its, std::min(q.ite, q.ide - 1), 2, q.kde - 1, q.jts, std::min(q.jte, q.jde - 1)};
+    if (!c.pert_coriolis && !empty(in)) {
+      for (int m = 0; m < ns; m++) {
+        Box sb = strips[m];
+        sb.i1 = std::min(sb.i1, cq.i1); sb.j1 = std::min(sb.j1, cq.j1); sb.k0 = cq.k0; sb.k1 = cq.k1;
+        LAUNCH3(this, k_invert_cqw, sb, o("cqw"));
+      }
+    } else {
+      LAUNCH3(this, k_invert_cqw, cq, o("cqw"));
+    }
+  }
 }
 
 }  // namespace wg
