@@ -106,6 +106,7 @@ __global__ void k_calc_ww(const Geo g, Box b, cfp u, cfp v, cfp mup, cfp mub, fp
   const float my0 = A2(g.msfuy, i, j), my1 = A2(g.msfuy, i + 1, j);
   const float mvi0 = A2(g.msfvx_inv, i, j), mvi1 = A2(g.msfvx_inv, i, j + 1);
   float dmdt = 0.f;
+#pragma unroll 4
   for (int k = 1; k <= ktf; k++) {
     const float c1h = g.c1h[k], c2h = g.c2h[k];
     const float divv = msftx * g.dnw[k] *
@@ -116,6 +117,7 @@ __global__ void k_calc_ww(const Geo g, Box b, cfp u, cfp v, cfp mup, cfp mub, fp
   }
   float wprev = 0.f;
   A3(ww, i, 1, j) = 0.f;
+#pragma unroll 4
   for (int k = 2; k <= ktf; k++) {
     const float divv = A3(ww, i, k, j);
     wprev = wprev - g.dnw[k - 1] * g.c1h[k - 1] * dmdt - divv;
