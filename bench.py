@@ -37,6 +37,8 @@ ALGO_ACCESSES = {
     "k_advance_uv<true>": 18,          # advance_uv 14 + ru_m, rv_m read and written
     "k_advance_w<true>": 25,           # advance_w 19 + calc_p_rho (al, p, pm1 r/w) + sumflux (ww_m r/w); alt, c2a, t_2, t_1 shared
     "k_advect_scalar_fast<theta>": 7, "k_advect_scalar_fast": 5,
+    "k_mom_u_fast": 6, "k_mom_v_fast": 6, "k_mom_w_fast": 6, "k_ph_fast": 6,     # interior forms of k_tend_u/v/w/ph
+    "k_pd_scale_fast": 6, "k_pd_tend_fast": 7,
 }
 
 
