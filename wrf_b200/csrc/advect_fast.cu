@@ -25,8 +25,11 @@ __device__ __forceinline__ float adv_vface(const Geo &g, int kk, int ktf, float 
 }
 
 // THETA: also rk_addtend_dry's part for theta (module_em.F:1068-1078): + t_tendf/msfty + (c1h*mut+c2h)*h_diabatic/msfty
+#ifndef ADV_MINB
+#define ADV_MINB 6
+#endif
 template <bool THETA>
-__global__ void __launch_bounds__(128, 6) k_advect_scalar_fast(const Geo g, Box b, cfp q, cfp ru, cfp rv, cfp rom, cfp mut, cfp t_tendf,
+__global__ void __launch_bounds__(128, ADV_MINB) k_advect_scalar_fast(const Geo g, Box b, cfp q, cfp ru, cfp rv, cfp rom, cfp mut, cfp t_tendf,
                                                            cfp h_diabatic, fp tend) {
   const int lane = threadIdx.x;
   const int i_raw = b.i0 + blockIdx.x * 31 + lane;

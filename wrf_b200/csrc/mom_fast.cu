@@ -28,6 +28,17 @@ struct MomIn {
   cfp ru_tendf, rv_tendf, rw_tendf;
 };
 
+// resident blocks per SM the register allocation aims at (measured, profiles/README.md r1o/r1p: more
+// warps beat more registers until the spills start)
+#ifndef PH_MINB
+#define PH_MINB 7
+#endif
+#ifndef MOM_MINB
+#define MOM_MINB 6
+#endif
+#ifndef MOMW_MINB
+#define MOMW_MINB 7
+#endif
 #define MOM_THREAD_SETUP                                                     \
   const int lane = threadIdx.x;                                              \
   const int i_raw = b.i0 + blockIdx.x * 31 + lane;                           \
@@ -40,7 +51,7 @@ struct MomIn {
 
 // ===========================================================================
 // ru_tend at (i, 1..kde-1, j); level kde is zero (rk_tendency zeroes the whole array, module_em.F:370-428)
-__global__ void __launch_bounds__(128, 4) k_mom_u_fast(const Geo g, Box b, MomIn s, fp ru_tend) {
+__global__ void __launch_bounds__(128, MOM_MINB) k_mom_u_fast(const Geo g, Box b, MomIn s, fp ru_tend) {
   MOM_THREAD_SETUP;
   cfp u = s.u, ru = s.ru, rv = s.rv, rom = s.ww;
   // ---- column constants
@@ -146,7 +157,7 @@ __global__ void __launch_bounds__(128, 4) k_mom_u_fast(const Geo g, Box b, MomIn
 
 // ===========================================================================
 // rv_tend at (i, 1..kde-1, j)
-__global__ void __launch_bounds__(128, 4) k_mom_v_fast(const Geo g, Box b, MomIn s, fp rv_tend) {
+__global__ void __launch_bounds__(128, MOM_MINB) k_mom_v_fast(const Geo g, Box b, MomIn s, fp rv_tend) {
   MOM_THREAD_SETUP;
   cfp v = s.v, ru = s.ru, rv = s.rv, rom = s.ww;
   const float msfvy = A2(g.msfvy, i, j), msfvx = A2(g.msfvx, i, j), msfvx_inv = A2(g.msfvx_inv, i, j);
@@ -247,7 +258,7 @@ __global__ void __launch_bounds__(128, 4) k_mom_v_fast(const Geo g, Box b, MomIn
 // ===========================================================================
 // rw_tend at (i, 1..kde, j).  Also pg_buoy_w's side effect cqw <- 1/(1+cqw) at levels 2..kde-1 (:2489):
 // the column's thread is the only reader of cqw(i,:,j) here, and it carries cqw(k-1) in a register.
-__global__ void __launch_bounds__(128, 4) k_mom_w_fast(const Geo g, Box b, MomIn s, fp rw_tend, fp cqw_inout) {
+__global__ void __launch_bounds__(128, MOMW_MINB) k_mom_w_fast(const Geo g, Box b, MomIn s, fp rw_tend, fp cqw_inout) {
   MOM_THREAD_SETUP;
   (void)ktf;
   cfp w = s.w, ru = s.ru, rv = s.rv, rom = s.ww;
@@ -358,7 +369,7 @@ __global__ void __launch_bounds__(128, 4) k_mom_w_fast(const Geo g, Box b, MomIn
 // ph_tend at (i, 1..kde, j): rhs_ph (module_big_step_utilities_em.F:1365-2181, 6th-order branch) +
 // rk_addtend_dry, the sums of tend_ph_pt<true> (tend.cu) with the vertical operands rolling in registers
 struct PhIn { cfp ph, phb, u, v, w, ww, mut, muu, muv, ph_tendf; };
-__global__ void __launch_bounds__(128, 6) k_ph_fast(const Geo g, Box b, PhIn s, fp ph_tend) {
+__global__ void __launch_bounds__(128, PH_MINB) k_ph_fast(const Geo g, Box b, PhIn s, fp ph_tend) {
   TID2;
   const int kde = g.kde;
   cfp ph = s.ph, phb = s.phb;

@@ -118,6 +118,9 @@ __device__ __forceinline__ HiLo pd_z(const Geo &g, const Coef &cf, int kk, float
   return f;
 }
 
+#ifndef PD_MINB
+#define PD_MINB 6
+#endif
 #define PD_THREAD_SETUP                                                      \
   const int lane = threadIdx.x;                                              \
   const int i_raw = b.i0 + blockIdx.x * 31 + lane;                           \
@@ -130,7 +133,7 @@ __device__ __forceinline__ HiLo pd_z(const Geo &g, const Coef &cf, int kk, float
   const Coef &cf = g
 
 // pass 1: scale(i, 1..ktf, j) = limiter factor of the cell (:7681-7776)
-__global__ void __launch_bounds__(128, 4) k_pd_scale_fast(const Geo g, Box b, PdFastIn s, fp scale) {
+__global__ void __launch_bounds__(128, PD_MINB) k_pd_scale_fast(const Geo g, Box b, PdFastIn s, fp scale) {
   PD_THREAD_SETUP;
   const PdCol c = pd_col(g, s, i, j);
   const float msftx = A2(g.msftx, i, j), msfty = A2(g.msfty, i, j);
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(128, 4) k_pd_scale_fast(const Geo g, Box b, Pd
 
 // pass 2: tendency(i, 1..ktf, j) = - limited flux divergence (:7778-7883).  A face's high-order part is
 // scaled by its donor cell (:7764-7773), so the limited value of a face is the same seen from either side.
-__global__ void __launch_bounds__(128, 4) k_pd_tend_fast(const Geo g, Box b, PdFastIn s, cfp scale, fp tend) {
+__global__ void __launch_bounds__(128, PD_MINB) k_pd_tend_fast(const Geo g, Box b, PdFastIn s, cfp scale, fp tend) {
   PD_THREAD_SETUP;
   const PdCol c = pd_col(g, s, i, j);
   const float msftx = A2(g.msftx, i, j);
