@@ -286,7 +286,7 @@ def cpu_baseline(args, quick=False):
     threads = o.set_threads(args.cpu_threads or os.cpu_count() or 1)
     o.start_domain()
     o.step(1)
-    steps = 1 if quick else max(1, args.steps)
+    steps = 8 if quick else max(1, args.steps)      # ~5-10 s of CPU work on the sample
     t0 = time.perf_counter()
     o.step(steps)
     dt = (time.perf_counter() - t0) / steps

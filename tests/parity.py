@@ -16,6 +16,30 @@ TOL_REL_L2 = 0.0
 STEP_TOL_REL_L2 = 1.0e-5
 
 
+def with_map_factors(case, amp=0.04):
+    """Give a case smoothly varying map factors and a full set of Coriolis / rotation fields (f, e, sina,
+    cosa).  Every shipped ideal case has msf == 1 and e == 0, which would hide a wrong map factor or a
+    dropped curvature term in a kernel; here the seven staggered factors all differ from one another."""
+    d = case.dims
+    jj, ii = np.meshgrid(np.arange(d.jms, d.jme + 1, dtype=np.float64), np.arange(d.ims, d.ime + 1, dtype=np.float64), indexing="ij")
+    nx, ny = float(d.ide - d.ids), float(d.jde - d.jds)
+
+    def m(pi, pj, sx=0.0, sy=0.0):
+        return (1.0 + amp * np.sin(2 * np.pi * (ii + sx) / nx * pi + 0.3) * np.cos(2 * np.pi * (jj + sy) / ny * pj + 0.7)).astype(np.float32)
+
+    f = case.fields
+    f["msftx"], f["msfty"] = m(1, 1), m(1, 2)
+    f["msfux"], f["msfuy"] = m(1, 1, -0.5), m(1, 2, -0.5)
+    f["msfvx"], f["msfvy"] = m(1, 1, 0.0, -0.5), m(1, 2, 0.0, -0.5)
+    f["msfvx_inv"] = (np.float32(1.0) / f["msfvx"]).astype(np.float32)
+    lat = (0.6 + 0.1 * np.sin(2 * np.pi * jj / ny)).astype(np.float64)
+    f["f"] = (1.4584e-4 * np.sin(lat)).astype(np.float32)
+    f["e"] = (1.4584e-4 * np.cos(lat)).astype(np.float32)
+    rot = 0.2 * np.sin(2 * np.pi * ii / nx)
+    f["sina"], f["cosa"] = np.sin(rot).astype(np.float32), np.cos(rot).astype(np.float32)
+    return case
+
+
 def small_cases():
     """name -> Case; sizes the oracle finishes in about a second per step.  Together they cover
     every lateral boundary type, both advection options, Kessler, the three damping options and
@@ -38,6 +62,9 @@ def small_cases():
                                      zdamp=8000.0, dampcoef=0.2, scalar_adv_opt=0, num_scalar=1, u_scale=1.5),
         "rk2_sym_x": make_case("synthetic", nx=30, ny=28, nz=15, periodic=False, bubble_lattice=20000.0, noise=0.05,
                                calm=True, rk_ord=2, open_xs=0, open_xe=0, symmetric_xs=1, symmetric_xe=1, time_step_sound=4),
+        # non-trivial map factors, f, e, sina, cosa: doubly periodic (the interior kernels do every point) and open
+        "mapfac": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=1)),
+        "mapfac_open": with_map_factors(make_case("quarter_ss", nx=30, ny=28, nz=19, w_damping=1)),
     }
 
 

@@ -12,7 +12,8 @@ from wrf_b200 import Solver
 pytestmark = pytest.mark.gpu
 
 CASES = None
-ALL = ["hill2d_x", "quarter_ss", "quarter_ss_nopd", "b_wave", "les", "periodic", "b_wave_lid", "quarter_ss_opts", "rk2_sym_x"]
+ALL = ["hill2d_x", "quarter_ss", "quarter_ss_nopd", "b_wave", "les", "periodic", "b_wave_lid", "quarter_ss_opts", "rk2_sym_x",
+       "mapfac", "mapfac_open"]
 
 
 def cases():
