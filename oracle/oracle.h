@@ -177,6 +177,14 @@ void rk_addtend_dry(const Cx &x, A3 ru_tend, A3 rv_tend, A3 rw_tend, A3 ph_tend,
                     int rk_step, A3 h_diabatic, A2 mut);
 void ww_split(const Cx &x, A3 wwE, A3 wwI, A3 ww);
 void set_w_surface(const Cx &x, A3 w, A3 u, A3 v);
+// diffusion.cpp (diff_opt = 1, km_opt = 1: constant K on coordinate surfaces)
+void horizontal_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT, A1 c1, A1 c2, float xk);
+void horizontal_diffusion_3dmp(const Cx &x, A3 field, A3 tendency, A2 MUT, A1 c1, A1 c2, A3 base_3d, float xk);
+void vertical_diffusion(const Cx &x, char name, A3 field, A3 tendency, A1 c1, A1 c2, A3 alt, A2 MUT, float kvdif);
+void vertical_diffusion_mp(const Cx &x, A3 field, A3 tendency, A1 base, A1 c1, A1 c2, A3 alt, A2 MUT, float kvdif);
+void vertical_diffusion_3dmp(const Cx &x, A3 field, A3 tendency, A3 base_3d, A1 c1, A1 c2, A3 alt, A2 MUT, float kvdif);
+void vertical_diffusion_u(const Cx &x, A3 field, A3 tendency, A1 u_base, A1 c1h, A1 c2h, A3 alt, A2 muu, float kvdif);
+void vertical_diffusion_v(const Cx &x, A3 field, A3 tendency, A1 v_base, A1 c1h, A1 c2h, A3 alt, A2 muv, float kvdif);
 // advect.cpp
 void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut);
 void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut);

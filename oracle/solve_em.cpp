@@ -13,7 +13,7 @@ static const char *k3d[] = {
     "ru_m", "rv_m", "ww_m", "ru_tend", "rv_tend", "u_save", "v_save", "t_save", "h_diabatic",
     "ru_tendf", "rv_tendf", "rw_tend", "rw_tendf", "w_save", "ww1", "wwE", "wwI",
     "ph_tend", "ph_tendf", "ph_save", "t_tend", "t_tendf", "t_2save", "advect_tend",
-    "alpha", "a", "gamma", "c2a", "cqu", "cqv", "cqw", "pm1",
+    "alpha", "a", "gamma", "c2a", "cqu", "cqv", "cqw", "pm1", "t_init",
     "rho", "th_phy", "pi_phy", "p_phy", "z", "z_at_w", "dz8w", "qv_diabatic", "qc_diabatic", nullptr};
 static const char *k2d[] = {"mu_1", "mu_2", "mub", "mudf", "muu", "muus", "muv", "muvs", "mut", "muts",
                             "muave", "mu_save", "mu_tend", "mu_tendf",
@@ -174,6 +174,21 @@ void Oracle::rk_tendency(int rk_step) {
   if (c.pert_coriolis) par([&](const Cx &xt) { perturbation_coriolis(xt, ru, rv, rw, ru_tend, rv_tend, rw_tend, muu, muv, a3("phb"), ph); });
   else par([&](const Cx &xt) { coriolis(xt, ru, rv, rw, ru_tend, rv_tend, rw_tend); });
   par([&](const Cx &xt) { curvature(xt, ru, rv, rw, u, v, w, ru_tend, rv_tend, rw_tend); });
+  if (rk_step == 1 && c.diff_opt == 1) {   // forward_step: diff_opt1, module_em.F:802-878 (bl_pbl_physics = 0)
+    // xkmhd = grid%xkmh = khdif and xkhh = khdif/prandtl everywhere (isotropic_km, module_diffusion_em.F:1718-1772)
+    const float prandtl = 1.f / 3.0f;
+    const float xkmh = c.khdif, xkhh = c.khdif / prandtl, kvdif = c.kvdif;
+    A3 alt = a3("alt");
+    par([&](const Cx &xt) { horizontal_diffusion(xt, 'u', u, a3("ru_tendf"), mut, xt.c1h, xt.c2h, xkmh); });
+    par([&](const Cx &xt) { horizontal_diffusion(xt, 'v', v, a3("rv_tendf"), mut, xt.c1h, xt.c2h, xkmh); });
+    par([&](const Cx &xt) { horizontal_diffusion(xt, 'w', w, a3("rw_tendf"), mut, xt.c1f, xt.c2f, xkmh); });
+    par([&](const Cx &xt) { horizontal_diffusion_3dmp(xt, t, a3("t_tendf"), mut, xt.c1h, xt.c2h, a3("t_init"), xkhh); });
+    par([&](const Cx &xt) { vertical_diffusion_u(xt, u, a3("ru_tendf"), xt.u_base, xt.c1h, xt.c2h, alt, muu, kvdif); });
+    par([&](const Cx &xt) { vertical_diffusion_v(xt, v, a3("rv_tendf"), xt.v_base, xt.c1h, xt.c2h, alt, muv, kvdif); });
+    par([&](const Cx &xt) { vertical_diffusion(xt, 'w', w, a3("rw_tendf"), xt.c1f, xt.c2f, alt, mut, kvdif); });
+    const float kvdq = 3.f * kvdif;
+    par([&](const Cx &xt) { vertical_diffusion_3dmp(xt, t, a3("t_tendf"), a3("t_init"), xt.c1h, xt.c2h, alt, mut, kvdq); });
+  }
   if (rk_step == 1 && c.damp_opt == 2)
     par([&](const Cx &xt) { rk_rayleigh_damp(xt, a3("ru_tendf"), a3("rv_tendf"), a3("rw_tendf"), a3("t_tendf"), u, v, w, t, mut, muu, muv, ph, a3("phb")); });
   par([&](const Cx &xt) { rk_addtend_dry(xt, ru_tend, rv_tend, rw_tend, ph_tend, t_tend, a3("ru_tendf"), a3("rv_tendf"), a3("rw_tendf"), a3("ph_tendf"),
@@ -302,6 +317,15 @@ void Oracle::rk_scalar_step(int rk_step) {
       par([&](const Cx &xt) { advect_scalar_pd(xt, a3(s.f), a3(s.o), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE"), a2("muts"), a2("mub"), a2("mu_1"), dt_rk); });
     else
       par([&](const Cx &xt) { advect_scalar(xt, a3(s.f), a3(s.f), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE"), a2("muts")); });
+    if (rk_step == 1 && c.diff_opt == 1) {   // rk_step_1: diff_opt1, module_em.F:1378-1419 (xkmhd = grid%xkhh, solve_em.F:2230)
+      const float prandtl = 1.f / 3.0f;
+      const float xkhh = c.khdif / prandtl, kvdq = c.kvdif / prandtl;
+      par([&](const Cx &xt) { horizontal_diffusion(xt, 'm', a3(s.f), a3(s.t), a2("muts"), xt.c1h, xt.c2h, xkhh); });
+      if (s.f == "moist_qv")
+        par([&](const Cx &xt) { vertical_diffusion_mp(xt, a3(s.f), a3(s.t), xt.qv_base, xt.c1h, xt.c2h, a3("alt"), a2("muts"), kvdq); });
+      else
+        par([&](const Cx &xt) { vertical_diffusion(xt, 'm', a3(s.f), a3(s.t), xt.c1h, xt.c2h, a3("alt"), a2("muts"), kvdq); });
+    }
     par([&](const Cx &xt) { rk_update_scalar(xt, a3(s.o), a3(s.f), a3(s.t), a3("advect_tend"), a2("mu_1"), a2("mu_2"), a2("mub"), rk_step, dt_rk); });
   }
 }

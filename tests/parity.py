@@ -65,6 +65,12 @@ def small_cases():
         # non-trivial map factors, f, e, sina, cosa: doubly periodic (the interior kernels do every point) and open
         "mapfac": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=1)),
         "mapfac_open": with_map_factors(make_case("quarter_ss", nx=30, ny=28, nz=19, w_damping=1)),
+        # constant-K diffusion on coordinate surfaces (diff_opt 1 / km_opt 1): open + Kessler (qv uses
+        # the base-state form), doubly periodic with map factors and a passive scalar, and em_b_wave as shipped (K = 0)
+        "diffusion": make_case("quarter_ss", nx=26, ny=24, nz=21, diff_opt=1, km_opt=1, khdif=500.0, kvdif=100.0),
+        "diffusion_periodic": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=1,
+                                                         diff_opt=1, km_opt=1, khdif=300.0, kvdif=50.0)),
+        "b_wave_shipped": make_case("b_wave", nx=21, ny=31, nz=17, diff_opt=1, km_opt=1, khdif=0.0, kvdif=0.0),
     }
 
 

@@ -198,3 +198,32 @@ def test_hill2d_x_mountain_wave_matches_documented_solution():
     assert 0.07 <= amp <= 0.14, amp                 # U hm / a = 0.1 m/s (grows slowly with height as rho^-1/2)
     # and the 2-D case stays 2-D: no v, no y variation
     assert np.abs(o.get("v_2")).max() == 0.0
+
+
+def test_constant_k_diffusion_decays_a_sinusoid_at_the_analytic_rate():
+    """diff_opt = 1 / km_opt = 1 (module_big_step_utilities_em.F:2715-2950 for a mass-point field): a passive scalar
+    sin(2 pi x / L) in a resting, horizontally uniform atmosphere is only touched by horizontal_diffusion('m') with
+    K = xkhh = khdif / prandtl = 3 khdif (module_diffusion_em.F:1718-1772, solve_em.F:2230).  The centred operator
+    has the eigenvalue -K (2 - 2 cos(2 pi dx / L)) / dx^2, so after n forward-Euler steps the amplitude is
+    (1 - dt K (2 - 2 cos(k dx)) / dx^2)^n exactly, up to rounding."""
+    nx, L = 33, 32                                  # 32 mass points per period
+    case = make_case("b_wave", nx=nx, ny=12, nz=11, calm=True, num_scalar=1, scalar_adv_opt=1,      # periodic x, no bubble, at rest
+                     diff_opt=1, km_opt=1, khdif=1.0e6, kvdif=0.0)
+    d = case.dims
+    ii = np.arange(d.ims, d.ime + 1, dtype=np.float64)
+    prof = (1.0 + 0.5 * np.sin(2 * np.pi * (ii - 1) / L)).astype(np.float32)
+    s = case.fields["scalar_1"]
+    s[:] = prof[None, None, :]
+    s[:, -1, :] = 0
+    o = Oracle(case)
+    o.start_domain()
+    n = 20
+    o.step(n)
+    c = case.config
+    K = np.float64(c.khdif) * 3.0
+    lam = 1.0 - c.dt * K * (2.0 - 2.0 * np.cos(2 * np.pi / L)) / c.dx ** 2
+    got = o.get("scalar_1")[4 - d.jms, 3, 1 - d.ims:1 - d.ims + L].astype(np.float64)
+    amp = 2.0 * np.abs(np.fft.rfft(got - got.mean())[1]) / L
+    assert abs(amp / 0.5 - lam ** n) < 2e-4 * lam ** n, (amp / 0.5, lam ** n)
+    assert abs(got.mean() - 1.0) < 1e-5                               # diffusion conserves the mean
+    assert np.abs(o.get("w_2")).max() < 1e-3                          # and the atmosphere stayed at rest

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 CASES = None
 ALL = ["hill2d_x", "quarter_ss", "quarter_ss_nopd", "b_wave", "les", "periodic", "b_wave_lid", "quarter_ss_opts", "rk2_sym_x",
-       "mapfac", "mapfac_open"]
+       "mapfac", "mapfac_open", "diffusion", "diffusion_periodic", "b_wave_shipped"]
 
 
 def cases():
@@ -79,9 +79,23 @@ def test_solve_em_host_round_trip():
     a.close(); b.close()
 
 
+def test_shipped_hill2d_x_diffusion_settings_are_the_identity():
+    """em_hill2d_x ships diff_opt = 2, km_opt = 1, khdif = kvdif = 0: every diffusion tendency is a product with a
+    zero eddy viscosity, so the step must equal the diff_opt = 0 step bit for bit (and is accepted at create)."""
+    from wrf_b200 import make_case
+    a = Solver(make_case("hill2d_x", nx=62, ny=3, nz=21))
+    b = Solver(make_case("hill2d_x", nx=62, ny=3, nz=21, diff_opt=2, km_opt=1, khdif=0.0, kvdif=0.0))
+    for s in (a, b):
+        s.start_domain(); s.step(2)
+    for n in ["u_2", "v_2", "w_2", "t_2", "ph_2", "mu_2", "moist_qv"]:
+        assert np.array_equal(a.get(n), b.get(n)), n
+    a.close(); b.close()
+
+
 def test_unsupported_namelist_fails_loudly():
     from wrf_b200 import WrfGpuError, make_case
     case = make_case("quarter_ss", nx=26, ny=24, nz=21)
-    case.config.diff_opt = 2
+    case.config.diff_opt = 2        # TKE closure: a 'next' row
+    case.config.km_opt = 2
     with pytest.raises(WrfGpuError):
         Solver(case)

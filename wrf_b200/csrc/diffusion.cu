@@ -1,0 +1,193 @@
+// diffusion.cu -- constant-K diffusion on coordinate surfaces (diff_opt = 1, km_opt = 1):
+// horizontal_diffusion (module_big_step_utilities_em.F:2715), horizontal_diffusion_3dmp (:2954),
+// vertical_diffusion (:3064), vertical_diffusion_mp (:3192), vertical_diffusion_3dmp (:3286),
+// vertical_diffusion_u (:3382), vertical_diffusion_v (:3485), called on the first RK substep from
+// rk_tendency (module_em.F:802-878) and rk_scalar_tend (:1378-1419).
+//
+// One launch per tendency array: the thread of a point adds the horizontal term and then the vertical
+// term, in the reference's order, each inside the reference's own loop ranges.  The reference's row
+// buffer vflux(i,k) is a pure function of the column, so vflux(k) and vflux(k-1) are evaluated at the
+// point (vflux(0) = vflux(1), vflux(ktf) = 0 as in the reference).
+//
+// The eddy viscosities xkmh / xkhh the reference reads from arrays are the constants khdif and
+// khdif/prandtl on every element (isotropic_km, module_diffusion_em.F:1718-1772, then HALO_EM_TKE_E and
+// phy_bc): the kernels take the number and keep the averaging expressions as written.
+#include "common.cuh"
+
+namespace wg {
+
+enum { DIFF_U = 0, DIFF_V = 1, DIFF_W = 2, DIFF_THETA = 3, DIFF_QV = 4, DIFF_SCALAR = 5 };
+
+struct DiffIn {
+  cfp field, mut, mass_v, alt, base_3d;   // mut: horizontal mass; mass_v: muu / muv / mut of the vertical term
+  const float *base_1d;                   // u_base / v_base / qv_base (origin shifted), or null
+  float xk, kvdif;                        // horizontal K of this field, vertical K of this field
+};
+
+template <int KIND>
+__global__ void k_diffuse(const Geo g, Box b, DiffIn s, fp tendency) {
+  TID3;
+  const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, kde = g.kde;
+  const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte, kts = 1;
+  const int ktf = kde - 1;
+  const float rdx = g.rdx, rdy = g.rdy, xk = s.xk, kvdif = s.kvdif;
+  cfp field = s.field, MUT = s.mut, alt = s.alt;
+  float t = A3(tendency, i, k, j);
+  // ------------------------------------------------------------------ horizontal
+  {
+    int i_start, i_end, j_start, j_end, k_start = kts;
+    if (KIND == DIFF_U) {
+      i_start = its; i_end = ite; j_start = jts; j_end = min(jte, jde - 1);
+      if (g.open_xs) i_start = max(ids + 1, its);
+      if (g.open_xe) i_end = min(ide - 1, ite);
+      if (g.open_ys) j_start = max(jds + 1, jts);
+      if (g.open_ye) j_end = min(jde - 2, jte);
+      if (g.periodic_x) { i_start = its; i_end = ite; }
+    } else if (KIND == DIFF_V) {
+      i_start = its; i_end = min(ite, ide - 1); j_start = jts; j_end = jte;
+      if (g.open_xs) i_start = max(ids + 1, its);
+      if (g.open_xe) i_end = min(ide - 2, ite);
+      if (g.open_ys) j_start = max(jds + 1, jts);
+      if (g.open_ye) j_end = min(jde - 1, jte);
+      if (g.periodic_x) { i_start = its; i_end = min(ite, ide - 1); }
+    } else {
+      i_start = its; i_end = min(ite, ide - 1); j_start = jts; j_end = min(jte, jde - 1);
+      if (g.open_xs) i_start = max(ids + 1, its);
+      if (g.open_xe) i_end = min(ide - 2, ite);
+      if (g.open_ys) j_start = max(jds + 1, jts);
+      if (g.open_ye) j_end = min(jde - 2, jte);
+      if (g.periodic_x) { i_start = its; i_end = min(ite, ide - 1); }
+      if (KIND == DIFF_W) k_start = kts + 1;
+    }
+    if (i >= i_start && i <= i_end && j >= j_start && j <= j_end && k >= k_start && k <= ktf) {
+      const float c1 = KIND == DIFF_W ? g.c1f[k] : g.c1h[k], c2 = KIND == DIFF_W ? g.c2f[k] : g.c2h[k];
+      float mrdx, mkrdxm, mkrdxp, mrdy, mkrdym, mkrdyp;
+      if (KIND == DIFF_U) {
+        mkrdxm = (A2(g.msftx, i - 1, j) / A2(g.msfty, i - 1, j)) * (c1 * A2(MUT, i - 1, j) + c2) * xk * rdx;
+        mkrdxp = (A2(g.msftx, i, j) / A2(g.msfty, i, j)) * (c1 * A2(MUT, i, j) + c2) * xk * rdx;
+        mrdx = A2(g.msfux, i, j) * A2(g.msfuy, i, j) * rdx;
+        mkrdym = ((A2(g.msfuy, i, j) + A2(g.msfuy, i, j - 1)) / (A2(g.msfux, i, j) + A2(g.msfux, i, j - 1))) *
+                 0.25f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j - 1) + c2) + (c1 * A2(MUT, i - 1, j - 1) + c2) + (c1 * A2(MUT, i - 1, j) + c2)) *
+                 0.25f * (xk + xk + xk + xk) * rdy;
+        mkrdyp = ((A2(g.msfuy, i, j) + A2(g.msfuy, i, j + 1)) / (A2(g.msfux, i, j) + A2(g.msfux, i, j + 1))) *
+                 0.25f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j + 1) + c2) + (c1 * A2(MUT, i - 1, j + 1) + c2) + (c1 * A2(MUT, i - 1, j) + c2)) *
+                 0.25f * (xk + xk + xk + xk) * rdy;
+        mrdy = A2(g.msfux, i, j) * A2(g.msfuy, i, j) * rdy;
+      } else if (KIND == DIFF_V) {
+        mkrdxm = ((A2(g.msfvx, i, j) + A2(g.msfvx, i - 1, j)) / (A2(g.msfvy, i, j) + A2(g.msfvy, i - 1, j))) *
+                 0.25f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j - 1) + c2) + (c1 * A2(MUT, i - 1, j - 1) + c2) + (c1 * A2(MUT, i - 1, j) + c2)) *
+                 0.25f * (xk + xk + xk + xk) * rdx;
+        mkrdxp = ((A2(g.msfvx, i, j) + A2(g.msfvx, i + 1, j)) / (A2(g.msfvy, i, j) + A2(g.msfvy, i + 1, j))) *
+                 0.25f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j - 1) + c2) + (c1 * A2(MUT, i + 1, j - 1) + c2) + (c1 * A2(MUT, i + 1, j) + c2)) *
+                 0.25f * (xk + xk + xk + xk) * rdx;
+        mrdx = A2(g.msfvx, i, j) * A2(g.msfvy, i, j) * rdx;
+        mkrdym = (A2(g.msfty, i, j - 1) / A2(g.msftx, i, j - 1)) * xk * rdy;
+        mkrdyp = (A2(g.msfty, i, j) / A2(g.msftx, i, j)) * xk * rdy;
+        mrdy = A2(g.msfvx, i, j) * A2(g.msfvy, i, j) * rdy;
+      } else if (KIND == DIFF_W) {
+        mkrdxm = (A2(g.msfux, i, j) / A2(g.msfuy, i, j)) *
+                 0.25f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i - 1, j) + c2) + (c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i - 1, j) + c2)) *
+                 0.25f * (xk + xk + xk + xk) * rdx;
+        mkrdxp = (A2(g.msfux, i + 1, j) / A2(g.msfuy, i + 1, j)) *
+                 0.25f * ((c1 * A2(MUT, i + 1, j) + c2) + (c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i + 1, j) + c2) + (c1 * A2(MUT, i, j) + c2)) *
+                 0.25f * (xk + xk + xk + xk) * rdx;
+        mrdx = A2(g.msftx, i, j) * A2(g.msfty, i, j) * rdx;
+        mkrdym = (A2(g.msfvy, i, j) * A2(g.msfvx_inv, i, j)) *
+                 0.25f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j - 1) + c2) + (c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j - 1) + c2)) *
+                 0.25f * (xk + xk + xk + xk) * rdy;
+        mkrdyp = (A2(g.msfvy, i, j + 1) * A2(g.msfvx_inv, i, j + 1)) *
+                 0.25f * ((c1 * A2(MUT, i, j + 1) + c2) + (c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j + 1) + c2) + (c1 * A2(MUT, i, j) + c2)) *
+                 0.25f * (xk + xk + xk + xk) * rdy;
+        mrdy = A2(g.msftx, i, j) * A2(g.msfty, i, j) * rdy;
+      } else {
+        mkrdxm = (A2(g.msfux, i, j) / A2(g.msfuy, i, j)) * 0.5f * (xk + xk) * 0.5f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i - 1, j) + c2)) * rdx;
+        mkrdxp = (A2(g.msfux, i + 1, j) / A2(g.msfuy, i + 1, j)) * 0.5f * (xk + xk) * 0.5f * ((c1 * A2(MUT, i + 1, j) + c2) + (c1 * A2(MUT, i, j) + c2)) * rdx;
+        mrdx = A2(g.msftx, i, j) * A2(g.msfty, i, j) * rdx;
+        mkrdym = (A2(g.msfvy, i, j) * A2(g.msfvx_inv, i, j)) * 0.5f * (xk + xk) * 0.5f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j - 1) + c2)) * rdy;
+        mkrdyp = (A2(g.msfvy, i, j + 1) * A2(g.msfvx_inv, i, j + 1)) * 0.5f * (xk + xk) * 0.5f * ((c1 * A2(MUT, i, j + 1) + c2) + (c1 * A2(MUT, i, j) + c2)) * rdy;
+        mrdy = A2(g.msftx, i, j) * A2(g.msfty, i, j) * rdy;
+      }
+      const float fc = A3(field, i, k, j), fe = A3(field, i + 1, k, j), fw = A3(field, i - 1, k, j), fn = A3(field, i, k, j + 1), fs = A3(field, i, k, j - 1);
+      if (KIND == DIFF_THETA) {
+        cfp bs = s.base_3d;
+        const float bc = A3(bs, i, k, j), be = A3(bs, i + 1, k, j), bw = A3(bs, i - 1, k, j), bn = A3(bs, i, k, j + 1), bso = A3(bs, i, k, j - 1);
+        t = t + (mrdx * (mkrdxp * (fe - fc - be + bc) - mkrdxm * (fc - fw - bc + bw)) + mrdy * (mkrdyp * (fn - fc - bn + bc) - mkrdym * (fc - fs - bc + bso)));
+      } else {
+        t = t + (mrdx * (mkrdxp * (fe - fc) - mkrdxm * (fc - fw)) + mrdy * (mkrdyp * (fn - fc) - mkrdym * (fc - fs)));
+      }
+    }
+  }
+  // ------------------------------------------------------------------ vertical (bl_pbl_physics = 0)
+  {
+    int i_start = its, i_end = min(ite, ide - 1), j_start = jts, j_end = min(jte, jde - 1);
+    int k_lo = kts, k_hi = ktf;
+    if (KIND == DIFF_U) {
+      i_end = ite;
+      if (g.open_xs) i_start = max(ids + 1, its);
+      if (g.open_xe) i_end = min(ide - 1, ite);
+      if (g.periodic_x) { i_start = its; i_end = ite; }
+      k_hi = ktf - 1;
+    } else if (KIND == DIFF_V) {
+      if (g.open_ys) j_start = max(jds + 1, jts);
+      if (g.open_ye) j_end = min(jde - 1, jte);
+      k_hi = ktf - 1;
+    } else if (KIND == DIFF_W) {
+      k_lo = kts + 1;
+    }
+    if (i >= i_start && i <= i_end && j >= j_start && j <= j_end && k >= k_lo && k <= k_hi) {
+      // vflux(kk), kk = kts..ktf-1, of this column; vflux(ktf) = 0; vflux(0) = vflux(1) (not for w)
+      auto vflux = [&](int kk) -> float {
+        if (kk == ktf) return 0.f;
+        if (kk == 0) kk = 1;
+        if (KIND == DIFF_W) return (kvdif / A3(alt, i, kk, j)) * g.rdnw[kk] * (A3(field, i, kk + 1, j) - A3(field, i, kk, j));
+        if (KIND == DIFF_U)
+          return kvdif * g.rdn[kk + 1] / (0.25f * (A3(alt, i, kk, j) + A3(alt, i - 1, kk, j) + A3(alt, i, kk + 1, j) + A3(alt, i - 1, kk + 1, j))) *
+                 (A3(field, i, kk + 1, j) - A3(field, i, kk, j) - s.base_1d[kk + 1] + s.base_1d[kk]);
+        if (KIND == DIFF_V)
+          return kvdif * g.rdn[kk + 1] / (0.25f * (A3(alt, i, kk, j) + A3(alt, i, kk, j - 1) + A3(alt, i, kk + 1, j) + A3(alt, i, kk + 1, j - 1))) *
+                 (A3(field, i, kk + 1, j) - A3(field, i, kk, j) - s.base_1d[kk + 1] + s.base_1d[kk]);
+        if (KIND == DIFF_THETA)
+          return kvdif * g.rdn[kk + 1] / (0.5f * (A3(alt, i, kk, j) + A3(alt, i, kk + 1, j))) *
+                 (A3(field, i, kk + 1, j) - A3(field, i, kk, j) - A3(s.base_3d, i, kk + 1, j) + A3(s.base_3d, i, kk, j));
+        if (KIND == DIFF_QV)
+          return kvdif * g.rdn[kk + 1] / (0.5f * (A3(alt, i, kk, j) + A3(alt, i, kk + 1, j))) *
+                 (A3(field, i, kk + 1, j) - A3(field, i, kk, j) - s.base_1d[kk + 1] + s.base_1d[kk]);
+        return kvdif * g.rdn[kk + 1] / (0.5f * (A3(alt, i, kk, j) + A3(alt, i, kk + 1, j))) * (A3(field, i, kk + 1, j) - A3(field, i, kk, j));
+      };
+      const float vk = vflux(k), vkm1 = vflux(k - 1);
+      cfp mv = s.mass_v;
+      if (KIND == DIFF_W)
+        t = t + g.rdn[k] * WG_G * WG_G / (g.c1f[k] * A2(mv, i, j) + g.c2f[k]) / (0.5f * (A3(alt, i, k, j) + A3(alt, i, k - 1, j))) * (vk - vkm1);
+      else if (KIND == DIFF_U)
+        t = t + WG_G * WG_G * g.rdnw[k] / (g.c1h[k] * A2(mv, i, j) + g.c2h[k]) / (0.5f * (A3(alt, i - 1, k, j) + A3(alt, i, k, j))) * (vk - vkm1);
+      else if (KIND == DIFF_V)
+        t = t + WG_G * WG_G * g.rdnw[k] / (g.c1h[k] * A2(mv, i, j) + g.c2h[k]) / (0.5f * (A3(alt, i, k, j - 1) + A3(alt, i, k, j))) * (vk - vkm1);
+      else
+        t = t + WG_G * WG_G / (g.c1h[k] * A2(mv, i, j) + g.c2h[k]) / A3(alt, i, k, j) * g.rdnw[k] * (vk - vkm1);
+    }
+  }
+  A3(tendency, i, k, j) = t;
+}
+
+// which = DIFF_*; adds the diffusion of `field` to `tendency` on the whole tile
+void launch_diffuse(Solver *s, int which, cfp field, fp tendency, float xk, float kvdif) {
+  const Geo &q = s->g;
+  Box tile{q.its, q.ite, 1, q.kde, q.jts, q.jte};
+  DiffIn in;
+  in.field = field; in.mut = s->o("mut"); in.mass_v = s->o("mut"); in.alt = s->o("alt"); in.base_3d = nullptr; in.base_1d = nullptr;
+  in.xk = xk; in.kvdif = kvdif;
+  switch (which) {
+    case DIFF_U: in.mass_v = s->o("muu"); in.base_1d = s->o("u_base"); LAUNCH3(s, k_diffuse<DIFF_U>, tile, in, tendency); break;
+    case DIFF_V: in.mass_v = s->o("muv"); in.base_1d = s->o("v_base"); LAUNCH3(s, k_diffuse<DIFF_V>, tile, in, tendency); break;
+    case DIFF_W: LAUNCH3(s, k_diffuse<DIFF_W>, tile, in, tendency); break;
+    case DIFF_THETA: in.base_3d = s->o("t_init"); LAUNCH3(s, k_diffuse<DIFF_THETA>, tile, in, tendency); break;
+    case DIFF_QV:     // rk_scalar_tend passes grid%muts as mut (solve_em.F:2219)
+      in.mut = s->o("muts"); in.mass_v = s->o("muts"); in.base_1d = s->o("qv_base");
+      LAUNCH3(s, k_diffuse<DIFF_QV>, tile, in, tendency); break;
+    default:
+      in.mut = s->o("muts"); in.mass_v = s->o("muts");
+      LAUNCH3(s, k_diffuse<DIFF_SCALAR>, tile, in, tendency); break;
+  }
+}
+
+}  // namespace wg

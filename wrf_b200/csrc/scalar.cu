@@ -269,6 +269,10 @@ void Solver::rk_scalar_step(int rk_step) {
       const int nst = edge_strips(mass, in, strips);
       for (int m = 0; m < nst; m++) LAUNCH3(this, k_advect_scalar, strips[m], o(s.f), o("ru_m"), o("rv_m"), o("ww_m"), o("advect_tend"));
     }
+    if (rk_step == 1 && c.diff_opt == 1) {   // rk_step_1: diff_opt1 (module_em.F:1378-1419): K = xkhh, kvdq = kvdif/prandtl
+      const float prandtl = 1.f / 3.0f;
+      launch_diffuse(this, s.f == "moist_qv" ? 4 : 5, o(s.f), o(s.t), c.khdif / prandtl, c.kvdif / prandtl);
+    }
     LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
   }
 }

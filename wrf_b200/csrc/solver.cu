@@ -13,7 +13,7 @@ static const char *k3d[] = {
     "ru_m", "rv_m", "ww_m", "ru_tend", "rv_tend", "u_save", "v_save", "t_save", "h_diabatic",
     "ru_tendf", "rv_tendf", "rw_tend", "rw_tendf", "w_save", "ww1",
     "ph_tend", "ph_tendf", "ph_save", "t_tend", "t_tendf", "t_2save", "advect_tend",
-    "alpha", "a", "gamma", "c2a", "cqu", "cqv", "cqw", "pm1", "rho", "pd_scale", nullptr};
+    "alpha", "a", "gamma", "c2a", "cqu", "cqv", "cqw", "pm1", "rho", "pd_scale", "t_init", nullptr};
 static const char *k3d_mp[] = {"th_phy", "pi_phy", "z", "dz8w", "qv_diabatic", "qc_diabatic", nullptr};
 static const char *k2d[] = {"mu_1", "mu_2", "mub", "mudf", "muu", "muus", "muv", "muvs", "mut", "muts",
                             "muave", "mu_save", "mu_tend", "mu_tendf",
@@ -36,7 +36,17 @@ static void check_config(const wrfgpu_config &c) {
   if (!c.non_hydrostatic) bad("hydrostatic option");
   if (c.damp_opt != 0 && c.damp_opt != 2 && c.damp_opt != 3) bad("damp_opt must be 0, 2 or 3");
   if (c.zadvect_implicit != 0) bad("zadvect_implicit (IEVA)");
-  if (c.diff_opt != 0 || c.km_opt != 0 || c.diff_6th_opt != 0) bad("diff_opt/km_opt/diff_6th_opt must be 0 (diffusion is a 'next' row)");
+  // diffusion: constant K on coordinate surfaces (diff_opt 1 / km_opt 1) is on the device; with
+  // km_opt = 1 and khdif = kvdif = 0 the physical-space form (diff_opt 2: shipped em_hill2d_x) adds exact zeros
+  // to zero-initialised tendencies, i.e. it is the identity, and is accepted as such.  Everything else
+  // (TKE / Smagorinsky closures, 6th-order filter) is a 'next' row.
+  if (c.diff_6th_opt != 0) bad("diff_6th_opt must be 0");
+  if (c.diff_opt != 0) {
+    if (c.km_opt != 1) bad("km_opt must be 1 (constant K) when diff_opt is not 0; the TKE/Smagorinsky closures are a 'next' row");
+    if (c.diff_opt == 2 && (c.khdif != 0.f || c.kvdif != 0.f)) bad("diff_opt = 2 is only accepted with khdif = kvdif = 0 (then it is the identity)");
+    if (c.diff_opt != 1 && c.diff_opt != 2) bad("diff_opt must be 0, 1 or 2");
+    if (c.khdif < 0.f || c.kvdif < 0.f) bad("khdif, kvdif must not be negative");
+  } else if (c.km_opt != 0 && c.km_opt != 1) bad("km_opt must be 0 or 1");
   if (c.mp_physics != 0 && c.mp_physics != 1) bad("mp_physics must be 0 or 1 (Kessler)");
   if (c.mp_physics == 1 && c.num_moist != 3) bad("Kessler needs num_moist = 3 (qv,qc,qr)");
   if (c.hypsometric_opt != 1 && c.hypsometric_opt != 2) bad("hypsometric_opt must be 1 or 2");

@@ -942,6 +942,14 @@ void Solver::rk_tendency(int rk_step, bool zero_save) {
   // the *_save arrays and mu_tend/mu_save are zeroed by rk_tendency (module_em.F:370-428)
   if (zero_save) LAUNCH3(this, k_zero3, tile, o("u_save"), o("v_save"), o("w_save"), o("ph_save"), o("t_save"));
   LAUNCH2(this, k_zero2, tile, o("mu_tend"), o("mu_save"));
+  if (rk_step == 1 && c.diff_opt == 1) {   // forward_step: diff_opt1 (module_em.F:802-878), before rk_rayleigh_damp
+    const float prandtl = 1.f / 3.0f;    // share/module_model_constants.F:86
+    const float xkmh = c.khdif, xkhh = c.khdif / prandtl;
+    launch_diffuse(this, 0, o("u_2"), o("ru_tendf"), xkmh, c.kvdif);
+    launch_diffuse(this, 1, o("v_2"), o("rv_tendf"), xkmh, c.kvdif);
+    launch_diffuse(this, 2, o("w_2"), o("rw_tendf"), xkmh, c.kvdif);
+    launch_diffuse(this, 3, o("t_2"), o("t_tendf"), xkhh, 3.f * c.kvdif);
+  }
   if (rk_step == 1 && c.damp_opt == 2) {
     const int jm = std::min(q.jte, q.jde - 1), im = std::min(q.ite, q.ide - 1);
     for (int kind = 0; kind < 3; kind++) {

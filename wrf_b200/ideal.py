@@ -507,6 +507,7 @@ def make_case(name="quarter_ss", nx=None, ny=None, nz=None, **over) -> Case:
     fl["w_2"] = np.zeros_like(T)
     fl["mu_1"], fl["mu_2"], fl["mub"], fl["ht"] = MU.copy(), MU.copy(), MUB, HT
     fl["phb"], fl["pb"], fl["alb"], fl["p"], fl["al"], fl["alt"] = PHB, PB, ALB, P, AL, ALT
+    fl["t_init"] = bcast(col["t_init"])      # dry base-state theta - t0 (module_initialize_ideal.F), the base_3d of the 3dmp diffusion
     if c.num_moist >= 1:
         fl["moist_qv"] = QV
     ones = np.ones((nj, ni), F)
