@@ -90,6 +90,7 @@ SUBROUTINE solve_em ( grid , config_flags  &
       CALL add('ph_1',grid%ph_1); CALL add('ph_2',grid%ph_2); CALL add('phb',grid%phb); CALL add('pb',grid%pb)
       CALL add('alb',grid%alb); CALL add('p',grid%p); CALL add('al',grid%al); CALL add('alt',grid%alt)
       CALL add('h_diabatic',grid%h_diabatic)
+      CALL add('t_init',grid%t_init)      ! base state of the theta diffusion (diff_opt = 1)
       CALL add('moist_qv', moist(:,:,:,P_QV))
       IF ( config_flags%mp_physics == 1 ) THEN
          CALL add('moist_qc', moist(:,:,:,P_QC)); CALL add('moist_qr', moist(:,:,:,P_QR))
