@@ -1,6 +1,6 @@
 """gpurun helper: phase-by-phase diff table and whole-step diff for the small cases."""
 import sys, time
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from tests import parity
 from tests.oracle_lib import Oracle
 from wrf_b200 import Solver
