@@ -34,6 +34,7 @@ ALGO_ACCESSES = {
     "k_calc_p_rho_phi": 7, "k_advect_scalar": 5, "k_update_scalar": 3, "k_pd_scale": 6, "k_pd_tend": 7,
     "k_update_scalar_pd": 2, "k_zero3": 5, "k_invert_cqw": 2, "k_kessler": 20,
     # fused forms (what wrfgpu_step launches): DISTINCT fields of the fused routines, so lower than the sum of the parts
+    "k_advance_mu_t<true>": 11, "k_advance_mu_t<false>": 11,
     "k_advance_uv<true>": 18,          # advance_uv 14 + ru_m, rv_m read and written
     "k_advance_w<true>": 25,           # advance_w 19 + calc_p_rho (al, p, pm1 r/w) + sumflux (ww_m r/w); alt, c2a, t_2, t_1 shared
     "k_advect_scalar_fast<theta>": 7, "k_advect_scalar_fast": 5,

@@ -361,6 +361,11 @@ __device__ __forceinline__ Mt2 mt_load2(const Geo &g, const MuTArgs &a, int i, i
   m.ue = A3(a.u, i + 1, k, j); m.u0 = A3(a.u, i, k, j); m.t1e = A3(a.t_1, i + 1, k, j); m.t1w = A3(a.t_1, i - 1, k, j);
   return m;
 }
+// FINAL_AVE (the form wrfgpu_step uses, paired with k_advance_w<true>): t_ave receives the finished time average
+// t_2ave of advance_w (:1314-1317) instead of the old theta'' -- this thread holds every operand of it (old and new
+// theta'', t_1, muave, muts), and advance_w then reads one field in its upward sweep instead of reading t_2, t_1,
+// t_2ave and writing t_2ave back: 12 B per point and launch less DRAM traffic in the DRAM-bound kernel.
+template <bool FINAL_AVE>
 __device__ __forceinline__ void advance_mu_t_column(const Geo &g, const Coef &cf, float dts, const MuTArgs &a, int i, int j) {
   const int k_end = g.kde - 1;
   const float msftx = A2(g.msftx, i, j), msfty = A2(g.msfty, i, j);
@@ -381,13 +386,16 @@ __device__ __forceinline__ void advance_mu_t_column(const Geo &g, const Coef &cf
     if (k < k_end) A3(a.ww, i, k + 1, j) = dvdxi;
     c1 = n1;
   }
+  float muts_new, muave_new;
   {
     const float mu_old = A2(a.mu, i, j);
     const float mu_new = mu_old + dts * (dmdt + mu_tend);
     A2(a.mu, i, j) = mu_new;
     A2(a.mudf, i, j) = (dmdt + mu_tend);
-    A2(a.muts, i, j) = A2(a.mut, i, j) + mu_new;
-    A2(a.muave, i, j) = .5f * ((1.f + g.epssm) * mu_new + (1.f - g.epssm) * mu_old);
+    muts_new = A2(a.mut, i, j) + mu_new;
+    A2(a.muts, i, j) = muts_new;
+    muave_new = .5f * ((1.f + g.epssm) * mu_new + (1.f - g.epssm) * mu_old);
+    A2(a.muave, i, j) = muave_new;
   }
   // pass 2: ww recurrence (:1109-1121), then the theta update which needs ww(k), ww(k+1)
   // ww(1) is not touched by the recurrence; ww(k) -= ww_1(k) for k = 1..k_end
@@ -407,22 +415,28 @@ __device__ __forceinline__ void advance_mu_t_column(const Geo &g, const Coef &cf
       wdtn_kp1 = wkp1 * (cf.fnm[k + 1] * c2.t1u + cf.fnp[k + 1] * t1_k);
     }   // else wdtn(kde) = 0
     const float told = c2.t;
-    A3(a.t_ave, i, k, j) = told;
+    if (!FINAL_AVE) A3(a.t_ave, i, k, j) = told;
     float tn = told + msfty * dts * c2.ft;
     tn = tn - dts * msfty *
                   (msftx * (.5f * g.rdy * (c2.vn * (c2.t1n + t1_k) - c2.v0 * (t1_k + c2.t1s)) +
                             .5f * g.rdx * (c2.ue * (c2.t1e + t1_k) - c2.u0 * (t1_k + c2.t1w))) +
                    cf.rdnw[k] * (wdtn_kp1 - wdtn_k));
     A3(a.t, i, k, j) = tn;
+    if (FINAL_AVE) {   // t_2ave(k) of advance_w (:1314-1317)
+      float tv = .5f * ((1.f + g.epssm) * tn + (1.f - g.epssm) * told);
+      tv = (tv + (cf.c1h[k] * muave_new) * WG_T0) / ((cf.c1h[k] * muts_new + cf.c2h[k]) * (WG_T0 + t1_k));
+      A3(a.t_ave, i, k, j) = tv;
+    }
     wdtn_k = wdtn_kp1;
     t1_k = c2.t1u;
     c2 = n2;
   }
 }
+template <bool FINAL_AVE>
 __global__ void __launch_bounds__(128, MT_MINB) k_advance_mu_t(const Geo g, Box b, float dts, MuTArgs a) {
   COEF_CONST;
   TID2;
-  advance_mu_t_column(g, cf, dts, a, i, j);
+  advance_mu_t_column<FINAL_AVE>(g, cf, dts, a, i, j);
 }
 
 // ---------------------------------------------------------------------------
@@ -442,6 +456,7 @@ struct WFuse { int iteration, nsmall; fp al, p, pm1, ww_m, ru_m, rv_m; cfp mu, w
 // operand; a value that the reference recomputes at the next level is computed once and carried,
 // which is bit-identical.
 struct WUp { float w_kp1, pht_kp1, ph_kp1, ph1_kp2, phb_kp2, ww_kp2, rwt, cqw, c2a, alt, t2, t2a, t1, a, alpha; };
+template <bool FUSE>
 __device__ __forceinline__ WUp w_load_up(const Geo &g, const WArgs &a, int i, int k, int j) {
   WUp q;
   const int kde = g.kde;
@@ -449,7 +464,9 @@ __device__ __forceinline__ WUp w_load_up(const Geo &g, const WArgs &a, int i, in
   q.ph1_kp2 = 0.f; q.phb_kp2 = 0.f; q.ww_kp2 = 0.f;
   if (k + 2 <= kde) { q.ph1_kp2 = A3(a.ph_1, i, k + 2, j); q.phb_kp2 = A3(a.phb, i, k + 2, j); q.ww_kp2 = A3(a.ww, i, k + 2, j); }
   q.rwt = A3(a.rw_tend, i, k, j); q.cqw = A3(a.cqw, i, k, j); q.c2a = A3(a.c2a, i, k, j); q.alt = A3(a.alt, i, k, j);
-  q.t2 = A3(a.t_2, i, k, j); q.t2a = A3(a.t_2ave, i, k, j); q.t1 = A3(a.t_1, i, k, j);
+  q.t2a = A3(a.t_2ave, i, k, j);
+  q.t2 = 0.f; q.t1 = 0.f;
+  if (!FUSE) { q.t2 = A3(a.t_2, i, k, j); q.t1 = A3(a.t_1, i, k, j); }   // FUSE: t_2ave is already the finished average (k_advance_mu_t<true>)
   q.a = A3(a.a, i, k, j); q.alpha = A3(a.alpha, i, k, j);
   return q;
 }
@@ -496,10 +513,14 @@ __device__ __forceinline__ void advance_w_column(const Geo &g, const Coef &cf, f
   // ---- level 1: t_2ave(1) (:1314-1317) and the carried products
   float t2ave_km1, c2a_km1, alt_km1;
   {
-    const float t1v = A3(a.t_1, i, 1, j);
-    float tv = .5f * ((1.f + epssm) * A3(a.t_2, i, 1, j) + (1.f - epssm) * A3(a.t_2ave, i, 1, j));
-    tv = (tv + (cf.c1h[1] * muave) * WG_T0) / ((cf.c1h[1] * muts + cf.c2h[1]) * (WG_T0 + t1v));
-    A3(a.t_2ave, i, 1, j) = tv;
+    float tv;
+    if (FUSE) tv = A3(a.t_2ave, i, 1, j);
+    else {
+      const float t1v = A3(a.t_1, i, 1, j);
+      tv = .5f * ((1.f + epssm) * A3(a.t_2, i, 1, j) + (1.f - epssm) * A3(a.t_2ave, i, 1, j));
+      tv = (tv + (cf.c1h[1] * muave) * WG_T0) / ((cf.c1h[1] * muts + cf.c2h[1]) * (WG_T0 + t1v));
+      A3(a.t_2ave, i, 1, j) = tv;
+    }
     t2ave_km1 = tv; c2a_km1 = A3(a.c2a, i, 1, j); alt_km1 = A3(a.alt, i, 1, j);
   }
   // layer integral of -omega dphi/deta: wdwn(kk+1) of the reference (:1318-1345)
@@ -535,14 +556,18 @@ __device__ __forceinline__ void advance_w_column(const Geo &g, const Coef &cf, f
   float cpre_km1 = c2a_km1 * cf.rdnw[1] / (cf.c1h[1] * mut + cf.c2h[1]);
   float cat_km1 = c2a_km1 * alt_km1 * t2ave_km1;
   float wprev = w1;                                                              // w(k-1) after elimination
-  WUp q = w_load_up(g, a, i, 2, j);
+  WUp q = w_load_up<FUSE>(g, a, i, 2, j);
   for (int k = 2; k <= k_end; k++) {
     WUp qn;
-    if (k < k_end) qn = w_load_up(g, a, i, k + 1, j);
+    if (k < k_end) qn = w_load_up<FUSE>(g, a, i, k + 1, j);
     // t_2ave(k) (:1314-1317)
-    float tv = .5f * ((1.f + epssm) * q.t2 + (1.f - epssm) * q.t2a);
-    tv = (tv + (cf.c1h[k] * muave) * WG_T0) / ((cf.c1h[k] * muts + cf.c2h[k]) * (WG_T0 + q.t1));
-    A3(a.t_2ave, i, k, j) = tv;
+    float tv;
+    if (FUSE) tv = q.t2a;
+    else {
+      tv = .5f * ((1.f + epssm) * q.t2 + (1.f - epssm) * q.t2a);
+      tv = (tv + (cf.c1h[k] * muave) * WG_T0) / ((cf.c1h[k] * muts + cf.c2h[k]) * (WG_T0 + q.t1));
+      A3(a.t_2ave, i, k, j) = tv;
+    }
     // rhs(k+1): needs layer k+1 (levels k+1, k+2) unless k+1 = kde
     float lay_kp1 = 0.f;
     if (k + 1 <= k_end) lay_kp1 = layer(k + 1, q.ph1_kp2, ph1_kp1, q.phb_kp2, phb_kp1, q.ww_kp2, ww_kp1);
@@ -787,12 +812,14 @@ static MuTArgs mu_t_args(Solver *s) {
   return a;
 }
 
-void Solver::advance_mu_t(int rk_step) {
+void Solver::advance_mu_t(int rk_step, bool final_ave) {
   const Geo &q = g;
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
   MuTArgs a = mu_t_args(this);
-  LAUNCH2(this, k_advance_mu_t, (Box{q.its, std::min(q.ite, q.ide - 1), 1, 1, q.jts, std::min(q.jte, q.jde - 1)}), dts_rk, a);
+  const Box mass{q.its, std::min(q.ite, q.ide - 1), 1, 1, q.jts, std::min(q.jte, q.jde - 1)};
+  if (final_ave) LAUNCH2(this, k_advance_mu_t<true>, mass, dts_rk, a);    // only together with advance_w_fused
+  else LAUNCH2(this, k_advance_mu_t<false>, mass, dts_rk, a);
 }
 
 static WArgs w_args(Solver *s) {

@@ -192,7 +192,7 @@ struct Solver {
   void advance_uv(int rk_step);
   void advance_uv_fused(int rk_step, int iteration);
   void sumflux_w(int rk_step, int iteration);
-  void advance_mu_t(int rk_step);
+  void advance_mu_t(int rk_step, bool final_ave = false);   // final_ave: see k_advance_mu_t<true>
   void advance_w(int rk_step);
   void advance_w_fused(int rk_step, int iteration);
   void sumflux(int rk_step, int iteration);

@@ -257,7 +257,7 @@ void Solver::step() {
     for (int it = 1; it <= ns; it++) {
       { PHASE("advance_uv"); advance_uv_fused(rk_step, it); }
       halo("HALO_EM_C");
-      { PHASE("advance_mu_t"); advance_mu_t(rk_step); }
+      { PHASE("advance_mu_t"); advance_mu_t(rk_step, true); }
       { PHASE("advance_w"); advance_w_fused(rk_step, it); }
     }
     { PHASE("small_step_finish"); small_step_finish(rk_step); }
