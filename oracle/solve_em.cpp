@@ -528,7 +528,7 @@ extern "C" int oracle_start_domain(orc::Oracle *o) {
   OGUARD({
     o->halo("HALO_EM_INIT");   // HALO_EM_INIT_1..5, dyn_em/start_em.F
     for (const char *n : {"phb"}) o->bc(n, 'w');
-    for (const char *n : {"pb", "alb", "p", "al", "alt"}) o->bc(n, 't');
+    for (const char *n : {"pb", "alb", "p", "al", "alt", "t_init"}) o->bc(n, 't');   // start_em.F:1723
     for (const char *n : {"mub", "ht", "msftx", "msfty", "f", "e", "sina", "cosa"}) o->bc(n, 't');
     for (const char *n : {"msfux", "msfuy"}) o->bc(n, 'u');
     for (const char *n : {"msfvx", "msfvx_inv", "msfvy"}) o->bc(n, 'v');

@@ -54,7 +54,7 @@ static const HaloDef kHalos[] = {
     {"HALO_EM_E_5", 3, "u_1,u_2,v_1,v_2,w_1,w_2,t_1,t_2,ph_1,ph_2", "mu_1,mu_2"},
     // start_domain_em (dyn_em/start_em.F): HALO_EM_INIT_1..5 carry the base state, map factors and both time levels
     {"HALO_EM_INIT", 4,
-     "phb,pb,alb,p,al,alt,u_1,u_2,v_1,v_2,w_1,w_2,t_1,t_2,ph_1,ph_2,@moist,@moist_old,@scalar,@scalar_old",
+     "phb,pb,alb,p,al,alt,t_init,u_1,u_2,v_1,v_2,w_1,w_2,t_1,t_2,ph_1,ph_2,@moist,@moist_old,@scalar,@scalar_old",
      "mub,ht,msftx,msfty,f,e,sina,cosa,msfux,msfuy,msfvx,msfvx_inv,msfvy,mu_1,mu_2"},
 };
 

@@ -246,7 +246,7 @@ void Solver::end_of_step() {
 // the part of start_domain_em (dyn_em/start_em.F) the hot path needs before step 1
 void Solver::start_domain() {
   halo("HALO_EM_INIT");
-  std::vector<BcItem> it = {{"phb", 'w'}, {"pb", 't'}, {"alb", 't'}, {"p", 't'}, {"al", 't'}, {"alt", 't'},
+  std::vector<BcItem> it = {{"phb", 'w'}, {"pb", 't'}, {"alb", 't'}, {"p", 't'}, {"al", 't'}, {"alt", 't'}, {"t_init", 't'},
                             {"mub", 't'}, {"ht", 't'}, {"msftx", 't'}, {"msfty", 't'}, {"f", 't'}, {"e", 't'}, {"sina", 't'}, {"cosa", 't'},
                             {"msfux", 'u'}, {"msfuy", 'u'}, {"msfvx", 'v'}, {"msfvx_inv", 'v'}, {"msfvy", 'v'},
                             {"u_1", 'U'}, {"u_2", 'U'}, {"v_1", 'V'}, {"v_2", 'V'}, {"w_1", 'w'}, {"w_2", 'w'},
