@@ -107,8 +107,8 @@ __device__ __forceinline__ void coef_to_smem(const Geo &g, Coef &sc) {
   __syncthreads();
 }
 #endif
-// per kernel, whichever measured faster (profiles/README.md, r1e): shared memory for k_advance_w
-// (many coefficients per level), the constant bank for k_advance_uv / k_advance_mu_t (few)
+// per kernel, whichever measured faster (profiles/README.md, r1e, r1u): shared memory for k_advance_w and
+// k_advance_mu_t (many coefficient reads per level), the constant bank for k_advance_uv (few)
 #define COEF_SMEM __shared__ Coef sc_; coef_to_smem(g, sc_); const Coef &cf = sc_
 #define COEF_CONST const Coef &cf = g
 
