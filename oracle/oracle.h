@@ -192,6 +192,9 @@ void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
 void advect_scalar(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut);
 void advect_scalar_pd(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom,
                       A2 mut, A2 mub, A2 mu_old, float dt);
+// advect_mono.cpp
+void advect_scalar_mono(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom, A3 romI,
+                        A2 mut, A2 mub, A2 mu_old, float dt);
 // small_step.cpp
 void small_step_prep(const Cx &x, A3 u_1, A3 u_2, A3 v_1, A3 v_2, A3 w_1, A3 w_2, A3 t_1, A3 t_2,
                      A3 ph_1, A3 ph_2, A2 mub, A2 mu_1, A2 mu_2, A2 muu, A2 muus, A2 muv, A2 muvs,

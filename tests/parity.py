@@ -71,6 +71,10 @@ def small_cases():
         "diffusion_periodic": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=1,
                                                          diff_opt=1, km_opt=1, khdif=300.0, kvdif=50.0)),
         "b_wave_shipped": make_case("b_wave", nx=21, ny=31, nz=17, diff_opt=1, km_opt=1, khdif=0.0, kvdif=0.0),
+        # monotonic scalar advection (*_adv_opt = 2): open + Kessler species, and doubly periodic tracers with map factors
+        "mono": make_case("quarter_ss", nx=26, ny=24, nz=21, moist_adv_opt=2),
+        "mono_periodic": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=2,
+                                                    scalar_adv_opt=2, moist_adv_opt=2)),
     }
 
 

@@ -188,6 +188,173 @@ __global__ void k_pd_tend(const Geo g, Box b, PdIn s, cfp scale, Box lim, fp ten
   A3(tend, i, k, j) = t;
 }
 
+
+// ===========================================================================================
+// advect_scalar_mono (module_advect_em.F:9495-10560): the monotonic limiter, *_adv_opt = 2.
+// Same two-pass structure as the positive-definite path above: pass 1 writes the two per-cell factors
+// scale_in / scale_out, pass 2 re-evaluates the face fluxes, scales each high-order part by
+// min(scale_in(receiver), scale_out(donor)) (:10385-10416) and writes the tendency.
+__device__ __forceinline__ float mflux4(float qm2, float qm1, float q0, float qp1) {
+  return (7.f / 12.f) * (q0 + qm1) - (1.f / 12.f) * (qp1 + qm2);
+}
+__device__ __forceinline__ float mflux3(float qm2, float qm1, float q0, float qp1, float ua) {   // no sign(time_step) here (:9590-9592)
+  return mflux4(qm2, qm1, q0, qp1) + sign1(ua) * (1.f / 12.f) * ((qp1 - qm2) - 3.f * (q0 - qm1));
+}
+__device__ __forceinline__ float mflux6(float qm3, float qm2, float qm1, float q0, float qp1, float qp2) {
+  return (37.f / 60.f) * (q0 + qm1) - (2.f / 15.f) * (qp1 + qm2) + (1.f / 60.f) * (qp2 + qm3);
+}
+__device__ __forceinline__ float mflux5(float qm3, float qm2, float qm1, float q0, float qp1, float qp2, float ua) {
+  return mflux6(qm3, qm2, qm1, q0, qp1, qp2) - sign1(ua) * (1.f / 60.f) * ((qp2 - qm3) - 5.f * (qp1 - qm2) + 10.f * (q0 - qm1));
+}
+__device__ __forceinline__ float mflux_upwind(float qm1, float q0, float cr) {   // :9602-9603
+  return 0.5f * (1.f + sign1(cr)) * qm1 + 0.5f * (1.f - sign1(cr)) * q0;
+}
+struct MFace { float hi, lo, cr; bool ok; };   // hi = high-order minus upwind, lo = upwind flux, cr: cr > 0 means flow from the lower-index cell
+
+__device__ __forceinline__ MFace mono_face_x(const Geo &g, const PdIn &s, int ii, int k, int j, bool dxs, bool dxe) {
+  MFace f;
+  const int ord = pd_order(ii, dxs, dxe, g.ids, g.ide);
+  f.ok = ord != 0;
+  if (!f.ok) { f.hi = 0.f; f.lo = 0.f; f.cr = 0.f; return f; }
+  const float vel = A3(s.ru, ii, k, j);
+  f.cr = vel;
+  f.lo = vel * mflux_upwind(A3(s.q_old, ii - 1, k, j), A3(s.q_old, ii, k, j), f.cr);
+  float h;
+  if (ord == 5) h = vel * mflux5(A3(s.q, ii - 3, k, j), A3(s.q, ii - 2, k, j), A3(s.q, ii - 1, k, j), A3(s.q, ii, k, j), A3(s.q, ii + 1, k, j), A3(s.q, ii + 2, k, j), vel);
+  else if (ord == 3) h = vel * mflux3(A3(s.q, ii - 2, k, j), A3(s.q, ii - 1, k, j), A3(s.q, ii, k, j), A3(s.q, ii + 1, k, j), vel);
+  else h = 0.5f * (A3(s.ru, ii, k, j)) * (A3(s.q, ii, k, j) + A3(s.q, ii - 1, k, j));
+  f.hi = h - f.lo;
+  return f;
+}
+__device__ __forceinline__ MFace mono_face_y(const Geo &g, const PdIn &s, int i, int k, int jj, bool dys, bool dye) {
+  MFace f;
+  const int ord = pd_order(jj, dys, dye, g.jds, g.jde);
+  f.ok = ord != 0;
+  if (!f.ok) { f.hi = 0.f; f.lo = 0.f; f.cr = 0.f; return f; }
+  const float vel = A3(s.rv, i, k, jj);
+  f.cr = vel;
+  f.lo = vel * mflux_upwind(A3(s.q_old, i, k, jj - 1), A3(s.q_old, i, k, jj), f.cr);
+  float h;
+  if (ord == 5) h = vel * mflux5(A3(s.q, i, k, jj - 3), A3(s.q, i, k, jj - 2), A3(s.q, i, k, jj - 1), A3(s.q, i, k, jj), A3(s.q, i, k, jj + 1), A3(s.q, i, k, jj + 2), vel);
+  else if (ord == 3) h = vel * mflux3(A3(s.q, i, k, jj - 2), A3(s.q, i, k, jj - 1), A3(s.q, i, k, jj), A3(s.q, i, k, jj + 1), vel);
+  else h = 0.5f * A3(s.rv, i, k, jj) * (A3(s.q, i, k, jj) + A3(s.q, i, k, jj - 1));
+  f.hi = h - f.lo;
+  return f;
+}
+__device__ __forceinline__ MFace mono_face_z(const Geo &g, const PdIn &s, int i, int kk, int j) {
+  MFace f;
+  const int ktf = g.kde - 1;
+  f.ok = kk >= 2 && kk <= ktf;          // faces 1 and kde carry no flux and no bound (:10096-10101)
+  if (!f.ok) { f.hi = 0.f; f.lo = 0.f; f.cr = 0.f; return f; }
+  const float vel = A3(s.rom, i, kk, j);
+  f.cr = -vel;
+  f.lo = vel * mflux_upwind(A3(s.q_old, i, kk - 1, j), A3(s.q_old, i, kk, j), f.cr);
+  float h;
+  if (kk == 2 || kk == ktf) h = A3(s.rom, i, kk, j) * (g.fnm[kk] * A3(s.q, i, kk, j) + g.fnp[kk] * A3(s.q, i, kk - 1, j));
+  else h = vel * mflux3(A3(s.q, i, kk - 2, j), A3(s.q, i, kk - 1, j), A3(s.q, i, kk, j), A3(s.q, i, kk + 1, j), -vel);
+  f.hi = h - f.lo;
+  return f;
+}
+
+// pass 1: scale_in, scale_out of a cell of the limiter box (:10322-10383)
+__global__ void k_mono_scale(const Geo g, Box b, PdIn s, fp scale_in, fp scale_out) {
+  TID3;
+  const bool dxs = !(g.periodic_x || g.sym_xs), dxe = !(g.periodic_x || g.sym_xe);
+  const bool dys = !(g.periodic_y || g.sym_ys), dye = !(g.periodic_y || g.sym_ye);
+  const MFace x0 = mono_face_x(g, s, i, k, j, dxs, dxe), x1 = mono_face_x(g, s, i + 1, k, j, dxs, dxe);
+  const MFace y0 = mono_face_y(g, s, i, k, j, dys, dye), y1 = mono_face_y(g, s, i, k, j + 1, dys, dye);
+  const MFace z0 = mono_face_z(g, s, i, k, j), z1 = mono_face_z(g, s, i, k + 1, j);
+  // bounds: the cell's own old value and the old value of every neighbour that is upwind of a computed face
+  const float qo = A3(s.q_old, i, k, j);
+  float qmax = qo, qmin = qo;
+  auto take = [&](float v) { qmax = fmaxf(qmax, v); qmin = fminf(qmin, v); };
+  if (x0.ok && x0.cr > 0.f) take(A3(s.q_old, i - 1, k, j));
+  if (x1.ok && !(x1.cr > 0.f)) take(A3(s.q_old, i + 1, k, j));
+  if (y0.ok && y0.cr > 0.f) take(A3(s.q_old, i, k, j - 1));
+  if (y1.ok && !(y1.cr > 0.f)) take(A3(s.q_old, i, k, j + 1));
+  if (z0.ok && z0.cr > 0.f) take(A3(s.q_old, i, k - 1, j));
+  if (z1.ok && !(z1.cr > 0.f)) take(A3(s.q_old, i, k + 1, j));
+  const float msftx = A2(g.msftx, i, j), msfty = A2(g.msfty, i, j);
+  const float c1h = g.c1h[k], c2h = g.c2h[k];
+  // romI = wwI = 0 without implicit vertical advection (zadvect_implicit is rejected at create)
+  const float ieva_corr = (c1h * A2(s.mut, i, j) + c2h) + s.dt * msfty * g.rdnw[k] * (0.f - 0.f);
+  const float ph_upwind = ((c1h * A2(s.mub, i, j) + c2h) + (c1h * A2(s.mu_old, i, j))) * qo -
+                          s.dt * (msftx * msfty * (g.rdx * (x1.lo - x0.lo) + g.rdy * (y1.lo - y0.lo)) + msfty * g.rdnw[k] * (z1.lo - z0.lo));
+  const float flux_in = -s.dt * ((msftx * msfty) * (g.rdx * (fminf(0.f, x1.hi) - fmaxf(0.f, x0.hi)) + g.rdy * (fminf(0.f, y1.hi) - fmaxf(0.f, y0.hi))) +
+                                 msfty * g.rdnw[k] * (fmaxf(0.f, z1.hi) - fminf(0.f, z0.hi)));
+  const float ph_hi = ieva_corr * qmax - ph_upwind;
+  float si = 1.f, so = 1.f;
+  if (flux_in > ph_hi) si = fmaxf(0.f, ph_hi / (flux_in + 1.e-20f));
+  const float flux_out = s.dt * ((msftx * msfty) * (g.rdx * (fmaxf(0.f, x1.hi) - fminf(0.f, x0.hi)) + g.rdy * (fmaxf(0.f, y1.hi) - fminf(0.f, y0.hi))) +
+                                 msfty * g.rdnw[k] * (fminf(0.f, z1.hi) - fmaxf(0.f, z0.hi)));
+  const float ph_low = ph_upwind - ieva_corr * qmin;
+  if (flux_out > ph_low) so = fmaxf(0.f, ph_low / (flux_out + 1.e-20f));
+  A3(scale_in, i, k, j) = si;
+  A3(scale_out, i, k, j) = so;
+}
+
+// pass 2: limited flux divergence (:10385-10556) + open-boundary terms (:10019-10083)
+__global__ void k_mono_tend(const Geo g, Box b, PdIn s, cfp scale_in, cfp scale_out, Box lim, fp tend) {
+  TID3;
+  const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde;
+  const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
+  const bool dxs = !(g.periodic_x || g.sym_xs), dxe = !(g.periodic_x || g.sym_xe);
+  const bool dys = !(g.periodic_y || g.sym_ys), dye = !(g.periodic_y || g.sym_ye);
+  cfp q = s.q, q_old = s.q_old, ru = s.ru, rv = s.rv;
+  // factors of a cell, 1 outside the limiter box (the reference initialises both arrays to 1)
+  auto in_lim = [&](int ii, int kk, int jj) { return !(ii < lim.i0 || ii > lim.i1 || jj < lim.j0 || jj > lim.j1 || kk < lim.k0 || kk > lim.k1); };
+  auto sin_at = [&](int ii, int kk, int jj) -> float { return in_lim(ii, kk, jj) ? A3(scale_in, ii, kk, jj) : 1.f; };
+  auto sout_at = [&](int ii, int kk, int jj) -> float { return in_lim(ii, kk, jj) ? A3(scale_out, ii, kk, jj) : 1.f; };
+  float t = 0.f;
+  const int i_end = min(ite, ide - 1), j_end = min(jte, jde - 1);
+  if (g.open_xs && i == ids) {
+    const float ub = fminf(0.5f * (A3(ru, ids, k, j) + A3(ru, ids + 1, k, j)), 0.f);
+    t = t - g.rdx * (ub * (A3(q_old, ids + 1, k, j) - A3(q_old, ids, k, j)) + A3(q, ids, k, j) * (A3(ru, ids + 1, k, j) - A3(ru, ids, k, j)));
+  }
+  if (g.open_xe && ite == ide && i == i_end) {
+    const float ub = fmaxf(0.5f * (A3(ru, ide - 1, k, j) + A3(ru, ide, k, j)), 0.f);
+    t = t - g.rdx * (ub * (A3(q_old, i_end, k, j) - A3(q_old, i_end - 1, k, j)) + A3(q, i_end, k, j) * (A3(ru, ide, k, j) - A3(ru, ide - 1, k, j)));
+  }
+  if (g.open_ys && j == jds) {
+    const float vb = fminf(0.5f * (A3(rv, i, k, jds) + A3(rv, i, k, jds + 1)), 0.f);
+    t = t - g.rdy * (vb * (A3(q_old, i, k, jds + 1) - A3(q_old, i, k, jds)) + A3(q, i, k, jds) * (A3(rv, i, k, jds + 1) - A3(rv, i, k, jds)));
+  }
+  if (g.open_ye && jte == jde && j == j_end) {
+    const float vb = fmaxf(0.5f * (A3(rv, i, k, jde - 1) + A3(rv, i, k, jde)), 0.f);
+    t = t - g.rdy * (vb * (A3(q_old, i, k, j_end) - A3(q_old, i, k, j_end - 1)) + A3(q, i, k, j_end) * (A3(rv, i, k, jde) - A3(rv, i, k, jde - 1)));
+  }
+  // the reference scales the faces in its own loops (x: i_start..i_end+1, y: j_start..j_end+1, z: k = 2..ktf of the
+  // limiter box); a face outside them keeps its value, which is what the factor 1 of sin_at / sout_at gives
+  {
+    const MFace z0 = mono_face_z(g, s, i, k, j), z1 = mono_face_z(g, s, i, k + 1, j);
+    float h0 = z0.hi, h1 = z1.hi;
+    if (z0.ok) h0 = (h0 < 0.f ? fminf(sin_at(i, k, j), sout_at(i, k - 1, j)) : fminf(sout_at(i, k, j), sin_at(i, k - 1, j))) * h0;
+    if (z1.ok) h1 = (h1 < 0.f ? fminf(sin_at(i, k + 1, j), sout_at(i, k, j)) : fminf(sout_at(i, k + 1, j), sin_at(i, k, j))) * h1;
+    t = t - g.rdnw[k] * (h1 - h0 + z1.lo - z0.lo);
+  }
+  {
+    const int i_lo = dxs ? max(its, ids + 1) : its, i_hi = dxe ? min(ite, ide - 2) : min(ite, ide - 1);
+    if (i >= i_lo && i <= i_hi) {
+      const MFace x0 = mono_face_x(g, s, i, k, j, dxs, dxe), x1 = mono_face_x(g, s, i + 1, k, j, dxs, dxe);
+      float h0 = x0.hi, h1 = x1.hi;
+      h0 = (h0 > 0.f ? fminf(sin_at(i, k, j), sout_at(i - 1, k, j)) : fminf(sout_at(i, k, j), sin_at(i - 1, k, j))) * h0;
+      h1 = (h1 > 0.f ? fminf(sin_at(i + 1, k, j), sout_at(i, k, j)) : fminf(sout_at(i + 1, k, j), sin_at(i, k, j))) * h1;
+      t = t - A2(g.msftx, i, j) * (g.rdx * (h1 - h0 + x1.lo - x0.lo));
+    }
+  }
+  {
+    const int j_lo = dys ? max(jts, jds + 1) : jts, j_hi = dye ? min(jte, jde - 2) : min(jte, jde - 1);
+    if (j >= j_lo && j <= j_hi) {
+      const MFace y0 = mono_face_y(g, s, i, k, j, dys, dye), y1 = mono_face_y(g, s, i, k, j + 1, dys, dye);
+      float h0 = y0.hi, h1 = y1.hi;
+      h0 = (h0 > 0.f ? fminf(sin_at(i, k, j), sout_at(i, k, j - 1)) : fminf(sout_at(i, k, j), sin_at(i, k, j - 1))) * h0;
+      h1 = (h1 > 0.f ? fminf(sin_at(i, k, j + 1), sout_at(i, k, j)) : fminf(sout_at(i, k, j + 1), sin_at(i, k, j))) * h1;
+      t = t - A2(g.msftx, i, j) * (g.rdy * (h1 - h0 + y1.lo - y0.lo));
+    }
+  }
+  A3(tend, i, k, j) = t;
+}
+
 // rk_update_scalar_pd (module_em.F:1803-1916)
 __global__ void k_update_scalar_pd(const Geo g, Box b, float dt, fp scalar, fp sc_tend, cfp mu_old, cfp mu_new, cfp mu_base) {
   TID3;
@@ -223,7 +390,7 @@ void Solver::rk_scalar_step(int rk_step) {
   if (last) {
     std::vector<BcItem> items;
     for (auto &s : species)
-      if (s.adv_opt == 1) {
+      if (s.adv_opt == 1 || s.adv_opt == 2) {   // /= ORIGINAL and /= WENO_SCALAR (solve_em.F:1850-1977)
         LAUNCH3(this, k_update_scalar_pd, mass, dt_rk, o(s.o), o(s.t), o("mu_1"), o("mu_1"), o("mub"));
         items.push_back({s.o, 'p'});
       }
@@ -233,7 +400,7 @@ void Solver::rk_scalar_step(int rk_step) {
   const bool dxs = !(c.periodic_x || c.symmetric_xs), dxe = !(c.periodic_x || c.symmetric_xe);
   const bool dys = !(c.periodic_y || c.symmetric_ys), dye = !(c.periodic_y || c.symmetric_ye);
   for (auto &s : species) {
-    if (last && s.adv_opt == 1) {
+    if (last && (s.adv_opt == 1 || s.adv_opt == 2)) {
       PdIn in;
       in.q = o(s.f); in.q_old = o(s.o); in.ru = o("ru_m"); in.rv = o("rv_m"); in.rom = o("ww_m");
       in.mut = o("muts"); in.mub = o("mub"); in.mu_old = o("mu_1"); in.dt = dt_rk;
@@ -249,6 +416,12 @@ void Solver::rk_scalar_step(int rk_step) {
       if (c.open_ye && dye) lim.j1 = std::min(q.jte + 1, q.jde - 2);
       // "a" is free between calc_coef_w uses only until the next small_step_prep: use advect scratch "alpha"?  No:
       // the limiter factor gets its own scratch so that a, alpha, gamma stay comparable with the oracle.
+      if (s.adv_opt == 2) {   // monotonic limiter: gather kernels on the whole limiter box / mass points
+        LAUNCH3(this, k_mono_scale, lim, in, o("pd_scale"), o("pd_scale2"));
+        LAUNCH3(this, k_mono_tend, mass, in, o("pd_scale"), o("pd_scale2"), lim, o("advect_tend"));
+        LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
+        continue;
+      }
       // k-marching kernels (pd_fast.cu) where every face is 5th order, the gather kernels on the strips around
       Box sfast = lim, tfast = interior_box(q);
       tfast.k1 = ktf;

@@ -13,7 +13,7 @@ static const char *k3d[] = {
     "ru_m", "rv_m", "ww_m", "ru_tend", "rv_tend", "u_save", "v_save", "t_save", "h_diabatic",
     "ru_tendf", "rv_tendf", "rw_tend", "rw_tendf", "w_save", "ww1",
     "ph_tend", "ph_tendf", "ph_save", "t_tend", "t_tendf", "t_2save", "advect_tend",
-    "alpha", "a", "gamma", "c2a", "cqu", "cqv", "cqw", "pm1", "rho", "pd_scale", "t_init", nullptr};
+    "alpha", "a", "gamma", "c2a", "cqu", "cqv", "cqw", "pm1", "rho", "pd_scale", "pd_scale2", "t_init", nullptr};
 static const char *k3d_mp[] = {"th_phy", "pi_phy", "z", "dz8w", "qv_diabatic", "qc_diabatic", nullptr};
 static const char *k2d[] = {"mu_1", "mu_2", "mub", "mudf", "muu", "muus", "muv", "muvs", "mut", "muts",
                             "muave", "mu_save", "mu_tend", "mu_tendf",
@@ -30,8 +30,8 @@ static void check_config(const wrfgpu_config &c) {
   if (c.rk_ord != 3 && c.rk_ord != 2) bad("rk_ord must be 2 or 3");
   if (c.h_mom_adv_order != 5 || c.h_sca_adv_order != 5) bad("h_*_adv_order must be 5");
   if (c.v_mom_adv_order != 3 || c.v_sca_adv_order != 3) bad("v_*_adv_order must be 3");
-  if (c.moist_adv_opt != 0 && c.moist_adv_opt != 1) bad("moist_adv_opt must be 0 (original) or 1 (positive-definite)");
-  if (c.scalar_adv_opt != 0 && c.scalar_adv_opt != 1) bad("scalar_adv_opt must be 0 or 1");
+  if (c.moist_adv_opt < 0 || c.moist_adv_opt > 2) bad("moist_adv_opt must be 0 (original), 1 (positive-definite) or 2 (monotonic)");
+  if (c.scalar_adv_opt < 0 || c.scalar_adv_opt > 2) bad("scalar_adv_opt must be 0, 1 or 2");
   if (c.momentum_adv_opt != 1) bad("momentum_adv_opt must be 1");
   if (!c.non_hydrostatic) bad("hydrostatic option");
   if (c.damp_opt != 0 && c.damp_opt != 2 && c.damp_opt != 3) bad("damp_opt must be 0, 2 or 3");
