@@ -866,7 +866,7 @@ void Solver::sumflux(int rk_step, int iteration) {
 // the part of sumflux the fused advance_uv leaves: ww_m (all levels) and the level-kde reset of ru_m, rv_m
 __global__ void k_sumflux_w(const Geo g, Box b, int iteration, int nsmall, cfp ww, cfp ww_lin, fp ru_m, fp rv_m, fp ww_m) {
   TID3;
-  const int mini = min(g.ide - 1, g.ite), minj = min(g.jde - 1, g.jte), mink = g.kde - 1;
+  const int mini = min(g.ide - 1, g.ite), minj = min(g.jde - 1, g.jte);
   const bool dw = (i <= mini && j <= minj);
   float cq = 0.f;
   if (iteration != 1) cq = A3(ww_m, i, k, j);

@@ -292,9 +292,7 @@ __device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i,
 }
 __global__ void k_tend_u(const Geo g, Box b, TendIn s, fp ru_tend) {
   TID3;
-  const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, ktf = g.kde - 1, kde = g.kde;
-  const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
-  (void)ids; (void)jds; (void)ktf; (void)kde; (void)its; (void)jts;
+  const int jde = g.jde, ktf = g.kde - 1, jte = g.jte;
   if (k > ktf || j > min(jte, jde - 1)) { A3(ru_tend, i, k, j) = 0.f; return; }
   A3(ru_tend, i, k, j) = interior_pt(g, i, j) ? tend_u_pt<true>(g, s, i, k, j) : tend_u_pt<false>(g, s, i, k, j);
 }
@@ -471,9 +469,7 @@ __device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i,
 }
 __global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
   TID3;
-  const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, ktf = g.kde - 1, kde = g.kde;
-  const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
-  (void)ids; (void)jds; (void)ktf; (void)kde; (void)its; (void)jts;
+  const int ide = g.ide, ktf = g.kde - 1, ite = g.ite;
   if (k > ktf || i > min(ite, ide - 1)) { A3(rv_tend, i, k, j) = 0.f; return; }
   A3(rv_tend, i, k, j) = interior_pt(g, i, j) ? tend_v_pt<true>(g, s, i, k, j) : tend_v_pt<false>(g, s, i, k, j);
 }
@@ -483,7 +479,7 @@ __global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
 // cqw is read here un-inverted; k_invert_cqw applies cqw <- 1/(1+cqw) (:2489) afterwards.
 template <bool FAST>
 __device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i, int k, int j) {
-  const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, kde = g.kde, ktf = g.kde - 1;
+  const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, kde = g.kde;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
   const Deg dg = degrade(g);
   const float sg = g.sgn_ts;
