@@ -90,7 +90,15 @@ __global__ void k_prep_3d(const Geo g, Box b, cfp u, cfp v, cfp w, cfp muu, cfp 
 
 // calc_ww_cp, module_big_step_utilities_em.F:640-782.  One thread per column; pass 1
 // stores divv(k) in ww(k+1) while summing dmdt, pass 2 turns it into ww in place.
-__global__ void k_calc_ww(const Geo g, Box b, cfp u, cfp v, cfp mup, cfp mub, fp ww) {
+#ifndef WW_MINB
+#define WW_MINB 16    // r1w: 6.5 ms per step at 16 resident blocks, 7.5 at 12, 10.6 at 8
+#endif
+#ifndef WW_UNROLL
+#define WW_UNROLL 4
+#endif
+#define WW_PRAGMA_(x) _Pragma(#x)
+#define WW_PRAGMA(x) WW_PRAGMA_(x)
+__global__ void __launch_bounds__(128, WW_MINB) k_calc_ww(const Geo g, Box b, cfp u, cfp v, cfp mup, cfp mub, fp ww) {
   TID2;
   const int ktf = g.kde - 1, kte = g.kde;
   if (i > min(g.ite, g.ide - 1)) {   // i = ide column: only the ww(:,1,:) / ww(:,kte,:) reset (:744-749)
@@ -106,7 +114,7 @@ __global__ void k_calc_ww(const Geo g, Box b, cfp u, cfp v, cfp mup, cfp mub, fp
   const float my0 = A2(g.msfuy, i, j), my1 = A2(g.msfuy, i + 1, j);
   const float mvi0 = A2(g.msfvx_inv, i, j), mvi1 = A2(g.msfvx_inv, i, j + 1);
   float dmdt = 0.f;
-#pragma unroll 4
+  WW_PRAGMA(unroll WW_UNROLL)
   for (int k = 1; k <= ktf; k++) {
     const float c1h = g.c1h[k], c2h = g.c2h[k];
     const float divv = msftx * g.dnw[k] *
@@ -117,7 +125,7 @@ __global__ void k_calc_ww(const Geo g, Box b, cfp u, cfp v, cfp mup, cfp mub, fp
   }
   float wprev = 0.f;
   A3(ww, i, 1, j) = 0.f;
-#pragma unroll 4
+  WW_PRAGMA(unroll WW_UNROLL)
   for (int k = 2; k <= ktf; k++) {
     const float divv = A3(ww, i, k, j);
     wprev = wprev - g.dnw[k - 1] * g.c1h[k - 1] * dmdt - divv;
