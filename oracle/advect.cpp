@@ -37,6 +37,30 @@ inline void degrade_flags(const Cx &x, int xe_off, int ye_off, bool &dxs, bool &
   if (x.c.periodic_y || x.c.symmetric_ys || (x.jts > x.jds + 3)) dys = false;
   if (x.c.periodic_y || x.c.symmetric_ye || (x.jte < x.jde - ye_off)) dye = false;
 }
+// 5th-order WENO face flux (Jiang and Shu 1996) of advect_scalar_weno / advect_scalar_wenopd
+// (module_advect_em.F:8095-8124, 8803-8835).  m3..p2 are the six values around the face (q(-3) .. q(+2)),
+// `upw` = the wind blows from the low-index side.  The candidate fluxes and smoothness indicators are REAL
+// expressions assigned to DOUBLE PRECISION variables; the weights are double precision (eps = 1.d-40, pw = 2).
+inline float weno5(float vel, bool upw, float m3, float m2, float m1, float p0, float p1, float p2) {
+  float qim2, qim1, qi, qip1, qip2;
+  if (upw) { qip2 = p1; qip1 = p0; qi = m1; qim1 = m2; qim2 = m3; }
+  else { qip2 = m2; qip1 = m1; qi = p0; qim1 = p1; qim2 = p2; }
+  const double f0 = (double)(1.f / 3.f * qim2 - 7.f / 6.f * qim1 + 11.f / 6.f * qi);
+  const double f1 = (double)(-1.f / 6.f * qim1 + 5.f / 6.f * qi + 1.f / 3.f * qip1);
+  const double f2 = (double)(1.f / 3.f * qi + 5.f / 6.f * qip1 - 1.f / 6.f * qip2);
+  const float a0 = qim2 - 2.f * qim1 + qi, b0 = qim2 - 4.f * qim1 + 3.f * qi;
+  const float a1 = qim1 - 2.f * qi + qip1, b1 = qim1 - qip1;
+  const float a2 = qi - 2.f * qip1 + qip2, b2 = qip2 - 4.f * qip1 + 3.f * qi;
+  const double beta0 = (double)(13.f / 12.f * (a0 * a0) + 1.f / 4.f * (b0 * b0));
+  const double beta1 = (double)(13.f / 12.f * (a1 * a1) + 1.f / 4.f * (b1 * b1));
+  const double beta2 = (double)(13.f / 12.f * (a2 * a2) + 1.f / 4.f * (b2 * b2));
+  const double gi0 = 1.0 / 10.0, gi1 = 6.0 / 10.0, gi2 = 3.0 / 10.0, eps = 1.0e-40;
+  const double wi0 = gi0 / ((eps + beta0) * (eps + beta0));
+  const double wi1 = gi1 / ((eps + beta1) * (eps + beta1));
+  const double wi2 = gi2 / ((eps + beta2) * (eps + beta2));
+  const double sumwk = wi0 + wi1 + wi2;
+  return (float)((double)vel * (wi0 * f0 + wi1 * f1 + wi2 * f2) / sumwk);
+}
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -971,6 +995,147 @@ void advect_scalar_pd(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A
     for (int k = kts; k <= ktf; k++)
       for (int i = i_start; i <= i_end; i++)
         tendency(i, k, j) = tendency(i, k, j) - msftx(i, j) * (rdy * (fqy(i, k, j + 1) - fqy(i, k, j) + fqyl(i, k, j + 1) - fqyl(i, k, j)));
+}
+
+// module_advect_em.F:7889-8569: 5th-order WENO in all three directions, "adapted from COMMAS";
+// *_adv_opt = 3 (WENO_SCALAR) on the last RK substep, and theta with it (module_em.F:603-621).  Loop structure,
+// degraded faces next to non-periodic boundaries and the open-boundary terms are advect_scalar's; horz_order and
+// vert_order are forced to 5 (:8009-8010): WENO for k = kts+3..ktf-2, flux3 at kts+2 and ktf-1, 2nd order at
+// kts+1 and ktf.  The statement functions are the pre-divided ones (:7974-7981), flux3 without sign(time_step).
+void advect_scalar_weno(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom) {
+  const int ids = x.ids, ide = x.ide, jds = x.jds, jde = x.jde;
+  const int its = x.its, ite = x.ite, jts = x.jts, jte = x.jte, kts = x.kts, kte = x.kte;
+  const int ktf = std::min(kte, x.kde - 1);
+  const A1 &fzm = x.fnm, &fzp = x.fnp, &rdzw = x.rdnw;
+  const float rdx = x.rdx, rdy = x.rdy;
+  const float sgn_ts = (float)(x.time_step >= 0 ? 1 : -1);
+  auto flux3 = [](float q_im2, float q_im1, float q_i, float q_ip1, float ua) {
+    return ((7.f / 12.f) * (q_i + q_im1) - (1.f / 12.f) * (q_ip1 + q_im2)) + sign1(ua) * (1.f / 12.f) * ((q_ip1 - q_im2) - 3.f * (q_i - q_im1));
+  };
+  bool degrade_xs, degrade_xe, degrade_ys, degrade_ye;
+  degrade_flags(x, 3, 4, degrade_xs, degrade_xe, degrade_ys, degrade_ye);   // :8017-8031
+  Row fq0(its, ite, kte), fq1(its, ite, kte), fqx(its, ite, kte), vflux(its, ite, kte);
+
+  // y
+  int i_start = its, i_end = std::min(ite, ide - 1), j_start = jts, j_end = std::min(jte, jde - 1);
+  int j_start_f = j_start, j_end_f = j_end + 1;
+  if (degrade_ys) { j_start = std::max(jts, jds + 1); j_start_f = jds + 3; }
+  if (degrade_ye) { j_end = std::min(jte, jde - 2); j_end_f = jde - 3; }
+  Row *jp1 = &fq1, *jp0 = &fq0;
+  for (int j = j_start; j <= j_end + 1; j++) {
+    Row &fqy = *jp1;
+    const bool full = j >= j_start_f && j <= j_end_f;
+    const bool second = !full && (j == jds + 1 || j == jde - 1), third = !full && !second && (j == jds + 2 || j == jde - 2);
+    if (full || second || third)
+      for (int k = kts; k <= ktf; k++)
+        for (int i = i_start; i <= i_end; i++) {
+          if (full) {
+            float vel = 0.5f * (rv(i, k, j) + rv(i, k, j));     // is = js = ks = 0
+            fqy(i, k) = weno5(vel, vel * sgn_ts >= 0.0f, field(i, k, j - 3), field(i, k, j - 2), field(i, k, j - 1), field(i, k, j),
+                              field(i, k, j + 1), field(i, k, j + 2));
+          } else if (second) {
+            fqy(i, k) = 0.5f * rv(i, k, j) * (field(i, k, j) + field(i, k, j - 1));
+          } else {
+            float vel = rv(i, k, j);
+            fqy(i, k) = vel * flux3(field(i, k, j - 2), field(i, k, j - 1), field(i, k, j), field(i, k, j + 1), vel);
+          }
+        }
+    if (j > j_start)
+      for (int k = kts; k <= ktf; k++)
+        for (int i = i_start; i <= i_end; i++) {
+          float mrdy = x.msftx(i, j - 1) * rdy;
+          tendency(i, k, j - 1) = tendency(i, k, j - 1) - mrdy * ((*jp1)(i, k) - (*jp0)(i, k));
+        }
+    std::swap(jp1, jp0);
+  }
+
+  // x
+  i_start = its; i_end = std::min(ite, ide - 1); j_start = jts; j_end = std::min(jte, jde - 1);
+  int i_start_f = i_start, i_end_f = i_end + 1;
+  if (degrade_xs) { i_start = std::max(ids + 1, its); i_start_f = std::min(i_start + 2, ids + 3); }
+  if (degrade_xe) { i_end = std::min(ide - 2, ite); i_end_f = ide - 3; }
+  for (int j = j_start; j <= j_end; j++) {
+    for (int k = kts; k <= ktf; k++)
+      for (int i = i_start_f; i <= i_end_f; i++) {
+        float vel = 0.5f * (ru(i, k, j) + ru(i, k, j));
+        fqx(i, k) = weno5(vel, vel * sgn_ts >= 0.0f, field(i - 3, k, j), field(i - 2, k, j), field(i - 1, k, j), field(i, k, j),
+                          field(i + 1, k, j), field(i + 2, k, j));
+      }
+    auto low = [&](int i) {
+      if (i == ids + 1 || i == ide - 1)
+        for (int k = kts; k <= ktf; k++) fqx(i, k) = 0.5f * (ru(i, k, j)) * (field(i, k, j) + field(i - 1, k, j));
+      if (i == ids + 2 || i == ide - 2)
+        for (int k = kts; k <= ktf; k++) {
+          float vel = ru(i, k, j);
+          fqx(i, k) = vel * flux3(field(i - 2, k, j), field(i - 1, k, j), field(i, k, j), field(i + 1, k, j), vel);
+        }
+    };
+    if (degrade_xs)
+      for (int i = i_start; i <= i_start_f - 1; i++) if (i == ids + 1 || i == ids + 2) low(i);
+    if (degrade_xe)
+      for (int i = i_end_f + 1; i <= i_end + 1; i++) if (i == ide - 1 || i == ide - 2) low(i);
+    for (int k = kts; k <= ktf; k++)
+      for (int i = i_start; i <= i_end; i++) {
+        float mrdx = x.msftx(i, j) * rdx;
+        tendency(i, k, j) = tendency(i, k, j) - mrdx * (fqx(i + 1, k) - fqx(i, k));
+      }
+  }
+
+  // open boundary terms (:8402-8466)
+  i_start = its; i_end = std::min(ite, ide - 1); j_start = jts; j_end = std::min(jte, jde - 1);
+  if (x.c.open_xs && its == ids)
+    for (int j = j_start; j <= j_end; j++)
+      for (int k = kts; k <= ktf; k++) {
+        float ub = std::min(0.5f * (ru(its, k, j) + ru(its + 1, k, j)), 0.f);
+        tendency(its, k, j) = tendency(its, k, j) -
+                              rdx * (ub * (field_old(its + 1, k, j) - field_old(its, k, j)) + field(its, k, j) * (ru(its + 1, k, j) - ru(its, k, j)));
+      }
+  if (x.c.open_xe && ite == ide)
+    for (int j = j_start; j <= j_end; j++)
+      for (int k = kts; k <= ktf; k++) {
+        float ub = std::max(0.5f * (ru(ite - 1, k, j) + ru(ite, k, j)), 0.f);
+        tendency(i_end, k, j) = tendency(i_end, k, j) -
+                                rdx * (ub * (field_old(i_end, k, j) - field_old(i_end - 1, k, j)) + field(i_end, k, j) * (ru(ite, k, j) - ru(ite - 1, k, j)));
+      }
+  if (x.c.open_ys && jts == jds)
+    for (int k = kts; k <= ktf; k++)
+      for (int i = i_start; i <= i_end; i++) {
+        float vb = std::min(0.5f * (rv(i, k, jts) + rv(i, k, jts + 1)), 0.f);
+        tendency(i, k, jts) = tendency(i, k, jts) -
+                              rdy * (vb * (field_old(i, k, jts + 1) - field_old(i, k, jts)) + field(i, k, jts) * (rv(i, k, jts + 1) - rv(i, k, jts)));
+      }
+  if (x.c.open_ye && jte == jde)
+    for (int k = kts; k <= ktf; k++)
+      for (int i = i_start; i <= i_end; i++) {
+        float vb = std::max(0.5f * (rv(i, k, jte - 1) + rv(i, k, jte)), 0.f);
+        tendency(i, k, j_end) = tendency(i, k, j_end) -
+                                rdy * (vb * (field_old(i, k, j_end) - field_old(i, k, j_end - 1)) + field(i, k, j_end) * (rv(i, k, jte) - rv(i, k, jte - 1)));
+      }
+
+  // vertical (:8476-8565)
+  for (int i = i_start; i <= i_end; i++) { vflux(i, kts) = 0.f; vflux(i, kte) = 0.f; }
+  for (int j = j_start; j <= j_end; j++) {
+    for (int k = kts + 3; k <= ktf - 2; k++)
+      for (int i = i_start; i <= i_end; i++) {
+        float vel = 0.5f * (rom(i, k, j) + rom(i, k, j));
+        vflux(i, k) = weno5(vel, -vel * sgn_ts >= 0.0f, field(i, k - 3, j), field(i, k - 2, j), field(i, k - 1, j), field(i, k, j),
+                            field(i, k + 1, j), field(i, k + 2, j));
+      }
+    for (int i = i_start; i <= i_end; i++) {
+      int k = kts + 1;
+      vflux(i, k) = rom(i, k, j) * (fzm(k) * field(i, k, j) + fzp(k) * field(i, k - 1, j));
+      k = kts + 2;
+      float vel = rom(i, k, j);
+      vflux(i, k) = vel * flux3(field(i, k - 2, j), field(i, k - 1, j), field(i, k, j), field(i, k + 1, j), -vel);
+      k = ktf - 1;
+      vel = rom(i, k, j);
+      vflux(i, k) = vel * flux3(field(i, k - 2, j), field(i, k - 1, j), field(i, k, j), field(i, k + 1, j), -vel);
+      k = ktf;
+      vflux(i, k) = rom(i, k, j) * (fzm(k) * field(i, k, j) + fzp(k) * field(i, k - 1, j));
+    }
+    for (int k = kts; k <= ktf; k++)
+      for (int i = i_start; i <= i_end; i++) tendency(i, k, j) = tendency(i, k, j) - rdzw(k) * (vflux(i, k + 1) - vflux(i, k));
+  }
 }
 
 }  // namespace orc

@@ -165,7 +165,10 @@ void Oracle::rk_tendency(int rk_step) {
   par([&](const Cx &xt) { advect_u(xt, u, u, ru_tend, ru, rv, wwE, mut); });
   par([&](const Cx &xt) { advect_v(xt, v, v, rv_tend, ru, rv, wwE, mut); });
   par([&](const Cx &xt) { advect_w(xt, w, w, rw_tend, ru, rv, wwE, mut); });
-  par([&](const Cx &xt) { advect_scalar(xt, t, t, t_tend, ru, rv, wwE, mut); });
+  // theta goes with the scalars' WENO option on the last RK substep (module_em.F:603-621)
+  const bool weno_t = (c.scalar_adv_opt == 3 || c.scalar_adv_opt == 4 || c.moist_adv_opt == 3 || c.moist_adv_opt == 4) && rk_step == c.rk_ord;
+  if (weno_t) par([&](const Cx &xt) { advect_scalar_weno(xt, t, t, t_tend, ru, rv, wwE); });
+  else par([&](const Cx &xt) { advect_scalar(xt, t, t, t_tend, ru, rv, wwE, mut); });
   par([&](const Cx &xt) { rhs_ph(xt, ph_tend, u, v, wwE, ph, ph, a3("phb"), w, mut, muu, muv); });
   par([&](const Cx &xt) { horizontal_pressure_gradient(xt, ru_tend, rv_tend, ph, a3("alt"), a3("p"), a3("pb"), a3("al"), a3("php"), a3("cqu"), a3("cqv"), muu, muv, mu); });
   par([&](const Cx &xt) { pg_buoy_w(xt, rw_tend, a3("p"), a3("cqw"), mu, mub); });
@@ -315,6 +318,8 @@ void Oracle::rk_scalar_step(int rk_step) {
     par([&](const Cx &xt) { zero_tend(xt, a3("advect_tend")); });
     if (rk_step == rk_order && s.adv_opt == 1)
       par([&](const Cx &xt) { advect_scalar_pd(xt, a3(s.f), a3(s.o), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE"), a2("muts"), a2("mub"), a2("mu_1"), dt_rk); });
+    else if (rk_step == rk_order && s.adv_opt == 3)   // WENO_SCALAR, module_em.F:1300-1312
+      par([&](const Cx &xt) { advect_scalar_weno(xt, a3(s.f), a3(s.f), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE")); });
     else if (rk_step == rk_order && s.adv_opt == 2)   // MONOTONIC, module_em.F:1282-1298
       par([&](const Cx &xt) { advect_scalar_mono(xt, a3(s.f), a3(s.o), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE"), a3("wwI"), a2("muts"), a2("mub"), a2("mu_1"), dt_rk); });
     else
