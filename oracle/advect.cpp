@@ -758,8 +758,10 @@ void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
 // ---------------------------------------------------------------------------
 // module_advect_em.F:6069-7885, horz_order 5 (:6505-6779), vert_order 3
 // (:7595-7645), limiter (:7681-7776), flux divergence (:7778-7883)
+// `weno` = advect_scalar_wenopd (:8573-9490, *_adv_opt = 4): the same routine with the 5th-order fluxes replaced by
+// the WENO flux and, in the vertical, WENO on k = kts+3..ktf-2 (flux3 stays at kts+2 and ktf-1) (:9217-9262).
 void advect_scalar_pd(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom,
-                      A2 mut, A2 mub, A2 mu_old, float dt) {
+                      A2 mut, A2 mub, A2 mu_old, float dt, bool weno) {
   const int ids = x.ids, ide = x.ide, jds = x.jds, jde = x.jde, kde = x.kde;
   const int its = x.its, ite = x.ite, jts = x.jts, jte = x.jte, kts = x.kts, kte = x.kte;
   const int ktf = std::min(kte, kde - 1);
@@ -822,7 +824,9 @@ void advect_scalar_pd(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A
         float vel = rv(i, k, j);
         float cr = vel * dt / dy / mu;
         fqyl(i, k, j) = mu * (dy / dt) * flux_upwind(field_old(i, k, j - 1), field_old(i, k, j), cr);
-        if (mode == 5)
+        if (mode == 5 && weno)
+          fqy(i, k, j) = weno5(vel, vel * sgn >= 0.0f, field(i, k, j - 3), field(i, k, j - 2), field(i, k, j - 1), field(i, k, j), field(i, k, j + 1), field(i, k, j + 2));
+        else if (mode == 5)
           fqy(i, k, j) = vel * flux5(field(i, k, j - 3), field(i, k, j - 2), field(i, k, j - 1), field(i, k, j), field(i, k, j + 1), field(i, k, j + 2), vel);
         else if (mode == 2)
           fqy(i, k, j) = 0.5f * rv(i, k, j) * (field(i, k, j) + field(i, k, j - 1));
@@ -852,7 +856,9 @@ void advect_scalar_pd(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A
         cr = vel * dt / dx / mu;
       }
       fqxl(i, k, j) = mu * (dx / dt) * flux_upwind(field_old(i - 1, k, j), field_old(i, k, j), cr);
-      if (mode == 5)
+      if (mode == 5 && weno)
+        fqx(i, k, j) = weno5(vel, vel * sgn >= 0.0f, field(i - 3, k, j), field(i - 2, k, j), field(i - 1, k, j), field(i, k, j), field(i + 1, k, j), field(i + 2, k, j));
+      else if (mode == 5)
         fqx(i, k, j) = vel * flux5(field(i - 3, k, j), field(i - 2, k, j), field(i - 1, k, j), field(i, k, j), field(i + 1, k, j), field(i + 2, k, j), vel);
       else if (mode == 2)
         fqx(i, k, j) = 0.5f * (ru(i, k, j)) * (field(i, k, j) + field(i - 1, k, j));
@@ -926,7 +932,10 @@ void advect_scalar_pd(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A
       for (int i = i_start; i <= i_end; i++) {
         dolow(i, k);
         float vel = rom(i, k, j);
-        fqz(i, k, j) = vel * flux3(field(i, k - 2, j), field(i, k - 1, j), field(i, k, j), field(i, k + 1, j), -vel);
+        if (weno && k >= kts + 3 && k <= ktf - 2)
+          fqz(i, k, j) = weno5(vel, -vel * sgn >= 0.0f, field(i, k - 3, j), field(i, k - 2, j), field(i, k - 1, j), field(i, k, j), field(i, k + 1, j), field(i, k + 2, j));
+        else
+          fqz(i, k, j) = vel * flux3(field(i, k - 2, j), field(i, k - 1, j), field(i, k, j), field(i, k + 1, j), -vel);
         fqz(i, k, j) = fqz(i, k, j) - fqzl(i, k, j);
       }
     for (int i = i_start; i <= i_end; i++) {
@@ -1025,7 +1034,7 @@ void advect_scalar_weno(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru,
   for (int j = j_start; j <= j_end + 1; j++) {
     Row &fqy = *jp1;
     const bool full = j >= j_start_f && j <= j_end_f;
-    const bool second = !full && (j == jds + 1 || j == jde - 1), third = !full && !second && (j == jds + 2 || j == jde - 2);
+    const bool second = !full && (j == jds + 1 || (j == jde - 1 && j != jds + 2)), third = !full && !second && (j == jds + 2 || j == jde - 2);
     if (full || second || third)
       for (int k = kts; k <= ktf; k++)
         for (int i = i_start; i <= i_end; i++) {

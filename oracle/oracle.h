@@ -191,7 +191,7 @@ void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
 void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut);
 void advect_scalar(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut);
 void advect_scalar_pd(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom,
-                      A2 mut, A2 mub, A2 mu_old, float dt);
+                      A2 mut, A2 mub, A2 mu_old, float dt, bool weno = false);
 void advect_scalar_weno(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom);
 // advect_mono.cpp
 void advect_scalar_mono(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom, A3 romI,

@@ -303,21 +303,21 @@ void Oracle::rk_scalar_step(int rk_step) {
     sp.push_back({"scalar_" + std::to_string(s), "scalar_old_" + std::to_string(s), "scalar_tend_" + std::to_string(s), c.scalar_adv_opt});
   if (rk_step == rk_order)
     for (auto &s : sp)
-      if (s.adv_opt == 1 || s.adv_opt == 2) par([&](const Cx &xt) { rk_update_scalar_pd(xt, a3(s.o), a3(s.t), a2("mu_1"), a2("mu_1"), a2("mub"), dt_rk); });
+      if (s.adv_opt == 1 || s.adv_opt == 2 || s.adv_opt == 4) par([&](const Cx &xt) { rk_update_scalar_pd(xt, a3(s.o), a3(s.t), a2("mu_1"), a2("mu_1"), a2("mub"), dt_rk); });
   if (rk_step == rk_order) {
     bool any = false;
-    for (auto &s : sp) any |= (s.adv_opt == 1 || s.adv_opt == 2);   // /= ORIGINAL and /= WENO_SCALAR, solve_em.F:1850-1977
+    for (auto &s : sp) any |= (s.adv_opt == 1 || s.adv_opt == 2 || s.adv_opt == 4);   // /= ORIGINAL and /= WENO_SCALAR, solve_em.F:1850-1977
     if (any) halo("HALO_EM_MOIST_OLD_E_7");   // + PERIOD_BDY_EM_MOIST_OLD (and the SCALAR_OLD twins), solve_em.F:1878-2142
     for (auto &s : sp)
-      if (s.adv_opt == 1 || s.adv_opt == 2) bc(s.o, 'p');
+      if (s.adv_opt == 1 || s.adv_opt == 2 || s.adv_opt == 4) bc(s.o, 'p');
   }
   halo("HALO_EM_D");   // + PERIOD_EM_DA, solve_em.F:2179-2181
   for (auto &s : sp) {
     // rk_scalar_tend, module_em.F:1096-1442
     par([&](const Cx &xt) { ww_split(xt, a3("wwE"), a3("wwI"), a3("ww_m")); });
     par([&](const Cx &xt) { zero_tend(xt, a3("advect_tend")); });
-    if (rk_step == rk_order && s.adv_opt == 1)
-      par([&](const Cx &xt) { advect_scalar_pd(xt, a3(s.f), a3(s.o), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE"), a2("muts"), a2("mub"), a2("mu_1"), dt_rk); });
+    if (rk_step == rk_order && (s.adv_opt == 1 || s.adv_opt == 4))   // POSITIVEDEF :1266-1280, WENOPD_SCALAR :1314-1327
+      par([&](const Cx &xt) { advect_scalar_pd(xt, a3(s.f), a3(s.o), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE"), a2("muts"), a2("mub"), a2("mu_1"), dt_rk, s.adv_opt == 4); });
     else if (rk_step == rk_order && s.adv_opt == 3)   // WENO_SCALAR, module_em.F:1300-1312
       par([&](const Cx &xt) { advect_scalar_weno(xt, a3(s.f), a3(s.f), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE")); });
     else if (rk_step == rk_order && s.adv_opt == 2)   // MONOTONIC, module_em.F:1282-1298

@@ -75,6 +75,14 @@ def small_cases():
         "mono": make_case("quarter_ss", nx=26, ny=24, nz=21, moist_adv_opt=2),
         "mono_periodic": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=2,
                                                     scalar_adv_opt=2, moist_adv_opt=2)),
+        # 5th-order WENO scalar advection (*_adv_opt = 3; theta follows on the last RK substep) and WENO inside the
+        # positive-definite limiter (*_adv_opt = 4): open + Kessler species, and doubly periodic tracers with map factors
+        "weno": make_case("quarter_ss", nx=26, ny=24, nz=21, moist_adv_opt=3),
+        "weno_periodic": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=2,
+                                                    scalar_adv_opt=3, moist_adv_opt=3)),
+        "wenopd": make_case("quarter_ss", nx=26, ny=24, nz=21, moist_adv_opt=4),
+        "wenopd_periodic": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=2,
+                                                      scalar_adv_opt=4, moist_adv_opt=3)),
     }
 
 

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 CASES = None
 ALL = ["hill2d_x", "quarter_ss", "quarter_ss_nopd", "b_wave", "les", "periodic", "b_wave_lid", "quarter_ss_opts", "rk2_sym_x",
        "mapfac", "mapfac_open", "diffusion", "diffusion_periodic", "b_wave_shipped",
-       "mono", "mono_periodic"]
+       "mono", "mono_periodic", "weno", "weno_periodic", "wenopd", "wenopd_periodic"]
 
 
 def cases():

@@ -12,10 +12,17 @@
 // cell (:7764-7773) and writes the tendency.  Flux values are pure functions of the
 // inputs, so recomputation is bit-identical to the stored version.
 #include "common.cuh"
+#include "weno.cuh"
 
 namespace wg {
 
 __global__ void k_advect_scalar(const Geo g, Box b, cfp q, cfp ru, cfp rv, cfp rom, fp tend);   // tend.cu
+
+// advect_scalar_weno on the mass points (*_adv_opt = 3, last RK substep, module_em.F:1300-1312)
+__global__ void k_advect_scalar_weno(const Geo g, Box b, cfp q, cfp ru, cfp rv, cfp rom, fp tend) {
+  TID3;
+  A3(tend, i, k, j) = advect_scalar_weno_pt(g, q, q, ru, rv, rom, i, k, j);
+}
 
 // statement functions of advect_scalar_pd (:6169-6186) -- note the pre-divided constants
 __device__ __forceinline__ float pflux4(float qm2, float qm1, float q0, float qp1) {
@@ -37,6 +44,7 @@ __device__ __forceinline__ float flux_upwind(float qm1, float q0, float cr) {
 struct PdIn {
   cfp q, q_old, ru, rv, rom, mut, mub, mu_old;
   float dt;
+  bool weno;   // advect_scalar_wenopd (*_adv_opt = 4): WENO in place of the 5th-order fluxes, and on k = 4..ktf-2
 };
 struct Face { float hi, lo; bool ok; };   // hi = high-order minus low, lo = upwind flux
 
@@ -63,7 +71,8 @@ __device__ __forceinline__ Face pd_face_x(const Geo &g, const PdIn &s, int ii, i
   else { vel = A3(s.ru, ii, k, j); cr = vel * s.dt / dx / mu; }
   f.lo = mu * (dx / s.dt) * flux_upwind(A3(s.q_old, ii - 1, k, j), A3(s.q_old, ii, k, j), cr);
   float h;
-  if (ord == 5) h = vel * pflux5(A3(s.q, ii - 3, k, j), A3(s.q, ii - 2, k, j), A3(s.q, ii - 1, k, j), A3(s.q, ii, k, j), A3(s.q, ii + 1, k, j), A3(s.q, ii + 2, k, j), vel, g.sgn_ts);
+  if (ord == 5 && s.weno) h = weno5(vel, vel * g.sgn_ts >= 0.0f, A3(s.q, ii - 3, k, j), A3(s.q, ii - 2, k, j), A3(s.q, ii - 1, k, j), A3(s.q, ii, k, j), A3(s.q, ii + 1, k, j), A3(s.q, ii + 2, k, j));
+  else if (ord == 5) h = vel * pflux5(A3(s.q, ii - 3, k, j), A3(s.q, ii - 2, k, j), A3(s.q, ii - 1, k, j), A3(s.q, ii, k, j), A3(s.q, ii + 1, k, j), A3(s.q, ii + 2, k, j), vel, g.sgn_ts);
   else if (ord == 3) h = vel * pflux3(A3(s.q, ii - 2, k, j), A3(s.q, ii - 1, k, j), A3(s.q, ii, k, j), A3(s.q, ii + 1, k, j), vel, g.sgn_ts);
   else h = 0.5f * (A3(s.ru, ii, k, j)) * (A3(s.q, ii, k, j) + A3(s.q, ii - 1, k, j));
   f.hi = h - f.lo;
@@ -81,7 +90,8 @@ __device__ __forceinline__ Face pd_face_y(const Geo &g, const PdIn &s, int i, in
   const float cr = vel * s.dt / dy / mu;
   f.lo = mu * (dy / s.dt) * flux_upwind(A3(s.q_old, i, k, jj - 1), A3(s.q_old, i, k, jj), cr);
   float h;
-  if (ord == 5) h = vel * pflux5(A3(s.q, i, k, jj - 3), A3(s.q, i, k, jj - 2), A3(s.q, i, k, jj - 1), A3(s.q, i, k, jj), A3(s.q, i, k, jj + 1), A3(s.q, i, k, jj + 2), vel, g.sgn_ts);
+  if (ord == 5 && s.weno) h = weno5(vel, vel * g.sgn_ts >= 0.0f, A3(s.q, i, k, jj - 3), A3(s.q, i, k, jj - 2), A3(s.q, i, k, jj - 1), A3(s.q, i, k, jj), A3(s.q, i, k, jj + 1), A3(s.q, i, k, jj + 2));
+  else if (ord == 5) h = vel * pflux5(A3(s.q, i, k, jj - 3), A3(s.q, i, k, jj - 2), A3(s.q, i, k, jj - 1), A3(s.q, i, k, jj), A3(s.q, i, k, jj + 1), A3(s.q, i, k, jj + 2), vel, g.sgn_ts);
   else if (ord == 3) h = vel * pflux3(A3(s.q, i, k, jj - 2), A3(s.q, i, k, jj - 1), A3(s.q, i, k, jj), A3(s.q, i, k, jj + 1), vel, g.sgn_ts);
   else h = 0.5f * A3(s.rv, i, k, jj) * (A3(s.q, i, k, jj) + A3(s.q, i, k, jj - 1));
   f.hi = h - f.lo;
@@ -100,6 +110,8 @@ __device__ __forceinline__ Face pd_face_z(const Geo &g, const PdIn &s, int i, in
   f.lo = mu * (dz / s.dt) * flux_upwind(A3(s.q_old, i, kk - 1, j), A3(s.q_old, i, kk, j), cr);
   float h;
   if (kk == 2 || kk == ktf) h = A3(s.rom, i, kk, j) * (g.fnm[kk] * A3(s.q, i, kk, j) + g.fnp[kk] * A3(s.q, i, kk - 1, j));
+  else if (s.weno && kk >= 4 && kk <= ktf - 2)   // :9217-9262
+    h = weno5(vel, -vel * g.sgn_ts >= 0.0f, A3(s.q, i, kk - 3, j), A3(s.q, i, kk - 2, j), A3(s.q, i, kk - 1, j), A3(s.q, i, kk, j), A3(s.q, i, kk + 1, j), A3(s.q, i, kk + 2, j));
   else h = vel * pflux3(A3(s.q, i, kk - 2, j), A3(s.q, i, kk - 1, j), A3(s.q, i, kk, j), A3(s.q, i, kk + 1, j), -vel, g.sgn_ts);
   f.hi = h - f.lo;
   return f;
@@ -390,7 +402,7 @@ void Solver::rk_scalar_step(int rk_step) {
   if (last) {
     std::vector<BcItem> items;
     for (auto &s : species)
-      if (s.adv_opt == 1 || s.adv_opt == 2) {   // /= ORIGINAL and /= WENO_SCALAR (solve_em.F:1850-1977)
+      if (s.adv_opt == 1 || s.adv_opt == 2 || s.adv_opt == 4) {   // /= ORIGINAL and /= WENO_SCALAR (solve_em.F:1850-1977)
         LAUNCH3(this, k_update_scalar_pd, mass, dt_rk, o(s.o), o(s.t), o("mu_1"), o("mu_1"), o("mub"));
         items.push_back({s.o, 'p'});
       }
@@ -400,10 +412,10 @@ void Solver::rk_scalar_step(int rk_step) {
   const bool dxs = !(c.periodic_x || c.symmetric_xs), dxe = !(c.periodic_x || c.symmetric_xe);
   const bool dys = !(c.periodic_y || c.symmetric_ys), dye = !(c.periodic_y || c.symmetric_ye);
   for (auto &s : species) {
-    if (last && (s.adv_opt == 1 || s.adv_opt == 2)) {
+    if (last && (s.adv_opt == 1 || s.adv_opt == 2 || s.adv_opt == 4)) {
       PdIn in;
       in.q = o(s.f); in.q_old = o(s.o); in.ru = o("ru_m"); in.rv = o("rv_m"); in.rom = o("ww_m");
-      in.mut = o("muts"); in.mub = o("mub"); in.mu_old = o("mu_1"); in.dt = dt_rk;
+      in.mut = o("muts"); in.mub = o("mub"); in.mu_old = o("mu_1"); in.dt = dt_rk; in.weno = s.adv_opt == 4;
       // limiter box (:7683-7710)
       Box lim{q.its - 1, im + 1, 1, ktf, q.jts - 1, jm + 1};
       if (dxs) lim.i0 = std::max(q.its - 1, q.ids);
@@ -422,6 +434,12 @@ void Solver::rk_scalar_step(int rk_step) {
         LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
         continue;
       }
+      if (s.adv_opt == 4) {   // WENO inside the positive-definite limiter: the gather kernels everywhere
+        LAUNCH3(this, k_pd_scale, lim, in, o("pd_scale"));
+        LAUNCH3(this, k_pd_tend, mass, in, o("pd_scale"), lim, o("advect_tend"));
+        LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
+        continue;
+      }
       // k-marching kernels (pd_fast.cu) where every face is 5th order, the gather kernels on the strips around
       Box sfast = lim, tfast = interior_box(q);
       tfast.k1 = ktf;
@@ -434,6 +452,8 @@ void Solver::rk_scalar_step(int rk_step) {
       launch_pd_fast(this, 2, tfast, in.q, in.q_old, dt_rk, o("advect_tend"));
       nst = edge_strips(mass, tfast, strips);
       for (int m = 0; m < nst; m++) LAUNCH3(this, k_pd_tend, strips[m], in, o("pd_scale"), lim, o("advect_tend"));
+    } else if (last && s.adv_opt == 3) {   // WENO_SCALAR (module_em.F:1300-1312)
+      LAUNCH3(this, k_advect_scalar_weno, mass, o(s.f), o("ru_m"), o("rv_m"), o("ww_m"), o("advect_tend"));
     } else {
       Box in = interior_box(q);
       in.k1 = ktf;

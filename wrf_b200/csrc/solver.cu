@@ -30,8 +30,8 @@ static void check_config(const wrfgpu_config &c) {
   if (c.rk_ord != 3 && c.rk_ord != 2) bad("rk_ord must be 2 or 3");
   if (c.h_mom_adv_order != 5 || c.h_sca_adv_order != 5) bad("h_*_adv_order must be 5");
   if (c.v_mom_adv_order != 3 || c.v_sca_adv_order != 3) bad("v_*_adv_order must be 3");
-  if (c.moist_adv_opt < 0 || c.moist_adv_opt > 2) bad("moist_adv_opt must be 0 (original), 1 (positive-definite) or 2 (monotonic)");
-  if (c.scalar_adv_opt < 0 || c.scalar_adv_opt > 2) bad("scalar_adv_opt must be 0, 1 or 2");
+  if (c.moist_adv_opt < 0 || c.moist_adv_opt > 4) bad("moist_adv_opt must be 0 (original), 1 (positive-definite), 2 (monotonic), 3 (WENO) or 4 (WENO, positive-definite)");
+  if (c.scalar_adv_opt < 0 || c.scalar_adv_opt > 4) bad("scalar_adv_opt must be 0 ... 4");
   if (c.momentum_adv_opt != 1) bad("momentum_adv_opt must be 1");
   if (!c.non_hydrostatic) bad("hydrostatic option");
   if (c.damp_opt != 0 && c.damp_opt != 2 && c.damp_opt != 3) bad("damp_opt must be 0, 2 or 3");

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "libm_port.h"
 #include "flux.cuh"
+#include "weno.cuh"
 
 namespace wg {
 
@@ -709,6 +710,16 @@ __global__ void k_tend_t(const Geo g, Box b, TendIn s, fp t_tend) {
   A3(t_tend, i, k, j) = t;
 }
 
+// t_tend on the last RK substep when a scalar family uses WENO (module_em.F:603-621): advect_scalar_weno(theta)
+__global__ void k_tend_t_weno(const Geo g, Box b, TendIn s, fp t_tend) {
+  TID3;
+  if (k > g.kde - 1 || i > min(g.ite, g.ide - 1) || j > min(g.jte, g.jde - 1)) { A3(t_tend, i, k, j) = 0.f; return; }
+  float t = advect_scalar_weno_pt(g, s.t, s.t, s.ru, s.rv, s.ww, i, k, j);
+  const float msfty = A2(g.msfty, i, j);
+  t = t + A3(s.t_tendf, i, k, j) / msfty + (g.c1h[k] * A2(s.mut, i, j) + g.c2h[k]) * A3(s.h_diabatic, i, k, j) / msfty;
+  A3(t_tend, i, k, j) = t;
+}
+
 // external entry for the scalar path (scalar.cu)
 __global__ void k_advect_scalar(const Geo g, Box b, cfp q, cfp ru, cfp rv, cfp rom, fp tend) {
   TID3;
@@ -978,7 +989,10 @@ void Solver::rk_tendency(int rk_step, bool zero_save) {
     LAUNCH3(this, k_tend_v, tile, s, o("rv_tend"));
     LAUNCH3(this, k_tend_w, tile, s, o("rw_tend"));
   }
-  {   // theta: k-marching flux-sharing kernel on the interior, the gather kernel on the edge strips
+  const bool weno_t = (c.scalar_adv_opt == 3 || c.scalar_adv_opt == 4 || c.moist_adv_opt == 3 || c.moist_adv_opt == 4) && rk_step == c.rk_ord;
+  if (weno_t) {   // theta follows the scalars' WENO option on the last substep: gather kernel on the whole tile
+    LAUNCH3(this, k_tend_t_weno, tile, s, o("t_tend"));
+  } else {   // theta: k-marching flux-sharing kernel on the interior, the gather kernel on the edge strips
     launch_advect_scalar_fast(this, true, in, s.t, s.ru, s.rv, s.ww, s.mut, s.t_tendf, s.h_diabatic, o("t_tend"));
     for (int m = 0; m < ns; m++) LAUNCH3(this, k_tend_t, strips[m], s, o("t_tend"));
   }
