@@ -8,8 +8,44 @@
 namespace orc {
 
 namespace {
+// 5th-order WENO face flux (Jiang and Shu 1996) of advect_scalar_weno / advect_scalar_wenopd
+// (module_advect_em.F:8095-8124, 8803-8835).  m3..p2 are the six values around the face (q(-3) .. q(+2)),
+// `upw` = the wind blows from the low-index side.  The candidate fluxes and smoothness indicators are REAL
+// expressions assigned to DOUBLE PRECISION variables; the weights are double precision (pw = 2; eps = 1.d-40 for scalars,
+// 1.d-18 in advect_weno_u/v/w :10950).
+inline float weno5(float vel, bool upw, float m3, float m2, float m1, float p0, float p1, float p2, double eps = 1.0e-40) {
+  float qim2, qim1, qi, qip1, qip2;
+  if (upw) { qip2 = p1; qip1 = p0; qi = m1; qim1 = m2; qim2 = m3; }
+  else { qip2 = m2; qip1 = m1; qi = p0; qim1 = p1; qim2 = p2; }
+  const double f0 = (double)(1.f / 3.f * qim2 - 7.f / 6.f * qim1 + 11.f / 6.f * qi);
+  const double f1 = (double)(-1.f / 6.f * qim1 + 5.f / 6.f * qi + 1.f / 3.f * qip1);
+  const double f2 = (double)(1.f / 3.f * qi + 5.f / 6.f * qip1 - 1.f / 6.f * qip2);
+  const float a0 = qim2 - 2.f * qim1 + qi, b0 = qim2 - 4.f * qim1 + 3.f * qi;
+  const float a1 = qim1 - 2.f * qi + qip1, b1 = qim1 - qip1;
+  const float a2 = qi - 2.f * qip1 + qip2, b2 = qip2 - 4.f * qip1 + 3.f * qi;
+  const double beta0 = (double)(13.f / 12.f * (a0 * a0) + 1.f / 4.f * (b0 * b0));
+  const double beta1 = (double)(13.f / 12.f * (a1 * a1) + 1.f / 4.f * (b1 * b1));
+  const double beta2 = (double)(13.f / 12.f * (a2 * a2) + 1.f / 4.f * (b2 * b2));
+  const double gi0 = 1.0 / 10.0, gi1 = 6.0 / 10.0, gi2 = 3.0 / 10.0;
+  const double wi0 = gi0 / ((eps + beta0) * (eps + beta0));
+  const double wi1 = gi1 / ((eps + beta1) * (eps + beta1));
+  const double wi2 = gi2 / ((eps + beta2) * (eps + beta2));
+  const double sumwk = wi0 + wi1 + wi2;
+  return (float)((double)vel * (wi0 * f0 + wi1 * f1 + wi2 * f2) / sumwk);
+}
 struct Flux {
   float sgn_ts;  // sign(1,time_step)
+  bool weno = false;   // advect_weno_u/v/w (:10876-13041, momentum_adv_opt = 3): WENO in place of flux5, vert_order 5 structure
+  // vel * flux5(...) of a horizontal face, or the WENO face flux
+  inline float h5(float vel, float m3, float m2, float m1, float p0, float p1, float p2) const {
+    if (weno) return weno5(vel, vel * sgn_ts >= 0.0f, m3, m2, m1, p0, p1, p2, 1.0e-18);
+    return vel * flux5(m3, m2, m1, p0, p1, p2, vel);
+  }
+  // vertical face k: flux3 under vert_order 3; with weno the 5th-order structure, WENO on k = kts+3 .. k5max
+  inline float v35(int k, int k5min, int k5max, float vel, float m3, float m2, float m1, float p0, float p1, float p2) const {
+    if (weno && k >= k5min && k <= k5max) return weno5(vel, -vel * sgn_ts >= 0.0f, m3, m2, m1, p0, p1, p2, 1.0e-18);
+    return vel * flux3(m2, m1, p0, p1, -vel);
+  }
   // module_advect_em.F:202-213 statement functions
   inline float flux4(float q_im2, float q_im1, float q_i, float q_ip1) const {
     return (7.f * (q_i + q_im1) - (q_ip1 + q_im2)) / 12.0f;
@@ -37,42 +73,18 @@ inline void degrade_flags(const Cx &x, int xe_off, int ye_off, bool &dxs, bool &
   if (x.c.periodic_y || x.c.symmetric_ys || (x.jts > x.jds + 3)) dys = false;
   if (x.c.periodic_y || x.c.symmetric_ye || (x.jte < x.jde - ye_off)) dye = false;
 }
-// 5th-order WENO face flux (Jiang and Shu 1996) of advect_scalar_weno / advect_scalar_wenopd
-// (module_advect_em.F:8095-8124, 8803-8835).  m3..p2 are the six values around the face (q(-3) .. q(+2)),
-// `upw` = the wind blows from the low-index side.  The candidate fluxes and smoothness indicators are REAL
-// expressions assigned to DOUBLE PRECISION variables; the weights are double precision (eps = 1.d-40, pw = 2).
-inline float weno5(float vel, bool upw, float m3, float m2, float m1, float p0, float p1, float p2) {
-  float qim2, qim1, qi, qip1, qip2;
-  if (upw) { qip2 = p1; qip1 = p0; qi = m1; qim1 = m2; qim2 = m3; }
-  else { qip2 = m2; qip1 = m1; qi = p0; qim1 = p1; qim2 = p2; }
-  const double f0 = (double)(1.f / 3.f * qim2 - 7.f / 6.f * qim1 + 11.f / 6.f * qi);
-  const double f1 = (double)(-1.f / 6.f * qim1 + 5.f / 6.f * qi + 1.f / 3.f * qip1);
-  const double f2 = (double)(1.f / 3.f * qi + 5.f / 6.f * qip1 - 1.f / 6.f * qip2);
-  const float a0 = qim2 - 2.f * qim1 + qi, b0 = qim2 - 4.f * qim1 + 3.f * qi;
-  const float a1 = qim1 - 2.f * qi + qip1, b1 = qim1 - qip1;
-  const float a2 = qi - 2.f * qip1 + qip2, b2 = qip2 - 4.f * qip1 + 3.f * qi;
-  const double beta0 = (double)(13.f / 12.f * (a0 * a0) + 1.f / 4.f * (b0 * b0));
-  const double beta1 = (double)(13.f / 12.f * (a1 * a1) + 1.f / 4.f * (b1 * b1));
-  const double beta2 = (double)(13.f / 12.f * (a2 * a2) + 1.f / 4.f * (b2 * b2));
-  const double gi0 = 1.0 / 10.0, gi1 = 6.0 / 10.0, gi2 = 3.0 / 10.0, eps = 1.0e-40;
-  const double wi0 = gi0 / ((eps + beta0) * (eps + beta0));
-  const double wi1 = gi1 / ((eps + beta1) * (eps + beta1));
-  const double wi2 = gi2 / ((eps + beta2) * (eps + beta2));
-  const double sumwk = wi0 + wi1 + wi2;
-  return (float)((double)vel * (wi0 * f0 + wi1 * f1 + wi2 * f2) / sumwk);
-}
 }  // namespace
 
 // ---------------------------------------------------------------------------
 // module_advect_em.F:126-1526, horz_order 5 (:486-745), open BC (:1240-1334),
 // vert_order 3 (:1470-1498)
-void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut) {
+void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut, bool weno) {
   const int ids = x.ids, ide = x.ide, jds = x.jds, jde = x.jde;
   const int its = x.its, ite = x.ite, jts = x.jts, jte = x.jte, kts = x.kts, kte = x.kte;
   const int ktf = std::min(kte, x.kde - 1);
   const A1 &c1 = x.c1h, &c2 = x.c2h, &fzm = x.fnm, &fzp = x.fnp, &rdzw = x.rdnw;
   const float rdx = x.rdx, rdy = x.rdy;
-  Flux F{(float)(x.time_step >= 0 ? 1 : -1)};
+  Flux F{(float)(x.time_step >= 0 ? 1 : -1), weno};
   bool degrade_xs, degrade_xe, degrade_ys, degrade_ye;
   degrade_flags(x, 2, 4, degrade_xs, degrade_xe, degrade_ys, degrade_ye);
   Row fq0(its, ite, kte), fq1(its, ite, kte), fqx(its, ite, kte), vflux(its, ite, kte);
@@ -92,7 +104,7 @@ void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
       for (int k = kts; k <= ktf; k++)
         for (int i = i_start; i <= i_end; i++) {
           float vel = 0.5f * (rv(i, k, j) + rv(i - 1, k, j));
-          fqy(i, k) = vel * F.flux5(u(i, k, j - 3), u(i, k, j - 2), u(i, k, j - 1), u(i, k, j), u(i, k, j + 1), u(i, k, j + 2), vel);
+          fqy(i, k) = F.h5(vel, u(i, k, j - 3), u(i, k, j - 2), u(i, k, j - 1), u(i, k, j), u(i, k, j + 1), u(i, k, j + 2));
         }
     } else if (j == jds + 1) {
       for (int k = kts; k <= ktf; k++)
@@ -131,7 +143,7 @@ void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
     for (int k = kts; k <= ktf; k++)
       for (int i = i_start_f; i <= i_end_f; i++) {
         float vel = 0.5f * (ru(i, k, j) + ru(i - 1, k, j));
-        fqx(i, k) = vel * F.flux5(u(i - 3, k, j), u(i - 2, k, j), u(i - 1, k, j), u(i, k, j), u(i + 1, k, j), u(i + 2, k, j), vel);
+        fqx(i, k) = F.h5(vel, u(i - 3, k, j), u(i - 2, k, j), u(i - 1, k, j), u(i, k, j), u(i + 1, k, j), u(i + 2, k, j));
       }
     if (degrade_xs) {
       if (i_start == ids + 1) {
@@ -225,7 +237,7 @@ void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
     for (int k = kts + 2; k <= ktf - 1; k++)
       for (int i = i_start; i <= i_end; i++) {
         float vel = 0.5f * (rom(i - 1, k, j) + rom(i, k, j));
-        vflux(i, k) = vel * F.flux3(u(i, k - 2, j), u(i, k - 1, j), u(i, k, j), u(i, k + 1, j), -vel);
+        vflux(i, k) = F.v35(k, kts + 3, ktf - 2, vel, u(i, k - 3, j), u(i, k - 2, j), u(i, k - 1, j), u(i, k, j), u(i, k + 1, j), u(i, k + 2, j));
       }
     for (int i = i_start; i <= i_end; i++) {
       int k = kts + 1;
@@ -241,13 +253,13 @@ void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
 // ---------------------------------------------------------------------------
 // module_advect_em.F:1530-3024, horz_order 5 (:1904-2171), open BC (:2690-2800),
 // vert_order 3 (:2961-2995)
-void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut) {
+void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut, bool weno) {
   const int ids = x.ids, ide = x.ide, jds = x.jds, jde = x.jde;
   const int its = x.its, ite = x.ite, jts = x.jts, jte = x.jte, kts = x.kts, kte = x.kte;
   const int ktf = std::min(kte, x.kde - 1);
   const A1 &c1 = x.c1h, &c2 = x.c2h, &fzm = x.fnm, &fzp = x.fnp, &rdzw = x.rdnw;
   const float rdx = x.rdx, rdy = x.rdy;
-  Flux F{(float)(x.time_step >= 0 ? 1 : -1)};
+  Flux F{(float)(x.time_step >= 0 ? 1 : -1), weno};
   bool degrade_xs, degrade_xe, degrade_ys, degrade_ye;
   degrade_flags(x, 3, 3, degrade_xs, degrade_xe, degrade_ys, degrade_ye);
   Row fq0(its, ite, kte), fq1(its, ite, kte), fqx(its, ite, kte), vflux(its, ite, kte);
@@ -263,7 +275,7 @@ void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
       for (int k = kts; k <= ktf; k++)
         for (int i = i_start; i <= i_end; i++) {
           float vel = 0.5f * (rv(i, k, j) + rv(i, k, j - 1));
-          fqy(i, k) = vel * F.flux5(v(i, k, j - 3), v(i, k, j - 2), v(i, k, j - 1), v(i, k, j), v(i, k, j + 1), v(i, k, j + 2), vel);
+          fqy(i, k) = F.h5(vel, v(i, k, j - 3), v(i, k, j - 2), v(i, k, j - 1), v(i, k, j), v(i, k, j + 1), v(i, k, j + 2));
         }
     } else if (j == jds + 1) {
       for (int k = kts; k <= ktf; k++)
@@ -309,7 +321,7 @@ void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
     for (int k = kts; k <= ktf; k++)
       for (int i = i_start_f; i <= i_end_f; i++) {
         float vel = 0.5f * (ru(i, k, j) + ru(i, k, j - 1));
-        fqx(i, k) = vel * F.flux5(v(i - 3, k, j), v(i - 2, k, j), v(i - 1, k, j), v(i, k, j), v(i + 1, k, j), v(i + 2, k, j), vel);
+        fqx(i, k) = F.h5(vel, v(i - 3, k, j), v(i - 2, k, j), v(i - 1, k, j), v(i, k, j), v(i + 1, k, j), v(i + 2, k, j));
       }
     if (degrade_xs) {
       for (int i = i_start; i <= i_start_f - 1; i++) {
@@ -397,7 +409,7 @@ void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
     for (int k = kts + 2; k <= ktf - 1; k++)
       for (int i = i_start; i <= i_end; i++) {
         float vel = 0.5f * (rom(i, k, j) + rom(i, k, j - 1));
-        vflux(i, k) = vel * F.flux3(v(i, k - 2, j), v(i, k - 1, j), v(i, k, j), v(i, k + 1, j), -vel);
+        vflux(i, k) = F.v35(k, kts + 3, ktf - 2, vel, v(i, k - 3, j), v(i, k - 2, j), v(i, k - 1, j), v(i, k, j), v(i, k + 1, j), v(i, k + 2, j));
       }
     for (int i = i_start; i <= i_end; i++) {
       int k = kts + 1;
@@ -559,14 +571,14 @@ void advect_scalar(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 r
 // ---------------------------------------------------------------------------
 // module_advect_em.F:4364-6065, horz_order 5 (:4784-5096), open BC (:5689-5820),
 // vert_order 3 (:5996-6031).  rdzu = rdn.
-void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut) {
+void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut, bool weno) {
   (void)mut;
   const int ids = x.ids, ide = x.ide, jds = x.jds, jde = x.jde;
   const int its = x.its, ite = x.ite, jts = x.jts, jte = x.jte, kts = x.kts, kte = x.kte;
   const int ktf = std::min(kte, x.kde - 1);
   const A1 &fzm = x.fnm, &fzp = x.fnp, &rdzu = x.rdn;
   const float rdx = x.rdx, rdy = x.rdy;
-  Flux F{(float)(x.time_step >= 0 ? 1 : -1)};
+  Flux F{(float)(x.time_step >= 0 ? 1 : -1), weno};
   bool degrade_xs, degrade_xe, degrade_ys, degrade_ye;
   degrade_flags(x, 3, 4, degrade_xs, degrade_xe, degrade_ys, degrade_ye);
   Row fq0(its, ite, kte), fq1(its, ite, kte), fqx(its, ite, kte), vflux(its, ite, kte);
@@ -588,7 +600,7 @@ void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
       for (int k = kts + 1; k <= ktf + 1; k++)
         for (int i = i_start; i <= i_end; i++) {
           float vel = vely(i, k, j);
-          fqy(i, k) = vel * F.flux5(w(i, k, j - 3), w(i, k, j - 2), w(i, k, j - 1), w(i, k, j), w(i, k, j + 1), w(i, k, j + 2), vel);
+          fqy(i, k) = F.h5(vel, w(i, k, j - 3), w(i, k, j - 2), w(i, k, j - 1), w(i, k, j), w(i, k, j + 1), w(i, k, j + 2));
         }
     } else if (j == jds + 1) {
       for (int k = kts + 1; k <= ktf + 1; k++)
@@ -626,7 +638,7 @@ void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
     for (int k = kts + 1; k <= ktf + 1; k++)
       for (int i = i_start_f; i <= i_end_f; i++) {
         float vel = velx(i, k, j);
-        fqx(i, k) = vel * F.flux5(w(i - 3, k, j), w(i - 2, k, j), w(i - 1, k, j), w(i, k, j), w(i + 1, k, j), w(i + 2, k, j), vel);
+        fqx(i, k) = F.h5(vel, w(i - 3, k, j), w(i - 2, k, j), w(i - 1, k, j), w(i, k, j), w(i + 1, k, j), w(i + 2, k, j));
       }
     if (degrade_xs)
       for (int i = i_start; i <= i_start_f - 1; i++) {
@@ -740,7 +752,7 @@ void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
     for (int k = kts + 2; k <= ktf; k++)
       for (int i = i_start; i <= i_end; i++) {
         float vel = 0.5f * (rom(i, k, j) + rom(i, k - 1, j));
-        vflux(i, k) = vel * F.flux3(w(i, k - 2, j), w(i, k - 1, j), w(i, k, j), w(i, k + 1, j), -vel);
+        vflux(i, k) = F.v35(k, kts + 3, ktf - 1, vel, w(i, k - 3, j), w(i, k - 2, j), w(i, k - 1, j), w(i, k, j), w(i, k + 1, j), w(i, k + 2, j));
       }
     for (int i = i_start; i <= i_end; i++) {
       int k = kts + 1;

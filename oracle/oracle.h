@@ -186,9 +186,9 @@ void vertical_diffusion_3dmp(const Cx &x, A3 field, A3 tendency, A3 base_3d, A1 
 void vertical_diffusion_u(const Cx &x, A3 field, A3 tendency, A1 u_base, A1 c1h, A1 c2h, A3 alt, A2 muu, float kvdif);
 void vertical_diffusion_v(const Cx &x, A3 field, A3 tendency, A1 v_base, A1 c1h, A1 c2h, A3 alt, A2 muv, float kvdif);
 // advect.cpp
-void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut);
-void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut);
-void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut);
+void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut, bool weno = false);
+void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut, bool weno = false);
+void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut, bool weno = false);
 void advect_scalar(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut);
 void advect_scalar_pd(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom,
                       A2 mut, A2 mub, A2 mu_old, float dt, bool weno = false);

@@ -162,9 +162,11 @@ void Oracle::rk_tendency(int rk_step) {
   par([&](const Cx &xt) { zero_tend2d(xt, a2("mu_tend")); });
   par([&](const Cx &xt) { zero_tend2d(xt, a2("mu_save")); });
   par([&](const Cx &xt) { ww_split(xt, wwE, wwI, ww); });
-  par([&](const Cx &xt) { advect_u(xt, u, u, ru_tend, ru, rv, wwE, mut); });
-  par([&](const Cx &xt) { advect_v(xt, v, v, rv_tend, ru, rv, wwE, mut); });
-  par([&](const Cx &xt) { advect_w(xt, w, w, rw_tend, ru, rv, wwE, mut); });
+  // momentum_adv_opt = 3 (WENO_MOM, Registry.EM_COMMON:3273): advect_weno_u/v/w on the last RK substep (module_em.F:491-600)
+  const bool weno_m = c.momentum_adv_opt == 3 && rk_step == c.rk_ord;
+  par([&](const Cx &xt) { advect_u(xt, u, u, ru_tend, ru, rv, wwE, mut, weno_m); });
+  par([&](const Cx &xt) { advect_v(xt, v, v, rv_tend, ru, rv, wwE, mut, weno_m); });
+  par([&](const Cx &xt) { advect_w(xt, w, w, rw_tend, ru, rv, wwE, mut, weno_m); });
   // theta goes with the scalars' WENO option on the last RK substep (module_em.F:603-621)
   const bool weno_t = (c.scalar_adv_opt == 3 || c.scalar_adv_opt == 4 || c.moist_adv_opt == 3 || c.moist_adv_opt == 4) && rk_step == c.rk_ord;
   if (weno_t) par([&](const Cx &xt) { advect_scalar_weno(xt, t, t, t_tend, ru, rv, wwE); });

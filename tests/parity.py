@@ -83,6 +83,12 @@ def small_cases():
         "wenopd": make_case("quarter_ss", nx=26, ny=24, nz=21, moist_adv_opt=4),
         "wenopd_periodic": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=2,
                                                       scalar_adv_opt=4, moist_adv_opt=3)),
+        # WENO momentum advection (momentum_adv_opt = 3, advect_weno_u/v/w on the last RK substep): open + Kessler,
+        # doubly periodic with map factors, and periodic x / symmetric y with the rigid lid (w flux at the top)
+        "weno_mom": make_case("quarter_ss", nx=26, ny=24, nz=21, momentum_adv_opt=3, moist_adv_opt=4),
+        "weno_mom_periodic": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=1,
+                                                        momentum_adv_opt=3)),
+        "weno_mom_b_wave": make_case("b_wave", nx=21, ny=31, nz=17, momentum_adv_opt=3, top_lid=1),
     }
 
 

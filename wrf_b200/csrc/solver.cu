@@ -32,7 +32,7 @@ static void check_config(const wrfgpu_config &c) {
   if (c.v_mom_adv_order != 3 || c.v_sca_adv_order != 3) bad("v_*_adv_order must be 3");
   if (c.moist_adv_opt < 0 || c.moist_adv_opt > 4) bad("moist_adv_opt must be 0 (original), 1 (positive-definite), 2 (monotonic), 3 (WENO) or 4 (WENO, positive-definite)");
   if (c.scalar_adv_opt < 0 || c.scalar_adv_opt > 4) bad("scalar_adv_opt must be 0 ... 4");
-  if (c.momentum_adv_opt != 1) bad("momentum_adv_opt must be 1");
+  if (c.momentum_adv_opt != 1 && c.momentum_adv_opt != 3) bad("momentum_adv_opt must be 1 (original) or 3 (WENO)");
   if (!c.non_hydrostatic) bad("hydrostatic option");
   if (c.damp_opt != 0 && c.damp_opt != 2 && c.damp_opt != 3) bad("damp_opt must be 0, 2 or 3");
   if (c.zadvect_implicit != 0) bad("zadvect_implicit (IEVA)");

@@ -118,7 +118,7 @@ __device__ __forceinline__ float pert_wind(const Geo &g, cfp r_in, cfp ph, cfp p
 
 // ===========================================================================
 // ru_tend: advect_u (:126) + pgf x (:2320-2400) + coriolis (:3700-3735) + curvature + addtend
-template <bool FAST>
+template <bool FAST, bool WENO = false>
 __device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i, int k, int j) {
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, ktf = g.kde - 1;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
@@ -141,7 +141,7 @@ __device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i,
         const int ord = FAST ? 5 : face_order(jj, dg.ys, dg.ye, jds + 1, jds + 2, jde - 1, jde - 2);
         if (ord == 5) {
           const float vel = 0.5f * (A3(rv, i, k, jj) + A3(rv, i - 1, k, jj));
-          fq[m] = vel * flux5(YSTENCIL(u, i, k, jj), vel, sg);
+          fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, YSTENCIL(u, i, k, jj), 1.0e-18) : vel * flux5(YSTENCIL(u, i, k, jj), vel, sg);
         } else if (ord == 3) {
           const float vel = 0.5f * (A3(rv, i, k, jj) + A3(rv, i - 1, k, jj));
           fq[m] = vel * flux3(A3(u, i, k, jj - 2), A3(u, i, k, jj - 1), A3(u, i, k, jj), A3(u, i, k, jj + 1), vel, sg);
@@ -164,7 +164,7 @@ __device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i,
         const int ord = FAST ? 5 : face_order(ii, dg.xs, dg.xe, ids + 1, ids + 2, ide, ide - 1);
         if (ord == 5) {
           const float vel = 0.5f * (A3(ru, ii, k, j) + A3(ru, ii - 1, k, j));
-          fq[m] = vel * flux5(XSTENCIL(u, ii, k, j), vel, sg);
+          fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, XSTENCIL(u, ii, k, j), 1.0e-18) : vel * flux5(XSTENCIL(u, ii, k, j), vel, sg);
         } else if (ord == 3) {
           const float vel = 0.5f * (A3(ru, ii, k, j) + A3(ru, ii - 1, k, j));
           fq[m] = vel * flux3(A3(u, ii - 2, k, j), A3(u, ii - 1, k, j), A3(u, ii, k, j), A3(u, ii + 1, k, j), vel, sg);
@@ -226,7 +226,10 @@ __device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i,
           vf[m] = 0.5f * (A3(rom, i, kk, j) + A3(rom, i - 1, kk, j)) * (g.fnm[kk] * A3(u, i, kk, j) + g.fnp[kk] * A3(u, i, kk - 1, j));
         else {
           const float vel = 0.5f * (A3(rom, i - 1, kk, j) + A3(rom, i, kk, j));
-          vf[m] = vel * flux3(A3(u, i, kk - 2, j), A3(u, i, kk - 1, j), A3(u, i, kk, j), A3(u, i, kk + 1, j), -vel, sg);
+          if (WENO && kk >= 4 && kk <= ktf - 2)   // vert_order 5 structure of advect_weno_u
+            vf[m] = weno5(vel, -vel * sg >= 0.0f, A3(u, i, kk - 3, j), A3(u, i, kk - 2, j), A3(u, i, kk - 1, j), A3(u, i, kk, j), A3(u, i, kk + 1, j), A3(u, i, kk + 2, j), 1.0e-18);
+          else
+            vf[m] = vel * flux3(A3(u, i, kk - 2, j), A3(u, i, kk - 1, j), A3(u, i, kk, j), A3(u, i, kk + 1, j), -vel, sg);
         }
       }
       t = t - g.rdnw[k] * (vf[1] - vf[0]);
@@ -298,9 +301,16 @@ __global__ void k_tend_u(const Geo g, Box b, TendIn s, fp ru_tend) {
   A3(ru_tend, i, k, j) = interior_pt(g, i, j) ? tend_u_pt<true>(g, s, i, k, j) : tend_u_pt<false>(g, s, i, k, j);
 }
 
+// momentum_adv_opt = 3 on the last RK substep: advect_weno_u (module_advect_em.F:10876) in place of advect_u
+__global__ void k_tend_u_weno(const Geo g, Box b, TendIn s, fp ru_tend) {
+  TID3;
+  if (k > g.kde - 1 || j > min(g.jte, g.jde - 1)) { A3(ru_tend, i, k, j) = 0.f; return; }
+  A3(ru_tend, i, k, j) = tend_u_pt<false, true>(g, s, i, k, j);
+}
+
 // ===========================================================================
 // rv_tend: advect_v (:1530) + pgf y + coriolis + curvature + addtend
-template <bool FAST>
+template <bool FAST, bool WENO = false>
 __device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i, int k, int j) {
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, ktf = g.kde - 1;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
@@ -319,7 +329,7 @@ __device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i,
         const int ord = FAST ? 5 : face_order(jj, dg.ys, dg.ye, jds + 1, jds + 2, jde, jde - 1);
         if (ord == 5) {
           const float vel = 0.5f * (A3(rv, i, k, jj) + A3(rv, i, k, jj - 1));
-          fq[m] = vel * flux5(YSTENCIL(v, i, k, jj), vel, sg);
+          fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, YSTENCIL(v, i, k, jj), 1.0e-18) : vel * flux5(YSTENCIL(v, i, k, jj), vel, sg);
         } else if (ord == 3) {
           const float vel = 0.5f * (A3(rv, i, k, jj) + A3(rv, i, k, jj - 1));
           fq[m] = vel * flux3(A3(v, i, k, jj - 2), A3(v, i, k, jj - 1), A3(v, i, k, jj), A3(v, i, k, jj + 1), vel, sg);
@@ -345,7 +355,7 @@ __device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i,
         const int ord = FAST ? 5 : face_order(ii, dg.xs, dg.xe, ids + 1, ids + 2, ide - 1, ide - 2);
         if (ord == 5) {
           const float vel = 0.5f * (A3(ru, ii, k, j) + A3(ru, ii, k, j - 1));
-          fq[m] = vel * flux5(XSTENCIL(v, ii, k, j), vel, sg);
+          fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, XSTENCIL(v, ii, k, j), 1.0e-18) : vel * flux5(XSTENCIL(v, ii, k, j), vel, sg);
         } else if (ord == 3) {
           const float vel = 0.5f * (A3(ru, ii, k, j) + A3(ru, ii, k, j - 1));
           fq[m] = vel * flux3(A3(v, ii - 2, k, j), A3(v, ii - 1, k, j), A3(v, ii, k, j), A3(v, ii + 1, k, j), vel, sg);
@@ -406,7 +416,10 @@ __device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i,
           vf[m] = 0.5f * (A3(rom, i, kk, j) + A3(rom, i, kk, j - 1)) * (g.fnm[kk] * A3(v, i, kk, j) + g.fnp[kk] * A3(v, i, kk - 1, j));
         else {
           const float vel = 0.5f * (A3(rom, i, kk, j) + A3(rom, i, kk, j - 1));
-          vf[m] = vel * flux3(A3(v, i, kk - 2, j), A3(v, i, kk - 1, j), A3(v, i, kk, j), A3(v, i, kk + 1, j), -vel, sg);
+          if (WENO && kk >= 4 && kk <= ktf - 2)   // vert_order 5 structure of advect_weno_v
+            vf[m] = weno5(vel, -vel * sg >= 0.0f, A3(v, i, kk - 3, j), A3(v, i, kk - 2, j), A3(v, i, kk - 1, j), A3(v, i, kk, j), A3(v, i, kk + 1, j), A3(v, i, kk + 2, j), 1.0e-18);
+          else
+            vf[m] = vel * flux3(A3(v, i, kk - 2, j), A3(v, i, kk - 1, j), A3(v, i, kk, j), A3(v, i, kk + 1, j), -vel, sg);
         }
       }
       t = t - (A2(g.msfvy, i, j) / A2(g.msfvx, i, j)) * g.rdnw[k] * (vf[1] - vf[0]);
@@ -475,10 +488,16 @@ __global__ void k_tend_v(const Geo g, Box b, TendIn s, fp rv_tend) {
   A3(rv_tend, i, k, j) = interior_pt(g, i, j) ? tend_v_pt<true>(g, s, i, k, j) : tend_v_pt<false>(g, s, i, k, j);
 }
 
+__global__ void k_tend_v_weno(const Geo g, Box b, TendIn s, fp rv_tend) {   // advect_weno_v (:11523)
+  TID3;
+  if (k > g.kde - 1 || i > min(g.ite, g.ide - 1)) { A3(rv_tend, i, k, j) = 0.f; return; }
+  A3(rv_tend, i, k, j) = tend_v_pt<false, true>(g, s, i, k, j);
+}
+
 // ===========================================================================
 // rw_tend: advect_w (:4364) + pg_buoy_w (:2419) + w_damp (:2503) + coriolis + curvature + addtend
 // cqw is read here un-inverted; k_invert_cqw applies cqw <- 1/(1+cqw) (:2489) afterwards.
-template <bool FAST>
+template <bool FAST, bool WENO = false>
 __device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i, int k, int j) {
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, kde = g.kde;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
@@ -503,7 +522,7 @@ __device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i,
           const int jj = j + m;
           const int ord = FAST ? 5 : face_order(jj, dg.ys, dg.ye, jds + 1, jds + 2, jde - 1, jde - 2);
           const float vel = WVEL(rv, i, jj);
-          if (ord == 5) fq[m] = vel * flux5(YSTENCIL(w, i, k, jj), vel, sg);
+          if (ord == 5) fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, YSTENCIL(w, i, k, jj), 1.0e-18) : vel * flux5(YSTENCIL(w, i, k, jj), vel, sg);
           else if (ord == 3) fq[m] = vel * flux3(A3(w, i, k, jj - 2), A3(w, i, k, jj - 1), A3(w, i, k, jj), A3(w, i, k, jj + 1), vel, sg);
           else fq[m] = 0.5f * (vel) * (A3(w, i, k, jj) + A3(w, i, k, jj - 1));
         }
@@ -521,7 +540,7 @@ __device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i,
           const int ii = i + m;
           const int ord = FAST ? 5 : face_order(ii, dg.xs, dg.xe, ids + 1, ids + 2, ide - 1, ide - 2);
           const float vel = WVEL(ru, ii, j);
-          if (ord == 5) fq[m] = vel * flux5(XSTENCIL(w, ii, k, j), vel, sg);
+          if (ord == 5) fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, XSTENCIL(w, ii, k, j), 1.0e-18) : vel * flux5(XSTENCIL(w, ii, k, j), vel, sg);
           else if (ord == 3) fq[m] = vel * flux3(A3(w, ii - 2, k, j), A3(w, ii - 1, k, j), A3(w, ii, k, j), A3(w, ii + 1, k, j), vel, sg);
           else fq[m] = 0.5f * (vel) * (A3(w, ii, k, j) + A3(w, ii - 1, k, j));
         }
@@ -564,6 +583,8 @@ __device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i,
       auto vflux = [&](int kk) -> float {
         if (kk == 2 || kk == kde) return 0.25f * (A3(rom, i, kk, j) + A3(rom, i, kk - 1, j)) * (A3(w, i, kk, j) + A3(w, i, kk - 1, j));
         const float vel = 0.5f * (A3(rom, i, kk, j) + A3(rom, i, kk - 1, j));
+        if (WENO && kk >= 4 && kk <= kde - 2)   // vert_order 5 structure of advect_weno_w (:12959-13037)
+          return weno5(vel, -vel * sg >= 0.0f, A3(w, i, kk - 3, j), A3(w, i, kk - 2, j), A3(w, i, kk - 1, j), A3(w, i, kk, j), A3(w, i, kk + 1, j), A3(w, i, kk + 2, j), 1.0e-18);
         return vel * flux3(A3(w, i, kk - 2, j), A3(w, i, kk - 1, j), A3(w, i, kk, j), A3(w, i, kk + 1, j), -vel, sg);
       };
       if (!top) t = t - g.rdn[k] * (vflux(k + 1) - vflux(k));
@@ -614,6 +635,12 @@ __global__ void k_tend_w(const Geo g, Box b, TendIn s, fp rw_tend) {
   (void)ids; (void)jds; (void)ktf; (void)kde; (void)its; (void)jts;
   if (i > min(ite, ide - 1) || j > min(jte, jde - 1)) { A3(rw_tend, i, k, j) = 0.f; return; }
   A3(rw_tend, i, k, j) = interior_pt(g, i, j) ? tend_w_pt<true>(g, s, i, k, j) : tend_w_pt<false>(g, s, i, k, j);
+}
+
+__global__ void k_tend_w_weno(const Geo g, Box b, TendIn s, fp rw_tend) {   // advect_weno_w (:12218)
+  TID3;
+  if (i > min(g.ite, g.ide - 1) || j > min(g.jte, g.jde - 1)) { A3(rw_tend, i, k, j) = 0.f; return; }
+  A3(rw_tend, i, k, j) = tend_w_pt<false, true>(g, s, i, k, j);
 }
 
 // cqw <- 1/(1+cqw), module_big_step_utilities_em.F:2489
@@ -976,7 +1003,12 @@ void Solver::rk_tendency(int rk_step, bool zero_save) {
   const Box in = interior_box(q);
   Box strips[4];
   const int ns = edge_strips(tile, in, strips);
-  if (!c.pert_coriolis && !empty(in)) {
+  const bool weno_m = c.momentum_adv_opt == 3 && rk_step == c.rk_ord;   // WENO_MOM, module_em.F:491-600
+  if (weno_m) {
+    LAUNCH3(this, k_tend_u_weno, tile, s, o("ru_tend"));
+    LAUNCH3(this, k_tend_v_weno, tile, s, o("rv_tend"));
+    LAUNCH3(this, k_tend_w_weno, tile, s, o("rw_tend"));
+  } else if (!c.pert_coriolis && !empty(in)) {
     // momentum: k-marching kernels on the interior (mom_fast.cu), the gather kernels on the edge strips
     for (int which = 0; which < 3; which++) launch_mom_fast(this, which, in);
     for (int m = 0; m < ns; m++) {
@@ -1004,7 +1036,7 @@ void Solver::rk_tendency(int rk_step, bool zero_save) {
   }
   {   // cqw <- 1/(1+cqw): done by k_mom_w_fast on the interior, here on what is left of the mass points
     const Box cq{q.its, std::min(q.ite, q.ide - 1), 2, q.kde - 1, q.jts, std::min(q.jte, q.jde - 1)};
-    if (!c.pert_coriolis && !empty(in)) {
+    if (!weno_m && !c.pert_coriolis && !empty(in)) {
       for (int m = 0; m < ns; m++) {
         Box sb = strips[m];
         sb.i1 = std::min(sb.i1, cq.i1); sb.j1 = std::min(sb.j1, cq.j1); sb.k0 = cq.k0; sb.k1 = cq.k1;

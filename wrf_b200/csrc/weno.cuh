@@ -13,7 +13,7 @@
 namespace wg {
 
 // m3 .. p2 are the six values around the face (q(-3) .. q(+2)); upw = the wind blows from the low-index side
-__device__ __forceinline__ float weno5(float vel, bool upw, float m3, float m2, float m1, float p0, float p1, float p2) {
+__device__ __forceinline__ float weno5(float vel, bool upw, float m3, float m2, float m1, float p0, float p1, float p2, const double eps = 1.0e-40) {
   const float qim2 = upw ? m3 : p2, qim1 = upw ? m2 : p1, qi = upw ? m1 : p0, qip1 = upw ? p0 : m1, qip2 = upw ? p1 : m2;
   const double f0 = (double)(1.f / 3.f * qim2 - 7.f / 6.f * qim1 + 11.f / 6.f * qi);
   const double f1 = (double)(-1.f / 6.f * qim1 + 5.f / 6.f * qi + 1.f / 3.f * qip1);
@@ -24,7 +24,7 @@ __device__ __forceinline__ float weno5(float vel, bool upw, float m3, float m2, 
   const double beta0 = (double)(13.f / 12.f * (a0 * a0) + 1.f / 4.f * (b0 * b0));
   const double beta1 = (double)(13.f / 12.f * (a1 * a1) + 1.f / 4.f * (b1 * b1));
   const double beta2 = (double)(13.f / 12.f * (a2 * a2) + 1.f / 4.f * (b2 * b2));
-  const double gi0 = 1.0 / 10.0, gi1 = 6.0 / 10.0, gi2 = 3.0 / 10.0, eps = 1.0e-40;
+  const double gi0 = 1.0 / 10.0, gi1 = 6.0 / 10.0, gi2 = 3.0 / 10.0;   // eps: 1.d-40 for scalars (:7968), 1.d-18 for momentum (:10950)
   const double wi0 = gi0 / ((eps + beta0) * (eps + beta0));
   const double wi1 = gi1 / ((eps + beta1) * (eps + beta1));
   const double wi2 = gi2 / ((eps + beta2) * (eps + beta2));
