@@ -193,6 +193,16 @@ void advect_scalar(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 r
 void advect_scalar_pd(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom,
                       A2 mut, A2 mub, A2 mu_old, float dt, bool weno = false);
 void advect_scalar_weno(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom);
+// ieva.cpp (module_ieva_em.F)
+void ww_split_ieva(const Cx &x, A3 wwE, A3 wwI, A3 u, A3 v, A3 ww, A2 mut, float dt);
+void calc_mut_old(const Cx &x, A2 mut_old, A2 mub, A2 mu_old);
+void calc_mut_new(const Cx &x, A3 u, A3 v, A2 mut_old, A2 muu, A2 muv, A2 mut_new, float dt);
+void advect_ph_implicit(const Cx &x, A3 pho, A3 tendency, A3 phb, A3 wwI, A2 mut, float dt_rk);
+void advect_s_implicit(const Cx &x, A3 s_old, A3 tendency, A3 rom, A2 mut_old, A2 mut_new, float dt_rk);
+void advect_u_implicit(const Cx &x, A3 u_old, A3 tendency, A3 rom, A2 muu_old, A2 muu_new, float dt_rk);
+void advect_v_implicit(const Cx &x, A3 v_old, A3 tendency, A3 rom, A2 muv_old, A2 muv_new, float dt_rk);
+void advect_w_implicit(const Cx &x, A3 w_old, A3 tendency, A3 utend, A3 vtend, A3 rom, A3 ph_new, A3 ph_old, A3 ph_tend,
+                       A2 mut_old, A2 mut, A2 mut_new, float dt_rk);
 // advect_mono.cpp
 void advect_scalar_mono(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom, A3 romI,
                         A2 mut, A2 mub, A2 mu_old, float dt);

@@ -17,6 +17,7 @@ static const char *k3d[] = {
     "rho", "th_phy", "pi_phy", "p_phy", "z", "z_at_w", "dz8w", "qv_diabatic", "qc_diabatic", nullptr};
 static const char *k2d[] = {"mu_1", "mu_2", "mub", "mudf", "muu", "muus", "muv", "muvs", "mut", "muts",
                             "muave", "mu_save", "mu_tend", "mu_tendf",
+                            "mut_old", "mut_new", "muu_old", "muu_new", "muv_old", "muv_new",   // IEVA locals of rk_tendency (module_em.F:343-347)
                             "msftx", "msfty", "msfux", "msfuy", "msfvx", "msfvx_inv", "msfvy",
                             "f", "e", "sina", "cosa", "ht", "rainnc", "rainncv", nullptr};
 static const char *k1d[] = {"znu", "znw", "fnm", "fnp", "rdnw", "rdn", "dnw", "dn",
@@ -161,17 +162,36 @@ void Oracle::rk_tendency(int rk_step) {
     par([&](const Cx &xt) { zero_tend(xt, z); });
   par([&](const Cx &xt) { zero_tend2d(xt, a2("mu_tend")); });
   par([&](const Cx &xt) { zero_tend2d(xt, a2("mu_save")); });
-  par([&](const Cx &xt) { ww_split(xt, wwE, wwI, ww); });
+  // IEVA (zadvect_implicit > 0) on the last RK substep, CHK_IEVA module_ieva_em.F:13-43
+  const bool ieva = c.zadvect_implicit > 0 && rk_step == c.rk_ord;
+  const float dt_step = c.dt / (float)(c.rk_ord - rk_step + 1);
+  A2 mut_old = a2("mut_old"), mut_new = a2("mut_new");
+  if (ieva) {   // module_em.F:438-480
+    par([&](const Cx &xt) { ww_split_ieva(xt, wwE, wwI, u, v, ww, mut, c.dt); });
+    par([&](const Cx &xt) { calc_mut_old(xt, mut_old, mub, a2("mu_1")); });
+    par([&](const Cx &xt) { calc_mut_new(xt, u, v, mut_old, muu, muv, mut_new, c.dt); });
+    par([&](const Cx &xt) { calc_mu_uv_1(xt, mut_old, a2("muu_old"), a2("muv_old")); });
+    par([&](const Cx &xt) { calc_mu_uv_1(xt, mut_new, a2("muu_new"), a2("muv_new")); });
+  } else {
+    par([&](const Cx &xt) { ww_split(xt, wwE, wwI, ww); });
+  }
   // momentum_adv_opt = 3 (WENO_MOM, Registry.EM_COMMON:3273): advect_weno_u/v/w on the last RK substep (module_em.F:491-600)
   const bool weno_m = c.momentum_adv_opt == 3 && rk_step == c.rk_ord;
   par([&](const Cx &xt) { advect_u(xt, u, u, ru_tend, ru, rv, wwE, mut, weno_m); });
+  if (ieva) par([&](const Cx &xt) { advect_u_implicit(xt, a3("u_1"), ru_tend, wwI, a2("muu_old"), a2("muu_new"), dt_step); });
   par([&](const Cx &xt) { advect_v(xt, v, v, rv_tend, ru, rv, wwE, mut, weno_m); });
+  if (ieva) par([&](const Cx &xt) { advect_v_implicit(xt, a3("v_1"), rv_tend, wwI, a2("muv_old"), a2("muv_new"), dt_step); });
   par([&](const Cx &xt) { advect_w(xt, w, w, rw_tend, ru, rv, wwE, mut, weno_m); });
   // theta goes with the scalars' WENO option on the last RK substep (module_em.F:603-621)
   const bool weno_t = (c.scalar_adv_opt == 3 || c.scalar_adv_opt == 4 || c.moist_adv_opt == 3 || c.moist_adv_opt == 4) && rk_step == c.rk_ord;
   if (weno_t) par([&](const Cx &xt) { advect_scalar_weno(xt, t, t, t_tend, ru, rv, wwE); });
   else par([&](const Cx &xt) { advect_scalar(xt, t, t, t_tend, ru, rv, wwE, mut); });
+  if (ieva) par([&](const Cx &xt) { advect_s_implicit(xt, a3("t_1"), t_tend, wwI, mut_old, mut_new, dt_step); });
   par([&](const Cx &xt) { rhs_ph(xt, ph_tend, u, v, wwE, ph, ph, a3("phb"), w, mut, muu, muv); });
+  if (ieva) {   // module_em.F:682-715
+    par([&](const Cx &xt) { advect_ph_implicit(xt, a3("ph_1"), ph_tend, a3("phb"), wwI, mut, dt_step); });
+    par([&](const Cx &xt) { advect_w_implicit(xt, a3("w_1"), rw_tend, ru_tend, rv_tend, wwI, ph, a3("ph_1"), ph_tend, mut_old, mut, mut_new, dt_step); });
+  }
   par([&](const Cx &xt) { horizontal_pressure_gradient(xt, ru_tend, rv_tend, ph, a3("alt"), a3("p"), a3("pb"), a3("al"), a3("php"), a3("cqu"), a3("cqv"), muu, muv, mu); });
   par([&](const Cx &xt) { pg_buoy_w(xt, rw_tend, a3("p"), a3("cqw"), mu, mub); });
   float mv, mh;
@@ -314,9 +334,23 @@ void Oracle::rk_scalar_step(int rk_step) {
       if (s.adv_opt == 1 || s.adv_opt == 2 || s.adv_opt == 4) bc(s.o, 'p');
   }
   halo("HALO_EM_D");   // + PERIOD_EM_DA, solve_em.F:2179-2181
+  if (c.zadvect_implicit > 0 && rk_step == rk_order && !sp.empty()) {
+    // WW_SPLIT below reads u_1, v_1 one point beyond the tile.  The Registry exchanges the _1 fields only at the end of a
+    // step (HALO_EM_D3_5 / E_5), i.e. before small_step_prep refreshes their interior, so under DM the reference reads
+    // one-step-old halo values here and its IEVA results depend on the decomposition.  Deliberate deviation: exchange
+    // them (and refresh the physical boundary zone) so that N ranks equal 1 rank; open-boundary cases are unaffected.
+    halo("HALO_EM_IEVA");
+    bc("u_1", 'U'); bc("v_1", 'V');
+  }
   for (auto &s : sp) {
     // rk_scalar_tend, module_em.F:1096-1442
-    par([&](const Cx &xt) { ww_split(xt, a3("wwE"), a3("wwI"), a3("ww_m")); });
+    const bool ieva = c.zadvect_implicit > 0 && rk_step == rk_order;   // module_em.F:1216-1243
+    if (ieva) {
+      par([&](const Cx &xt) { ww_split_ieva(xt, a3("wwE"), a3("wwI"), a3("u_1"), a3("v_1"), a3("ww_m"), a2("muts"), c.dt); });
+      par([&](const Cx &xt) { calc_mut_old(xt, a2("mut_old"), a2("mub"), a2("mu_1")); });
+    } else {
+      par([&](const Cx &xt) { ww_split(xt, a3("wwE"), a3("wwI"), a3("ww_m")); });
+    }
     par([&](const Cx &xt) { zero_tend(xt, a3("advect_tend")); });
     if (rk_step == rk_order && (s.adv_opt == 1 || s.adv_opt == 4))   // POSITIVEDEF :1266-1280, WENOPD_SCALAR :1314-1327
       par([&](const Cx &xt) { advect_scalar_pd(xt, a3(s.f), a3(s.o), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE"), a2("muts"), a2("mub"), a2("mu_1"), dt_rk, s.adv_opt == 4); });
@@ -326,6 +360,8 @@ void Oracle::rk_scalar_step(int rk_step) {
       par([&](const Cx &xt) { advect_scalar_mono(xt, a3(s.f), a3(s.o), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE"), a3("wwI"), a2("muts"), a2("mub"), a2("mu_1"), dt_rk); });
     else
       par([&](const Cx &xt) { advect_scalar(xt, a3(s.f), a3(s.f), a3("advect_tend"), a3("ru_m"), a3("rv_m"), a3("wwE"), a2("muts")); });
+    if (ieva)   // module_em.F:1346-1364: mut_new = mut (= muts)
+      par([&](const Cx &xt) { advect_s_implicit(xt, a3(s.o), a3("advect_tend"), a3("wwI"), a2("mut_old"), a2("muts"), dt_rk); });
     if (rk_step == 1 && c.diff_opt == 1) {   // rk_step_1: diff_opt1, module_em.F:1378-1419 (xkmhd = grid%xkhh, solve_em.F:2230)
       const float prandtl = 1.f / 3.0f;
       const float xkhh = c.khdif / prandtl, kvdq = c.kvdif / prandtl;

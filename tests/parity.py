@@ -40,6 +40,34 @@ def with_map_factors(case, amp=0.04):
     return case
 
 
+def with_updraft(case, wmax, conv=25.0):
+    """Add an updraft core to a case: a Gaussian blob of `wmax` m/s in w and, because the first step diagnoses ww from
+    the divergence of (u, v) and not from w, winds converging below and diverging aloft (`conv` m/s) that imply the same
+    kind of core.  The vertical Courant number then exceeds IEVA's threshold from the first step on, so that WW_SPLIT
+    hands part of ww to the implicit solver (wwI /= 0)."""
+    d = case.dims
+    nz = d.kde
+    jj = np.arange(d.jms, d.jme + 1, dtype=np.float64)[:, None, None]
+    ii = np.arange(d.ims, d.ime + 1, dtype=np.float64)[None, None, :]
+    kk = np.arange(case.fields["w_2"].shape[1], dtype=np.float64)[None, :, None]
+    ic, jc = 0.5 * (d.ids + d.ide), 0.5 * (d.jds + d.jde)
+    xh, yh = (ii - ic) / 4.0, (jj - jc) / 4.0
+    blob = (wmax * np.exp(-(xh ** 2 + yh ** 2 + ((kk - nz / 3.0) / (nz / 5.0)) ** 2))).astype(np.float32)
+    blob[:, 0, :] = 0
+    blob[:, nz - 1:, :] = 0
+    prof = np.cos(np.pi * (kk + 0.5) / (nz - 1))
+    prof[:, nz - 1:, :] = 0
+    up = (-conv * (xh - 0.125) * np.exp(-((xh - 0.125) ** 2 + yh ** 2)) * prof).astype(np.float32)     # u points sit half a cell west
+    vp = (-conv * (yh - 0.125) * np.exp(-(xh ** 2 + (yh - 0.125) ** 2)) * prof).astype(np.float32)
+    if d.jde - d.jds < 4:      # 2-D (x, z) cases keep v = 0 and no y variation
+        blob = np.broadcast_to(blob[blob.shape[0] // 2][None], blob.shape).copy()
+        up = np.broadcast_to((-conv * (xh - 0.125) * np.exp(-((xh - 0.125) ** 2)) * prof).astype(np.float32), up.shape).copy()
+        vp = np.zeros_like(vp)
+    for n, a in (("w_2", blob), ("w_1", blob), ("u_2", up), ("u_1", up), ("v_2", vp), ("v_1", vp)):
+        case.fields[n] = (case.fields[n] + a).astype(np.float32)
+    return case
+
+
 def small_cases():
     """name -> Case; sizes the oracle finishes in about a second per step.  Together they cover
     every lateral boundary type, both advection options, Kessler, the three damping options and
@@ -89,6 +117,15 @@ def small_cases():
         "weno_mom_periodic": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=1,
                                                         momentum_adv_opt=3)),
         "weno_mom_b_wave": make_case("b_wave", nx=21, ny=31, nz=17, momentum_adv_opt=3, top_lid=1),
+        # implicit-explicit vertical advection (zadvect_implicit = 1, module_ieva_em.F) with an updraft strong enough to
+        # make wwI non-zero: open + Kessler + PD, doubly periodic with map factors + monotonic / PD tracers, and over
+        # the hill (terrain slopes in advect_w_implicit's lower boundary row) together with the WENO options
+        "ieva": with_updraft(make_case("quarter_ss", nx=26, ny=24, nz=41, zadvect_implicit=1, dt=20.0, time_step=20), 60.0),
+        "ieva_periodic": with_updraft(with_map_factors(make_case("synthetic", nx=34, ny=30, nz=33, bubble_lattice=20000.0, noise=0.05,
+                                                                  num_scalar=2, scalar_adv_opt=2, moist_adv_opt=1, zadvect_implicit=1,
+                                                                  dt=20.0, time_step=20)), 60.0),
+        "ieva_weno_hill": with_updraft(make_case("hill2d_x", nx=62, ny=3, nz=41, zadvect_implicit=1, momentum_adv_opt=3,
+                                                 moist_adv_opt=3), 60.0, conv=70.0),
     }
 
 

@@ -287,6 +287,40 @@ def test_weno_switches_theta_advection_on_the_last_substep_only():
     assert np.sqrt(((ta - tb) ** 2).mean()) < 0.1 * np.sqrt(((ta - t0) ** 2).mean())
 
 
+def test_ieva_splits_the_mass_flux_and_conserves_tracer_mass():
+    """module_ieva_em.F: WW_SPLIT hands the part of ww above the adjusted Courant limit to the implicit solver:
+    wwE + wwI = ww, both carry the sign of ww, the explicit part's Courant number stays below alpha_max = 1.1
+    (:7-8, :262-281), and wwI is non-zero in the updraft core.  The implicit upwind scheme is in flux form: a tracer
+    advected through the core has the mass budget of the explicit run (and, with the positive-definite limiter on the
+    explicit part, keeps its sign),
+    and the solution stays close to the explicit one where both are stable."""
+    got = {}
+    for opt in (0, 1):
+        case = parity.with_updraft(make_case("synthetic", nx=34, ny=30, nz=33, bubble_lattice=20000.0, noise=0.05, num_scalar=1,
+                                             scalar_adv_opt=1, zadvect_implicit=opt, dt=20.0, time_step=20), 60.0)
+        o = Oracle(case)
+        o.start_domain()
+        m0 = (interior(o, "scalar_1").astype(np.float64) * _mass(o)).sum()
+        o.step(4)
+        s = interior(o, "scalar_1")
+        m1 = (s.astype(np.float64) * _mass(o)).sum()
+        got[opt] = (abs(m1 - m0) / m0, float(s.min()), interior(o, "w_2").astype(np.float64), interior(o, "t_2").astype(np.float64))
+        if opt == 1:
+            ww, wwE, wwI = (interior(o, n).astype(np.float64) for n in ("ww_m", "wwE", "wwI"))
+            assert np.abs(wwI).max() > 1.0                                   # the implicit part is active ...
+            assert np.abs(wwE + wwI - ww).max() <= 1e-6 * np.abs(ww).max()   # ... a split, not a change, of ww
+            assert (wwE * ww >= 0).all() and (wwI * ww >= 0).all()
+            d, c = case.dims, case.config
+            mass = o.get("c1f")[None, :d.kde - 1, None] * interior(o, "muts").astype(np.float64)[:, None, :] + o.get("c2f")[None, :d.kde - 1, None]
+            cr = np.abs(wwE) * c.dt * np.abs(o.get("rdnw").astype(np.float64))[None, :d.kde - 1, None] / mass
+            assert cr.max() <= 1.1 + 1e-5, cr.max()
+    assert abs(got[1][0] - got[0][0]) < 2e-4, (got[0][0], got[1][0])         # the implicit part moves no tracer mass of its own
+    assert got[1][1] > -1e-6                                                 # positive definite with the implicit part
+    assert np.isfinite(got[1][2]).all()
+    assert np.abs(got[1][2] - got[0][2]).max() < 0.25 * np.abs(got[0][2]).max()   # same flow as the explicit scheme
+    assert np.abs(got[1][3] - got[0][3]).max() < 1.0
+
+
 def _mass(o):
     """(c1h*mu + c2h) per mass point of the interior, shape (j, k, i)"""
     d = o.case.dims

@@ -15,7 +15,7 @@ CASES = None
 ALL = ["hill2d_x", "quarter_ss", "quarter_ss_nopd", "b_wave", "les", "periodic", "b_wave_lid", "quarter_ss_opts", "rk2_sym_x",
        "mapfac", "mapfac_open", "diffusion", "diffusion_periodic", "b_wave_shipped",
        "mono", "mono_periodic", "weno", "weno_periodic", "wenopd", "wenopd_periodic",
-       "weno_mom", "weno_mom_periodic", "weno_mom_b_wave"]
+       "weno_mom", "weno_mom_periodic", "weno_mom_b_wave", "ieva", "ieva_periodic", "ieva_weno_hill"]
 
 
 def cases():
@@ -78,6 +78,18 @@ def test_drift_100_steps(name):
         worst = max(worst, parity.rel_l2_field(o, n, a, b))
         assert np.array_equal(a, b), (n, worst)
     assert np.abs(s.get("w_2")).max() > 0.5          # and the flow is far from trivial by then
+    s.close()
+
+
+@pytest.mark.parametrize("name", ["ieva", "ieva_periodic"])
+def test_ieva_three_steps_bit_exact(name):
+    """IEVA with a non-zero implicit part (wwI) on every step: three steps stay identical to the oracle, including
+    the split mass fluxes and the mass estimates of the last substep."""
+    o, s = _pair(name)
+    o.step(3); s.step(3)
+    assert np.abs(o.get("wwI")).max() > 0.0
+    rep = parity.diff_report(o, s)
+    assert not rep, rep[:5]
     s.close()
 
 

@@ -187,7 +187,10 @@ struct Solver {
   void rk_step_prep(int rk_step);
   void rk_phys_bc_dry_1();
   void init_zero_tendency();
-  void rk_tendency(int rk_step, bool zero_save = true);   // zero_save = false: small_step_prep(rk_step, true) writes those zeros
+  void rk_tendency(int rk_step, bool zero_save = true);
+  // IEVA (ieva.cu): WW_SPLIT + mass estimates; one implicit column solve (0 scalar, 1 u, 2 v, 3 ph, 4 w)
+  void ieva_split(bool dry, const float *u, const float *v, const float *ww, const float *mut, bool active = true);
+  void ieva_implicit(int which, float *tendency, const float *q_old, const float *mu_old, const float *mu_new, float dt_rk);   // zero_save = false: small_step_prep(rk_step, true) writes those zeros
   void small_step_prep(int rk_step, bool zero_rest = false);
   void advance_uv(int rk_step);
   void advance_uv_fused(int rk_step, int iteration);

@@ -50,6 +50,11 @@ static const HaloDef kHalos[] = {
     {"HALO_EM_THETAM", 3, "h_diabatic", ""},
     // end of step (:4437-4449): HALO_EM_D3_5 :3456 (3) + PERIOD_BDY_EM_D3 :3547, species :3521 (4)
     {"HALO_EM_D3_5", 3, "u_1,u_2,v_1,v_2,w_1,w_2,t_1,t_2,ph_1,ph_2", "mu_1,mu_2"},
+    // IEVA only, before rk_scalar_tend's WW_SPLIT on the last RK substep (module_em.F:1222): that call reads u_1, v_1 one
+    // point beyond the tile, but the Registry exchanges the _1 fields only at the end of a step (HALO_EM_D3_5 / E_5), before
+    // small_step_prep refreshes their interior -- under DM the reference reads one-step-old halo values there and its IEVA
+    // results depend on the decomposition.  This exchange (not in the Registry) makes N ranks equal 1 rank.
+    {"HALO_EM_IEVA", 2, "u_1,v_1", ""},
     // very end (:4781-4846): HALO_EM_E_5 :3458 (3) after set_w_surface
     {"HALO_EM_E_5", 3, "u_1,u_2,v_1,v_2,w_1,w_2,t_1,t_2,ph_1,ph_2", "mu_1,mu_2"},
     // start_domain_em (dyn_em/start_em.F): HALO_EM_INIT_1..5 carry the base state, map factors and both time levels

@@ -44,6 +44,7 @@ __device__ __forceinline__ float flux_upwind(float qm1, float q0, float cr) {
 struct PdIn {
   cfp q, q_old, ru, rv, rom, mut, mub, mu_old;
   float dt;
+  cfp romI;    // wwI under IEVA (advect_scalar_mono's ieva_corr, module_advect_em.F:10383), else null
   bool weno;   // advect_scalar_wenopd (*_adv_opt = 4): WENO in place of the 5th-order fluxes, and on k = 4..ktf-2
 };
 struct Face { float hi, lo; bool ok; };   // hi = high-order minus low, lo = upwind flux
@@ -288,8 +289,9 @@ __global__ void k_mono_scale(const Geo g, Box b, PdIn s, fp scale_in, fp scale_o
   if (z1.ok && !(z1.cr > 0.f)) take(A3(s.q_old, i, k + 1, j));
   const float msftx = A2(g.msftx, i, j), msfty = A2(g.msfty, i, j);
   const float c1h = g.c1h[k], c2h = g.c2h[k];
-  // romI = wwI = 0 without implicit vertical advection (zadvect_implicit is rejected at create)
-  const float ieva_corr = (c1h * A2(s.mut, i, j) + c2h) + s.dt * msfty * g.rdnw[k] * (0.f - 0.f);
+  // romI = wwI, identically 0 without implicit vertical advection
+  const float dromI = s.romI ? (A3(s.romI, i, k + 1, j) - A3(s.romI, i, k, j)) : (0.f - 0.f);
+  const float ieva_corr = (c1h * A2(s.mut, i, j) + c2h) + s.dt * msfty * g.rdnw[k] * dromI;
   const float ph_upwind = ((c1h * A2(s.mub, i, j) + c2h) + (c1h * A2(s.mu_old, i, j))) * qo -
                           s.dt * (msftx * msfty * (g.rdx * (x1.lo - x0.lo) + g.rdy * (y1.lo - y0.lo)) + msfty * g.rdnw[k] * (z1.lo - z0.lo));
   const float flux_in = -s.dt * ((msftx * msfty) * (g.rdx * (fminf(0.f, x1.hi) - fmaxf(0.f, x0.hi)) + g.rdy * (fminf(0.f, y1.hi) - fmaxf(0.f, y0.hi))) +
@@ -409,12 +411,20 @@ void Solver::rk_scalar_step(int rk_step) {
     if (!items.empty()) { halo("HALO_EM_MOIST_OLD_E_7"); bc(items); }
   }
   halo("HALO_EM_D");
+  // IEVA on the last substep (module_em.F:1216-1243): the explicit schemes see wwE, the implicit solve takes wwI
+  const bool ieva = c.zadvect_implicit > 0 && last;
+  if (ieva && !species.empty()) {   // see HALO_EM_IEVA in halo.cu: current u_1, v_1 around the tile for WW_SPLIT
+    halo("HALO_EM_IEVA");
+    bc({{"u_1", 'U'}, {"v_1", 'V'}});
+  }
+  if (c.zadvect_implicit > 0 && !species.empty()) ieva_split(false, o("u_1"), o("v_1"), o("ww_m"), o("muts"), ieva);
+  cfp rom = ieva ? o("wwE") : o("ww_m");
   const bool dxs = !(c.periodic_x || c.symmetric_xs), dxe = !(c.periodic_x || c.symmetric_xe);
   const bool dys = !(c.periodic_y || c.symmetric_ys), dye = !(c.periodic_y || c.symmetric_ye);
   for (auto &s : species) {
     if (last && (s.adv_opt == 1 || s.adv_opt == 2 || s.adv_opt == 4)) {
       PdIn in;
-      in.q = o(s.f); in.q_old = o(s.o); in.ru = o("ru_m"); in.rv = o("rv_m"); in.rom = o("ww_m");
+      in.q = o(s.f); in.q_old = o(s.o); in.ru = o("ru_m"); in.rv = o("rv_m"); in.rom = rom; in.romI = ieva ? o("wwI") : nullptr;
       in.mut = o("muts"); in.mub = o("mub"); in.mu_old = o("mu_1"); in.dt = dt_rk; in.weno = s.adv_opt == 4;
       // limiter box (:7683-7710)
       Box lim{q.its - 1, im + 1, 1, ktf, q.jts - 1, jm + 1};
@@ -431,12 +441,14 @@ void Solver::rk_scalar_step(int rk_step) {
       if (s.adv_opt == 2) {   // monotonic limiter: gather kernels on the whole limiter box / mass points
         LAUNCH3(this, k_mono_scale, lim, in, o("pd_scale"), o("pd_scale2"));
         LAUNCH3(this, k_mono_tend, mass, in, o("pd_scale"), o("pd_scale2"), lim, o("advect_tend"));
+        if (ieva) ieva_implicit(0, o("advect_tend"), o(s.o), o("mut_old"), o("muts"), dt_rk);
         LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
         continue;
       }
-      if (s.adv_opt == 4) {   // WENO inside the positive-definite limiter: the gather kernels everywhere
+      if (s.adv_opt == 4 || ieva) {   // WENO inside the positive-definite limiter, or IEVA's wwE: the gather kernels everywhere
         LAUNCH3(this, k_pd_scale, lim, in, o("pd_scale"));
         LAUNCH3(this, k_pd_tend, mass, in, o("pd_scale"), lim, o("advect_tend"));
+        if (ieva) ieva_implicit(0, o("advect_tend"), o(s.o), o("mut_old"), o("muts"), dt_rk);
         LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
         continue;
       }
@@ -453,15 +465,16 @@ void Solver::rk_scalar_step(int rk_step) {
       nst = edge_strips(mass, tfast, strips);
       for (int m = 0; m < nst; m++) LAUNCH3(this, k_pd_tend, strips[m], in, o("pd_scale"), lim, o("advect_tend"));
     } else if (last && s.adv_opt == 3) {   // WENO_SCALAR (module_em.F:1300-1312)
-      LAUNCH3(this, k_advect_scalar_weno, mass, o(s.f), o("ru_m"), o("rv_m"), o("ww_m"), o("advect_tend"));
+      LAUNCH3(this, k_advect_scalar_weno, mass, o(s.f), o("ru_m"), o("rv_m"), rom, o("advect_tend"));
     } else {
       Box in = interior_box(q);
       in.k1 = ktf;
-      launch_advect_scalar_fast(this, false, in, o(s.f), o("ru_m"), o("rv_m"), o("ww_m"), nullptr, nullptr, nullptr, o("advect_tend"));
+      launch_advect_scalar_fast(this, false, in, o(s.f), o("ru_m"), o("rv_m"), rom, nullptr, nullptr, nullptr, o("advect_tend"));
       Box strips[4];
       const int nst = edge_strips(mass, in, strips);
-      for (int m = 0; m < nst; m++) LAUNCH3(this, k_advect_scalar, strips[m], o(s.f), o("ru_m"), o("rv_m"), o("ww_m"), o("advect_tend"));
+      for (int m = 0; m < nst; m++) LAUNCH3(this, k_advect_scalar, strips[m], o(s.f), o("ru_m"), o("rv_m"), rom, o("advect_tend"));
     }
+    if (ieva) ieva_implicit(0, o("advect_tend"), o(s.o), o("mut_old"), o("muts"), dt_rk);   // module_em.F:1346-1364: mut_new = mut (= muts)
     if (rk_step == 1 && c.diff_opt == 1) {   // rk_step_1: diff_opt1 (module_em.F:1378-1419): K = xkhh, kvdq = kvdif/prandtl
       const float prandtl = 1.f / 3.0f;
       launch_diffuse(this, s.f == "moist_qv" ? 4 : 5, o(s.f), o(s.t), c.khdif / prandtl, c.kvdif / prandtl);

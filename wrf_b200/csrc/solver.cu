@@ -35,7 +35,7 @@ static void check_config(const wrfgpu_config &c) {
   if (c.momentum_adv_opt != 1 && c.momentum_adv_opt != 3) bad("momentum_adv_opt must be 1 (original) or 3 (WENO)");
   if (!c.non_hydrostatic) bad("hydrostatic option");
   if (c.damp_opt != 0 && c.damp_opt != 2 && c.damp_opt != 3) bad("damp_opt must be 0, 2 or 3");
-  if (c.zadvect_implicit != 0) bad("zadvect_implicit (IEVA)");
+  if (c.zadvect_implicit < 0) bad("zadvect_implicit must be 0 or positive (IEVA on the last RK substep)");
   // diffusion: constant K on coordinate surfaces (diff_opt 1 / km_opt 1) is on the device; with
   // km_opt = 1 and khdif = kvdif = 0 the physical-space form (diff_opt 2: shipped em_hill2d_x) adds exact zeros
   // to zero-initialised tendencies, i.e. it is the identity, and is accepted as such.  Everything else
@@ -76,6 +76,10 @@ Solver::Solver(const wrfgpu_dims &d_, const wrfgpu_config &c_, int dev) : d(d_),
   if (c.mp_physics) for (int i = 0; k3d_mp[i]; i++) add(k3d_mp[i], 3);
   for (int i = 0; k2d[i]; i++) add(k2d[i], 2);
   for (int i = 0; k1d[i]; i++) add(k1d[i], 1);
+  if (c.zadvect_implicit > 0) {   // IEVA: wwE / wwI and the locals of rk_tendency (module_em.F:343-347)
+    add("wwE", 3); add("wwI", 3);
+    for (const char *n : {"mut_old", "mut_new", "muu_old", "muu_new", "muv_old", "muv_new"}) add(n, 2);
+  }
   for (int s = 0; s < c.num_moist; s++) {
     Species sp{std::string("moist_") + moist_names[s], std::string("moist_old_") + moist_names[s],
                std::string("moist_tend_") + moist_names[s], c.moist_adv_opt};

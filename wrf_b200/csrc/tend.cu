@@ -84,6 +84,7 @@ struct TendIn {
   cfp p, pb, al, alt, php, cqu, cqv, cqw, h_diabatic;
   cfp mut, muu, muv, mu, mub;
   cfp ru_tendf, rv_tendf, rw_tendf, ph_tendf, t_tendf;
+  cfp rom;   // the vertical mass flux the explicit advection sees: ww, or wwE under IEVA (module_ieva_em.F:49)
 };
 
 // perturbation_coriolis (:3854-4173): ru, rv minus the mass-coupled base-state wind interpolated
@@ -118,14 +119,15 @@ __device__ __forceinline__ float pert_wind(const Geo &g, cfp r_in, cfp ph, cfp p
 
 // ===========================================================================
 // ru_tend: advect_u (:126) + pgf x (:2320-2400) + coriolis (:3700-3735) + curvature + addtend
-template <bool FAST, bool WENO = false>
-__device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i, int k, int j) {
+template <bool FAST, bool WENO = false, int PART = 0>   // PART (IEVA): 1 = advection only, 2 = everything after it, starting from t0
+__device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i, int k, int j, float t0 = 0.f) {
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, ktf = g.kde - 1;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
   const Deg dg = degrade(g);
   const float sg = g.sgn_ts;
-  cfp u = s.u, ru = s.ru, rv = s.rv, rom = s.ww;
-  float t = 0.f;
+  cfp u = s.u, ru = s.ru, rv = s.rv, rom = s.rom;
+  float t = t0;
+  if (PART != 2) {
   // --- y flux divergence
   {
     int i_s = its, i_e = ite;
@@ -235,6 +237,8 @@ __device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i,
       t = t - g.rdnw[k] * (vf[1] - vf[0]);
     }
   }
+  }
+  if (PART == 1) return t;
   // --- horizontal pressure gradient, x (:2320-2400)
   {
     int i_s = its, i_e = ite;
@@ -310,14 +314,15 @@ __global__ void k_tend_u_weno(const Geo g, Box b, TendIn s, fp ru_tend) {
 
 // ===========================================================================
 // rv_tend: advect_v (:1530) + pgf y + coriolis + curvature + addtend
-template <bool FAST, bool WENO = false>
-__device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i, int k, int j) {
+template <bool FAST, bool WENO = false, int PART = 0>
+__device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i, int k, int j, float t0 = 0.f) {
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, ktf = g.kde - 1;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
   const Deg dg = degrade(g);
   const float sg = g.sgn_ts;
-  cfp v = s.v, ru = s.ru, rv = s.rv, rom = s.ww;
-  float t = 0.f;
+  cfp v = s.v, ru = s.ru, rv = s.rv, rom = s.rom;
+  float t = t0;
+  if (PART != 2) {
   // --- y flux divergence
   {
     const int j_lo = dg.ys ? max(jts, jds + 1) : jts, j_hi = dg.ye ? min(jte, jde - 1) : jte;
@@ -425,6 +430,8 @@ __device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i,
       t = t - (A2(g.msfvy, i, j) / A2(g.msfvx, i, j)) * g.rdnw[k] * (vf[1] - vf[0]);
     }
   }
+  }
+  if (PART == 1) return t;
   // --- horizontal pressure gradient, y (:2230-2300)
   {
     int j_s = jts, j_e = jte;
@@ -497,14 +504,14 @@ __global__ void k_tend_v_weno(const Geo g, Box b, TendIn s, fp rv_tend) {   // a
 // ===========================================================================
 // rw_tend: advect_w (:4364) + pg_buoy_w (:2419) + w_damp (:2503) + coriolis + curvature + addtend
 // cqw is read here un-inverted; k_invert_cqw applies cqw <- 1/(1+cqw) (:2489) afterwards.
-template <bool FAST, bool WENO = false>
-__device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i, int k, int j) {
+template <bool FAST, bool WENO = false, int PART = 0>
+__device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i, int k, int j, float t0 = 0.f) {
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, kde = g.kde;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
   const Deg dg = degrade(g);
   const float sg = g.sgn_ts;
-  cfp w = s.w, ru = s.ru, rv = s.rv, rom = s.ww;
-  float t = 0.f;
+  cfp w = s.w, ru = s.ru, rv = s.rv, rom = s.rom;
+  float t = t0;
   if (k >= 2) {
     const bool top = (k == kde);
     const float fa = top ? (2.f - g.fnm[k - 1]) : g.fnm[k];
@@ -512,6 +519,7 @@ __device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i,
     const int ka = top ? k - 1 : k, kb = top ? k - 2 : k - 1;
     // vel at a face: interior  fzm(k)*r(k)+fzp(k)*r(k-1);  top  (2-fzm(k-1))*r(k-1)-fzp(k-1)*r(k-2)
 #define WVEL(r, ii, jj) (top ? (fa * A3(r, ii, ka, jj) - fb * A3(r, ii, kb, jj)) : (fa * A3(r, ii, ka, jj) + fb * A3(r, ii, kb, jj)))
+    if (PART != 2) {
     // --- y
     {
       const int j_lo = dg.ys ? max(jts, jds + 1) : jts, j_hi = dg.ye ? min(jte, jde - 2) : min(jte, jde - 1);
@@ -590,6 +598,8 @@ __device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i,
       if (!top) t = t - g.rdn[k] * (vflux(k + 1) - vflux(k));
       else t = t + 2.f * g.rdn[k - 1] * (vflux(k));
     }
+    }
+    if (PART == 1) return t;
     // --- pg_buoy_w (:2419-2499)
     {
       const float mu = A2(s.mu, i, j), mub = A2(s.mub, i, j), rmsf = (1.f / A2(g.msfty, i, j));
@@ -625,6 +635,7 @@ __device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i,
                                  (fzm * (A3(s.v, i, k, j) + A3(s.v, i, k, j + 1)) + fzp * (A3(s.v, i, k - 1, j) + A3(s.v, i, k - 1, j + 1))));
     }
   }
+  if (PART == 1) return t;
   t = t + A3(s.rw_tendf, i, k, j) / A2(g.msfty, i, j);
   return t;
 }
@@ -730,8 +741,8 @@ __device__ __forceinline__ float advect_scalar_pt(const Geo &g, cfp q, cfp q_old
 __global__ void k_tend_t(const Geo g, Box b, TendIn s, fp t_tend) {
   TID3;
   if (k > g.kde - 1 || i > min(g.ite, g.ide - 1) || j > min(g.jte, g.jde - 1)) { A3(t_tend, i, k, j) = 0.f; return; }
-  float t = interior_pt(g, i, j) ? advect_scalar_pt<true>(g, s.t, s.t, s.ru, s.rv, s.ww, i, k, j)
-                               : advect_scalar_pt<false>(g, s.t, s.t, s.ru, s.rv, s.ww, i, k, j);
+  float t = interior_pt(g, i, j) ? advect_scalar_pt<true>(g, s.t, s.t, s.ru, s.rv, s.rom, i, k, j)
+                               : advect_scalar_pt<false>(g, s.t, s.t, s.ru, s.rv, s.rom, i, k, j);
   const float msfty = A2(g.msfty, i, j);
   t = t + A3(s.t_tendf, i, k, j) / msfty + (g.c1h[k] * A2(s.mut, i, j) + g.c2h[k]) * A3(s.h_diabatic, i, k, j) / msfty;
   A3(t_tend, i, k, j) = t;
@@ -741,7 +752,7 @@ __global__ void k_tend_t(const Geo g, Box b, TendIn s, fp t_tend) {
 __global__ void k_tend_t_weno(const Geo g, Box b, TendIn s, fp t_tend) {
   TID3;
   if (k > g.kde - 1 || i > min(g.ite, g.ide - 1) || j > min(g.jte, g.jde - 1)) { A3(t_tend, i, k, j) = 0.f; return; }
-  float t = advect_scalar_weno_pt(g, s.t, s.t, s.ru, s.rv, s.ww, i, k, j);
+  float t = advect_scalar_weno_pt(g, s.t, s.t, s.ru, s.rv, s.rom, i, k, j);
   const float msfty = A2(g.msfty, i, j);
   t = t + A3(s.t_tendf, i, k, j) / msfty + (g.c1h[k] * A2(s.mut, i, j) + g.c2h[k]) * A3(s.h_diabatic, i, k, j) / msfty;
   A3(t_tend, i, k, j) = t;
@@ -756,13 +767,13 @@ __global__ void k_advect_scalar(const Geo g, Box b, cfp q, cfp ru, cfp rv, cfp r
 
 // ===========================================================================
 // ph_tend: rhs_ph (:1365-2181, 6th-order branch) + rk_addtend_dry
-template <bool FAST>
-__device__ __forceinline__ float tend_ph_pt(const Geo &g, const TendIn &s, int i, int k, int j) {
+template <bool FAST, int PART = 0>
+__device__ __forceinline__ float tend_ph_pt(const Geo &g, const TendIn &s, int i, int k, int j, float t0 = 0.f) {
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, kde = g.kde, kte = g.kde;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
-  cfp ph = s.ph, phb = s.phb, u = s.u, v = s.v, ww = s.ww;
+  cfp ph = s.ph, phb = s.phb, u = s.u, v = s.v, ww = s.rom;
   const float msfty = A2(g.msfty, i, j);
-  float t = 0.f;
+  float t = t0;
   if (k >= 2) {
     const float c1f = g.c1f[k], c2f = g.c2f[k];
     if (k <= kte - 1) {
@@ -872,6 +883,7 @@ __device__ __forceinline__ float tend_ph_pt(const Geo &g, const TendIn &s, int i
       t = t - (A2(g.msftx, i, j) / msfty) * g.rdx * mass * (+ur * (A3(ph, i, k, j) - A3(ph, i - 1, k, j)));
     }
   }
+  if (PART == 1) return t;
   t = t + A3(s.ph_tendf, i, k, j) / msfty;
   return t;
 }
@@ -882,6 +894,53 @@ __global__ void k_tend_ph(const Geo g, Box b, TendIn s, fp ph_tend) {
   (void)ids; (void)jds; (void)ktf; (void)kde; (void)its; (void)jts;
   if (i > min(ite, ide - 1) || j > min(jte, jde - 1)) { A3(ph_tend, i, k, j) = 0.f; return; }
   A3(ph_tend, i, k, j) = interior_pt(g, i, j) ? tend_ph_pt<true>(g, s, i, k, j) : tend_ph_pt<false>(g, s, i, k, j);
+}
+
+// ===========================================================================
+// IEVA (module_ieva_em.F), last RK substep: each tendency is built in three launches -- PART 1 the explicit advection
+// (with wwE), then the implicit column solve on the stored tendency (ieva.cu), then PART 2 everything the fused kernels
+// add after the advection, starting from the stored value.  Gather kernels on the whole tile.
+template <int PART>
+__global__ void k_tend_u_part(const Geo g, Box b, TendIn s, fp ru_tend, int weno) {
+  TID3;
+  if (k > g.kde - 1 || j > min(g.jte, g.jde - 1)) { if (PART == 1) A3(ru_tend, i, k, j) = 0.f; return; }
+  const float t0 = PART == 2 ? A3(ru_tend, i, k, j) : 0.f;
+  A3(ru_tend, i, k, j) = weno ? tend_u_pt<false, true, PART>(g, s, i, k, j, t0) : tend_u_pt<false, false, PART>(g, s, i, k, j, t0);
+}
+template <int PART>
+__global__ void k_tend_v_part(const Geo g, Box b, TendIn s, fp rv_tend, int weno) {
+  TID3;
+  if (k > g.kde - 1 || i > min(g.ite, g.ide - 1)) { if (PART == 1) A3(rv_tend, i, k, j) = 0.f; return; }
+  const float t0 = PART == 2 ? A3(rv_tend, i, k, j) : 0.f;
+  A3(rv_tend, i, k, j) = weno ? tend_v_pt<false, true, PART>(g, s, i, k, j, t0) : tend_v_pt<false, false, PART>(g, s, i, k, j, t0);
+}
+template <int PART>
+__global__ void k_tend_w_part(const Geo g, Box b, TendIn s, fp rw_tend, int weno) {
+  TID3;
+  if (i > min(g.ite, g.ide - 1) || j > min(g.jte, g.jde - 1)) { if (PART == 1) A3(rw_tend, i, k, j) = 0.f; return; }
+  const float t0 = PART == 2 ? A3(rw_tend, i, k, j) : 0.f;
+  A3(rw_tend, i, k, j) = weno ? tend_w_pt<false, true, PART>(g, s, i, k, j, t0) : tend_w_pt<false, false, PART>(g, s, i, k, j, t0);
+}
+template <int PART>
+__global__ void k_tend_ph_part(const Geo g, Box b, TendIn s, fp ph_tend) {
+  TID3;
+  if (i > min(g.ite, g.ide - 1) || j > min(g.jte, g.jde - 1)) { if (PART == 1) A3(ph_tend, i, k, j) = 0.f; return; }
+  if (PART == 1) A3(ph_tend, i, k, j) = tend_ph_pt<false, 1>(g, s, i, k, j);
+  else A3(ph_tend, i, k, j) = A3(ph_tend, i, k, j) + A3(s.ph_tendf, i, k, j) / A2(g.msfty, i, j);
+}
+template <int PART>
+__global__ void k_tend_t_part(const Geo g, Box b, TendIn s, fp t_tend, int weno) {
+  TID3;
+  if (k > g.kde - 1 || i > min(g.ite, g.ide - 1) || j > min(g.jte, g.jde - 1)) { if (PART == 1) A3(t_tend, i, k, j) = 0.f; return; }
+  if (PART == 1) {
+    A3(t_tend, i, k, j) = weno ? advect_scalar_weno_pt(g, s.t, s.t, s.ru, s.rv, s.rom, i, k, j)
+                               : advect_scalar_pt<false>(g, s.t, s.t, s.ru, s.rv, s.rom, i, k, j);
+  } else {
+    const float msfty = A2(g.msfty, i, j);
+    float t = A3(t_tend, i, k, j);
+    t = t + A3(s.t_tendf, i, k, j) / msfty + (g.c1h[k] * A2(s.mut, i, j) + g.c2h[k]) * A3(s.h_diabatic, i, k, j) / msfty;
+    A3(t_tend, i, k, j) = t;
+  }
 }
 
 // ===========================================================================
@@ -994,7 +1053,7 @@ void Solver::rk_tendency(int rk_step, bool zero_save) {
   }
   TendIn s;
   s.u = o("u_2"); s.v = o("v_2"); s.w = o("w_2"); s.t = o("t_2"); s.ph = o("ph_2"); s.phb = o("phb");
-  s.ru = o("ru"); s.rv = o("rv"); s.rw = o("rw"); s.ww = o("ww");
+  s.ru = o("ru"); s.rv = o("rv"); s.rw = o("rw"); s.ww = o("ww"); s.rom = o("ww");
   s.p = o("p"); s.pb = o("pb"); s.al = o("al"); s.alt = o("alt"); s.php = o("php");
   s.cqu = o("cqu"); s.cqv = o("cqv"); s.cqw = o("cqw"); s.h_diabatic = o("h_diabatic");
   s.mut = o("mut"); s.muu = o("muu"); s.muv = o("muv"); s.mu = o("mu_2"); s.mub = o("mub");
@@ -1004,6 +1063,31 @@ void Solver::rk_tendency(int rk_step, bool zero_save) {
   Box strips[4];
   const int ns = edge_strips(tile, in, strips);
   const bool weno_m = c.momentum_adv_opt == 3 && rk_step == c.rk_ord;   // WENO_MOM, module_em.F:491-600
+  const bool weno_t = (c.scalar_adv_opt == 3 || c.scalar_adv_opt == 4 || c.moist_adv_opt == 3 || c.moist_adv_opt == 4) && rk_step == c.rk_ord;
+  if (c.zadvect_implicit > 0 && rk_step != c.rk_ord) ieva_split(true, s.u, s.v, o("ww"), s.mut, false);
+  if (c.zadvect_implicit > 0 && rk_step == c.rk_ord) {   // IEVA, CHK_IEVA module_ieva_em.F:13-43; order of module_em.F:438-715
+    const float dt_step = c.dt / (float)(c.rk_ord - rk_step + 1);
+    ieva_split(true, s.u, s.v, o("ww"), s.mut);
+    s.rom = o("wwE");
+    LAUNCH3(this, k_tend_u_part<1>, tile, s, o("ru_tend"), (int)weno_m);
+    ieva_implicit(1, o("ru_tend"), o("u_1"), o("muu_old"), o("muu_new"), dt_step);
+    LAUNCH3(this, k_tend_v_part<1>, tile, s, o("rv_tend"), (int)weno_m);
+    ieva_implicit(2, o("rv_tend"), o("v_1"), o("muv_old"), o("muv_new"), dt_step);
+    LAUNCH3(this, k_tend_w_part<1>, tile, s, o("rw_tend"), (int)weno_m);
+    LAUNCH3(this, k_tend_t_part<1>, tile, s, o("t_tend"), (int)weno_t);
+    ieva_implicit(0, o("t_tend"), o("t_1"), o("mut_old"), o("mut_new"), dt_step);
+    LAUNCH3(this, k_tend_ph_part<1>, tile, s, o("ph_tend"));
+    ieva_implicit(3, o("ph_tend"), nullptr, nullptr, nullptr, dt_step);
+    ieva_implicit(4, o("rw_tend"), nullptr, nullptr, nullptr, dt_step);
+    LAUNCH3(this, k_tend_u_part<2>, tile, s, o("ru_tend"), (int)weno_m);
+    LAUNCH3(this, k_tend_v_part<2>, tile, s, o("rv_tend"), (int)weno_m);
+    LAUNCH3(this, k_tend_w_part<2>, tile, s, o("rw_tend"), (int)weno_m);
+    LAUNCH3(this, k_tend_t_part<2>, tile, s, o("t_tend"), (int)weno_t);
+    LAUNCH3(this, k_tend_ph_part<2>, tile, s, o("ph_tend"));
+    const Box cq{q.its, std::min(q.ite, q.ide - 1), 2, q.kde - 1, q.jts, std::min(q.jte, q.jde - 1)};
+    LAUNCH3(this, k_invert_cqw, cq, o("cqw"));
+    return;
+  }
   if (weno_m) {
     LAUNCH3(this, k_tend_u_weno, tile, s, o("ru_tend"));
     LAUNCH3(this, k_tend_v_weno, tile, s, o("rv_tend"));
@@ -1021,11 +1105,10 @@ void Solver::rk_tendency(int rk_step, bool zero_save) {
     LAUNCH3(this, k_tend_v, tile, s, o("rv_tend"));
     LAUNCH3(this, k_tend_w, tile, s, o("rw_tend"));
   }
-  const bool weno_t = (c.scalar_adv_opt == 3 || c.scalar_adv_opt == 4 || c.moist_adv_opt == 3 || c.moist_adv_opt == 4) && rk_step == c.rk_ord;
   if (weno_t) {   // theta follows the scalars' WENO option on the last substep: gather kernel on the whole tile
     LAUNCH3(this, k_tend_t_weno, tile, s, o("t_tend"));
   } else {   // theta: k-marching flux-sharing kernel on the interior, the gather kernel on the edge strips
-    launch_advect_scalar_fast(this, true, in, s.t, s.ru, s.rv, s.ww, s.mut, s.t_tendf, s.h_diabatic, o("t_tend"));
+    launch_advect_scalar_fast(this, true, in, s.t, s.ru, s.rv, s.rom, s.mut, s.t_tendf, s.h_diabatic, o("t_tend"));
     for (int m = 0; m < ns; m++) LAUNCH3(this, k_tend_t, strips[m], s, o("t_tend"));
   }
   if (!empty(in)) {   // ph: k-marching kernel on the interior (mom_fast.cu), the gather kernel on the edge strips
