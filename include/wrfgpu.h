@@ -52,9 +52,10 @@ typedef struct wrfgpu_config {
   int time_step_sound;                   /* 0 => derived, solve_em.F:446-462 */
   int h_mom_adv_order, v_mom_adv_order;  /* 5 / 3 */
   int h_sca_adv_order, v_sca_adv_order;  /* 5 / 3 */
-  int moist_adv_opt, scalar_adv_opt;     /* 0 = original, 1 = positive-definite
+  int moist_adv_opt, scalar_adv_opt;     /* 0 = original, 1 = positive-definite, 2 = monotonic,
+                                            3 = WENO, 4 = WENO + positive-definite
                                             (Registry.EM_COMMON:3275-3279) */
-  int momentum_adv_opt;                  /* 1 */
+  int momentum_adv_opt;                  /* 1 = original, 3 = WENO (Registry.EM_COMMON:3272-3273) */
   int non_hydrostatic;                   /* 1 */
   int top_lid;                           /* 0/1 */
   int damp_opt;                          /* 0, 2 (rk_rayleigh_damp), 3 (implicit w) */
@@ -63,7 +64,7 @@ typedef struct wrfgpu_config {
   int use_theta_m;                       /* 0/1 */
   int hypsometric_opt;                   /* 1/2 */
   int phi_adv_z;                         /* 1/2 */
-  int zadvect_implicit;                  /* must be 0 */
+  int zadvect_implicit;                  /* > 0: IEVA on the last RK substep (module_ieva_em.F) */
   int diff_opt, km_opt;                  /* must be 0 on device */
   int diff_6th_opt;                      /* must be 0 */
   int mp_physics;                        /* 0 = none(passive qv), 1 = Kessler */
