@@ -115,6 +115,22 @@ int  wrfgpu_num_fields(const wrfgpu_solver *s);
 const char *wrfgpu_field_name(const wrfgpu_solver *s, int idx);
 void *wrfgpu_field_devptr(wrfgpu_solver *s, const char *name);
 
+/* -- history / restart snapshots --------------------------- */
+/* replaces the contract "the host grid% arrays are current when
+ * med_before_solve_io runs" (frame/module_integrate.F:406;
+ * share/mediation_integrate.F: med_before_solve_io -> med_hist_out,
+ * med_restart_out at the history / restart alarms).  _begin copies the listed
+ * fields device-to-device into staging buffers on the compute stream and
+ * returns; the device-to-host copies into pinned memory overlap the following
+ * time steps on a second stream.  _wait blocks until they have landed; _host
+ * then returns the pinned buffer of one field (valid until the next _begin;
+ * NULL if the field is not part of the current snapshot).  _busy: 1 while the
+ * copies are in flight, 0 when done, -1 on error. */
+int  wrfgpu_snapshot_begin(wrfgpu_solver *s, int nfields, const char *const *names);
+int  wrfgpu_snapshot_wait (wrfgpu_solver *s);
+int  wrfgpu_snapshot_busy (wrfgpu_solver *s);
+const float *wrfgpu_snapshot_host(wrfgpu_solver *s, const char *name, size_t *n);
+
 /* -- the hot path -------------------------------------------------------- */
 /* one model time step of one domain = dyn_em/solve_em.F:578-4848 with the
  * state resident in HBM */

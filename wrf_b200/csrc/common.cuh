@@ -147,6 +147,7 @@ struct Solver {
   float *d_cfl = nullptr;   // 2 floats: max_vert_cfl, max_horiz_cfl
   // halo exchange state (HaloState, halo.cu)
   void *comm = nullptr;
+  void *snapshot = nullptr;   // history.cu: staging / pinned buffers of wrfgpu_snapshot_*
   int rank = 0, nranks = 1;
   // phase / kernel timing (cudaEvents on `stream`, only when switched on)
   bool timing = false;
@@ -260,6 +261,7 @@ inline bool empty(const Box &b) { return b.i1 < b.i0 || b.k1 < b.k0 || b.j1 < b.
   if (i > b.i1 || j > b.j1) return;
 
 void halo_destroy(Solver *s);   // halo.cu
+void snapshot_destroy(Solver *s);   // history.cu
 // advect_fast.cu
 Box interior_box(const Geo &q);
 int edge_strips(const Box &tile, const Box &in, Box out[4]);

@@ -125,6 +125,7 @@ Solver::~Solver() {
   cudaSetDevice(device);
   for (auto &kv : fields) cudaFree(kv.second.d);
   halo_destroy(this);
+  snapshot_destroy(this);
   cudaFree(d_cfl);
   if (stream && own_stream) cudaStreamDestroy(stream);
 }

@@ -14,7 +14,8 @@ MODULE module_wrfgpu
    PUBLIC :: wrfgpu_dims, wrfgpu_config, wrfgpu_check
    PUBLIC :: wrfgpu_create, wrfgpu_destroy, wrfgpu_last_error, wrfgpu_upload, wrfgpu_download, wrfgpu_step, &
              wrfgpu_solve_em, wrfgpu_start_domain, wrfgpu_sync, wrfgpu_comm_unique_id, wrfgpu_comm_init, &
-             wrfgpu_compute_mesh, wrfgpu_patch_dims, wrfgpu_field_size
+             wrfgpu_compute_mesh, wrfgpu_patch_dims, wrfgpu_field_size, &
+             wrfgpu_snapshot_begin, wrfgpu_snapshot_wait, wrfgpu_snapshot_busy, wrfgpu_snapshot_host
 
    ! wrfgpu_dims: the three index triplets of get_ijk_from_grid (dyn_em/solve_em.F:288-296)
    TYPE, BIND(C) :: wrfgpu_dims
@@ -72,6 +73,28 @@ MODULE module_wrfgpu
          TYPE(c_ptr), VALUE :: handle
          INTEGER(c_int), VALUE :: nfields
          TYPE(c_ptr), INTENT(IN) :: names(*), host(*)
+      END FUNCTION
+      ! history / restart alarms (share/mediation_integrate.F med_before_solve_io): stage the stream's fields and go on
+      ! stepping; wait + wrfgpu_snapshot_host give the pinned host copy that med_hist_out / med_restart_out unpack
+      INTEGER(c_int) FUNCTION wrfgpu_snapshot_begin(handle, nfields, names) BIND(C, name='wrfgpu_snapshot_begin')
+         IMPORT :: c_int, c_ptr
+         TYPE(c_ptr), VALUE :: handle
+         INTEGER(c_int), VALUE :: nfields
+         TYPE(c_ptr), INTENT(IN) :: names(*)
+      END FUNCTION
+      INTEGER(c_int) FUNCTION wrfgpu_snapshot_wait(handle) BIND(C, name='wrfgpu_snapshot_wait')
+         IMPORT :: c_int, c_ptr
+         TYPE(c_ptr), VALUE :: handle
+      END FUNCTION
+      INTEGER(c_int) FUNCTION wrfgpu_snapshot_busy(handle) BIND(C, name='wrfgpu_snapshot_busy')
+         IMPORT :: c_int, c_ptr
+         TYPE(c_ptr), VALUE :: handle
+      END FUNCTION
+      TYPE(c_ptr) FUNCTION wrfgpu_snapshot_host(handle, name, n) BIND(C, name='wrfgpu_snapshot_host')
+         IMPORT :: c_ptr, c_char, c_size_t
+         TYPE(c_ptr), VALUE :: handle
+         CHARACTER(KIND=c_char), INTENT(IN) :: name(*)
+         INTEGER(c_size_t), INTENT(OUT) :: n
       END FUNCTION
       INTEGER(c_int) FUNCTION wrfgpu_start_domain(handle) BIND(C, name='wrfgpu_start_domain')
          IMPORT :: c_int, c_ptr

@@ -30,6 +30,7 @@ ABI_SYMBOLS = (
     "wrfgpu_step", "wrfgpu_solve_em", "wrfgpu_sync", "wrfgpu_set_stream", "wrfgpu_kernel_report", "wrfgpu_launch_count", "wrfgpu_phase_ms", "wrfgpu_set_physical_bc",
     "wrfgpu_compute_mesh", "wrfgpu_patch_dims", "wrfgpu_comm_unique_id", "wrfgpu_comm_init", "wrfgpu_comm_init_local", "wrfgpu_halo",
     "wrfgpu_halo_spec", "wrfgpu_halo_box", "wrfgpu_halo_bytes",
+    "wrfgpu_snapshot_begin", "wrfgpu_snapshot_wait", "wrfgpu_snapshot_busy", "wrfgpu_snapshot_host",
 ) + tuple("wrfgpu_" + p for p in PHASES)
 
 
@@ -54,6 +55,7 @@ def load():
         lib.wrfgpu_launch_count.restype = ctypes.c_longlong
         lib.wrfgpu_phase_ms.restype = ctypes.c_double
         lib.wrfgpu_kernel_report.restype = ctypes.c_size_t
+        lib.wrfgpu_snapshot_host.restype = ctypes.c_void_p
         _LIB = lib
     return _LIB
 
@@ -144,6 +146,34 @@ class Solver:
 
     def halo(self, name):
         self._chk(self.lib.wrfgpu_halo(self.h, name.encode()))
+
+    # ---- history / restart snapshots ----
+    def snapshot_begin(self, names):
+        """Stage `names` for output: returns as soon as the device-to-device copies are enqueued; the time loop may go on."""
+        n = len(names)
+        self._chk(self.lib.wrfgpu_snapshot_begin(self.h, ctypes.c_int(n), (ctypes.c_char_p * n)(*[s.encode() for s in names])))
+        self._snap_names = list(names)
+
+    def snapshot_busy(self) -> bool:
+        r = int(self.lib.wrfgpu_snapshot_busy(self.h))
+        if r < 0:
+            raise WrfGpuError(self.lib.wrfgpu_last_error().decode())
+        return bool(r)
+
+    def snapshot_wait(self):
+        """Block until the snapshot has landed in pinned host memory; returns {name: array shaped like get(name)} (copies)."""
+        self._chk(self.lib.wrfgpu_snapshot_wait(self.h))
+        out = {}
+        for name in getattr(self, "_snap_names", []):
+            n = ctypes.c_size_t(0)
+            p = self.lib.wrfgpu_snapshot_host(self.h, name.encode(), ctypes.byref(n))
+            if not p:
+                raise WrfGpuError(f"no snapshot of '{name}'")
+            a = np.ctypeslib.as_array((ctypes.c_float * n.value).from_address(p)).copy()
+            d = self.case.dims
+            ni, nk, nj = d.ime - d.ims + 1, d.kme - d.kms + 1, d.jme - d.jms + 1
+            out[name] = a.reshape(nj, nk, ni) if n.value == ni * nk * nj else (a.reshape(nj, ni) if n.value == ni * nj else a)
+        return out
 
     # ---- ranks ----
     @staticmethod
