@@ -134,3 +134,55 @@ def test_history_stream_writes_wrfout_from_the_device(tmp_path):
     assert "QRAIN" in nc.variables and "RAINNC" in nc.variables
     nc.close()
     a.close(); b.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# restart: the reference's regression suite asks a restarted run to reproduce the continuous one bit for bit
+# (tools/regtest.csh, "restart" comparisons with BIT4BIT).  Same criterion here, through a wrfrst file.
+PROG = ["u_2", "v_2", "w_2", "t_2", "ph_2", "mu_2", "u_1", "v_1", "w_1", "t_1", "ph_1", "mu_1", "p", "al"]
+
+
+def _restart_round_trip(make, case, tmp_path, n1=3, n2=3):
+    import dataclasses
+    cont = make(case)
+    cont.start_domain(); cont.step(n1 + n2)
+    first = make(case)
+    first.start_domain(); first.step(n1)
+    names = wrfout.stream_fields(first.names(), "r")
+    w = wrfout.WrfOut(str(tmp_path / "wrfrst_d01"), case.dims, case.config)
+    w.write(wrfout.time_string("0001-01-01_00:00:00", n1 * case.config.dt), {n: first.get(n) for n in names})
+    w.close()
+    fields = wrfout.read_fields(w.path, case.dims)
+    second = make(dataclasses.replace(case, fields=fields))
+    second.start_domain(); second.step(n2)
+    prog = PROG + [n for n in cont.names() if n.startswith(("moist_q", "scalar_")) and "old" not in n and "tend" not in n]
+    prog += [n for n in ("rainnc", "h_diabatic") if n in cont.names()]
+    bad = [n for n in prog if not np.array_equal(_owned(case, cont.get(n)), _owned(case, second.get(n)))]
+    for m in (cont, first, second):
+        if hasattr(m, "close"):
+            m.close()
+    return bad
+
+
+def _owned(case, a):
+    d = case.dims
+    if a.ndim == 3:
+        return a[d.jds - d.jms:d.jde - d.jms + 1, :, d.ids - d.ims:d.ide - d.ims + 1]
+    if a.ndim == 2:
+        return a[d.jds - d.jms:d.jde - d.jms + 1, d.ids - d.ims:d.ide - d.ims + 1]
+    return a
+
+
+@pytest.mark.parametrize("name", ["quarter_ss", "periodic", "b_wave", "hill2d_x", "diffusion", "ieva_periodic"])
+def test_restart_reproduces_the_continuous_run_oracle(name, tmp_path):
+    from tests.oracle_lib import Oracle
+    bad = _restart_round_trip(Oracle, parity.small_cases()[name], tmp_path)
+    assert not bad, bad
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["quarter_ss", "periodic", "ieva_periodic"])
+def test_restart_reproduces_the_continuous_run_gpu(name, tmp_path):
+    from wrf_b200 import Solver
+    bad = _restart_round_trip(Solver, parity.small_cases()[name], tmp_path)
+    assert not bad, bad

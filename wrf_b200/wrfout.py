@@ -54,6 +54,7 @@ _STATE = [
     ("msfux", "MAPFAC_UX", "X", "Map scale factor on u-grid, x direction", "", "hr"),
     ("msfuy", "MAPFAC_UY", "X", "Map scale factor on u-grid, y direction", "", "hr"),
     ("msfvx", "MAPFAC_VX", "Y", "Map scale factor on v-grid, x direction", "", "hr"),
+    ("msfvx_inv", "MF_VX_INV", "Y", "Inverse map scale factor on v-grid, x direction", "", "hr"),
     ("msfvy", "MAPFAC_VY", "Y", "Map scale factor on v-grid, y direction", "", "hr"),
     ("f", "F", "", "Coriolis sine latitude term", "s-1", "hr"),
     ("e", "E", "", "Coriolis cosine latitude term", "s-1", "hr"),
@@ -75,6 +76,11 @@ _STATE = [
     ("c4h", "C4H", "", "half levels, c4h = (eta-bh)*(p0-pt)", "Pa", "hr"),
     ("c3f", "C3F", "Z", "full levels, c3f = bf", "Dimensionless", "hr"),
     ("c4f", "C4F", "Z", "full levels, c4f = (eta-bf)*(p0-pt)", "Pa", "hr"),
+    ("u_base", "U_BASE", "", "BASE STATE X WIND IN IDEALIZED CASES", "", "r"),
+    ("v_base", "V_BASE", "", "BASE STATE Y WIND IN IDEALIZED CASES", "", "r"),
+    ("t_base", "T_BASE", "", "BASE STATE T IN IDEALIZED CASES", "K", "r"),
+    ("qv_base", "QV_BASE", "", "BASE STATE QV IN IDEALIZED CASES", "", "r"),
+    ("z_base", "Z_BASE", "", "BASE STATE HEIGHT IN IDEALIZED CASES", "", "r"),
 ]
 # restart also needs the second time level of the prognostic fields
 _RESTART_EXTRA = [("u_1", "U_1", "X"), ("v_1", "V_1", "Y"), ("w_1", "W_1", "Z"), ("ph_1", "PH_1", "Z"), ("t_1", "THM_1", ""), ("mu_1", "MU_1", "")]
@@ -89,6 +95,50 @@ def stream_fields(available, stream="h"):
         out += [f for f in available if f.startswith(("scalar_", "moist_old_", "scalar_old_")) and "tend" not in f]
     else:
         out += [f for f in available if f.startswith("scalar_") and "old" not in f and "tend" not in f]
+    return out
+
+
+def _field_of(varname):
+    for f, name, _, _, _, _ in _STATE:
+        if name == varname:
+            return f
+    for f, name, _ in _RESTART_EXTRA:
+        if name == varname:
+            return f
+    return varname.lower()
+
+
+def read_fields(path, dims, rec=-1):
+    """Read one time record of a wrfout / wrfrst file written by WrfOut back into arrays of the solver's memory shape
+    ((nj, nk, ni) / (nj, ni) / (nk,), zero outside the patch).  With a restart file this is the reference's restart read
+    (share/mediation_wrfmain.F med_initialdata_input with config_flags%restart, input_restart): feed the arrays to a new
+    solver and call start_domain, which refills halos and boundary zones as start_domain_em does on a restart."""
+    from scipy.io import netcdf_file
+    d = dims
+    nj, nk, ni = d.jme - d.jms + 1, d.kme - d.kms + 1, d.ime - d.ims + 1
+    out = {}
+    nc = netcdf_file(path, "r", mmap=False)
+    try:
+        i0 = int(getattr(nc, "WEST-EAST_PATCH_START_UNSTAG"))
+        j0 = int(getattr(nc, "SOUTH-NORTH_PATCH_START_UNSTAG"))
+        for name, v in nc.variables.items():
+            if name in ("Times", "T"):
+                continue
+            a = np.asarray(v[rec], dtype=np.float32)
+            if a.ndim == 3:
+                full = np.zeros((nj, nk, ni), np.float32)
+                k, j, i = a.shape
+                full[j0 - d.jms:j0 - d.jms + j, :k, i0 - d.ims:i0 - d.ims + i] = a.transpose(1, 0, 2)
+            elif a.ndim == 2:
+                full = np.zeros((nj, ni), np.float32)
+                j, i = a.shape
+                full[j0 - d.jms:j0 - d.jms + j, i0 - d.ims:i0 - d.ims + i] = a
+            else:
+                full = np.zeros(nk, np.float32)
+                full[:a.shape[0]] = a
+            out[_field_of(name)] = full
+    finally:
+        nc.close()
     return out
 
 
