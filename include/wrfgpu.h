@@ -66,7 +66,7 @@ typedef struct wrfgpu_config {
   int phi_adv_z;                         /* 1/2 */
   int zadvect_implicit;                  /* > 0: IEVA on the last RK substep (module_ieva_em.F) */
   int diff_opt, km_opt;                  /* must be 0 on device */
-  int diff_6th_opt;                      /* must be 0 */
+  int diff_6th_opt;                      /* 0, 1 or 2 (sixth_order_diffusion; 2 = no up-gradient fluxes) */
   int mp_physics;                        /* 0 = none(passive qv), 1 = Kessler */
   int time_step;                         /* integer namelist time_step; only its
                                             sign is used (module_advect_em.F:204) */
@@ -85,6 +85,11 @@ typedef struct wrfgpu_config {
   int num_scalar;                        /* 0..8 */
   /* RSL_LITE process mesh (external/RSL_LITE/module_dm.F:98-175) */
   int ntasks_x, ntasks_y, mytask;        /* mytask = mytask_y*ntasks_x + mytask_x */
+  /* 6th-order horizontal filter (Registry.EM_COMMON:2860-2863, 2893-2896) */
+  float diff_6th_factor;                 /* 0.12 */
+  float diff_6th_thresh;                 /* 0.10 */
+  int diff_6th_slopeopt;                 /* 0/1: taper the filter over steep terrain */
+  int moist_mix6_off, scalar_mix6_off;   /* 1 = no 6th-order filter on that family */
 } wrfgpu_config;
 
 typedef struct wrfgpu_solver wrfgpu_solver;   /* opaque */

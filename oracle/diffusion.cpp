@@ -279,4 +279,122 @@ void vertical_diffusion_v(const Cx &x, A3 field, A3 tendency, A1 v_base, A1 c1h,
   }
 }
 
+// module_big_step_utilities_em.F:6220-6620 sixth_order_diffusion (Knievel et al. 2007): the 6th-order horizontal filter
+// of diff_6th_opt = 1, 2 (2: fluxes that run up the gradient are dropped), optionally tapered over steep terrain
+// (diff_6th_slopeopt), added to the *_tendf arrays on the first RK substep (module_em.F:880-930, 1421-1437).
+void sixth_order_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT, float dt, A1 c1, A1 c2, A3 phb) {
+  const int ids = x.ids, ide = x.ide, jds = x.jds, jde = x.jde;
+  const int its = x.its, ite = x.ite, jts = x.jts, jte = x.jte, kts = x.kts;
+  const int ktf = std::min(x.kte, x.kde - 1);
+  const int opt = x.c.diff_6th_opt;
+  const float rdx = x.rdx, rdy = x.rdy;
+  const A2 &msfux = x.msfux, &msfuy = x.msfuy, &msfvx = x.msfvx, &msfvy = x.msfvy, &msftx = x.msftx, &msfty = x.msfty;
+  const float diff_6th_coef = x.c.diff_6th_factor * 0.015625f / (2.0f * dt);
+  int i_start = its, i_end, j_start = jts, j_end, k_start = kts, k_end = ktf;
+  if (name == 'u') {
+    i_end = ite; j_end = std::min(jde - 1, jte);
+    if (x.c.open_xs) i_start = std::max(its, ids + 3);
+    if (x.c.open_ys) j_start = std::max(jts, jds + 3);
+    if (x.c.open_xe) i_end = std::min(ite, ide - 3);
+    if (x.c.open_ye) j_end = std::min(jte, jde - 4);
+  } else if (name == 'v') {
+    i_end = std::min(ide - 1, ite); j_end = jte;
+    if (x.c.open_xs) i_start = std::max(its, ids + 3);
+    if (x.c.open_ys) j_start = std::max(jts, jds + 3);
+    if (x.c.open_xe) i_end = std::min(ite, ide - 4);
+    if (x.c.open_ye) j_end = std::min(jte, jde - 3);
+    if (x.c.open_xs) {   // sic (:6333): "open_xs .or. specified" restricts all four sides
+      i_start = std::max(its, ids + 3); i_end = std::min(ite, ide - 4);
+      j_start = std::max(jts, jds + 3); j_end = std::min(jte, jde - 3);
+    }
+  } else {
+    i_end = std::min(ide - 1, ite); j_end = std::min(jde - 1, jte);
+    if (x.c.open_xs) i_start = std::max(its, ids + 3);
+    if (x.c.open_ys) j_start = std::max(jts, jds + 3);
+    if (x.c.open_xe) i_end = std::min(ite, ide - 4);
+    if (x.c.open_ye) j_end = std::min(jte, jde - 4);
+    if (name == 'w') k_start = kts + 1;
+  }
+  for (int j = j_start; j <= j_end; j++)
+    for (int k = k_start; k <= k_end; k++)
+      for (int i = i_start; i <= i_end; i++) {
+        float dflux_x_p0 = (10.0f * (field(i, k, j) - field(i - 1, k, j)) - 5.0f * (field(i + 1, k, j) - field(i - 2, k, j)) + (field(i + 2, k, j) - field(i - 3, k, j)));
+        float dflux_x_p1 = (10.0f * (field(i + 1, k, j) - field(i, k, j)) - 5.0f * (field(i + 2, k, j) - field(i - 1, k, j)) + (field(i + 3, k, j) - field(i - 2, k, j)));
+        if (opt == 2) {
+          if (dflux_x_p0 * (field(i, k, j) - field(i - 1, k, j)) <= 0.0f) dflux_x_p0 = 0.0f;
+          if (dflux_x_p1 * (field(i + 1, k, j) - field(i, k, j)) <= 0.0f) dflux_x_p1 = 0.0f;
+        }
+        float slopedamp_p0 = 1.f, slopedamp_p1 = 1.f;
+        if (x.c.diff_6th_slopeopt >= 1) {
+          const float dx = 1.f / rdx;
+          const float dzthresh = x.c.diff_6th_thresh * 9.81f * dx;
+          float dzmax_p0, dzmax_p1;
+          if (name == 'u') {
+            dzmax_p0 = std::max(std::fabs(phb(i, k, j) - phb(i - 1, k, j)) * msfux(i, j), std::fabs(phb(i - 1, k, j) - phb(i - 2, k, j)) * msfux(i - 1, j));
+            dzmax_p1 = std::max(std::fabs(phb(i + 1, k, j) - phb(i, k, j)) * msfux(i + 1, j), std::fabs(phb(i, k, j) - phb(i - 1, k, j)) * msfux(i, j));
+          } else if (name == 'v') {
+            dzmax_p0 = std::max(std::fabs(phb(i, k, j) - phb(i - 1, k, j)) * msfux(i, j), std::fabs(phb(i, k, j - 1) - phb(i - 1, k, j - 1)) * msfux(i, j - 1));
+            dzmax_p1 = std::max(std::fabs(phb(i + 1, k, j) - phb(i, k, j)) * msfux(i + 1, j), std::fabs(phb(i + 1, k, j - 1) - phb(i, k, j - 1)) * msfux(i + 1, j - 1));
+          } else {
+            dzmax_p0 = std::fabs(phb(i, k, j) - phb(i - 1, k, j)) * msfux(i, j);
+            dzmax_p1 = std::fabs(phb(i + 1, k, j) - phb(i, k, j)) * msfux(i + 1, j);
+          }
+          slopedamp_p0 = std::max(1.f - (dzmax_p0 / dzthresh), 0.f);
+          slopedamp_p1 = std::max(1.f - (dzmax_p1 / dzthresh), 0.f);
+        }
+        float mu_avg_p0, mu_avg_p1, tendency_x, tendency_y;
+        if (name == 'u') {
+          mu_avg_p0 = (c1(k) * MUT(i - 1, j) + c2(k));
+          mu_avg_p1 = (c1(k) * MUT(i, j) + c2(k));
+          tendency_x = diff_6th_coef * msfux(i, j) * ((slopedamp_p1 * mu_avg_p1 * dflux_x_p1) - (slopedamp_p0 * mu_avg_p0 * dflux_x_p0));
+        } else if (name == 'v') {
+          mu_avg_p0 = 0.25f * ((c1(k) * MUT(i - 1, j - 1) + c2(k)) + (c1(k) * MUT(i, j - 1) + c2(k)) + (c1(k) * MUT(i - 1, j) + c2(k)) + (c1(k) * MUT(i, j) + c2(k)));
+          mu_avg_p1 = 0.25f * ((c1(k) * MUT(i, j - 1) + c2(k)) + (c1(k) * MUT(i + 1, j - 1) + c2(k)) + (c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i + 1, j) + c2(k)));
+          tendency_x = diff_6th_coef * msfvx(i, j) * ((slopedamp_p1 * mu_avg_p1 * dflux_x_p1) - (slopedamp_p0 * mu_avg_p0 * dflux_x_p0));
+        } else {
+          mu_avg_p0 = 0.5f * ((c1(k) * MUT(i - 1, j) + c2(k)) + (c1(k) * MUT(i, j) + c2(k)));
+          mu_avg_p1 = 0.5f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i + 1, j) + c2(k)));
+          tendency_x = diff_6th_coef * msftx(i, j) * ((slopedamp_p1 * mu_avg_p1 * dflux_x_p1) - (slopedamp_p0 * mu_avg_p0 * dflux_x_p0));
+        }
+        float dflux_y_p0 = (10.0f * (field(i, k, j) - field(i, k, j - 1)) - 5.0f * (field(i, k, j + 1) - field(i, k, j - 2)) + (field(i, k, j + 2) - field(i, k, j - 3)));
+        float dflux_y_p1 = (10.0f * (field(i, k, j + 1) - field(i, k, j)) - 5.0f * (field(i, k, j + 2) - field(i, k, j - 1)) + (field(i, k, j + 3) - field(i, k, j - 2)));
+        if (opt == 2) {
+          if (dflux_y_p0 * (field(i, k, j) - field(i, k, j - 1)) <= 0.0f) dflux_y_p0 = 0.0f;
+          if (dflux_y_p1 * (field(i, k, j + 1) - field(i, k, j)) <= 0.0f) dflux_y_p1 = 0.0f;
+        }
+        slopedamp_p0 = 1.f; slopedamp_p1 = 1.f;
+        if (x.c.diff_6th_slopeopt >= 1) {
+          const float dy = 1.f / rdy;
+          const float dzthresh = x.c.diff_6th_thresh * 9.81f * dy;
+          float dzmax_p0, dzmax_p1;
+          if (name == 'u') {
+            dzmax_p0 = std::max(std::fabs(phb(i, k, j) - phb(i, k, j - 1)) * msfvy(i, j), std::fabs(phb(i - 1, k, j) - phb(i - 1, k, j - 1)) * msfvy(i - 1, j));
+            dzmax_p1 = std::max(std::fabs(phb(i, k, j + 1) - phb(i, k, j)) * msfvy(i, j + 1), std::fabs(phb(i - 1, k, j + 1) - phb(i - 1, k, j)) * msfvy(i - 1, j + 1));
+          } else if (name == 'v') {
+            dzmax_p0 = std::max(std::fabs(phb(i, k, j) - phb(i, k, j - 1)) * msfvy(i, j), std::fabs(phb(i, k, j - 1) - phb(i, k, j - 2)) * msfvy(i, j - 1));
+            dzmax_p1 = std::max(std::fabs(phb(i, k, j + 1) - phb(i, k, j)) * msfvy(i, j + 1), std::fabs(phb(i, k, j) - phb(i, k, j - 1)) * msfvy(i, j));
+          } else {
+            dzmax_p0 = std::fabs(phb(i, k, j) - phb(i, k, j - 1)) * msfvy(i, j);
+            dzmax_p1 = std::fabs(phb(i, k, j + 1) - phb(i, k, j)) * msfvy(i, j + 1);
+          }
+          slopedamp_p0 = std::max(1.f - (dzmax_p0 / dzthresh), 0.f);
+          slopedamp_p1 = std::max(1.f - (dzmax_p1 / dzthresh), 0.f);
+        }
+        if (name == 'u') {
+          mu_avg_p0 = 0.25f * ((c1(k) * MUT(i - 1, j - 1) + c2(k)) + (c1(k) * MUT(i, j - 1) + c2(k)) + (c1(k) * MUT(i - 1, j) + c2(k)) + (c1(k) * MUT(i, j) + c2(k)));
+          mu_avg_p1 = 0.25f * ((c1(k) * MUT(i - 1, j) + c2(k)) + (c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i - 1, j + 1) + c2(k)) + (c1(k) * MUT(i, j + 1) + c2(k)));
+          tendency_y = diff_6th_coef * msfuy(i, j) * ((slopedamp_p1 * mu_avg_p1 * dflux_y_p1) - (slopedamp_p0 * mu_avg_p0 * dflux_y_p0));
+        } else if (name == 'v') {
+          mu_avg_p0 = (c1(k) * MUT(i, j - 1) + c2(k));
+          mu_avg_p1 = (c1(k) * MUT(i, j) + c2(k));
+          tendency_y = diff_6th_coef * msfvy(i, j) * ((slopedamp_p1 * mu_avg_p1 * dflux_y_p1) - (slopedamp_p0 * mu_avg_p0 * dflux_y_p0));
+        } else {
+          mu_avg_p0 = 0.5f * ((c1(k) * MUT(i, j - 1) + c2(k)) + (c1(k) * MUT(i, j) + c2(k)));
+          mu_avg_p1 = 0.5f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i, j + 1) + c2(k)));
+          tendency_y = diff_6th_coef * msfty(i, j) * ((slopedamp_p1 * mu_avg_p1 * dflux_y_p1) - (slopedamp_p0 * mu_avg_p0 * dflux_y_p0));
+        }
+        tendency(i, k, j) = tendency(i, k, j) + tendency_x + tendency_y;
+      }
+}
+
 }  // namespace orc

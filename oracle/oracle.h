@@ -182,6 +182,7 @@ void horizontal_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT,
 void horizontal_diffusion_3dmp(const Cx &x, A3 field, A3 tendency, A2 MUT, A1 c1, A1 c2, A3 base_3d, float xk);
 void vertical_diffusion(const Cx &x, char name, A3 field, A3 tendency, A1 c1, A1 c2, A3 alt, A2 MUT, float kvdif);
 void vertical_diffusion_mp(const Cx &x, A3 field, A3 tendency, A1 base, A1 c1, A1 c2, A3 alt, A2 MUT, float kvdif);
+void sixth_order_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT, float dt, A1 c1, A1 c2, A3 phb);
 void vertical_diffusion_3dmp(const Cx &x, A3 field, A3 tendency, A3 base_3d, A1 c1, A1 c2, A3 alt, A2 MUT, float kvdif);
 void vertical_diffusion_u(const Cx &x, A3 field, A3 tendency, A1 u_base, A1 c1h, A1 c2h, A3 alt, A2 muu, float kvdif);
 void vertical_diffusion_v(const Cx &x, A3 field, A3 tendency, A1 v_base, A1 c1h, A1 c2h, A3 alt, A2 muv, float kvdif);

@@ -214,6 +214,13 @@ void Oracle::rk_tendency(int rk_step) {
     const float kvdq = 3.f * kvdif;
     par([&](const Cx &xt) { vertical_diffusion_3dmp(xt, t, a3("t_tendf"), a3("t_init"), xt.c1h, xt.c2h, alt, mut, kvdq); });
   }
+  if (rk_step == 1 && c.diff_6th_opt != 0) {   // module_em.F:880-930
+    A3 phb = a3("phb");
+    par([&](const Cx &xt) { sixth_order_diffusion(xt, 'u', u, a3("ru_tendf"), mut, c.dt, xt.c1h, xt.c2h, phb); });
+    par([&](const Cx &xt) { sixth_order_diffusion(xt, 'v', v, a3("rv_tendf"), mut, c.dt, xt.c1h, xt.c2h, phb); });
+    par([&](const Cx &xt) { sixth_order_diffusion(xt, 'w', w, a3("rw_tendf"), mut, c.dt, xt.c1f, xt.c2f, phb); });
+    par([&](const Cx &xt) { sixth_order_diffusion(xt, 'm', t, a3("t_tendf"), mut, c.dt, xt.c1h, xt.c2h, phb); });
+  }
   if (rk_step == 1 && c.damp_opt == 2)
     par([&](const Cx &xt) { rk_rayleigh_damp(xt, a3("ru_tendf"), a3("rv_tendf"), a3("rw_tendf"), a3("t_tendf"), u, v, w, t, mut, muu, muv, ph, a3("phb")); });
   par([&](const Cx &xt) { rk_addtend_dry(xt, ru_tend, rv_tend, rw_tend, ph_tend, t_tend, a3("ru_tendf"), a3("rv_tendf"), a3("rw_tendf"), a3("ph_tendf"),
@@ -316,13 +323,13 @@ void Oracle::rk_scalar_step(int rk_step) {
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
   const int rk_order = c.rk_ord;
-  struct Sp { std::string f, o, t; int adv_opt; };
+  struct Sp { std::string f, o, t; int adv_opt; bool moist; };
   std::vector<Sp> sp;
   for (int s = 0; s < c.num_moist; s++)
     sp.push_back({std::string("moist_") + moist_names[s], std::string("moist_old_") + moist_names[s],
-                  std::string("moist_tend_") + moist_names[s], c.moist_adv_opt});
+                  std::string("moist_tend_") + moist_names[s], c.moist_adv_opt, true});
   for (int s = 1; s <= c.num_scalar; s++)
-    sp.push_back({"scalar_" + std::to_string(s), "scalar_old_" + std::to_string(s), "scalar_tend_" + std::to_string(s), c.scalar_adv_opt});
+    sp.push_back({"scalar_" + std::to_string(s), "scalar_old_" + std::to_string(s), "scalar_tend_" + std::to_string(s), c.scalar_adv_opt, false});
   if (rk_step == rk_order)
     for (auto &s : sp)
       if (s.adv_opt == 1 || s.adv_opt == 2 || s.adv_opt == 4) par([&](const Cx &xt) { rk_update_scalar_pd(xt, a3(s.o), a3(s.t), a2("mu_1"), a2("mu_1"), a2("mub"), dt_rk); });
@@ -371,6 +378,8 @@ void Oracle::rk_scalar_step(int rk_step) {
       else
         par([&](const Cx &xt) { vertical_diffusion(xt, 'm', a3(s.f), a3(s.t), xt.c1h, xt.c2h, a3("alt"), a2("muts"), kvdq); });
     }
+    if (rk_step == 1 && c.diff_6th_opt != 0 && !(s.moist ? c.moist_mix6_off : c.scalar_mix6_off))   // module_em.F:1421-1437 (dt_step = dt_rk)
+      par([&](const Cx &xt) { sixth_order_diffusion(xt, 'm', a3(s.f), a3(s.t), a2("muts"), dt_rk, xt.c1h, xt.c2h, a3("phb")); });
     par([&](const Cx &xt) { rk_update_scalar(xt, a3(s.o), a3(s.f), a3(s.t), a3("advect_tend"), a2("mu_1"), a2("mu_2"), a2("mub"), rk_step, dt_rk); });
   }
 }

@@ -120,6 +120,12 @@ def small_cases():
         # implicit-explicit vertical advection (zadvect_implicit = 1, module_ieva_em.F) with an updraft strong enough to
         # make wwI non-zero: open + Kessler + PD, doubly periodic with map factors + monotonic / PD tracers, and over
         # the hill (terrain slopes in advect_w_implicit's lower boundary row) together with the WENO options
+        # 6th-order horizontal filter (diff_6th_opt 1 / 2, sixth_order_diffusion): open + Kessler with the up-gradient fluxes
+        # dropped, doubly periodic with map factors (scalars exempted by scalar_mix6_off), over the hill with the slope taper
+        "diff6": make_case("quarter_ss", nx=26, ny=24, nz=21, diff_6th_opt=2),
+        "diff6_periodic": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=2,
+                                                     diff_6th_opt=1, diff_6th_factor=0.2, scalar_mix6_off=1)),
+        "diff6_hill": make_case("hill2d_x", nx=62, ny=3, nz=21, diff_6th_opt=2, diff_6th_slopeopt=1, diff_6th_thresh=0.004),
         "ieva": with_updraft(make_case("quarter_ss", nx=26, ny=24, nz=41, zadvect_implicit=1, dt=20.0, time_step=20), 60.0),
         "ieva_periodic": with_updraft(with_map_factors(make_case("synthetic", nx=34, ny=30, nz=33, bubble_lattice=20000.0, noise=0.05,
                                                                   num_scalar=2, scalar_adv_opt=2, moist_adv_opt=1, zadvect_implicit=1,

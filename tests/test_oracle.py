@@ -229,6 +229,39 @@ def test_constant_k_diffusion_decays_a_sinusoid_at_the_analytic_rate():
     assert np.abs(o.get("w_2")).max() < 1e-3                          # and the atmosphere stayed at rest
 
 
+def test_sixth_order_filter_damps_the_two_delta_x_wave_at_the_documented_rate():
+    """sixth_order_diffusion (module_big_step_utilities_em.F:6220): for q = (-1)^i the flux differences are +-32 q, so the
+    tendency is -64 * (factor * 0.015625 / (2 dt')) * mu * q = -(factor / (2 dt')) mu q: the filter removes factor / 2 of a
+    2 dx wave per direction and time step dt' ("diff_6th_factor = 0.12: 12 % of the 2 dx checkerboard per step").  For the
+    scalars rk_scalar_tend passes dt' = dt_rk = dt / 3 of the first substep (module_em.F:1423-1426) while the tendency acts
+    over the whole step, so a passive scalar in a resting atmosphere loses 3 * factor / 2 per step; a 4 dx wave,
+    by the same algebra (flux differences -+ 8 q ... ), loses an eighth of that; diff_6th_opt = 2 changes neither
+    (all fluxes run down the gradient), and scalar_mix6_off switches the filter off."""
+    nx, factor = 33, 0.12
+    ii = None
+    got = {}
+    for label, kw, wave in (("2dx", dict(diff_6th_opt=1), 2), ("2dx_opt2", dict(diff_6th_opt=2), 2), ("4dx", dict(diff_6th_opt=1), 4),
+                            ("off", dict(diff_6th_opt=1, scalar_mix6_off=1), 2)):
+        case = make_case("b_wave", nx=nx, ny=12, nz=11, calm=True, num_scalar=1, scalar_adv_opt=1, diff_6th_factor=factor, **kw)
+        d = case.dims
+        ii = np.arange(d.ims, d.ime + 1, dtype=np.float64)
+        prof = (1.0 + 0.5 * np.cos(2 * np.pi * (ii - 1) / wave)).astype(np.float32)
+        s = case.fields["scalar_1"]
+        s[:] = prof[None, None, :]
+        s[:, -1, :] = 0
+        o = Oracle(case)
+        o.start_domain()
+        o.step(3)
+        row = o.get("scalar_1")[4 - d.jms, 3, 1 - d.ims:1 - d.ims + 32].astype(np.float64)
+        amp = 2.0 * np.abs(np.fft.rfft(row - row.mean())[32 // wave]) / 32 / (2.0 if wave == 2 else 1.0)
+        got[label] = amp / 0.5
+        assert abs(row.mean() - 1.0) < 1e-5
+    assert abs(got["2dx"] - (1.0 - 1.5 * factor) ** 3) < 1e-4, got
+    assert abs(got["2dx_opt2"] - got["2dx"]) < 1e-6, got
+    assert abs(got["4dx"] - (1.0 - 1.5 * factor / 8.0) ** 3) < 1e-4, got
+    assert abs(got["off"] - 1.0) < 1e-6, got
+
+
 def test_monotonic_advection_creates_no_new_extrema():
     """advect_scalar_mono (module_advect_em.F:9495-10560, "monotonic advection option ... Smolarkiewicz MWR 1989"):
     a top-hat tracer advected through the sheared supercell environment stays inside its initial range [0, 1]

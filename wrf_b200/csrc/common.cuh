@@ -271,6 +271,8 @@ void launch_advect_scalar_fast(Solver *s, bool theta, const Box &in, cfp q, cfp 
 // pd_fast.cu: pass 1 = limiter factor on bx -> out, pass 2 = limited flux divergence on bx -> out
 void launch_pd_fast(Solver *s, int pass, const Box &bx, cfp q, cfp q_old, float dt, fp out);
 // diffusion.cu: adds the constant-K diffusion of `field` to `tendency` (which = 0 u, 1 v, 2 w, 3 theta, 4 qv, 5 other scalar)
+// sixth_order_diffusion of `field` added to `tendency` (which as above; anything >= 3 = mass points)
+void launch_diff6(Solver *s, int which, const float *field, float *tendency, const float *mut, float dt);
 void launch_diffuse(Solver *s, int which, cfp field, fp tendency, float xk, float kvdif);
 // mom_fast.cu: which = 0 ru_tend, 1 rv_tend, 2 rw_tend on the interior box
 void launch_mom_fast(Solver *s, int which, const Box &in);

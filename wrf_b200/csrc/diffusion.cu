@@ -190,4 +190,139 @@ void launch_diffuse(Solver *s, int which, cfp field, fp tendency, float xk, floa
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// sixth_order_diffusion (module_big_step_utilities_em.F:6220-6620): the 6th-order horizontal filter of diff_6th_opt = 1, 2,
+// added to the *_tendf arrays on the first RK substep (module_em.F:880-930, 1421-1437).  KIND: DIFF_U, DIFF_V, DIFF_W, else mass.
+struct Diff6In {
+  cfp field, mut, phb;
+  float coef;        // diff_6th_factor * 0.015625 / (2 dt)
+  float thresh;      // diff_6th_thresh
+  int opt, slopeopt;
+  Box r;             // the reference's loop ranges for this variable
+};
+
+template <int KIND>
+__global__ void k_diff6(const Geo g, Box b, Diff6In s, fp tendency) {
+  TID3;
+  cfp field = s.field, MUT = s.mut, phb = s.phb;
+  const float *c1 = KIND == DIFF_W ? g.c1f : g.c1h, *c2 = KIND == DIFF_W ? g.c2f : g.c2h;
+  float dflux_x_p0 = (10.0f * (A3(field, i, k, j) - A3(field, i - 1, k, j)) - 5.0f * (A3(field, i + 1, k, j) - A3(field, i - 2, k, j)) + (A3(field, i + 2, k, j) - A3(field, i - 3, k, j)));
+  float dflux_x_p1 = (10.0f * (A3(field, i + 1, k, j) - A3(field, i, k, j)) - 5.0f * (A3(field, i + 2, k, j) - A3(field, i - 1, k, j)) + (A3(field, i + 3, k, j) - A3(field, i - 2, k, j)));
+  if (s.opt == 2) {
+    if (dflux_x_p0 * (A3(field, i, k, j) - A3(field, i - 1, k, j)) <= 0.0f) dflux_x_p0 = 0.0f;
+    if (dflux_x_p1 * (A3(field, i + 1, k, j) - A3(field, i, k, j)) <= 0.0f) dflux_x_p1 = 0.0f;
+  }
+  float slopedamp_p0 = 1.f, slopedamp_p1 = 1.f;
+  if (s.slopeopt >= 1) {
+    const float dx = 1.f / g.rdx;
+    const float dzthresh = s.thresh * 9.81f * dx;
+    float dzmax_p0, dzmax_p1;
+    if (KIND == DIFF_U) {
+      dzmax_p0 = fmaxf(fabsf(A3(phb, i, k, j) - A3(phb, i - 1, k, j)) * A2(g.msfux, i, j), fabsf(A3(phb, i - 1, k, j) - A3(phb, i - 2, k, j)) * A2(g.msfux, i - 1, j));
+      dzmax_p1 = fmaxf(fabsf(A3(phb, i + 1, k, j) - A3(phb, i, k, j)) * A2(g.msfux, i + 1, j), fabsf(A3(phb, i, k, j) - A3(phb, i - 1, k, j)) * A2(g.msfux, i, j));
+    } else if (KIND == DIFF_V) {
+      dzmax_p0 = fmaxf(fabsf(A3(phb, i, k, j) - A3(phb, i - 1, k, j)) * A2(g.msfux, i, j), fabsf(A3(phb, i, k, j - 1) - A3(phb, i - 1, k, j - 1)) * A2(g.msfux, i, j - 1));
+      dzmax_p1 = fmaxf(fabsf(A3(phb, i + 1, k, j) - A3(phb, i, k, j)) * A2(g.msfux, i + 1, j), fabsf(A3(phb, i + 1, k, j - 1) - A3(phb, i, k, j - 1)) * A2(g.msfux, i + 1, j - 1));
+    } else {
+      dzmax_p0 = fabsf(A3(phb, i, k, j) - A3(phb, i - 1, k, j)) * A2(g.msfux, i, j);
+      dzmax_p1 = fabsf(A3(phb, i + 1, k, j) - A3(phb, i, k, j)) * A2(g.msfux, i + 1, j);
+    }
+    slopedamp_p0 = fmaxf(1.f - (dzmax_p0 / dzthresh), 0.f);
+    slopedamp_p1 = fmaxf(1.f - (dzmax_p1 / dzthresh), 0.f);
+  }
+  float mu_avg_p0, mu_avg_p1, tendency_x, tendency_y;
+  if (KIND == DIFF_U) {
+    mu_avg_p0 = (c1[k] * A2(MUT, i - 1, j) + c2[k]);
+    mu_avg_p1 = (c1[k] * A2(MUT, i, j) + c2[k]);
+    tendency_x = s.coef * A2(g.msfux, i, j) * ((slopedamp_p1 * mu_avg_p1 * dflux_x_p1) - (slopedamp_p0 * mu_avg_p0 * dflux_x_p0));
+  } else if (KIND == DIFF_V) {
+    mu_avg_p0 = 0.25f * ((c1[k] * A2(MUT, i - 1, j - 1) + c2[k]) + (c1[k] * A2(MUT, i, j - 1) + c2[k]) + (c1[k] * A2(MUT, i - 1, j) + c2[k]) + (c1[k] * A2(MUT, i, j) + c2[k]));
+    mu_avg_p1 = 0.25f * ((c1[k] * A2(MUT, i, j - 1) + c2[k]) + (c1[k] * A2(MUT, i + 1, j - 1) + c2[k]) + (c1[k] * A2(MUT, i, j) + c2[k]) + (c1[k] * A2(MUT, i + 1, j) + c2[k]));
+    tendency_x = s.coef * A2(g.msfvx, i, j) * ((slopedamp_p1 * mu_avg_p1 * dflux_x_p1) - (slopedamp_p0 * mu_avg_p0 * dflux_x_p0));
+  } else {
+    mu_avg_p0 = 0.5f * ((c1[k] * A2(MUT, i - 1, j) + c2[k]) + (c1[k] * A2(MUT, i, j) + c2[k]));
+    mu_avg_p1 = 0.5f * ((c1[k] * A2(MUT, i, j) + c2[k]) + (c1[k] * A2(MUT, i + 1, j) + c2[k]));
+    tendency_x = s.coef * A2(g.msftx, i, j) * ((slopedamp_p1 * mu_avg_p1 * dflux_x_p1) - (slopedamp_p0 * mu_avg_p0 * dflux_x_p0));
+  }
+  float dflux_y_p0 = (10.0f * (A3(field, i, k, j) - A3(field, i, k, j - 1)) - 5.0f * (A3(field, i, k, j + 1) - A3(field, i, k, j - 2)) + (A3(field, i, k, j + 2) - A3(field, i, k, j - 3)));
+  float dflux_y_p1 = (10.0f * (A3(field, i, k, j + 1) - A3(field, i, k, j)) - 5.0f * (A3(field, i, k, j + 2) - A3(field, i, k, j - 1)) + (A3(field, i, k, j + 3) - A3(field, i, k, j - 2)));
+  if (s.opt == 2) {
+    if (dflux_y_p0 * (A3(field, i, k, j) - A3(field, i, k, j - 1)) <= 0.0f) dflux_y_p0 = 0.0f;
+    if (dflux_y_p1 * (A3(field, i, k, j + 1) - A3(field, i, k, j)) <= 0.0f) dflux_y_p1 = 0.0f;
+  }
+  slopedamp_p0 = 1.f; slopedamp_p1 = 1.f;
+  if (s.slopeopt >= 1) {
+    const float dy = 1.f / g.rdy;
+    const float dzthresh = s.thresh * 9.81f * dy;
+    float dzmax_p0, dzmax_p1;
+    if (KIND == DIFF_U) {
+      dzmax_p0 = fmaxf(fabsf(A3(phb, i, k, j) - A3(phb, i, k, j - 1)) * A2(g.msfvy, i, j), fabsf(A3(phb, i - 1, k, j) - A3(phb, i - 1, k, j - 1)) * A2(g.msfvy, i - 1, j));
+      dzmax_p1 = fmaxf(fabsf(A3(phb, i, k, j + 1) - A3(phb, i, k, j)) * A2(g.msfvy, i, j + 1), fabsf(A3(phb, i - 1, k, j + 1) - A3(phb, i - 1, k, j)) * A2(g.msfvy, i - 1, j + 1));
+    } else if (KIND == DIFF_V) {
+      dzmax_p0 = fmaxf(fabsf(A3(phb, i, k, j) - A3(phb, i, k, j - 1)) * A2(g.msfvy, i, j), fabsf(A3(phb, i, k, j - 1) - A3(phb, i, k, j - 2)) * A2(g.msfvy, i, j - 1));
+      dzmax_p1 = fmaxf(fabsf(A3(phb, i, k, j + 1) - A3(phb, i, k, j)) * A2(g.msfvy, i, j + 1), fabsf(A3(phb, i, k, j) - A3(phb, i, k, j - 1)) * A2(g.msfvy, i, j));
+    } else {
+      dzmax_p0 = fabsf(A3(phb, i, k, j) - A3(phb, i, k, j - 1)) * A2(g.msfvy, i, j);
+      dzmax_p1 = fabsf(A3(phb, i, k, j + 1) - A3(phb, i, k, j)) * A2(g.msfvy, i, j + 1);
+    }
+    slopedamp_p0 = fmaxf(1.f - (dzmax_p0 / dzthresh), 0.f);
+    slopedamp_p1 = fmaxf(1.f - (dzmax_p1 / dzthresh), 0.f);
+  }
+  if (KIND == DIFF_U) {
+    mu_avg_p0 = 0.25f * ((c1[k] * A2(MUT, i - 1, j - 1) + c2[k]) + (c1[k] * A2(MUT, i, j - 1) + c2[k]) + (c1[k] * A2(MUT, i - 1, j) + c2[k]) + (c1[k] * A2(MUT, i, j) + c2[k]));
+    mu_avg_p1 = 0.25f * ((c1[k] * A2(MUT, i - 1, j) + c2[k]) + (c1[k] * A2(MUT, i, j) + c2[k]) + (c1[k] * A2(MUT, i - 1, j + 1) + c2[k]) + (c1[k] * A2(MUT, i, j + 1) + c2[k]));
+    tendency_y = s.coef * A2(g.msfuy, i, j) * ((slopedamp_p1 * mu_avg_p1 * dflux_y_p1) - (slopedamp_p0 * mu_avg_p0 * dflux_y_p0));
+  } else if (KIND == DIFF_V) {
+    mu_avg_p0 = (c1[k] * A2(MUT, i, j - 1) + c2[k]);
+    mu_avg_p1 = (c1[k] * A2(MUT, i, j) + c2[k]);
+    tendency_y = s.coef * A2(g.msfvy, i, j) * ((slopedamp_p1 * mu_avg_p1 * dflux_y_p1) - (slopedamp_p0 * mu_avg_p0 * dflux_y_p0));
+  } else {
+    mu_avg_p0 = 0.5f * ((c1[k] * A2(MUT, i, j - 1) + c2[k]) + (c1[k] * A2(MUT, i, j) + c2[k]));
+    mu_avg_p1 = 0.5f * ((c1[k] * A2(MUT, i, j) + c2[k]) + (c1[k] * A2(MUT, i, j + 1) + c2[k]));
+    tendency_y = s.coef * A2(g.msfty, i, j) * ((slopedamp_p1 * mu_avg_p1 * dflux_y_p1) - (slopedamp_p0 * mu_avg_p0 * dflux_y_p0));
+  }
+  A3(tendency, i, k, j) = A3(tendency, i, k, j) + tendency_x + tendency_y;
+}
+
+// which = DIFF_U / DIFF_V / DIFF_W / anything else (mass points); adds the filter of `field` to `tendency`
+void launch_diff6(Solver *s, int which, cfp field, fp tendency, cfp mut, float dt) {
+  const Geo &q = s->g;
+  const wrfgpu_config &c = s->c;
+  const int ktf = q.kde - 1;
+  Box r{q.its, 0, 1, ktf, q.jts, 0};
+  if (which == DIFF_U) {
+    r.i1 = q.ite; r.j1 = std::min(q.jde - 1, q.jte);
+    if (c.open_xs) r.i0 = std::max(q.its, q.ids + 3);
+    if (c.open_ys) r.j0 = std::max(q.jts, q.jds + 3);
+    if (c.open_xe) r.i1 = std::min(q.ite, q.ide - 3);
+    if (c.open_ye) r.j1 = std::min(q.jte, q.jde - 4);
+  } else if (which == DIFF_V) {
+    r.i1 = std::min(q.ide - 1, q.ite); r.j1 = q.jte;
+    if (c.open_xs) r.i0 = std::max(q.its, q.ids + 3);
+    if (c.open_ys) r.j0 = std::max(q.jts, q.jds + 3);
+    if (c.open_xe) r.i1 = std::min(q.ite, q.ide - 4);
+    if (c.open_ye) r.j1 = std::min(q.jte, q.jde - 3);
+    if (c.open_xs) {   // sic (:6333): "open_xs .or. specified" restricts all four sides
+      r.i0 = std::max(q.its, q.ids + 3); r.i1 = std::min(q.ite, q.ide - 4);
+      r.j0 = std::max(q.jts, q.jds + 3); r.j1 = std::min(q.jte, q.jde - 3);
+    }
+  } else {
+    r.i1 = std::min(q.ide - 1, q.ite); r.j1 = std::min(q.jde - 1, q.jte);
+    if (c.open_xs) r.i0 = std::max(q.its, q.ids + 3);
+    if (c.open_ys) r.j0 = std::max(q.jts, q.jds + 3);
+    if (c.open_xe) r.i1 = std::min(q.ite, q.ide - 4);
+    if (c.open_ye) r.j1 = std::min(q.jte, q.jde - 4);
+    if (which == DIFF_W) r.k0 = 2;
+  }
+  Diff6In in;
+  in.field = field; in.mut = mut; in.phb = s->o("phb");
+  in.coef = c.diff_6th_factor * 0.015625f / (2.0f * dt);
+  in.thresh = c.diff_6th_thresh; in.opt = c.diff_6th_opt; in.slopeopt = c.diff_6th_slopeopt;
+  in.r = r;
+  if (which == DIFF_U) LAUNCH3(s, k_diff6<DIFF_U>, r, in, tendency);
+  else if (which == DIFF_V) LAUNCH3(s, k_diff6<DIFF_V>, r, in, tendency);
+  else if (which == DIFF_W) LAUNCH3(s, k_diff6<DIFF_W>, r, in, tendency);
+  else LAUNCH3(s, k_diff6<DIFF_SCALAR>, r, in, tendency);
+}
+
 }  // namespace wg

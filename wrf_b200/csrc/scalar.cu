@@ -479,6 +479,8 @@ void Solver::rk_scalar_step(int rk_step) {
       const float prandtl = 1.f / 3.0f;
       launch_diffuse(this, s.f == "moist_qv" ? 4 : 5, o(s.f), o(s.t), c.khdif / prandtl, c.kvdif / prandtl);
     }
+    if (rk_step == 1 && c.diff_6th_opt != 0 && !(s.f.rfind("moist_", 0) == 0 ? c.moist_mix6_off : c.scalar_mix6_off))
+      launch_diff6(this, 5, o(s.f), o(s.t), o("muts"), dt_rk);   // module_em.F:1421-1437 (dt_step = dt_rk)
     LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
   }
 }

@@ -40,7 +40,7 @@ static void check_config(const wrfgpu_config &c) {
   // km_opt = 1 and khdif = kvdif = 0 the physical-space form (diff_opt 2: shipped em_hill2d_x) adds exact zeros
   // to zero-initialised tendencies, i.e. it is the identity, and is accepted as such.  Everything else
   // (TKE / Smagorinsky closures, 6th-order filter) is a 'next' row.
-  if (c.diff_6th_opt != 0) bad("diff_6th_opt must be 0");
+  if (c.diff_6th_opt < 0 || c.diff_6th_opt > 2) bad("diff_6th_opt must be 0, 1 or 2");
   if (c.diff_opt != 0) {
     if (c.km_opt != 1) bad("km_opt must be 1 (constant K) when diff_opt is not 0; the TKE/Smagorinsky closures are a 'next' row");
     if (c.diff_opt == 2 && (c.khdif != 0.f || c.kvdif != 0.f)) bad("diff_opt = 2 is only accepted with khdif = kvdif = 0 (then it is the identity)");

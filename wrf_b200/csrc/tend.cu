@@ -1043,6 +1043,12 @@ void Solver::rk_tendency(int rk_step, bool zero_save) {
     launch_diffuse(this, 2, o("w_2"), o("rw_tendf"), xkmh, c.kvdif);
     launch_diffuse(this, 3, o("t_2"), o("t_tendf"), xkhh, 3.f * c.kvdif);
   }
+  if (rk_step == 1 && c.diff_6th_opt != 0) {   // module_em.F:880-930
+    launch_diff6(this, 0, o("u_2"), o("ru_tendf"), o("mut"), c.dt);
+    launch_diff6(this, 1, o("v_2"), o("rv_tendf"), o("mut"), c.dt);
+    launch_diff6(this, 2, o("w_2"), o("rw_tendf"), o("mut"), c.dt);
+    launch_diff6(this, 3, o("t_2"), o("t_tendf"), o("mut"), c.dt);
+  }
   if (rk_step == 1 && c.damp_opt == 2) {
     const int jm = std::min(q.jte, q.jde - 1), im = std::min(q.ite, q.ide - 1);
     for (int kind = 0; kind < 3; kind++) {

@@ -39,6 +39,8 @@ MODULE module_wrfgpu
       REAL(c_float)  :: dt, dx, dy, epssm, smdiv, emdiv, dampcoef, zdamp, w_crit_cfl
       REAL(c_float)  :: p_top, cf1, cf2, cf3, cfn, cfn1, khdif, kvdif
       INTEGER(c_int) :: num_moist, num_scalar, ntasks_x, ntasks_y, mytask
+      REAL(c_float)  :: diff_6th_factor, diff_6th_thresh
+      INTEGER(c_int) :: diff_6th_slopeopt, moist_mix6_off, scalar_mix6_off
    END TYPE wrfgpu_config
 
    INTERFACE

@@ -71,6 +71,9 @@ SUBROUTINE solve_em ( grid , config_flags  &
       c%khdif = config_flags%khdif; c%kvdif = config_flags%kvdif
       c%num_moist = num_moist - PARAM_FIRST_SCALAR + 1;  c%num_scalar = 0
       c%ntasks_x = ntasks_x; c%ntasks_y = ntasks_y; c%mytask = mytask
+      c%diff_6th_factor = config_flags%diff_6th_factor; c%diff_6th_thresh = config_flags%diff_6th_thresh
+      c%diff_6th_slopeopt = config_flags%diff_6th_slopeopt
+      c%moist_mix6_off = MERGE(1,0,config_flags%moist_mix6_off); c%scalar_mix6_off = MERGE(1,0,config_flags%scalar_mix6_off)
       device = MOD(mytask, 8)                        ! one rank per GPU of the box
       CALL wrfgpu_check( wrfgpu_create(d, c, device, handle(id)), 'wrfgpu_create' )
 #ifdef DM_PARALLEL

@@ -62,7 +62,9 @@ class Config(ctypes.Structure):
         + [(n, ctypes.c_float) for n in (
             "dt", "dx", "dy", "epssm", "smdiv", "emdiv", "dampcoef", "zdamp", "w_crit_cfl",
             "p_top", "cf1", "cf2", "cf3", "cfn", "cfn1", "khdif", "kvdif")]
-        + [(n, ctypes.c_int) for n in ("num_moist", "num_scalar", "ntasks_x", "ntasks_y", "mytask")])
+        + [(n, ctypes.c_int) for n in ("num_moist", "num_scalar", "ntasks_x", "ntasks_y", "mytask")]
+        + [(n, ctypes.c_float) for n in ("diff_6th_factor", "diff_6th_thresh")]
+        + [(n, ctypes.c_int) for n in ("diff_6th_slopeopt", "moist_mix6_off", "scalar_mix6_off")])
 
 
 def default_config(**kw) -> Config:
@@ -82,6 +84,7 @@ def default_config(**kw) -> Config:
     c.epssm, c.smdiv, c.emdiv = 0.1, 0.1, 0.01
     c.dampcoef, c.zdamp = 0.2, 5000.0
     c.w_crit_cfl = 1.2
+    c.diff_6th_factor, c.diff_6th_thresh = 0.12, 0.10
     c.ntasks_x = c.ntasks_y = 1
     for k, v in kw.items():
         setattr(c, k, v)
