@@ -130,6 +130,17 @@ def small_cases():
         "ieva_periodic": with_updraft(with_map_factors(make_case("synthetic", nx=34, ny=30, nz=33, bubble_lattice=20000.0, noise=0.05,
                                                                   num_scalar=2, scalar_adv_opt=2, moist_adv_opt=1, zadvect_implicit=1,
                                                                   dt=20.0, time_step=20)), 60.0),
+        # edges of the envelope: the most levels a Geo carries (126), a domain with no point further than 4 from an open
+        # boundary (every fast-kernel box empty), rk_ord = 2 with every optional scheme at once under a rigid lid, and a
+        # negative time_step (sign(1,time_step) flips the upwind bias of every odd-order flux, module_advect_em.F:204)
+        "tall": make_case("quarter_ss", nx=14, ny=13, nz=126),
+        "tiny": make_case("quarter_ss", nx=10, ny=9, nz=11),
+        "rk2_everything": with_updraft(make_case("synthetic", nx=30, ny=28, nz=33, periodic=False, bubble_lattice=20000.0, noise=0.05,
+                                                 rk_ord=2, time_step_sound=4, zadvect_implicit=1, momentum_adv_opt=3, moist_adv_opt=3,
+                                                 num_scalar=1, scalar_adv_opt=4, dt=20.0, time_step=20, top_lid=1, diff_6th_opt=2,
+                                                 diff_opt=1, km_opt=1, khdif=200.0, kvdif=20.0), 40.0, conv=20.0),
+        "backward": make_case("synthetic", nx=30, ny=28, nz=15, bubble_lattice=20000.0, noise=0.05, num_scalar=1, scalar_adv_opt=3,
+                              momentum_adv_opt=3, time_step=-12),
         "ieva_weno_hill": with_updraft(make_case("hill2d_x", nx=62, ny=3, nz=41, zadvect_implicit=1, momentum_adv_opt=3,
                                                  moist_adv_opt=3), 60.0, conv=70.0),
     }
