@@ -35,16 +35,26 @@ inline float weno5(float vel, bool upw, float m3, float m2, float m1, float p0, 
 }
 struct Flux {
   float sgn_ts;  // sign(1,time_step)
-  bool weno = false;   // advect_weno_u/v/w (:10876-13041, momentum_adv_opt = 3): WENO in place of flux5, vert_order 5 structure
+  bool weno = false;
+  // h_*_adv_order = 6 / v_*_adv_order = 4: "EXACTLY the same [code] EXCEPT the 5th order and 3rd operators are used in
+  // place of the 6th and 4th order operators" (module_advect_em.F:488-491, 829-830, and the vert_order 4 / 3 blocks)
+  bool h_even = false, v_even = false;
+  // horizontal 3rd / 4th-order face value next to a boundary, vertical 3rd / 4th-order face value
+  inline float h3(float q_im2, float q_im1, float q_i, float q_ip1, float ua) const {
+    return (h_even && !weno) ? flux4(q_im2, q_im1, q_i, q_ip1) : flux3(q_im2, q_im1, q_i, q_ip1, ua);
+  }
+  inline float v3(float q_im2, float q_im1, float q_i, float q_ip1, float ua) const {
+    return (v_even && !weno) ? flux4(q_im2, q_im1, q_i, q_ip1) : flux3(q_im2, q_im1, q_i, q_ip1, ua);
+  }   // advect_weno_u/v/w (:10876-13041, momentum_adv_opt = 3): WENO in place of flux5, vert_order 5 structure
   // vel * flux5(...) of a horizontal face, or the WENO face flux
   inline float h5(float vel, float m3, float m2, float m1, float p0, float p1, float p2) const {
     if (weno) return weno5(vel, vel * sgn_ts >= 0.0f, m3, m2, m1, p0, p1, p2, 1.0e-18);
-    return vel * flux5(m3, m2, m1, p0, p1, p2, vel);
+    return vel * flux5(m3, m2, m1, p0, p1, p2, vel);   // flux6 when h_even
   }
   // vertical face k: flux3 under vert_order 3; with weno the 5th-order structure, WENO on k = kts+3 .. k5max
   inline float v35(int k, int k5min, int k5max, float vel, float m3, float m2, float m1, float p0, float p1, float p2) const {
     if (weno && k >= k5min && k <= k5max) return weno5(vel, -vel * sgn_ts >= 0.0f, m3, m2, m1, p0, p1, p2, 1.0e-18);
-    return vel * flux3(m2, m1, p0, p1, -vel);
+    return vel * v3(m2, m1, p0, p1, -vel);
   }
   // module_advect_em.F:202-213 statement functions
   inline float flux4(float q_im2, float q_im1, float q_i, float q_ip1) const {
@@ -57,6 +67,7 @@ struct Flux {
     return (37.f * (q_i + q_im1) - 8.f * (q_ip1 + q_im2) + (q_ip2 + q_im3)) / 60.0f;
   }
   inline float flux5(float q_im3, float q_im2, float q_im1, float q_i, float q_ip1, float q_ip2, float ua) const {
+    if (h_even) return flux6(q_im3, q_im2, q_im1, q_i, q_ip1, q_ip2);
     return flux6(q_im3, q_im2, q_im1, q_i, q_ip1, q_ip2) -
            sgn_ts * sign1(ua) * ((q_ip2 - q_im3) - 5.f * (q_ip1 - q_im2) + 10.f * (q_i - q_im1)) / 60.0f;
   }
@@ -84,7 +95,7 @@ void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
   const int ktf = std::min(kte, x.kde - 1);
   const A1 &c1 = x.c1h, &c2 = x.c2h, &fzm = x.fnm, &fzp = x.fnp, &rdzw = x.rdnw;
   const float rdx = x.rdx, rdy = x.rdy;
-  Flux F{(float)(x.time_step >= 0 ? 1 : -1), weno};
+  Flux F{(float)(x.time_step >= 0 ? 1 : -1), weno, x.c.h_mom_adv_order == 6, x.c.v_mom_adv_order == 4};
   bool degrade_xs, degrade_xe, degrade_ys, degrade_ye;
   degrade_flags(x, 2, 4, degrade_xs, degrade_xe, degrade_ys, degrade_ye);
   Row fq0(its, ite, kte), fq1(its, ite, kte), fqx(its, ite, kte), vflux(its, ite, kte);
@@ -113,7 +124,7 @@ void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
       for (int k = kts; k <= ktf; k++)
         for (int i = i_start; i <= i_end; i++) {
           float vel = 0.5f * (rv(i, k, j) + rv(i - 1, k, j));
-          fqy(i, k) = vel * F.flux3(u(i, k, j - 2), u(i, k, j - 1), u(i, k, j), u(i, k, j + 1), vel);
+          fqy(i, k) = vel * F.h3(u(i, k, j - 2), u(i, k, j - 1), u(i, k, j), u(i, k, j + 1), vel);
         }
     } else if (j == jde - 1) {
       for (int k = kts; k <= ktf; k++)
@@ -122,7 +133,7 @@ void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
       for (int k = kts; k <= ktf; k++)
         for (int i = i_start; i <= i_end; i++) {
           float vel = 0.5f * (rv(i, k, j) + rv(i - 1, k, j));
-          fqy(i, k) = vel * F.flux3(u(i, k, j - 2), u(i, k, j - 1), u(i, k, j), u(i, k, j + 1), vel);
+          fqy(i, k) = vel * F.h3(u(i, k, j - 2), u(i, k, j - 1), u(i, k, j), u(i, k, j + 1), vel);
         }
     }
     if (j > j_start)
@@ -156,7 +167,7 @@ void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
       int i = ids + 2;
       for (int k = kts; k <= ktf; k++) {
         float vel = 0.5f * (ru(i, k, j) + ru(i - 1, k, j));
-        fqx(i, k) = vel * F.flux3(u(i - 2, k, j), u(i - 1, k, j), u(i, k, j), u(i + 1, k, j), vel);
+        fqx(i, k) = vel * F.h3(u(i - 2, k, j), u(i - 1, k, j), u(i, k, j), u(i + 1, k, j), vel);
       }
     }
     if (degrade_xe) {
@@ -170,7 +181,7 @@ void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
       for (int k = kts; k <= ktf; k++) {
         int i = ide - 1;
         float vel = 0.5f * (ru(i, k, j) + ru(i - 1, k, j));
-        fqx(i, k) = vel * F.flux3(u(i - 2, k, j), u(i - 1, k, j), u(i, k, j), u(i + 1, k, j), vel);
+        fqx(i, k) = vel * F.h3(u(i - 2, k, j), u(i - 1, k, j), u(i, k, j), u(i + 1, k, j), vel);
       }
     }
     for (int k = kts; k <= ktf; k++)
@@ -259,7 +270,7 @@ void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
   const int ktf = std::min(kte, x.kde - 1);
   const A1 &c1 = x.c1h, &c2 = x.c2h, &fzm = x.fnm, &fzp = x.fnp, &rdzw = x.rdnw;
   const float rdx = x.rdx, rdy = x.rdy;
-  Flux F{(float)(x.time_step >= 0 ? 1 : -1), weno};
+  Flux F{(float)(x.time_step >= 0 ? 1 : -1), weno, x.c.h_mom_adv_order == 6, x.c.v_mom_adv_order == 4};
   bool degrade_xs, degrade_xe, degrade_ys, degrade_ye;
   degrade_flags(x, 3, 3, degrade_xs, degrade_xe, degrade_ys, degrade_ye);
   Row fq0(its, ite, kte), fq1(its, ite, kte), fqx(its, ite, kte), vflux(its, ite, kte);
@@ -287,7 +298,7 @@ void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
       for (int k = kts; k <= ktf; k++)
         for (int i = i_start; i <= i_end; i++) {
           float vel = 0.5f * (rv(i, k, j) + rv(i, k, j - 1));
-          fqy(i, k) = vel * F.flux3(v(i, k, j - 2), v(i, k, j - 1), v(i, k, j), v(i, k, j + 1), vel);
+          fqy(i, k) = vel * F.h3(v(i, k, j - 2), v(i, k, j - 1), v(i, k, j), v(i, k, j + 1), vel);
         }
     } else if (j == jde) {
       for (int k = kts; k <= ktf; k++)
@@ -299,7 +310,7 @@ void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
       for (int k = kts; k <= ktf; k++)
         for (int i = i_start; i <= i_end; i++) {
           float vel = 0.5f * (rv(i, k, j) + rv(i, k, j - 1));
-          fqy(i, k) = vel * F.flux3(v(i, k, j - 2), v(i, k, j - 1), v(i, k, j), v(i, k, j + 1), vel);
+          fqy(i, k) = vel * F.h3(v(i, k, j - 2), v(i, k, j - 1), v(i, k, j), v(i, k, j + 1), vel);
         }
     }
     if (j > j_start)
@@ -330,7 +341,7 @@ void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
         if (i == ids + 2)
           for (int k = kts; k <= ktf; k++) {
             float vel = 0.5f * (ru(i, k, j) + ru(i, k, j - 1));
-            fqx(i, k) = vel * F.flux3(v(i - 2, k, j), v(i - 1, k, j), v(i, k, j), v(i + 1, k, j), vel);
+            fqx(i, k) = vel * F.h3(v(i - 2, k, j), v(i - 1, k, j), v(i, k, j), v(i + 1, k, j), vel);
           }
       }
     }
@@ -342,7 +353,7 @@ void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
         if (i == ide - 2)
           for (int k = kts; k <= ktf; k++) {
             float vel = 0.5f * (ru(i, k, j) + ru(i, k, j - 1));
-            fqx(i, k) = vel * F.flux3(v(i - 2, k, j), v(i - 1, k, j), v(i, k, j), v(i + 1, k, j), vel);
+            fqx(i, k) = vel * F.h3(v(i - 2, k, j), v(i - 1, k, j), v(i, k, j), v(i + 1, k, j), vel);
           }
       }
     }
@@ -433,7 +444,7 @@ void advect_scalar(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 r
   const int ktf = std::min(kte, x.kde - 1);
   const A1 &fzm = x.fnm, &fzp = x.fnp, &rdzw = x.rdnw;
   const float rdx = x.rdx, rdy = x.rdy;
-  Flux F{(float)(x.time_step >= 0 ? 1 : -1)};
+  Flux F{(float)(x.time_step >= 0 ? 1 : -1), false, x.c.h_sca_adv_order == 6, x.c.v_sca_adv_order == 4};
   bool degrade_xs, degrade_xe, degrade_ys, degrade_ye;
   degrade_flags(x, 3, 4, degrade_xs, degrade_xe, degrade_ys, degrade_ye);
   Row fq0(its, ite, kte), fq1(its, ite, kte), fqx(its, ite, kte), vflux(its, ite, kte);
@@ -459,7 +470,7 @@ void advect_scalar(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 r
       for (int k = kts; k <= ktf; k++)
         for (int i = i_start; i <= i_end; i++) {
           float vel = rv(i, k, j);
-          fqy(i, k) = vel * F.flux3(field(i, k, j - 2), field(i, k, j - 1), field(i, k, j), field(i, k, j + 1), vel);
+          fqy(i, k) = vel * F.h3(field(i, k, j - 2), field(i, k, j - 1), field(i, k, j), field(i, k, j + 1), vel);
         }
     } else if (j == jde - 1) {
       for (int k = kts; k <= ktf; k++)
@@ -468,7 +479,7 @@ void advect_scalar(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 r
       for (int k = kts; k <= ktf; k++)
         for (int i = i_start; i <= i_end; i++) {
           float vel = rv(i, k, j);
-          fqy(i, k) = vel * F.flux3(field(i, k, j - 2), field(i, k, j - 1), field(i, k, j), field(i, k, j + 1), vel);
+          fqy(i, k) = vel * F.h3(field(i, k, j - 2), field(i, k, j - 1), field(i, k, j), field(i, k, j + 1), vel);
         }
     }
     if (j > j_start)
@@ -498,7 +509,7 @@ void advect_scalar(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 r
         if (i == ids + 2)
           for (int k = kts; k <= ktf; k++) {
             float vel = ru(i, k, j);
-            fqx(i, k) = vel * F.flux3(field(i - 2, k, j), field(i - 1, k, j), field(i, k, j), field(i + 1, k, j), vel);
+            fqx(i, k) = vel * F.h3(field(i - 2, k, j), field(i - 1, k, j), field(i, k, j), field(i + 1, k, j), vel);
           }
       }
     if (degrade_xe)
@@ -508,7 +519,7 @@ void advect_scalar(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 r
         if (i == ide - 2)
           for (int k = kts; k <= ktf; k++) {
             float vel = ru(i, k, j);
-            fqx(i, k) = vel * F.flux3(field(i - 2, k, j), field(i - 1, k, j), field(i, k, j), field(i + 1, k, j), vel);
+            fqx(i, k) = vel * F.h3(field(i - 2, k, j), field(i - 1, k, j), field(i, k, j), field(i + 1, k, j), vel);
           }
       }
     for (int k = kts; k <= ktf; k++)
@@ -555,7 +566,7 @@ void advect_scalar(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 r
     for (int k = kts + 2; k <= ktf - 1; k++)
       for (int i = i_start; i <= i_end; i++) {
         float vel = rom(i, k, j);
-        vflux(i, k) = vel * F.flux3(field(i, k - 2, j), field(i, k - 1, j), field(i, k, j), field(i, k + 1, j), -vel);
+        vflux(i, k) = vel * F.v3(field(i, k - 2, j), field(i, k - 1, j), field(i, k, j), field(i, k + 1, j), -vel);
       }
     for (int i = i_start; i <= i_end; i++) {
       int k = kts + 1;
@@ -578,7 +589,7 @@ void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
   const int ktf = std::min(kte, x.kde - 1);
   const A1 &fzm = x.fnm, &fzp = x.fnp, &rdzu = x.rdn;
   const float rdx = x.rdx, rdy = x.rdy;
-  Flux F{(float)(x.time_step >= 0 ? 1 : -1), weno};
+  Flux F{(float)(x.time_step >= 0 ? 1 : -1), weno, x.c.h_mom_adv_order == 6, x.c.v_mom_adv_order == 4};
   bool degrade_xs, degrade_xe, degrade_ys, degrade_ye;
   degrade_flags(x, 3, 4, degrade_xs, degrade_xe, degrade_ys, degrade_ye);
   Row fq0(its, ite, kte), fq1(its, ite, kte), fqx(its, ite, kte), vflux(its, ite, kte);
@@ -609,7 +620,7 @@ void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
       for (int k = kts + 1; k <= ktf + 1; k++)
         for (int i = i_start; i <= i_end; i++) {
           float vel = vely(i, k, j);
-          fqy(i, k) = vel * F.flux3(w(i, k, j - 2), w(i, k, j - 1), w(i, k, j), w(i, k, j + 1), vel);
+          fqy(i, k) = vel * F.h3(w(i, k, j - 2), w(i, k, j - 1), w(i, k, j), w(i, k, j + 1), vel);
         }
     } else if (j == jde - 1) {
       for (int k = kts + 1; k <= ktf + 1; k++)
@@ -618,7 +629,7 @@ void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
       for (int k = kts + 1; k <= ktf + 1; k++)
         for (int i = i_start; i <= i_end; i++) {
           float vel = vely(i, k, j);
-          fqy(i, k) = vel * F.flux3(w(i, k, j - 2), w(i, k, j - 1), w(i, k, j), w(i, k, j + 1), vel);
+          fqy(i, k) = vel * F.h3(w(i, k, j - 2), w(i, k, j - 1), w(i, k, j), w(i, k, j + 1), vel);
         }
     }
     if (j > j_start)
@@ -647,7 +658,7 @@ void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
         if (i == ids + 2)
           for (int k = kts + 1; k <= ktf + 1; k++) {
             float vel = velx(i, k, j);
-            fqx(i, k) = vel * F.flux3(w(i - 2, k, j), w(i - 1, k, j), w(i, k, j), w(i + 1, k, j), vel);
+            fqx(i, k) = vel * F.h3(w(i - 2, k, j), w(i - 1, k, j), w(i, k, j), w(i + 1, k, j), vel);
           }
       }
     if (degrade_xe)
@@ -657,7 +668,7 @@ void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
         if (i == ide - 2)
           for (int k = kts + 1; k <= ktf + 1; k++) {
             float vel = velx(i, k, j);
-            fqx(i, k) = vel * F.flux3(w(i - 2, k, j), w(i - 1, k, j), w(i, k, j), w(i + 1, k, j), vel);
+            fqx(i, k) = vel * F.h3(w(i - 2, k, j), w(i - 1, k, j), w(i, k, j), w(i + 1, k, j), vel);
           }
       }
     for (int k = kts + 1; k <= ktf + 1; k++)
@@ -786,13 +797,23 @@ void advect_scalar_pd(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A
   auto flux4 = [](float q_im2, float q_im1, float q_i, float q_ip1) {
     return (7.f / 12.f) * (q_i + q_im1) - (1.f / 12.f) * (q_ip1 + q_im2);
   };
-  auto flux3 = [&](float q_im2, float q_im1, float q_i, float q_ip1, float ua) {
+  // h_sca_adv_order = 6 / v_sca_adv_order = 4: the same code with flux6 / flux4 (:6229-6503, :7544-7593); the WENO variant
+  // keeps its own structure whatever the orders say
+  const bool h_even = x.c.h_sca_adv_order == 6 && !weno, v_even = x.c.v_sca_adv_order == 4 && !weno;
+  auto flux3o = [&](float q_im2, float q_im1, float q_i, float q_ip1, float ua) {
     return flux4(q_im2, q_im1, q_i, q_ip1) + sgn * sign1(ua) * (1.f / 12.f) * ((q_ip1 - q_im2) - 3.f * (q_i - q_im1));
+  };
+  auto flux3 = [&](float q_im2, float q_im1, float q_i, float q_ip1, float ua) {   // horizontal faces
+    return h_even ? flux4(q_im2, q_im1, q_i, q_ip1) : flux3o(q_im2, q_im1, q_i, q_ip1, ua);
+  };
+  auto vflux3 = [&](float q_im2, float q_im1, float q_i, float q_ip1, float ua) {  // vertical faces
+    return v_even ? flux4(q_im2, q_im1, q_i, q_ip1) : flux3o(q_im2, q_im1, q_i, q_ip1, ua);
   };
   auto flux6 = [](float q_im3, float q_im2, float q_im1, float q_i, float q_ip1, float q_ip2) {
     return (37.f / 60.f) * (q_i + q_im1) - (2.f / 15.f) * (q_ip1 + q_im2) + (1.f / 60.f) * (q_ip2 + q_im3);
   };
   auto flux5 = [&](float q_im3, float q_im2, float q_im1, float q_i, float q_ip1, float q_ip2, float ua) {
+    if (h_even) return flux6(q_im3, q_im2, q_im1, q_i, q_ip1, q_ip2);
     return flux6(q_im3, q_im2, q_im1, q_i, q_ip1, q_ip2) -
            sgn * sign1(ua) * (1.f / 60.f) * ((q_ip2 - q_im3) - 5.f * (q_ip1 - q_im2) + 10.f * (q_i - q_im1));
   };
@@ -947,7 +968,7 @@ void advect_scalar_pd(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A
         if (weno && k >= kts + 3 && k <= ktf - 2)
           fqz(i, k, j) = weno5(vel, -vel * sgn >= 0.0f, field(i, k - 3, j), field(i, k - 2, j), field(i, k - 1, j), field(i, k, j), field(i, k + 1, j), field(i, k + 2, j));
         else
-          fqz(i, k, j) = vel * flux3(field(i, k - 2, j), field(i, k - 1, j), field(i, k, j), field(i, k + 1, j), -vel);
+          fqz(i, k, j) = vel * vflux3(field(i, k - 2, j), field(i, k - 1, j), field(i, k, j), field(i, k + 1, j), -vel);
         fqz(i, k, j) = fqz(i, k, j) - fqzl(i, k, j);
       }
     for (int i = i_start; i <= i_end; i++) {

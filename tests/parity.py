@@ -141,6 +141,12 @@ def small_cases():
                                                  diff_opt=1, km_opt=1, khdif=200.0, kvdif=20.0), 40.0, conv=20.0),
         "backward": make_case("synthetic", nx=30, ny=28, nz=15, bubble_lattice=20000.0, noise=0.05, num_scalar=1, scalar_adv_opt=3,
                               momentum_adv_opt=3, time_step=-12),
+        # even advection orders (h 6 / v 4: the same code with flux6 / flux4): all four at once with open boundaries, Kessler
+        # and the PD limiter; doubly periodic with map factors and h 6 only; mixed per family with periodic x / symmetric y
+        "order64": make_case("quarter_ss", nx=26, ny=24, nz=21, h_mom_adv_order=6, v_mom_adv_order=4, h_sca_adv_order=6, v_sca_adv_order=4),
+        "order63_periodic": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=2,
+                                                       scalar_adv_opt=0, h_mom_adv_order=6, h_sca_adv_order=6)),
+        "order_mixed": make_case("b_wave", nx=21, ny=31, nz=17, h_mom_adv_order=6, v_sca_adv_order=4, moist_adv_opt=4, momentum_adv_opt=3),
         "ieva_weno_hill": with_updraft(make_case("hill2d_x", nx=62, ny=3, nz=41, zadvect_implicit=1, momentum_adv_opt=3,
                                                  moist_adv_opt=3), 60.0, conv=70.0),
     }

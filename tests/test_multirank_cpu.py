@@ -80,7 +80,7 @@ def _check(case, ntx, nty, nsteps=2):
 
 
 @pytest.mark.parametrize("mesh", [(1, 2), (2, 1), (2, 2)])
-@pytest.mark.parametrize("name", ["quarter_ss", "periodic", "b_wave", "hill2d_x_wide", "les", "diffusion", "diffusion_periodic", "mono", "mono_periodic", "weno", "wenopd_periodic", "weno_mom", "ieva", "ieva_periodic", "diff6", "diff6_periodic"])
+@pytest.mark.parametrize("name", ["quarter_ss", "periodic", "b_wave", "hill2d_x_wide", "les", "diffusion", "diffusion_periodic", "mono", "mono_periodic", "weno", "wenopd_periodic", "weno_mom", "ieva", "ieva_periodic", "diff6", "diff6_periodic", "order64"])
 def test_n_rank_oracle_equals_single_rank(name, mesh):
     cases = parity.small_cases()
     cases["hill2d_x_wide"] = make_case("hill2d_x", nx=62, ny=9, nz=21)

@@ -262,6 +262,34 @@ def test_sixth_order_filter_damps_the_two_delta_x_wave_at_the_documented_rate():
     assert abs(got["off"] - 1.0) < 1e-6, got
 
 
+def test_even_order_advection_is_the_odd_order_without_its_dissipation():
+    """h_sca_adv_order = 6 uses flux6 where 5 uses flux5 = flux6 - sign(u)/60 * (6th difference) (module_advect_em.F:202-213,
+    3394-3400): the extra term is purely dissipative.  A 10 dx sine wave carried by the ADVECT_KERNEL harness's uniform
+    flow (Courant number C = 0.45 per loop) keeps the same phase under both orders, and the 5th-order amplitude is the
+    6th-order one times exp(-N C (2 sin(k dx / 2))^6 / 60), the damping of that term alone."""
+    res = {}
+    nloops, wl = 40, 10.0
+    for h in (5, 6):
+        case = parity.tophat_case(0)
+        case.config.h_sca_adv_order = h
+        d = case.dims
+        ii = np.arange(d.ims, d.ime + 1, dtype=np.float64)
+        q = (1.0 + 0.5 * np.sin(2 * np.pi * (ii - 1) / wl)).astype(np.float32)
+        for n in ("scalar_1", "scalar_old_1"):
+            case.fields[n][:] = q[None, None, :]
+        o = Oracle(case)
+        parity.feeder_loop(o, nloops)
+        row = o.get("scalar_1")[1 - d.jms, 3, 1 - d.ims:1 - d.ims + 90].astype(np.float64)
+        f = np.fft.rfft(row - row.mean())[9]
+        res[h] = (2 * np.abs(f) / 90 / 0.5, np.angle(f), row.mean())
+    courant = 90.0 * 5.0 / 1000.0
+    want = np.exp(-nloops * courant * (2 * np.sin(np.pi / wl)) ** 6 / 60.0)
+    assert abs(res[5][0] / res[6][0] - want) < 2e-4, (res, want)
+    assert abs(res[5][1] - res[6][1]) < 1e-3                    # same phase speed
+    assert res[6][0] > 0.985                                    # what is left is RK3's own damping
+    assert abs(res[5][2] - 1.0) < 1e-6 and abs(res[6][2] - 1.0) < 1e-6
+
+
 def test_monotonic_advection_creates_no_new_extrema():
     """advect_scalar_mono (module_advect_em.F:9495-10560, "monotonic advection option ... Smolarkiewicz MWR 1989"):
     a top-hat tracer advected through the sheared supercell environment stays inside its initial range [0, 1]

@@ -50,6 +50,9 @@ struct GeoBase {
   float rdx, rdy, dt, cf1, cf2, cf3, cfn, cfn1;
   float epssm, smdiv, emdiv, dampcoef, zdamp, w_crit_cfl, p_top;
   float sgn_ts;                    // sign(1,time_step)
+  // factor of the upwind term of the momentum / scalar fluxes, horizontal / vertical: sgn_ts for the odd orders (5, 3),
+  // 0 for the even ones (h_*_adv_order = 6, v_*_adv_order = 4), which are the same operators without that term
+  float sg_hm, sg_vm, sg_hs, sg_vs;
   // base-state sounding (Rayleigh damping, perturbation Coriolis only): origin-shifted global pointers
   const float *u_base, *v_base, *t_base, *z_base;
   // 2-D fields, origin shifted: A2(f,i,j)

@@ -63,6 +63,7 @@ __device__ __forceinline__ int pd_order(int f, bool dlo, bool dhi, int lo_edge, 
 __device__ __forceinline__ Face pd_face_x(const Geo &g, const PdIn &s, int ii, int k, int j, bool dxs, bool dxe) {
   Face f;
   const int ord = pd_order(ii, dxs, dxe, g.ids, g.ide);
+  const float sgh = s.weno ? g.sgn_ts : g.sg_hs;   // h_sca_adv_order = 6: flux6 / flux4, i.e. no upwind term
   f.ok = ord != 0;
   if (!f.ok) { f.hi = 0.f; f.lo = 0.f; return f; }
   const float dx = 2.f / (A2(g.msfty, ii, j) + A2(g.msfty, ii - 1, j)) / g.rdx;
@@ -73,8 +74,8 @@ __device__ __forceinline__ Face pd_face_x(const Geo &g, const PdIn &s, int ii, i
   f.lo = mu * (dx / s.dt) * flux_upwind(A3(s.q_old, ii - 1, k, j), A3(s.q_old, ii, k, j), cr);
   float h;
   if (ord == 5 && s.weno) h = weno5(vel, vel * g.sgn_ts >= 0.0f, A3(s.q, ii - 3, k, j), A3(s.q, ii - 2, k, j), A3(s.q, ii - 1, k, j), A3(s.q, ii, k, j), A3(s.q, ii + 1, k, j), A3(s.q, ii + 2, k, j));
-  else if (ord == 5) h = vel * pflux5(A3(s.q, ii - 3, k, j), A3(s.q, ii - 2, k, j), A3(s.q, ii - 1, k, j), A3(s.q, ii, k, j), A3(s.q, ii + 1, k, j), A3(s.q, ii + 2, k, j), vel, g.sgn_ts);
-  else if (ord == 3) h = vel * pflux3(A3(s.q, ii - 2, k, j), A3(s.q, ii - 1, k, j), A3(s.q, ii, k, j), A3(s.q, ii + 1, k, j), vel, g.sgn_ts);
+  else if (ord == 5) h = vel * pflux5(A3(s.q, ii - 3, k, j), A3(s.q, ii - 2, k, j), A3(s.q, ii - 1, k, j), A3(s.q, ii, k, j), A3(s.q, ii + 1, k, j), A3(s.q, ii + 2, k, j), vel, sgh);
+  else if (ord == 3) h = vel * pflux3(A3(s.q, ii - 2, k, j), A3(s.q, ii - 1, k, j), A3(s.q, ii, k, j), A3(s.q, ii + 1, k, j), vel, sgh);
   else h = 0.5f * (A3(s.ru, ii, k, j)) * (A3(s.q, ii, k, j) + A3(s.q, ii - 1, k, j));
   f.hi = h - f.lo;
   return f;
@@ -83,6 +84,7 @@ __device__ __forceinline__ Face pd_face_x(const Geo &g, const PdIn &s, int ii, i
 __device__ __forceinline__ Face pd_face_y(const Geo &g, const PdIn &s, int i, int k, int jj, bool dys, bool dye) {
   Face f;
   const int ord = pd_order(jj, dys, dye, g.jds, g.jde);
+  const float sgh = s.weno ? g.sgn_ts : g.sg_hs;
   f.ok = ord != 0;
   if (!f.ok) { f.hi = 0.f; f.lo = 0.f; return f; }
   const float dy = 2.f / (A2(g.msftx, i, jj) + A2(g.msftx, i, jj - 1)) / g.rdy;
@@ -92,8 +94,8 @@ __device__ __forceinline__ Face pd_face_y(const Geo &g, const PdIn &s, int i, in
   f.lo = mu * (dy / s.dt) * flux_upwind(A3(s.q_old, i, k, jj - 1), A3(s.q_old, i, k, jj), cr);
   float h;
   if (ord == 5 && s.weno) h = weno5(vel, vel * g.sgn_ts >= 0.0f, A3(s.q, i, k, jj - 3), A3(s.q, i, k, jj - 2), A3(s.q, i, k, jj - 1), A3(s.q, i, k, jj), A3(s.q, i, k, jj + 1), A3(s.q, i, k, jj + 2));
-  else if (ord == 5) h = vel * pflux5(A3(s.q, i, k, jj - 3), A3(s.q, i, k, jj - 2), A3(s.q, i, k, jj - 1), A3(s.q, i, k, jj), A3(s.q, i, k, jj + 1), A3(s.q, i, k, jj + 2), vel, g.sgn_ts);
-  else if (ord == 3) h = vel * pflux3(A3(s.q, i, k, jj - 2), A3(s.q, i, k, jj - 1), A3(s.q, i, k, jj), A3(s.q, i, k, jj + 1), vel, g.sgn_ts);
+  else if (ord == 5) h = vel * pflux5(A3(s.q, i, k, jj - 3), A3(s.q, i, k, jj - 2), A3(s.q, i, k, jj - 1), A3(s.q, i, k, jj), A3(s.q, i, k, jj + 1), A3(s.q, i, k, jj + 2), vel, sgh);
+  else if (ord == 3) h = vel * pflux3(A3(s.q, i, k, jj - 2), A3(s.q, i, k, jj - 1), A3(s.q, i, k, jj), A3(s.q, i, k, jj + 1), vel, sgh);
   else h = 0.5f * A3(s.rv, i, k, jj) * (A3(s.q, i, k, jj) + A3(s.q, i, k, jj - 1));
   f.hi = h - f.lo;
   return f;
@@ -104,6 +106,7 @@ __device__ __forceinline__ Face pd_face_z(const Geo &g, const PdIn &s, int i, in
   f.ok = true;
   if (kk == 1 || kk == g.kde) { f.hi = 0.f; f.lo = 0.f; return f; }
   const int ktf = g.kde - 1;
+  const float sgv = s.weno ? g.sgn_ts : g.sg_vs;   // v_sca_adv_order = 4: flux4
   const float dz = 2.f / (g.rdnw[kk] + g.rdnw[kk - 1]);
   const float mu = 0.5f * ((g.c1h[kk] * A2(s.mut, i, j) + g.c2h[kk]) + (g.c1h[kk] * A2(s.mut, i, j) + g.c2h[kk]));
   const float vel = A3(s.rom, i, kk, j);
@@ -113,7 +116,7 @@ __device__ __forceinline__ Face pd_face_z(const Geo &g, const PdIn &s, int i, in
   if (kk == 2 || kk == ktf) h = A3(s.rom, i, kk, j) * (g.fnm[kk] * A3(s.q, i, kk, j) + g.fnp[kk] * A3(s.q, i, kk - 1, j));
   else if (s.weno && kk >= 4 && kk <= ktf - 2)   // :9217-9262
     h = weno5(vel, -vel * g.sgn_ts >= 0.0f, A3(s.q, i, kk - 3, j), A3(s.q, i, kk - 2, j), A3(s.q, i, kk - 1, j), A3(s.q, i, kk, j), A3(s.q, i, kk + 1, j), A3(s.q, i, kk + 2, j));
-  else h = vel * pflux3(A3(s.q, i, kk - 2, j), A3(s.q, i, kk - 1, j), A3(s.q, i, kk, j), A3(s.q, i, kk + 1, j), -vel, g.sgn_ts);
+  else h = vel * pflux3(A3(s.q, i, kk - 2, j), A3(s.q, i, kk - 1, j), A3(s.q, i, kk, j), A3(s.q, i, kk + 1, j), -vel, sgv);
   f.hi = h - f.lo;
   return f;
 }
@@ -419,6 +422,7 @@ void Solver::rk_scalar_step(int rk_step) {
   }
   if (c.zadvect_implicit > 0 && !species.empty()) ieva_split(false, o("u_1"), o("v_1"), o("ww_m"), o("muts"), ieva);
   cfp rom = ieva ? o("wwE") : o("ww_m");
+  const bool dflt_s = c.h_sca_adv_order == 5 && c.v_sca_adv_order == 3;   // the k-marching kernels exist for these
   const bool dxs = !(c.periodic_x || c.symmetric_xs), dxe = !(c.periodic_x || c.symmetric_xe);
   const bool dys = !(c.periodic_y || c.symmetric_ys), dye = !(c.periodic_y || c.symmetric_ye);
   for (auto &s : species) {
@@ -445,7 +449,7 @@ void Solver::rk_scalar_step(int rk_step) {
         LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
         continue;
       }
-      if (s.adv_opt == 4 || ieva) {   // WENO inside the positive-definite limiter, or IEVA's wwE: the gather kernels everywhere
+      if (s.adv_opt == 4 || ieva || !dflt_s) {   // WENO inside the positive-definite limiter, or IEVA's wwE: the gather kernels everywhere
         LAUNCH3(this, k_pd_scale, lim, in, o("pd_scale"));
         LAUNCH3(this, k_pd_tend, mass, in, o("pd_scale"), lim, o("advect_tend"));
         if (ieva) ieva_implicit(0, o("advect_tend"), o(s.o), o("mut_old"), o("muts"), dt_rk);
@@ -466,6 +470,8 @@ void Solver::rk_scalar_step(int rk_step) {
       for (int m = 0; m < nst; m++) LAUNCH3(this, k_pd_tend, strips[m], in, o("pd_scale"), lim, o("advect_tend"));
     } else if (last && s.adv_opt == 3) {   // WENO_SCALAR (module_em.F:1300-1312)
       LAUNCH3(this, k_advect_scalar_weno, mass, o(s.f), o("ru_m"), o("rv_m"), rom, o("advect_tend"));
+    } else if (!dflt_s) {   // orders other than (5, 3): the gather kernel everywhere
+      LAUNCH3(this, k_advect_scalar, mass, o(s.f), o("ru_m"), o("rv_m"), rom, o("advect_tend"));
     } else {
       Box in = interior_box(q);
       in.k1 = ktf;

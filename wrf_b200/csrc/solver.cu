@@ -28,8 +28,10 @@ static void check_config(const wrfgpu_config &c) {
   auto bad = [](const std::string &m) { throw std::runtime_error("wrfgpu: unsupported configuration: " + m); };
   if (c.specified || c.nested || c.polar) bad("specified/nested/polar lateral boundaries are not on the device path");
   if (c.rk_ord != 3 && c.rk_ord != 2) bad("rk_ord must be 2 or 3");
-  if (c.h_mom_adv_order != 5 || c.h_sca_adv_order != 5) bad("h_*_adv_order must be 5");
-  if (c.v_mom_adv_order != 3 || c.v_sca_adv_order != 3) bad("v_*_adv_order must be 3");
+  if ((c.h_mom_adv_order != 5 && c.h_mom_adv_order != 6) || (c.h_sca_adv_order != 5 && c.h_sca_adv_order != 6)) bad("h_*_adv_order must be 5 or 6");
+  if ((c.v_mom_adv_order != 3 && c.v_mom_adv_order != 4) || (c.v_sca_adv_order != 3 && c.v_sca_adv_order != 4)) bad("v_*_adv_order must be 3 or 4");
+  if ((c.moist_adv_opt == 2 || c.scalar_adv_opt == 2) && (c.h_sca_adv_order != 5 || c.v_sca_adv_order != 3))
+    bad("monotonic advection (*_adv_opt = 2) needs h_sca_adv_order = 5 and v_sca_adv_order = 3");
   if (c.moist_adv_opt < 0 || c.moist_adv_opt > 4) bad("moist_adv_opt must be 0 (original), 1 (positive-definite), 2 (monotonic), 3 (WENO) or 4 (WENO, positive-definite)");
   if (c.scalar_adv_opt < 0 || c.scalar_adv_opt > 4) bad("scalar_adv_opt must be 0 ... 4");
   if (c.momentum_adv_opt != 1 && c.momentum_adv_opt != 3) bad("momentum_adv_opt must be 1 (original) or 3 (WENO)");
@@ -186,6 +188,8 @@ void Solver::build_geo() {
   q.epssm = c.epssm; q.smdiv = c.smdiv; q.emdiv = c.emdiv; q.dampcoef = c.dampcoef; q.zdamp = c.zdamp;
   q.w_crit_cfl = c.w_crit_cfl; q.p_top = c.p_top;
   q.sgn_ts = c.time_step >= 0 ? 1.f : -1.f;
+  q.sg_hm = c.h_mom_adv_order == 6 ? 0.f : q.sgn_ts; q.sg_vm = c.v_mom_adv_order == 4 ? 0.f : q.sgn_ts;
+  q.sg_hs = c.h_sca_adv_order == 6 ? 0.f : q.sgn_ts; q.sg_vs = c.v_sca_adv_order == 4 ? 0.f : q.sgn_ts;
   coef_dirty = true;   // fnm ... c4f are copied from the device fields before the next launch (sync_coef)
   q.u_base = o("u_base"); q.v_base = o("v_base"); q.t_base = o("t_base"); q.z_base = o("z_base");
   q.msftx = o("msftx"); q.msfty = o("msfty"); q.msfux = o("msfux"); q.msfuy = o("msfuy"); q.msfvx = o("msfvx");

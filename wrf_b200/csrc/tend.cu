@@ -125,6 +125,8 @@ __device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i,
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
   const Deg dg = degrade(g);
   const float sg = g.sgn_ts;
+  // even orders (h 6 / v 4) are the odd ones without the upwind term: its factor is 0 then; WENO keeps sign(time_step)
+  const float sgh = WENO ? sg : g.sg_hm, sgv = WENO ? sg : g.sg_vm;
   cfp u = s.u, ru = s.ru, rv = s.rv, rom = s.rom;
   float t = t0;
   if (PART != 2) {
@@ -143,10 +145,10 @@ __device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i,
         const int ord = FAST ? 5 : face_order(jj, dg.ys, dg.ye, jds + 1, jds + 2, jde - 1, jde - 2);
         if (ord == 5) {
           const float vel = 0.5f * (A3(rv, i, k, jj) + A3(rv, i - 1, k, jj));
-          fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, YSTENCIL(u, i, k, jj), 1.0e-18) : vel * flux5(YSTENCIL(u, i, k, jj), vel, sg);
+          fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, YSTENCIL(u, i, k, jj), 1.0e-18) : vel * flux5(YSTENCIL(u, i, k, jj), vel, sgh);
         } else if (ord == 3) {
           const float vel = 0.5f * (A3(rv, i, k, jj) + A3(rv, i - 1, k, jj));
-          fq[m] = vel * flux3(A3(u, i, k, jj - 2), A3(u, i, k, jj - 1), A3(u, i, k, jj), A3(u, i, k, jj + 1), vel, sg);
+          fq[m] = vel * flux3(A3(u, i, k, jj - 2), A3(u, i, k, jj - 1), A3(u, i, k, jj), A3(u, i, k, jj + 1), vel, sgh);
         } else {
           fq[m] = 0.25f * (A3(rv, i, k, jj) + A3(rv, i - 1, k, jj)) * (A3(u, i, k, jj) + A3(u, i, k, jj - 1));
         }
@@ -166,10 +168,10 @@ __device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i,
         const int ord = FAST ? 5 : face_order(ii, dg.xs, dg.xe, ids + 1, ids + 2, ide, ide - 1);
         if (ord == 5) {
           const float vel = 0.5f * (A3(ru, ii, k, j) + A3(ru, ii - 1, k, j));
-          fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, XSTENCIL(u, ii, k, j), 1.0e-18) : vel * flux5(XSTENCIL(u, ii, k, j), vel, sg);
+          fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, XSTENCIL(u, ii, k, j), 1.0e-18) : vel * flux5(XSTENCIL(u, ii, k, j), vel, sgh);
         } else if (ord == 3) {
           const float vel = 0.5f * (A3(ru, ii, k, j) + A3(ru, ii - 1, k, j));
-          fq[m] = vel * flux3(A3(u, ii - 2, k, j), A3(u, ii - 1, k, j), A3(u, ii, k, j), A3(u, ii + 1, k, j), vel, sg);
+          fq[m] = vel * flux3(A3(u, ii - 2, k, j), A3(u, ii - 1, k, j), A3(u, ii, k, j), A3(u, ii + 1, k, j), vel, sgh);
         } else {
           fq[m] = 0.25f * (A3(ru, ii, k, j) + A3(ru, ii - 1, k, j)) * (A3(u, ii, k, j) + A3(u, ii - 1, k, j));
         }
@@ -231,7 +233,7 @@ __device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i,
           if (WENO && kk >= 4 && kk <= ktf - 2)   // vert_order 5 structure of advect_weno_u
             vf[m] = weno5(vel, -vel * sg >= 0.0f, A3(u, i, kk - 3, j), A3(u, i, kk - 2, j), A3(u, i, kk - 1, j), A3(u, i, kk, j), A3(u, i, kk + 1, j), A3(u, i, kk + 2, j), 1.0e-18);
           else
-            vf[m] = vel * flux3(A3(u, i, kk - 2, j), A3(u, i, kk - 1, j), A3(u, i, kk, j), A3(u, i, kk + 1, j), -vel, sg);
+            vf[m] = vel * flux3(A3(u, i, kk - 2, j), A3(u, i, kk - 1, j), A3(u, i, kk, j), A3(u, i, kk + 1, j), -vel, sgv);
         }
       }
       t = t - g.rdnw[k] * (vf[1] - vf[0]);
@@ -320,6 +322,8 @@ __device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i,
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
   const Deg dg = degrade(g);
   const float sg = g.sgn_ts;
+  // even orders (h 6 / v 4) are the odd ones without the upwind term: its factor is 0 then; WENO keeps sign(time_step)
+  const float sgh = WENO ? sg : g.sg_hm, sgv = WENO ? sg : g.sg_vm;
   cfp v = s.v, ru = s.ru, rv = s.rv, rom = s.rom;
   float t = t0;
   if (PART != 2) {
@@ -334,10 +338,10 @@ __device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i,
         const int ord = FAST ? 5 : face_order(jj, dg.ys, dg.ye, jds + 1, jds + 2, jde, jde - 1);
         if (ord == 5) {
           const float vel = 0.5f * (A3(rv, i, k, jj) + A3(rv, i, k, jj - 1));
-          fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, YSTENCIL(v, i, k, jj), 1.0e-18) : vel * flux5(YSTENCIL(v, i, k, jj), vel, sg);
+          fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, YSTENCIL(v, i, k, jj), 1.0e-18) : vel * flux5(YSTENCIL(v, i, k, jj), vel, sgh);
         } else if (ord == 3) {
           const float vel = 0.5f * (A3(rv, i, k, jj) + A3(rv, i, k, jj - 1));
-          fq[m] = vel * flux3(A3(v, i, k, jj - 2), A3(v, i, k, jj - 1), A3(v, i, k, jj), A3(v, i, k, jj + 1), vel, sg);
+          fq[m] = vel * flux3(A3(v, i, k, jj - 2), A3(v, i, k, jj - 1), A3(v, i, k, jj), A3(v, i, k, jj + 1), vel, sgh);
         } else {
           fq[m] = 0.25f * (A3(rv, i, k, jj) + A3(rv, i, k, jj - 1)) * (A3(v, i, k, jj) + A3(v, i, k, jj - 1));
         }
@@ -360,10 +364,10 @@ __device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i,
         const int ord = FAST ? 5 : face_order(ii, dg.xs, dg.xe, ids + 1, ids + 2, ide - 1, ide - 2);
         if (ord == 5) {
           const float vel = 0.5f * (A3(ru, ii, k, j) + A3(ru, ii, k, j - 1));
-          fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, XSTENCIL(v, ii, k, j), 1.0e-18) : vel * flux5(XSTENCIL(v, ii, k, j), vel, sg);
+          fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, XSTENCIL(v, ii, k, j), 1.0e-18) : vel * flux5(XSTENCIL(v, ii, k, j), vel, sgh);
         } else if (ord == 3) {
           const float vel = 0.5f * (A3(ru, ii, k, j) + A3(ru, ii, k, j - 1));
-          fq[m] = vel * flux3(A3(v, ii - 2, k, j), A3(v, ii - 1, k, j), A3(v, ii, k, j), A3(v, ii + 1, k, j), vel, sg);
+          fq[m] = vel * flux3(A3(v, ii - 2, k, j), A3(v, ii - 1, k, j), A3(v, ii, k, j), A3(v, ii + 1, k, j), vel, sgh);
         } else {
           fq[m] = 0.25f * (A3(ru, ii, k, j) + A3(ru, ii, k, j - 1)) * (A3(v, ii, k, j) + A3(v, ii - 1, k, j));
         }
@@ -424,7 +428,7 @@ __device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i,
           if (WENO && kk >= 4 && kk <= ktf - 2)   // vert_order 5 structure of advect_weno_v
             vf[m] = weno5(vel, -vel * sg >= 0.0f, A3(v, i, kk - 3, j), A3(v, i, kk - 2, j), A3(v, i, kk - 1, j), A3(v, i, kk, j), A3(v, i, kk + 1, j), A3(v, i, kk + 2, j), 1.0e-18);
           else
-            vf[m] = vel * flux3(A3(v, i, kk - 2, j), A3(v, i, kk - 1, j), A3(v, i, kk, j), A3(v, i, kk + 1, j), -vel, sg);
+            vf[m] = vel * flux3(A3(v, i, kk - 2, j), A3(v, i, kk - 1, j), A3(v, i, kk, j), A3(v, i, kk + 1, j), -vel, sgv);
         }
       }
       t = t - (A2(g.msfvy, i, j) / A2(g.msfvx, i, j)) * g.rdnw[k] * (vf[1] - vf[0]);
@@ -510,6 +514,8 @@ __device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i,
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
   const Deg dg = degrade(g);
   const float sg = g.sgn_ts;
+  // even orders (h 6 / v 4) are the odd ones without the upwind term: its factor is 0 then; WENO keeps sign(time_step)
+  const float sgh = WENO ? sg : g.sg_hm, sgv = WENO ? sg : g.sg_vm;
   cfp w = s.w, ru = s.ru, rv = s.rv, rom = s.rom;
   float t = t0;
   if (k >= 2) {
@@ -530,8 +536,8 @@ __device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i,
           const int jj = j + m;
           const int ord = FAST ? 5 : face_order(jj, dg.ys, dg.ye, jds + 1, jds + 2, jde - 1, jde - 2);
           const float vel = WVEL(rv, i, jj);
-          if (ord == 5) fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, YSTENCIL(w, i, k, jj), 1.0e-18) : vel * flux5(YSTENCIL(w, i, k, jj), vel, sg);
-          else if (ord == 3) fq[m] = vel * flux3(A3(w, i, k, jj - 2), A3(w, i, k, jj - 1), A3(w, i, k, jj), A3(w, i, k, jj + 1), vel, sg);
+          if (ord == 5) fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, YSTENCIL(w, i, k, jj), 1.0e-18) : vel * flux5(YSTENCIL(w, i, k, jj), vel, sgh);
+          else if (ord == 3) fq[m] = vel * flux3(A3(w, i, k, jj - 2), A3(w, i, k, jj - 1), A3(w, i, k, jj), A3(w, i, k, jj + 1), vel, sgh);
           else fq[m] = 0.5f * (vel) * (A3(w, i, k, jj) + A3(w, i, k, jj - 1));
         }
         const float mrdy = A2(g.msftx, i, j) * g.rdy;
@@ -548,8 +554,8 @@ __device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i,
           const int ii = i + m;
           const int ord = FAST ? 5 : face_order(ii, dg.xs, dg.xe, ids + 1, ids + 2, ide - 1, ide - 2);
           const float vel = WVEL(ru, ii, j);
-          if (ord == 5) fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, XSTENCIL(w, ii, k, j), 1.0e-18) : vel * flux5(XSTENCIL(w, ii, k, j), vel, sg);
-          else if (ord == 3) fq[m] = vel * flux3(A3(w, ii - 2, k, j), A3(w, ii - 1, k, j), A3(w, ii, k, j), A3(w, ii + 1, k, j), vel, sg);
+          if (ord == 5) fq[m] = WENO ? weno5(vel, vel * sg >= 0.0f, XSTENCIL(w, ii, k, j), 1.0e-18) : vel * flux5(XSTENCIL(w, ii, k, j), vel, sgh);
+          else if (ord == 3) fq[m] = vel * flux3(A3(w, ii - 2, k, j), A3(w, ii - 1, k, j), A3(w, ii, k, j), A3(w, ii + 1, k, j), vel, sgh);
           else fq[m] = 0.5f * (vel) * (A3(w, ii, k, j) + A3(w, ii - 1, k, j));
         }
         const float mrdx = A2(g.msftx, i, j) * g.rdx;
@@ -593,7 +599,7 @@ __device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i,
         const float vel = 0.5f * (A3(rom, i, kk, j) + A3(rom, i, kk - 1, j));
         if (WENO && kk >= 4 && kk <= kde - 2)   // vert_order 5 structure of advect_weno_w (:12959-13037)
           return weno5(vel, -vel * sg >= 0.0f, A3(w, i, kk - 3, j), A3(w, i, kk - 2, j), A3(w, i, kk - 1, j), A3(w, i, kk, j), A3(w, i, kk + 1, j), A3(w, i, kk + 2, j), 1.0e-18);
-        return vel * flux3(A3(w, i, kk - 2, j), A3(w, i, kk - 1, j), A3(w, i, kk, j), A3(w, i, kk + 1, j), -vel, sg);
+        return vel * flux3(A3(w, i, kk - 2, j), A3(w, i, kk - 1, j), A3(w, i, kk, j), A3(w, i, kk + 1, j), -vel, sgv);
       };
       if (!top) t = t - g.rdn[k] * (vflux(k + 1) - vflux(k));
       else t = t + 2.f * g.rdn[k - 1] * (vflux(k));
@@ -667,7 +673,7 @@ __device__ __forceinline__ float advect_scalar_pt(const Geo &g, cfp q, cfp q_old
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, ktf = g.kde - 1;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
   const Deg dg = degrade(g);
-  const float sg = g.sgn_ts;
+  const float sgh = g.sg_hs, sgv = g.sg_vs;   // 0 for the even orders (h 6 / v 4): no upwind term
   float t = 0.f;
   {
     const int j_lo = dg.ys ? max(jts, jds + 1) : jts, j_hi = dg.ye ? min(jte, jde - 2) : min(jte, jde - 1);
@@ -678,8 +684,8 @@ __device__ __forceinline__ float advect_scalar_pt(const Geo &g, cfp q, cfp q_old
         const int jj = j + m;
         const int ord = FAST ? 5 : face_order(jj, dg.ys, dg.ye, jds + 1, jds + 2, jde - 1, jde - 2);
         const float vel = A3(rv, i, k, jj);
-        if (ord == 5) fq[m] = vel * flux5(YSTENCIL(q, i, k, jj), vel, sg);
-        else if (ord == 3) fq[m] = vel * flux3(A3(q, i, k, jj - 2), A3(q, i, k, jj - 1), A3(q, i, k, jj), A3(q, i, k, jj + 1), vel, sg);
+        if (ord == 5) fq[m] = vel * flux5(YSTENCIL(q, i, k, jj), vel, sgh);
+        else if (ord == 3) fq[m] = vel * flux3(A3(q, i, k, jj - 2), A3(q, i, k, jj - 1), A3(q, i, k, jj), A3(q, i, k, jj + 1), vel, sgh);
         else fq[m] = 0.5f * vel * (A3(q, i, k, jj) + A3(q, i, k, jj - 1));
       }
       const float mrdy = A2(g.msftx, i, j) * g.rdy;
@@ -695,8 +701,8 @@ __device__ __forceinline__ float advect_scalar_pt(const Geo &g, cfp q, cfp q_old
         const int ii = i + m;
         const int ord = FAST ? 5 : face_order(ii, dg.xs, dg.xe, ids + 1, ids + 2, ide - 1, ide - 2);
         const float vel = A3(ru, ii, k, j);
-        if (ord == 5) fq[m] = vel * flux5(XSTENCIL(q, ii, k, j), vel, sg);
-        else if (ord == 3) fq[m] = vel * flux3(A3(q, ii - 2, k, j), A3(q, ii - 1, k, j), A3(q, ii, k, j), A3(q, ii + 1, k, j), vel, sg);
+        if (ord == 5) fq[m] = vel * flux5(XSTENCIL(q, ii, k, j), vel, sgh);
+        else if (ord == 3) fq[m] = vel * flux3(A3(q, ii - 2, k, j), A3(q, ii - 1, k, j), A3(q, ii, k, j), A3(q, ii + 1, k, j), vel, sgh);
         else fq[m] = 0.5f * (vel) * (A3(q, ii, k, j) + A3(q, ii - 1, k, j));
       }
       const float mrdx = A2(g.msftx, i, j) * g.rdx;
@@ -729,7 +735,7 @@ __device__ __forceinline__ float advect_scalar_pt(const Geo &g, cfp q, cfp q_old
       else if (kk == 2 || kk == ktf) vf[m] = A3(rom, i, kk, j) * (g.fnm[kk] * A3(q, i, kk, j) + g.fnp[kk] * A3(q, i, kk - 1, j));
       else {
         const float vel = A3(rom, i, kk, j);
-        vf[m] = vel * flux3(A3(q, i, kk - 2, j), A3(q, i, kk - 1, j), A3(q, i, kk, j), A3(q, i, kk + 1, j), -vel, sg);
+        vf[m] = vel * flux3(A3(q, i, kk - 2, j), A3(q, i, kk - 1, j), A3(q, i, kk, j), A3(q, i, kk + 1, j), -vel, sgv);
       }
     }
     t = t - g.rdnw[k] * (vf[1] - vf[0]);
@@ -1094,11 +1100,13 @@ void Solver::rk_tendency(int rk_step, bool zero_save) {
     LAUNCH3(this, k_invert_cqw, cq, o("cqw"));
     return;
   }
+  // the k-marching interior kernels exist for the default orders (5, 3); other orders take the gather kernels everywhere
+  const bool dflt_m = c.h_mom_adv_order == 5 && c.v_mom_adv_order == 3, dflt_s = c.h_sca_adv_order == 5 && c.v_sca_adv_order == 3;
   if (weno_m) {
     LAUNCH3(this, k_tend_u_weno, tile, s, o("ru_tend"));
     LAUNCH3(this, k_tend_v_weno, tile, s, o("rv_tend"));
     LAUNCH3(this, k_tend_w_weno, tile, s, o("rw_tend"));
-  } else if (!c.pert_coriolis && !empty(in)) {
+  } else if (dflt_m && !c.pert_coriolis && !empty(in)) {
     // momentum: k-marching kernels on the interior (mom_fast.cu), the gather kernels on the edge strips
     for (int which = 0; which < 3; which++) launch_mom_fast(this, which, in);
     for (int m = 0; m < ns; m++) {
@@ -1113,6 +1121,8 @@ void Solver::rk_tendency(int rk_step, bool zero_save) {
   }
   if (weno_t) {   // theta follows the scalars' WENO option on the last substep: gather kernel on the whole tile
     LAUNCH3(this, k_tend_t_weno, tile, s, o("t_tend"));
+  } else if (!dflt_s) {
+    LAUNCH3(this, k_tend_t, tile, s, o("t_tend"));
   } else {   // theta: k-marching flux-sharing kernel on the interior, the gather kernel on the edge strips
     launch_advect_scalar_fast(this, true, in, s.t, s.ru, s.rv, s.rom, s.mut, s.t_tendf, s.h_diabatic, o("t_tend"));
     for (int m = 0; m < ns; m++) LAUNCH3(this, k_tend_t, strips[m], s, o("t_tend"));
@@ -1125,7 +1135,7 @@ void Solver::rk_tendency(int rk_step, bool zero_save) {
   }
   {   // cqw <- 1/(1+cqw): done by k_mom_w_fast on the interior, here on what is left of the mass points
     const Box cq{q.its, std::min(q.ite, q.ide - 1), 2, q.kde - 1, q.jts, std::min(q.jte, q.jde - 1)};
-    if (!weno_m && !c.pert_coriolis && !empty(in)) {
+    if (!weno_m && dflt_m && !c.pert_coriolis && !empty(in)) {
       for (int m = 0; m < ns; m++) {
         Box sb = strips[m];
         sb.i1 = std::min(sb.i1, cq.i1); sb.j1 = std::min(sb.j1, cq.j1); sb.k0 = cq.k0; sb.k1 = cq.k1;
