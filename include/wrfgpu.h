@@ -65,7 +65,7 @@ typedef struct wrfgpu_config {
   int hypsometric_opt;                   /* 1/2 */
   int phi_adv_z;                         /* 1/2 */
   int zadvect_implicit;                  /* > 0: IEVA on the last RK substep (module_ieva_em.F) */
-  int diff_opt, km_opt;                  /* must be 0 on device */
+  int diff_opt, km_opt;                  /* 0; 1/1 constant K; 1/4 2-D Smagorinsky */
   int diff_6th_opt;                      /* 0, 1 or 2 (sixth_order_diffusion; 2 = no up-gradient fluxes) */
   int mp_physics;                        /* 0 = none(passive qv), 1 = Kessler */
   int time_step;                         /* integer namelist time_step; only its
@@ -90,6 +90,10 @@ typedef struct wrfgpu_config {
   float diff_6th_thresh;                 /* 0.10 */
   int diff_6th_slopeopt;                 /* 0/1: taper the filter over steep terrain */
   int moist_mix6_off, scalar_mix6_off;   /* 1 = no 6th-order filter on that family */
+  /* eddy-viscosity closures (Registry.EM_COMMON rconfig c_s, c_k, mix_full_fields) */
+  float c_s;                             /* Smagorinsky coefficient, 0.25 (km_opt = 3, 4) */
+  float c_k;                             /* TKE coefficient, 0.15 (km_opt = 2; not on the device yet) */
+  int mix_full_fields;                   /* 0/1: vertical shear of the full u, v in defor13/23 instead of u - u_base */
 } wrfgpu_config;
 
 typedef struct wrfgpu_solver wrfgpu_solver;   /* opaque */
@@ -165,6 +169,9 @@ int wrfgpu_start_domain     (wrfgpu_solver *s);               /* start_em.F: BC 
 int wrfgpu_rk_step_prep     (wrfgpu_solver *s, int rk_step);  /* module_em.F:37            */
 int wrfgpu_rk_phys_bc_dry_1 (wrfgpu_solver *s);               /* solve_em.F:726-754        */
 int wrfgpu_init_zero_tendency(wrfgpu_solver *s);              /* module_em.F:1920          */
+int wrfgpu_diffusion_prep   (wrfgpu_solver *s);               /* module_first_rk_step_part2.F:427-680:
+                                                                 compute_diff_metrics, cal_deform_and_div,
+                                                                 calculate_km_kh (km_opt 4), phy_bc */
 int wrfgpu_rk_tendency      (wrfgpu_solver *s, int rk_step);  /* module_em.F:190 + :959    */
 int wrfgpu_small_step_prep  (wrfgpu_solver *s, int rk_step);  /* module_small_step_em.F:16,
                                                                  calc_p_rho(0) :438, calc_coef_w :570,

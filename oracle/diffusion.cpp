@@ -7,14 +7,14 @@
 // The eddy-viscosity arrays xkmh / xkhh the reference passes in are filled by isotropic_km
 // (module_diffusion_em.F:1718-1772) with the constants khdif and khdif/prandtl on every mass point, then
 // exchanged (HALO_EM_TKE_E) and extended by phy_bc's set_physical_bc3d: every element the routines below
-// read holds the same number, so the restatement takes that number `xk` instead of an array and keeps
-// the averaging expressions (0.25*(xk+xk+xk+xk) ...) as written.
+// read holds the same number: the routines take an `XK` (oracle.h), which is either that number or -- for the
+// closures that compute K (smag2d_km, deform.cpp) -- the xkmh / xkhh array itself, indexed as in the reference.
 #include "oracle.h"
 
 namespace orc {
 
 // name: 'u', 'v', 'w' or anything else for a mass-point field ("m")
-void horizontal_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT, A1 c1, A1 c2, float xk) {
+void horizontal_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT, A1 c1, A1 c2, XK xkmhd) {
   const int ids = x.ids, ide = x.ide, jds = x.jds, jde = x.jde, kde = x.kde;
   const int its = x.its, ite = x.ite, jts = x.jts, jte = x.jte, kts = x.kts, kte = x.kte;
   const wrfgpu_config &cf = x.c;
@@ -35,15 +35,15 @@ void horizontal_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT,
     for (int j = j_start; j <= j_end; j++)
       for (int k = kts; k <= ktf; k++)
         for (int i = i_start; i <= i_end; i++) {
-          mkrdxm = (msftx(i - 1, j) / msfty(i - 1, j)) * (c1(k) * MUT(i - 1, j) + c2(k)) * xk * rdx;
-          mkrdxp = (msftx(i, j) / msfty(i, j)) * (c1(k) * MUT(i, j) + c2(k)) * xk * rdx;
+          mkrdxm = (msftx(i - 1, j) / msfty(i - 1, j)) * (c1(k) * MUT(i - 1, j) + c2(k)) * xkmhd(i - 1, k, j) * rdx;
+          mkrdxp = (msftx(i, j) / msfty(i, j)) * (c1(k) * MUT(i, j) + c2(k)) * xkmhd(i, k, j) * rdx;
           mrdx = msfux(i, j) * msfuy(i, j) * rdx;
           mkrdym = ((msfuy(i, j) + msfuy(i, j - 1)) / (msfux(i, j) + msfux(i, j - 1))) *
                    0.25f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i, j - 1) + c2(k)) + (c1(k) * MUT(i - 1, j - 1) + c2(k)) + (c1(k) * MUT(i - 1, j) + c2(k))) *
-                   0.25f * (xk + xk + xk + xk) * rdy;
+                   0.25f * (xkmhd(i, k, j) + xkmhd(i, k, j - 1) + xkmhd(i - 1, k, j - 1) + xkmhd(i - 1, k, j)) * rdy;
           mkrdyp = ((msfuy(i, j) + msfuy(i, j + 1)) / (msfux(i, j) + msfux(i, j + 1))) *
                    0.25f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i, j + 1) + c2(k)) + (c1(k) * MUT(i - 1, j + 1) + c2(k)) + (c1(k) * MUT(i - 1, j) + c2(k))) *
-                   0.25f * (xk + xk + xk + xk) * rdy;
+                   0.25f * (xkmhd(i, k, j) + xkmhd(i, k, j + 1) + xkmhd(i - 1, k, j + 1) + xkmhd(i - 1, k, j)) * rdy;
           mrdy = msfux(i, j) * msfuy(i, j) * rdy;
           tendency(i, k, j) = tendency(i, k, j) + (mrdx * (mkrdxp * (field(i + 1, k, j) - field(i, k, j)) - mkrdxm * (field(i, k, j) - field(i - 1, k, j))) +
                                                    mrdy * (mkrdyp * (field(i, k, j + 1) - field(i, k, j)) - mkrdym * (field(i, k, j) - field(i, k, j - 1))));
@@ -63,13 +63,13 @@ void horizontal_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT,
         for (int i = i_start; i <= i_end; i++) {
           mkrdxm = ((msfvx(i, j) + msfvx(i - 1, j)) / (msfvy(i, j) + msfvy(i - 1, j))) *
                    0.25f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i, j - 1) + c2(k)) + (c1(k) * MUT(i - 1, j - 1) + c2(k)) + (c1(k) * MUT(i - 1, j) + c2(k))) *
-                   0.25f * (xk + xk + xk + xk) * rdx;
+                   0.25f * (xkmhd(i, k, j) + xkmhd(i, k, j - 1) + xkmhd(i - 1, k, j - 1) + xkmhd(i - 1, k, j)) * rdx;
           mkrdxp = ((msfvx(i, j) + msfvx(i + 1, j)) / (msfvy(i, j) + msfvy(i + 1, j))) *
                    0.25f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i, j - 1) + c2(k)) + (c1(k) * MUT(i + 1, j - 1) + c2(k)) + (c1(k) * MUT(i + 1, j) + c2(k))) *
-                   0.25f * (xk + xk + xk + xk) * rdx;
+                   0.25f * (xkmhd(i, k, j) + xkmhd(i, k, j - 1) + xkmhd(i + 1, k, j - 1) + xkmhd(i + 1, k, j)) * rdx;
           mrdx = msfvx(i, j) * msfvy(i, j) * rdx;
-          mkrdym = (msfty(i, j - 1) / msftx(i, j - 1)) * xk * rdy;
-          mkrdyp = (msfty(i, j) / msftx(i, j)) * xk * rdy;
+          mkrdym = (msfty(i, j - 1) / msftx(i, j - 1)) * xkmhd(i, k, j - 1) * rdy;
+          mkrdyp = (msfty(i, j) / msftx(i, j)) * xkmhd(i, k, j) * rdy;
           mrdy = msfvx(i, j) * msfvy(i, j) * rdy;
           tendency(i, k, j) = tendency(i, k, j) + (mrdx * (mkrdxp * (field(i + 1, k, j) - field(i, k, j)) - mkrdxm * (field(i, k, j) - field(i - 1, k, j))) +
                                                    mrdy * (mkrdyp * (field(i, k, j + 1) - field(i, k, j)) - mkrdym * (field(i, k, j) - field(i, k, j - 1))));
@@ -87,17 +87,17 @@ void horizontal_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT,
         for (int i = i_start; i <= i_end; i++) {
           mkrdxm = (msfux(i, j) / msfuy(i, j)) *
                    0.25f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i - 1, j) + c2(k)) + (c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i - 1, j) + c2(k))) *
-                   0.25f * (xk + xk + xk + xk) * rdx;
+                   0.25f * (xkmhd(i, k, j) + xkmhd(i - 1, k, j) + xkmhd(i, k - 1, j) + xkmhd(i - 1, k - 1, j)) * rdx;
           mkrdxp = (msfux(i + 1, j) / msfuy(i + 1, j)) *
                    0.25f * ((c1(k) * MUT(i + 1, j) + c2(k)) + (c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i + 1, j) + c2(k)) + (c1(k) * MUT(i, j) + c2(k))) *
-                   0.25f * (xk + xk + xk + xk) * rdx;
+                   0.25f * (xkmhd(i + 1, k, j) + xkmhd(i, k, j) + xkmhd(i + 1, k - 1, j) + xkmhd(i, k - 1, j)) * rdx;
           mrdx = msftx(i, j) * msfty(i, j) * rdx;
           mkrdym = (msfvy(i, j) * msfvx_inv(i, j)) *
                    0.25f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i, j - 1) + c2(k)) + (c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i, j - 1) + c2(k))) *
-                   0.25f * (xk + xk + xk + xk) * rdy;
+                   0.25f * (xkmhd(i, k, j) + xkmhd(i, k, j - 1) + xkmhd(i, k - 1, j) + xkmhd(i, k - 1, j - 1)) * rdy;
           mkrdyp = (msfvy(i, j + 1) * msfvx_inv(i, j + 1)) *
                    0.25f * ((c1(k) * MUT(i, j + 1) + c2(k)) + (c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i, j + 1) + c2(k)) + (c1(k) * MUT(i, j) + c2(k))) *
-                   0.25f * (xk + xk + xk + xk) * rdy;
+                   0.25f * (xkmhd(i, k, j + 1) + xkmhd(i, k, j) + xkmhd(i, k - 1, j + 1) + xkmhd(i, k - 1, j)) * rdy;
           mrdy = msftx(i, j) * msfty(i, j) * rdy;
           tendency(i, k, j) = tendency(i, k, j) + (mrdx * (mkrdxp * (field(i + 1, k, j) - field(i, k, j)) - mkrdxm * (field(i, k, j) - field(i - 1, k, j))) +
                                                    mrdy * (mkrdyp * (field(i, k, j + 1) - field(i, k, j)) - mkrdym * (field(i, k, j) - field(i, k, j - 1))));
@@ -113,11 +113,11 @@ void horizontal_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT,
     for (int j = j_start; j <= j_end; j++)
       for (int k = kts; k <= ktf; k++)
         for (int i = i_start; i <= i_end; i++) {
-          mkrdxm = (msfux(i, j) / msfuy(i, j)) * 0.5f * (xk + xk) * 0.5f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i - 1, j) + c2(k))) * rdx;
-          mkrdxp = (msfux(i + 1, j) / msfuy(i + 1, j)) * 0.5f * (xk + xk) * 0.5f * ((c1(k) * MUT(i + 1, j) + c2(k)) + (c1(k) * MUT(i, j) + c2(k))) * rdx;
+          mkrdxm = (msfux(i, j) / msfuy(i, j)) * 0.5f * (xkmhd(i, k, j) + xkmhd(i - 1, k, j)) * 0.5f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i - 1, j) + c2(k))) * rdx;
+          mkrdxp = (msfux(i + 1, j) / msfuy(i + 1, j)) * 0.5f * (xkmhd(i + 1, k, j) + xkmhd(i, k, j)) * 0.5f * ((c1(k) * MUT(i + 1, j) + c2(k)) + (c1(k) * MUT(i, j) + c2(k))) * rdx;
           mrdx = msftx(i, j) * msfty(i, j) * rdx;
-          mkrdym = (msfvy(i, j) * msfvx_inv(i, j)) * 0.5f * (xk + xk) * 0.5f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i, j - 1) + c2(k))) * rdy;
-          mkrdyp = (msfvy(i, j + 1) * msfvx_inv(i, j + 1)) * 0.5f * (xk + xk) * 0.5f * ((c1(k) * MUT(i, j + 1) + c2(k)) + (c1(k) * MUT(i, j) + c2(k))) * rdy;
+          mkrdym = (msfvy(i, j) * msfvx_inv(i, j)) * 0.5f * (xkmhd(i, k, j) + xkmhd(i, k, j - 1)) * 0.5f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i, j - 1) + c2(k))) * rdy;
+          mkrdyp = (msfvy(i, j + 1) * msfvx_inv(i, j + 1)) * 0.5f * (xkmhd(i, k, j + 1) + xkmhd(i, k, j)) * 0.5f * ((c1(k) * MUT(i, j + 1) + c2(k)) + (c1(k) * MUT(i, j) + c2(k))) * rdy;
           mrdy = msftx(i, j) * msfty(i, j) * rdy;
           tendency(i, k, j) = tendency(i, k, j) + (mrdx * (mkrdxp * (field(i + 1, k, j) - field(i, k, j)) - mkrdxm * (field(i, k, j) - field(i - 1, k, j))) +
                                                    mrdy * (mkrdyp * (field(i, k, j + 1) - field(i, k, j)) - mkrdym * (field(i, k, j) - field(i, k, j - 1))));
@@ -126,7 +126,7 @@ void horizontal_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT,
 }
 
 // :2954-3060, mass-point field minus a 3-D base state (theta - t_init)
-void horizontal_diffusion_3dmp(const Cx &x, A3 field, A3 tendency, A2 MUT, A1 c1, A1 c2, A3 base_3d, float xk) {
+void horizontal_diffusion_3dmp(const Cx &x, A3 field, A3 tendency, A2 MUT, A1 c1, A1 c2, A3 base_3d, XK xkmhd) {
   const int ids = x.ids, ide = x.ide, jds = x.jds, jde = x.jde, kde = x.kde;
   const int its = x.its, ite = x.ite, jts = x.jts, jte = x.jte, kts = x.kts, kte = x.kte;
   const wrfgpu_config &cf = x.c;
@@ -144,11 +144,11 @@ void horizontal_diffusion_3dmp(const Cx &x, A3 field, A3 tendency, A2 MUT, A1 c1
   for (int j = j_start; j <= j_end; j++)
     for (int k = kts; k <= ktf; k++)
       for (int i = i_start; i <= i_end; i++) {
-        const float mkrdxm = (msfux(i, j) / msfuy(i, j)) * 0.5f * (xk + xk) * 0.5f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i - 1, j) + c2(k))) * rdx;
-        const float mkrdxp = (msfux(i + 1, j) / msfuy(i + 1, j)) * 0.5f * (xk + xk) * 0.5f * ((c1(k) * MUT(i + 1, j) + c2(k)) + (c1(k) * MUT(i, j) + c2(k))) * rdx;
+        const float mkrdxm = (msfux(i, j) / msfuy(i, j)) * 0.5f * (xkmhd(i, k, j) + xkmhd(i - 1, k, j)) * 0.5f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i - 1, j) + c2(k))) * rdx;
+        const float mkrdxp = (msfux(i + 1, j) / msfuy(i + 1, j)) * 0.5f * (xkmhd(i + 1, k, j) + xkmhd(i, k, j)) * 0.5f * ((c1(k) * MUT(i + 1, j) + c2(k)) + (c1(k) * MUT(i, j) + c2(k))) * rdx;
         const float mrdx = msftx(i, j) * msfty(i, j) * rdx;
-        const float mkrdym = (msfvy(i, j) * msfvx_inv(i, j)) * 0.5f * (xk + xk) * 0.5f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i, j - 1) + c2(k))) * rdy;
-        const float mkrdyp = (msfvy(i, j + 1) * msfvx_inv(i, j + 1)) * 0.5f * (xk + xk) * 0.5f * ((c1(k) * MUT(i, j + 1) + c2(k)) + (c1(k) * MUT(i, j) + c2(k))) * rdy;
+        const float mkrdym = (msfvy(i, j) * msfvx_inv(i, j)) * 0.5f * (xkmhd(i, k, j) + xkmhd(i, k, j - 1)) * 0.5f * ((c1(k) * MUT(i, j) + c2(k)) + (c1(k) * MUT(i, j - 1) + c2(k))) * rdy;
+        const float mkrdyp = (msfvy(i, j + 1) * msfvx_inv(i, j + 1)) * 0.5f * (xkmhd(i, k, j + 1) + xkmhd(i, k, j)) * 0.5f * ((c1(k) * MUT(i, j + 1) + c2(k)) + (c1(k) * MUT(i, j) + c2(k))) * rdy;
         const float mrdy = msftx(i, j) * msfty(i, j) * rdy;
         tendency(i, k, j) = tendency(i, k, j) +
                             (mrdx * (mkrdxp * (field(i + 1, k, j) - field(i, k, j) - base_3d(i + 1, k, j) + base_3d(i, k, j)) -

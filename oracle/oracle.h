@@ -79,6 +79,15 @@ struct Cx {
   A2 msftx, msfty, msfux, msfuy, msfvx, msfvx_inv, msfvy, f, e, sina, cosa, ht;
 };
 
+// eddy viscosity argument of the horizontal diffusion routines: the array xkmhd(i,k,j) of the reference, or the
+// constant every element of it holds when km_opt = 1 (isotropic_km)
+struct XK {
+  float c = 0.f; A3 a;
+  XK(float c_) : c(c_) {}
+  XK(A3 a_) : a(a_) {}
+  inline float operator()(int i, int k, int j) const { return a.p ? a(i, k, j) : c; }
+};
+
 inline float sign1(float a) { return std::copysign(1.0f, a); }  // SIGN(1.,a)
 
 struct Oracle {
@@ -110,6 +119,7 @@ struct Oracle {
   void rk_step_prep(int rk_step);
   void rk_phys_bc_dry_1();
   void init_zero_tendency();
+  void diffusion_prep();              // first_rk_step_part2: metrics, deformation, K (km_opt = 4)
   void rk_tendency(int rk_step);      // rk_tendency + rk_addtend_dry
   void small_step_prep(int rk_step);  // + calc_p_rho(0) + calc_coef_w + bc fills
   void advance_uv(int rk_step);
@@ -178,14 +188,19 @@ void rk_addtend_dry(const Cx &x, A3 ru_tend, A3 rv_tend, A3 rw_tend, A3 ph_tend,
 void ww_split(const Cx &x, A3 wwE, A3 wwI, A3 ww);
 void set_w_surface(const Cx &x, A3 w, A3 u, A3 v);
 // diffusion.cpp (diff_opt = 1, km_opt = 1: constant K on coordinate surfaces)
-void horizontal_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT, A1 c1, A1 c2, float xk);
-void horizontal_diffusion_3dmp(const Cx &x, A3 field, A3 tendency, A2 MUT, A1 c1, A1 c2, A3 base_3d, float xk);
+void horizontal_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT, A1 c1, A1 c2, XK xk);
+void horizontal_diffusion_3dmp(const Cx &x, A3 field, A3 tendency, A2 MUT, A1 c1, A1 c2, A3 base_3d, XK xk);
 void vertical_diffusion(const Cx &x, char name, A3 field, A3 tendency, A1 c1, A1 c2, A3 alt, A2 MUT, float kvdif);
 void vertical_diffusion_mp(const Cx &x, A3 field, A3 tendency, A1 base, A1 c1, A1 c2, A3 alt, A2 MUT, float kvdif);
 void sixth_order_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT, float dt, A1 c1, A1 c2, A3 phb);
 void vertical_diffusion_3dmp(const Cx &x, A3 field, A3 tendency, A3 base_3d, A1 c1, A1 c2, A3 alt, A2 MUT, float kvdif);
 void vertical_diffusion_u(const Cx &x, A3 field, A3 tendency, A1 u_base, A1 c1h, A1 c2h, A3 alt, A2 muu, float kvdif);
 void vertical_diffusion_v(const Cx &x, A3 field, A3 tendency, A1 v_base, A1 c1h, A1 c2h, A3 alt, A2 muv, float kvdif);
+// deform.cpp (first_rk_step_part2's diffusion preamble: metrics, deformation, 2-D Smagorinsky K)
+void compute_diff_metrics(const Cx &x, A3 ph, A3 phb, A3 z, A3 rdz, A3 rdzw, A3 zx, A3 zy);
+void cal_deform_and_div(const Cx &x, A3 u, A3 v, A3 w, A3 div, A3 defor11, A3 defor22, A3 defor33, A3 defor12, A3 defor13,
+                        A3 defor23, A3 rdz, A3 rdzw, A3 zx, A3 zy);
+void smag2d_km(const Cx &x, A3 xkmh, A3 xkmv, A3 xkhh, A3 xkhv, A3 defor11, A3 defor22, A3 defor12, A3 rdzw, A3 zx, A3 zy);
 // advect.cpp
 void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut, bool weno = false);
 void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut, bool weno = false);

@@ -42,6 +42,9 @@ Oracle::Oracle(const wrfgpu_dims &d_, const wrfgpu_config &c_) : d(d_), c(c_) {
     add("scalar_old_" + std::to_string(s), 3);
     add("scalar_tend_" + std::to_string(s), 3);
   }
+  if (c.diff_opt != 0 && c.km_opt >= 2)   // closures that compute K: metrics, deformation, K arrays (Registry.EM_COMMON state)
+    for (const char *n : {"zx", "zy", "rdz", "rdzw", "div", "defor11", "defor22", "defor33", "defor12", "defor13", "defor23",
+                          "xkmh", "xkmv", "xkhh", "xkhv"}) add(n, 3);
   // harmless defaults so that an un-set map factor does not divide by zero
   for (const char *m : {"msftx", "msfty", "msfux", "msfuy", "msfvx", "msfvx_inv", "msfvy"})
     std::fill(data[m].begin(), data[m].end(), 1.f);
@@ -152,6 +155,28 @@ void Oracle::init_zero_tendency() {
   for (int s = 1; s <= c.num_scalar; s++) zero_tend(x, a3("scalar_tend_" + std::to_string(s)));
 }
 
+// first_rk_step_part2 (dyn_em/module_first_rk_step_part2.F:427-680, :758-760): metrics of the physical-space
+// diffusion, deformation and divergence, the eddy viscosities and their boundary fills.  Run for the closures that
+// compute K (km_opt = 4 here); with km_opt = 1 every K element is a constant the diffusion routines take directly.
+void Oracle::diffusion_prep() {
+  if (c.diff_opt == 0 || c.km_opt < 2) return;
+  if (c.km_opt != 4 || c.diff_opt != 1) throw std::runtime_error("oracle: only km_opt = 4 with diff_opt = 1 is restated");
+  A3 ph = a3("ph_2"), phb = a3("phb"), z = a3("z"), rdz = a3("rdz"), rdzw = a3("rdzw"), zx = a3("zx"), zy = a3("zy");
+  par([&](const Cx &xt) { compute_diff_metrics(xt, ph, phb, z, rdz, rdzw, zx, zy); });
+  halo("HALO_EM_TKE_C");   // + PERIOD_BDY_EM_A1, :446-447
+  bc("rdzw", 'w'); bc("rdz", 'w'); bc("z", 'w'); bc("zx", 'e'); bc("zy", 'f');
+  par([&](const Cx &xt) {
+    cal_deform_and_div(xt, a3("u_2"), a3("v_2"), a3("w_2"), a3("div"), a3("defor11"), a3("defor22"), a3("defor33"), a3("defor12"),
+                       a3("defor13"), a3("defor23"), rdz, rdzw, zx, zy);
+  });
+  halo("HALO_EM_TKE_D");   // :571
+  par([&](const Cx &xt) {
+    smag2d_km(xt, a3("xkmh"), a3("xkmv"), a3("xkhh"), a3("xkhv"), a3("defor11"), a3("defor22"), a3("defor12"), rdzw, zx, zy);
+  });
+  halo("HALO_EM_TKE_E");   // + PERIOD_BDY_EM_PHY_BC, HALO_EM_PHYS_DIFFUSION, :644-650, :759
+  bc("xkmh", 't'); bc("xkhh", 't');   // phy_bc, module_diffusion_em.F:5901 (the diff_opt = 2 part fills the rest)
+}
+
 // module_em.F:190-955 rk_tendency followed by rk_addtend_dry (solve_em.F:881-1007)
 void Oracle::rk_tendency(int rk_step) {
   A3 ru_tend = a3("ru_tend"), rv_tend = a3("rv_tend"), rw_tend = a3("rw_tend"), ph_tend = a3("ph_tend"), t_tend = a3("t_tend");
@@ -202,7 +227,8 @@ void Oracle::rk_tendency(int rk_step) {
   if (rk_step == 1 && c.diff_opt == 1) {   // forward_step: diff_opt1, module_em.F:802-878 (bl_pbl_physics = 0)
     // xkmhd = grid%xkmh = khdif and xkhh = khdif/prandtl everywhere (isotropic_km, module_diffusion_em.F:1718-1772)
     const float prandtl = 1.f / 3.0f;
-    const float xkmh = c.khdif, xkhh = c.khdif / prandtl, kvdif = c.kvdif;
+    const float kvdif = c.kvdif;
+    const XK xkmh = c.km_opt == 1 ? XK(c.khdif) : XK(a3("xkmh")), xkhh = c.km_opt == 1 ? XK(c.khdif / prandtl) : XK(a3("xkhh"));
     A3 alt = a3("alt");
     par([&](const Cx &xt) { horizontal_diffusion(xt, 'u', u, a3("ru_tendf"), mut, xt.c1h, xt.c2h, xkmh); });
     par([&](const Cx &xt) { horizontal_diffusion(xt, 'v', v, a3("rv_tendf"), mut, xt.c1h, xt.c2h, xkmh); });
@@ -371,7 +397,8 @@ void Oracle::rk_scalar_step(int rk_step) {
       par([&](const Cx &xt) { advect_s_implicit(xt, a3(s.o), a3("advect_tend"), a3("wwI"), a2("mut_old"), a2("muts"), dt_rk); });
     if (rk_step == 1 && c.diff_opt == 1) {   // rk_step_1: diff_opt1, module_em.F:1378-1419 (xkmhd = grid%xkhh, solve_em.F:2230)
       const float prandtl = 1.f / 3.0f;
-      const float xkhh = c.khdif / prandtl, kvdq = c.kvdif / prandtl;
+      const float kvdq = c.kvdif / prandtl;
+      const XK xkhh = c.km_opt == 1 ? XK(c.khdif / prandtl) : XK(a3("xkhh"));
       par([&](const Cx &xt) { horizontal_diffusion(xt, 'm', a3(s.f), a3(s.t), a2("muts"), xt.c1h, xt.c2h, xkhh); });
       if (s.f == "moist_qv")
         par([&](const Cx &xt) { vertical_diffusion_mp(xt, a3(s.f), a3(s.t), xt.qv_base, xt.c1h, xt.c2h, a3("alt"), a2("muts"), kvdq); });
@@ -495,6 +522,7 @@ void Oracle::step() {
     halo("HALO_EM_A");   // + PERIOD_BDY_EM_A, solve_em.F:708,715
     rk_phys_bc_dry_1();
     if (rk_step == 1) init_zero_tendency();
+    if (rk_step == 1) diffusion_prep();
     rk_tendency(rk_step);
     small_step_prep(rk_step);
     for (int it = 1; it <= ns; it++) {
@@ -560,6 +588,7 @@ int oracle_rk_step_prep(Oracle *o, int rk) { OGUARD(o->rk_step_prep(rk)) }
 int oracle_rk_phys_bc_dry_1(Oracle *o) { OGUARD(o->rk_phys_bc_dry_1()) }
 int oracle_init_zero_tendency(Oracle *o) { OGUARD(o->init_zero_tendency()) }
 int oracle_rk_tendency(Oracle *o, int rk) { OGUARD(o->rk_tendency(rk)) }
+int oracle_diffusion_prep(Oracle *o) { OGUARD(o->diffusion_prep()) }
 int oracle_small_step_prep(Oracle *o, int rk) { OGUARD(o->small_step_prep(rk)) }
 int oracle_advance_uv(Oracle *o, int rk) { OGUARD(o->advance_uv(rk)) }
 int oracle_advance_mu_t(Oracle *o, int rk) { OGUARD(o->advance_mu_t(rk)) }

@@ -147,6 +147,14 @@ def small_cases():
         "order63_periodic": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=2,
                                                        scalar_adv_opt=0, h_mom_adv_order=6, h_sca_adv_order=6)),
         "order_mixed": make_case("b_wave", nx=21, ny=31, nz=17, h_mom_adv_order=6, v_sca_adv_order=4, moist_adv_opt=4, momentum_adv_opt=3),
+        # 2-D Smagorinsky closure on coordinate surfaces (diff_opt 1 / km_opt 4, the usual real-data setting):
+        # open + Kessler, doubly periodic with map factors and tracers, over the hill (terrain slopes zx in the deformation),
+        # periodic x / symmetric y with vertical constant-K mixing on top
+        "smag2d": make_case("quarter_ss", nx=26, ny=24, nz=21, diff_opt=1, km_opt=4),
+        "smag2d_periodic": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=2,
+                                                      diff_opt=1, km_opt=4, c_s=0.5)),
+        "smag2d_hill": make_case("hill2d_x", nx=62, ny=3, nz=21, diff_opt=1, km_opt=4, mix_full_fields=1),
+        "smag2d_b_wave": make_case("b_wave", nx=21, ny=31, nz=17, diff_opt=1, km_opt=4, kvdif=5.0),
         "ieva_weno_hill": with_updraft(make_case("hill2d_x", nx=62, ny=3, nz=41, zadvect_implicit=1, momentum_adv_opt=3,
                                                  moist_adv_opt=3), 60.0, conv=70.0),
     }
@@ -206,7 +214,7 @@ def phase_sequence(case):
         ns = 1 if (c.rk_ord == 3 and rk == 1) else (nss // 2 if rk < c.rk_ord else nss)
         seq += [("rk_step_prep", (rk,)), ("rk_phys_bc_dry_1", ())]
         if rk == 1:
-            seq.append(("init_zero_tendency", ()))
+            seq += [("init_zero_tendency", ()), ("diffusion_prep", ())]
         seq += [("rk_tendency", (rk,)), ("small_step_prep", (rk,))]
         for it in range(1, ns + 1):
             seq += [("advance_uv", (rk,)), ("advance_mu_t", (rk,)), ("advance_w", (rk,)), ("sumflux", (rk, it)), ("calc_p_rho", (it,))]

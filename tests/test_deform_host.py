@@ -1,0 +1,76 @@
+"""The diffusion preamble (compute_diff_metrics, cal_deform_and_div, smag2d_km -- SURVEY.md 8f-1) on the device is written
+as __host__ __device__ point functions (wrf_b200/csrc/deform.cuh).  Here the same header is compiled for the host
+(tests/deform_shim.cu, nvcc, no GPU needed), run in plain loops and compared with the oracle's restatement of the reference
+routines bit for bit, on every lateral boundary type -- so the GPU parity tests of these kernels only have to confirm that
+the device evaluates the same IEEE operations."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.oracle_lib import Oracle
+from tests.parity import small_cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "_build")
+ORDER = ("ph_2", "phb", "u_2", "v_2", "w_2", "z", "rdz", "rdzw", "zx", "zy", "div", "defor11", "defor22", "defor33", "defor12", "defor13",
+         "defor23", "xkmh", "xkmv", "xkhh", "xkhv", "msftx", "msfty", "msfux", "msfuy", "msfvx", "msfvy", "fnm", "fnp", "dn", "dnw",
+         "u_base", "v_base")
+OUT = ORDER[5:21]
+
+
+@pytest.fixture(scope="module")
+def shim():
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, "deform_shim.so")
+    src = os.path.join(ROOT, "tests", "deform_shim.cu")
+    deps = [src] + [os.path.join(ROOT, "wrf_b200", "csrc", f) for f in ("deform.cuh", "common.cuh")] + [os.path.join(ROOT, "include", "wrfgpu.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in deps):
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-o", so, src])
+    L = ctypes.CDLL(so)
+    L.deform_shim_run.restype = ctypes.c_int
+    return L
+
+
+def run_shim(L, case, arrays, stage):
+    ptrs = (ctypes.c_void_p * len(ORDER))(*[arrays[n].ctypes.data for n in ORDER])
+    assert L.deform_shim_run(ctypes.c_int(stage), ctypes.byref(case.dims), ctypes.byref(case.config), ptrs) == 0
+
+
+@pytest.mark.parametrize("name", ["smag2d", "smag2d_periodic", "smag2d_hill", "smag2d_b_wave"])
+def test_device_point_functions_equal_the_oracle(shim, name):
+    case = small_cases()[name]
+    o = Oracle(case)
+    o.start_domain()
+    o.step(2)   # the state (and the stale contents of the 16 work fields) of a running model
+    for ph, args in (("rk_step_prep", (1,)), ("rk_phys_bc_dry_1", ()), ("init_zero_tendency", ())):
+        o.call(ph, *args)
+    arrays = {n: np.ascontiguousarray(o.get(n)).copy() for n in ORDER}
+    applier = Oracle(case)   # set_physical_bc of the oracle, applied to the shim's arrays between the stages
+
+    def bc(n, var):
+        applier.set(n, arrays[n])
+        applier.bc(n, var)
+        arrays[n][...] = applier.get(n)
+
+    run_shim(shim, case, arrays, 1)
+    for n, var in (("rdzw", "w"), ("rdz", "w"), ("z", "w"), ("zx", "e"), ("zy", "f")):
+        bc(n, var)
+    run_shim(shim, case, arrays, 2)
+    run_shim(shim, case, arrays, 3)
+    bc("xkmh", "t"); bc("xkhh", "t")
+    o.call("diffusion_prep")
+    ref = {n: o.get(n) for n in OUT}
+    bad = []
+    for n in OUT:
+        a, b = arrays[n].view(np.uint32), ref[n].view(np.uint32)
+        if not np.array_equal(a, b):
+            w = np.argwhere(a != b)
+            bad.append((n, len(w), w[:3].tolist(), float(np.abs(arrays[n] - ref[n]).max())))
+    assert not bad, bad
+    assert float(ref["xkmh"].max()) > 0.0

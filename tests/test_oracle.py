@@ -229,6 +229,46 @@ def test_constant_k_diffusion_decays_a_sinusoid_at_the_analytic_rate():
     assert np.abs(o.get("w_2")).max() < 1e-3                          # and the atmosphere stayed at rest
 
 
+def test_smag2d_k_of_a_sheared_jet_is_the_documented_formula():
+    """diff_opt = 1 / km_opt = 4 (smag2d_km, module_diffusion_em.F:1934-2043): K_h = c_s^2 l^2 |D| with l^2 = dx dy and
+    D^2 = 0.25 (D11 - D22)^2 + D12^2 (4-point average of D12 to the mass point).  For v = V sin(2 pi x / L) on a flat,
+    Cartesian, periodic-x grid D11 = D22 = 0 and D12 = dv/dx (cal_deform_and_div :611-870 without its terrain terms), so with
+    the centred differences the code uses K(i) = c_s^2 dx dy |V (sin(k x_{i+1}) - sin(k x_{i-1})) / (2 dx)| -- the x-average
+    of the two D12 that flank a mass point; xkhh = K / prandtl = 3 K; and the tendency of v is the divergence of K dv/dx."""
+    nx, L, V = 33, 32, 8.0
+    case = make_case("b_wave", nx=nx, ny=12, nz=11, calm=True, diff_opt=1, km_opt=4, c_s=0.25)
+    d, c = case.dims, case.config
+    ii = np.arange(d.ims, d.ime + 1, dtype=np.float64)
+    vprof = (V * np.sin(2 * np.pi * (ii - 1) / L)).astype(np.float32)          # v sits at the mass-point x
+    for n in ("v_1", "v_2"):
+        case.fields[n][:] = vprof[None, None, :]
+        case.fields[n][:, -1, :] = 0
+    o = Oracle(case)
+    o.start_domain()
+    for ph, args in (("rk_step_prep", (1,)), ("rk_phys_bc_dry_1", ()), ("init_zero_tendency", ()), ("diffusion_prep", ())):
+        o.call(ph, *args)
+    j, k = 5 - d.jms, 3
+    sl = slice(1 - d.ims, 1 - d.ims + L)
+    x = np.arange(L, dtype=np.float64)
+    kk = 2 * np.pi / L
+    d12_u = V * (np.sin(kk * x) - np.sin(kk * (x - 1))) / c.dx                 # D12 at the u-point west of mass point i
+    want = c.c_s ** 2 * c.dx * c.dy * np.abs(0.5 * (d12_u + np.roll(d12_u, -1)))
+    got = o.get("xkmh")[j, k, sl].astype(np.float64)
+    assert np.allclose(got, want, rtol=2e-5, atol=1e-3 * want.max()), np.abs(got - want).max()
+    assert np.allclose(o.get("xkhh")[j, k, sl], 3.0 * got, rtol=1e-6)
+    assert np.abs(o.get("defor11")[j, k, sl]).max() < 1e-9 and np.abs(o.get("defor13")).max() == 0.0
+    assert want.max() > 5.0e3                                                   # a K that matters on this grid (dx = 100 km)
+    # the diffusion tendency it feeds: rv_tendf = d/dx ( mu K_u dv/dx ) with K_u the 4-point average to the u-point
+    o.call("rk_tendency", 1)
+    mu = float(o.get("mut")[j, 1 - d.ims])
+    c1, c2 = float(o.get("c1h")[k]), float(o.get("c2h")[k])
+    ku = 0.5 * (got + np.roll(got, 1))
+    flux = (c1 * mu + c2) * ku * d12_u
+    want_t = (np.roll(flux, -1) - flux) / c.dx
+    got_t = o.get("rv_tendf")[j, k, sl].astype(np.float64)
+    assert np.allclose(got_t, want_t, rtol=1e-4, atol=2e-4 * np.abs(want_t).max()), np.abs(got_t - want_t).max()
+
+
 def test_sixth_order_filter_damps_the_two_delta_x_wave_at_the_documented_rate():
     """sixth_order_diffusion (module_big_step_utilities_em.F:6220): for q = (-1)^i the flux differences are +-32 q, so the
     tendency is -64 * (factor * 0.015625 / (2 dt')) * mu * q = -(factor / (2 dt')) mu q: the filter removes factor / 2 of a

@@ -1,0 +1,56 @@
+// deform.cu -- the diffusion preamble of the first RK substep for the closures that compute K
+// (first_rk_step_part2, dyn_em/module_first_rk_step_part2.F:427-680): compute_diff_metrics, cal_deform_and_div,
+// the eddy viscosities (smag2d_km, km_opt = 4), their exchanges (HALO_EM_TKE_C / _D / _E) and boundary fills.
+// Three launches per time step; the point functions and their derivation are in deform.cuh.
+#include "deform.cuh"
+
+namespace wg {
+
+__global__ void k_diff_metrics(const Geo g, Box b, cfp ph, cfp phb, fp z, fp rdz, fp rdzw, fp zx, fp zy) {
+  TID3;
+  diff_metrics_point(g, i, k, j, ph, phb, z, rdz, rdzw, zx, zy);
+}
+
+__global__ void k_deform(const Geo g, Box b, DefR r, DefIn s, DefOut o) {
+  TID3;
+  deform_point(g, r, s, o, i, k, j);
+}
+
+__global__ void k_smag2d(const Geo g, Box b, SmagIn s, fp xkmh, fp xkmv, fp xkhh, fp xkhv) {
+  TID3;
+  smag2d_point(g, s, i, k, j, xkmh, xkmv, xkhh, xkhv);
+}
+
+void Solver::diffusion_prep() {
+  if (c.diff_opt == 0 || c.km_opt < 2) return;   // km_opt = 1: K is a constant the diffusion kernels take by value
+  const Geo &q = g;
+  // compute_diff_metrics: rdz, rdzw on rows jts-1..jte, the rest on the tile
+  LAUNCH3(this, k_diff_metrics, (Box{q.its, q.ite, 1, q.kde, q.jts - 1, q.jte}), o("ph_2"), o("phb"), o("z"), o("rdz"), o("rdzw"), o("zx"), o("zy"));
+  halo("HALO_EM_TKE_C");   // + PERIOD_BDY_EM_A1 (:446-447)
+  bc({{"rdzw", 'w'}, {"rdz", 'w'}, {"z", 'w'}, {"zx", 'e'}, {"zy", 'f'}});
+  // cal_deform_and_div
+  DefIn in;
+  in.u = o("u_2"); in.v = o("v_2"); in.w = o("w_2"); in.rdz = o("rdz"); in.rdzw = o("rdzw"); in.zx = o("zx"); in.zy = o("zy");
+  in.dn = o("dn"); in.dnw = o("dnw"); in.u_base = o("u_base"); in.v_base = o("v_base");
+  DefOut out;
+  out.div = o("div"); out.defor11 = o("defor11"); out.defor22 = o("defor22"); out.defor33 = o("defor33");
+  out.defor12 = o("defor12"); out.defor13 = o("defor13"); out.defor23 = o("defor23");
+  const DefR r = def_ranges(q, c.mix_full_fields);
+  LAUNCH3(this, k_deform, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), r, in, out);
+  halo("HALO_EM_TKE_D");   // :571
+  // calculate_km_kh -> smag2d_km on its computed range (module_diffusion_em.F:1974-1989)
+  int i_start = q.its, i_end = std::min(q.ite, q.ide - 1), j_start = q.jts, j_end = std::min(q.jte, q.jde - 1);
+  if (q.open_xs) i_start = std::max(q.ids + 1, q.its);
+  if (q.open_xe) i_end = std::min(q.ide - 2, q.ite);
+  if (q.open_ys) j_start = std::max(q.jds + 1, q.jts);
+  if (q.open_ye) j_end = std::min(q.jde - 2, q.jte);
+  if (q.periodic_x) { i_start = q.its; i_end = std::min(q.ite, q.ide - 1); }
+  SmagIn sm;
+  sm.defor11 = o("defor11"); sm.defor22 = o("defor22"); sm.defor12 = o("defor12"); sm.rdzw = o("rdzw"); sm.zx = o("zx"); sm.zy = o("zy");
+  sm.dx = c.dx; sm.dy = c.dy; sm.c_s = c.c_s; sm.diff_opt = c.diff_opt;
+  LAUNCH3(this, k_smag2d, (Box{i_start, i_end, 1, q.kde - 1, j_start, j_end}), sm, o("xkmh"), o("xkmv"), o("xkhh"), o("xkhv"));
+  halo("HALO_EM_TKE_E");   // + PERIOD_BDY_EM_PHY_BC, HALO_EM_PHYS_DIFFUSION (:644-650, :759)
+  bc({{"xkmh", 't'}, {"xkhh", 't'}});   // phy_bc (module_diffusion_em.F:5901), diff_opt = 1 part
+}
+
+}  // namespace wg

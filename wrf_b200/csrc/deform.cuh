@@ -1,0 +1,253 @@
+// deform.cuh -- point functions of the diffusion preamble: compute_diff_metrics
+// (dyn_em/module_diffusion_em.F:6882-7129), cal_deform_and_div (:17-1189) and smag2d_km (:1934-2043).
+//
+// The reference sweeps tile-sized work arrays (hat, hatavg, tmp1) through a dozen loop nests per tensor component.
+// Every one of them is a pure function of a few neighbouring points of u, v, w and the metrics, so here the thread
+// of a point evaluates them in registers, in the reference's order of operations, and writes each output once:
+// no work arrays, one pass over memory.  The functions are __host__ __device__ so that tests/deform_shim.cu can run
+// exactly this code on the CPU against the oracle.
+//
+// The reference finishes defor12 / defor13 / defor23 by copying the first computed row / column onto the domain
+// edge it skipped (:826-870, :1143-1187), in the order west, south, east, north.  The net effect of the four copies
+// is "take the value of the nearest computed point", which is what the thread of an edge point evaluates (DefR holds
+// the computed ranges and which edges are copied).  Elements the reference never writes are not written here either.
+#pragma once
+#include "common.cuh"
+
+namespace wg {
+
+#ifdef __CUDACC__
+#define WG_HD __host__ __device__ __forceinline__
+#else
+#define WG_HD inline
+#endif
+
+struct DefIn {
+  cfp u, v, w, rdz, rdzw, zx, zy;
+  const float *dn, *dnw, *u_base, *v_base;   // origin shifted 1-D
+};
+struct DefOut { fp div, defor11, defor22, defor33, defor12, defor13, defor23; };
+
+// loop ranges of cal_deform_and_div on this tile
+struct DefR {
+  int a_ie, a_je;                              // defor11/22/33, div: its..a_ie, jts..a_je
+  int i0_12, i1_12, j0_12, j1_12;              // defor12 computed range
+  int cxs12, cys12, cxe12, cye12;              // ... and its edge copies
+  int i0_13, i1_13, j0_13, j1_13;              // defor13
+  int i0_23, i1_23, j0_23, j1_23;              // defor23
+  int cxs, cys, cxe, cye;                      // edge copies of defor13 and defor23 (ranges of the defor23 block)
+  int ktf, kte, mix_full_fields;
+};
+
+inline DefR def_ranges(const GeoBase &g, int mix_full_fields) {
+  DefR r;
+  const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
+  r.kte = g.kde; r.ktf = g.kde - 1; r.mix_full_fields = mix_full_fields;
+  r.a_ie = ite < ide - 1 ? ite : ide - 1; r.a_je = jte < jde - 1 ? jte : jde - 1;
+  int i_start = its, i_end = ite, j_start = jts, j_end = jte;
+  if (g.open_xs) i_start = ids + 1 > its ? ids + 1 : its;
+  if (g.open_xe) i_end = ide - 1 < ite ? ide - 1 : ite;
+  if (g.open_ys) j_start = jds + 1 > jts ? jds + 1 : jts;
+  if (g.open_ye) j_end = jde - 1 < jte ? jde - 1 : jte;
+  if (g.periodic_x) { i_start = its; i_end = ite; }
+  r.i0_12 = i_start; r.i1_12 = i_end; r.j0_12 = j_start; r.j1_12 = j_end;
+  r.cxs12 = !g.periodic_x && i_start == ids + 1; r.cys12 = !g.periodic_y && j_start == jds + 1;
+  r.cxe12 = !g.periodic_x && i_end == ide - 1; r.cye12 = !g.periodic_y && j_end == jde - 1;
+  i_start = its; i_end = r.a_ie; j_start = jts; j_end = r.a_je;
+  if (g.open_xs) i_start = ids + 1 > its ? ids + 1 : its;
+  if (g.open_ys) j_start = jds + 1 > jts ? jds + 1 : jts;
+  if (g.periodic_x) i_start = its;
+  if (g.periodic_y) j_end = jte < jde ? jte : jde;
+  r.i0_23 = i_start; r.i1_23 = g.periodic_x ? r.a_ie : i_end; r.j0_23 = j_start; r.j1_23 = j_end;
+  r.i0_13 = i_start; r.i1_13 = g.periodic_x ? (ite < ide ? ite : ide) : i_end; r.j0_13 = j_start; r.j1_13 = j_end;
+  r.cxs = !g.periodic_x && r.i0_23 == ids + 1; r.cys = !g.periodic_y && r.j0_23 == jds + 1;
+  r.cxe = !g.periodic_x && r.i1_23 == ide - 1; r.cye = !g.periodic_y && r.j1_23 == jde - 1;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------ compute_diff_metrics
+// thread box: i in its..ite, k in 1..kte, j in jts-1..jte
+WG_HD void diff_metrics_point(const Geo &g, int i, int k, int j, cfp ph, cfp phb, fp z, fp rdz, fp rdzw, fp zx, fp zy) {
+  const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
+  const int ktf = g.kde - 1;
+  const int i_end = min(ite, ide - 1), j_end = min(jte, jde - 1);
+  const float rdx = g.rdx, rdy = g.rdy;
+  if (i <= i_end && k <= ktf) {   // rows jts-1..jte (:6928-6965)
+    const float zw0 = (A3(ph, i, k, j) + A3(phb, i, k, j)) / WG_G, zw1 = (A3(ph, i, k + 1, j) + A3(phb, i, k + 1, j)) / WG_G;
+    A3(rdzw, i, k, j) = 1.0f / (zw1 - zw0);
+    if (k == 1) A3(rdz, i, 1, j) = 2.f / (zw1 - zw0);
+    else {
+      const float zwm = (A3(ph, i, k - 1, j) + A3(phb, i, k - 1, j)) / WG_G;
+      A3(rdz, i, k, j) = 2.0f / (zw1 - zwm);
+    }
+  }
+  if (j < jts) return;
+  // zx (:6972-6990; columns ids and ide :7010-7055)
+  if (j <= j_end) {
+    if (i >= max(ids + 1, its) && i <= i_end) {
+      float v = rdx * (A3(phb, i, k, j) - A3(phb, i - 1, k, j)) / WG_G;
+      v = v + rdx * (A3(ph, i, k, j) - A3(ph, i - 1, k, j)) / WG_G;
+      A3(zx, i, k, j) = v;
+    } else if (((i == ids && its == ids) || (i == ide && ite == ide)) && k <= ktf) {
+      float v = 0.0f;
+      if (g.periodic_x) {
+        v = rdx * (A3(phb, i, k, j) - A3(phb, i - 1, k, j)) / WG_G;
+        v = v + rdx * (A3(ph, i, k, j) - A3(ph, i - 1, k, j)) / WG_G;
+      }
+      A3(zx, i, k, j) = v;
+    }
+  }
+  // zy (:6992-7008; rows jds and jde :7057-7110)
+  if (i <= i_end) {
+    if (j >= max(jds + 1, jts) && j <= j_end) {
+      float v = rdy * (A3(phb, i, k, j) - A3(phb, i, k, j - 1)) / WG_G;
+      v = v + rdy * (A3(ph, i, k, j) - A3(ph, i, k, j - 1)) / WG_G;
+      A3(zy, i, k, j) = v;
+    } else if (((j == jds && jts == jds) || (j == jde && jte == jde)) && k <= ktf) {
+      float v = 0.0f;
+      if (g.periodic_y) {
+        v = rdy * (A3(phb, i, k, j) - A3(phb, i, k, j - 1)) / WG_G;
+        v = v + rdy * (A3(ph, i, k, j) - A3(ph, i, k, j - 1)) / WG_G;
+      }
+      A3(zy, i, k, j) = v;
+    }
+    if (j <= j_end && k <= ktf) A3(z, i, k, j) = 0.5f * (A3(ph, i, k, j) + A3(phb, i, k, j) + A3(ph, i, k + 1, j) + A3(phb, i, k + 1, j)) / WG_G;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ cal_deform_and_div
+WG_HD float hat_(const Geo &g, cfp vel, cfp msf, int i, int k, int j) { return A3(vel, i, k, j) / A2(msf, i, j); }
+// hatavg of the two columns A = (ia,ja), B = (ib,jb) at w-level k (:230-262 and the three blocks like it)
+WG_HD float hatavg_(const Geo &g, cfp vel, cfp msf, int ia, int ja, int ib, int jb, int k, int kte, float cft1, float cft2) {
+  if (k == 1)
+    return 0.5f * (g.cf1 * hat_(g, vel, msf, ia, 1, ja) + g.cf2 * hat_(g, vel, msf, ia, 2, ja) + g.cf3 * hat_(g, vel, msf, ia, 3, ja) +
+                   g.cf1 * hat_(g, vel, msf, ib, 1, jb) + g.cf2 * hat_(g, vel, msf, ib, 2, jb) + g.cf3 * hat_(g, vel, msf, ib, 3, jb));
+  if (k == kte)
+    return 0.5f * (cft1 * (hat_(g, vel, msf, ia, kte - 1, ja) + hat_(g, vel, msf, ib, kte - 1, jb)) +
+                   cft2 * (hat_(g, vel, msf, ia, kte - 2, ja) + hat_(g, vel, msf, ib, kte - 2, jb)));
+  return 0.5f * (g.fnm[k] * (hat_(g, vel, msf, ia, k, ja) + hat_(g, vel, msf, ib, k, jb)) +
+                 g.fnp[k] * (hat_(g, vel, msf, ia, k - 1, ja) + hat_(g, vel, msf, ib, k - 1, jb)));
+}
+
+WG_HD float defor12_at(const Geo &g, const DefIn &s, int i, int k, int j, int kte, float cft1, float cft2) {
+  cfp zx = s.zx, zy = s.zy, rdzw = s.rdzw;
+  const float mm = 0.25f * (A2(g.msfux, i, j - 1) + A2(g.msfux, i, j)) * (A2(g.msfvy, i - 1, j) + A2(g.msfvy, i, j));
+  const float tmpzy = 0.25f * (A3(zy, i - 1, k, j) + A3(zy, i, k, j) + A3(zy, i - 1, k + 1, j) + A3(zy, i, k + 1, j));
+  float tmp1 = (hatavg_(g, s.u, g.msfux, i, j - 1, i, j, k + 1, kte, cft1, cft2) - hatavg_(g, s.u, g.msfux, i, j - 1, i, j, k, kte, cft1, cft2)) *
+               0.25f * tmpzy * (A3(rdzw, i, k, j) + A3(rdzw, i - 1, k, j) + A3(rdzw, i - 1, k, j - 1) + A3(rdzw, i, k, j - 1));
+  float d12 = mm * (g.rdy * (hat_(g, s.u, g.msfux, i, k, j) - hat_(g, s.u, g.msfux, i, k, j - 1)) - tmp1);
+  const float tmpzx = 0.25f * (A3(zx, i, k, j - 1) + A3(zx, i, k, j) + A3(zx, i, k + 1, j - 1) + A3(zx, i, k + 1, j));
+  tmp1 = (hatavg_(g, s.v, g.msfvy, i - 1, j, i, j, k + 1, kte, cft1, cft2) - hatavg_(g, s.v, g.msfvy, i - 1, j, i, j, k, kte, cft1, cft2)) *
+         0.25f * tmpzx * (A3(rdzw, i, k, j) + A3(rdzw, i, k, j - 1) + A3(rdzw, i - 1, k, j - 1) + A3(rdzw, i - 1, k, j));
+  d12 = d12 + mm * (g.rdx * (hat_(g, s.v, g.msfvy, i, k, j) - hat_(g, s.v, g.msfvy, i - 1, k, j)) - tmp1);
+  return d12;
+}
+
+// k in 1..kte; 0 at k = 1 and k = kte
+WG_HD float defor13_at(const Geo &g, const DefIn &s, int i, int k, int j, int kte, int mix_full_fields) {
+  if (k == 1 || k == kte) return 0.0f;
+  cfp w = s.w, rdz = s.rdz, u = s.u;
+  const float mm = A2(g.msfux, i, j) * A2(g.msfuy, i, j);
+  const float h00 = hat_(g, w, g.msfty, i, k, j), h0p = hat_(g, w, g.msfty, i, k + 1, j), hm0 = hat_(g, w, g.msfty, i - 1, k, j),
+              hmp = hat_(g, w, g.msfty, i - 1, k + 1, j), h0m = hat_(g, w, g.msfty, i, k - 1, j), hmm = hat_(g, w, g.msfty, i - 1, k - 1, j);
+  const float hak = 0.25f * (h00 + h0p + hm0 + hmp), hakm = 0.25f * (h0m + h00 + hmm + hm0);
+  float tmp1 = (hak - hakm) * A3(s.zx, i, k, j) * 0.5f * (A3(rdz, i, k, j) + A3(rdz, i - 1, k, j));
+  float d = mm * (g.rdx * (h00 - hm0) - tmp1);
+  if (mix_full_fields) tmp1 = (A3(u, i, k, j) - A3(u, i, k - 1, j)) * 0.5f * (A3(rdz, i, k, j) + A3(rdz, i - 1, k, j));
+  else tmp1 = (A3(u, i, k, j) - s.u_base[k] - A3(u, i, k - 1, j) + s.u_base[k - 1]) * 0.5f * (A3(rdz, i, k, j) + A3(rdz, i - 1, k, j));
+  return d + tmp1;
+}
+WG_HD float defor23_at(const Geo &g, const DefIn &s, int i, int k, int j, int kte, int mix_full_fields) {
+  if (k == 1 || k == kte) return 0.0f;
+  cfp w = s.w, rdz = s.rdz, v = s.v;
+  const float mm = A2(g.msfvx, i, j) * A2(g.msfvy, i, j);
+  const float h00 = hat_(g, w, g.msftx, i, k, j), h0p = hat_(g, w, g.msftx, i, k + 1, j), hm0 = hat_(g, w, g.msftx, i, k, j - 1),
+              hmp = hat_(g, w, g.msftx, i, k + 1, j - 1), h0m = hat_(g, w, g.msftx, i, k - 1, j), hmm = hat_(g, w, g.msftx, i, k - 1, j - 1);
+  const float hak = 0.25f * (h00 + h0p + hm0 + hmp), hakm = 0.25f * (h0m + h00 + hmm + hm0);
+  float tmp1 = (hak - hakm) * A3(s.zy, i, k, j) * 0.5f * (A3(rdz, i, k, j) + A3(rdz, i, k, j - 1));
+  float d = mm * (g.rdy * (h00 - hm0) - tmp1);
+  if (mix_full_fields) tmp1 = (A3(v, i, k, j) - A3(v, i, k - 1, j)) * 0.5f * (A3(rdz, i, k, j) + A3(rdz, i, k, j - 1));
+  else tmp1 = (A3(v, i, k, j) - s.v_base[k] - A3(v, i, k - 1, j) + s.v_base[k - 1]) * 0.5f * (A3(rdz, i, k, j) + A3(rdz, i, k, j - 1));
+  return d + tmp1;
+}
+
+// thread box: i in its..ite, k in 1..kte, j in jts..jte
+WG_HD void deform_point(const Geo &g, const DefR &r, const DefIn &s, const DefOut &o, int i, int k, int j) {
+  const int kte = r.kte, ktf = r.ktf;
+  const float cft2 = -0.5f * s.dnw[kte - 1] / s.dn[kte - 1];
+  const float cft1 = 1.0f - cft2;
+  cfp zx = s.zx, zy = s.zy, rdzw = s.rdzw, w = s.w;
+  // defor11, defor22, defor33, div (:205-609)
+  if (i <= r.a_ie && j <= r.a_je && k <= ktf) {
+    const float mm = A2(g.msftx, i, j) * A2(g.msfty, i, j);
+    const float tmpzx = 0.25f * (A3(zx, i, k, j) + A3(zx, i + 1, k, j) + A3(zx, i, k + 1, j) + A3(zx, i + 1, k + 1, j));
+    float tmp1 = (hatavg_(g, s.u, g.msfuy, i, j, i + 1, j, k + 1, kte, cft1, cft2) - hatavg_(g, s.u, g.msfuy, i, j, i + 1, j, k, kte, cft1, cft2)) *
+                 tmpzx * A3(rdzw, i, k, j);
+    tmp1 = mm * (g.rdx * (hat_(g, s.u, g.msfuy, i + 1, k, j) - hat_(g, s.u, g.msfuy, i, k, j)) - tmp1);
+    A3(o.defor11, i, k, j) = 2.0f * tmp1;
+    float div = tmp1;
+    const float tmpzy = 0.25f * (A3(zy, i, k, j) + A3(zy, i, k, j + 1) + A3(zy, i, k + 1, j) + A3(zy, i, k + 1, j + 1));
+    tmp1 = (hatavg_(g, s.v, g.msfvx, i, j, i, j + 1, k + 1, kte, cft1, cft2) - hatavg_(g, s.v, g.msfvx, i, j, i, j + 1, k, kte, cft1, cft2)) *
+           tmpzy * A3(rdzw, i, k, j);
+    tmp1 = mm * (g.rdy * (hat_(g, s.v, g.msfvx, i, k, j + 1) - hat_(g, s.v, g.msfvx, i, k, j)) - tmp1);
+    A3(o.defor22, i, k, j) = 2.0f * tmp1;
+    div = div + tmp1;
+    tmp1 = (A3(w, i, k + 1, j) - A3(w, i, k, j)) * A3(rdzw, i, k, j);
+    A3(o.defor33, i, k, j) = 2.0f * tmp1;
+    div = div + tmp1;
+    A3(o.div, i, k, j) = div;
+  }
+  // defor12 (:611-870)
+  if (k <= ktf) {
+    int ic = i, jc = j;
+    if (r.cxs12 && i == g.ids) ic = g.ids + 1;
+    if (r.cxe12 && i == g.ide) ic = g.ide - 1;
+    if (r.cys12 && j == g.jds) jc = g.jds + 1;
+    if (r.cye12 && j == g.jde) jc = g.jde - 1;
+    if (ic >= r.i0_12 && ic <= r.i1_12 && jc >= r.j0_12 && jc <= r.j1_12) A3(o.defor12, i, k, j) = defor12_at(g, s, ic, k, jc, kte, cft1, cft2);
+  }
+  // defor13, defor23 (:872-1187)
+  {
+    int ic = i, jc = j;
+    if (r.cxs && i == g.ids) ic = g.ids + 1;
+    if (r.cxe && i == g.ide) ic = g.ide - 1;
+    if (r.cys && j == g.jds) jc = g.jds + 1;
+    if (r.cye && j == g.jde) jc = g.jde - 1;
+    if (ic >= r.i0_13 && ic <= r.i1_13 && jc >= r.j0_13 && jc <= r.j1_13) A3(o.defor13, i, k, j) = defor13_at(g, s, ic, k, jc, kte, r.mix_full_fields);
+    if (ic >= r.i0_23 && ic <= r.i1_23 && jc >= r.j0_23 && jc <= r.j1_23) A3(o.defor23, i, k, j) = defor23_at(g, s, ic, k, jc, kte, r.mix_full_fields);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ smag2d_km
+struct SmagIn { cfp defor11, defor22, defor12, rdzw, zx, zy; float dx, dy, c_s; int diff_opt; };
+// thread box: the computed range of smag2d_km (:1974-1989), k in 1..ktf
+WG_HD void smag2d_point(const Geo &g, const SmagIn &s, int i, int k, int j, fp xkmh, fp xkmv, fp xkhh, fp xkhv) {
+  const float pr = 1.f / 3.f;   // prandtl, share/module_model_constants.F
+  cfp defor11 = s.defor11, defor22 = s.defor22, defor12 = s.defor12, zx = s.zx, zy = s.zy;
+  float def2 = 0.25f * ((A3(defor11, i, k, j) - A3(defor22, i, k, j)) * (A3(defor11, i, k, j) - A3(defor22, i, k, j)));
+  float tmp = 0.25f * (A3(defor12, i, k, j) + A3(defor12, i, k, j + 1) + A3(defor12, i + 1, k, j) + A3(defor12, i + 1, k, j + 1));
+  def2 = def2 + tmp * tmp;
+  const float mlen_h = sqrtf(s.dx / A2(g.msftx, i, j) * s.dy / A2(g.msfty, i, j));
+  tmp = sqrtf(def2);
+  float km = s.c_s * s.c_s * mlen_h * mlen_h * tmp;
+  km = fminf(km, 10.f * mlen_h);
+  float kh = km / pr;
+  if (s.diff_opt == 2) {
+    const float dxm = s.dx / A2(g.msftx, i, j), dym = s.dy / A2(g.msfty, i, j);
+    const float tmpzx = (0.25f * (fabsf(A3(zx, i, k, j)) + fabsf(A3(zx, i + 1, k, j)) + fabsf(A3(zx, i, k + 1, j)) + fabsf(A3(zx, i + 1, k + 1, j))) *
+                         A3(s.rdzw, i, k, j) * dxm);
+    const float tmpzy = (0.25f * (fabsf(A3(zy, i, k, j)) + fabsf(A3(zy, i, k, j + 1)) + fabsf(A3(zy, i, k + 1, j)) + fabsf(A3(zy, i, k + 1, j + 1))) *
+                         A3(s.rdzw, i, k, j) * dym);
+    const float alpha = fmaxf(sqrtf(tmpzx * tmpzx + tmpzy * tmpzy), 1.0f);
+    const float def_limit = fmaxf(10.f / mlen_h, 1.e-3f);
+    if (tmp > def_limit) km = km / (alpha * alpha);
+    else km = km / (alpha);
+    kh = km / pr;
+  }
+  A3(xkmh, i, k, j) = km;
+  A3(xkmv, i, k, j) = km;
+  A3(xkhh, i, k, j) = kh;
+  A3(xkhv, i, k, j) = 0.f;
+}
+
+}  // namespace wg

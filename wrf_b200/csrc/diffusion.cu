@@ -22,9 +22,13 @@ struct DiffIn {
   cfp field, mut, mass_v, alt, base_3d;   // mut: horizontal mass; mass_v: muu / muv / mut of the vertical term
   const float *base_1d;                   // u_base / v_base / qv_base (origin shifted), or null
   float xk, kvdif;                        // horizontal K of this field, vertical K of this field
+  cfp xkarr;                              // ARR: the horizontal K is this array (xkmh / xkhh of a closure) instead of xk
 };
 
-template <int KIND>
+// ARR = false: every element of the reference's xkmhd array holds the constant xk (km_opt = 1), the averaging
+// expressions are kept; ARR = true: the array computed by k_smag2d (km_opt = 4), indexed as in the reference
+#define XK(i_, k_, j_) (ARR ? A3(s.xkarr, i_, k_, j_) : xk)
+template <int KIND, bool ARR>
 __global__ void k_diffuse(const Geo g, Box b, DiffIn s, fp tendency) {
   TID3;
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, kde = g.kde;
@@ -63,48 +67,48 @@ __global__ void k_diffuse(const Geo g, Box b, DiffIn s, fp tendency) {
       const float c1 = KIND == DIFF_W ? g.c1f[k] : g.c1h[k], c2 = KIND == DIFF_W ? g.c2f[k] : g.c2h[k];
       float mrdx, mkrdxm, mkrdxp, mrdy, mkrdym, mkrdyp;
       if (KIND == DIFF_U) {
-        mkrdxm = (A2(g.msftx, i - 1, j) / A2(g.msfty, i - 1, j)) * (c1 * A2(MUT, i - 1, j) + c2) * xk * rdx;
-        mkrdxp = (A2(g.msftx, i, j) / A2(g.msfty, i, j)) * (c1 * A2(MUT, i, j) + c2) * xk * rdx;
+        mkrdxm = (A2(g.msftx, i - 1, j) / A2(g.msfty, i - 1, j)) * (c1 * A2(MUT, i - 1, j) + c2) * XK(i - 1, k, j) * rdx;
+        mkrdxp = (A2(g.msftx, i, j) / A2(g.msfty, i, j)) * (c1 * A2(MUT, i, j) + c2) * XK(i, k, j) * rdx;
         mrdx = A2(g.msfux, i, j) * A2(g.msfuy, i, j) * rdx;
         mkrdym = ((A2(g.msfuy, i, j) + A2(g.msfuy, i, j - 1)) / (A2(g.msfux, i, j) + A2(g.msfux, i, j - 1))) *
                  0.25f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j - 1) + c2) + (c1 * A2(MUT, i - 1, j - 1) + c2) + (c1 * A2(MUT, i - 1, j) + c2)) *
-                 0.25f * (xk + xk + xk + xk) * rdy;
+                 0.25f * (XK(i, k, j) + XK(i, k, j - 1) + XK(i - 1, k, j - 1) + XK(i - 1, k, j)) * rdy;
         mkrdyp = ((A2(g.msfuy, i, j) + A2(g.msfuy, i, j + 1)) / (A2(g.msfux, i, j) + A2(g.msfux, i, j + 1))) *
                  0.25f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j + 1) + c2) + (c1 * A2(MUT, i - 1, j + 1) + c2) + (c1 * A2(MUT, i - 1, j) + c2)) *
-                 0.25f * (xk + xk + xk + xk) * rdy;
+                 0.25f * (XK(i, k, j) + XK(i, k, j + 1) + XK(i - 1, k, j + 1) + XK(i - 1, k, j)) * rdy;
         mrdy = A2(g.msfux, i, j) * A2(g.msfuy, i, j) * rdy;
       } else if (KIND == DIFF_V) {
         mkrdxm = ((A2(g.msfvx, i, j) + A2(g.msfvx, i - 1, j)) / (A2(g.msfvy, i, j) + A2(g.msfvy, i - 1, j))) *
                  0.25f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j - 1) + c2) + (c1 * A2(MUT, i - 1, j - 1) + c2) + (c1 * A2(MUT, i - 1, j) + c2)) *
-                 0.25f * (xk + xk + xk + xk) * rdx;
+                 0.25f * (XK(i, k, j) + XK(i, k, j - 1) + XK(i - 1, k, j - 1) + XK(i - 1, k, j)) * rdx;
         mkrdxp = ((A2(g.msfvx, i, j) + A2(g.msfvx, i + 1, j)) / (A2(g.msfvy, i, j) + A2(g.msfvy, i + 1, j))) *
                  0.25f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j - 1) + c2) + (c1 * A2(MUT, i + 1, j - 1) + c2) + (c1 * A2(MUT, i + 1, j) + c2)) *
-                 0.25f * (xk + xk + xk + xk) * rdx;
+                 0.25f * (XK(i, k, j) + XK(i, k, j - 1) + XK(i + 1, k, j - 1) + XK(i + 1, k, j)) * rdx;
         mrdx = A2(g.msfvx, i, j) * A2(g.msfvy, i, j) * rdx;
-        mkrdym = (A2(g.msfty, i, j - 1) / A2(g.msftx, i, j - 1)) * xk * rdy;
-        mkrdyp = (A2(g.msfty, i, j) / A2(g.msftx, i, j)) * xk * rdy;
+        mkrdym = (A2(g.msfty, i, j - 1) / A2(g.msftx, i, j - 1)) * XK(i, k, j - 1) * rdy;
+        mkrdyp = (A2(g.msfty, i, j) / A2(g.msftx, i, j)) * XK(i, k, j) * rdy;
         mrdy = A2(g.msfvx, i, j) * A2(g.msfvy, i, j) * rdy;
       } else if (KIND == DIFF_W) {
         mkrdxm = (A2(g.msfux, i, j) / A2(g.msfuy, i, j)) *
                  0.25f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i - 1, j) + c2) + (c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i - 1, j) + c2)) *
-                 0.25f * (xk + xk + xk + xk) * rdx;
+                 0.25f * (XK(i, k, j) + XK(i - 1, k, j) + XK(i, k - 1, j) + XK(i - 1, k - 1, j)) * rdx;
         mkrdxp = (A2(g.msfux, i + 1, j) / A2(g.msfuy, i + 1, j)) *
                  0.25f * ((c1 * A2(MUT, i + 1, j) + c2) + (c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i + 1, j) + c2) + (c1 * A2(MUT, i, j) + c2)) *
-                 0.25f * (xk + xk + xk + xk) * rdx;
+                 0.25f * (XK(i + 1, k, j) + XK(i, k, j) + XK(i + 1, k - 1, j) + XK(i, k - 1, j)) * rdx;
         mrdx = A2(g.msftx, i, j) * A2(g.msfty, i, j) * rdx;
         mkrdym = (A2(g.msfvy, i, j) * A2(g.msfvx_inv, i, j)) *
                  0.25f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j - 1) + c2) + (c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j - 1) + c2)) *
-                 0.25f * (xk + xk + xk + xk) * rdy;
+                 0.25f * (XK(i, k, j) + XK(i, k, j - 1) + XK(i, k - 1, j) + XK(i, k - 1, j - 1)) * rdy;
         mkrdyp = (A2(g.msfvy, i, j + 1) * A2(g.msfvx_inv, i, j + 1)) *
                  0.25f * ((c1 * A2(MUT, i, j + 1) + c2) + (c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j + 1) + c2) + (c1 * A2(MUT, i, j) + c2)) *
-                 0.25f * (xk + xk + xk + xk) * rdy;
+                 0.25f * (XK(i, k, j + 1) + XK(i, k, j) + XK(i, k - 1, j + 1) + XK(i, k - 1, j)) * rdy;
         mrdy = A2(g.msftx, i, j) * A2(g.msfty, i, j) * rdy;
       } else {
-        mkrdxm = (A2(g.msfux, i, j) / A2(g.msfuy, i, j)) * 0.5f * (xk + xk) * 0.5f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i - 1, j) + c2)) * rdx;
-        mkrdxp = (A2(g.msfux, i + 1, j) / A2(g.msfuy, i + 1, j)) * 0.5f * (xk + xk) * 0.5f * ((c1 * A2(MUT, i + 1, j) + c2) + (c1 * A2(MUT, i, j) + c2)) * rdx;
+        mkrdxm = (A2(g.msfux, i, j) / A2(g.msfuy, i, j)) * 0.5f * (XK(i, k, j) + XK(i - 1, k, j)) * 0.5f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i - 1, j) + c2)) * rdx;
+        mkrdxp = (A2(g.msfux, i + 1, j) / A2(g.msfuy, i + 1, j)) * 0.5f * (XK(i + 1, k, j) + XK(i, k, j)) * 0.5f * ((c1 * A2(MUT, i + 1, j) + c2) + (c1 * A2(MUT, i, j) + c2)) * rdx;
         mrdx = A2(g.msftx, i, j) * A2(g.msfty, i, j) * rdx;
-        mkrdym = (A2(g.msfvy, i, j) * A2(g.msfvx_inv, i, j)) * 0.5f * (xk + xk) * 0.5f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j - 1) + c2)) * rdy;
-        mkrdyp = (A2(g.msfvy, i, j + 1) * A2(g.msfvx_inv, i, j + 1)) * 0.5f * (xk + xk) * 0.5f * ((c1 * A2(MUT, i, j + 1) + c2) + (c1 * A2(MUT, i, j) + c2)) * rdy;
+        mkrdym = (A2(g.msfvy, i, j) * A2(g.msfvx_inv, i, j)) * 0.5f * (XK(i, k, j) + XK(i, k, j - 1)) * 0.5f * ((c1 * A2(MUT, i, j) + c2) + (c1 * A2(MUT, i, j - 1) + c2)) * rdy;
+        mkrdyp = (A2(g.msfvy, i, j + 1) * A2(g.msfvx_inv, i, j + 1)) * 0.5f * (XK(i, k, j + 1) + XK(i, k, j)) * 0.5f * ((c1 * A2(MUT, i, j + 1) + c2) + (c1 * A2(MUT, i, j) + c2)) * rdy;
         mrdy = A2(g.msftx, i, j) * A2(g.msfty, i, j) * rdy;
       }
       const float fc = A3(field, i, k, j), fe = A3(field, i + 1, k, j), fw = A3(field, i - 1, k, j), fn = A3(field, i, k, j + 1), fs = A3(field, i, k, j - 1);
@@ -170,23 +174,23 @@ __global__ void k_diffuse(const Geo g, Box b, DiffIn s, fp tendency) {
 }
 
 // which = DIFF_*; adds the diffusion of `field` to `tendency` on the whole tile
-void launch_diffuse(Solver *s, int which, cfp field, fp tendency, float xk, float kvdif) {
+void launch_diffuse(Solver *s, int which, cfp field, fp tendency, float xk, float kvdif, cfp xkarr) {
   const Geo &q = s->g;
   Box tile{q.its, q.ite, 1, q.kde, q.jts, q.jte};
   DiffIn in;
   in.field = field; in.mut = s->o("mut"); in.mass_v = s->o("mut"); in.alt = s->o("alt"); in.base_3d = nullptr; in.base_1d = nullptr;
-  in.xk = xk; in.kvdif = kvdif;
+  in.xk = xk; in.kvdif = kvdif; in.xkarr = xkarr;
   switch (which) {
-    case DIFF_U: in.mass_v = s->o("muu"); in.base_1d = s->o("u_base"); LAUNCH3(s, k_diffuse<DIFF_U>, tile, in, tendency); break;
-    case DIFF_V: in.mass_v = s->o("muv"); in.base_1d = s->o("v_base"); LAUNCH3(s, k_diffuse<DIFF_V>, tile, in, tendency); break;
-    case DIFF_W: LAUNCH3(s, k_diffuse<DIFF_W>, tile, in, tendency); break;
-    case DIFF_THETA: in.base_3d = s->o("t_init"); LAUNCH3(s, k_diffuse<DIFF_THETA>, tile, in, tendency); break;
+    case DIFF_U: in.mass_v = s->o("muu"); in.base_1d = s->o("u_base"); if (xkarr) LAUNCH3(s, (k_diffuse<DIFF_U, true>), tile, in, tendency); else LAUNCH3(s, (k_diffuse<DIFF_U, false>), tile, in, tendency); break;
+    case DIFF_V: in.mass_v = s->o("muv"); in.base_1d = s->o("v_base"); if (xkarr) LAUNCH3(s, (k_diffuse<DIFF_V, true>), tile, in, tendency); else LAUNCH3(s, (k_diffuse<DIFF_V, false>), tile, in, tendency); break;
+    case DIFF_W: if (xkarr) LAUNCH3(s, (k_diffuse<DIFF_W, true>), tile, in, tendency); else LAUNCH3(s, (k_diffuse<DIFF_W, false>), tile, in, tendency); break;
+    case DIFF_THETA: in.base_3d = s->o("t_init"); if (xkarr) LAUNCH3(s, (k_diffuse<DIFF_THETA, true>), tile, in, tendency); else LAUNCH3(s, (k_diffuse<DIFF_THETA, false>), tile, in, tendency); break;
     case DIFF_QV:     // rk_scalar_tend passes grid%muts as mut (solve_em.F:2219)
       in.mut = s->o("muts"); in.mass_v = s->o("muts"); in.base_1d = s->o("qv_base");
-      LAUNCH3(s, k_diffuse<DIFF_QV>, tile, in, tendency); break;
+      if (xkarr) LAUNCH3(s, (k_diffuse<DIFF_QV, true>), tile, in, tendency); else LAUNCH3(s, (k_diffuse<DIFF_QV, false>), tile, in, tendency); break;
     default:
       in.mut = s->o("muts"); in.mass_v = s->o("muts");
-      LAUNCH3(s, k_diffuse<DIFF_SCALAR>, tile, in, tendency); break;
+      if (xkarr) LAUNCH3(s, (k_diffuse<DIFF_SCALAR, true>), tile, in, tendency); else LAUNCH3(s, (k_diffuse<DIFF_SCALAR, false>), tile, in, tendency); break;
   }
 }
 

@@ -55,6 +55,13 @@ static const HaloDef kHalos[] = {
     // small_step_prep refreshes their interior -- under DM the reference reads one-step-old halo values there and its IEVA
     // results depend on the decomposition.  This exchange (not in the Registry) makes N ranks equal 1 rank.
     {"HALO_EM_IEVA", 2, "u_1,v_1", ""},
+    // diffusion preamble of the first RK substep (first_rk_step_part2, module_first_rk_step_part2.F), closures that compute K:
+    // metrics (:446-447): HALO_EM_TKE_C :3438 (1) + PERIOD_BDY_EM_A1 :3539 (3); its u_2, v_2 are current since HALO_EM_E_5
+    {"HALO_EM_TKE_C", 3, "z,zx,zy,rdz,rdzw", ""},
+    // deformation (:571): HALO_EM_TKE_D :3439 (1)
+    {"HALO_EM_TKE_D", 1, "defor11,defor22,defor33,defor12,defor13,defor23,div", ""},
+    // eddy viscosities (:644-650, :759): HALO_EM_TKE_E :3440 (1) + PERIOD_BDY_EM_PHY_BC :3540 (2) + HALO_EM_PHYS_DIFFUSION :3432 (1)
+    {"HALO_EM_TKE_E", 2, "xkmv,xkmh,xkhv,xkhh,div,defor11,defor22,defor33,defor12,defor13,defor23", ""},
     // very end (:4781-4846): HALO_EM_E_5 :3458 (3) after set_w_surface
     {"HALO_EM_E_5", 3, "u_1,u_2,v_1,v_2,w_1,w_2,t_1,t_2,ph_1,ph_2", "mu_1,mu_2"},
     // start_domain_em (dyn_em/start_em.F): HALO_EM_INIT_1..5 carry the base state, map factors and both time levels

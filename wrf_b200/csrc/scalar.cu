@@ -483,7 +483,7 @@ void Solver::rk_scalar_step(int rk_step) {
     if (ieva) ieva_implicit(0, o("advect_tend"), o(s.o), o("mut_old"), o("muts"), dt_rk);   // module_em.F:1346-1364: mut_new = mut (= muts)
     if (rk_step == 1 && c.diff_opt == 1) {   // rk_step_1: diff_opt1 (module_em.F:1378-1419): K = xkhh, kvdq = kvdif/prandtl
       const float prandtl = 1.f / 3.0f;
-      launch_diffuse(this, s.f == "moist_qv" ? 4 : 5, o(s.f), o(s.t), c.khdif / prandtl, c.kvdif / prandtl);
+      launch_diffuse(this, s.f == "moist_qv" ? 4 : 5, o(s.f), o(s.t), c.khdif / prandtl, c.kvdif / prandtl, c.km_opt == 1 ? nullptr : o("xkhh"));
     }
     if (rk_step == 1 && c.diff_6th_opt != 0 && !(s.f.rfind("moist_", 0) == 0 ? c.moist_mix6_off : c.scalar_mix6_off))
       launch_diff6(this, 5, o(s.f), o(s.t), o("muts"), dt_rk);   // module_em.F:1421-1437 (dt_step = dt_rk)

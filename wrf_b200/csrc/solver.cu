@@ -38,13 +38,15 @@ static void check_config(const wrfgpu_config &c) {
   if (!c.non_hydrostatic) bad("hydrostatic option");
   if (c.damp_opt != 0 && c.damp_opt != 2 && c.damp_opt != 3) bad("damp_opt must be 0, 2 or 3");
   if (c.zadvect_implicit < 0) bad("zadvect_implicit must be 0 or positive (IEVA on the last RK substep)");
-  // diffusion: constant K on coordinate surfaces (diff_opt 1 / km_opt 1) is on the device; with
-  // km_opt = 1 and khdif = kvdif = 0 the physical-space form (diff_opt 2: shipped em_hill2d_x) adds exact zeros
-  // to zero-initialised tendencies, i.e. it is the identity, and is accepted as such.  Everything else
-  // (TKE / Smagorinsky closures, 6th-order filter) is a 'next' row.
+  // diffusion: on coordinate surfaces (diff_opt 1) with constant K (km_opt 1) or the 2-D Smagorinsky
+  // closure (km_opt 4, deform.cu) is on the device; with km_opt = 1 and khdif = kvdif = 0 the physical-space form
+  // (diff_opt 2: shipped em_hill2d_x) adds exact zeros to zero-initialised tendencies, i.e. it is the identity, and
+  // is accepted as such.  The rest (physical-space diffusion with non-zero K, TKE / 3-D Smagorinsky) is a 'next' row.
   if (c.diff_6th_opt < 0 || c.diff_6th_opt > 2) bad("diff_6th_opt must be 0, 1 or 2");
   if (c.diff_opt != 0) {
-    if (c.km_opt != 1) bad("km_opt must be 1 (constant K) when diff_opt is not 0; the TKE/Smagorinsky closures are a 'next' row");
+    if (c.km_opt != 1 && !(c.km_opt == 4 && c.diff_opt == 1))
+      bad("km_opt must be 1 (constant K), or 4 (2-D Smagorinsky) with diff_opt = 1; the TKE / 3-D Smagorinsky closures are a 'next' row");
+    if (c.km_opt == 4 && !(c.c_s > 0.f)) bad("c_s must be positive with km_opt = 4");
     if (c.diff_opt == 2 && (c.khdif != 0.f || c.kvdif != 0.f)) bad("diff_opt = 2 is only accepted with khdif = kvdif = 0 (then it is the identity)");
     if (c.diff_opt != 1 && c.diff_opt != 2) bad("diff_opt must be 0, 1 or 2");
     if (c.khdif < 0.f || c.kvdif < 0.f) bad("khdif, kvdif must not be negative");
@@ -78,6 +80,11 @@ Solver::Solver(const wrfgpu_dims &d_, const wrfgpu_config &c_, int dev) : d(d_),
   if (c.mp_physics) for (int i = 0; k3d_mp[i]; i++) add(k3d_mp[i], 3);
   for (int i = 0; k2d[i]; i++) add(k2d[i], 2);
   for (int i = 0; k1d[i]; i++) add(k1d[i], 1);
+  if (c.diff_opt != 0 && c.km_opt >= 2) {   // closures that compute K: metrics, deformation, K arrays (deform.cu)
+    if (!c.mp_physics) add("z", 3);
+    for (const char *n : {"zx", "zy", "rdz", "rdzw", "div", "defor11", "defor22", "defor33", "defor12", "defor13", "defor23",
+                          "xkmh", "xkmv", "xkhh", "xkhv"}) add(n, 3);
+  }
   if (c.zadvect_implicit > 0) {   // IEVA: wwE / wwI and the locals of rk_tendency (module_em.F:343-347)
     add("wwE", 3); add("wwI", 3);
     for (const char *n : {"mut_old", "mut_new", "muu_old", "muu_new", "muv_old", "muv_new"}) add(n, 2);
@@ -260,6 +267,7 @@ void Solver::step() {
     halo("HALO_EM_A");
     { PHASE("bc"); rk_phys_bc_dry_1(); }
     if (rk_step == 1) { PHASE("rk_tendency"); init_zero_tendency(); }
+    if (rk_step == 1) { PHASE("diffusion_prep"); diffusion_prep(); }
     // the zeroing of u_save ... t_save (module_em.F:370-428) is folded into small_step_prep's sweep: nothing reads them in between
     { PHASE("rk_tendency"); rk_tendency(rk_step, false); }
     { PHASE("small_step_prep"); small_step_prep(rk_step, true); }
@@ -386,6 +394,7 @@ int wrfgpu_start_domain(wrfgpu_solver *s) { GUARD(s->s.start_domain()) }
 int wrfgpu_rk_step_prep(wrfgpu_solver *s, int rk) { GUARD(s->s.rk_step_prep(rk)) }
 int wrfgpu_rk_phys_bc_dry_1(wrfgpu_solver *s) { GUARD(s->s.rk_phys_bc_dry_1()) }
 int wrfgpu_init_zero_tendency(wrfgpu_solver *s) { GUARD(s->s.init_zero_tendency()) }
+int wrfgpu_diffusion_prep(wrfgpu_solver *s) { GUARD(s->s.diffusion_prep()) }
 int wrfgpu_rk_tendency(wrfgpu_solver *s, int rk) { GUARD(s->s.rk_tendency(rk)) }
 int wrfgpu_small_step_prep(wrfgpu_solver *s, int rk) { GUARD(s->s.small_step_prep(rk)) }
 int wrfgpu_advance_uv(wrfgpu_solver *s, int rk) { GUARD(s->s.advance_uv(rk)) }

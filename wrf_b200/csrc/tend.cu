@@ -1044,10 +1044,11 @@ void Solver::rk_tendency(int rk_step, bool zero_save) {
   if (rk_step == 1 && c.diff_opt == 1) {   // forward_step: diff_opt1 (module_em.F:802-878), before rk_rayleigh_damp
     const float prandtl = 1.f / 3.0f;    // share/module_model_constants.F:86
     const float xkmh = c.khdif, xkhh = c.khdif / prandtl;
-    launch_diffuse(this, 0, o("u_2"), o("ru_tendf"), xkmh, c.kvdif);
-    launch_diffuse(this, 1, o("v_2"), o("rv_tendf"), xkmh, c.kvdif);
-    launch_diffuse(this, 2, o("w_2"), o("rw_tendf"), xkmh, c.kvdif);
-    launch_diffuse(this, 3, o("t_2"), o("t_tendf"), xkhh, 3.f * c.kvdif);
+    cfp kmh = c.km_opt == 1 ? nullptr : o("xkmh"), khh = c.km_opt == 1 ? nullptr : o("xkhh");   // K arrays of diffusion_prep (deform.cu)
+    launch_diffuse(this, 0, o("u_2"), o("ru_tendf"), xkmh, c.kvdif, kmh);
+    launch_diffuse(this, 1, o("v_2"), o("rv_tendf"), xkmh, c.kvdif, kmh);
+    launch_diffuse(this, 2, o("w_2"), o("rw_tendf"), xkmh, c.kvdif, kmh);
+    launch_diffuse(this, 3, o("t_2"), o("t_tendf"), xkhh, 3.f * c.kvdif, khh);
   }
   if (rk_step == 1 && c.diff_6th_opt != 0) {   // module_em.F:880-930
     launch_diff6(this, 0, o("u_2"), o("ru_tendf"), o("mut"), c.dt);

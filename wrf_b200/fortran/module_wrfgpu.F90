@@ -41,6 +41,8 @@ MODULE module_wrfgpu
       INTEGER(c_int) :: num_moist, num_scalar, ntasks_x, ntasks_y, mytask
       REAL(c_float)  :: diff_6th_factor, diff_6th_thresh
       INTEGER(c_int) :: diff_6th_slopeopt, moist_mix6_off, scalar_mix6_off
+      REAL(c_float)  :: c_s, c_k
+      INTEGER(c_int) :: mix_full_fields
    END TYPE wrfgpu_config
 
    INTERFACE

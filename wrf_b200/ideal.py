@@ -64,7 +64,9 @@ class Config(ctypes.Structure):
             "p_top", "cf1", "cf2", "cf3", "cfn", "cfn1", "khdif", "kvdif")]
         + [(n, ctypes.c_int) for n in ("num_moist", "num_scalar", "ntasks_x", "ntasks_y", "mytask")]
         + [(n, ctypes.c_float) for n in ("diff_6th_factor", "diff_6th_thresh")]
-        + [(n, ctypes.c_int) for n in ("diff_6th_slopeopt", "moist_mix6_off", "scalar_mix6_off")])
+        + [(n, ctypes.c_int) for n in ("diff_6th_slopeopt", "moist_mix6_off", "scalar_mix6_off")]
+        + [(n, ctypes.c_float) for n in ("c_s", "c_k")]
+        + [("mix_full_fields", ctypes.c_int)])
 
 
 def default_config(**kw) -> Config:
@@ -85,6 +87,7 @@ def default_config(**kw) -> Config:
     c.dampcoef, c.zdamp = 0.2, 5000.0
     c.w_crit_cfl = 1.2
     c.diff_6th_factor, c.diff_6th_thresh = 0.12, 0.10
+    c.c_s, c.c_k = 0.25, 0.15
     c.ntasks_x = c.ntasks_y = 1
     for k, v in kw.items():
         setattr(c, k, v)

@@ -19,7 +19,7 @@ from .ideal import Case, Config, Dims
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-PHASES = ("rk_step_prep", "rk_phys_bc_dry_1", "init_zero_tendency", "rk_tendency", "small_step_prep",
+PHASES = ("rk_step_prep", "rk_phys_bc_dry_1", "init_zero_tendency", "diffusion_prep", "rk_tendency", "small_step_prep",
           "advance_uv", "advance_mu_t", "advance_w", "sumflux", "calc_p_rho", "small_step_finish",
           "rk_scalar_step", "calc_p_rho_phi", "rk_phys_bc_dry_2", "microphysics", "end_of_step", "start_domain")
 
