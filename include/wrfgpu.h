@@ -65,7 +65,8 @@ typedef struct wrfgpu_config {
   int hypsometric_opt;                   /* 1/2 */
   int phi_adv_z;                         /* 1/2 */
   int zadvect_implicit;                  /* > 0: IEVA on the last RK substep (module_ieva_em.F) */
-  int diff_opt, km_opt;                  /* 0; 1/1 constant K; 1/4 2-D Smagorinsky */
+  int diff_opt, km_opt;                  /* diff_opt 0, 1 (coordinate surfaces), 2 (physical space);
+                                            km_opt 1 (constant K) or 4 (2-D Smagorinsky) */
   int diff_6th_opt;                      /* 0, 1 or 2 (sixth_order_diffusion; 2 = no up-gradient fluxes) */
   int mp_physics;                        /* 0 = none(passive qv), 1 = Kessler */
   int time_step;                         /* integer namelist time_step; only its
@@ -94,6 +95,10 @@ typedef struct wrfgpu_config {
   float c_s;                             /* Smagorinsky coefficient, 0.25 (km_opt = 3, 4) */
   float c_k;                             /* TKE coefficient, 0.15 (km_opt = 2; not on the device yet) */
   int mix_full_fields;                   /* 0/1: vertical shear of the full u, v in defor13/23 instead of u - u_base */
+  /* surface fluxes of the physical-space vertical diffusion (diff_opt = 2; module_diffusion_em.F:4160-4353) */
+  int isfflx;                            /* 0: drag and heat flux from the two constants below; 1, 2: from ustm / hfx / qfx */
+  float tke_drag_coefficient;            /* 0. */
+  float tke_heat_flux;                   /* 0. (K m/s) */
 } wrfgpu_config;
 
 typedef struct wrfgpu_solver wrfgpu_solver;   /* opaque */

@@ -201,6 +201,23 @@ void compute_diff_metrics(const Cx &x, A3 ph, A3 phb, A3 z, A3 rdz, A3 rdzw, A3 
 void cal_deform_and_div(const Cx &x, A3 u, A3 v, A3 w, A3 div, A3 defor11, A3 defor22, A3 defor33, A3 defor12, A3 defor13,
                         A3 defor23, A3 rdz, A3 rdzw, A3 zx, A3 zy);
 void smag2d_km(const Cx &x, A3 xkmh, A3 xkmv, A3 xkhh, A3 xkhv, A3 defor11, A3 defor22, A3 defor12, A3 rdzw, A3 zx, A3 zy);
+// diffusion2.cpp (diff_opt = 2: diffusion in physical space, called from first_rk_step_part2)
+void phy_prep_rho(const Cx &x, A3 rho, A3 alt, const A3 *qv);
+void horizontal_diffusion_u_2(const Cx &x, A3 tendency, A3 defor11, A3 defor12, A3 xkmh, A3 zx, A3 zy, A3 rdzw, A3 rho);
+void horizontal_diffusion_v_2(const Cx &x, A3 tendency, A3 defor12, A3 defor22, A3 xkmh, A3 zx, A3 zy, A3 rdzw, A3 rho);
+void horizontal_diffusion_w_2(const Cx &x, A3 tendency, A3 defor13, A3 defor23, A3 xkmv, A3 zx, A3 zy, A3 rdz, A3 rho);
+void horizontal_diffusion_s(const Cx &x, A3 tendency, A3 var, A3 xkhh, A3 zx, A3 zy, A3 rdzw, A3 rho);
+void vertical_diffusion_u_2(const Cx &x, A3 tendency, A3 defor13, A3 xkmv, A3 rho);
+void vertical_diffusion_v_2(const Cx &x, A3 tendency, A3 defor23, A3 xkmv, A3 rho);
+void vertical_diffusion_w_2(const Cx &x, A3 tendency, A3 defor33, A3 xkmh, A3 rho);
+void vertical_diffusion_s(const Cx &x, A3 tendency, A3 var_in, const A1 *base, A3 xkhv, A3 rdz, A3 rho);
+void surface_drag(const Cx &x, A3 ru_tendf, A3 rv_tendf, A3 u_2, A3 v_2, A3 rho, A2 ust);
+void surface_heat_flux(const Cx &x, A3 rt_tendf, A3 t_2, const A3 *qv, A3 rho, A2 hfx, A2 qfx);
+void surface_moisture_flux(const Cx &x, A3 qv_tendf, A2 qfx);
+// diff_opt = 2 with constant K = 0 and no surface fluxes adds exact zeros to zero-initialised tendencies
+inline bool diff2_is_identity(const wrfgpu_config &c) {
+  return c.diff_opt == 2 && c.km_opt == 1 && c.khdif == 0.f && c.kvdif == 0.f && c.isfflx == 0 && c.tke_drag_coefficient == 0.f && c.tke_heat_flux == 0.f;
+}
 // advect.cpp
 void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut, bool weno = false);
 void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut, bool weno = false);

@@ -42,9 +42,11 @@ Oracle::Oracle(const wrfgpu_dims &d_, const wrfgpu_config &c_) : d(d_), c(c_) {
     add("scalar_old_" + std::to_string(s), 3);
     add("scalar_tend_" + std::to_string(s), 3);
   }
-  if (c.diff_opt != 0 && c.km_opt >= 2)   // closures that compute K: metrics, deformation, K arrays (Registry.EM_COMMON state)
+  if (c.diff_opt != 0 && (c.km_opt >= 2 || (c.diff_opt == 2 && !diff2_is_identity(c)))) {   // metrics, deformation, K arrays (Registry.EM_COMMON state)
+    for (const char *n : {"ustm", "hfx", "qfx"}) add(n, 2);
     for (const char *n : {"zx", "zy", "rdz", "rdzw", "div", "defor11", "defor22", "defor33", "defor12", "defor13", "defor23",
                           "xkmh", "xkmv", "xkhh", "xkhv"}) add(n, 3);
+  }
   // harmless defaults so that an un-set map factor does not divide by zero
   for (const char *m : {"msftx", "msfty", "msfux", "msfuy", "msfvx", "msfvx_inv", "msfvy"})
     std::fill(data[m].begin(), data[m].end(), 1.f);
@@ -159,22 +161,69 @@ void Oracle::init_zero_tendency() {
 // diffusion, deformation and divergence, the eddy viscosities and their boundary fills.  Run for the closures that
 // compute K (km_opt = 4 here); with km_opt = 1 every K element is a constant the diffusion routines take directly.
 void Oracle::diffusion_prep() {
-  if (c.diff_opt == 0 || c.km_opt < 2) return;
-  if (c.km_opt != 4 || c.diff_opt != 1) throw std::runtime_error("oracle: only km_opt = 4 with diff_opt = 1 is restated");
+  if (c.diff_opt == 0) return;
+  if (c.diff_opt == 1 && c.km_opt == 1) return;   // every K element is a constant the diffusion routines of rk_tendency take directly
+  if (diff2_is_identity(c)) return;               // diff_opt = 2 with all coefficients zero adds exact zeros (shipped em_hill2d_x)
+  if (c.km_opt != 4 && !(c.km_opt == 1 && c.diff_opt == 2)) throw std::runtime_error("oracle: km_opt 2 / 3 are not restated");
   A3 ph = a3("ph_2"), phb = a3("phb"), z = a3("z"), rdz = a3("rdz"), rdzw = a3("rdzw"), zx = a3("zx"), zy = a3("zy");
+  A3 xkmh = a3("xkmh"), xkmv = a3("xkmv"), xkhh = a3("xkhh"), xkhv = a3("xkhv"), rho = a3("rho");
+  if (c.diff_opt == 2) {   // phy_prep (first_rk_step_part1): the density the stresses are built with
+    if (c.num_moist >= 1) { A3 qv = a3("moist_qv"); par([&](const Cx &xt) { phy_prep_rho(xt, rho, a3("alt"), &qv); }); }
+    else par([&](const Cx &xt) { phy_prep_rho(xt, rho, a3("alt"), nullptr); });
+  }
   par([&](const Cx &xt) { compute_diff_metrics(xt, ph, phb, z, rdz, rdzw, zx, zy); });
   halo("HALO_EM_TKE_C");   // + PERIOD_BDY_EM_A1, :446-447
+  if (c.diff_opt == 2) { halo("HALO_EM_TKE_C_SFC"); bc("ustm", 't'); }   // ustm of HALO_EM_TKE_C, set_physical_bc2d :492
   bc("rdzw", 'w'); bc("rdz", 'w'); bc("z", 'w'); bc("zx", 'e'); bc("zy", 'f');
   par([&](const Cx &xt) {
     cal_deform_and_div(xt, a3("u_2"), a3("v_2"), a3("w_2"), a3("div"), a3("defor11"), a3("defor22"), a3("defor33"), a3("defor12"),
                        a3("defor13"), a3("defor23"), rdz, rdzw, zx, zy);
   });
   halo("HALO_EM_TKE_D");   // :571
-  par([&](const Cx &xt) {
-    smag2d_km(xt, a3("xkmh"), a3("xkmv"), a3("xkhh"), a3("xkhv"), a3("defor11"), a3("defor22"), a3("defor12"), rdzw, zx, zy);
-  });
+  if (c.km_opt == 1) {     // isotropic_km, module_diffusion_em.F:1718-1772
+    const float prandtl = 1.f / 3.0f;
+    const float khdif3 = c.khdif / prandtl, kvdif3 = c.kvdif / prandtl;
+    for (int j = x.jts; j <= std::min(x.jte, x.jde - 1); j++)
+      for (int k = x.kts; k <= x.kte; k++)
+        for (int i = x.its; i <= std::min(x.ite, x.ide - 1); i++) {
+          xkmh(i, k, j) = c.khdif; xkmv(i, k, j) = c.kvdif; xkhh(i, k, j) = khdif3; xkhv(i, k, j) = kvdif3;
+        }
+  } else {
+    par([&](const Cx &xt) { smag2d_km(xt, xkmh, xkmv, xkhh, xkhv, a3("defor11"), a3("defor22"), a3("defor12"), rdzw, zx, zy); });
+  }
   halo("HALO_EM_TKE_E");   // + PERIOD_BDY_EM_PHY_BC, HALO_EM_PHYS_DIFFUSION, :644-650, :759
-  bc("xkmh", 't'); bc("xkhh", 't');   // phy_bc, module_diffusion_em.F:5901 (the diff_opt = 2 part fills the rest)
+  bc("xkmh", 't'); bc("xkhh", 't');   // phy_bc, module_diffusion_em.F:5901
+  if (c.diff_opt != 2) return;
+  bc("xkmv", 't'); bc("xkhv", 't'); bc("div", 't'); bc("defor11", 't'); bc("defor22", 't'); bc("defor33", 't');
+  bc("defor12", 'd'); bc("defor13", 'e'); bc("defor23", 'f'); bc("rho", 't');
+  // vertical diffusion first and then horizontal (module_first_rk_step_part2.F:1019-1122; bl_pbl_physics = 0)
+  A3 u = a3("u_2"), v = a3("v_2"), t = a3("t_2");
+  A3 ru_tendf = a3("ru_tendf"), rv_tendf = a3("rv_tendf"), rw_tendf = a3("rw_tendf"), t_tendf = a3("t_tendf");
+  par([&](const Cx &xt) { vertical_diffusion_u_2(xt, ru_tendf, a3("defor13"), xkmv, rho); });
+  par([&](const Cx &xt) { vertical_diffusion_v_2(xt, rv_tendf, a3("defor23"), xkmv, rho); });
+  par([&](const Cx &xt) { vertical_diffusion_w_2(xt, rw_tendf, a3("defor33"), xkmh, rho); });
+  par([&](const Cx &xt) { surface_drag(xt, ru_tendf, rv_tendf, u, v, rho, a2("ustm")); });
+  const A1 *tb = c.mix_full_fields ? nullptr : &x.t_base, *qb = c.mix_full_fields ? nullptr : &x.qv_base;
+  par([&](const Cx &xt) { vertical_diffusion_s(xt, t_tendf, t, tb, xkhv, rdz, rho); });
+  {
+    A3 qv; if (c.num_moist >= 1) qv = a3("moist_qv");
+    par([&](const Cx &xt) { surface_heat_flux(xt, t_tendf, t, c.num_moist >= 1 ? &qv : nullptr, rho, a2("hfx"), a2("qfx")); });
+  }
+  for (int sp = 0; sp < c.num_moist; sp++) {
+    A3 q = a3(std::string("moist_") + moist_names[sp]), qt = a3(std::string("moist_tend_") + moist_names[sp]);
+    par([&](const Cx &xt) { vertical_diffusion_s(xt, qt, q, sp == 0 ? qb : nullptr, xkhv, rdz, rho); });
+    if (sp == 0) par([&](const Cx &xt) { surface_moisture_flux(xt, qt, a2("qfx")); });
+  }
+  for (int sp = 1; sp <= c.num_scalar; sp++)
+    par([&](const Cx &xt) { vertical_diffusion_s(xt, a3("scalar_tend_" + std::to_string(sp)), a3("scalar_" + std::to_string(sp)), nullptr, xkhv, rdz, rho); });
+  par([&](const Cx &xt) { horizontal_diffusion_u_2(xt, ru_tendf, a3("defor11"), a3("defor12"), xkmh, zx, zy, rdzw, rho); });
+  par([&](const Cx &xt) { horizontal_diffusion_v_2(xt, rv_tendf, a3("defor12"), a3("defor22"), xkmh, zx, zy, rdzw, rho); });
+  par([&](const Cx &xt) { horizontal_diffusion_w_2(xt, rw_tendf, a3("defor13"), a3("defor23"), xkmv, zx, zy, rdz, rho); });
+  par([&](const Cx &xt) { horizontal_diffusion_s(xt, t_tendf, t, xkhh, zx, zy, rdzw, rho); });
+  for (int sp = 0; sp < c.num_moist; sp++)
+    par([&](const Cx &xt) { horizontal_diffusion_s(xt, a3(std::string("moist_tend_") + moist_names[sp]), a3(std::string("moist_") + moist_names[sp]), xkhh, zx, zy, rdzw, rho); });
+  for (int sp = 1; sp <= c.num_scalar; sp++)
+    par([&](const Cx &xt) { horizontal_diffusion_s(xt, a3("scalar_tend_" + std::to_string(sp)), a3("scalar_" + std::to_string(sp)), xkhh, zx, zy, rdzw, rho); });
 }
 
 // module_em.F:190-955 rk_tendency followed by rk_addtend_dry (solve_em.F:881-1007)

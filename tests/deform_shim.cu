@@ -2,19 +2,25 @@
 // functions of the diffusion preamble (metrics, deformation, 2-D Smagorinsky K) in plain loops on the CPU, so that the
 // exact code the kernels of deform.cu execute can be compared with the oracle bit for bit without a GPU.
 // Test infrastructure; compiled with nvcc (host code only is run) and -ffp-contract=off.
-#include "../wrf_b200/csrc/deform.cuh"
+#include "../wrf_b200/csrc/diffusion2.cuh"
 #include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
 
 using namespace wg;
 
-enum { PH, PHB, U, V, W, Z, RDZ, RDZW, ZX, ZY, DIV, D11, D22, D33, D12, D13, D23, XKMH, XKMV, XKHH, XKHV,
-       MSFTX, MSFTY, MSFUX, MSFUY, MSFVX, MSFVY, FNM, FNP, DN, DNW, UBASE, VBASE, NPTR };
-
-extern "C" int deform_shim_run(int stage, const wrfgpu_dims *dp, const wrfgpu_config *cp, float *const *ptr) {
+// stage: 0 rho, 1 metrics, 2 deformation, 3 smag2d K, 4 isotropic K, 5 diff_opt = 2 tendencies of u, v, w, theta,
+// 6 diff_opt = 2 tendency of the species names[nn-2] (field) / names[nn-1] (tendency) -- which = 1 for qv, else 2
+extern "C" int deform_shim_run(int stage, const wrfgpu_dims *dp, const wrfgpu_config *cp, int nn, const char *const *names, float *const *ptrs,
+                               int which) {
   const wrfgpu_dims &d = *dp;
   const wrfgpu_config &c = *cp;
+  std::map<std::string, float *> tab;
+  for (int n = 0; n < nn; n++) tab[names[n]] = ptrs[n];
   Geo *gp = new Geo();   // ~7 KB
   Geo &g = *gp;
+  memset(gp, 0, sizeof(Geo));
   g.ids = d.ids; g.ide = d.ide; g.jds = d.jds; g.jde = d.jde; g.kds = d.kds; g.kde = d.kde;
   g.ims = d.ims; g.ime = d.ime; g.jms = d.jms; g.jme = d.jme; g.kms = d.kms; g.kme = d.kme;
   g.ips = d.ips; g.ipe = d.ipe; g.jps = d.jps; g.jpe = d.jpe;
@@ -25,39 +31,80 @@ extern "C" int deform_shim_run(int stage, const wrfgpu_dims *dp, const wrfgpu_co
   g.open_xs = c.open_xs; g.open_xe = c.open_xe; g.open_ys = c.open_ys; g.open_ye = c.open_ye;
   g.rdx = 1.f / c.dx; g.rdy = 1.f / c.dy; g.cf1 = c.cf1; g.cf2 = c.cf2; g.cf3 = c.cf3;
   const long o3 = d.ims + (long)d.kms * g.ni + (long)d.jms * g.ni * g.nk, o2 = d.ims + (long)d.jms * g.ni, o1 = d.kms;
-  auto p3 = [&](int n) { return ptr[n] - o3; };
-  auto p2 = [&](int n) { return ptr[n] - o2; };
-  auto p1 = [&](int n) { return ptr[n] - o1; };
-  g.msftx = p2(MSFTX); g.msfty = p2(MSFTY); g.msfux = p2(MSFUX); g.msfuy = p2(MSFUY); g.msfvx = p2(MSFVX); g.msfvy = p2(MSFVY);
-  for (int k = d.kms; k <= d.kme; k++) { g.fnm[k] = p1(FNM)[k]; g.fnp[k] = p1(FNP)[k]; }
-  if (stage == 1) {
+  auto p3 = [&](const char *n) -> float * { auto it = tab.find(n); return it == tab.end() ? nullptr : it->second - o3; };
+  auto p2 = [&](const char *n) -> float * { return tab.at(n) - o2; };
+  auto p1 = [&](const char *n) -> float * { return tab.at(n) - o1; };
+  g.msftx = p2("msftx"); g.msfty = p2("msfty"); g.msfux = p2("msfux"); g.msfuy = p2("msfuy"); g.msfvx = p2("msfvx"); g.msfvy = p2("msfvy");
+  for (int k = d.kms; k <= d.kme; k++) { g.fnm[k] = p1("fnm")[k]; g.fnp[k] = p1("fnp")[k]; g.dnw[k] = p1("dnw")[k]; }
+  const int ie = std::min(g.ite, g.ide - 1), je = std::min(g.jte, g.jde - 1);
+  if (stage == 0) {
+    for (int j = g.jts; j <= je; j++)
+      for (int k = 1; k <= g.kde - 1; k++)
+        for (int i = g.its; i <= ie; i++) rho_point(g, i, k, j, p3("alt"), p3("moist_qv"), p3("rho"));
+  } else if (stage == 1) {
     for (int j = g.jts - 1; j <= g.jte; j++)
       for (int k = 1; k <= g.kde; k++)
-        for (int i = g.its; i <= g.ite; i++) diff_metrics_point(g, i, k, j, p3(PH), p3(PHB), p3(Z), p3(RDZ), p3(RDZW), p3(ZX), p3(ZY));
+        for (int i = g.its; i <= g.ite; i++) diff_metrics_point(g, i, k, j, p3("ph_2"), p3("phb"), p3("z"), p3("rdz"), p3("rdzw"), p3("zx"), p3("zy"));
   } else if (stage == 2) {
     DefIn in;
-    in.u = p3(U); in.v = p3(V); in.w = p3(W); in.rdz = p3(RDZ); in.rdzw = p3(RDZW); in.zx = p3(ZX); in.zy = p3(ZY);
-    in.dn = p1(DN); in.dnw = p1(DNW); in.u_base = p1(UBASE); in.v_base = p1(VBASE);
+    in.u = p3("u_2"); in.v = p3("v_2"); in.w = p3("w_2"); in.rdz = p3("rdz"); in.rdzw = p3("rdzw"); in.zx = p3("zx"); in.zy = p3("zy");
+    in.dn = p1("dn"); in.dnw = p1("dnw"); in.u_base = p1("u_base"); in.v_base = p1("v_base");
     DefOut out;
-    out.div = p3(DIV); out.defor11 = p3(D11); out.defor22 = p3(D22); out.defor33 = p3(D33); out.defor12 = p3(D12); out.defor13 = p3(D13);
-    out.defor23 = p3(D23);
+    out.div = p3("div"); out.defor11 = p3("defor11"); out.defor22 = p3("defor22"); out.defor33 = p3("defor33"); out.defor12 = p3("defor12");
+    out.defor13 = p3("defor13"); out.defor23 = p3("defor23");
     const DefR r = def_ranges(g, c.mix_full_fields);
     for (int j = g.jts; j <= g.jte; j++)
       for (int k = 1; k <= g.kde; k++)
         for (int i = g.its; i <= g.ite; i++) deform_point(g, r, in, out, i, k, j);
-  } else {
-    int i_start = g.its, i_end = std::min(g.ite, g.ide - 1), j_start = g.jts, j_end = std::min(g.jte, g.jde - 1);   // as Solver::diffusion_prep
+  } else if (stage == 3) {
+    int i_start = g.its, i_end = ie, j_start = g.jts, j_end = je;   // as Solver::diffusion_prep
     if (g.open_xs) i_start = std::max(g.ids + 1, g.its);
     if (g.open_xe) i_end = std::min(g.ide - 2, g.ite);
     if (g.open_ys) j_start = std::max(g.jds + 1, g.jts);
     if (g.open_ye) j_end = std::min(g.jde - 2, g.jte);
-    if (g.periodic_x) { i_start = g.its; i_end = std::min(g.ite, g.ide - 1); }
+    if (g.periodic_x) { i_start = g.its; i_end = ie; }
     SmagIn sm;
-    sm.defor11 = p3(D11); sm.defor22 = p3(D22); sm.defor12 = p3(D12); sm.rdzw = p3(RDZW); sm.zx = p3(ZX); sm.zy = p3(ZY);
+    sm.defor11 = p3("defor11"); sm.defor22 = p3("defor22"); sm.defor12 = p3("defor12"); sm.rdzw = p3("rdzw"); sm.zx = p3("zx"); sm.zy = p3("zy");
     sm.dx = c.dx; sm.dy = c.dy; sm.c_s = c.c_s; sm.diff_opt = c.diff_opt;
     for (int j = j_start; j <= j_end; j++)
       for (int k = 1; k <= g.kde - 1; k++)
-        for (int i = i_start; i <= i_end; i++) smag2d_point(g, sm, i, k, j, p3(XKMH), p3(XKMV), p3(XKHH), p3(XKHV));
+        for (int i = i_start; i <= i_end; i++) smag2d_point(g, sm, i, k, j, p3("xkmh"), p3("xkmv"), p3("xkhh"), p3("xkhv"));
+  } else if (stage == 4) {
+    const float prandtl = 1.f / 3.0f;   // as Solver::diffusion2_isotropic_km
+    const float khdif3 = c.khdif / prandtl, kvdif3 = c.kvdif / prandtl;
+    float *xkmh = p3("xkmh"), *xkmv = p3("xkmv"), *xkhh = p3("xkhh"), *xkhv = p3("xkhv");
+    for (int j = g.jts; j <= je; j++)
+      for (int k = 1; k <= g.kde; k++)
+        for (int i = g.its; i <= ie; i++) { A3(xkmh, i, k, j) = c.khdif; A3(xkmv, i, k, j) = c.kvdif; A3(xkhh, i, k, j) = khdif3; A3(xkhv, i, k, j) = kvdif3; }
+  } else {
+    D2In s;   // as Solver::diffusion2_tendencies
+    s.defor11 = p3("defor11"); s.defor22 = p3("defor22"); s.defor33 = p3("defor33"); s.defor12 = p3("defor12"); s.defor13 = p3("defor13");
+    s.defor23 = p3("defor23"); s.xkmh = p3("xkmh"); s.xkmv = p3("xkmv"); s.xkhh = p3("xkhh"); s.xkhv = p3("xkhv"); s.zx = p3("zx"); s.zy = p3("zy");
+    s.rdz = p3("rdz"); s.rdzw = p3("rdzw"); s.rho = p3("rho"); s.dn = p1("dn");
+    s.u = p3("u_2"); s.v = p3("v_2"); s.t = p3("t_2"); s.qv = p3("moist_qv");
+    s.ustm = p2("ustm"); s.hfx_in = p2("hfx"); s.qfx = p2("qfx"); s.hfx_out = p2("hfx");
+    s.isfflx = c.isfflx; s.use_theta_m = c.use_theta_m; s.cd0 = c.tke_drag_coefficient; s.heat_flux = c.tke_heat_flux;
+    const R4 ru = d2_range(g, 'u'), rv = d2_range(g, 'v'), rm = d2_range(g, 'm');
+    const float *tb = c.mix_full_fields ? nullptr : p1("t_base"), *qb = c.mix_full_fields ? nullptr : p1("qv_base");
+    if (stage == 5) {
+      for (int j = g.jts; j <= g.jte; j++)
+        for (int k = 1; k <= g.kde - 1; k++)
+          for (int i = g.its; i <= g.ite; i++) {
+            diff2_u_point(g, s, ru, i, k, j, p3("ru_tendf"));
+            diff2_v_point(g, s, rv, i, k, j, p3("rv_tendf"));
+          }
+      for (int j = rm.j0; j <= rm.j1; j++)
+        for (int k = 2; k <= g.kde - 1; k++)
+          for (int i = rm.i0; i <= rm.i1; i++) diff2_w_point(g, s, i, k, j, p3("rw_tendf"));
+      for (int j = g.jts; j <= g.jte; j++)
+        for (int k = 1; k <= g.kde - 1; k++)
+          for (int i = g.its; i <= g.ite; i++) diff2_s_point(g, s, rm, 0, p3("t_2"), tb, s.xkhv, s.xkhh, i, k, j, p3("t_tendf"));
+    } else {
+      float *var = p3(names[nn - 2]), *tend = p3(names[nn - 1]);
+      for (int j = g.jts; j <= g.jte; j++)
+        for (int k = 1; k <= g.kde - 1; k++)
+          for (int i = g.its; i <= g.ite; i++) diff2_s_point(g, s, rm, which, var, which == 1 ? qb : nullptr, s.xkhv, s.xkhh, i, k, j, tend);
+    }
   }
   delete gp;
   return 0;

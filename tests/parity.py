@@ -40,6 +40,16 @@ def with_map_factors(case, amp=0.04):
     return case
 
 
+def with_surface_fluxes(case):
+    """ustm, hfx, qfx as a host-side surface-layer scheme would hand them over (isfflx 1 / 2): smooth, non-zero patterns"""
+    d = case.dims
+    jj, ii = np.meshgrid(np.arange(d.jms, d.jme + 1), np.arange(d.ims, d.ime + 1), indexing="ij")
+    case.fields["ustm"] = (0.25 + 0.1 * np.sin(0.37 * ii + 0.9 * jj)).astype(np.float32)
+    case.fields["hfx"] = (80.0 + 40.0 * np.cos(0.21 * ii - 0.5 * jj)).astype(np.float32)
+    case.fields["qfx"] = (2.0e-5 * (1.0 + 0.5 * np.sin(0.13 * ii + 0.4 * jj))).astype(np.float32)
+    return case
+
+
 def with_updraft(case, wmax, conv=25.0):
     """Add an updraft core to a case: a Gaussian blob of `wmax` m/s in w and, because the first step diagnoses ww from
     the divergence of (u, v) and not from w, winds converging below and diverging aloft (`conv` m/s) that imply the same
@@ -155,6 +165,16 @@ def small_cases():
                                                       diff_opt=1, km_opt=4, c_s=0.5)),
         "smag2d_hill": make_case("hill2d_x", nx=62, ny=3, nz=21, diff_opt=1, km_opt=4, mix_full_fields=1),
         "smag2d_b_wave": make_case("b_wave", nx=21, ny=31, nz=17, diff_opt=1, km_opt=4, kvdif=5.0),
+        # diffusion in physical space (diff_opt 2: vertical_diffusion_2 + horizontal_diffusion_2 with the cal_titau stresses):
+        # constant K with open boundaries, Kessler, namelist drag and heat flux; 2-D Smagorinsky K, doubly periodic with map
+        # factors, tracers and full-field mixing; constant K over the hill (the terrain-slope terms) with surface fluxes from a
+        # host-side surface scheme (isfflx 1); Smagorinsky K with periodic x / symmetric y
+        "diff2": make_case("quarter_ss", nx=26, ny=24, nz=21, diff_opt=2, km_opt=1, khdif=300.0, kvdif=100.0, tke_drag_coefficient=0.003,
+                           tke_heat_flux=0.05),
+        "diff2_periodic": with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=2,
+                                                     diff_opt=2, km_opt=4, c_s=0.5, mix_full_fields=1)),
+        "diff2_hill": with_surface_fluxes(make_case("hill2d_x", nx=62, ny=3, nz=21, diff_opt=2, km_opt=1, khdif=100.0, kvdif=30.0, isfflx=1)),
+        "diff2_b_wave": make_case("b_wave", nx=21, ny=31, nz=17, diff_opt=2, km_opt=4, isfflx=2, tke_heat_flux=0.02),
         "ieva_weno_hill": with_updraft(make_case("hill2d_x", nx=62, ny=3, nz=41, zadvect_implicit=1, momentum_adv_opt=3,
                                                  moist_adv_opt=3), 60.0, conv=70.0),
     }

@@ -16,10 +16,10 @@ from tests.parity import small_cases
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "tests", "_build")
-ORDER = ("ph_2", "phb", "u_2", "v_2", "w_2", "z", "rdz", "rdzw", "zx", "zy", "div", "defor11", "defor22", "defor33", "defor12", "defor13",
-         "defor23", "xkmh", "xkmv", "xkhh", "xkhv", "msftx", "msfty", "msfux", "msfuy", "msfvx", "msfvy", "fnm", "fnp", "dn", "dnw",
-         "u_base", "v_base")
-OUT = ORDER[5:21]
+IN3 = ("ph_2", "phb", "u_2", "v_2", "w_2", "t_2", "alt")
+OUT3 = ("z", "rdz", "rdzw", "zx", "zy", "div", "defor11", "defor22", "defor33", "defor12", "defor13", "defor23", "xkmh", "xkmv", "xkhh", "xkhv")
+D2 = ("rho", "ru_tendf", "rv_tendf", "rw_tendf", "t_tendf", "ustm", "hfx", "qfx")
+REST = ("msftx", "msfty", "msfux", "msfuy", "msfvx", "msfvy", "fnm", "fnp", "dn", "dnw", "u_base", "v_base", "t_base", "qv_base")
 
 
 @pytest.fixture(scope="module")
@@ -29,7 +29,7 @@ def shim():
     os.makedirs(BUILD, exist_ok=True)
     so = os.path.join(BUILD, "deform_shim.so")
     src = os.path.join(ROOT, "tests", "deform_shim.cu")
-    deps = [src] + [os.path.join(ROOT, "wrf_b200", "csrc", f) for f in ("deform.cuh", "common.cuh")] + [os.path.join(ROOT, "include", "wrfgpu.h")]
+    deps = [src] + [os.path.join(ROOT, "wrf_b200", "csrc", f) for f in ("deform.cuh", "diffusion2.cuh", "common.cuh")] + [os.path.join(ROOT, "include", "wrfgpu.h")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-o", so, src])
     L = ctypes.CDLL(so)
@@ -37,20 +37,28 @@ def shim():
     return L
 
 
-def run_shim(L, case, arrays, stage):
-    ptrs = (ctypes.c_void_p * len(ORDER))(*[arrays[n].ctypes.data for n in ORDER])
-    assert L.deform_shim_run(ctypes.c_int(stage), ctypes.byref(case.dims), ctypes.byref(case.config), ptrs) == 0
+def run_shim(L, case, arrays, stage, last=(), which=0):
+    names = [n for n in arrays if n not in last] + list(last)
+    cn = (ctypes.c_char_p * len(names))(*[n.encode() for n in names])
+    ptrs = (ctypes.c_void_p * len(names))(*[arrays[n].ctypes.data for n in names])
+    assert L.deform_shim_run(ctypes.c_int(stage), ctypes.byref(case.dims), ctypes.byref(case.config), ctypes.c_int(len(names)), cn, ptrs,
+                             ctypes.c_int(which)) == 0
 
 
-@pytest.mark.parametrize("name", ["smag2d", "smag2d_periodic", "smag2d_hill", "smag2d_b_wave"])
+@pytest.mark.parametrize("name", ["smag2d", "smag2d_periodic", "smag2d_hill", "smag2d_b_wave", "diff2", "diff2_periodic", "diff2_hill", "diff2_b_wave"])
 def test_device_point_functions_equal_the_oracle(shim, name):
     case = small_cases()[name]
+    c = case.config
     o = Oracle(case)
     o.start_domain()
-    o.step(2)   # the state (and the stale contents of the 16 work fields) of a running model
+    o.step(2)   # the state (and the stale contents of the work fields) of a running model
     for ph, args in (("rk_step_prep", (1,)), ("rk_phys_bc_dry_1", ()), ("init_zero_tendency", ())):
         o.call(ph, *args)
-    arrays = {n: np.ascontiguousarray(o.get(n)).copy() for n in ORDER}
+    species = [(n, n.replace("moist_", "moist_tend_").replace("scalar_", "scalar_tend_")) for n in o.names()
+               if n.startswith(("moist_q", "scalar_")) and "old" not in n and "tend" not in n]
+    have = set(o.names())
+    names = [n for n in IN3 + OUT3 + D2 + REST if n in have] + [n for pair in species for n in pair]
+    arrays = {n: np.ascontiguousarray(o.get(n)).copy() for n in names}
     applier = Oracle(case)   # set_physical_bc of the oracle, applied to the shim's arrays between the stages
 
     def bc(n, var):
@@ -58,19 +66,32 @@ def test_device_point_functions_equal_the_oracle(shim, name):
         applier.bc(n, var)
         arrays[n][...] = applier.get(n)
 
+    if c.diff_opt == 2:
+        run_shim(shim, case, arrays, 0)
     run_shim(shim, case, arrays, 1)
     for n, var in (("rdzw", "w"), ("rdz", "w"), ("z", "w"), ("zx", "e"), ("zy", "f")):
         bc(n, var)
     run_shim(shim, case, arrays, 2)
-    run_shim(shim, case, arrays, 3)
+    run_shim(shim, case, arrays, 4 if c.km_opt == 1 else 3)
     bc("xkmh", "t"); bc("xkhh", "t")
+    out = list(OUT3)
+    if c.diff_opt == 2:
+        for n, var in (("xkmv", "t"), ("xkhv", "t"), ("div", "t"), ("defor11", "t"), ("defor22", "t"), ("defor33", "t"), ("defor12", "d"),
+                       ("defor13", "e"), ("defor23", "f"), ("rho", "t")):
+            bc(n, var)
+        run_shim(shim, case, arrays, 5)
+        for f, t in species:
+            run_shim(shim, case, arrays, 6, last=(f, t), which=1 if f == "moist_qv" else 2)
+        out += ["rho", "ru_tendf", "rv_tendf", "rw_tendf", "t_tendf", "hfx"] + [t for _, t in species]
     o.call("diffusion_prep")
-    ref = {n: o.get(n) for n in OUT}
     bad = []
-    for n in OUT:
-        a, b = arrays[n].view(np.uint32), ref[n].view(np.uint32)
+    for n in out:
+        ref = o.get(n)
+        a, b = arrays[n].view(np.uint32), ref.view(np.uint32)
         if not np.array_equal(a, b):
             w = np.argwhere(a != b)
-            bad.append((n, len(w), w[:3].tolist(), float(np.abs(arrays[n] - ref[n]).max())))
+            bad.append((n, len(w), w[:3].tolist(), float(np.abs(arrays[n] - ref).max())))
     assert not bad, bad
-    assert float(ref["xkmh"].max()) > 0.0
+    assert float(o.get("xkmh").max()) > 0.0
+    if c.diff_opt == 2:
+        assert all(float(np.abs(o.get(n)).max()) > 0.0 for n in ("ru_tendf", "rw_tendf", "t_tendf"))

@@ -269,6 +269,52 @@ def test_smag2d_k_of_a_sheared_jet_is_the_documented_formula():
     assert np.allclose(got_t, want_t, rtol=1e-4, atol=2e-4 * np.abs(want_t).max()), np.abs(got_t - want_t).max()
 
 
+def test_physical_space_diffusion_decays_a_sinusoid_and_a_vertical_profile_at_the_analytic_rates():
+    """diff_opt = 2 / km_opt = 1 (horizontal_diffusion_s, vertical_diffusion_s, module_diffusion_em.F:3711, :4789): over flat
+    terrain the physical-space operator is d/dx(rho K dq/dx) / rho_hyd with K = xkhh = khdif / prandtl = 3 khdif, so a passive
+    sin(2 pi x / L) decays by 1 - dt K (2 - 2 cos(k dx)) / dx^2 per step up to the ratio of the moist density rho = (1 + qv) / alt
+    the stresses are built with to the dry hydrostatic mass the tendency is divided by (a few 1e-4 here); the mean is conserved.
+    In the vertical (kvdif, xkhv = 3 kvdif) the flux -rho K dq/dz vanishes at the surface and the top, so the column integral of
+    the tendency of any profile (here one linear in z) is zero."""
+    nx, L = 33, 32
+    case = make_case("b_wave", nx=nx, ny=12, nz=11, calm=True, num_scalar=2, scalar_adv_opt=1, diff_opt=2, km_opt=1, khdif=1.0e6, kvdif=30.0)
+    d, c = case.dims, case.config
+    ii = np.arange(d.ims, d.ime + 1, dtype=np.float64)
+    prof = (1.0 + 0.5 * np.sin(2 * np.pi * (ii - 1) / L)).astype(np.float32)
+    s = case.fields["scalar_1"]
+    s[:] = prof[None, None, :]
+    s[:, -1, :] = 0
+    o = Oracle(case)
+    o.start_domain()
+    # scalar_2 = height of the mass level: linear in z
+    for ph, args in (("rk_step_prep", (1,)), ("rk_phys_bc_dry_1", ()), ("init_zero_tendency", ()), ("diffusion_prep", ())):
+        o.call(ph, *args)
+    z = o.get("z").copy()
+    z[:, -1, :] = 0
+    o = Oracle(case)
+    o.set("scalar_2", z * 1.0e-3)
+    o.start_domain()
+    for ph, args in (("rk_step_prep", (1,)), ("rk_phys_bc_dry_1", ()), ("init_zero_tendency", ()), ("diffusion_prep", ())):
+        o.call(ph, *args)
+    t2 = o.get("scalar_tend_2")[4 - d.jms, :-1, 1 - d.ims:1 - d.ims + L].astype(np.float64)
+    dnw = o.get("dnw")[:-1].astype(np.float64)
+    col = (t2 * dnw[:, None]).sum(axis=0)                                 # sum_k tend dnw / g = H3(top) - H3(surface) = 0
+    assert np.abs(col).max() < 1e-5 * np.abs(t2 * dnw[:, None]).sum(axis=0).max()
+    assert np.abs(t2).max() > 0.1                                         # rho K dq/dz is not uniform: rho falls with height
+    o = Oracle(case)
+    o.start_domain()
+    n = 20
+    o.step(n)
+    c = case.config
+    K = np.float64(c.khdif) * 3.0
+    lam = 1.0 - c.dt * K * (2.0 - 2.0 * np.cos(2 * np.pi / L)) / c.dx ** 2
+    got = o.get("scalar_1")[4 - d.jms, 3, 1 - d.ims:1 - d.ims + L].astype(np.float64)
+    amp = 2.0 * np.abs(np.fft.rfft(got - got.mean())[1]) / L
+    assert abs(amp / 0.5 - lam ** n) < 1.5e-3 * lam ** n, (amp / 0.5, lam ** n)
+    assert abs(got.mean() - 1.0) < 1e-5                               # diffusion conserves the mean
+    assert np.abs(o.get("w_2")).max() < 1e-3                          # and the atmosphere stayed at rest
+
+
 def test_sixth_order_filter_damps_the_two_delta_x_wave_at_the_documented_rate():
     """sixth_order_diffusion (module_big_step_utilities_em.F:6220): for q = (-1)^i the flux differences are +-32 q, so the
     tendency is -64 * (factor * 0.015625 / (2 dt')) * mu * q = -(factor / (2 dt')) mu q: the filter removes factor / 2 of a

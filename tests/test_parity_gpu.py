@@ -17,7 +17,8 @@ ALL = ["hill2d_x", "quarter_ss", "quarter_ss_nopd", "b_wave", "les", "periodic",
        "mono", "mono_periodic", "weno", "weno_periodic", "wenopd", "wenopd_periodic",
        "weno_mom", "weno_mom_periodic", "weno_mom_b_wave", "ieva", "ieva_periodic", "ieva_weno_hill",
        "diff6", "diff6_periodic", "diff6_hill", "tall", "tiny", "rk2_everything", "backward",
-       "order64", "order63_periodic", "order_mixed", "smag2d", "smag2d_periodic", "smag2d_hill", "smag2d_b_wave"]
+       "order64", "order63_periodic", "order_mixed", "smag2d", "smag2d_periodic", "smag2d_hill", "smag2d_b_wave",
+       "diff2", "diff2_periodic", "diff2_hill", "diff2_b_wave"]
 
 
 def cases():

@@ -191,7 +191,10 @@ struct Solver {
   void rk_step_prep(int rk_step);
   void rk_phys_bc_dry_1();
   void init_zero_tendency();
-  void diffusion_prep();   // deform.cu: first_rk_step_part2's metrics, deformation, K (km_opt = 4)
+  void diffusion_prep();   // deform.cu: first_rk_step_part2's metrics, deformation, K (km_opt = 4), diff_opt = 2 tendencies
+  void diffusion2_rho();   // diffusion2.cu
+  void diffusion2_isotropic_km();
+  void diffusion2_tendencies();
   void rk_tendency(int rk_step, bool zero_save = true);
   // IEVA (ieva.cu): WW_SPLIT + mass estimates; one implicit column solve (0 scalar, 1 u, 2 v, 3 ph, 4 w)
   void ieva_split(bool dry, const float *u, const float *v, const float *ww, const float *mut, bool active = true);
@@ -278,6 +281,8 @@ void launch_pd_fast(Solver *s, int pass, const Box &bx, cfp q, cfp q_old, float 
 // sixth_order_diffusion of `field` added to `tendency` (which as above; anything >= 3 = mass points)
 void launch_diff6(Solver *s, int which, const float *field, float *tendency, const float *mut, float dt);
 void launch_diffuse(Solver *s, int which, cfp field, fp tendency, float xk, float kvdif, cfp xkarr = nullptr);
+// diffusion2.cu: diff_opt = 2 with constant K = 0 and no surface fluxes adds exact zeros
+bool diff2_is_identity(const wrfgpu_config &c);
 // mom_fast.cu: which = 0 ru_tend, 1 rv_tend, 2 rw_tend on the interior box
 void launch_mom_fast(Solver *s, int which, const Box &in);
 

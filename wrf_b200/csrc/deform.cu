@@ -22,11 +22,15 @@ __global__ void k_smag2d(const Geo g, Box b, SmagIn s, fp xkmh, fp xkmv, fp xkhh
 }
 
 void Solver::diffusion_prep() {
-  if (c.diff_opt == 0 || c.km_opt < 2) return;   // km_opt = 1: K is a constant the diffusion kernels take by value
+  if (c.diff_opt == 0) return;
+  if (c.diff_opt == 1 && c.km_opt == 1) return;   // K is a constant the diffusion kernels of rk_tendency take by value
+  if (diff2_is_identity(c)) return;               // diff_opt = 2 with all coefficients zero adds exact zeros (shipped em_hill2d_x)
   const Geo &q = g;
+  if (c.diff_opt == 2) diffusion2_rho();
   // compute_diff_metrics: rdz, rdzw on rows jts-1..jte, the rest on the tile
   LAUNCH3(this, k_diff_metrics, (Box{q.its, q.ite, 1, q.kde, q.jts - 1, q.jte}), o("ph_2"), o("phb"), o("z"), o("rdz"), o("rdzw"), o("zx"), o("zy"));
   halo("HALO_EM_TKE_C");   // + PERIOD_BDY_EM_A1 (:446-447)
+  if (c.diff_opt == 2) { halo("HALO_EM_TKE_C_SFC"); bc({{"ustm", 't'}}); }   // ustm of HALO_EM_TKE_C, set_physical_bc2d :492
   bc({{"rdzw", 'w'}, {"rdz", 'w'}, {"z", 'w'}, {"zx", 'e'}, {"zy", 'f'}});
   // cal_deform_and_div
   DefIn in;
@@ -38,6 +42,8 @@ void Solver::diffusion_prep() {
   const DefR r = def_ranges(q, c.mix_full_fields);
   LAUNCH3(this, k_deform, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), r, in, out);
   halo("HALO_EM_TKE_D");   // :571
+  if (c.km_opt == 1) diffusion2_isotropic_km();
+  else {
   // calculate_km_kh -> smag2d_km on its computed range (module_diffusion_em.F:1974-1989)
   int i_start = q.its, i_end = std::min(q.ite, q.ide - 1), j_start = q.jts, j_end = std::min(q.jte, q.jde - 1);
   if (q.open_xs) i_start = std::max(q.ids + 1, q.its);
@@ -49,8 +55,10 @@ void Solver::diffusion_prep() {
   sm.defor11 = o("defor11"); sm.defor22 = o("defor22"); sm.defor12 = o("defor12"); sm.rdzw = o("rdzw"); sm.zx = o("zx"); sm.zy = o("zy");
   sm.dx = c.dx; sm.dy = c.dy; sm.c_s = c.c_s; sm.diff_opt = c.diff_opt;
   LAUNCH3(this, k_smag2d, (Box{i_start, i_end, 1, q.kde - 1, j_start, j_end}), sm, o("xkmh"), o("xkmv"), o("xkhh"), o("xkhv"));
+  }
   halo("HALO_EM_TKE_E");   // + PERIOD_BDY_EM_PHY_BC, HALO_EM_PHYS_DIFFUSION (:644-650, :759)
   bc({{"xkmh", 't'}, {"xkhh", 't'}});   // phy_bc (module_diffusion_em.F:5901), diff_opt = 1 part
+  if (c.diff_opt == 2) diffusion2_tendencies();
 }
 
 }  // namespace wg

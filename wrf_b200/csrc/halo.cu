@@ -58,12 +58,16 @@ static const HaloDef kHalos[] = {
     // diffusion preamble of the first RK substep (first_rk_step_part2, module_first_rk_step_part2.F), closures that compute K:
     // metrics (:446-447): HALO_EM_TKE_C :3438 (1) + PERIOD_BDY_EM_A1 :3539 (3); its u_2, v_2 are current since HALO_EM_E_5
     {"HALO_EM_TKE_C", 3, "z,zx,zy,rdz,rdzw", ""},
+    // the 2-D part of HALO_EM_TKE_C (ustm; diff_opt = 2 only: the surface drag averages it to the u and v points)
+    {"HALO_EM_TKE_C_SFC", 1, "", "ustm"},
     // deformation (:571): HALO_EM_TKE_D :3439 (1)
     {"HALO_EM_TKE_D", 1, "defor11,defor22,defor33,defor12,defor13,defor23,div", ""},
     // eddy viscosities (:644-650, :759): HALO_EM_TKE_E :3440 (1) + PERIOD_BDY_EM_PHY_BC :3540 (2) + HALO_EM_PHYS_DIFFUSION :3432 (1)
-    {"HALO_EM_TKE_E", 2, "xkmv,xkmh,xkhv,xkhh,div,defor11,defor22,defor33,defor12,defor13,defor23", ""},
-    // very end (:4781-4846): HALO_EM_E_5 :3458 (3) after set_w_surface
-    {"HALO_EM_E_5", 3, "u_1,u_2,v_1,v_2,w_1,w_2,t_1,t_2,ph_1,ph_2", "mu_1,mu_2"},
+    {"HALO_EM_TKE_E", 2, "xkmv,xkmh,xkhv,xkhh,div,defor11,defor22,defor33,defor12,defor13,defor23,rho", ""},
+    // very end (:4781-4846): HALO_EM_E_5 :3458 (3) after set_w_surface -- NOT followed by a PERIOD_* closure or a set_physical_bc
+    // in the reference, so the periodic ghost zone keeps the w_2(k=1) of before set_w_surface (what the boundary fill of a
+    // single rank leaves there as well): negative width = no closure.  cal_deform_and_div is the one reader of that value.
+    {"HALO_EM_E_5", -3, "u_1,u_2,v_1,v_2,w_1,w_2,t_1,t_2,ph_1,ph_2", "mu_1,mu_2"},
     // start_domain_em (dyn_em/start_em.F): HALO_EM_INIT_1..5 carry the base state, map factors and both time levels
     {"HALO_EM_INIT", 4,
      "phb,pb,alb,p,al,alt,t_init,u_1,u_2,v_1,v_2,w_1,w_2,t_1,t_2,ph_1,ph_2,@moist,@moist_old,@scalar,@scalar_old",
@@ -105,16 +109,20 @@ static bool halo_fields(const wrfgpu_config &c, const std::string &name, int &wi
 // ---------------------------------------------------------------------------------------------
 // strip geometry.  dir: 0 = -y, 1 = +y (Y phase), 2 = -x, 3 = +x (X phase)
 struct Strip { int peer; int is, ie, js, je; };
+// A negative width means "HALO only": an exchange the reference does not follow with a PERIOD_* closure, so the ghost zone
+// beyond a periodic domain edge keeps what the last closure / set_physical_bc put there (see HALO_EM_E_5 in the table).
 static bool halo_box(const wrfgpu_dims &d, const wrfgpu_config &c, int w, int dir, bool send, Strip &s) {
   const int ntx = std::max(1, c.ntasks_x), nty = std::max(1, c.ntasks_y);
   const int mx = c.mytask % ntx, my = c.mytask / ntx;
+  const bool closure = w > 0;
+  if (w < 0) w = -w;
   bool wrap = false;
   int px = mx, py = my;
   switch (dir) {
-    case 0: if (my > 0) py = my - 1; else if (c.periodic_y && nty > 1) { py = nty - 1; wrap = true; } else return false; break;
-    case 1: if (my < nty - 1) py = my + 1; else if (c.periodic_y && nty > 1) { py = 0; wrap = true; } else return false; break;
-    case 2: if (mx > 0) px = mx - 1; else if (c.periodic_x && ntx > 1) { px = ntx - 1; wrap = true; } else return false; break;
-    default: if (mx < ntx - 1) px = mx + 1; else if (c.periodic_x && ntx > 1) { px = 0; wrap = true; } else return false; break;
+    case 0: if (my > 0) py = my - 1; else if (c.periodic_y && nty > 1 && closure) { py = nty - 1; wrap = true; } else return false; break;
+    case 1: if (my < nty - 1) py = my + 1; else if (c.periodic_y && nty > 1 && closure) { py = 0; wrap = true; } else return false; break;
+    case 2: if (mx > 0) px = mx - 1; else if (c.periodic_x && ntx > 1 && closure) { px = ntx - 1; wrap = true; } else return false; break;
+    default: if (mx < ntx - 1) px = mx + 1; else if (c.periodic_x && ntx > 1 && closure) { px = 0; wrap = true; } else return false; break;
   }
   s.peer = py * ntx + px;
   // extent along the exchanged dimension: [lo, hi] of the patch, domain [ds, de]
@@ -141,7 +149,7 @@ static bool halo_box(const wrfgpu_dims &d, const wrfgpu_config &c, int w, int di
     s.is = a; s.ie = b;
     // rows include the y halo just received, so corners arrive in two hops (c_code.c:587 JMAX/JMIN clip to
     // the domain; with a split periodic y the ghost rows beyond the domain came from the wrap and go along)
-    const int ext = (c.periodic_y && nty > 1) ? w : 0;
+    const int ext = (c.periodic_y && nty > 1 && closure) ? w : 0;
     s.js = std::max(d.jps - w, d.jds - ext); s.je = std::min(d.jpe + w, d.jde + ext);
   }
   return true;

@@ -42,7 +42,8 @@ MODULE module_wrfgpu
       REAL(c_float)  :: diff_6th_factor, diff_6th_thresh
       INTEGER(c_int) :: diff_6th_slopeopt, moist_mix6_off, scalar_mix6_off
       REAL(c_float)  :: c_s, c_k
-      INTEGER(c_int) :: mix_full_fields
+      INTEGER(c_int) :: mix_full_fields, isfflx
+      REAL(c_float)  :: tke_drag_coefficient, tke_heat_flux
    END TYPE wrfgpu_config
 
    INTERFACE

@@ -66,7 +66,8 @@ class Config(ctypes.Structure):
         + [(n, ctypes.c_float) for n in ("diff_6th_factor", "diff_6th_thresh")]
         + [(n, ctypes.c_int) for n in ("diff_6th_slopeopt", "moist_mix6_off", "scalar_mix6_off")]
         + [(n, ctypes.c_float) for n in ("c_s", "c_k")]
-        + [("mix_full_fields", ctypes.c_int)])
+        + [("mix_full_fields", ctypes.c_int), ("isfflx", ctypes.c_int)]
+        + [(n, ctypes.c_float) for n in ("tke_drag_coefficient", "tke_heat_flux")])
 
 
 def default_config(**kw) -> Config:
