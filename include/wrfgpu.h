@@ -66,7 +66,8 @@ typedef struct wrfgpu_config {
   int phi_adv_z;                         /* 1/2 */
   int zadvect_implicit;                  /* > 0: IEVA on the last RK substep (module_ieva_em.F) */
   int diff_opt, km_opt;                  /* diff_opt 0, 1 (coordinate surfaces), 2 (physical space);
-                                            km_opt 1 (constant K) or 4 (2-D Smagorinsky) */
+                                            km_opt 1 (constant K), 3 (3-D Smagorinsky) or 4 (2-D Smagorinsky)
+                                             */
   int diff_6th_opt;                      /* 0, 1 or 2 (sixth_order_diffusion; 2 = no up-gradient fluxes) */
   int mp_physics;                        /* 0 = none(passive qv), 1 = Kessler */
   int time_step;                         /* integer namelist time_step; only its
@@ -99,6 +100,9 @@ typedef struct wrfgpu_config {
   int isfflx;                            /* 0: drag and heat flux from the two constants below; 1, 2: from ustm / hfx / qfx */
   float tke_drag_coefficient;            /* 0. */
   float tke_heat_flux;                   /* 0. (K m/s) */
+  /* 3-D Smagorinsky closure (km_opt = 3; smag_km, module_diffusion_em.F:1777) */
+  int mix_isotropic;                     /* 0 = separate horizontal / vertical length scales, 1 = (dx dy dz)^(1/3) */
+  float mix_upper_bound;                 /* 0.1: K <= mix_upper_bound * l^2 / dt */
 } wrfgpu_config;
 
 typedef struct wrfgpu_solver wrfgpu_solver;   /* opaque */

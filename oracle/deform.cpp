@@ -450,4 +450,175 @@ void smag2d_km(const Cx &x, A3 xkmh, A3 xkmv, A3 xkhh, A3 xkhv, A3 defor11, A3 d
       }
 }
 
+// the thermodynamic part of phy_prep that calculate_N2 reads (module_big_step_utilities_em.F:4818-4912): th_phy, p_phy,
+// t_phy = th_phy * pi_phy on the tile's mass points, and p8w, t8w at the surface (level 1) as 2-D fields
+void phy_prep_thermo(const Cx &x, A3 t, const A3 *qv, A3 p, A3 pb, A3 ph, A3 phb, A3 th_phy, A3 p_phy, A3 t_phy, A2 p8w_sfc, A2 t8w_sfc) {
+  const int i_start = x.its, i_end = std::min(x.ite, x.ide - 1), j_start = x.jts, j_end = std::min(x.jte, x.jde - 1);
+  const int k_start = x.kts, k_end = std::min(x.kte, x.kde - 1);
+  for (int j = j_start; j <= j_end; j++)
+    for (int k = k_start; k <= k_end; k++)
+      for (int i = i_start; i <= i_end; i++) {
+        if (x.c.use_theta_m == 1 && qv) th_phy(i, k, j) = (t(i, k, j) + t0) / (1.f + r_v / r_d * (*qv)(i, k, j));
+        else th_phy(i, k, j) = t(i, k, j) + t0;
+        p_phy(i, k, j) = p(i, k, j) + pb(i, k, j);
+        const float pi_phy = std::pow(p_phy(i, k, j) / p1000mb, rcp);
+        t_phy(i, k, j) = th_phy(i, k, j) * pi_phy;
+      }
+  for (int j = j_start; j <= j_end; j++)
+    for (int i = i_start; i <= i_end; i++) {
+      const float zw1 = (phb(i, 1, j) + ph(i, 1, j)) / g, zw2 = (phb(i, 2, j) + ph(i, 2, j)) / g, zw3 = (phb(i, 3, j) + ph(i, 3, j)) / g;
+      const float z0 = zw1;
+      const float z1 = 0.5f * (zw1 + zw2);
+      const float z2 = 0.5f * (zw2 + zw3);
+      const float w1 = (z0 - z2) / (z1 - z2);
+      const float w2 = 1.f - w1;
+      p8w_sfc(i, j) = w1 * p_phy(i, 1, j) + w2 * p_phy(i, 2, j);
+      t8w_sfc(i, j) = w1 * t_phy(i, 1, j) + w2 * t_phy(i, 2, j);
+    }
+}
+
+// module_diffusion_em.F:1485-1712; moist species qv, qc (no ice on this path: P_QI is not allocated)
+void calculate_N2(const Cx &x, A3 BN2, const A3 *qv, const A3 *qc, A3 theta, A3 t, A3 p, A2 p8w_sfc, A2 t8w_sfc, A3 rdz, A3 rdzw) {
+  const int ids = x.ids, ide = x.ide, jds = x.jds, jde = x.jde, kde = x.kde;
+  const int its = x.its, ite = x.ite, jts = x.jts, jte = x.jte, kts = x.kts, kte = x.kte;
+  const wrfgpu_config &cf = x.c;
+  const A1 &dnw = x.dnw, &dn = x.dn;
+  const float cf1 = x.cf1, cf2 = x.cf2, cf3 = x.cf3;
+  const bool spec = cf.specified || cf.nested;
+  const float qc_cr = 0.00001f;
+  const int ktf = std::min(kte, kde - 1), ktes1 = kte - 1, ktes2 = kte - 2;
+  int i_start = its, i_end = std::min(ite, ide - 1), j_start = jts, j_end = std::min(jte, jde - 1);
+  if (cf.open_xs || spec) i_start = std::max(ids + 1, its);
+  if (cf.open_xe || spec) i_end = std::min(ide - 2, ite);
+  if (cf.open_ys || spec) j_start = std::max(jds + 1, jts);
+  if (cf.open_ye || spec) j_end = std::min(jde - 2, jte);
+  if (cf.periodic_x) i_start = its;
+  if (cf.periodic_x) i_end = std::min(ite, ide - 1);
+  Loc3 l1(x), l2(x), l3(x);
+  Loc2 m1(x), m2(x);
+  A3 tmp1 = l1.a, qvs = l2.a, qctmp = l3.a;
+  A2 tmp1sfc = m1.a, tmp1top = m2.a;
+  auto QV = [&](int i, int k, int j) -> float { return qv ? (*qv)(i, k, j) : 0.f; };   // moist(:,:,:,P_QV): the zero dummy slot without qv
+  for (int j = j_start; j <= j_end; j++)
+    for (int k = kts; k <= ktf; k++)
+      for (int i = i_start; i <= i_end; i++) qctmp(i, k, j) = qc ? (*qc)(i, k, j) : 0.0f;
+  for (const A3 *sp : {qv, qc}) {
+    if (!sp) continue;
+    for (int j = j_start; j <= j_end; j++)
+      for (int k = kts; k <= ktf; k++)
+        for (int i = i_start; i <= i_end; i++) tmp1(i, k, j) = tmp1(i, k, j) + (*sp)(i, k, j);
+    for (int j = j_start; j <= j_end; j++)
+      for (int i = i_start; i <= i_end; i++) {
+        tmp1sfc(i, j) = tmp1sfc(i, j) + cf1 * (*sp)(i, 1, j) + cf2 * (*sp)(i, 2, j) + cf3 * (*sp)(i, 3, j);
+        tmp1top(i, j) = tmp1top(i, j) + (*sp)(i, ktes1, j) + ((*sp)(i, ktes1, j) - (*sp)(i, ktes2, j)) * 0.5f * dnw(ktes1) / dn(ktes1);
+      }
+  }
+  for (int j = j_start; j <= j_end; j++)
+    for (int k = kts; k <= ktf; k++)
+      for (int i = i_start; i <= i_end; i++) {
+        const float tc = t(i, k, j) - svpt0;
+        const float es = 1000.0f * svp1 * std::exp(svp2 * tc / (t(i, k, j) - svp3));
+        qvs(i, k, j) = ep_2 * es / (p(i, k, j) - es);
+      }
+  float tmpdz, xlvqv, coefa, thetaep1, thetaem1;
+  for (int j = j_start; j <= j_end; j++)
+    for (int k = kts + 1; k <= ktf - 1; k++)
+      for (int i = i_start; i <= i_end; i++) {
+        tmpdz = 1.0f / rdz(i, k, j) + 1.0f / rdz(i, k + 1, j);
+        if (QV(i, k, j) >= qvs(i, k, j) || qctmp(i, k, j) >= qc_cr) {
+          xlvqv = xlv * QV(i, k, j);
+          coefa = (1.0f + xlvqv / r_d / t(i, k, j)) / (1.0f + xlv * xlvqv / cp / r_v / t(i, k, j) / t(i, k, j)) / theta(i, k, j);
+          thetaep1 = theta(i, k + 1, j) * (1.0f + xlv * qvs(i, k + 1, j) / cp / t(i, k + 1, j));
+          thetaem1 = theta(i, k - 1, j) * (1.0f + xlv * qvs(i, k - 1, j) / cp / t(i, k - 1, j));
+          BN2(i, k, j) = g * (coefa * (thetaep1 - thetaem1) / tmpdz - (tmp1(i, k + 1, j) - tmp1(i, k - 1, j)) / tmpdz);
+        } else {
+          BN2(i, k, j) = g * ((theta(i, k + 1, j) - theta(i, k - 1, j)) / theta(i, k, j) / tmpdz + 1.61f * (QV(i, k + 1, j) - QV(i, k - 1, j)) / tmpdz -
+                              (tmp1(i, k + 1, j) - tmp1(i, k - 1, j)) / tmpdz);
+        }
+      }
+  const int k = kts;
+  for (int j = j_start; j <= j_end; j++)
+    for (int i = i_start; i <= i_end; i++) {
+      tmpdz = 1.0f / rdz(i, k + 1, j) + 0.5f / rdzw(i, k, j);
+      const float thetasfc = t8w_sfc(i, j) / std::pow(p8w_sfc(i, j) / p1000mb, r_d / cp);
+      if (QV(i, k, j) >= qvs(i, k, j) || qctmp(i, k, j) >= qc_cr) {
+        const float qvsfc = cf1 * qvs(i, 1, j) + cf2 * qvs(i, 2, j) + cf3 * qvs(i, 3, j);
+        xlvqv = xlv * QV(i, k, j);
+        coefa = (1.0f + xlvqv / r_d / t(i, k, j)) / (1.0f + xlv * xlvqv / cp / r_v / t(i, k, j) / t(i, k, j)) / theta(i, k, j);
+        thetaep1 = theta(i, k + 1, j) * (1.0f + xlv * qvs(i, k + 1, j) / cp / t(i, k + 1, j));
+        const float thetaesfc = thetasfc * (1.0f + xlv * qvsfc / cp / t8w_sfc(i, j));
+        BN2(i, k, j) = g * (coefa * (thetaep1 - thetaesfc) / tmpdz - (tmp1(i, k + 1, j) - tmp1sfc(i, j)) / tmpdz);
+      } else {
+        const float qvsfc = cf1 * QV(i, 1, j) + cf2 * QV(i, 2, j) + cf3 * QV(i, 3, j);
+        tmpdz = 1.f / rdzw(i, k, j);
+        BN2(i, k, j) = g * ((theta(i, k + 1, j) - theta(i, k, j)) / theta(i, k, j) / tmpdz + 1.61f * (QV(i, k + 1, j) - qvsfc) / tmpdz -
+                            (tmp1(i, k + 1, j) - tmp1sfc(i, j)) / tmpdz);
+      }
+    }
+  for (int j = j_start; j <= j_end; j++)
+    for (int i = i_start; i <= i_end; i++) BN2(i, ktf, j) = BN2(i, ktf - 1, j);
+}
+
+// module_diffusion_em.F:1777-1928 (prandtl = 1/3)
+void smag_km(const Cx &x, A3 xkmh, A3 xkmv, A3 xkhh, A3 xkhv, A3 BN2, A3 defor11, A3 defor22, A3 defor33, A3 defor12, A3 defor13, A3 defor23,
+             A3 rdzw) {
+  const int ids = x.ids, ide = x.ide, jds = x.jds, jde = x.jde, kde = x.kde;
+  const int its = x.its, ite = x.ite, jts = x.jts, jte = x.jte, kts = x.kts, kte = x.kte;
+  const wrfgpu_config &cf = x.c;
+  const A2 &msftx = x.msftx, &msfty = x.msfty;
+  const float dx = cf.dx, dy = cf.dy, dt = cf.dt, mix_upper_bound = cf.mix_upper_bound;
+  const bool spec = cf.specified || cf.nested;
+  Loc3 l1(x);
+  A3 def2 = l1.a;
+  const int ktf = std::min(kte, kde - 1);
+  int i_start = its, i_end = std::min(ite, ide - 1), j_start = jts, j_end = std::min(jte, jde - 1);
+  if (cf.open_xs || spec) i_start = std::max(ids + 1, its);
+  if (cf.open_xe || spec) i_end = std::min(ide - 2, ite);
+  if (cf.open_ys || spec) j_start = std::max(jds + 1, jts);
+  if (cf.open_ye || spec) j_end = std::min(jde - 2, jte);
+  if (cf.periodic_x) i_start = its;
+  if (cf.periodic_x) i_end = std::min(ite, ide - 1);
+  const float pr = 1.f / 3.f, c_s = cf.c_s;
+  float tmp;
+  for (int j = j_start; j <= j_end; j++)
+    for (int k = kts; k <= ktf; k++)
+      for (int i = i_start; i <= i_end; i++) {
+        def2(i, k, j) = 0.5f * (defor11(i, k, j) * defor11(i, k, j) + defor22(i, k, j) * defor22(i, k, j) + defor33(i, k, j) * defor33(i, k, j));
+        tmp = 0.25f * (defor12(i, k, j) + defor12(i, k, j + 1) + defor12(i + 1, k, j) + defor12(i + 1, k, j + 1));
+        def2(i, k, j) = def2(i, k, j) + tmp * tmp;
+        tmp = 0.25f * (defor13(i, k + 1, j) + defor13(i, k, j) + defor13(i + 1, k + 1, j) + defor13(i + 1, k, j));
+        def2(i, k, j) = def2(i, k, j) + tmp * tmp;
+        tmp = 0.25f * (defor23(i, k + 1, j) + defor23(i, k, j) + defor23(i, k + 1, j + 1) + defor23(i, k, j + 1));
+        def2(i, k, j) = def2(i, k, j) + tmp * tmp;
+      }
+  for (int j = j_start; j <= j_end; j++)
+    for (int k = kts; k <= ktf; k++)
+      for (int i = i_start; i <= i_end; i++) {
+        tmp = std::max(0.f, def2(i, k, j) - BN2(i, k, j) / pr);
+        tmp = std::sqrt(tmp);   // tmp**0.5
+        if (cf.mix_isotropic == 0) {
+          const float mlen_h = std::sqrt(dx / msftx(i, j) * dy / msfty(i, j));
+          const float mlen_v = 1.f / rdzw(i, k, j);
+          xkmh(i, k, j) = std::max(c_s * c_s * mlen_h * mlen_h * tmp, 1.0E-6f * mlen_h * mlen_h);
+          xkmh(i, k, j) = std::min(xkmh(i, k, j), mix_upper_bound * mlen_h * mlen_h / dt);
+          xkmv(i, k, j) = std::max(c_s * c_s * mlen_v * mlen_v * tmp, 1.0E-6f * mlen_v * mlen_v);
+          xkmv(i, k, j) = std::min(xkmv(i, k, j), mix_upper_bound * mlen_v * mlen_v / dt);
+          xkhh(i, k, j) = xkmh(i, k, j) / pr;
+          xkhh(i, k, j) = std::min(xkhh(i, k, j), mix_upper_bound * mlen_h * mlen_h / dt);
+          xkhv(i, k, j) = xkmv(i, k, j) / pr;
+          xkhv(i, k, j) = std::min(xkhv(i, k, j), mix_upper_bound * mlen_v * mlen_v / dt);
+        } else {
+          const float deltas = std::pow(dx / msftx(i, j) * dy / msfty(i, j) / rdzw(i, k, j), 0.33333333f);
+          xkmh(i, k, j) = std::max(c_s * c_s * deltas * deltas * tmp, 1.0E-6f * deltas * deltas);
+          xkmh(i, k, j) = std::min(xkmh(i, k, j), mix_upper_bound * dx / msftx(i, j) * dy / msfty(i, j) / dt);
+          xkmv(i, k, j) = xkmh(i, k, j);
+          xkmv(i, k, j) = std::min(xkmv(i, k, j), mix_upper_bound / rdzw(i, k, j) / rdzw(i, k, j) / dt);
+          xkhh(i, k, j) = xkmh(i, k, j) / pr;
+          xkhh(i, k, j) = std::min(xkhh(i, k, j), mix_upper_bound * dx / msftx(i, j) * dy / msfty(i, j) / dt);
+          xkhv(i, k, j) = xkmv(i, k, j) / pr;
+          xkhv(i, k, j) = std::min(xkhv(i, k, j), mix_upper_bound / rdzw(i, k, j) / rdzw(i, k, j) / dt);
+        }
+      }
+}
+
 }  // namespace orc

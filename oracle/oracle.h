@@ -200,6 +200,10 @@ void vertical_diffusion_v(const Cx &x, A3 field, A3 tendency, A1 v_base, A1 c1h,
 void compute_diff_metrics(const Cx &x, A3 ph, A3 phb, A3 z, A3 rdz, A3 rdzw, A3 zx, A3 zy);
 void cal_deform_and_div(const Cx &x, A3 u, A3 v, A3 w, A3 div, A3 defor11, A3 defor22, A3 defor33, A3 defor12, A3 defor13,
                         A3 defor23, A3 rdz, A3 rdzw, A3 zx, A3 zy);
+void phy_prep_thermo(const Cx &x, A3 t, const A3 *qv, A3 p, A3 pb, A3 ph, A3 phb, A3 th_phy, A3 p_phy, A3 t_phy, A2 p8w_sfc, A2 t8w_sfc);
+void calculate_N2(const Cx &x, A3 BN2, const A3 *qv, const A3 *qc, A3 theta, A3 t, A3 p, A2 p8w_sfc, A2 t8w_sfc, A3 rdz, A3 rdzw);
+void smag_km(const Cx &x, A3 xkmh, A3 xkmv, A3 xkhh, A3 xkhv, A3 BN2, A3 defor11, A3 defor22, A3 defor33, A3 defor12, A3 defor13, A3 defor23,
+             A3 rdzw);
 void smag2d_km(const Cx &x, A3 xkmh, A3 xkmv, A3 xkhh, A3 xkhv, A3 defor11, A3 defor22, A3 defor12, A3 rdzw, A3 zx, A3 zy);
 // diffusion2.cpp (diff_opt = 2: diffusion in physical space, called from first_rk_step_part2)
 void phy_prep_rho(const Cx &x, A3 rho, A3 alt, const A3 *qv);

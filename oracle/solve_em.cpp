@@ -43,7 +43,8 @@ Oracle::Oracle(const wrfgpu_dims &d_, const wrfgpu_config &c_) : d(d_), c(c_) {
     add("scalar_tend_" + std::to_string(s), 3);
   }
   if (c.diff_opt != 0 && (c.km_opt >= 2 || (c.diff_opt == 2 && !diff2_is_identity(c)))) {   // metrics, deformation, K arrays (Registry.EM_COMMON state)
-    for (const char *n : {"ustm", "hfx", "qfx"}) add(n, 2);
+    for (const char *n : {"ustm", "hfx", "qfx", "p8w_sfc", "t8w_sfc"}) add(n, 2);
+    for (const char *n : {"bn2", "t_phy"}) add(n, 3);
     for (const char *n : {"zx", "zy", "rdz", "rdzw", "div", "defor11", "defor22", "defor33", "defor12", "defor13", "defor23",
                           "xkmh", "xkmv", "xkhh", "xkhv"}) add(n, 3);
   }
@@ -164,7 +165,7 @@ void Oracle::diffusion_prep() {
   if (c.diff_opt == 0) return;
   if (c.diff_opt == 1 && c.km_opt == 1) return;   // every K element is a constant the diffusion routines of rk_tendency take directly
   if (diff2_is_identity(c)) return;               // diff_opt = 2 with all coefficients zero adds exact zeros (shipped em_hill2d_x)
-  if (c.km_opt != 4 && !(c.km_opt == 1 && c.diff_opt == 2)) throw std::runtime_error("oracle: km_opt 2 / 3 are not restated");
+  if (c.km_opt != 4 && c.km_opt != 3 && !(c.km_opt == 1 && c.diff_opt == 2)) throw std::runtime_error("oracle: km_opt 2 (TKE) is not restated");
   A3 ph = a3("ph_2"), phb = a3("phb"), z = a3("z"), rdz = a3("rdz"), rdzw = a3("rdzw"), zx = a3("zx"), zy = a3("zy");
   A3 xkmh = a3("xkmh"), xkmv = a3("xkmv"), xkhh = a3("xkhh"), xkhv = a3("xkhv"), rho = a3("rho");
   if (c.diff_opt == 2) {   // phy_prep (first_rk_step_part1): the density the stresses are built with
@@ -188,6 +189,18 @@ void Oracle::diffusion_prep() {
         for (int i = x.its; i <= std::min(x.ite, x.ide - 1); i++) {
           xkmh(i, k, j) = c.khdif; xkmv(i, k, j) = c.kvdif; xkhh(i, k, j) = khdif3; xkhv(i, k, j) = kvdif3;
         }
+  } else if (c.km_opt == 3) {   // calculate_N2 (on phy_prep's th_phy, t_phy, p_phy, p8w, t8w) and smag_km
+    A3 qv, qc;
+    if (c.num_moist >= 1) qv = a3("moist_qv");
+    if (c.num_moist >= 2) qc = a3("moist_qc");
+    const A3 *pqv = c.num_moist >= 1 ? &qv : nullptr, *pqc = c.num_moist >= 2 ? &qc : nullptr;
+    par([&](const Cx &xt) {
+      phy_prep_thermo(xt, a3("t_2"), pqv, a3("p"), a3("pb"), ph, phb, a3("th_phy"), a3("p_phy"), a3("t_phy"), a2("p8w_sfc"), a2("t8w_sfc"));
+    });
+    par([&](const Cx &xt) { calculate_N2(xt, a3("bn2"), pqv, pqc, a3("th_phy"), a3("t_phy"), a3("p_phy"), a2("p8w_sfc"), a2("t8w_sfc"), rdz, rdzw); });
+    par([&](const Cx &xt) {
+      smag_km(xt, xkmh, xkmv, xkhh, xkhv, a3("bn2"), a3("defor11"), a3("defor22"), a3("defor33"), a3("defor12"), a3("defor13"), a3("defor23"), rdzw);
+    });
   } else {
     par([&](const Cx &xt) { smag2d_km(xt, xkmh, xkmv, xkhh, xkhv, a3("defor11"), a3("defor22"), a3("defor12"), rdzw, zx, zy); });
   }

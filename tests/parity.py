@@ -50,6 +50,15 @@ def with_surface_fluxes(case):
     return case
 
 
+def with_cloud(case):
+    """cloud water above the threshold of calculate_N2's saturated branch (qc >= 1e-5) in a box of the domain"""
+    d = case.dims
+    qc = case.fields.setdefault("moist_qc", np.zeros_like(case.fields["moist_qv"]))
+    j0, i0 = (d.jde // 3) - d.jms, (d.ide // 3) - d.ims
+    qc[j0:j0 + d.jde // 3, 1:9, i0:i0 + d.ide // 3] = 2.0e-4
+    return case
+
+
 def with_updraft(case, wmax, conv=25.0):
     """Add an updraft core to a case: a Gaussian blob of `wmax` m/s in w and, because the first step diagnoses ww from
     the divergence of (u, v) and not from w, winds converging below and diverging aloft (`conv` m/s) that imply the same
@@ -175,6 +184,13 @@ def small_cases():
                                                      diff_opt=2, km_opt=4, c_s=0.5, mix_full_fields=1)),
         "diff2_hill": with_surface_fluxes(make_case("hill2d_x", nx=62, ny=3, nz=21, diff_opt=2, km_opt=1, khdif=100.0, kvdif=30.0, isfflx=1)),
         "diff2_b_wave": make_case("b_wave", nx=21, ny=31, nz=17, diff_opt=2, km_opt=4, isfflx=2, tke_heat_flux=0.02),
+        # 3-D Smagorinsky closure (km_opt 3: calculate_N2 with its saturated branch, smag_km) feeding the physical-space diffusion:
+        # open + Kessler with a cloud and an updraft; doubly periodic, map factors, isotropic length scale; and feeding the
+        # coordinate-surface diffusion over the hill
+        "smag3d": with_cloud(with_updraft(make_case("quarter_ss", nx=26, ny=24, nz=21, diff_opt=2, km_opt=3, c_s=0.25), 30.0)),
+        "smag3d_periodic": with_updraft(with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=1,
+                                                                   diff_opt=2, km_opt=3, mix_isotropic=1, mix_full_fields=1)), 30.0),
+        "smag3d_hill": with_updraft(make_case("hill2d_x", nx=62, ny=3, nz=21, diff_opt=1, km_opt=3, kvdif=10.0), 20.0, conv=70.0),
         "ieva_weno_hill": with_updraft(make_case("hill2d_x", nx=62, ny=3, nz=41, zadvect_implicit=1, momentum_adv_opt=3,
                                                  moist_adv_opt=3), 60.0, conv=70.0),
     }

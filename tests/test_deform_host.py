@@ -16,9 +16,9 @@ from tests.parity import small_cases
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "tests", "_build")
-IN3 = ("ph_2", "phb", "u_2", "v_2", "w_2", "t_2", "alt")
+IN3 = ("ph_2", "phb", "u_2", "v_2", "w_2", "t_2", "alt", "p", "pb")
 OUT3 = ("z", "rdz", "rdzw", "zx", "zy", "div", "defor11", "defor22", "defor33", "defor12", "defor13", "defor23", "xkmh", "xkmv", "xkhh", "xkhv")
-D2 = ("rho", "ru_tendf", "rv_tendf", "rw_tendf", "t_tendf", "ustm", "hfx", "qfx")
+D2 = ("bn2", "rho", "ru_tendf", "rv_tendf", "rw_tendf", "t_tendf", "ustm", "hfx", "qfx")
 REST = ("msftx", "msfty", "msfux", "msfuy", "msfvx", "msfvy", "fnm", "fnp", "dn", "dnw", "u_base", "v_base", "t_base", "qv_base")
 
 
@@ -45,7 +45,8 @@ def run_shim(L, case, arrays, stage, last=(), which=0):
                              ctypes.c_int(which)) == 0
 
 
-@pytest.mark.parametrize("name", ["smag2d", "smag2d_periodic", "smag2d_hill", "smag2d_b_wave", "diff2", "diff2_periodic", "diff2_hill", "diff2_b_wave"])
+@pytest.mark.parametrize("name", ["smag2d", "smag2d_periodic", "smag2d_hill", "smag2d_b_wave", "diff2", "diff2_periodic", "diff2_hill", "diff2_b_wave",
+                                  "smag3d", "smag3d_periodic", "smag3d_hill"])
 def test_device_point_functions_equal_the_oracle(shim, name):
     case = small_cases()[name]
     c = case.config
@@ -72,9 +73,9 @@ def test_device_point_functions_equal_the_oracle(shim, name):
     for n, var in (("rdzw", "w"), ("rdz", "w"), ("z", "w"), ("zx", "e"), ("zy", "f")):
         bc(n, var)
     run_shim(shim, case, arrays, 2)
-    run_shim(shim, case, arrays, 4 if c.km_opt == 1 else 3)
+    run_shim(shim, case, arrays, {1: 4, 3: 7, 4: 3}[c.km_opt])
     bc("xkmh", "t"); bc("xkhh", "t")
-    out = list(OUT3)
+    out = list(OUT3) + (["bn2"] if c.km_opt == 3 else [])
     if c.diff_opt == 2:
         for n, var in (("xkmv", "t"), ("xkhv", "t"), ("div", "t"), ("defor11", "t"), ("defor22", "t"), ("defor33", "t"), ("defor12", "d"),
                        ("defor13", "e"), ("defor23", "f"), ("rho", "t")):
@@ -93,5 +94,8 @@ def test_device_point_functions_equal_the_oracle(shim, name):
             bad.append((n, len(w), w[:3].tolist(), float(np.abs(arrays[n] - ref).max())))
     assert not bad, bad
     assert float(o.get("xkmh").max()) > 0.0
+    if name == "smag3d":   # both branches of calculate_N2 and both limits of smag_km are exercised
+        lo = float(o.get("xkmh")[o.get("xkmh") > 0].min())
+        assert float(o.get("xkmh").max()) > 1.5 * lo and float(o.get("bn2").min()) < 0.0 < float(o.get("bn2").max())
     if c.diff_opt == 2:
         assert all(float(np.abs(o.get(n)).max()) > 0.0 for n in ("ru_tendf", "rw_tendf", "t_tendf"))

@@ -21,6 +21,11 @@ __global__ void k_smag2d(const Geo g, Box b, SmagIn s, fp xkmh, fp xkmv, fp xkhh
   smag2d_point(g, s, i, k, j, xkmh, xkmv, xkhh, xkhv);
 }
 
+__global__ void k_smag3d(const Geo g, Box b, Smag3In s, fp bn2, fp xkmh, fp xkmv, fp xkhh, fp xkhv) {
+  TID3;
+  smag3d_point(g, s, i, k, j, bn2, xkmh, xkmv, xkhh, xkhv);
+}
+
 void Solver::diffusion_prep() {
   if (c.diff_opt == 0) return;
   if (c.diff_opt == 1 && c.km_opt == 1) return;   // K is a constant the diffusion kernels of rk_tendency take by value
@@ -51,10 +56,21 @@ void Solver::diffusion_prep() {
   if (q.open_ys) j_start = std::max(q.jds + 1, q.jts);
   if (q.open_ye) j_end = std::min(q.jde - 2, q.jte);
   if (q.periodic_x) { i_start = q.its; i_end = std::min(q.ite, q.ide - 1); }
+  if (c.km_opt == 3) {   // calculate_N2 + smag_km in one launch
+    Smag3In s3;
+    s3.t_2 = o("t_2"); s3.qv = c.num_moist >= 1 ? o("moist_qv") : nullptr; s3.qc = c.num_moist >= 2 ? o("moist_qc") : nullptr;
+    s3.p = o("p"); s3.pb = o("pb"); s3.ph = o("ph_2"); s3.phb = o("phb"); s3.rdz = o("rdz"); s3.rdzw = o("rdzw");
+    s3.defor11 = o("defor11"); s3.defor22 = o("defor22"); s3.defor33 = o("defor33"); s3.defor12 = o("defor12"); s3.defor13 = o("defor13");
+    s3.defor23 = o("defor23"); s3.dn = o("dn");
+    s3.dx = c.dx; s3.dy = c.dy; s3.dt = c.dt; s3.c_s = c.c_s; s3.mix_upper_bound = c.mix_upper_bound; s3.mix_isotropic = c.mix_isotropic;
+    s3.use_theta_m = c.use_theta_m;
+    LAUNCH3(this, k_smag3d, (Box{i_start, i_end, 1, q.kde - 1, j_start, j_end}), s3, o("bn2"), o("xkmh"), o("xkmv"), o("xkhh"), o("xkhv"));
+  } else {
   SmagIn sm;
   sm.defor11 = o("defor11"); sm.defor22 = o("defor22"); sm.defor12 = o("defor12"); sm.rdzw = o("rdzw"); sm.zx = o("zx"); sm.zy = o("zy");
   sm.dx = c.dx; sm.dy = c.dy; sm.c_s = c.c_s; sm.diff_opt = c.diff_opt;
   LAUNCH3(this, k_smag2d, (Box{i_start, i_end, 1, q.kde - 1, j_start, j_end}), sm, o("xkmh"), o("xkmv"), o("xkhh"), o("xkhv"));
+  }
   }
   halo("HALO_EM_TKE_E");   // + PERIOD_BDY_EM_PHY_BC, HALO_EM_PHYS_DIFFUSION (:644-650, :759)
   bc({{"xkmh", 't'}, {"xkhh", 't'}});   // phy_bc (module_diffusion_em.F:5901), diff_opt = 1 part

@@ -13,14 +13,11 @@
 // the computed ranges and which edges are copied).  Elements the reference never writes are not written here either.
 #pragma once
 #include "common.cuh"
+#include "libm_port.h"
 
 namespace wg {
 
-#ifdef __CUDACC__
-#define WG_HD __host__ __device__ __forceinline__
-#else
-#define WG_HD inline
-#endif
+// WG_HD (__host__ __device__ __forceinline__ under nvcc) comes from libm_port.h
 
 struct DefIn {
   cfp u, v, w, rdz, rdzw, zx, zy;
@@ -248,6 +245,130 @@ WG_HD void smag2d_point(const Geo &g, const SmagIn &s, int i, int k, int j, fp x
   A3(xkmv, i, k, j) = km;
   A3(xkhh, i, k, j) = kh;
   A3(xkhv, i, k, j) = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------ calculate_N2 + smag_km
+// km_opt = 3 (module_diffusion_em.F:1485-1712, :1777-1928).  The reference reads th_phy, t_phy, p_phy, p8w, t8w of phy_prep
+// (module_big_step_utilities_em.F:4818-4912); they are pure functions of the column's t_2, qv, p, pb, ph, phb, evaluated
+// here at the three levels a point needs (one powf and one expf per level, the glibc restatements of libm_port.h).
+#define WG_XLV 2.5e6f
+#define WG_SVP1 0.6112f
+#define WG_SVP2 17.67f
+#define WG_SVP3 29.65f
+#define WG_SVPT0 273.15f
+#define WG_EP_2 (WG_RD / WG_RV)
+struct Smag3In {
+  cfp t_2, qv, qc, p, pb, ph, phb, rdz, rdzw, defor11, defor22, defor33, defor12, defor13, defor23;   // qv, qc may be null
+  const float *dn;
+  float dx, dy, dt, c_s, mix_upper_bound;
+  int mix_isotropic, use_theta_m;
+};
+struct Thermo { float theta, t, p, qvs; };
+WG_HD Thermo thermo_at(const Geo &g, const Smag3In &s, int i, int k, int j) {
+  Thermo r;
+  if (s.use_theta_m == 1 && s.qv) r.theta = (A3(s.t_2, i, k, j) + WG_T0) / (1.f + WG_RV / WG_RD * A3(s.qv, i, k, j));
+  else r.theta = A3(s.t_2, i, k, j) + WG_T0;
+  r.p = A3(s.p, i, k, j) + A3(s.pb, i, k, j);
+  const float pi_phy = wg_libm::powf_(r.p / WG_P0, WG_RCP);
+  r.t = r.theta * pi_phy;
+  const float tc = r.t - WG_SVPT0;
+  const float es = 1000.0f * WG_SVP1 * wg_libm::expf_(WG_SVP2 * tc / (r.t - WG_SVP3));
+  r.qvs = WG_EP_2 * es / (r.p - es);
+  return r;
+}
+// BN2(i,k,j) for k in 1..ktf-1 (the caller maps ktf to ktf-1, :1707-1711)
+WG_HD float bn2_at(const Geo &g, const Smag3In &s, int i, int k, int j) {
+  const float qc_cr = 0.00001f;
+  cfp rdz = s.rdz, rdzw = s.rdzw;
+  auto QV = [&](int kk) -> float { return s.qv ? A3(s.qv, i, kk, j) : 0.f; };
+  auto TMP1 = [&](int kk) -> float {   // qv + qc (P_QI is not allocated on this path)
+    float v = 0.f;
+    if (s.qv) v = v + A3(s.qv, i, kk, j);
+    if (s.qc) v = v + A3(s.qc, i, kk, j);
+    return v;
+  };
+  const Thermo c = thermo_at(g, s, i, k, j), up = thermo_at(g, s, i, k + 1, j);
+  const float qctmp = s.qc ? A3(s.qc, i, k, j) : 0.0f;
+  const bool sat = QV(k) >= c.qvs || qctmp >= qc_cr;
+  if (k >= 2) {
+    const Thermo dn_ = thermo_at(g, s, i, k - 1, j);
+    const float tmpdz = 1.0f / A3(rdz, i, k, j) + 1.0f / A3(rdz, i, k + 1, j);
+    if (sat) {
+      const float xlvqv = WG_XLV * QV(k);
+      const float coefa = (1.0f + xlvqv / WG_RD / c.t) / (1.0f + WG_XLV * xlvqv / WG_CP / WG_RV / c.t / c.t) / c.theta;
+      const float thetaep1 = up.theta * (1.0f + WG_XLV * up.qvs / WG_CP / up.t);
+      const float thetaem1 = dn_.theta * (1.0f + WG_XLV * dn_.qvs / WG_CP / dn_.t);
+      return WG_G * (coefa * (thetaep1 - thetaem1) / tmpdz - (TMP1(k + 1) - TMP1(k - 1)) / tmpdz);
+    }
+    return WG_G * ((up.theta - dn_.theta) / c.theta / tmpdz + 1.61f * (QV(k + 1) - QV(k - 1)) / tmpdz - (TMP1(k + 1) - TMP1(k - 1)) / tmpdz);
+  }
+  // k = 1: the surface values (:1663-1703); p8w, t8w at level 1 as phy_prep interpolates them (:4893-4903)
+  float tmp1sfc = 0.f;
+  if (s.qv) tmp1sfc = tmp1sfc + g.cf1 * A3(s.qv, i, 1, j) + g.cf2 * A3(s.qv, i, 2, j) + g.cf3 * A3(s.qv, i, 3, j);
+  if (s.qc) tmp1sfc = tmp1sfc + g.cf1 * A3(s.qc, i, 1, j) + g.cf2 * A3(s.qc, i, 2, j) + g.cf3 * A3(s.qc, i, 3, j);
+  const float zw1 = (A3(s.phb, i, 1, j) + A3(s.ph, i, 1, j)) / WG_G, zw2 = (A3(s.phb, i, 2, j) + A3(s.ph, i, 2, j)) / WG_G,
+              zw3 = (A3(s.phb, i, 3, j) + A3(s.ph, i, 3, j)) / WG_G;
+  const float z0 = zw1, z1 = 0.5f * (zw1 + zw2), z2 = 0.5f * (zw2 + zw3);
+  const float w1 = (z0 - z2) / (z1 - z2);
+  const float w2 = 1.f - w1;
+  const float p8w = w1 * c.p + w2 * up.p, t8w = w1 * c.t + w2 * up.t;
+  float tmpdz = 1.0f / A3(rdz, i, k + 1, j) + 0.5f / A3(rdzw, i, k, j);
+  const float thetasfc = t8w / wg_libm::powf_(p8w / WG_P0, WG_RD / WG_CP);
+  if (sat) {
+    const Thermo l3 = thermo_at(g, s, i, 3, j);
+    const float qvsfc = g.cf1 * c.qvs + g.cf2 * up.qvs + g.cf3 * l3.qvs;
+    const float xlvqv = WG_XLV * QV(k);
+    const float coefa = (1.0f + xlvqv / WG_RD / c.t) / (1.0f + WG_XLV * xlvqv / WG_CP / WG_RV / c.t / c.t) / c.theta;
+    const float thetaep1 = up.theta * (1.0f + WG_XLV * up.qvs / WG_CP / up.t);
+    const float thetaesfc = thetasfc * (1.0f + WG_XLV * qvsfc / WG_CP / t8w);
+    return WG_G * (coefa * (thetaep1 - thetaesfc) / tmpdz - (TMP1(k + 1) - tmp1sfc) / tmpdz);
+  }
+  const float qvsfc = g.cf1 * QV(1) + g.cf2 * QV(2) + g.cf3 * QV(3);
+  tmpdz = 1.f / A3(rdzw, i, k, j);
+  return WG_G * ((up.theta - c.theta) / c.theta / tmpdz + 1.61f * (QV(k + 1) - qvsfc) / tmpdz - (TMP1(k + 1) - tmp1sfc) / tmpdz);
+}
+// thread box: the computed range of smag_km (:1816-1831), k in 1..ktf
+WG_HD void smag3d_point(const Geo &g, const Smag3In &s, int i, int k, int j, fp bn2, fp xkmh, fp xkmv, fp xkhh, fp xkhv) {
+  const int ktf = g.kde - 1;
+  const float pr = 1.f / 3.f;
+  cfp defor11 = s.defor11, defor22 = s.defor22, defor33 = s.defor33, defor12 = s.defor12, defor13 = s.defor13, defor23 = s.defor23;
+  const float BN2 = bn2_at(g, s, i, k == ktf ? ktf - 1 : k, j);
+  A3(bn2, i, k, j) = BN2;
+  float def2 = 0.5f * (A3(defor11, i, k, j) * A3(defor11, i, k, j) + A3(defor22, i, k, j) * A3(defor22, i, k, j) + A3(defor33, i, k, j) * A3(defor33, i, k, j));
+  float tmp = 0.25f * (A3(defor12, i, k, j) + A3(defor12, i, k, j + 1) + A3(defor12, i + 1, k, j) + A3(defor12, i + 1, k, j + 1));
+  def2 = def2 + tmp * tmp;
+  tmp = 0.25f * (A3(defor13, i, k + 1, j) + A3(defor13, i, k, j) + A3(defor13, i + 1, k + 1, j) + A3(defor13, i + 1, k, j));
+  def2 = def2 + tmp * tmp;
+  tmp = 0.25f * (A3(defor23, i, k + 1, j) + A3(defor23, i, k, j) + A3(defor23, i, k + 1, j + 1) + A3(defor23, i, k, j + 1));
+  def2 = def2 + tmp * tmp;
+  tmp = fmaxf(0.f, def2 - BN2 / pr);
+  tmp = sqrtf(tmp);
+  const float c_s = s.c_s, mub = s.mix_upper_bound, dt = s.dt, dx = s.dx, dy = s.dy;
+  const float rdzw = A3(s.rdzw, i, k, j), mtx = A2(g.msftx, i, j), mty = A2(g.msfty, i, j);
+  float km_h, km_v, kh_h, kh_v;
+  if (s.mix_isotropic == 0) {
+    const float mlen_h = sqrtf(dx / mtx * dy / mty);
+    const float mlen_v = 1.f / rdzw;
+    km_h = fmaxf(c_s * c_s * mlen_h * mlen_h * tmp, 1.0E-6f * mlen_h * mlen_h);
+    km_h = fminf(km_h, mub * mlen_h * mlen_h / dt);
+    km_v = fmaxf(c_s * c_s * mlen_v * mlen_v * tmp, 1.0E-6f * mlen_v * mlen_v);
+    km_v = fminf(km_v, mub * mlen_v * mlen_v / dt);
+    kh_h = km_h / pr;
+    kh_h = fminf(kh_h, mub * mlen_h * mlen_h / dt);
+    kh_v = km_v / pr;
+    kh_v = fminf(kh_v, mub * mlen_v * mlen_v / dt);
+  } else {
+    const float deltas = wg_libm::powf_(dx / mtx * dy / mty / rdzw, 0.33333333f);
+    km_h = fmaxf(c_s * c_s * deltas * deltas * tmp, 1.0E-6f * deltas * deltas);
+    km_h = fminf(km_h, mub * dx / mtx * dy / mty / dt);
+    km_v = km_h;
+    km_v = fminf(km_v, mub / rdzw / rdzw / dt);
+    kh_h = km_h / pr;
+    kh_h = fminf(kh_h, mub * dx / mtx * dy / mty / dt);
+    kh_v = km_v / pr;
+    kh_v = fminf(kh_v, mub / rdzw / rdzw / dt);
+  }
+  A3(xkmh, i, k, j) = km_h; A3(xkmv, i, k, j) = km_v; A3(xkhh, i, k, j) = kh_h; A3(xkhv, i, k, j) = kh_v;
 }
 
 }  // namespace wg

@@ -44,9 +44,11 @@ static void check_config(const wrfgpu_config &c) {
   // is accepted as such.  The rest (physical-space diffusion with non-zero K, TKE / 3-D Smagorinsky) is a 'next' row.
   if (c.diff_6th_opt < 0 || c.diff_6th_opt > 2) bad("diff_6th_opt must be 0, 1 or 2");
   if (c.diff_opt != 0) {
-    if (c.km_opt != 1 && c.km_opt != 4)
-      bad("km_opt must be 1 (constant K) or 4 (2-D Smagorinsky); the TKE / 3-D Smagorinsky closures are a 'next' row");
-    if (c.km_opt == 4 && !(c.c_s > 0.f)) bad("c_s must be positive with km_opt = 4");
+    if (c.km_opt != 1 && c.km_opt != 3 && c.km_opt != 4)
+      bad("km_opt must be 1 (constant K), 3 (3-D Smagorinsky) or 4 (2-D Smagorinsky); the TKE closure is a 'next' row");
+    if (c.km_opt == 3 && !(c.mix_upper_bound > 0.f)) bad("mix_upper_bound must be positive with km_opt = 3");
+    if (c.km_opt == 3 && c.mix_isotropic != 0 && c.mix_isotropic != 1) bad("mix_isotropic must be 0 or 1");
+    if (c.km_opt >= 3 && !(c.c_s > 0.f)) bad("c_s must be positive with km_opt = 3, 4");
     if (c.isfflx < 0 || c.isfflx > 2) bad("isfflx must be 0, 1 or 2");
     if (c.diff_opt != 1 && c.diff_opt != 2) bad("diff_opt must be 0, 1 or 2");
     if (c.khdif < 0.f || c.kvdif < 0.f) bad("khdif, kvdif must not be negative");
@@ -82,6 +84,7 @@ Solver::Solver(const wrfgpu_dims &d_, const wrfgpu_config &c_, int dev) : d(d_),
   for (int i = 0; k1d[i]; i++) add(k1d[i], 1);
   if (c.diff_opt != 0 && (c.km_opt >= 2 || (c.diff_opt == 2 && !diff2_is_identity(c)))) {   // metrics, deformation, K arrays (deform.cu)
     if (!c.mp_physics) add("z", 3);
+    if (c.km_opt == 3) add("bn2", 3);
     for (const char *n : {"ustm", "hfx", "qfx"}) add(n, 2);   // surface fluxes of a host-side surface scheme (isfflx 1, 2); zero otherwise
     for (const char *n : {"zx", "zy", "rdz", "rdzw", "div", "defor11", "defor22", "defor33", "defor12", "defor13", "defor23",
                           "xkmh", "xkmv", "xkhh", "xkhv"}) add(n, 3);

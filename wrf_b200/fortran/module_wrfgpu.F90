@@ -44,6 +44,8 @@ MODULE module_wrfgpu
       REAL(c_float)  :: c_s, c_k
       INTEGER(c_int) :: mix_full_fields, isfflx
       REAL(c_float)  :: tke_drag_coefficient, tke_heat_flux
+      INTEGER(c_int) :: mix_isotropic
+      REAL(c_float)  :: mix_upper_bound
    END TYPE wrfgpu_config
 
    INTERFACE

@@ -67,7 +67,8 @@ class Config(ctypes.Structure):
         + [(n, ctypes.c_int) for n in ("diff_6th_slopeopt", "moist_mix6_off", "scalar_mix6_off")]
         + [(n, ctypes.c_float) for n in ("c_s", "c_k")]
         + [("mix_full_fields", ctypes.c_int), ("isfflx", ctypes.c_int)]
-        + [(n, ctypes.c_float) for n in ("tke_drag_coefficient", "tke_heat_flux")])
+        + [(n, ctypes.c_float) for n in ("tke_drag_coefficient", "tke_heat_flux")]
+        + [("mix_isotropic", ctypes.c_int), ("mix_upper_bound", ctypes.c_float)])
 
 
 def default_config(**kw) -> Config:
@@ -89,6 +90,7 @@ def default_config(**kw) -> Config:
     c.w_crit_cfl = 1.2
     c.diff_6th_factor, c.diff_6th_thresh = 0.12, 0.10
     c.c_s, c.c_k = 0.25, 0.15
+    c.mix_upper_bound = 0.1
     c.ntasks_x = c.ntasks_y = 1
     for k, v in kw.items():
         setattr(c, k, v)
