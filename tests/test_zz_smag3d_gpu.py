@@ -1,9 +1,9 @@
 """GPU parity of the 3-D Smagorinsky closure (km_opt = 3: calculate_N2 + smag_km in k_smag3d, wrf_b200/csrc/deform.cuh).
 
-These cases were added after the round's GPU budget was spent: the kernel body is pinned bit for bit against the oracle on
-the CPU (tests/test_deform_host.py runs the same __host__ __device__ point functions, including the restated glibc
-powf / expf the device uses), but the kernel itself has not run on a B200 yet.  They live in a file that sorts last so that
-`pytest -x` reaches them after every test that has."""
+The kernel body is pinned bit for bit against the oracle on the CPU (tests/test_deform_host.py runs the same
+__host__ __device__ point functions, including the restated glibc powf / expf the device uses).  On the B200 the five-step
+test below has passed (profiles/README.md, run r1zh); the phase-by-phase test had not been run when the round's GPU budget
+ran out, so the file sorts last: `pytest -x` reaches it after every test that has run on a GPU."""
 import pytest
 
 from tests import parity
