@@ -103,6 +103,9 @@ typedef struct wrfgpu_config {
   /* 3-D Smagorinsky closure (km_opt = 3; smag_km, module_diffusion_em.F:1777) */
   int mix_isotropic;                     /* 0 = separate horizontal / vertical length scales, 1 = (dx dy dz)^(1/3) */
   float mix_upper_bound;                 /* 0.1: K <= mix_upper_bound * l^2 / dt */
+  /* 1.5-order TKE closure (km_opt = 2 with diff_opt = 2): the prognostic tke_1 / tke_2 (Registry.EM_COMMON:312) */
+  int tke_adv_opt;                       /* as scalar_adv_opt (Registry.EM_COMMON:2884) */
+  float tke_upper_bound;                 /* 1000. (bound_tke, module_em.F:2616) */
 } wrfgpu_config;
 
 typedef struct wrfgpu_solver wrfgpu_solver;   /* opaque */

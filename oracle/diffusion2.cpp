@@ -255,7 +255,7 @@ void horizontal_diffusion_w_2(const Cx &x, A3 tendency, A3 defor13, A3 defor23, 
 }
 
 // :3711-3998 (doing_tke = .false.)
-void horizontal_diffusion_s(const Cx &x, A3 tendency, A3 var, A3 xkhh, A3 zx, A3 zy, A3 rdzw, A3 rho) {
+void horizontal_diffusion_s(const Cx &x, A3 tendency, A3 var, A3 xkhh, A3 zx, A3 zy, A3 rdzw, A3 rho, bool doing_tke) {
   const int kts = x.kts, kte = x.kte, ktf = std::min(x.kte, x.kde - 1);
   const int ktes1 = kte - 1, ktes2 = kte - 2;
   const A1 &fnm = x.fnm, &fnp = x.fnp, &dnw = x.dnw, &dn = x.dn;
@@ -265,6 +265,12 @@ void horizontal_diffusion_s(const Cx &x, A3 tendency, A3 var, A3 xkhh, A3 zx, A3
   const int i_start = r.i_start, i_end = r.i_end, j_start = r.j_start, j_end = r.j_end;
   Loc3 l1(x), l2(x), l3(x), l4(x), l5(x), l6(x), l7(x);
   A3 H1avg = l1.a, H2avg = l2.a, H1 = l3.a, H2 = l4.a, xkxavg = l5.a, zx_at_m = l6.a, zy_at_m = l7.a;
+  Loc3 l8(x);
+  A3 tmptendf = l8.a;
+  if (doing_tke)
+    for (int j = j_start; j <= j_end; j++)
+      for (int k = kts; k <= ktf; k++)
+        for (int i = i_start; i <= i_end; i++) tmptendf(i, k, j) = tendency(i, k, j);
   for (int j = j_start; j <= j_end; j++)
     for (int k = kts; k <= ktf; k++)
       for (int i = i_start; i <= i_end + 1; i++) xkxavg(i, k, j) = 0.5f * (xkhh(i - 1, k, j) + xkhh(i, k, j)) * 0.5f * (rho(i - 1, k, j) + rho(i, k, j));
@@ -334,6 +340,10 @@ void horizontal_diffusion_s(const Cx &x, A3 tendency, A3 var, A3 xkhh, A3 zx, A3
                                                      msftx(i, j) * zx_at_m(i, k, j) * (H1avg(i, k + 1, j) - H1avg(i, k, j)) * rdzw(i, k, j) -
                                                      msfty(i, j) * zy_at_m(i, k, j) * (H2avg(i, k + 1, j) - H2avg(i, k, j)) * rdzw(i, k, j));
       }
+  if (doing_tke)
+    for (int j = j_start; j <= j_end; j++)
+      for (int k = kts; k <= ktf; k++)
+        for (int i = i_start; i <= i_end; i++) tendency(i, k, j) = tmptendf(i, k, j) + 2.f * (tendency(i, k, j) - tmptendf(i, k, j));
 }
 
 // :4463-4570
@@ -393,12 +403,16 @@ void vertical_diffusion_w_2(const Cx &x, A3 tendency, A3 defor33, A3 xkmh, A3 rh
       for (int i = r.i_start; i <= r.i_end; i++) tendency(i, k, j) = tendency(i, k, j) + g * (titau3(i, k, j) - titau3(i, k - 1, j)) / dn(k);
 }
 // :4789-4906 (doing_tke = .false.); var(i,k,j) - base(k) when base is given (the var_mix copies of the driver, :4239-4256, :4312-4330)
-void vertical_diffusion_s(const Cx &x, A3 tendency, A3 var_in, const A1 *base, A3 xkhv, A3 rdz, A3 rho) {
+void vertical_diffusion_s(const Cx &x, A3 tendency, A3 var_in, const A1 *base, A3 xkhv, A3 rdz, A3 rho, bool doing_tke) {
   const int kts = x.kts, kte = x.kte, ktf = std::min(x.kte, x.kde - 1);
   const A1 &fnm = x.fnm, &fnp = x.fnp, &dnw = x.dnw;
   const R4 r = range(x, 'm');
-  Loc3 l1(x), l2(x);
-  A3 H3 = l1.a, var = l2.a;
+  Loc3 l1(x), l2(x), l3(x);
+  A3 H3 = l1.a, var = l2.a, tmptendf = l3.a;
+  if (doing_tke)
+    for (int j = r.j_start; j <= r.j_end; j++)
+      for (int k = kts; k <= ktf; k++)
+        for (int i = r.i_start; i <= r.i_end; i++) tmptendf(i, k, j) = tendency(i, k, j);
   for (int j = x.jts; j <= std::min(x.jte, x.jde - 1); j++)
     for (int k = kts; k <= kte - 1; k++)
       for (int i = x.its; i <= std::min(x.ite, x.ide - 1); i++) var(i, k, j) = base ? var_in(i, k, j) - (*base)(k) : var_in(i, k, j);
@@ -417,6 +431,10 @@ void vertical_diffusion_s(const Cx &x, A3 tendency, A3 var_in, const A1 *base, A
   for (int j = r.j_start; j <= r.j_end; j++)
     for (int k = kts; k <= ktf; k++)
       for (int i = r.i_start; i <= r.i_end; i++) tendency(i, k, j) = tendency(i, k, j) + g * (H3(i, k + 1, j) - H3(i, k, j)) / dnw(k);
+  if (doing_tke)
+    for (int j = r.j_start; j <= r.j_end; j++)
+      for (int k = kts; k <= ktf; k++)
+        for (int i = r.i_start; i <= r.i_end; i++) tendency(i, k, j) = tmptendf(i, k, j) + 2.f * (tendency(i, k, j) - tmptendf(i, k, j));
 }
 
 // the surface momentum and heat / moisture fluxes of vertical_diffusion_2 (:4160-4236, :4262-4300, :4338-4353)

@@ -105,6 +105,10 @@ struct Oracle {
   void (*halo_cb)(void *ctx, const char *name) = nullptr;
   void *halo_ctx = nullptr;
   void halo(const char *name) { if (halo_cb) halo_cb(halo_ctx, name); }
+  // km_opt = 2: the prognostic tke is carried as one more species of the scalar family (scalar_N = tke_2, scalar_old_N = tke_1,
+  // scalar_tend_N = tke_tend with N = num_scalar + 1), advected with tke_adv_opt
+  int tke_index() const { return (c.km_opt == 2 && c.diff_opt == 2) ? c.num_scalar + 1 : 0; }
+  int nsc() const { return c.num_scalar + (tke_index() ? 1 : 0); }
   int nthreads = 1;   // j-tiles run on std::threads like the reference's OpenMP tiles (solve_em.F:652-674)
   template <class Fn> void par(Fn fn);
 
@@ -210,11 +214,11 @@ void phy_prep_rho(const Cx &x, A3 rho, A3 alt, const A3 *qv);
 void horizontal_diffusion_u_2(const Cx &x, A3 tendency, A3 defor11, A3 defor12, A3 xkmh, A3 zx, A3 zy, A3 rdzw, A3 rho);
 void horizontal_diffusion_v_2(const Cx &x, A3 tendency, A3 defor12, A3 defor22, A3 xkmh, A3 zx, A3 zy, A3 rdzw, A3 rho);
 void horizontal_diffusion_w_2(const Cx &x, A3 tendency, A3 defor13, A3 defor23, A3 xkmv, A3 zx, A3 zy, A3 rdz, A3 rho);
-void horizontal_diffusion_s(const Cx &x, A3 tendency, A3 var, A3 xkhh, A3 zx, A3 zy, A3 rdzw, A3 rho);
+void horizontal_diffusion_s(const Cx &x, A3 tendency, A3 var, A3 xkhh, A3 zx, A3 zy, A3 rdzw, A3 rho, bool doing_tke = false);
 void vertical_diffusion_u_2(const Cx &x, A3 tendency, A3 defor13, A3 xkmv, A3 rho);
 void vertical_diffusion_v_2(const Cx &x, A3 tendency, A3 defor23, A3 xkmv, A3 rho);
 void vertical_diffusion_w_2(const Cx &x, A3 tendency, A3 defor33, A3 xkmh, A3 rho);
-void vertical_diffusion_s(const Cx &x, A3 tendency, A3 var_in, const A1 *base, A3 xkhv, A3 rdz, A3 rho);
+void vertical_diffusion_s(const Cx &x, A3 tendency, A3 var_in, const A1 *base, A3 xkhv, A3 rdz, A3 rho, bool doing_tke = false);
 void surface_drag(const Cx &x, A3 ru_tendf, A3 rv_tendf, A3 u_2, A3 v_2, A3 rho, A2 ust);
 void surface_heat_flux(const Cx &x, A3 rt_tendf, A3 t_2, const A3 *qv, A3 rho, A2 hfx, A2 qfx);
 void surface_moisture_flux(const Cx &x, A3 qv_tendf, A2 qfx);
@@ -222,6 +226,13 @@ void surface_moisture_flux(const Cx &x, A3 qv_tendf, A2 qfx);
 inline bool diff2_is_identity(const wrfgpu_config &c) {
   return c.diff_opt == 2 && c.km_opt == 1 && c.khdif == 0.f && c.kvdif == 0.f && c.isfflx == 0 && c.tke_drag_coefficient == 0.f && c.tke_heat_flux == 0.f;
 }
+// tke.cpp (km_opt = 2)
+void phy_prep_top(const Cx &x, A3 ph, A3 phb, A3 p_phy, A3 t_phy, A2 p8w_top, A2 t8w_top);
+void tke_km(const Cx &x, A3 xkmh, A3 xkmv, A3 xkhh, A3 xkhv, A3 BN2, A3 tke, A2 p8w_sfc, A2 t8w_sfc, A2 p8w_top, A2 t8w_top, A3 theta, A3 rdz,
+            A3 rdzw);
+void tke_rhs(const Cx &x, A3 tendency, A3 BN2, A3 defor11, A3 defor22, A3 defor33, A3 defor12, A3 defor13, A3 defor23, A3 u, A3 v, A3 tke, A2 mu,
+             A3 theta, A3 xkmh, A3 xkmv, A3 xkhv, A3 rdzw, A2 hfx, const A3 *qv, A2 ust, A3 rho);
+void bound_tke(const Cx &x, A3 tke, float tke_upper_bound);
 // advect.cpp
 void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut, bool weno = false);
 void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2 mut, bool weno = false);

@@ -37,7 +37,7 @@ Oracle::Oracle(const wrfgpu_dims &d_, const wrfgpu_config &c_) : d(d_), c(c_) {
     add(std::string("moist_old_") + moist_names[s], 3);
     add(std::string("moist_tend_") + moist_names[s], 3);
   }
-  for (int s = 1; s <= c.num_scalar; s++) {
+  for (int s = 1; s <= nsc(); s++) {
     add("scalar_" + std::to_string(s), 3);
     add("scalar_old_" + std::to_string(s), 3);
     add("scalar_tend_" + std::to_string(s), 3);
@@ -45,6 +45,8 @@ Oracle::Oracle(const wrfgpu_dims &d_, const wrfgpu_config &c_) : d(d_), c(c_) {
   if (c.diff_opt != 0 && (c.km_opt >= 2 || (c.diff_opt == 2 && !diff2_is_identity(c)))) {   // metrics, deformation, K arrays (Registry.EM_COMMON state)
     for (const char *n : {"ustm", "hfx", "qfx", "p8w_sfc", "t8w_sfc"}) add(n, 2);
     for (const char *n : {"bn2", "t_phy"}) add(n, 3);
+    for (const char *n : {"p8w_top", "t8w_top"}) add(n, 2);
+    // (the prognostic tke rides as the last species of the scalar family, added by the nsc() loop above: tke_2 / tke_1 / tke_tend)
     for (const char *n : {"zx", "zy", "rdz", "rdzw", "div", "defor11", "defor22", "defor33", "defor12", "defor13", "defor23",
                           "xkmh", "xkmv", "xkhh", "xkhv"}) add(n, 3);
   }
@@ -155,7 +157,7 @@ void Oracle::init_zero_tendency() {
   for (const char *n : {"ru_tendf", "rv_tendf", "rw_tendf", "ph_tendf", "t_tendf"}) zero_tend(x, a3(n));
   par([&](const Cx &xt) { zero_tend2d(xt, a2("mu_tendf")); });
   for (int s = 0; s < c.num_moist; s++) zero_tend(x, a3(std::string("moist_tend_") + moist_names[s]));
-  for (int s = 1; s <= c.num_scalar; s++) zero_tend(x, a3("scalar_tend_" + std::to_string(s)));
+  for (int s = 1; s <= nsc(); s++) zero_tend(x, a3("scalar_tend_" + std::to_string(s)));
 }
 
 // first_rk_step_part2 (dyn_em/module_first_rk_step_part2.F:427-680, :758-760): metrics of the physical-space
@@ -165,7 +167,7 @@ void Oracle::diffusion_prep() {
   if (c.diff_opt == 0) return;
   if (c.diff_opt == 1 && c.km_opt == 1) return;   // every K element is a constant the diffusion routines of rk_tendency take directly
   if (diff2_is_identity(c)) return;               // diff_opt = 2 with all coefficients zero adds exact zeros (shipped em_hill2d_x)
-  if (c.km_opt != 4 && c.km_opt != 3 && !(c.km_opt == 1 && c.diff_opt == 2)) throw std::runtime_error("oracle: km_opt 2 (TKE) is not restated");
+  if (c.km_opt == 2 && c.diff_opt != 2) throw std::runtime_error("oracle: km_opt 2 (TKE) needs diff_opt 2 (tke_rhs is only called there)");
   A3 ph = a3("ph_2"), phb = a3("phb"), z = a3("z"), rdz = a3("rdz"), rdzw = a3("rdzw"), zx = a3("zx"), zy = a3("zy");
   A3 xkmh = a3("xkmh"), xkmv = a3("xkmv"), xkhh = a3("xkhh"), xkhv = a3("xkhv"), rho = a3("rho");
   if (c.diff_opt == 2) {   // phy_prep (first_rk_step_part1): the density the stresses are built with
@@ -189,7 +191,7 @@ void Oracle::diffusion_prep() {
         for (int i = x.its; i <= std::min(x.ite, x.ide - 1); i++) {
           xkmh(i, k, j) = c.khdif; xkmv(i, k, j) = c.kvdif; xkhh(i, k, j) = khdif3; xkhv(i, k, j) = kvdif3;
         }
-  } else if (c.km_opt == 3) {   // calculate_N2 (on phy_prep's th_phy, t_phy, p_phy, p8w, t8w) and smag_km
+  } else if (c.km_opt == 3 || c.km_opt == 2) {   // calculate_N2 (on phy_prep's th_phy, t_phy, p_phy, p8w, t8w), then smag_km or tke_km
     A3 qv, qc;
     if (c.num_moist >= 1) qv = a3("moist_qv");
     if (c.num_moist >= 2) qc = a3("moist_qc");
@@ -198,9 +200,17 @@ void Oracle::diffusion_prep() {
       phy_prep_thermo(xt, a3("t_2"), pqv, a3("p"), a3("pb"), ph, phb, a3("th_phy"), a3("p_phy"), a3("t_phy"), a2("p8w_sfc"), a2("t8w_sfc"));
     });
     par([&](const Cx &xt) { calculate_N2(xt, a3("bn2"), pqv, pqc, a3("th_phy"), a3("t_phy"), a3("p_phy"), a2("p8w_sfc"), a2("t8w_sfc"), rdz, rdzw); });
-    par([&](const Cx &xt) {
-      smag_km(xt, xkmh, xkmv, xkhh, xkhv, a3("bn2"), a3("defor11"), a3("defor22"), a3("defor33"), a3("defor12"), a3("defor13"), a3("defor23"), rdzw);
-    });
+    if (c.km_opt == 3) {
+      par([&](const Cx &xt) {
+        smag_km(xt, xkmh, xkmv, xkhh, xkhv, a3("bn2"), a3("defor11"), a3("defor22"), a3("defor33"), a3("defor12"), a3("defor13"), a3("defor23"), rdzw);
+      });
+    } else {
+      par([&](const Cx &xt) { phy_prep_top(xt, ph, phb, a3("p_phy"), a3("t_phy"), a2("p8w_top"), a2("t8w_top")); });
+      par([&](const Cx &xt) {
+        tke_km(xt, xkmh, xkmv, xkhh, xkhv, a3("bn2"), a3("scalar_" + std::to_string(tke_index())), a2("p8w_sfc"), a2("t8w_sfc"), a2("p8w_top"),
+               a2("t8w_top"), a3("th_phy"), rdz, rdzw);
+      });
+    }
   } else {
     par([&](const Cx &xt) { smag2d_km(xt, xkmh, xkmv, xkhh, xkhv, a3("defor11"), a3("defor22"), a3("defor12"), rdzw, zx, zy); });
   }
@@ -212,6 +222,14 @@ void Oracle::diffusion_prep() {
   // vertical diffusion first and then horizontal (module_first_rk_step_part2.F:1019-1122; bl_pbl_physics = 0)
   A3 u = a3("u_2"), v = a3("v_2"), t = a3("t_2");
   A3 ru_tendf = a3("ru_tendf"), rv_tendf = a3("rv_tendf"), rw_tendf = a3("rw_tendf"), t_tendf = a3("t_tendf");
+  const std::string tk = tke_index() ? std::to_string(tke_index()) : std::string();
+  if (tke_index()) {   // tke_rhs (:904-940), before the diffusion
+    A3 qv; if (c.num_moist >= 1) qv = a3("moist_qv");
+    par([&](const Cx &xt) {
+      tke_rhs(xt, a3("scalar_tend_" + tk), a3("bn2"), a3("defor11"), a3("defor22"), a3("defor33"), a3("defor12"), a3("defor13"), a3("defor23"), u, v,
+              a3("scalar_" + tk), a2("mut"), a3("th_phy"), xkmh, xkmv, xkhv, rdzw, a2("hfx"), c.num_moist >= 1 ? &qv : nullptr, a2("ustm"), rho);
+    });
+  }
   par([&](const Cx &xt) { vertical_diffusion_u_2(xt, ru_tendf, a3("defor13"), xkmv, rho); });
   par([&](const Cx &xt) { vertical_diffusion_v_2(xt, rv_tendf, a3("defor23"), xkmv, rho); });
   par([&](const Cx &xt) { vertical_diffusion_w_2(xt, rw_tendf, a3("defor33"), xkmh, rho); });
@@ -227,16 +245,20 @@ void Oracle::diffusion_prep() {
     par([&](const Cx &xt) { vertical_diffusion_s(xt, qt, q, sp == 0 ? qb : nullptr, xkhv, rdz, rho); });
     if (sp == 0) par([&](const Cx &xt) { surface_moisture_flux(xt, qt, a2("qfx")); });
   }
-  for (int sp = 1; sp <= c.num_scalar; sp++)
-    par([&](const Cx &xt) { vertical_diffusion_s(xt, a3("scalar_tend_" + std::to_string(sp)), a3("scalar_" + std::to_string(sp)), nullptr, xkhv, rdz, rho); });
+  for (int sp = 1; sp <= nsc(); sp++) {
+    const bool is_tke = sp == tke_index();   // tke: K = xkmv, doing_tke (:4302-4308)
+    par([&](const Cx &xt) { vertical_diffusion_s(xt, a3("scalar_tend_" + std::to_string(sp)), a3("scalar_" + std::to_string(sp)), nullptr, is_tke ? xkmv : xkhv, rdz, rho, is_tke); });
+  }
   par([&](const Cx &xt) { horizontal_diffusion_u_2(xt, ru_tendf, a3("defor11"), a3("defor12"), xkmh, zx, zy, rdzw, rho); });
   par([&](const Cx &xt) { horizontal_diffusion_v_2(xt, rv_tendf, a3("defor12"), a3("defor22"), xkmh, zx, zy, rdzw, rho); });
   par([&](const Cx &xt) { horizontal_diffusion_w_2(xt, rw_tendf, a3("defor13"), a3("defor23"), xkmv, zx, zy, rdz, rho); });
   par([&](const Cx &xt) { horizontal_diffusion_s(xt, t_tendf, t, xkhh, zx, zy, rdzw, rho); });
   for (int sp = 0; sp < c.num_moist; sp++)
     par([&](const Cx &xt) { horizontal_diffusion_s(xt, a3(std::string("moist_tend_") + moist_names[sp]), a3(std::string("moist_") + moist_names[sp]), xkhh, zx, zy, rdzw, rho); });
-  for (int sp = 1; sp <= c.num_scalar; sp++)
-    par([&](const Cx &xt) { horizontal_diffusion_s(xt, a3("scalar_tend_" + std::to_string(sp)), a3("scalar_" + std::to_string(sp)), xkhh, zx, zy, rdzw, rho); });
+  for (int sp = 1; sp <= nsc(); sp++) {
+    const bool is_tke = sp == tke_index();   // tke: K = xkmh, doing_tke (:2968-2982)
+    par([&](const Cx &xt) { horizontal_diffusion_s(xt, a3("scalar_tend_" + std::to_string(sp)), a3("scalar_" + std::to_string(sp)), is_tke ? xkmh : xkhh, zx, zy, rdzw, rho, is_tke); });
+  }
 }
 
 // module_em.F:190-955 rk_tendency followed by rk_addtend_dry (solve_em.F:881-1007)
@@ -416,8 +438,9 @@ void Oracle::rk_scalar_step(int rk_step) {
   for (int s = 0; s < c.num_moist; s++)
     sp.push_back({std::string("moist_") + moist_names[s], std::string("moist_old_") + moist_names[s],
                   std::string("moist_tend_") + moist_names[s], c.moist_adv_opt, true});
-  for (int s = 1; s <= c.num_scalar; s++)
-    sp.push_back({"scalar_" + std::to_string(s), "scalar_old_" + std::to_string(s), "scalar_tend_" + std::to_string(s), c.scalar_adv_opt, false});
+  for (int s = 1; s <= nsc(); s++)
+    sp.push_back({"scalar_" + std::to_string(s), "scalar_old_" + std::to_string(s), "scalar_tend_" + std::to_string(s),
+                  s == tke_index() ? c.tke_adv_opt : c.scalar_adv_opt, false});
   if (rk_step == rk_order)
     for (auto &s : sp)
       if (s.adv_opt == 1 || s.adv_opt == 2 || s.adv_opt == 4) par([&](const Cx &xt) { rk_update_scalar_pd(xt, a3(s.o), a3(s.t), a2("mu_1"), a2("mu_1"), a2("mub"), dt_rk); });
@@ -470,6 +493,8 @@ void Oracle::rk_scalar_step(int rk_step) {
     if (rk_step == 1 && c.diff_6th_opt != 0 && !(s.moist ? c.moist_mix6_off : c.scalar_mix6_off))   // module_em.F:1421-1437 (dt_step = dt_rk)
       par([&](const Cx &xt) { sixth_order_diffusion(xt, 'm', a3(s.f), a3(s.t), a2("muts"), dt_rk, xt.c1h, xt.c2h, a3("phb")); });
     par([&](const Cx &xt) { rk_update_scalar(xt, a3(s.o), a3(s.f), a3(s.t), a3("advect_tend"), a2("mu_1"), a2("mu_2"), a2("mub"), rk_step, dt_rk); });
+    if (tke_index() && s.f == "scalar_" + std::to_string(tke_index()))   // bound the tke (solve_em.F:2437-2445)
+      par([&](const Cx &xt) { bound_tke(xt, a3(s.f), c.tke_upper_bound); });
   }
 }
 
@@ -484,7 +509,7 @@ void Oracle::rk_phys_bc_dry_2() {
   halo("HALO_EM_MOIST_E_7");   // HALO_EM_MOIST_E_5/7, SCALAR_E_5/7, solve_em.F:3359-3447
   bc("u_2", 'U'); bc("v_2", 'V'); bc("w_2", 'w'); bc("t_2", 'p'); bc("ph_2", 'w'); bc("mu_2", 't');
   for (int s = 0; s < c.num_moist; s++) bc(std::string("moist_") + moist_names[s], 'p');
-  for (int s = 1; s <= c.num_scalar; s++) bc("scalar_" + std::to_string(s), 'p');
+  for (int s = 1; s <= nsc(); s++) bc("scalar_" + std::to_string(s), 'p');
 }
 
 // moist_physics_prep_em / kessler / moist_physics_finish_em, solve_em.F:3629-4115
@@ -560,7 +585,7 @@ void Oracle::end_of_step() {
   bc("u_1", 'U'); bc("u_2", 'U'); bc("v_1", 'V'); bc("v_2", 'V'); bc("w_1", 'w'); bc("w_2", 'w');
   bc("t_1", 'p'); bc("t_2", 'p'); bc("ph_1", 'w'); bc("ph_2", 'w'); bc("mu_1", 't'); bc("mu_2", 't');
   for (int s = 0; s < c.num_moist; s++) bc(std::string("moist_") + moist_names[s], 'p');
-  for (int s = 1; s <= c.num_scalar; s++) bc("scalar_" + std::to_string(s), 'p');
+  for (int s = 1; s <= nsc(); s++) bc("scalar_" + std::to_string(s), 'p');
   halo("HALO_EM_C");           // + PERIOD_BDY_EM_E, solve_em.F:4730-4731
   par([&](const Cx &xt) { set_w_surface(xt, a3("w_2"), a3("u_2"), a3("v_2")); });
   halo("HALO_EM_E_5");         // solve_em.F:4781-4846

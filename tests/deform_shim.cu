@@ -11,7 +11,8 @@
 using namespace wg;
 
 // stage: 0 rho, 1 metrics, 2 deformation, 3 smag2d K, 7 calculate_N2 + smag_km, 4 isotropic K, 5 diff_opt = 2 tendencies of u, v, w, theta,
-// 6 diff_opt = 2 tendency of the species names[nn-2] (field) / names[nn-1] (tendency) -- which = 1 for qv, else 2
+// 6 diff_opt = 2 tendency of the species names[nn-2] (field) / names[nn-1] (tendency) -- which = 1 for qv, 3 for tke, else 2;
+// 8 calculate_N2 + tke_km, 9 tke_rhs
 extern "C" int deform_shim_run(int stage, const wrfgpu_dims *dp, const wrfgpu_config *cp, int nn, const char *const *names, float *const *ptrs,
                                int which) {
   const wrfgpu_dims &d = *dp;
@@ -85,6 +86,30 @@ extern "C" int deform_shim_run(int stage, const wrfgpu_dims *dp, const wrfgpu_co
     for (int j = j_start; j <= j_end; j++)
       for (int k = 1; k <= g.kde - 1; k++)
         for (int i = i_start; i <= i_end; i++) smag3d_point(g, s3, i, k, j, p3("bn2"), p3("xkmh"), p3("xkmv"), p3("xkhh"), p3("xkhv"));
+  } else if (stage == 8 || stage == 9) {   // tke_km / tke_rhs, inputs as deform.cu's tke_in()
+    int i_start = g.its, i_end = ie, j_start = g.jts, j_end = je;
+    if (g.open_xs) i_start = std::max(g.ids + 1, g.its);
+    if (g.open_xe) i_end = std::min(g.ide - 2, g.ite);
+    if (g.open_ys) j_start = std::max(g.jds + 1, g.jts);
+    if (g.open_ye) j_end = std::min(g.jde - 2, g.jte);
+    if (g.periodic_x) { i_start = g.its; i_end = ie; }
+    for (int k = d.kms; k <= d.kme; k++) { g.c1h[k] = p1("c1h")[k]; g.c2h[k] = p1("c2h")[k]; }
+    TkeIn t;
+    Smag3In &s3 = t.th;
+    s3.t_2 = p3("t_2"); s3.qv = p3("moist_qv"); s3.qc = p3("moist_qc"); s3.p = p3("p"); s3.pb = p3("pb"); s3.ph = p3("ph_2"); s3.phb = p3("phb");
+    s3.rdz = p3("rdz"); s3.rdzw = p3("rdzw"); s3.defor11 = p3("defor11"); s3.defor22 = p3("defor22"); s3.defor33 = p3("defor33");
+    s3.defor12 = p3("defor12"); s3.defor13 = p3("defor13"); s3.defor23 = p3("defor23"); s3.dn = p1("dn");
+    s3.dx = c.dx; s3.dy = c.dy; s3.dt = c.dt; s3.c_s = c.c_s; s3.mix_upper_bound = c.mix_upper_bound; s3.mix_isotropic = c.mix_isotropic;
+    s3.use_theta_m = c.use_theta_m;
+    t.tke = p3("tke_2"); t.bn2 = p3("bn2"); t.xkmh = p3("xkmh"); t.xkmv = p3("xkmv"); t.xkhv = p3("xkhv"); t.u = p3("u_2"); t.v = p3("v_2");
+    t.mut = p2("mut"); t.rho = p3("rho"); t.hfx = p2("hfx"); t.ustm = p2("ustm");
+    t.c_k = c.c_k; t.cd0 = c.tke_drag_coefficient; t.heat_flux = c.tke_heat_flux; t.isfflx = c.isfflx; t.diff_opt = c.diff_opt;
+    for (int j = j_start; j <= j_end; j++)
+      for (int k = 1; k <= g.kde - 1; k++)
+        for (int i = i_start; i <= i_end; i++) {
+          if (stage == 8) tke_km_point(g, t, i, k, j, p3("bn2"), p3("xkmh"), p3("xkmv"), p3("xkhh"), p3("xkhv"));
+          else tke_rhs_point(g, t, i, k, j, p3("tke_tend"));
+        }
   } else if (stage == 4) {
     const float prandtl = 1.f / 3.0f;   // as Solver::diffusion2_isotropic_km
     const float khdif3 = c.khdif / prandtl, kvdif3 = c.kvdif / prandtl;
@@ -119,7 +144,9 @@ extern "C" int deform_shim_run(int stage, const wrfgpu_dims *dp, const wrfgpu_co
       float *var = p3(names[nn - 2]), *tend = p3(names[nn - 1]);
       for (int j = g.jts; j <= g.jte; j++)
         for (int k = 1; k <= g.kde - 1; k++)
-          for (int i = g.its; i <= g.ite; i++) diff2_s_point(g, s, rm, which, var, which == 1 ? qb : nullptr, s.xkhv, s.xkhh, i, k, j, tend);
+          for (int i = g.its; i <= g.ite; i++)
+            diff2_s_point(g, s, rm, which == 3 ? 2 : which, var, which == 1 ? qb : nullptr, which == 3 ? s.xkmv : s.xkhv, which == 3 ? s.xkmh : s.xkhh, i, k, j,
+                          tend, which == 3 ? 1 : 0);
     }
   }
   delete gp;

@@ -50,6 +50,18 @@ def with_surface_fluxes(case):
     return case
 
 
+def with_tke(case):
+    """a smooth, positive initial tke (both time levels) so that every term of tke_rhs acts from the first step"""
+    d, c = case.dims, case.config
+    kk, jj, ii = np.meshgrid(np.arange(d.kms, d.kme + 1), np.arange(d.jms, d.jme + 1), np.arange(d.ims, d.ime + 1), indexing="ij")
+    a = (0.6 * np.exp(-kk / 6.0) * (1.0 + 0.5 * np.sin(0.41 * ii + 0.23 * jj))).astype(np.float32).transpose(1, 0, 2)
+    a[:, -1, :] = 0
+    n = c.num_scalar + 1
+    case.fields["scalar_%d" % n] = a.copy()
+    case.fields["scalar_old_%d" % n] = a.copy()
+    return case
+
+
 def with_cloud(case):
     """cloud water above the threshold of calculate_N2's saturated branch (qc >= 1e-5) in a box of the domain"""
     d = case.dims
@@ -191,6 +203,14 @@ def small_cases():
         "smag3d_periodic": with_updraft(with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05, num_scalar=1,
                                                                    diff_opt=2, km_opt=3, mix_isotropic=1, mix_full_fields=1)), 30.0),
         "smag3d_hill": with_updraft(make_case("hill2d_x", nx=62, ny=3, nz=21, diff_opt=1, km_opt=3, kvdif=10.0), 20.0, conv=70.0),
+        # 1.5-order TKE closure (km_opt 2 with diff_opt 2: tke_km, tke_rhs, the prognostic tke advected, mixed and bounded) -- the
+        # closure of the shipped em_quarter_ss and em_les namelists: open + Kessler as shipped (mix_full_fields), doubly periodic
+        # with the isotropic length scale, namelist drag / heat flux and a tracer, over the hill with fluxes from a surface scheme
+        "tke": with_tke(with_cloud(with_updraft(make_case("quarter_ss", nx=26, ny=24, nz=21, diff_opt=2, km_opt=2, mix_full_fields=1), 30.0))),
+        "tke_periodic": with_tke(with_updraft(with_map_factors(make_case("synthetic", nx=34, ny=30, nz=17, bubble_lattice=20000.0, noise=0.05,
+                                                                         num_scalar=1, diff_opt=2, km_opt=2, mix_isotropic=1, tke_adv_opt=2,
+                                                                         tke_drag_coefficient=0.003, tke_heat_flux=0.05)), 30.0)),
+        "tke_hill": with_tke(with_surface_fluxes(make_case("hill2d_x", nx=62, ny=3, nz=21, diff_opt=2, km_opt=2, isfflx=1))),
         "ieva_weno_hill": with_updraft(make_case("hill2d_x", nx=62, ny=3, nz=41, zadvect_implicit=1, momentum_adv_opt=3,
                                                  moist_adv_opt=3), 60.0, conv=70.0),
     }

@@ -19,7 +19,7 @@ BUILD = os.path.join(ROOT, "tests", "_build")
 IN3 = ("ph_2", "phb", "u_2", "v_2", "w_2", "t_2", "alt", "p", "pb")
 OUT3 = ("z", "rdz", "rdzw", "zx", "zy", "div", "defor11", "defor22", "defor33", "defor12", "defor13", "defor23", "xkmh", "xkmv", "xkhh", "xkhv")
 D2 = ("bn2", "rho", "ru_tendf", "rv_tendf", "rw_tendf", "t_tendf", "ustm", "hfx", "qfx")
-REST = ("msftx", "msfty", "msfux", "msfuy", "msfvx", "msfvy", "fnm", "fnp", "dn", "dnw", "u_base", "v_base", "t_base", "qv_base")
+REST = ("mut", "c1h", "c2h", "msftx", "msfty", "msfux", "msfuy", "msfvx", "msfvy", "fnm", "fnp", "dn", "dnw", "u_base", "v_base", "t_base", "qv_base")
 
 
 @pytest.fixture(scope="module")
@@ -46,7 +46,7 @@ def run_shim(L, case, arrays, stage, last=(), which=0):
 
 
 @pytest.mark.parametrize("name", ["smag2d", "smag2d_periodic", "smag2d_hill", "smag2d_b_wave", "diff2", "diff2_periodic", "diff2_hill", "diff2_b_wave",
-                                  "smag3d", "smag3d_periodic", "smag3d_hill"])
+                                  "smag3d", "smag3d_periodic", "smag3d_hill", "tke", "tke_periodic", "tke_hill"])
 def test_device_point_functions_equal_the_oracle(shim, name):
     case = small_cases()[name]
     c = case.config
@@ -60,6 +60,11 @@ def test_device_point_functions_equal_the_oracle(shim, name):
     have = set(o.names())
     names = [n for n in IN3 + OUT3 + D2 + REST if n in have] + [n for pair in species for n in pair]
     arrays = {n: np.ascontiguousarray(o.get(n)).copy() for n in names}
+    tke = None
+    if c.km_opt == 2:   # the tke species is the last one of the scalar family; the shim takes it under its Registry names
+        tke = "scalar_%d" % (c.num_scalar + 1)
+        arrays["tke_2"] = arrays[tke]
+        arrays["tke_tend"] = arrays[tke.replace("scalar_", "scalar_tend_")]
     applier = Oracle(case)   # set_physical_bc of the oracle, applied to the shim's arrays between the stages
 
     def bc(n, var):
@@ -73,16 +78,18 @@ def test_device_point_functions_equal_the_oracle(shim, name):
     for n, var in (("rdzw", "w"), ("rdz", "w"), ("z", "w"), ("zx", "e"), ("zy", "f")):
         bc(n, var)
     run_shim(shim, case, arrays, 2)
-    run_shim(shim, case, arrays, {1: 4, 3: 7, 4: 3}[c.km_opt])
+    run_shim(shim, case, arrays, {1: 4, 2: 8, 3: 7, 4: 3}[c.km_opt])
     bc("xkmh", "t"); bc("xkhh", "t")
-    out = list(OUT3) + (["bn2"] if c.km_opt == 3 else [])
+    out = list(OUT3) + (["bn2"] if c.km_opt in (2, 3) else [])
     if c.diff_opt == 2:
         for n, var in (("xkmv", "t"), ("xkhv", "t"), ("div", "t"), ("defor11", "t"), ("defor22", "t"), ("defor33", "t"), ("defor12", "d"),
                        ("defor13", "e"), ("defor23", "f"), ("rho", "t")):
             bc(n, var)
+        if tke:
+            run_shim(shim, case, arrays, 9)
         run_shim(shim, case, arrays, 5)
         for f, t in species:
-            run_shim(shim, case, arrays, 6, last=(f, t), which=1 if f == "moist_qv" else 2)
+            run_shim(shim, case, arrays, 6, last=(f, t), which=1 if f == "moist_qv" else (3 if f == tke else 2))
         out += ["rho", "ru_tendf", "rv_tendf", "rw_tendf", "t_tendf", "hfx"] + [t for _, t in species]
     o.call("diffusion_prep")
     bad = []
@@ -94,6 +101,9 @@ def test_device_point_functions_equal_the_oracle(shim, name):
             bad.append((n, len(w), w[:3].tolist(), float(np.abs(arrays[n] - ref).max())))
     assert not bad, bad
     assert float(o.get("xkmh").max()) > 0.0
+    if tke:
+        tt = o.get(tke.replace("scalar_", "scalar_tend_"))
+        assert float(tt.max()) > 0.0 > float(tt.min())        # production and dissipation both act
     if name == "smag3d":   # both branches of calculate_N2 and both limits of smag_km are exercised
         lo = float(o.get("xkmh")[o.get("xkmh") > 0].min())
         assert float(o.get("xkmh").max()) > 1.5 * lo and float(o.get("bn2").min()) < 0.0 < float(o.get("bn2").max())

@@ -315,6 +315,42 @@ def test_physical_space_diffusion_decays_a_sinusoid_and_a_vertical_profile_at_th
     assert np.abs(o.get("w_2")).max() < 1e-3                          # and the atmosphere stayed at rest
 
 
+def test_tke_closure_decays_at_rest_and_grows_in_the_supercell_updraft():
+    """km_opt = 2 / diff_opt = 2 (tke_km, tke_rhs, bound_tke -- the closure of the shipped em_quarter_ss and em_les namelists).
+    (i) In a resting, stably stratified, horizontally uniform atmosphere there is no shear production and the buoyancy term is a
+    sink, so an initial tke can only decay: the domain total falls monotonically, tke stays within [0, tke_upper_bound] and the
+    air stays at rest.  (ii) With the shipped em_quarter_ss closure settings the 3 K bubble's updraft spins tke up from exactly
+    zero (tke_seed lets K start from the floor), and only where there is shear."""
+    case = make_case("b_wave", nx=17, ny=12, nz=11, calm=True, diff_opt=2, km_opt=2, mix_full_fields=1)
+    d = case.dims
+    kk = np.arange(d.kms, d.kme + 1, dtype=np.float32)
+    t0 = (0.5 * np.exp(-kk / 4.0))[None, :, None] * np.ones_like(case.fields["t_2"])
+    t0[:, -1, :] = 0
+    case.fields["scalar_1"] = t0.copy(); case.fields["scalar_old_1"] = t0.copy()
+    o = Oracle(case)
+    o.start_domain()
+    own = (slice(1 - d.jms, d.jde - d.jms), slice(0, d.kde - 1), slice(1 - d.ims, d.ide - d.ims))
+    tot = [float(o.get("scalar_1")[own].astype(np.float64).sum())]
+    for _ in range(5):
+        o.step(2)
+        tke = o.get("scalar_1")[own]
+        assert tke.min() >= 0.0 and tke.max() <= case.config.tke_upper_bound
+        tot.append(float(tke.astype(np.float64).sum()))
+    assert all(b < a for a, b in zip(tot, tot[1:])) and tot[-1] < 0.9 * tot[0], tot
+    assert np.abs(o.get("w_2")).max() < 1e-3 and np.abs(o.get("u_2") - o.get("u_2")[own[0], :, :][:1, :, own[2]].mean()).max() < 50.0
+    case = make_case("quarter_ss", nx=26, ny=24, nz=21, diff_opt=2, km_opt=2, mix_full_fields=1)
+    o = Oracle(case)
+    o.set_threads(8)
+    o.start_domain()
+    assert float(np.abs(o.get("scalar_1")).max()) == 0.0
+    o.step(50)
+    tke, w = o.get("scalar_1"), o.get("w_2")
+    assert tke.min() >= 0.0 and 0.01 < tke.max() < 10.0
+    j, k, i = np.unravel_index(np.argmax(tke), tke.shape)
+    assert np.abs(w[max(j - 3, 0):j + 4, :, max(i - 3, 0):i + 4]).max() > 0.5 * np.abs(w).max()      # tke sits at the updraft
+    assert float(o.get("xkmh").max()) > 10.0 * float(o.get("xkmh")[o.get("xkmh") > 0].min())
+
+
 def test_sixth_order_filter_damps_the_two_delta_x_wave_at_the_documented_rate():
     """sixth_order_diffusion (module_big_step_utilities_em.F:6220): for q = (-1)^i the flux differences are +-32 q, so the
     tendency is -64 * (factor * 0.015625 / (2 dt')) * mu * q = -(factor / (2 dt')) mu q: the filter removes factor / 2 of a

@@ -146,6 +146,9 @@ struct Solver {
   std::vector<Species> species;
   int num_sound_steps = 0;
   float dts = 0.f;
+  // km_opt = 2: the prognostic tke rides as one more species of the scalar family (scalar_N = tke_2, scalar_old_N = tke_1,
+  // scalar_tend_N = tke_tend, N = num_scalar + 1; the Registry names are aliases), advected with tke_adv_opt
+  int tke_index() const { return (c.km_opt == 2 && c.diff_opt == 2) ? c.num_scalar + 1 : 0; }
   long long launches = 0;
   float *d_cfl = nullptr;   // 2 floats: max_vert_cfl, max_horiz_cfl
   // halo exchange state (HaloState, halo.cu)
@@ -195,6 +198,7 @@ struct Solver {
   void diffusion2_rho();   // diffusion2.cu
   void diffusion2_isotropic_km();
   void diffusion2_tendencies();
+  void tke_rhs();          // deform.cu
   void rk_tendency(int rk_step, bool zero_save = true);
   // IEVA (ieva.cu): WW_SPLIT + mass estimates; one implicit column solve (0 scalar, 1 u, 2 v, 3 ph, 4 w)
   void ieva_split(bool dry, const float *u, const float *v, const float *ww, const float *mut, bool active = true);

@@ -26,6 +26,43 @@ __global__ void k_smag3d(const Geo g, Box b, Smag3In s, fp bn2, fp xkmh, fp xkmv
   smag3d_point(g, s, i, k, j, bn2, xkmh, xkmv, xkhh, xkhv);
 }
 
+__global__ void k_tke_km(const Geo g, Box b, TkeIn s, fp bn2, fp xkmh, fp xkmv, fp xkhh, fp xkhv) {
+  TID3;
+  tke_km_point(g, s, i, k, j, bn2, xkmh, xkmv, xkhh, xkhv);
+}
+__global__ void k_tke_rhs(const Geo g, Box b, TkeIn s, fp tendency) {
+  TID3;
+  tke_rhs_point(g, s, i, k, j, tendency);
+}
+
+// inputs of tke_km / tke_rhs
+static TkeIn tke_in(Solver *S) {
+  const wrfgpu_config &c = S->c;
+  TkeIn t;
+  Smag3In &s3 = t.th;
+  s3.t_2 = S->o("t_2"); s3.qv = c.num_moist >= 1 ? S->o("moist_qv") : nullptr; s3.qc = c.num_moist >= 2 ? S->o("moist_qc") : nullptr;
+  s3.p = S->o("p"); s3.pb = S->o("pb"); s3.ph = S->o("ph_2"); s3.phb = S->o("phb"); s3.rdz = S->o("rdz"); s3.rdzw = S->o("rdzw");
+  s3.defor11 = S->o("defor11"); s3.defor22 = S->o("defor22"); s3.defor33 = S->o("defor33"); s3.defor12 = S->o("defor12");
+  s3.defor13 = S->o("defor13"); s3.defor23 = S->o("defor23"); s3.dn = S->o("dn");
+  s3.dx = c.dx; s3.dy = c.dy; s3.dt = c.dt; s3.c_s = c.c_s; s3.mix_upper_bound = c.mix_upper_bound; s3.mix_isotropic = c.mix_isotropic;
+  s3.use_theta_m = c.use_theta_m;
+  t.tke = S->o("tke_2"); t.bn2 = S->o("bn2"); t.xkmh = S->o("xkmh"); t.xkmv = S->o("xkmv"); t.xkhv = S->o("xkhv"); t.u = S->o("u_2");
+  t.v = S->o("v_2"); t.mut = S->o("mut"); t.rho = S->o("rho"); t.hfx = S->o("hfx"); t.ustm = S->o("ustm");
+  t.c_k = c.c_k; t.cd0 = c.tke_drag_coefficient; t.heat_flux = c.tke_heat_flux; t.isfflx = c.isfflx; t.diff_opt = c.diff_opt;
+  return t;
+}
+// tke_rhs (module_first_rk_step_part2.F:904-940) on tke_km's range
+void Solver::tke_rhs() {
+  const Geo &q = g;
+  int i_start = q.its, i_end = std::min(q.ite, q.ide - 1), j_start = q.jts, j_end = std::min(q.jte, q.jde - 1);
+  if (q.open_xs) i_start = std::max(q.ids + 1, q.its);
+  if (q.open_xe) i_end = std::min(q.ide - 2, q.ite);
+  if (q.open_ys) j_start = std::max(q.jds + 1, q.jts);
+  if (q.open_ye) j_end = std::min(q.jde - 2, q.jte);
+  if (q.periodic_x) { i_start = q.its; i_end = std::min(q.ite, q.ide - 1); }
+  LAUNCH3(this, k_tke_rhs, (Box{i_start, i_end, 1, q.kde - 1, j_start, j_end}), tke_in(this), o("tke_tend"));
+}
+
 void Solver::diffusion_prep() {
   if (c.diff_opt == 0) return;
   if (c.diff_opt == 1 && c.km_opt == 1) return;   // K is a constant the diffusion kernels of rk_tendency take by value
@@ -56,7 +93,9 @@ void Solver::diffusion_prep() {
   if (q.open_ys) j_start = std::max(q.jds + 1, q.jts);
   if (q.open_ye) j_end = std::min(q.jde - 2, q.jte);
   if (q.periodic_x) { i_start = q.its; i_end = std::min(q.ite, q.ide - 1); }
-  if (c.km_opt == 3) {   // calculate_N2 + smag_km in one launch
+  if (c.km_opt == 2) {   // calculate_N2 + tke_km in one launch
+    LAUNCH3(this, k_tke_km, (Box{i_start, i_end, 1, q.kde - 1, j_start, j_end}), tke_in(this), o("bn2"), o("xkmh"), o("xkmv"), o("xkhh"), o("xkhv"));
+  } else if (c.km_opt == 3) {   // calculate_N2 + smag_km in one launch
     Smag3In s3;
     s3.t_2 = o("t_2"); s3.qv = c.num_moist >= 1 ? o("moist_qv") : nullptr; s3.qc = c.num_moist >= 2 ? o("moist_qc") : nullptr;
     s3.p = o("p"); s3.pb = o("pb"); s3.ph = o("ph_2"); s3.phb = o("phb"); s3.rdz = o("rdz"); s3.rdzw = o("rdzw");

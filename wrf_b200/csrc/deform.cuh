@@ -371,4 +371,166 @@ WG_HD void smag3d_point(const Geo &g, const Smag3In &s, int i, int k, int j, fp 
   A3(xkmh, i, k, j) = km_h; A3(xkmv, i, k, j) = km_v; A3(xkhh, i, k, j) = kh_h; A3(xkhv, i, k, j) = kh_v;
 }
 
+// ------------------------------------------------------------------------------------------ tke_km, tke_rhs (km_opt = 2)
+// module_diffusion_em.F:2049-2335 (tke_km), :2341-2405 (calc_l_scale), :6099-6228 (tke_rhs = tke_shear :6529 + tke_buoyancy
+// :6234 + tke_dissip :6384 + the limiter of the sink)
+struct TkeIn {
+  Smag3In th;                       // the thermodynamic inputs of calculate_N2 / tke_km and the deformation tensor
+  cfp tke, bn2, xkmh, xkmv, xkhv, u, v, mut, rho, hfx, ustm;
+  float c_k, cd0, heat_flux;
+  int isfflx, diff_opt;
+};
+WG_HD float theta_at(const Geo &g, const Smag3In &s, int i, int k, int j) {
+  if (s.use_theta_m == 1 && s.qv) return (A3(s.t_2, i, k, j) + WG_T0) / (1.f + WG_RV / WG_RD * A3(s.qv, i, k, j));
+  return A3(s.t_2, i, k, j) + WG_T0;
+}
+WG_HD float l_scale_at(const Geo &g, const TkeIn &s, int i, int k, int j, float deltas) {
+  float l = deltas;
+  const float bn2 = A3(s.bn2, i, k, j);
+  if (bn2 > 1.0e-6f) {
+    const float tmp = sqrtf(fmaxf(A3(s.tke, i, k, j), 1.0e-6f));
+    l = 0.76f * tmp / sqrtf(bn2);
+    l = fminf(l, deltas);
+    l = fmaxf(l, 0.001f * deltas);
+  }
+  return l;
+}
+// thread box: the computed range of tke_km, k in 1..ktf; writes BN2 (calculate_N2) and the four K arrays
+WG_HD void tke_km_point(const Geo &g, const TkeIn &s, int i, int k, int j, fp bn2, fp xkmh, fp xkmv, fp xkhh, fp xkhv) {
+  const Smag3In &t = s.th;
+  const int ktf = g.kde - 1, kde = g.kde;
+  const float prandtl = 1.f / 3.0f;
+  cfp rdz = t.rdz, rdzw = t.rdzw;
+  const float BN2 = bn2_at(g, t, i, k == ktf ? ktf - 1 : k, j);
+  A3(bn2, i, k, j) = BN2;
+  float tke_seed = 0.f;
+  if (s.isfflx == 0) {
+    if (s.diff_opt == 2) { if (s.cd0 < 1.e-10f && s.heat_flux < 1.e-10f) tke_seed = 1.e-06f; }
+    else tke_seed = 1.e-06f;
+  }
+  const float mtx = A2(g.msftx, i, j), mty = A2(g.msfty, i, j), dx = t.dx, dy = t.dy, dt = t.dt, mub = t.mix_upper_bound;
+  const float tmp = sqrtf(fmaxf(A3(s.tke, i, k, j), tke_seed));
+  float km_h, km_v, kh_h, kh_v;
+  if (t.mix_isotropic == 0) {
+    float dthrdn;
+    if (k == 1) {
+      const Thermo c = thermo_at(g, t, i, 1, j), up = thermo_at(g, t, i, 2, j);
+      const float zw1 = (A3(t.phb, i, 1, j) + A3(t.ph, i, 1, j)) / WG_G, zw2 = (A3(t.phb, i, 2, j) + A3(t.ph, i, 2, j)) / WG_G,
+                  zw3 = (A3(t.phb, i, 3, j) + A3(t.ph, i, 3, j)) / WG_G;
+      const float z0 = zw1, z1 = 0.5f * (zw1 + zw2), z2 = 0.5f * (zw2 + zw3);
+      const float w1 = (z0 - z2) / (z1 - z2);
+      const float w2 = 1.f - w1;
+      const float p8w = w1 * c.p + w2 * up.p, t8w = w1 * c.t + w2 * up.t;
+      const float tmpdz = 1.0f / A3(rdzw, i, 2, j) + 1.0f / A3(rdzw, i, 1, j);
+      const float thetasfc = t8w / wg_libm::powf_(p8w / WG_P0, WG_RD / WG_CP);
+      dthrdn = (up.theta - thetasfc) / tmpdz;
+    } else if (k == ktf) {
+      const Thermo a = thermo_at(g, t, i, kde - 1, j), b = thermo_at(g, t, i, kde - 2, j);
+      const float zwe = (A3(t.phb, i, kde, j) + A3(t.ph, i, kde, j)) / WG_G, zwf = (A3(t.phb, i, ktf, j) + A3(t.ph, i, ktf, j)) / WG_G,
+                  zwg = (A3(t.phb, i, ktf - 1, j) + A3(t.ph, i, ktf - 1, j)) / WG_G;
+      const float z0 = zwe, z1 = 0.5f * (zwf + zwe), z2 = 0.5f * (zwg + zwf);
+      const float w1 = (z0 - z2) / (z1 - z2);
+      const float w2 = 1.f - w1;
+      const float p8w = wg_libm::expf_(w1 * wg_libm::logf_(a.p) + w2 * wg_libm::logf_(b.p)), t8w = w1 * a.t + w2 * b.t;
+      const float tmpdz = 1.0f / A3(rdz, i, k, j) + 0.5f / A3(rdzw, i, k, j);
+      const float thetatop = t8w / wg_libm::powf_(p8w / WG_P0, WG_RD / WG_CP);
+      dthrdn = (thetatop - theta_at(g, t, i, k - 1, j)) / tmpdz;
+    } else {
+      const float tmpdz = 1.0f / A3(rdz, i, k + 1, j) + 1.0f / A3(rdz, i, k, j);
+      dthrdn = (theta_at(g, t, i, k + 1, j) - theta_at(g, t, i, k - 1, j)) / tmpdz;
+    }
+    const float mlen_h = sqrtf(dx / mtx * dy / mty);
+    const float deltas = 1.0f / A3(rdzw, i, k, j);
+    float mlen_v = deltas;
+    if (dthrdn > 0.f) {
+      const float mlen_s = 0.76f * tmp / sqrtf(fabsf(WG_G / theta_at(g, t, i, k, j) * dthrdn));
+      mlen_v = fminf(mlen_v, mlen_s);
+    }
+    km_h = fmaxf(s.c_k * tmp * mlen_h, 1.0E-6f * mlen_h * mlen_h);
+    km_h = fminf(km_h, mub * mlen_h * mlen_h / dt);
+    km_v = fmaxf(s.c_k * tmp * mlen_v, 1.0E-6f * deltas * deltas);
+    km_v = fminf(km_v, mub * deltas * deltas / dt);
+    const float pr_inv_h = 1.f / prandtl;
+    const float pr_inv_v = 1.0f + 2.0f * mlen_v / deltas;
+    kh_h = km_h * pr_inv_h;
+    kh_v = km_v * pr_inv_v;
+  } else {
+    const float rz = A3(rdzw, i, k, j);
+    const float deltas = wg_libm::powf_(dx / mtx * dy / mty / rz, 0.33333333f);
+    // calc_l_scale reads BN2 and tke of this very point: use the value just computed (the bn2 field is being written)
+    float l = deltas;
+    if (BN2 > 1.0e-6f) {
+      const float tt = sqrtf(fmaxf(A3(s.tke, i, k, j), 1.0e-6f));
+      l = 0.76f * tt / sqrtf(BN2);
+      l = fminf(l, deltas);
+      l = fmaxf(l, 0.001f * deltas);
+    }
+    km_h = s.c_k * tmp * l;
+    km_h = fminf(mub * dx / mtx * dy / mty / dt, km_h);
+    km_v = s.c_k * tmp * l;
+    km_v = fminf(mub / rz / rz / dt, km_v);
+    const float pr_inv = 1.0f + 2.0f * l / deltas;
+    kh_h = fminf(mub * dx / mtx * dy / mty / dt, km_h * pr_inv);
+    kh_v = fminf(mub / rz / rz / dt, km_v * pr_inv);
+  }
+  A3(xkmh, i, k, j) = km_h; A3(xkmv, i, k, j) = km_v; A3(xkhh, i, k, j) = kh_h; A3(xkhv, i, k, j) = kh_v;
+}
+// thread box: the computed range of tke_rhs (the same as tke_km's), k in 1..ktf
+WG_HD void tke_rhs_point(const Geo &g, const TkeIn &s, int i, int k, int j, fp tendency) {
+  const Smag3In &t = s.th;
+  const int ktf = g.kde - 1;
+  cfp defor11 = t.defor11, defor22 = t.defor22, defor33 = t.defor33, defor12 = t.defor12, defor13 = t.defor13, defor23 = t.defor23, u = s.u, v = s.v;
+  const float mass = g.c1h[k] * A2(s.mut, i, j) + g.c2h[k];
+  const float xkmh = A3(s.xkmh, i, k, j), xkmv = A3(s.xkmv, i, k, j), xkhv = A3(s.xkhv, i, k, j);
+  float td = A3(tendency, i, k, j);
+  auto sq = [](float a) { return a * a; };
+  // tke_shear
+  td = td + 0.5f * mass * xkmh * (A3(defor11, i, k, j) * A3(defor11, i, k, j));
+  td = td + 0.5f * mass * xkmh * (A3(defor22, i, k, j) * A3(defor22, i, k, j));
+  td = td + 0.5f * mass * xkmv * (A3(defor33, i, k, j) * A3(defor33, i, k, j));
+  float avg = 0.25f * (sq(A3(defor12, i, k, j)) + sq(A3(defor12, i, k, j + 1)) + sq(A3(defor12, i + 1, k, j)) + sq(A3(defor12, i + 1, k, j + 1)));
+  td = td + mass * xkmh * avg;
+  auto d13 = [&](int ii, int kk) -> float { return (kk == 1 || kk == ktf + 1) ? 0.0f : A3(defor13, ii, kk, j); };
+  auto d23 = [&](int jj, int kk) -> float { return (kk == 1 || kk == ktf + 1) ? 0.0f : A3(defor23, i, kk, jj); };
+  avg = 0.25f * (sq(d13(i, k + 1)) + sq(d13(i, k)) + sq(d13(i + 1, k + 1)) + sq(d13(i + 1, k)));
+  td = td + mass * xkmv * avg;
+  float absU = 0.f, Cd = 0.f;
+  if (k == 1) {
+    const float a = A3(u, i, k, j) + A3(u, i + 1, k, j), b = A3(v, i, k, j) + A3(v, i, k, j + 1);
+    absU = 0.5f * sqrtf(a * a + b * b);
+    if (s.isfflx == 0) Cd = s.cd0;
+    else { absU = absU + 1.e-10f; Cd = (A2(s.ustm, i, j) * A2(s.ustm, i, j)) / (absU * absU); }
+    td = td + mass * ((A3(u, i, k, j) + A3(u, i + 1, k, j)) * 0.5f * Cd * absU * (A3(defor13, i, 2, j) + A3(defor13, i + 1, 2, j)) * 0.5f);
+  }
+  avg = 0.25f * (sq(d23(j, k + 1)) + sq(d23(j, k)) + sq(d23(j + 1, k + 1)) + sq(d23(j + 1, k)));
+  td = td + mass * xkmv * avg;
+  if (k == 1) td = td + mass * ((A3(v, i, k, j) + A3(v, i, k, j + 1)) * 0.5f * Cd * absU * (A3(defor23, i, 2, j) + A3(defor23, i, 2, j + 1)) * 0.5f);
+  // tke_buoyancy
+  const float BN2 = A3(s.bn2, i, k, j);
+  if (k >= 2) td = td - mass * xkhv * BN2;
+  else {
+    float heat_flux;
+    if (s.isfflx == 0 || s.isfflx == 2) heat_flux = s.heat_flux;
+    else {
+      const float cpm = WG_CP * (1.f + 0.8f * (t.qv ? A3(t.qv, i, k, j) : 0.f));
+      heat_flux = (A2(s.hfx, i, j) / cpm) / A3(s.rho, i, k, j);
+    }
+    td = td - mass * ((xkhv * BN2) - (WG_G / theta_at(g, t, i, k, j)) * heat_flux) / 2.f;
+  }
+  // tke_dissip
+  {
+    const float ce1 = (s.c_k / 0.10f) * 0.19f;
+    const float ce2 = fmaxf(0.0f, 0.93f - ce1);
+    const float deltas = wg_libm::powf_(t.dx / A2(g.msftx, i, j) * t.dy / A2(g.msfty, i, j) / A3(t.rdzw, i, k, j), 0.33333333f);
+    const float l_scale = l_scale_at(g, s, i, k, j, deltas);
+    const float tketmp = fmaxf(A3(s.tke, i, k, j), 1.0e-6f);
+    float coefc;
+    if (k == 1 || k == ktf) coefc = 3.9f;
+    else coefc = ce1 + ce2 * l_scale / deltas;
+    td = td - mass * coefc * wg_libm::powf_(tketmp, 1.5f) / l_scale;
+  }
+  td = fmaxf(td, -mass * fmaxf(0.0f, A3(s.tke, i, k, j)) / t.dt);
+  A3(tendency, i, k, j) = td;
+}
+
 }  // namespace wg

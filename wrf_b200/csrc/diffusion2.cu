@@ -25,9 +25,9 @@ __global__ void k_diff2_w(const Geo g, Box b, D2In s, fp tendency) {
   TID3;
   diff2_w_point(g, s, i, k, j, tendency);
 }
-__global__ void k_diff2_s(const Geo g, Box b, D2In s, R4 r, int which, cfp var, const float *base, cfp xkhv, cfp xkhh, fp tendency) {
+__global__ void k_diff2_s(const Geo g, Box b, D2In s, R4 r, int which, cfp var, const float *base, cfp xkhv, cfp xkhh, fp tendency, int doing_tke) {
   TID3;
-  diff2_s_point(g, s, r, which, var, base, xkhv, xkhh, i, k, j, tendency);
+  diff2_s_point(g, s, r, which, var, base, xkhv, xkhh, i, k, j, tendency, doing_tke);
 }
 
 bool diff2_is_identity(const wrfgpu_config &c) {
@@ -62,14 +62,18 @@ void Solver::diffusion2_tendencies() {
   s.isfflx = c.isfflx; s.use_theta_m = c.use_theta_m; s.cd0 = c.tke_drag_coefficient; s.heat_flux = c.tke_heat_flux;
   const R4 ru = d2_range(q, 'u'), rv = d2_range(q, 'v'), rm = d2_range(q, 'm');
   const Box tile{q.its, q.ite, 1, q.kde - 1, q.jts, q.jte};
+  if (tke_index()) tke_rhs();   // before the diffusion (module_first_rk_step_part2.F:904-940)
   LAUNCH3(this, k_diff2_u, tile, s, ru, o("ru_tendf"));
   LAUNCH3(this, k_diff2_v, tile, s, rv, o("rv_tendf"));
   LAUNCH3(this, k_diff2_w, (Box{rm.i0, rm.i1, 2, q.kde - 1, rm.j0, rm.j1}), s, o("rw_tendf"));
   const float *tb = c.mix_full_fields ? nullptr : o("t_base"), *qb = c.mix_full_fields ? nullptr : o("qv_base");
-  LAUNCH3(this, k_diff2_s, tile, s, rm, 0, o("t_2"), tb, o("xkhv"), o("xkhh"), o("t_tendf"));
-  for (auto &sp : species)
-    LAUNCH3(this, k_diff2_s, tile, s, rm, sp.f == "moist_qv" ? 1 : 2, o(sp.f), sp.f == "moist_qv" ? qb : (const float *)nullptr, o("xkhv"), o("xkhh"),
-            o(sp.t));
+  LAUNCH3(this, k_diff2_s, tile, s, rm, 0, o("t_2"), tb, o("xkhv"), o("xkhh"), o("t_tendf"), 0);
+  const std::string tke_name = tke_index() ? "scalar_" + std::to_string(tke_index()) : std::string("-");
+  for (auto &sp : species) {
+    const bool is_tke = sp.f == tke_name;   // tke mixes with K_m and doing_tke (:4302-4308, :2968-2982)
+    LAUNCH3(this, k_diff2_s, tile, s, rm, sp.f == "moist_qv" ? 1 : 2, o(sp.f), sp.f == "moist_qv" ? qb : (const float *)nullptr,
+            is_tke ? o("xkmv") : o("xkhv"), is_tke ? o("xkmh") : o("xkhh"), o(sp.t), is_tke ? 1 : 0);
+  }
 }
 
 }  // namespace wg

@@ -204,8 +204,9 @@ WG_HD void diff2_w_point(const Geo &g, const D2In &s, int i, int k, int j, fp te
 // ---- scalars (vertical_diffusion_s :4789, the surface heat / moisture flux :4262-4353, horizontal_diffusion_s :3711)
 // which: 0 theta (t_2; vertical part on t_2 - t_base unless mix_full_fields), 1 qv (vertical part on qv - qv_base unless
 // mix_full_fields), 2 any other species.  base: origin-shifted 1-D array or null.  thread box: the tile's mass points, k in 1..ktf
+// doing_tke: the tke species (K = xkmv / xkmh passed as xkhv / xkhh): each of the two terms is added twice (:4893-4903, :3985-3995)
 WG_HD void diff2_s_point(const Geo &g, const D2In &s, const R4 &r, int which, cfp var, const float *base, cfp xkhv, cfp xkhh, int i, int k, int j,
-                         fp tendency) {
+                         fp tendency, int doing_tke = 0) {
   const int ktf = g.kde - 1, kte = g.kde;
   const bool in = in_r4(r, i, j);
   const bool flux = k == 1 && which != 2 && i <= min(g.ite, g.ide - 1) && j <= min(g.jte, g.jde - 1);
@@ -220,7 +221,9 @@ WG_HD void diff2_s_point(const Geo &g, const D2In &s, const R4 &r, int which, cf
       xkxavg = xkxavg * (g.fnm[kk] * A3(rho, i, kk, j) + g.fnp[kk] * A3(rho, i, kk - 1, j));
       return -xkxavg * (vm(kk) - vm(kk - 1)) * A3(rdz, i, kk, j);
     };
+    const float t0 = t;
     t = t + WG_G * (H3(k + 1) - H3(k)) / g.dnw[k];
+    if (doing_tke) t = t0 + 2.f * (t - t0);
   }
   if (flux) {
     if (which == 0) {
@@ -280,10 +283,12 @@ WG_HD void diff2_s_point(const Geo &g, const D2In &s, const R4 &r, int which, cf
     const float zy_at_m = 0.25f * (A3(zy, i, k, j) + A3(zy, i, k, j + 1) + A3(zy, i, k + 1, j) + A3(zy, i, k + 1, j + 1));
     const float mrdx = A2(g.msftx, i, j) * g.rdx;
     const float mrdy = A2(g.msfty, i, j) * g.rdy;
+    const float t0 = t;
     t = t + WG_G / (g.dnw[k] * A3(rdzw, i, k, j)) *
                 (mrdx * (H1(i + 1, k) - H1(i, k)) + mrdy * (H2(j + 1, k) - H2(j, k)) -
                  A2(g.msftx, i, j) * zx_at_m * (H1avg(k + 1) - H1avg(k)) * A3(rdzw, i, k, j) -
                  A2(g.msfty, i, j) * zy_at_m * (H2avg(k + 1) - H2avg(k)) * A3(rdzw, i, k, j));
+    if (doing_tke) t = t0 + 2.f * (t - t0);
   }
   A3(tendency, i, k, j) = t;
 }

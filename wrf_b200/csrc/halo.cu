@@ -88,6 +88,7 @@ static void split(const std::string &s, std::vector<std::string> &out) {
 static bool halo_fields(const wrfgpu_config &c, const std::string &name, int &width, std::vector<std::string> &f3,
                         std::vector<std::string> &f2) {
   static const char *mn[] = {"qv", "qc", "qr"};
+  const int nsc = c.num_scalar + ((c.km_opt == 2 && c.diff_opt == 2) ? 1 : 0);   // + the tke species (Solver::tke_index)
   for (const HaloDef &h : kHalos) {
     if (name != h.name) continue;
     width = h.width;
@@ -96,8 +97,8 @@ static bool halo_fields(const wrfgpu_config &c, const std::string &name, int &wi
     for (auto &t : raw) {
       if (t == "@moist") for (int s = 0; s < c.num_moist; s++) f3.push_back(std::string("moist_") + mn[s]);
       else if (t == "@moist_old") for (int s = 0; s < c.num_moist; s++) f3.push_back(std::string("moist_old_") + mn[s]);
-      else if (t == "@scalar") for (int s = 1; s <= c.num_scalar; s++) f3.push_back("scalar_" + std::to_string(s));
-      else if (t == "@scalar_old") for (int s = 1; s <= c.num_scalar; s++) f3.push_back("scalar_old_" + std::to_string(s));
+      else if (t == "@scalar") for (int s = 1; s <= nsc; s++) f3.push_back("scalar_" + std::to_string(s));
+      else if (t == "@scalar_old") for (int s = 1; s <= nsc; s++) f3.push_back("scalar_old_" + std::to_string(s));
       else f3.push_back(t);
     }
     split(h.f2, f2);

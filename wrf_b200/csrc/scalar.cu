@@ -397,7 +397,14 @@ __global__ void k_update_scalar(const Geo g, Box b, int rk_step, float dt, fp sc
   A3(scalar_2, i, k, j) = ((g.c1h[k] * muold + g.c2h[k]) * s1 + dt * tendency) / (g.c1h[k] * munew + g.c2h[k]);
 }
 
+// bound_tke (module_em.F:2616-2646), after the update of the tke species (solve_em.F:2437-2445)
+__global__ void k_bound_tke(const Geo g, Box b, float tke_upper_bound, fp tke) {
+  TID3;
+  A3(tke, i, k, j) = fminf(tke_upper_bound, fmaxf(A3(tke, i, k, j), 0.f));
+}
+
 void Solver::rk_scalar_step(int rk_step) {
+  const std::string tke_name = tke_index() ? "scalar_" + std::to_string(tke_index()) : std::string("-");
   const Geo &q = g;
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
@@ -446,14 +453,14 @@ void Solver::rk_scalar_step(int rk_step) {
         LAUNCH3(this, k_mono_scale, lim, in, o("pd_scale"), o("pd_scale2"));
         LAUNCH3(this, k_mono_tend, mass, in, o("pd_scale"), o("pd_scale2"), lim, o("advect_tend"));
         if (ieva) ieva_implicit(0, o("advect_tend"), o(s.o), o("mut_old"), o("muts"), dt_rk);
-        LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
+        { LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub")); if (s.f == tke_name) LAUNCH3(this, k_bound_tke, mass, c.tke_upper_bound, o(s.f)); }
         continue;
       }
       if (s.adv_opt == 4 || ieva || !dflt_s) {   // WENO inside the positive-definite limiter, or IEVA's wwE: the gather kernels everywhere
         LAUNCH3(this, k_pd_scale, lim, in, o("pd_scale"));
         LAUNCH3(this, k_pd_tend, mass, in, o("pd_scale"), lim, o("advect_tend"));
         if (ieva) ieva_implicit(0, o("advect_tend"), o(s.o), o("mut_old"), o("muts"), dt_rk);
-        LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
+        { LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub")); if (s.f == tke_name) LAUNCH3(this, k_bound_tke, mass, c.tke_upper_bound, o(s.f)); }
         continue;
       }
       // k-marching kernels (pd_fast.cu) where every face is 5th order, the gather kernels on the strips around
@@ -487,7 +494,7 @@ void Solver::rk_scalar_step(int rk_step) {
     }
     if (rk_step == 1 && c.diff_6th_opt != 0 && !(s.f.rfind("moist_", 0) == 0 ? c.moist_mix6_off : c.scalar_mix6_off))
       launch_diff6(this, 5, o(s.f), o(s.t), o("muts"), dt_rk);   // module_em.F:1421-1437 (dt_step = dt_rk)
-    LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
+    { LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub")); if (s.f == tke_name) LAUNCH3(this, k_bound_tke, mass, c.tke_upper_bound, o(s.f)); }
   }
 }
 

@@ -44,11 +44,15 @@ static void check_config(const wrfgpu_config &c) {
   // is accepted as such.  The rest (physical-space diffusion with non-zero K, TKE / 3-D Smagorinsky) is a 'next' row.
   if (c.diff_6th_opt < 0 || c.diff_6th_opt > 2) bad("diff_6th_opt must be 0, 1 or 2");
   if (c.diff_opt != 0) {
-    if (c.km_opt != 1 && c.km_opt != 3 && c.km_opt != 4)
-      bad("km_opt must be 1 (constant K), 3 (3-D Smagorinsky) or 4 (2-D Smagorinsky); the TKE closure is a 'next' row");
-    if (c.km_opt == 3 && !(c.mix_upper_bound > 0.f)) bad("mix_upper_bound must be positive with km_opt = 3");
-    if (c.km_opt == 3 && c.mix_isotropic != 0 && c.mix_isotropic != 1) bad("mix_isotropic must be 0 or 1");
+    if (c.km_opt < 1 || c.km_opt > 4) bad("km_opt must be 1 (constant K), 2 (TKE), 3 (3-D Smagorinsky) or 4 (2-D Smagorinsky)");
+    if (c.km_opt == 2 && c.diff_opt != 2) bad("km_opt = 2 (TKE) needs diff_opt = 2: tke_rhs is only called there (module_first_rk_step_part2.F:904)");
+    if (c.km_opt == 2 && (c.tke_adv_opt < 0 || c.tke_adv_opt > 4)) bad("tke_adv_opt must be 0 ... 4");
+    if (c.km_opt == 2 && c.diff_6th_opt != 0) bad("the 6th-order filter on tke (tke_mix6_off) is not on the device path");
+    if (c.km_opt == 2 && !(c.c_k > 0.f)) bad("c_k must be positive with km_opt = 2");
+    if ((c.km_opt == 2 || c.km_opt == 3) && !(c.mix_upper_bound > 0.f)) bad("mix_upper_bound must be positive with km_opt = 2, 3");
+    if ((c.km_opt == 2 || c.km_opt == 3) && c.mix_isotropic != 0 && c.mix_isotropic != 1) bad("mix_isotropic must be 0 or 1");
     if (c.km_opt >= 3 && !(c.c_s > 0.f)) bad("c_s must be positive with km_opt = 3, 4");
+    if (c.num_scalar > 7 && c.km_opt == 2) bad("at most 7 scalars with km_opt = 2 (tke is carried as one more)");
     if (c.isfflx < 0 || c.isfflx > 2) bad("isfflx must be 0, 1 or 2");
     if (c.diff_opt != 1 && c.diff_opt != 2) bad("diff_opt must be 0, 1 or 2");
     if (c.khdif < 0.f || c.kvdif < 0.f) bad("khdif, kvdif must not be negative");
@@ -84,7 +88,7 @@ Solver::Solver(const wrfgpu_dims &d_, const wrfgpu_config &c_, int dev) : d(d_),
   for (int i = 0; k1d[i]; i++) add(k1d[i], 1);
   if (c.diff_opt != 0 && (c.km_opt >= 2 || (c.diff_opt == 2 && !diff2_is_identity(c)))) {   // metrics, deformation, K arrays (deform.cu)
     if (!c.mp_physics) add("z", 3);
-    if (c.km_opt == 3) add("bn2", 3);
+    if (c.km_opt == 3 || c.km_opt == 2) add("bn2", 3);
     for (const char *n : {"ustm", "hfx", "qfx"}) add(n, 2);   // surface fluxes of a host-side surface scheme (isfflx 1, 2); zero otherwise
     for (const char *n : {"zx", "zy", "rdz", "rdzw", "div", "defor11", "defor22", "defor33", "defor12", "defor13", "defor23",
                           "xkmh", "xkmv", "xkhh", "xkhv"}) add(n, 3);
@@ -99,9 +103,9 @@ Solver::Solver(const wrfgpu_dims &d_, const wrfgpu_config &c_, int dev) : d(d_),
     add(sp.f, 3); add(sp.o, 3); add(sp.t, 3);
     species.push_back(sp);
   }
-  for (int s = 1; s <= c.num_scalar; s++) {
+  for (int s = 1; s <= c.num_scalar + (tke_index() ? 1 : 0); s++) {
     Species sp{"scalar_" + std::to_string(s), "scalar_old_" + std::to_string(s), "scalar_tend_" + std::to_string(s),
-               c.scalar_adv_opt};
+               s == tke_index() ? c.tke_adv_opt : c.scalar_adv_opt};
     add(sp.f, 3); add(sp.o, 3); add(sp.t, 3);
     species.push_back(sp);
   }
@@ -172,7 +176,12 @@ void Solver::add(const std::string &n, int kind) {
   names.push_back(n);
 }
 
-Field &Solver::F(const std::string &n) {
+Field &Solver::F(const std::string &n0) {
+  std::string n = n0;
+  if (tke_index()) {   // Registry names of the tke species
+    const std::string N = std::to_string(tke_index());
+    if (n0 == "tke_2") n = "scalar_" + N; else if (n0 == "tke_1") n = "scalar_old_" + N; else if (n0 == "tke_tend") n = "scalar_tend_" + N;
+  }
   auto it = fields.find(n);
   if (it == fields.end()) throw std::runtime_error("wrfgpu: unknown field '" + n + "'");
   return it->second;

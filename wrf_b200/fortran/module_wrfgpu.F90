@@ -46,6 +46,8 @@ MODULE module_wrfgpu
       REAL(c_float)  :: tke_drag_coefficient, tke_heat_flux
       INTEGER(c_int) :: mix_isotropic
       REAL(c_float)  :: mix_upper_bound
+      INTEGER(c_int) :: tke_adv_opt
+      REAL(c_float)  :: tke_upper_bound
    END TYPE wrfgpu_config
 
    INTERFACE

@@ -77,6 +77,7 @@ SUBROUTINE solve_em ( grid , config_flags  &
       c%c_s = config_flags%c_s; c%c_k = config_flags%c_k; c%mix_full_fields = MERGE(1,0,config_flags%mix_full_fields)
       c%isfflx = config_flags%isfflx; c%tke_drag_coefficient = config_flags%tke_drag_coefficient; c%tke_heat_flux = config_flags%tke_heat_flux
       c%mix_isotropic = config_flags%mix_isotropic; c%mix_upper_bound = config_flags%mix_upper_bound
+      c%tke_adv_opt = config_flags%tke_adv_opt; c%tke_upper_bound = config_flags%tke_upper_bound
       device = MOD(mytask, 8)                        ! one rank per GPU of the box
       CALL wrfgpu_check( wrfgpu_create(d, c, device, handle(id)), 'wrfgpu_create' )
 #ifdef DM_PARALLEL

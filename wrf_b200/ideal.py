@@ -68,7 +68,7 @@ class Config(ctypes.Structure):
         + [(n, ctypes.c_float) for n in ("c_s", "c_k")]
         + [("mix_full_fields", ctypes.c_int), ("isfflx", ctypes.c_int)]
         + [(n, ctypes.c_float) for n in ("tke_drag_coefficient", "tke_heat_flux")]
-        + [("mix_isotropic", ctypes.c_int), ("mix_upper_bound", ctypes.c_float)])
+        + [("mix_isotropic", ctypes.c_int), ("mix_upper_bound", ctypes.c_float), ("tke_adv_opt", ctypes.c_int), ("tke_upper_bound", ctypes.c_float)])
 
 
 def default_config(**kw) -> Config:
@@ -91,6 +91,7 @@ def default_config(**kw) -> Config:
     c.diff_6th_factor, c.diff_6th_thresh = 0.12, 0.10
     c.c_s, c.c_k = 0.25, 0.15
     c.mix_upper_bound = 0.1
+    c.tke_adv_opt, c.tke_upper_bound = 1, 1000.0
     c.ntasks_x = c.ntasks_y = 1
     for k, v in kw.items():
         setattr(c, k, v)
