@@ -85,31 +85,30 @@ void Solver::diffusion_prep() {
   LAUNCH3(this, k_deform, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), r, in, out);
   halo("HALO_EM_TKE_D");   // :571
   if (c.km_opt == 1) diffusion2_isotropic_km();
-  else {
-  // calculate_km_kh -> smag2d_km on its computed range (module_diffusion_em.F:1974-1989)
-  int i_start = q.its, i_end = std::min(q.ite, q.ide - 1), j_start = q.jts, j_end = std::min(q.jte, q.jde - 1);
-  if (q.open_xs) i_start = std::max(q.ids + 1, q.its);
-  if (q.open_xe) i_end = std::min(q.ide - 2, q.ite);
-  if (q.open_ys) j_start = std::max(q.jds + 1, q.jts);
-  if (q.open_ye) j_end = std::min(q.jde - 2, q.jte);
-  if (q.periodic_x) { i_start = q.its; i_end = std::min(q.ite, q.ide - 1); }
-  if (c.km_opt == 2) {   // calculate_N2 + tke_km in one launch
-    LAUNCH3(this, k_tke_km, (Box{i_start, i_end, 1, q.kde - 1, j_start, j_end}), tke_in(this), o("bn2"), o("xkmh"), o("xkmv"), o("xkhh"), o("xkhv"));
-  } else if (c.km_opt == 3) {   // calculate_N2 + smag_km in one launch
-    Smag3In s3;
-    s3.t_2 = o("t_2"); s3.qv = c.num_moist >= 1 ? o("moist_qv") : nullptr; s3.qc = c.num_moist >= 2 ? o("moist_qc") : nullptr;
-    s3.p = o("p"); s3.pb = o("pb"); s3.ph = o("ph_2"); s3.phb = o("phb"); s3.rdz = o("rdz"); s3.rdzw = o("rdzw");
-    s3.defor11 = o("defor11"); s3.defor22 = o("defor22"); s3.defor33 = o("defor33"); s3.defor12 = o("defor12"); s3.defor13 = o("defor13");
-    s3.defor23 = o("defor23"); s3.dn = o("dn");
-    s3.dx = c.dx; s3.dy = c.dy; s3.dt = c.dt; s3.c_s = c.c_s; s3.mix_upper_bound = c.mix_upper_bound; s3.mix_isotropic = c.mix_isotropic;
-    s3.use_theta_m = c.use_theta_m;
-    LAUNCH3(this, k_smag3d, (Box{i_start, i_end, 1, q.kde - 1, j_start, j_end}), s3, o("bn2"), o("xkmh"), o("xkmv"), o("xkhh"), o("xkhv"));
-  } else {
-  SmagIn sm;
-  sm.defor11 = o("defor11"); sm.defor22 = o("defor22"); sm.defor12 = o("defor12"); sm.rdzw = o("rdzw"); sm.zx = o("zx"); sm.zy = o("zy");
-  sm.dx = c.dx; sm.dy = c.dy; sm.c_s = c.c_s; sm.diff_opt = c.diff_opt;
-  LAUNCH3(this, k_smag2d, (Box{i_start, i_end, 1, q.kde - 1, j_start, j_end}), sm, o("xkmh"), o("xkmv"), o("xkhh"), o("xkhv"));
-  }
+  else {   // calculate_km_kh on the range its closures share (module_diffusion_em.F:1816-1831, :1974-1989, :2078-2093)
+    int i_start = q.its, i_end = std::min(q.ite, q.ide - 1), j_start = q.jts, j_end = std::min(q.jte, q.jde - 1);
+    if (q.open_xs) i_start = std::max(q.ids + 1, q.its);
+    if (q.open_xe) i_end = std::min(q.ide - 2, q.ite);
+    if (q.open_ys) j_start = std::max(q.jds + 1, q.jts);
+    if (q.open_ye) j_end = std::min(q.jde - 2, q.jte);
+    if (q.periodic_x) { i_start = q.its; i_end = std::min(q.ite, q.ide - 1); }
+    if (c.km_opt == 2) {   // calculate_N2 + tke_km in one launch
+      LAUNCH3(this, k_tke_km, (Box{i_start, i_end, 1, q.kde - 1, j_start, j_end}), tke_in(this), o("bn2"), o("xkmh"), o("xkmv"), o("xkhh"), o("xkhv"));
+    } else if (c.km_opt == 3) {   // calculate_N2 + smag_km in one launch
+      Smag3In s3;
+      s3.t_2 = o("t_2"); s3.qv = c.num_moist >= 1 ? o("moist_qv") : nullptr; s3.qc = c.num_moist >= 2 ? o("moist_qc") : nullptr;
+      s3.p = o("p"); s3.pb = o("pb"); s3.ph = o("ph_2"); s3.phb = o("phb"); s3.rdz = o("rdz"); s3.rdzw = o("rdzw");
+      s3.defor11 = o("defor11"); s3.defor22 = o("defor22"); s3.defor33 = o("defor33"); s3.defor12 = o("defor12"); s3.defor13 = o("defor13");
+      s3.defor23 = o("defor23"); s3.dn = o("dn");
+      s3.dx = c.dx; s3.dy = c.dy; s3.dt = c.dt; s3.c_s = c.c_s; s3.mix_upper_bound = c.mix_upper_bound; s3.mix_isotropic = c.mix_isotropic;
+      s3.use_theta_m = c.use_theta_m;
+      LAUNCH3(this, k_smag3d, (Box{i_start, i_end, 1, q.kde - 1, j_start, j_end}), s3, o("bn2"), o("xkmh"), o("xkmv"), o("xkhh"), o("xkhv"));
+    } else {
+      SmagIn sm;
+      sm.defor11 = o("defor11"); sm.defor22 = o("defor22"); sm.defor12 = o("defor12"); sm.rdzw = o("rdzw"); sm.zx = o("zx"); sm.zy = o("zy");
+      sm.dx = c.dx; sm.dy = c.dy; sm.c_s = c.c_s; sm.diff_opt = c.diff_opt;
+      LAUNCH3(this, k_smag2d, (Box{i_start, i_end, 1, q.kde - 1, j_start, j_end}), sm, o("xkmh"), o("xkmv"), o("xkhh"), o("xkhv"));
+    }
   }
   halo("HALO_EM_TKE_E");   // + PERIOD_BDY_EM_PHY_BC, HALO_EM_PHYS_DIFFUSION (:644-650, :759)
   bc({{"xkmh", 't'}, {"xkhh", 't'}});   // phy_bc (module_diffusion_em.F:5901), diff_opt = 1 part
