@@ -29,3 +29,13 @@ def test_five_steps_bit_exact(name):
     o.step(5); s.step(5)
     rep = parity.diff_report(o, s)
     assert not rep, rep[:10]
+
+
+@pytest.mark.parametrize("mesh", [(1, 2), (2, 2)])
+@pytest.mark.parametrize("name", ["smag3d_periodic", "tke", "tke_periodic"])
+def test_n_rank_gpu_equals_single_rank(name, mesh):
+    """the reference's BIT4BIT criterion on the device for the two closures (the tke species travels with the scalar halos)"""
+    from tests.test_multi_gpu import _run
+    bad, sent = _run(parity.small_cases()[name], *mesh, nsteps=2)
+    assert not bad, bad[:8]
+    assert all(b > 0 for b in sent)
