@@ -106,6 +106,9 @@ typedef struct wrfgpu_config {
   /* 1.5-order TKE closure (km_opt = 2 with diff_opt = 2): the prognostic tke_1 / tke_2 (Registry.EM_COMMON:312) */
   int tke_adv_opt;                       /* as scalar_adv_opt (Registry.EM_COMMON:2884) */
   float tke_upper_bound;                 /* 1000. (bound_tke, module_em.F:2616) */
+  /* w_damp's CFL maxima (module_big_step_utilities_em.F:2503-2711) are folded into grid%max_vert_cfl /
+   * max_horiz_cfl only with the adaptive time step (solve_em.F:914-930); 1 = compute them on the device */
+  int use_adaptive_time_step;
 } wrfgpu_config;
 
 typedef struct wrfgpu_solver wrfgpu_solver;   /* opaque */
@@ -168,6 +171,10 @@ int  wrfgpu_set_stream(wrfgpu_solver *s, void *cuda_stream);
 /* per-kernel cudaEvent statistics collected while phase timing is on, as text
  * lines "kernel count total_ms"; returns the buffer size needed */
 size_t wrfgpu_kernel_report(wrfgpu_solver *s, char *buf, size_t cap);
+/* grid%max_vert_cfl / grid%max_horiz_cfl (solve_em.F:914-930): the running maxima of w_damp's Courant numbers over
+ * every RK substep since the last reset, over all ranks of the mesh (the wrf_dm_maxval of adapt_timestep,
+ * dyn_em/adapt_timestep_em.F).  Needs use_adaptive_time_step = 1.  reset != 0 zeroes them after the read. */
+int  wrfgpu_max_cfl(wrfgpu_solver *s, float *max_vert_cfl, float *max_horiz_cfl, int reset);
 /* number of kernels this library launched since create (bench "gpu_launches") */
 long long wrfgpu_launch_count(const wrfgpu_solver *s);
 /* cudaEvent timing of the kernels launched by phase `name` since the last

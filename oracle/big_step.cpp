@@ -621,7 +621,7 @@ void pg_buoy_w(const Cx &x, A3 rw_tend, A3 p, A3 cqw, A2 muf, A2 mubf) {
   }
 }
 
-// module_big_step_utilities_em.F:2503-2711 (zadvect_implicit = 0, not polar)
+// module_big_step_utilities_em.F:2503-2711 (not polar)
 void w_damp(const Cx &x, A3 rw_tend, float &max_vert_cfl, float &max_horiz_cfl, A3 u, A3 v, A3 ww,
             A3 w, A2 mut) {
   const int itf = std::min(x.ite, x.ide - 1), jtf = std::min(x.jte, x.jde - 1);
@@ -629,7 +629,7 @@ void w_damp(const Cx &x, A3 rw_tend, float &max_vert_cfl, float &max_horiz_cfl, 
   max_vert_cfl = 0.f;
   max_horiz_cfl = 0.f;
   const float w_crit_cfl = x.c.w_crit_cfl;
-  const float w_damp_on = w_beta;
+  const float w_damp_on = x.c.zadvect_implicit > 0 ? w_crit_cfl : w_beta;   // :2602-2608
   const float dt = x.dt;
   for (int j = x.jts; j <= jtf; j++)
     for (int k = 2; k <= x.kde - 1; k++)

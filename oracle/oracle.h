@@ -109,6 +109,8 @@ struct Oracle {
   // scalar_tend_N = tke_tend with N = num_scalar + 1), advected with tke_adv_opt
   int tke_index() const { return (c.km_opt == 2 && c.diff_opt == 2) ? c.num_scalar + 1 : 0; }
   int nsc() const { return c.num_scalar + (tke_index() ? 1 : 0); }
+  // grid%max_vert_cfl, grid%max_horiz_cfl (solve_em.F:914-930): running maxima of w_damp's Courant numbers
+  float max_vert_cfl = 0.f, max_horiz_cfl = 0.f;
   int nthreads = 1;   // j-tiles run on std::threads like the reference's OpenMP tiles (solve_em.F:652-674)
   template <class Fn> void par(Fn fn);
 

@@ -305,6 +305,10 @@ void Oracle::rk_tendency(int rk_step) {
   par([&](const Cx &xt) { pg_buoy_w(xt, rw_tend, a3("p"), a3("cqw"), mu, mub); });
   float mv, mh;
   w_damp(x, rw_tend, mv, mh, u, v, ww, w, mut);
+  if (c.use_adaptive_time_step) {   // solve_em.F:914-922
+    if (mh > max_horiz_cfl) max_horiz_cfl = mh;
+    if (mv > max_vert_cfl) max_vert_cfl = mv;
+  }
   if (c.pert_coriolis) par([&](const Cx &xt) { perturbation_coriolis(xt, ru, rv, rw, ru_tend, rv_tend, rw_tend, muu, muv, a3("phb"), ph); });
   else par([&](const Cx &xt) { coriolis(xt, ru, rv, rw, ru_tend, rv_tend, rw_tend); });
   par([&](const Cx &xt) { curvature(xt, ru, rv, rw, u, v, w, ru_tend, rv_tend, rw_tend); });
@@ -668,6 +672,11 @@ int oracle_set_halo_callback(Oracle *o, void (*cb)(void *, const char *), void *
 float *oracle_field_ptr(Oracle *o, const char *name) {
   auto it = o->data.find(name);
   return it == o->data.end() ? nullptr : it->second.data();
+}
+int oracle_max_cfl(Oracle *o, float *mv, float *mh, int reset) {
+  *mv = o->max_vert_cfl; *mh = o->max_horiz_cfl;
+  if (reset) o->max_vert_cfl = o->max_horiz_cfl = 0.f;
+  return 0;
 }
 int oracle_set_threads(Oracle *o, int n) { o->nthreads = n < 1 ? 1 : n; return o->nthreads; }
 int oracle_step(Oracle *o, int n) { OGUARD(for (int i = 0; i < n; i++) o->step()) }

@@ -65,6 +65,11 @@ class Oracle:
     def call(self, phase, *args):
         self._chk(getattr(self.lib, "oracle_" + phase)(self.h, *[ctypes.c_int(int(x)) for x in args]))
 
+    def max_cfl(self, reset=False):
+        mv, mh = ctypes.c_float(), ctypes.c_float()
+        self._chk(self.lib.oracle_max_cfl(self.h, ctypes.byref(mv), ctypes.byref(mh), ctypes.c_int(int(reset))))
+        return mv.value, mh.value
+
     def set_threads(self, n):
         return int(self.lib.oracle_set_threads(self.h, ctypes.c_int(int(n))))
 

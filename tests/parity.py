@@ -158,6 +158,10 @@ def small_cases():
                                                      diff_6th_opt=1, diff_6th_factor=0.2, scalar_mix6_off=1)),
         "diff6_hill": make_case("hill2d_x", nx=62, ny=3, nz=21, diff_6th_opt=2, diff_6th_slopeopt=1, diff_6th_thresh=0.004),
         "ieva": with_updraft(make_case("quarter_ss", nx=26, ny=24, nz=41, zadvect_implicit=1, dt=20.0, time_step=20), 60.0),
+        # w_damp with IEVA: damping starts at w_crit_cfl instead of w_beta = 1 (module_big_step_utilities_em.F:2602-2608);
+        # the updraft has vertical Courant numbers on both sides of 2 and between 1 and 2; also the CFL maxima (adaptive dt)
+        "ieva_wdamp": with_updraft(make_case("quarter_ss", nx=26, ny=24, nz=41, zadvect_implicit=1, dt=20.0, time_step=20, w_damping=1,
+                                             w_crit_cfl=2.0, use_adaptive_time_step=1), 60.0, conv=60.0),
         "ieva_periodic": with_updraft(with_map_factors(make_case("synthetic", nx=34, ny=30, nz=33, bubble_lattice=20000.0, noise=0.05,
                                                                   num_scalar=2, scalar_adv_opt=2, moist_adv_opt=1, zadvect_implicit=1,
                                                                   dt=20.0, time_step=20)), 60.0),
@@ -281,6 +285,12 @@ def phase_sequence(case):
     return seq
 
 
+# Scratch arrays of the oracle the device never materialises in a phase: the closures' phy_prep (th_phy of
+# module_big_step_utilities_em.F:5394, read by calculate_N2) is evaluated in registers by k_smag3d / k_tke_km; the device's
+# th_phy only exists for Kessler and is written by its own moist_physics_prep in the microphysics phase (compared there).
+NOT_MATERIALISED = {("diffusion_prep", "th_phy")}
+
+
 def run_phase_parity(case, verbose=False):
     """Run one step phase by phase; the GPU input of every phase is the oracle's state.
     Returns list of failures (phase, field, n, maxabs, rel)."""
@@ -296,7 +306,7 @@ def run_phase_parity(case, verbose=False):
         s.call(phase, *args)
         rep = diff_report(o, s, fields)
         for r in rep:
-            ok = False   # any differing bit is a failure
+            ok = (phase, r[0]) in NOT_MATERIALISED   # any differing bit of anything else is a failure
             if verbose or not ok:
                 print(f"  {'ok ' if ok else 'BAD'} {phase}{args}: {r[0]:12s} n={r[1]:7d} maxabs={r[2]:.3e} rel_l2={r[3]:.3e}")
             if not ok:

@@ -1,10 +1,9 @@
 """GPU parity of the 3-D Smagorinsky closure (km_opt = 3: calculate_N2 + smag_km in k_smag3d, wrf_b200/csrc/deform.cuh) and of
-the TKE closure (km_opt = 2: k_tke_km, k_tke_rhs, k_bound_tke, the doing_tke flag of k_diff2_s).
+the TKE closure (km_opt = 2: k_tke_km, k_tke_rhs, k_bound_tke, the doing_tke flag of k_diff2_s) over several steps and
+over N ranks; the phase-by-phase and one-step cases are in test_parity_gpu.py (ALL).
 
-The kernel body is pinned bit for bit against the oracle on the CPU (tests/test_deform_host.py runs the same
-__host__ __device__ point functions, including the restated glibc powf / expf the device uses).  On the B200 the five-step
-test below has passed (profiles/README.md, run r1zh); the phase-by-phase test had not been run when the round's GPU budget
-ran out, and the three tke cases have not run on a GPU at all, so the file sorts last: `pytest -x` reaches it after every test that has run on a GPU."""
+The kernel bodies are also pinned bit for bit against the oracle on the CPU (tests/test_deform_host.py runs the same
+__host__ __device__ point functions, including the restated glibc powf / expf the device uses)."""
 import pytest
 
 from tests import parity
@@ -13,12 +12,6 @@ from wrf_b200 import Solver
 
 pytestmark = pytest.mark.gpu
 NAMES = ["smag3d", "smag3d_periodic", "smag3d_hill", "tke", "tke_periodic", "tke_hill"]
-
-
-@pytest.mark.parametrize("name", NAMES)
-def test_phase_parity(name):
-    fails = parity.run_phase_parity(parity.small_cases()[name])
-    assert not fails, fails[:10]
 
 
 @pytest.mark.parametrize("name", NAMES)

@@ -535,3 +535,36 @@ def test_quarter_ss_supercell_with_documented_default_mixing():
     assert 3.0e-3 < qr.max() < 2.0e-2, qr.max()     # several g/kg of rain water
     assert rain.max() > 1.0                         # mm at the ground under the core
     assert interior(o, "moist_qv").min() >= 0.0 and interior(o, "moist_qc").min() >= 0.0 and qr.min() >= 0.0   # PD advection + Kessler
+
+
+def test_w_damp_starts_at_w_crit_cfl_with_ieva():
+    """module_big_step_utilities_em.F:2602-2608: with zadvect_implicit > 0 the damping of w starts at w_crit_cfl, without it
+    at w_beta = 1; between the two thresholds an IEVA run must leave rw_tend alone (the term -sign(w)*0.3*(cfl - w_crit_cfl)*mass
+    would be positive there: it would accelerate w).  The case has Courant numbers in (1, 2) and above 2."""
+    from tests.parity import small_cases
+    base = small_cases()["ieva_wdamp"]
+    tend = {}
+    for damping in (0, 1):
+        case = small_cases()["ieva_wdamp"]
+        case.config.w_damping = damping
+        o = Oracle(case)
+        o.start_domain()
+        for ph, args in (("rk_step_prep", (1,)), ("rk_phys_bc_dry_1", ()), ("init_zero_tendency", ()), ("rk_tendency", (1,))):
+            o.call(ph, *args)
+        tend[damping] = o.get("rw_tend").copy()
+        if damping:
+            ww, mut = o.get("ww"), o.get("mut")
+            c1f, c2f, rdnw = o.get("c1f"), o.get("c2f"), o.get("rdnw")
+            d = case.dims
+            with np.errstate(invalid="ignore", divide="ignore"):     # the memory halo holds zeros
+                cfl = np.abs(ww / (c1f[None, :, None] * mut[:, None, :] + c2f[None, :, None]) * rdnw[None, :, None] * np.float32(case.config.dt))
+            sl = (slice(d.jps - d.jms, d.jpe - d.jms), slice(1, d.kde - 1), slice(d.ips - d.ims, d.ipe - d.ims))
+            cfl = cfl[sl]
+            changed = (tend[1] != tend[0])[sl]
+            between = (cfl > 1.0) & (cfl <= 2.0)
+            assert between.sum() > 20 and (cfl > 2.0).sum() > 20
+            assert not changed[between].any()           # untouched below w_crit_cfl
+            assert changed[cfl > 2.0].all()             # damped above it
+            mv, mh = o.max_cfl()
+            assert abs(mv - cfl.max()) <= 1e-6 * mv and 0 < mh < 1
+    assert base.config.zadvect_implicit == 1 and base.config.w_crit_cfl == 2.0

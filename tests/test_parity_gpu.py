@@ -15,10 +15,11 @@ CASES = None
 ALL = ["hill2d_x", "quarter_ss", "quarter_ss_nopd", "b_wave", "les", "periodic", "b_wave_lid", "quarter_ss_opts", "rk2_sym_x",
        "mapfac", "mapfac_open", "diffusion", "diffusion_periodic", "b_wave_shipped",
        "mono", "mono_periodic", "weno", "weno_periodic", "wenopd", "wenopd_periodic",
-       "weno_mom", "weno_mom_periodic", "weno_mom_b_wave", "ieva", "ieva_periodic", "ieva_weno_hill",
+       "weno_mom", "weno_mom_periodic", "weno_mom_b_wave", "ieva", "ieva_wdamp", "ieva_periodic", "ieva_weno_hill",
        "diff6", "diff6_periodic", "diff6_hill", "tall", "tiny", "rk2_everything", "backward",
        "order64", "order63_periodic", "order_mixed", "smag2d", "smag2d_periodic", "smag2d_hill", "smag2d_b_wave",
-       "diff2", "diff2_periodic", "diff2_hill", "diff2_b_wave"]
+       "diff2", "diff2_periodic", "diff2_hill", "diff2_b_wave",
+       "smag3d", "smag3d_periodic", "smag3d_hill", "tke", "tke_periodic", "tke_hill"]
 
 
 def cases():
@@ -96,6 +97,22 @@ def test_ieva_three_steps_bit_exact(name):
     s.close()
 
 
+def test_w_damp_cfl_maxima_equal_the_oracle():
+    """a7: max_vert_cfl / max_horiz_cfl (w_damp's reduction, consumed by the adaptive time step, solve_em.F:914-930) equal
+    the oracle's bit for bit after every step, and the reset works"""
+    case = cases()["ieva_wdamp"]
+    o, s = Oracle(case), Solver(case)
+    o.start_domain(); s.start_domain()
+    for n in range(3):
+        o.step(1); s.step(1)
+        a, b = s.max_cfl(reset=(n == 1)), o.max_cfl(reset=(n == 1))
+        assert a == b, (n, a, b)
+        assert a[0] > 2.0 and 0.0 < a[1] < 1.0     # the updraft exceeds w_crit_cfl = 2; horizontal Courant numbers are ordinary
+    s.close()
+    with pytest.raises(Exception):
+        Solver(cases()["quarter_ss"]).max_cfl()
+
+
 def test_solve_em_host_round_trip():
     """the strict drop-in call (host arrays in, one solve_em, host arrays out) equals
     stepping the resident state."""
@@ -125,10 +142,28 @@ def test_shipped_hill2d_x_diffusion_settings_are_the_identity():
     a.close(); b.close()
 
 
-def test_unsupported_namelist_fails_loudly():
+REJECTED = [
+    ("polar", dict(polar=1)),                                   # polar filters: out of scope
+    ("momentum_adv_opt=2", dict(momentum_adv_opt=2)),           # no such option in the Registry
+    ("km_opt=2 needs diff_opt=2", dict(diff_opt=1, km_opt=2)),  # tke_rhs is only called from the diff_opt=2 branch
+    ("odd time_step_sound", dict(time_step_sound=5)),           # solve_em.F:607-610
+    ("hydrostatic", dict(non_hydrostatic=0)),
+    ("damp_opt=1", dict(damp_opt=1)),
+    ("global lat-lon", dict(map_proj=6)),
+    ("h_sca_adv_order=4", dict(h_sca_adv_order=4)),
+    ("mp_physics=2", dict(mp_physics=2)),
+    ("conflicting bc", dict(periodic_x=1, open_xs=1)),
+]
+
+
+@pytest.mark.parametrize("why,overrides", REJECTED, ids=[r[0] for r in REJECTED])
+def test_unsupported_namelist_fails_loudly(why, overrides):
+    """no CPU fallback and no silent approximation: a namelist value the device path does not implement is an error at
+    wrfgpu_create (the Fortran shim turns it into wrf_error_fatal)"""
     from wrf_b200 import WrfGpuError, make_case
     case = make_case("quarter_ss", nx=26, ny=24, nz=21)
-    case.config.diff_opt = 2        # TKE closure: a 'next' row
-    case.config.km_opt = 2
+    for k, v in overrides.items():
+        assert hasattr(case.config, k), k
+        setattr(case.config, k, v)
     with pytest.raises(WrfGpuError):
         Solver(case)

@@ -49,6 +49,7 @@ struct GeoBase {
   int num_moist;
   float rdx, rdy, dt, cf1, cf2, cf3, cfn, cfn1;
   float epssm, smdiv, emdiv, dampcoef, zdamp, w_crit_cfl, p_top;
+  float w_damp_on;                 // vertical Courant number where w_damp starts: w_crit_cfl with IEVA, w_beta = 1 without (:2602-2608)
   float sgn_ts;                    // sign(1,time_step)
   // factor of the upwind term of the momentum / scalar fluxes, horizontal / vertical: sgn_ts for the odd orders (5, 3),
   // 0 for the even ones (h_*_adv_order = 6, v_*_adv_order = 4), which are the same operators without that term
@@ -272,6 +273,7 @@ inline bool empty(const Box &b) { return b.i1 < b.i0 || b.k1 < b.k0 || b.j1 < b.
   if (i > b.i1 || j > b.j1) return;
 
 void halo_destroy(Solver *s);   // halo.cu
+void halo_max2(Solver *s, float *d2, float out[2]);   // halo.cu: max over the ranks of the mesh of two non-negative device floats
 void snapshot_destroy(Solver *s);   // history.cu
 // advect_fast.cu
 Box interior_box(const Geo &q);

@@ -229,6 +229,7 @@ struct Nccl {
   int (*CommInitRank)(void **, int, Id128, int) = nullptr;
   int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(void *) = nullptr;
@@ -248,6 +249,7 @@ static Nccl &nccl() {
     n.CommInitRank = (int (*)(void **, int, Id128, int))dlsym(n.h, "ncclCommInitRank");
     n.Send = (int (*)(const void *, size_t, int, int, void *, cudaStream_t))dlsym(n.h, "ncclSend");
     n.Recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))dlsym(n.h, "ncclRecv");
+    n.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(n.h, "ncclAllReduce");
     n.GroupStart = (int (*)())dlsym(n.h, "ncclGroupStart");
     n.GroupEnd = (int (*)())dlsym(n.h, "ncclGroupEnd");
     n.CommDestroy = (int (*)(void *))dlsym(n.h, "ncclCommDestroy");
@@ -288,6 +290,7 @@ struct HaloState {
   size_t cap = 0;                     // floats per buffer
   cudaEvent_t packed = nullptr, consumed = nullptr;
   long long exchanges = 0, bytes_sent = 0;
+  float max2[2] = {0.f, 0.f};         // halo_max2's host copy (local groups)
 };
 
 static HaloState &hs(Solver *s) {
@@ -419,6 +422,30 @@ static void exchange_phase(Solver *s, int width, const std::vector<Field *> &fld
       s->kpost();
       s->launches++;
     }
+}
+
+// wrf_dm_maxval's role for grid%max_vert_cfl / max_horiz_cfl (dyn_em/adapt_timestep_em.F): ncclAllReduce(max) between
+// processes; solvers of one process compare their host copies between two barriers.
+void halo_max2(Solver *s, float *d2, float out[2]) {
+  if (s->nranks > 1) {
+    HaloState &h = hs(s);
+    if (h.local) {
+      CUDA_CHECK(cudaMemcpyAsync(h.max2, d2, 2 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+      CUDA_CHECK(cudaStreamSynchronize(s->stream));
+      h.local->barrier();
+      out[0] = out[1] = 0.f;
+      for (Solver *r : h.local->ranks) { out[0] = std::max(out[0], hs(r).max2[0]); out[1] = std::max(out[1], hs(r).max2[1]); }
+      h.local->barrier();
+      CUDA_CHECK(cudaMemcpyAsync(d2, out, 2 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+      CUDA_CHECK(cudaStreamSynchronize(s->stream));
+      return;
+    }
+    Nccl &n = nccl();
+    if (!h.comm || !n.AllReduce) throw std::runtime_error("wrfgpu: CFL maxima on a multi-rank mesh before wrfgpu_comm_init");
+    nccl_check(n.AllReduce(d2, d2, 2, 7 /*ncclFloat*/, 2 /*ncclMax*/, h.comm, s->stream), "AllReduce");
+  }
+  CUDA_CHECK(cudaMemcpyAsync(out, d2, 2 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_CHECK(cudaStreamSynchronize(s->stream));
 }
 
 void Solver::halo(const std::string &name) {

@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(128, MOMW_MINB) k_mom_w_fast(const Geo g, Box 
       if (g.w_damping == 1) {
         const float mass = (g.c1f[k] * mut + g.c2f[k]);
         const float vert_cfl = fabsf(rom_k / mass * g.rdnw[k] * g.dt);
-        if (vert_cfl > 1.0f) t = t - sign1(w1) * 0.3f * (vert_cfl - g.w_crit_cfl) * mass;
+        if (vert_cfl > g.w_damp_on) t = t - sign1(w1) * 0.3f * (vert_cfl - g.w_crit_cfl) * mass;
       }
       // ---- coriolis (:3839-3844) and curvature (:4459-4463)
       const float fzm = g.fnm[k], fzp = g.fnp[k];

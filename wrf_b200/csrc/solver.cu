@@ -110,6 +110,7 @@ Solver::Solver(const wrfgpu_dims &d_, const wrfgpu_config &c_, int dev) : d(d_),
     species.push_back(sp);
   }
   CUDA_CHECK(cudaMalloc(&d_cfl, 2 * sizeof(float)));
+  CUDA_CHECK(cudaMemset(d_cfl, 0, 2 * sizeof(float)));
   // map factors default to 1 so an un-set factor cannot divide by zero
   for (const char *m : {"msftx", "msfty", "msfux", "msfuy", "msfvx", "msfvx_inv", "msfvy"}) {
     Field &f = F(m);
@@ -207,6 +208,7 @@ void Solver::build_geo() {
   q.cf1 = c.cf1; q.cf2 = c.cf2; q.cf3 = c.cf3; q.cfn = c.cfn; q.cfn1 = c.cfn1;
   q.epssm = c.epssm; q.smdiv = c.smdiv; q.emdiv = c.emdiv; q.dampcoef = c.dampcoef; q.zdamp = c.zdamp;
   q.w_crit_cfl = c.w_crit_cfl; q.p_top = c.p_top;
+  q.w_damp_on = c.zadvect_implicit > 0 ? c.w_crit_cfl : 1.0f;   // module_big_step_utilities_em.F:2602-2608 (w_beta = 1)
   q.sgn_ts = c.time_step >= 0 ? 1.f : -1.f;
   q.sg_hm = c.h_mom_adv_order == 6 ? 0.f : q.sgn_ts; q.sg_vm = c.v_mom_adv_order == 4 ? 0.f : q.sgn_ts;
   q.sg_hs = c.h_sca_adv_order == 6 ? 0.f : q.sgn_ts; q.sg_vs = c.v_sca_adv_order == 4 ? 0.f : q.sgn_ts;
@@ -380,6 +382,15 @@ int wrfgpu_solve_em(wrfgpu_solver *s, int n_in, const char *const *in_names, con
 }
 int wrfgpu_sync(wrfgpu_solver *s) { GUARD({ CUDA_CHECK(cudaStreamSynchronize(s->s.stream)); CUDA_CHECK(cudaGetLastError()); }) }
 long long wrfgpu_launch_count(const wrfgpu_solver *s) { return s->s.launches; }
+int wrfgpu_max_cfl(wrfgpu_solver *s, float *max_vert_cfl, float *max_horiz_cfl, int reset) {
+  GUARD({
+    if (!s->s.c.use_adaptive_time_step) throw std::runtime_error("wrfgpu_max_cfl: the CFL maxima are only computed with use_adaptive_time_step = 1");
+    float h[2];
+    wg::halo_max2(&s->s, s->s.d_cfl, h);
+    *max_vert_cfl = h[0]; *max_horiz_cfl = h[1];
+    if (reset) CUDA_CHECK(cudaMemsetAsync(s->s.d_cfl, 0, 2 * sizeof(float), s->s.stream));
+  })
+}
 int wrfgpu_set_stream(wrfgpu_solver *s, void *cuda_stream) {
   GUARD({
     CUDA_CHECK(cudaStreamSynchronize(s->s.stream));

@@ -624,7 +624,7 @@ __device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i,
       if (g.w_damping == 1) {
         const float mass = (g.c1f[k] * A2(s.mut, i, j) + g.c2f[k]);
         const float vert_cfl = fabsf(A3(s.ww, i, k, j) / mass * g.rdnw[k] * g.dt);
-        if (vert_cfl > 1.0f) t = t - sign1(A3(w, i, k, j)) * 0.3f * (vert_cfl - g.w_crit_cfl) * mass;
+        if (vert_cfl > g.w_damp_on) t = t - sign1(A3(w, i, k, j)) * 0.3f * (vert_cfl - g.w_crit_cfl) * mass;
       }
       // --- coriolis (:3839-3844) and curvature (:4459-4463)
       const float fzm = g.fnm[k], fzp = g.fnp[k];
@@ -1007,6 +1007,30 @@ __global__ void k_rayleigh(const Geo g, Box b, int kind, cfp u, cfp v, cfp w, cf
   }
 }
 
+// w_damp's CFL maxima (module_big_step_utilities_em.F:2503-2711): max over j = jts..jtf, k = 2..kde-1, i = its..itf of
+// vert_cfl and horiz_cfl, the same real*4 expressions.  The maximum of non-negative floats is order independent and their
+// bit patterns order like integers: warp shuffle, then one atomicMax per warp into cfl[0] (vertical), cfl[1] (horizontal).
+__global__ void k_cfl_max(const Geo g, Box b, cfp u, cfp v, cfp ww, cfp mut, unsigned *cfl) {
+  const int i = b.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = b.k0 + blockIdx.y * blockDim.y + threadIdx.y;
+  const int j = b.j0 + blockIdx.z * blockDim.z + threadIdx.z;
+  float vc = 0.f, hc = 0.f;
+  if (i <= b.i1 && k <= b.k1 && j <= b.j1) {
+    vc = fabsf(A3(ww, i, k, j) / (g.c1f[k] * A2(mut, i, j) + g.c2f[k]) * g.rdnw[k] * g.dt);
+    hc = fmaxf(fabsf(A3(u, i, k, j) * g.rdx * A2(g.msfux, i, j) * g.dt), fabsf(A3(v, i, k, j) * g.rdy * A2(g.msfvy, i, j) * g.dt));
+    if (!(vc >= 0.f)) vc = 0.f;   // NaN never wins a Fortran '>' comparison
+    if (!(hc >= 0.f)) hc = 0.f;
+  }
+  for (int m = 16; m > 0; m >>= 1) {
+    vc = fmaxf(vc, __shfl_xor_sync(0xffffffffu, vc, m));
+    hc = fmaxf(hc, __shfl_xor_sync(0xffffffffu, hc, m));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(cfl, __float_as_uint(vc));
+    atomicMax(cfl + 1, __float_as_uint(hc));
+  }
+}
+
 __global__ void k_zero3(const Geo g, Box b, fp a0, fp a1, fp a2, fp a3, fp a4) {
   TID3;
   const long x = (long)i + (long)k * g.sk + (long)j * g.sj;
@@ -1072,6 +1096,10 @@ void Solver::rk_tendency(int rk_step, bool zero_save) {
   s.mut = o("mut"); s.muu = o("muu"); s.muv = o("muv"); s.mu = o("mu_2"); s.mub = o("mub");
   s.ru_tendf = o("ru_tendf"); s.rv_tendf = o("rv_tendf"); s.rw_tendf = o("rw_tendf"); s.ph_tendf = o("ph_tendf");
   s.t_tendf = o("t_tendf");
+  if (c.use_adaptive_time_step) {   // solve_em.F:914-922: the maxima are only consumed by the adaptive time step
+    const Box cb{q.its, std::min(q.ite, q.ide - 1), 2, q.kde - 1, q.jts, std::min(q.jte, q.jde - 1)};
+    LAUNCH3(this, k_cfl_max, cb, s.u, s.v, s.ww, s.mut, (unsigned *)d_cfl);
+  }
   const Box in = interior_box(q);
   Box strips[4];
   const int ns = edge_strips(tile, in, strips);

@@ -68,7 +68,8 @@ class Config(ctypes.Structure):
         + [(n, ctypes.c_float) for n in ("c_s", "c_k")]
         + [("mix_full_fields", ctypes.c_int), ("isfflx", ctypes.c_int)]
         + [(n, ctypes.c_float) for n in ("tke_drag_coefficient", "tke_heat_flux")]
-        + [("mix_isotropic", ctypes.c_int), ("mix_upper_bound", ctypes.c_float), ("tke_adv_opt", ctypes.c_int), ("tke_upper_bound", ctypes.c_float)])
+        + [("mix_isotropic", ctypes.c_int), ("mix_upper_bound", ctypes.c_float), ("tke_adv_opt", ctypes.c_int), ("tke_upper_bound", ctypes.c_float),
+           ("use_adaptive_time_step", ctypes.c_int)])
 
 
 def default_config(**kw) -> Config:

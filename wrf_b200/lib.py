@@ -27,7 +27,7 @@ PHASES = ("rk_step_prep", "rk_phys_bc_dry_1", "init_zero_tendency", "diffusion_p
 ABI_SYMBOLS = (
     "wrfgpu_create", "wrfgpu_destroy", "wrfgpu_last_error", "wrfgpu_version", "wrfgpu_field_size", "wrfgpu_set_field",
     "wrfgpu_get_field", "wrfgpu_upload", "wrfgpu_download", "wrfgpu_num_fields", "wrfgpu_field_name", "wrfgpu_field_devptr",
-    "wrfgpu_step", "wrfgpu_solve_em", "wrfgpu_sync", "wrfgpu_set_stream", "wrfgpu_kernel_report", "wrfgpu_launch_count", "wrfgpu_phase_ms", "wrfgpu_set_physical_bc",
+    "wrfgpu_step", "wrfgpu_solve_em", "wrfgpu_sync", "wrfgpu_set_stream", "wrfgpu_kernel_report", "wrfgpu_launch_count", "wrfgpu_max_cfl", "wrfgpu_phase_ms", "wrfgpu_set_physical_bc",
     "wrfgpu_compute_mesh", "wrfgpu_patch_dims", "wrfgpu_comm_unique_id", "wrfgpu_comm_init", "wrfgpu_comm_init_local", "wrfgpu_halo",
     "wrfgpu_halo_spec", "wrfgpu_halo_box", "wrfgpu_halo_bytes",
     "wrfgpu_snapshot_begin", "wrfgpu_snapshot_wait", "wrfgpu_snapshot_busy", "wrfgpu_snapshot_host",
@@ -194,6 +194,12 @@ class Solver:
     def halo_bytes(self) -> int:
         self.lib.wrfgpu_halo_bytes.restype = ctypes.c_longlong
         return int(self.lib.wrfgpu_halo_bytes(self.h))
+
+    def max_cfl(self, reset=False):
+        """grid%max_vert_cfl, grid%max_horiz_cfl (solve_em.F:914-930) over all ranks; needs use_adaptive_time_step = 1"""
+        mv, mh = ctypes.c_float(), ctypes.c_float()
+        self._chk(self.lib.wrfgpu_max_cfl(self.h, ctypes.byref(mv), ctypes.byref(mh), ctypes.c_int(int(reset))))
+        return mv.value, mh.value
 
     def launch_count(self) -> int:
         return int(self.lib.wrfgpu_launch_count(self.h))
