@@ -107,7 +107,9 @@ def test_w_damp_cfl_maxima_equal_the_oracle():
         o.step(1); s.step(1)
         a, b = s.max_cfl(reset=(n == 1)), o.max_cfl(reset=(n == 1))
         assert a == b, (n, a, b)
-        assert a[0] > 2.0 and 0.0 < a[1] < 1.0     # the updraft exceeds w_crit_cfl = 2; horizontal Courant numbers are ordinary
+        if n < 2:      # the initial updraft exceeds w_crit_cfl = 2 (the damping has tamed it by the third step, after the reset)
+            assert a[0] > 2.0
+        assert 0.0 < a[1] < 1.0                    # horizontal Courant numbers are ordinary
     s.close()
     with pytest.raises(Exception):
         Solver(cases()["quarter_ss"]).max_cfl()

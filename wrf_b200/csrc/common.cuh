@@ -128,7 +128,8 @@ struct Field {
   float *d = nullptr;   // device allocation
   float *o = nullptr;   // origin-shifted pointer
   int kind = 3;         // 3, 2, 1
-  size_t n = 0;
+  size_t n = 0;         // floats of the caller's (host) array: (ime-ims+1) per row
+  size_t nd = 0;        // floats of the device allocation: Solver::pitch() per row
 };
 
 struct Species {
@@ -155,6 +156,7 @@ struct Solver {
   // halo exchange state (HaloState, halo.cu)
   void *comm = nullptr;
   void *snapshot = nullptr;   // history.cu: staging / pinned buffers of wrfgpu_snapshot_*
+  void *tile_maps = nullptr;  // tend_tile.cu: the TMA tensor maps of the tile-staged tendency kernel
   int rank = 0, nranks = 1;
   // phase / kernel timing (cudaEvents on `stream`, only when switched on)
   bool timing = false;
@@ -186,6 +188,9 @@ struct Solver {
   Solver(const wrfgpu_dims &d, const wrfgpu_config &c, int device);
   ~Solver();
   void add(const std::string &n, int kind);
+  size_t pitch() const { return ((size_t)(d.ime - d.ims + 1) + 31) / 32 * 32; }   // device row length in floats
+  void copy_in(Field &f, const float *host, cudaMemcpyKind kind);
+  void copy_out(const Field &f, float *host, cudaMemcpyKind kind, cudaStream_t st);
   Field &F(const std::string &n);
   float *o(const std::string &n) { return F(n).o; }   // origin-shifted
   void build_geo();
@@ -289,6 +294,10 @@ void launch_diff6(Solver *s, int which, const float *field, float *tendency, con
 void launch_diffuse(Solver *s, int which, cfp field, fp tendency, float xk, float kvdif, cfp xkarr = nullptr);
 // diffusion2.cu: diff_opt = 2 with constant K = 0 and no surface fluxes adds exact zeros
 bool diff2_is_identity(const wrfgpu_config &c);
+// tend_tile.cu: all five dry tendencies of the interior box in one TMA-staged kernel
+bool tend_tile_enabled();
+void launch_tend_tile(Solver *s, const Box &in);
+void tend_tile_destroy(Solver *s);
 // mom_fast.cu: which = 0 ru_tend, 1 rv_tend, 2 rw_tend on the interior box
 void launch_mom_fast(Solver *s, int which, const Box &in);
 

@@ -50,7 +50,7 @@ void snapshot_begin(Solver *s, int nf, const char *const *names) {
       CUDA_CHECK(cudaMalloc(&b.stage, f.n * sizeof(float)));
       CUDA_CHECK(cudaMallocHost(&b.host, f.n * sizeof(float)));
     }
-    CUDA_CHECK(cudaMemcpyAsync(b.stage, f.d, f.n * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+    s->copy_out(f, b.stage, cudaMemcpyDeviceToDevice, s->stream);   // staging holds the caller's (unpadded) layout
     p->current.push_back(names[i]);
   }
   CUDA_CHECK(cudaEventRecord(p->staged, s->stream));

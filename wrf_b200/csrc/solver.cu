@@ -114,8 +114,8 @@ Solver::Solver(const wrfgpu_dims &d_, const wrfgpu_config &c_, int dev) : d(d_),
   // map factors default to 1 so an un-set factor cannot divide by zero
   for (const char *m : {"msftx", "msfty", "msfux", "msfuy", "msfvx", "msfvx_inv", "msfvy"}) {
     Field &f = F(m);
-    std::vector<float> ones(f.n, 1.f);
-    CUDA_CHECK(cudaMemcpy(f.d, ones.data(), f.n * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> ones(f.nd, 1.f);
+    CUDA_CHECK(cudaMemcpy(f.d, ones.data(), f.nd * sizeof(float), cudaMemcpyHostToDevice));
   }
   if (c.time_step_sound == 0) {   // solve_em.F:446-462
     float spacing = std::min(c.dx, c.dy);
@@ -144,6 +144,7 @@ Solver::~Solver() {
   for (auto &kv : fields) cudaFree(kv.second.d);
   halo_destroy(this);
   snapshot_destroy(this);
+  tend_tile_destroy(this);
   cudaFree(d_cfl);
   if (stream && own_stream) cudaStreamDestroy(stream);
 }
@@ -161,20 +162,38 @@ void Solver::flush_timing() {
   pending.clear();
 }
 
+// Device rows are padded to a multiple of 32 floats (Solver::pitch): every (k,j) row starts on a 128-byte line and the
+// strides are multiples of 16 bytes, which the TMA tensor maps of the tile-staged kernels need (tend_tile.cu).  The host
+// arrays keep the caller's extents, so uploads / downloads are pitched copies (xfer below).
 void Solver::add(const std::string &n, int kind) {
   Field f;
   f.kind = kind;
   const size_t ni = d.ime - d.ims + 1, nk = d.kme - d.kms + 1, nj = d.jme - d.jms + 1;
+  const size_t np = pitch();
   f.n = kind == 3 ? ni * nk * nj : (kind == 2 ? ni * nj : nk);
-  CUDA_CHECK(cudaMalloc(&f.d, f.n * sizeof(float)));
-  CUDA_CHECK(cudaMemset(f.d, 0, f.n * sizeof(float)));
+  f.nd = kind == 3 ? np * nk * nj : (kind == 2 ? np * nj : nk);
+  CUDA_CHECK(cudaMalloc(&f.d, f.nd * sizeof(float)));
+  CUDA_CHECK(cudaMemset(f.d, 0, f.nd * sizeof(float)));
   long off = 0;
-  if (kind == 3) off = (long)d.ims + (long)d.kms * (long)ni + (long)d.jms * (long)(ni * nk);
-  else if (kind == 2) off = (long)d.ims + (long)d.jms * (long)ni;
+  if (kind == 3) off = (long)d.ims + (long)d.kms * (long)np + (long)d.jms * (long)(np * nk);
+  else if (kind == 2) off = (long)d.ims + (long)d.jms * (long)np;
   else off = d.kms;
   f.o = f.d - off;
   fields[n] = f;
   names.push_back(n);
+}
+
+// host (contiguous rows of ni floats) <-> device (rows of pitch() floats); `host` may also be device memory (bench.py
+// builds its synthetic state on the GPU)
+void Solver::copy_in(Field &f, const float *host, cudaMemcpyKind kind) {
+  if (f.kind == 1) { CUDA_CHECK(cudaMemcpyAsync(f.d, host, f.n * sizeof(float), kind, stream)); return; }
+  const size_t ni = d.ime - d.ims + 1;
+  CUDA_CHECK(cudaMemcpy2DAsync(f.d, pitch() * sizeof(float), host, ni * sizeof(float), ni * sizeof(float), f.n / ni, kind, stream));
+}
+void Solver::copy_out(const Field &f, float *host, cudaMemcpyKind kind, cudaStream_t st) {
+  if (f.kind == 1) { CUDA_CHECK(cudaMemcpyAsync(host, f.d, f.n * sizeof(float), kind, st)); return; }
+  const size_t ni = d.ime - d.ims + 1;
+  CUDA_CHECK(cudaMemcpy2DAsync(host, ni * sizeof(float), f.d, pitch() * sizeof(float), ni * sizeof(float), f.n / ni, kind, st));
 }
 
 Field &Solver::F(const std::string &n0) {
@@ -194,7 +213,7 @@ void Solver::build_geo() {
   q.ims = d.ims; q.ime = d.ime; q.jms = d.jms; q.jme = d.jme; q.kms = d.kms; q.kme = d.kme;
   q.ips = d.ips; q.ipe = d.ipe; q.jps = d.jps; q.jpe = d.jpe;
   q.its = d.ips; q.ite = d.ipe; q.jts = d.jps; q.jte = d.jpe;
-  q.ni = d.ime - d.ims + 1; q.nk = d.kme - d.kms + 1; q.nj = d.jme - d.jms + 1;
+  q.ni = (int)pitch(); q.nk = d.kme - d.kms + 1; q.nj = d.jme - d.jms + 1;   // ni = the device row pitch (>= ime-ims+1)
   q.sk = q.ni; q.sj = (long)q.ni * q.nk;
   if ((long)q.ni * q.nk * q.nj >= (1L << 31)) throw std::runtime_error("wrfgpu: a patch of more than 2^31 points per field is not supported");
   q.isk = q.ni; q.isj = q.ni * q.nk;
@@ -346,8 +365,8 @@ static void xfer(Solver &S, const char *name, const float *in, float *out, size_
   cudaMemcpyKind kind = in ? (dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
                            : (dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost);
   if (in && f.kind == 1) S.coef_dirty = true;
-  if (in) CUDA_CHECK(cudaMemcpyAsync(f.d, in, n * sizeof(float), kind, S.stream));
-  else CUDA_CHECK(cudaMemcpyAsync(out, f.d, n * sizeof(float), kind, S.stream));
+  if (in) S.copy_in(f, in, kind);
+  else S.copy_out(f, out, kind, S.stream);
   if (!async) CUDA_CHECK(cudaStreamSynchronize(S.stream));
 }
 int wrfgpu_set_field(wrfgpu_solver *s, const char *name, const float *host, size_t n) { GUARD(xfer(s->s, name, host, nullptr, n, false)) }

@@ -1131,6 +1131,23 @@ void Solver::rk_tendency(int rk_step, bool zero_save) {
   }
   // the k-marching interior kernels exist for the default orders (5, 3); other orders take the gather kernels everywhere
   const bool dflt_m = c.h_mom_adv_order == 5 && c.v_mom_adv_order == 3, dflt_s = c.h_sca_adv_order == 5 && c.v_sca_adv_order == 3;
+  // default orders, no WENO, no perturbation Coriolis: the five tendencies of the interior in one tile-staged kernel
+  // (tend_tile.cu), the gather kernels on the edge strips
+  if (!weno_m && !weno_t && dflt_m && dflt_s && !c.pert_coriolis && !empty(in) && tend_tile_enabled()) {
+    launch_tend_tile(this, in);
+    for (int m = 0; m < ns; m++) {
+      LAUNCH3(this, k_tend_u, strips[m], s, o("ru_tend"));
+      LAUNCH3(this, k_tend_v, strips[m], s, o("rv_tend"));
+      LAUNCH3(this, k_tend_w, strips[m], s, o("rw_tend"));
+      LAUNCH3(this, k_tend_t, strips[m], s, o("t_tend"));
+      LAUNCH3(this, k_tend_ph, strips[m], s, o("ph_tend"));
+      const Box cq{q.its, std::min(q.ite, q.ide - 1), 2, q.kde - 1, q.jts, std::min(q.jte, q.jde - 1)};
+      Box sb = strips[m];
+      sb.i1 = std::min(sb.i1, cq.i1); sb.j1 = std::min(sb.j1, cq.j1); sb.k0 = cq.k0; sb.k1 = cq.k1;
+      LAUNCH3(this, k_invert_cqw, sb, o("cqw"));
+    }
+    return;
+  }
   if (weno_m) {
     LAUNCH3(this, k_tend_u_weno, tile, s, o("ru_tend"));
     LAUNCH3(this, k_tend_v_weno, tile, s, o("rv_tend"));
