@@ -238,6 +238,12 @@ int wrfgpu_halo_spec(const wrfgpu_config *c, const char *halo_name, int *width, 
  * has no neighbour there (external/RSL_LITE/c_code.c:405-700, period.c, module_dm.F:2761) */
 int wrfgpu_halo_box(const wrfgpu_dims *d, const wrfgpu_config *c, int width, int dir, int send,
                     int *peer, int *is, int *ie, int *js, int *je);
+/* A HALO_EM_x merged with its PERIOD_* twin carries the PERIOD width (e.g. HALO_EM_A 1, PERIOD_BDY_EM_A 2): a neighbour
+ * inside the domain only gets the Registry's HALO width, which this returns (Registry.EM_COMMON:3425, :3447-3450);
+ * _box2 is wrfgpu_halo_box with that width for links that do not cross a periodic edge (0 = the same as `width`). */
+int wrfgpu_halo_regular_width(const char *halo_name, int width);
+int wrfgpu_halo_box2(const wrfgpu_dims *d, const wrfgpu_config *c, int width, int regular_width, int dir, int send,
+                     int *peer, int *is, int *ie, int *js, int *je);
 /* bytes this rank has sent in halo exchanges since create (bench: NVLink traffic) */
 long long wrfgpu_halo_bytes(const wrfgpu_solver *s);
 

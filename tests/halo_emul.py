@@ -27,10 +27,15 @@ def halo_spec(config, name):
     return w.value, [f for f in buf.value.decode().split(",") if f]
 
 
-def halo_box(dims, config, width, direction, send):
+def regular_width(name, width):
+    """the Registry's HALO width towards a neighbour inside the domain (the PERIOD width applies across a periodic edge)"""
+    return int(wrf_b200.load().wrfgpu_halo_regular_width(name.encode(), ctypes.c_int(width)))
+
+
+def halo_box(dims, config, width, direction, send, hwidth=0):
     lib = wrf_b200.load()
     v = [ctypes.c_int(0) for _ in range(5)]
-    ok = lib.wrfgpu_halo_box(ctypes.byref(dims), ctypes.byref(config), width, direction, 1 if send else 0, *[ctypes.byref(x) for x in v])
+    ok = lib.wrfgpu_halo_box2(ctypes.byref(dims), ctypes.byref(config), width, hwidth, direction, 1 if send else 0, *[ctypes.byref(x) for x in v])
     if not ok:
         return None
     peer, i0, i1, j0, j1 = [x.value for x in v]
@@ -104,14 +109,15 @@ class HaloEmulator:
         if c.ntasks_x * c.ntasks_y == 1:
             return
         width, fields = halo_spec(c, name)
+        hw = regular_width(name, width)
         views = [v for v in (self.view(f) for f in fields) if v is not None]
         for d0 in (0, 2):                              # Y phase, then X phase
             sends, recvs, rboxes = {}, {}, {}
             for q in (d0, d0 + 1):
-                sb = halo_box(d, c, width, q, True)
+                sb = halo_box(d, c, width, q, True, hw)
                 if sb is None:
                     continue
-                rb = halo_box(d, c, width, q, False)
+                rb = halo_box(d, c, width, q, False, hw)
                 peer, i0, i1, j0, j1 = sb
                 sj, si = slice(j0 - d.jms, j1 - d.jms + 1), slice(i0 - d.ims, i1 - d.ims + 1)
                 sends[q] = (peer, np.concatenate([(v[sj, :, si] if v.ndim == 3 else v[sj, si]).ravel() for v in views]))

@@ -90,3 +90,29 @@ def test_halo_is_neighbour_interior():
             assert np.array_equal(aa, gg), (s.case.name, n, int((aa != gg).sum()))
     for s in ranks:
         s.close()
+
+
+@pytest.mark.parametrize("mesh", [(1, 2), (2, 2)])
+@pytest.mark.parametrize("name", ["quarter_ss", "periodic", "tke_periodic"])
+def test_peer_window_transport_between_solvers_of_one_process(name, mesh, monkeypatch):
+    """the transport the multi-process runs use (k_halo_direct: packs into the neighbour's receive buffer, ready / ack
+    counters in the neighbour's window) between solvers that share this GPU: same bits as the single-rank run"""
+    monkeypatch.setenv("WRFGPU_HALO_DIRECT", "1")
+    bad, sent = _run(parity.small_cases()[name], *mesh, nsteps=3)
+    assert not bad, bad[:8]
+    assert all(b > 0 for b in sent)
+
+
+def test_processes_exchange_through_cuda_ipc_windows():
+    """ranks as processes, one per GPU (what bench.py runs under torchrun and wrf.exe under mpirun): the neighbours' windows
+    are mapped through CUDA IPC handles exchanged over NCCL.  Needs two GPUs."""
+    import os, subprocess, sys
+    if _ndev() < 2:
+        pytest.skip("one GPU on this box: the IPC path needs one GPU per process")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root, WRFGPU_HALO="direct")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", os.path.join(root, "tests", "ipc_rank_main.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("IPC_RANK_OK") == 2, r.stdout[-2000:]

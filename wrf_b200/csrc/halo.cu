@@ -74,6 +74,15 @@ static const HaloDef kHalos[] = {
      "mub,ht,msftx,msfty,f,e,sina,cosa,msfux,msfuy,msfvx,msfvx_inv,msfvy,mu_1,mu_2"},
 };
 
+// Registry width of the HALO_* part where it is narrower than the PERIOD_* part it is merged with (Registry.EM_COMMON:3425,
+// :3447-3450: 4-point stencils = width 1): a neighbour inside the domain gets the HALO width, the neighbour across a split
+// periodic edge the PERIOD width.  Halves the bytes of the four most frequent exchanges.
+static int regular_width(const std::string &name, int width) {
+  for (const char *n : {"HALO_EM_A", "HALO_EM_B", "HALO_EM_C", "HALO_EM_C2"})
+    if (name == n) return 1;
+  return width;
+}
+
 static void split(const std::string &s, std::vector<std::string> &out) {
   size_t a = 0;
   while (a < s.size()) {
@@ -112,11 +121,13 @@ static bool halo_fields(const wrfgpu_config &c, const std::string &name, int &wi
 struct Strip { int peer; int is, ie, js, je; };
 // A negative width means "HALO only": an exchange the reference does not follow with a PERIOD_* closure, so the ghost zone
 // beyond a periodic domain edge keeps what the last closure / set_physical_bc put there (see HALO_EM_E_5 in the table).
-static bool halo_box(const wrfgpu_dims &d, const wrfgpu_config &c, int w, int dir, bool send, Strip &s) {
+// hw: the width towards a neighbour inside the domain (0 = the same as w, the width across a periodic edge)
+static bool halo_box(const wrfgpu_dims &d, const wrfgpu_config &c, int w, int dir, bool send, Strip &s, int hw = 0) {
   const int ntx = std::max(1, c.ntasks_x), nty = std::max(1, c.ntasks_y);
   const int mx = c.mytask % ntx, my = c.mytask / ntx;
   const bool closure = w > 0;
   if (w < 0) w = -w;
+  if (hw <= 0) hw = w;
   bool wrap = false;
   int px = mx, py = my;
   switch (dir) {
@@ -126,6 +137,7 @@ static bool halo_box(const wrfgpu_dims &d, const wrfgpu_config &c, int w, int di
     default: if (mx < ntx - 1) px = mx + 1; else if (c.periodic_x && ntx > 1 && closure) { px = 0; wrap = true; } else return false; break;
   }
   s.peer = py * ntx + px;
+  if (!wrap) w = hw;
   // extent along the exchanged dimension: [lo, hi] of the patch, domain [ds, de]
   const bool isy = dir < 2;
   const int ps = isy ? d.jps : d.ips, pe = isy ? d.jpe : d.ipe, ds = isy ? d.jds : d.ids, de = isy ? d.jde : d.ide;
@@ -230,6 +242,7 @@ struct Nccl {
   int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(void *) = nullptr;
@@ -250,6 +263,7 @@ static Nccl &nccl() {
     n.Send = (int (*)(const void *, size_t, int, int, void *, cudaStream_t))dlsym(n.h, "ncclSend");
     n.Recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))dlsym(n.h, "ncclRecv");
     n.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(n.h, "ncclAllReduce");
+    n.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(n.h, "ncclAllGather");
     n.GroupStart = (int (*)())dlsym(n.h, "ncclGroupStart");
     n.GroupEnd = (int (*)())dlsym(n.h, "ncclGroupEnd");
     n.CommDestroy = (int (*)(void *))dlsym(n.h, "ncclCommDestroy");
@@ -291,7 +305,106 @@ struct HaloState {
   cudaEvent_t packed = nullptr, consumed = nullptr;
   long long exchanges = 0, bytes_sent = 0;
   float max2[2] = {0.f, 0.f};         // halo_max2's host copy (local groups)
+  // direct transport (see "peer windows" below)
+  bool direct = false;
+  char *win = nullptr;                // this rank's window: flags + 4 directions x 2 parities of receive buffers
+  size_t win_cap = 0;                 // floats per receive buffer
+  std::vector<char *> peer_win;       // the windows of the other ranks as this rank addresses them (nullptr: not opened)
+  std::vector<bool> peer_ipc;         // opened with cudaIpcOpenMemHandle (to be closed)
+  unsigned seq[4] = {0, 0, 0, 0};     // exchanges done per direction; the n-th uses receive buffer n & 1
+  unsigned *d_count = nullptr;        // 4 block counters of the put / get kernels
 };
+
+// ---------------------------------------------------------------------------------------------
+// Direct transport over peer windows: no library call and no host synchronisation on the exchange path.
+// Every rank owns a window in its HBM: per direction (0 = -y, 1 = +y, 2 = -x, 3 = +x) a `ready` and an `ack` counter and two
+// receive buffers.  Neighbours address each other's windows directly: CUDA IPC handles between processes (one per GPU:
+// bench.py under torchrun, wrf.exe under mpirun; the handles travel once through ncclAllGather), plain pointers between the
+// solvers of one process.  The n-th exchange of a rank towards direction q:
+//   k_halo_put  waits until ack[q] >= n - 2 (the neighbour has emptied the buffer of exchange n - 2, which had the same
+//               parity), packs the strip straight INTO THE NEIGHBOUR'S receive buffer (q^1, n & 1) -- stores over NVLink --
+//               and, when the last block is through, publishes ready[q^1] = n in the neighbour's window (release, system scope);
+//   k_halo_get  waits for its own ready[q] >= n, unpacks its receive buffer (q, n & 1) and, last block, writes
+//               ack[q^1] = n into the neighbour's window.
+// Both kernels run on the solver's stream like any other kernel of the step, so an exchange is two launches per phase and
+// costs NVLink latency instead of two NCCL groups (8 GPUs, r1: ~156 ncclSend/Recv kernels and their rendezvous per step).
+// Every spin is bounded and ends in a trap: a lost neighbour becomes a CUDA error, never a hung GPU.
+#define WIN_HDR 256
+__host__ __device__ inline unsigned *win_ready(char *w, int dir) { return reinterpret_cast<unsigned *>(w) + dir; }
+__host__ __device__ inline unsigned *win_ack(char *w, int dir) { return reinterpret_cast<unsigned *>(w + 64) + dir; }
+__host__ __device__ inline float *win_buf(char *w, int dir, unsigned parity, size_t cap) {
+  return reinterpret_cast<float *>(w + WIN_HDR) + ((size_t)dir * 2 + parity) * cap;
+}
+
+struct LinkArgs {                 // per strip (two per phase)
+  unsigned *wait_flag[2];         // local flag to wait on (put: ack[q]; get: ready[q]); nullptr = no wait
+  unsigned wait_val[2];
+  unsigned *post_flag[2];         // remote flag the last block writes (put: neighbour's ready[q^1]; get: neighbour's ack[q^1])
+  unsigned post_val[2];
+  unsigned *count[2];             // local block counter (zero between launches)
+  unsigned nblocks[2];
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// The waits of a phase as a kernel of their own (two threads): used between solvers that SHARE a GPU, where hundreds of
+// spinning blocks inside the copy kernels could hold the registers a neighbour's compute kernel (256 threads x 128
+// registers, 91 KB of shared memory) needs to run and reach its own put -- a deadlock by starvation.  One warp cannot.
+__global__ void k_halo_wait(LinkArgs l) {
+  const int sd = threadIdx.x;
+  if (sd < 2 && l.wait_flag[sd]) {
+    int spin = 0;
+    while ((int)(ld_acquire_sys(l.wait_flag[sd]) - l.wait_val[sd]) < 0) {
+      if (++spin > (1 << 26)) __trap();
+      __nanosleep(64);
+    }
+  }
+}
+
+// GET = false: fields -> a.buf (the neighbour's receive buffer); GET = true: a.buf (my receive buffer) -> fields
+template <bool GET>
+__global__ void k_halo_direct(const GeoBase g, HaloArgs a, LinkArgs l) {
+  const int f = blockIdx.z % a.n, sd = blockIdx.z / a.n;
+  if (!a.active[sd]) return;
+  if (threadIdx.x == 0 && l.wait_flag[sd]) {
+    int spin = 0;
+    while ((int)(ld_acquire_sys(l.wait_flag[sd]) - l.wait_val[sd]) < 0) {
+      if (++spin > (1 << 26)) __trap();      // seconds: the neighbour is gone
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  const int ni = a.ie[sd] - a.is[sd] + 1, nj = a.je[sd] - a.js[sd] + 1;
+  const bool is3d = a.is3d[f];
+  const int nk = is3d ? a.nk : 1;
+  const int total = ni * nj * nk;
+  float *buf = a.buf[sd] + a.off[f] * (long)ni * nj;
+  float *fld = a.p[f];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int row = e / ni, ii = e - row * ni;
+    const int jj = row / nk, kk = row - jj * nk;
+    const int i = a.is[sd] + ii, j = a.js[sd] + jj, k = 1 + kk;
+    const long x = is3d ? ((long)i + (long)k * g.sk + (long)j * g.sj) : ((long)i + (long)j * g.ni);
+    if (GET) fld[x] = __ldcg(buf + e);       // written by the neighbour's GPU: never through this SM's L1
+    else buf[e] = fld[x];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();                  // cumulative: the block's stores are ordered before the counter / flag
+    if (atomicAdd(l.count[sd], 1u) == l.nblocks[sd] - 1) {
+      *l.count[sd] = 0;
+      __threadfence_system();
+      st_release_sys(l.post_flag[sd], l.post_val[sd]);
+    }
+  }
+}
 
 static HaloState &hs(Solver *s) {
   if (!s->comm) s->comm = new HaloState();
@@ -316,6 +429,10 @@ void halo_destroy(Solver *s) {
   if (!s->comm) return;
   HaloState &h = hs(s);
   for (int d = 0; d < 4; d++) { cudaFree(h.send[d]); cudaFree(h.recv[d]); }
+  for (size_t r = 0; r < h.peer_win.size(); r++)
+    if (h.peer_win[r] && h.peer_ipc[r]) cudaIpcCloseMemHandle(h.peer_win[r]);
+  if (h.win) cudaFree(h.win);
+  if (h.d_count) cudaFree(h.d_count);
   if (h.packed) cudaEventDestroy(h.packed);
   if (h.consumed) cudaEventDestroy(h.consumed);
   if (h.comm && nccl().CommDestroy) nccl().CommDestroy(h.comm);
@@ -337,7 +454,7 @@ static void launch_copy(Solver *s, bool unpack, HaloArgs &a) {
 }
 
 // one phase (Y: dirs 0,1; X: dirs 2,3) of one exchange
-static void exchange_phase(Solver *s, int width, const std::vector<Field *> &flds, int d0) {
+static void exchange_phase(Solver *s, int width, int hwidth, const std::vector<Field *> &flds, int d0) {
   HaloState &h = hs(s);
   HaloArgs snd{}, rcv{};
   snd.n = rcv.n = (int)flds.size();
@@ -353,24 +470,82 @@ static void exchange_phase(Solver *s, int width, const std::vector<Field *> &fld
   bool has[2];
   size_t nsend[2] = {0, 0}, nrecv[2] = {0, 0}, need = 0;
   for (int q = 0; q < 2; q++) {
-    has[q] = halo_box(s->d, s->c, width, d0 + q, true, ss[q]);
+    has[q] = halo_box(s->d, s->c, width, d0 + q, true, ss[q], hwidth);
     if (has[q]) {
-      halo_box(s->d, s->c, width, d0 + q, false, rs[q]);
+      halo_box(s->d, s->c, width, d0 + q, false, rs[q], hwidth);
       nsend[q] = (size_t)unit * (ss[q].ie - ss[q].is + 1) * (ss[q].je - ss[q].js + 1);
       nrecv[q] = (size_t)unit * (rs[q].ie - rs[q].is + 1) * (rs[q].je - rs[q].js + 1);
       need = std::max(need, std::max(nsend[q], nrecv[q]));
     }
   }
   if (!has[0] && !has[1]) {
-    if (h.local) { h.local->barrier(); h.local->barrier(); }   // keep the collective call pattern aligned
+    if (h.local) { h.local->barrier(); if (!h.direct) h.local->barrier(); }   // keep the collective call pattern aligned
     return;
   }
-  if (h.local) {
-    // buffer growth must be collective-safe: peers read our pointers only after the barrier below
-    ensure_buffers(s, need);
-  } else {
-    ensure_buffers(s, need);
+  if (h.direct) {   // peer windows: pack into the neighbour's receive buffer, unpack mine (see k_halo_direct)
+    if (need > h.win_cap) throw std::runtime_error("wrfgpu: halo strip larger than the peer window (halo_capacity)");
+    LinkArgs put{}, get{};
+    for (int q = 0; q < 2; q++) {
+      snd.active[q] = rcv.active[q] = has[q];
+      if (!has[q]) continue;
+      const int dir = d0 + q;
+      const unsigned n = ++h.seq[dir];
+      char *pw = h.peer_win[ss[q].peer];
+      if (!pw) throw std::runtime_error("wrfgpu: no peer window for rank " + std::to_string(ss[q].peer));
+      snd.is[q] = ss[q].is; snd.ie[q] = ss[q].ie; snd.js[q] = ss[q].js; snd.je[q] = ss[q].je;
+      snd.buf[q] = win_buf(pw, dir ^ 1, n & 1u, h.win_cap);
+      rcv.is[q] = rs[q].is; rcv.ie[q] = rs[q].ie; rcv.js[q] = rs[q].js; rcv.je[q] = rs[q].je;
+      rcv.buf[q] = win_buf(h.win, dir, n & 1u, h.win_cap);
+      put.wait_flag[q] = n >= 3 ? win_ack(h.win, dir) : nullptr; put.wait_val[q] = n - 2;
+      put.post_flag[q] = win_ready(pw, dir ^ 1); put.post_val[q] = n;
+      put.count[q] = h.d_count + q;
+      get.wait_flag[q] = win_ready(h.win, dir); get.wait_val[q] = n;
+      get.post_flag[q] = win_ack(pw, dir ^ 1); get.post_val[q] = n;
+      get.count[q] = h.d_count + 2 + q;
+    }
+    for (int pass = 0; pass < 2; pass++) {
+      HaloArgs &a = pass ? rcv : snd;
+      LinkArgs &l = pass ? get : put;
+      long total = 0;
+      for (int q = 0; q < 2; q++)
+        if (a.active[q]) total = std::max(total, (long)(a.ie[q] - a.is[q] + 1) * (a.je[q] - a.js[q] + 1) * a.nk);
+      dim3 grid((unsigned)std::min(512L, (total + 255) / 256), 1, (unsigned)(2 * a.n));
+      for (int q = 0; q < 2; q++) l.nblocks[q] = grid.x * (unsigned)a.n;
+      if (h.local && (l.wait_flag[0] || l.wait_flag[1])) {   // solvers sharing a GPU: wait in a kernel of one warp
+        s->kpre("k_halo_wait");
+        k_halo_wait<<<1, 32, 0, s->stream>>>(l);
+        s->kpost();
+        s->launches++;
+        l.wait_flag[0] = l.wait_flag[1] = nullptr;
+      }
+      s->kpre(pass ? "k_halo_get" : "k_halo_put");
+      if (pass) k_halo_direct<true><<<grid, 256, 0, s->stream>>>(s->g, a, l);
+      else k_halo_direct<false><<<grid, 256, 0, s->stream>>>(s->g, a, l);
+      s->kpost();
+      s->launches++;
+      // Solvers of ONE process share a CUDA context: an implicitly synchronising call of one host thread (cudaMalloc, a
+      // first-launch module load) would wait for a spinning get kernel of another whose put has not been launched yet.
+      // A host barrier between the two launches rules that out: when a get kernel starts, every put it can wait for is
+      // already in a stream.  Processes (one context per GPU) need no such thing.
+      if (pass == 0 && h.local) h.local->barrier();
+    }
+    h.exchanges++;
+    h.bytes_sent += (long long)((nsend[0] + nsend[1]) * sizeof(float));
+    const bool isy_d = d0 == 0;
+    const bool close_d = isy_d ? (s->c.periodic_x && s->c.ntasks_x == 1) : (s->c.periodic_y && s->c.ntasks_y == 1);
+    if (close_d)
+      for (int q = 0; q < 2; q++) {
+        if (!has[q]) continue;
+        const int a0 = isy_d ? rs[q].js : rs[q].is, a1 = isy_d ? rs[q].je : rs[q].ie;
+        const int lines = (a1 - a0 + 1) * s->g.nk;
+        s->kpre("k_halo_close");
+        k_halo_close<<<dim3((unsigned)((lines + 127) / 128), 1, (unsigned)rcv.n), 128, 0, s->stream>>>(s->g, rcv, isy_d ? 1 : 0, a0, a1);
+        s->kpost();
+        s->launches++;
+      }
+    return;
   }
+  ensure_buffers(s, need);
   for (int q = 0; q < 2; q++) {
     snd.active[q] = rcv.active[q] = has[q];
     if (!has[q]) continue;
@@ -424,6 +599,85 @@ static void exchange_phase(Solver *s, int width, const std::vector<Field *> &fld
     }
 }
 
+// floats of the largest strip any exchange of this solver packs (all fields of a batch, the wider of the two widths,
+// the longer side of the patch plus corners)
+static size_t halo_capacity(Solver *s) {
+  size_t cap = 0;
+  // the same number on every rank (the neighbours index each other's windows with it): the largest patch of the mesh
+  const int ntx = std::max(1, s->c.ntasks_x), nty = std::max(1, s->c.ntasks_y);
+  const size_t side = (size_t)std::max((s->d.ide - s->d.ids + ntx) / ntx, (s->d.jde - s->d.jds + nty) / nty) + 2;
+  for (const HaloDef &hd : kHalos) {
+    int width = 0;
+    std::vector<std::string> f3, f2;
+    halo_fields(s->c, hd.name, width, f3, f2);
+    const size_t w = (size_t)std::abs(width);
+    size_t unit = 0, nf = 0;
+    for (auto &n : f3) if (s->fields.count(n)) { unit += s->g.nk; nf++; }
+    for (auto &n : f2) if (s->fields.count(n)) { unit += 1; nf++; }
+    (void)nf;
+    cap = std::max(cap, unit * (w + 1) * (side + 2 * w + 2));
+  }
+  return cap + 64;
+}
+
+static void direct_alloc(Solver *s) {
+  HaloState &h = hs(s);
+  h.win_cap = (halo_capacity(s) + 31) / 32 * 32;
+  const size_t bytes = WIN_HDR + 8 * h.win_cap * sizeof(float);
+  CUDA_CHECK(cudaMalloc(&h.win, bytes));
+  CUDA_CHECK(cudaMemset(h.win, 0, WIN_HDR));
+  CUDA_CHECK(cudaMalloc(&h.d_count, 4 * sizeof(unsigned)));
+  CUDA_CHECK(cudaMemset(h.d_count, 0, 4 * sizeof(unsigned)));
+  h.peer_win.assign(s->nranks, nullptr);
+  h.peer_ipc.assign(s->nranks, false);
+  CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+// which ranks this rank ever exchanges with
+static std::vector<int> halo_peers(Solver *s) {
+  std::vector<int> out;
+  for (int w : {4, -3})          // with and without the periodic closure
+    for (int dir = 0; dir < 4; dir++) {
+      Strip st;
+      if (halo_box(s->d, s->c, w, dir, true, st) && std::find(out.begin(), out.end(), st.peer) == out.end()) out.push_back(st.peer);
+    }
+  return out;
+}
+
+// ranks are processes: exchange the windows' IPC handles through NCCL and map the neighbours' windows
+static void direct_setup_ipc(Solver *s) {
+  HaloState &h = hs(s);
+  Nccl &n = nccl();
+  if (!n.AllGather) throw std::runtime_error("wrfgpu: ncclAllGather not found");
+  direct_alloc(s);
+  struct Rec { cudaIpcMemHandle_t handle; unsigned long long cap; char pad[56]; };
+  static_assert(sizeof(Rec) == 128, "Rec");
+  Rec mine{};
+  CUDA_CHECK(cudaIpcGetMemHandle(&mine.handle, h.win));
+  mine.cap = h.win_cap;
+  Rec *d_all = nullptr;
+  CUDA_CHECK(cudaMalloc(&d_all, sizeof(Rec) * s->nranks));
+  CUDA_CHECK(cudaMemcpy(d_all + s->rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice));
+  nccl_check(n.AllGather(d_all + s->rank, d_all, sizeof(Rec), 0 /*ncclChar*/, h.comm, s->stream), "AllGather");
+  CUDA_CHECK(cudaStreamSynchronize(s->stream));
+  std::vector<Rec> all(s->nranks);
+  CUDA_CHECK(cudaMemcpy(all.data(), d_all, sizeof(Rec) * s->nranks, cudaMemcpyDeviceToHost));
+  cudaFree(d_all);
+  for (int r : halo_peers(s)) {
+    if (r == s->rank) { h.peer_win[r] = h.win; continue; }
+    if (all[r].cap != h.win_cap) throw std::runtime_error("wrfgpu: peer windows of different sizes");
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      throw std::runtime_error(std::string("wrfgpu: cudaIpcOpenMemHandle failed (") + cudaGetErrorString(e) + ")");
+    }
+    h.peer_win[r] = (char *)p;
+    h.peer_ipc[r] = true;
+  }
+  h.direct = true;
+}
+
 // wrf_dm_maxval's role for grid%max_vert_cfl / max_horiz_cfl (dyn_em/adapt_timestep_em.F): ncclAllReduce(max) between
 // processes; solvers of one process compare their host copies between two barriers.
 void halo_max2(Solver *s, float *d2, float out[2]) {
@@ -458,8 +712,9 @@ void Solver::halo(const std::string &name) {
   for (auto &n : f2) if (fields.count(n)) all.push_back(&F(n));
   for (size_t pos = 0; pos < all.size(); pos += HALO_MAX) {
     std::vector<Field *> batch(all.begin() + pos, all.begin() + std::min(all.size(), pos + HALO_MAX));
-    exchange_phase(this, width, batch, 0);   // Y
-    exchange_phase(this, width, batch, 2);   // X (j range includes the rows just received)
+    const int hw = regular_width(name, width);
+    exchange_phase(this, width, hw, batch, 0);   // Y
+    exchange_phase(this, width, hw, batch, 2);   // X (j range includes the rows just received)
   }
 }
 
@@ -484,11 +739,18 @@ int wrfgpu_halo_spec(const wrfgpu_config *c, const char *halo_name, int *width, 
 
 int wrfgpu_halo_box(const wrfgpu_dims *d, const wrfgpu_config *c, int width, int dir, int send, int *peer, int *is, int *ie,
                     int *js, int *je) {
+  return wrfgpu_halo_box2(d, c, width, 0, dir, send, peer, is, ie, js, je);
+}
+
+int wrfgpu_halo_box2(const wrfgpu_dims *d, const wrfgpu_config *c, int width, int regular_width, int dir, int send, int *peer,
+                     int *is, int *ie, int *js, int *je) {
   wg::Strip s;
-  if (!wg::halo_box(*d, *c, width, dir, send != 0, s)) return 0;
+  if (!wg::halo_box(*d, *c, width, dir, send != 0, s, regular_width)) return 0;
   *peer = s.peer; *is = s.is; *ie = s.ie; *js = s.js; *je = s.je;
   return 1;
 }
+
+int wrfgpu_halo_regular_width(const char *halo_name, int width) { return wg::regular_width(halo_name, width); }
 
 int wrfgpu_comm_unique_id(void *id128) {
   wg::Nccl &n = wg::nccl();
@@ -507,6 +769,16 @@ int wrfgpu_comm_init(wrfgpu_solver *s, const void *id128, int rank, int nranks) 
     wg::Id128 id;
     memcpy(id.b, id128, 128);
     wg::nccl_check(n.CommInitRank(&h.comm, nranks, id, rank), "CommInitRank");
+    // halos travel through peer windows (CUDA IPC over NVLink); WRFGPU_HALO=nccl keeps ncclSend/ncclRecv (A/B runs)
+    const char *mode = getenv("WRFGPU_HALO");
+    if (!(mode && !strcmp(mode, "nccl"))) {
+      try { wg::direct_setup_ipc(&S); }
+      catch (const std::exception &e) {
+        if (mode && !strcmp(mode, "direct")) throw;
+        fprintf(stderr, "wrfgpu: rank %d: peer windows unavailable (%s); halos go through ncclSend/ncclRecv\n", rank, e.what());
+        wg::hs(&S).direct = false;
+      }
+    }
     return 0;
   } catch (const std::exception &e) { g_wrfgpu_err = e.what(); return 1; }
 }
@@ -514,11 +786,15 @@ int wrfgpu_comm_init(wrfgpu_solver *s, const void *id128, int rank, int nranks) 
 int wrfgpu_comm_init_local(wrfgpu_solver *const *all, int n) {
   try {
     auto *grp = new wg::LocalGroup();
+    bool distinct = n > 1;    // every rank on its own GPU: the peer-window transport (their kernels run concurrently for sure)
     for (int r = 0; r < n; r++) {
       Solver &S = all[r]->s;
       if (S.nranks != n || S.rank != r) throw std::runtime_error("wrfgpu_comm_init_local: solvers must be given in rank order");
       grp->ranks.push_back(&S);
+      for (int q = 0; q < r; q++) distinct = distinct && all[q]->s.device != S.device;
     }
+    const char *mode = getenv("WRFGPU_HALO_DIRECT");   // 1: also between solvers that share a GPU (tests; needs concurrent kernels)
+    const bool direct = (mode && mode[0] == '1') || (distinct && !(mode && mode[0] == '0'));
     for (int r = 0; r < n; r++) {
       Solver &S = all[r]->s;
       CUDA_CHECK(cudaSetDevice(S.device));
@@ -537,6 +813,17 @@ int wrfgpu_comm_init_local(wrfgpu_solver *const *all, int n) {
           if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(e);
           cudaGetLastError();
         }
+      }
+    }
+    if (direct) {
+      for (int r = 0; r < n; r++) { CUDA_CHECK(cudaSetDevice(all[r]->s.device)); wg::direct_alloc(&all[r]->s); }
+      for (int r = 0; r < n; r++) {
+        wg::HaloState &h = wg::hs(&all[r]->s);
+        for (int q = 0; q < n; q++) {
+          if (wg::hs(&all[q]->s).win_cap != h.win_cap) throw std::runtime_error("wrfgpu_comm_init_local: peer windows of different sizes");
+          h.peer_win[q] = wg::hs(&all[q]->s).win;
+        }
+        h.direct = true;
       }
     }
     return 0;

@@ -96,7 +96,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
 // everywhere.  Worth a test per column because the tendf / h_diabatic numerators are exactly zero until a physics scheme
 // fills them, and a zero numerator sends nvcc's IEEE division down its ~70-instruction slow path (FCHK): five of those per
 // point were 18 % of this kernel's instructions (ncu r2j).
-__device__ __forceinline__ float div_msf(float x, float msf, bool msf_is_one) { return msf_is_one ? x : x / msf; }
+__device__ __forceinline__ float div_msf(float x, float msf, bool msf_is_one) {
+  float r = x;
+  if (!msf_is_one) {
+    asm volatile("" ::: "memory");   // keeps the division inside the branch (nvcc otherwise evaluates it speculatively and selects)
+    r = x / msf;
+  }
+  return r;
+}
 
 #ifndef TT_MINB
 #define TT_MINB 2

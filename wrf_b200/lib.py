@@ -29,7 +29,7 @@ ABI_SYMBOLS = (
     "wrfgpu_get_field", "wrfgpu_upload", "wrfgpu_download", "wrfgpu_num_fields", "wrfgpu_field_name", "wrfgpu_field_devptr",
     "wrfgpu_step", "wrfgpu_solve_em", "wrfgpu_sync", "wrfgpu_set_stream", "wrfgpu_kernel_report", "wrfgpu_launch_count", "wrfgpu_max_cfl", "wrfgpu_phase_ms", "wrfgpu_set_physical_bc",
     "wrfgpu_compute_mesh", "wrfgpu_patch_dims", "wrfgpu_comm_unique_id", "wrfgpu_comm_init", "wrfgpu_comm_init_local", "wrfgpu_halo",
-    "wrfgpu_halo_spec", "wrfgpu_halo_box", "wrfgpu_halo_bytes",
+    "wrfgpu_halo_spec", "wrfgpu_halo_box", "wrfgpu_halo_box2", "wrfgpu_halo_regular_width", "wrfgpu_halo_bytes",
     "wrfgpu_snapshot_begin", "wrfgpu_snapshot_wait", "wrfgpu_snapshot_busy", "wrfgpu_snapshot_host",
 ) + tuple("wrfgpu_" + p for p in PHASES)
 
