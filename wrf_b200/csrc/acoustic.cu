@@ -804,7 +804,9 @@ void Solver::advance_uv_fused(int rk_step, int iteration) {
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
   UvFuse fz{iteration, ns, o("ru_m"), o("rv_m"), o("u_save"), o("v_save")};
-  LAUNCH2(this, k_advance_uv<true>, (Box{q.its, q.ite, 1, 1, q.jts, q.jte}), dts_rk, uv_args(this), fz);
+  const UvArgs ua = uv_args(this);
+  // HALO_EM_C (solve_em.F:1382) overlaps the interior of the kernel that produces u, v
+  overlapped(Box{q.its, q.ite, 1, 1, q.jts, q.jte}, "HALO_EM_C", [&](const Box &bx) { LAUNCH2(this, k_advance_uv<true>, bx, dts_rk, ua, fz); });
 }
 
 static MuTArgs mu_t_args(Solver *s) {
@@ -850,8 +852,9 @@ void Solver::advance_w_fused(int rk_step, int iteration) {
   rk_params(rk_step, dt_rk, dts_rk, ns);
   if (q.kde < 5) throw std::runtime_error("wrfgpu: the fused column kernel needs at least 5 levels");
   WFuse fz{iteration, ns, o("al"), o("p"), o("pm1"), o("ww_m"), o("ru_m"), o("rv_m"), o("mu_2"), o("ww1")};
-  LAUNCH2(this, k_advance_w<true>, (Box{q.its, q.ite, 1, 1, q.jts, q.jte}), dts_rk, w_args(this), fz);
-  halo("HALO_EM_C2");
+  const WArgs wa = w_args(this);
+  // HALO_EM_C2 (solve_em.F:1659) overlaps the interior of the column kernel that produces ph, al, p
+  overlapped(Box{q.its, q.ite, 1, 1, q.jts, q.jte}, "HALO_EM_C2", [&](const Box &bx) { LAUNCH2(this, k_advance_w<true>, bx, dts_rk, wa, fz); });
   bc({{"ph_2", 'w'}, {"al", 'p'}, {"p", 'p'}, {"muts", 't'}, {"mu_2", 't'}, {"mudf", 't'}});
 }
 

@@ -231,6 +231,26 @@ struct Solver {
   void bc(const std::vector<BcItem> &items);
   // halo.cu
   void halo(const std::string &name);
+  // Overlap of an exchange with the kernel that produces its data (north star: "overlapped with interior-tile compute"):
+  // the producer runs first on the RING of the patch (the points within 3 of a side that has a neighbour: everything a send
+  // strip holds), then the exchange goes to a second stream while the producer does the interior on the main stream; the
+  // main stream joins before the first consumer of the halo.  `launch(box)` must give the same values for any partition
+  // of the box (the column kernels of the acoustic loop do: they read no neighbour of the fields they update).
+  cudaStream_t hstream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap = true;                 // WRFGPU_OVERLAP=0 switches it off (A/B runs)
+  void halo_begin(const std::string &name);
+  void halo_end();
+  int ring_split(const Box &full, int w, Box ring[4], Box &inner);
+  template <class F> void overlapped(const Box &full, const char *halo_name, F launch) {
+    Box ring[4], inner;
+    const int n = (nranks > 1 && overlap) ? ring_split(full, 3, ring, inner) : 0;
+    if (n == 0) { launch(full); halo(halo_name); return; }
+    for (int m = 0; m < n; m++) launch(ring[m]);
+    halo_begin(halo_name);
+    if (inner.i0 <= inner.i1 && inner.j0 <= inner.j1) launch(inner);
+    halo_end();
+  }
 };
 
 // launch helpers -------------------------------------------------------------

@@ -431,6 +431,7 @@ void halo_destroy(Solver *s) {
   for (int d = 0; d < 4; d++) { cudaFree(h.send[d]); cudaFree(h.recv[d]); }
   for (size_t r = 0; r < h.peer_win.size(); r++)
     if (h.peer_win[r] && h.peer_ipc[r]) cudaIpcCloseMemHandle(h.peer_win[r]);
+  if (s->hstream) { cudaStreamDestroy(s->hstream); cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); s->hstream = nullptr; }
   if (h.win) cudaFree(h.win);
   if (h.d_count) cudaFree(h.d_count);
   if (h.packed) cudaEventDestroy(h.packed);
@@ -701,6 +702,43 @@ void halo_max2(Solver *s, float *d2, float out[2]) {
   CUDA_CHECK(cudaMemcpyAsync(out, d2, 2 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
   CUDA_CHECK(cudaStreamSynchronize(s->stream));
 }
+
+// the strips of `full` within w of a patch side across which this rank has a neighbour (mesh or periodic wrap), and the rest
+int Solver::ring_split(const Box &full, int w, Box ring[4], Box &inner) {
+  Strip st;
+  bool link[4];
+  for (int dir = 0; dir < 4; dir++) link[dir] = halo_box(d, c, 4, dir, true, st);
+  inner = full;
+  int n = 0;
+  if (link[0]) { ring[n++] = Box{full.i0, full.i1, full.k0, full.k1, full.j0, std::min(full.j1, full.j0 + w - 1)}; inner.j0 = full.j0 + w; }
+  if (link[1] && inner.j0 <= full.j1) {
+    const int j0 = std::max(inner.j0, full.j1 - w + 1);
+    ring[n++] = Box{full.i0, full.i1, full.k0, full.k1, j0, full.j1}; inner.j1 = j0 - 1;
+  }
+  if (inner.j0 > inner.j1) return n;
+  if (link[2]) { ring[n++] = Box{full.i0, std::min(full.i1, full.i0 + w - 1), full.k0, full.k1, inner.j0, inner.j1}; inner.i0 = full.i0 + w; }
+  if (link[3] && inner.i0 <= full.i1) {
+    const int i0 = std::max(inner.i0, full.i1 - w + 1);
+    ring[n++] = Box{i0, full.i1, full.k0, full.k1, inner.j0, inner.j1}; inner.i1 = i0 - 1;
+  }
+  return n;
+}
+
+void Solver::halo_begin(const std::string &name) {
+  if (!hstream) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&hstream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  CUDA_CHECK(cudaEventRecord(ev_fork, stream));
+  CUDA_CHECK(cudaStreamWaitEvent(hstream, ev_fork, 0));
+  std::swap(stream, hstream);
+  try { halo(name); } catch (...) { std::swap(stream, hstream); throw; }
+  std::swap(stream, hstream);
+  CUDA_CHECK(cudaEventRecord(ev_join, hstream));
+}
+
+void Solver::halo_end() { CUDA_CHECK(cudaStreamWaitEvent(stream, ev_join, 0)); }
 
 void Solver::halo(const std::string &name) {
   if (nranks == 1) return;   // a single task: every HALO_*.inc is a no-op, periodic closure is set_physical_bc's job

@@ -136,6 +136,7 @@ Solver::Solver(const wrfgpu_dims &d_, const wrfgpu_config &c_, int dev) : d(d_),
   }
   rank = c.mytask;
   nranks = std::max(1, c.ntasks_x * c.ntasks_y);
+  if (const char *e = getenv("WRFGPU_OVERLAP")) overlap = e[0] != '0';
   build_geo();
 }
 
@@ -306,8 +307,7 @@ void Solver::step() {
     { PHASE("rk_tendency"); rk_tendency(rk_step, false); }
     { PHASE("small_step_prep"); small_step_prep(rk_step, true); }
     for (int it = 1; it <= ns; it++) {
-      { PHASE("advance_uv"); advance_uv_fused(rk_step, it); }
-      halo("HALO_EM_C");
+      { PHASE("advance_uv"); advance_uv_fused(rk_step, it); }   // + HALO_EM_C, overlapped with the kernel's interior
       { PHASE("advance_mu_t"); advance_mu_t(rk_step, true); }
       { PHASE("advance_w"); advance_w_fused(rk_step, it); }
     }
