@@ -116,3 +116,12 @@ def test_processes_exchange_through_cuda_ipc_windows():
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("IPC_RANK_OK") == 2, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("name", ["quarter_ss", "periodic"])
+def test_exchange_overlapped_with_the_interior_of_its_producer(name, monkeypatch):
+    """WRFGPU_OVERLAP=1: advance_uv / advance_w run on the ring of the patch first, HALO_EM_C / HALO_EM_C2 then travel on a
+    priority stream while the interior is computed.  Same bits as the single-rank run."""
+    monkeypatch.setenv("WRFGPU_OVERLAP", "1")
+    bad, sent = _run(parity.small_cases()[name], 2, 2, nsteps=3)
+    assert not bad, bad[:8]

@@ -236,20 +236,37 @@ struct Solver {
   // strip holds), then the exchange goes to a second stream while the producer does the interior on the main stream; the
   // main stream joins before the first consumer of the halo.  `launch(box)` must give the same values for any partition
   // of the box (the column kernels of the acoustic loop do: they read no neighbour of the fields they update).
-  cudaStream_t hstream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool overlap = true;                 // WRFGPU_OVERLAP=0 switches it off (A/B runs)
-  void halo_begin(const std::string &name);
-  void halo_end();
+  // The ring strips and the exchange run on high-priority streams (their few blocks are scheduled ahead of the interior's
+  // pending blocks), one stream per strip so that the four latency-bound column marches run side by side.
+  cudaStream_t hstream = nullptr, rstream[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ring[4] = {nullptr, nullptr, nullptr, nullptr};
+  // Measured on 4 and 8 B200 (profiles/README.md, r2v-r2x): with the peer-window transport an acoustic exchange costs
+  // 55-90 us, less than the four latency-bound ring launches cost the producer, so the split loses 0.6-1 % of the step.
+  // It is therefore OFF unless WRFGPU_OVERLAP=1; tests/test_multi_gpu.py runs it for the bits.
+  bool overlap = false;
+  void overlap_streams();
   int ring_split(const Box &full, int w, Box ring[4], Box &inner);
   template <class F> void overlapped(const Box &full, const char *halo_name, F launch) {
     Box ring[4], inner;
     const int n = (nranks > 1 && overlap) ? ring_split(full, 3, ring, inner) : 0;
     if (n == 0) { launch(full); halo(halo_name); return; }
-    for (int m = 0; m < n; m++) launch(ring[m]);
-    halo_begin(halo_name);
-    if (inner.i0 <= inner.i1 && inner.j0 <= inner.j1) launch(inner);
-    halo_end();
+    overlap_streams();
+    CUDA_CHECK(cudaEventRecord(ev_fork, stream));
+    cudaStream_t main_stream = stream;
+    for (int m = 0; m < n; m++) {      // ring first, on the priority streams
+      CUDA_CHECK(cudaStreamWaitEvent(rstream[m], ev_fork, 0));
+      stream = rstream[m];
+      try { launch(ring[m]); } catch (...) { stream = main_stream; throw; }
+      stream = main_stream;
+      CUDA_CHECK(cudaEventRecord(ev_ring[m], rstream[m]));
+      CUDA_CHECK(cudaStreamWaitEvent(hstream, ev_ring[m], 0));
+    }
+    if (inner.i0 <= inner.i1 && inner.j0 <= inner.j1) launch(inner);      // the bulk, on the main stream
+    stream = hstream;                  // the exchange, behind the ring
+    try { halo(halo_name); } catch (...) { stream = main_stream; throw; }
+    stream = main_stream;
+    CUDA_CHECK(cudaEventRecord(ev_join, hstream));
+    CUDA_CHECK(cudaStreamWaitEvent(stream, ev_join, 0));
   }
 };
 
@@ -277,7 +294,8 @@ inline bool empty(const Box &b) { return b.i1 < b.i0 || b.k1 < b.k0 || b.j1 < b.
   do {                                                                               \
     Box b_ = (box);                                                                  \
     if (!empty(b_)) {                                                                \
-      const dim3 &t_ = (S)->blk2;                                                    \
+      /* strips a few columns wide (the ring of an overlapped exchange): 4 x 32 threads instead of 128 x 1 */ \
+      const dim3 t_ = (b_.i1 - b_.i0 < 4) ? dim3(4, 32, 1) : (S)->blk2;             \
       dim3 gr_((unsigned)((b_.i1 - b_.i0 + t_.x) / t_.x), (unsigned)((b_.j1 - b_.j0 + t_.y) / t_.y)); \
       if ((S)->coef_dirty) (S)->sync_coef();                                         \
       (S)->kpre(#kern);                                                              \

@@ -368,9 +368,21 @@ __global__ void k_halo_wait(LinkArgs l) {
   }
 }
 
-// GET = false: fields -> a.buf (the neighbour's receive buffer); GET = true: a.buf (my receive buffer) -> fields
-template <bool GET>
-__global__ void k_halo_direct(const GeoBase g, HaloArgs a, LinkArgs l) {
+// PUT: fields -> a.buf (the neighbour's receive buffer); GET: a.buf (my receive buffer) -> fields.  MODE 0 = put, 1 = get,
+// 2 = both in one launch (processes: blockIdx.y = 0 packs with `a`, `l`; blockIdx.y = 1 unpacks with `a2`, `l2`; the put
+// blocks have the lower block indices, so they are dispatched first, and nothing in a launch waits for the same launch).
+struct HaloPair { HaloArgs a; LinkArgs l; };
+#ifndef HU
+#define HU 8
+#endif
+#ifndef HALO_TPB
+#define HALO_TPB 512
+#endif
+template <int MODE>
+__global__ void k_halo_direct(const GeoBase g, const HaloPair pp, const HaloPair pg) {
+  const bool GET = MODE == 1 || (MODE == 2 && blockIdx.y == 1);
+  const HaloArgs &a = GET ? pg.a : pp.a;
+  const LinkArgs &l = GET ? pg.l : pp.l;
   const int f = blockIdx.z % a.n, sd = blockIdx.z / a.n;
   if (!a.active[sd]) return;
   if (threadIdx.x == 0 && l.wait_flag[sd]) {
@@ -387,13 +399,26 @@ __global__ void k_halo_direct(const GeoBase g, HaloArgs a, LinkArgs l) {
   const int total = ni * nj * nk;
   float *buf = a.buf[sd] + a.off[f] * (long)ni * nj;
   float *fld = a.p[f];
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int row = e / ni, ii = e - row * ni;
-    const int jj = row / nk, kk = row - jj * nk;
-    const int i = a.is[sd] + ii, j = a.js[sd] + jj, k = 1 + kk;
-    const long x = is3d ? ((long)i + (long)k * g.sk + (long)j * g.sj) : ((long)i + (long)j * g.ni);
-    if (GET) fld[x] = __ldcg(buf + e);       // written by the neighbour's GPU: never through this SM's L1
-    else buf[e] = fld[x];
+  // HU elements per thread and trip: the loads of a trip are independent, so their latencies overlap
+  const int stride = gridDim.x * blockDim.x;
+  for (int e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += HU * stride) {
+    long x[HU];
+    float v[HU];
+#pragma unroll
+    for (int u = 0; u < HU; u++) {
+      const int e = e0 + u * stride;
+      const int ee = e < total ? e : e0;
+      const int row = ee / ni, ii = ee - row * ni;
+      const int jj = row / nk, kk = row - jj * nk;
+      const int i = a.is[sd] + ii, j = a.js[sd] + jj, k = 1 + kk;
+      x[u] = is3d ? ((long)i + (long)k * g.sk + (long)j * g.sj) : ((long)i + (long)j * g.ni);
+      v[u] = GET ? __ldcg(buf + ee) : fld[x[u]];       // a receive buffer is written by the neighbour's GPU: never through L1
+    }
+#pragma unroll
+    for (int u = 0; u < HU; u++) {
+      const int e = e0 + u * stride;
+      if (e < total) { if (GET) fld[x[u]] = v[u]; else buf[e] = v[u]; }
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -431,7 +456,10 @@ void halo_destroy(Solver *s) {
   for (int d = 0; d < 4; d++) { cudaFree(h.send[d]); cudaFree(h.recv[d]); }
   for (size_t r = 0; r < h.peer_win.size(); r++)
     if (h.peer_win[r] && h.peer_ipc[r]) cudaIpcCloseMemHandle(h.peer_win[r]);
-  if (s->hstream) { cudaStreamDestroy(s->hstream); cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); s->hstream = nullptr; }
+  if (s->hstream) {
+    cudaStreamDestroy(s->hstream); cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); s->hstream = nullptr;
+    for (int m = 0; m < 4; m++) { cudaStreamDestroy(s->rstream[m]); cudaEventDestroy(s->ev_ring[m]); }
+  }
   if (h.win) cudaFree(h.win);
   if (h.d_count) cudaFree(h.d_count);
   if (h.packed) cudaEventDestroy(h.packed);
@@ -504,15 +532,26 @@ static void exchange_phase(Solver *s, int width, int hwidth, const std::vector<F
       get.post_flag[q] = win_ack(pw, dir ^ 1); get.post_val[q] = n;
       get.count[q] = h.d_count + 2 + q;
     }
-    for (int pass = 0; pass < 2; pass++) {
-      HaloArgs &a = pass ? rcv : snd;
-      LinkArgs &l = pass ? get : put;
-      long total = 0;
-      for (int q = 0; q < 2; q++)
-        if (a.active[q]) total = std::max(total, (long)(a.ie[q] - a.is[q] + 1) * (a.je[q] - a.js[q] + 1) * a.nk);
-      dim3 grid((unsigned)std::min(512L, (total + 255) / 256), 1, (unsigned)(2 * a.n));
-      for (int q = 0; q < 2; q++) l.nblocks[q] = grid.x * (unsigned)a.n;
-      if (h.local && (l.wait_flag[0] || l.wait_flag[1])) {   // solvers sharing a GPU: wait in a kernel of one warp
+    long total = 0;
+    for (int q = 0; q < 2; q++)
+      if (has[q]) total = std::max(total, std::max((long)(snd.ie[q] - snd.is[q] + 1) * (snd.je[q] - snd.js[q] + 1),
+                                                    (long)(rcv.ie[q] - rcv.is[q] + 1) * (rcv.je[q] - rcv.js[q] + 1)) * snd.nk);
+    // about two blocks per SM in all: every block ends with a system-scope fence and an atomic, and strips are small
+    const long per_fs = std::max(1L, 296L / (2 * snd.n));
+    const unsigned gx = (unsigned)std::min(per_fs, (total + HU * HALO_TPB - 1) / (HU * HALO_TPB));
+    for (int q = 0; q < 2; q++) put.nblocks[q] = get.nblocks[q] = gx * (unsigned)snd.n;
+    HaloPair pp{snd, put}, pg{rcv, get};
+    if (!h.local) {   // processes: pack and unpack in one launch
+      s->kpre("k_halo_exchange");
+      k_halo_direct<2><<<dim3(gx, 2, (unsigned)(2 * snd.n)), HALO_TPB, 0, s->stream>>>(s->g, pp, pg);
+      s->kpost();
+      s->launches++;
+    }
+    for (int pass = 0; pass < 2 && h.local; pass++) {
+      HaloPair &pr = pass ? pg : pp;
+      LinkArgs &l = pr.l;
+      dim3 grid(gx, 1, (unsigned)(2 * snd.n));
+      if (l.wait_flag[0] || l.wait_flag[1]) {   // solvers sharing a GPU: wait in a kernel of one warp
         s->kpre("k_halo_wait");
         k_halo_wait<<<1, 32, 0, s->stream>>>(l);
         s->kpost();
@@ -520,8 +559,8 @@ static void exchange_phase(Solver *s, int width, int hwidth, const std::vector<F
         l.wait_flag[0] = l.wait_flag[1] = nullptr;
       }
       s->kpre(pass ? "k_halo_get" : "k_halo_put");
-      if (pass) k_halo_direct<true><<<grid, 256, 0, s->stream>>>(s->g, a, l);
-      else k_halo_direct<false><<<grid, 256, 0, s->stream>>>(s->g, a, l);
+      if (pass) k_halo_direct<1><<<grid, HALO_TPB, 0, s->stream>>>(s->g, pp, pr);
+      else k_halo_direct<0><<<grid, HALO_TPB, 0, s->stream>>>(s->g, pr, pg);
       s->kpost();
       s->launches++;
       // Solvers of ONE process share a CUDA context: an implicitly synchronising call of one host thread (cudaMalloc, a
@@ -724,21 +763,18 @@ int Solver::ring_split(const Box &full, int w, Box ring[4], Box &inner) {
   return n;
 }
 
-void Solver::halo_begin(const std::string &name) {
-  if (!hstream) {
-    CUDA_CHECK(cudaStreamCreateWithFlags(&hstream, cudaStreamNonBlocking));
-    CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+void Solver::overlap_streams() {
+  if (hstream) return;
+  int lo = 0, hi = 0;
+  CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // hi = the greatest priority (numerically lowest)
+  CUDA_CHECK(cudaStreamCreateWithPriority(&hstream, cudaStreamNonBlocking, hi));
+  CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  for (int m = 0; m < 4; m++) {
+    CUDA_CHECK(cudaStreamCreateWithPriority(&rstream[m], cudaStreamNonBlocking, hi));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_ring[m], cudaEventDisableTiming));
   }
-  CUDA_CHECK(cudaEventRecord(ev_fork, stream));
-  CUDA_CHECK(cudaStreamWaitEvent(hstream, ev_fork, 0));
-  std::swap(stream, hstream);
-  try { halo(name); } catch (...) { std::swap(stream, hstream); throw; }
-  std::swap(stream, hstream);
-  CUDA_CHECK(cudaEventRecord(ev_join, hstream));
 }
-
-void Solver::halo_end() { CUDA_CHECK(cudaStreamWaitEvent(stream, ev_join, 0)); }
 
 void Solver::halo(const std::string &name) {
   if (nranks == 1) return;   // a single task: every HALO_*.inc is a no-op, periodic closure is set_physical_bc's job

@@ -136,7 +136,7 @@ Solver::Solver(const wrfgpu_dims &d_, const wrfgpu_config &c_, int dev) : d(d_),
   }
   rank = c.mytask;
   nranks = std::max(1, c.ntasks_x * c.ntasks_y);
-  if (const char *e = getenv("WRFGPU_OVERLAP")) overlap = e[0] != '0';
+  if (const char *e = getenv("WRFGPU_OVERLAP")) overlap = e[0] == '1';
   build_geo();
 }
 
