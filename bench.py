@@ -40,6 +40,8 @@ ALGO_ACCESSES = {
     "k_advect_scalar_fast<theta>": 7, "k_advect_scalar_fast": 5,
     "k_mom_u_fast": 6, "k_mom_v_fast": 6, "k_mom_w_fast": 6, "k_ph_fast": 6,     # interior forms of k_tend_u/v/w/ph
     "k_pd_scale_fast": 6, "k_pd_tend_fast": 7,
+    # the whole rk_tendency + rk_addtend_dry phase of the interior in one TMA-staged kernel: 24 fields in, 5 tendencies + cqw out
+    "k_tend_tile": 30,
 }
 
 
@@ -119,6 +121,41 @@ def tile_case_on_device(small, nx, ny, nz, device, ntx=1, nty=1, rank=0):
     return big, out
 
 
+def state_checksum(s, names, dev, world):
+    """Decomposition-independent checksum of the owned points of `names` + a finiteness check.  Every point contributes
+    bits(value) x odd_hash(global i, k, j) in wrap-around 64-bit arithmetic; the per-rank sums add up to the same number
+    for any patch mesh, so the N-GPU run can be compared with the 1-GPU run at the size that is timed (the reference's
+    BIT4BIT criterion, tools/regtest.csh:14-18)."""
+    import torch
+    import torch.distributed as dist
+    from wrf_b200 import decomp
+    d = s.case.dims
+    ni, nk, nj = d.ime - d.ims + 1, d.kme - d.kms + 1, d.jme - d.jms + 1
+    out, finite = {}, True
+    for n in names:
+        t = torch.empty(s.size(n), dtype=torch.float32, device=dev)
+        s.get(n, out=t)
+        t = t.view(nj, nk, ni) if t.numel() == ni * nk * nj else t.view(nj, 1, ni)
+        ie = d.ipe if n in decomp.XSTAG else min(d.ipe, d.ide - 1)
+        je = d.jpe if n in decomp.YSTAG else min(d.jpe, d.jde - 1)
+        own = t[d.jps - d.jms:je - d.jms + 1, :, d.ips - d.ims:ie - d.ims + 1]
+        finite = finite and bool(torch.isfinite(own).all().item())
+        gj = torch.arange(d.jps, je + 1, device=dev, dtype=torch.int64)[:, None, None]
+        gk = torch.arange(1, own.shape[1] + 1, device=dev, dtype=torch.int64)[None, :, None]
+        gi = torch.arange(d.ips, ie + 1, device=dev, dtype=torch.int64)[None, None, :]
+        h = ((gi * 73856093) ^ (gk * 19349663) ^ (gj * 83492791)) | 1
+        bits = own.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+        acc = (bits * h).sum()
+        if world > 1:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        out[n] = "%016x" % (int(acc.item()) & 0xFFFFFFFFFFFFFFFF)
+    if world > 1:
+        f = torch.tensor([1 if finite else 0], device=dev)
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        finite = bool(f.item())
+    return out, finite
+
+
 def measured_traffic():
     """per-kernel DRAM bytes per grid point from the last committed `ncu --set full` capture"""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -146,7 +183,12 @@ def run_ours(args):
 
     nx, ny, nz = args.nx, args.ny, args.nz
     lat = 50
-    small = make_case("synthetic", nx=lat + 1, ny=lat + 1, nz=nz, bubble_lattice=lat * 2000.0)
+    moist = args.workload == "moist"
+    if moist:   # the shipped em_quarter_ss physics: Kessler (qv, qc, qr), diff_opt 2 / km_opt 2 (prognostic tke), PD advection
+        small = make_case("synthetic", nx=lat + 1, ny=lat + 1, nz=nz, bubble_lattice=lat * 2000.0, mp_physics=1, num_moist=3,
+                          diff_opt=2, km_opt=2, mix_full_fields=1, damp_opt=2, zdamp=5000.0, dampcoef=0.003)
+    else:
+        small = make_case("synthetic", nx=lat + 1, ny=lat + 1, nz=nz, bubble_lattice=lat * 2000.0)
     case, dev_fields = tile_case_on_device(small, nx, ny, nz, dev, ntx, nty, rank)
     s = Solver(case, device=local, upload=False)
     stream = torch.cuda.current_stream()
@@ -166,7 +208,8 @@ def run_ours(args):
     d = case.dims
     my_pts = (min(d.ipe, d.ide - 1) - d.ips + 1) * (min(d.jpe, d.jde - 1) - d.jps + 1) * (nz - 1)
     ns = c.time_step_sound
-    bytes_pt = algorithmic_bytes_per_point_step(c.num_moist, c.num_moist + c.num_scalar, ns, c.mp_physics)
+    n_adv = c.num_moist + c.num_scalar + (1 if (c.km_opt == 2 and c.diff_opt == 2) else 0)      # species advected (tke is one)
+    bytes_pt = algorithmic_bytes_per_point_step(c.num_moist, n_adv, ns, c.mp_physics) + (584 if moist else 0)   # + DESIGN.md diffusion family
 
     def barrier():
         torch.cuda.synchronize()
@@ -201,6 +244,10 @@ def run_ours(args):
     halo_bytes = (s.halo_bytes() - hb0) / args.steps
     ms_per_step = ms / args.steps
     value = npts / (ms_per_step * 1e-3)
+    # the state after exactly warmup + steps steps: finite, and the same numbers on any number of GPUs
+    checksum, finite = state_checksum(s, ["u_2", "w_2", "t_2", "mu_2"], dev, world)
+    if not finite:
+        raise SystemExit("bench.py: the state is not finite after the timed steps -- no throughput number")
 
     # ---- per-kernel times (events on the same stream, outside the timed region)
     s.phase_timing(True)
@@ -209,7 +256,8 @@ def run_ours(args):
     s.phase_timing(False)
     barrier()
     tot = sum(v[1] for v in rep.values())
-    top = max(rep.items(), key=lambda kv: kv[1][1])
+    # the dominant COMPUTE kernel (the exchange kernels' times include waiting for the neighbour)
+    top = max(((k, v) for k, v in rep.items() if "halo" not in k), key=lambda kv: kv[1][1])
     peak, peak_src = measured_peak()
     kname, (kn, kms) = top
     acc = ALGO_ACCESSES.get(kname, ALGO_ACCESSES.get(kname.split("<")[0], 0))
@@ -226,13 +274,16 @@ def run_ours(args):
     if world > 1:
         roofline["halo"] = {"bytes_sent_per_rank_per_step": int(halo_bytes),
                             "GBs_per_rank": round(halo_bytes / (ms_per_step * 1e-3) / 1e9, 2),
-                            "nvlink_peak_GBs_per_direction": 770.0, "transport": "ncclSend/ncclRecv"}
+                            "nvlink_peak_GBs_per_direction": 770.0,
+                            "transport": ("ncclSend/ncclRecv" if os.environ.get("WRFGPU_HALO") == "nccl" else
+                                          "peer windows over CUDA IPC: packed straight into the neighbour's buffer by one kernel per phase")}
 
     # ---- end to end through the drop-in call with host buffers
     if args.no_e2e:      # tuning runs only: the line is not a bench result without e2e
         if rank == 0:
-            print(json.dumps({"tuning_run": True, "ms_per_step": round(ms_per_step, 3), "value": value, "gpu_launches": int(launches),
-                              "step_frac": roofline["step"]["frac"], "kernels_ms_per_step": roofline["kernels_ms_per_step"]}), flush=True)
+            print(json.dumps({"tuning_run": True, "workload": args.workload, "ms_per_step": round(ms_per_step, 3), "value": value,
+                              "gpu_launches": int(launches), "step_frac": roofline["step"]["frac"], "checksum": checksum,
+                              "kernels_ms_per_step": roofline["kernels_ms_per_step"]}), flush=True)
         s.close()
         if world > 1:
             dist.barrier()
@@ -260,22 +311,55 @@ def run_ours(args):
     line = {"metric": "grid-pt RK3 steps/s", "value": value, "unit": "grid-pt-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"synthetic em_quarter_ss {nx}x{ny}x{nz} (e_we x e_sn x e_vert), dx=2km, dt=12s, ns={ns}, "
-                                   f"periodic x/y, dry (passive qv, moist_adv_opt=1), {ntx}x{nty} patch mesh, 1 patch per GPU",
+            "config": {"workload": f"synthetic em_quarter_ss {nx}x{ny}x{nz} (e_we x e_sn x e_vert), dx=2km, dt=12s, ns={ns}, periodic x/y, "
+                                   + ("Kessler + diff_opt=2/km_opt=2 (qv, qc, qr, tke; the shipped em_quarter_ss physics), " if moist else
+                                      "dry (passive qv, moist_adv_opt=1), ") + f"{ntx}x{nty} patch mesh, 1 patch per GPU",
                        "grid_points": npts, "l2_policy": "working set (tens of GB per step) is far larger than the 126 MB L2",
                        "timing": "CUDA events on the launching stream, max over ranks"},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary()}
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "checksum": {"after_steps": args.warmup + args.steps, "finite": finite, "fields": checksum,
+                         "note": "sum over owned points of bits(value) x odd_hash(global i,k,j) mod 2^64: identical for every patch mesh"}}
+    s.close()
+    del s
+    torch.cuda.empty_cache()
+    if world == 1 and not moist and not args.no_second_workload:
+        line["second_workload"] = second_workload(args)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, quick=True)
         print(json.dumps(line), flush=True)
-    s.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def second_workload(args):
+    """the shipped em_quarter_ss physics (Kessler + TKE closure) at the same size, a short resident-state measurement in a
+    child process (fresh device memory); reported inside the dry line, it is not the headline number"""
+    cmd = [sys.executable, os.path.abspath(__file__), "--workload", "moist", "--steps", "3", "--warmup", "3", "--no-e2e",
+           "--nx", str(args.nx), "--ny", str(args.ny), "--nz", str(args.nz)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        top = sorted(d["kernels_ms_per_step"].items(), key=lambda kv: -kv[1])[:8]
+        return {"workload": "synthetic em_quarter_ss, Kessler + diff_opt=2/km_opt=2 (qv, qc, qr, tke)", "ms_per_step": d["ms_per_step"],
+                "value": d["value"], "unit": "grid-pt-steps/s", "step_roofline_frac": d["step_frac"], "steps": 3, "warmup": 3,
+                "top_kernels_ms_per_step": dict(top), "checksum": d["checksum"]}
+    except Exception as e:   # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
 # ---------------------------------------------------------------------------
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(args, quick=False):
     """The CPU restatement (oracle/) on a bounded sample of the same workload."""
     from tests.oracle_lib import Oracle
@@ -295,7 +379,8 @@ def cpu_baseline(args, quick=False):
     return {"value": npts / dt, "unit": "grid-pt-steps/s", "cores": threads, "kind": "port",
             "sample": f"oracle/ (C++ restatement, -O2 -ffp-contract=off, j-tiles on {threads} threads) on {n + 1}x{n + 1}x{args.nz} "
                       f"of the same synthetic workload, {steps} step(s), {dt:.2f} s/step",
-            "host_cpus": os.cpu_count()}
+            "host_cpus": os.cpu_count(), "cpu_model": cpu_model(),
+            "label": "vs-port: the repo's own CPU restatement of solve_em on a cache-friendly sample, NOT wrf.exe (no Fortran compiler here)"}
 
 
 def run_reference(args):
@@ -330,6 +415,9 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs: skip the end-to-end leg and print a short line")
+    ap.add_argument("--workload", default="dry", choices=["dry", "moist"],
+                    help="dry = the headline configuration (BASELINE.json configs[4]); moist = the same domain with the shipped em_quarter_ss physics")
+    ap.add_argument("--no-second-workload", action="store_true", help="skip the short moist + TKE measurement appended to the 1-GPU line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
