@@ -50,6 +50,12 @@ def with_surface_fluxes(case):
     return case
 
 
+def shipped_case(name):
+    import os
+    from wrf_b200 import shipped
+    return shipped.init_domain(os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures", name))
+
+
 def with_tke(case):
     """a smooth, positive initial tke (both time levels) so that every term of tke_rhs acts from the first step"""
     d, c = case.dims, case.config
@@ -215,6 +221,13 @@ def small_cases():
                                                                          num_scalar=1, diff_opt=2, km_opt=2, mix_isotropic=1, tke_adv_opt=2,
                                                                          tke_drag_coefficient=0.003, tke_heat_flux=0.05)), 30.0)),
         "tke_hill": with_tke(with_surface_fluxes(make_case("hill2d_x", nx=62, ny=3, nz=21, diff_opt=2, km_opt=2, isfflx=1))),
+        # C1-C4 exactly as shipped: test/em_*/namelist.input + input_sounding / input_jet (tests/fixtures, unchanged copies) through
+        # wrf_b200/shipped.py (= ideal.exe + start_em), at the shipped dimensions 202x3x41, 42x42x41, 41x81x65, 40x40x40.  em_les
+        # selects sf_sfclay_physics = 1 (host-side physics): its friction velocity is stood in for by a smooth pattern.
+        "shipped_hill2d_x": shipped_case("em_hill2d_x"),
+        "shipped_quarter_ss": shipped_case("em_quarter_ss"),
+        "shipped_b_wave": shipped_case("em_b_wave"),
+        "shipped_les": with_surface_fluxes(shipped_case("em_les")),
         "ieva_weno_hill": with_updraft(make_case("hill2d_x", nx=62, ny=3, nz=41, zadvect_implicit=1, momentum_adv_opt=3,
                                                  moist_adv_opt=3), 60.0, conv=70.0),
     }

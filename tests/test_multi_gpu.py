@@ -57,6 +57,13 @@ def test_n_rank_gpu_equals_single_rank(name, mesh):
     assert all(b > 0 for b in sent)
 
 
+@pytest.mark.parametrize("mesh", [(1, 2), (2, 2)])
+def test_shipped_b_wave_on_2_and_4_ranks(mesh):
+    """BASELINE config C3: em_b_wave as shipped (41x81x65, periodic x / symmetric y, input_jet) at 2 and 4 ranks"""
+    bad, sent = _run(parity.small_cases()["shipped_b_wave"], *mesh, nsteps=2)
+    assert not bad, bad[:8]
+
+
 def test_2x4_mesh_like_the_8_gpu_bench():
     """the mesh mpaspect gives 8 tasks (module_dm.F:98-116), on a periodic domain with uneven patches"""
     case = wrf_b200.make_case("synthetic", nx=43, ny=54, nz=13, bubble_lattice=20000.0, noise=0.05, num_scalar=1)

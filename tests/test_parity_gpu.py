@@ -19,7 +19,8 @@ ALL = ["hill2d_x", "quarter_ss", "quarter_ss_nopd", "b_wave", "les", "periodic",
        "diff6", "diff6_periodic", "diff6_hill", "tall", "tiny", "rk2_everything", "backward",
        "order64", "order63_periodic", "order_mixed", "smag2d", "smag2d_periodic", "smag2d_hill", "smag2d_b_wave",
        "diff2", "diff2_periodic", "diff2_hill", "diff2_b_wave",
-       "smag3d", "smag3d_periodic", "smag3d_hill", "tke", "tke_periodic", "tke_hill"]
+       "smag3d", "smag3d_periodic", "smag3d_hill", "tke", "tke_periodic", "tke_hill",
+       "shipped_hill2d_x", "shipped_quarter_ss", "shipped_b_wave", "shipped_les"]
 
 
 def cases():
@@ -82,6 +83,19 @@ def test_drift_100_steps(name):
         worst = max(worst, parity.rel_l2_field(o, n, a, b))
         assert np.array_equal(a, b), (n, worst)
     assert np.abs(s.get("w_2")).max() > 0.5          # and the flow is far from trivial by then
+    s.close()
+
+
+@pytest.mark.parametrize("name", ["shipped_hill2d_x", "shipped_quarter_ss", "shipped_b_wave", "shipped_les"])
+def test_shipped_configurations_ten_steps_bit_exact(name):
+    """BASELINE configs C1-C4 as shipped (namelist.input, input_sounding / input_jet, shipped dimensions and closures): ten
+    steps on the device equal the oracle bit for bit in every field"""
+    o, s = _pair(name)
+    o.set_threads(8)
+    o.step(10); s.step(10)
+    rep = parity.diff_report(o, s)
+    assert not rep, rep[:5]
+    assert np.isfinite(s.get("w_2")).all() and np.abs(s.get("w_2")).max() > 0.0
     s.close()
 
 
