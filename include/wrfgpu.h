@@ -121,6 +121,8 @@ int  wrfgpu_create (const wrfgpu_dims *d, const wrfgpu_config *c, int device,
 int  wrfgpu_destroy(wrfgpu_solver *s);
 const char *wrfgpu_last_error(void);
 int  wrfgpu_version(void);
+/* CUDA devices visible to this process (the Fortran shim maps rank -> device with it); 0 when there is none */
+int  wrfgpu_device_count(void);
 
 /* -- state transfer ------------------------------------------------------ */
 /* Registry names without the grid% prefix: "u_2","t_1","mu_2","phb","fnm",

@@ -73,3 +73,91 @@ def test_product_does_not_import_oracle():
                 if re.search(r"liboracle|oracle/|import oracle|from oracle|oracle_lib", t):
                     bad.append(fn)
     assert not bad, bad
+
+
+def _build_driver():
+    import subprocess
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "abi_driver")
+    libdir = os.path.join(ROOT, "wrf_b200")
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "abi_driver.c"), "-L" + libdir, "-lwrfgpu",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def _write_state(case, path):
+    import numpy as np
+    with open(path, "wb") as f:
+        f.write(bytes(case.dims)); f.write(bytes(case.config))
+        f.write(np.int32(len(case.fields)).tobytes())
+        for k, a in case.fields.items():
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            f.write(k.encode().ljust(24, b"\0")[:24]); f.write(np.int64(a.size).tobytes()); f.write(a.tobytes())
+
+
+def _read_state(path):
+    import numpy as np
+    out = {}
+    with open(path, "rb") as f:
+        n = int(np.frombuffer(f.read(4), np.int32)[0])
+        for _ in range(n):
+            name = f.read(24).split(b"\0")[0].decode()
+            cnt = int(np.frombuffer(f.read(8), np.int64)[0])
+            out[name] = np.frombuffer(f.read(4 * cnt), np.float32).copy()
+    return out
+
+
+def test_c_driver_links_against_the_abi_and_fails_loudly_without_a_gpu(have_gpu, tmp_path):
+    """tests/abi_driver.c (the Fortran shim's call sequence in C) compiles against include/wrfgpu.h and links with
+    libwrfgpu.so; on a box without a GPU it ends like the shim: a fatal message, no CPU path"""
+    import subprocess
+    exe = _build_driver()
+    if have_gpu:
+        pytest.skip("a GPU is present; the run itself is test_c_driver_replays_the_shim_call_sequence")
+    case = wrf_b200.make_case("quarter_ss", nx=12, ny=12, nz=9)
+    st = str(tmp_path / "state.bin")
+    _write_state(case, st)
+    r = subprocess.run([exe, st, "1", str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert r.returncode == 3, (r.returncode, r.stderr)
+    assert "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_driver_replays_the_shim_call_sequence(tmp_path):
+    """create -> upload (pointer table) -> start_domain -> step x n -> download through plain C equals the ctypes mirror"""
+    import subprocess
+    import numpy as np
+    exe = _build_driver()
+    case = wrf_b200.make_case("quarter_ss", nx=26, ny=24, nz=21, diff_opt=2, km_opt=2, mix_full_fields=1)
+    st, out = str(tmp_path / "state.bin"), str(tmp_path / "out.bin")
+    _write_state(case, st)
+    r = subprocess.run([exe, st, "3", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = _read_state(out)
+    s = wrf_b200.Solver(case)
+    s.start_domain(); s.step(3)
+    assert {"u_2", "w_2", "t_2", "ph_2", "mu_2", "moist_qv", "moist_qr", "scalar_1", "rainnc"} <= set(got)
+    for n, a in got.items():
+        assert np.array_equal(a, s.get(n).ravel()), n
+    s.close()
+
+
+def test_fortran_binding_lists_the_header_members():
+    """the BIND(C) types of wrf_b200/fortran/module_wrfgpu.F90 name the members of wrfgpu_dims / wrfgpu_config in the
+    header's order and with the header's types (the shim cannot be compiled here, so at least its layout is pinned)"""
+    src = open(os.path.join(ROOT, "wrf_b200", "fortran", "module_wrfgpu.F90")).read()
+    for cname, cls in (("wrfgpu_dims", wrf_b200.Dims), ("wrfgpu_config", wrf_b200.Config)):
+        body = re.search(r"TYPE, BIND\(C\) :: %s(.*?)END TYPE %s" % (cname, cname), src, flags=re.S).group(1)
+        names = []
+        for ln in body.splitlines():
+            ln = ln.split("!")[0].strip()
+            m = re.match(r"(INTEGER\(c_int\)|REAL\(c_float\))\s*::\s*(.*)", ln)
+            if m:
+                names += [(x.strip(), "int" if "INTEGER" in m.group(1) else "float") for x in m.group(2).split(",")]
+        mine = [(n, "int" if t is ctypes.c_int else "float") for n, t in cls._fields_]
+        assert names == mine, cname
+    shim = open(os.path.join(ROOT, "wrf_b200", "fortran", "solve_em_gpu.F90")).read()
+    for member, _ in wrf_b200.Config._fields_:
+        assert re.search(r"\bc%%%s\b" % member, shim), f"solve_em_gpu.F90 never sets c%{member}"
+    assert "Is_alarm_tstep(grid%domain_clock, grid%alarms(HISTORY_ALARM))" in shim and "restart_flag_alarm_rings" not in shim

@@ -336,7 +336,12 @@ thread_local std::string g_wrfgpu_err;
 extern "C" {
 
 const char *wrfgpu_last_error(void) { return g_err.c_str(); }
-int wrfgpu_version(void) { return 100; }
+int wrfgpu_version(void) { return 200; }
+int wrfgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
 
 int wrfgpu_create(const wrfgpu_dims *d, const wrfgpu_config *c, int device, wrfgpu_solver **out) {
   try { *out = new wrfgpu_solver(*d, *c, device); return 0; }

@@ -5,7 +5,8 @@
 ! asks for: wrf.exe stays Fortran, the Registry-defined state stays in TYPE(domain), and this
 ! module hands the addresses of grid%u_2, grid%t_2, ... to the C-ABI.  No Fortran compiler exists
 ! in the image this was developed in, so the module has been desk-checked against
-! include/wrfgpu.h (struct member order, by-value vs by-reference) but not compiled here.
+! include/wrfgpu.h (struct member order, by-value vs by-reference; tests/test_abi.py also compares the
+! member lists of the two BIND(C) types below with the header) but not compiled here.
 !
 MODULE module_wrfgpu
    USE, INTRINSIC :: iso_c_binding
@@ -14,7 +15,7 @@ MODULE module_wrfgpu
    PUBLIC :: wrfgpu_dims, wrfgpu_config, wrfgpu_check
    PUBLIC :: wrfgpu_create, wrfgpu_destroy, wrfgpu_last_error, wrfgpu_upload, wrfgpu_download, wrfgpu_step, &
              wrfgpu_solve_em, wrfgpu_start_domain, wrfgpu_sync, wrfgpu_comm_unique_id, wrfgpu_comm_init, &
-             wrfgpu_compute_mesh, wrfgpu_patch_dims, wrfgpu_field_size, &
+             wrfgpu_compute_mesh, wrfgpu_patch_dims, wrfgpu_field_size, wrfgpu_device_count, wrfgpu_max_cfl, &
              wrfgpu_snapshot_begin, wrfgpu_snapshot_wait, wrfgpu_snapshot_busy, wrfgpu_snapshot_host
 
    ! wrfgpu_dims: the three index triplets of get_ijk_from_grid (dyn_em/solve_em.F:288-296)
@@ -48,6 +49,7 @@ MODULE module_wrfgpu
       REAL(c_float)  :: mix_upper_bound
       INTEGER(c_int) :: tke_adv_opt
       REAL(c_float)  :: tke_upper_bound
+      INTEGER(c_int) :: use_adaptive_time_step
    END TYPE wrfgpu_config
 
    INTERFACE
@@ -120,6 +122,15 @@ MODULE module_wrfgpu
          TYPE(c_ptr), VALUE :: handle
          INTEGER(c_int), VALUE :: n_in, n_out
          TYPE(c_ptr), INTENT(IN) :: in_names(*), in_host(*), out_names(*), out_host(*)
+      END FUNCTION
+      INTEGER(c_int) FUNCTION wrfgpu_device_count() BIND(C, name='wrfgpu_device_count')
+         IMPORT :: c_int
+      END FUNCTION
+      INTEGER(c_int) FUNCTION wrfgpu_max_cfl(handle, max_vert_cfl, max_horiz_cfl, reset) BIND(C, name='wrfgpu_max_cfl')
+         IMPORT :: c_int, c_ptr, c_float
+         TYPE(c_ptr), VALUE :: handle
+         REAL(c_float), INTENT(OUT) :: max_vert_cfl, max_horiz_cfl
+         INTEGER(c_int), VALUE :: reset
       END FUNCTION
       INTEGER(c_int) FUNCTION wrfgpu_sync(handle) BIND(C, name='wrfgpu_sync')
          IMPORT :: c_int, c_ptr

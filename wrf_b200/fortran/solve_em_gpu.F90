@@ -4,46 +4,75 @@
 ! argument list (grid, config_flags, <dummy_new_args.inc>), so share/solve_interface.F:50-55 and
 ! everything above it are unchanged.  dyn_em/Makefile lists this object instead of solve_em.o
 ! (INTEGRATION.md).  The Registry state stays where the Registry put it -- grid%u_2, grid%t_2,
-! grid%mu_2, grid%ph_2, moist(:,:,:,P_QV) ... -- and is mirrored in HBM; between history /
-! restart alarms the device copy is the live one and the host arrays are refreshed only when
-! med_after_solve_io is about to read them (restart_flag / Is_alarm_tstep, solve_em.F:360-374).
+! grid%mu_2, grid%ph_2, grid%tke_2, moist(:,:,:,P_QV), scalar(:,:,:,n) ... -- and is mirrored in HBM;
+! between history / restart alarms the device copy is the live one and the host arrays are refreshed
+! only when med_after_solve_io is about to read them: the reference's own test for "an alarm rings at
+! the end of this step", Is_alarm_tstep on grid%alarms(HISTORY_ALARM) / (restart_alarm)
+! (dyn_em/solve_em.F:360-374, frame/module_domain.F:2484).
 !
-! Not compiled in the development image (no Fortran compiler); kept deliberately small so that
-! everything that needs testing lives behind the C-ABI, where the parity tests exercise it.
+! What the device does not do is host-side physics: first_rk_step_part1 (radiation, surface layer,
+! PBL, cumulus; dyn_em/solve_em.F:807-871) is not called, so a namelist that selects any of them is
+! refused with wrf_error_fatal instead of running without their tendencies.  Diffusion (diff_opt,
+! km_opt), Kessler microphysics and the boundary fills run on the device.
+!
+! Not compiled in the development image (no Fortran compiler).  tests/abi_driver.c replays this file's
+! call sequence -- wrfgpu_create with a filled wrfgpu_config, the pointer tables of wrfgpu_upload,
+! wrfgpu_start_domain, wrfgpu_step, wrfgpu_download -- from C against the same library, so every entry
+! point is exercised the way this shim uses it.
 !
 SUBROUTINE solve_em ( grid , config_flags  &
 #include "dummy_new_args.inc"
                     )
-   USE module_domain,          ONLY : domain, get_ijk_from_grid, domain_get_current_time
-   USE module_configure,       ONLY : grid_config_rec_type, PARAM_FIRST_SCALAR, P_QV, P_QC, P_QR
+   USE module_state_description
+   USE module_domain,          ONLY : domain, get_ijk_from_grid, is_alarm_tstep
+   USE module_domain_type,     ONLY : history_alarm, restart_alarm
+   USE module_configure,       ONLY : grid_config_rec_type
    USE module_driver_constants
+#ifdef DM_PARALLEL
    USE module_dm,              ONLY : ntasks_x, ntasks_y, mytask, local_communicator
+#endif
    USE module_wrf_error
    USE module_wrfgpu
    USE, INTRINSIC :: iso_c_binding
    IMPLICIT NONE
+#ifdef DM_PARALLEL
+   INCLUDE 'mpif.h'
+#endif
 
    TYPE(domain) , TARGET          :: grid
    TYPE (grid_config_rec_type) , INTENT(IN) :: config_flags
 #include "dummy_new_decl.inc"
 
-   INTEGER, PARAMETER :: MAXF = 96
+   INTEGER, PARAMETER :: MAXF = 128
    TYPE(c_ptr), SAVE :: handle(max_domains) = c_null_ptr
    LOGICAL,     SAVE :: resident(max_domains) = .FALSE.
    TYPE(wrfgpu_dims)   :: d
    TYPE(wrfgpu_config) :: c
    CHARACTER(len=24, kind=c_char), TARGET, SAVE :: nm(MAXF)
    TYPE(c_ptr) :: names(MAXF), host(MAXF)
-   INTEGER :: nf, id, ierr, device
+   INTEGER :: nf, id, ierr, device, ndev, n, nsc, my_rank, nx_tasks, ny_tasks
    INTEGER :: ids, ide, jds, jde, kds, kde, ims, ime, jms, jme, kms, kme, ips, ipe, jps, jpe, kps, kpe
    CHARACTER(kind=c_char) :: ncclid(128)
+   CHARACTER(len=16) :: sname
    LOGICAL :: host_needs_state
+   REAL(c_float) :: cfl_v, cfl_h
 
    id = grid%id
    CALL get_ijk_from_grid ( grid , ids, ide, jds, jde, kds, kde, ims, ime, jms, jme, kms, kme, &
                                    ips, ipe, jps, jpe, kps, kpe )
+#ifdef DM_PARALLEL
+   my_rank = mytask; nx_tasks = ntasks_x; ny_tasks = ntasks_y
+#else
+   my_rank = 0; nx_tasks = 1; ny_tasks = 1
+#endif
+   nsc = num_scalar - PARAM_FIRST_SCALAR + 1        ! species of the scalar family (slot 1 is the Registry's dummy)
 
    IF ( .NOT. c_associated(handle(id)) ) THEN
+      ! host-side physics would need first_rk_step_part1/2 and their *_tendf arrays: refuse instead of dropping them
+      IF ( config_flags%ra_lw_physics /= 0 .OR. config_flags%ra_sw_physics /= 0 .OR. config_flags%sf_sfclay_physics /= 0 .OR. &
+           config_flags%sf_surface_physics /= 0 .OR. config_flags%bl_pbl_physics /= 0 .OR. config_flags%cu_physics /= 0 ) &
+         CALL wrf_error_fatal( 'solve_em (wrfgpu): radiation / surface / PBL / cumulus physics run on the host '// &
+                               '(first_rk_step_part1) and are not wired into this solver' )
       d = wrfgpu_dims(ids, ide, jds, jde, kds, kde, ims, ime, jms, jme, kms, kme, ips, ipe, jps, jpe, kps, kpe)
       c%periodic_x   = MERGE(1,0,config_flags%periodic_x);   c%periodic_y   = MERGE(1,0,config_flags%periodic_y)
       c%symmetric_xs = MERGE(1,0,config_flags%symmetric_xs); c%symmetric_xe = MERGE(1,0,config_flags%symmetric_xe)
@@ -69,8 +98,8 @@ SUBROUTINE solve_em ( grid , config_flags  &
       c%dampcoef = config_flags%dampcoef; c%zdamp = config_flags%zdamp; c%w_crit_cfl = config_flags%w_crit_cfl
       c%p_top = grid%p_top; c%cf1 = grid%cf1; c%cf2 = grid%cf2; c%cf3 = grid%cf3; c%cfn = grid%cfn; c%cfn1 = grid%cfn1
       c%khdif = config_flags%khdif; c%kvdif = config_flags%kvdif
-      c%num_moist = num_moist - PARAM_FIRST_SCALAR + 1;  c%num_scalar = 0
-      c%ntasks_x = ntasks_x; c%ntasks_y = ntasks_y; c%mytask = mytask
+      c%num_moist = num_moist - PARAM_FIRST_SCALAR + 1;  c%num_scalar = nsc
+      c%ntasks_x = nx_tasks; c%ntasks_y = ny_tasks; c%mytask = my_rank
       c%diff_6th_factor = config_flags%diff_6th_factor; c%diff_6th_thresh = config_flags%diff_6th_thresh
       c%diff_6th_slopeopt = config_flags%diff_6th_slopeopt
       c%moist_mix6_off = MERGE(1,0,config_flags%moist_mix6_off); c%scalar_mix6_off = MERGE(1,0,config_flags%scalar_mix6_off)
@@ -78,13 +107,16 @@ SUBROUTINE solve_em ( grid , config_flags  &
       c%isfflx = config_flags%isfflx; c%tke_drag_coefficient = config_flags%tke_drag_coefficient; c%tke_heat_flux = config_flags%tke_heat_flux
       c%mix_isotropic = config_flags%mix_isotropic; c%mix_upper_bound = config_flags%mix_upper_bound
       c%tke_adv_opt = config_flags%tke_adv_opt; c%tke_upper_bound = config_flags%tke_upper_bound
-      device = MOD(mytask, 8)                        ! one rank per GPU of the box
+      c%use_adaptive_time_step = MERGE(1,0,config_flags%use_adaptive_time_step)
+      ndev = wrfgpu_device_count()
+      IF ( ndev < 1 ) CALL wrf_error_fatal( 'solve_em (wrfgpu): no CUDA device on this node (there is no CPU fallback)' )
+      device = MOD(my_rank, ndev)                    ! one rank per GPU of the node, ranks placed node by node
       CALL wrfgpu_check( wrfgpu_create(d, c, device, handle(id)), 'wrfgpu_create' )
 #ifdef DM_PARALLEL
-      IF ( ntasks_x*ntasks_y > 1 ) THEN             ! NCCL bootstrap over the communicator RSL_LITE already has
-         IF ( mytask == 0 ) CALL wrfgpu_check( wrfgpu_comm_unique_id(ncclid), 'wrfgpu_comm_unique_id' )
-         CALL MPI_Bcast( ncclid, 128, MPI_CHARACTER, 0, local_communicator, ierr )
-         CALL wrfgpu_check( wrfgpu_comm_init(handle(id), ncclid, mytask, ntasks_x*ntasks_y), 'wrfgpu_comm_init' )
+      IF ( nx_tasks*ny_tasks > 1 ) THEN             ! bootstrap over the communicator RSL_LITE already has
+         IF ( my_rank == 0 ) CALL wrfgpu_check( wrfgpu_comm_unique_id(ncclid), 'wrfgpu_comm_unique_id' )
+         CALL MPI_Bcast( ncclid, 128, MPI_BYTE, 0, local_communicator, ierr )
+         CALL wrfgpu_check( wrfgpu_comm_init(handle(id), ncclid, my_rank, nx_tasks*ny_tasks), 'wrfgpu_comm_init' )
       END IF
 #endif
    END IF
@@ -102,11 +134,20 @@ SUBROUTINE solve_em ( grid , config_flags  &
       IF ( config_flags%mp_physics == 1 ) THEN
          CALL add('moist_qc', moist(:,:,:,P_QC)); CALL add('moist_qr', moist(:,:,:,P_QR))
       END IF
+      DO n = 1, nsc                                  ! scalar(:,:,:,PARAM_FIRST_SCALAR+n-1) <-> "scalar_n"
+         WRITE(sname,'(A,I0)') 'scalar_', n
+         CALL add(TRIM(sname), scalar(:,:,:,PARAM_FIRST_SCALAR+n-1))
+      END DO
+      IF ( config_flags%km_opt == 2 .AND. config_flags%diff_opt == 2 ) THEN   ! the prognostic tke of the 1.5-order closure
+         CALL add('tke_1',grid%tke_1); CALL add('tke_2',grid%tke_2)
+      END IF
       CALL add2('mu_1',grid%mu_1); CALL add2('mu_2',grid%mu_2); CALL add2('mub',grid%mub); CALL add2('ht',grid%ht)
       CALL add2('msftx',grid%msftx); CALL add2('msfty',grid%msfty); CALL add2('msfux',grid%msfux); CALL add2('msfuy',grid%msfuy)
       CALL add2('msfvx',grid%msfvx); CALL add2('msfvx_inv',grid%msfvx_inv); CALL add2('msfvy',grid%msfvy)
       CALL add2('f',grid%f); CALL add2('e',grid%e); CALL add2('sina',grid%sina); CALL add2('cosa',grid%cosa)
-      CALL add2('rainnc',grid%rainnc); CALL add2('rainncv',grid%rainncv)
+      IF ( config_flags%mp_physics == 1 ) THEN
+         CALL add2('rainnc',grid%rainnc); CALL add2('rainncv',grid%rainncv)
+      END IF
       CALL add1('znu',grid%znu); CALL add1('znw',grid%znw); CALL add1('fnm',grid%fnm); CALL add1('fnp',grid%fnp)
       CALL add1('rdnw',grid%rdnw); CALL add1('rdn',grid%rdn); CALL add1('dnw',grid%dnw); CALL add1('dn',grid%dn)
       CALL add1('c1h',grid%c1h); CALL add1('c2h',grid%c2h); CALL add1('c1f',grid%c1f); CALL add1('c2f',grid%c2f)
@@ -118,11 +159,30 @@ SUBROUTINE solve_em ( grid , config_flags  &
       resident(id) = .TRUE.
    END IF
 
+   ! ---- surface fluxes of the physical-space vertical diffusion: allocation-time zeros without a surface-layer scheme
+   !      (a scheme would make this shim refuse above), uploaded so that the device sees what grid% holds
+   IF ( config_flags%diff_opt == 2 .AND. config_flags%isfflx /= 0 ) THEN
+      nf = 0
+      CALL add2('ustm',grid%ustm); CALL add2('hfx',grid%hfx); CALL add2('qfx',grid%qfx)
+      CALL wrfgpu_check( wrfgpu_upload(handle(id), nf, names, host), 'wrfgpu_upload(ustm,hfx,qfx)' )
+   END IF
+
+   ! ---- the reference's bookkeeping of this call (solve_em.F:360-374)
+   host_needs_state = Is_alarm_tstep(grid%domain_clock, grid%alarms(restart_alarm)) .OR. &
+                      Is_alarm_tstep(grid%domain_clock, grid%alarms(HISTORY_ALARM))
+   grid%itimestep = grid%itimestep + 1
+   grid%dtbc = grid%dtbc + grid%dt
+
    ! ---- the step: dyn_em/solve_em.F:578-4848 on the device
    CALL wrfgpu_check( wrfgpu_step(handle(id), 1), 'wrfgpu_step' )
 
-   ! ---- device -> host only when the host is about to read the state (history/restart/diagnostics)
-   host_needs_state = grid%restart_flag_alarm_rings .OR. grid%history_alarm_rings   ! see INTEGRATION.md for the exact test
+   IF ( config_flags%use_adaptive_time_step ) THEN     ! solve_em.F:914-930: what adapt_timestep reads next call
+      CALL wrfgpu_check( wrfgpu_max_cfl(handle(id), cfl_v, cfl_h, 1), 'wrfgpu_max_cfl' )
+      grid%max_vert_cfl = MAX(grid%max_vert_cfl, cfl_v); grid%max_horiz_cfl = MAX(grid%max_horiz_cfl, cfl_h)
+      grid%max_cfl_val = MAX(grid%max_cfl_val, grid%max_vert_cfl, grid%max_horiz_cfl)
+   END IF
+
+   ! ---- device -> host only when the host is about to read the state (history / restart output after this step)
    IF ( host_needs_state ) THEN
       nf = 0
       CALL add('u_1',grid%u_1); CALL add('u_2',grid%u_2); CALL add('v_1',grid%v_1); CALL add('v_2',grid%v_2)
@@ -133,24 +193,34 @@ SUBROUTINE solve_em ( grid , config_flags  &
       IF ( config_flags%mp_physics == 1 ) THEN
          CALL add('moist_qc', moist(:,:,:,P_QC)); CALL add('moist_qr', moist(:,:,:,P_QR))
       END IF
-      CALL add2('mu_1',grid%mu_1); CALL add2('mu_2',grid%mu_2); CALL add2('rainnc',grid%rainnc); CALL add2('rainncv',grid%rainncv)
+      DO n = 1, nsc
+         WRITE(sname,'(A,I0)') 'scalar_', n
+         CALL add(TRIM(sname), scalar(:,:,:,PARAM_FIRST_SCALAR+n-1))
+      END DO
+      IF ( config_flags%km_opt == 2 .AND. config_flags%diff_opt == 2 ) THEN
+         CALL add('tke_1',grid%tke_1); CALL add('tke_2',grid%tke_2)
+      END IF
+      CALL add2('mu_1',grid%mu_1); CALL add2('mu_2',grid%mu_2)
+      IF ( config_flags%mp_physics == 1 ) THEN
+         CALL add2('rainnc',grid%rainnc); CALL add2('rainncv',grid%rainncv)
+      END IF
       CALL wrfgpu_check( wrfgpu_download(handle(id), nf, names, host), 'wrfgpu_download' )
    END IF
 
 CONTAINS
    SUBROUTINE add(name, a)
       CHARACTER(len=*), INTENT(IN) :: name
-      REAL, TARGET, INTENT(IN) :: a(:,:,:)          ! (ims:ime,kms:kme,jms:jme), contiguous
+      REAL, TARGET, CONTIGUOUS, INTENT(IN) :: a(:,:,:)          ! (ims:ime,kms:kme,jms:jme)
       nf = nf + 1; nm(nf) = TRIM(name)//c_null_char; names(nf) = c_loc(nm(nf)); host(nf) = c_loc(a)
    END SUBROUTINE
    SUBROUTINE add2(name, a)
       CHARACTER(len=*), INTENT(IN) :: name
-      REAL, TARGET, INTENT(IN) :: a(:,:)
+      REAL, TARGET, CONTIGUOUS, INTENT(IN) :: a(:,:)
       nf = nf + 1; nm(nf) = TRIM(name)//c_null_char; names(nf) = c_loc(nm(nf)); host(nf) = c_loc(a)
    END SUBROUTINE
    SUBROUTINE add1(name, a)
       CHARACTER(len=*), INTENT(IN) :: name
-      REAL, TARGET, INTENT(IN) :: a(:)
+      REAL, TARGET, CONTIGUOUS, INTENT(IN) :: a(:)
       nf = nf + 1; nm(nf) = TRIM(name)//c_null_char; names(nf) = c_loc(nm(nf)); host(nf) = c_loc(a)
    END SUBROUTINE
 END SUBROUTINE solve_em

@@ -25,7 +25,7 @@ PHASES = ("rk_step_prep", "rk_phys_bc_dry_1", "init_zero_tendency", "diffusion_p
 
 # every symbol include/wrfgpu.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = (
-    "wrfgpu_create", "wrfgpu_destroy", "wrfgpu_last_error", "wrfgpu_version", "wrfgpu_field_size", "wrfgpu_set_field",
+    "wrfgpu_create", "wrfgpu_destroy", "wrfgpu_last_error", "wrfgpu_version", "wrfgpu_device_count", "wrfgpu_field_size", "wrfgpu_set_field",
     "wrfgpu_get_field", "wrfgpu_upload", "wrfgpu_download", "wrfgpu_num_fields", "wrfgpu_field_name", "wrfgpu_field_devptr",
     "wrfgpu_step", "wrfgpu_solve_em", "wrfgpu_sync", "wrfgpu_set_stream", "wrfgpu_kernel_report", "wrfgpu_launch_count", "wrfgpu_max_cfl", "wrfgpu_phase_ms", "wrfgpu_set_physical_bc",
     "wrfgpu_compute_mesh", "wrfgpu_patch_dims", "wrfgpu_comm_unique_id", "wrfgpu_comm_init", "wrfgpu_comm_init_local", "wrfgpu_halo",
