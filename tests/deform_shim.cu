@@ -141,12 +141,13 @@ extern "C" int deform_shim_run(int stage, const wrfgpu_dims *dp, const wrfgpu_co
         for (int k = 1; k <= g.kde - 1; k++)
           for (int i = g.its; i <= g.ite; i++) diff2_s_point(g, s, rm, 0, p3("t_2"), tb, s.xkhv, s.xkhh, i, k, j, p3("t_tendf"));
     } else {
+      // the species go through the k-marching form the device launches (diff2_s_column); theta above through the point form,
+      // so both are pinned against the oracle here
       float *var = p3(names[nn - 2]), *tend = p3(names[nn - 1]);
       for (int j = g.jts; j <= g.jte; j++)
-        for (int k = 1; k <= g.kde - 1; k++)
-          for (int i = g.its; i <= g.ite; i++)
-            diff2_s_point(g, s, rm, which == 3 ? 2 : which, var, which == 1 ? qb : nullptr, which == 3 ? s.xkmv : s.xkhv, which == 3 ? s.xkmh : s.xkhh, i, k, j,
-                          tend, which == 3 ? 1 : 0);
+        for (int i = g.its; i <= g.ite; i++)
+          diff2_s_column(g, s, rm, which == 3 ? 2 : which, var, which == 1 ? qb : nullptr, which == 3 ? s.xkmv : s.xkhv, which == 3 ? s.xkmh : s.xkhh, i, j,
+                         tend, which == 3 ? 1 : 0);
     }
   }
   delete gp;

@@ -30,6 +30,13 @@ __global__ void k_diff2_s(const Geo g, Box b, D2In s, R4 r, int which, cfp var, 
   diff2_s_point(g, s, r, which, var, base, xkhv, xkhh, i, k, j, tendency, doing_tke);
 }
 
+// one thread per column: every H1 / H2 face flux once per level (diff2_s_column)
+__global__ void __launch_bounds__(128) k_diff2_s_march(const Geo g, Box b, D2In s, R4 r, int which, cfp var, const float *base, cfp xkhv, cfp xkhh,
+                                                         fp tendency, int doing_tke) {
+  TID2;
+  diff2_s_column(g, s, r, which, var, base, xkhv, xkhh, i, j, tendency, doing_tke);
+}
+
 bool diff2_is_identity(const wrfgpu_config &c) {
   return c.diff_opt == 2 && c.km_opt == 1 && c.khdif == 0.f && c.kvdif == 0.f && c.isfflx == 0 && c.tke_drag_coefficient == 0.f &&
          c.tke_heat_flux == 0.f;
@@ -67,11 +74,12 @@ void Solver::diffusion2_tendencies() {
   LAUNCH3(this, k_diff2_v, tile, s, rv, o("rv_tendf"));
   LAUNCH3(this, k_diff2_w, (Box{rm.i0, rm.i1, 2, q.kde - 1, rm.j0, rm.j1}), s, o("rw_tendf"));
   const float *tb = c.mix_full_fields ? nullptr : o("t_base"), *qb = c.mix_full_fields ? nullptr : o("qv_base");
-  LAUNCH3(this, k_diff2_s, tile, s, rm, 0, o("t_2"), tb, o("xkhv"), o("xkhh"), o("t_tendf"), 0);
+  const Box cols{q.its, q.ite, 1, 1, q.jts, q.jte};
+  LAUNCH2(this, k_diff2_s_march, cols, s, rm, 0, o("t_2"), tb, o("xkhv"), o("xkhh"), o("t_tendf"), 0);
   const std::string tke_name = tke_index() ? "scalar_" + std::to_string(tke_index()) : std::string("-");
   for (auto &sp : species) {
     const bool is_tke = sp.f == tke_name;   // tke mixes with K_m and doing_tke (:4302-4308, :2968-2982)
-    LAUNCH3(this, k_diff2_s, tile, s, rm, sp.f == "moist_qv" ? 1 : 2, o(sp.f), sp.f == "moist_qv" ? qb : (const float *)nullptr,
+    LAUNCH2(this, k_diff2_s_march, cols, s, rm, sp.f == "moist_qv" ? 1 : 2, o(sp.f), sp.f == "moist_qv" ? qb : (const float *)nullptr,
             is_tke ? o("xkmv") : o("xkhv"), is_tke ? o("xkmh") : o("xkhh"), o(sp.t), is_tke ? 1 : 0);
   }
 }

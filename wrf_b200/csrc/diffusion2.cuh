@@ -205,71 +205,102 @@ WG_HD void diff2_w_point(const Geo &g, const D2In &s, int i, int k, int j, fp te
 // which: 0 theta (t_2; vertical part on t_2 - t_base unless mix_full_fields), 1 qv (vertical part on qv - qv_base unless
 // mix_full_fields), 2 any other species.  base: origin-shifted 1-D array or null.  thread box: the tile's mass points, k in 1..ktf
 // doing_tke: the tke species (K = xkmv / xkmh passed as xkhv / xkhh): each of the two terms is added twice (:4893-4903, :3985-3995)
+//
+// The pieces below are shared by the reference form (diff2_s_point: everything of a point evaluated on the spot) and by the
+// k-marching kernel of diffusion2.cu (each face flux evaluated once per column and level and carried in registers).
+// var averaged to the w-level kk of the face between columns (ia,ja) and (ib,jb); B is the "minus" neighbour
+WG_HD float d2s_havg(const Geo &g, const D2In &s, cfp var, int ia, int ja, int ib, int jb, int kk) {
+  const int ktf = g.kde - 1, kte = g.kde;
+  if (kk == 1)
+    return 0.5f * (g.cf1 * A3(var, ia, 1, ja) + g.cf2 * A3(var, ia, 2, ja) + g.cf3 * A3(var, ia, 3, ja) + g.cf1 * A3(var, ib, 1, jb) +
+                   g.cf2 * A3(var, ib, 2, jb) + g.cf3 * A3(var, ib, 3, jb));
+  if (kk == ktf + 1)
+    return 0.5f * (A3(var, ia, kte - 1, ja) + (A3(var, ia, kte - 1, ja) - A3(var, ia, kte - 2, ja)) * 0.5f * g.dnw[kte - 1] / s.dn[kte - 1] +
+                   A3(var, ib, kte - 1, jb) + (A3(var, ib, kte - 1, jb) - A3(var, ib, kte - 2, jb)) * 0.5f * g.dnw[kte - 1] / s.dn[kte - 1]);
+  return 0.5f * (g.fnm[kk] * (A3(var, ib, kk, jb) + A3(var, ia, kk, ja)) + g.fnp[kk] * (A3(var, ib, kk - 1, jb) + A3(var, ia, kk - 1, ja)));
+}
+// x-flux at the u-point ii of level kk; hlo, hhi = d2s_havg(ii, j, ii-1, j, kk / kk+1)
+WG_HD float d2s_H1(const Geo &g, const D2In &s, cfp var, cfp xkhh, int ii, int kk, int j, float hlo, float hhi) {
+  cfp rho = s.rho, rdzw = s.rdzw, zx = s.zx;
+  const float xkxavg = 0.5f * (A3(xkhh, ii - 1, kk, j) + A3(xkhh, ii, kk, j)) * 0.5f * (A3(rho, ii - 1, kk, j) + A3(rho, ii, kk, j));
+  const float tmpzx = 0.5f * (A3(zx, ii, kk, j) + A3(zx, ii, kk + 1, j));
+  const float rdzu = 2.f / (1.f / A3(rdzw, ii, kk, j) + 1.f / A3(rdzw, ii - 1, kk, j));
+  return -A2(g.msfux, ii, j) * xkxavg * (g.rdx * (A3(var, ii, kk, j) - A3(var, ii - 1, kk, j)) - tmpzx * (hhi - hlo) * rdzu);
+}
+// y-flux at the v-point jj of level kk; hlo, hhi = d2s_havg(i, jj, i, jj-1, kk / kk+1)
+WG_HD float d2s_H2(const Geo &g, const D2In &s, cfp var, cfp xkhh, int i, int kk, int jj, float hlo, float hhi) {
+  cfp rho = s.rho, rdzw = s.rdzw, zy = s.zy;
+  const float xkxavg = 0.5f * (A3(xkhh, i, kk, jj - 1) + A3(xkhh, i, kk, jj)) * 0.5f * (A3(rho, i, kk, jj - 1) + A3(rho, i, kk, jj));
+  const float tmpzy = 0.5f * (A3(zy, i, kk, jj) + A3(zy, i, kk + 1, jj));
+  const float rdzv = 2.f / (1.f / A3(rdzw, i, kk, jj) + 1.f / A3(rdzw, i, kk, jj - 1));
+  return -A2(g.msfvy, i, jj) * xkxavg * (g.rdy * (A3(var, i, kk, jj) - A3(var, i, kk, jj - 1)) - tmpzy * (hhi - hlo) * rdzv);
+}
+// vertical flux at the w-level kk of the column
+WG_HD float d2s_H3(const Geo &g, const D2In &s, cfp var, const float *base, cfp xkhv, int i, int kk, int j) {
+  if (kk == 1 || kk == g.kde) return 0.f;
+  cfp rho = s.rho, rdz = s.rdz;
+  float xkxavg = g.fnm[kk] * A3(xkhv, i, kk, j) + g.fnp[kk] * A3(xkhv, i, kk - 1, j);
+  xkxavg = xkxavg * (g.fnm[kk] * A3(rho, i, kk, j) + g.fnp[kk] * A3(rho, i, kk - 1, j));
+  const float va = base ? A3(var, i, kk, j) - base[kk] : A3(var, i, kk, j);
+  const float vb = base ? A3(var, i, kk - 1, j) - base[kk - 1] : A3(var, i, kk - 1, j);
+  return -xkxavg * (va - vb) * A3(rdz, i, kk, j);
+}
+// the surface heat / moisture flux of level 1 added to t
+WG_HD float d2s_surface_flux(const Geo &g, const D2In &s, int which, int i, int j, float t) {
+  cfp rho = s.rho;
+  if (which == 0) {
+    const float q = s.qv ? A3(s.qv, i, 1, j) : 0.f;
+    const float cpm = WG_CP * (1.f + 0.8f * q);
+    const float theta = (s.use_theta_m == 1 && s.qv) ? (A3(s.t, i, 1, j) + WG_T0) / (1.f + WG_RV / WG_RD * q) : A3(s.t, i, 1, j) + WG_T0;
+    if (s.isfflx == 0 || s.isfflx == 2) {
+      const float heat_flux = s.heat_flux;
+      A2(s.hfx_out, i, j) = heat_flux * cpm * A3(rho, i, 1, j);
+      if (s.use_theta_m == 1)
+        t = t - WG_G * heat_flux * (1.f + WG_RVOVRD * q) * A3(rho, i, 1, j) / g.dnw[1] - WG_G * 1.61f * theta * A2(s.qfx, i, j) / g.dnw[1];
+      else
+        t = t - WG_G * heat_flux * A3(rho, i, 1, j) / g.dnw[1];
+    } else {
+      const float heat_flux = A2(s.hfx_in, i, j) / cpm;
+      if (s.use_theta_m == 1) t = t - WG_G * heat_flux * (1.f + WG_RVOVRD * q) / g.dnw[1] - WG_G * 1.61f * theta * A2(s.qfx, i, j) / g.dnw[1];
+      else t = t - WG_G * heat_flux / g.dnw[1];
+    }
+  } else if (s.isfflx != 0) {
+    t = t - WG_G * A2(s.qfx, i, j) / g.dnw[1];
+  }
+  return t;
+}
+// the horizontal term of a point from its face fluxes: h1w/h1e = H1(i / i+1, k), h2s/h2n = H2(j / j+1, k), a1lo/a1hi =
+// H1avg(k / k+1), a2lo/a2hi = H2avg(k / k+1)
+WG_HD float d2s_horizontal(const Geo &g, const D2In &s, int i, int k, int j, float h1w, float h1e, float h2s, float h2n, float a1lo,
+                           float a1hi, float a2lo, float a2hi) {
+  cfp rdzw = s.rdzw, zx = s.zx, zy = s.zy;
+  const float zx_at_m = 0.25f * (A3(zx, i, k, j) + A3(zx, i + 1, k, j) + A3(zx, i, k + 1, j) + A3(zx, i + 1, k + 1, j));
+  const float zy_at_m = 0.25f * (A3(zy, i, k, j) + A3(zy, i, k, j + 1) + A3(zy, i, k + 1, j) + A3(zy, i, k + 1, j + 1));
+  const float mrdx = A2(g.msftx, i, j) * g.rdx;
+  const float mrdy = A2(g.msfty, i, j) * g.rdy;
+  return WG_G / (g.dnw[k] * A3(rdzw, i, k, j)) *
+         (mrdx * (h1e - h1w) + mrdy * (h2n - h2s) - A2(g.msftx, i, j) * zx_at_m * (a1hi - a1lo) * A3(rdzw, i, k, j) -
+          A2(g.msfty, i, j) * zy_at_m * (a2hi - a2lo) * A3(rdzw, i, k, j));
+}
 WG_HD void diff2_s_point(const Geo &g, const D2In &s, const R4 &r, int which, cfp var, const float *base, cfp xkhv, cfp xkhh, int i, int k, int j,
                          fp tendency, int doing_tke = 0) {
-  const int ktf = g.kde - 1, kte = g.kde;
+  const int ktf = g.kde - 1;
   const bool in = in_r4(r, i, j);
   const bool flux = k == 1 && which != 2 && i <= min(g.ite, g.ide - 1) && j <= min(g.jte, g.jde - 1);
   if (!in && !flux) return;
-  cfp rho = s.rho, rdz = s.rdz, rdzw = s.rdzw, zx = s.zx, zy = s.zy;
   float t = A3(tendency, i, k, j);
   if (in) {
-    auto vm = [&](int kk) -> float { return base ? A3(var, i, kk, j) - base[kk] : A3(var, i, kk, j); };
-    auto H3 = [&](int kk) -> float {
-      if (kk == 1 || kk == ktf + 1) return 0.f;
-      float xkxavg = g.fnm[kk] * A3(xkhv, i, kk, j) + g.fnp[kk] * A3(xkhv, i, kk - 1, j);
-      xkxavg = xkxavg * (g.fnm[kk] * A3(rho, i, kk, j) + g.fnp[kk] * A3(rho, i, kk - 1, j));
-      return -xkxavg * (vm(kk) - vm(kk - 1)) * A3(rdz, i, kk, j);
-    };
     const float t0 = t;
-    t = t + WG_G * (H3(k + 1) - H3(k)) / g.dnw[k];
+    t = t + WG_G * (d2s_H3(g, s, var, base, xkhv, i, k + 1, j) - d2s_H3(g, s, var, base, xkhv, i, k, j)) / g.dnw[k];
     if (doing_tke) t = t0 + 2.f * (t - t0);
   }
-  if (flux) {
-    if (which == 0) {
-      const float q = s.qv ? A3(s.qv, i, 1, j) : 0.f;
-      const float cpm = WG_CP * (1.f + 0.8f * q);
-      const float theta = (s.use_theta_m == 1 && s.qv) ? (A3(s.t, i, 1, j) + WG_T0) / (1.f + WG_RV / WG_RD * q) : A3(s.t, i, 1, j) + WG_T0;
-      if (s.isfflx == 0 || s.isfflx == 2) {
-        const float heat_flux = s.heat_flux;
-        A2(s.hfx_out, i, j) = heat_flux * cpm * A3(rho, i, 1, j);
-        if (s.use_theta_m == 1)
-          t = t - WG_G * heat_flux * (1.f + WG_RVOVRD * q) * A3(rho, i, 1, j) / g.dnw[1] - WG_G * 1.61f * theta * A2(s.qfx, i, j) / g.dnw[1];
-        else
-          t = t - WG_G * heat_flux * A3(rho, i, 1, j) / g.dnw[1];
-      } else {
-        const float heat_flux = A2(s.hfx_in, i, j) / cpm;
-        if (s.use_theta_m == 1) t = t - WG_G * heat_flux * (1.f + WG_RVOVRD * q) / g.dnw[1] - WG_G * 1.61f * theta * A2(s.qfx, i, j) / g.dnw[1];
-        else t = t - WG_G * heat_flux / g.dnw[1];
-      }
-    } else if (s.isfflx != 0) {
-      t = t - WG_G * A2(s.qfx, i, j) / g.dnw[1];
-    }
-  }
+  if (flux) t = d2s_surface_flux(g, s, which, i, j, t);
   if (in) {
-    // var averaged to the w-level kk of the face between columns (ia,ja) and (ib,jb); B is the "minus" neighbour
-    auto havg = [&](int ia, int ja, int ib, int jb, int kk) -> float {
-      if (kk == 1)
-        return 0.5f * (g.cf1 * A3(var, ia, 1, ja) + g.cf2 * A3(var, ia, 2, ja) + g.cf3 * A3(var, ia, 3, ja) + g.cf1 * A3(var, ib, 1, jb) +
-                       g.cf2 * A3(var, ib, 2, jb) + g.cf3 * A3(var, ib, 3, jb));
-      if (kk == ktf + 1)
-        return 0.5f * (A3(var, ia, kte - 1, ja) + (A3(var, ia, kte - 1, ja) - A3(var, ia, kte - 2, ja)) * 0.5f * g.dnw[kte - 1] / s.dn[kte - 1] +
-                       A3(var, ib, kte - 1, jb) + (A3(var, ib, kte - 1, jb) - A3(var, ib, kte - 2, jb)) * 0.5f * g.dnw[kte - 1] / s.dn[kte - 1]);
-      return 0.5f * (g.fnm[kk] * (A3(var, ib, kk, jb) + A3(var, ia, kk, ja)) + g.fnp[kk] * (A3(var, ib, kk - 1, jb) + A3(var, ia, kk - 1, ja)));
+    auto H1 = [&](int ii, int kk) -> float {
+      return d2s_H1(g, s, var, xkhh, ii, kk, j, d2s_havg(g, s, var, ii, j, ii - 1, j, kk), d2s_havg(g, s, var, ii, j, ii - 1, j, kk + 1));
     };
-    auto H1 = [&](int ii, int kk) -> float {   // x-flux at the u-point ii
-      const float xkxavg = 0.5f * (A3(xkhh, ii - 1, kk, j) + A3(xkhh, ii, kk, j)) * 0.5f * (A3(rho, ii - 1, kk, j) + A3(rho, ii, kk, j));
-      const float tmpzx = 0.5f * (A3(zx, ii, kk, j) + A3(zx, ii, kk + 1, j));
-      const float rdzu = 2.f / (1.f / A3(rdzw, ii, kk, j) + 1.f / A3(rdzw, ii - 1, kk, j));
-      return -A2(g.msfux, ii, j) * xkxavg *
-             (g.rdx * (A3(var, ii, kk, j) - A3(var, ii - 1, kk, j)) - tmpzx * (havg(ii, j, ii - 1, j, kk + 1) - havg(ii, j, ii - 1, j, kk)) * rdzu);
-    };
-    auto H2 = [&](int jj, int kk) -> float {   // y-flux at the v-point jj
-      const float xkxavg = 0.5f * (A3(xkhh, i, kk, jj - 1) + A3(xkhh, i, kk, jj)) * 0.5f * (A3(rho, i, kk, jj - 1) + A3(rho, i, kk, jj));
-      const float tmpzy = 0.5f * (A3(zy, i, kk, jj) + A3(zy, i, kk + 1, jj));
-      const float rdzv = 2.f / (1.f / A3(rdzw, i, kk, jj) + 1.f / A3(rdzw, i, kk, jj - 1));
-      return -A2(g.msfvy, i, jj) * xkxavg *
-             (g.rdy * (A3(var, i, kk, jj) - A3(var, i, kk, jj - 1)) - tmpzy * (havg(i, jj, i, jj - 1, kk + 1) - havg(i, jj, i, jj - 1, kk)) * rdzv);
+    auto H2 = [&](int jj, int kk) -> float {
+      return d2s_H2(g, s, var, xkhh, i, kk, jj, d2s_havg(g, s, var, i, jj, i, jj - 1, kk), d2s_havg(g, s, var, i, jj, i, jj - 1, kk + 1));
     };
     auto H1avg = [&](int kk) -> float {
       if (kk == 1 || kk == ktf + 1) return 0.f;
@@ -279,18 +310,70 @@ WG_HD void diff2_s_point(const Geo &g, const D2In &s, const R4 &r, int which, cf
       if (kk == 1 || kk == ktf + 1) return 0.f;
       return 0.5f * (g.fnm[kk] * (H2(j + 1, kk) + H2(j, kk)) + g.fnp[kk] * (H2(j + 1, kk - 1) + H2(j, kk - 1)));
     };
-    const float zx_at_m = 0.25f * (A3(zx, i, k, j) + A3(zx, i + 1, k, j) + A3(zx, i, k + 1, j) + A3(zx, i + 1, k + 1, j));
-    const float zy_at_m = 0.25f * (A3(zy, i, k, j) + A3(zy, i, k, j + 1) + A3(zy, i, k + 1, j) + A3(zy, i, k + 1, j + 1));
-    const float mrdx = A2(g.msftx, i, j) * g.rdx;
-    const float mrdy = A2(g.msfty, i, j) * g.rdy;
     const float t0 = t;
-    t = t + WG_G / (g.dnw[k] * A3(rdzw, i, k, j)) *
-                (mrdx * (H1(i + 1, k) - H1(i, k)) + mrdy * (H2(j + 1, k) - H2(j, k)) -
-                 A2(g.msftx, i, j) * zx_at_m * (H1avg(k + 1) - H1avg(k)) * A3(rdzw, i, k, j) -
-                 A2(g.msfty, i, j) * zy_at_m * (H2avg(k + 1) - H2avg(k)) * A3(rdzw, i, k, j));
+    t = t + d2s_horizontal(g, s, i, k, j, H1(i, k), H1(i + 1, k), H2(j, k), H2(j + 1, k), H1avg(k), H1avg(k + 1), H2avg(k), H2avg(k + 1));
     if (doing_tke) t = t0 + 2.f * (t - t0);
   }
   A3(tendency, i, k, j) = t;
+}
+
+// the same sums with a thread per column marching k: H1 / H2 of the level above are evaluated once (four per point and
+// level instead of twelve) and the level's and the one below roll in registers, like the w-level averages they difference
+WG_HD void diff2_s_column(const Geo &g, const D2In &s, const R4 &r, int which, cfp var, const float *base, cfp xkhv, cfp xkhh, int i, int j,
+                          fp tendency, int doing_tke) {
+  const int ktf = g.kde - 1;
+  const bool in = in_r4(r, i, j);
+  const bool flux = which != 2 && i <= min(g.ite, g.ide - 1) && j <= min(g.jte, g.jde - 1);
+  if (!in) {
+    if (flux) A3(tendency, i, 1, j) = d2s_surface_flux(g, s, which, i, j, A3(tendency, i, 1, j));
+    return;
+  }
+  // w-level averages of the four faces at levels k (lo) and k+1 (hi), and the face fluxes at k-1 (m), k (c), k+1 (p)
+  float aw_lo = d2s_havg(g, s, var, i, j, i - 1, j, 1), ae_lo = d2s_havg(g, s, var, i + 1, j, i, j, 1);
+  float as_lo = d2s_havg(g, s, var, i, j, i, j - 1, 1), an_lo = d2s_havg(g, s, var, i, j + 1, i, j, 1);
+  float aw_hi = d2s_havg(g, s, var, i, j, i - 1, j, 2), ae_hi = d2s_havg(g, s, var, i + 1, j, i, j, 2);
+  float as_hi = d2s_havg(g, s, var, i, j, i, j - 1, 2), an_hi = d2s_havg(g, s, var, i, j + 1, i, j, 2);
+  float h1w_m = 0.f, h1e_m = 0.f, h2s_m = 0.f, h2n_m = 0.f;
+  float h1w_c = d2s_H1(g, s, var, xkhh, i, 1, j, aw_lo, aw_hi), h1e_c = d2s_H1(g, s, var, xkhh, i + 1, 1, j, ae_lo, ae_hi);
+  float h2s_c = d2s_H2(g, s, var, xkhh, i, 1, j, as_lo, as_hi), h2n_c = d2s_H2(g, s, var, xkhh, i, 1, j + 1, an_lo, an_hi);
+  float h3_lo = 0.f;   // H3(1) = 0
+  for (int k = 1; k <= ktf; k++) {
+    // level k+1 of the face fluxes (needed by H1avg(k+1) for k+1 <= ktf)
+    float h1w_p = 0.f, h1e_p = 0.f, h2s_p = 0.f, h2n_p = 0.f;
+    if (k + 1 <= ktf) {
+      aw_lo = aw_hi; ae_lo = ae_hi; as_lo = as_hi; an_lo = an_hi;
+      aw_hi = d2s_havg(g, s, var, i, j, i - 1, j, k + 2); ae_hi = d2s_havg(g, s, var, i + 1, j, i, j, k + 2);
+      as_hi = d2s_havg(g, s, var, i, j, i, j - 1, k + 2); an_hi = d2s_havg(g, s, var, i, j + 1, i, j, k + 2);
+      h1w_p = d2s_H1(g, s, var, xkhh, i, k + 1, j, aw_lo, aw_hi); h1e_p = d2s_H1(g, s, var, xkhh, i + 1, k + 1, j, ae_lo, ae_hi);
+      h2s_p = d2s_H2(g, s, var, xkhh, i, k + 1, j, as_lo, as_hi); h2n_p = d2s_H2(g, s, var, xkhh, i, k + 1, j + 1, an_lo, an_hi);
+    }
+    float t = A3(tendency, i, k, j);
+    {
+      const float h3_hi = d2s_H3(g, s, var, base, xkhv, i, k + 1, j);
+      const float t0 = t;
+      t = t + WG_G * (h3_hi - h3_lo) / g.dnw[k];
+      if (doing_tke) t = t0 + 2.f * (t - t0);
+      h3_lo = h3_hi;
+    }
+    if (k == 1 && flux) t = d2s_surface_flux(g, s, which, i, j, t);
+    {
+      float a1lo = 0.f, a1hi = 0.f, a2lo = 0.f, a2hi = 0.f;
+      if (k != 1) {
+        a1lo = 0.5f * (g.fnm[k] * (h1e_c + h1w_c) + g.fnp[k] * (h1e_m + h1w_m));
+        a2lo = 0.5f * (g.fnm[k] * (h2n_c + h2s_c) + g.fnp[k] * (h2n_m + h2s_m));
+      }
+      if (k + 1 != ktf + 1) {
+        a1hi = 0.5f * (g.fnm[k + 1] * (h1e_p + h1w_p) + g.fnp[k + 1] * (h1e_c + h1w_c));
+        a2hi = 0.5f * (g.fnm[k + 1] * (h2n_p + h2s_p) + g.fnp[k + 1] * (h2n_c + h2s_c));
+      }
+      const float t0 = t;
+      t = t + d2s_horizontal(g, s, i, k, j, h1w_c, h1e_c, h2s_c, h2n_c, a1lo, a1hi, a2lo, a2hi);
+      if (doing_tke) t = t0 + 2.f * (t - t0);
+    }
+    A3(tendency, i, k, j) = t;
+    h1w_m = h1w_c; h1e_m = h1e_c; h2s_m = h2s_c; h2n_m = h2n_c;
+    h1w_c = h1w_p; h1e_c = h1e_p; h2s_c = h2s_p; h2n_c = h2n_p;
+  }
 }
 
 // phy_prep's density (module_big_step_utilities_em.F:4856) on the tile's mass points, k in 1..ktf
