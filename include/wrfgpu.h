@@ -46,7 +46,8 @@ typedef struct wrfgpu_config {
   int periodic_x, periodic_y;
   int symmetric_xs, symmetric_xe, symmetric_ys, symmetric_ye;
   int open_xs, open_xe, open_ys, open_ye;
-  int specified, nested, polar;          /* must be 0: out of scope, rejected */
+  int specified, nested, polar;          /* must be 0: specified / nested lateral boundaries are not built,
+                                            polar filters are out of scope; rejected at create */
   /* &dynamics */
   int rk_ord;                            /* 3 (2 also accepted) */
   int time_step_sound;                   /* 0 => derived, solve_em.F:446-462 */
@@ -66,8 +67,8 @@ typedef struct wrfgpu_config {
   int phi_adv_z;                         /* 1/2 */
   int zadvect_implicit;                  /* > 0: IEVA on the last RK substep (module_ieva_em.F) */
   int diff_opt, km_opt;                  /* diff_opt 0, 1 (coordinate surfaces), 2 (physical space);
-                                            km_opt 1 (constant K), 3 (3-D Smagorinsky) or 4 (2-D Smagorinsky)
-                                             */
+                                            km_opt 1 (constant K), 2 (1.5-order TKE; needs diff_opt 2), 3 (3-D
+                                            Smagorinsky) or 4 (2-D Smagorinsky) */
   int diff_6th_opt;                      /* 0, 1 or 2 (sixth_order_diffusion; 2 = no up-gradient fluxes) */
   int mp_physics;                        /* 0 = none(passive qv), 1 = Kessler */
   int time_step;                         /* integer namelist time_step; only its
@@ -94,7 +95,7 @@ typedef struct wrfgpu_config {
   int moist_mix6_off, scalar_mix6_off;   /* 1 = no 6th-order filter on that family */
   /* eddy-viscosity closures (Registry.EM_COMMON rconfig c_s, c_k, mix_full_fields) */
   float c_s;                             /* Smagorinsky coefficient, 0.25 (km_opt = 3, 4) */
-  float c_k;                             /* TKE coefficient, 0.15 (km_opt = 2; not on the device yet) */
+  float c_k;                             /* TKE coefficient, 0.15 (km_opt = 2) */
   int mix_full_fields;                   /* 0/1: vertical shear of the full u, v in defor13/23 instead of u - u_base */
   /* surface fluxes of the physical-space vertical diffusion (diff_opt = 2; module_diffusion_em.F:4160-4353) */
   int isfflx;                            /* 0: drag and heat flux from the two constants below; 1, 2: from ustm / hfx / qfx */

@@ -23,12 +23,12 @@ for w in $what; do
       echo "sanitize rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/${tag}_sanitize.log | tail -3 ;;
     launches)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv \
-        python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_launches.log 2>&1
+        python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-second-workload > gpurun_out/${tag}_launches.log 2>&1
       tail -1 gpurun_out/${tag}_launches.log | cut -c1-200 ;;
     full)
       # skip start_domain and the warm-up step, then one whole step of the main kernels
       timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"$MAIN" --launch-skip ${SKIP:-70} --launch-count ${COUNT:-70} \
-        -o /tmp/${tag}_full -f python bench.py --steps 1 --warmup 1 --nx 500 --ny 500 --no-cpu-baseline > gpurun_out/${tag}_full.log 2>&1
+        -o /tmp/${tag}_full -f python bench.py --steps 1 --warmup 1 --nx 500 --ny 500 --no-cpu-baseline --no-second-workload > gpurun_out/${tag}_full.log 2>&1
       tail -1 gpurun_out/${tag}_full.log | cut -c1-200
       ncu -i /tmp/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_raw.csv 2>/dev/null
       for kn in ${SRC_KERNELS:-k_mom_u_fast k_advance_uv k_advance_w k_advance_mu_t k_advect_scalar_fast k_pd_tend_fast}; do

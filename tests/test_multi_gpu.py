@@ -132,3 +132,12 @@ def test_exchange_overlapped_with_the_interior_of_its_producer(name, monkeypatch
     monkeypatch.setenv("WRFGPU_OVERLAP", "1")
     bad, sent = _run(parity.small_cases()[name], 2, 2, nsteps=3)
     assert not bad, bad[:8]
+
+
+def test_n_ranks_equal_one_rank_at_a_size_where_every_kernel_runs_its_interior_path():
+    """the BIT4BIT criterion at 500 x 500 x 40 (the parity cases are at most 62 points wide: there the TMA-staged tendency
+    kernel, the k-marching kernels and the halo transport only ever see a handful of tiles)"""
+    case = wrf_b200.make_case("synthetic", nx=501, ny=501, nz=41, bubble_lattice=100000.0, num_scalar=1)
+    bad, sent = _run(case, 2, 2, nsteps=2)
+    assert not bad, bad[:8]
+    assert all(b > 1.0e7 for b in sent)

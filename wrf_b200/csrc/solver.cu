@@ -38,10 +38,10 @@ static void check_config(const wrfgpu_config &c) {
   if (!c.non_hydrostatic) bad("hydrostatic option");
   if (c.damp_opt != 0 && c.damp_opt != 2 && c.damp_opt != 3) bad("damp_opt must be 0, 2 or 3");
   if (c.zadvect_implicit < 0) bad("zadvect_implicit must be 0 or positive (IEVA on the last RK substep)");
-  // diffusion: on coordinate surfaces (diff_opt 1) with constant K (km_opt 1) or the 2-D Smagorinsky
-  // closure (km_opt 4, deform.cu) is on the device; with km_opt = 1 and khdif = kvdif = 0 the physical-space form
-  // (diff_opt 2: shipped em_hill2d_x) adds exact zeros to zero-initialised tendencies, i.e. it is the identity, and
-  // is accepted as such.  The rest (physical-space diffusion with non-zero K, TKE / 3-D Smagorinsky) is a 'next' row.
+  // diffusion: on coordinate surfaces (diff_opt 1) and in physical space (diff_opt 2), each with constant K
+  // (km_opt 1), the 2-D or 3-D Smagorinsky closure (km_opt 4, 3; deform.cu) and, with diff_opt 2, the 1.5-order TKE
+  // closure (km_opt 2) -- every combination the shipped ideal namelists select.  What check_config still refuses is
+  // listed in DESIGN.md section 2.
   if (c.diff_6th_opt < 0 || c.diff_6th_opt > 2) bad("diff_6th_opt must be 0, 1 or 2");
   if (c.diff_opt != 0) {
     if (c.km_opt < 1 || c.km_opt > 4) bad("km_opt must be 1 (constant K), 2 (TKE), 3 (3-D Smagorinsky) or 4 (2-D Smagorinsky)");
