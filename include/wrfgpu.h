@@ -46,8 +46,9 @@ typedef struct wrfgpu_config {
   int periodic_x, periodic_y;
   int symmetric_xs, symmetric_xe, symmetric_ys, symmetric_ye;
   int open_xs, open_xe, open_ys, open_ye;
-  int specified, nested, polar;          /* must be 0: specified / nested lateral boundaries are not built,
-                                            polar filters are out of scope; rejected at create */
+  int specified, nested, polar;          /* specified / nested: the lateral boundary zone is driven by the boundary arrays
+                                            (the zone widths are at the end of this struct); polar must be 0
+                                            (polar filters are out of scope; rejected at create) */
   /* &dynamics */
   int rk_ord;                            /* 3 (2 also accepted) */
   int time_step_sound;                   /* 0 => derived, solve_em.F:446-462 */
@@ -110,6 +111,11 @@ typedef struct wrfgpu_config {
   /* w_damp's CFL maxima (module_big_step_utilities_em.F:2503-2711) are folded into grid%max_vert_cfl /
    * max_horiz_cfl only with the adaptive time step (solve_em.F:914-930); 1 = compute them on the device */
   int use_adaptive_time_step;
+  /* specified / nested lateral boundaries (&bdy_control; share/module_bc.F:1122-2693, dyn_em/module_bc_em.F:17-700) */
+  int spec_bdy_width;                    /* 5: rows held by the boundary arrays */
+  int spec_zone;                         /* 1: outer rows set from the boundary file */
+  int relax_zone;                        /* 4: rows relaxed towards it (spec_zone + relax_zone = spec_bdy_width) */
+  int have_bcs_moist, have_bcs_scalar;   /* 0/1: every moist species / scalar has boundary arrays (always so when nested) */
 } wrfgpu_config;
 
 typedef struct wrfgpu_solver wrfgpu_solver;   /* opaque */

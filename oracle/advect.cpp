@@ -101,8 +101,8 @@ void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
   Row fq0(its, ite, kte), fq1(its, ite, kte), fqx(its, ite, kte), vflux(its, ite, kte);
 
   int i_start = its, i_end = ite;
-  if (x.c.open_xs) i_start = std::max(ids + 1, its);
-  if (x.c.open_xe) i_end = std::min(ide - 1, ite);
+  if (x.oxs()) i_start = std::max(ids + 1, its);
+  if (x.oxe()) i_end = std::min(ide - 1, ite);
   if (x.c.periodic_x) { i_start = its; i_end = ite; }
   int j_start = jts, j_end = std::min(jte, jde - 1);
   int j_start_f = j_start, j_end_f = j_end + 1;
@@ -161,6 +161,7 @@ void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
         int i = ids + 1;
         for (int k = kts; k <= ktf; k++) {
           float ub = u(i - 1, k, j);
+          if (x.spec && u(i, k, j) < 0.f) ub = u(i, k, j);   // specified uses upstream normal wind at boundaries (:698)
           fqx(i, k) = 0.25f * (ru(i, k, j) + ru(i - 1, k, j)) * (u(i, k, j) + ub);
         }
       }
@@ -175,6 +176,7 @@ void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
         int i = ide;
         for (int k = kts; k <= ktf; k++) {
           float ub = u(i, k, j);
+          if (x.spec && u(i - 1, k, j) > 0.f) ub = u(i - 1, k, j);   // :720
           fqx(i, k) = 0.25f * (ru(i, k, j) + ru(i - 1, k, j)) * (u(i - 1, k, j) + ub);
         }
       }
@@ -240,8 +242,8 @@ void advect_u(const Cx &x, A3 u, A3 u_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
 
   // vertical advection (:1336-1498); note the reference tests open_ys/open_ye here
   i_start = its; i_end = ite; j_start = jts; j_end = std::min(jte, jde - 1);
-  if (x.c.open_ys) i_start = std::max(ids + 1, its);
-  if (x.c.open_ye) i_end = std::min(ide - 1, ite);
+  if (x.oys()) i_start = std::max(ids + 1, its);
+  if (x.oye()) i_end = std::min(ide - 1, ite);
   if (x.c.periodic_x) { i_start = its; i_end = ite; }
   for (int i = i_start; i <= i_end; i++) { vflux(i, kts) = 0.f; vflux(i, kte) = 0.f; }
   for (int j = j_start; j <= j_end; j++) {
@@ -292,6 +294,7 @@ void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
       for (int k = kts; k <= ktf; k++)
         for (int i = i_start; i <= i_end; i++) {
           float vb = v(i, k, j - 1);
+          if (x.spec && v(i, k, j) < 0.f) vb = v(i, k, j);   // specified uses upstream normal wind at boundaries (:1985)
           fqy(i, k) = 0.25f * (rv(i, k, j) + rv(i, k, j - 1)) * (v(i, k, j) + vb);
         }
     } else if (j == jds + 2) {
@@ -304,6 +307,7 @@ void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
       for (int k = kts; k <= ktf; k++)
         for (int i = i_start; i <= i_end; i++) {
           float vb = v(i, k, j);
+          if (x.spec && v(i, k, j - 1) > 0.f) vb = v(i, k, j - 1);   // :2007
           fqy(i, k) = 0.25f * (rv(i, k, j) + rv(i, k, j - 1)) * (vb + v(i, k, j - 1));
         }
     } else if (j == jde - 1) {
@@ -323,8 +327,8 @@ void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
   }
 
   i_start = its; i_end = std::min(ite, ide - 1); j_start = jts; j_end = jte;
-  if (x.c.open_ys) j_start = std::max(jds + 1, jts);
-  if (x.c.open_ye) j_end = std::min(jde - 1, jte);
+  if (x.oys()) j_start = std::max(jds + 1, jts);
+  if (x.oye()) j_end = std::min(jde - 1, jte);
   int i_start_f = i_start, i_end_f = i_end + 1;
   if (degrade_xs) { i_start = std::max(ids + 1, its); i_start_f = std::min(i_start + 2, ids + 3); }
   if (degrade_xe) { i_end = std::min(ide - 2, ite); i_end_f = ide - 3; }
@@ -414,8 +418,8 @@ void advect_v(const Cx &x, A3 v, A3 v_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
   // vertical (:2802-2995)
   i_start = its; i_end = std::min(ite, ide - 1); j_start = jts; j_end = jte;
   for (int i = i_start; i <= i_end; i++) { vflux(i, kts) = 0.f; vflux(i, kte) = 0.f; }
-  if (x.c.open_ys) j_start = std::max(jds + 1, jts);
-  if (x.c.open_ye) j_end = std::min(jde - 1, jte);
+  if (x.oys()) j_start = std::max(jds + 1, jts);
+  if (x.oye()) j_end = std::min(jde - 1, jte);
   for (int j = j_start; j <= j_end; j++) {
     for (int k = kts + 2; k <= ktf - 1; k++)
       for (int i = i_start; i <= i_end; i++) {
@@ -989,6 +993,12 @@ void advect_scalar_pd(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A
   if (degrade_xe) i_end = std::min(ite + 1, ide - 1);
   if (degrade_ys) j_start = std::max(jts - 1, jds);
   if (degrade_ye) j_end = std::min(jte + 1, jde - 1);
+  if (x.spec) {   // :7697-7702
+    if (degrade_xs) i_start = std::max(its - 1, ids + 1);
+    if (degrade_xe) i_end = std::min(ite + 1, ide - 2);
+    if (degrade_ys) j_start = std::max(jts - 1, jds + 1);
+    if (degrade_ye) j_end = std::min(jte + 1, jde - 2);
+  }
   if (x.c.open_xs && degrade_xs) i_start = std::max(its - 1, ids + 1);
   if (x.c.open_xe && degrade_xe) i_end = std::min(ite + 1, ide - 2);
   if (x.c.open_ys && degrade_ys) j_start = std::max(jts - 1, jds + 1);

@@ -69,7 +69,7 @@ void set_physical_bc3d(const Cx &x, A3 dat, char variable_in) {
             for (int i = 1; i <= bdyzone; i++) dat(ide + i, k, j) = dat(ide - i, k, j);
       }
     }
-    if (x.c.open_xs && its == ids && open_bc_copy) {
+    if (x.oxs() && its == ids && open_bc_copy) {
       for (int j = jts - bdyzone; j <= std::min(jte, jde + jstag) + bdyzone; j++)
         for (int k = kts; k <= k_end; k++) {
           dat(ids - 1, k, j) = dat(ids, k, j);
@@ -77,7 +77,7 @@ void set_physical_bc3d(const Cx &x, A3 dat, char variable_in) {
           dat(ids - 3, k, j) = dat(ids, k, j);
         }
     }
-    if (x.c.open_xe && ite == ide && open_bc_copy) {
+    if (x.oxe() && ite == ide && open_bc_copy) {
       if (variable != 'u' && variable != 'x') {
         for (int j = jts - bdyzone; j <= std::min(jte, jde + jstag) + bdyzone; j++)
           for (int k = kts; k <= k_end; k++) {
@@ -142,7 +142,7 @@ void set_physical_bc3d(const Cx &x, A3 dat, char variable_in) {
             for (int i = i_start; i <= i_end; i++) dat(i, k, jde + j) = dat(i, k, jde - j);
       }
     }
-    if (x.c.open_ys && jts == jds && open_bc_copy) {
+    if (x.oys() && jts == jds && open_bc_copy) {
       for (int k = kts; k <= k_end; k++)
         for (int i = i_start; i <= i_end; i++) {
           dat(i, k, jds - 1) = dat(i, k, jds);
@@ -150,7 +150,7 @@ void set_physical_bc3d(const Cx &x, A3 dat, char variable_in) {
           dat(i, k, jds - 3) = dat(i, k, jds);
         }
     }
-    if (x.c.open_ye && jte == jde && open_bc_copy) {
+    if (x.oye() && jte == jde && open_bc_copy) {
       if (variable != 'v' && variable != 'y') {
         for (int k = kts; k <= k_end; k++)
           for (int i = i_start; i <= i_end; i++) {
@@ -221,14 +221,14 @@ void set_physical_bc2d(const Cx &x, A2 dat, char variable_in) {
           for (int i = 0; i <= bdyzone - 1; i++) dat(ide + i, j) = dat(ide - i, j);
       }
     }
-    if (x.c.open_xs && its == ids && open_bc_copy) {
+    if (x.oxs() && its == ids && open_bc_copy) {
       for (int j = j0; j <= j1; j++) {
         dat(ids - 1, j) = dat(ids, j);
         dat(ids - 2, j) = dat(ids, j);
         dat(ids - 3, j) = dat(ids, j);
       }
     }
-    if (x.c.open_xe && ite == ide && open_bc_copy) {
+    if (x.oxe() && ite == ide && open_bc_copy) {
       if (variable != 'u' && variable != 'x') {
         for (int j = j0; j <= j1; j++) {
           dat(ide, j) = dat(ide - 1, j);
@@ -283,14 +283,14 @@ void set_physical_bc2d(const Cx &x, A2 dat, char variable_in) {
           for (int i = istart; i <= iend; i++) dat(i, jde + j) = dat(i, jde - j);
       }
     }
-    if (x.c.open_ys && jts == jds && open_bc_copy) {
+    if (x.oys() && jts == jds && open_bc_copy) {
       for (int i = istart; i <= iend; i++) {
         dat(i, jds - 1) = dat(i, jds);
         dat(i, jds - 2) = dat(i, jds);
         dat(i, jds - 3) = dat(i, jds);
       }
     }
-    if (x.c.open_ye && jte == jde && open_bc_copy) {
+    if (x.oye() && jte == jde && open_bc_copy) {
       if (variable != 'v' && variable != 'y') {
         for (int i = istart; i <= iend; i++) {
           dat(i, jde) = dat(i, jde - 1);

@@ -370,32 +370,32 @@ void rhs_ph(const Cx &x, A3 ph_tend, A3 u, A3 v, A3 ww, A3 ph, A3 ph_old, A3 phb
   };
   int i_start = its, j_start = jts;
   itf = std::min(ite, ide - 1); jtf = std::min(jte, jde - 1);
-  if (x.c.open_ys) j_start = std::max(jts, jds + 3);
-  if (x.c.open_ye) jtf = std::min(jtf, jde - 4);
+  if (x.oys()) j_start = std::max(jts, jds + 3);
+  if (x.oye()) jtf = std::min(jtf, jde - 4);
   for (int j = j_start; j <= jtf; j++) {
     for (int k = 2; k <= kte - 1; k++)
       for (int i = i_start; i <= itf; i++) y6(i, k, j, false);
     for (int i = i_start; i <= itf; i++) y6(i, kte, j, true);
   }
-  if (x.c.open_ys && jts <= jds + 2 && jds + 2 <= jte) {
+  if (x.oys() && jts <= jds + 2 && jds + 2 <= jte) {
     int j = jds + 2;
     for (int k = 2; k <= kte - 1; k++)
       for (int i = i_start; i <= itf; i++) y4(i, k, j, false);
     for (int i = i_start; i <= itf; i++) y4(i, kte, j, true);
   }
-  if (x.c.open_ye && jts <= jde - 3 && jde - 3 <= jte) {
+  if (x.oye() && jts <= jde - 3 && jde - 3 <= jte) {
     int j = jde - 3;
     for (int k = 2; k <= kte - 1; k++)
       for (int i = i_start; i <= itf; i++) y4(i, k, j, false);
     for (int i = i_start; i <= itf; i++) y4(i, kte, j, true);
   }
-  if (x.c.open_ys && jts <= jds + 1 && jds + 1 <= jte) {
+  if (x.oys() && jts <= jds + 1 && jds + 1 <= jte) {
     int j = jds + 1;
     for (int k = 2; k <= kte - 1; k++)
       for (int i = i_start; i <= itf; i++) y2(i, k, j, false);
     for (int i = i_start; i <= itf; i++) y2(i, kte, j, true);
   }
-  if (x.c.open_ye && jts <= jde - 2 && jde - 2 <= jte) {
+  if (x.oye() && jts <= jde - 2 && jde - 2 <= jte) {
     int j = jde - 2;
     for (int k = 2; k <= kte - 1; k++)
       for (int i = i_start; i <= itf; i++) y2(i, k, j, false);
@@ -439,8 +439,8 @@ void rhs_ph(const Cx &x, A3 ph_tend, A3 u, A3 v, A3 ww, A3 ph, A3 ph_old, A3 phb
   };
   i_start = its; j_start = jts;
   itf = std::min(ite, ide - 1); jtf = std::min(jte, jde - 1);
-  if (x.c.open_xs) i_start = std::max(its, ids + 3);
-  if (x.c.open_xe) itf = std::min(itf, ide - 4);
+  if (x.oxs()) i_start = std::max(its, ids + 3);
+  if (x.oxe()) itf = std::min(itf, ide - 4);
   for (int j = j_start; j <= jtf; j++) {
     for (int k = 2; k <= kte - 1; k++)
       for (int i = i_start; i <= itf; i++) x6(i, k, j, false);
@@ -460,13 +460,13 @@ void rhs_ph(const Cx &x, A3 ph_tend, A3 u, A3 v, A3 ww, A3 ph, A3 ph_old, A3 phb
       x4(i, kte, j, true);
     }
   }
-  if (x.c.open_xs && its <= ids + 1 && ids + 1 <= ite) {
+  if (x.oxs() && its <= ids + 1 && ids + 1 <= ite) {
     int i = ids + 1;
     for (int j = j_start; j <= jtf; j++)
       for (int k = 2; k <= kte - 1; k++) x2(i, k, j, false);
     for (int j = j_start; j <= jtf; j++) x2(i, kte, j, true);
   }
-  if (x.c.open_xe && its <= ide - 2 && ide - 2 <= ite) {
+  if (x.oxe() && its <= ide - 2 && ide - 2 <= ite) {
     int i = ide - 2;
     for (int j = j_start; j <= jtf; j++)
       for (int k = 2; k <= kte - 1; k++) x2(i, k, j, false);
@@ -538,8 +538,8 @@ void horizontal_pressure_gradient(const Cx &x, A3 ru_tend, A3 rv_tend, A3 ph, A3
   auto dpn = [&](int i, int k) -> float & { return dpn_[(i - its) + k * ni]; };
   int itf = std::min(ite, ide - 1), jtf = jte, ktf = std::min(x.kte, kde - 1);
   int i_start = its, j_start = jts;
-  if (x.c.open_ys && jts == jds) j_start = jts + 1;
-  if (x.c.open_ye && jte == jde) jtf = jtf - 1;
+  if (x.oys() && jts == jds) j_start = jts + 1;
+  if (x.oye() && jte == jde) jtf = jtf - 1;
   for (int j = j_start; j <= jtf; j++) {
     int k = 1;
     for (int i = i_start; i <= itf; i++) {
@@ -566,8 +566,8 @@ void horizontal_pressure_gradient(const Cx &x, A3 ru_tend, A3 rv_tend, A3 ph, A3
   }
   itf = ite; jtf = std::min(jte, jde - 1);
   i_start = its; j_start = jts;
-  if (x.c.open_xs && its == ids) i_start = its + 1;
-  if (x.c.open_xe && ite == ide) itf = itf - 1;
+  if (x.oxs() && its == ids) i_start = its + 1;
+  if (x.oxe() && ite == ide) itf = itf - 1;
   if (x.c.periodic_x) { i_start = its; itf = ite; }
   for (int j = j_start; j <= jtf; j++) {
     int k = 1;
@@ -652,8 +652,8 @@ void coriolis(const Cx &x, A3 ru, A3 rv, A3 rw, A3 ru_tend, A3 rv_tend, A3 rw_te
   const A2 &f = x.f, &e = x.e, &sina = x.sina, &cosa = x.cosa;
   const A1 &fzm = x.fnm, &fzp = x.fnp;
   int i_start = its, i_end = ite;
-  if (x.c.open_xs) i_start = std::max(ids + 1, its);
-  if (x.c.open_xe) i_end = std::min(ide - 1, ite);
+  if (x.oxs()) i_start = std::max(ids + 1, its);
+  if (x.oxe()) i_end = std::min(ide - 1, ite);
   if (x.c.periodic_x) { i_start = its; i_end = ite; }
   for (int j = jts; j <= std::min(jte, jde - 1); j++)
     for (int k = kts; k <= ktf; k++)
@@ -664,8 +664,8 @@ void coriolis(const Cx &x, A3 ru, A3 rv, A3 rw, A3 ru_tend, A3 rv_tend, A3 rw_te
                            0.5f * (e(i, j) + e(i - 1, j)) * 0.5f * (cosa(i, j) + cosa(i - 1, j)) * 0.25f *
                                (rw(i - 1, k + 1, j) + rw(i - 1, k, j) + rw(i, k + 1, j) + rw(i, k, j));
   int j_start = jts, j_end = jte;
-  if (x.c.open_ys) j_start = std::max(jds + 1, jts);
-  if (x.c.open_ye) j_end = std::min(jde - 1, jte);
+  if (x.oys()) j_start = std::max(jds + 1, jts);
+  if (x.oye()) j_end = std::min(jde - 1, jte);
   for (int j = j_start; j <= j_end; j++)
     for (int k = kts; k <= ktf; k++)
       for (int i = its; i <= std::min(ide - 1, ite); i++)
@@ -697,8 +697,8 @@ void perturbation_coriolis(const Cx &x, A3 ru_in, A3 rv_in, A3 rw, A3 ru_tend, A
   auto ru = [&](int i, int k, int j) -> float & { return ru_[(i - its + 1) + (size_t)(k - kts) * ni + (size_t)(j - jts + 1) * ni * nk]; };
   auto rv = [&](int i, int k, int j) -> float & { return rv_[(i - its + 1) + (size_t)(k - kts) * ni + (size_t)(j - jts + 1) * ni * nk]; };
   int i_start = its, i_end = ite;
-  if (x.c.open_xs) i_start = std::max(ids + 1, its);
-  if (x.c.open_xe) i_end = std::min(ide - 1, ite);
+  if (x.oxs()) i_start = std::max(ids + 1, its);
+  if (x.oxe()) i_end = std::min(ide - 1, ite);
   if (x.c.periodic_x) { i_start = its; i_end = ite; }
 
   auto zv = [&](int i, int k, int j) {
@@ -755,8 +755,8 @@ void perturbation_coriolis(const Cx &x, A3 ru_in, A3 rv_in, A3 rw, A3 ru_tend, A
                                  (rw(ite - 1, k + 1, j) + rw(ite - 1, k, j) + rw(ite - 1, k + 1, j) + rw(ite - 1, k, j));
   }
   int j_start = jts, j_end = jte;
-  if (x.c.open_ys) j_start = std::max(jds + 1, jts);
-  if (x.c.open_ye) j_end = std::min(jde - 1, jte);
+  if (x.oys()) j_start = std::max(jds + 1, jts);
+  if (x.oye()) j_end = std::min(jde - 1, jte);
   for (int j = j_start - 1; j <= j_end; j++)
     for (int k = kts + 1; k <= ktf - 1; k++)
       for (int i = its; i <= std::min(ite, ide - 1) + 1; i++) {
@@ -826,31 +826,31 @@ void curvature(const Cx &x, A3 ru, A3 rv, A3 rw, A3 u, A3 v, A3 w, A3 ru_tend, A
   std::vector<float> vx_((size_t)ni * nk * nj, 0.f);
   auto vxgm = [&](int i, int k, int j) -> float & { return vx_[(i - its + 1) + (size_t)(k - kts) * ni + (size_t)(j - jts + 1) * ni * nk]; };
   int i_start = its - 1, i_end = ite, j_start = jts - 1, j_end = jte;
-  if (x.c.open_xs && its == ids) i_start = its;
-  if (x.c.open_xe && ite == ide) i_end = ite - 1;
-  if (x.c.open_ys && jts == jds) j_start = jts;
-  if (x.c.open_ye && jte == jde) j_end = jte - 1;
+  if (x.oxs() && its == ids) i_start = its;
+  if (x.oxe() && ite == ide) i_end = ite - 1;
+  if (x.oys() && jts == jds) j_start = jts;
+  if (x.oye() && jte == jde) j_end = jte - 1;
   if (x.c.periodic_x) { i_start = its - 1; i_end = ite; }
   for (int j = j_start; j <= j_end; j++)
     for (int k = kts; k <= ktf; k++)
       for (int i = i_start; i <= i_end; i++)
         vxgm(i, k, j) = 0.5f * (u(i, k, j) + u(i + 1, k, j)) * (x.msfvx(i, j + 1) - x.msfvx(i, j)) * rdy -
                         0.5f * (v(i, k, j) + v(i, k, j + 1)) * (x.msfuy(i + 1, j) - x.msfuy(i, j)) * rdx;
-  if (x.c.open_xs && its == ids)
+  if ((x.c.open_xs || (x.spec && !x.c.periodic_x)) && its == ids)
     for (int j = jts; j <= jte - 1; j++)
       for (int k = kts; k <= ktf; k++) vxgm(its - 1, k, j) = vxgm(its, k, j);
-  if (x.c.open_xe && ite == ide)
+  if ((x.c.open_xe || (x.spec && !x.c.periodic_x)) && ite == ide)
     for (int j = jts; j <= jte - 1; j++)
       for (int k = kts; k <= ktf; k++) vxgm(ite, k, j) = vxgm(ite - 1, k, j);
-  if (x.c.open_ys && jts == jds)
+  if (x.oys() && jts == jds)
     for (int k = kts; k <= ktf; k++)
       for (int i = its - 1; i <= ite; i++) vxgm(i, k, jts - 1) = vxgm(i, k, jts);
-  if (x.c.open_ye && jte == jde)
+  if (x.oye() && jte == jde)
     for (int k = kts; k <= ktf; k++)
       for (int i = its - 1; i <= ite; i++) vxgm(i, k, jte) = vxgm(i, k, jte - 1);
   i_start = its;
-  if (x.c.open_xs) i_start = std::max(ids + 1, its);
-  if (x.c.open_xe) i_end = std::min(ide - 1, ite);
+  if (x.oxs()) i_start = std::max(ids + 1, its);
+  if (x.oxe()) i_end = std::min(ide - 1, ite);
   if (x.c.periodic_x) { i_start = its; i_end = ite; }
   for (int j = jts; j <= std::min(jde - 1, jte); j++)
     for (int k = kts; k <= ktf; k++)
@@ -860,8 +860,8 @@ void curvature(const Cx &x, A3 ru, A3 rv, A3 rw, A3 u, A3 v, A3 w, A3 ru_tend, A
                                (rv(i - 1, k, j + 1) + rv(i, k, j + 1) + rv(i - 1, k, j) + rv(i, k, j)) -
                            u(i, k, j) * reradius * 0.25f * (rw(i - 1, k + 1, j) + rw(i - 1, k, j) + rw(i, k + 1, j) + rw(i, k, j));
   j_start = jts;
-  if (x.c.open_ys) j_start = std::max(jds + 1, jts);
-  if (x.c.open_ye) j_end = std::min(jde - 1, jte);
+  if (x.oys()) j_start = std::max(jds + 1, jts);
+  if (x.oye()) j_end = std::min(jde - 1, jte);
   for (int j = j_start; j <= j_end; j++)
     for (int k = kts; k <= ktf; k++)
       for (int i = its; i <= std::min(ite, ide - 1); i++)

@@ -297,13 +297,17 @@ void sixth_order_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT
     if (x.c.open_ys) j_start = std::max(jts, jds + 3);
     if (x.c.open_xe) i_end = std::min(ite, ide - 3);
     if (x.c.open_ye) j_end = std::min(jte, jde - 4);
+    if (x.spec) {   // :6354
+      i_start = std::max(its, ids + 3); i_end = std::min(ite, ide - 3);
+      j_start = std::max(jts, jds + 3); j_end = std::min(jte, jde - 4);
+    }
   } else if (name == 'v') {
     i_end = std::min(ide - 1, ite); j_end = jte;
     if (x.c.open_xs) i_start = std::max(its, ids + 3);
     if (x.c.open_ys) j_start = std::max(jts, jds + 3);
     if (x.c.open_xe) i_end = std::min(ite, ide - 4);
     if (x.c.open_ye) j_end = std::min(jte, jde - 3);
-    if (x.c.open_xs) {   // sic (:6333): "open_xs .or. specified" restricts all four sides
+    if (x.c.open_xs || x.spec) {   // sic (:6381): "open_xs .or. specified" restricts all four sides
       i_start = std::max(its, ids + 3); i_end = std::min(ite, ide - 4);
       j_start = std::max(jts, jds + 3); j_end = std::min(jte, jde - 3);
     }
@@ -313,6 +317,10 @@ void sixth_order_diffusion(const Cx &x, char name, A3 field, A3 tendency, A2 MUT
     if (x.c.open_ys) j_start = std::max(jts, jds + 3);
     if (x.c.open_xe) i_end = std::min(ite, ide - 4);
     if (x.c.open_ye) j_end = std::min(jte, jde - 4);
+    if (x.spec) {   // :6408, :6435
+      i_start = std::max(its, ids + 3); i_end = std::min(ide - 4, ite);
+      j_start = std::max(jts, jds + 3); j_end = std::min(jde - 4, jte);
+    }
     if (name == 'w') k_start = kts + 1;
   }
   for (int j = j_start; j <= j_end; j++)

@@ -71,6 +71,13 @@ struct Cx {
   float rdx, rdy, dt;
   float cf1, cf2, cf3, cfn, cfn1;
   int time_step;
+  // specified / nested lateral boundaries: `specified = config_flags%specified .or. config_flags%nested`,
+  // the local most routines of the reference build; o?? = "open_?? .or. specified" as nearly every loop-range test reads
+  bool spec = false;
+  inline bool oxs() const { return c.open_xs || spec; }
+  inline bool oxe() const { return c.open_xe || spec; }
+  inline bool oys() const { return c.open_ys || spec; }
+  inline bool oye() const { return c.open_ye || spec; }
   // 1-D coefficient arrays (Registry.EM_COMMON:349-354, registry.hyb_coord)
   A1 znu, znw, fnm, fnp, rdnw, rdn, dnw, dn;
   A1 c1h, c2h, c1f, c2f, c3h, c4h, c3f, c4f;
@@ -86,6 +93,23 @@ struct XK {
   XK(float c_) : c(c_) {}
   XK(A3 a_) : a(a_) {}
   inline float operator()(int i, int k, int j) const { return a.p ? a(i, k, j) : c; }
+};
+
+// one field's boundary arrays (Registry.EM_COMMON 'b' entries: <f>_bxs/_bxe/_bys/_bye and the tendencies <f>_btxs ...):
+// x sides are (jms:jme, kds:kde, spec_bdy_width), y sides (ims:ime, kds:kde, spec_bdy_width); mu has one level.
+// side: 0 = Y-start, 1 = Y-end, 2 = X-start, 3 = X-end
+struct Bdy {
+  const float *v[4] = {nullptr, nullptr, nullptr, nullptr}, *t[4] = {nullptr, nullptr, nullptr, nullptr};
+  int ims = 0, jms = 0, ni = 0, nj = 0, nk = 0;
+  inline long at(int side, int along, int k, int b) const {
+    return side < 2 ? (long)(along - ims) + (long)(k - 1) * ni + (long)(b - 1) * ni * nk : (long)(along - jms) + (long)(k - 1) * nj + (long)(b - 1) * nj * nk;
+  }
+  inline float val(int side, int along, int k, int b) const { return v[side][at(side, along, k, b)]; }
+  inline float tend(int side, int along, int k, int b) const { return t[side][at(side, along, k, b)]; }
+};
+struct A1x {   // fcx(1:spec_bdy_width), gcx
+  const float *p = nullptr;
+  inline float operator()(int b) const { return p[b - 1]; }
 };
 
 inline float sign1(float a) { return std::copysign(1.0f, a); }  // SIGN(1.,a)
@@ -111,6 +135,14 @@ struct Oracle {
   int nsc() const { return c.num_scalar + (tke_index() ? 1 : 0); }
   // grid%max_vert_cfl, grid%max_horiz_cfl (solve_em.F:914-930): running maxima of w_damp's Courant numbers
   float max_vert_cfl = 0.f, max_horiz_cfl = 0.f;
+  // specified / nested lateral boundaries: grid%dtbc (time since the boundary arrays were valid; solve_em.F:377) and the
+  // boundary arrays of `field` ("u", "v", "w", "ph", "t", "mu", "moist_qv", "scalar_1", ...)
+  float dtbc = 0.f;
+  bool spec() const { return c.specified || c.nested; }
+  bool has_bdy(const std::string &field) const { return data.count(field + "_bxs") != 0; }
+  Bdy bdy(const std::string &field);
+  void add_raw(const std::string &n, size_t count);
+  void spec_final();                  // solve_em.F:4540-4722
   int nthreads = 1;   // j-tiles run on std::threads like the reference's OpenMP tiles (solve_em.F:652-674)
   template <class Fn> void par(Fn fn);
 
@@ -256,6 +288,21 @@ void advect_w_implicit(const Cx &x, A3 w_old, A3 tendency, A3 utend, A3 vtend, A
 // advect_mono.cpp
 void advect_scalar_mono(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru, A3 rv, A3 rom, A3 romI,
                         A2 mut, A2 mub, A2 mu_old, float dt);
+// bdy.cpp (specified / nested lateral boundaries: share/module_bc.F:1122-2456, dyn_em/module_bc_em.F:17-700)
+void relax_bdy_dry(const Cx &x, A3 ru_tendf, A3 rv_tendf, A3 ph_tendf, A3 t_tendf, A3 rw_tendf, A2 mu_tend, A3 ru, A3 rv, A3 ph, A3 t, A3 w,
+                   A2 mu, A2 mut, const Bdy &bu, const Bdy &bv, const Bdy &bph, const Bdy &bt, const Bdy &bw, const Bdy &bmu, float dtbc,
+                   A1x fcx, A1x gcx);
+void relax_bdy_scalar(const Cx &x, A3 scalar_tend, A3 scalar, A2 mu, const Bdy &B, float dtbc, A1x fcx, A1x gcx);
+void spec_bdy_dry(const Cx &x, A3 ru_tend, A3 rv_tend, A3 ph_tend, A3 t_tend, A3 rw_tend, A2 mu_tend, const Bdy &bu, const Bdy &bv,
+                  const Bdy &bph, const Bdy &bt, const Bdy &bw, const Bdy &bmu);
+void spec_bdy_scalar(const Cx &x, A3 scalar_tend, const Bdy &B);
+void spec_bdyupdate(const Cx &x, A3 field, A3 field_tend, float dt, char variable);
+void spec_bdyupdate(const Cx &x, A2 field, A2 field_tend, float dt);
+void spec_bdyupdate_ph(const Cx &x, A3 ph_save, A3 field, A3 field_tend, A2 mu_tend, A2 muts, A1 c1, A1 c2, float dt);
+void zero_grad_bdy(const Cx &x, A3 field, char variable);
+void flow_dep_bdy(const Cx &x, A3 field, A3 u, A3 v);
+void spec_bdy_final(const Cx &x, A3 field, A2 mu, A1 c1, A1 c2, A2 msf, const Bdy &B, char variable, float dtbc);
+void spec_bdy_final(const Cx &x, A2 field, A2 mu, A1 c1, A1 c2, A2 msf, const Bdy &B, float dtbc);
 // small_step.cpp
 void small_step_prep(const Cx &x, A3 u_1, A3 u_2, A3 v_1, A3 v_2, A3 w_1, A3 w_2, A3 t_1, A3 t_2,
                      A3 ph_1, A3 ph_2, A2 mub, A2 mu_1, A2 mu_2, A2 muu, A2 muus, A2 muv, A2 muvs,

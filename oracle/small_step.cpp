@@ -235,7 +235,7 @@ void calc_coef_w(const Cx &x, A3 a, A3 alpha, A3 gamma, A2 mut, A3 cqw, A3 c2a, 
   }
 }
 
-// dyn_em/module_small_step_em.F:654-965 (no specified/nested/polar)
+// dyn_em/module_small_step_em.F:654-965 (no polar)
 void advance_uv(const Cx &x, A3 u, A3 ru_tend, A3 v, A3 rv_tend, A3 p, A3 pb, A3 ph, A3 php,
                 A3 alt, A3 al, A2 mu, A2 muu, A3 cqu, A2 muv, A3 cqv, A2 mudf, float dts) {
   const int ids = x.ids, ide = x.ide, jds = x.jds, jde = x.jde, kde = x.kde;
@@ -246,6 +246,14 @@ void advance_uv(const Cx &x, A3 u, A3 ru_tend, A3 v, A3 rv_tend, A3 p, A3 pb, A3
   int i_start = its, i_end = std::min(ite, ide - 1), j_start = jts, j_end = std::min(jte, jde - 1);
   int k_start = x.kts, k_end = x.kte - 1;
   int i_endu = ite, j_endv = jte;
+  if (x.spec) {   // :734-751
+    const int sz = x.c.spec_zone;
+    i_start = std::max(its, ids + sz); i_end = std::min(ite, ide - sz - 1);
+    j_start = std::max(jts, jds + sz); j_end = std::min(jte, jde - sz - 1);
+    k_end = std::min(x.kte, kde - 1);
+    i_endu = std::min(ite, ide - sz); j_endv = std::min(jte, jde - sz);
+    if (x.c.periodic_x) { i_start = its; i_end = std::min(ite, ide - 1); i_endu = ite; }
+  }
   int i_start_up = i_start, i_end_up = i_endu;
   int j_start_vp = j_start, j_end_vp = j_endv;
   if ((x.c.open_xs || x.c.symmetric_xs) && its == ids) i_start_up++;
@@ -343,9 +351,13 @@ void advance_mu_t(const Cx &x, A3 ww, A3 ww_1, A3 u, A3 u_1, A3 v, A3 v_1, A2 mu
                   A2 mu_tend, float dts, float epssm) {
   const int kde = x.kde;
   const int its = x.its;
-  const int i_start = x.its, i_end = std::min(x.ite, x.ide - 1);
-  const int j_start = x.jts, j_end = std::min(x.jte, x.jde - 1);
+  int i_start = x.its, i_end = std::min(x.ite, x.ide - 1);
+  int j_start = x.jts, j_end = std::min(x.jte, x.jde - 1);
   const int k_start = x.kts, k_end = x.kte - 1;
+  if (x.spec) {   // :1054-1063
+    if (!x.c.periodic_x) { i_start = std::max(x.its, x.ids + 1); i_end = std::min(x.ite, x.ide - 2); }
+    j_start = std::max(x.jts, x.jds + 1); j_end = std::min(x.jte, x.jde - 2);
+  }
   const A1 &c1h = x.c1h, &c2h = x.c2h, &dnw = x.dnw, &fnm = x.fnm, &fnp = x.fnp, &rdnw = x.rdnw;
   const float rdx = x.rdx, rdy = x.rdy;
   const int ni = x.ite - its + 2, nk = kde + 1;
@@ -414,9 +426,13 @@ void advance_w(const Cx &x, A3 w, A3 rw_tend, A3 ww, A3 w_save, A3 u, A3 v, A2 m
                A3 c2a, A3 cqw, A3 alt, A3 a, A3 alpha, A3 gamma, float dts, float epssm) {
   (void)mu1;
   const int kde = x.kde, its = x.its;
-  const int i_start = x.its, i_end = std::min(x.ite, x.ide - 1);
-  const int j_start = x.jts, j_end = std::min(x.jte, x.jde - 1);
+  int i_start = x.its, i_end = std::min(x.ite, x.ide - 1);
+  int j_start = x.jts, j_end = std::min(x.jte, x.jde - 1);
   const int k_end = x.kte - 1;
+  if (x.spec) {   // :1273-1282
+    if (!x.c.periodic_x) { i_start = std::max(x.its, x.ids + 1); i_end = std::min(x.ite, x.ide - 2); }
+    j_start = std::max(x.jts, x.jds + 1); j_end = std::min(x.jte, x.jde - 2);
+  }
   const A1 &c1h = x.c1h, &c2h = x.c2h, &c1f = x.c1f, &c2f = x.c2f;
   const A1 &fnm = x.fnm, &fnp = x.fnp, &rdnw = x.rdnw, &rdn = x.rdn;
   const float rdx = x.rdx, rdy = x.rdy, cf1 = x.cf1, cf2 = x.cf2, cf3 = x.cf3;

@@ -50,6 +50,24 @@ Oracle::Oracle(const wrfgpu_dims &d_, const wrfgpu_config &c_) : d(d_), c(c_) {
     for (const char *n : {"zx", "zy", "rdz", "rdzw", "div", "defor11", "defor22", "defor33", "defor12", "defor13", "defor23",
                           "xkmh", "xkmv", "xkhh", "xkhv"}) add(n, 3);
   }
+  if (spec()) {   // boundary arrays of the specified / nested zone (Registry.EM_COMMON 'b' entries), fcx / gcx (lbc_fcx_gcx)
+    if (c.spec_bdy_width < 1 || c.spec_zone < 0 || c.relax_zone < c.spec_zone || c.relax_zone + 1 > c.spec_bdy_width)
+      throw std::runtime_error("oracle: spec_bdy_width / spec_zone / relax_zone");
+    const size_t W = c.spec_bdy_width, ni = d.ime - d.ims + 1, nj = d.jme - d.jms + 1, nk = d.kde - d.kds + 1;
+    add_raw("fcx", W); add_raw("gcx", W);
+    auto add_bdy = [&](const std::string &f, size_t levels) {
+      for (const char *t : {"_b", "_bt"}) {
+        add_raw(f + t + "xs", nj * levels * W); add_raw(f + t + "xe", nj * levels * W);
+        add_raw(f + t + "ys", ni * levels * W); add_raw(f + t + "ye", ni * levels * W);
+      }
+    };
+    for (const char *f : {"u", "v", "w", "ph", "t"}) add_bdy(f, nk);
+    add_bdy("mu", 1);
+    for (int s = 0; s < c.num_moist; s++)
+      if (s == 0 || c.nested || c.have_bcs_moist) add_bdy(std::string("moist_") + moist_names[s], nk);
+    if (c.nested || c.have_bcs_scalar)
+      for (int s = 1; s <= c.num_scalar; s++) add_bdy("scalar_" + std::to_string(s), nk);
+  }
   // harmless defaults so that an un-set map factor does not divide by zero
   for (const char *m : {"msftx", "msfty", "msfux", "msfuy", "msfvx", "msfvx_inv", "msfvy"})
     std::fill(data[m].begin(), data[m].end(), 1.f);
@@ -67,6 +85,22 @@ void Oracle::add(const std::string &n, int k) {
   names.push_back(n);
   kind[n] = k;
   data[n].assign(k == 3 ? n3 : (k == 2 ? n2 : n1), 0.f);
+}
+void Oracle::add_raw(const std::string &n, size_t count) {
+  names.push_back(n);
+  kind[n] = 4;
+  data[n].assign(count, 0.f);
+}
+Bdy Oracle::bdy(const std::string &f) {
+  Bdy B;
+  static const char *sfx[4] = {"ys", "ye", "xs", "xe"};
+  for (int q = 0; q < 4; q++) {
+    B.v[q] = data.at(f + "_b" + sfx[q]).data();
+    B.t[q] = data.at(f + "_bt" + sfx[q]).data();
+  }
+  B.ims = d.ims; B.jms = d.jms; B.ni = d.ime - d.ims + 1; B.nj = d.jme - d.jms + 1;
+  B.nk = f == "mu" ? 1 : d.kde - d.kds + 1;
+  return B;
 }
 A3 Oracle::a3(const std::string &n) {
   auto it = data.find(n);
@@ -97,6 +131,7 @@ void Oracle::refresh_cx() {
   x.rdx = 1.f / c.dx; x.rdy = 1.f / c.dy; x.dt = c.dt;
   x.cf1 = c.cf1; x.cf2 = c.cf2; x.cf3 = c.cf3; x.cfn = c.cfn; x.cfn1 = c.cfn1;
   x.time_step = c.time_step;
+  x.spec = c.specified || c.nested;
   x.znu = a1("znu"); x.znw = a1("znw"); x.fnm = a1("fnm"); x.fnp = a1("fnp");
   x.rdnw = a1("rdnw"); x.rdn = a1("rdn"); x.dnw = a1("dnw"); x.dn = a1("dn");
   x.c1h = a1("c1h"); x.c2h = a1("c2h"); x.c1f = a1("c1f"); x.c2f = a1("c2f");
@@ -337,9 +372,21 @@ void Oracle::rk_tendency(int rk_step) {
   }
   if (rk_step == 1 && c.damp_opt == 2)
     par([&](const Cx &xt) { rk_rayleigh_damp(xt, a3("ru_tendf"), a3("rv_tendf"), a3("rw_tendf"), a3("t_tendf"), u, v, w, t, mut, muu, muv, ph, a3("phb")); });
+  const A1x fcx{spec() ? data.at("fcx").data() : nullptr}, gcx{spec() ? data.at("gcx").data() : nullptr};
+  if (spec() && rk_step == 1) {   // solve_em.F:937-968: the relaxation tendencies land in the *_save arrays zeroed above
+    const Bdy bu = bdy("u"), bv = bdy("v"), bph = bdy("ph"), bt = bdy("t"), bw = bdy("w"), bmu = bdy("mu");
+    par([&](const Cx &xt) {
+      relax_bdy_dry(xt, a3("u_save"), a3("v_save"), a3("ph_save"), a3("t_save"), a3("w_save"), a2("mu_tend"), ru, rv, ph, t, w, mu, mut, bu, bv, bph,
+                    bt, bw, bmu, dtbc, fcx, gcx);
+    });
+  }
   par([&](const Cx &xt) { rk_addtend_dry(xt, ru_tend, rv_tend, rw_tend, ph_tend, t_tend, a3("ru_tendf"), a3("rv_tendf"), a3("rw_tendf"), a3("ph_tendf"),
                  a3("t_tendf"), a3("u_save"), a3("v_save"), a3("w_save"), a3("ph_save"), a3("t_save"), a2("mu_tend"), a2("mu_tendf"),
                  rk_step, a3("h_diabatic"), mut); });
+  if (spec()) {   // solve_em.F:982-1007
+    const Bdy bu = bdy("u"), bv = bdy("v"), bph = bdy("ph"), bt = bdy("t"), bw = bdy("w"), bmu = bdy("mu");
+    par([&](const Cx &xt) { spec_bdy_dry(xt, ru_tend, rv_tend, ph_tend, t_tend, rw_tend, a2("mu_tend"), bu, bv, bph, bt, bw, bmu); });
+  }
 }
 
 // solve_em.F:1089-1263
@@ -363,6 +410,10 @@ void Oracle::advance_uv(int rk_step) {
   rk_params(rk_step, dt_rk, dts_rk, ns);
   par([&](const Cx &xt) { orc::advance_uv(xt, a3("u_2"), a3("ru_tend"), a3("v_2"), a3("rv_tend"), a3("p"), a3("pb"), a3("ph_2"), a3("php"), a3("alt"), a3("al"),
                   a2("mu_2"), a2("muu"), a3("cqu"), a2("muv"), a3("cqv"), a2("mudf"), dts_rk); });
+  if (spec()) {   // solve_em.F:1344-1365
+    par([&](const Cx &xt) { spec_bdyupdate(xt, a3("u_2"), a3("ru_tend"), dts_rk, 'u'); });
+    par([&](const Cx &xt) { spec_bdyupdate(xt, a3("v_2"), a3("rv_tend"), dts_rk, 'v'); });
+  }
 }
 void Oracle::advance_mu_t(int rk_step) {
   float dt_rk, dts_rk; int ns;
@@ -370,6 +421,11 @@ void Oracle::advance_mu_t(int rk_step) {
   par([&](const Cx &xt) { orc::advance_mu_t(xt, a3("ww"), a3("ww1"), a3("u_2"), a3("u_save"), a3("v_2"), a3("v_save"), a2("mu_2"), a2("mut"), a2("muave"),
                     a2("muts"), a2("muu"), a2("muv"), a2("mudf"), a3("t_2"), a3("t_save"), a3("t_2save"), a3("t_tend"), a2("mu_tend"),
                     dts_rk, c.epssm); });
+  if (spec()) {   // solve_em.F:1459-1490
+    par([&](const Cx &xt) { spec_bdyupdate(xt, a3("t_2"), a3("t_tend"), dts_rk, 't'); });
+    par([&](const Cx &xt) { spec_bdyupdate(xt, a2("mu_2"), a2("mu_tend"), dts_rk); });
+    par([&](const Cx &xt) { spec_bdyupdate(xt, a2("muts"), a2("mu_tend"), dts_rk); });
+  }
 }
 void Oracle::advance_w(int rk_step) {
   float dt_rk, dts_rk; int ns;
@@ -383,6 +439,11 @@ void Oracle::sumflux(int rk_step, int iteration) {
   rk_params(rk_step, dt_rk, dts_rk, ns);
   par([&](const Cx &xt) { orc::sumflux(xt, a3("u_2"), a3("v_2"), a3("ww"), a3("u_save"), a3("v_save"), a3("ww1"), a2("muu"), a2("muv"), a3("ru_m"), a3("rv_m"),
                a3("ww_m"), iteration, ns); });
+  if (spec()) {   // solve_em.F:1582-1620 (non_hydrostatic)
+    par([&](const Cx &xt) { spec_bdyupdate_ph(xt, a3("ph_save"), a3("ph_2"), a3("ph_tend"), a2("mu_tend"), a2("muts"), xt.c1f, xt.c2f, dts_rk); });
+    if (c.specified) par([&](const Cx &xt) { zero_grad_bdy(xt, a3("w_2"), 'w'); });
+    else par([&](const Cx &xt) { spec_bdyupdate(xt, a3("w_2"), a3("rw_tend"), dts_rk, 'h'); });
+  }
 }
 void Oracle::calc_p_rho(int iteration) {
   par([&](const Cx &xt) { orc::calc_p_rho(xt, a3("al"), a3("p"), a3("ph_2"), a3("alt"), a3("t_2"), a3("t_save"), a3("c2a"), a3("pm1"), a2("mu_2"), a2("muts"),
@@ -421,10 +482,18 @@ static void rk_update_scalar_pd(const Cx &x, A3 scalar, A3 sc_tend, A2 mu_old, A
 static void rk_update_scalar(const Cx &x, A3 scalar_1, A3 scalar_2, A3 sc_tend, A3 advect_tend, A2 mu_old, A2 mu_new, A2 mu_base,
                              int rk_step, float dt) {
   const int itf = std::min(x.ite, x.ide - 1), jtf = std::min(x.jte, x.jde - 1), ktf = std::min(x.kte, x.kde - 1);
+  // the advective tendency is not used in the specified zone (:1671-1678); sc_tend is (the *_spc ranges)
+  int i_start = x.its, i_end = itf, j_start = x.jts, j_end = jtf;
+  if (x.spec) {
+    const int sz = x.c.spec_zone;
+    if (!x.c.periodic_x) { i_start = std::max(x.its, x.ids + sz); i_end = std::min(x.ite, x.ide - sz - 1); }
+    j_start = std::max(x.jts, x.jds + sz); j_end = std::min(x.jte, x.jde - sz - 1);
+  }
   for (int j = x.jts; j <= jtf; j++)
     for (int k = x.kts; k <= ktf; k++)
       for (int i = x.its; i <= itf; i++) {
-        float tendency = advect_tend(i, k, j) * x.msfty(i, j);
+        float tendency = 0.f;
+        if (i >= i_start && i <= i_end && j >= j_start && j <= j_end) tendency = advect_tend(i, k, j) * x.msfty(i, j);
         tendency = tendency + sc_tend(i, k, j);
         float muold = mu_old(i, j) + mu_base(i, j), munew = mu_new(i, j) + mu_base(i, j);
         if (rk_step == 1) scalar_1(i, k, j) = scalar_2(i, k, j);
@@ -496,9 +565,19 @@ void Oracle::rk_scalar_step(int rk_step) {
     }
     if (rk_step == 1 && c.diff_6th_opt != 0 && !(s.moist ? c.moist_mix6_off : c.scalar_mix6_off))   // module_em.F:1421-1437 (dt_step = dt_rk)
       par([&](const Cx &xt) { sixth_order_diffusion(xt, 'm', a3(s.f), a3(s.t), a2("muts"), dt_rk, xt.c1h, xt.c2h, a3("phb")); });
+    const bool is_tke = tke_index() && s.f == "scalar_" + std::to_string(tke_index());
+    if (spec() && rk_step == 1 && has_bdy(s.f)) {   // solve_em.F:2261-2296 (moist), :2808-2843 (scalar): qv, or every species with boundary arrays
+      const Bdy B = bdy(s.f);
+      const A1x fcx{data.at("fcx").data()}, gcx{data.at("gcx").data()};
+      par([&](const Cx &xt) { relax_bdy_scalar(xt, a3(s.t), a3(s.f), a2("mut"), B, dtbc, fcx, gcx); });
+      par([&](const Cx &xt) { spec_bdy_scalar(xt, a3(s.t), B); });
+    }
     par([&](const Cx &xt) { rk_update_scalar(xt, a3(s.o), a3(s.f), a3(s.t), a3("advect_tend"), a2("mu_1"), a2("mu_2"), a2("mub"), rk_step, dt_rk); });
-    if (tke_index() && s.f == "scalar_" + std::to_string(tke_index()))   // bound the tke (solve_em.F:2437-2445)
+    if (is_tke)   // bound the tke (solve_em.F:2437-2445)
       par([&](const Cx &xt) { bound_tke(xt, a3(s.f), c.tke_upper_bound); });
+    // zero gradient on outflow / zero on inflow: moist species without boundary arrays (solve_em.F:2342-2355, specified only), tke (:2446-2456)
+    if ((s.moist && c.specified && !c.have_bcs_moist && s.f != "moist_qv") || (is_tke && spec()))
+      par([&](const Cx &xt) { flow_dep_bdy(xt, a3(s.f), a3("ru_m"), a3("rv_m")); });
   }
 }
 
@@ -519,7 +598,11 @@ void Oracle::rk_phys_bc_dry_2() {
 // moist_physics_prep_em / kessler / moist_physics_finish_em, solve_em.F:3629-4115
 void Oracle::microphysics() {
   if (c.mp_physics == 0) return;
-  const int i_start = x.its, i_end = std::min(x.ite, x.ide - 1), j_start = x.jts, j_end = std::min(x.jte, x.jde - 1);
+  // solve_em.F:3623-3645: the specified zone is left out (sz rows; all of x when periodic_x)
+  const int sz = spec() ? c.spec_zone : 0;
+  const int i_start = c.periodic_x ? std::max(x.its, x.ids) : std::max(x.its, x.ids + sz);
+  const int i_end = c.periodic_x ? std::min(x.ite, x.ide - 1) : std::min(x.ite, x.ide - 1 - sz);
+  const int j_start = std::max(x.jts, x.jds + sz), j_end = std::min(x.jte, x.jde - 1 - sz);
   const int k_start = x.kts, kte = x.kte, k_end = std::min(x.kte, x.kde - 1);
   const float dt = c.dt;
   A3 t_new = a3("t_2"), rho = a3("rho"), al = a3("al"), alb = a3("alb"), p = a3("p"), pb = a3("pb"), ph = a3("ph_2"), phb = a3("phb");
@@ -554,7 +637,7 @@ void Oracle::microphysics() {
       }
   // microphysics_driver -> kessler with kte = kde-1 (solve_em.F: KTE=min(k_end,kde-1))
   Cx xk = x;
-  xk.ite = i_end; xk.jte = j_end; xk.kte = k_end;
+  xk.its = i_start; xk.ite = i_end; xk.jts = j_start; xk.jte = j_end; xk.kte = k_end;
   { Cx keep = x; x = xk; par([&](const Cx &xt) { kessler(xt, th_phy, qv, qc, qr, rho, pii, dt, z, dz8w, a2("rainnc"), a2("rainncv")); }); x = keep; }
   // module_big_step_utilities_em.F:5593-5784 (no_mp_heating = 0, mp_tend_lim = 10.)
   const float mp_tend_lim = 10.f;
@@ -590,13 +673,34 @@ void Oracle::end_of_step() {
   bc("t_1", 'p'); bc("t_2", 'p'); bc("ph_1", 'w'); bc("ph_2", 'w'); bc("mu_1", 't'); bc("mu_2", 't');
   for (int s = 0; s < c.num_moist; s++) bc(std::string("moist_") + moist_names[s], 'p');
   for (int s = 1; s <= nsc(); s++) bc("scalar_" + std::to_string(s), 'p');
+  if (spec()) spec_final();
   halo("HALO_EM_C");           // + PERIOD_BDY_EM_E, solve_em.F:4730-4731
   par([&](const Cx &xt) { set_w_surface(xt, a3("w_2"), a3("u_2"), a3("v_2")); });
   halo("HALO_EM_E_5");         // solve_em.F:4781-4846
 }
 
+// solve_em.F:4540-4722: force the specified rows to the boundary-file values (no drift from summing tendencies)
+void Oracle::spec_final() {
+  par([&](const Cx &xt) { spec_bdy_final(xt, a3("u_2"), a2("muus"), xt.c1h, xt.c2h, xt.msfuy, bdy("u"), 'u', dtbc); });
+  par([&](const Cx &xt) { spec_bdy_final(xt, a3("v_2"), a2("muvs"), xt.c1h, xt.c2h, xt.msfvx, bdy("v"), 'v', dtbc); });
+  if (c.nested) par([&](const Cx &xt) { spec_bdy_final(xt, a3("w_2"), a2("muts"), xt.c1f, xt.c2f, xt.msfty, bdy("w"), 'w', dtbc); });
+  par([&](const Cx &xt) { spec_bdy_final(xt, a3("t_2"), a2("muts"), xt.c1h, xt.c2h, xt.msfty, bdy("t"), 't', dtbc); });
+  par([&](const Cx &xt) { spec_bdy_final(xt, a3("ph_2"), a2("muts"), xt.c1f, xt.c2f, xt.msfty, bdy("ph"), 'h', dtbc); });
+  par([&](const Cx &xt) { spec_bdy_final(xt, a2("mu_2"), a2("muts"), xt.c1h, xt.c2h, xt.msfty, bdy("mu"), dtbc); });
+  for (int s = 0; s < c.num_moist; s++) {
+    const std::string f = std::string("moist_") + moist_names[s];
+    if (has_bdy(f)) par([&](const Cx &xt) { spec_bdy_final(xt, a3(f), a2("muts"), xt.c1h, xt.c2h, xt.msfty, bdy(f), 't', dtbc); });
+  }
+  if (c.nested)
+    for (int s = 1; s <= c.num_scalar; s++) {
+      const std::string f = "scalar_" + std::to_string(s);
+      par([&](const Cx &xt) { spec_bdy_final(xt, a3(f), a2("muts"), xt.c1h, xt.c2h, xt.msfty, bdy(f), 't', dtbc); });
+    }
+}
+
 void Oracle::step() {
   const int rk_order = c.rk_ord;
+  dtbc = dtbc + c.dt;   // solve_em.F:377
   // solve_em.F:520-550 initialize_moist_old + bc
   if (c.num_moist >= 1) {
     A3 mo = a3("moist_old_qv"), m = a3("moist_qv");
@@ -678,6 +782,8 @@ int oracle_max_cfl(Oracle *o, float *mv, float *mh, int reset) {
   if (reset) o->max_vert_cfl = o->max_horiz_cfl = 0.f;
   return 0;
 }
+int oracle_set_dtbc(Oracle *o, float dtbc) { o->dtbc = dtbc; return 0; }
+float oracle_get_dtbc(Oracle *o) { return o->dtbc; }
 int oracle_set_threads(Oracle *o, int n) { o->nthreads = n < 1 ? 1 : n; return o->nthreads; }
 int oracle_step(Oracle *o, int n) { OGUARD(for (int i = 0; i < n; i++) o->step()) }
 int oracle_rk_step_prep(Oracle *o, int rk) { OGUARD(o->rk_step_prep(rk)) }
@@ -714,6 +820,6 @@ extern "C" int oracle_start_domain(orc::Oracle *o) {
     o->bc("u_1", 'U'); o->bc("u_2", 'U'); o->bc("v_1", 'V'); o->bc("v_2", 'V'); o->bc("w_1", 'w'); o->bc("w_2", 'w');
     o->bc("t_1", 'p'); o->bc("t_2", 'p'); o->bc("ph_1", 'w'); o->bc("ph_2", 'w'); o->bc("mu_1", 't'); o->bc("mu_2", 't');
     for (auto &n : o->names)
-      if (n.rfind("moist_", 0) == 0 || n.rfind("scalar_", 0) == 0) o->bc(n, 'p');
+      if ((n.rfind("moist_", 0) == 0 || n.rfind("scalar_", 0) == 0) && o->kind[n] == 3) o->bc(n, 'p');
   })
 }

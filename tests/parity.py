@@ -105,6 +105,24 @@ def with_updraft(case, wmax, conv=25.0):
     return case
 
 
+def with_boundary_zone(case):
+    """Boundary arrays for a specified / nested case (wrf_b200/bdy.py): the values real.exe would store for the first
+    boundary time (the case's own mass-coupled initial state) and tendencies that are not zero -- a slow drift of the
+    boundary values with a wave along each side, so that the relaxation, the specified-zone tendencies, the small-step
+    updates and the end-of-step reset all have something to do."""
+    from wrf_b200 import bdy
+
+    def tend(name, v):
+        wave = np.sin(np.arange(v.shape[-1]) * 0.3 + len(name))[None, None, :]
+        lev = np.cos(np.arange(v.shape[1]) * 0.2)[None, :, None]
+        return (1.0e-4 * v * (0.5 + 0.5 * wave * lev)).astype(np.float32)
+
+    return bdy.add_boundary_arrays(case, tend, spec_exp=0.33)
+
+
+SPEC = dict(open_xs=0, open_xe=0, open_ys=0, open_ye=0, spec_bdy_width=5, spec_zone=1, relax_zone=4)
+
+
 class LazyCases(dict):
     """name -> Case, each built the first time it is asked for (building all ~55 states takes several seconds and most
     tests want one): the values of the dict literal in _all_cases are compiled one by one and evaluated on demand."""
@@ -272,6 +290,20 @@ def _all_cases():
         "shipped_quarter_ss": shipped_case("em_quarter_ss"),
         "shipped_b_wave": shipped_case("em_b_wave"),
         "shipped_les": with_surface_fluxes(shipped_case("em_les")),
+        # specified / nested lateral boundaries: relaxation + specified zone driven by boundary arrays with non-zero
+        # tendencies.  Kessler with flow-dependent qc, qr; the real-data dynamics (2-D Smagorinsky on coordinate surfaces, w_damping,
+        # damp_opt 3, map factors, a tracer without boundary arrays); a nest (w and every species relaxed too); boundary arrays for
+        # every moist species with the 6th-order filter and even-order advection; the TKE closure in physical space
+        "specified": with_boundary_zone(make_case("quarter_ss", nx=30, ny=28, nz=19, specified=1, **SPEC)),
+        "specified_real": with_boundary_zone(with_map_factors(make_case("quarter_ss", nx=30, ny=28, nz=19, specified=1, diff_opt=1, km_opt=4,
+                                                                         w_damping=1, damp_opt=3, zdamp=8000.0, dampcoef=0.2, num_scalar=1,
+                                                                         mp_physics=0, num_moist=1, **SPEC))),
+        "nested": with_boundary_zone(make_case("quarter_ss", nx=30, ny=28, nz=19, nested=1, num_scalar=1, **SPEC)),
+        "specified_bcs_moist": with_boundary_zone(make_case("quarter_ss", nx=30, ny=28, nz=19, specified=1, have_bcs_moist=1, diff_6th_opt=2,
+                                                            h_mom_adv_order=6, v_mom_adv_order=4, h_sca_adv_order=6, v_sca_adv_order=4,
+                                                            moist_adv_opt=0, **SPEC)),
+        "specified_tke": with_boundary_zone(with_tke(with_updraft(make_case("quarter_ss", nx=30, ny=28, nz=19, specified=1, diff_opt=2, km_opt=2,
+                                                                            mix_full_fields=1, **SPEC), 20.0))),
         "ieva_weno_hill": with_updraft(make_case("hill2d_x", nx=62, ny=3, nz=41, zadvect_implicit=1, momentum_adv_opt=3,
                                                  moist_adv_opt=3), 60.0, conv=70.0),
     }

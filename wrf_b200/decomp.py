@@ -42,6 +42,14 @@ def window(gd: Dims, pd: Dims):
     return (slice(pd.jms - gd.jms, pd.jme - gd.jms + 1), slice(pd.ims - gd.ims, pd.ime - gd.ims + 1))
 
 
+def bdy_side(name: str) -> str:
+    """'x' / 'y' for a boundary array name (<f>_bxs, <f>_btye, ...), '' for every other field"""
+    for t in ("_bx", "_btx", "_by", "_bty"):
+        if name[-len(t) - 1:-1] == t and name[-1] in "se":
+            return t[-1]
+    return ""
+
+
 def split_case(case: Case, ntasks_x: int, ntasks_y: int, poison: bool = False):
     """global Case -> list of per-rank Cases (rank = my*ntasks_x + mx, module_dm.F:135-175).
     poison=True overwrites everything a rank does not own with NaN, so that a test fails unless the
@@ -54,6 +62,10 @@ def split_case(case: Case, ntasks_x: int, ntasks_y: int, poison: bool = False):
         sj, si = window(gd, pd)
         fl = {}
         for k, a in case.fields.items():
+            side = bdy_side(k)
+            if side:     # boundary arrays (spec_bdy_width, levels, jms:jme | ims:ime): cut along the side (wrf_b200/bdy.py)
+                fl[k] = np.ascontiguousarray(a[..., sj if side == "x" else si]).copy()
+                continue
             if a.ndim == 3:
                 b = np.ascontiguousarray(a[sj, :, si]).copy()
             elif a.ndim == 2:

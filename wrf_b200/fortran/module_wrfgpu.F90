@@ -50,6 +50,7 @@ MODULE module_wrfgpu
       INTEGER(c_int) :: tke_adv_opt
       REAL(c_float)  :: tke_upper_bound
       INTEGER(c_int) :: use_adaptive_time_step
+      INTEGER(c_int) :: spec_bdy_width, spec_zone, relax_zone, have_bcs_moist, have_bcs_scalar
    END TYPE wrfgpu_config
 
    INTERFACE

@@ -69,7 +69,8 @@ class Config(ctypes.Structure):
         + [("mix_full_fields", ctypes.c_int), ("isfflx", ctypes.c_int)]
         + [(n, ctypes.c_float) for n in ("tke_drag_coefficient", "tke_heat_flux")]
         + [("mix_isotropic", ctypes.c_int), ("mix_upper_bound", ctypes.c_float), ("tke_adv_opt", ctypes.c_int), ("tke_upper_bound", ctypes.c_float),
-           ("use_adaptive_time_step", ctypes.c_int)])
+           ("use_adaptive_time_step", ctypes.c_int)]
+        + [(n, ctypes.c_int) for n in ("spec_bdy_width", "spec_zone", "relax_zone", "have_bcs_moist", "have_bcs_scalar")])
 
 
 def default_config(**kw) -> Config:
