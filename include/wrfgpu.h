@@ -175,6 +175,15 @@ int  wrfgpu_solve_em(wrfgpu_solver *s,
                      int n_in,  const char *const *in_names,  const float *const *in_host,
                      int n_out, const char *const *out_names, float *const *out_host);
 int  wrfgpu_sync(wrfgpu_solver *s);
+/* specified / nested lateral boundaries.  The boundary arrays are fields like any other: "<f>_bxs", "<f>_bxe",
+ * "<f>_bys", "<f>_bye" and the tendencies "<f>_btxs" ... "<f>_btye" for f = u, v, w, ph, t, mu, moist_qv (and every moist
+ * species / scalar_N that has them), in the reference's layout (jms:jme | ims:ime, kds:kde, spec_bdy_width), mu with one
+ * level (Registry.EM_COMMON 'b' entries); "fcx", "gcx" are the relaxation weights start_em computes (lbc_fcx_gcx,
+ * dyn_em/module_bc_em.F:1297).  grid%dtbc, the time since the arrays were valid, is advanced by every step
+ * (solve_em.F:377); the host sets it back to 0 when it uploads the next boundary time (share/input_wrf.F:1834,
+ * mediation_integrate.F:1529). */
+int  wrfgpu_set_dtbc(wrfgpu_solver *s, float dtbc);
+int  wrfgpu_get_dtbc(wrfgpu_solver *s, float *dtbc);
 /* run on the caller's CUDA stream (cudaStream_t) instead of the solver's own */
 int  wrfgpu_set_stream(wrfgpu_solver *s, void *cuda_stream);
 /* per-kernel cudaEvent statistics collected while phase timing is on, as text

@@ -70,6 +70,13 @@ class Oracle:
         self._chk(self.lib.oracle_max_cfl(self.h, ctypes.byref(mv), ctypes.byref(mh), ctypes.c_int(int(reset))))
         return mv.value, mh.value
 
+    def set_dtbc(self, dtbc):
+        self.lib.oracle_set_dtbc(self.h, ctypes.c_float(dtbc))
+
+    def dtbc(self):
+        self.lib.oracle_get_dtbc.restype = ctypes.c_float
+        return float(self.lib.oracle_get_dtbc(self.h))
+
     def set_threads(self, n):
         return int(self.lib.oracle_set_threads(self.h, ctypes.c_int(int(n))))
 

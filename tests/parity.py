@@ -385,6 +385,8 @@ def run_phase_parity(case, verbose=False):
     Returns list of failures (phase, field, n, maxabs, rel)."""
     o, s = Oracle(case), Solver(case)
     o.start_domain(); s.start_domain()
+    if case.config.specified or case.config.nested:   # grid%dtbc as solve_em leaves it for the first step (solve_em.F:377)
+        o.set_dtbc(case.config.dt); s.set_dtbc(case.config.dt)
     fails = []
     rep = diff_report(o, s)
     for r in rep:

@@ -83,7 +83,8 @@ def _check(case, ntx, nty, nsteps=2):
 
 @pytest.mark.parametrize("mesh", [(1, 2), (2, 1), (2, 2)])
 @pytest.mark.parametrize("name", ["quarter_ss", "periodic", "b_wave", "hill2d_x_wide", "les", "diffusion", "diffusion_periodic", "mono", "mono_periodic", "weno", "wenopd_periodic", "weno_mom", "ieva", "ieva_periodic", "diff6", "diff6_periodic", "order64",
-                                  "smag2d", "smag2d_periodic", "smag2d_b_wave", "diff2", "diff2_periodic", "diff2_hill_wide", "diff2_b_wave", "smag3d", "smag3d_periodic", "tke", "tke_periodic"])
+                                  "smag2d", "smag2d_periodic", "smag2d_b_wave", "diff2", "diff2_periodic", "diff2_hill_wide", "diff2_b_wave", "smag3d", "smag3d_periodic", "tke", "tke_periodic",
+                                  "specified", "specified_real", "nested", "specified_bcs_moist", "specified_tke"])
 def test_n_rank_oracle_equals_single_rank(name, mesh):
     cases = parity.small_cases()
     cases["hill2d_x_wide"] = make_case("hill2d_x", nx=62, ny=9, nz=21)

@@ -8,6 +8,7 @@ import pytest
 from tests import parity
 from tests.oracle_lib import Oracle
 from wrf_b200 import Solver
+from wrf_b200.decomp import bdy_side as parity_bdy_side
 
 pytestmark = pytest.mark.gpu
 
@@ -20,7 +21,8 @@ ALL = ["hill2d_x", "quarter_ss", "quarter_ss_nopd", "b_wave", "les", "periodic",
        "order64", "order63_periodic", "order_mixed", "smag2d", "smag2d_periodic", "smag2d_hill", "smag2d_b_wave",
        "diff2", "diff2_periodic", "diff2_hill", "diff2_b_wave",
        "smag3d", "smag3d_periodic", "smag3d_hill", "tke", "tke_periodic", "tke_hill",
-       "shipped_hill2d_x", "shipped_quarter_ss", "shipped_b_wave", "shipped_les"]
+       "shipped_hill2d_x", "shipped_quarter_ss", "shipped_b_wave", "shipped_les",
+       "specified", "specified_real", "nested", "specified_bcs_moist", "specified_tke"]
 
 
 def cases():
@@ -99,6 +101,35 @@ def test_shipped_configurations_ten_steps_bit_exact(name):
     s.close()
 
 
+@pytest.mark.parametrize("name", ["specified", "specified_real", "nested", "specified_bcs_moist", "specified_tke"])
+def test_boundary_zone_twelve_steps_bit_exact(name):
+    """f3: specified / nested lateral boundaries.  Twelve steps with a new boundary time read after the sixth (the host
+    uploads fresh boundary arrays and resets dtbc, as share/input_wrf.F does): every field equals the oracle bit for bit,
+    the specified rows hold exactly the boundary file's value at the end of each step, and grid%dtbc follows."""
+    case = cases()[name]
+    o, s = _pair(name)
+    d, c = case.dims, case.config
+    for n in range(12):
+        if n == 6:     # next boundary time: the old values advanced by six steps of their tendencies, new tendencies
+            for f in [k for k in case.fields if "_bt" in k and parity_bdy_side(k)]:
+                val = f.replace("_bt", "_b")
+                new = (case.fields[val] + np.float32(6 * c.dt) * case.fields[f]).astype(np.float32)
+                o.set(val, new); s.set(val, new)
+                o.set(f, -0.5 * case.fields[f]); s.set(f, -0.5 * case.fields[f])
+            o.set_dtbc(0.0); s.set_dtbc(0.0)
+        o.step(1); s.step(1)
+        assert s.dtbc() == o.dtbc() and abs(s.dtbc() - ((n % 6) + 1) * c.dt) < 1e-3
+    rep = parity.diff_report(o, s)
+    assert not rep, rep[:5]
+    # spec_bdy_final: mu_2 on the outermost row is the boundary value + dtbc * tendency
+    mu, bx, bt = s.get("mu_2"), s.get("mu_bxs").reshape(c.spec_bdy_width, 1, -1), s.get("mu_btxs").reshape(c.spec_bdy_width, 1, -1)
+    j0, j1 = d.jds + 1 - d.jms, d.jde - 2 - d.jms
+    want = (bx[0, 0, j0:j1 + 1] + np.float32(s.dtbc()) * bt[0, 0, j0:j1 + 1]).astype(np.float32)
+    assert np.array_equal(mu[j0:j1 + 1, d.ids - d.ims], want)
+    assert np.isfinite(s.get("w_2")).all() and np.abs(s.get("w_2")).max() > 0.0
+    s.close()
+
+
 @pytest.mark.parametrize("name", ["ieva", "ieva_periodic"])
 def test_ieva_three_steps_bit_exact(name):
     """IEVA with a non-zero implicit part (wwI) on every step: three steps stay identical to the oracle, including
@@ -169,6 +200,12 @@ REJECTED = [
     ("h_sca_adv_order=4", dict(h_sca_adv_order=4)),
     ("mp_physics=2", dict(mp_physics=2)),
     ("conflicting bc", dict(periodic_x=1, open_xs=1)),
+    # specified / nested boundaries are built for all four sides and the non-WENO, non-monotonic, non-IEVA options
+    ("specified with open sides", dict(specified=1, spec_bdy_width=5, spec_zone=1, relax_zone=4)),
+    ("specified and nested", dict(specified=1, nested=1, open_xs=0, open_xe=0, open_ys=0, open_ye=0, spec_bdy_width=5, spec_zone=1, relax_zone=4)),
+    ("specified with WENO", dict(specified=1, open_xs=0, open_xe=0, open_ys=0, open_ye=0, spec_bdy_width=5, spec_zone=1, relax_zone=4, moist_adv_opt=3)),
+    ("specified with IEVA", dict(specified=1, open_xs=0, open_xe=0, open_ys=0, open_ye=0, spec_bdy_width=5, spec_zone=1, relax_zone=4, zadvect_implicit=1)),
+    ("relax_zone outside spec_bdy_width", dict(specified=1, open_xs=0, open_xe=0, open_ys=0, open_ye=0, spec_bdy_width=4, spec_zone=1, relax_zone=4)),
 ]
 
 

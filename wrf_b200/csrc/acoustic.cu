@@ -239,20 +239,27 @@ __global__ void __launch_bounds__(128, UV_MINB) k_advance_uv(const Geo g, Box b,
   TID2;
   const int ids = g.ids, ide = g.ide, jds = g.jds, jde = g.jde, kde = g.kde;
   const int its = g.its, ite = g.ite, jts = g.jts, jte = g.jte;
-  const int i_start = its, i_end = min(ite, ide - 1), j_start = jts, j_end = min(jte, jde - 1);
+  int i_start = its, i_end = min(ite, ide - 1), j_start = jts, j_end = min(jte, jde - 1), i_endu = ite, j_endv = jte;
+  if (g.spec) {   // :734-751: the specified rows are not advanced here (spec_bdyupdate does it)
+    const int sz = g.spec_zone;
+    i_start = max(its, ids + sz); i_end = min(ite, ide - sz - 1);
+    j_start = max(jts, jds + sz); j_end = min(jte, jde - sz - 1);
+    i_endu = min(ite, ide - sz); j_endv = min(jte, jde - sz);
+    if (g.periodic_x) { i_start = its; i_end = min(ite, ide - 1); i_endu = ite; }
+  }
   const float dx = 1.f / g.rdx, dy = 1.f / g.rdy;
   // ---- which of the reference's loop ranges this column is in (:734-797)
-  int i_start_up = i_start, i_end_up = ite, i_s_t = i_start, i_e_t = ite;
+  int i_start_up = i_start, i_end_up = i_endu, i_s_t = i_start, i_e_t = i_endu;
   if ((g.open_xs || g.sym_xs) && its == ids) i_start_up++;
   if ((g.open_xe || g.sym_xe) && ite == ide) i_end_up--;
   if (g.sym_xs && its == ids) i_s_t++;
   if (g.sym_xe && ite == ide) i_e_t--;
-  int j_start_vp = j_start, j_end_vp = jte, j_s_t = j_start, j_e_t = jte;
+  int j_start_vp = j_start, j_end_vp = j_endv, j_s_t = j_start, j_e_t = j_endv;
   if ((g.open_ys || g.sym_ys) && jts == jds) j_start_vp++;
   if ((g.open_ye || g.sym_ye) && jte == jde) j_end_vp--;
   if (g.sym_ys && jts == jds) j_s_t++;
   if (g.sym_ye && jte == jde) j_e_t--;
-  const bool u_row = j <= j_end, v_col = i <= i_end;
+  const bool u_row = j >= j_start && j <= j_end, v_col = i >= i_start && i <= i_end;
   const bool u_tend = u_row && i >= i_s_t && i <= i_e_t, u_pg = u_row && i >= i_start_up && i <= i_end_up;
   const bool v_tend = v_col && j >= j_s_t && j <= j_e_t, v_pg = v_tend && j >= j_start_vp && j <= j_end_vp;
   if (!FUSE && !u_tend && !u_pg && !v_tend) return;
@@ -796,6 +803,7 @@ void Solver::advance_uv(int rk_step) {
   rk_params(rk_step, dt_rk, dts_rk, ns);
   UvFuse fz{0, 0, nullptr, nullptr, nullptr, nullptr};
   LAUNCH2(this, k_advance_uv<false>, (Box{q.its, q.ite, 1, 1, q.jts, q.jte}), dts_rk, uv_args(this), fz);
+  if (spec()) spec_update_uv(dts_rk);   // solve_em.F:1344-1365
 }
 
 // advance_uv + the u, v part of sumflux(iteration); the ww part is k_sumflux_w (after advance_w)
@@ -822,9 +830,10 @@ void Solver::advance_mu_t(int rk_step, bool final_ave) {
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
   MuTArgs a = mu_t_args(this);
-  const Box mass{q.its, std::min(q.ite, q.ide - 1), 1, 1, q.jts, std::min(q.jte, q.jde - 1)};
+  const Box mass = spec() ? spec_mass_box() : Box{q.its, std::min(q.ite, q.ide - 1), 1, 1, q.jts, std::min(q.jte, q.jde - 1)};
   if (final_ave) LAUNCH2(this, k_advance_mu_t<true>, mass, dts_rk, a);    // only together with advance_w_fused
   else LAUNCH2(this, k_advance_mu_t<false>, mass, dts_rk, a);
+  if (spec()) spec_update_tmu(dts_rk);   // solve_em.F:1459-1490
 }
 
 static WArgs w_args(Solver *s) {
@@ -841,7 +850,17 @@ void Solver::advance_w(int rk_step) {
   float dt_rk, dts_rk; int ns;
   rk_params(rk_step, dt_rk, dts_rk, ns);
   WFuse fz{};
-  LAUNCH2(this, k_advance_w<false>, (Box{q.its, std::min(q.ite, q.ide - 1), 1, 1, q.jts, std::min(q.jte, q.jde - 1)}), dts_rk, w_args(this), fz);
+  const Box mass = spec() ? spec_mass_box() : Box{q.its, std::min(q.ite, q.ide - 1), 1, 1, q.jts, std::min(q.jte, q.jde - 1)};
+  LAUNCH2(this, k_advance_w<false>, mass, dts_rk, w_args(this), fz);
+}
+
+// the columns advance_mu_t and advance_w update with specified / nested boundaries (module_small_step_em.F:1054-1063, :1273-1282):
+// one row in from every side, whatever spec_zone is
+Box Solver::spec_mass_box() const {
+  const Geo &q = g;
+  Box bx{q.its, std::min(q.ite, q.ide - 1), 1, 1, std::max(q.jts, q.jds + 1), std::min(q.jte, q.jde - 2)};
+  if (!q.periodic_x) { bx.i0 = std::max(q.its, q.ids + 1); bx.i1 = std::min(q.ite, q.ide - 2); }
+  return bx;
 }
 
 // advance_w + sumflux (ww part) + calc_p_rho(iteration) in one column kernel, then the exchange and
@@ -864,6 +883,7 @@ void Solver::sumflux(int rk_step, int iteration) {
   rk_params(rk_step, dt_rk, dts_rk, ns);
   LAUNCH3(this, k_sumflux, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), iteration, ns, o("u_2"), o("v_2"), o("ww"), o("u_save"),
           o("v_save"), o("ww1"), o("muu"), o("muv"), o("ru_m"), o("rv_m"), o("ww_m"));
+  if (spec()) spec_update_phw(dts_rk);   // solve_em.F:1582-1620, between sumflux and calc_p_rho
 }
 
 // the part of sumflux the fused advance_uv leaves: ww_m (all levels) and the level-kde reset of ru_m, rv_m

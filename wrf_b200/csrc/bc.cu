@@ -97,14 +97,14 @@ __global__ void k_bc_x(const GeoBase g, BcBatch bb) {
         else { for (int i = 0; i <= BDY - 1; i++) D(ide + i) = D(ide - i); }
       }
     }
-    if (g.open_xs && its == ids && q.open_bc_copy) {
+    if (g.oxs() && its == ids && q.open_bc_copy) {
       const int a0 = is3d ? jts - BDY : j0, a1 = is3d ? min(jte, jde + q.jstag) + BDY : j1;
       if (j >= a0 && j <= a1) {
         const float s = D(ids);
         D(ids - 1) = s; D(ids - 2) = s; D(ids - 3) = s;
       }
     }
-    if (g.open_xe && ite == ide && q.open_bc_copy) {
+    if (g.oxe() && ite == ide && q.open_bc_copy) {
       if (v != 'u' && v != 'x') {
         const int a0 = is3d ? jts - BDY : j0, a1 = is3d ? min(jte, jde + q.jstag) + BDY : j1;
         if (j >= a0 && j <= a1) {
@@ -163,11 +163,11 @@ __global__ void k_bc_y(const GeoBase g, BcBatch bb) {
       else if (v == 'v') { for (int j = 1; j <= BDY; j++) D(jde + j) = -D(jde - j); }
       else { for (int j = 1; j <= BDY; j++) D(jde + j) = D(jde - j); }
     }
-    if (g.open_ys && jts == jds && q.open_bc_copy) {
+    if (g.oys() && jts == jds && q.open_bc_copy) {
       const float s = D(jds);
       D(jds - 1) = s; D(jds - 2) = s; D(jds - 3) = s;
     }
-    if (g.open_ye && jte == jde && q.open_bc_copy) {
+    if (g.oye() && jte == jde && q.open_bc_copy) {
       if (v != 'v' && v != 'y') {
         const float s = D(jde - 1);
         D(jde) = s; D(jde + 1) = s; D(jde + 2) = s;

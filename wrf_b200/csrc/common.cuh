@@ -42,9 +42,17 @@ struct GeoBase {
   int ips, ipe, jps, jpe;
   int its, ite, jts, jte;          // tile == patch (numtiles = 1)
   int ni, nk, nj;
+  int hni, hnj;                    // row / column lengths of the caller's arrays (ime-ims+1, jme-jms+1): the boundary arrays keep them
   long sk, sj;                     // strides of k and j in a 3-D field
   int isk, isj;                    // the same as 32-bit ints: element indices fit (checked at create)
   int periodic_x, periodic_y, sym_xs, sym_xe, sym_ys, sym_ye, open_xs, open_xe, open_ys, open_ye;
+  // specified / nested lateral boundaries: spec = config_flags%specified .or. config_flags%nested; nearly
+  // every loop-range test of the reference reads "open_?? .or. specified" (o??() below), the radiative blocks open_?? alone
+  int spec, spec_zone, relax_zone;
+  __host__ __device__ bool oxs() const { return open_xs || spec; }
+  __host__ __device__ bool oxe() const { return open_xe || spec; }
+  __host__ __device__ bool oys() const { return open_ys || spec; }
+  __host__ __device__ bool oye() const { return open_ye || spec; }
   int top_lid, phi_adv_z, damp_opt, w_damping, pert_coriolis, use_theta_m, hypsometric_opt, rk_ord;
   int num_moist;
   float rdx, rdy, dt, cf1, cf2, cf3, cfn, cfn1;
@@ -130,7 +138,11 @@ struct Field {
   int kind = 3;         // 3, 2, 1
   size_t n = 0;         // floats of the caller's (host) array: (ime-ims+1) per row
   size_t nd = 0;        // floats of the device allocation: Solver::pitch() per row
+  bool raw = false;     // a contiguous array that is not a model field (boundary arrays, fcx / gcx): kind 1 copies, no coefficient refresh
 };
+
+// the eight boundary arrays of one field (bdy.cu), sides in the order Y-start, Y-end, X-start, X-end
+struct BdyArr { const float *v[4], *t[4]; int nk; };
 
 struct Species {
   std::string f, o, t;  // field, old, tend names
@@ -153,6 +165,23 @@ struct Solver {
   int tke_index() const { return (c.km_opt == 2 && c.diff_opt == 2) ? c.num_scalar + 1 : 0; }
   long long launches = 0;
   float *d_cfl = nullptr;   // 2 floats: max_vert_cfl, max_horiz_cfl
+  // specified / nested lateral boundaries (bdy.cu): grid%dtbc, the time since the boundary arrays were valid (solve_em.F:377;
+  // reset by the host when it uploads the next boundary time, wrfgpu_set_dtbc)
+  float dtbc = 0.f;
+  bool spec() const { return c.specified || c.nested; }
+  void add_raw(const std::string &n, size_t count);
+  void add_bdy(const std::string &field, int levels);
+  bool has_bdy(const std::string &field) const;
+  BdyArr bdy_arr(const std::string &field);
+  void relax_bdy_dry(bool store_save);
+  void spec_bdy_dry();
+  void spec_update_uv(float dts_rk);
+  void spec_update_tmu(float dts_rk);
+  void spec_update_phw(float dts_rk);
+  void bdy_scalar(const Species &sp);
+  void flow_dep_bdy(const std::string &field);
+  void spec_final();
+  Box spec_mass_box() const;
   // halo exchange state (HaloState, halo.cu)
   void *comm = nullptr;
   void *snapshot = nullptr;   // history.cu: staging / pinned buffers of wrfgpu_snapshot_*
@@ -206,6 +235,7 @@ struct Solver {
   void diffusion2_tendencies();
   void tke_rhs();          // deform.cu
   void rk_tendency(int rk_step, bool zero_save = true);
+  void rk_tendency_main(int rk_step, bool zero_save);
   // IEVA (ieva.cu): WW_SPLIT + mass estimates; one implicit column solve (0 scalar, 1 u, 2 v, 3 ph, 4 w)
   void ieva_split(bool dry, const float *u, const float *v, const float *ww, const float *mut, bool active = true);
   void ieva_implicit(int which, float *tendency, const float *q_old, const float *mu_old, const float *mu_new, float dt_rk);   // zero_save = false: small_step_prep(rk_step, true) writes those zeros

@@ -55,10 +55,10 @@ static TkeIn tke_in(Solver *S) {
 void Solver::tke_rhs() {
   const Geo &q = g;
   int i_start = q.its, i_end = std::min(q.ite, q.ide - 1), j_start = q.jts, j_end = std::min(q.jte, q.jde - 1);
-  if (q.open_xs) i_start = std::max(q.ids + 1, q.its);
-  if (q.open_xe) i_end = std::min(q.ide - 2, q.ite);
-  if (q.open_ys) j_start = std::max(q.jds + 1, q.jts);
-  if (q.open_ye) j_end = std::min(q.jde - 2, q.jte);
+  if (q.oxs()) i_start = std::max(q.ids + 1, q.its);
+  if (q.oxe()) i_end = std::min(q.ide - 2, q.ite);
+  if (q.oys()) j_start = std::max(q.jds + 1, q.jts);
+  if (q.oye()) j_end = std::min(q.jde - 2, q.jte);
   if (q.periodic_x) { i_start = q.its; i_end = std::min(q.ite, q.ide - 1); }
   LAUNCH3(this, k_tke_rhs, (Box{i_start, i_end, 1, q.kde - 1, j_start, j_end}), tke_in(this), o("tke_tend"));
 }
@@ -87,10 +87,10 @@ void Solver::diffusion_prep() {
   if (c.km_opt == 1) diffusion2_isotropic_km();
   else {   // calculate_km_kh on the range its closures share (module_diffusion_em.F:1816-1831, :1974-1989, :2078-2093)
     int i_start = q.its, i_end = std::min(q.ite, q.ide - 1), j_start = q.jts, j_end = std::min(q.jte, q.jde - 1);
-    if (q.open_xs) i_start = std::max(q.ids + 1, q.its);
-    if (q.open_xe) i_end = std::min(q.ide - 2, q.ite);
-    if (q.open_ys) j_start = std::max(q.jds + 1, q.jts);
-    if (q.open_ye) j_end = std::min(q.jde - 2, q.jte);
+    if (q.oxs()) i_start = std::max(q.ids + 1, q.its);
+    if (q.oxe()) i_end = std::min(q.ide - 2, q.ite);
+    if (q.oys()) j_start = std::max(q.jds + 1, q.jts);
+    if (q.oye()) j_end = std::min(q.jde - 2, q.jte);
     if (q.periodic_x) { i_start = q.its; i_end = std::min(q.ite, q.ide - 1); }
     if (c.km_opt == 2) {   // calculate_N2 + tke_km in one launch
       LAUNCH3(this, k_tke_km, (Box{i_start, i_end, 1, q.kde - 1, j_start, j_end}), tke_in(this), o("bn2"), o("xkmh"), o("xkmv"), o("xkhh"), o("xkhv"));

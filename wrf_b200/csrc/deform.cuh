@@ -42,17 +42,17 @@ inline DefR def_ranges(const GeoBase &g, int mix_full_fields) {
   r.kte = g.kde; r.ktf = g.kde - 1; r.mix_full_fields = mix_full_fields;
   r.a_ie = ite < ide - 1 ? ite : ide - 1; r.a_je = jte < jde - 1 ? jte : jde - 1;
   int i_start = its, i_end = ite, j_start = jts, j_end = jte;
-  if (g.open_xs) i_start = ids + 1 > its ? ids + 1 : its;
-  if (g.open_xe) i_end = ide - 1 < ite ? ide - 1 : ite;
-  if (g.open_ys) j_start = jds + 1 > jts ? jds + 1 : jts;
-  if (g.open_ye) j_end = jde - 1 < jte ? jde - 1 : jte;
+  if (g.oxs()) i_start = ids + 1 > its ? ids + 1 : its;
+  if (g.oxe()) i_end = ide - 1 < ite ? ide - 1 : ite;
+  if (g.oys()) j_start = jds + 1 > jts ? jds + 1 : jts;
+  if (g.oye()) j_end = jde - 1 < jte ? jde - 1 : jte;
   if (g.periodic_x) { i_start = its; i_end = ite; }
   r.i0_12 = i_start; r.i1_12 = i_end; r.j0_12 = j_start; r.j1_12 = j_end;
   r.cxs12 = !g.periodic_x && i_start == ids + 1; r.cys12 = !g.periodic_y && j_start == jds + 1;
   r.cxe12 = !g.periodic_x && i_end == ide - 1; r.cye12 = !g.periodic_y && j_end == jde - 1;
   i_start = its; i_end = r.a_ie; j_start = jts; j_end = r.a_je;
-  if (g.open_xs) i_start = ids + 1 > its ? ids + 1 : its;
-  if (g.open_ys) j_start = jds + 1 > jts ? jds + 1 : jts;
+  if (g.oxs()) i_start = ids + 1 > its ? ids + 1 : its;
+  if (g.oys()) j_start = jds + 1 > jts ? jds + 1 : jts;
   if (g.periodic_x) i_start = its;
   if (g.periodic_y) j_end = jte < jde ? jte : jde;
   r.i0_23 = i_start; r.i1_23 = g.periodic_x ? r.a_ie : i_end; r.j0_23 = j_start; r.j1_23 = j_end;

@@ -42,24 +42,24 @@ __global__ void k_diffuse(const Geo g, Box b, DiffIn s, fp tendency) {
     int i_start, i_end, j_start, j_end, k_start = kts;
     if (KIND == DIFF_U) {
       i_start = its; i_end = ite; j_start = jts; j_end = min(jte, jde - 1);
-      if (g.open_xs) i_start = max(ids + 1, its);
-      if (g.open_xe) i_end = min(ide - 1, ite);
-      if (g.open_ys) j_start = max(jds + 1, jts);
-      if (g.open_ye) j_end = min(jde - 2, jte);
+      if (g.oxs()) i_start = max(ids + 1, its);
+      if (g.oxe()) i_end = min(ide - 1, ite);
+      if (g.oys()) j_start = max(jds + 1, jts);
+      if (g.oye()) j_end = min(jde - 2, jte);
       if (g.periodic_x) { i_start = its; i_end = ite; }
     } else if (KIND == DIFF_V) {
       i_start = its; i_end = min(ite, ide - 1); j_start = jts; j_end = jte;
-      if (g.open_xs) i_start = max(ids + 1, its);
-      if (g.open_xe) i_end = min(ide - 2, ite);
-      if (g.open_ys) j_start = max(jds + 1, jts);
-      if (g.open_ye) j_end = min(jde - 1, jte);
+      if (g.oxs()) i_start = max(ids + 1, its);
+      if (g.oxe()) i_end = min(ide - 2, ite);
+      if (g.oys()) j_start = max(jds + 1, jts);
+      if (g.oye()) j_end = min(jde - 1, jte);
       if (g.periodic_x) { i_start = its; i_end = min(ite, ide - 1); }
     } else {
       i_start = its; i_end = min(ite, ide - 1); j_start = jts; j_end = min(jte, jde - 1);
-      if (g.open_xs) i_start = max(ids + 1, its);
-      if (g.open_xe) i_end = min(ide - 2, ite);
-      if (g.open_ys) j_start = max(jds + 1, jts);
-      if (g.open_ye) j_end = min(jde - 2, jte);
+      if (g.oxs()) i_start = max(ids + 1, its);
+      if (g.oxe()) i_end = min(ide - 2, ite);
+      if (g.oys()) j_start = max(jds + 1, jts);
+      if (g.oye()) j_end = min(jde - 2, jte);
       if (g.periodic_x) { i_start = its; i_end = min(ite, ide - 1); }
       if (KIND == DIFF_W) k_start = kts + 1;
     }
@@ -127,13 +127,13 @@ __global__ void k_diffuse(const Geo g, Box b, DiffIn s, fp tendency) {
     int k_lo = kts, k_hi = ktf;
     if (KIND == DIFF_U) {
       i_end = ite;
-      if (g.open_xs) i_start = max(ids + 1, its);
-      if (g.open_xe) i_end = min(ide - 1, ite);
+      if (g.oxs()) i_start = max(ids + 1, its);
+      if (g.oxe()) i_end = min(ide - 1, ite);
       if (g.periodic_x) { i_start = its; i_end = ite; }
       k_hi = ktf - 1;
     } else if (KIND == DIFF_V) {
-      if (g.open_ys) j_start = max(jds + 1, jts);
-      if (g.open_ye) j_end = min(jde - 1, jte);
+      if (g.oys()) j_start = max(jds + 1, jts);
+      if (g.oye()) j_end = min(jde - 1, jte);
       k_hi = ktf - 1;
     } else if (KIND == DIFF_W) {
       k_lo = kts + 1;
@@ -300,13 +300,17 @@ void launch_diff6(Solver *s, int which, cfp field, fp tendency, cfp mut, float d
     if (c.open_ys) r.j0 = std::max(q.jts, q.jds + 3);
     if (c.open_xe) r.i1 = std::min(q.ite, q.ide - 3);
     if (c.open_ye) r.j1 = std::min(q.jte, q.jde - 4);
+    if (q.spec) {   // :6354
+      r.i0 = std::max(q.its, q.ids + 3); r.i1 = std::min(q.ite, q.ide - 3);
+      r.j0 = std::max(q.jts, q.jds + 3); r.j1 = std::min(q.jte, q.jde - 4);
+    }
   } else if (which == DIFF_V) {
     r.i1 = std::min(q.ide - 1, q.ite); r.j1 = q.jte;
     if (c.open_xs) r.i0 = std::max(q.its, q.ids + 3);
     if (c.open_ys) r.j0 = std::max(q.jts, q.jds + 3);
     if (c.open_xe) r.i1 = std::min(q.ite, q.ide - 4);
     if (c.open_ye) r.j1 = std::min(q.jte, q.jde - 3);
-    if (c.open_xs) {   // sic (:6333): "open_xs .or. specified" restricts all four sides
+    if (c.open_xs || q.spec) {   // sic (:6381): "open_xs .or. specified" restricts all four sides
       r.i0 = std::max(q.its, q.ids + 3); r.i1 = std::min(q.ite, q.ide - 4);
       r.j0 = std::max(q.jts, q.jds + 3); r.j1 = std::min(q.jte, q.jde - 3);
     }
@@ -316,6 +320,10 @@ void launch_diff6(Solver *s, int which, cfp field, fp tendency, cfp mut, float d
     if (c.open_ys) r.j0 = std::max(q.jts, q.jds + 3);
     if (c.open_xe) r.i1 = std::min(q.ite, q.ide - 4);
     if (c.open_ye) r.j1 = std::min(q.jte, q.jde - 4);
+    if (q.spec) {   // :6408, :6435
+      r.i0 = std::max(q.its, q.ids + 3); r.i1 = std::min(q.ide - 4, q.ite);
+      r.j0 = std::max(q.jts, q.jds + 3); r.j1 = std::min(q.jde - 4, q.jte);
+    }
     if (which == DIFF_W) r.k0 = 2;
   }
   Diff6In in;

@@ -32,24 +32,24 @@ inline R4 d2_range(const GeoBase &g, char kind) {
   R4 r;
   if (kind == 'u') {
     r = {its, ite, jts, mn(jte, jde - 1)};
-    if (g.open_xs) r.i0 = mx(ids + 1, its);
-    if (g.open_xe) r.i1 = mn(ide - 1, ite);
-    if (g.open_ys) r.j0 = mx(jds + 1, jts);
-    if (g.open_ye) r.j1 = mn(jde - 2, jte);
+    if (g.oxs()) r.i0 = mx(ids + 1, its);
+    if (g.oxe()) r.i1 = mn(ide - 1, ite);
+    if (g.oys()) r.j0 = mx(jds + 1, jts);
+    if (g.oye()) r.j1 = mn(jde - 2, jte);
     if (g.periodic_x) { r.i0 = its; r.i1 = ite; }
   } else if (kind == 'v') {
     r = {its, mn(ite, ide - 1), jts, jte};
-    if (g.open_xs) r.i0 = mx(ids + 1, its);
-    if (g.open_xe) r.i1 = mn(ide - 2, ite);
-    if (g.open_ys) r.j0 = mx(jds + 1, jts);
-    if (g.open_ye) r.j1 = mn(jde - 1, jte);
+    if (g.oxs()) r.i0 = mx(ids + 1, its);
+    if (g.oxe()) r.i1 = mn(ide - 2, ite);
+    if (g.oys()) r.j0 = mx(jds + 1, jts);
+    if (g.oye()) r.j1 = mn(jde - 1, jte);
     if (g.periodic_x) { r.i0 = its; r.i1 = mn(ite, ide - 1); }
   } else {
     r = {its, mn(ite, ide - 1), jts, mn(jte, jde - 1)};
-    if (g.open_xs) r.i0 = mx(ids + 1, its);
-    if (g.open_xe) r.i1 = mn(ide - 2, ite);
-    if (g.open_ys) r.j0 = mx(jds + 1, jts);
-    if (g.open_ye) r.j1 = mn(jde - 2, jte);
+    if (g.oxs()) r.i0 = mx(ids + 1, its);
+    if (g.oxe()) r.i1 = mn(ide - 2, ite);
+    if (g.oys()) r.j0 = mx(jds + 1, jts);
+    if (g.oye()) r.j1 = mn(jde - 2, jte);
     if (g.periodic_x) { r.i0 = its; r.i1 = mn(ite, ide - 1); }
   }
   return r;

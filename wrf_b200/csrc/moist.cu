@@ -205,7 +205,10 @@ void Solver::microphysics() {
   a.pi_phy = o("pi_phy"); a.z = o("z"); a.dz8w = o("dz8w"); a.rainnc = o("rainnc"); a.rainncv = o("rainncv");
   a.al = o("al"); a.alb = o("alb"); a.p = o("p"); a.pb = o("pb"); a.ph = o("ph_2"); a.phb = o("phb");
   a.dt = c.dt;
-  LAUNCH2(this, k_kessler, (Box{q.its, std::min(q.ite, q.ide - 1), 1, 1, q.jts, std::min(q.jte, q.jde - 1)}), a);
+  // solve_em.F:3623-3645: the specified rows are left out (sz rows; all of x when periodic_x)
+  const int sz = spec() ? c.spec_zone : 0, szx = c.periodic_x ? 0 : sz;
+  LAUNCH2(this, k_kessler, (Box{std::max(q.its, q.ids + szx), std::min(q.ite, q.ide - 1 - szx), 1, 1, std::max(q.jts, q.jds + sz),
+                                std::min(q.jte, q.jde - 1 - sz)}), a);
   halo("HALO_EM_THETAM");
   bc({{"h_diabatic", 'p'}});
 }
@@ -237,6 +240,7 @@ void Solver::end_of_step() {
                             {"t_1", 'p'}, {"t_2", 'p'}, {"ph_1", 'w'}, {"ph_2", 'w'}, {"mu_1", 't'}, {"mu_2", 't'}};
   for (auto &s : species) it.push_back({s.f, 'p'});
   bc(it);
+  if (spec()) spec_final();   // solve_em.F:4540-4722
   halo("HALO_EM_C");
   LAUNCH2(this, k_set_w_surface, (Box{q.its, std::min(q.ite, q.ide - 1), 1, 1, q.jts, std::min(q.jte, q.jde - 1)}), o("w_2"), o("u_2"),
           o("v_2"));

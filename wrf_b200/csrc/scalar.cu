@@ -388,7 +388,11 @@ __global__ void k_update_scalar_pd(const Geo g, Box b, float dt, fp scalar, fp s
 __global__ void k_update_scalar(const Geo g, Box b, int rk_step, float dt, fp scalar_1, fp scalar_2, cfp sc_tend, cfp advect_tend,
                                 cfp mu_old, cfp mu_new, cfp mu_base) {
   TID3;
-  float tendency = A3(advect_tend, i, k, j) * A2(g.msfty, i, j);
+  // the advective tendency is not used in the specified rows (:1671-1678); sc_tend (there: the boundary file's) is
+  const int sz = g.spec_zone;
+  const bool adv = !g.spec || ((g.periodic_x || (i >= g.ids + sz && i <= g.ide - sz - 1)) && j >= g.jds + sz && j <= g.jde - sz - 1);
+  float tendency = 0.f;
+  if (adv) tendency = A3(advect_tend, i, k, j) * A2(g.msfty, i, j);
   tendency = tendency + A3(sc_tend, i, k, j);
   const float muold = A2(mu_old, i, j) + A2(mu_base, i, j), munew = A2(mu_new, i, j) + A2(mu_base, i, j);
   float s1;
@@ -432,6 +436,15 @@ void Solver::rk_scalar_step(int rk_step) {
   const bool dflt_s = c.h_sca_adv_order == 5 && c.v_sca_adv_order == 3;   // the k-marching kernels exist for these
   const bool dxs = !(c.periodic_x || c.symmetric_xs), dxe = !(c.periodic_x || c.symmetric_xe);
   const bool dys = !(c.periodic_y || c.symmetric_ys), dye = !(c.periodic_y || c.symmetric_ye);
+  // what follows rk_scalar_tend for one species (solve_em.F:2261-2355, :2437-2456, :2808-2843)
+  auto update = [&](const Species &s) {
+    const bool moist = s.f.rfind("moist_", 0) == 0, is_tke = s.f == tke_name;
+    if (spec() && rk_step == 1 && has_bdy(s.f)) bdy_scalar(s);   // relax_bdy_scalar + spec_bdy_scalar: qv, or every species with boundary arrays
+    LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
+    if (is_tke) LAUNCH3(this, k_bound_tke, mass, c.tke_upper_bound, o(s.f));
+    // zero gradient on outflow / zero on inflow: moist species without boundary arrays (specified only), tke
+    if ((moist && c.specified && !c.have_bcs_moist && s.f != "moist_qv") || (is_tke && spec())) flow_dep_bdy(s.f);
+  };
   for (auto &s : species) {
     if (last && (s.adv_opt == 1 || s.adv_opt == 2 || s.adv_opt == 4)) {
       PdIn in;
@@ -443,6 +456,12 @@ void Solver::rk_scalar_step(int rk_step) {
       if (dxe) lim.i1 = std::min(q.ite + 1, q.ide - 1);
       if (dys) lim.j0 = std::max(q.jts - 1, q.jds);
       if (dye) lim.j1 = std::min(q.jte + 1, q.jde - 1);
+      if (spec()) {   // :7697-7702
+        if (dxs) lim.i0 = std::max(q.its - 1, q.ids + 1);
+        if (dxe) lim.i1 = std::min(q.ite + 1, q.ide - 2);
+        if (dys) lim.j0 = std::max(q.jts - 1, q.jds + 1);
+        if (dye) lim.j1 = std::min(q.jte + 1, q.jde - 2);
+      }
       if (c.open_xs && dxs) lim.i0 = std::max(q.its - 1, q.ids + 1);
       if (c.open_xe && dxe) lim.i1 = std::min(q.ite + 1, q.ide - 2);
       if (c.open_ys && dys) lim.j0 = std::max(q.jts - 1, q.jds + 1);
@@ -453,14 +472,14 @@ void Solver::rk_scalar_step(int rk_step) {
         LAUNCH3(this, k_mono_scale, lim, in, o("pd_scale"), o("pd_scale2"));
         LAUNCH3(this, k_mono_tend, mass, in, o("pd_scale"), o("pd_scale2"), lim, o("advect_tend"));
         if (ieva) ieva_implicit(0, o("advect_tend"), o(s.o), o("mut_old"), o("muts"), dt_rk);
-        { LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub")); if (s.f == tke_name) LAUNCH3(this, k_bound_tke, mass, c.tke_upper_bound, o(s.f)); }
+        update(s);
         continue;
       }
       if (s.adv_opt == 4 || ieva || !dflt_s) {   // WENO inside the positive-definite limiter, or IEVA's wwE: the gather kernels everywhere
         LAUNCH3(this, k_pd_scale, lim, in, o("pd_scale"));
         LAUNCH3(this, k_pd_tend, mass, in, o("pd_scale"), lim, o("advect_tend"));
         if (ieva) ieva_implicit(0, o("advect_tend"), o(s.o), o("mut_old"), o("muts"), dt_rk);
-        { LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub")); if (s.f == tke_name) LAUNCH3(this, k_bound_tke, mass, c.tke_upper_bound, o(s.f)); }
+        update(s);
         continue;
       }
       // k-marching kernels (pd_fast.cu) where every face is 5th order, the gather kernels on the strips around
@@ -494,7 +513,7 @@ void Solver::rk_scalar_step(int rk_step) {
     }
     if (rk_step == 1 && c.diff_6th_opt != 0 && !(s.f.rfind("moist_", 0) == 0 ? c.moist_mix6_off : c.scalar_mix6_off))
       launch_diff6(this, 5, o(s.f), o(s.t), o("muts"), dt_rk);   // module_em.F:1421-1437 (dt_step = dt_rk)
-    { LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub")); if (s.f == tke_name) LAUNCH3(this, k_bound_tke, mass, c.tke_upper_bound, o(s.f)); }
+    update(s);
   }
 }
 

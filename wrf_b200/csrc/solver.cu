@@ -26,7 +26,18 @@ static const char *moist_names[] = {"qv", "qc", "qr"};
 
 static void check_config(const wrfgpu_config &c) {
   auto bad = [](const std::string &m) { throw std::runtime_error("wrfgpu: unsupported configuration: " + m); };
-  if (c.specified || c.nested || c.polar) bad("specified/nested/polar lateral boundaries are not on the device path");
+  if (c.polar) bad("polar boundary conditions / filters are not on the device path");
+  if (c.specified && c.nested) bad("specified and nested are exclusive");
+  if (c.specified || c.nested) {
+    if (c.periodic_x || c.periodic_y || c.open_xs || c.open_xe || c.open_ys || c.open_ye || c.symmetric_xs || c.symmetric_xe ||
+        c.symmetric_ys || c.symmetric_ye)
+      bad("specified / nested boundaries on all four sides only (the periodic_x channel of the reference is not on the device path)");
+    if (c.spec_bdy_width < 2 || c.spec_zone < 1 || c.relax_zone <= c.spec_zone || c.relax_zone + 1 > c.spec_bdy_width)
+      bad("need 1 <= spec_zone < relax_zone < spec_bdy_width");
+    if (c.momentum_adv_opt != 1 || c.moist_adv_opt > 1 || c.scalar_adv_opt > 1 || (c.km_opt == 2 && c.tke_adv_opt > 1))
+      bad("specified / nested boundaries with monotonic or WENO advection");
+    if (c.zadvect_implicit > 0) bad("specified / nested boundaries with IEVA");
+  }
   if (c.rk_ord != 3 && c.rk_ord != 2) bad("rk_ord must be 2 or 3");
   if ((c.h_mom_adv_order != 5 && c.h_mom_adv_order != 6) || (c.h_sca_adv_order != 5 && c.h_sca_adv_order != 6)) bad("h_*_adv_order must be 5 or 6");
   if ((c.v_mom_adv_order != 3 && c.v_mom_adv_order != 4) || (c.v_sca_adv_order != 3 && c.v_sca_adv_order != 4)) bad("v_*_adv_order must be 3 or 4");
@@ -108,6 +119,18 @@ Solver::Solver(const wrfgpu_dims &d_, const wrfgpu_config &c_, int dev) : d(d_),
                s == tke_index() ? c.tke_adv_opt : c.scalar_adv_opt};
     add(sp.f, 3); add(sp.o, 3); add(sp.t, 3);
     species.push_back(sp);
+  }
+  if (spec()) {   // boundary arrays (Registry.EM_COMMON 'b' entries) and the relaxation weights of lbc_fcx_gcx
+    if (d.ide - d.ids < 2 * c.spec_bdy_width + 2 || d.jde - d.jds < 2 * c.spec_bdy_width + 2)
+      throw std::runtime_error("wrfgpu: the domain is too small for its boundary zone");
+    const int nk = d.kde - d.kds + 1;
+    add_raw("fcx", c.spec_bdy_width); add_raw("gcx", c.spec_bdy_width);
+    for (const char *f : {"u", "v", "w", "ph", "t"}) add_bdy(f, nk);
+    add_bdy("mu", 1);
+    for (auto &sp : species) {
+      const bool moist = sp.f.rfind("moist_", 0) == 0, is_tke = tke_index() && sp.f == "scalar_" + std::to_string(tke_index());
+      if (moist ? (sp.f == "moist_qv" || c.nested || c.have_bcs_moist) : (!is_tke && (c.nested || c.have_bcs_scalar))) add_bdy(sp.f, nk);
+    }
   }
   CUDA_CHECK(cudaMalloc(&d_cfl, 2 * sizeof(float)));
   CUDA_CHECK(cudaMemset(d_cfl, 0, 2 * sizeof(float)));
@@ -214,6 +237,7 @@ void Solver::build_geo() {
   q.ims = d.ims; q.ime = d.ime; q.jms = d.jms; q.jme = d.jme; q.kms = d.kms; q.kme = d.kme;
   q.ips = d.ips; q.ipe = d.ipe; q.jps = d.jps; q.jpe = d.jpe;
   q.its = d.ips; q.ite = d.ipe; q.jts = d.jps; q.jte = d.jpe;
+  q.hni = d.ime - d.ims + 1; q.hnj = d.jme - d.jms + 1;
   q.ni = (int)pitch(); q.nk = d.kme - d.kms + 1; q.nj = d.jme - d.jms + 1;   // ni = the device row pitch (>= ime-ims+1)
   q.sk = q.ni; q.sj = (long)q.ni * q.nk;
   if ((long)q.ni * q.nk * q.nj >= (1L << 31)) throw std::runtime_error("wrfgpu: a patch of more than 2^31 points per field is not supported");
@@ -221,6 +245,7 @@ void Solver::build_geo() {
   q.periodic_x = c.periodic_x; q.periodic_y = c.periodic_y;
   q.sym_xs = c.symmetric_xs; q.sym_xe = c.symmetric_xe; q.sym_ys = c.symmetric_ys; q.sym_ye = c.symmetric_ye;
   q.open_xs = c.open_xs; q.open_xe = c.open_xe; q.open_ys = c.open_ys; q.open_ye = c.open_ye;
+  q.spec = (c.specified || c.nested) ? 1 : 0; q.spec_zone = c.spec_zone; q.relax_zone = c.relax_zone;
   q.top_lid = c.top_lid; q.phi_adv_z = c.phi_adv_z; q.damp_opt = c.damp_opt; q.w_damping = c.w_damping;
   q.pert_coriolis = c.pert_coriolis; q.use_theta_m = c.use_theta_m; q.hypsometric_opt = c.hypsometric_opt;
   q.rk_ord = c.rk_ord; q.num_moist = c.num_moist;
@@ -289,6 +314,7 @@ struct PhaseTimer {
 // one model step, dyn_em/solve_em.F:520-4848
 void Solver::step() {
   const int rk_order = c.rk_ord;
+  dtbc = dtbc + c.dt;   // solve_em.F:377
   if (c.num_moist >= 1) {   // initialize_moist_old + bc (solve_em.F:520-550)
     LAUNCH3(this, k_copy_box, (Box{g.its, std::min(g.ite, g.ide - 1), 1, g.kde - 1, g.jts, std::min(g.jte, g.jde - 1)}),
             (const float *)o("moist_qv"), o("moist_old_qv"));
@@ -307,6 +333,12 @@ void Solver::step() {
     { PHASE("rk_tendency"); rk_tendency(rk_step, false); }
     { PHASE("small_step_prep"); small_step_prep(rk_step, true); }
     for (int it = 1; it <= ns; it++) {
+      if (spec()) {   // the specified rows are advanced between the kernels (solve_em.F:1344-1620): no fusion across them
+        { PHASE("advance_uv"); advance_uv(rk_step); halo("HALO_EM_C"); }
+        { PHASE("advance_mu_t"); advance_mu_t(rk_step); }
+        { PHASE("advance_w"); advance_w(rk_step); sumflux(rk_step, it); calc_p_rho(it); }
+        continue;
+      }
       { PHASE("advance_uv"); advance_uv_fused(rk_step, it); }   // + HALO_EM_C, overlapped with the kernel's interior
       { PHASE("advance_mu_t"); advance_mu_t(rk_step, true); }
       { PHASE("advance_w"); advance_w_fused(rk_step, it); }
@@ -369,7 +401,7 @@ static void xfer(Solver &S, const char *name, const float *in, float *out, size_
   cudaGetLastError();
   cudaMemcpyKind kind = in ? (dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
                            : (dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost);
-  if (in && f.kind == 1) S.coef_dirty = true;
+  if (in && f.kind == 1 && !f.raw) S.coef_dirty = true;
   if (in) S.copy_in(f, in, kind);
   else S.copy_out(f, out, kind, S.stream);
   if (!async) CUDA_CHECK(cudaStreamSynchronize(S.stream));
@@ -415,6 +447,8 @@ int wrfgpu_max_cfl(wrfgpu_solver *s, float *max_vert_cfl, float *max_horiz_cfl, 
     if (reset) CUDA_CHECK(cudaMemsetAsync(s->s.d_cfl, 0, 2 * sizeof(float), s->s.stream));
   })
 }
+int wrfgpu_set_dtbc(wrfgpu_solver *s, float dtbc) { GUARD(s->s.dtbc = dtbc) }
+int wrfgpu_get_dtbc(wrfgpu_solver *s, float *dtbc) { GUARD(*dtbc = s->s.dtbc) }
 int wrfgpu_set_stream(wrfgpu_solver *s, void *cuda_stream) {
   GUARD({
     CUDA_CHECK(cudaStreamSynchronize(s->s.stream));

@@ -71,10 +71,10 @@ __device__ __forceinline__ float dpn_at(const Geo &g, cfp p, int i, int kk, int 
 // vxgm of curvature (:4230-4290) with the open-boundary copies folded into index clamps
 template <bool FAST>
 __device__ __forceinline__ float vxgm_at(const Geo &g, cfp u, cfp v, int i, int k, int j) {
-  if (!FAST && g.open_xs && i == g.ids - 1) i = g.ids;
-  if (!FAST && g.open_xe && i == g.ide) i = g.ide - 1;
-  if (!FAST && g.open_ys && j == g.jds - 1) j = g.jds;
-  if (!FAST && g.open_ye && j == g.jde) j = g.jde - 1;
+  if (!FAST && (g.open_xs || (g.spec && !g.periodic_x)) && i == g.ids - 1) i = g.ids;
+  if (!FAST && (g.open_xe || (g.spec && !g.periodic_x)) && i == g.ide) i = g.ide - 1;
+  if (!FAST && g.oys() && j == g.jds - 1) j = g.jds;
+  if (!FAST && g.oye() && j == g.jde) j = g.jde - 1;
   return 0.5f * (A3(u, i, k, j) + A3(u, i + 1, k, j)) * (A2(g.msfvx, i, j + 1) - A2(g.msfvx, i, j)) * g.rdy -
          0.5f * (A3(v, i, k, j) + A3(v, i, k, j + 1)) * (A2(g.msfuy, i + 1, j) - A2(g.msfuy, i, j)) * g.rdx;
 }
@@ -133,8 +133,8 @@ __device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i,
   // --- y flux divergence
   {
     int i_s = its, i_e = ite;
-    if (g.open_xs) i_s = max(ids + 1, its);
-    if (g.open_xe) i_e = min(ide - 1, ite);
+    if (g.oxs()) i_s = max(ids + 1, its);
+    if (g.oxe()) i_e = min(ide - 1, ite);
     if (g.periodic_x) { i_s = its; i_e = ite; }
     const int j_lo = dg.ys ? max(jts, jds + 1) : jts, j_hi = dg.ye ? min(jte, jde - 2) : min(jte, jde - 1);
     if (FAST || (i >= i_s && i <= i_e && j >= j_lo && j <= j_hi)) {
@@ -173,7 +173,12 @@ __device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i,
           const float vel = 0.5f * (A3(ru, ii, k, j) + A3(ru, ii - 1, k, j));
           fq[m] = vel * flux3(A3(u, ii - 2, k, j), A3(u, ii - 1, k, j), A3(u, ii, k, j), A3(u, ii + 1, k, j), vel, sgh);
         } else {
-          fq[m] = 0.25f * (A3(ru, ii, k, j) + A3(ru, ii - 1, k, j)) * (A3(u, ii, k, j) + A3(u, ii - 1, k, j));
+          float ua = A3(u, ii, k, j), ub = A3(u, ii - 1, k, j);
+          if (g.spec) {   // specified uses upstream normal wind at boundaries (:698, :720)
+            if (ii == ids + 1) { if (ua < 0.f) ub = ua; }
+            else if (ub > 0.f) ua = ub;
+          }
+          fq[m] = 0.25f * (A3(ru, ii, k, j) + A3(ru, ii - 1, k, j)) * (ua + ub);
         }
       }
       const float mrdx = A2(g.msfux, i, j) * g.rdx;
@@ -217,8 +222,8 @@ __device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i,
   // --- vertical (:1336-1498; the reference tests open_ys/open_ye for the i range)
   {
     int i_s = its, i_e = ite;
-    if (g.open_ys) i_s = max(ids + 1, its);
-    if (g.open_ye) i_e = min(ide - 1, ite);
+    if (g.oys()) i_s = max(ids + 1, its);
+    if (g.oye()) i_e = min(ide - 1, ite);
     if (g.periodic_x) { i_s = its; i_e = ite; }
     if (FAST || (i >= i_s && i <= i_e)) {
       float vf[2];
@@ -244,8 +249,8 @@ __device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i,
   // --- horizontal pressure gradient, x (:2320-2400)
   {
     int i_s = its, i_e = ite;
-    if (g.open_xs && its == ids) i_s = its + 1;
-    if (g.open_xe && ite == ide) i_e = ite - 1;
+    if (g.oxs() && its == ids) i_s = its + 1;
+    if (g.oxe() && ite == ide) i_e = ite - 1;
     if (g.periodic_x) { i_s = its; i_e = ite; }
     if (FAST || (i >= i_s && i <= i_e)) {
       const float mr = A2(g.msfux, i, j) / A2(g.msfuy, i, j);
@@ -262,8 +267,8 @@ __device__ __forceinline__ float tend_u_pt(const Geo &g, const TendIn &s, int i,
   // --- coriolis (:3700-3735) and curvature (:4292-4330)
   {
     int i_s = its, i_e = ite;
-    if (g.open_xs) i_s = max(ids + 1, its);
-    if (g.open_xe) i_e = min(ide - 1, ite);
+    if (g.oxs()) i_s = max(ids + 1, its);
+    if (g.oxe()) i_e = min(ide - 1, ite);
     if (g.periodic_x) { i_s = its; i_e = ite; }
     if (FAST || (i >= i_s && i <= i_e)) {
       const float rvavg = 0.25f * (A3(rv, i - 1, k, j + 1) + A3(rv, i, k, j + 1) + A3(rv, i - 1, k, j) + A3(rv, i, k, j));
@@ -343,7 +348,12 @@ __device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i,
           const float vel = 0.5f * (A3(rv, i, k, jj) + A3(rv, i, k, jj - 1));
           fq[m] = vel * flux3(A3(v, i, k, jj - 2), A3(v, i, k, jj - 1), A3(v, i, k, jj), A3(v, i, k, jj + 1), vel, sgh);
         } else {
-          fq[m] = 0.25f * (A3(rv, i, k, jj) + A3(rv, i, k, jj - 1)) * (A3(v, i, k, jj) + A3(v, i, k, jj - 1));
+          float va = A3(v, i, k, jj), vb = A3(v, i, k, jj - 1);
+          if (g.spec) {   // specified uses upstream normal wind at boundaries (:1985, :2007)
+            if (jj == jds + 1) { if (va < 0.f) vb = va; }
+            else if (vb > 0.f) va = vb;
+          }
+          fq[m] = 0.25f * (A3(rv, i, k, jj) + A3(rv, i, k, jj - 1)) * (va + vb);
         }
       }
       const float mrdy = A2(g.msfvy, i, j) * g.rdy;
@@ -353,8 +363,8 @@ __device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i,
   // --- x flux divergence
   {
     int j_s = jts, j_e = jte;
-    if (g.open_ys) j_s = max(jds + 1, jts);
-    if (g.open_ye) j_e = min(jde - 1, jte);
+    if (g.oys()) j_s = max(jds + 1, jts);
+    if (g.oye()) j_e = min(jde - 1, jte);
     const int i_lo = dg.xs ? max(ids + 1, its) : its, i_hi = dg.xe ? min(ide - 2, ite) : min(ite, ide - 1);
     if (FAST || (j >= j_s && j <= j_e && i >= i_lo && i <= i_hi)) {
       float fq[2];
@@ -413,8 +423,8 @@ __device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i,
   // --- vertical (:2802-2995)
   {
     int j_s = jts, j_e = jte;
-    if (g.open_ys) j_s = max(jds + 1, jts);
-    if (g.open_ye) j_e = min(jde - 1, jte);
+    if (g.oys()) j_s = max(jds + 1, jts);
+    if (g.oye()) j_e = min(jde - 1, jte);
     if (FAST || (j >= j_s && j <= j_e)) {
       float vf[2];
 #pragma unroll
@@ -439,8 +449,8 @@ __device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i,
   // --- horizontal pressure gradient, y (:2230-2300)
   {
     int j_s = jts, j_e = jte;
-    if (g.open_ys && jts == jds) j_s = jts + 1;
-    if (g.open_ye && jte == jde) j_e = jte - 1;
+    if (g.oys() && jts == jds) j_s = jts + 1;
+    if (g.oye() && jte == jde) j_e = jte - 1;
     if (FAST || (j >= j_s && j <= j_e)) {
       const float mr = A2(g.msfvy, i, j) / A2(g.msfvx, i, j);
       float dpy = mr * .5f * g.rdy * (g.c1h[k] * A2(s.muv, i, j) + g.c2h[k]) *
@@ -456,8 +466,8 @@ __device__ __forceinline__ float tend_v_pt(const Geo &g, const TendIn &s, int i,
   // --- coriolis (:3745-3765), curvature (:4340-4380)
   {
     int j_s = jts, j_e = jte;
-    if (g.open_ys) j_s = max(jds + 1, jts);
-    if (g.open_ye) j_e = min(jde - 1, jte);
+    if (g.oys()) j_s = max(jds + 1, jts);
+    if (g.oye()) j_e = min(jde - 1, jte);
     if (FAST || (j >= j_s && j <= j_e)) {
       const float rwsum = (A3(s.rw, i, k + 1, j - 1) + A3(s.rw, i, k, j - 1) + A3(s.rw, i, k + 1, j) + A3(s.rw, i, k, j));
       const float ruavg = 0.25f * (A3(ru, i, k, j) + A3(ru, i + 1, k, j) + A3(ru, i, k, j - 1) + A3(ru, i + 1, k, j - 1));
@@ -798,14 +808,14 @@ __device__ __forceinline__ float tend_ph_pt(const Geo &g, const TendIn &s, int i
     // --- y advection
     {
       int j6s = jts, j6e = min(jte, jde - 1);
-      if (g.open_ys) j6s = max(jts, jds + 3);
-      if (g.open_ye) j6e = min(j6e, jde - 4);
+      if (g.oys()) j6s = max(jts, jds + 3);
+      if (g.oye()) j6e = min(j6e, jde - 4);
       int mode = 0;
       if (FAST || (j >= j6s && j <= j6e)) mode = 6;
-      else if (g.open_ys && j == jds + 2) mode = 4;
-      else if (g.open_ye && j == jde - 3) mode = 4;
-      else if (g.open_ys && j == jds + 1) mode = 2;
-      else if (g.open_ye && j == jde - 2) mode = 2;
+      else if (g.oys() && j == jds + 2) mode = 4;
+      else if (g.oye() && j == jde - 3) mode = 4;
+      else if (g.oys() && j == jds + 1) mode = 2;
+      else if (g.oye() && j == jde - 2) mode = 2;
       // a row can match more than one of the reference's blocks only on tiny domains
       if (mode) {
         const float va = top ? (g.cfn * A3(v, i, k - 1, j + 1) + g.cfn1 * A3(v, i, k - 2, j + 1)) : (A3(v, i, k, j + 1) + A3(v, i, k - 1, j + 1));
@@ -832,14 +842,14 @@ __device__ __forceinline__ float tend_ph_pt(const Geo &g, const TendIn &s, int i
     // --- x advection
     {
       int i6s = its, i6e = min(ite, ide - 1);
-      if (g.open_xs) i6s = max(its, ids + 3);
-      if (g.open_xe) i6e = min(i6e, ide - 4);
+      if (g.oxs()) i6s = max(its, ids + 3);
+      if (g.oxe()) i6e = min(i6e, ide - 4);
       int mode = 0;
       if (FAST || (i >= i6s && i <= i6e)) mode = 6;
       else if (g.open_xs && i == ids + 2) mode = 4;
       else if (g.open_xe && i == ide - 3) mode = 4;
-      else if (g.open_xs && i == ids + 1) mode = 2;
-      else if (g.open_xe && i == ide - 2) mode = 2;
+      else if (g.oxs() && i == ids + 1) mode = 2;
+      else if (g.oxe() && i == ide - 2) mode = 2;
       if (mode) {
         const float ua = top ? (g.cfn * A3(u, i + 1, k - 1, j) + g.cfn1 * A3(u, i + 1, k - 2, j)) : (A3(u, i + 1, k, j) + A3(u, i + 1, k - 1, j));
         const float ub = top ? (g.cfn * A3(u, i, k - 1, j) + g.cfn1 * A3(u, i, k - 2, j)) : (A3(u, i, k, j) + A3(u, i, k - 1, j));
@@ -1060,6 +1070,11 @@ void Solver::init_zero_tendency() {
 }
 
 void Solver::rk_tendency(int rk_step, bool zero_save) {
+  rk_tendency_main(rk_step, zero_save);
+  if (spec()) spec_bdy_dry();   // solve_em.F:982-1007, after rk_addtend_dry
+}
+
+void Solver::rk_tendency_main(int rk_step, bool zero_save) {
   const Geo &q = g;
   Box tile{q.its, q.ite, 1, q.kde, q.jts, q.jte};
   // the *_save arrays and mu_tend/mu_save are zeroed by rk_tendency (module_em.F:370-428)
@@ -1088,6 +1103,9 @@ void Solver::rk_tendency(int rk_step, bool zero_save) {
               o("muv"), o("ru_tendf"), o("rv_tendf"), o("rw_tendf"), o("t_tendf"));
     }
   }
+  // relax_bdy_dry (solve_em.F:937-968) + the first-substep half of rk_addtend_dry: it only reads the state, so it can go
+  // ahead of the tendency kernels, which add *_tendf last; it must follow every other contribution to *_tendf
+  if (spec() && rk_step == 1) relax_bdy_dry(zero_save);
   TendIn s;
   s.u = o("u_2"); s.v = o("v_2"); s.w = o("w_2"); s.t = o("t_2"); s.ph = o("ph_2"); s.phb = o("phb");
   s.ru = o("ru"); s.rv = o("rv"); s.rw = o("rw"); s.ww = o("ww"); s.rom = o("ww");

@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")"
 name=$1; shift
 out=../variants; mkdir -p $out /tmp/wgv_$name
-for f in solver bc prep tend tend_tile advect_fast mom_fast pd_fast diffusion deform diffusion2 acoustic ieva scalar moist halo history decomp; do
+for f in solver bc prep tend tend_tile advect_fast mom_fast pd_fast diffusion deform diffusion2 acoustic ieva scalar moist bdy halo history decomp; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC "$@" -c $f.cu -o /tmp/wgv_$name/$f.o &
 done
 wait

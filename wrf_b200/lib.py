@@ -27,7 +27,7 @@ PHASES = ("rk_step_prep", "rk_phys_bc_dry_1", "init_zero_tendency", "diffusion_p
 ABI_SYMBOLS = (
     "wrfgpu_create", "wrfgpu_destroy", "wrfgpu_last_error", "wrfgpu_version", "wrfgpu_device_count", "wrfgpu_field_size", "wrfgpu_set_field",
     "wrfgpu_get_field", "wrfgpu_upload", "wrfgpu_download", "wrfgpu_num_fields", "wrfgpu_field_name", "wrfgpu_field_devptr",
-    "wrfgpu_step", "wrfgpu_solve_em", "wrfgpu_sync", "wrfgpu_set_stream", "wrfgpu_kernel_report", "wrfgpu_launch_count", "wrfgpu_max_cfl", "wrfgpu_phase_ms", "wrfgpu_set_physical_bc",
+    "wrfgpu_step", "wrfgpu_solve_em", "wrfgpu_sync", "wrfgpu_set_dtbc", "wrfgpu_get_dtbc", "wrfgpu_set_stream", "wrfgpu_kernel_report", "wrfgpu_launch_count", "wrfgpu_max_cfl", "wrfgpu_phase_ms", "wrfgpu_set_physical_bc",
     "wrfgpu_compute_mesh", "wrfgpu_patch_dims", "wrfgpu_comm_unique_id", "wrfgpu_comm_init", "wrfgpu_comm_init_local", "wrfgpu_halo",
     "wrfgpu_halo_spec", "wrfgpu_halo_box", "wrfgpu_halo_box2", "wrfgpu_halo_regular_width", "wrfgpu_halo_bytes",
     "wrfgpu_snapshot_begin", "wrfgpu_snapshot_wait", "wrfgpu_snapshot_busy", "wrfgpu_snapshot_host",
@@ -125,6 +125,15 @@ class Solver:
 
     def sync(self):
         self._chk(self.lib.wrfgpu_sync(self.h))
+
+    def set_dtbc(self, dtbc: float):
+        """grid%dtbc: seconds since the uploaded boundary arrays were valid (0 right after a boundary time was read)"""
+        self._chk(self.lib.wrfgpu_set_dtbc(self.h, ctypes.c_float(dtbc)))
+
+    def dtbc(self) -> float:
+        v = ctypes.c_float()
+        self._chk(self.lib.wrfgpu_get_dtbc(self.h, ctypes.byref(v)))
+        return v.value
 
     def solve_em(self, in_names, in_ptrs, out_names, out_ptrs):
         """Strict drop-in call: upload `in`, one solve_em, download `out` (host pointers as ints)."""
