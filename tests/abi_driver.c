@@ -1,6 +1,7 @@
 /* abi_driver.c -- replays, from plain C, the exact call sequence of wrf_b200/fortran/solve_em_gpu.F90 against
  * libwrfgpu.so: wrfgpu_device_count, wrfgpu_create with a filled wrfgpu_dims / wrfgpu_config, the (name, pointer) tables of
- * wrfgpu_upload, wrfgpu_start_domain, wrfgpu_step one step at a time, wrfgpu_download of the shim's field list, and
+ * wrfgpu_upload (the boundary arrays of a specified / nested domain among them), wrfgpu_start_domain, wrfgpu_set_dtbc and
+ * wrfgpu_step one step at a time, wrfgpu_download of the shim's field list, and
  * wrfgpu_last_error on failure.  The Fortran shim cannot be compiled in the development image; this driver pins the
  * boundary the shim binds (include/wrfgpu.h) with a caller that is not Python.
  *
@@ -12,7 +13,7 @@
 #include <string.h>
 #include "../include/wrfgpu.h"
 
-#define MAXF 160
+#define MAXF 384
 static void die(const char *where) {
   fprintf(stderr, "abi_driver: %s: %s\n", where, wrfgpu_last_error());
   exit(2);
@@ -53,8 +54,12 @@ int main(int argc, char **argv) {
   if (wrfgpu_upload(s, nf, names, host)) die("wrfgpu_upload");
   if (wrfgpu_start_domain(s)) die("wrfgpu_start_domain");
   const int nsteps = atoi(argv[2]);
-  for (int n = 0; n < nsteps; n++)
+  float dtbc = 0.f;                      /* grid%dtbc: the boundary arrays above were just read */
+  for (int n = 0; n < nsteps; n++) {
+    if ((c.specified || c.nested) && wrfgpu_set_dtbc(s, dtbc)) die("wrfgpu_set_dtbc");   /* the shim, before every step */
+    dtbc = dtbc + c.dt;                  /* solve_em.F:377 on the host copy */
     if (wrfgpu_step(s, 1)) die("wrfgpu_step");
+  }
   /* the shim's download list (history / restart alarm) */
   const char *want[] = {"u_1", "u_2", "v_1", "v_2", "w_1", "w_2", "t_1", "t_2", "ph_1", "ph_2", "p", "al", "alt", "ww", "h_diabatic",
                         "moist_qv", "moist_qc", "moist_qr", "scalar_1", "scalar_2", "tke_1", "tke_2", "mu_1", "mu_2", "rainnc", "rainncv"};

@@ -15,7 +15,7 @@ MODULE module_wrfgpu
    PUBLIC :: wrfgpu_dims, wrfgpu_config, wrfgpu_check
    PUBLIC :: wrfgpu_create, wrfgpu_destroy, wrfgpu_last_error, wrfgpu_upload, wrfgpu_download, wrfgpu_step, &
              wrfgpu_solve_em, wrfgpu_start_domain, wrfgpu_sync, wrfgpu_comm_unique_id, wrfgpu_comm_init, &
-             wrfgpu_compute_mesh, wrfgpu_patch_dims, wrfgpu_field_size, wrfgpu_device_count, wrfgpu_max_cfl, &
+             wrfgpu_compute_mesh, wrfgpu_patch_dims, wrfgpu_field_size, wrfgpu_device_count, wrfgpu_max_cfl, wrfgpu_set_dtbc, &
              wrfgpu_snapshot_begin, wrfgpu_snapshot_wait, wrfgpu_snapshot_busy, wrfgpu_snapshot_host
 
    ! wrfgpu_dims: the three index triplets of get_ijk_from_grid (dyn_em/solve_em.F:288-296)
@@ -132,6 +132,11 @@ MODULE module_wrfgpu
          TYPE(c_ptr), VALUE :: handle
          REAL(c_float), INTENT(OUT) :: max_vert_cfl, max_horiz_cfl
          INTEGER(c_int), VALUE :: reset
+      END FUNCTION
+      INTEGER(c_int) FUNCTION wrfgpu_set_dtbc(handle, dtbc) BIND(C, name='wrfgpu_set_dtbc')
+         IMPORT :: c_int, c_ptr, c_float
+         TYPE(c_ptr), VALUE :: handle
+         REAL(c_float), VALUE :: dtbc
       END FUNCTION
       INTEGER(c_int) FUNCTION wrfgpu_sync(handle) BIND(C, name='wrfgpu_sync')
          IMPORT :: c_int, c_ptr

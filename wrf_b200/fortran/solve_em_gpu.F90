@@ -10,6 +10,10 @@
 ! the end of this step", Is_alarm_tstep on grid%alarms(HISTORY_ALARM) / (restart_alarm)
 ! (dyn_em/solve_em.F:360-374, frame/module_domain.F:2484).
 !
+! Specified / nested lateral boundaries: grid%u_bxs ... grid%mu_btye, moist_b*, scalar_b* and grid%fcx / gcx are uploaded
+! whenever the host has refilled them (grid%dtbc == 0); relaxation, the specified rows and their end-of-step reset run on
+! the device.
+!
 ! What the device does not do is host-side physics: first_rk_step_part1 (radiation, surface layer,
 ! PBL, cumulus; dyn_em/solve_em.F:807-871) is not called, so a namelist that selects any of them is
 ! refused with wrf_error_fatal instead of running without their tendencies.  Diffusion (diff_opt,
@@ -43,14 +47,14 @@ SUBROUTINE solve_em ( grid , config_flags  &
    TYPE (grid_config_rec_type) , INTENT(IN) :: config_flags
 #include "dummy_new_decl.inc"
 
-   INTEGER, PARAMETER :: MAXF = 128
+   INTEGER, PARAMETER :: MAXF = 384
    TYPE(c_ptr), SAVE :: handle(max_domains) = c_null_ptr
    LOGICAL,     SAVE :: resident(max_domains) = .FALSE.
    TYPE(wrfgpu_dims)   :: d
    TYPE(wrfgpu_config) :: c
    CHARACTER(len=24, kind=c_char), TARGET, SAVE :: nm(MAXF)
    TYPE(c_ptr) :: names(MAXF), host(MAXF)
-   INTEGER :: nf, id, ierr, device, ndev, n, nsc, my_rank, nx_tasks, ny_tasks
+   INTEGER :: nf, id, ierr, device, ndev, n, m, nsc, my_rank, nx_tasks, ny_tasks
    INTEGER :: ids, ide, jds, jde, kds, kde, ims, ime, jms, jme, kms, kme, ips, ipe, jps, jpe, kps, kpe
    CHARACTER(kind=c_char) :: ncclid(128)
    CHARACTER(len=16) :: sname
@@ -108,6 +112,8 @@ SUBROUTINE solve_em ( grid , config_flags  &
       c%mix_isotropic = config_flags%mix_isotropic; c%mix_upper_bound = config_flags%mix_upper_bound
       c%tke_adv_opt = config_flags%tke_adv_opt; c%tke_upper_bound = config_flags%tke_upper_bound
       c%use_adaptive_time_step = MERGE(1,0,config_flags%use_adaptive_time_step)
+      c%spec_bdy_width = config_flags%spec_bdy_width; c%spec_zone = grid%spec_zone; c%relax_zone = grid%relax_zone
+      c%have_bcs_moist = MERGE(1,0,config_flags%have_bcs_moist); c%have_bcs_scalar = MERGE(1,0,config_flags%have_bcs_scalar)
       ndev = wrfgpu_device_count()
       IF ( ndev < 1 ) CALL wrf_error_fatal( 'solve_em (wrfgpu): no CUDA device on this node (there is no CPU fallback)' )
       device = MOD(my_rank, ndev)                    ! one rank per GPU of the node, ranks placed node by node
@@ -167,6 +173,40 @@ SUBROUTINE solve_em ( grid , config_flags  &
       CALL wrfgpu_check( wrfgpu_upload(handle(id), nf, names, host), 'wrfgpu_upload(ustm,hfx,qfx)' )
    END IF
 
+   ! ---- specified / nested lateral boundaries: the boundary arrays change when share/input_wrf.F reads the next boundary
+   !      time or med_nest_force refills them, and both reset grid%dtbc to 0 (input_wrf.F:1834, mediation_force_domain.F:206);
+   !      the device keeps its own dtbc, advanced by wrfgpu_step exactly as solve_em.F:377 advances grid%dtbc below
+   IF ( config_flags%specified .OR. config_flags%nested ) THEN
+      IF ( grid%dtbc == 0. ) THEN
+         nf = 0
+         CALL add1('fcx',grid%fcx); CALL add1('gcx',grid%gcx)
+         CALL addb('u', grid%u_bxs, grid%u_bxe, grid%u_bys, grid%u_bye, grid%u_btxs, grid%u_btxe, grid%u_btys, grid%u_btye)
+         CALL addb('v', grid%v_bxs, grid%v_bxe, grid%v_bys, grid%v_bye, grid%v_btxs, grid%v_btxe, grid%v_btys, grid%v_btye)
+         CALL addb('w', grid%w_bxs, grid%w_bxe, grid%w_bys, grid%w_bye, grid%w_btxs, grid%w_btxe, grid%w_btys, grid%w_btye)
+         CALL addb('ph', grid%ph_bxs, grid%ph_bxe, grid%ph_bys, grid%ph_bye, grid%ph_btxs, grid%ph_btxe, grid%ph_btys, grid%ph_btye)
+         CALL addb('t', grid%t_bxs, grid%t_bxe, grid%t_bys, grid%t_bye, grid%t_btxs, grid%t_btxe, grid%t_btys, grid%t_btye)
+         CALL addb('mu', grid%mu_bxs, grid%mu_bxe, grid%mu_bys, grid%mu_bye, grid%mu_btxs, grid%mu_btxe, grid%mu_btys, grid%mu_btye)
+         CALL addb('moist_qv', moist_bxs(:,:,:,P_QV), moist_bxe(:,:,:,P_QV), moist_bys(:,:,:,P_QV), moist_bye(:,:,:,P_QV), &
+                   moist_btxs(:,:,:,P_QV), moist_btxe(:,:,:,P_QV), moist_btys(:,:,:,P_QV), moist_btye(:,:,:,P_QV))
+         IF ( config_flags%mp_physics == 1 .AND. ( config_flags%nested .OR. config_flags%have_bcs_moist ) ) THEN
+            CALL addb('moist_qc', moist_bxs(:,:,:,P_QC), moist_bxe(:,:,:,P_QC), moist_bys(:,:,:,P_QC), moist_bye(:,:,:,P_QC), &
+                      moist_btxs(:,:,:,P_QC), moist_btxe(:,:,:,P_QC), moist_btys(:,:,:,P_QC), moist_btye(:,:,:,P_QC))
+            CALL addb('moist_qr', moist_bxs(:,:,:,P_QR), moist_bxe(:,:,:,P_QR), moist_bys(:,:,:,P_QR), moist_bye(:,:,:,P_QR), &
+                      moist_btxs(:,:,:,P_QR), moist_btxe(:,:,:,P_QR), moist_btys(:,:,:,P_QR), moist_btye(:,:,:,P_QR))
+         END IF
+         IF ( config_flags%nested .OR. config_flags%have_bcs_scalar ) THEN
+            DO n = 1, nsc
+               WRITE(sname,'(A,I0)') 'scalar_', n
+               m = PARAM_FIRST_SCALAR+n-1
+               CALL addb(TRIM(sname), scalar_bxs(:,:,:,m), scalar_bxe(:,:,:,m), scalar_bys(:,:,:,m), scalar_bye(:,:,:,m), &
+                         scalar_btxs(:,:,:,m), scalar_btxe(:,:,:,m), scalar_btys(:,:,:,m), scalar_btye(:,:,:,m))
+            END DO
+         END IF
+         CALL wrfgpu_check( wrfgpu_upload(handle(id), nf, names, host), 'wrfgpu_upload(boundary arrays)' )
+      END IF
+      CALL wrfgpu_check( wrfgpu_set_dtbc(handle(id), grid%dtbc), 'wrfgpu_set_dtbc' )
+   END IF
+
    ! ---- the reference's bookkeeping of this call (solve_em.F:360-374)
    host_needs_state = Is_alarm_tstep(grid%domain_clock, grid%alarms(restart_alarm)) .OR. &
                       Is_alarm_tstep(grid%domain_clock, grid%alarms(HISTORY_ALARM))
@@ -217,6 +257,12 @@ CONTAINS
       CHARACTER(len=*), INTENT(IN) :: name
       REAL, TARGET, CONTIGUOUS, INTENT(IN) :: a(:,:)
       nf = nf + 1; nm(nf) = TRIM(name)//c_null_char; names(nf) = c_loc(nm(nf)); host(nf) = c_loc(a)
+   END SUBROUTINE
+   SUBROUTINE addb(f, bxs, bxe, bys, bye, btxs, btxe, btys, btye)   ! the eight boundary arrays of one field
+      CHARACTER(len=*), INTENT(IN) :: f
+      REAL, TARGET, CONTIGUOUS, INTENT(IN) :: bxs(:,:,:), bxe(:,:,:), bys(:,:,:), bye(:,:,:), btxs(:,:,:), btxe(:,:,:), btys(:,:,:), btye(:,:,:)
+      CALL add(f//'_bxs', bxs);   CALL add(f//'_bxe', bxe);   CALL add(f//'_bys', bys);   CALL add(f//'_bye', bye)
+      CALL add(f//'_btxs', btxs); CALL add(f//'_btxe', btxe); CALL add(f//'_btys', btys); CALL add(f//'_btye', btye)
    END SUBROUTINE
    SUBROUTINE add1(name, a)
       CHARACTER(len=*), INTENT(IN) :: name
