@@ -9,6 +9,9 @@
 // Thomas forward/backward sweeps) live in registers.
 #include "common.cuh"
 #include "libm_port.h"
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
 
 namespace wg {
 
@@ -372,8 +375,12 @@ __device__ __forceinline__ Mt2 mt_load2(const Geo &g, const MuTArgs &a, int i, i
 // t_2ave of advance_w (:1314-1317) instead of the old theta'' -- this thread holds every operand of it (old and new
 // theta'', t_1, muave, muts), and advance_w then reads one field in its upward sweep instead of reading t_2, t_1,
 // t_2ave and writing t_2ave back: 12 B per point and launch less DRAM traffic in the DRAM-bound kernel.
-template <bool FINAL_AVE>
-__device__ __forceinline__ void advance_mu_t_column(const Geo &g, const Coef &cf, float dts, const MuTArgs &a, int i, int j) {
+// ld1(k) / ld2(k) deliver the operands of level k of the two sweeps (Mt1 / Mt2): straight from global memory
+// (k_advance_mu_t) or from the shared-memory ring the bulk-copy engine fills (k_advance_mu_t_st).  `active` = false:
+// a thread that only keeps a block-wide pipeline in step (it computes a copy of a neighbouring column and stores nothing).
+template <bool FINAL_AVE, class Ld1, class Ld2, class Mid>
+__device__ __forceinline__ void advance_mu_t_column(const Geo &g, const Coef &cf, float dts, const MuTArgs &a, int i, int j, bool active, Ld1 ld1,
+                                                    Ld2 ld2, Mid between_sweeps) {
   const int k_end = g.kde - 1;
   const float msftx = A2(g.msftx, i, j), msfty = A2(g.msfty, i, j);
   const float muu0 = A2(a.muu, i, j), muu1 = A2(a.muu, i + 1, j), muv0 = A2(a.muv, i, j), muv1 = A2(a.muv, i, j + 1);
@@ -381,58 +388,61 @@ __device__ __forceinline__ void advance_mu_t_column(const Geo &g, const Coef &cf
   const float mu_tend = A2(a.mu_tend, i, j);
   // pass 1: dvdxi(k) (parked in ww(k+1)) and its column integral dmdt
   float dmdt = 0.f;
-  Mt1 c1 = mt_load1(g, a, i, 1, j);
+  Mt1 c1 = ld1(1);
   for (int k = 1; k <= k_end; k++) {
     Mt1 n1;
-    if (k < k_end) n1 = mt_load1(g, a, i, k + 1, j);
+    if (k < k_end) n1 = ld1(k + 1);
     const float c1h = cf.c1h[k], c2h = cf.c2h[k];
     const float dvdxi = msftx * msfty *
                         (g.rdy * ((c1.vn + (c1h * muv1 + c2h) * c1.vsn * mvi1) - (c1.v0 + (c1h * muv0 + c2h) * c1.vs0 * mvi0)) +
                          g.rdx * ((c1.ue + (c1h * muu1 + c2h) * c1.use / my1) - (c1.u0 + (c1h * muu0 + c2h) * c1.us0 / my0)));
     dmdt = dmdt + cf.dnw[k] * dvdxi;
-    if (k < k_end) A3(a.ww, i, k + 1, j) = dvdxi;
+    if (k < k_end && active) A3(a.ww, i, k + 1, j) = dvdxi;
     c1 = n1;
   }
   float muts_new, muave_new;
   {
     const float mu_old = A2(a.mu, i, j);
     const float mu_new = mu_old + dts * (dmdt + mu_tend);
-    A2(a.mu, i, j) = mu_new;
-    A2(a.mudf, i, j) = (dmdt + mu_tend);
     muts_new = A2(a.mut, i, j) + mu_new;
-    A2(a.muts, i, j) = muts_new;
     muave_new = .5f * ((1.f + g.epssm) * mu_new + (1.f - g.epssm) * mu_old);
-    A2(a.muave, i, j) = muave_new;
+    if (active) {
+      A2(a.mu, i, j) = mu_new;
+      A2(a.mudf, i, j) = (dmdt + mu_tend);
+      A2(a.muts, i, j) = muts_new;
+      A2(a.muave, i, j) = muave_new;
+    }
   }
+  between_sweeps();
   // pass 2: ww recurrence (:1109-1121), then the theta update which needs ww(k), ww(k+1)
   // ww(1) is not touched by the recurrence; ww(k) -= ww_1(k) for k = 1..k_end
   float w_rec = A3(a.ww, i, 1, j);             // ww(i,1,j) before the subtraction
-  A3(a.ww, i, 1, j) = w_rec - A3(a.ww_1, i, 1, j);
+  if (active) A3(a.ww, i, 1, j) = w_rec - A3(a.ww_1, i, 1, j);
   float wdtn_k = 0.f;                          // wdtn(1) = 0
   float t1_k = A3(a.t_1, i, 1, j);
-  Mt2 c2 = mt_load2(g, a, i, 1, j, k_end);
+  Mt2 c2 = ld2(1);
   for (int k = 1; k <= k_end; k++) {
     Mt2 n2;
-    if (k < k_end) n2 = mt_load2(g, a, i, k + 1, j, k_end);
+    if (k < k_end) n2 = ld2(k + 1);
     float wdtn_kp1 = 0.f;
     if (k + 1 <= k_end) {
       w_rec = w_rec - cf.dnw[k] * ((cf.c1h[k] * dmdt) + c2.dv + (cf.c1h[k] * mu_tend)) / msfty;
       const float wkp1 = w_rec - c2.ww1;
-      A3(a.ww, i, k + 1, j) = wkp1;
+      if (active) A3(a.ww, i, k + 1, j) = wkp1;
       wdtn_kp1 = wkp1 * (cf.fnm[k + 1] * c2.t1u + cf.fnp[k + 1] * t1_k);
     }   // else wdtn(kde) = 0
     const float told = c2.t;
-    if (!FINAL_AVE) A3(a.t_ave, i, k, j) = told;
+    if (!FINAL_AVE && active) A3(a.t_ave, i, k, j) = told;
     float tn = told + msfty * dts * c2.ft;
     tn = tn - dts * msfty *
                   (msftx * (.5f * g.rdy * (c2.vn * (c2.t1n + t1_k) - c2.v0 * (t1_k + c2.t1s)) +
                             .5f * g.rdx * (c2.ue * (c2.t1e + t1_k) - c2.u0 * (t1_k + c2.t1w))) +
                    cf.rdnw[k] * (wdtn_kp1 - wdtn_k));
-    A3(a.t, i, k, j) = tn;
+    if (active) A3(a.t, i, k, j) = tn;
     if (FINAL_AVE) {   // t_2ave(k) of advance_w (:1314-1317)
       float tv = .5f * ((1.f + g.epssm) * tn + (1.f - g.epssm) * told);
       tv = (tv + (cf.c1h[k] * muave_new) * WG_T0) / ((cf.c1h[k] * muts_new + cf.c2h[k]) * (WG_T0 + t1_k));
-      A3(a.t_ave, i, k, j) = tv;
+      if (active) A3(a.t_ave, i, k, j) = tv;
     }
     wdtn_k = wdtn_kp1;
     t1_k = c2.t1u;
@@ -446,7 +456,129 @@ template <bool FINAL_AVE>
 __global__ void __launch_bounds__(128, MT_MINB) k_advance_mu_t(const Geo g, Box b, float dts, MuTArgs a) {
   MT_COEF;
   TID2;
-  advance_mu_t_column<FINAL_AVE>(g, cf, dts, a, i, j);
+  const int k_end = g.kde - 1;
+  advance_mu_t_column<FINAL_AVE>(
+      g, cf, dts, a, i, j, true, [&](int k) { return mt_load1(g, a, i, k, j); }, [&](int k) { return mt_load2(g, a, i, k, j, k_end); }, [] {});
+}
+
+// ---------------------------------------------------------------------------
+// The same column march with its operands staged by the bulk-copy engine (cp.async.bulk, the 1-D form of TMA): a block is
+// 128 columns of one j row; per level one thread issues one 544-byte row copy per operand stream (6 in the first sweep,
+// 10 in the second) into a ring of MTS_STAGES levels, an mbarrier per slot counts the bytes in, and every thread then
+// takes its operands -- its own column and the i-1 / i+1 neighbours -- from shared memory.  The register prefetch of
+// k_advance_mu_t keeps one level of loads in flight per warp and pays for it in registers; the ring keeps MTS_STAGES - 1
+// levels in flight without holding a register.  Arithmetic: advance_mu_t_column, unchanged.
+// Measured at 2000x2000x80 (profiles/README.md, mts1-mts3): 46.1 -> 42.4 ms per step with 3 stages at 8 blocks per SM;
+// 2, 4 or 5 stages (7 / 6 blocks) and one-instruction issue by ten lanes were all slower (48.5-54.5, 47.1).
+#ifndef MTS_STAGES
+#define MTS_STAGES 3
+#endif
+#define MTS_RW 136          // floats per staged row: 128 columns + the i-1 / i+1 neighbours + the slack of a 16-byte aligned start
+#define MTS_ROWS 10
+#ifndef MTS_MINB
+#define MTS_MINB 8
+#endif
+__device__ __forceinline__ uint32_t mts_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mts_bulk(uint32_t dst, const float *src, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"((uint32_t)(MTS_RW * sizeof(float))), "r"(bar)
+               : "memory");
+}
+// bounded wait: a lost completion becomes a trap (an error the host reports), never a hung GPU
+__device__ __forceinline__ void mts_wait(uint32_t bar, uint32_t parity) {
+  for (int spin = 0; spin < (1 << 24); spin++) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
+template <bool FINAL_AVE>
+__global__ void __launch_bounds__(128, MTS_MINB) k_advance_mu_t_st(const Geo g, Box b, float dts, MuTArgs a) {
+  MT_COEF;
+  __shared__ __align__(128) float ring[MTS_STAGES][MTS_ROWS][MTS_RW];
+  __shared__ __align__(8) unsigned long long bars[MTS_STAGES];
+  const int tx = threadIdx.x;
+  const int i0 = b.i0 + blockIdx.x * 128, j = b.j0 + blockIdx.y;
+  const bool active = i0 + tx <= b.i1;
+  const int i = active ? i0 + tx : b.i1;             // idle threads shadow the last column (and store nothing)
+  const int s0 = (i0 - 1 - g.ims) & ~3;              // 16-byte aligned start of the staged rows, in floats from the row start
+  const int ix = (i - g.ims) - s0;                   // this column in a staged row (>= 1)
+  const int k_end = g.kde - 1;
+  if (tx == 0) {
+    for (int q = 0; q < MTS_STAGES; q++)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mts_smem(&bars[q])), "r"(1u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // level L lives in slot (L-1) % MTS_STAGES; it is that slot's ((L-1) / MTS_STAGES)-th use of the sweep
+  auto row = [&](const float *f, int L, int jj) { return &A3(f, g.ims + s0, L, jj); };
+  auto issue1 = [&](int L) {
+    const int q = (L - 1) % MTS_STAGES;
+    const uint32_t bar = mts_smem(&bars[q]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(6 * MTS_RW * sizeof(float))) : "memory");
+    mts_bulk(mts_smem(ring[q][0]), row(a.v, L, j), bar);     mts_bulk(mts_smem(ring[q][1]), row(a.v, L, j + 1), bar);
+    mts_bulk(mts_smem(ring[q][2]), row(a.v_1, L, j), bar);   mts_bulk(mts_smem(ring[q][3]), row(a.v_1, L, j + 1), bar);
+    mts_bulk(mts_smem(ring[q][4]), row(a.u, L, j), bar);     mts_bulk(mts_smem(ring[q][5]), row(a.u_1, L, j), bar);
+  };
+  auto issue2 = [&](int L) {
+    const int q = (L - 1) % MTS_STAGES;
+    const uint32_t bar = mts_smem(&bars[q]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(10 * MTS_RW * sizeof(float))) : "memory");
+    mts_bulk(mts_smem(ring[q][0]), row(a.ww, L, j), bar);      mts_bulk(mts_smem(ring[q][1]), row(a.ww_1, L, j), bar);
+    mts_bulk(mts_smem(ring[q][2]), row(a.t_1, L, j - 1), bar); mts_bulk(mts_smem(ring[q][3]), row(a.t_1, L, j), bar);
+    mts_bulk(mts_smem(ring[q][4]), row(a.t_1, L, j + 1), bar); mts_bulk(mts_smem(ring[q][5]), row(a.t, L, j), bar);
+    mts_bulk(mts_smem(ring[q][6]), row(a.ft, L, j), bar);      mts_bulk(mts_smem(ring[q][7]), row(a.v, L, j), bar);
+    mts_bulk(mts_smem(ring[q][8]), row(a.v, L, j + 1), bar);   mts_bulk(mts_smem(ring[q][9]), row(a.u, L, j), bar);
+  };
+  // uses of slot q during the first sweep: the parity of a second-sweep wait continues from there
+  auto uses1 = [&](int q) { return q <= k_end - 1 ? (k_end - 1 - q) / MTS_STAGES + 1 : 0; };
+  auto wait_level = [&](int L, int sweep) {
+    const int q = (L - 1) % MTS_STAGES;
+    const int n = (L - 1) / MTS_STAGES + (sweep == 2 ? uses1(q) : 0);
+    mts_wait(mts_smem(&bars[q]), (uint32_t)(n & 1));
+  };
+  if (tx == 0)
+    for (int L = 1; L <= MTS_STAGES && L <= k_end; L++) issue1(L);
+  auto ld1 = [&](int k) {
+    wait_level(k, 1);
+    const int q = (k - 1) % MTS_STAGES;
+    Mt1 m;
+    m.v0 = ring[q][0][ix]; m.vn = ring[q][1][ix]; m.vs0 = ring[q][2][ix]; m.vsn = ring[q][3][ix];
+    m.u0 = ring[q][4][ix]; m.ue = ring[q][4][ix + 1]; m.us0 = ring[q][5][ix]; m.use = ring[q][5][ix + 1];
+    __syncthreads();                                       // everyone has taken level k: its slot is free
+    if (tx == 0 && k + MTS_STAGES <= k_end) issue1(k + MTS_STAGES);
+    return m;
+  };
+  auto between = [&] {
+    // the first sweep parked dvdxi in ww with ordinary stores; the second sweep's bulk copies read it back
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (tx == 0)
+      for (int L = 1; L <= MTS_STAGES && L <= k_end; L++) issue2(L);
+  };
+  auto ld2 = [&](int k) {
+    wait_level(k, 2);
+    if (k + 1 <= k_end) wait_level(k + 1, 2);
+    const int q = (k - 1) % MTS_STAGES, qn = k % MTS_STAGES;
+    Mt2 m;
+    m.dv = 0.f; m.ww1 = 0.f; m.t1u = 0.f;
+    if (k + 1 <= k_end) { m.dv = ring[qn][0][ix]; m.ww1 = ring[qn][1][ix]; m.t1u = ring[qn][3][ix]; }
+    m.t1s = ring[q][2][ix]; m.t1w = ring[q][3][ix - 1]; m.t1e = ring[q][3][ix + 1]; m.t1n = ring[q][4][ix];
+    m.t = ring[q][5][ix]; m.ft = ring[q][6][ix]; m.v0 = ring[q][7][ix]; m.vn = ring[q][8][ix];
+    m.u0 = ring[q][9][ix]; m.ue = ring[q][9][ix + 1];
+    __syncthreads();                                       // level k's slot is free (level k+1's is read again by the next call)
+    if (tx == 0 && k + MTS_STAGES <= k_end) issue2(k + MTS_STAGES);
+    return m;
+  };
+  advance_mu_t_column<FINAL_AVE>(g, cf, dts, a, i, j, active, ld1, ld2, between);
 }
 
 // ---------------------------------------------------------------------------
@@ -831,7 +963,16 @@ void Solver::advance_mu_t(int rk_step, bool final_ave) {
   rk_params(rk_step, dt_rk, dts_rk, ns);
   MuTArgs a = mu_t_args(this);
   const Box mass = spec() ? spec_mass_box() : Box{q.its, std::min(q.ite, q.ide - 1), 1, 1, q.jts, std::min(q.jte, q.jde - 1)};
-  if (final_ave) LAUNCH2(this, k_advance_mu_t<true>, mass, dts_rk, a);    // only together with advance_w_fused
+  static const bool staged = [] { const char *e = getenv("WRFGPU_MT"); return !(e && !strcmp(e, "column")); }();
+  if (staged && !empty(mass) && mass.i1 - mass.i0 >= 4) {   // operands staged by the bulk-copy engine (k_advance_mu_t_st); WRFGPU_MT=column: the register-prefetch form
+    const dim3 gr((unsigned)((mass.i1 - mass.i0 + 128) / 128), (unsigned)(mass.j1 - mass.j0 + 1));
+    if (coef_dirty) sync_coef();
+    kpre(final_ave ? "k_advance_mu_t_st<true>" : "k_advance_mu_t_st<false>");
+    if (final_ave) k_advance_mu_t_st<true><<<gr, 128, 0, stream>>>(g, mass, dts_rk, a);
+    else k_advance_mu_t_st<false><<<gr, 128, 0, stream>>>(g, mass, dts_rk, a);
+    kpost();
+    launches++;
+  } else if (final_ave) LAUNCH2(this, k_advance_mu_t<true>, mass, dts_rk, a);    // only together with advance_w_fused
   else LAUNCH2(this, k_advance_mu_t<false>, mass, dts_rk, a);
   if (spec()) spec_update_tmu(dts_rk);   // solve_em.F:1459-1490
 }
