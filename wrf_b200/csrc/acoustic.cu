@@ -468,15 +468,20 @@ __global__ void __launch_bounds__(128, MT_MINB) k_advance_mu_t(const Geo g, Box 
 // takes its operands -- its own column and the i-1 / i+1 neighbours -- from shared memory.  The register prefetch of
 // k_advance_mu_t keeps one level of loads in flight per warp and pays for it in registers; the ring keeps MTS_STAGES - 1
 // levels in flight without holding a register.  Arithmetic: advance_mu_t_column, unchanged.
-// Measured at 2000x2000x80 (profiles/README.md, mts1-mts3): 46.1 -> 42.4 ms per step with 3 stages at 8 blocks per SM;
-// 2, 4 or 5 stages (7 / 6 blocks) and one-instruction issue by ten lanes were all slower (48.5-54.5, 47.1).
+// Measured at 2000x2000x80 (profiles/README.md, mts1-mts8): the register-prefetch kernel 46.1 ms per step; staged with a
+// block-wide barrier per level 42.4; with a producer warp and full / empty mbarriers (below) 38.9 at 3 stages, 37.2 at 4
+// (the default: 8 consumer warps per block, 4 blocks per SM), 40.3 at 5 or 6 stages (3 blocks), 37.9 with 16 consumer warps.
 #ifndef MTS_STAGES
-#define MTS_STAGES 3
+#define MTS_STAGES 4
 #endif
-#define MTS_RW 136          // floats per staged row: 128 columns + the i-1 / i+1 neighbours + the slack of a 16-byte aligned start
+#ifndef MTS_CW
+#define MTS_CW 8            // consumer warps per block (32 columns each); one more warp issues the copies
+#endif
+#define MTS_NCOL (32 * MTS_CW)
+#define MTS_RW (MTS_NCOL + 8)   // floats per staged row: the columns + the i-1 / i+1 neighbours + the slack of a 16-byte aligned start
 #define MTS_ROWS 10
 #ifndef MTS_MINB
-#define MTS_MINB 8
+#define MTS_MINB 4
 #endif
 __device__ __forceinline__ uint32_t mts_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mts_bulk(uint32_t dst, const float *src, uint32_t bar) {
@@ -484,6 +489,7 @@ __device__ __forceinline__ void mts_bulk(uint32_t dst, const float *src, uint32_
                "r"((uint32_t)(MTS_RW * sizeof(float))), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void mts_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 // bounded wait: a lost completion becomes a trap (an error the host reports), never a hung GPU
 __device__ __forceinline__ void mts_wait(uint32_t bar, uint32_t parity) {
   for (int spin = 0; spin < (1 << 24); spin++) {
@@ -500,82 +506,93 @@ __device__ __forceinline__ void mts_wait(uint32_t bar, uint32_t parity) {
   __trap();
 }
 
+// Roles: warps 0 .. MTS_CW-1 march their 32 columns each; the last warp's lane 0 is the producer.  The two sweeps are one
+// sequence of 2 k_end "events" (event e < k_end: level e+1 of the first sweep, then the levels of the second); event e
+// lives in slot e % MTS_STAGES.  full[q] (count 1 + the bytes of the copies) tells the consumers that a slot has landed,
+// empty[q] (count MTS_CW: lane 0 of every consumer warp) tells the producer that they are done with it, `sweep` that the
+// first sweep's stores of dvdxi into ww are visible to the copy engine.  No block-wide barrier inside the march: the warps
+// drift by up to a ring's depth (the first version synchronised the block once per level and spent a third of its stall
+// cycles there, ncu mtsp).
 template <bool FINAL_AVE>
-__global__ void __launch_bounds__(128, MTS_MINB) k_advance_mu_t_st(const Geo g, Box b, float dts, MuTArgs a) {
+__global__ void __launch_bounds__(32 * (MTS_CW + 1), MTS_MINB) k_advance_mu_t_st(const Geo g, Box b, float dts, MuTArgs a) {
   MT_COEF;
-  __shared__ __align__(128) float ring[MTS_STAGES][MTS_ROWS][MTS_RW];
-  __shared__ __align__(8) unsigned long long bars[MTS_STAGES];
-  const int tx = threadIdx.x;
-  const int i0 = b.i0 + blockIdx.x * 128, j = b.j0 + blockIdx.y;
-  const bool active = i0 + tx <= b.i1;
-  const int i = active ? i0 + tx : b.i1;             // idle threads shadow the last column (and store nothing)
+  extern __shared__ __align__(128) float mts_dyn[];   // the ring: more than the 48 KB a static array may take
+  float (*ring)[MTS_ROWS][MTS_RW] = reinterpret_cast<float (*)[MTS_ROWS][MTS_RW]>(mts_dyn);
+  __shared__ __align__(8) unsigned long long full[MTS_STAGES], empty[MTS_STAGES], sweep;
+  const int tx = threadIdx.x, lane = tx & 31;
+  const int i0 = b.i0 + blockIdx.x * MTS_NCOL, j = b.j0 + blockIdx.y;
   const int s0 = (i0 - 1 - g.ims) & ~3;              // 16-byte aligned start of the staged rows, in floats from the row start
-  const int ix = (i - g.ims) - s0;                   // this column in a staged row (>= 1)
   const int k_end = g.kde - 1;
   if (tx == 0) {
-    for (int q = 0; q < MTS_STAGES; q++)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mts_smem(&bars[q])), "r"(1u) : "memory");
+    for (int q = 0; q < MTS_STAGES; q++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mts_smem(&full[q])), "r"(1u) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mts_smem(&empty[q])), "r"((uint32_t)MTS_CW) : "memory");
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mts_smem(&sweep)), "r"((uint32_t)MTS_CW) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  // level L lives in slot (L-1) % MTS_STAGES; it is that slot's ((L-1) / MTS_STAGES)-th use of the sweep
-  auto row = [&](const float *f, int L, int jj) { return &A3(f, g.ims + s0, L, jj); };
-  auto issue1 = [&](int L) {
-    const int q = (L - 1) % MTS_STAGES;
-    const uint32_t bar = mts_smem(&bars[q]);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(6 * MTS_RW * sizeof(float))) : "memory");
-    mts_bulk(mts_smem(ring[q][0]), row(a.v, L, j), bar);     mts_bulk(mts_smem(ring[q][1]), row(a.v, L, j + 1), bar);
-    mts_bulk(mts_smem(ring[q][2]), row(a.v_1, L, j), bar);   mts_bulk(mts_smem(ring[q][3]), row(a.v_1, L, j + 1), bar);
-    mts_bulk(mts_smem(ring[q][4]), row(a.u, L, j), bar);     mts_bulk(mts_smem(ring[q][5]), row(a.u_1, L, j), bar);
+  if (tx >= MTS_NCOL) {   // ---- producer
+    if (lane != 0) return;
+    auto row = [&](const float *f, int L, int jj) { return &A3(f, g.ims + s0, L, jj); };
+    for (int e = 0; e < 2 * k_end; e++) {
+      const int q = e % MTS_STAGES, n = e / MTS_STAGES;
+      if (n > 0) mts_wait(mts_smem(&empty[q]), (uint32_t)((n - 1) & 1));
+      if (e == k_end) mts_wait(mts_smem(&sweep), 0u);
+      const uint32_t bar = mts_smem(&full[q]);
+      if (e < k_end) {
+        const int L = e + 1;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(6 * MTS_RW * sizeof(float))) : "memory");
+        mts_bulk(mts_smem(ring[q][0]), row(a.v, L, j), bar);     mts_bulk(mts_smem(ring[q][1]), row(a.v, L, j + 1), bar);
+        mts_bulk(mts_smem(ring[q][2]), row(a.v_1, L, j), bar);   mts_bulk(mts_smem(ring[q][3]), row(a.v_1, L, j + 1), bar);
+        mts_bulk(mts_smem(ring[q][4]), row(a.u, L, j), bar);     mts_bulk(mts_smem(ring[q][5]), row(a.u_1, L, j), bar);
+      } else {
+        const int L = e - k_end + 1;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(10 * MTS_RW * sizeof(float))) : "memory");
+        mts_bulk(mts_smem(ring[q][0]), row(a.ww, L, j), bar);      mts_bulk(mts_smem(ring[q][1]), row(a.ww_1, L, j), bar);
+        mts_bulk(mts_smem(ring[q][2]), row(a.t_1, L, j - 1), bar); mts_bulk(mts_smem(ring[q][3]), row(a.t_1, L, j), bar);
+        mts_bulk(mts_smem(ring[q][4]), row(a.t_1, L, j + 1), bar); mts_bulk(mts_smem(ring[q][5]), row(a.t, L, j), bar);
+        mts_bulk(mts_smem(ring[q][6]), row(a.ft, L, j), bar);      mts_bulk(mts_smem(ring[q][7]), row(a.v, L, j), bar);
+        mts_bulk(mts_smem(ring[q][8]), row(a.v, L, j + 1), bar);   mts_bulk(mts_smem(ring[q][9]), row(a.u, L, j), bar);
+      }
+    }
+    return;
+  }
+  // ---- consumers
+  const bool active = i0 + tx <= b.i1;
+  const int i = active ? i0 + tx : b.i1;             // idle threads shadow the last column (and store nothing)
+  const int ix = (i - g.ims) - s0;                   // this column in a staged row (>= 1)
+  auto wait_event = [&](int e) { mts_wait(mts_smem(&full[e % MTS_STAGES]), (uint32_t)((e / MTS_STAGES) & 1)); };
+  auto release = [&](int e) {
+    __syncwarp();
+    if (lane == 0) mts_arrive(mts_smem(&empty[e % MTS_STAGES]));
   };
-  auto issue2 = [&](int L) {
-    const int q = (L - 1) % MTS_STAGES;
-    const uint32_t bar = mts_smem(&bars[q]);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(10 * MTS_RW * sizeof(float))) : "memory");
-    mts_bulk(mts_smem(ring[q][0]), row(a.ww, L, j), bar);      mts_bulk(mts_smem(ring[q][1]), row(a.ww_1, L, j), bar);
-    mts_bulk(mts_smem(ring[q][2]), row(a.t_1, L, j - 1), bar); mts_bulk(mts_smem(ring[q][3]), row(a.t_1, L, j), bar);
-    mts_bulk(mts_smem(ring[q][4]), row(a.t_1, L, j + 1), bar); mts_bulk(mts_smem(ring[q][5]), row(a.t, L, j), bar);
-    mts_bulk(mts_smem(ring[q][6]), row(a.ft, L, j), bar);      mts_bulk(mts_smem(ring[q][7]), row(a.v, L, j), bar);
-    mts_bulk(mts_smem(ring[q][8]), row(a.v, L, j + 1), bar);   mts_bulk(mts_smem(ring[q][9]), row(a.u, L, j), bar);
-  };
-  // uses of slot q during the first sweep: the parity of a second-sweep wait continues from there
-  auto uses1 = [&](int q) { return q <= k_end - 1 ? (k_end - 1 - q) / MTS_STAGES + 1 : 0; };
-  auto wait_level = [&](int L, int sweep) {
-    const int q = (L - 1) % MTS_STAGES;
-    const int n = (L - 1) / MTS_STAGES + (sweep == 2 ? uses1(q) : 0);
-    mts_wait(mts_smem(&bars[q]), (uint32_t)(n & 1));
-  };
-  if (tx == 0)
-    for (int L = 1; L <= MTS_STAGES && L <= k_end; L++) issue1(L);
   auto ld1 = [&](int k) {
-    wait_level(k, 1);
-    const int q = (k - 1) % MTS_STAGES;
+    const int e = k - 1, q = e % MTS_STAGES;
+    wait_event(e);
     Mt1 m;
     m.v0 = ring[q][0][ix]; m.vn = ring[q][1][ix]; m.vs0 = ring[q][2][ix]; m.vsn = ring[q][3][ix];
     m.u0 = ring[q][4][ix]; m.ue = ring[q][4][ix + 1]; m.us0 = ring[q][5][ix]; m.use = ring[q][5][ix + 1];
-    __syncthreads();                                       // everyone has taken level k: its slot is free
-    if (tx == 0 && k + MTS_STAGES <= k_end) issue1(k + MTS_STAGES);
+    release(e);
     return m;
   };
   auto between = [&] {
     // the first sweep parked dvdxi in ww with ordinary stores; the second sweep's bulk copies read it back
     asm volatile("fence.proxy.async;" ::: "memory");
-    __syncthreads();
-    if (tx == 0)
-      for (int L = 1; L <= MTS_STAGES && L <= k_end; L++) issue2(L);
+    __syncwarp();
+    if (lane == 0) mts_arrive(mts_smem(&sweep));
   };
   auto ld2 = [&](int k) {
-    wait_level(k, 2);
-    if (k + 1 <= k_end) wait_level(k + 1, 2);
-    const int q = (k - 1) % MTS_STAGES, qn = k % MTS_STAGES;
+    const int e = k_end + k - 1, q = e % MTS_STAGES, qn = (e + 1) % MTS_STAGES;
+    wait_event(e);
+    if (k + 1 <= k_end) wait_event(e + 1);
     Mt2 m;
     m.dv = 0.f; m.ww1 = 0.f; m.t1u = 0.f;
     if (k + 1 <= k_end) { m.dv = ring[qn][0][ix]; m.ww1 = ring[qn][1][ix]; m.t1u = ring[qn][3][ix]; }
     m.t1s = ring[q][2][ix]; m.t1w = ring[q][3][ix - 1]; m.t1e = ring[q][3][ix + 1]; m.t1n = ring[q][4][ix];
     m.t = ring[q][5][ix]; m.ft = ring[q][6][ix]; m.v0 = ring[q][7][ix]; m.vn = ring[q][8][ix];
     m.u0 = ring[q][9][ix]; m.ue = ring[q][9][ix + 1];
-    __syncthreads();                                       // level k's slot is free (level k+1's is read again by the next call)
-    if (tx == 0 && k + MTS_STAGES <= k_end) issue2(k + MTS_STAGES);
+    release(e);                                            // level k's slot (level k+1's is read again by the next call)
     return m;
   };
   advance_mu_t_column<FINAL_AVE>(g, cf, dts, a, i, j, active, ld1, ld2, between);
@@ -965,11 +982,19 @@ void Solver::advance_mu_t(int rk_step, bool final_ave) {
   const Box mass = spec() ? spec_mass_box() : Box{q.its, std::min(q.ite, q.ide - 1), 1, 1, q.jts, std::min(q.jte, q.jde - 1)};
   static const bool staged = [] { const char *e = getenv("WRFGPU_MT"); return !(e && !strcmp(e, "column")); }();
   if (staged && !empty(mass) && mass.i1 - mass.i0 >= 4) {   // operands staged by the bulk-copy engine (k_advance_mu_t_st); WRFGPU_MT=column: the register-prefetch form
-    const dim3 gr((unsigned)((mass.i1 - mass.i0 + 128) / 128), (unsigned)(mass.j1 - mass.j0 + 1));
+    const dim3 gr((unsigned)((mass.i1 - mass.i0 + MTS_NCOL) / MTS_NCOL), (unsigned)(mass.j1 - mass.j0 + 1));
+    const int nthr = 32 * (MTS_CW + 1);
+    const size_t ring_bytes = sizeof(float) * MTS_STAGES * MTS_ROWS * MTS_RW;
+    static const bool attr = [&] {
+      CUDA_CHECK(cudaFuncSetAttribute(k_advance_mu_t_st<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+      CUDA_CHECK(cudaFuncSetAttribute(k_advance_mu_t_st<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+      return true;
+    }();
+    (void)attr;
     if (coef_dirty) sync_coef();
     kpre(final_ave ? "k_advance_mu_t_st<true>" : "k_advance_mu_t_st<false>");
-    if (final_ave) k_advance_mu_t_st<true><<<gr, 128, 0, stream>>>(g, mass, dts_rk, a);
-    else k_advance_mu_t_st<false><<<gr, 128, 0, stream>>>(g, mass, dts_rk, a);
+    if (final_ave) k_advance_mu_t_st<true><<<gr, nthr, ring_bytes, stream>>>(g, mass, dts_rk, a);
+    else k_advance_mu_t_st<false><<<gr, nthr, ring_bytes, stream>>>(g, mass, dts_rk, a);
     kpost();
     launches++;
   } else if (final_ave) LAUNCH2(this, k_advance_mu_t<true>, mass, dts_rk, a);    // only together with advance_w_fused
