@@ -130,6 +130,22 @@ def test_boundary_zone_twelve_steps_bit_exact(name):
     s.close()
 
 
+def test_register_prefetch_form_of_advance_mu_t_is_still_exact():
+    """WRFGPU_MT=column selects k_advance_mu_t (operands prefetched into registers) instead of k_advance_mu_t_st (operands
+    staged by the bulk-copy engine); the switch is read once per process, so the check runs in a child: phase parity and
+    one whole step of two cases"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, WRFGPU_MT="column", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_parity_gpu.py"), "-x", "-q", "-k",
+                        "(phase_parity or full_step) and (quarter_ss or periodic or specified_real) and not shipped"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-1000:]
+
+
 @pytest.mark.parametrize("name", ["ieva", "ieva_periodic"])
 def test_ieva_three_steps_bit_exact(name):
     """IEVA with a non-zero implicit part (wwI) on every step: three steps stay identical to the oracle, including

@@ -985,12 +985,11 @@ void Solver::advance_mu_t(int rk_step, bool final_ave) {
     const dim3 gr((unsigned)((mass.i1 - mass.i0 + MTS_NCOL) / MTS_NCOL), (unsigned)(mass.j1 - mass.j0 + 1));
     const int nthr = 32 * (MTS_CW + 1);
     const size_t ring_bytes = sizeof(float) * MTS_STAGES * MTS_ROWS * MTS_RW;
-    static const bool attr = [&] {
+    if (!mt_smem_set) {   // per device, hence per Solver
       CUDA_CHECK(cudaFuncSetAttribute(k_advance_mu_t_st<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
       CUDA_CHECK(cudaFuncSetAttribute(k_advance_mu_t_st<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
-      return true;
-    }();
-    (void)attr;
+      mt_smem_set = true;
+    }
     if (coef_dirty) sync_coef();
     kpre(final_ave ? "k_advance_mu_t_st<true>" : "k_advance_mu_t_st<false>");
     if (final_ave) k_advance_mu_t_st<true><<<gr, nthr, ring_bytes, stream>>>(g, mass, dts_rk, a);

@@ -165,6 +165,7 @@ struct Solver {
   int tke_index() const { return (c.km_opt == 2 && c.diff_opt == 2) ? c.num_scalar + 1 : 0; }
   long long launches = 0;
   float *d_cfl = nullptr;   // 2 floats: max_vert_cfl, max_horiz_cfl
+  bool mt_smem_set = false; // acoustic.cu: the dynamic shared memory size of k_advance_mu_t_st has been set on this device
   // specified / nested lateral boundaries (bdy.cu): grid%dtbc, the time since the boundary arrays were valid (solve_em.F:377;
   // reset by the host when it uploads the next boundary time, wrfgpu_set_dtbc)
   float dtbc = 0.f;
