@@ -492,6 +492,9 @@ __device__ __forceinline__ void mts_bulk(uint32_t dst, const float *src, uint32_
 __device__ __forceinline__ void mts_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 // bounded wait: a lost completion becomes a trap (an error the host reports), never a hung GPU
 __device__ __forceinline__ void mts_wait(uint32_t bar, uint32_t parity) {
+#ifndef MTS_UNROLL_WAIT
+#pragma unroll 1
+#endif
   for (int spin = 0; spin < (1 << 24); spin++) {
     uint32_t ok;
     asm volatile(
