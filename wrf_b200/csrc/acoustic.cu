@@ -96,6 +96,96 @@ __global__ void k_ssp_3d(const Geo g, Box b, int rk_step, int zero_rest, SspArgs
   }
 }
 
+// The same sweep with 16-byte accesses: a thread owns four consecutive columns (a 16-byte aligned group of the padded
+// device row), loads every operand of the group with one LDG.128 and stores a result with one STG.128 when all four
+// lanes take the same branch (all but the groups that straddle its, ite or the last mass column).  26 streams at 128-byte
+// warp requests ran at 0.66 of the copy bandwidth; a warp request is now 512 contiguous bytes per stream.
+__device__ __forceinline__ void ld4(const float *p, float v[4]) {
+  const float4 q = *reinterpret_cast<const float4 *>(p);
+  v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+// lanes lo..hi (0..3, inclusive) of the group are to be written
+__device__ __forceinline__ void st4(float *p, const float v[4], int lo, int hi) {
+  if (lo == 0 && hi == 3) *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  else {
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (q >= lo && q <= hi) p[q] = v[q];
+  }
+}
+__global__ void k_ssp_3d_v4(const Geo g, Box b, int rk_step, int zero_rest, SspArgs a) {
+  // b.i0 / b.i1: first and last GROUP index of the row (column = ims + 4 * group + lane)
+  const int gi = b.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = b.k0 + blockIdx.y * blockDim.y + threadIdx.y;
+  const int j = b.j0 + blockIdx.z * blockDim.z + threadIdx.z;
+  if (gi > b.i1 || k > b.k1 || j > b.j1) return;
+  const int i = g.ims + 4 * gi;                 // column of lane 0
+  const int kde = g.kde;
+  const int i_m = min(g.ite, g.ide - 1);        // last mass column
+  const bool jm = j <= min(g.jte, g.jde - 1), km = k <= kde - 1;
+  // lanes inside the tile, and inside the mass columns
+  const int lo = max(g.its - i, 0), hi = min(g.ite - i, 3), him = min(i_m - i, 3);
+  const float c1h = g.c1h[k], c2h = g.c2h[k], c1f = g.c1f[k], c2f = g.c2f[k];
+  float zero[4] = {0.f, 0.f, 0.f, 0.f};
+  if (km && jm) {   // u points: every column of the tile
+    float u2[4], u1[4], muus[4], muu[4], my[4], out[4];
+    ld4(&A3(a.u_2, i, k, j), u2); ld4(&A2(a.muus, i, j), muus); ld4(&A2(a.muu, i, j), muu); ld4(&A2(g.msfuy, i, j), my);
+    if (rk_step == 1) { for (int q = 0; q < 4; q++) u1[q] = u2[q]; st4(&A3(a.u_1, i, k, j), u2, lo, hi); }
+    else ld4(&A3(a.u_1, i, k, j), u1);
+    st4(&A3(a.u_save, i, k, j), u2, lo, hi);
+    for (int q = 0; q < 4; q++) out[q] = ((c1h * muus[q] + c2h) * u1[q] - (c1h * muu[q] + c2h) * u2[q]) / my[q];
+    st4(&A3(a.u_2, i, k, j), out, lo, hi);
+  } else if (zero_rest) st4(&A3(a.u_save, i, k, j), zero, lo, hi);
+  if (km) {   // v points: the mass columns; the last u column (if any) only gets zero_rest's zero
+    if (him >= lo) {
+      float v2[4], v1[4], muvs[4], muv[4], mi[4], out[4];
+      ld4(&A3(a.v_2, i, k, j), v2); ld4(&A2(a.muvs, i, j), muvs); ld4(&A2(a.muv, i, j), muv); ld4(&A2(g.msfvx_inv, i, j), mi);
+      if (rk_step == 1) { for (int q = 0; q < 4; q++) v1[q] = v2[q]; st4(&A3(a.v_1, i, k, j), v2, lo, him); }
+      else ld4(&A3(a.v_1, i, k, j), v1);
+      st4(&A3(a.v_save, i, k, j), v2, lo, him);
+      for (int q = 0; q < 4; q++) out[q] = ((c1h * muvs[q] + c2h) * v1[q] - (c1h * muv[q] + c2h) * v2[q]) * mi[q];
+      st4(&A3(a.v_2, i, k, j), out, lo, him);
+    }
+    if (zero_rest && hi > him) st4(&A3(a.v_save, i, k, j), zero, max(him + 1, lo), hi);
+  } else if (zero_rest) st4(&A3(a.v_save, i, k, j), zero, lo, hi);
+  if (jm) {
+    if (him >= lo) {
+      float muts[4], mut[4];
+      ld4(&A2(a.muts, i, j), muts); ld4(&A2(a.mut, i, j), mut);
+      if (km) {
+        float t2[4], t1[4], pb[4], p[4], alt[4], out[4];
+        ld4(&A3(a.t_2, i, k, j), t2); ld4(&A3(a.pb, i, k, j), pb); ld4(&A3(a.p, i, k, j), p); ld4(&A3(a.alt, i, k, j), alt);
+        if (rk_step == 1) { for (int q = 0; q < 4; q++) t1[q] = t2[q]; st4(&A3(a.t_1, i, k, j), t2, lo, him); }
+        else ld4(&A3(a.t_1, i, k, j), t1);
+        for (int q = 0; q < 4; q++) out[q] = WG_CPOVCV * (pb[q] + p[q]) / alt[q];
+        st4(&A3(a.c2a, i, k, j), out, lo, him);
+        st4(&A3(a.t_save, i, k, j), t2, lo, him);
+        for (int q = 0; q < 4; q++) out[q] = (c1h * muts[q] + c2h) * t1[q] - (c1h * mut[q] + c2h) * t2[q];
+        st4(&A3(a.t_2, i, k, j), out, lo, him);
+      } else if (zero_rest) st4(&A3(a.t_save, i, k, j), zero, lo, him);
+      float w2[4], p2[4], w1[4], p1[4], my[4], ww[4], out[4];
+      ld4(&A3(a.w_2, i, k, j), w2); ld4(&A3(a.ph_2, i, k, j), p2); ld4(&A2(g.msfty, i, j), my); ld4(&A3(a.ww, i, k, j), ww);
+      if (rk_step == 1) {
+        for (int q = 0; q < 4; q++) { w1[q] = w2[q]; p1[q] = p2[q]; }
+        st4(&A3(a.w_1, i, k, j), w2, lo, him); st4(&A3(a.ph_1, i, k, j), p2, lo, him);
+      } else { ld4(&A3(a.w_1, i, k, j), w1); ld4(&A3(a.ph_1, i, k, j), p1); }
+      st4(&A3(a.w_save, i, k, j), w2, lo, him);
+      for (int q = 0; q < 4; q++) out[q] = ((c1f * muts[q] + c2f) * w1[q] - (c1f * mut[q] + c2f) * w2[q]) / my[q];
+      st4(&A3(a.w_2, i, k, j), out, lo, him);
+      st4(&A3(a.ph_save, i, k, j), p2, lo, him);
+      for (int q = 0; q < 4; q++) out[q] = p1[q] - p2[q];
+      st4(&A3(a.ph_2, i, k, j), out, lo, him);
+      st4(&A3(a.ww_save, i, k, j), ww, lo, him);
+    }
+    if (zero_rest && hi > him) {
+      const int l2 = max(him + 1, lo);
+      st4(&A3(a.w_save, i, k, j), zero, l2, hi); st4(&A3(a.ph_save, i, k, j), zero, l2, hi); st4(&A3(a.t_save, i, k, j), zero, l2, hi);
+    }
+  } else if (zero_rest) {
+    st4(&A3(a.w_save, i, k, j), zero, lo, hi); st4(&A3(a.ph_save, i, k, j), zero, lo, hi); st4(&A3(a.t_save, i, k, j), zero, lo, hi);
+  }
+}
+
 // calc_p_rho (:438-566), non-hydrostatic
 __global__ void k_calc_p_rho(const Geo g, Box b, int step, fp al, fp p, cfp ph, cfp alt, cfp t_2, cfp t_1, cfp c2a, fp pm1,
                              cfp mu, cfp mut) {
@@ -930,7 +1020,11 @@ void Solver::small_step_prep(int rk_step, bool zero_rest) {
   a.u_save = o("u_save"); a.v_save = o("v_save"); a.w_save = o("w_save"); a.t_save = o("t_save"); a.ph_save = o("ph_save");
   a.ww_save = o("ww1"); a.c2a = o("c2a"); a.ww = o("ww"); a.pb = o("pb"); a.p = o("p"); a.alt = o("alt");
   a.muu = o("muu"); a.muus = o("muus"); a.muv = o("muv"); a.muvs = o("muvs"); a.mut = o("mut"); a.muts = o("muts");
-  LAUNCH3(this, k_ssp_3d, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), rk_step, zero_rest ? 1 : 0, a);
+  static const bool vec4 = [] { const char *e = getenv("WRFGPU_SSP"); return !(e && !strcmp(e, "scalar")); }();
+  if (vec4)   // four columns per thread, 16-byte accesses; the box counts groups of four from the start of the memory row
+    LAUNCH3(this, k_ssp_3d_v4, (Box{(q.its - q.ims) / 4, (q.ite - q.ims) / 4, 1, q.kde, q.jts, q.jte}), rk_step, zero_rest ? 1 : 0, a);
+  else
+    LAUNCH3(this, k_ssp_3d, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), rk_step, zero_rest ? 1 : 0, a);
   const int im = std::min(q.ite, q.ide - 1), jm = std::min(q.jte, q.jde - 1);
   LAUNCH3(this, k_calc_p_rho, (Box{q.its, im, 1, q.kde - 1, q.jts, jm}), 0, o("al"), o("p"), o("ph_2"), o("alt"), o("t_2"),
           o("t_save"), o("c2a"), o("pm1"), o("mu_2"), o("muts"));
