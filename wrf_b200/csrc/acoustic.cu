@@ -100,19 +100,6 @@ __global__ void k_ssp_3d(const Geo g, Box b, int rk_step, int zero_rest, SspArgs
 // device row), loads every operand of the group with one LDG.128 and stores a result with one STG.128 when all four
 // lanes take the same branch (all but the groups that straddle its, ite or the last mass column).  26 streams at 128-byte
 // warp requests ran at 0.66 of the copy bandwidth; a warp request is now 512 contiguous bytes per stream.
-__device__ __forceinline__ void ld4(const float *p, float v[4]) {
-  const float4 q = *reinterpret_cast<const float4 *>(p);
-  v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-}
-// lanes lo..hi (0..3, inclusive) of the group are to be written
-__device__ __forceinline__ void st4(float *p, const float v[4], int lo, int hi) {
-  if (lo == 0 && hi == 3) *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  else {
-#pragma unroll
-    for (int q = 0; q < 4; q++)
-      if (q >= lo && q <= hi) p[q] = v[q];
-  }
-}
 __global__ void k_ssp_3d_v4(const Geo g, Box b, int rk_step, int zero_rest, SspArgs a) {
   // b.i0 / b.i1: first and last GROUP index of the row (column = ims + 4 * group + lane)
   const int gi = b.i0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -205,6 +192,29 @@ __global__ void k_calc_p_rho(const Geo g, Box b, int step, fp al, fp p, cfp ph, 
     A3(pm1, i, k, j) = after_load(ptmp, pold);   // see common.cuh: keep the store behind the load
   }
   A3(p, i, k, j) = pv;
+}
+
+// calc_p_rho with 16-byte accesses (mass columns: lanes lo..him of a group)
+__global__ void k_calc_p_rho_v4(const Geo g, Box b, int step, fp al, fp p, cfp ph, cfp alt, cfp t_2, cfp t_1, cfp c2a, fp pm1,
+                                cfp mu, cfp mut) {
+  TID3_V4;
+  (void)hi;
+  if (him < lo) return;
+  const float c1h = g.c1h[k], c2h = g.c2h[k];
+  float m[4], mt[4], altv[4], t1[4], ph1[4], ph0[4], c2[4], t2[4], alv[4], pv[4], pold[4], ptmp[4];
+  ld4(&A2(mu, i, j), m); ld4(&A2(mut, i, j), mt); ld4(&A3(alt, i, k, j), altv); ld4(&A3(t_1, i, k, j), t1);
+  ld4(&A3(ph, i, k + 1, j), ph1); ld4(&A3(ph, i, k, j), ph0); ld4(&A3(c2a, i, k, j), c2); ld4(&A3(t_2, i, k, j), t2);
+  if (step != 0) ld4(&A3(pm1, i, k, j), pold);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    alv[q] = -1.f / (c1h * mt[q] + c2h) * (altv[q] * (c1h * m[q]) + g.rdnw[k] * (ph1[q] - ph0[q]));
+    pv[q] = c2[q] * (altv[q] * (t2[q] - (c1h * m[q]) * t1[q]) / ((c1h * mt[q] + c2h) * (WG_T0 + t1[q])) - alv[q]);
+    ptmp[q] = pv[q];
+    if (step != 0) { pv[q] = pv[q] + g.smdiv * (pv[q] - pold[q]); ptmp[q] = after_load(ptmp[q], pold[q]); }
+  }
+  st4(&A3(al, i, k, j), alv, lo, him);
+  st4(&A3(pm1, i, k, j), ptmp, lo, him);
+  st4(&A3(p, i, k, j), pv, lo, him);
 }
 
 // calc_coef_w (:570-650): column recurrence for the tridiagonal factors
@@ -1006,6 +1016,69 @@ __global__ void k_ssf(const Geo g, Box b, int last, float dts, int nsmall, SsfAr
   }
 }
 
+// k_ssf with 16-byte accesses (see k_ssp_3d_v4): b.i0 / b.i1 count groups of four columns from the start of the memory row
+__global__ void k_ssf_v4(const Geo g, Box b, int last, float dts, int nsmall, SsfArgs a) {
+  const int gi = b.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = b.k0 + blockIdx.y * blockDim.y + threadIdx.y;
+  const int j = b.j0 + blockIdx.z * blockDim.z + threadIdx.z;
+  if (gi > b.i1 || k > b.k1 || j > b.j1) return;
+  const int i = g.ims + 4 * gi;
+  const int kde = g.kde;
+  const bool jm = j <= min(g.jte, g.jde - 1), km = k <= kde - 1;
+  const int lo = max(g.its - i, 0), hi = min(g.ite - i, 3), him = min(min(g.ite, g.ide - 1) - i, 3);
+  const float c1h = g.c1h[k], c2h = g.c2h[k];
+  float x[4], sv[4], m1[4], m2[4], ms[4], out[4];
+  if (km && him >= lo) {   // v
+    ld4(&A3(a.v_2, i, k, j), x); ld4(&A3(a.v_save, i, k, j), sv); ld4(&A2(a.muv, i, j), m1); ld4(&A2(a.muvs, i, j), m2); ld4(&A2(g.msfvx, i, j), ms);
+#pragma unroll
+    for (int q = 0; q < 4; q++) out[q] = (ms[q] * x[q] + sv[q] * (c1h * m1[q] + c2h)) / (c1h * m2[q] + c2h);
+    st4(&A3(a.v_2, i, k, j), out, lo, him);
+  }
+  if (km && jm) {   // u
+    ld4(&A3(a.u_2, i, k, j), x); ld4(&A3(a.u_save, i, k, j), sv); ld4(&A2(a.muu, i, j), m1); ld4(&A2(a.muus, i, j), m2); ld4(&A2(g.msfuy, i, j), ms);
+#pragma unroll
+    for (int q = 0; q < 4; q++) out[q] = (ms[q] * x[q] + sv[q] * (c1h * m1[q] + c2h)) / (c1h * m2[q] + c2h);
+    st4(&A3(a.u_2, i, k, j), out, lo, hi);
+  }
+  if (jm && him >= lo) {
+    float mut[4], muts[4];
+    ld4(&A2(a.mut, i, j), mut); ld4(&A2(a.muts, i, j), muts);
+    const float c1f = g.c1f[k], c2f = g.c2f[k];
+    ld4(&A3(a.w_2, i, k, j), x); ld4(&A3(a.w_save, i, k, j), sv); ld4(&A2(g.msfty, i, j), ms);
+#pragma unroll
+    for (int q = 0; q < 4; q++) out[q] = (ms[q] * x[q] + sv[q] * (c1f * mut[q] + c2f)) / (c1f * muts[q] + c2f);
+    st4(&A3(a.w_2, i, k, j), out, lo, him);
+    ld4(&A3(a.ph_2, i, k, j), x); ld4(&A3(a.ph_save, i, k, j), sv);
+#pragma unroll
+    for (int q = 0; q < 4; q++) out[q] = x[q] + sv[q];
+    st4(&A3(a.ph_2, i, k, j), out, lo, him);
+    ld4(&A3(a.ww, i, k, j), x); ld4(&A3(a.ww1, i, k, j), sv);
+#pragma unroll
+    for (int q = 0; q < 4; q++) out[q] = x[q] + sv[q];
+    st4(&A3(a.ww, i, k, j), out, lo, him);
+    if (km) {
+      ld4(&A3(a.t_2, i, k, j), x); ld4(&A3(a.t_save, i, k, j), sv);
+      if (!last) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) out[q] = (x[q] + sv[q] * (c1h * mut[q] + c2h)) / (c1h * muts[q] + c2h);
+      } else {
+        float hd[4];
+        ld4(&A3(a.h_diabatic, i, k, j), hd);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          out[q] = (x[q] - dts * (float)nsmall * (c1h * mut[q] + c2h) * hd[q] + sv[q] * (c1h * mut[q] + c2h)) / (c1h * muts[q] + c2h);
+      }
+      st4(&A3(a.t_2, i, k, j), out, lo, him);
+    }
+    if (k == 1) {
+      ld4(&A2(a.mu_2, i, j), x); ld4(&A2(a.mu_save, i, j), sv);
+#pragma unroll
+      for (int q = 0; q < 4; q++) out[q] = x[q] + sv[q];
+      st4(&A2(a.mu_2, i, j), out, lo, him);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 void Solver::small_step_prep(int rk_step, bool zero_rest) {
   const Geo &q = g;
@@ -1026,8 +1099,13 @@ void Solver::small_step_prep(int rk_step, bool zero_rest) {
   else
     LAUNCH3(this, k_ssp_3d, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), rk_step, zero_rest ? 1 : 0, a);
   const int im = std::min(q.ite, q.ide - 1), jm = std::min(q.jte, q.jde - 1);
-  LAUNCH3(this, k_calc_p_rho, (Box{q.its, im, 1, q.kde - 1, q.jts, jm}), 0, o("al"), o("p"), o("ph_2"), o("alt"), o("t_2"),
-          o("t_save"), o("c2a"), o("pm1"), o("mu_2"), o("muts"));
+  if (vec4) {
+    Box bx = box_v4(q, 1, q.kde - 1);
+    bx.j1 = jm;
+    LAUNCH3(this, k_calc_p_rho_v4, bx, 0, o("al"), o("p"), o("ph_2"), o("alt"), o("t_2"), o("t_save"), o("c2a"), o("pm1"), o("mu_2"), o("muts"));
+  } else
+    LAUNCH3(this, k_calc_p_rho, (Box{q.its, im, 1, q.kde - 1, q.jts, jm}), 0, o("al"), o("p"), o("ph_2"), o("alt"), o("t_2"),
+            o("t_save"), o("c2a"), o("pm1"), o("mu_2"), o("muts"));
   LAUNCH2(this, k_calc_coef_w, (Box{q.its, im, 1, 1, q.jts, jm}), dts_rk, o("a"), o("alpha"), o("gamma"), o("mut"), o("cqw"),
           o("c2a"));
   halo("HALO_EM_B");
@@ -1186,7 +1264,9 @@ void Solver::small_step_finish(int rk_step) {
   a.ww1 = o("ww1"); a.mut = o("mut"); a.muts = o("muts"); a.muu = o("muu"); a.muus = o("muus"); a.muv = o("muv"); a.muvs = o("muvs");
   a.u_save = o("u_save"); a.v_save = o("v_save"); a.w_save = o("w_save"); a.t_save = o("t_save"); a.ph_save = o("ph_save");
   a.mu_save = o("mu_save"); a.h_diabatic = o("h_diabatic");
-  LAUNCH3(this, k_ssf, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), rk_step == c.rk_ord ? 1 : 0, dts_rk, ns, a);
+  static const bool vec4 = [] { const char *e = getenv("WRFGPU_SSP"); return !(e && !strcmp(e, "scalar")); }();
+  if (vec4) LAUNCH3(this, k_ssf_v4, (Box{(q.its - q.ims) / 4, (q.ite - q.ims) / 4, 1, q.kde, q.jts, q.jte}), rk_step == c.rk_ord ? 1 : 0, dts_rk, ns, a);
+  else LAUNCH3(this, k_ssf, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), rk_step == c.rk_ord ? 1 : 0, dts_rk, ns, a);
   if (rk_step == c.rk_ord) bc({{"ru_m", 'u'}, {"rv_m", 'v'}, {"ww_m", 'w'}, {"mut", 't'}, {"muts", 't'}});
 }
 

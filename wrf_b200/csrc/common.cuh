@@ -305,6 +305,8 @@ struct Solver {
 inline dim3 grid3(const Box &b, const dim3 &t) {   // thread block t = (i, k, j)
   return dim3((unsigned)((b.i1 - b.i0 + t.x) / t.x), (unsigned)((b.k1 - b.k0 + t.y) / t.y), (unsigned)((b.j1 - b.j0 + t.z) / t.z));
 }
+// the tile [its, ite] x [k0, k1] x [jts, jte] as groups of four columns counted from ims (the *_v4 kernels)
+inline Box box_v4(const Geo &q, int k0, int k1) { return Box{(q.its - q.ims) / 4, (q.ite - q.ims) / 4, k0, k1, q.jts, q.jte}; }
 inline bool empty(const Box &b) { return b.i1 < b.i0 || b.k1 < b.k0 || b.j1 < b.j0; }
 
 #define WG_BX 128
@@ -336,6 +338,31 @@ inline bool empty(const Box &b) { return b.i1 < b.i0 || b.k1 < b.k0 || b.j1 < b.
     }                                                                                \
   } while (0)
 
+// 16-byte accesses of the streaming kernels (k_ssp_3d_v4, k_ssf_v4, k_prep_3d_v4, ...): a thread owns a 16-byte aligned
+// group of four columns of the padded device row; p points at lane 0
+#ifdef __CUDACC__
+__device__ __forceinline__ void ld4(const float *p, float v[4]) {
+  const float4 q = *reinterpret_cast<const float4 *>(p);
+  v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+// lanes lo..hi (0..3, inclusive) of the group are to be written
+__device__ __forceinline__ void st4(float *p, const float v[4], int lo, int hi) {
+  if (lo == 0 && hi == 3) *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  else {
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (q >= lo && q <= hi) p[q] = v[q];
+  }
+}
+#endif
+// thread -> (group of four columns, k, j) of a box whose i0 / i1 count groups from the start of the memory row
+#define TID3_V4                                               \
+  const int gi_ = b.i0 + blockIdx.x * blockDim.x + threadIdx.x; \
+  const int k = b.k0 + blockIdx.y * blockDim.y + threadIdx.y; \
+  const int j = b.j0 + blockIdx.z * blockDim.z + threadIdx.z; \
+  if (gi_ > b.i1 || k > b.k1 || j > b.j1) return;             \
+  const int i = g.ims + 4 * gi_;                              \
+  const int lo = max(g.its - i, 0), hi = min(g.ite - i, 3), him = min(min(g.ite, g.ide - 1) - i, 3);
 #define TID3                                              \
   const int i = b.i0 + blockIdx.x * blockDim.x + threadIdx.x; \
   const int k = b.k0 + blockIdx.y * blockDim.y + threadIdx.y; \

@@ -5,6 +5,8 @@
 // The reference makes seven separate sweeps (module_big_step_utilities_em.F:26,329,
 // 640,787,910,1227,3587).  Algorithmic bytes: 16+n_moist field accesses per point.
 #include "common.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace wg {
 
@@ -88,6 +90,100 @@ __global__ void k_prep_3d(const Geo g, Box b, cfp u, cfp v, cfp w, cfp muu, cfp 
   }
 }
 
+// the same with 16-byte accesses (four columns per thread, see ld4 / st4 in common.cuh)
+__global__ void k_prep_3d_v4(const Geo g, Box b, cfp u, cfp v, cfp w, cfp muu, cfp muv, cfp mut, fp ru, fp rv, fp rw,
+                             MoistPtrs mp, fp cqu, fp cqv, fp cqw, cfp al, cfp alb, fp alt, cfp ph, cfp phb, fp php) {
+  TID3_V4;
+  const int ktf = g.kde - 1;
+  const bool jm = j <= min(g.jte, g.jde - 1), km = k <= ktf;
+  const float c1h = g.c1h[k], c2h = g.c2h[k];
+  float x[4], m[4], ms[4], out[4];
+  float mq[3][4];           // the species at (i, k, j), reused by the three cq averages
+  if (km && mp.n >= 1)
+#pragma unroll
+    for (int s = 0; s < 3; s++)
+      if (s < mp.n) ld4(&A3(mp.m[s], i, k, j), mq[s]);
+  if (km && jm) {
+    ld4(&A3(u, i, k, j), x); ld4(&A2(muu, i, j), m); ld4(&A2(g.msfuy, i, j), ms);
+#pragma unroll
+    for (int q = 0; q < 4; q++) out[q] = x[q] * (c1h * m[q] + c2h) / ms[q];
+    st4(&A3(ru, i, k, j), out, lo, hi);
+#pragma unroll
+    for (int q = 0; q < 4; q++) out[q] = 1.f;
+    if (mp.n >= 1) {
+      float qtot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        if (s >= mp.n) continue;
+        const float west = A3(mp.m[s], i - 1, k, j);
+#pragma unroll
+        for (int q = 0; q < 4; q++) qtot[q] = qtot[q] + mq[s][q] + (q == 0 ? west : mq[s][q > 0 ? q - 1 : 0]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) out[q] = 1.f / (1.f + 0.5f * qtot[q]);
+    }
+    st4(&A3(cqu, i, k, j), out, lo, hi);
+  }
+  if (km && him >= lo) {
+    ld4(&A3(v, i, k, j), x); ld4(&A2(muv, i, j), m); ld4(&A2(g.msfvx_inv, i, j), ms);
+#pragma unroll
+    for (int q = 0; q < 4; q++) out[q] = x[q] * (c1h * m[q] + c2h) * ms[q];
+    st4(&A3(rv, i, k, j), out, lo, him);
+#pragma unroll
+    for (int q = 0; q < 4; q++) out[q] = 1.f;
+    if (mp.n >= 1) {
+      float qtot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        if (s >= mp.n) continue;
+        float south[4];
+        ld4(&A3(mp.m[s], i, k, j - 1), south);
+#pragma unroll
+        for (int q = 0; q < 4; q++) qtot[q] = qtot[q] + mq[s][q] + south[q];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) out[q] = 1.f / (1.f + 0.5f * qtot[q]);
+    }
+    st4(&A3(cqv, i, k, j), out, lo, him);
+  }
+  if (jm && him >= lo) {
+    ld4(&A3(w, i, k, j), x); ld4(&A2(mut, i, j), m); ld4(&A2(g.msfty, i, j), ms);
+    const float c1f = g.c1f[k], c2f = g.c2f[k];
+#pragma unroll
+    for (int q = 0; q < 4; q++) out[q] = x[q] * (c1f * m[q] + c2f) / ms[q];
+    st4(&A3(rw, i, k, j), out, lo, him);
+    if (km) {
+      if (k >= 2) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) out[q] = 0.f;
+        if (mp.n >= 1) {
+          float qtot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int s = 0; s < 3; s++) {
+            if (s >= mp.n) continue;
+            float below[4];
+            ld4(&A3(mp.m[s], i, k - 1, j), below);
+#pragma unroll
+            for (int q = 0; q < 4; q++) qtot[q] = qtot[q] + mq[s][q] + below[q];
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) out[q] = 0.5f * qtot[q];
+        }
+        st4(&A3(cqw, i, k, j), out, lo, him);
+      }
+      float a0[4], a1[4], p0[4], p1[4], b0[4], b1[4];
+      ld4(&A3(al, i, k, j), a0); ld4(&A3(alb, i, k, j), a1);
+#pragma unroll
+      for (int q = 0; q < 4; q++) out[q] = a0[q] + a1[q];
+      st4(&A3(alt, i, k, j), out, lo, him);
+      ld4(&A3(phb, i, k, j), b0); ld4(&A3(phb, i, k + 1, j), b1); ld4(&A3(ph, i, k, j), p0); ld4(&A3(ph, i, k + 1, j), p1);
+#pragma unroll
+      for (int q = 0; q < 4; q++) out[q] = 0.5f * (b0[q] + b1[q] + p0[q] + p1[q]);
+      st4(&A3(php, i, k, j), out, lo, him);
+    }
+  }
+}
+
 // calc_ww_cp, module_big_step_utilities_em.F:640-782.  One thread per column; pass 1
 // stores divv(k) in ww(k+1) while summing dmdt, pass 2 turns it into ww in place.
 #ifndef WW_MINB
@@ -141,9 +237,15 @@ void Solver::rk_step_prep(int) {
   mp.n = c.num_moist;
   static const char *mn[] = {"moist_qv", "moist_qc", "moist_qr"};
   for (int s = 0; s < 3; s++) mp.m[s] = s < mp.n ? o(mn[s]) : nullptr;
-  LAUNCH3(this, k_prep_3d, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), o("u_2"), o("v_2"), o("w_2"), o("muu"), o("muv"),
-          o("mut"), o("ru"), o("rv"), o("rw"), mp, o("cqu"), o("cqv"), o("cqw"), o("al"), o("alb"), o("alt"), o("ph_2"),
-          o("phb"), o("php"));
+  static const bool vec4 = [] { const char *e = getenv("WRFGPU_SSP"); return !(e && !strcmp(e, "scalar")); }();
+  if (vec4)
+    LAUNCH3(this, k_prep_3d_v4, box_v4(q, 1, q.kde), o("u_2"), o("v_2"), o("w_2"), o("muu"), o("muv"),
+            o("mut"), o("ru"), o("rv"), o("rw"), mp, o("cqu"), o("cqv"), o("cqw"), o("al"), o("alb"), o("alt"), o("ph_2"),
+            o("phb"), o("php"));
+  else
+    LAUNCH3(this, k_prep_3d, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), o("u_2"), o("v_2"), o("w_2"), o("muu"), o("muv"),
+            o("mut"), o("ru"), o("rv"), o("rw"), mp, o("cqu"), o("cqv"), o("cqw"), o("al"), o("alb"), o("alt"), o("ph_2"),
+            o("phb"), o("php"));
   LAUNCH2(this, k_calc_ww, (Box{q.its, q.ite, 1, 1, q.jts, std::min(q.jte, q.jde - 1)}), o("u_2"), o("v_2"), o("mu_2"),
           o("mub"), o("ww"));
 }

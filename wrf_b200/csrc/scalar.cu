@@ -12,6 +12,8 @@
 // cell (:7764-7773) and writes the tendency.  Flux values are pure functions of the
 // inputs, so recomputation is bit-identical to the stored version.
 #include "common.cuh"
+#include <cstdlib>
+#include <cstring>
 #include "weno.cuh"
 
 namespace wg {
@@ -401,6 +403,49 @@ __global__ void k_update_scalar(const Geo g, Box b, int rk_step, float dt, fp sc
   A3(scalar_2, i, k, j) = ((g.c1h[k] * muold + g.c2h[k]) * s1 + dt * tendency) / (g.c1h[k] * munew + g.c2h[k]);
 }
 
+// the two updates with 16-byte accesses (mass columns: lanes lo..him of a group of four)
+__global__ void k_update_scalar_pd_v4(const Geo g, Box b, float dt, fp scalar, fp sc_tend, cfp mu_old, cfp mu_new, cfp mu_base) {
+  TID3_V4;
+  (void)hi;
+  if (him < lo) return;
+  float tend_in[4], s_in[4], mo[4], mn[4], mb[4], out[4], z[4];
+  ld4(&A3(sc_tend, i, k, j), tend_in); ld4(&A3(scalar, i, k, j), s_in);
+  ld4(&A2(mu_old, i, j), mo); ld4(&A2(mu_new, i, j), mn); ld4(&A2(mu_base, i, j), mb);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    float tendency = 0.f;
+    tendency = tendency + tend_in[q];
+    const float muold = mo[q] + mb[q], munew = mn[q] + mb[q];
+    out[q] = ((g.c1h[k] * muold + g.c2h[k]) * s_in[q] + dt * tendency) / (g.c1h[k] * munew + g.c2h[k]);
+    z[q] = after_load(0.f, tend_in[q]);
+  }
+  st4(&A3(scalar, i, k, j), out, lo, him);
+  st4(&A3(sc_tend, i, k, j), z, lo, him);
+}
+__global__ void k_update_scalar_v4(const Geo g, Box b, int rk_step, float dt, fp scalar_1, fp scalar_2, cfp sc_tend, cfp advect_tend,
+                                   cfp mu_old, cfp mu_new, cfp mu_base) {
+  TID3_V4;
+  (void)hi;
+  if (him < lo) return;
+  const int sz = g.spec_zone;
+  const bool adv_j = !g.spec || (j >= g.jds + sz && j <= g.jde - sz - 1);
+  float at[4], my[4], st[4], mo[4], mn[4], mb[4], s1[4], out[4];
+  ld4(&A3(advect_tend, i, k, j), at); ld4(&A2(g.msfty, i, j), my); ld4(&A3(sc_tend, i, k, j), st);
+  ld4(&A2(mu_old, i, j), mo); ld4(&A2(mu_new, i, j), mn); ld4(&A2(mu_base, i, j), mb);
+  if (rk_step == 1) { ld4(&A3(scalar_2, i, k, j), s1); st4(&A3(scalar_1, i, k, j), s1, lo, him); }
+  else ld4(&A3(scalar_1, i, k, j), s1);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const bool adv = adv_j && (!g.spec || g.periodic_x || (i + q >= g.ids + sz && i + q <= g.ide - sz - 1));
+    const float adv_t = at[q] * my[q];
+    float tendency = adv ? adv_t : 0.f;
+    tendency = tendency + st[q];
+    const float muold = mo[q] + mb[q], munew = mn[q] + mb[q];
+    out[q] = ((g.c1h[k] * muold + g.c2h[k]) * s1[q] + dt * tendency) / (g.c1h[k] * munew + g.c2h[k]);
+  }
+  st4(&A3(scalar_2, i, k, j), out, lo, him);
+}
+
 // bound_tke (module_em.F:2616-2646), after the update of the tke species (solve_em.F:2437-2445)
 __global__ void k_bound_tke(const Geo g, Box b, float tke_upper_bound, fp tke) {
   TID3;
@@ -414,12 +459,16 @@ void Solver::rk_scalar_step(int rk_step) {
   rk_params(rk_step, dt_rk, dts_rk, ns);
   const int im = std::min(q.ite, q.ide - 1), jm = std::min(q.jte, q.jde - 1), ktf = q.kde - 1;
   Box mass{q.its, im, 1, ktf, q.jts, jm};
+  Box mass4 = box_v4(q, 1, ktf);   // the same points as groups of four columns (the *_v4 kernels mask the lanes)
+  mass4.j1 = jm;
+  static const bool vec4 = [] { const char *e = getenv("WRFGPU_SSP"); return !(e && !strcmp(e, "scalar")); }();
   const bool last = rk_step == c.rk_ord;
   if (last) {
     std::vector<BcItem> items;
     for (auto &s : species)
       if (s.adv_opt == 1 || s.adv_opt == 2 || s.adv_opt == 4) {   // /= ORIGINAL and /= WENO_SCALAR (solve_em.F:1850-1977)
-        LAUNCH3(this, k_update_scalar_pd, mass, dt_rk, o(s.o), o(s.t), o("mu_1"), o("mu_1"), o("mub"));
+        if (vec4) LAUNCH3(this, k_update_scalar_pd_v4, mass4, dt_rk, o(s.o), o(s.t), o("mu_1"), o("mu_1"), o("mub"));
+        else LAUNCH3(this, k_update_scalar_pd, mass, dt_rk, o(s.o), o(s.t), o("mu_1"), o("mu_1"), o("mub"));
         items.push_back({s.o, 'p'});
       }
     if (!items.empty()) { halo("HALO_EM_MOIST_OLD_E_7"); bc(items); }
@@ -440,7 +489,8 @@ void Solver::rk_scalar_step(int rk_step) {
   auto update = [&](const Species &s) {
     const bool moist = s.f.rfind("moist_", 0) == 0, is_tke = s.f == tke_name;
     if (spec() && rk_step == 1 && has_bdy(s.f)) bdy_scalar(s);   // relax_bdy_scalar + spec_bdy_scalar: qv, or every species with boundary arrays
-    LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
+    if (vec4) LAUNCH3(this, k_update_scalar_v4, mass4, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
+    else LAUNCH3(this, k_update_scalar, mass, rk_step, dt_rk, o(s.o), o(s.f), o(s.t), o("advect_tend"), o("mu_1"), o("mu_2"), o("mub"));
     if (is_tke) LAUNCH3(this, k_bound_tke, mass, c.tke_upper_bound, o(s.f));
     // zero gradient on outflow / zero on inflow: moist species without boundary arrays (specified only), tke
     if ((moist && c.specified && !c.have_bcs_moist && s.f != "moist_qv") || (is_tke && spec())) flow_dep_bdy(s.f);

@@ -296,6 +296,15 @@ __global__ void k_copy_box(const Geo g, Box b, const float *__restrict__ src, fl
   A3(dst, i, k, j) = A3(src, i, k, j);
 }
 
+__global__ void k_copy_box_v4(const Geo g, Box b, const float *__restrict__ src, float *__restrict__ dst) {   // mass columns, 16-byte accesses
+  TID3_V4;
+  (void)hi;
+  if (him < lo) return;
+  float v[4];
+  ld4(&A3(src, i, k, j), v);
+  st4(&A3(dst, i, k, j), v, lo, him);
+}
+
 struct PhaseTimer {
   Solver *s; const char *name; cudaEvent_t a, b;
   PhaseTimer(Solver *s_, const char *n) : s(s_), name(n) {
@@ -316,8 +325,9 @@ void Solver::step() {
   const int rk_order = c.rk_ord;
   dtbc = dtbc + c.dt;   // solve_em.F:377
   if (c.num_moist >= 1) {   // initialize_moist_old + bc (solve_em.F:520-550)
-    LAUNCH3(this, k_copy_box, (Box{g.its, std::min(g.ite, g.ide - 1), 1, g.kde - 1, g.jts, std::min(g.jte, g.jde - 1)}),
-            (const float *)o("moist_qv"), o("moist_old_qv"));
+    Box bx = box_v4(g, 1, g.kde - 1);
+    bx.j1 = std::min(g.jte, g.jde - 1);
+    LAUNCH3(this, k_copy_box_v4, bx, (const float *)o("moist_qv"), o("moist_old_qv"));
     halo("HALO_EM_MOIST_OLD_E_7");
     bc({{"moist_old_qv", 'p'}});
   }

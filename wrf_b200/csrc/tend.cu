@@ -1041,14 +1041,15 @@ __global__ void k_cfl_max(const Geo g, Box b, cfp u, cfp v, cfp ww, cfp mut, uns
   }
 }
 
-__global__ void k_zero3(const Geo g, Box b, fp a0, fp a1, fp a2, fp a3, fp a4) {
-  TID3;
-  const long x = (long)i + (long)k * g.sk + (long)j * g.sj;
-  if (a0) a0[x] = 0.f;
-  if (a1) a1[x] = 0.f;
-  if (a2) a2[x] = 0.f;
-  if (a3) a3[x] = 0.f;
-  if (a4) a4[x] = 0.f;
+__global__ void k_zero3_v4(const Geo g, Box b, fp a0, fp a1, fp a2, fp a3, fp a4) {   // 16-byte stores, four columns per thread
+  TID3_V4;
+  (void)him;
+  const float z[4] = {0.f, 0.f, 0.f, 0.f};
+  if (a0) st4(&A3(a0, i, k, j), z, lo, hi);
+  if (a1) st4(&A3(a1, i, k, j), z, lo, hi);
+  if (a2) st4(&A3(a2, i, k, j), z, lo, hi);
+  if (a3) st4(&A3(a3, i, k, j), z, lo, hi);
+  if (a4) st4(&A3(a4, i, k, j), z, lo, hi);
 }
 __global__ void k_zero2(const Geo g, Box b, fp a0, fp a1) {
   TID2;
@@ -1060,12 +1061,12 @@ __global__ void k_zero2(const Geo g, Box b, fp a0, fp a1) {
 void Solver::init_zero_tendency() {
   const Geo &q = g;
   Box tile{q.its, q.ite, 1, q.kde, q.jts, q.jte};
-  LAUNCH3(this, k_zero3, tile, o("ru_tendf"), o("rv_tendf"), o("rw_tendf"), o("ph_tendf"), o("t_tendf"));
+  LAUNCH3(this, k_zero3_v4, box_v4(q, 1, q.kde), o("ru_tendf"), o("rv_tendf"), o("rw_tendf"), o("ph_tendf"), o("t_tendf"));
   LAUNCH2(this, k_zero2, tile, o("mu_tendf"), (float *)nullptr);
   for (size_t s = 0; s < species.size(); s += 5) {
     float *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     for (size_t m = 0; m < 5 && s + m < species.size(); m++) p[m] = o(species[s + m].t);
-    LAUNCH3(this, k_zero3, tile, p[0], p[1], p[2], p[3], p[4]);
+    LAUNCH3(this, k_zero3_v4, box_v4(q, 1, q.kde), p[0], p[1], p[2], p[3], p[4]);
   }
 }
 
@@ -1078,7 +1079,7 @@ void Solver::rk_tendency_main(int rk_step, bool zero_save) {
   const Geo &q = g;
   Box tile{q.its, q.ite, 1, q.kde, q.jts, q.jte};
   // the *_save arrays and mu_tend/mu_save are zeroed by rk_tendency (module_em.F:370-428)
-  if (zero_save) LAUNCH3(this, k_zero3, tile, o("u_save"), o("v_save"), o("w_save"), o("ph_save"), o("t_save"));
+  if (zero_save) LAUNCH3(this, k_zero3_v4, box_v4(q, 1, q.kde), o("u_save"), o("v_save"), o("w_save"), o("ph_save"), o("t_save"));
   LAUNCH2(this, k_zero2, tile, o("mu_tend"), o("mu_save"));
   if (rk_step == 1 && c.diff_opt == 1) {   // forward_step: diff_opt1 (module_em.F:802-878), before rk_rayleigh_damp
     const float prandtl = 1.f / 3.0f;    // share/module_model_constants.F:86
