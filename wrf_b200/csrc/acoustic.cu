@@ -263,6 +263,62 @@ __global__ void k_calc_coef_w(const Geo g, Box b, float dts, fp a, fp alpha, fp 
   }
 }
 
+// calc_coef_w with four columns per thread: 16-byte accesses and four independent recurrences in flight
+__global__ void k_calc_coef_w_v4(const Geo g, Box b, float dts, fp a, fp alpha, fp gamma, cfp mut, cfp cqw, cfp c2a) {
+  COEF_SMEM;
+  TID2_V4;
+  if (him < lo) return;
+  const int kde = g.kde;
+  const float lid_flag = g.top_lid ? 0.f : 1.f;
+  const float x0 = .5f * dts * WG_G * (1.f + g.epssm);
+  const float cof = x0 * x0;
+  float mt[4], c2top[4], out[4], zero[4] = {0.f, 0.f, 0.f, 0.f}, a_top[4];
+  ld4(&A2(mut, i, j), mt); ld4(&A3(c2a, i, kde - 1, j), c2top);
+  {
+    const int k = kde - 1;
+    st4(&A3(a, i, 2, j), zero, lo, him);
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      a_top[q] = -2.f * cof * (cf.rdnw[kde - 1] * cf.rdnw[kde - 1]) * c2top[q] * lid_flag / ((cf.c1h[k] * mt[q] + cf.c2h[k]) * (cf.c1f[k] * mt[q] + cf.c2f[k]));
+    st4(&A3(a, i, kde, j), a_top, lo, him);
+    st4(&A3(gamma, i, 1, j), zero, lo, him);
+  }
+  float gam_prev[4] = {0.f, 0.f, 0.f, 0.f}, c2a_km1[4];
+  ld4(&A3(c2a, i, 1, j), c2a_km1);
+  for (int k = 2; k <= kde - 1; k++) {
+    float cq[4], c2a_k[4], ak[4], al[4];
+    ld4(&A3(cqw, i, k, j), cq); ld4(&A3(c2a, i, k, j), c2a_k);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (k == 2) ak[q] = 0.f;
+      else ak[q] = -cq[q] * cof * cf.rdn[k] * cf.rdnw[k - 1] * c2a_km1[q] / ((cf.c1h[k - 1] * mt[q] + cf.c2h[k - 1]) * (cf.c1f[k - 1] * mt[q] + cf.c2f[k - 1]));
+      const float bb = 1.f + cq[q] * cof * cf.rdn[k] *
+                                 (cf.rdnw[k] * c2a_k[q] / ((cf.c1h[k] * mt[q] + cf.c2h[k]) * (cf.c1f[k] * mt[q] + cf.c2f[k])) +
+                                  cf.rdnw[k - 1] * c2a_km1[q] / ((cf.c1h[k - 1] * mt[q] + cf.c2h[k - 1]) * (cf.c1f[k] * mt[q] + cf.c2f[k])));
+      const float cc = -cq[q] * cof * cf.rdn[k] * cf.rdnw[k] * c2a_k[q] / ((cf.c1h[k] * mt[q] + cf.c2h[k]) * (cf.c1f[k + 1] * mt[q] + cf.c2f[k + 1]));
+      al[q] = 1.f / (bb - ak[q] * gam_prev[q]);
+      gam_prev[q] = cc * al[q];
+      c2a_km1[q] = c2a_k[q];
+    }
+    if (k > 2) st4(&A3(a, i, k, j), ak, lo, him);
+    st4(&A3(alpha, i, k, j), al, lo, him);
+    st4(&A3(gamma, i, k, j), gam_prev, lo, him);
+  }
+  {
+    const int k = kde;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const float bb = 1.f + 2.f * cof * (cf.rdnw[kde - 1] * cf.rdnw[kde - 1]) * c2top[q] / ((cf.c1h[k - 1] * mt[q] + cf.c2h[k - 1]) * (cf.c1f[k] * mt[q] + cf.c2f[k]));
+      const float cc = 0.f;
+      const float al = 1.f / (bb - a_top[q] * gam_prev[q]);
+      out[q] = al;
+      gam_prev[q] = cc * al;
+    }
+    st4(&A3(alpha, i, kde, j), out, lo, him);
+    st4(&A3(gamma, i, kde, j), gam_prev, lo, him);
+  }
+}
+
 // ---------------------------------------------------------------------------
 struct UvArgs {
   fp u, v;
@@ -1106,8 +1162,13 @@ void Solver::small_step_prep(int rk_step, bool zero_rest) {
   } else
     LAUNCH3(this, k_calc_p_rho, (Box{q.its, im, 1, q.kde - 1, q.jts, jm}), 0, o("al"), o("p"), o("ph_2"), o("alt"), o("t_2"),
             o("t_save"), o("c2a"), o("pm1"), o("mu_2"), o("muts"));
-  LAUNCH2(this, k_calc_coef_w, (Box{q.its, im, 1, 1, q.jts, jm}), dts_rk, o("a"), o("alpha"), o("gamma"), o("mut"), o("cqw"),
-          o("c2a"));
+  if (vec4) {
+    Box bx = box_v4(q, 1, 1);
+    bx.j1 = jm;
+    LAUNCH2(this, k_calc_coef_w_v4, bx, dts_rk, o("a"), o("alpha"), o("gamma"), o("mut"), o("cqw"), o("c2a"));
+  } else
+    LAUNCH2(this, k_calc_coef_w, (Box{q.its, im, 1, 1, q.jts, jm}), dts_rk, o("a"), o("alpha"), o("gamma"), o("mut"), o("cqw"),
+            o("c2a"));
   halo("HALO_EM_B");
   bc({{"ru_tend", 'u'}, {"rv_tend", 'v'}, {"ph_2", 'w'}, {"al", 'p'}, {"p", 'p'}, {"t_1", 'p'}, {"t_save", 't'},
       {"mu_1", 't'}, {"mu_2", 't'}, {"mudf", 't'}});

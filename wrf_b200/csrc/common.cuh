@@ -355,6 +355,13 @@ __device__ __forceinline__ void st4(float *p, const float v[4], int lo, int hi) 
   }
 }
 #endif
+// column kernels: thread -> (group of four columns, j)
+#define TID2_V4                                               \
+  const int gi_ = b.i0 + blockIdx.x * blockDim.x + threadIdx.x; \
+  const int j = b.j0 + blockIdx.y * blockDim.y + threadIdx.y; \
+  if (gi_ > b.i1 || j > b.j1) return;                         \
+  const int i = g.ims + 4 * gi_;                              \
+  const int lo = max(g.its - i, 0), him = min(min(g.ite, g.ide - 1) - i, 3);
 // thread -> (group of four columns, k, j) of a box whose i0 / i1 count groups from the start of the memory row
 #define TID3_V4                                               \
   const int gi_ = b.i0 + blockIdx.x * blockDim.x + threadIdx.x; \

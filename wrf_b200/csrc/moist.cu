@@ -3,6 +3,8 @@
 // (:5394-5589) and moist_physics_finish_em (:5593-5784), set_w_surface
 // (module_bc_em.F:1196-1270) and the end-of-step / start-of-run boundary fills.
 #include "common.cuh"
+#include <cstdlib>
+#include <cstring>
 #include "libm_port.h"
 
 namespace wg {
@@ -42,8 +44,53 @@ __global__ void k_calc_p_rho_phi(const Geo g, Box b, fp al, cfp alb, cfp mu, cfp
   A3(p, i, k, j) = pv;
 }
 
+// calc_p_rho_phi with 16-byte accesses (mass columns: lanes lo..him of a group of four)
+__global__ void k_calc_p_rho_phi_v4(const Geo g, Box b, fp al, cfp alb, cfp mu, cfp muts, cfp ph, cfp phb, fp p, cfp pb, cfp t, cfp qv) {
+  TID3_V4;
+  (void)hi;
+  if (him < lo) return;
+  float mts[4], m[4], ph1[4], ph0[4], pb1[4], pb0[4], ab[4], tv[4], q4[4], pbv[4], alv[4], pv[4];
+  ld4(&A2(muts, i, j), mts); ld4(&A3(ph, i, k + 1, j), ph1); ld4(&A3(ph, i, k, j), ph0); ld4(&A3(alb, i, k, j), ab);
+  ld4(&A3(t, i, k, j), tv); ld4(&A3(pb, i, k, j), pbv);
+  if (g.hypsometric_opt == 1) ld4(&A2(mu, i, j), m);
+  else { ld4(&A3(phb, i, k + 1, j), pb1); ld4(&A3(phb, i, k, j), pb0); }
+  if (g.num_moist >= 1 && g.use_theta_m != 1) ld4(&A3(qv, i, k, j), q4);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    if (g.hypsometric_opt == 1) {
+      alv[q] = -1.f / (g.c1h[k] * mts[q] + g.c2h[k]) * (ab[q] * (g.c1h[k] * m[q]) + g.rdnw[k] * (ph1[q] - ph0[q]));
+    } else {
+      const float pfu = g.c3f[k + 1] * mts[q] + g.c4f[k + 1] + g.p_top;
+      const float pfd = g.c3f[k] * mts[q] + g.c4f[k] + g.p_top;
+      const float phm = g.c3h[k] * mts[q] + g.c4h[k] + g.p_top;
+      alv[q] = (ph1[q] - ph0[q] + pb1[q] - pb0[q]) / phm / log_f(pfd / pfu) - ab[q];
+    }
+    if (g.num_moist >= 1) {
+      float temp;
+      if (g.use_theta_m == 1) temp = (WG_RD * (WG_T0 + tv[q])) / (WG_P0 * (alv[q] + ab[q]));
+      else {
+        const float qvf = 1.f + WG_RVOVRD * q4[q];
+        temp = (WG_RD * (WG_T0 + tv[q]) * qvf) / (WG_P0 * (alv[q] + ab[q]));
+      }
+      pv[q] = pow_f(temp, WG_CPOVCV) * WG_P0 - pbv[q];
+    } else {
+      pv[q] = WG_P0 * pow_f((WG_RD * (WG_T0 + tv[q])) / (WG_P0 * (alv[q] + ab[q])), WG_CPOVCV) - pbv[q];
+    }
+  }
+  st4(&A3(al, i, k, j), alv, lo, him);
+  st4(&A3(p, i, k, j), pv, lo, him);
+}
+
 void Solver::calc_p_rho_phi() {
   const Geo &q = g;
+  static const bool vec4 = [] { const char *e = getenv("WRFGPU_SSP"); return !(e && !strcmp(e, "scalar")); }();
+  if (vec4) {
+    Box bx = box_v4(q, 1, q.kde - 1);
+    bx.j1 = std::min(q.jte, q.jde - 1);
+    LAUNCH3(this, k_calc_p_rho_phi_v4, bx, o("al"), o("alb"), o("mu_2"), o("muts"), o("ph_2"), o("phb"), o("p"), o("pb"), o("t_2"),
+            c.num_moist >= 1 ? o("moist_qv") : o("t_2"));
+    return;
+  }
   LAUNCH3(this, k_calc_p_rho_phi, (Box{q.its, std::min(q.ite, q.ide - 1), 1, q.kde - 1, q.jts, std::min(q.jte, q.jde - 1)}), o("al"),
           o("alb"), o("mu_2"), o("muts"), o("ph_2"), o("phb"), o("p"), o("pb"), o("t_2"), c.num_moist >= 1 ? o("moist_qv") : o("t_2"));
 }
