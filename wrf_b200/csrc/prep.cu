@@ -230,6 +230,63 @@ __global__ void __launch_bounds__(128, WW_MINB) k_calc_ww(const Geo g, Box b, cf
   A3(ww, i, kte, j) = 0.f;
 }
 
+// calc_ww_cp with four columns per thread: 16-byte accesses, four independent column sums in flight
+__global__ void __launch_bounds__(128, 6) k_calc_ww_v4(const Geo g, Box b, cfp u, cfp v, cfp mup, cfp mub, fp ww) {
+  const int gi_ = b.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = b.j0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (gi_ > b.i1 || j > b.j1) return;
+  const int i = g.ims + 4 * gi_;
+  const int lo = max(g.its - i, 0), hi = min(g.ite - i, 3), him = min(min(g.ite, g.ide - 1) - i, 3);
+  const int ktf = g.kde - 1, kte = g.kde;
+  const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+  if (hi > him) {   // the i = ide column of the tile: only the ww(:,1,:) / ww(:,kte,:) reset (:744-749)
+    st4(&A3(ww, i, 1, j), zero, max(him + 1, lo), hi);
+    st4(&A3(ww, i, kte, j), zero, max(him + 1, lo), hi);
+  }
+  if (him < lo) return;
+  float mp[4], mb[4], mps[4], mbs[4], mpn[4], mbn[4], msftx[4], my[4], mvi0[4], mvi1[4];
+  ld4(&A2(mup, i, j), mp); ld4(&A2(mub, i, j), mb); ld4(&A2(mup, i, j - 1), mps); ld4(&A2(mub, i, j - 1), mbs);
+  ld4(&A2(mup, i, j + 1), mpn); ld4(&A2(mub, i, j + 1), mbn); ld4(&A2(g.msftx, i, j), msftx); ld4(&A2(g.msfuy, i, j), my);
+  ld4(&A2(g.msfvx_inv, i, j), mvi0); ld4(&A2(g.msfvx_inv, i, j + 1), mvi1);
+  const float mp_w = A2(mup, i - 1, j), mb_w = A2(mub, i - 1, j), mp_e = A2(mup, i + 4, j), mb_e = A2(mub, i + 4, j), my_e = A2(g.msfuy, i + 4, j);
+  float muu0[4], muu1[4], muv0[4], muv1[4], my1[4], dmdt[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const float pw = q == 0 ? mp_w : mp[q > 0 ? q - 1 : 0], bw = q == 0 ? mb_w : mb[q > 0 ? q - 1 : 0];
+    const float pe = q == 3 ? mp_e : mp[q < 3 ? q + 1 : 3], be = q == 3 ? mb_e : mb[q < 3 ? q + 1 : 3];
+    muu0[q] = 0.5f * (mp[q] + mb[q] + pw + bw);
+    muu1[q] = 0.5f * (pe + be + mp[q] + mb[q]);
+    muv0[q] = 0.5f * (mp[q] + mb[q] + mps[q] + mbs[q]);
+    muv1[q] = 0.5f * (mpn[q] + mbn[q] + mp[q] + mb[q]);
+    my1[q] = q == 3 ? my_e : my[q < 3 ? q + 1 : 3];
+  }
+  for (int k = 1; k <= ktf; k++) {
+    const float c1h = g.c1h[k], c2h = g.c2h[k];
+    float ug[4], v0[4], v1[4], divv[4];
+    ld4(&A3(u, i, k, j), ug); ld4(&A3(v, i, k, j), v0); ld4(&A3(v, i, k, j + 1), v1);
+    const float u_e = A3(u, i + 4, k, j);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const float ue = q == 3 ? u_e : ug[q < 3 ? q + 1 : 3];
+      divv[q] = msftx[q] * g.dnw[k] *
+                (g.rdx * ((c1h * muu1[q] + c2h) * ue / my1[q] - (c1h * muu0[q] + c2h) * ug[q] / my[q]) +
+                 g.rdy * ((c1h * muv1[q] + c2h) * v1[q] * mvi1[q] - (c1h * muv0[q] + c2h) * v0[q] * mvi0[q]));
+      dmdt[q] = dmdt[q] + divv[q];
+    }
+    st4(&A3(ww, i, k + 1, j), divv, lo, him);
+  }
+  float wprev[4] = {0.f, 0.f, 0.f, 0.f};
+  st4(&A3(ww, i, 1, j), zero, lo, him);
+  for (int k = 2; k <= ktf; k++) {
+    float divv[4];
+    ld4(&A3(ww, i, k, j), divv);
+#pragma unroll
+    for (int q = 0; q < 4; q++) wprev[q] = wprev[q] - g.dnw[k - 1] * g.c1h[k - 1] * dmdt[q] - divv[q];
+    st4(&A3(ww, i, k, j), wprev, lo, him);
+  }
+  st4(&A3(ww, i, kte, j), zero, lo, him);
+}
+
 void Solver::rk_step_prep(int) {
   const Geo &q = g;
   LAUNCH2(this, k_prep_mu, (Box{q.its, q.ite, 1, 1, q.jts, q.jte}), o("mu_2"), o("mub"), o("mut"), o("muu"), o("muv"));
@@ -246,8 +303,13 @@ void Solver::rk_step_prep(int) {
     LAUNCH3(this, k_prep_3d, (Box{q.its, q.ite, 1, q.kde, q.jts, q.jte}), o("u_2"), o("v_2"), o("w_2"), o("muu"), o("muv"),
             o("mut"), o("ru"), o("rv"), o("rw"), mp, o("cqu"), o("cqv"), o("cqw"), o("al"), o("alb"), o("alt"), o("ph_2"),
             o("phb"), o("php"));
-  LAUNCH2(this, k_calc_ww, (Box{q.its, q.ite, 1, 1, q.jts, std::min(q.jte, q.jde - 1)}), o("u_2"), o("v_2"), o("mu_2"),
-          o("mub"), o("ww"));
+  if (vec4) {
+    Box bx = box_v4(q, 1, 1);
+    bx.j1 = std::min(q.jte, q.jde - 1);
+    LAUNCH2(this, k_calc_ww_v4, bx, o("u_2"), o("v_2"), o("mu_2"), o("mub"), o("ww"));
+  } else
+    LAUNCH2(this, k_calc_ww, (Box{q.its, q.ite, 1, 1, q.jts, std::min(q.jte, q.jde - 1)}), o("u_2"), o("v_2"), o("mu_2"),
+            o("mub"), o("ww"));
 }
 
 // solve_em.F:726-754 (rk_phys_bc_dry_1 = module_bc_em.F:960-1041, then rho, al, ph_2)
