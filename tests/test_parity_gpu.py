@@ -134,15 +134,16 @@ def test_boundary_zone_twelve_steps_bit_exact(name):
     s.close()
 
 
-def test_register_prefetch_form_of_advance_mu_t_is_still_exact():
+def test_alternative_kernel_forms_are_still_exact():
     """WRFGPU_MT=column selects k_advance_mu_t (operands prefetched into registers) instead of k_advance_mu_t_st (operands
-    staged by the bulk-copy engine); the switch is read once per process, so the check runs in a child: phase parity and
-    one whole step of two cases"""
+    staged by the bulk-copy engine), WRFGPU_SSP=scalar the one-point-per-thread streaming kernels instead of the *_v4
+    ones (four columns per thread, 16-byte accesses); the switches are read once per process, so the check runs in a
+    child: phase parity and one whole step of a few cases"""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, WRFGPU_MT="column", PYTHONPATH=root)
+    env = dict(os.environ, WRFGPU_MT="column", WRFGPU_SSP="scalar", PYTHONPATH=root)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_parity_gpu.py"), "-x", "-q", "-k",
                         "(phase_parity or full_step) and (quarter_ss or periodic or specified_real) and not shipped"],
                        env=env, capture_output=True, text=True, timeout=900)
