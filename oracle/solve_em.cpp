@@ -782,6 +782,18 @@ int oracle_max_cfl(Oracle *o, float *mv, float *mh, int reset) {
   if (reset) o->max_vert_cfl = o->max_horiz_cfl = 0.f;
   return 0;
 }
+// the physical constants of oracle.h by their names in share/module_model_constants.F (tests/test_reference_tables.py)
+int oracle_constant(const char *name, float *value) {
+  static const std::map<std::string, float> k = {
+      {"g", orc::g}, {"r_d", orc::r_d}, {"cp", orc::cp}, {"r_v", orc::r_v}, {"cv", orc::cv}, {"cvpm", orc::cvpm}, {"rcp", orc::rcp},
+      {"p1000mb", orc::p1000mb}, {"t0", orc::t0}, {"p0", orc::p0}, {"cpovcv", orc::cpovcv}, {"rvovrd", orc::rvovrd},
+      {"reradius", orc::reradius}, {"cb", orc::cb}, {"xlv", orc::xlv}, {"rhowater", orc::rhowater}, {"svp1", orc::svp1},
+      {"svp2", orc::svp2}, {"svp3", orc::svp3}, {"svpt0", orc::svpt0}, {"ep_2", orc::ep_2}};
+  auto it = k.find(name);
+  if (it == k.end()) return 1;
+  *value = it->second;
+  return 0;
+}
 int oracle_set_dtbc(Oracle *o, float dtbc) { o->dtbc = dtbc; return 0; }
 float oracle_get_dtbc(Oracle *o) { return o->dtbc; }
 int oracle_set_threads(Oracle *o, int n) { o->nthreads = n < 1 ? 1 : n; return o->nthreads; }

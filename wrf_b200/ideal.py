@@ -89,7 +89,7 @@ def default_config(**kw) -> Config:
     c.time_step = 1
     c.epssm, c.smdiv, c.emdiv = 0.1, 0.1, 0.01
     c.dampcoef, c.zdamp = 0.2, 5000.0
-    c.w_crit_cfl = 1.2
+    c.w_crit_cfl = 1.0      # Registry.EM_COMMON:2842
     c.diff_6th_factor, c.diff_6th_thresh = 0.12, 0.10
     c.c_s, c.c_k = 0.25, 0.15
     c.mix_upper_bound = 0.1

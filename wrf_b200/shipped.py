@@ -68,14 +68,16 @@ def read_namelist(path):
 
 
 # Registry.EM_COMMON rconfig defaults of the entries the path reads (namelist.input only lists what it changes)
+# Registry/Registry.EM_COMMON rconfig defaults (+ registry.hyb_coord for hybrid_opt, etac), pinned against the reference by
+# tests/test_reference_tables.py.  -1 = "has to be set in namelist.input" (diff_opt, km_opt: share/module_check_a_mundo.F:320-325).
 REGISTRY_DEFAULTS = dict(
-    rk_ord=3, time_step_sound=10, h_mom_adv_order=5, v_mom_adv_order=3, h_sca_adv_order=5, v_sca_adv_order=3,
-    moist_adv_opt=1, scalar_adv_opt=1, tke_adv_opt=1, momentum_adv_opt=1, non_hydrostatic=True, top_lid=False, damp_opt=0,
+    rk_ord=3, time_step_sound=0, h_mom_adv_order=5, v_mom_adv_order=3, h_sca_adv_order=5, v_sca_adv_order=3,
+    moist_adv_opt=1, scalar_adv_opt=1, tke_adv_opt=1, momentum_adv_opt=1, non_hydrostatic=True, top_lid=False, damp_opt=3,
     zdamp=5000.0, dampcoef=0.2, w_damping=0, pert_coriolis=False, use_theta_m=1, hypsometric_opt=2, phi_adv_z=1, zadvect_implicit=0,
-    w_crit_cfl=1.2, diff_opt=1, km_opt=1, diff_6th_opt=0, diff_6th_factor=0.12, diff_6th_thresh=0.10, diff_6th_slopeopt=0,
+    w_crit_cfl=1.0, diff_opt=-1, km_opt=-1, diff_6th_opt=0, diff_6th_factor=0.12, diff_6th_thresh=0.10, diff_6th_slopeopt=0,
     moist_mix6_off=False, scalar_mix6_off=False, khdif=0.0, kvdif=0.0, c_s=0.25, c_k=0.15, mix_full_fields=False, mix_isotropic=0,
     mix_upper_bound=0.1, tke_upper_bound=1000.0, tke_drag_coefficient=0.0, tke_heat_flux=0.0, epssm=0.1, smdiv=0.1, emdiv=0.01,
-    hybrid_opt=2, etac=0.2, mp_physics=0, isfflx=1, use_adaptive_time_step=False, specified=False, nested=False, polar=False,
+    hybrid_opt=2, etac=0.2, mp_physics=-1, isfflx=1, use_adaptive_time_step=False, specified=False, nested=False, polar=False,
     periodic_x=False, periodic_y=False, symmetric_xs=False, symmetric_xe=False, symmetric_ys=False, symmetric_ye=False,
     open_xs=False, open_xe=False, open_ys=False, open_ye=False)
 
@@ -99,6 +101,10 @@ def config_from_namelist(nl, dom=1):
               "scalar_adv_opt", "tke_adv_opt", "momentum_adv_opt", "damp_opt", "w_damping", "use_theta_m", "hypsometric_opt", "phi_adv_z",
               "zadvect_implicit", "diff_opt", "km_opt", "diff_6th_opt", "diff_6th_slopeopt", "mix_isotropic", "mp_physics", "isfflx"):
         setattr(c, n, int(v(n)))
+    if c.diff_opt == -1 or c.km_opt == -1:     # share/module_check_a_mundo.F:320-325
+        raise ValueError("Both km_opt and diff_opt need to be set in the namelist.input file.")
+    if c.mp_physics == -1:                     # no physics_suite fills it in for the idealised cases
+        raise ValueError("mp_physics needs to be set in the namelist.input file.")
     for n in ("non_hydrostatic", "top_lid", "pert_coriolis", "mix_full_fields", "moist_mix6_off", "scalar_mix6_off", "use_adaptive_time_step",
               "periodic_x", "periodic_y", "symmetric_xs", "symmetric_xe", "symmetric_ys", "symmetric_ye", "open_xs", "open_xe", "open_ys",
               "open_ye", "specified", "nested", "polar"):
