@@ -1191,3 +1191,15 @@ void advect_scalar_weno(const Cx &x, A3 field, A3 field_old, A3 tendency, A3 ru,
 }
 
 }  // namespace orc
+
+// the flux operators by their order, for tests/test_reference_tables.py (which evaluates the reference's own statement
+// functions, module_advect_em.F:202-213, from their source text): q = q_im3..q_ip2 (orders 5, 6) or q_im2..q_ip1 (3, 4)
+extern "C" float oracle_flux(int order, const float *q, float ua, int time_step) {
+  orc::Flux F{(float)(time_step >= 0 ? 1 : -1), false, false, false};
+  switch (order) {
+    case 3: return F.flux3(q[0], q[1], q[2], q[3], ua);
+    case 4: return F.flux4(q[0], q[1], q[2], q[3]);
+    case 5: return F.flux5(q[0], q[1], q[2], q[3], q[4], q[5], ua);
+    default: return F.flux6(q[0], q[1], q[2], q[3], q[4], q[5]);
+  }
+}

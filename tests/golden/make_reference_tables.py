@@ -6,6 +6,7 @@ product's host logic to (tests/test_reference_tables.py):
               with Fortran's left-to-right rules
   halos       Registry/Registry.EM_COMMON: every `halo` / `period` line of dyn_em (name -> [[stencil points | width, fields]])
   rconfig     Registry/Registry.EM_COMMON: default of every namelist variable wrf_b200/shipped.py knows
+  flux_operators  dyn_em/module_advect_em.F:202-213: the statement functions flux3 / flux4 / flux5 / flux6 as source text
 
     python tests/golden/make_reference_tables.py        # rewrites the JSON; commit it together with this script
 """
@@ -21,9 +22,11 @@ WANT = ["g", "r_d", "cp", "r_v", "cv", "cvpm", "rcp", "p1000mb", "t0", "p0", "cp
         "svp1", "svp2", "svp3", "svpt0", "ep_2"]
 
 
-def f32_eval(expr, env):
-    """evaluate a Fortran real*4 constant expression (+ - * / parentheses, names, literals) operation by operation in float32"""
-    toks = re.findall(r"[A-Za-z_]\w*|\d+\.?\d*(?:[eE][+-]?\d+)?|\.\d+(?:[eE][+-]?\d+)?|[-+*/()]", expr)
+def f32_eval(expr, env, funcs=None):
+    """evaluate a Fortran real*4 expression (+ - * / parentheses, names, literals, calls of `funcs`) operation by operation in
+    float32, left to right within a precedence level as the standard prescribes"""
+    funcs = funcs or {}
+    toks = re.findall(r"[A-Za-z_]\w*|\d+\.?\d*(?:[eE][+-]?\d+)?|\.\d+(?:[eE][+-]?\d+)?|[-+*/(),]", expr)
     pos = [0]
 
     def peek():
@@ -44,6 +47,14 @@ def f32_eval(expr, env):
         if t == "+":
             return atom()
         if re.match(r"[A-Za-z_]", t):
+            if t.lower() in funcs and peek() == "(":
+                take()
+                args = [addsub()]
+                while peek() == ",":
+                    take()
+                    args.append(addsub())
+                take()
+                return np.float32(funcs[t.lower()](*args))
             return env[t.lower()]
         return np.float32(float(t))
 
@@ -82,6 +93,24 @@ def constants():
     return out
 
 
+def flux_operators():
+    """the statement functions flux3 ... flux6 of advect_u (dyn_em/module_advect_em.F:202-213), continuation lines joined"""
+    src = open(os.path.join(REF, "dyn_em", "module_advect_em.F")).read().split("\n")
+    out, n = {}, 0
+    while n < len(src) and len(out) < 4:
+        m = re.match(r"\s*(flux[3456])\(([^)]*)\)\s*=\s*&?\s*$|\s*(flux[3456])\(([^)]*)\)\s*=(.*)$", src[n])
+        if m:
+            name = m.group(1) or m.group(3)
+            args = [a.strip() for a in (m.group(2) or m.group(4)).split(",")]
+            text = (m.group(5) or "")
+            while text.rstrip().endswith("&") or not text.strip():
+                n += 1
+                text = text.rstrip().rstrip("&") + " " + src[n].strip()
+            out[name] = {"args": args, "expr": " ".join(text.replace("&", " ").split())}
+        n += 1
+    return out
+
+
 def halos():
     out = {}
     for ln in open(os.path.join(REF, "Registry", "Registry.EM_COMMON")):
@@ -113,8 +142,8 @@ if __name__ == "__main__":
     import sys
     sys.path.insert(0, ROOT)
     from wrf_b200 import shipped
-    tables = {"_source": "wrf-model/WRF, files share/module_model_constants.F and Registry/Registry.EM_COMMON", "constants": constants(),
-              "halos": halos(), "rconfig": rconfig(set(shipped.REGISTRY_DEFAULTS))}
+    tables = {"_source": "wrf-model/WRF, files share/module_model_constants.F, Registry/Registry.EM_COMMON, dyn_em/module_advect_em.F", "constants": constants(),
+              "halos": halos(), "rconfig": rconfig(set(shipped.REGISTRY_DEFAULTS)), "flux_operators": flux_operators()}
     with open(os.path.join(ROOT, "tests", "golden", "reference_tables.json"), "w") as f:
         json.dump(tables, f, indent=1, sort_keys=True)
     print({k: len(v) for k, v in tables.items() if isinstance(v, dict)})

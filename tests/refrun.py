@@ -1,0 +1,190 @@
+"""Runs one routine of the reference (through tests/fortran_subset.py) on the state an Oracle object holds, bound exactly
+as dyn_em/solve_em.F binds it: the CALL statement of the routine is read from solve_em.F and every actual argument
+is resolved to the oracle's field of that name (grid%u_2 -> "u_2", ww1 -> "ww1", ...), to a dimension, a namelist value
+or a step scalar.  Test infrastructure; needs the reference tree (/root/reference), i.e. the build container."""
+from __future__ import annotations
+
+import os
+import re
+
+import numpy as np
+
+from tests.fortran_subset import Library, _cpp, _strip_comment, module_parameters
+
+REF = "/root/reference"
+f32 = np.float32
+_CONSTANTS = None
+
+
+def have_reference():
+    return os.path.isdir(os.path.join(REF, "dyn_em"))
+
+
+def call_statement(routine, occurrence=0, path="dyn_em/solve_em.F"):
+    """the occurrence-th `CALL routine (...)` of a reference file as (positional actuals, keyword actuals)"""
+    lines = [_strip_comment(ln).rstrip() for ln in _cpp(open(os.path.join(REF, path), errors="replace").read().split("\n"), {"DM_PARALLEL": 1})]
+    cur, found = "", []
+    for ln in lines:
+        t = ln.strip()
+        if not t or t.startswith("!$"):
+            continue
+        if cur:
+            cur += " " + (t[1:] if t.startswith("&") else t)
+        else:
+            cur = t
+        if cur.endswith("&"):
+            cur = cur[:-1]
+            continue
+        m = re.match(r"call\s+%s\s*\((.*)\)\s*$" % re.escape(routine), cur, re.I)
+        if m:
+            found.append(m.group(1))
+        cur = ""
+    text = found[occurrence]
+    args, depth, piece = [], 0, ""
+    for ch in text:
+        depth += ch == "("
+        depth -= ch == ")"
+        if ch == "," and depth == 0:
+            args.append(piece.strip())
+            piece = ""
+        else:
+            piece += ch
+    args.append(piece.strip())
+    pos, kw = [], {}
+    for a in args:
+        m = re.match(r"([A-Za-z_]\w*)\s*=\s*(.+)$", a)
+        if m and not re.match(r"[A-Za-z_]\w*\s*==", a):
+            kw[m.group(1).lower()] = m.group(2).strip()
+        else:
+            pos.append(a)
+    return pos, kw
+
+
+CONFIG_FLAGS = ("periodic_x", "periodic_y", "symmetric_xs", "symmetric_xe", "symmetric_ys", "symmetric_ye", "open_xs", "open_xe", "open_ys",
+                "open_ye", "specified", "nested", "polar", "non_hydrostatic", "top_lid", "pert_coriolis", "mix_full_fields")
+CONFIG_INT = ("damp_opt", "w_damping", "diff_opt", "km_opt", "h_mom_adv_order", "v_mom_adv_order", "h_sca_adv_order", "v_sca_adv_order",
+              "time_step", "rk_ord", "spec_zone", "relax_zone", "spec_bdy_width", "use_theta_m", "hypsometric_opt", "phi_adv_z", "map_proj",
+              "zadvect_implicit", "momentum_adv_opt", "diff_6th_opt", "diff_6th_slopeopt", "mix_isotropic", "isfflx")
+CONFIG_REAL = ("dampcoef", "zdamp", "w_crit_cfl", "khdif", "kvdif", "epssm", "smdiv", "emdiv", "diff_6th_factor", "diff_6th_thresh", "c_s", "c_k",
+               "mix_upper_bound", "tke_upper_bound", "tke_drag_coefficient", "tke_heat_flux", "dx", "dy", "dt", "p_top")
+
+
+SOURCES = ("dyn_em/module_em.F", "dyn_em/module_advect_em.F", "dyn_em/module_big_step_utilities_em.F", "dyn_em/module_small_step_em.F",
+           "dyn_em/module_bc_em.F", "dyn_em/module_ieva_em.F", "dyn_em/module_diffusion_em.F", "share/module_bc.F")
+_LIBRARY = None
+
+
+def library(time_step):
+    """every SUBROUTINE of the path's reference files, translated on first use (tests/fortran_subset.Library)"""
+    global _CONSTANTS, _LIBRARY
+    if _LIBRARY is None:
+        _CONSTANTS = module_parameters(os.path.join(REF, "share", "module_model_constants.F"))
+        # module_state_description: one INTEGER PARAMETER per Registry `package` (original_mom = 1, weno_mom = 3, positivedef = 1, ...)
+        for ln in open(os.path.join(REF, "Registry", "Registry.EM_COMMON"), errors="replace"):
+            m = re.match(r"package\s+(\w+)\s+\w+==(-?\d+)\b", ln)
+            if m:
+                _CONSTANTS.setdefault(m.group(1).lower(), (int(m.group(2)), "i"))
+        comp = dict([(k, "l") for k in CONFIG_FLAGS] + [(k, "i") for k in CONFIG_INT] + [(k, "r") for k in CONFIG_REAL])
+        types = {"config_flags": comp}
+
+        def fatal(*a, **k):
+            raise RuntimeError("wrf_error_fatal called by the reference routine")
+
+        hooks = {"nl_get_time_step": lambda _id, _ts: {1: _LIBRARY.time_step}, "wrf_error_fatal": fatal, "wrf_debug": lambda *a, **k: {},
+                 "wrf_message": lambda *a, **k: {}}
+        _LIBRARY = Library([os.path.join(REF, f) for f in SOURCES], defines={"EM_CORE": 1}, types=types, constants=_CONSTANTS, hooks=hooks)
+    _LIBRARY.time_step = int(time_step)
+    return _LIBRARY
+
+
+class _Flags(dict):
+    """config_flags: namelist entries the path does not carry are off / zero (rad_nudge, polar, ...)"""
+
+    def __missing__(self, key):
+        return 0
+
+
+class RefCall:
+    def __init__(self, src_file, routine, occurrence=0, call_path="dyn_em/solve_em.F", defines=None, alias=None):
+        self.R = library(1).routine(routine)
+        self.pos, self.kw = call_statement(routine, occurrence, call_path)
+        self.alias = alias or {}
+        self.absent = set()            # array actuals the oracle has no field for (bound to zeros)
+
+    def bind(self, oracle, scalars):
+        """-> (kwargs for the routine, {oracle field name: array in Fortran index order})"""
+        case = oracle.case
+        d, c = case.dims, case.config
+        R = self.R
+        actual = dict(zip(R.dummies, self.pos))
+        actual.update(self.kw)
+        fields, args = {}, {}
+        cfg = _Flags({k: bool(getattr(c, k)) for k in CONFIG_FLAGS if hasattr(c, k)})
+        cfg.update({k: int(getattr(c, k)) for k in CONFIG_INT if hasattr(c, k)})
+        cfg.update({k: f32(getattr(c, k)) for k in CONFIG_REAL if hasattr(c, k)})
+        dims = {n: getattr(d, n) for n in ("ids", "ide", "jds", "jde", "kds", "kde", "ims", "ime", "jms", "jme", "kms", "kme")}
+        dims.update(ips=d.ips, ipe=d.ipe, jps=d.jps, jpe=d.jpe, kps=d.kds, kpe=d.kde)
+        tile = {"grid%i_start(ij)": d.ips, "grid%i_end(ij)": d.ipe, "grid%j_start(ij)": d.jps, "grid%j_end(ij)": d.jpe, "k_start": d.kds,
+                "k_end": d.kde}
+        tile.update({"num_3d_m": c.num_moist + 1, "num_3d_s": c.num_scalar + 1, "grid%u_frame": f32(0), "grid%v_frame": f32(0),
+                     "max_vert_cfl_tmp(ij)": f32(0), "max_horiz_cfl_tmp(ij)": f32(0), "grid%id": 1, "grid%itimestep": 1})
+        have = set(oracle.names())
+        for dummy in R.dummies:
+            if dummy not in actual:
+                raise KeyError(f"{R.name}: no actual argument for {dummy}")
+            a = actual[dummy].strip().lower().replace(" ", "")
+            a = self.alias.get(a, a)
+            key = a[5:] if a.startswith("grid%") else a
+            if dummy in R.dims:
+                if key not in have:          # an array of options the path does not have (physics tendencies, ...): zeros
+                    ni, nk, nj = d.ime - d.ims + 1, d.kme - d.kms + 1, d.jme - d.jms + 1
+                    rank = len(R.dims[dummy])
+                    self.absent.add(key)
+                    args[dummy] = np.zeros({3: (ni, nk, nj), 2: (ni, nj), 1: (nk,)}[rank], np.float32)
+                    continue
+                if key not in fields:
+                    x = np.array(oracle.get(key), dtype=np.float32)
+                    fields[key] = np.ascontiguousarray(x.transpose(2, 1, 0) if x.ndim == 3 else (x.T if x.ndim == 2 else x))
+                args[dummy] = fields[key]
+            elif R.kind.get(dummy) == "t":
+                args[dummy] = cfg
+            elif a in tile:
+                args[dummy] = tile[a]
+            elif key in dims:
+                args[dummy] = dims[key]
+            elif key in scalars:
+                args[dummy] = scalars[key]
+            elif a.startswith("config_flags%"):
+                args[dummy] = cfg[a.split("%", 1)[1]]
+            elif key in ("rdx", "rdy"):
+                args[dummy] = f32(f32(1.0) / f32(c.dx if key == "rdx" else c.dy))
+            elif key in cfg:
+                args[dummy] = cfg[key]
+            elif hasattr(c, key):
+                v = getattr(c, key)
+                args[dummy] = f32(v) if R.kind.get(dummy) == "r" else int(v)
+            elif key in _CONSTANTS:                  # a module PARAMETER passed as an actual (t0, g, ...)
+                args[dummy] = _CONSTANTS[key][0]
+            elif re.fullmatch(r"[-+]?\d+", a):
+                args[dummy] = int(a)
+            else:
+                raise KeyError(f"{R.name}: cannot resolve {dummy} <- {a}")
+        return args, fields
+
+    def run(self, oracle, **scalars):
+        library(oracle.case.config.time_step)
+        args, fields = self.bind(oracle, scalars)
+        self.R(**args)
+        out = {}
+        for k, v in fields.items():
+            out[k] = np.ascontiguousarray(v.transpose(2, 1, 0) if v.ndim == 3 else (v.T if v.ndim == 2 else v))
+        return out
+
+
+def interior(case, a, stag=""):
+    """the domain points of an oracle-ordered array (what the routines own; halo rows are the boundary fills' business)"""
+    d = case.dims
+    ie = d.ide if "x" in stag else d.ide - 1
+    je = d.jde if "y" in stag else d.jde - 1
+    sj, si = slice(d.jds - d.jms, je - d.jms + 1), slice(d.ids - d.ims, ie - d.ims + 1)
+    return a[sj, ..., si] if a.ndim >= 2 else a

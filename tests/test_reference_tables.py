@@ -28,6 +28,7 @@ def test_fixture_is_what_the_reference_tree_holds():
     assert m.constants() == TABLES["constants"]
     assert m.halos() == TABLES["halos"]
     assert m.rconfig(set(shipped.REGISTRY_DEFAULTS)) == TABLES["rconfig"]
+    assert m.flux_operators() == TABLES["flux_operators"]
 
 
 def test_oracle_constants_are_module_model_constants():
@@ -113,3 +114,42 @@ def test_exchange_table_is_the_registry_s(ours):
     else:
         assert abs(regular) == hmax, (regular, hmax)
     assert abs(width) == max(abs(regular), pmax), (width, regular, pmax)
+
+
+def _generator():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mrt", os.path.join(HERE, "golden", "make_reference_tables.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("time_step", [12, -12])
+def test_flux_operators_are_the_reference_statement_functions(time_step):
+    """flux3 ... flux6 as the reference writes them (statement functions of advect_u, kept as source text in the fixture),
+    evaluated operation by operation in real*4, against the oracle's operators: same bits for every argument"""
+    ops = TABLES["flux_operators"]
+    assert sorted(ops) == ["flux3", "flux4", "flux5", "flux6"]
+    ev = _generator().f32_eval
+    lib = load_oracle()
+    lib.oracle_flux.restype = ctypes.c_float
+    f32 = np.float32
+
+    def sign(a, b):
+        return f32(abs(a)) if (b >= 0 and not (b == 0 and np.signbit(b))) else f32(-abs(a))
+
+    funcs = {"sign": sign}
+    for name in ("flux4", "flux6", "flux3", "flux5"):     # the even ones first: the odd ones call them
+        rec = ops[name]
+        funcs[name] = (lambda rec: lambda *a: ev(rec["expr"], dict(zip(rec["args"], [f32(x) for x in a]), time_step=f32(time_step)), funcs))(rec)
+    rng = np.random.default_rng(11)
+    for n in range(400):
+        scale = f32(10.0 ** rng.integers(-3, 4))
+        q = (rng.standard_normal(6) * scale).astype(f32)
+        ua = f32(rng.standard_normal() * 30.0) if n % 7 else f32(0.0)
+        for order, nq in ((3, 4), (4, 4), (5, 6), (6, 6)):
+            qq = q[:nq] if nq == 6 else q[1:5]
+            want = funcs["flux%d" % order](*[f32(x) for x in qq], ua)
+            buf = (ctypes.c_float * nq)(*[float(x) for x in qq])
+            got = f32(lib.oracle_flux(order, buf, ctypes.c_float(float(ua)), ctypes.c_int(time_step)))
+            assert got.view(np.uint32) == f32(want).view(np.uint32), (order, qq, ua, got, want)
