@@ -22,7 +22,7 @@ import numpy as np
 
 f32 = np.float32
 _libm = ctypes.CDLL(ctypes.util.find_library("m"))
-for _n in ("cosf", "sinf", "atanf", "expf", "logf", "sqrtf", "tanhf", "acosf", "asinf"):
+for _n in ("cosf", "sinf", "atanf", "expf", "logf", "sqrtf", "tanhf", "acosf", "asinf", "tanf"):
     getattr(_libm, _n).restype = ctypes.c_float
     getattr(_libm, _n).argtypes = [ctypes.c_float]
 _libm.powf.restype = ctypes.c_float
@@ -41,15 +41,16 @@ def _idiv(a, b):          # Fortran integer division truncates towards zero
 
 def _powi(x, n):          # libgcc __powisf2: the multiply sequence gfortran uses for real ** integer
     m = abs(int(n))
-    x = f32(x)
-    y = x if (m & 1) else f32(1.0)
+    T = np.float64 if isinstance(x, np.float64) else f32        # __powidf2 for a double precision base
+    x = T(x)
+    y = x if (m & 1) else T(1.0)
     m >>= 1
     while m:
-        x = f32(x * x)
+        x = T(x * x)
         if m & 1:
-            y = f32(y * x)
+            y = T(y * x)
         m >>= 1
-    return f32(f32(1.0) / y) if n < 0 else y
+    return T(T(1.0) / y) if n < 0 else y
 
 
 def _sign(a, b):
@@ -57,8 +58,19 @@ def _sign(a, b):
     return -abs(a) if neg else abs(a)
 
 
-RUNTIME = dict(f32=f32, f64=np.float64, _idiv=_idiv, _powi=_powi, _sign=_sign, _cos=_m1("cosf"), _sin=_m1("sinf"), _atan=_m1("atanf"),
-               _exp=_m1("expf"), _log=_m1("logf"), _sqrt=_m1("sqrtf"), _tanh=_m1("tanhf"), _acos=_m1("acosf"), _asin=_m1("asinf"),
+def _fit(a, shape):
+    """the actual array seen through the dummy's declared shape when the ranks differ (a view: only extent-1 axes come or go)"""
+    if a is None or not isinstance(a, np.ndarray) or a.ndim == len(shape):
+        return a
+    if [n for n in a.shape if n != 1] != [n for n in shape if n != 1]:
+        raise NotImplementedError(f"sequence association of shape {a.shape} with {shape}")
+    v = a.reshape(shape)
+    assert np.shares_memory(v, a)
+    return v
+
+
+RUNTIME = dict(_fit=_fit, f32=f32, f64=np.float64, _idiv=_idiv, _powi=_powi, _sign=_sign, _cos=_m1("cosf"), _sin=_m1("sinf"), _atan=_m1("atanf"),
+               _exp=_m1("expf"), _log=_m1("logf"), _sqrt=_m1("sqrtf"), _tanh=_m1("tanhf"), _acos=_m1("acosf"), _asin=_m1("asinf"), _tan=_m1("tanf"),
                _powf=lambda a, b: f32(_libm.powf(float(f32(a)), float(f32(b)))), np=np)
 
 
@@ -157,12 +169,12 @@ def statements(path, name, defines=None):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # expressions
-_TOK = re.compile(r"\s*('[^']*'|\"[^\"]*\"|\d+\.\d*(?:[ed][+-]?\d+)?|\.\d+(?:[ed][+-]?\d+)?|\d+(?:[ed][+-]?\d+)?|\.(?:lt|le|gt|ge|eq|ne|and|or|not|true|false|eqv|neqv)\."
+_TOK = re.compile(r"\s*('[^']*'|\"[^\"]*\"|\d+\.(?!(?:lt|le|gt|ge|eq|ne|and|or|not|eqv|neqv)\.)\d*(?:[ed][+-]?\d+)?|\.\d+(?:[ed][+-]?\d+)?|\d+(?:[ed][+-]?\d+)?|\.(?:lt|le|gt|ge|eq|ne|and|or|not|true|false|eqv|neqv)\."
                   r"|[a-z_]\w*|\*\*|==|/=|<=|>=|[-+*/()<>,:%=])")
 _REL = {".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">=", ".eq.": "==", ".ne.": "!=", "<": "<", "<=": "<=", ">": ">", ">=": ">=", "==": "==",
         "/=": "!="}
 _INTR1 = {"cos": "_cos", "sin": "_sin", "atan": "_atan", "exp": "_exp", "log": "_log", "alog": "_log", "sqrt": "_sqrt", "tanh": "_tanh",
-          "acos": "_acos", "asin": "_asin"}
+          "acos": "_acos", "asin": "_asin", "tan": "_tan"}
 
 
 def tokenize(s):
@@ -330,18 +342,29 @@ class Routine:
         self.is_function = bool(m) and m.group(3) == "function"
         self.result_kind = {"real": "r", "integer": "i", "logical": "l", None: None}[m.group(2) if m else None]
         self.kind, self.dims, self.params, self.stmtfn, self.derived, self.optional = {}, {}, {}, {}, set(), set()
+        self.implicit_none = False
         body = st[1:-1]
         if self.is_function and self.result_kind:
             self.kind[name] = self.result_kind
         n = 0
         while n < len(body) and self._declaration(body[n]):
             n += 1
-        self.py = self._translate(body[n:])
+        rest = []                      # declarations may follow statement-function definitions (advect_u: LOGICAL :: specified)
+        for st in body[n:]:
+            if "::" in st and re.match(r"(real|integer|logical|double precision)\b", st) and self._declaration(st):
+                continue
+            rest.append(st)
+        self.py = self._translate(rest)
         self.fn = None
 
     # -- declarations
     def _declaration(self, s):
-        if s.startswith(("implicit", "use ", "external", "intrinsic", "save")):
+        if s.startswith("implicit"):
+            self.implicit_none = True
+            return True
+        if s.startswith(("use ", "external", "intrinsic", "save")):
+            return True
+        if re.match(r"character\s*\*\s*\d+", s):        # message buffers: never part of the arithmetic
             return True
         m = None
         mt = re.match(r"(real|integer|logical|double precision|character|type\s*\(\s*\w+\s*\))\s*(\([^)]*\))?\s*(,|::)", s)
@@ -350,11 +373,13 @@ class Routine:
             m = re.match(r"(.*)$", s)      # placeholder match object; the pieces are taken below
             base, attrs, ents = mt.group(1), s[mt.end(3) - len(mt.group(3)):sep], s[sep + 2:]
         if not m:
-            m2 = re.match(r"(real|integer|logical)\s+([a-z_].*)$", s)        # old style: REAL a, b
+            m2 = re.match(r"(real|integer|logical|type\s*\(\s*\w+\s*\))\s+([a-z_].*)$", s)        # old style: REAL a, b
             if not m2:
                 return False
             base, attrs, ents = m2.group(1), "", m2.group(2)
         k = {"real": "r", "integer": "i", "logical": "l", "double precision": "d", "character": "c"}.get(base.split("(")[0].strip(), "t")
+        if k == "r" and mt and mt.group(2) and re.fullmatch(r"\(\s*(kind\s*=\s*)?8\s*\)", mt.group(2)):
+            k = "d"                     # REAL(KIND=8)
         dim = None
         md = re.search(r"dimension\s*\(", attrs)
         if md:
@@ -479,7 +504,7 @@ class Routine:
             t = ty[0] if ty[0] != "i" or ty[1] == "i" else ty[0]
             out = f"_sign({src[0]}, {src[1]})"
             return (f"f32({out})" if t == "r" else out), t
-        if fn in ("real", "float"):
+        if fn in ("real", "float", "sngl"):
             return f"f32({src[0]})", "r"
         if fn in ("int", "ifix"):
             return f"int({src[0]})", "i"
@@ -489,6 +514,12 @@ class Routine:
             return (f"int(np.fmod({src[0]}, {src[1]}))", "i") if ty[0] == "i" else (f"f32(np.fmod({src[0]}, {src[1]}))", "r")
         if fn == "dble":
             return f"f64({src[0]})", "d"
+        if fn == "ichar":
+            return f"ord({src[0]})", "i"
+        if fn == "char":
+            return f"chr({src[0]})", "c"
+        if fn == "trim":
+            return f"({src[0]}).rstrip()", "c"
         if fn == "present":
             return f"({src[0]} is not None)", "l"
         if fn in _INTR1:
@@ -509,6 +540,13 @@ class Routine:
 
         for nm in self.dummies:
             emit(f"v_{nm} = A[{nm!r}]")
+        for nm in self.dummies:          # sequence association: a 2-D actual for a (ims:ime, 1:1, jms:jme) dummy (calculate_full of mu)
+            if nm in self.dims and all(d.strip() not in (":", "*") for d in self.dims[nm]):
+                shape = []
+                for d in self.dims[nm]:
+                    lo, hi = (d.split(":") + ["1"])[:2] if ":" in d else ("1", d)
+                    shape.append(f"({self.expr(hi)[0]}) - ({self.expr(lo)[0]}) + 1")
+                emit(f"v_{nm} = _fit(v_{nm}, ({', '.join(shape)},))")
         for nm, init in self.params.items():
             src, t = self.expr(init)
             emit(f"v_{nm} = {self.conv(src, t, self.kind[nm])}")
@@ -569,7 +607,14 @@ class Routine:
                 emit("pass")
                 blocks.append(("do", label))
                 continue
-            if re.match(r"do\s*$", s) or re.match(r"do\s+while", s):
+            mw = re.match(r"do\s*while\s*\(", s)
+            if mw:
+                emit(f"while {self.expr(self._paren_after(s, 2))[0]}:")
+                ind += 1
+                emit("pass")
+                blocks.append(("do", label))
+                continue
+            if re.match(r"do\s*$", s):
                 raise NotImplementedError(s)
             if s.startswith("if"):
                 cond = self._paren_after(s, 2)
@@ -617,12 +662,15 @@ class Routine:
         if s == "exit":
             emit("break")
             return
-        if s == "continue":
+        if s == "continue" or re.match(r"(write\s*\(|print\s*\*)", s):      # diagnostics text is not part of the arithmetic
             emit("pass")
             return
         if s.startswith("call "):
             if re.match(r"call\s+(wrf_debug|wrf_message)\b", s):
                 emit("pass")
+                return
+            if re.match(r"call\s+wrf_error_fatal3?\b", s):
+                emit(f"raise RuntimeError({s!r})")
                 return
             mc = re.match(r"call\s+([a-z_]\w*)\s*(\((.*)\))?\s*$", s)
             if not mc or self.library is None:
@@ -667,6 +715,8 @@ class Routine:
             emit(f"    return {self.conv(src, t, self.kind.get(nm, 'r'))}")
             return
         src, t = self.expr(rhs)
+        if nm not in self.kind and not self.implicit_none and not ml.group(2):
+            self.kind[nm] = "i" if nm[0] in "ijklmn" else "r"      # Fortran's implicit typing (ww_split's cw_max)
         if nm not in self.kind:
             raise NotImplementedError(f"undeclared {nm!r}")
         val = self.conv(src, t, self.kind[nm])
@@ -694,10 +744,12 @@ class Routine:
             return self.fn(args)
 
 
-def module_parameters(path):
+def module_parameters(path, known=None, header_only=False):
     """the REAL / INTEGER PARAMETERs of a module file (share/module_model_constants.F), evaluated in order with real*4
-    semantics: name -> (value, 'r' | 'i')"""
-    out = {}
+    semantics: name -> (value, 'r' | 'i').  header_only: stop at CONTAINS (the module-level declarations of a file of
+    routines); known: constants the expressions may use"""
+    out = dict(known or {})
+    mine = {}
 
     class _M(Routine):
         def __init__(self):          # only the expression machinery
@@ -707,6 +759,8 @@ def module_parameters(path):
     tr = _M()
     for ln in open(path, errors="replace"):
         ln = _strip_comment(ln).strip().lower()
+        if header_only and ln == "contains":
+            break
         m = re.match(r"(real|integer)\s*,\s*parameter\s*::\s*([a-z_]\w*)\s*=\s*(.+)$", ln)
         if not m:
             continue
@@ -716,8 +770,8 @@ def module_parameters(path):
             continue
         want = "r" if m.group(1) == "real" else "i"
         val = eval(tr.conv(src, t, want), dict(RUNTIME))
-        out[m.group(2)] = (val, want)
-    return out
+        out[m.group(2)] = mine[m.group(2)] = (val, want)
+    return mine
 
 
 class Library:

@@ -4,11 +4,14 @@ is resolved to the oracle's field of that name (grid%u_2 -> "u_2", ww1 -> "ww1",
 or a step scalar.  Test infrastructure; needs the reference tree (/root/reference), i.e. the build container."""
 from __future__ import annotations
 
+import ctypes
 import os
 import re
 
 import numpy as np
 
+from wrf_b200 import decomp
+from wrf_b200.ideal import Config
 from tests.fortran_subset import Library, _cpp, _strip_comment, module_parameters
 
 REF = "/root/reference"
@@ -84,7 +87,12 @@ def library(time_step):
             m = re.match(r"package\s+(\w+)\s+\w+==(-?\d+)\b", ln)
             if m:
                 _CONSTANTS.setdefault(m.group(1).lower(), (int(m.group(2)), "i"))
+        for f in SOURCES:          # module-level PARAMETERs of the files themselves (alpha_min of module_ieva_em, bdyzone of module_bc)
+            for k, v in module_parameters(os.path.join(REF, f), _CONSTANTS, header_only=True).items():
+                _CONSTANTS.setdefault(k, v)
         comp = dict([(k, "l") for k in CONFIG_FLAGS] + [(k, "i") for k in CONFIG_INT] + [(k, "r") for k in CONFIG_REAL])
+        for k, ct in Config._fields_:            # every namelist entry the path's configuration carries
+            comp.setdefault(k, "r" if ct is ctypes.c_float else "i")
         types = {"config_flags": comp}
 
         def fatal(*a, **k):
@@ -104,50 +112,93 @@ class _Flags(dict):
         return 0
 
 
-class RefCall:
-    def __init__(self, src_file, routine, occurrence=0, call_path="dyn_em/solve_em.F", defines=None, alias=None):
-        self.R = library(1).routine(routine)
-        self.pos, self.kw = call_statement(routine, occurrence, call_path)
-        self.alias = alias or {}
+def _fortran_order(x):
+    return np.ascontiguousarray(x.transpose(2, 1, 0) if x.ndim == 3 else (x.T if x.ndim == 2 else x))
+
+
+class RefState:
+    """The oracle's fields as the reference routines see them: Fortran index order (i,k,j), fetched from the oracle on first
+    use and then owned by the reference side, so that a sequence of reference calls works on its own results."""
+
+    def __init__(self, oracle):
+        self.oracle = oracle
+        self.have = set(oracle.names())
+        self.fields = {}
         self.absent = set()            # array actuals the oracle has no field for (bound to zeros)
 
-    def bind(self, oracle, scalars):
-        """-> (kwargs for the routine, {oracle field name: array in Fortran index order})"""
+    def array(self, key):
+        if key not in self.fields:
+            x = np.array(self.oracle.get(key), dtype=np.float32)
+            side = decomp.bdy_side(key)
+            if side:        # a boundary array: (spec_bdy_width, levels, along) in C order = Fortran's (jms:jme | ims:ime, kds:kde | 1, width)
+                d, W = self.oracle.case.dims, self.oracle.case.config.spec_bdy_width
+                along = (d.jme - d.jms + 1) if side == "x" else (d.ime - d.ims + 1)
+                x = x.reshape(W, x.size // (W * along), along)
+            self.fields[key] = _fortran_order(x)
+        return self.fields[key]
+
+    def result(self, key):
+        """a field after the reference calls, in the oracle's (j,k,i) order"""
+        return _fortran_order(self.fields[key])
+
+
+class RefCall:
+    def __init__(self, routine, occurrence=0, call_path="dyn_em/solve_em.F", alias=None, actuals=None):
+        """actuals: {dummy: actual text} for a routine solve_em reaches through a driver this path does not translate
+        (first_rk_step_part2's calculate_km_kh -> isotropic_km); dummies it leaves out are bound by their own names"""
+        self.R = library(1).routine(routine)
+        if actuals is None:
+            self.pos, self.kw = call_statement(routine, occurrence, call_path)
+        else:
+            self.pos, self.kw = [], {d: actuals.get(d, d) for d in self.R.dummies}
+        self.alias = alias or {}
+
+    def bind(self, state, scalars):
+        """-> kwargs for the routine; arrays are the RefState's (shared between calls)"""
+        oracle = state.oracle
         case = oracle.case
         d, c = case.dims, case.config
         R = self.R
         actual = dict(zip(R.dummies, self.pos))
         actual.update(self.kw)
-        fields, args = {}, {}
+        args = {}
         cfg = _Flags({k: bool(getattr(c, k)) for k in CONFIG_FLAGS if hasattr(c, k)})
         cfg.update({k: int(getattr(c, k)) for k in CONFIG_INT if hasattr(c, k)})
         cfg.update({k: f32(getattr(c, k)) for k in CONFIG_REAL if hasattr(c, k)})
+        for k, ct in Config._fields_:
+            cfg.setdefault(k, f32(getattr(c, k)) if ct is ctypes.c_float else int(getattr(c, k)))
         dims = {n: getattr(d, n) for n in ("ids", "ide", "jds", "jde", "kds", "kde", "ims", "ime", "jms", "jme", "kms", "kme")}
-        dims.update(ips=d.ips, ipe=d.ipe, jps=d.jps, jpe=d.jpe, kps=d.kds, kpe=d.kde)
+        dims.update(ips=d.ips, ipe=d.ipe, jps=d.jps, jpe=d.jpe, kps=d.kds, kpe=d.kde, its=d.ips, ite=d.ipe, jts=d.jps, jte=d.jpe,
+                    kts=d.kds, kte=d.kde)
         tile = {"grid%i_start(ij)": d.ips, "grid%i_end(ij)": d.ipe, "grid%j_start(ij)": d.jps, "grid%j_end(ij)": d.jpe, "k_start": d.kds,
                 "k_end": d.kde}
         tile.update({"num_3d_m": c.num_moist + 1, "num_3d_s": c.num_scalar + 1, "grid%u_frame": f32(0), "grid%v_frame": f32(0),
                      "max_vert_cfl_tmp(ij)": f32(0), "max_horiz_cfl_tmp(ij)": f32(0), "grid%id": 1, "grid%itimestep": 1})
-        have = set(oracle.names())
         for dummy in R.dummies:
             if dummy not in actual:
+                if dummy in R.optional:
+                    continue
                 raise KeyError(f"{R.name}: no actual argument for {dummy}")
             a = actual[dummy].strip().lower().replace(" ", "")
             a = self.alias.get(a, a)
+            if not isinstance(a, str):               # an alias may give the value itself
+                args[dummy] = a
+                continue
             key = a[5:] if a.startswith("grid%") else a
             if dummy in R.dims:
-                if key not in have:          # an array of options the path does not have (physics tendencies, ...): zeros
+                if key not in state.have:        # an array of options the path does not have (physics tendencies, ...): zeros
                     ni, nk, nj = d.ime - d.ims + 1, d.kme - d.kms + 1, d.jme - d.jms + 1
                     rank = len(R.dims[dummy])
-                    self.absent.add(key)
-                    args[dummy] = np.zeros({3: (ni, nk, nj), 2: (ni, nj), 1: (nk,)}[rank], np.float32)
+                    state.absent.add(key)
+                    if key not in state.fields:
+                        state.fields[key] = np.zeros({4: (ni, nk, nj, 1), 3: (ni, nk, nj), 2: (ni, nj), 1: (nk,)}[rank], np.float32)
+                    args[dummy] = state.fields[key]
                     continue
-                if key not in fields:
-                    x = np.array(oracle.get(key), dtype=np.float32)
-                    fields[key] = np.ascontiguousarray(x.transpose(2, 1, 0) if x.ndim == 3 else (x.T if x.ndim == 2 else x))
-                args[dummy] = fields[key]
+                args[dummy] = state.array(key)
             elif R.kind.get(dummy) == "t":
                 args[dummy] = cfg
+            elif a in scalars:
+                args[dummy] = scalars[a]
             elif a in tile:
                 args[dummy] = tile[a]
             elif key in dims:
@@ -167,18 +218,19 @@ class RefCall:
                 args[dummy] = _CONSTANTS[key][0]
             elif re.fullmatch(r"[-+]?\d+", a):
                 args[dummy] = int(a)
+            elif re.fullmatch(r"[-+]?\d*\.\d*", a):
+                args[dummy] = f32(a)
+            elif a in (".true.", ".false."):
+                args[dummy] = a == ".true."
+            elif re.fullmatch(r"'[^']*'", a):
+                args[dummy] = a[1:-1]
             else:
                 raise KeyError(f"{R.name}: cannot resolve {dummy} <- {a}")
-        return args, fields
+        return args
 
-    def run(self, oracle, **scalars):
-        library(oracle.case.config.time_step)
-        args, fields = self.bind(oracle, scalars)
-        self.R(**args)
-        out = {}
-        for k, v in fields.items():
-            out[k] = np.ascontiguousarray(v.transpose(2, 1, 0) if v.ndim == 3 else (v.T if v.ndim == 2 else v))
-        return out
+    def run(self, state, **scalars):
+        library(state.oracle.case.config.time_step)
+        return self.R(**self.bind(state, scalars))
 
 
 def interior(case, a, stag=""):

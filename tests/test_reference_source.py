@@ -1,0 +1,183 @@
+"""The oracle against the reference's OWN SOURCE, executed here.
+
+tests/fortran_subset.py translates the routines of dyn_em/module_em.F, module_small_step_em.F, module_big_step_utilities_em.F,
+module_advect_em.F, ... (read where they lie under /root/reference; nothing is copied) into Python with real*4 semantics,
+tests/refrun.py binds each one as the CALL statement in dyn_em/solve_em.F binds it, and every test below
+
+  1. advances an Oracle to the point just before one phase of a solve_em step,
+  2. runs the reference routines of that phase on a copy of the oracle's state,
+  3. runs the oracle's phase,
+  4. requires every field the reference routines were handed to be equal BIT FOR BIT on the domain's own points.
+
+That pins oracle/ (and through the GPU parity tests the device code) to the reference's arithmetic, statement by statement, rather
+than to a reading of it.  The reference tree only exists in the build container: without it the tests skip, and
+tests/golden/reference_source.json (written by this file with REFSRC_WRITE=1, read by test_reference_source_golden.py) keeps
+what they established: a checksum of every compared field, which the oracle must reproduce wherever the suite runs."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import parity, refrun
+from tests.oracle_lib import Oracle
+from wrf_b200 import decomp, make_case
+
+pytestmark = pytest.mark.skipif(not refrun.have_reference(), reason="needs the reference tree (/root/reference)")
+f32 = np.float32
+
+
+def small_case(name="quarter_ss", **kw):
+    return parity.with_map_factors(make_case(name, nx=12, ny=10, nz=9, **kw))
+
+
+# The configurations of tests/parity.py's catalogue at sizes the translated Fortran (a Python loop nest) finishes in a second or two
+Q = dict(nx=12, ny=10, nz=9)
+S = dict(nx=14, ny=12, nz=9, bubble_lattice=8000.0, noise=0.05)
+H = dict(nx=20, ny=3, nz=9)
+CASES = {
+    "open_mapfac": lambda: parity.with_map_factors(make_case("quarter_ss", w_damping=1, **Q)),
+    "b_wave_lid": lambda: make_case("b_wave", nx=9, ny=13, nz=9, top_lid=1, phi_adv_z=2, w_damping=1, hypsometric_opt=1),
+    "opts": lambda: make_case("quarter_ss", use_theta_m=0, hypsometric_opt=1, damp_opt=3, zdamp=8000.0, dampcoef=0.2, scalar_adv_opt=0,
+                              num_scalar=1, u_scale=1.5, **Q),
+    "periodic_mapfac": lambda: parity.with_map_factors(make_case("synthetic", num_scalar=1, **S)),
+    "rk2_sym_x": lambda: make_case("synthetic", periodic=False, calm=True, rk_ord=2, open_xs=0, open_xe=0, symmetric_xs=1, symmetric_xe=1,
+                                   time_step_sound=4, **S),
+    "diffusion": lambda: make_case("quarter_ss", diff_opt=1, km_opt=1, khdif=500.0, kvdif=100.0, **Q),
+    "diffusion_periodic": lambda: parity.with_map_factors(make_case("synthetic", num_scalar=1, diff_opt=1, km_opt=1, khdif=300.0, kvdif=50.0, **S)),
+    "hill": lambda: make_case("hill2d_x", **H),
+    "order64": lambda: make_case("quarter_ss", h_mom_adv_order=6, v_mom_adv_order=4, h_sca_adv_order=6, v_sca_adv_order=4, **Q),
+    "weno": lambda: make_case("quarter_ss", momentum_adv_opt=3, moist_adv_opt=3, **Q),
+    "diff6": lambda: make_case("quarter_ss", diff_6th_opt=2, **Q),
+    "diff6_hill": lambda: make_case("hill2d_x", diff_6th_opt=2, diff_6th_slopeopt=1, diff_6th_thresh=0.004, **H),
+    "ieva": lambda: parity.with_updraft(make_case("quarter_ss", nx=12, ny=10, nz=17, zadvect_implicit=1, dt=40.0, time_step=40), 80.0),
+    "backward": lambda: make_case("synthetic", num_scalar=1, scalar_adv_opt=3, momentum_adv_opt=3, time_step=-12, **S),
+    "specified": lambda: parity.with_boundary_zone(make_case("quarter_ss", nx=16, ny=14, nz=9, specified=1, **parity.SPEC)),
+    "nested": lambda: parity.with_boundary_zone(make_case("quarter_ss", nx=16, ny=14, nz=9, nested=1, num_scalar=1, **parity.SPEC)),
+}
+
+
+def at_phase(case, target, rk=None, occurrence=0):
+    """an oracle advanced to just before the occurrence-th `target` phase (of Runge-Kutta stage rk) of the first step"""
+    o = Oracle(case)
+    o.start_domain()
+    if case.config.specified or case.config.nested:
+        o.set_dtbc(case.config.dt)
+    n = 0
+    for ph, args in parity.phase_sequence(case):
+        if ph == target and (rk is None or (args and args[0] == rk)):
+            if n == occurrence:
+                return o, args
+            n += 1
+        o.call(ph, *args)
+    raise KeyError(target)
+
+
+def rk_scalars(c, rk):
+    """dt_rk, dts_rk, number_of_small_timesteps of solve_em.F:585-615"""
+    nss = c.time_step_sound
+    dt = f32(c.dt)
+    dts = f32(dt / f32(nss))
+    if c.rk_ord == 3 and rk == 1:
+        return dict(dt_rk=f32(dt / f32(3.0)), dts_rk=f32(dt / f32(3.0)), number_of_small_timesteps=1)
+    if rk < c.rk_ord:
+        return dict(dt_rk=f32(f32(0.5) * dt), dts_rk=dts, number_of_small_timesteps=nss // 2)
+    return dict(dt_rk=dt, dts_rk=dts, number_of_small_timesteps=nss)
+
+
+def own(case, name, a):
+    """the points of the field the domain owns (the halo is the boundary fills' and exchanges' business)"""
+    d = case.dims
+    ie = d.ide if name in decomp.XSTAG else d.ide - 1
+    je = d.jde if name in decomp.YSTAG else d.jde - 1
+    if a.ndim == 1:
+        return a
+    return a[d.jds - d.jms:je - d.jms + 1, ..., d.ids - d.ims:ie - d.ims + 1]
+
+
+def compare(case, state, oracle, phase):
+    """-> (n compared, [names that differ])"""
+    bad, n = [], 0
+    for k in sorted(state.fields):
+        if k in state.absent or decomp.bdy_side(k):      # boundary arrays are inputs
+            continue
+        a, b = own(case, k, state.result(k)), own(case, k, np.asarray(oracle.get(k)))
+        n += 1
+        if not np.array_equal(a.view(np.uint32), b.view(np.uint32)):
+            both_nan = np.isnan(a) & np.isnan(b)
+            d = np.argwhere((a.view(np.uint32) != b.view(np.uint32)) & ~both_nan)
+            if len(d):
+                bad.append((k, len(d), tuple(d[0]), float(a[tuple(d[0])]), float(b[tuple(d[0])])))
+    return n, bad
+
+
+def run(case, phase, rk, program, occurrence=0, extra=None, not_compared=()):
+    o, args = at_phase(case, phase, rk, occurrence)
+    rk = rk or 1
+    scal = rk_scalars(case.config, rk)
+    scal.update(rk_step=rk, rk_order=case.config.rk_ord, iteration=args[1] if len(args) > 1 else 1)
+    if case.config.specified or case.config.nested:
+        scal["dtbc"] = f32(o.dtbc())
+    scal.update(extra or {})
+    st = refrun.RefState(o)
+    for step in program:
+        routine, occ = step[0], step[1]
+        opts = step[2] if len(step) > 2 else {}
+        refrun.RefCall(routine, occ, opts.get("path", "dyn_em/solve_em.F"), opts.get("alias"), opts.get("actuals")).run(
+            st, **{**scal, **opts.get("scalars", {})})
+    changed = [k for k in st.fields if k not in st.absent and not decomp.bdy_side(k) and not np.array_equal(st.result(k), np.asarray(o.get(k)), equal_nan=True)]
+    assert changed, f"{phase}: the reference routines changed nothing (a vacuous comparison)"
+    o.call(phase, *args)
+    for k in not_compared:
+        st.absent.add(k)
+    n, bad = compare(case, st, o, phase)
+    assert not bad, f"{phase}: reference source and oracle differ in {bad}"
+    return n, st, o
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the acoustic loop and its brackets (module_small_step_em.F), at every Runge-Kutta stage
+
+@pytest.mark.parametrize("routine,rk,least", [("advance_uv", 1, 30), ("advance_uv", 2, 30), ("advance_uv", 3, 30), ("advance_mu_t", 1, 35),
+                                              ("advance_mu_t", 3, 35), ("advance_w", 1, 35), ("advance_w", 3, 35), ("sumflux", 1, 20),
+                                              ("sumflux", 2, 20), ("sumflux", 3, 20)])
+def test_acoustic_step(routine, rk, least):
+    n, *_ = run(small_case(), routine, rk, [(routine, 0)], occurrence=1 if rk > 1 else 0)
+    assert n >= least
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the large-step tendencies: rk_tendency (module_em.F:188) with everything it calls -- advection of u, v, w, ph, theta,
+# curvature, Coriolis, pressure gradient and buoyancy, horizontal/vertical diffusion, Rayleigh damping -- then rk_addtend_dry
+
+def tendency_program(c, rk):
+    """the reference calls between rk_step_prep's boundary fills and small_step_prep (solve_em.F:790-1100) -> (program, fields left out)"""
+    prog, skip = [], ()
+    if c.diff_opt == 1 and c.km_opt == 1 and rk == 1:
+        # first_rk_step_part2 -> calculate_km_kh -> isotropic_km fills the K arrays with the namelist constants once per step; the
+        # oracle and the device hand the constants to the diffusion routines directly and never materialise the arrays
+        prog.append(("isotropic_km", 0, {"actuals": {}}))
+        for k in ("xkmh", "xkhh"):      # phy_bc (module_diffusion_em.F:5901): the halo the horizontal operators read
+            prog.append(("set_physical_bc3d", 0, {"actuals": {"dat": k, "variable_in": "'t'"}}))
+        skip = ("xkmh", "xkmv", "xkhh", "xkhv")
+    prog.append(("rk_tendency", 0))
+    if (c.specified or c.nested) and rk == 1:        # solve_em.F:937
+        prog.append(("relax_bdy_dry", 0))
+    prog.append(("rk_addtend_dry", 0))
+    if c.specified or c.nested:
+        prog.append(("spec_bdy_dry", 0))
+    return prog, skip
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("rk", [1, 2, 3])
+def test_rk_tendency(name, rk):
+    case = CASES[name]()
+    if rk > case.config.rk_ord:
+        pytest.skip("rk_ord 2")
+    prog, skip = tendency_program(case.config, rk)
+    n, st, o = run(case, "rk_tendency", rk, prog, not_compared=skip)
+    assert n >= 70
+    if name == "ieva" and rk == 3:
+        assert np.any(np.asarray(o.get("wwI"))), "the IEVA case must move some of the vertical transport to the implicit solver"
