@@ -486,6 +486,8 @@ class Routine:
         if tok not in self.kind and tok in self.constants:
             v, t = self.constants[tok]
             return (f"f32({float(v)!r})" if t == "r" else repr(int(v))), t
+        if tok not in self.kind and self.library is not None and tok in self.library.globals:
+            return f"_G[{tok!r}]", "i"            # a USEd module variable (p_qv, ...), looked up when the routine runs
         if tok not in self.kind:
             raise NotImplementedError(f"undeclared name {tok!r} (IMPLICIT NONE expected)")
         return f"v_{tok}", self.kind[tok]
@@ -669,6 +671,17 @@ class Routine:
             if re.match(r"call\s+(wrf_debug|wrf_message)\b", s):
                 emit("pass")
                 return
+            mv = re.match(r"call\s+(vpow|vspow)\s*\((.*)\)\s*$", s)
+            if mv:          # frame/libmassv.F:375-381 (VPOW is vspow unless DOUBLE_PRECISION): z(j) = y(j)**x(j), j = 1..n, on array
+                z, y, x, cnt = self._split(mv.group(2))          # elements passed as the start of a run along the first dimension
+                def run_of(text):
+                    me = re.match(r"([a-z_]\w*)\s*\((.*)\)$", text.strip())
+                    subs = [self.expr(t)[0] for t in self._split(me.group(2))]
+                    subs[0] = f"({subs[0]}) + _n"
+                    return self.index(me.group(1), subs)
+                emit(f"for _n in range({self.expr(cnt)[0]}):")
+                emit(f"    {run_of(z)} = _powf({run_of(y)}, {run_of(x)})")
+                return
             if re.match(r"call\s+wrf_error_fatal3?\b", s):
                 emit(f"raise RuntimeError({s!r})")
                 return
@@ -731,6 +744,7 @@ class Routine:
     def __call__(self, **args):
         if self.fn is None:
             ns = dict(RUNTIME)
+            ns["_G"] = self.library.globals if self.library is not None else {}
             ns["_call"] = self.library.call if self.library is not None else None
             ns["_callf"] = self.library.callf if self.library is not None else None
             exec(compile(self.py, f"<{self.name} of {self.path}>", "exec"), ns)
@@ -780,6 +794,7 @@ class Library:
 
     def __init__(self, files, defines=None, types=None, constants=None, hooks=None):
         self.where, self.cache = {}, {}
+        self.globals = {}              # USEd module variables (integers), by name
         self.defines, self.types, self.constants, self.hooks = defines or {}, types or {}, constants or {}, hooks or {}
         for path in files:
             for ln in open(path, errors="replace"):

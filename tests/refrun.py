@@ -82,6 +82,7 @@ def library(time_step):
     global _CONSTANTS, _LIBRARY
     if _LIBRARY is None:
         _CONSTANTS = module_parameters(os.path.join(REF, "share", "module_model_constants.F"))
+        _CONSTANTS["param_first_scalar"] = (2, "i")          # tools/gen_mod_state_descr.c:69
         # module_state_description: one INTEGER PARAMETER per Registry `package` (original_mom = 1, weno_mom = 3, positivedef = 1, ...)
         for ln in open(os.path.join(REF, "Registry", "Registry.EM_COMMON"), errors="replace"):
             m = re.match(r"package\s+(\w+)\s+\w+==(-?\d+)\b", ln)
@@ -101,8 +102,19 @@ def library(time_step):
         hooks = {"nl_get_time_step": lambda _id, _ts: {1: _LIBRARY.time_step}, "wrf_error_fatal": fatal, "wrf_debug": lambda *a, **k: {},
                  "wrf_message": lambda *a, **k: {}}
         _LIBRARY = Library([os.path.join(REF, f) for f in SOURCES], defines={"EM_CORE": 1}, types=types, constants=_CONSTANTS, hooks=hooks)
+        _LIBRARY.globals.update({q: 1 for q in ("p_qv", "p_qc", "p_qr", "p_qi", "p_qs", "p_qg", "p_qh", "p_qni", "p_qnc")})
     _LIBRARY.time_step = int(time_step)
     return _LIBRARY
+
+
+def set_species(c):
+    """module_state_description's species indices for this configuration (set_scalar_indices_from_config): active species count up
+    from PARAM_FIRST_SCALAR = 2 (tools/gen_mod_state_descr.c:69), inactive ones are 1"""
+    g = library(c.time_step).globals
+    for n, q in enumerate(("p_qv", "p_qc", "p_qr")):
+        g[q] = n + 2 if n < c.num_moist else 1
+    for q in ("p_qi", "p_qs", "p_qg", "p_qh", "p_qni", "p_qnc"):
+        g[q] = 1
 
 
 class _Flags(dict):
@@ -122,12 +134,33 @@ class RefState:
 
     def __init__(self, oracle):
         self.oracle = oracle
-        self.have = set(oracle.names())
+        self.have = set(oracle.names()) | {"moist", "moist_old", "moist_tend", "scalar", "scalar_old", "scalar_tend"}
         self.fields = {}
         self.absent = set()            # array actuals the oracle has no field for (bound to zeros)
 
+    def groups(self):
+        """the 4-D species arrays of the Registry (moist, scalar, their _old and _tend forms) -> the oracle's per-species fields;
+        Fortran index 1 is the unused slot below PARAM_FIRST_SCALAR"""
+        c = self.oracle.case.config
+        out = {}
+        for fam, mid in (("moist", ""), ("moist_old", "old_"), ("moist_tend", "tend_")):
+            out[fam] = ["moist_" + mid + q for q in ("qv", "qc", "qr")[:c.num_moist]]
+        for fam, mid in (("scalar", ""), ("scalar_old", "old_"), ("scalar_tend", "tend_")):
+            out[fam] = ["scalar_" + mid + str(n) for n in range(1, c.num_scalar + 1)]
+        return out
+
     def array(self, key):
         if key not in self.fields:
+            for fam, members in self.groups().items():
+                if key == fam or key in members:
+                    d = self.oracle.case.dims
+                    a4 = np.zeros((d.ime - d.ims + 1, d.kme - d.kms + 1, d.jme - d.jms + 1, len(members) + 1), np.float32)
+                    for n, m in enumerate(members):
+                        a4[..., n + 1] = _fortran_order(np.array(self.oracle.get(m), dtype=np.float32))
+                        self.fields[m] = a4[..., n + 1]
+                    self.fields[fam] = a4
+                    self.absent.add(fam)          # compared through its members
+                    return self.fields[key]
             x = np.array(self.oracle.get(key), dtype=np.float32)
             side = decomp.bdy_side(key)
             if side:        # a boundary array: (spec_bdy_width, levels, along) in C order = Fortran's (jms:jme | ims:ime, kds:kde | 1, width)
@@ -172,6 +205,7 @@ class RefCall:
                     kts=d.kds, kte=d.kde)
         tile = {"grid%i_start(ij)": d.ips, "grid%i_end(ij)": d.ipe, "grid%j_start(ij)": d.jps, "grid%j_end(ij)": d.jpe, "k_start": d.kds,
                 "k_end": d.kde}
+        tile.update({"num_moist": c.num_moist + 1, "num_scalar": c.num_scalar + 1, "n_moist": c.num_moist + 1})
         tile.update({"num_3d_m": c.num_moist + 1, "num_3d_s": c.num_scalar + 1, "grid%u_frame": f32(0), "grid%v_frame": f32(0),
                      "max_vert_cfl_tmp(ij)": f32(0), "max_horiz_cfl_tmp(ij)": f32(0), "grid%id": 1, "grid%itimestep": 1})
         for dummy in R.dummies:
@@ -229,7 +263,7 @@ class RefCall:
         return args
 
     def run(self, state, **scalars):
-        library(state.oracle.case.config.time_step)
+        set_species(state.oracle.case.config)
         return self.R(**self.bind(state, scalars))
 
 

@@ -181,3 +181,71 @@ def test_rk_tendency(name, rk):
     assert n >= 70
     if name == "ieva" and rk == 3:
         assert np.any(np.asarray(o.get("wwI"))), "the IEVA case must move some of the vertical transport to the implicit solver"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the brackets of the acoustic loop and the diagnostics
+
+SOME = ["open_mapfac", "b_wave_lid", "opts", "periodic_mapfac", "rk2_sym_x", "hill", "specified"]
+
+
+@pytest.mark.parametrize("name", SOME)
+@pytest.mark.parametrize("rk", [1, 2])
+def test_rk_step_prep(name, rk):
+    n, *_ = run(CASES[name](), "rk_step_prep", rk, [("rk_step_prep", 0)])
+    assert n >= 25
+
+
+@pytest.mark.parametrize("name", SOME)
+@pytest.mark.parametrize("rk", [1, 2])
+def test_small_step_prep(name, rk):
+    """small_step_prep, calc_p_rho(step 0) and calc_coef_w (solve_em.F:1100-1175)"""
+    n, *_ = run(CASES[name](), "small_step_prep", rk, [("small_step_prep", 0), ("calc_p_rho", 0), ("calc_coef_w", 0)])
+    assert n >= 40
+
+
+@pytest.mark.parametrize("name", SOME)
+def test_calc_p_rho(name):
+    """the pressure / inverse density diagnosis inside the acoustic loop (solve_em.F:1623), second small step of stage 2 or 3"""
+    case = CASES[name]()
+    n, *_ = run(case, "calc_p_rho", None, [("calc_p_rho", 1)], occurrence=2, extra={"iteration": 2})
+    assert n >= 10
+
+
+@pytest.mark.parametrize("name", SOME)
+@pytest.mark.parametrize("rk", [1, 3])
+def test_small_step_finish(name, rk):
+    case = CASES[name]()
+    rk = min(rk, case.config.rk_ord)
+    n, *_ = run(case, "small_step_finish", rk, [("calc_mu_uv_1", 0), ("small_step_finish", 0)])
+    assert n >= 30
+
+
+@pytest.mark.parametrize("name", SOME)
+def test_calc_p_rho_phi(name):
+    n, *_ = run(CASES[name](), "calc_p_rho_phi", None, [("calc_p_rho_phi", 0)], occurrence=1)
+    assert n >= 10
+
+
+def acoustic_program(c, routine):
+    """a routine of the acoustic loop with the specified-zone updates solve_em.F makes right after it (:1344-1365, :1459-1490,
+    :1582-1620)"""
+    prog = [(routine, 0)]
+    if not (c.specified or c.nested):
+        return prog
+    if routine == "advance_uv":
+        prog += [("spec_bdyupdate", 0), ("spec_bdyupdate", 1)]
+    if routine == "advance_mu_t":
+        prog += [("spec_bdyupdate", 2), ("spec_bdyupdate", 3), ("spec_bdyupdate", 4)]
+    if routine == "sumflux":
+        prog += [("spec_bdyupdate_ph", 0), ("zero_grad_bdy", 0) if c.specified else ("spec_bdyupdate", 5)]
+    return prog
+
+
+@pytest.mark.parametrize("name", ["specified", "nested", "periodic_mapfac", "b_wave_lid", "hill", "rk2_sym_x"])
+@pytest.mark.parametrize("routine", ["advance_uv", "advance_mu_t", "advance_w", "sumflux"])
+def test_acoustic_step_configurations(name, routine):
+    case = CASES[name]()
+    rk = case.config.rk_ord
+    n, *_ = run(case, routine, rk, acoustic_program(case.config, routine), occurrence=1)
+    assert n >= 20
