@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes
 import ctypes.util
+import os
 import re
 
 import numpy as np
@@ -354,7 +355,12 @@ class Routine:
             if "::" in st and re.match(r"(real|integer|logical|double precision)\b", st) and self._declaration(st):
                 continue
             rest.append(st)
-        self.py = self._translate(rest)
+        try:
+            self.py = self._translate(rest)
+        except NotImplementedError as e:
+            if "[in " not in str(e):
+                raise NotImplementedError(f"{e} [in {name} of {os.path.basename(path)}]") from e
+            raise
         self.fn = None
 
     # -- declarations
@@ -643,6 +649,14 @@ class Routine:
         ret = [nm for nm in self.dummies if nm not in self.dims and self.kind.get(nm) in ("r", "i", "l", "d")]
         return "return {" + ", ".join(f"{nm!r}: v_{nm}" for nm in ret) + "}"
 
+    def _array_dummy(self, callee, key, position):
+        """does the callee declare the dummy this actual lands on as an array?"""
+        if self.library is None or callee not in self.library.where:
+            return False
+        R = self.library.routine(callee)
+        dummy = key if key else (R.dummies[position] if position < len(R.dummies) else None)
+        return dummy in R.dims
+
     @staticmethod
     def _paren_after(s, pos):
         start = s.index("(", pos)
@@ -692,7 +706,19 @@ class Routine:
             for n_arg, a in enumerate(self._split(mc.group(3)) if mc.group(3) and mc.group(3).strip() else []):
                 mk = re.match(r"([a-z_]\w*)\s*=\s*([^=].*)$", a)
                 key, text = (mk.group(1), mk.group(2).strip()) if mk else (None, a.strip())
-                if re.fullmatch(r"[a-z_]\w*", text) and text in self.kind:      # a variable: arrays and derived types go by reference
+                me = re.match(r"([a-z_]\w*)\s*\((.*)\)$", text)
+                if me and me.group(1) in self.dims and mc.group(1) not in self.library.hooks and self._array_dummy(mc.group(1), key, n_arg):
+                    # an element as the start of a slab (sequence association): moist(ims,kms,jms,im) -> the species' 3-D array
+                    nm_a, subs = me.group(1), [t.strip() for t in self._split(me.group(2))]
+                    lows = [(d.split(":")[0].strip() if ":" in d else "1") for d in self.dims[nm_a]]
+                    lead = 0
+                    while lead < len(subs) and subs[lead] == lows[lead]:
+                        lead += 1
+                    if lead == 0 or len(subs) != len(lows):
+                        raise NotImplementedError(f"array element actual {text!r}")
+                    idx = [":"] * lead + [f"({self.expr(t)[0]}) - ({self.expr(lo)[0]})" for t, lo in zip(subs[lead:], lows[lead:])]
+                    src = f"v_{nm_a}[{', '.join(idx)}]"
+                elif re.fullmatch(r"[a-z_]\w*", text) and text in self.kind:      # a variable: arrays and derived types go by reference
                     src = f"v_{text}"
                     if text not in self.dims and self.kind[text] in "ridl":
                         back.append((key if key else n_arg, text))
@@ -733,7 +759,9 @@ class Routine:
         if nm not in self.kind:
             raise NotImplementedError(f"undeclared {nm!r}")
         val = self.conv(src, t, self.kind[nm])
-        if ml.group(2):
+        if ml.group(2) and all(x.strip() == ":" for x in self._split(ml.group(3))):
+            emit(f"v_{nm}[...] = {val}")                 # a(:,:,:) = scalar
+        elif ml.group(2):
             subs = [self.expr(x)[0] for x in self._split(ml.group(3))]
             emit(f"{self.index(nm, subs)} = {val}")
         elif nm in self.dims:

@@ -42,7 +42,10 @@ def call_statement(routine, occurrence=0, path="dyn_em/solve_em.F"):
         if m:
             found.append(m.group(1))
         cur = ""
-    text = found[occurrence]
+    if isinstance(occurrence, str):          # the call whose argument list mentions this text (the scalar loop's: "scalar_tend(")
+        text = next(t for t in found if occurrence in t.lower().replace(" ", ""))
+    else:
+        text = found[occurrence]
     args, depth, piece = [], 0, ""
     for ch in text:
         depth += ch == "("

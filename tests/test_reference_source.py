@@ -49,6 +49,10 @@ CASES = {
     "hill": lambda: make_case("hill2d_x", **H),
     "order64": lambda: make_case("quarter_ss", h_mom_adv_order=6, v_mom_adv_order=4, h_sca_adv_order=6, v_sca_adv_order=4, **Q),
     "weno": lambda: make_case("quarter_ss", momentum_adv_opt=3, moist_adv_opt=3, **Q),
+    "mono": lambda: make_case("quarter_ss", moist_adv_opt=2, **Q),
+    "mono_periodic": lambda: parity.with_map_factors(make_case("synthetic", num_scalar=2, scalar_adv_opt=2, moist_adv_opt=2, **S)),
+    "wenopd": lambda: make_case("quarter_ss", moist_adv_opt=4, **Q),
+    "wenopd_periodic": lambda: parity.with_map_factors(make_case("synthetic", num_scalar=2, scalar_adv_opt=4, moist_adv_opt=3, **S)),
     "diff6": lambda: make_case("quarter_ss", diff_6th_opt=2, **Q),
     "diff6_hill": lambda: make_case("hill2d_x", diff_6th_opt=2, diff_6th_slopeopt=1, diff_6th_thresh=0.004, **H),
     "ieva": lambda: parity.with_updraft(make_case("quarter_ss", nx=12, ny=10, nz=17, zadvect_implicit=1, dt=40.0, time_step=40), 80.0),
@@ -249,3 +253,63 @@ def test_acoustic_step_configurations(name, routine):
     rk = case.config.rk_ord
     n, *_ = run(case, routine, rk, acoustic_program(case.config, routine), occurrence=1)
     assert n >= 20
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the scalar step (solve_em.F:1845-2955): rk_update_scalar_pd, rk_scalar_tend with every advection option, the species'
+# boundary-zone tendencies, rk_update_scalar, flow_dep_bdy -- species by species as the moist and scalar loops run them
+
+def species_alias(fam, member, index_var):
+    """the slab actuals of one species, moist(ims,kms,jms,im) ..., as the oracle's per-species field names"""
+    tail = member[len(fam) + 1:]                      # qv | 1
+    al = {f"{fam}(ims,kms,jms,{index_var})": member, f"{fam}_old(ims,kms,jms,{index_var})": f"{fam}_old_{tail}",
+          f"{fam}_tend(ims,kms,jms,{index_var})": f"{fam}_tend_{tail}"}
+    for side in ("xs", "xe", "ys", "ye"):
+        first = "jms" if side[0] == "x" else "ims"
+        al[f"{fam}_b{side}({first},kms,1,{index_var})"] = f"{member}_b{side}"
+        al[f"{fam}_bt{side}({first},kms,1,{index_var})"] = f"{member}_bt{side}"
+    return al
+
+
+def scalar_program(c, rk, have):
+    prog = []
+    fams = [("moist", ["moist_" + q for q in ("qv", "qc", "qr")[:c.num_moist]], "im", c.moist_adv_opt, 0),
+            ("scalar", ["scalar_%d" % n for n in range(1, c.num_scalar + 1)], "is", c.scalar_adv_opt, 1)]
+    last = rk == c.rk_ord
+    for fam, members, iv, adv, nth in fams:                 # solve_em.F:1849-1977
+        if last and adv in (1, 2, 4):
+            for n, m in enumerate(members):
+                prog.append(("rk_update_scalar_pd", fam + "_tend(", {"alias": species_alias(fam, m, "im"), "scalars": {"im": n + 2}}))
+    for fam, members, iv, adv, nth in fams:
+        if last and adv in (1, 2, 4):
+            for m in members:                              # set_physical_bc3d on the _old fields (:1897-1907, :1960-1970)
+                old = species_alias(fam, m, iv)[f"{fam}_old(ims,kms,jms,{iv})"]
+                prog.append(("set_physical_bc3d", 0, {"actuals": {"dat": old, "variable_in": "'p'"}}))
+    for fam, members, iv, adv, nth in fams:
+        for n, m in enumerate(members):
+            opts = {"alias": species_alias(fam, m, iv), "scalars": {iv: n + 2, "tenddec": False}}
+            occ = fam + "_tend("
+            prog.append(("rk_scalar_tend", occ, opts))
+            spec = c.specified or c.nested
+            if spec and rk == 1 and (m + "_bxs") in have:
+                prog.append(("relax_bdy_scalar", occ, opts))
+                prog.append(("spec_bdy_scalar", occ, opts))
+            prog.append(("rk_update_scalar", occ, opts))
+            if fam == "moist" and c.specified and not c.have_bcs_moist and m != "moist_qv":
+                prog.append(("flow_dep_bdy", 0, opts))
+    return prog
+
+
+SCALAR_CASES = ["mono", "mono_periodic", "wenopd", "wenopd_periodic", "order64", "open_mapfac", "opts", "periodic_mapfac", "rk2_sym_x", "weno", "diffusion", "diff6", "specified", "nested", "ieva"]
+
+
+@pytest.mark.parametrize("name", SCALAR_CASES)
+@pytest.mark.parametrize("rk", [1, 3])
+def test_rk_scalar_step(name, rk):
+    case = CASES[name]()
+    c = case.config
+    rk = min(rk, c.rk_ord)
+    if c.num_moist + c.num_scalar == 0:
+        pytest.skip("no species")
+    n, *_ = run(case, "rk_scalar_step", rk, scalar_program(c, rk, set(case.fields)), not_compared=("h_tendency", "z_tendency"))
+    assert n >= 15
