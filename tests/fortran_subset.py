@@ -70,7 +70,11 @@ def _fit(a, shape):
     return v
 
 
-RUNTIME = dict(_fit=_fit, f32=f32, f64=np.float64, _idiv=_idiv, _powi=_powi, _sign=_sign, _cos=_m1("cosf"), _sin=_m1("sinf"), _atan=_m1("atanf"),
+def _dim(a, b):
+    return (a - b) if a > b else (a - a)
+
+
+RUNTIME = dict(_fit=_fit, _dim=_dim, f32=f32, f64=np.float64, _idiv=_idiv, _powi=_powi, _sign=_sign, _cos=_m1("cosf"), _sin=_m1("sinf"), _atan=_m1("atanf"),
                _exp=_m1("expf"), _log=_m1("logf"), _sqrt=_m1("sqrtf"), _tanh=_m1("tanhf"), _acos=_m1("acosf"), _asin=_m1("asinf"), _tan=_m1("tanf"),
                _powf=lambda a, b: f32(_libm.powf(float(f32(a)), float(f32(b)))), np=np)
 
@@ -522,6 +526,10 @@ class Routine:
             return (f"int(np.fmod({src[0]}, {src[1]}))", "i") if ty[0] == "i" else (f"f32(np.fmod({src[0]}, {src[1]}))", "r")
         if fn == "dble":
             return f"f64({src[0]})", "d"
+        if fn == "dim":                 # positive difference
+            t = "r" if "r" in ty else "i"
+            a, b = self.conv(src[0], ty[0], t), self.conv(src[1], ty[1], t)
+            return (f"_dim({a}, {b})", t)
         if fn == "ichar":
             return f"ord({src[0]})", "i"
         if fn == "char":

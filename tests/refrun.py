@@ -76,7 +76,8 @@ CONFIG_REAL = ("dampcoef", "zdamp", "w_crit_cfl", "khdif", "kvdif", "epssm", "sm
 
 
 SOURCES = ("dyn_em/module_em.F", "dyn_em/module_advect_em.F", "dyn_em/module_big_step_utilities_em.F", "dyn_em/module_small_step_em.F",
-           "dyn_em/module_bc_em.F", "dyn_em/module_ieva_em.F", "dyn_em/module_diffusion_em.F", "share/module_bc.F")
+           "dyn_em/module_bc_em.F", "dyn_em/module_ieva_em.F", "dyn_em/module_diffusion_em.F", "share/module_bc.F",
+           "phys/module_mp_kessler.F")
 _LIBRARY = None
 
 
@@ -97,6 +98,10 @@ def library(time_step):
         comp = dict([(k, "l") for k in CONFIG_FLAGS] + [(k, "i") for k in CONFIG_INT] + [(k, "r") for k in CONFIG_REAL])
         for k, ct in Config._fields_:            # every namelist entry the path's configuration carries
             comp.setdefault(k, "r" if ct is ctypes.c_float else "i")
+        for ln in open(os.path.join(REF, "Registry", "Registry.EM_COMMON"), errors="replace"):     # and every other rconfig entry, by its type
+            f = ln.split()
+            if len(f) >= 3 and f[0] == "rconfig" and f[1] in ("real", "integer", "logical"):
+                comp.setdefault(f[2].lower(), f[1][0])
         types = {"config_flags": comp}
 
         def fatal(*a, **k):
@@ -120,11 +125,36 @@ def set_species(c):
         g[q] = 1
 
 
+_REGISTRY = None
+
+
+def registry_default(key):
+    """the Registry default of a namelist entry the path's configuration does not carry (mp_tend_lim = 10., no_mp_heating = 0,
+    rad_nudge = 0, ...): the value config_flags holds in a run whose namelist does not mention it"""
+    global _REGISTRY
+    if _REGISTRY is None:
+        _REGISTRY = {}
+        for ln in open(os.path.join(REF, "Registry", "Registry.EM_COMMON"), errors="replace"):
+            f = ln.split()
+            if len(f) >= 6 and f[0] == "rconfig":
+                kind, name, val = f[1], f[2].lower(), f[5]
+                try:
+                    if kind == "real":
+                        _REGISTRY[name] = f32(val.rstrip("fF"))
+                    elif kind == "integer":
+                        _REGISTRY[name] = int(val)
+                    elif kind == "logical":
+                        _REGISTRY[name] = val.lower().strip(".") in ("true", "t")
+                except ValueError:
+                    pass
+    return _REGISTRY.get(key, 0)
+
+
 class _Flags(dict):
-    """config_flags: namelist entries the path does not carry are off / zero (rad_nudge, polar, ...)"""
+    """config_flags: namelist entries the path does not carry have their Registry defaults"""
 
     def __missing__(self, key):
-        return 0
+        return registry_default(key)
 
 
 def _fortran_order(x):
@@ -216,6 +246,9 @@ class RefCall:
                 if dummy in R.optional:
                     continue
                 raise KeyError(f"{R.name}: no actual argument for {dummy}")
+            if not isinstance(actual[dummy], str):       # the value itself
+                args[dummy] = actual[dummy]
+                continue
             a = actual[dummy].strip().lower().replace(" ", "")
             a = self.alias.get(a, a)
             if not isinstance(a, str):               # an alias may give the value itself

@@ -100,13 +100,15 @@ def own(case, name, a):
     return a[d.jds - d.jms:je - d.jms + 1, ..., d.ids - d.ims:ie - d.ims + 1]
 
 
-def compare(case, state, oracle, phase):
-    """-> (n compared, [names that differ])"""
+def compare(case, state, oracle, phase, whole=False):
+    """-> (n compared, [names that differ]); whole: halo included (the boundary fills)"""
     bad, n = [], 0
     for k in sorted(state.fields):
         if k in state.absent or decomp.bdy_side(k):      # boundary arrays are inputs
             continue
-        a, b = own(case, k, state.result(k)), own(case, k, np.asarray(oracle.get(k)))
+        a, b = state.result(k), np.asarray(oracle.get(k))
+        if not whole:
+            a, b = own(case, k, a), own(case, k, b)
         n += 1
         if not np.array_equal(a.view(np.uint32), b.view(np.uint32)):
             both_nan = np.isnan(a) & np.isnan(b)
@@ -116,7 +118,7 @@ def compare(case, state, oracle, phase):
     return n, bad
 
 
-def run(case, phase, rk, program, occurrence=0, extra=None, not_compared=()):
+def run(case, phase, rk, program, occurrence=0, extra=None, not_compared=(), whole=False):
     o, args = at_phase(case, phase, rk, occurrence)
     rk = rk or 1
     scal = rk_scalars(case.config, rk)
@@ -135,7 +137,7 @@ def run(case, phase, rk, program, occurrence=0, extra=None, not_compared=()):
     o.call(phase, *args)
     for k in not_compared:
         st.absent.add(k)
-    n, bad = compare(case, st, o, phase)
+    n, bad = compare(case, st, o, phase, whole)
     assert not bad, f"{phase}: reference source and oracle differ in {bad}"
     return n, st, o
 
@@ -313,3 +315,56 @@ def test_rk_scalar_step(name, rk):
         pytest.skip("no species")
     n, *_ = run(case, "rk_scalar_step", rk, scalar_program(c, rk, set(case.fields)), not_compared=("h_tendency", "z_tendency"))
     assert n >= 15
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the physical boundary fills (share/module_bc.F set_physical_bc3d / 2d through module_bc_em.F's rk_phys_bc_dry_1 / _2): periodic,
+# symmetric, open and specified edges; the WHOLE memory arrays are compared, halo and corners included
+
+BC_CASES = ["open_mapfac", "periodic_mapfac", "b_wave_lid", "rk2_sym_x", "specified", "hill"]
+
+
+@pytest.mark.parametrize("name", BC_CASES)
+def test_rk_phys_bc_dry_1(name):
+    prog = [("rk_phys_bc_dry_1", 0), ("set_physical_bc3d", "grid%rho,"), ("set_physical_bc3d", "grid%al,"), ("set_physical_bc3d", "grid%ph_2,'w'")]
+    n, *_ = run(CASES[name](), "rk_phys_bc_dry_1", None, prog, occurrence=1, whole=True)
+    assert n >= 12
+
+
+@pytest.mark.parametrize("name", BC_CASES)
+def test_rk_phys_bc_dry_2(name):
+    case = CASES[name]()
+    c = case.config
+    prog = [("rk_phys_bc_dry_2", 0)]
+    for fam, members, iv in (("moist", ["moist_" + q for q in ("qv", "qc", "qr")[:c.num_moist]], "im"),
+                             ("scalar", ["scalar_%d" % n for n in range(1, c.num_scalar + 1)], "is")):
+        for m in members:
+            prog.append(("set_physical_bc3d", 0, {"actuals": {"dat": m, "variable_in": "'p'"}}))
+    n, *_ = run(case, "rk_phys_bc_dry_2", None, prog, whole=True)
+    assert n >= 6
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# microphysics (solve_em.F:3623-4115): moist_physics_prep_em, phys/module_mp_kessler.F as microphysics_driver calls it, and
+# moist_physics_finish_em -- expf / logf / powf / sqrtf through the host libm on both sides
+
+@pytest.mark.parametrize("name", ["open_mapfac", "opts", "specified", "weno"])
+def test_microphysics(name):
+    case = parity.with_cloud(CASES[name]())
+    c, d = case.config, case.dims
+    assert c.mp_physics == 1
+    qc = case.fields["moist_qc"]
+    qc[qc > 0] = 2.5e-3                                 # above the autoconversion threshold
+    qr = case.fields.setdefault("moist_qr", np.zeros_like(qc))
+    qr[:, 2:7, d.ide // 2 - d.ims:] = 1.5e-3            # rain falling through cloudy and through dry air (accretion, evaporation, fallout)
+    sz = c.spec_zone if (c.specified or c.nested) else 0          # solve_em.F:3623-3645
+    tile = dict(its=max(d.ips, d.ids + sz), ite=min(d.ipe, d.ide - 1 - sz), jts=max(d.jps, d.jds + sz), jte=min(d.jpe, d.jde - 1 - sz))
+    alias = {"moist(ims,kms,jms,p_qv)": "moist_qv", "moist(ims,kms,jms,p_qc)": "moist_qc"}
+    kess = {"t": "th_phy", "qv": "moist_qv", "qc": "moist_qc", "qr": "moist_qr", "pii": "pi_phy", "dt_in": "dt", "xlv": "xlv", "cp": "cp", "ep2": "ep_2",
+            "kte": min(d.kde, d.kde - 1)}
+    prog = [("moist_physics_prep_em", 0, {"alias": alias, "scalars": {"dtm": f32(c.dt), **tile}}),
+            ("kessler", 0, {"actuals": kess, "scalars": tile}),
+            ("moist_physics_finish_em", 0, {"alias": alias, "scalars": {"dtm": f32(c.dt), **tile}})]
+    n, st, o = run(case, "microphysics", None, prog)
+    assert n >= 20
+    assert np.any(np.asarray(o.get("rainncv")) > 0) and np.any(np.asarray(o.get("moist_qc")) > 0)
