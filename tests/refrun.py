@@ -141,8 +141,8 @@ def registry_default(key):
                 try:
                     if kind == "real":
                         _REGISTRY[name] = f32(val.rstrip("fF"))
-                    elif kind == "integer":
-                        _REGISTRY[name] = int(val)
+                    elif kind == "integer":      # -1 = "must be chosen" (the physics selectors): off, as the namelists of this path set them
+                        _REGISTRY[name] = max(int(val), 0)
                     elif kind == "logical":
                         _REGISTRY[name] = val.lower().strip(".") in ("true", "t")
                 except ValueError:
