@@ -146,7 +146,7 @@ def statements(path, name, defines=None):
     lines = [_strip_comment(ln).rstrip() for ln in lines]
     out, cur, on = [], "", False
     start = re.compile(r"^\s*((real|integer|logical)\s+)?(subroutine|function)\s+%s\b" % re.escape(name), re.I)
-    end = re.compile(r"^\s*end\s*(subroutine|function)\s+%s\b" % re.escape(name), re.I)
+    end = re.compile(r"^\s*end\s*(subroutine|function)(\s+%s\b|\s*$)" % re.escape(name), re.I)
     for ln in lines:
         if not ln.strip():
             continue
@@ -584,11 +584,44 @@ class Routine:
         while n < len(body):
             s = body[n]
             n += 1
-            m = re.match(r"([a-z_]\w*)\s*:\s*(do\b.*|if\b.*)$", s)
+            m = re.match(r"([a-z_]\w*)\s*:\s*(do\b.*|if\b.*|select\b.*)$", s)
             label = None
             if m and not re.match(r"[a-z_]\w*\s*:\s*:", s):
                 label, s = m.group(1), m.group(2)
             if re.match(r"(end\s*do|enddo)\b", s):
+                ind -= 1
+                blocks.pop()
+                continue
+            msel = re.match(r"select\s*case\s*\(", s)
+            if msel:                    # SELECT CASE -> an if / elif chain on the selector's value
+                nsel = sum(1 for b in blocks if b[0] == "select")
+                emit(f"_sel{nsel} = {self.expr(self._paren_after(s, 6))[0]}")
+                emit("if False:")
+                ind += 1
+                emit("pass")
+                blocks.append(("select", label))
+                continue
+            if re.match(r"case\s+default\b", s):
+                ind -= 1
+                emit("else:")
+                ind += 1
+                emit("pass")
+                continue
+            if re.match(r"case\s*\(", s):
+                nsel = sum(1 for b in blocks if b[0] == "select") - 1
+                tests = []
+                for v in self._split(self._paren_after(s, 4)):
+                    if ":" in v:
+                        lo, hi = [t.strip() for t in v.split(":")]
+                        tests.append(" and ".join(([f"_sel{nsel} >= {self.expr(lo)[0]}"] if lo else []) + ([f"_sel{nsel} <= {self.expr(hi)[0]}"] if hi else [])))
+                    else:
+                        tests.append(f"_sel{nsel} == {self.expr(v)[0]}")
+                ind -= 1
+                emit("elif " + " or ".join(f"({t})" for t in tests) + ":")
+                ind += 1
+                emit("pass")
+                continue
+            if re.match(r"end\s*select\b", s):
                 ind -= 1
                 blocks.pop()
                 continue

@@ -111,6 +111,8 @@ def library(time_step):
                  "wrf_message": lambda *a, **k: {}}
         _LIBRARY = Library([os.path.join(REF, f) for f in SOURCES], defines={"EM_CORE": 1}, types=types, constants=_CONSTANTS, hooks=hooks)
         _LIBRARY.globals.update({q: 1 for q in ("p_qv", "p_qc", "p_qr", "p_qi", "p_qs", "p_qg", "p_qh", "p_qni", "p_qnc")})
+        # the NBA stress arrays of sfs_opt > 0 (not on this path): their species indices are 1 = unused
+        _LIBRARY.globals.update({q: 1 for q in ("p_m11", "p_m12", "p_m13", "p_m22", "p_m23", "p_m33", "p_r12", "p_r13", "p_r23", "p_smnsmn")})
     _LIBRARY.time_step = int(time_step)
     return _LIBRARY
 
@@ -238,6 +240,8 @@ class RefCall:
                     kts=d.kds, kte=d.kde)
         tile = {"grid%i_start(ij)": d.ips, "grid%i_end(ij)": d.ipe, "grid%j_start(ij)": d.jps, "grid%j_end(ij)": d.jpe, "k_start": d.kds,
                 "k_end": d.kde}
+        tile["grid%warm_rain"] = c.mp_physics == 1          # mp_init, phys/module_physics_init.F:4463-4481 (Kessler)
+        tile.update({"num_nba_mij": 1, "num_nba_rij": 1, "n_nba_mij": 1, "n_nba_rij": 1})
         tile.update({"num_moist": c.num_moist + 1, "num_scalar": c.num_scalar + 1, "n_moist": c.num_moist + 1})
         tile.update({"num_3d_m": c.num_moist + 1, "num_3d_s": c.num_scalar + 1, "grid%u_frame": f32(0), "grid%v_frame": f32(0),
                      "max_vert_cfl_tmp(ij)": f32(0), "max_horiz_cfl_tmp(ij)": f32(0), "grid%id": 1, "grid%itimestep": 1})

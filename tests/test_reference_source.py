@@ -53,6 +53,18 @@ CASES = {
     "mono_periodic": lambda: parity.with_map_factors(make_case("synthetic", num_scalar=2, scalar_adv_opt=2, moist_adv_opt=2, **S)),
     "wenopd": lambda: make_case("quarter_ss", moist_adv_opt=4, **Q),
     "wenopd_periodic": lambda: parity.with_map_factors(make_case("synthetic", num_scalar=2, scalar_adv_opt=4, moist_adv_opt=3, **S)),
+    "smag2d": lambda: make_case("quarter_ss", diff_opt=1, km_opt=4, **Q),
+    "smag2d_hill": lambda: make_case("hill2d_x", diff_opt=1, km_opt=4, mix_full_fields=1, **H),
+    "diff2": lambda: make_case("quarter_ss", diff_opt=2, km_opt=1, khdif=300.0, kvdif=100.0, tke_drag_coefficient=0.003, tke_heat_flux=0.05, **Q),
+    "diff2_periodic": lambda: parity.with_map_factors(make_case("synthetic", num_scalar=2, diff_opt=2, km_opt=4, c_s=0.5, mix_full_fields=1, **S)),
+    "diff2_hill": lambda: parity.with_surface_fluxes(make_case("hill2d_x", diff_opt=2, km_opt=1, khdif=100.0, kvdif=30.0, isfflx=1, **H)),
+    "smag3d": lambda: parity.with_cloud(parity.with_updraft(make_case("quarter_ss", diff_opt=2, km_opt=3, c_s=0.25, **Q), 30.0)),
+    "smag3d_periodic": lambda: parity.with_updraft(parity.with_map_factors(make_case("synthetic", num_scalar=1, diff_opt=2, km_opt=3, mix_isotropic=1,
+                                                                                     mix_full_fields=1, **S)), 30.0),
+    "tke": lambda: parity.with_tke(parity.with_cloud(parity.with_updraft(make_case("quarter_ss", diff_opt=2, km_opt=2, mix_full_fields=1, **Q), 30.0))),
+    "tke_periodic": lambda: parity.with_tke(parity.with_updraft(parity.with_map_factors(make_case(
+        "synthetic", num_scalar=1, diff_opt=2, km_opt=2, mix_isotropic=1, tke_adv_opt=2, tke_drag_coefficient=0.003, tke_heat_flux=0.05, **S)), 30.0)),
+    "tke_hill": lambda: parity.with_tke(parity.with_surface_fluxes(make_case("hill2d_x", diff_opt=2, km_opt=2, isfflx=1, **H))),
     "diff6": lambda: make_case("quarter_ss", diff_6th_opt=2, **Q),
     "diff6_hill": lambda: make_case("hill2d_x", diff_6th_opt=2, diff_6th_slopeopt=1, diff_6th_thresh=0.004, **H),
     "ieva": lambda: parity.with_updraft(make_case("quarter_ss", nx=12, ny=10, nz=17, zadvect_implicit=1, dt=40.0, time_step=40), 80.0),
@@ -368,3 +380,78 @@ def test_microphysics(name):
     n, st, o = run(case, "microphysics", None, prog)
     assert n >= 20
     assert np.any(np.asarray(o.get("rainncv")) > 0) and np.any(np.asarray(o.get("moist_qc")) > 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the end of the step (solve_em.F:4175-4759): calc_p_rho_phi, the boundary fills of both time levels, spec_bdy_final on every
+# field with boundary arrays, set_w_surface
+
+def final_program(c, have):
+    prog = [("calc_p_rho_phi", 1), ("set_phys_bc_dry_2", 0)]
+    species = [("moist", "moist_" + q, "im", n + 2) for n, q in enumerate(("qv", "qc", "qr")[:c.num_moist])]
+    species += [("scalar", "scalar_%d" % n, "is", n + 1) for n in range(1, c.num_scalar + 1)]
+    for fam, m, iv, idx in species:
+        prog.append(("set_physical_bc3d", 0, {"actuals": {"dat": m, "variable_in": "'p'"}}))
+    if c.specified or c.nested:
+        for f in ("grid%u_2,", "grid%v_2,") + (("grid%w_2,",) if c.nested else ()) + ("grid%t_2,", "grid%ph_2,", "grid%mu_2,"):
+            prog.append(("spec_bdy_final", f))
+        for fam, m, iv, idx in species:
+            if (m + "_bxs") in have and (fam == "moist" or c.nested):
+                prog.append(("spec_bdy_final", fam + "(ims,kms,jms," + iv + ")", {"alias": species_alias(fam, m, iv), "scalars": {iv: idx}}))
+    prog.append(("set_w_surface", 0, {"scalars": {"fill_w_flag": False}}))
+    return prog
+
+
+@pytest.mark.parametrize("name", ["open_mapfac", "periodic_mapfac", "hill", "b_wave_lid", "specified", "nested"])
+def test_end_of_step(name):
+    case = CASES[name]()
+    n, *_ = run(case, "end_of_step", None, final_program(case.config, set(case.fields)))
+    assert n >= 20
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# first_rk_step_part1 / part2 as far as the path goes: phy_prep, compute_diff_metrics and its boundary fills, cal_deform_and_div,
+# calculate_km_kh (calculate_N2 + isotropic / 2-D and 3-D Smagorinsky / TKE closures), phy_bc, tke_rhs, vertical_diffusion_2,
+# horizontal_diffusion_2 (module_diffusion_em.F)
+
+PART1, PART2 = "dyn_em/module_first_rk_step_part1.F", "dyn_em/module_first_rk_step_part2.F"
+
+
+def tke_alias(c):
+    n = c.num_scalar + 1
+    return {"grid%tke_2": f"scalar_{n}", "grid%tke_1": f"scalar_old_{n}", "tke_tend": f"scalar_tend_{n}"} if c.km_opt == 2 else {}
+
+
+def diffusion_program(c):
+    al = tke_alias(c)
+    al.update({"moist(ims,kms,jms,p_qv)": "moist_qv"})
+    o2 = {"path": PART2, "alias": al, "scalars": {"num_chem": 1, "num_tracer": 1}}
+    prog = [("phy_prep", 0, {"path": PART1})]
+    prog.append(("compute_diff_metrics", 0, o2))
+    for text in ("grid%rdzw,", "grid%rdz,", "grid%z,", "grid%zx,", "grid%zy,"):
+        prog.append(("set_physical_bc3d", text, o2))
+    if c.diff_opt == 2:
+        prog.append(("set_physical_bc2d", "grid%ustm,", o2))
+    prog += [("cal_deform_and_div", 0, o2), ("calculate_km_kh", 0, o2), ("phy_bc", 0, o2)]
+    if c.diff_opt == 2:
+        if c.km_opt == 2:
+            prog.append(("tke_rhs", 0, o2))
+        prog += [("vertical_diffusion_2", 0, o2), ("horizontal_diffusion_2", 0, o2)]
+    return prog
+
+
+DIFFUSION_CASES = ["smag2d", "smag2d_hill", "diff2", "diff2_periodic", "diff2_hill", "smag3d", "smag3d_periodic", "tke", "tke_periodic", "tke_hill"]
+
+
+@pytest.mark.parametrize("name", DIFFUSION_CASES)
+def test_diffusion_prep(name):
+    case = CASES[name]()
+    c = case.config
+    # phy_prep's outputs the closures of this configuration never read are not materialised by the oracle (nor by the device)
+    skip = ["pi_phy", "z_at_w", "dz8w"]
+    if c.km_opt not in (2, 3):
+        skip += ["th_phy", "p_phy", "t_phy", "bn2"]
+    if c.diff_opt != 2:
+        skip += ["rho"]
+    n, *_ = run(case, "diffusion_prep", None, diffusion_program(c), not_compared=skip)
+    assert n >= 25
