@@ -13,7 +13,6 @@ That pins oracle/ (and through the GPU parity tests the device code) to the refe
 than to a reading of it.  The reference tree only exists in the build container: without it the tests skip, and
 tests/golden/reference_source.json (written by this file with REFSRC_WRITE=1, read by test_reference_source_golden.py) keeps
 what they established: a checksum of every compared field, which the oracle must reproduce wherever the suite runs."""
-import hashlib
 import json
 import os
 
@@ -21,100 +20,26 @@ import numpy as np
 import pytest
 
 from tests import parity, refrun
-from tests.oracle_lib import Oracle
-from wrf_b200 import decomp, make_case
+from tests.refcases import CASES, at_phase, build, digest, own, rk_scalars
+from wrf_b200 import decomp
 
 pytestmark = pytest.mark.skipif(not refrun.have_reference(), reason="needs the reference tree (/root/reference)")
 f32 = np.float32
 
 
-def small_case(name="quarter_ss", **kw):
-    return parity.with_map_factors(make_case(name, nx=12, ny=10, nz=9, **kw))
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "reference_source.json")
+RECORD = [] if os.environ.get("REFSRC_WRITE") == "1" else None
 
 
-# The configurations of tests/parity.py's catalogue at sizes the translated Fortran (a Python loop nest) finishes in a second or two
-Q = dict(nx=12, ny=10, nz=9)
-S = dict(nx=14, ny=12, nz=9, bubble_lattice=8000.0, noise=0.05)
-H = dict(nx=20, ny=3, nz=9)
-CASES = {
-    "open_mapfac": lambda: parity.with_map_factors(make_case("quarter_ss", w_damping=1, **Q)),
-    "b_wave_lid": lambda: make_case("b_wave", nx=9, ny=13, nz=9, top_lid=1, phi_adv_z=2, w_damping=1, hypsometric_opt=1),
-    "opts": lambda: make_case("quarter_ss", use_theta_m=0, hypsometric_opt=1, damp_opt=3, zdamp=8000.0, dampcoef=0.2, scalar_adv_opt=0,
-                              num_scalar=1, u_scale=1.5, **Q),
-    "periodic_mapfac": lambda: parity.with_map_factors(make_case("synthetic", num_scalar=1, **S)),
-    "rk2_sym_x": lambda: make_case("synthetic", periodic=False, calm=True, rk_ord=2, open_xs=0, open_xe=0, symmetric_xs=1, symmetric_xe=1,
-                                   time_step_sound=4, **S),
-    "diffusion": lambda: make_case("quarter_ss", diff_opt=1, km_opt=1, khdif=500.0, kvdif=100.0, **Q),
-    "diffusion_periodic": lambda: parity.with_map_factors(make_case("synthetic", num_scalar=1, diff_opt=1, km_opt=1, khdif=300.0, kvdif=50.0, **S)),
-    "hill": lambda: make_case("hill2d_x", **H),
-    "order64": lambda: make_case("quarter_ss", h_mom_adv_order=6, v_mom_adv_order=4, h_sca_adv_order=6, v_sca_adv_order=4, **Q),
-    "weno": lambda: make_case("quarter_ss", momentum_adv_opt=3, moist_adv_opt=3, **Q),
-    "mono": lambda: make_case("quarter_ss", moist_adv_opt=2, **Q),
-    "mono_periodic": lambda: parity.with_map_factors(make_case("synthetic", num_scalar=2, scalar_adv_opt=2, moist_adv_opt=2, **S)),
-    "wenopd": lambda: make_case("quarter_ss", moist_adv_opt=4, **Q),
-    "wenopd_periodic": lambda: parity.with_map_factors(make_case("synthetic", num_scalar=2, scalar_adv_opt=4, moist_adv_opt=3, **S)),
-    "smag2d": lambda: make_case("quarter_ss", diff_opt=1, km_opt=4, **Q),
-    "smag2d_hill": lambda: make_case("hill2d_x", diff_opt=1, km_opt=4, mix_full_fields=1, **H),
-    "diff2": lambda: make_case("quarter_ss", diff_opt=2, km_opt=1, khdif=300.0, kvdif=100.0, tke_drag_coefficient=0.003, tke_heat_flux=0.05, **Q),
-    "diff2_periodic": lambda: parity.with_map_factors(make_case("synthetic", num_scalar=2, diff_opt=2, km_opt=4, c_s=0.5, mix_full_fields=1, **S)),
-    "diff2_hill": lambda: parity.with_surface_fluxes(make_case("hill2d_x", diff_opt=2, km_opt=1, khdif=100.0, kvdif=30.0, isfflx=1, **H)),
-    "smag3d": lambda: parity.with_cloud(parity.with_updraft(make_case("quarter_ss", diff_opt=2, km_opt=3, c_s=0.25, **Q), 30.0)),
-    "smag3d_periodic": lambda: parity.with_updraft(parity.with_map_factors(make_case("synthetic", num_scalar=1, diff_opt=2, km_opt=3, mix_isotropic=1,
-                                                                                     mix_full_fields=1, **S)), 30.0),
-    "tke": lambda: parity.with_tke(parity.with_cloud(parity.with_updraft(make_case("quarter_ss", diff_opt=2, km_opt=2, mix_full_fields=1, **Q), 30.0))),
-    "tke_periodic": lambda: parity.with_tke(parity.with_updraft(parity.with_map_factors(make_case(
-        "synthetic", num_scalar=1, diff_opt=2, km_opt=2, mix_isotropic=1, tke_adv_opt=2, tke_drag_coefficient=0.003, tke_heat_flux=0.05, **S)), 30.0)),
-    "tke_hill": lambda: parity.with_tke(parity.with_surface_fluxes(make_case("hill2d_x", diff_opt=2, km_opt=2, isfflx=1, **H))),
-    "specified_tke": lambda: parity.with_boundary_zone(parity.with_tke(parity.with_updraft(make_case(
-        "quarter_ss", nx=16, ny=14, nz=9, specified=1, diff_opt=2, km_opt=2, mix_full_fields=1, **parity.SPEC), 20.0))),
-    "specified_real": lambda: parity.with_boundary_zone(parity.with_map_factors(make_case(
-        "quarter_ss", nx=16, ny=14, nz=9, specified=1, diff_opt=1, km_opt=4, w_damping=1, damp_opt=3, zdamp=8000.0, dampcoef=0.2, num_scalar=1,
-        mp_physics=0, num_moist=1, **parity.SPEC))),
-    "diff6": lambda: make_case("quarter_ss", diff_6th_opt=2, **Q),
-    "diff6_hill": lambda: make_case("hill2d_x", diff_6th_opt=2, diff_6th_slopeopt=1, diff_6th_thresh=0.004, **H),
-    "ieva": lambda: parity.with_updraft(make_case("quarter_ss", nx=12, ny=10, nz=17, zadvect_implicit=1, dt=40.0, time_step=40), 80.0),
-    "backward": lambda: make_case("synthetic", num_scalar=1, scalar_adv_opt=3, momentum_adv_opt=3, time_step=-12, **S),
-    "specified": lambda: parity.with_boundary_zone(make_case("quarter_ss", nx=16, ny=14, nz=9, specified=1, **parity.SPEC)),
-    "nested": lambda: parity.with_boundary_zone(make_case("quarter_ss", nx=16, ny=14, nz=9, nested=1, num_scalar=1, **parity.SPEC)),
-}
-
-
-def at_phase(case, target, rk=None, occurrence=0):
-    """an oracle advanced to just before the occurrence-th `target` phase (of Runge-Kutta stage rk) of the first step"""
-    o = Oracle(case)
-    o.start_domain()
-    if case.config.specified or case.config.nested:
-        o.set_dtbc(case.config.dt)
-    n = 0
-    for ph, args in parity.phase_sequence(case):
-        if ph == target and (rk is None or (args and args[0] == rk)):
-            if n == occurrence:
-                return o, args
-            n += 1
-        o.call(ph, *args)
-    raise KeyError(target)
-
-
-def rk_scalars(c, rk):
-    """dt_rk, dts_rk, number_of_small_timesteps of solve_em.F:585-615"""
-    nss = c.time_step_sound
-    dt = f32(c.dt)
-    dts = f32(dt / f32(nss))
-    if c.rk_ord == 3 and rk == 1:
-        return dict(dt_rk=f32(dt / f32(3.0)), dts_rk=f32(dt / f32(3.0)), number_of_small_timesteps=1)
-    if rk < c.rk_ord:
-        return dict(dt_rk=f32(f32(0.5) * dt), dts_rk=dts, number_of_small_timesteps=nss // 2)
-    return dict(dt_rk=dt, dts_rk=dts, number_of_small_timesteps=nss)
-
-
-def own(case, name, a):
-    """the points of the field the domain owns (the halo is the boundary fills' and exchanges' business)"""
-    d = case.dims
-    ie = d.ide if name in decomp.XSTAG else d.ide - 1
-    je = d.jde if name in decomp.YSTAG else d.jde - 1
-    if a.ndim == 1:
-        return a
-    return a[d.jds - d.jms:je - d.jms + 1, ..., d.ids - d.ims:ie - d.ims + 1]
+@pytest.fixture(scope="module", autouse=True)
+def _write_golden():
+    """REFSRC_WRITE=1 python -m pytest tests/test_reference_source.py  regenerates tests/golden/reference_source.json: for every
+    comparison made here, a digest of each field as the REFERENCE's routines left it (own points, or the whole array for the boundary
+    fills).  tests/test_reference_source_golden.py holds the oracle to those digests where the reference tree is absent."""
+    yield
+    if RECORD is not None:
+        with open(GOLDEN, "w") as f:
+            json.dump({"generator": "REFSRC_WRITE=1 python -m pytest tests/test_reference_source.py", "records": RECORD}, f, separators=(",", ":"), sort_keys=True)
 
 
 def compare(case, state, oracle, phase, whole=False):
@@ -137,7 +62,7 @@ def compare(case, state, oracle, phase, whole=False):
 
 def run(case, phase, rk, program, occurrence=0, extra=None, not_compared=(), whole=False):
     o, args = at_phase(case, phase, rk, occurrence)
-    rk = rk or 1
+    rk_in, rk = rk, rk or 1
     scal = rk_scalars(case.config, rk)
     scal.update(rk_step=rk, rk_order=case.config.rk_ord, iteration=args[1] if len(args) > 1 else 1)
     if case.config.specified or case.config.nested:
@@ -156,6 +81,14 @@ def run(case, phase, rk, program, occurrence=0, extra=None, not_compared=(), who
         st.absent.add(k)
     n, bad = compare(case, st, o, phase, whole)
     assert not bad, f"{phase}: reference source and oracle differ in {bad}"
+    if RECORD is not None:
+        fields = {}
+        for k in sorted(st.fields):
+            if k in st.absent or decomp.bdy_side(k):
+                continue
+            a = st.result(k)
+            fields[k] = digest(a if whole else own(case, k, a))
+        RECORD.append({"case": case.refname, "phase": phase, "rk": rk_in, "occurrence": occurrence, "whole": whole, "fields": fields})
     return n, st, o
 
 
@@ -166,7 +99,7 @@ def run(case, phase, rk, program, occurrence=0, extra=None, not_compared=(), who
                                               ("advance_mu_t", 3, 35), ("advance_w", 1, 35), ("advance_w", 3, 35), ("sumflux", 1, 20),
                                               ("sumflux", 2, 20), ("sumflux", 3, 20)])
 def test_acoustic_step(routine, rk, least):
-    n, *_ = run(small_case(), routine, rk, [(routine, 0)], occurrence=1 if rk > 1 else 0)
+    n, *_ = run(build("small"), routine, rk, [(routine, 0)], occurrence=1 if rk > 1 else 0)
     assert n >= least
 
 
@@ -196,7 +129,7 @@ def tendency_program(c, rk):
 @pytest.mark.parametrize("name", sorted(CASES))
 @pytest.mark.parametrize("rk", [1, 2, 3])
 def test_rk_tendency(name, rk):
-    case = CASES[name]()
+    case = build(name)
     if rk > case.config.rk_ord:
         pytest.skip("rk_ord 2")
     prog, skip = tendency_program(case.config, rk)
@@ -215,7 +148,7 @@ SOME = ["open_mapfac", "b_wave_lid", "opts", "periodic_mapfac", "rk2_sym_x", "hi
 @pytest.mark.parametrize("name", SOME)
 @pytest.mark.parametrize("rk", [1, 2])
 def test_rk_step_prep(name, rk):
-    n, *_ = run(CASES[name](), "rk_step_prep", rk, [("rk_step_prep", 0)])
+    n, *_ = run(build(name), "rk_step_prep", rk, [("rk_step_prep", 0)])
     assert n >= 25
 
 
@@ -223,14 +156,14 @@ def test_rk_step_prep(name, rk):
 @pytest.mark.parametrize("rk", [1, 2])
 def test_small_step_prep(name, rk):
     """small_step_prep, calc_p_rho(step 0) and calc_coef_w (solve_em.F:1100-1175)"""
-    n, *_ = run(CASES[name](), "small_step_prep", rk, [("small_step_prep", 0), ("calc_p_rho", 0), ("calc_coef_w", 0)])
+    n, *_ = run(build(name), "small_step_prep", rk, [("small_step_prep", 0), ("calc_p_rho", 0), ("calc_coef_w", 0)])
     assert n >= 40
 
 
 @pytest.mark.parametrize("name", SOME)
 def test_calc_p_rho(name):
     """the pressure / inverse density diagnosis inside the acoustic loop (solve_em.F:1623), second small step of stage 2 or 3"""
-    case = CASES[name]()
+    case = build(name)
     n, *_ = run(case, "calc_p_rho", None, [("calc_p_rho", 1)], occurrence=2, extra={"iteration": 2})
     assert n >= 10
 
@@ -238,7 +171,7 @@ def test_calc_p_rho(name):
 @pytest.mark.parametrize("name", SOME)
 @pytest.mark.parametrize("rk", [1, 3])
 def test_small_step_finish(name, rk):
-    case = CASES[name]()
+    case = build(name)
     rk = min(rk, case.config.rk_ord)
     n, *_ = run(case, "small_step_finish", rk, [("calc_mu_uv_1", 0), ("small_step_finish", 0)])
     assert n >= 30
@@ -246,7 +179,7 @@ def test_small_step_finish(name, rk):
 
 @pytest.mark.parametrize("name", SOME)
 def test_calc_p_rho_phi(name):
-    n, *_ = run(CASES[name](), "calc_p_rho_phi", None, [("calc_p_rho_phi", 0)], occurrence=1)
+    n, *_ = run(build(name), "calc_p_rho_phi", None, [("calc_p_rho_phi", 0)], occurrence=1)
     assert n >= 10
 
 
@@ -268,7 +201,7 @@ def acoustic_program(c, routine):
 @pytest.mark.parametrize("name", ["specified", "nested", "periodic_mapfac", "b_wave_lid", "hill", "rk2_sym_x"])
 @pytest.mark.parametrize("routine", ["advance_uv", "advance_mu_t", "advance_w", "sumflux"])
 def test_acoustic_step_configurations(name, routine):
-    case = CASES[name]()
+    case = build(name)
     rk = case.config.rk_ord
     n, *_ = run(case, routine, rk, acoustic_program(case.config, routine), occurrence=1)
     assert n >= 20
@@ -336,7 +269,7 @@ SCALAR_CASES = ["smag2d", "diff2_periodic", "tke", "tke_periodic", "tke_hill", "
 @pytest.mark.parametrize("name", SCALAR_CASES)
 @pytest.mark.parametrize("rk", [1, 3])
 def test_rk_scalar_step(name, rk):
-    case = CASES[name]()
+    case = build(name)
     c = case.config
     rk = min(rk, c.rk_ord)
     if c.num_moist + c.num_scalar == 0:
@@ -360,13 +293,13 @@ BC_CASES = ["open_mapfac", "periodic_mapfac", "b_wave_lid", "rk2_sym_x", "specif
 @pytest.mark.parametrize("name", BC_CASES)
 def test_rk_phys_bc_dry_1(name):
     prog = [("rk_phys_bc_dry_1", 0), ("set_physical_bc3d", "grid%rho,"), ("set_physical_bc3d", "grid%al,"), ("set_physical_bc3d", "grid%ph_2,'w'")]
-    n, *_ = run(CASES[name](), "rk_phys_bc_dry_1", None, prog, occurrence=1, whole=True)
+    n, *_ = run(build(name), "rk_phys_bc_dry_1", None, prog, occurrence=1, whole=True)
     assert n >= 12
 
 
 @pytest.mark.parametrize("name", BC_CASES)
 def test_rk_phys_bc_dry_2(name):
-    case = CASES[name]()
+    case = build(name)
     c = case.config
     prog = [("rk_phys_bc_dry_2", 0)]
     for fam, members, iv in (("moist", ["moist_" + q for q in ("qv", "qc", "qr")[:c.num_moist]], "im"),
@@ -381,15 +314,11 @@ def test_rk_phys_bc_dry_2(name):
 # microphysics (solve_em.F:3623-4115): moist_physics_prep_em, phys/module_mp_kessler.F as microphysics_driver calls it, and
 # moist_physics_finish_em -- expf / logf / powf / sqrtf through the host libm on both sides
 
-@pytest.mark.parametrize("name", ["open_mapfac", "opts", "specified", "weno"])
+@pytest.mark.parametrize("name", ["rain_open_mapfac", "rain_opts", "rain_specified", "rain_weno"])
 def test_microphysics(name):
-    case = parity.with_cloud(CASES[name]())
+    case = build(name)
     c, d = case.config, case.dims
     assert c.mp_physics == 1
-    qc = case.fields["moist_qc"]
-    qc[qc > 0] = 2.5e-3                                 # above the autoconversion threshold
-    qr = case.fields.setdefault("moist_qr", np.zeros_like(qc))
-    qr[:, 2:7, d.ide // 2 - d.ims:] = 1.5e-3            # rain falling through cloudy and through dry air (accretion, evaporation, fallout)
     sz = c.spec_zone if (c.specified or c.nested) else 0          # solve_em.F:3623-3645
     tile = dict(its=max(d.ips, d.ids + sz), ite=min(d.ipe, d.ide - 1 - sz), jts=max(d.jps, d.jds + sz), jte=min(d.jpe, d.jde - 1 - sz))
     alias = {"moist(ims,kms,jms,p_qv)": "moist_qv", "moist(ims,kms,jms,p_qc)": "moist_qc"}
@@ -425,7 +354,7 @@ def final_program(c, have):
 
 @pytest.mark.parametrize("name", ["open_mapfac", "periodic_mapfac", "hill", "b_wave_lid", "specified", "nested"])
 def test_end_of_step(name):
-    case = CASES[name]()
+    case = build(name)
     n, *_ = run(case, "end_of_step", None, final_program(case.config, set(case.fields)))
     assert n >= 20
 
@@ -466,7 +395,7 @@ DIFFUSION_CASES = ["smag2d", "smag2d_hill", "diff2", "diff2_periodic", "diff2_hi
 
 @pytest.mark.parametrize("name", DIFFUSION_CASES)
 def test_diffusion_prep(name):
-    case = CASES[name]()
+    case = build(name)
     c = case.config
     # phy_prep's outputs the closures of this configuration never read are not materialised by the oracle (nor by the device)
     skip = ["pi_phy", "z_at_w", "dz8w"]

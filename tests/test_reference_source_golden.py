@@ -1,0 +1,41 @@
+"""The oracle against what the reference's own source computed (tests/test_reference_source.py), from a committed fixture.
+
+tests/golden/reference_source.json holds, for every phase / Runge-Kutta stage / configuration that module compares, a digest of every
+field as the REFERENCE's Fortran routines left it when they were executed in the build container (through tests/fortran_subset.py, on
+the state an Oracle had reached).  This module needs no reference tree: it brings an Oracle to the same point, runs the oracle's phase
+and requires the same digests -- so the pin travels with the repository (the GPU box has no /root/reference), and a change of the
+oracle, the compiler or libm that moves a single bit of any of these fields fails here.
+
+Regenerate (build container only):  REFSRC_WRITE=1 python -m pytest tests/test_reference_source.py"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.refcases import at_phase, build, digest, own
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "reference_source.json")
+RECORDS = json.load(open(GOLDEN))["records"] if os.path.exists(GOLDEN) else []
+
+
+def test_fixture_is_there():
+    assert len(RECORDS) >= 200, "tests/golden/reference_source.json is missing or short: regenerate it in the build container"
+    phases = {r["phase"] for r in RECORDS}
+    assert {"rk_step_prep", "rk_tendency", "small_step_prep", "advance_uv", "advance_mu_t", "advance_w", "sumflux", "calc_p_rho",
+            "small_step_finish", "rk_scalar_step", "calc_p_rho_phi", "microphysics", "diffusion_prep", "end_of_step", "rk_phys_bc_dry_1",
+            "rk_phys_bc_dry_2"} <= phases
+
+
+@pytest.mark.parametrize("n", range(len(RECORDS)))
+def test_oracle_reproduces_reference_digest(n):
+    r = RECORDS[n]
+    case = build(r["case"])
+    o, args = at_phase(case, r["phase"], r["rk"], r["occurrence"])
+    o.call(r["phase"], *args)
+    bad = []
+    for k, want in r["fields"].items():
+        a = np.asarray(o.get(k))
+        if digest(a if r["whole"] else own(case, k, a)) != want:
+            bad.append(k)
+    assert not bad, f"{r['case']} {r['phase']} rk {r['rk']}: the oracle no longer equals the reference source in {bad}"
