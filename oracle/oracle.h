@@ -4,12 +4,16 @@
 // tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs may load it, and only as the checker / CPU baseline.
 //
-// PARITY UNPINNED: the reference ships no golden outputs for this path
-//  and no Fortran compiler exists in the build container, so this
-// restatement could not be diffed against wrf.exe here.  It follows the
-// reference routine by routine (file:line cited on each function), in real*4,
-// Fortran evaluation order, compiled with -ffp-contract=off like the GNU stanza
-// of arch/configure.defaults:774-814 (no FMA).
+// PARITY PIN: the reference ships no golden outputs for this path
+// and no Fortran compiler exists in the build container, so this restatement
+// could not be diffed against wrf.exe.  It is pinned instead to the reference's
+// own routines EXECUTED FROM THEIR SOURCE (tests/fortran_subset.py translates
+// them with real*4 semantics; tests/test_reference_source.py compares every phase
+// of the step bit for bit over 38 configurations; the resulting digests travel as
+// tests/golden/reference_source.json).  It follows the reference routine by
+// routine (file:line cited on each function), in real*4, Fortran evaluation
+// order, compiled with -ffp-contract=off like the GNU stanza of
+// arch/configure.defaults:774-814 (no FMA).
 #pragma once
 #include <cmath>
 #include <cstring>

@@ -810,7 +810,10 @@ class Routine:
         else:
             emit(f"v_{nm} = {val}")
 
+    calls = 0          # how often the routine ran (the inventory of tests/golden/reference_source.json)
+
     def __call__(self, **args):
+        self.calls += 1
         if self.fn is None:
             ns = dict(RUNTIME)
             ns["_G"] = self.library.globals if self.library is not None else {}

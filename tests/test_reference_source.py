@@ -39,7 +39,9 @@ def _write_golden():
     yield
     if RECORD is not None:
         with open(GOLDEN, "w") as f:
-            json.dump({"generator": "REFSRC_WRITE=1 python -m pytest tests/test_reference_source.py", "records": RECORD}, f, separators=(",", ":"), sort_keys=True)
+            ran = {k: r.calls for k, r in sorted(refrun.library(1).cache.items()) if r.calls}
+            json.dump({"generator": "REFSRC_WRITE=1 python -m pytest tests/test_reference_source.py", "records": RECORD,
+                       "routines_executed": ran}, f, separators=(",", ":"), sort_keys=True)
 
 
 def compare(case, state, oracle, phase, whole=False):
@@ -142,7 +144,7 @@ def test_rk_tendency(name, rk):
 # ---------------------------------------------------------------------------------------------------------------------
 # the brackets of the acoustic loop and the diagnostics
 
-SOME = ["open_mapfac", "b_wave_lid", "opts", "periodic_mapfac", "rk2_sym_x", "hill", "specified"]
+SOME = ["les", "open_mapfac", "b_wave_lid", "opts", "periodic_mapfac", "rk2_sym_x", "hill", "specified"]
 
 
 @pytest.mark.parametrize("name", SOME)
@@ -263,7 +265,7 @@ def scalar_program(c, rk, have):
     return prog
 
 
-SCALAR_CASES = ["smag2d", "diff2_periodic", "tke", "tke_periodic", "tke_hill", "specified_tke", "mono", "mono_periodic", "wenopd", "wenopd_periodic", "order64", "open_mapfac", "opts", "periodic_mapfac", "rk2_sym_x", "weno", "diffusion", "diff6", "specified", "nested", "ieva"]
+SCALAR_CASES = ["les", "smag2d", "diff2_periodic", "tke", "tke_periodic", "tke_hill", "specified_tke", "mono", "mono_periodic", "wenopd", "wenopd_periodic", "order64", "open_mapfac", "opts", "periodic_mapfac", "rk2_sym_x", "weno", "diffusion", "diff6", "specified", "nested", "ieva"]
 
 
 @pytest.mark.parametrize("name", SCALAR_CASES)
