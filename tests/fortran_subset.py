@@ -567,7 +567,10 @@ class Routine:
             src, t = self.expr(init)
             emit(f"v_{nm} = {self.conv(src, t, self.kind[nm])}")
         for nm, k in self.kind.items():
-            if nm in self.dummies or nm in self.params or k in "tc":
+            if nm in self.dummies or nm in self.params or k == "t":
+                continue
+            if k == "c":
+                emit(f"v_{nm} = ''")
                 continue
             if nm in self.dims:
                 shape = []

@@ -53,6 +53,9 @@ CASES = {
     "specified_real": lambda: parity.with_boundary_zone(parity.with_map_factors(make_case(
         "quarter_ss", nx=16, ny=14, nz=9, specified=1, diff_opt=1, km_opt=4, w_damping=1, damp_opt=3, zdamp=8000.0, dampcoef=0.2, num_scalar=1,
         mp_physics=0, num_moist=1, **parity.SPEC))),
+    "ieva_wdamp": lambda: parity.with_updraft(make_case("quarter_ss", nx=12, ny=10, nz=17, zadvect_implicit=1, dt=40.0, time_step=40, w_damping=1,
+                                                        w_crit_cfl=2.0, use_adaptive_time_step=1), 80.0, conv=60.0),
+    "adaptive": lambda: parity.with_updraft(parity.with_map_factors(make_case("quarter_ss", w_damping=1, use_adaptive_time_step=1, **Q)), 20.0),
     "les": lambda: parity.with_map_factors(make_case("les", **Q)),          # pert_coriolis, PD tracers, passive qv
     "diff6": lambda: make_case("quarter_ss", diff_6th_opt=2, **Q),
     "rain_open_mapfac": lambda: rainy(CASES["open_mapfac"]()),

@@ -108,7 +108,7 @@ def library(time_step):
             raise RuntimeError("wrf_error_fatal called by the reference routine")
 
         hooks = {"nl_get_time_step": lambda _id, _ts: {1: _LIBRARY.time_step}, "wrf_error_fatal": fatal, "wrf_debug": lambda *a, **k: {},
-                 "wrf_message": lambda *a, **k: {}}
+                 "wrf_message": lambda *a, **k: {}, "get_current_time_string": lambda *a, **k: {}, "get_current_grid_name": lambda *a, **k: {}}
         _LIBRARY = Library([os.path.join(REF, f) for f in SOURCES], defines={"EM_CORE": 1}, types=types, constants=_CONSTANTS, hooks=hooks)
         _LIBRARY.globals.update({q: 1 for q in ("p_qv", "p_qc", "p_qr", "p_qi", "p_qs", "p_qg", "p_qh", "p_qni", "p_qnc")})
         # the NBA stress arrays of sfs_opt > 0 (not on this path): their species indices are 1 = unused
@@ -172,6 +172,7 @@ class RefState:
         self.have = set(oracle.names()) | {"moist", "moist_old", "moist_tend", "scalar", "scalar_old", "scalar_tend"}
         self.fields = {}
         self.absent = set()            # array actuals the oracle has no field for (bound to zeros)
+        self.returns = []              # (routine, {scalar dummy: value after the call}) of every call made on this state
 
     def groups(self):
         """the 4-D species arrays of the Registry (moist, scalar, their _old and _tend forms) -> the oracle's per-species fields;

@@ -74,8 +74,9 @@ def run(case, phase, rk, program, occurrence=0, extra=None, not_compared=(), who
     for step in program:
         routine, occ = step[0], step[1]
         opts = step[2] if len(step) > 2 else {}
-        refrun.RefCall(routine, occ, opts.get("path", "dyn_em/solve_em.F"), opts.get("alias"), opts.get("actuals")).run(
+        ret = refrun.RefCall(routine, occ, opts.get("path", "dyn_em/solve_em.F"), opts.get("alias"), opts.get("actuals")).run(
             st, **{**scal, **opts.get("scalars", {})})
+        st.returns.append((routine, ret))            # the scalar dummies after the call (max_vert_cfl, ...)
     changed = [k for k in st.fields if k not in st.absent and not decomp.bdy_side(k) and not np.array_equal(st.result(k), np.asarray(o.get(k)), equal_nan=True)]
     assert changed, f"{phase}: the reference routines changed nothing (a vacuous comparison)"
     o.call(phase, *args)
@@ -143,6 +144,22 @@ def test_rk_tendency(name, rk):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # the brackets of the acoustic loop and the diagnostics
+
+@pytest.mark.parametrize("name", ["ieva_wdamp", "adaptive"])
+def test_w_damp_cfl_maxima(name):
+    """max_vert_cfl / max_horiz_cfl as w_damp returns them through rk_tendency (module_big_step_utilities_em.F:2503-2711), the input of
+    the adaptive time step (solve_em.F:914-930); with IEVA the damping starts at w_crit_cfl"""
+    case = build(name)
+    prog, skip = tendency_program(case.config, 1)
+    o, args = at_phase(case, "rk_tendency", 1)
+    o.max_cfl(reset=True)
+    n, st, o = run(case, "rk_tendency", 1, prog, not_compared=skip)
+    ret = dict(st.returns)["rk_tendency"]
+    mv, mh = o.max_cfl()
+    assert f32(ret["max_vert_cfl"]) == f32(mv) and f32(ret["max_horiz_cfl"]) == f32(mh) and mv > 0 and mh > 0
+    if name == "ieva_wdamp":
+        assert mv > 1.0, "the case must have vertical Courant numbers above the explicit limit"
+
 
 SOME = ["les", "open_mapfac", "b_wave_lid", "opts", "periodic_mapfac", "rk2_sym_x", "hill", "specified"]
 
