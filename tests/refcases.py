@@ -131,3 +131,19 @@ def own(case, name, a):
     return a[d.jds - d.jms:je - d.jms + 1, ..., d.ids - d.ims:ie - d.ims + 1]
 
 
+
+
+def oracle_feeder(adv_opt, loops, at=()):
+    """rk_scalar_step(1..3) per loop with the periodic fill at the end of the loop only, as the program does -> {loop: column}, row"""
+    o = Oracle(parity.tophat_case(adv_opt))
+    o.start_domain()
+    d = o.case.dims
+    row = lambda: np.asarray(o.get("scalar_1"))[2 - d.jms, 0, 1 - d.ims:91 - d.ims + 1]
+    cols = {}
+    for n in range(1, loops + 1):
+        for rk in (1, 2, 3):
+            o.call("rk_scalar_step", rk)
+        o.bc("scalar_1", "p")
+        if n in at:
+            cols[n] = [int(x) for x in np.rint((row() * f32(100)).astype(f32))]
+    return cols, row().copy()

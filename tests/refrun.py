@@ -23,9 +23,9 @@ def have_reference():
     return os.path.isdir(os.path.join(REF, "dyn_em"))
 
 
-def call_statement(routine, occurrence=0, path="dyn_em/solve_em.F"):
+def call_statement(routine, occurrence=0, path="dyn_em/solve_em.F", defines=None):
     """the occurrence-th `CALL routine (...)` of a reference file as (positional actuals, keyword actuals)"""
-    lines = [_strip_comment(ln).rstrip() for ln in _cpp(open(os.path.join(REF, path), errors="replace").read().split("\n"), {"DM_PARALLEL": 1})]
+    lines = [_strip_comment(ln).rstrip() for ln in _cpp(open(os.path.join(REF, path), errors="replace").read().split("\n"), defines or {"DM_PARALLEL": 1})]
     cur, found = "", []
     for ln in lines:
         t = ln.strip()

@@ -20,7 +20,7 @@ import numpy as np
 import pytest
 
 from tests import parity, refrun
-from tests.refcases import CASES, at_phase, build, digest, own, rk_scalars
+from tests.refcases import CASES, at_phase, build, digest, oracle_feeder, own, rk_scalars
 from wrf_b200 import decomp
 
 pytestmark = pytest.mark.skipif(not refrun.have_reference(), reason="needs the reference tree (/root/reference)")
@@ -424,3 +424,33 @@ def test_diffusion_prep(name):
         skip += ["rho"]
     n, *_ = run(case, "diffusion_prep", None, diffusion_program(c), not_compared=skip)
     assert n >= 25
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's own kernel harness, PROGRAM feeder (module_advect_em.F:10567-10870, -DADVECT_KERNEL), with its five
+# scalar_adv_opt settings: its advection kernels run from source inside the program's own loop (tests/feeder_ref.py), against
+# the oracle's rk_scalar_step driven the same way.  The harness's output -- the integer columns of NNNNNN.txt -- must be
+# reproduced exactly; the float rows agree to rounding (the program updates with dt*tendency/3., the model with (dt/3)*tendency).
+
+FEEDER_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "feeder_columns.json")
+
+
+@pytest.mark.parametrize("adv_opt", [0, 1, 2, 3, 4])
+def test_feeder_harness(adv_opt):
+    from tests.feeder_ref import Feeder
+    write = os.environ.get("REFSRC_FEEDER") == "1"         # REFSRC_FEEDER=1: the program's first output file, 000200.txt (10 minutes)
+    marks = (100, 200) if write else (8,)
+    F = Feeder(adv_opt)
+    ref = {}
+    for n in range(1, marks[-1] + 1):
+        F.loop()
+        if n in marks:
+            ref[n] = F.column()
+    cols, row = oracle_feeder(adv_opt, marks[-1], marks)
+    assert cols == ref, f"scalar_adv_opt {adv_opt}: the harness's output columns differ"
+    assert np.abs(row - F.row()).max() < 1e-5 and np.abs(F.row()).max() > 0.9
+    if write:
+        have = json.load(open(FEEDER_GOLDEN)) if os.path.exists(FEEDER_GOLDEN) else {}
+        have[str(adv_opt)] = {str(k): v for k, v in ref.items()}
+        have["generator"] = "REFSRC_FEEDER=1 python -m pytest tests/test_reference_source.py -k feeder_harness"
+        json.dump(have, open(FEEDER_GOLDEN, "w"), separators=(",", ":"), sort_keys=True)

@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.refcases import at_phase, build, digest, own
+from tests.refcases import at_phase, build, digest, oracle_feeder, own
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "reference_source.json")
 RECORDS = json.load(open(GOLDEN))["records"] if os.path.exists(GOLDEN) else []
@@ -39,3 +39,21 @@ def test_oracle_reproduces_reference_digest(n):
         if digest(a if r["whole"] else own(case, k, a)) != want:
             bad.append(k)
     assert not bad, f"{r['case']} {r['phase']} rk {r['rk']}: the oracle no longer equals the reference source in {bad}"
+
+
+FEEDER_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "feeder_columns.json")
+FEEDER = json.load(open(FEEDER_GOLDEN)) if os.path.exists(FEEDER_GOLDEN) else {}
+
+
+@pytest.mark.parametrize("adv_opt", [0, 1, 2, 3, 4])
+def test_feeder_output_files(adv_opt):
+    """PROGRAM feeder (dyn_em/module_advect_em.F:10567, the reference's own kernel harness): what it writes to 000200.txt -- NINT(field*100)
+    along x after 200 trips of its loop -- for each of its five scalar_adv_opt settings, obtained by running the reference's kernels from
+    source inside the program's loop (tests/feeder_ref.py; fixture tests/golden/feeder_columns.json).  The oracle's rk_scalar_step, driven
+    the same way, must write the same file; also half way (loop 100)."""
+    assert str(adv_opt) in FEEDER, "tests/golden/feeder_columns.json is missing: REFSRC_FEEDER=1 python -m pytest tests/test_reference_source.py -k feeder_harness"
+    want = {int(k): v for k, v in FEEDER[str(adv_opt)].items()}
+    cols, row = oracle_feeder(adv_opt, max(want), tuple(want))
+    assert cols == want
+    hat = np.array(want[200])
+    assert hat.max() >= 95 and (hat.min() >= 0 if adv_opt in (1, 2, 4) else hat.min() < 0)     # PD / monotonic / WENO-PD stay non-negative

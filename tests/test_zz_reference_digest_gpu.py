@@ -71,3 +71,28 @@ def test_device_reproduces_reference_digests(name):
         assert all(r["seen"] > r["occurrence"] for r in recs), "a recorded phase was never reached"
     finally:
         s.close()
+
+
+FEEDER_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "feeder_columns.json")
+FEEDER = json.load(open(FEEDER_GOLDEN)) if os.path.exists(FEEDER_GOLDEN) else {}
+
+
+@pytest.mark.parametrize("adv_opt", [0, 1, 2, 3, 4])
+def test_device_writes_the_feeder_output_files(adv_opt):
+    """PROGRAM feeder, the reference's own kernel harness (dyn_em/module_advect_em.F:10567): the device's scalar step, driven as the program
+    drives its kernels, must write the files the reference's kernels wrote (tests/golden/feeder_columns.json, made by tests/feeder_ref.py)."""
+    want = {int(k): v for k, v in FEEDER[str(adv_opt)].items()}
+    case = parity.tophat_case(adv_opt)
+    s = Solver(case)
+    try:
+        s.start_domain()
+        d = case.dims
+        for n in range(1, max(want) + 1):
+            for rk in (1, 2, 3):
+                s.call("rk_scalar_step", rk)
+            s.bc("scalar_1", "p")
+            if n in want:
+                row = np.asarray(s.get("scalar_1"))[2 - d.jms, 0, 1 - d.ims:91 - d.ims + 1]
+                assert [int(x) for x in np.rint((row * np.float32(100)).astype(np.float32))] == want[n], f"loop {n}"
+    finally:
+        s.close()
