@@ -56,4 +56,8 @@ def test_feeder_output_files(adv_opt):
     cols, row = oracle_feeder(adv_opt, max(want), tuple(want))
     assert cols == want
     hat = np.array(want[200])
-    assert hat.max() >= 95 and (hat.min() >= 0 if adv_opt in (1, 2, 4) else hat.min() < 0)     # PD / monotonic / WENO-PD stay non-negative
+    assert hat.max() >= 95
+    if adv_opt in (1, 2, 4):
+        assert hat.min() >= 0            # PD / monotonic / WENO-PD stay non-negative
+    if adv_opt == 0:
+        assert hat.min() < 0             # the unlimited 5th-order scheme undershoots
