@@ -376,6 +376,14 @@ class Routine:
             return True
         if re.match(r"character\s*\*\s*\d+", s):        # message buffers: never part of the arithmetic
             return True
+        mp = re.match(r"parameter\s*\((.*)\)\s*$", s)     # old style: INTEGER n / PARAMETER (n = 1000)
+        if mp:
+            for ent in self._split(mp.group(1)):
+                nm, init = [x.strip() for x in ent.split("=", 1)]
+                if nm not in self.kind:
+                    self.kind[nm] = "i" if nm[0] in "ijklmn" else "r"
+                self.params[nm] = init
+            return True
         m = None
         mt = re.match(r"(real|integer|logical|double precision|character|type\s*\(\s*\w+\s*\))\s*(\([^)]*\))?\s*(,|::)", s)
         if mt and "::" in s:

@@ -4,15 +4,18 @@ input_jet are read as the reference reads them, and the initial state follows dy
 read_input_jet :2200) and the first-trip diagnosis of start_domain_em (dyn_em/start_em.F:780-845: al and p re-derived from
 ph with the model's own hypsometric option), statement for statement in real*4.
 
-Differences that cannot be avoided without the reference's compiler, both documented where they occur:
+Difference that cannot be avoided without the reference's compiler, documented where it occurs:
   * em_les seeds its perturbation with RANDOM_NUMBER (module_initialize_ideal.F:1385): the stream is gfortran's; a
     deterministic hash of (i, j) takes its place (same amplitude, same four levels);
-  * transcendental functions are numpy's float32 ones (the time step itself uses the bit-exact libm restatement, the
-    initial state is data).
+  (x**y, EXP, LOG, COS go to the host libm's float routines -- powf, expf, logf, cosf -- exactly as gfortran's real*4 intrinsics do;
+  numpy's own float32 versions differ from them in the last bit now and then.  get_sounding / get_sounding_b_wave /
+  calc_jet_sounding below equal the reference's routines bit for bit on the shipped inputs: tests/test_reference_init.py.)
 
 Host language note: this is the role of ideal.exe, which is outside the hot path; Python is enough here."""
 from __future__ import annotations
 
+import ctypes
+import ctypes.util
 import math
 import os
 import re
@@ -22,6 +25,23 @@ import numpy as np
 
 from . import ideal
 from .ideal import F, Case, cvpm, g, p1000mb, r_d, r_v, rcp, rvovrd, t0
+
+_LIBM = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+
+
+def _libm(name, nargs):
+    """a real*4 intrinsic as gfortran evaluates it: the host libm's float routine, element by element"""
+    fn = getattr(_LIBM, name)
+    fn.restype, fn.argtypes = ctypes.c_float, [ctypes.c_float] * nargs
+    uf = np.frompyfunc(lambda *a: fn(*[float(x) for x in a]), nargs, 1)
+
+    def call(*a):
+        r = uf(*[np.asarray(x, dtype=F) for x in a])
+        return F(r) if np.ndim(r) == 0 else np.asarray(r, dtype=F)
+    return call
+
+
+powf, expf, logf, cosf = _libm("powf", 2), _libm("expf", 1), _libm("logf", 1), _libm("cosf", 1)
 
 HILL2D_X, QUARTER_SS, B_WAVE, LES = 1, 2, 7, 9      # Registry ideal_case values (share/module_model_constants / namelist &ideal)
 
@@ -169,19 +189,19 @@ def jet_sounding(jet, jp, dry):
     if dry:
         rel_hum = np.zeros(nz, F)
     else:
-        rel_hum = np.where(h > F(8000.0), F(0.1), F(1.0) - F(0.90) * (h / F(8000.0)) ** F(1.25)).astype(F)
+        rel_hum = np.where(h > F(8000.0), F(0.1), F(1.0) - F(0.90) * powf(h / F(8000.0), F(1.25))).astype(F)
         rel_hum = np.minimum(F(0.7), rel_hum)
     cpovcv = F(ideal.cp / (ideal.cp - r_d))
-    p = (p1000mb * (r_d * rho * th / p1000mb) ** cpovcv).astype(F)
+    p = (p1000mb * powf(r_d * rho * th / p1000mb, cpovcv)).astype(F)
     if not dry:
         svp1, svp2, svp3, svpt0, ep_2 = F(0.6112), F(17.67), F(29.65), F(273.15), F(r_d / r_v)
         for kk in range(nz):
-            tmppi = (p[kk] / p1000mb) ** rcp
+            tmppi = powf(p[kk] / p1000mb, rcp)
             temperature = tmppi * th[kk]
             if temperature > svpt0:
-                es = F(1000.0) * svp1 * np.exp(svp2 * (temperature - svpt0) / (temperature - svp3), dtype=F)
+                es = F(1000.0) * svp1 * expf(svp2 * (temperature - svpt0) / (temperature - svp3))
             else:
-                es = F(1000.0) * svp1 * np.exp(F(21.8745584) * (temperature - F(273.16)) / (temperature - F(7.66)), dtype=F)
+                es = F(1000.0) * svp1 * expf(F(21.8745584) * (temperature - F(273.16)) / (temperature - F(7.66)))
             qvs = ep_2 * es / (p[kk] - es)
             qv[kk] = rel_hum[kk] * qvs
             th[kk] = th[kk] / (F(1.0) + F(0.61) * qv[kk])
@@ -202,14 +222,14 @@ def get_sounding(snd, dry):
     nl = len(h)
     th_surf = F(snd["ts"])
     qvf = F(1.0) + rvovrd * qv[0]
-    rho_surf = F(1.0) / ((r_d / p1000mb) * th_surf * qvf * ((p_surf / p1000mb) ** cvpm))
+    rho_surf = F(1.0) / ((r_d / p1000mb) * th_surf * qvf * powf(p_surf / p1000mb, cvpm))
     rho, pm = np.zeros(nl, F), np.zeros(nl, F)
     qvf1 = F(1.0) + qv[0]
     rho[0] = rho_surf
     dz = h[0]
     for _ in range(10):
         pm[0] = p_surf - F(0.5) * dz * (rho_surf + rho[0]) * g * qvf1
-        rho[0] = F(1.0) / ((r_d / p1000mb) * th[0] * qvf * ((pm[0] / p1000mb) ** cvpm))
+        rho[0] = F(1.0) / ((r_d / p1000mb) * th[0] * qvf * powf(pm[0] / p1000mb, cvpm))
     for k in range(1, nl):
         rho[k] = rho[k - 1]
         dz = h[k] - h[k - 1]
@@ -219,7 +239,7 @@ def get_sounding(snd, dry):
             pm[k] = pm[k - 1] - F(0.5) * dz * (rho[k] + rho[k - 1]) * g * qvf1
             if pm[k] <= 0:
                 raise ValueError("Integrated pressure has gone negative - too cold for chosen height")
-            rho[k] = F(1.0) / ((r_d / p1000mb) * th[k] * qvf * ((pm[k] / p1000mb) ** cvpm))
+            rho[k] = F(1.0) / ((r_d / p1000mb) * th[k] * qvf * powf(pm[k] / p1000mb, cvpm))
     pd = np.zeros(nl, F)
     pd[nl - 1] = pm[nl - 1]
     for k in range(nl - 2, -1, -1):
@@ -287,7 +307,7 @@ def init_domain(rundir, dom=1) -> Case:
         fl["pb"][jj, :kde - 1, ii] = pl
         ti = (ideal.interp_0(dry_s["theta"], dry_s["p"], pl) - t0).astype(F)
         fl["t_init"][jj, :kde - 1, ii] = ti
-        fl["alb"][jj, :kde - 1, ii] = ((r_d / p1000mb) * (ti + t0) * (pl / p1000mb) ** cvpm).astype(F)
+        fl["alb"][jj, :kde - 1, ii] = ((r_d / p1000mb) * (ti + t0) * powf(pl / p1000mb, cvpm)).astype(F)
         phb = fl["phb"][jj, :, ii]
         phb[0] = g * ht[jj, ii]
         for kk in range(1, kde):
@@ -336,7 +356,7 @@ def init_domain(rundir, dom=1) -> Case:
             qvf1 = qvf1 * qvf2
             p[kk] = -F(0.5) * ((c1f[k] * mu1) + qvf1 * (c1f[k] * mub[jj, ii] + c2f[k])) / rdnw[kk] / qvf2
             qvf = F(1.0) + rvovrd * qv[kk]
-            alt[kk] = (r_d / p1000mb) * (t1[kk] + t0) * qvf * (((p[kk] + pbc[kk]) / p1000mb) ** cvpm)
+            alt[kk] = (r_d / p1000mb) * (t1[kk] + t0) * qvf * powf((p[kk] + pbc[kk]) / p1000mb, cvpm)
             al[kk] = alt[kk] - albc[kk]
             for kk in range(kde - 3, -1, -1):
                 k = kk + 1
@@ -345,7 +365,7 @@ def init_domain(rundir, dom=1) -> Case:
                 qvf1 = qvf1 * qvf2
                 p[kk] = p[kk + 1] - ((c1f[k] * mu1) + qvf1 * (c1f[k] * mub[jj, ii] + c2f[k])) / qvf2 / rdn[kk + 1]
                 qvf = F(1.0) + rvovrd * qv[kk]
-                alt[kk] = (r_d / p1000mb) * (t1[kk] + t0) * qvf * (((p[kk] + pbc[kk]) / p1000mb) ** cvpm)
+                alt[kk] = (r_d / p1000mb) * (t1[kk] + t0) * qvf * powf((p[kk] + pbc[kk]) / p1000mb, cvpm)
                 al[kk] = alt[kk] - albc[kk]
             ph = np.zeros(kde, F)
             for kk in range(1, kde):
@@ -369,7 +389,7 @@ def init_domain(rundir, dom=1) -> Case:
             if dth[k] != 0.0:
                 fl["t"][jj, k, ii] = fl["t"][jj, k, ii] + dth[k]
                 qvf = F(1.0) + rvovrd * fl["qv"][jj, k, ii]
-                fl["alt"][jj, k, ii] = (r_d / p1000mb) * (fl["t"][jj, k, ii] + t0) * qvf * (((fl["p"][jj, k, ii] + fl["pb"][jj, k, ii]) / p1000mb) ** cvpm)
+                fl["alt"][jj, k, ii] = (r_d / p1000mb) * (fl["t"][jj, k, ii] + t0) * qvf * powf((fl["p"][jj, k, ii] + fl["pb"][jj, k, ii]) / p1000mb, cvpm)
                 fl["al"][jj, k, ii] = fl["alt"][jj, k, ii] - fl["alb"][jj, k, ii]
                 hit = True
         if hit or case_id in (QUARTER_SS, B_WAVE, LES):      # the reference re-integrates every column of the loop
@@ -392,13 +412,13 @@ def init_domain(rundir, dom=1) -> Case:
                     xrad = F(c.dx) * F(i - nxc) / F(10000.0)
                     zrad = (zmid - F(1500.0)) / F(1500.0)
                     rad = np.sqrt(xrad * xrad + yrad * yrad + zrad * zrad, dtype=F)
-                    dth = np.where(rad <= F(1.0), delt * np.cos(F(0.5) * pi * rad, dtype=F) ** 2, F(0.0)).astype(F)
+                    dth = np.where(rad <= F(1.0), delt * cosf(F(0.5) * pi * rad) ** 2, F(0.0)).astype(F)
                 elif case_id == B_WAVE:
                     yrad = F(c.dy) * F(j - jde // 2 - 1) / F(2000000.0)
                     xrad = F(i - 1) / F(ide - 1)
                     zrad = (zmid - F(8000.0)) / F(8000.0)
                     rad = np.sqrt(yrad * yrad + zrad * zrad, dtype=F)
-                    tp = F(1.0) * np.cos(rad * piov2, dtype=F) * np.cos(rad * piov2, dtype=F) * np.cos(xrad * F(2.0) * pi + pi, dtype=F)
+                    tp = F(1.0) * cosf(rad * piov2) * cosf(rad * piov2) * cosf(xrad * F(2.0) * pi + pi)
                     dth = np.where(rad <= F(1.0), tp, F(0.0)).astype(F)
                 else:      # les: 0.1 (rand - 0.5) on the lowest four levels (RANDOM_NUMBER replaced, see the module docstring)
                     dth[:4] = F(0.1) * F(_hash01(i, j) - 0.5)
@@ -460,11 +480,11 @@ def init_domain(rundir, dom=1) -> Case:
         pfu = c3f[None, 1:kde, None] * (MUB + MU) + c4f[None, 1:kde, None] + p_top
         pfd = c3f[None, 0:kde - 1, None] * (MUB + MU) + c4f[None, 0:kde - 1, None] + p_top
         phm = c3h[None, kk, None] * (MUB + MU) + c4h[None, kk, None] + p_top
-        al = ((ph[:, 1:, :] - ph[:, :-1, :] + phb[:, 1:, :] - phb[:, :-1, :]) / phm / np.log(pfd / pfu, dtype=F) - alb).astype(F)
+        al = ((ph[:, 1:, :] - ph[:, :-1, :] + phb[:, 1:, :] - phb[:, :-1, :]) / phm / logf(pfd / pfu) - alb).astype(F)
     qvf = F(1.0) if c.use_theta_m == 1 else (F(1.0) + rvovrd * fl["qv"][sj, kk, si])
     cpovcv = F(ideal.cp / (ideal.cp - r_d))
     fl["al"][sj, kk, si] = al
-    fl["p"][sj, kk, si] = (p1000mb * ((r_d * (t0 + fl["t"][sj, kk, si]) * qvf) / (p1000mb * (al + alb))) ** cpovcv - fl["pb"][sj, kk, si]).astype(F)
+    fl["p"][sj, kk, si] = (p1000mb * powf((r_d * (t0 + fl["t"][sj, kk, si]) * qvf) / (p1000mb * (al + alb)), cpovcv) - fl["pb"][sj, kk, si]).astype(F)
     fl["alt"][sj, kk, si] = al + alb
 
     # ---- the fields of the C-ABI
