@@ -59,10 +59,11 @@ def _sign(a, b):
     return -abs(a) if neg else abs(a)
 
 
-def _fit(a, shape):
+def _fit(a, rank, shape_of):
     """the actual array seen through the dummy's declared shape when the ranks differ (a view: only extent-1 axes come or go)"""
-    if a is None or not isinstance(a, np.ndarray) or a.ndim == len(shape):
+    if a is None or not isinstance(a, np.ndarray) or a.ndim == rank:
         return a
+    shape = shape_of()
     if [n for n in a.shape if n != 1] != [n for n in shape if n != 1]:
         raise NotImplementedError(f"sequence association of shape {a.shape} with {shape}")
     v = a.reshape(shape)
@@ -70,11 +71,49 @@ def _fit(a, shape):
     return v
 
 
+class FArr:
+    """an array component of a derived-type object with its Fortran lower bounds (grid%u_2 -> (ims, kms, jms))"""
+
+    def __init__(self, a, lo):
+        self.a, self.lo = a, tuple(lo)
+
+    def idx(self, subs):
+        if len(subs) != len(self.lo):
+            raise IndexError(f"rank {len(self.lo)} component indexed with {len(subs)} subscripts")
+        return tuple(int(s) - l for s, l in zip(subs, self.lo))
+
+
+def _oget(obj, comp, subs):
+    if comp not in obj and hasattr(obj, "make"):
+        obj.make(comp, None if subs is None else len(subs))
+    v = obj[comp]
+    if subs is None:
+        return v.a if isinstance(v, FArr) else v
+    return v.a[v.idx(subs)]
+
+
+def _oset(obj, comp, subs, val):
+    if comp not in obj and hasattr(obj, "make") and subs is not None:
+        obj.make(comp, len(subs))
+    if subs is None:
+        if isinstance(obj.get(comp), FArr):
+            obj[comp].a[...] = val
+        else:
+            obj[comp] = val
+    else:
+        v = obj[comp]
+        v.a[v.idx(subs)] = val
+
+
+class _Obj(dict):
+    """a derived-type local the routine fills itself (config_flags of init_domain_rk, set by model_to_grid_config_rec)"""
+
+
 def _dim(a, b):
     return (a - b) if a > b else (a - a)
 
 
-RUNTIME = dict(_fit=_fit, _dim=_dim, f32=f32, f64=np.float64, _idiv=_idiv, _powi=_powi, _sign=_sign, _cos=_m1("cosf"), _sin=_m1("sinf"), _atan=_m1("atanf"),
+RUNTIME = dict(_fit=_fit, _dim=_dim, _oget=_oget, _oset=_oset, _Obj=_Obj, f32=f32, f64=np.float64, _idiv=_idiv, _powi=_powi, _sign=_sign, _cos=_m1("cosf"), _sin=_m1("sinf"), _atan=_m1("atanf"),
                _exp=_m1("expf"), _log=_m1("logf"), _sqrt=_m1("sqrtf"), _tanh=_m1("tanhf"), _acos=_m1("acosf"), _asin=_m1("asinf"), _tan=_m1("tanf"),
                _powf=lambda a, b: f32(_libm.powf(float(f32(a)), float(f32(b)))), np=np)
 
@@ -127,6 +166,24 @@ def _cpp(lines, defines):
     return out
 
 
+def _split_statements(text):
+    """a ; b ; c -> [a, b, c], leaving the ; inside character literals alone"""
+    out, cur, q = [], "", None
+    for ch in text:
+        if q:
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+        elif ch == ";":
+            out.append(cur)
+            cur = ""
+            continue
+        cur += ch
+    out.append(cur)
+    return out
+
+
 def _strip_comment(ln):
     q = None
     for n, ch in enumerate(ln):
@@ -140,9 +197,9 @@ def _strip_comment(ln):
     return ln
 
 
-def statements(path, name, defines=None):
-    """the statements of SUBROUTINE `name` in file `path`: comments dropped, continuations joined, lower case"""
-    lines = _cpp(open(path, errors="replace").read().split("\n"), defines or {})
+def statements(path, name, defines=None, text=None):
+    """the statements of SUBROUTINE `name` in file `path` (or in `text`): comments dropped, continuations joined, lower case"""
+    lines = _cpp((text if text is not None else open(path, errors="replace").read()).split("\n"), defines or {})
     lines = [_strip_comment(ln).rstrip() for ln in lines]
     out, cur, on = [], "", False
     start = re.compile(r"^\s*((real|integer|logical)\s+)?(subroutine|function)\s+%s\b" % re.escape(name), re.I)
@@ -163,7 +220,7 @@ def statements(path, name, defines=None):
         if cur.endswith("&"):
             cur = cur[:-1].rstrip()
             continue
-        for st in cur.split(";"):
+        for st in _split_statements(cur):
             if st.strip():
                 out.append(st.strip().lower())
         cur = ""
@@ -211,10 +268,18 @@ class Expr:
         return tok
 
     def parse(self):
-        r = self.or_()
+        r = self.eqv()
         if self.peek() is not None:
             raise NotImplementedError(f"trailing tokens {self.t[self.p:]} in {' '.join(self.t)}")
         return r
+
+    def eqv(self):
+        a, ta = self.or_()
+        while self.peek() in (".eqv.", ".neqv."):
+            op = "==" if self.take() == ".eqv." else "!="
+            b, _ = self.or_()
+            a, ta = f"(bool({a}) {op} bool({b}))", "l"
+        return a, ta
 
     def or_(self):
         a, ta = self.and_()
@@ -311,7 +376,7 @@ class Expr:
     def atom(self):
         tok = self.take()
         if tok == "(":
-            a, ta = self.or_()
+            a, ta = self.eqv()
             self.take(")")
             return f"({a})", ta
         if tok[0] in "'\"":
@@ -341,7 +406,7 @@ class Routine:
         self.library = library             # Library: resolves CALLs to other routines of the reference (or to Python hooks)
         self.types = types or {}           # derived-type argument name -> dict of components given at call time
         self.constants = constants or {}   # USEd module PARAMETERs: name -> (value, type letter), see module_parameters()
-        st = statements(path, name, defines)
+        st = statements(path, name, defines, library.texts.get(name) if library is not None else None)
         m = re.match(r"((real|integer|logical)\s+)?(subroutine|function)\s+\w+\s*\((.*)\)\s*$", st[0])
         self.dummies = [a.strip() for a in m.group(4).split(",")] if m and m.group(4).strip() else []
         self.is_function = bool(m) and m.group(3) == "function"
@@ -351,6 +416,11 @@ class Routine:
         body = st[1:-1]
         if self.is_function and self.result_kind:
             self.kind[name] = self.result_kind
+        if library is not None and name in library.inject:      # what a generated #include declares (dummy_new_args.inc: moist, ...)
+            extra_dummies, extra_decl = library.inject[name]
+            self.dummies += list(extra_dummies)
+            for d in extra_decl:
+                assert self._declaration(d.lower()), d
         n = 0
         while n < len(body) and self._declaration(body[n]):
             n += 1
@@ -484,9 +554,17 @@ class Routine:
         return f"v_{nm}[" + ", ".join(f"{s} - {lo}" for s, lo in zip(subs, lows)) + "]"
 
     def resolve(self, tok, ex):
-        if ex.peek() == "%":                          # config_flags%open_xs
+        if ex.peek() == "%":                          # config_flags%open_xs, grid%u_2(i,k,j), model_config_rec%ideal_case
             ex.take()
             comp = ex.take()
+            objects = self.library.objects if self.library is not None else {}
+            if tok in objects:
+                base = f"v_{tok}" if tok in self.kind else f"_G[{tok!r}]"
+                t = objects[tok].get(comp, objects[tok].get("*", "r"))
+                if ex.peek() == "(":
+                    subs = [a for a, _ in ex.args()]
+                    return f"_oget({base}, {comp!r}, ({', '.join(subs)},))", t
+                return f"_oget({base}, {comp!r}, None)", t
             return f"v_{tok}[{comp!r}]", self.types.get(tok, {}).get(comp, "l")
         if ex.peek() == "(":
             if tok in self.dims:
@@ -548,6 +626,8 @@ class Routine:
             return f"({src[0]} is not None)", "l"
         if fn in _INTR1:
             return f"{_INTR1[fn]}({self.conv(src[0], ty[0], 'r')})", "r"
+        if self.library is not None and fn in self.library.hooks:       # an EXTERNAL function supplied by the test (wrf_dm_on_monitor)
+            return f"_hookf({fn!r}, [{', '.join(src)}])", self.kind.get(fn, "r")
         if self.library is not None and fn in self.library.where:
             callee = self.library.routine(fn)
             if callee.is_function:
@@ -570,12 +650,15 @@ class Routine:
                 for d in self.dims[nm]:
                     lo, hi = (d.split(":") + ["1"])[:2] if ":" in d else ("1", d)
                     shape.append(f"({self.expr(hi)[0]}) - ({self.expr(lo)[0]}) + 1")
-                emit(f"v_{nm} = _fit(v_{nm}, ({', '.join(shape)},))")
+                emit(f"v_{nm} = _fit(v_{nm}, {len(shape)}, lambda: ({', '.join(shape)},))")
         for nm, init in self.params.items():
             src, t = self.expr(init)
             emit(f"v_{nm} = {self.conv(src, t, self.kind[nm])}")
         for nm, k in self.kind.items():
-            if nm in self.dummies or nm in self.params or k == "t":
+            if nm in self.dummies or nm in self.params:
+                continue
+            if k == "t":
+                emit(f"v_{nm} = _Obj()")
                 continue
             if k == "c":
                 emit(f"v_{nm} = ''")
@@ -792,6 +875,16 @@ class Routine:
         if eq < 0:
             raise NotImplementedError(f"statement {s!r}")
         lhs, rhs = s[:eq].strip(), s[eq + 1:].strip()
+        mo = re.match(r"([a-z_]\w*)\s*%\s*([a-z_]\w*)\s*(\((.*)\))?$", lhs)
+        if mo and self.library is not None and mo.group(1) in self.library.objects:
+            obj, comp = mo.group(1), mo.group(2)
+            table = self.library.objects[obj]
+            src, t = self.expr(rhs)
+            val = self.conv(src, t, table.get(comp, table.get("*", "r")))
+            base = f"v_{obj}" if obj in self.kind else f"_G[{obj!r}]"
+            subs = "None" if not mo.group(3) else "(" + ", ".join(self.expr(x)[0] for x in self._split(mo.group(4))) + ",)"
+            emit(f"_oset({base}, {comp!r}, {subs}, {val})")
+            return
         ml = re.match(r"([a-z_]\w*)\s*(\((.*)\))?$", lhs)
         if not ml:
             raise NotImplementedError(f"left-hand side {lhs!r}")
@@ -828,6 +921,7 @@ class Routine:
         if self.fn is None:
             ns = dict(RUNTIME)
             ns["_G"] = self.library.globals if self.library is not None else {}
+            ns["_hookf"] = (lambda nm, a: self.library.hooks[nm](*a)) if self.library is not None else None
             ns["_call"] = self.library.call if self.library is not None else None
             ns["_callf"] = self.library.callf if self.library is not None else None
             exec(compile(self.py, f"<{self.name} of {self.path}>", "exec"), ns)
@@ -852,6 +946,7 @@ def module_parameters(path, known=None, header_only=False):
         def __init__(self):          # only the expression machinery
             self.kind, self.dims, self.params, self.stmtfn, self.derived, self.types = {}, {}, {}, {}, set(), {}
             self.constants = out
+            self.library = None
 
     tr = _M()
     for ln in open(path, errors="replace"):
@@ -863,7 +958,7 @@ def module_parameters(path, known=None, header_only=False):
             continue
         try:
             src, t = tr.expr(m.group(3))
-        except NotImplementedError:
+        except (NotImplementedError, IndexError):
             continue
         want = "r" if m.group(1) == "real" else "i"
         val = eval(tr.conv(src, t, want), dict(RUNTIME))
@@ -877,13 +972,30 @@ class Library:
 
     def __init__(self, files, defines=None, types=None, constants=None, hooks=None):
         self.where, self.cache = {}, {}
-        self.globals = {}              # USEd module variables (integers), by name
+        self.globals = {}              # USEd module variables (integers, or objects such as model_config_rec), by name
+        self.texts = {}                # name -> source text of a routine assembled by the test (add_fragment)
+        self.inject = {}               # routine -> (extra dummy names, extra declaration statements) standing for a generated #include
+        self.objects = {}              # derived-type objects with array components: name -> {component: type letter, "*": default}
         self.defines, self.types, self.constants, self.hooks = defines or {}, types or {}, constants or {}, hooks or {}
         for path in files:
             for ln in open(path, errors="replace"):
                 m = re.match(r"\s*(?:(?:real|integer|logical)\s+)?(?:subroutine|function)\s+([a-z_]\w*)", ln, re.I)
                 if m:
                     self.where.setdefault(m.group(1).lower(), path)
+
+    def add_fragment(self, name, path, first, last, dummies, declarations, trim=0):
+        """a line range of a reference file (first/last: regular expressions matched against the lines, both inclusive) wrapped as
+        SUBROUTINE name(dummies) with the given declarations: a way to execute a block of a routine too large or too entangled to run
+        whole (the first-trip diagnosis inside start_domain_em); trim: lines to drop at the end (the ENDIF that closes an enclosing block).
+        The text is assembled in memory; nothing is written anywhere."""
+        lines = open(path, errors="replace").read().split("\n")
+        a = next(n for n, ln in enumerate(lines) if re.search(first, ln))
+        b = next(n for n, ln in enumerate(lines) if n > a and re.search(last, ln))
+        self.texts[name] = "\n".join([f"subroutine {name}({', '.join(dummies)})", "implicit none"] + list(declarations) + lines[a:b + 1 - trim]
+                                     + [f"end subroutine {name}"])
+        self.where[name] = path
+        self.cache.pop(name, None)
+        return a + 1, b + 1
 
     def routine(self, name):
         if name not in self.cache:

@@ -77,7 +77,7 @@ CONFIG_REAL = ("dampcoef", "zdamp", "w_crit_cfl", "khdif", "kvdif", "epssm", "sm
 
 SOURCES = ("dyn_em/module_em.F", "dyn_em/module_advect_em.F", "dyn_em/module_big_step_utilities_em.F", "dyn_em/module_small_step_em.F",
            "dyn_em/module_bc_em.F", "dyn_em/module_ieva_em.F", "dyn_em/module_diffusion_em.F", "share/module_bc.F",
-           "phys/module_mp_kessler.F", "dyn_em/module_initialize_ideal.F")
+           "phys/module_mp_kessler.F", "dyn_em/module_initialize_ideal.F", "dyn_em/module_init_utilities.F")
 _LIBRARY = None
 
 

@@ -61,3 +61,30 @@ def test_feeder_output_files(adv_opt):
         assert hat.min() >= 0            # PD / monotonic / WENO-PD stay non-negative
     if adv_opt == 0:
         assert hat.min() < 0             # the unlimited 5th-order scheme undershoots
+
+
+INIT_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "shipped_init.json")
+INIT = json.load(open(INIT_GOLDEN)) if os.path.exists(INIT_GOLDEN) else {}
+
+
+@pytest.mark.parametrize("name", ["em_quarter_ss", "em_hill2d_x", "em_les", "em_b_wave"])
+def test_shipped_initial_state_digests(name):
+    """wrf_b200/shipped.py's initial state for the four shipped run directories against digests of what the REFERENCE's init_domain_rk
+    (module_initialize_ideal.F) + the first trip of start_domain_em produced when executed from source in the build container
+    (tests/test_reference_init.py wrote tests/golden/shipped_init.json): 53 fields and 6 scalars per case, bit for bit."""
+    from wrf_b200 import shipped
+    assert name in INIT, "tests/golden/shipped_init.json is missing: REFSRC_WRITE=1 python -m pytest tests/test_reference_init.py -k initial_state"
+    case = shipped.init_domain(os.path.join(os.path.dirname(__file__), "fixtures", name))
+    d = case.dims
+    sj, si = slice(1 - d.jms, d.jde - d.jms + 1), slice(1 - d.ims, d.ide - d.ims + 1)
+    bad = []
+    for k, want in INIT[name].items():
+        if isinstance(want, float):
+            if np.float32(getattr(case.config, k)) != np.float32(want):
+                bad.append(k)
+            continue
+        a = case.fields[k]
+        if digest(a[sj, ..., si] if a.ndim >= 2 else a) != want:
+            bad.append(k)
+    assert not bad, f"{name}: {bad}"
+    assert len(INIT[name]) >= 55

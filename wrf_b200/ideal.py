@@ -219,12 +219,12 @@ def memory_dims(nx_stag, ny_stag, nz_stag, halo=5):
     return d
 
 
-def vertical_coords(kde, ztop, stretch=True):
-    """module_initialize_ideal.F:617-732."""
-    z_scale = F(8000.0 / ztop)
+def vertical_coords(kde, ztop, stretch=True, exp=np.exp):
+    """module_initialize_ideal.F:617-732.  exp: the real*4 EXP to use (shipped.py passes the host libm's expf, what ideal.exe calls)"""
+    z_scale = F(F(8000.0) / F(ztop))
     k = np.arange(kde, dtype=F)
     if stretch:
-        znw = ((np.exp(-(k) / F(kde - 1) / z_scale) - np.exp(F(-1.0) / z_scale)) / (F(1.0) - np.exp(F(-1.0) / z_scale))).astype(F)
+        znw = ((exp(-(k) / F(kde - 1) / z_scale) - exp(F(-1.0) / z_scale)) / (F(1.0) - exp(F(-1.0) / z_scale))).astype(F)
     else:
         znw = (F(1.0) - k / F(kde - 1)).astype(F)
     znw[0], znw[-1] = F(1.0), F(0.0)
@@ -245,11 +245,14 @@ def vertical_coords(kde, ztop, stretch=True):
     return o, sc
 
 
-def hybrid_coefs(v, p_top, hybrid_opt, etac=0.2):
-    """module_initialize_ideal.F:791-877."""
+def hybrid_coefs(v, p_top, hybrid_opt, etac=0.2, c3f=None):
+    """module_initialize_ideal.F:791-877.  c3f: the full-level B(eta) computed by the caller (shipped.py evaluates the cubic with
+    gfortran's multiply sequences for x**2, x**3, x**4)"""
     znw, znu = v["znw"], v["znu"]
     kde = len(znw)
-    if hybrid_opt in (0, 1):
+    if c3f is not None:
+        c3f = np.asarray(c3f, dtype=F)
+    elif hybrid_opt in (0, 1):
         c3f = znw.copy()
     else:
         e = F(etac)

@@ -43,6 +43,25 @@ def _libm(name, nargs):
 
 powf, expf, logf, cosf = _libm("powf", 2), _libm("expf", 1), _libm("logf", 1), _libm("cosf", 1)
 
+def interp_0(v_in, z_in, z_out):
+    """interp_0 (dyn_em/module_init_utilities.F:5-91), operand for operand: the table is NOT reversed when z decreases with the index
+    (pressure tables), the bracketing pair is the one the reference's downward scan finds first (the higher index pair on a tie), the
+    weight w2 belongs to the LOWER index, w1 = 1 - w2, result w1*v(kp) + w2*v(kp-1); the two extrapolation branches are the same
+    expression with kp = nz_in or 2 (their numerator and denominator are both negated, the quotient is bit-identical).  Vectorised over z_out."""
+    v_in, z_in = np.asarray(v_in, dtype=F), np.asarray(z_in, dtype=F)
+    h = np.asarray(z_out, dtype=F)
+    n = len(z_in)
+    if z_in[n - 1] > z_in[0]:
+        kp = np.searchsorted(z_in, h, side="right")            # nodes <= h: the pair (kp-1, kp) in 0-based indices
+    else:
+        kp = np.searchsorted(-z_in, -h, side="right")          # nodes >= h
+    kp = np.clip(kp, 1, n - 1)
+    w2 = ((h - z_in[kp]) / (z_in[kp - 1] - z_in[kp])).astype(F)
+    w1 = (F(1.0) - w2).astype(F)
+    out = ((w1 * v_in[kp]).astype(F) + (w2 * v_in[kp - 1]).astype(F)).astype(F)
+    return F(out) if np.ndim(out) == 0 else out
+
+
 HILL2D_X, QUARTER_SS, B_WAVE, LES = 1, 2, 7, 9      # Registry ideal_case values (share/module_model_constants / namelist &ideal)
 
 
@@ -271,7 +290,7 @@ def init_domain(rundir, dom=1) -> Case:
     ide, jde, kde = nx, ny, nz
     d = ideal.memory_dims(nx, ny, nz)
     stretch = case_id != LES
-    v, sc = ideal.vertical_coords(nz, gp["ztop"], stretch)
+    v, sc = ideal.vertical_coords(nz, gp["ztop"], stretch, exp=expf)
     for k_, val in sc.items():
         setattr(c, k_, float(val))
     pi = F(2.0) * np.arcsin(F(1.0), dtype=F)
@@ -283,9 +302,22 @@ def init_domain(rundir, dom=1) -> Case:
     else:
         snd = read_sounding(os.path.join(rundir, "input_sounding"))
         dry_s = get_sounding(snd, dry=True)
-    p_top = F(ideal.interp_0(dry_s["p"], dry_s["zk"], F(gp["ztop"])))
+    p_top = F(interp_0(dry_s["p"], dry_s["zk"], F(gp["ztop"])))
     c.p_top = float(p_top)
-    hy = ideal.hybrid_coefs(v, float(p_top), gp["hybrid_opt"], gp["etac"])
+    c3f = None
+    if gp["hybrid_opt"] == 2:       # :795-809, x**n as gfortran expands it (__powisf2: x*x, x*(x*x), (x*x)*(x*x))
+        e, znw = F(gp["etac"]), v["znw"]
+        sq = lambda x: (x * x).astype(F) if isinstance(x, np.ndarray) else F(x * x)
+        cube = lambda x: (x * sq(x)).astype(F) if isinstance(x, np.ndarray) else F(x * sq(x))
+        B1 = F(F(F(2.0) * sq(e)) * F(F(1.0) - e))
+        B2 = F(-e * F(F(F(4.0) - F(F(3.0) * e)) - cube(e)))
+        B3 = F(F(2.0) * F(F(1.0) - cube(e)))
+        B4 = F(-F(F(1.0) - sq(e)))
+        B5 = sq(sq(F(F(1.0) - e)))
+        c3f = ((((B1 + (B2 * znw).astype(F)).astype(F) + (B3 * sq(znw)).astype(F)).astype(F) + (B4 * cube(znw)).astype(F)).astype(F) / B5).astype(F)
+        c3f[znw < e] = 0
+        c3f[0], c3f[-1] = 1, 0
+    hy = ideal.hybrid_coefs(v, float(p_top), gp["hybrid_opt"], gp["etac"], c3f=c3f)
     c3h, c4h, c1h, c2h, c1f, c2f, c3f, c4f = (hy[n] for n in ("c3h", "c4h", "c1h", "c2h", "c1f", "c2f", "c3f", "c4f"))
     dnw, rdnw, rdn = v["dnw"], v["rdnw"], v["rdn"]
 
@@ -301,11 +333,11 @@ def init_domain(rundir, dom=1) -> Case:
             ht[:, I0 + i] = hm / (F(1.0) + (F(i - icm) / xa) ** 2)
     # base state (:962-985), every column of the patch (flat terrain: one column, copied)
     def base_column(jj, ii):
-        p_surf = F(ideal.interp_0(dry_s["p"], dry_s["zk"], F(g * ht[jj, ii] / g)))
+        p_surf = F(interp_0(dry_s["p"], dry_s["zk"], F(g * ht[jj, ii] / g)))
         mub[jj, ii] = p_surf - p_top
         pl = (c3h[:kde - 1] * (p_surf - p_top) + c4h[:kde - 1] + p_top).astype(F)
         fl["pb"][jj, :kde - 1, ii] = pl
-        ti = (ideal.interp_0(dry_s["theta"], dry_s["p"], pl) - t0).astype(F)
+        ti = (interp_0(dry_s["theta"], dry_s["p"], pl) - t0).astype(F)
         fl["t_init"][jj, :kde - 1, ii] = ti
         fl["alb"][jj, :kde - 1, ii] = ((r_d / p1000mb) * (ti + t0) * powf(pl / p1000mb, cvpm)).astype(F)
         phb = fl["phb"][jj, :, ii]
@@ -340,12 +372,12 @@ def init_domain(rundir, dom=1) -> Case:
                 if case_id == B_WAVE:
                     fl["u"][jj, :, ii] = col_cache["u"]
                 continue
-            pd_surf = F(ideal.interp_0(moist_s["pd"], moist_s["zk"], F(fl["phb"][jj, 0, ii] / g)))
+            pd_surf = F(interp_0(moist_s["pd"], moist_s["zk"], F(fl["phb"][jj, 0, ii] / g)))
             mu1 = F(pd_surf - p_top - mub[jj, ii])
             mu[jj, ii] = mu1
             pl = (c3h[:kde - 1] * (pd_surf - p_top) + c4h[:kde - 1] + p_top).astype(F)
-            qv = ideal.interp_0(moist_s["qv"], moist_s["pd"], pl).astype(F)
-            t1 = (ideal.interp_0(moist_s["theta"], moist_s["pd"], pl) - t0).astype(F)
+            qv = interp_0(moist_s["qv"], moist_s["pd"], pl).astype(F)
+            t1 = (interp_0(moist_s["theta"], moist_s["pd"], pl) - t0).astype(F)
             p = np.zeros(kde, F)
             pbc, albc = fl["pb"][jj, :, ii], fl["alb"][jj, :, ii]
             alt, al = np.zeros(kde, F), np.zeros(kde, F)
@@ -378,7 +410,7 @@ def init_domain(rundir, dom=1) -> Case:
             col_cache["mu"] = mu1
             if case_id == B_WAVE:
                 plu = (c3h[:kde] * (p_surf_last - p_top) + c4h[:kde] + p_top).astype(F)
-                fl["u"][jj, :, ii] = ideal.interp_0(moist_s["u"], moist_s["p"], plu)
+                fl["u"][jj, :, ii] = interp_0(moist_s["u"], moist_s["p"], plu)
                 col_cache["u"] = fl["u"][jj, :, ii].copy()
 
     # perturbation (:1098-1436) and hydrostatic rebalance of the columns it touched
@@ -438,9 +470,9 @@ def init_domain(rundir, dom=1) -> Case:
                     z_at_v = fl["phb"][jj - 1, 0, ii] / g
                 else:
                     z_at_v = F(0.5) * (fl["phb"][jj, 0, ii] + fl["phb"][jj - 1, 0, ii]) / g
-                ps = F(ideal.interp_0(wind_s["p"], wind_s["zk"], F(z_at_v)))
+                ps = F(interp_0(wind_s["p"], wind_s["zk"], F(z_at_v)))
                 pl = (c3h[:kde] * (ps - p_top) + c4h[:kde] + p_top).astype(F)
-                fl["v"][jj, :, ii] = ideal.interp_0(wind_s["v"], wind_s["p"], pl)
+                fl["v"][jj, :, ii] = interp_0(wind_s["v"], wind_s["p"], pl)
                 if case_id != HILL2D_X and i > its:       # flat: same profile everywhere
                     fl["v"][jj, :, I0 + its:I0 + min(ide - 1, ite) + 1] = fl["v"][jj, :, ii][:, None]
                     break
@@ -453,9 +485,9 @@ def init_domain(rundir, dom=1) -> Case:
                     z_at_u = fl["phb"][jj, 0, ii - 1] / g
                 else:
                     z_at_u = F(0.5) * (fl["phb"][jj, 0, ii] + fl["phb"][jj, 0, ii - 1]) / g
-                ps = F(ideal.interp_0(wind_s["p"], wind_s["zk"], F(z_at_u)))
+                ps = F(interp_0(wind_s["p"], wind_s["zk"], F(z_at_u)))
                 pl = (c3h[:kde] * (ps - p_top) + c4h[:kde] + p_top).astype(F)
-                fl["u"][jj, :, ii] = ideal.interp_0(wind_s["u"], wind_s["p"], pl)
+                fl["u"][jj, :, ii] = interp_0(wind_s["u"], wind_s["p"], pl)
     # base profiles from column (1,1) (:1579-1591)
     b1 = {n: np.zeros(nz, F) for n in ("u_base", "v_base", "t_base", "qv_base", "z_base")}
     j1, i1 = J0 + 1, I0 + 1
