@@ -17,6 +17,8 @@ from __future__ import annotations
 
 import numpy as np
 
+from .ideal import expf
+
 DRY = ("u", "v", "w", "ph", "t", "mu")
 SIDES = ("xs", "xe", "ys", "ye")
 
@@ -33,7 +35,7 @@ def lbc_fcx_gcx(c, spec_exp=0.0):
         fc = f32(f32(f32(0.1) / dt) * f32(sz + rz - loop)) / f32(rz - 1)
         gc = f32(f32(f32(f32(1.0) / dt) / f32(50.0)) * f32(sz + rz - loop)) / f32(rz - 1)
         if c.specified:
-            w = f32(np.exp(f32(-(loop - (sz + 1)) * f32(spec_exp))))
+            w = expf(f32(f32(-(loop - (sz + 1))) * f32(spec_exp)))      # EXP of gfortran's real*4 = the host libm's expf
             fc, gc = f32(fc * w), f32(gc * w)
         fcx[loop - 1], gcx[loop - 1] = fc, gc
     return fcx, gcx
@@ -51,11 +53,12 @@ def stuff_bdy(d, a, stagger, W):
     out = {s: np.zeros((W, nk, nj if s[0] == "x" else ni), np.float32) for s in SIDES}
     j0, j1 = d.jds - d.jms, jbe - d.jms          # rows of the field that exist on this stagger
     i0, i1 = d.ids - d.ims, ibe - d.ims
+    nc = nk if (a.ndim == 2 or stagger == "W") else nk - 1      # half-level fields: k = kds .. kde-1, the top row of the arrays stays untouched
     for b in range(1, W + 1):
-        out["xs"][b - 1, :, j0:j1 + 1] = a3[j0:j1 + 1, :nk, d.ids + b - 1 - d.ims].T
-        out["xe"][b - 1, :, j0:j1 + 1] = a3[j0:j1 + 1, :nk, ibe - (b - 1) - d.ims].T
-        out["ys"][b - 1, :, i0:i1 + 1] = a3[d.jds + b - 1 - d.jms, :nk, i0:i1 + 1]
-        out["ye"][b - 1, :, i0:i1 + 1] = a3[jbe - (b - 1) - d.jms, :nk, i0:i1 + 1]
+        out["xs"][b - 1, :nc, j0:j1 + 1] = a3[j0:j1 + 1, :nc, d.ids + b - 1 - d.ims].T
+        out["xe"][b - 1, :nc, j0:j1 + 1] = a3[j0:j1 + 1, :nc, ibe - (b - 1) - d.ims].T
+        out["ys"][b - 1, :nc, i0:i1 + 1] = a3[d.jds + b - 1 - d.jms, :nc, i0:i1 + 1]
+        out["ye"][b - 1, :nc, i0:i1 + 1] = a3[jbe - (b - 1) - d.jms, :nc, i0:i1 + 1]
     return out
 
 

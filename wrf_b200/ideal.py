@@ -19,6 +19,7 @@ Soundings are generated analytically instead of read from test/em_*/input_soundi
 from __future__ import annotations
 
 import ctypes
+import ctypes.util
 import math
 from dataclasses import dataclass, field
 
@@ -35,6 +36,24 @@ rcp = F(r_d / cp)
 p1000mb = F(100000.0)
 t0 = F(300.0)
 rvovrd = F(r_v / r_d)
+
+
+_LIBM = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+
+
+def _libm(name, nargs):
+    """a real*4 intrinsic as gfortran evaluates it: the host libm's float routine, element by element"""
+    fn = getattr(_LIBM, name)
+    fn.restype, fn.argtypes = ctypes.c_float, [ctypes.c_float] * nargs
+    uf = np.frompyfunc(lambda *a: fn(*[float(x) for x in a]), nargs, 1)
+
+    def call(*a):
+        r = uf(*[np.asarray(x, dtype=F) for x in a])
+        return F(r) if np.ndim(r) == 0 else np.asarray(r, dtype=F)
+    return call
+
+
+powf, expf, logf, cosf = _libm("powf", 2), _libm("expf", 1), _libm("logf", 1), _libm("cosf", 1)
 
 
 class Dims(ctypes.Structure):

@@ -14,8 +14,6 @@ Difference that cannot be avoided without the reference's compiler, documented w
 Host language note: this is the role of ideal.exe, which is outside the hot path; Python is enough here."""
 from __future__ import annotations
 
-import ctypes
-import ctypes.util
 import math
 import os
 import re
@@ -24,24 +22,7 @@ import struct
 import numpy as np
 
 from . import ideal
-from .ideal import F, Case, cvpm, g, p1000mb, r_d, r_v, rcp, rvovrd, t0
-
-_LIBM = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
-
-
-def _libm(name, nargs):
-    """a real*4 intrinsic as gfortran evaluates it: the host libm's float routine, element by element"""
-    fn = getattr(_LIBM, name)
-    fn.restype, fn.argtypes = ctypes.c_float, [ctypes.c_float] * nargs
-    uf = np.frompyfunc(lambda *a: fn(*[float(x) for x in a]), nargs, 1)
-
-    def call(*a):
-        r = uf(*[np.asarray(x, dtype=F) for x in a])
-        return F(r) if np.ndim(r) == 0 else np.asarray(r, dtype=F)
-    return call
-
-
-powf, expf, logf, cosf = _libm("powf", 2), _libm("expf", 1), _libm("logf", 1), _libm("cosf", 1)
+from .ideal import F, Case, cosf, cvpm, expf, g, logf, p1000mb, powf, r_d, r_v, rcp, rvovrd, t0
 
 def interp_0(v_in, z_in, z_out):
     """interp_0 (dyn_em/module_init_utilities.F:5-91), operand for operand: the table is NOT reversed when z decreases with the index
