@@ -593,7 +593,8 @@ void advect_w(const Cx &x, A3 w, A3 w_old, A3 tendency, A3 ru, A3 rv, A3 rom, A2
   const int ktf = std::min(kte, x.kde - 1);
   const A1 &fzm = x.fnm, &fzp = x.fnp, &rdzu = x.rdn;
   const float rdx = x.rdx, rdy = x.rdy;
-  Flux F{(float)(x.time_step >= 0 ? 1 : -1), weno, x.c.h_mom_adv_order == 6, x.c.v_mom_adv_order == 4};
+  // sic: w is advected with the SCALAR orders -- advect_w (:4463-4464) and advect_weno_w (:12339-12340) read h_sca_adv_order / v_sca_adv_order
+  Flux F{(float)(x.time_step >= 0 ? 1 : -1), weno, x.c.h_sca_adv_order == 6, x.c.v_sca_adv_order == 4};
   bool degrade_xs, degrade_xe, degrade_ys, degrade_ye;
   degrade_flags(x, 3, 4, degrade_xs, degrade_xe, degrade_ys, degrade_ye);
   Row fq0(its, ite, kte), fq1(its, ite, kte), fqx(its, ite, kte), vflux(its, ite, kte);

@@ -56,6 +56,17 @@ CASES = {
     "ieva_wdamp": lambda: parity.with_updraft(make_case("quarter_ss", nx=12, ny=10, nz=17, zadvect_implicit=1, dt=40.0, time_step=40, w_damping=1,
                                                         w_crit_cfl=2.0, use_adaptive_time_step=1), 80.0, conv=60.0),
     "adaptive": lambda: parity.with_updraft(parity.with_map_factors(make_case("quarter_ss", w_damping=1, use_adaptive_time_step=1, **Q)), 20.0),
+    "diff6_periodic": lambda: parity.with_map_factors(make_case("synthetic", num_scalar=2, diff_6th_opt=1, diff_6th_factor=0.2, scalar_mix6_off=1, **S)),
+    "order_mixed": lambda: make_case("b_wave", nx=9, ny=13, nz=9, h_mom_adv_order=6, v_sca_adv_order=4, moist_adv_opt=4, momentum_adv_opt=3),
+    "rk2_everything": lambda: parity.with_updraft(make_case("synthetic", nx=14, ny=12, nz=17, periodic=False, bubble_lattice=8000.0, noise=0.05, rk_ord=2,
+                                                            time_step_sound=4, zadvect_implicit=1, momentum_adv_opt=3, moist_adv_opt=3, num_scalar=1,
+                                                            scalar_adv_opt=4, dt=20.0, time_step=20, top_lid=1, diff_6th_opt=2, diff_opt=1, km_opt=1,
+                                                            khdif=200.0, kvdif=20.0), 40.0, conv=20.0),
+    "specified_bcs_moist": lambda: parity.with_boundary_zone(make_case("quarter_ss", nx=16, ny=14, nz=9, specified=1, have_bcs_moist=1, diff_6th_opt=2,
+                                                                       h_mom_adv_order=6, v_mom_adv_order=4, h_sca_adv_order=6, v_sca_adv_order=4,
+                                                                       moist_adv_opt=0, **parity.SPEC)),
+    "smag2d_b_wave": lambda: make_case("b_wave", nx=9, ny=13, nz=9, diff_opt=1, km_opt=4, kvdif=5.0),
+    "diff2_b_wave": lambda: make_case("b_wave", nx=9, ny=13, nz=9, diff_opt=2, km_opt=4, isfflx=2, tke_heat_flux=0.02),
     "les": lambda: parity.with_map_factors(make_case("les", **Q)),          # pert_coriolis, PD tracers, passive qv
     "diff6": lambda: make_case("quarter_ss", diff_6th_opt=2, **Q),
     "rain_open_mapfac": lambda: rainy(CASES["open_mapfac"]()),

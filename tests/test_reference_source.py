@@ -33,7 +33,7 @@ RECORD = [] if os.environ.get("REFSRC_WRITE") == "1" else None
 # out the combinations that repeat a code path already run (rk_tendency at the middle Runge-Kutta stage, and at the last stage for the
 # configurations whose last stage has nothing of its own), which the fixture replay of test_reference_source_golden.py still covers.
 FULL = RECORD is not None or os.environ.get("REFSRC_FULL") == "1"
-LAST_STAGE_DIFFERS = {"weno", "backward", "ieva", "ieva_wdamp", "wenopd", "wenopd_periodic", "rk2_sym_x", "specified", "open_mapfac",
+LAST_STAGE_DIFFERS = {"rk2_everything", "order_mixed", "weno", "backward", "ieva", "ieva_wdamp", "wenopd", "wenopd_periodic", "rk2_sym_x", "specified", "open_mapfac",
                       "periodic_mapfac", "smag2d", "tke", "les"}
 
 
@@ -252,6 +252,10 @@ def species_alias(fam, member, index_var):
 
 def scalar_program(c, rk, have):
     prog = []
+    if c.diff_opt == 1 and c.km_opt == 1 and rk == 1:          # the K arrays of isotropic_km, as in tendency_program
+        prog.append(("isotropic_km", 0, {"actuals": {}}))
+        for k in ("xkmh", "xkhh"):
+            prog.append(("set_physical_bc3d", 0, {"actuals": {"dat": k, "variable_in": "'t'"}}))
     fams = [("moist", ["moist_" + q for q in ("qv", "qc", "qr")[:c.num_moist]], "im", c.moist_adv_opt, 0),
             ("scalar", ["scalar_%d" % n for n in range(1, c.num_scalar + 1)], "is", c.scalar_adv_opt, 1)]
     last = rk == c.rk_ord
@@ -290,7 +294,7 @@ def scalar_program(c, rk, have):
     return prog
 
 
-SCALAR_CASES = ["les", "smag2d", "diff2_periodic", "tke", "tke_periodic", "tke_hill", "specified_tke", "mono", "mono_periodic", "wenopd", "wenopd_periodic", "order64", "open_mapfac", "opts", "periodic_mapfac", "rk2_sym_x", "weno", "diffusion", "diff6", "specified", "nested", "ieva"]
+SCALAR_CASES = ["diffusion_periodic", "diff6_periodic", "rk2_everything", "specified_bcs_moist", "les", "smag2d", "diff2_periodic", "tke", "tke_periodic", "tke_hill", "specified_tke", "mono", "mono_periodic", "wenopd", "wenopd_periodic", "order64", "open_mapfac", "opts", "periodic_mapfac", "rk2_sym_x", "weno", "diffusion", "diff6", "specified", "nested", "ieva"]
 
 
 @pytest.mark.parametrize("name", SCALAR_CASES)
@@ -301,7 +305,7 @@ def test_rk_scalar_step(name, rk):
     rk = min(rk, c.rk_ord)
     if c.num_moist + c.num_scalar == 0:
         pytest.skip("no species")
-    skip = ["h_tendency", "z_tendency"]
+    skip = ["h_tendency", "z_tendency", "xkmh", "xkmv", "xkhh", "xkhv"]
     if c.km_opt == 2 and c.num_scalar:
         # advect_tend is the per-species scratch rk_scalar_tend zeroes first: what it holds after the phase is the LAST species' flux
         # divergence, and solve_em.F steps the tke before the scalar family while the oracle keeps it as the family's last member
@@ -417,7 +421,7 @@ def diffusion_program(c):
     return prog
 
 
-DIFFUSION_CASES = ["smag2d", "smag2d_hill", "diff2", "diff2_periodic", "diff2_hill", "smag3d", "smag3d_periodic", "tke", "tke_periodic", "tke_hill"]
+DIFFUSION_CASES = ["smag2d_b_wave", "diff2_b_wave", "smag2d", "smag2d_hill", "diff2", "diff2_periodic", "diff2_hill", "smag3d", "smag3d_periodic", "tke", "tke_periodic", "tke_hill"]
 
 
 @pytest.mark.parametrize("name", DIFFUSION_CASES)

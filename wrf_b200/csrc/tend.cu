@@ -525,7 +525,8 @@ __device__ __forceinline__ float tend_w_pt(const Geo &g, const TendIn &s, int i,
   const Deg dg = degrade(g);
   const float sg = g.sgn_ts;
   // even orders (h 6 / v 4) are the odd ones without the upwind term: its factor is 0 then; WENO keeps sign(time_step)
-  const float sgh = WENO ? sg : g.sg_hm, sgv = WENO ? sg : g.sg_vm;
+  // sic: advect_w (:4463-4464) and advect_weno_w (:12339-12340) read h_sca_adv_order / v_sca_adv_order, not the momentum orders
+  const float sgh = WENO ? sg : g.sg_hs, sgv = WENO ? sg : g.sg_vs;
   cfp w = s.w, ru = s.ru, rv = s.rv, rom = s.rom;
   float t = t0;
   if (k >= 2) {
@@ -1167,22 +1168,31 @@ void Solver::rk_tendency_main(int rk_step, bool zero_save) {
     }
     return;
   }
+  // w is advected with the SCALAR orders (module_advect_em.F:4463-4464): its k-marching kernel (orders 5 / 3) needs dflt_s, not dflt_m
+  const bool fast_w = !weno_m && dflt_s && !c.pert_coriolis && !empty(in);
   if (weno_m) {
     LAUNCH3(this, k_tend_u_weno, tile, s, o("ru_tend"));
     LAUNCH3(this, k_tend_v_weno, tile, s, o("rv_tend"));
     LAUNCH3(this, k_tend_w_weno, tile, s, o("rw_tend"));
-  } else if (dflt_m && !c.pert_coriolis && !empty(in)) {
-    // momentum: k-marching kernels on the interior (mom_fast.cu), the gather kernels on the edge strips
-    for (int which = 0; which < 3; which++) launch_mom_fast(this, which, in);
-    for (int m = 0; m < ns; m++) {
-      LAUNCH3(this, k_tend_u, strips[m], s, o("ru_tend"));
-      LAUNCH3(this, k_tend_v, strips[m], s, o("rv_tend"));
-      LAUNCH3(this, k_tend_w, strips[m], s, o("rw_tend"));
-    }
   } else {
-    LAUNCH3(this, k_tend_u, tile, s, o("ru_tend"));
-    LAUNCH3(this, k_tend_v, tile, s, o("rv_tend"));
-    LAUNCH3(this, k_tend_w, tile, s, o("rw_tend"));
+    // momentum: k-marching kernels on the interior (mom_fast.cu), the gather kernels on the edge strips.  u and v follow the
+    // momentum orders, w the scalar ones (fast_w above)
+    if (dflt_m && !c.pert_coriolis && !empty(in)) {
+      for (int which = 0; which < 2; which++) launch_mom_fast(this, which, in);
+      for (int m = 0; m < ns; m++) {
+        LAUNCH3(this, k_tend_u, strips[m], s, o("ru_tend"));
+        LAUNCH3(this, k_tend_v, strips[m], s, o("rv_tend"));
+      }
+    } else {
+      LAUNCH3(this, k_tend_u, tile, s, o("ru_tend"));
+      LAUNCH3(this, k_tend_v, tile, s, o("rv_tend"));
+    }
+    if (fast_w) {
+      launch_mom_fast(this, 2, in);
+      for (int m = 0; m < ns; m++) LAUNCH3(this, k_tend_w, strips[m], s, o("rw_tend"));
+    } else {
+      LAUNCH3(this, k_tend_w, tile, s, o("rw_tend"));
+    }
   }
   if (weno_t) {   // theta follows the scalars' WENO option on the last substep: gather kernel on the whole tile
     LAUNCH3(this, k_tend_t_weno, tile, s, o("t_tend"));
@@ -1200,7 +1210,7 @@ void Solver::rk_tendency_main(int rk_step, bool zero_save) {
   }
   {   // cqw <- 1/(1+cqw): done by k_mom_w_fast on the interior, here on what is left of the mass points
     const Box cq{q.its, std::min(q.ite, q.ide - 1), 2, q.kde - 1, q.jts, std::min(q.jte, q.jde - 1)};
-    if (!weno_m && dflt_m && !c.pert_coriolis && !empty(in)) {
+    if (fast_w) {
       for (int m = 0; m < ns; m++) {
         Box sb = strips[m];
         sb.i1 = std::min(sb.i1, cq.i1); sb.j1 = std::min(sb.j1, cq.j1); sb.k0 = cq.k0; sb.k1 = cq.k1;
