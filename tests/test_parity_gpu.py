@@ -221,6 +221,7 @@ REJECTED = [
     ("h_sca_adv_order=4", dict(h_sca_adv_order=4)),
     ("mp_physics=2", dict(mp_physics=2)),
     ("conflicting bc", dict(periodic_x=1, open_xs=1)),
+    ("monotonic tke with h_sca_adv_order=6", dict(diff_opt=2, km_opt=2, tke_adv_opt=2, h_sca_adv_order=6)),   # wrf_error_fatal in the reference
     # specified / nested boundaries are built for all four sides and the non-WENO, non-monotonic, non-IEVA options
     ("specified with open sides", dict(specified=1, spec_bdy_width=5, spec_zone=1, relax_zone=4)),
     ("specified and nested", dict(specified=1, nested=1, open_xs=0, open_xe=0, open_ys=0, open_ye=0, spec_bdy_width=5, spec_zone=1, relax_zone=4)),

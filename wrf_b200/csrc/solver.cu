@@ -41,7 +41,8 @@ static void check_config(const wrfgpu_config &c) {
   if (c.rk_ord != 3 && c.rk_ord != 2) bad("rk_ord must be 2 or 3");
   if ((c.h_mom_adv_order != 5 && c.h_mom_adv_order != 6) || (c.h_sca_adv_order != 5 && c.h_sca_adv_order != 6)) bad("h_*_adv_order must be 5 or 6");
   if ((c.v_mom_adv_order != 3 && c.v_mom_adv_order != 4) || (c.v_sca_adv_order != 3 && c.v_sca_adv_order != 4)) bad("v_*_adv_order must be 3 or 4");
-  if ((c.moist_adv_opt == 2 || c.scalar_adv_opt == 2) && (c.h_sca_adv_order != 5 || c.v_sca_adv_order != 3))
+  // advect_scalar_mono has no other orders: the reference stops with "h_order not known" (module_advect_em.F), also for the tke
+  if ((c.moist_adv_opt == 2 || c.scalar_adv_opt == 2 || (c.km_opt == 2 && c.tke_adv_opt == 2)) && (c.h_sca_adv_order != 5 || c.v_sca_adv_order != 3))
     bad("monotonic advection (*_adv_opt = 2) needs h_sca_adv_order = 5 and v_sca_adv_order = 3");
   if (c.moist_adv_opt < 0 || c.moist_adv_opt > 4) bad("moist_adv_opt must be 0 (original), 1 (positive-definite), 2 (monotonic), 3 (WENO) or 4 (WENO, positive-definite)");
   if (c.scalar_adv_opt < 0 || c.scalar_adv_opt > 4) bad("scalar_adv_opt must be 0 ... 4");
