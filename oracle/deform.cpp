@@ -595,7 +595,7 @@ void smag_km(const Cx &x, A3 xkmh, A3 xkmv, A3 xkhh, A3 xkhv, A3 BN2, A3 defor11
     for (int k = kts; k <= ktf; k++)
       for (int i = i_start; i <= i_end; i++) {
         tmp = std::max(0.f, def2(i, k, j) - BN2(i, k, j) / pr);
-        tmp = std::sqrt(tmp);   // tmp**0.5
+        tmp = std::pow(tmp, 0.5f);   // tmp**0.5: gfortran calls powf unless -fno-signed-zeros; glibc's powf(x, .5) is not always sqrtf(x)
         if (cf.mix_isotropic == 0) {
           const float mlen_h = std::sqrt(dx / msftx(i, j) * dy / msfty(i, j));
           const float mlen_v = 1.f / rdzw(i, k, j);

@@ -107,7 +107,7 @@ void tke_km(const Cx &x, A3 xkmh, A3 xkmv, A3 xkhh, A3 xkhv, A3 BN2, A3 tke, A2 
           const float deltas = 1.0f / rdzw(i, k, j);
           float mlen_v = deltas;
           if (dthrdn(i, k, j) > 0.f) {
-            const float mlen_s = 0.76f * tmp / std::sqrt(std::fabs(g / theta(i, k, j) * dthrdn(i, k, j)));
+            const float mlen_s = 0.76f * tmp / std::pow(std::fabs(g / theta(i, k, j) * dthrdn(i, k, j)), 0.5f);   // (...)**0.5 = powf, see smag_km
             mlen_v = std::min(mlen_v, mlen_s);
           }
           xkmh(i, k, j) = std::max(c_k * tmp * mlen_h, 1.0E-6f * mlen_h * mlen_h);

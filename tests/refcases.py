@@ -67,6 +67,10 @@ CASES = {
                                                                        moist_adv_opt=0, **parity.SPEC)),
     "smag2d_b_wave": lambda: make_case("b_wave", nx=9, ny=13, nz=9, diff_opt=1, km_opt=4, kvdif=5.0),
     "diff2_b_wave": lambda: make_case("b_wave", nx=9, ny=13, nz=9, diff_opt=2, km_opt=4, isfflx=2, tke_heat_flux=0.02),
+    # a strong updraft under the 3-D Smagorinsky closure: two points where glibc's powf(x, 0.5) and sqrtf(x) differ (tmp**0.5 in smag_km)
+    "smag3d_pow": lambda: parity.with_updraft(make_case("quarter_ss", nx=12, ny=10, nz=17, diff_opt=2, km_opt=3, khdif=300.0, kvdif=50.0, use_theta_m=0,
+                                                        v_sca_adv_order=4, moist_adv_opt=3, momentum_adv_opt=3, damp_opt=0, rk_ord=2, zadvect_implicit=1,
+                                                        dt=40.0, time_step=40), 80.0),
     "les": lambda: parity.with_map_factors(make_case("les", **Q)),          # pert_coriolis, PD tracers, passive qv
     "diff6": lambda: make_case("quarter_ss", diff_6th_opt=2, **Q),
     "rain_open_mapfac": lambda: rainy(CASES["open_mapfac"]()),

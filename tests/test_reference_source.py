@@ -421,7 +421,7 @@ def diffusion_program(c):
     return prog
 
 
-DIFFUSION_CASES = ["smag2d_b_wave", "diff2_b_wave", "smag2d", "smag2d_hill", "diff2", "diff2_periodic", "diff2_hill", "smag3d", "smag3d_periodic", "tke", "tke_periodic", "tke_hill"]
+DIFFUSION_CASES = ["smag3d_pow", "smag2d_b_wave", "diff2_b_wave", "smag2d", "smag2d_hill", "diff2", "diff2_periodic", "diff2_hill", "smag3d", "smag3d_periodic", "tke", "tke_periodic", "tke_hill"]
 
 
 @pytest.mark.parametrize("name", DIFFUSION_CASES)

@@ -342,7 +342,7 @@ WG_HD void smag3d_point(const Geo &g, const Smag3In &s, int i, int k, int j, fp 
   tmp = 0.25f * (A3(defor23, i, k + 1, j) + A3(defor23, i, k, j) + A3(defor23, i, k + 1, j + 1) + A3(defor23, i, k, j + 1));
   def2 = def2 + tmp * tmp;
   tmp = fmaxf(0.f, def2 - BN2 / pr);
-  tmp = sqrtf(tmp);
+  tmp = wg_libm::powf_(tmp, 0.5f);   // tmp**0.5 (module_diffusion_em.F:1897, :1915) is powf for gfortran, and glibc's powf(x, .5) is not always sqrtf(x)
   const float c_s = s.c_s, mub = s.mix_upper_bound, dt = s.dt, dx = s.dx, dy = s.dy;
   const float rdzw = A3(s.rdzw, i, k, j), mtx = A2(g.msftx, i, j), mty = A2(g.msfty, i, j);
   float km_h, km_v, kh_h, kh_v;
@@ -443,7 +443,7 @@ WG_HD void tke_km_point(const Geo &g, const TkeIn &s, int i, int k, int j, fp bn
     const float deltas = 1.0f / A3(rdzw, i, k, j);
     float mlen_v = deltas;
     if (dthrdn > 0.f) {
-      const float mlen_s = 0.76f * tmp / sqrtf(fabsf(WG_G / theta_at(g, t, i, k, j) * dthrdn));
+      const float mlen_s = 0.76f * tmp / wg_libm::powf_(fabsf(WG_G / theta_at(g, t, i, k, j) * dthrdn), 0.5f);   // (...)**0.5 (:2212)
       mlen_v = fminf(mlen_v, mlen_s);
     }
     km_h = fmaxf(s.c_k * tmp * mlen_h, 1.0E-6f * mlen_h * mlen_h);
