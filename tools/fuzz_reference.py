@@ -39,6 +39,8 @@ for seed in range(seed0, seed0 + n):
     kw["pert_coriolis"] = R.choice([0, 1]); kw["rk_ord"] = R.choice([2, 3, 3]); kw["mix_full_fields"] = R.choice([0, 1])
     if R.random() < 0.2: kw["time_step"] = -12
     kw["epssm"] = R.choice([0.1, 0.3]); kw["smdiv"] = R.choice([0.1, 0.0]); kw["emdiv"] = R.choice([0.01, 0.0])
+    kw["hybrid_opt"] = R.choice([0, 2]); kw["time_step_sound"] = R.choice([2, 4, 6])
+    if base == "quarter_ss" and R.random() < 0.3: kw.update(mp_physics=0, num_moist=1)
     mode = R.choice(["plain", "spec", "nest", "ieva", "tke"]) if len(sys.argv) > 3 else "plain"
     wrap = []
     if mode in ("spec", "nest") and base in ("quarter_ss",):
@@ -89,6 +91,21 @@ for seed in range(seed0, seed0 + n):
         go("small_step_finish", rk, [("calc_mu_uv_1", 0), ("small_step_finish", 0)])
         if c.num_moist + c.num_scalar:
             go("rk_scalar_step", rk, scalar_program(c, rk, set(case.fields)), not_compared=["h_tendency", "z_tendency", "xkmh", "xkmv", "xkhh", "xkhv"])
+    if c.mp_physics == 1 and not (c.specified or c.nested):
+        from tests.refcases import rainy
+        import copy
+        d = case.dims
+        tile = dict(its=d.ips, ite=min(d.ipe, d.ide - 1), jts=d.jps, jte=min(d.jpe, d.jde - 1))
+        alias = {"moist(ims,kms,jms,p_qv)": "moist_qv", "moist(ims,kms,jms,p_qc)": "moist_qc"}
+        kess = {"t": "th_phy", "qv": "moist_qv", "qc": "moist_qc", "qr": "moist_qr", "pii": "pi_phy", "dt_in": "dt", "xlv": "xlv", "cp": "cp",
+                "ep2": "ep_2", "kte": d.kde - 1}
+        f32 = np.float32
+        keep = case
+        case = rainy(copy.deepcopy(case)); case.refname = keep.refname
+        go("microphysics", None, [("moist_physics_prep_em", 0, {"alias": alias, "scalars": {"dtm": f32(c.dt), **tile}}),
+                                   ("kessler", 0, {"actuals": kess, "scalars": tile}),
+                                   ("moist_physics_finish_em", 0, {"alias": alias, "scalars": {"dtm": f32(c.dt), **tile}})])
+        case = keep
     go("calc_p_rho_phi", None, [("calc_p_rho_phi", 0)], occurrence=1)
     go("end_of_step", None, final_program(c, set(case.fields)))
     print(seed, base, mode, "OK" if not bad else "DIFF", round(time.time() - t0, 1), {k: v for k, v in kw.items() if k not in ("bubble_lattice", "noise")} if bad else "", flush=True)
