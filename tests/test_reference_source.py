@@ -466,3 +466,38 @@ def test_feeder_harness(adv_opt):
         have[str(adv_opt)] = {str(k): v for k, v in ref.items()}
         have["generator"] = "REFSRC_FEEDER=1 python -m pytest tests/test_reference_source.py -k feeder_harness"
         json.dump(have, open(FEEDER_GOLDEN, "w"), separators=(",", ":"), sort_keys=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the boundary fills solve_em.F makes around the acoustic loop, each taken from its own CALL in solve_em.F (a fill the oracle makes that
+# solve_em.F does not have would not be found there), whole arrays compared
+
+def fills(pairs):
+    return [("set_physical_bc%dd" % rank, f"grid%{name},'{var}'") for name, var, rank in pairs]
+
+
+@pytest.mark.parametrize("name", ["open_mapfac", "periodic_mapfac", "b_wave_lid", "rk2_sym_x", "hill"])
+def test_fills_after_small_step_prep(name):
+    """solve_em.F:1180-1260"""
+    prog = [("small_step_prep", 0), ("calc_p_rho", 0), ("calc_coef_w", 0)] + fills(
+        [("ru_tend", "u", 3), ("rv_tend", "v", 3), ("ph_2", "w", 3), ("al", "p", 3), ("p", "p", 3), ("t_1", "p", 3), ("t_save", "t", 3),
+         ("mu_1", "t", 2), ("mu_2", "t", 2), ("mudf", "t", 2)])
+    n, *_ = run(build(name), "small_step_prep", 2, prog, whole=True)
+    assert n >= 40
+
+
+@pytest.mark.parametrize("name", ["open_mapfac", "periodic_mapfac", "b_wave_lid", "rk2_sym_x", "hill"])
+def test_fills_inside_the_acoustic_loop(name):
+    """solve_em.F:1660-1720"""
+    prog = [("calc_p_rho", 1)] + fills([("ph_2", "w", 3), ("al", "p", 3), ("p", "p", 3), ("muts", "t", 2), ("mu_2", "t", 2), ("mudf", "t", 2)])
+    n, *_ = run(build(name), "calc_p_rho", None, prog, occurrence=2, extra={"iteration": 2}, whole=True)
+    assert n >= 10
+
+
+@pytest.mark.parametrize("name", ["open_mapfac", "periodic_mapfac", "b_wave_lid", "hill"])
+def test_fills_after_the_last_small_step(name):
+    """solve_em.F:1800-1850: ru_m, rv_m, ww_m, mut, muts for the scalar step"""
+    case = build(name)
+    prog = [("calc_mu_uv_1", 0), ("small_step_finish", 0)] + fills([("ru_m", "u", 3), ("rv_m", "v", 3), ("ww_m", "w", 3), ("mut", "t", 2), ("muts", "t", 2)])
+    n, *_ = run(case, "small_step_finish", case.config.rk_ord, prog, whole=True)
+    assert n >= 30
