@@ -501,3 +501,46 @@ def test_fills_after_the_last_small_step(name):
     prog = [("calc_mu_uv_1", 0), ("small_step_finish", 0)] + fills([("ru_m", "u", 3), ("rv_m", "v", 3), ("ww_m", "w", 3), ("mut", "t", 2), ("muts", "t", 2)])
     n, *_ = run(case, "small_step_finish", case.config.rk_ord, prog, whole=True)
     assert n >= 30
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tiles: the reference's routines given ONE tile of the domain (grid%i_start(ij) ..., an interior tile and one on the domain edge) against
+# the oracle's whole-domain phase on that tile's points -- the loop-range logic that depends on where a tile lies (its > ids + 3 switches the
+# boundary treatment off, ...), which is what a patch of a decomposed run exercises
+
+@pytest.mark.parametrize("tile", [(5, 9, 4, 8), (1, 4, 1, 10), (8, 12, 6, 10)], ids=["interior", "west", "north-east"])
+@pytest.mark.parametrize("name,phase,rk", [("open_mapfac", "rk_tendency", 1), ("open_mapfac", "rk_tendency", 3), ("periodic_mapfac", "rk_tendency", 3),
+                                           ("order64", "rk_tendency", 3), ("weno", "rk_tendency", 3), ("open_mapfac", "advance_uv", 3),
+                                           ("open_mapfac", "advance_mu_t", 3), ("open_mapfac", "advance_w", 3), ("periodic_mapfac", "advance_uv", 3),
+                                           ("open_mapfac", "rk_scalar_step", 1), ("periodic_mapfac", "rk_scalar_step", 1)])
+def test_one_tile_of_the_reference(name, phase, rk, tile):
+    case = build(name)
+    d, c = case.dims, case.config
+    if phase == "rk_tendency":
+        prog = [p for p in tendency_program(c, rk)[0] if p[0] not in ("isotropic_km", "set_physical_bc3d")]
+    elif phase == "rk_scalar_step":
+        prog = [p for p in scalar_program(c, rk, set(case.fields)) if p[0] not in ("isotropic_km", "set_physical_bc3d")]
+    else:
+        prog = [(phase, 0)]
+    o, args = at_phase(case, phase, rk)
+    st = refrun.RefState(o)
+    scal = rk_scalars(c, rk)
+    i0, i1, j0, j1 = tile
+    scal.update(rk_step=rk, rk_order=c.rk_ord, iteration=1)
+    scal.update({"grid%i_start(ij)": i0, "grid%i_end(ij)": i1, "grid%j_start(ij)": j0, "grid%j_end(ij)": j1})
+    for step in prog:
+        opts = step[2] if len(step) > 2 else {}
+        refrun.RefCall(step[0], step[1], opts.get("path", "dyn_em/solve_em.F"), opts.get("alias"), opts.get("actuals")).run(
+            st, **{**scal, **opts.get("scalars", {})})
+    before = {k: np.asarray(o.get(k)).copy() for k in st.fields if k not in st.absent}
+    o.call(phase, *args)
+    sl = (slice(j0 - d.jms, j1 - d.jms + 1), Ellipsis, slice(i0 - d.ims, i1 - d.ims + 1))
+    bad, changed = [], 0
+    for k in sorted(before):
+        a, b = st.result(k), np.asarray(o.get(k))
+        if a.ndim < 2:
+            continue
+        changed += not np.array_equal(a[sl], before[k][sl], equal_nan=True)
+        if np.count_nonzero(~((a[sl] == b[sl]) | (np.isnan(a[sl]) & np.isnan(b[sl])))):
+            bad.append(k)
+    assert not bad and changed > 0, (bad, changed)
