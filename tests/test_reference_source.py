@@ -33,6 +33,10 @@ RECORD = [] if os.environ.get("REFSRC_WRITE") == "1" else None
 # out the combinations that repeat a code path already run (rk_tendency at the middle Runge-Kutta stage, and at the last stage for the
 # configurations whose last stage has nothing of its own), which the fixture replay of test_reference_source_golden.py still covers.
 FULL = RECORD is not None or os.environ.get("REFSRC_FULL") == "1"
+# the configurations of the default run: one per code path family (the others repeat paths with other boundary types or sizes)
+CORE = {"small", "open_mapfac", "periodic_mapfac", "b_wave_lid", "rk2_sym_x", "hill", "diffusion_periodic", "order_mixed", "weno", "backward",
+        "ieva", "ieva_wdamp", "specified", "nested", "smag2d", "diff2_hill", "smag3d_pow", "tke", "tke_periodic", "les", "mono", "wenopd",
+        "diff6_hill", "rk2_everything", "rain_open_mapfac"}
 LAST_STAGE_DIFFERS = {"rk2_everything", "order_mixed", "weno", "backward", "ieva", "ieva_wdamp", "wenopd", "wenopd_periodic", "rk2_sym_x", "specified", "open_mapfac",
                       "periodic_mapfac", "smag2d", "tke", "les"}
 
@@ -138,7 +142,7 @@ def tendency_program(c, rk):
 @pytest.mark.parametrize("name", sorted(CASES))
 @pytest.mark.parametrize("rk", [1, 2, 3])
 def test_rk_tendency(name, rk):
-    if not FULL and (rk == 2 or (rk == 3 and name not in LAST_STAGE_DIFFERS)):
+    if not FULL and (name not in CORE or rk == 2 or (rk == 3 and name not in LAST_STAGE_DIFFERS)):
         pytest.skip("REFSRC_FULL=1 runs it; its digests are in the fixture")
     case = build(name)
     if rk > case.config.rk_ord:
@@ -300,6 +304,8 @@ SCALAR_CASES = ["diffusion_periodic", "diff6_periodic", "rk2_everything", "speci
 @pytest.mark.parametrize("name", SCALAR_CASES)
 @pytest.mark.parametrize("rk", [1, 3])
 def test_rk_scalar_step(name, rk):
+    if not FULL and name not in CORE:
+        pytest.skip("REFSRC_FULL=1 runs it; its digests are in the fixture")
     case = build(name)
     c = case.config
     rk = min(rk, c.rk_ord)
@@ -426,6 +432,8 @@ DIFFUSION_CASES = ["smag3d_pow", "smag2d_b_wave", "diff2_b_wave", "smag2d", "sma
 
 @pytest.mark.parametrize("name", DIFFUSION_CASES)
 def test_diffusion_prep(name):
+    if not FULL and name not in CORE:
+        pytest.skip("REFSRC_FULL=1 runs it; its digests are in the fixture")
     case = build(name)
     c = case.config
     # phy_prep's outputs the closures of this configuration never read are not materialised by the oracle (nor by the device)
@@ -451,7 +459,7 @@ FEEDER_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "feeder_column
 def test_feeder_harness(adv_opt):
     from tests.feeder_ref import Feeder
     write = os.environ.get("REFSRC_FEEDER") == "1"         # REFSRC_FEEDER=1: the program's first output file, 000200.txt (10 minutes)
-    marks = (100, 200) if write else (4,)
+    marks = (100, 200) if write else (2,)
     F = Feeder(adv_opt)
     ref = {}
     for n in range(1, marks[-1] + 1):
