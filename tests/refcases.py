@@ -71,6 +71,10 @@ CASES = {
     "smag3d_pow": lambda: parity.with_updraft(make_case("quarter_ss", nx=12, ny=10, nz=17, diff_opt=2, km_opt=3, khdif=300.0, kvdif=50.0, use_theta_m=0,
                                                         v_sca_adv_order=4, moist_adv_opt=3, momentum_adv_opt=3, damp_opt=0, rk_ord=2, zadvect_implicit=1,
                                                         dt=40.0, time_step=40), 80.0),
+    # momentum and scalar orders apart, on a domain with a non-empty interior box: w (scalar orders) through its k-marching kernel next to
+    # u, v through the gather kernels, and the other way round
+    "w_fast_uv_gather": lambda: parity.with_map_factors(parity.with_updraft(make_case("quarter_ss", nx=20, ny=18, nz=9, h_mom_adv_order=6), 15.0)),
+    "uv_fast_w_gather": lambda: parity.with_map_factors(parity.with_updraft(make_case("quarter_ss", nx=20, ny=18, nz=9, h_sca_adv_order=6, v_sca_adv_order=4), 15.0)),
     "les": lambda: parity.with_map_factors(make_case("les", **Q)),          # pert_coriolis, PD tracers, passive qv
     "diff6": lambda: make_case("quarter_ss", diff_6th_opt=2, **Q),
     "rain_open_mapfac": lambda: rainy(CASES["open_mapfac"]()),
