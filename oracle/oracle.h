@@ -9,7 +9,7 @@
 // could not be diffed against wrf.exe.  It is pinned instead to the reference's
 // own routines EXECUTED FROM THEIR SOURCE (tests/fortran_subset.py translates
 // them with real*4 semantics; tests/test_reference_source.py compares every phase
-// of the step bit for bit over 47 configurations; the resulting digests travel as
+// of the step bit for bit over 49 configurations; the resulting digests travel as
 // tests/golden/reference_source.json).  It follows the reference routine by
 // routine (file:line cited on each function), in real*4, Fortran evaluation
 // order, compiled with -ffp-contract=off like the GNU stanza of
