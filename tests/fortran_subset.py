@@ -5,12 +5,28 @@ never copied) becomes a Python function that executes the same statements in the
 every REAL operation is one numpy float32 operation (round to nearest, no contraction: what gfortran -O2 emits for
 x86-64 without -ffast-math), INTEGER arithmetic is exact with Fortran's truncating division, x**n is the multiply
 sequence of __powisf2, transcendental intrinsics go to the host libm's float routines (cosf, atanf, powf, ...), which is
-what gfortran links.  The result is the reference's routine run on inputs of our choosing: tests/golden/
-make_reference_vectors.py stores such input / output pairs, tests/test_reference_vectors.py holds the oracle to them.
+what gfortran links.  The result is the reference's routine run on inputs of our choosing: tests/test_reference_source.py,
+test_reference_init.py and test_reference_bdy_host.py compare such runs with the oracle, with wrf_b200/shipped.py and with
+wrf_b200/bdy.py bit for bit, and tests/golden/reference_source.json, feeder_columns.json, shipped_init.json keep digests of what
+the reference produced for the machines that have no reference tree.
 
-Subset: IMPLICIT NONE routines with REAL / INTEGER / LOGICAL scalars and explicit-shape arrays, TYPE(...) arguments read
-through `%`, PARAMETERs, statement functions, assignment, DO / END DO (named or not, with CYCLE / EXIT), block and one-line
-IF, RETURN, cpp conditionals.  Anything else raises NotImplementedError when the routine is translated.
+Subset (whatever the ~120 routines of the path use; anything else raises NotImplementedError when a routine is translated):
+  declarations  REAL / INTEGER / LOGICAL / DOUBLE PRECISION / REAL(KIND=8), old style without `::`, PARAMETER attribute and statement,
+                initialised (SAVEd) locals, OPTIONAL, CHARACTER, implicit typing where IMPLICIT NONE is missing, declarations after
+                statement functions, TYPE(...) dummies and locals
+  statements    assignment (elements, whole arrays, a(:,:,:) = scalar), statement functions, DO / DO WHILE / END DO (named or not,
+                CYCLE / EXIT), block and one-line IF, SELECT CASE (values, ranges, DEFAULT), RETURN, `;`, WRITE / PRINT as no-ops,
+                CALL with positional, keyword and OPTIONAL arguments, scalars copied back, arrays by reference
+  association   an element as the start of a slab (moist(ims,kms,jms,im) -> a 3-D view), rank-changing dummies (2-D mu through
+                (ims:ime, 1:1, jms:jme)), the VPOW vector call of frame/libmassv.F
+  expressions   Fortran precedence and typing rules, mixed real*4 / real*8 / integer promotion, .EQV. / .NEQV., intrinsics
+                (MAX, MIN, ABS, SIGN, MOD, DIM, INT, NINT, REAL, SNGL, DBLE, ICHAR, CHAR, TRIM, PRESENT, the libm set)
+  program units internal FUNCTIONs, callees translated on first use (Library), Python hooks for what lies outside the subset (namelist
+                getters, message routines, file readers), module PARAMETERs and module variables, derived-type objects with array
+                components (grid%u_2(i,k,j), model_config_rec%...), a line range of a larger routine wrapped as a routine of its own
+                (Library.add_fragment), declarations standing in for a build-time #include (Library.inject), cpp conditionals
+One limitation to know about: the source is folded to lower case including character literals ('W' reads 'w'); callers pass
+character arguments in lower case.
 """
 from __future__ import annotations
 
