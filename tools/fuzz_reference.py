@@ -4,7 +4,7 @@ hypsometric option, Coriolis form, RK order, sign of time_step, acoustic coeffic
 boundaries, IEVA and the TKE closure), and every phase of a step is run from the reference's Fortran and from the oracle on the same state;
 any field that differs in a single bit is reported.  Build-container tool (needs /root/reference):
 
-    python tools/fuzz_reference.py <first seed> <count> [x]
+    python tools/fuzz_reference.py <first seed> <count> [x [bdy]]
 
 Equal or default values hide shared transliteration slips (w advected with the momentum orders went unnoticed as long as every case had
 h_mom = h_sca); drawing the options independently is what finds them.  Known, explained reports: IEVA with periodic boundaries (the
@@ -43,6 +43,9 @@ for seed in range(seed0, seed0 + n):
     if base == "quarter_ss" and R.random() < 0.3: kw.update(mp_physics=0, num_moist=1)
     mode = R.choice(["plain", "spec", "nest", "ieva", "tke"]) if len(sys.argv) > 3 else "plain"
     wrap = []
+    if len(sys.argv) > 4 and sys.argv[4] == "bdy":          # every seed a specified / nested configuration
+        mode, base, dims = R.choice(["spec", "nest"]), "quarter_ss", dict(nx=16, ny=14, nz=9)
+        kw.pop("bubble_lattice", None); kw.pop("noise", None); kw.pop("num_scalar", None)
     if mode in ("spec", "nest") and base in ("quarter_ss",):
         dims = dict(nx=16, ny=14, nz=9)
         kw.update(parity.SPEC); kw["specified" if mode == "spec" else "nested"] = 1
