@@ -219,8 +219,9 @@ def shipped_fields(case):
 @pytest.mark.parametrize("name", ["em_quarter_ss", "em_hill2d_x", "em_les", "em_b_wave"])
 def test_initial_state(name):
     write = os.environ.get("REFSRC_WRITE") == "1"
-    if name != "em_hill2d_x" and not (write or os.environ.get("REFSRC_FULL") == "1"):
-        pytest.skip("64 000 - 216 000 points take 25 s - over a minute through the translator: REFSRC_FULL=1 (the digests are in tests/golden/shipped_init.json)")
+    if not (write or os.environ.get("REFSRC_FULL") == "1"):
+        pytest.skip("25 000 - 216 000 points take 20 s - over a minute through the translator: REFSRC_FULL=1 runs it; the digests of what the "
+                    "reference produced are in tests/golden/shipped_init.json and checked by test_reference_source_golden.py")
     g, qv, c, d = reference_initial_state(name)
     ref = reference_fields(g, qv, d)
     case = shipped.init_domain(os.path.join(FIX, name))

@@ -34,9 +34,8 @@ RECORD = [] if os.environ.get("REFSRC_WRITE") == "1" else None
 # configurations whose last stage has nothing of its own), which the fixture replay of test_reference_source_golden.py still covers.
 FULL = RECORD is not None or os.environ.get("REFSRC_FULL") == "1"
 # the configurations of the default run: one per code path family (the others repeat paths with other boundary types or sizes)
-CORE = {"w_fast_uv_gather", "uv_fast_w_gather", "small", "open_mapfac", "periodic_mapfac", "b_wave_lid", "rk2_sym_x", "hill", "diffusion_periodic", "order_mixed", "weno", "backward",
-        "ieva", "ieva_wdamp", "specified", "nested", "smag2d", "diff2_hill", "smag3d_pow", "tke", "tke_periodic", "les", "mono", "wenopd",
-        "diff6_hill", "rk2_everything", "rain_open_mapfac"}
+CORE = {"w_fast_uv_gather", "uv_fast_w_gather", "open_mapfac", "periodic_mapfac", "b_wave_lid", "rk2_sym_x", "hill", "diffusion_periodic", "order_mixed",
+        "weno", "ieva_wdamp", "specified", "nested", "smag2d", "smag3d_pow", "tke_periodic", "les", "mono", "wenopd", "diff6_hill", "rk2_everything"}
 LAST_STAGE_DIFFERS = {"w_fast_uv_gather", "uv_fast_w_gather", "rk2_everything", "order_mixed", "weno", "backward", "ieva", "ieva_wdamp", "wenopd", "wenopd_periodic", "rk2_sym_x", "specified", "open_mapfac",
                       "periodic_mapfac", "smag2d", "tke", "les"}
 
